@@ -1,0 +1,736 @@
+// fpb_api.cu -- host side of the C ABI declared in include/fpb.h.
+//
+// Owns all device memory (met replica, particle SoA, grids), packs the
+// Fortran-layout met arrays into the device layout, replays the reference's
+// ran3 draw order in validation mode and launches the kernels of
+// fpb_kernels.cu / fpb_scatter.cu on one CUDA stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fpb_device.cuh"
+#include "fpb_scatter.cuh"
+
+// ------------------------------------------------------------ error state --
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),     \
+                  __FILE__, __LINE__);                                        \
+  } while (0)
+
+// ------------------------------------------------- host RNG (random_mod) --
+// Knuth's subtractive generator as published in Numerical Recipes ("ran3"),
+// which is what src/random_mod.f90:93-139 uses; needed on the host to fill
+// rannumb (src/FLEXPART.f90:56-59) and to replay the per-call table index
+// `nrand=int(ran3(idummy)*real(maxrand-1))+1` (src/advance.f90:153,
+// src/initialize.f90:68) in the reference's particle order.
+struct Ran3 {
+  int ma[56];
+  int inext = 0, inextp = 0;
+  bool seeded = false;
+  void seed(int idum) {
+    const int MBIG = 1000000000, MSEED = 161803398;
+    int mj = (MSEED - abs(idum)) % MBIG, mk = 1;
+    ma[55] = mj;
+    for (int i = 1; i <= 54; i++) {
+      int ii = (21 * i) % 55;
+      ma[ii] = mk;
+      mk = mj - mk;
+      if (mk < 0) mk += MBIG;
+      mj = ma[ii];
+    }
+    for (int k = 0; k < 4; k++)
+      for (int i = 1; i <= 55; i++) {
+        ma[i] -= ma[1 + (i + 30) % 55];
+        if (ma[i] < 0) ma[i] += MBIG;
+      }
+    inext = 0;
+    inextp = 31;
+    seeded = true;
+  }
+  // idum < 0 (or first use) re-seeds, then idum := 1
+  float next(int &idum) {
+    if (idum < 0 || !seeded) {
+      seed(idum);
+      idum = 1;
+    }
+    if (++inext == 56) inext = 1;
+    if (++inextp == 56) inextp = 1;
+    int mj = ma[inext] - ma[inextp];
+    if (mj < 0) mj += 1000000000;
+    ma[inext] = mj;
+    return (float)mj * (1.f / 1000000000.f);
+  }
+};
+
+// polar Box-Muller pair clipped to [-3,3]: src/random_mod.f90:70-90
+static void gasdev1(Ran3 &g, int &idum, float &r1, float &r2) {
+  float v1, v2, r;
+  do {
+    v1 = 2.f * g.next(idum) - 1.f;
+    v2 = 2.f * g.next(idum) - 1.f;
+    r = v1 * v1 + v2 * v2;
+  } while (r >= 1.0f || r == 0.0f);
+  // log evaluated in double and rounded once: the convention of the kernels'
+  // strict mode and of the oracle
+  float fac = sqrtf(-2.f * (float)log((double)r) / r);
+  r1 = std::min(3.f, std::max(-3.f, v1 * fac));
+  r2 = std::min(3.f, std::max(-3.f, v2 * fac));
+}
+
+// ------------------------------------------------------------------ handle --
+struct fpb_handle {
+  fpb_config cfg;
+  std::vector<float> height, xmass;
+  std::vector<int32_t> npart;
+  DevCfg d;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  // met: index = Fortran slot - 1
+  float4 *A[2] = {nullptr, nullptr}, *B[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
+  float *trop[2] = {nullptr, nullptr}, *vdep[2] = {nullptr, nullptr};
+  float *stage = nullptr;
+  size_t stage_n = 0;
+  int memind[2] = {1, 2}, memtime[2] = {0, 0}, lwindinterv = 1;
+  bool have_bracket = false;
+
+  DevParticles p{};
+  int numpart = 0;
+
+  float *d_height = nullptr, *d_xmass = nullptr;
+  int32_t *d_npart = nullptr;
+
+  float *d_rannumb = nullptr;
+  int maxrand = 0;
+  Ran3 ran3;
+  int idummy_init = -7, idummy_adv = -7; // SAVEd locals, src/advance.f90:120, src/initialize.f90:64
+  int32_t *d_nrand_init = nullptr, *d_nrand_adv = nullptr;
+  std::vector<int32_t> h_itra1, h_itramem, h_nrand_init, h_nrand_adv;
+
+  float *gridunc = nullptr, *griduncn = nullptr, *drygridunc = nullptr, *drygriduncn = nullptr;
+  float *creceptor = nullptr, *crec_acc = nullptr;
+  size_t n_grid = 0, n_gridn = 0, n_dry = 0, n_dryn = 0, n_rec = 0;
+
+  unsigned long long *d_stats = nullptr;
+  int64_t launches = 0;
+  ScatterWork scatter;
+};
+
+static void fill_devcfg(fpb_handle *h) {
+  const fpb_config &c = h->cfg;
+  DevCfg &d = h->d;
+  memset(&d, 0, sizeof d);
+  d.nx = c.nx; d.ny = c.ny; d.nz = c.nz;
+  d.nxd = c.nx;
+  d.nyd = (c.ny < c.nymax) ? c.ny + 1 : c.ny; // keep the row the reference's jyp can touch
+  d.nymax = c.nymax;
+  d.nxmin1 = c.nxmin1; d.nymin1 = c.nymin1;
+  d.dx = c.dx; d.dy = c.dy; d.xlon0 = c.xlon0; d.ylat0 = c.ylat0;
+  d.dxconst = c.dxconst; d.dyconst = c.dyconst;
+  d.xglobal = c.xglobal; d.nglobal = c.nglobal; d.sglobal = c.sglobal;
+  d.switchnorthg = c.switchnorthg; d.switchsouthg = c.switchsouthg;
+  memcpy(d.northpolemap, c.northpolemap, sizeof d.northpolemap);
+  memcpy(d.southpolemap, c.southpolemap, sizeof d.southpolemap);
+  d.eps = c.eps;
+  d.ldirect = c.ldirect; d.lsynctime = c.lsynctime; d.method = c.method;
+  d.mintime = c.mintime; d.ifine = c.ifine;
+  d.turbswitch = c.turbswitch; d.cblflag = c.cblflag; d.mdomainfill = c.mdomainfill;
+  d.mquasilag = c.mquasilag; d.lsettling = c.lsettling; d.turboff = c.turboff;
+  d.ctl = c.ctl; d.fine = c.fine; d.d_trop = c.d_trop; d.d_strat = c.d_strat;
+  d.turbmesoscale = c.turbmesoscale;
+  d.ind_samp = c.ind_samp; d.ioutputforeachrelease = c.ioutputforeachrelease;
+  d.lusekerneloutput = c.lusekerneloutput; d.lparticlecountoutput = c.lparticlecountoutput;
+  d.drydep = c.drydep; d.drybkdep = c.drybkdep; d.wetbkdep = c.wetbkdep;
+  d.nested_output = c.nested_output;
+  d.nspec = c.nspec;
+  for (int k = 0; k < FPB_MAXSPEC; k++) {
+    d.decay[k] = c.decay[k]; d.drydepspec[k] = c.drydepspec[k]; d.density[k] = c.density[k];
+    d.dquer[k] = c.dquer[k]; d.vsetaver[k] = c.vsetaver[k]; d.cunningham[k] = c.cunningham[k];
+  }
+  d.nageclass = c.nageclass;
+  for (int k = 0; k < FPB_MAXAGECLASS; k++) d.lage[k] = c.lage[k];
+  d.numxgrid = c.numxgrid; d.numygrid = c.numygrid; d.numzgrid = c.numzgrid;
+  d.dxout = c.dxout; d.dyout = c.dyout; d.xoutshift = c.xoutshift; d.youtshift = c.youtshift;
+  for (int k = 0; k < FPB_MAXZGRID; k++) d.outheight[k] = c.outheight[k];
+  d.numxgridn = c.numxgridn; d.numygridn = c.numygridn;
+  d.dxoutn = c.dxoutn; d.dyoutn = c.dyoutn; d.xoutshiftn = c.xoutshiftn; d.youtshiftn = c.youtshiftn;
+  d.maxpointspec_act = c.maxpointspec_act; d.nclassunc = c.nclassunc; d.maxageclass = c.maxageclass;
+  d.numreceptor = c.numreceptor;
+  for (int k = 0; k < FPB_MAXRECEPTOR; k++) {
+    d.xreceptor[k] = c.xreceptor[k]; d.yreceptor[k] = c.yreceptor[k]; d.receptorarea[k] = c.receptorarea[k];
+  }
+  d.numpoint = c.numpoint;
+  d.rng_mode = c.rng_mode;
+  d.seed = c.seed;
+  d.part_id_stride = c.part_id_stride ? c.part_id_stride : 1;
+  d.part_id_offset = c.part_id_offset;
+}
+
+// -------------------------------------------------------------- utilities --
+extern "C" const char *fpb_last_error(void) { return g_err.c_str(); }
+extern "C" int fpb_abi_version(void) { return FPB_ABI_VERSION; }
+extern "C" size_t fpb_config_sizeof(void) { return sizeof(fpb_config); }
+
+template <typename T>
+static int dalloc(T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void **)p, n * sizeof(T)));
+  CK(cudaMemset(*p, 0, n * sizeof(T)));
+  return 0;
+}
+#define DA(ptr, n)                      \
+  do {                                  \
+    if (dalloc(&(ptr), (n))) return 1;  \
+  } while (0)
+
+__global__ void fill_i32_kernel(int32_t *p, int32_t v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// dst[(k*nyd + jy)*nxd + ix].comp = src[(k*nymax + jy)*nxmax + ix]
+__global__ void pack_component_kernel(float *dst, int comp, int ncomp, const float *src,
+                                      int nxd, int nyd, int nk, int nxmax, int nymax) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)nxd * nyd * nk;
+  if (i >= n) return;
+  int ix = (int)(i % nxd);
+  size_t r = i / nxd;
+  int jy = (int)(r % nyd), k = (int)(r / nyd);
+  dst[i * ncomp + comp] = src[((size_t)k * nymax + jy) * nxmax + ix];
+}
+
+static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk) {
+  const fpb_config &c = h->cfg;
+  const DevCfg &d = h->d;
+  size_t nsrc = (size_t)c.nxmax * c.nymax * nk;
+  if (nsrc > h->stage_n) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    CK(cudaMalloc((void **)&h->stage, nsrc * sizeof(float)));
+    h->stage_n = nsrc;
+  }
+  size_t n = (size_t)d.nxd * d.nyd * nk;
+  if (src) {
+    CK(cudaMemcpyAsync(h->stage, src, nsrc * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CK(cudaMemsetAsync(h->stage, 0, nsrc * sizeof(float), h->stream));
+  }
+  pack_component_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+      dst, comp, ncomp, h->stage, d.nxd, d.nyd, nk, c.nxmax, c.nymax);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream)); // the caller may reuse its array
+  return 0;
+}
+
+// ------------------------------------------------------------------- init --
+extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
+  if (!cfg || !out) return fail("fpb_init: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != FPB_ABI_VERSION)
+    return fail("fpb_init: abi_version %d != %d", cfg->abi_version, FPB_ABI_VERSION);
+  if (cfg->nz > FPB_MAXNZ || cfg->nz < 2) return fail("fpb_init: nz=%d out of range (max %d)", cfg->nz, FPB_MAXNZ);
+  if (cfg->nspec < 1 || cfg->nspec > FPB_MAXSPEC) return fail("fpb_init: nspec=%d out of range", cfg->nspec);
+  if (cfg->nageclass < 1 || cfg->nageclass > FPB_MAXAGECLASS) return fail("fpb_init: nageclass out of range");
+  if (cfg->numzgrid < 1 || cfg->numzgrid > FPB_MAXZGRID) return fail("fpb_init: numzgrid out of range");
+  if (cfg->numreceptor < 0 || cfg->numreceptor > FPB_MAXRECEPTOR) return fail("fpb_init: numreceptor out of range");
+  if (!cfg->height) return fail("fpb_init: height is null");
+  if (cfg->maxpart < 1) return fail("fpb_init: maxpart < 1");
+  if (cfg->numpoint < 1 || !cfg->npart || !cfg->xmass) return fail("fpb_init: releases (numpoint/npart/xmass) missing");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("fpb_init: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("fpb_init: device %d not present", cfg->device);
+
+  fpb_handle *h = new fpb_handle();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  h->height.assign(cfg->height, cfg->height + cfg->nz);
+  h->npart.assign(cfg->npart, cfg->npart + cfg->numpoint);
+  // device xmass is packed [nspec][numpoint]
+  h->xmass.resize((size_t)cfg->nspec * cfg->numpoint);
+  for (int k = 0; k < cfg->nspec; k++)
+    for (int i = 0; i < cfg->numpoint; i++)
+      h->xmass[(size_t)k * cfg->numpoint + i] = cfg->xmass[i + (size_t)cfg->numpoint * k];
+  h->cfg.height = nullptr; h->cfg.npart = nullptr; h->cfg.xmass = nullptr;
+  fill_devcfg(h);
+  const DevCfg &d = h->d;
+  const fpb_config &c = h->cfg;
+
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  const size_t n3 = (size_t)d.nxd * d.nyd * c.nz, n2 = (size_t)d.nxd * d.nyd;
+  for (int s = 0; s < 2; s++) {
+    DA(h->A[s], n3); DA(h->B[s], n3); DA(h->S[s], n2);
+    DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
+  }
+  const size_t mp = (size_t)c.maxpart;
+  DA(h->p.xtra1, mp); DA(h->p.ytra1, mp); DA(h->p.ztra1, mp);
+  DA(h->p.itra1, mp); DA(h->p.npoint, mp); DA(h->p.nclass, mp); DA(h->p.idt, mp);
+  DA(h->p.itramem, mp); DA(h->p.itrasplit, mp);
+  DA(h->p.uap, mp); DA(h->p.ucp, mp); DA(h->p.uzp, mp);
+  DA(h->p.us, mp); DA(h->p.vs, mp); DA(h->p.ws, mp); DA(h->p.cbt, mp);
+  DA(h->p.xmass1, mp * c.nspec);
+  DA(h->p.xscav_frac1, mp * c.nspec);
+  h->p.maxpart = c.maxpart;
+  // itra1(:) = -999999999, src/FLEXPART.f90:315-317
+  fill_i32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
+  h->launches++;
+
+  DA(h->d_height, c.nz); DA(h->d_npart, c.numpoint); DA(h->d_xmass, h->xmass.size());
+  CK(cudaMemcpy(h->d_height, h->height.data(), c.nz * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_npart, h->npart.data(), c.numpoint * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_xmass, h->xmass.data(), h->xmass.size() * sizeof(float), cudaMemcpyHostToDevice));
+  DA(h->d_nrand_init, mp); DA(h->d_nrand_adv, mp);
+
+  const size_t outer = (size_t)c.nspec * c.maxpointspec_act * c.nclassunc * c.maxageclass;
+  h->n_grid = (size_t)c.numxgrid * c.numygrid * c.numzgrid * outer;
+  h->n_dry = (size_t)c.numxgrid * c.numygrid * outer;
+  DA(h->gridunc, h->n_grid); DA(h->drygridunc, h->n_dry);
+  if (c.nested_output == 1) {
+    h->n_gridn = (size_t)c.numxgridn * c.numygridn * c.numzgrid * outer;
+    h->n_dryn = (size_t)c.numxgridn * c.numygridn * outer;
+    DA(h->griduncn, h->n_gridn); DA(h->drygriduncn, h->n_dryn);
+  }
+  h->n_rec = (size_t)FPB_MAXRECEPTOR * c.nspec;
+  DA(h->creceptor, h->n_rec); DA(h->crec_acc, h->n_rec);
+  DA(h->d_stats, 8);
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+extern "C" int fpb_finalize(fpb_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int s = 0; s < 2; s++) {
+    cudaFree(h->A[s]); cudaFree(h->B[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
+  }
+  cudaFree(h->stage);
+  cudaFree(h->p.xtra1); cudaFree(h->p.ytra1); cudaFree(h->p.ztra1); cudaFree(h->p.itra1);
+  cudaFree(h->p.npoint); cudaFree(h->p.nclass); cudaFree(h->p.idt); cudaFree(h->p.itramem);
+  cudaFree(h->p.itrasplit); cudaFree(h->p.uap); cudaFree(h->p.ucp); cudaFree(h->p.uzp);
+  cudaFree(h->p.us); cudaFree(h->p.vs); cudaFree(h->p.ws); cudaFree(h->p.cbt);
+  cudaFree(h->p.xmass1); cudaFree(h->p.xscav_frac1);
+  cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
+  cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
+  cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
+  cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
+  scatter_free(h->scatter);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+// -------------------------------------------------------------------- RNG --
+extern "C" int fpb_set_rannumb(fpb_handle *h, const float *rannumb, int32_t n) {
+  if (!h || !rannumb || n < 16) return fail("fpb_set_rannumb: bad argument");
+  CK(cudaSetDevice(h->device));
+  if (h->d_rannumb) cudaFree(h->d_rannumb);
+  h->d_rannumb = nullptr;
+  // a few guard entries: the reference's wrap tests are one entry short in
+  // places (e.g. src/advance.f90:371 vs rannumb(nrand+1))
+  CK(cudaMalloc((void **)&h->d_rannumb, ((size_t)n + 16) * sizeof(float)));
+  CK(cudaMemset(h->d_rannumb, 0, ((size_t)n + 16) * sizeof(float)));
+  CK(cudaMemcpy(h->d_rannumb, rannumb, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  h->maxrand = n;
+  return 0;
+}
+
+extern "C" int fpb_fill_rannumb(fpb_handle *h, int32_t maxrand, int32_t idummy) {
+  if (!h || maxrand < 16) return fail("fpb_fill_rannumb: bad argument");
+  std::vector<float> t((size_t)maxrand + 2);
+  // 1-based like the Fortran loop, src/FLEXPART.f90:56-59
+  for (int i = 1; i <= maxrand - 1; i += 2) gasdev1(h->ran3, idummy, t[i], t[i + 1]);
+  gasdev1(h->ran3, idummy, t[maxrand], t[maxrand - 1]);
+  return fpb_set_rannumb(h, t.data() + 1, maxrand);
+}
+
+// -------------------------------------------------------------------- met --
+extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m) {
+  if (!h || !m) return fail("fpb_upload_met: null argument");
+  if (slot != 1 && slot != 2) return fail("fpb_upload_met: slot must be 1 or 2 (got %d)", slot);
+  if (!m->uu || !m->vv || !m->ww || !m->rho || !m->drhodz || !m->hmix || !m->ustar || !m->wstar ||
+      !m->oli || !m->tropopause)
+    return fail("fpb_upload_met: a mandatory field pointer is null");
+  const fpb_config &c = h->cfg;
+  if ((c.nglobal || c.sglobal) && (!m->uupol || !m->vvpol))
+    return fail("fpb_upload_met: uupol/vvpol required when a pole is in the domain");
+  if (c.lsettling && !m->tt) return fail("fpb_upload_met: tt required when lsettling");
+  if (c.drydep && !m->vdep) return fail("fpb_upload_met: vdep required when drydep");
+  CK(cudaSetDevice(h->device));
+  const int s = slot - 1;
+  float *A = (float *)h->A[s], *B = (float *)h->B[s], *S = (float *)h->S[s];
+  if (upload_component(h, A, 0, 4, m->uu, c.nz)) return 1;
+  if (upload_component(h, A, 1, 4, m->vv, c.nz)) return 1;
+  if (upload_component(h, A, 2, 4, m->ww, c.nz)) return 1;
+  if (upload_component(h, A, 3, 4, m->rho, c.nz)) return 1;
+  if (upload_component(h, B, 0, 4, m->drhodz, c.nz)) return 1;
+  if (upload_component(h, B, 1, 4, m->tt, c.nz)) return 1;
+  if (upload_component(h, B, 2, 4, m->uupol, c.nz)) return 1;
+  if (upload_component(h, B, 3, 4, m->vvpol, c.nz)) return 1;
+  if (upload_component(h, S, 0, 4, m->hmix, 1)) return 1;
+  if (upload_component(h, S, 1, 4, m->ustar, 1)) return 1;
+  if (upload_component(h, S, 2, 4, m->wstar, 1)) return 1;
+  if (upload_component(h, S, 3, 4, m->oli, 1)) return 1;
+  if (upload_component(h, h->trop[s], 0, 1, m->tropopause, 1)) return 1;
+  if (c.drydep) {
+    // host vdep(nxmax,nymax,maxspec): species k is "level" k
+    if (upload_component(h, h->vdep[s], 0, 1, m->vdep, c.nspec)) return 1;
+  }
+  return 0;
+}
+
+extern "C" int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2], const int32_t memtime[2],
+                                   int32_t lwindinterv) {
+  if (!h || !memind || !memtime) return fail("fpb_set_met_bracket: null argument");
+  if (!((memind[0] == 1 && memind[1] == 2) || (memind[0] == 2 && memind[1] == 1)))
+    return fail("fpb_set_met_bracket: memind must be a permutation of (1,2)");
+  if (memtime[0] == memtime[1]) return fail("fpb_set_met_bracket: memtime(1) == memtime(2)");
+  if (lwindinterv == 0) return fail("fpb_set_met_bracket: lwindinterv == 0");
+  h->memind[0] = memind[0]; h->memind[1] = memind[1];
+  h->memtime[0] = memtime[0]; h->memtime[1] = memtime[1];
+  h->lwindinterv = lwindinterv;
+  h->have_bracket = true;
+  return 0;
+}
+
+// -------------------------------------------------------------- particles --
+#define H2D(dst, src, T)                                                             \
+  do {                                                                               \
+    if (!(src)) return fail("fpb_push_particles: array " #src " is null");          \
+    CK(cudaMemcpyAsync((dst) + first, (src) + first, (size_t)count * sizeof(T),     \
+                       cudaMemcpyHostToDevice, h->stream));                          \
+  } while (0)
+#define D2H(dst, src, T)                                                             \
+  do {                                                                               \
+    if (dst)                                                                         \
+      CK(cudaMemcpyAsync((dst) + first, (src) + first, (size_t)count * sizeof(T),   \
+                         cudaMemcpyDeviceToHost, h->stream));                        \
+  } while (0)
+
+extern "C" int fpb_push_particles(fpb_handle *h, int32_t first, int32_t count, const fpb_particle_ptrs *p) {
+  if (!h || !p) return fail("fpb_push_particles: null argument");
+  if (count == 0) return 0;
+  if (first < 0 || count < 0 || (int64_t)first + count > h->cfg.maxpart)
+    return fail("fpb_push_particles: rows [%d,%d) outside capacity %d", first, first + count, h->cfg.maxpart);
+  CK(cudaSetDevice(h->device));
+  H2D(h->p.xtra1, p->xtra1, double); H2D(h->p.ytra1, p->ytra1, double); H2D(h->p.ztra1, p->ztra1, float);
+  H2D(h->p.itra1, p->itra1, int32_t); H2D(h->p.npoint, p->npoint, int32_t);
+  H2D(h->p.nclass, p->nclass, int32_t); H2D(h->p.idt, p->idt, int32_t);
+  H2D(h->p.itramem, p->itramem, int32_t);
+  if (p->itrasplit) H2D(h->p.itrasplit, p->itrasplit, int32_t);
+  H2D(h->p.uap, p->uap, float); H2D(h->p.ucp, p->ucp, float); H2D(h->p.uzp, p->uzp, float);
+  H2D(h->p.us, p->us, float); H2D(h->p.vs, p->vs, float); H2D(h->p.ws, p->ws, float);
+  H2D(h->p.cbt, p->cbt, int16_t);
+  if (!p->xmass1) return fail("fpb_push_particles: xmass1 is null");
+  for (int k = 0; k < h->cfg.nspec; k++) {
+    CK(cudaMemcpyAsync(h->p.xmass1 + (size_t)k * h->cfg.maxpart + first,
+                       p->xmass1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
+                       cudaMemcpyHostToDevice, h->stream));
+    if (p->xscav_frac1)
+      CK(cudaMemcpyAsync(h->p.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
+                         p->xscav_frac1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
+                         cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (first + count > h->numpart) h->numpart = first + count;
+  return 0;
+}
+
+extern "C" int fpb_set_numpart(fpb_handle *h, int32_t numpart) {
+  if (!h || numpart < 0 || numpart > h->cfg.maxpart) return fail("fpb_set_numpart: bad argument");
+  h->numpart = numpart;
+  return 0;
+}
+
+extern "C" int fpb_pull_particles(fpb_handle *h, int32_t first, int32_t count, const fpb_particle_ptrs *p) {
+  if (!h || !p) return fail("fpb_pull_particles: null argument");
+  if (count == 0) return 0;
+  if (first < 0 || count < 0 || (int64_t)first + count > h->cfg.maxpart)
+    return fail("fpb_pull_particles: rows [%d,%d) outside capacity %d", first, first + count, h->cfg.maxpart);
+  CK(cudaSetDevice(h->device));
+  D2H(p->xtra1, h->p.xtra1, double); D2H(p->ytra1, h->p.ytra1, double); D2H(p->ztra1, h->p.ztra1, float);
+  D2H(p->itra1, h->p.itra1, int32_t); D2H(p->npoint, h->p.npoint, int32_t);
+  D2H(p->nclass, h->p.nclass, int32_t); D2H(p->idt, h->p.idt, int32_t);
+  D2H(p->itramem, h->p.itramem, int32_t); D2H(p->itrasplit, h->p.itrasplit, int32_t);
+  D2H(p->uap, h->p.uap, float); D2H(p->ucp, h->p.ucp, float); D2H(p->uzp, h->p.uzp, float);
+  D2H(p->us, h->p.us, float); D2H(p->vs, h->p.vs, float); D2H(p->ws, h->p.ws, float);
+  D2H(p->cbt, h->p.cbt, int16_t);
+  for (int k = 0; k < h->cfg.nspec; k++) {
+    if (p->xmass1)
+      CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + first,
+                         h->p.xmass1 + (size_t)k * h->cfg.maxpart + first, (size_t)count * sizeof(float),
+                         cudaMemcpyDeviceToHost, h->stream));
+    if (p->xscav_frac1)
+      CK(cudaMemcpyAsync(p->xscav_frac1 + (size_t)k * p->ld + first,
+                         h->p.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
+                         (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------- step --
+static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat) {
+  d = h->d;
+  d.itime = itime;
+  d.ldeltat = ldeltat;
+  d.memtime[0] = h->memtime[0];
+  d.memtime[1] = h->memtime[1];
+  d.lwindinterv = h->lwindinterv;
+  d.maxrand = (h->cfg.rng_mode == FPB_RNG_PHILOX) ? (1 << 30) : h->maxrand;
+  d.numpart = h->numpart;
+}
+
+static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
+  DevMetSlot m;
+  const int s = fslot - 1;
+  m.A = h->A[s]; m.B = h->B[s]; m.S = h->S[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
+  return m;
+}
+
+// Validation RNG: replay `nrand=int(ran3(idummy)*real(maxrand-1))+1` in the
+// reference's order: one draw per initialize call and one per advance call,
+// particles in slot order (src/timemanager.f90:531-611).  Each routine owns a
+// SAVEd idummy=-7, so the FIRST call of each re-seeds the shared generator.
+static int replay_ran3_indices(fpb_handle *h, int itime) {
+  const int n = h->numpart;
+  h->h_itra1.resize(n); h->h_itramem.resize(n);
+  h->h_nrand_init.assign(n, 1); h->h_nrand_adv.assign(n, 1);
+  CK(cudaMemcpyAsync(h->h_itra1.data(), h->p.itra1, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_itramem.data(), h->p.itramem, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const float scale = (float)(h->maxrand - 1);
+  for (int j = 0; j < n; j++) {
+    if (h->h_itra1[j] != itime) continue;
+    if (h->h_itramem[j] == itime || itime == 0)
+      h->h_nrand_init[j] = (int)(h->ran3.next(h->idummy_init) * scale) + 1;
+    h->h_nrand_adv[j] = (int)(h->ran3.next(h->idummy_adv) * scale) + 1;
+  }
+  CK(cudaMemcpyAsync(h->d_nrand_init, h->h_nrand_init.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_nrand_adv, h->h_nrand_adv.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_stats *stats) {
+  if (!h) return fail("fpb_step: null handle");
+  if (!h->have_bracket) return fail("fpb_step: fpb_set_met_bracket has not been called");
+  CK(cudaSetDevice(h->device));
+  if (h->cfg.rng_mode != FPB_RNG_PHILOX && !h->d_rannumb) {
+    if (fpb_fill_rannumb(h, 1000000, -320)) return 1; // par_mod maxrand, FLEXPART.f90:47
+  }
+  if (h->cfg.cblflag == 1 && h->cfg.rng_mode == FPB_RNG_REFERENCE && h->cfg.math_mode != FPB_MATH_STRICT) {
+    // allowed, but CBL initial velocities use the "defined" draw
+  }
+  if (h->numpart == 0) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    return 0;
+  }
+  if (h->cfg.rng_mode == FPB_RNG_REFERENCE && replay_ran3_indices(h, itime)) return 1;
+
+  DevStepArgs a;
+  per_step_cfg(h, a.cfg, itime, ldeltat);
+  a.met[0] = slot_view(h, h->memind[0]);
+  a.met[1] = slot_view(h, h->memind[1]);
+  a.met_lit1 = slot_view(h, 1);
+  a.p = h->p;
+  a.height = h->d_height;
+  a.rannumb = h->d_rannumb;
+  a.npart = h->d_npart;
+  a.xmass = h->d_xmass;
+  a.nrand_init = h->d_nrand_init;
+  a.nrand_adv = h->d_nrand_adv;
+  a.drygridunc = h->drygridunc;
+  a.drygriduncn = h->drygriduncn;
+  a.stats = stats ? h->d_stats : nullptr;
+  if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+  if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_step_strict(a, h->stream);
+  else fpbk_step_fast(a, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (stats) {
+    unsigned long long hs[8];
+    CK(cudaMemcpyAsync(hs, h->d_stats, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    stats->n_active = (int64_t)hs[0]; stats->n_init = (int64_t)hs[1]; stats->n_terminated = (int64_t)hs[2];
+    stats->n_pbl = (int64_t)hs[3]; stats->n_substeps = (int64_t)hs[4]; stats->n_petterssen = (int64_t)hs[5];
+    stats->n_nan_cbl = (int64_t)hs[6];
+  } else {
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------- conccalc --
+__global__ void receptor_finalize_kernel(float *creceptor, float *acc, int numreceptor, int nspec,
+                                         float weight, const float *area /*unused*/, DevCfg c) {
+  int t = threadIdx.x;
+  if (t < numreceptor * nspec) {
+    int n = t / nspec, ks = t % nspec;
+    // creceptor(n,ks) += 2*weight*c(ks)/receptorarea(n), src/conccalc.f90:494-496
+    creceptor[n + FPB_MAXRECEPTOR * ks] += 2.f * weight * acc[n * nspec + ks] / c.receptorarea[n];
+    acc[n * nspec + ks] = 0.f;
+  }
+}
+
+extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
+  if (!h) return fail("fpb_conccalc: null handle");
+  if (h->cfg.ind_samp == -1 && !h->have_bracket) return fail("fpb_conccalc: no met bracket set");
+  if (h->numpart == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  DevConcArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.cfg.weight = weight;
+  a.met[0] = slot_view(h, h->memind[0]);
+  a.met[1] = slot_view(h, h->memind[1]);
+  a.p = h->p;
+  a.height = h->d_height;
+  a.gridunc = h->gridunc;
+  a.griduncn = h->griduncn;
+  a.crec_acc = h->crec_acc;
+  const bool strict = h->cfg.math_mode == FPB_MATH_STRICT;
+  if (h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
+    if (scatter_conccalc_deterministic(h->scatter, a, strict, h->stream, &h->launches)) return fail("%s", scatter_error());
+  } else {
+    if (strict) fpbk_conccalc_strict(a, h->stream); else fpbk_conccalc_fast(a, h->stream);
+    h->launches++;
+  }
+  if (h->cfg.numreceptor > 0) {
+    if (strict) fpbk_receptor_strict(a, h->stream); else fpbk_receptor_fast(a, h->stream);
+    receptor_finalize_kernel<<<1, 256, 0, h->stream>>>(h->creceptor, h->crec_acc, h->cfg.numreceptor,
+                                                      h->cfg.nspec, weight, nullptr, a.cfg);
+    h->launches += 2;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ grids --
+// device layout: species extent nspec; host layout: species extent maxspec
+static int fetch_one(fpb_handle *h, float *host, const float *dev, size_t inner, size_t ndev,
+                     std::vector<float> &tmp) {
+  if (!host || !dev) return 0;
+  const fpb_config &c = h->cfg;
+  tmp.resize(ndev);
+  CK(cudaMemcpyAsync(tmp.data(), dev, ndev * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t outer = (size_t)c.maxpointspec_act * c.nclassunc * c.maxageclass;
+  for (size_t o = 0; o < outer; o++) {
+    memcpy(host + o * c.maxspec * inner, tmp.data() + o * c.nspec * inner, (size_t)c.nspec * inner * sizeof(float));
+    if (c.maxspec > c.nspec)
+      memset(host + (o * c.maxspec + c.nspec) * inner, 0, (size_t)(c.maxspec - c.nspec) * inner * sizeof(float));
+  }
+  return 0;
+}
+
+extern "C" int fpb_zero_conc_grids(fpb_handle *h) {
+  if (!h) return fail("fpb_zero_conc_grids: null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->gridunc, 0, h->n_grid * sizeof(float), h->stream));
+  if (h->griduncn) CK(cudaMemsetAsync(h->griduncn, 0, h->n_gridn * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->creceptor, 0, h->n_rec * sizeof(float), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int fpb_fetch_grids(fpb_handle *h, float *gridunc, float *griduncn, float *drygridunc,
+                               float *drygriduncn, float *creceptor, int32_t zero_conc) {
+  if (!h) return fail("fpb_fetch_grids: null handle");
+  const fpb_config &c = h->cfg;
+  if (c.maxspec < c.nspec) return fail("fpb_fetch_grids: maxspec < nspec");
+  CK(cudaSetDevice(h->device));
+  std::vector<float> tmp;
+  if (fetch_one(h, gridunc, h->gridunc, (size_t)c.numxgrid * c.numygrid * c.numzgrid, h->n_grid, tmp)) return 1;
+  if (fetch_one(h, drygridunc, h->drygridunc, (size_t)c.numxgrid * c.numygrid, h->n_dry, tmp)) return 1;
+  if (c.nested_output == 1) {
+    if (fetch_one(h, griduncn, h->griduncn, (size_t)c.numxgridn * c.numygridn * c.numzgrid, h->n_gridn, tmp)) return 1;
+    if (fetch_one(h, drygriduncn, h->drygriduncn, (size_t)c.numxgridn * c.numygridn, h->n_dryn, tmp)) return 1;
+  }
+  if (creceptor) {
+    tmp.resize(h->n_rec);
+    CK(cudaMemcpyAsync(tmp.data(), h->creceptor, h->n_rec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(creceptor, 0, (size_t)FPB_MAXRECEPTOR * c.maxspec * sizeof(float));
+    memcpy(creceptor, tmp.data(), h->n_rec * sizeof(float)); // (maxreceptor, ks) with ks < nspec
+  }
+  if (zero_conc) return fpb_zero_conc_grids(h);
+  return 0;
+}
+
+__global__ void scale_dep_kernel(float *g, size_t n, size_t inner, int nspec, DevCfg c, const float f0,
+                                 const float f1, const float f2, const float f3, const float f4,
+                                 const float f5, const float f6, const float f7) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ks = (int)((i / inner) % nspec);
+  const float f[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+  g[i] *= f[ks];
+}
+
+extern "C" int fpb_scale_depgrids(fpb_handle *h, const float *factor) {
+  if (!h || !factor) return fail("fpb_scale_depgrids: null argument");
+  CK(cudaSetDevice(h->device));
+  float f[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+  for (int k = 0; k < h->cfg.nspec; k++) f[k] = factor[k];
+  const fpb_config &c = h->cfg;
+  scale_dep_kernel<<<(unsigned)((h->n_dry + 255) / 256), 256, 0, h->stream>>>(
+      h->drygridunc, h->n_dry, (size_t)c.numxgrid * c.numygrid, c.nspec, h->d, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+  h->launches++;
+  if (h->drygriduncn) {
+    scale_dep_kernel<<<(unsigned)((h->n_dryn + 255) / 256), 256, 0, h->stream>>>(
+        h->drygriduncn, h->n_dryn, (size_t)c.numxgridn * c.numygridn, c.nspec, h->d, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int fpb_grid_device_ptr(fpb_handle *h, int32_t which, void **dptr, size_t *nfloats) {
+  if (!h || !dptr || !nfloats) return fail("fpb_grid_device_ptr: null argument");
+  switch (which) {
+    case 0: *dptr = h->gridunc; *nfloats = h->n_grid; break;
+    case 1: *dptr = h->griduncn; *nfloats = h->n_gridn; break;
+    case 2: *dptr = h->drygridunc; *nfloats = h->n_dry; break;
+    case 3: *dptr = h->drygriduncn; *nfloats = h->n_dryn; break;
+    case 4: *dptr = h->creceptor; *nfloats = h->n_rec; break;
+    default: return fail("fpb_grid_device_ptr: which=%d", which);
+  }
+  return 0;
+}
+
+extern "C" int fpb_sort_particles(fpb_handle *h) {
+  if (!h) return fail("fpb_sort_particles: null handle");
+  return 0; // locality sort arrives with the sort kernels (fpb_scatter.cu)
+}
+
+extern "C" void *fpb_stream(fpb_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int64_t fpb_launch_count(fpb_handle *h) { return h ? h->launches : 0; }

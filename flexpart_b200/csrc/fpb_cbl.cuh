@@ -1,0 +1,176 @@
+// fpb_cbl.cuh -- skewed convective-boundary-layer scheme, device side.
+// Included inside the anonymous namespace of fpb_kernels.cu (uses its m_*
+// math layer).  Follows cbl (src/cbl.f90:70-212), re_initialize_particle
+// (src/re_initialize_particle.f90:44-91) and initialize_cbl_vel
+// (src/initialize_cbl_vel.f90:46-84): bi-Gaussian updraft/downdraft closure
+// of Luhar-Hibberd-Hurley with the Cassiani et al. (2015) density terms.
+
+__device__ __forceinline__ float cbl_cuberoot(float x) {
+  return copysignf(m_pow(fabsf(x), 0.333333333f), x);
+}
+
+__device__ __forceinline__ float cbl_transition(float h, float ol) {
+  float transition = 1.f;
+  if (-h / ol < 15.f) transition = (m_sin((((-h / ol) + 10.f) / 10.f) * PI_F)) / 2.f + 0.5f;
+  return transition;
+}
+
+// drift ath and diffusion bth of the CBL Langevin equation; sets flagrein
+// when the velocity is > 6 sigma from both modes.
+__device__ void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float h, float rhoa,
+                          float rhograd, float sigmaw, float dsigmawdz, float tlw, float ol,
+                          float &ath, float &bth, int &flagrein) {
+  const float usurad2 = 0.7071067812f, usurad2p = 0.3989422804f, C0 = 3.f,
+              costluar4 = 0.66667f, eps = 0.000001f;
+  const float dens = rhoa, ddens = rhograd;
+  const float timedir = (float)c.ldirect;
+  const float z = (zp / h);
+  const float transition = cbl_transition(h, ol);
+  const float w2 = (sigmaw * sigmaw);
+  const float dw2 = (2.f * sigmaw * dsigmawdz);
+  const float alfa = 2.f * w2 / (C0 * tlw);
+  const float wold = timedir * wp;
+  const float omz32 = m_pow(1.f - z, 3.f / 2.f);
+  const float w3 = ((1.2f * z * (omz32)) + eps) * (wst * wst * wst) * transition;
+  const float dw3 = (1.2f * ((omz32) + z * 1.5f * (m_pow(1.f - z, 1.f / 2.f)) * (-1.f))) *
+                    (wst * wst * wst) * (1.f / h) * transition;
+  const float w2_15 = m_pow(w2, 1.5f);
+  const float skew = w3 / (w2_15);
+  const float skew2 = skew * skew;
+  const float dskew = (dw3 * w2_15 - w3 * 1.5f * m_pow(w2, 0.5f) * dw2) / (w2 * w2 * w2);
+  const float radw2 = m_pow(w2, 0.5f);
+  const float dradw2 = 0.5f * m_pow(w2, -0.5f) * dw2;
+  const float fluarw = costluar4 * (cbl_cuberoot(skew));
+  const float fluarw2 = fluarw * fluarw;
+  float dfluarw, rluarw, xluarw, drluarw, dxluarw;
+  if (skew != 0.f) {
+    const float a1 = 1.f + fluarw2, a3 = 3.f + fluarw2;
+    const float a3sq = m_pow(a3, 2.f), a1_15 = m_pow(a1, 1.5f);
+    dfluarw = costluar4 * (1.f / 3.f) * cbl_cuberoot(m_pow(skew, -2.f)) * dskew;
+    rluarw = m_pow(a1, 3.f) * skew2 / (a3sq * fluarw2);
+    xluarw = a1_15 * skew / (a3 * fluarw);
+    drluarw = (((3.f * (a1 * a1) * (2.f * fluarw * dfluarw) * skew2) + (a1 * a1 * a1) * 2.f * skew * dskew) *
+                   a3sq * fluarw2 -
+               (a1 * a1 * a1) * skew2 *
+                   ((2.f * a3 * (2.f * fluarw * dfluarw) * fluarw2) + (a3 * a3) * 2.f * fluarw * dfluarw)) /
+              ((a3sq * fluarw2) * (a3sq * fluarw2));
+    dxluarw = (((1.5f * m_pow(a1, 0.5f) * (2.f * fluarw * dfluarw) * skew) + a1_15 * dskew) * a3 * fluarw -
+               a1_15 * skew * (3.f * dfluarw + 3.f * fluarw2 * dfluarw)) /
+              ((a3 * fluarw) * (a3 * fluarw));
+  } else {
+    dfluarw = 0.f; rluarw = 0.f; drluarw = 0.f; xluarw = 0.f; dxluarw = 0.f;
+  }
+  const float r4 = m_pow(4.f + rluarw, 0.5f);
+  const float aluarw = 0.5f * (1.f - xluarw / r4);
+  const float bluarw = 1.f - aluarw;
+  const float daluarw = -0.5f * ((dxluarw * r4) - (0.5f * xluarw * m_pow(4.f + rluarw, -0.5f) * drluarw)) /
+                        (4.f + rluarw);
+  const float dbluarw = -daluarw;
+  const float ra = bluarw / (aluarw * (1.f + fluarw2));
+  const float rb = aluarw / (bluarw * (1.f + fluarw2));
+  const float sra = m_pow(ra, 0.5f), srb = m_pow(rb, 0.5f);
+  const float sigmawa = radw2 * sra;
+  const float sigmawb = radw2 * srb;
+  const float dsigmawa =
+      dradw2 * sra +
+      radw2 * ((0.5f * m_pow(ra, -0.5f)) *
+               ((dbluarw * (aluarw * (1.f + fluarw2)) -
+                 bluarw * (daluarw * (1.f + fluarw2) + aluarw * 2.f * fluarw * dfluarw)) /
+                ((aluarw * (1.f + fluarw2)) * (aluarw * (1.f + fluarw2)))));
+  const float dsigmawb =
+      dradw2 * srb +
+      radw2 * ((0.5f * m_pow(rb, -0.5f)) *
+               ((daluarw * (bluarw * (1.f + fluarw2)) -
+                 aluarw * (dbluarw * (1.f + fluarw2) + bluarw * 2.f * fluarw * dfluarw)) /
+                ((bluarw * (1.f + fluarw2)) * (bluarw * (1.f + fluarw2)))));
+  const float wa = (fluarw * sigmawa), wb = (fluarw * sigmawb);
+  const float dwa = dfluarw * sigmawa + fluarw * dsigmawa;
+  const float dwb = dfluarw * sigmawb + fluarw * dsigmawb;
+  const float deltawa = wold - wa, deltawb = wold + wb;
+  const float wold2 = wold * wold;
+  const float sigmawa2 = sigmawa * sigmawa, sigmawb2 = sigmawb * sigmawb;
+  if (fabsf(deltawa) > 6.f * sigmawa && fabsf(deltawb) > 6.f * sigmawb) flagrein = 1;
+  const float pa = (usurad2p * (1.f / sigmawa)) * (m_exp(-(0.5f * (m_pow(deltawa / sigmawa, 2.f)))));
+  const float pb = (usurad2p * (1.f / sigmawb)) * (m_exp(-(0.5f * (m_pow(deltawb / sigmawb, 2.f)))));
+  const float ptot = dens * aluarw * pa + dens * bluarw * pb;
+  const float aperfa = deltawa * usurad2 / sigmawa;
+  const float aperfb = deltawb * usurad2 / sigmawb;
+  const float Phi =
+      -0.5f * (aluarw * dens * dwa + dens * wa * daluarw + aluarw * wa * ddens) * m_erf(aperfa) +
+      sigmawa *
+          (aluarw * dens * dsigmawa * (wold2 / sigmawa2 + 1.f) + sigmawa * dens * daluarw +
+           sigmawa * ddens * aluarw + aluarw * wold * dens / sigmawa2 * (sigmawa * dwa - wa * dsigmawa)) *
+          pa +
+      0.5f * (bluarw * dens * dwb + wb * dens * dbluarw + wb * bluarw * ddens) * m_erf(aperfb) +
+      sigmawb *
+          (bluarw * dens * dsigmawb * (wold2 / sigmawb2 + 1.f) + sigmawb * dens * dbluarw +
+           sigmawb * ddens * bluarw + bluarw * wold * dens / sigmawb2 * (-sigmawb * dwb + wb * dsigmawb)) *
+          pb;
+  const float Q = timedir * ((aluarw * dens * deltawa / sigmawa2) * pa + (bluarw * dens * deltawb / sigmawb2) * pb);
+  ath = (1.f / ptot) * (-(C0 / 2.f) * alfa * Q + Phi);
+  bth = m_sqrt(C0 * alfa);
+}
+
+// moment closure shared by re_initialize_particle / initialize_cbl_vel
+__device__ void cbl_split(float zp, float wst, float h, float sigmaw, float ol, float &aluarw,
+                          float &sigmawa, float &sigmawb, float &wa, float &wb) {
+  const float costluar4 = 0.66667f, eps = 0.000001f;
+  const float z = zp / h;
+  const float transition = cbl_transition(h, ol);
+  const float w2 = sigmaw * sigmaw;
+  const float w3 = (((1.2f * z * (m_pow(1.f - z, 3.f / 2.f))) + eps) * (wst * wst * wst)) * transition;
+  const float skew = w3 / (m_pow(w2, 1.5f));
+  const float skew2 = skew * skew;
+  const float radw2 = m_sqrt(w2);
+  const float fluarw = costluar4 * m_pow(skew, 0.333333333333333f);
+  const float fluarw2 = fluarw * fluarw;
+  const float rluarw = m_pow(1.f + fluarw2, 3.f) * skew2 / (m_pow(3.f + fluarw2, 2.f) * fluarw2);
+  const float xluarw = m_pow(rluarw, 0.5f);
+  aluarw = 0.5f * (1.f - xluarw / m_pow(4.f + rluarw, 0.5f));
+  const float bluarw = 1.f - aluarw;
+  sigmawa = radw2 * m_pow(bluarw / (aluarw * (1.f + fluarw2)), 0.5f);
+  sigmawb = radw2 * m_pow(aluarw / (bluarw * (1.f + fluarw2)), 0.5f);
+  wa = (fluarw * sigmawa);
+  wb = (fluarw * sigmawb);
+}
+
+// src/re_initialize_particle.f90:44-91 (draws continue in the rannumb stream)
+__device__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst, float h,
+                                 float sigmaw, float ol, float &wp, int &nrand) {
+  float aluarw, sigmawa, sigmawb, wa, wb;
+  nrand = nrand + 1;
+  float dcas1 = rng.get(nrand);
+  const float timedir = (float)c.ldirect;
+  cbl_split(zp, wst, h, sigmaw, ol, aluarw, sigmawa, sigmawb, wa, wb);
+  const float sgn = copysignf(1.f, wp) * timedir;
+  if (sgn > 0.f) { // updraft
+    for (int guard = 0; guard < 1000; guard++) {
+      wp = (dcas1 * sigmawa + wa);
+      if (!(wp < 0.f)) break;
+      nrand = nrand + 1;
+      dcas1 = rng.get(nrand);
+    }
+    wp = wp * timedir;
+  } else if (sgn < 0.f) { // downdraft
+    for (int guard = 0; guard < 1000; guard++) {
+      wp = (dcas1 * sigmawb - wb);
+      if (!(wp > 0.f)) break;
+      nrand = nrand + 1;
+      dcas1 = rng.get(nrand);
+    }
+    wp = wp * timedir;
+  }
+}
+
+// src/initialize_cbl_vel.f90:46-84.  The reference draws ran3 + gasdev from
+// the global sequential stream here; the device ("defined" behaviour, shared
+// with oracle/ strict_reference=0) takes the mode selector from the uniform
+// that chose the table index and the normal from the next table entry.
+__device__ float cbl_initial_velocity(const DevCfg &c, float dcas, float dcas1, float zp,
+                                      float wst, float h, float sigmaw, float ol) {
+  float aluarw, sigmawa, sigmawb, wa, wb;
+  const float timedir = (float)c.ldirect;
+  cbl_split(zp, wst, h, sigmaw, ol, aluarw, sigmawa, sigmawb, wa, wb);
+  if (dcas <= aluarw) return timedir * (dcas1 * sigmawa + wa);
+  return timedir * (dcas1 * sigmawb - wb);
+}

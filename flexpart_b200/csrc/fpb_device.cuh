@@ -1,0 +1,124 @@
+// fpb_device.cuh -- device-side types shared by the engine's kernels.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   met, per time slot:  A[k][jy][ix] = float4{uu,vv,ww,rho}
+//                        B[k][jy][ix] = float4{drhodz,tt,uupol,vvpol}
+//                        S[jy][ix]    = float4{hmix,ustar,wstar,oli}
+//                        trop[jy][ix], vdep[ks][jy][ix]
+//     -> the 4 values a bilinear corner needs sit in one 16-B word and the
+//        x-neighbour is the adjacent word: a corner PAIR is one 32-B sector.
+//   particles: structure of arrays, one array per com_mod variable
+//     (src/com_mod.f90:675-695), particle index fastest.
+//   grids: reference index order (src/outgrid_init.f90:192-201) packed to
+//     nspec species.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fpb.h"
+
+#define FPB_MAXNZ 160
+
+struct DevMetSlot {
+  const float4 *A;
+  const float4 *B;
+  const float4 *S;
+  const float *trop;
+  const float *vdep;
+};
+
+struct DevParticles {
+  double *xtra1, *ytra1;
+  float *ztra1;
+  int32_t *itra1, *npoint, *nclass, *idt, *itramem, *itrasplit;
+  float *uap, *ucp, *uzp, *us, *vs, *ws;
+  int16_t *cbt;
+  float *xmass1;      // [nspec][maxpart]
+  float *xscav_frac1; // [nspec][maxpart] or null
+  int32_t maxpart;
+};
+
+// Scalars the kernels read; passed by value as a __grid_constant__ kernel
+// parameter (constant bank), one copy per launch so several engine handles
+// can coexist in a process.
+struct DevCfg {
+  // met grid
+  int nx, ny, nz, nxd, nyd; // nxd/nyd: device extents of the packed met arrays
+  int nymax;
+  int nxmin1, nymin1;
+  float dx, dy, xlon0, ylat0, dxconst, dyconst;
+  int xglobal, nglobal, sglobal;
+  float switchnorthg, switchsouthg;
+  float northpolemap[9], southpolemap[9];
+  float eps;
+  // command
+  int ldirect, lsynctime, method, mintime, ifine;
+  int turbswitch, cblflag, mdomainfill, mquasilag, lsettling, turboff;
+  float ctl, fine, d_trop, d_strat, turbmesoscale;
+  int ind_samp, ioutputforeachrelease, lusekerneloutput, lparticlecountoutput;
+  int drydep, drybkdep, wetbkdep, nested_output;
+  // species
+  int nspec;
+  float decay[FPB_MAXSPEC];
+  int drydepspec[FPB_MAXSPEC];
+  float density[FPB_MAXSPEC], dquer[FPB_MAXSPEC], vsetaver[FPB_MAXSPEC],
+      cunningham[FPB_MAXSPEC];
+  int nageclass;
+  int lage[FPB_MAXAGECLASS];
+  // out grids
+  int numxgrid, numygrid, numzgrid;
+  float dxout, dyout, xoutshift, youtshift;
+  float outheight[FPB_MAXZGRID];
+  int numxgridn, numygridn;
+  float dxoutn, dyoutn, xoutshiftn, youtshiftn;
+  int maxpointspec_act, nclassunc, maxageclass;
+  int numreceptor;
+  float xreceptor[FPB_MAXRECEPTOR], yreceptor[FPB_MAXRECEPTOR],
+      receptorarea[FPB_MAXRECEPTOR];
+  int numpoint;
+  // per-step
+  int itime, ldeltat;
+  int memind[2];  // 0-based device slot of the older / newer field
+  int memtime[2];
+  int lwindinterv;
+  int maxrand;
+  int rng_mode;
+  unsigned long long seed;
+  int part_id_stride, part_id_offset;
+  int numpart;
+  float weight; // conccalc
+};
+
+struct DevStepArgs {
+  DevCfg cfg;
+  DevMetSlot met[2];   // [0] = memind(1) (older field), [1] = memind(2)
+  DevMetSlot met_lit1; // Fortran slot 1, for the reference's literal-slot reads
+  DevParticles p;
+  const float *height;   // [nz] 0-based (height[0] = level 1)
+  const float *rannumb;  // 0-based table, rannumb[i-1] = Fortran rannumb(i)
+  const int32_t *npart;  // [numpoint]
+  const float *xmass;    // [nspec][numpoint] (device-packed)
+  const int32_t *nrand_init; // reference RNG mode: per-slot nrand for initialize
+  const int32_t *nrand_adv;  //                      and for advance
+  float *drygridunc, *drygriduncn;
+  unsigned long long *stats; // 8 counters, fpb_step_stats order
+};
+
+struct DevConcArgs {
+  DevCfg cfg;
+  DevMetSlot met[2];   // ordered like DevStepArgs::met
+  DevParticles p;
+  const float *height;
+  float *gridunc, *griduncn;
+  float *crec_acc; // [numreceptor][nspec] accumulators of c(ks)
+};
+
+// launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
+#define FPB_DECL_LAUNCHERS(SUF)                                               \
+  void fpbk_step_##SUF(const DevStepArgs &a, cudaStream_t st);                \
+  void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
+  void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
+  void fpbk_conc_emit_##SUF(const DevConcArgs &a, int nest_sel, unsigned *keys, \
+                            float *vals, size_t nrec, cudaStream_t st);
+FPB_DECL_LAUNCHERS(fast)
+FPB_DECL_LAUNCHERS(strict)

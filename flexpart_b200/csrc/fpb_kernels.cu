@@ -1,0 +1,1551 @@
+// fpb_kernels.cu -- the particle-timestep kernels (sm_100a).
+//
+// Compiled twice into libfpb.so:
+//   -DFPB_STRICT=0            : production; FMA contraction on, float libm
+//   -DFPB_STRICT=1 --fmad=false: validation; every float operation rounded
+//                               once, transcendentals evaluated in double and
+//                               rounded once -> bit-comparable with oracle/.
+//
+// One thread owns one particle for the whole synchronisation interval:
+//   fpb_step_kernel      = timemanager particle-loop body  (src/timemanager.f90:531-712)
+//                          + initialize                    (src/initialize.f90:66-217)
+//                          + advance                       (src/advance.f90:133-985)
+//                          with interpol_all/misslev/wind/wind_short/vdep,
+//                          hanna/hanna1/hanna_short, cbl, windalign, the
+//                          polar-stereographic update (cmapf_mod), settling,
+//                          and drydepokernel(_nest).
+//   fpb_conccalc_kernel  = conccalc mother + nested grid    (src/conccalc.f90:50-444)
+//   fpb_receptor_kernel  = conccalc receptor loop           (src/conccalc.f90:451-498)
+//
+// The reference keeps its scratch in module globals (interpol_mod,
+// hanna_mod); here it is per-thread registers.  The nzmax-long profile cache
+// (indzindicator, src/advance.f90:310-331) becomes a two-entry cache of the
+// current level pair: a recomputed level gives the same bits because the
+// horizontal weights and the time weights are frozen for the whole call.
+#include <math.h>
+
+#include "fpb_device.cuh"
+
+#ifndef FPB_STRICT
+#define FPB_STRICT 0
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------- math ----
+#if FPB_STRICT
+__device__ __forceinline__ float m_exp(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float m_log(float x) { return (float)log((double)x); }
+__device__ __forceinline__ float m_pow(float a, float b) { return (float)pow((double)a, (double)b); }
+__device__ __forceinline__ float m_sin(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float m_cos(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float m_erf(float x) { return (float)erf((double)x); }
+#else
+__device__ __forceinline__ float m_exp(float x) { return expf(x); }
+__device__ __forceinline__ float m_log(float x) { return logf(x); }
+__device__ __forceinline__ float m_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ float m_sin(float x) { return sinf(x); }
+__device__ __forceinline__ float m_cos(float x) { return cosf(x); }
+__device__ __forceinline__ float m_erf(float x) { return erff(x); }
+#endif
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ int f_int(float x) { return (int)x; }   // Fortran int()
+__device__ __forceinline__ int d_int(double x) { return (int)x; }
+__device__ __forceinline__ int d_nint(double x) { return (int)round(x); } // nint()
+__device__ __forceinline__ double d_modulo(double a, double p) {
+  double r = fmod(a, p);
+  if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+  return r;
+}
+
+constexpr float PI_F = 3.14159265f;            // par_mod pi
+constexpr float PI180 = PI_F / 180.f;          // par_mod pi180
+constexpr float HREF = 15.f;                   // par_mod href
+constexpr float EPS2 = 1.e-9f;                 // advance.f90:107
+constexpr float EPS3 = 1.17549435e-38f;        // tiny(1.0)
+constexpr float EPS_SIG = 1.0e-30f;            // interpol_*.f90 eps
+constexpr float MINMASS = 0.0001f;             // par_mod minmass
+
+// ----------------------------------------------------------------- RNG ----
+// Philox4x32-10 (Salmon et al. 2011), counter = (particle id, time, stream, block)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+struct Rng {
+  const float *tab; // rannumb, 0-based
+  int maxrand;
+  int mode;
+  uint2 key;
+  uint32_t pid, tstep;
+  // FPB_RNG_PHILOX: cache of the last generated block of 4 normals
+  int cblk;
+  float cn[4];
+
+  // index stream: replaces ran3 (src/advance.f90:153, src/initialize.f90:68)
+  __device__ float uniform(uint32_t stream) const {
+    uint4 r = philox4x32_10(make_uint4(pid, tstep, stream, 0u), key);
+    return u01(r.x);
+  }
+  // Fortran rannumb(i)
+  __device__ float get(int i) {
+    if (mode != FPB_RNG_PHILOX) return __ldg(tab + (i - 1));
+    int blk = i >> 2;
+    if (blk != cblk) {
+      uint4 r = philox4x32_10(make_uint4(pid, tstep, 0x52414e44u, (uint32_t)blk), key);
+      // Box-Muller, clipped to +-3 like gasdev1 (src/random_mod.f90:86-89)
+      float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      float u2 = u01(r.y);
+      float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      float u4 = u01(r.w);
+      float ra = sqrtf(-2.f * __logf(u1)), rb = sqrtf(-2.f * __logf(u3));
+      float sa, ca, sb, cb;
+      __sincosf(6.28318530718f * u2, &sa, &ca);
+      __sincosf(6.28318530718f * u4, &sb, &cb);
+      cn[0] = fminf(fmaxf(ra * ca, -3.f), 3.f);
+      cn[1] = fminf(fmaxf(ra * sa, -3.f), 3.f);
+      cn[2] = fminf(fmaxf(rb * cb, -3.f), 3.f);
+      cn[3] = fminf(fmaxf(rb * sb, -3.f), 3.f);
+      cblk = blk;
+    }
+    int k = i & 3;
+    return k == 0 ? cn[0] : k == 1 ? cn[1] : k == 2 ? cn[2] : cn[3];
+  }
+};
+
+// ------------------------------------------------------------- gathers ----
+struct Lev { // one cached profile level (uprof(n) ... wsigprof(n))
+  float u, v, w, rho, rhograd, usig, vsig, wsig;
+};
+
+struct Hz { // horizontal + temporal interpolation weights (interpol_mod)
+  float p1, p2, p3, p4, dt1, dt2, dtt;
+  int o00, o10, o01, o11; // 2-D offsets of the 4 corners
+  int ngrid;
+};
+
+__device__ __forceinline__ void make_weights(const DevCfg &c, Hz &z, int itime_eff,
+                                             float xt, float yt, int ix, int jy,
+                                             int ixp, int jyp) {
+  // src/interpol_all.f90:57-71 (identical in interpol_wind, interpol_wind_short)
+  float ddx = xt - (float)ix, ddy = yt - (float)jy;
+  float rddx = 1.f - ddx, rddy = 1.f - ddy;
+  z.p1 = rddx * rddy;
+  z.p2 = ddx * rddy;
+  z.p3 = rddx * ddy;
+  z.p4 = ddx * ddy;
+  z.dt1 = (float)(itime_eff - c.memtime[0]);
+  z.dt2 = (float)(c.memtime[1] - itime_eff);
+  z.dtt = 1.f / (z.dt1 + z.dt2);
+  z.o00 = ix + c.nxd * jy;
+  z.o10 = ixp + c.nxd * jy;
+  z.o01 = ix + c.nxd * jyp;
+  z.o11 = ixp + c.nxd * jyp;
+}
+
+__device__ __forceinline__ float bil(const Hz &z, float a, float b, float c, float d) {
+  return z.p1 * a + z.p2 * b + z.p3 * c + z.p4 * d;
+}
+
+// first Fortran level index i in [2,nz] with height(i) > zt, minus 1
+// (the linear searches at src/interpol_all.f90:118-125 etc.; height is
+// strictly increasing so bisection returns the same index)
+__device__ __forceinline__ int find_indz(const float *sh, int nz, float zt) {
+  int lo = 2, hi = nz;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sh[mid - 1] > zt) hi = mid; else lo = mid + 1;
+  }
+  return lo - 1;
+}
+
+// one profile level: src/interpol_all.f90:135-238 == src/interpol_misslev.f90:56-157
+__device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot *met,
+                                              const Hz &z, int n, Lev &L) {
+  const int base = (n - 1) * (c.nxd * c.nyd);
+  float y1[2], y2[2], y3[2], r1[2], g1[2];
+  float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const float4 *A = met[m].A + base, *B = met[m].B + base;
+    float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
+    float4 Ba = __ldg(B + z.o00), Bb = __ldg(B + z.o10), Bc = __ldg(B + z.o01), Bd = __ldg(B + z.o11);
+    float ua, ub, uc, ud, va, vb, vc, vd;
+    if (z.ngrid < 0) {
+      ua = Ba.z; ub = Bb.z; uc = Bc.z; ud = Bd.z;
+      va = Ba.w; vb = Bb.w; vc = Bc.w; vd = Bd.w;
+    } else {
+      ua = Aa.x; ub = Ab.x; uc = Ac.x; ud = Ad.x;
+      va = Aa.y; vb = Ab.y; vc = Ac.y; vd = Ad.y;
+    }
+    y1[m] = bil(z, ua, ub, uc, ud);
+    y2[m] = bil(z, va, vb, vc, vd);
+    usl = usl + ua + ub + uc + ud;
+    vsl = vsl + va + vb + vc + vd;
+    usq = usq + ua * ua + ub * ub + uc * uc + ud * ud;
+    vsq = vsq + va * va + vb * vb + vc * vc + vd * vd;
+    y3[m] = bil(z, Aa.z, Ab.z, Ac.z, Ad.z);
+    g1[m] = bil(z, Ba.x, Bb.x, Bc.x, Bd.x);
+    r1[m] = bil(z, Aa.w, Ab.w, Ac.w, Ad.w);
+    wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
+    wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
+  }
+  L.u = (y1[0] * z.dt2 + y1[1] * z.dt1) * z.dtt;
+  L.v = (y2[0] * z.dt2 + y2[1] * z.dt1) * z.dtt;
+  L.w = (y3[0] * z.dt2 + y3[1] * z.dt1) * z.dtt;
+  L.rho = (r1[0] * z.dt2 + r1[1] * z.dt1) * z.dtt;
+  L.rhograd = (g1[0] * z.dt2 + g1[1] * z.dt1) * z.dtt;
+  float xaux = usq - usl * usl / 8.f;
+  L.usig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  xaux = vsq - vsl * vsl / 8.f;
+  L.vsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  xaux = wsq - wsl * wsl / 8.f;
+  L.wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+}
+
+// src/interpol_wind.f90:56-214 (SIGMA=true) / src/interpol_wind_short.f90:48-140
+template <bool SIGMA>
+__device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *met,
+                                            const Hz &z, const float *sh, float zt,
+                                            float &u, float &v, float &w, float &usig,
+                                            float &vsig, float &wsig) {
+  const int indz = find_indz(sh, c.nz, zt);
+  const float dz = 1.f / (sh[indz] - sh[indz - 1]);
+  const float dz1 = (zt - sh[indz - 1]) * dz;
+  const float dz2 = (sh[indz] - zt) * dz;
+  const int plane = c.nxd * c.nyd;
+  float uh[2], vh[2], wh[2];
+  float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    float u1[2], v1[2], w1[2];
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      const int base = (indz - 1 + n) * plane;
+      const float4 *A = met[m].A + base;
+      float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
+      float ua, ub, uc, ud, va, vb, vc, vd;
+      if (z.ngrid < 0) {
+        const float4 *B = met[m].B + base;
+        float4 Ba = __ldg(B + z.o00), Bb = __ldg(B + z.o10), Bc = __ldg(B + z.o01), Bd = __ldg(B + z.o11);
+        ua = Ba.z; ub = Bb.z; uc = Bc.z; ud = Bd.z;
+        va = Ba.w; vb = Bb.w; vc = Bc.w; vd = Bd.w;
+      } else {
+        ua = Aa.x; ub = Ab.x; uc = Ac.x; ud = Ad.x;
+        va = Aa.y; vb = Ab.y; vc = Ac.y; vd = Ad.y;
+      }
+      u1[n] = bil(z, ua, ub, uc, ud);
+      v1[n] = bil(z, va, vb, vc, vd);
+      w1[n] = bil(z, Aa.z, Ab.z, Ac.z, Ad.z);
+      if (SIGMA) {
+        usl = usl + ua + ub + uc + ud;
+        vsl = vsl + va + vb + vc + vd;
+        usq = usq + ua * ua + ub * ub + uc * uc + ud * ud;
+        vsq = vsq + va * va + vb * vb + vc * vc + vd * vd;
+        wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
+        wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
+      }
+    }
+    uh[m] = dz2 * u1[0] + dz1 * u1[1];
+    vh[m] = dz2 * v1[0] + dz1 * v1[1];
+    wh[m] = dz2 * w1[0] + dz1 * w1[1];
+  }
+  u = (uh[0] * z.dt2 + uh[1] * z.dt1) * z.dtt;
+  v = (vh[0] * z.dt2 + vh[1] * z.dt1) * z.dtt;
+  w = (wh[0] * z.dt2 + wh[1] * z.dt1) * z.dtt;
+  if (SIGMA) {
+    float xaux = usq - usl * usl / 16.f;
+    usig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 15.f);
+    xaux = vsq - vsl * vsl / 16.f;
+    vsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 15.f);
+    xaux = wsq - wsl * wsl / 16.f;
+    wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 15.f);
+  }
+}
+
+// --------------------------------------------------------- turbulence ----
+struct Turb { // hanna_mod
+  float ust, wst, ol, h, zeta, sigu, sigv, tlu, tlv, tlw, sigw, dsigwdz, dsigw2dz;
+};
+
+// src/interpol_all.f90:80-107
+__device__ __forceinline__ void interp_surface(const DevMetSlot *met, const Hz &z, Turb &t) {
+  float us1[2], ws1[2], ol1[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    float4 a = __ldg(met[m].S + z.o00), b = __ldg(met[m].S + z.o10),
+           c = __ldg(met[m].S + z.o01), d = __ldg(met[m].S + z.o11);
+    us1[m] = bil(z, a.y, b.y, c.y, d.y);
+    ws1[m] = bil(z, a.z, b.z, c.z, d.z);
+    ol1[m] = bil(z, a.w, b.w, c.w, d.w);
+  }
+  t.ust = (us1[0] * z.dt2 + us1[1] * z.dt1) * z.dtt;
+  t.wst = (ws1[0] * z.dt2 + ws1[1] * z.dt1) * z.dtt;
+  float oliaux = (ol1[0] * z.dt2 + ol1[1] * z.dt1) * z.dtt;
+  t.ol = (oliaux != 0.f) ? 1.f / oliaux : 99999.f;
+}
+
+// sigma_w, d(sigma_w)/dz and T_Lw of the unstable regime, shared by hanna and
+// hanna_short (src/hanna.f90:66-88, src/hanna_short.f90:59-77)
+__device__ __forceinline__ void hanna_unstable_w(Turb &t, float z) {
+  const float z23 = m_pow(t.zeta, 0.66666f);
+  t.sigw = m_sqrt(1.2f * (t.wst * t.wst) * (1.f - .9f * t.zeta) * z23 +
+                  (1.8f - 1.4f * t.zeta) * (t.ust * t.ust)) + 1.e-2f;
+  t.dsigwdz = 0.5f / t.sigw / t.h *
+              (-1.4f * (t.ust * t.ust) +
+               (t.wst * t.wst) * (0.8f * m_pow(fmaxf(t.zeta, 1.e-3f), -.33333f) - 1.8f * z23));
+  if (z < fabsf(t.ol))
+    t.tlw = 0.1f * z / (t.sigw * (0.55f - 0.38f * fabsf(z / t.ol)));
+  else if (t.zeta < 0.1f)
+    t.tlw = 0.59f * z / t.sigw;
+  else
+    t.tlw = 0.15f * t.h / t.sigw * (1.f - m_exp(-5.f * t.zeta));
+}
+
+// src/hanna.f90:42-106
+__device__ __forceinline__ void hanna(Turb &t, float z) {
+  if (t.h / fabsf(t.ol) < 1.f) {
+    t.ust = fmaxf(1.e-4f, t.ust);
+    float corr = z / t.ust;
+    t.sigu = 1.e-2f + 2.0f * t.ust * m_exp(-3.e-4f * corr);
+    t.sigw = 1.3f * t.ust * m_exp(-2.e-4f * corr);
+    t.dsigwdz = -2.e-4f * t.sigw;
+    t.sigw = t.sigw + 1.e-2f;
+    t.sigv = t.sigw;
+    t.tlu = 0.5f * z / t.sigw / (1.f + 1.5e-3f * corr);
+    t.tlv = t.tlu;
+    t.tlw = t.tlu;
+  } else if (t.ol < 0.f) {
+    t.sigu = 1.e-2f + t.ust * m_pow(12.f - 0.5f * t.h / t.ol, 0.33333f);
+    t.sigv = t.sigu;
+    hanna_unstable_w(t, z);
+    t.tlu = 0.15f * t.h / t.sigu;
+    t.tlv = t.tlu;
+  } else {
+    t.sigu = 1.e-2f + 2.f * t.ust * (1.f - t.zeta);
+    t.sigv = 1.e-2f + 1.3f * t.ust * (1.f - t.zeta);
+    t.sigw = t.sigv;
+    t.dsigwdz = -1.3f * t.ust / t.h;
+    t.tlu = 0.15f * t.h / t.sigu * (m_sqrt(t.zeta));
+    t.tlv = 0.467f * t.tlu;
+    t.tlw = 0.1f * t.h / t.sigw * m_pow(t.zeta, 0.8f);
+  }
+  t.tlu = fmaxf(10.f, t.tlu);
+  t.tlv = fmaxf(10.f, t.tlv);
+  t.tlw = fmaxf(30.f, t.tlw);
+  if (t.dsigwdz == 0.f) t.dsigwdz = 1.e-10f;
+}
+
+// src/hanna_short.f90:42-92
+__device__ __forceinline__ void hanna_short(Turb &t, float z) {
+  if (t.h / fabsf(t.ol) < 1.f) {
+    t.ust = fmaxf(1.e-4f, t.ust);
+    t.sigw = 1.3f * m_exp(-2.e-4f * z / t.ust);
+    t.dsigwdz = -2.e-4f * t.sigw;
+    t.sigw = t.sigw * t.ust + 1.e-2f;
+    t.tlw = 0.5f * z / t.sigw / (1.f + 1.5e-3f * z / t.ust);
+  } else if (t.ol < 0.f) {
+    hanna_unstable_w(t, z);
+  } else {
+    t.sigw = 1.e-2f + 1.3f * t.ust * (1.f - t.zeta);
+    t.dsigwdz = -1.3f * t.ust / t.h;
+    t.tlw = 0.1f * t.h / t.sigw * m_pow(t.zeta, 0.8f);
+  }
+  t.tlu = fmaxf(10.f, t.tlu);
+  t.tlv = fmaxf(10.f, t.tlv);
+  t.tlw = fmaxf(30.f, t.tlw);
+  if (t.dsigwdz == 0.f) t.dsigwdz = 1.e-10f;
+}
+
+// src/hanna1.f90:42-128
+__device__ __forceinline__ void hanna1(Turb &t, float z) {
+  if (t.h / fabsf(t.ol) < 1.f) {
+    t.ust = fmaxf(1.e-4f, t.ust);
+    t.sigu = 2.0f * t.ust * m_exp(-3.e-4f * z / t.ust);
+    t.sigu = fmaxf(t.sigu, 1.e-5f);
+    t.sigv = 1.3f * t.ust * m_exp(-2.e-4f * z / t.ust);
+    t.sigv = fmaxf(t.sigv, 1.e-5f);
+    t.sigw = t.sigv;
+    t.dsigw2dz = -6.76e-4f * t.ust * m_exp(-4.e-4f * z / t.ust);
+    t.tlu = 0.5f * z / t.sigw / (1.f + 1.5e-3f * z / t.ust);
+    t.tlv = t.tlu;
+    t.tlw = t.tlu;
+  } else if (t.ol < 0.f) {
+    t.sigu = t.ust * m_pow(12.f - 0.5f * t.h / t.ol, 0.33333f);
+    t.sigu = fmaxf(t.sigu, 1.e-6f);
+    t.sigv = t.sigu;
+    if (t.zeta < 0.03f) {
+      t.sigw = 0.96f * t.wst * m_pow(3.f * t.zeta - t.ol / t.h, 0.33333f);
+      t.dsigw2dz = 1.8432f * t.wst * t.wst / t.h * m_pow(3.f * t.zeta - t.ol / t.h, -0.33333f);
+    } else if (t.zeta < 0.4f) {
+      float s1 = 0.96f * m_pow(3.f * t.zeta - t.ol / t.h, 0.33333f);
+      float s2 = 0.763f * m_pow(t.zeta, 0.175f);
+      if (s1 < s2) {
+        t.sigw = t.wst * s1;
+        t.dsigw2dz = 1.8432f * t.wst * t.wst / t.h * m_pow(3.f * t.zeta - t.ol / t.h, -0.33333f);
+      } else {
+        t.sigw = t.wst * s2;
+        t.dsigw2dz = 0.203759f * t.wst * t.wst / t.h * m_pow(t.zeta, -0.65f);
+      }
+    } else if (t.zeta < 0.96f) {
+      t.sigw = 0.722f * t.wst * m_pow(1.f - t.zeta, 0.207f);
+      t.dsigw2dz = -.215812f * t.wst * t.wst / t.h * m_pow(1.f - t.zeta, -0.586f);
+    } else { // zeta in [0.96,1]; the reference leaves zeta == 1 undefined
+      t.sigw = 0.37f * t.wst;
+      t.dsigw2dz = 0.f;
+    }
+    t.sigw = fmaxf(t.sigw, 1.e-6f);
+    t.tlu = 0.15f * t.h / t.sigu;
+    t.tlv = t.tlu;
+    if (z < fabsf(t.ol))
+      t.tlw = 0.1f * z / (t.sigw * (0.55f - 0.38f * fabsf(z / t.ol)));
+    else if (t.zeta < 0.1f)
+      t.tlw = 0.59f * z / t.sigw;
+    else
+      t.tlw = 0.15f * t.h / t.sigw * (1.f - m_exp(-5.f * t.zeta));
+  } else {
+    t.sigu = 2.f * t.ust * (1.f - t.zeta);
+    t.sigv = 1.3f * t.ust * (1.f - t.zeta);
+    t.sigu = fmaxf(t.sigu, 1.e-6f);
+    t.sigv = fmaxf(t.sigv, 1.e-6f);
+    t.sigw = t.sigv;
+    t.dsigw2dz = 3.38f * t.ust * t.ust * (t.zeta - 1.f) / t.h;
+    t.tlu = 0.15f * t.h / t.sigu * (m_sqrt(t.zeta));
+    t.tlv = 0.467f * t.tlu;
+    t.tlw = 0.1f * t.h / t.sigw * m_pow(t.zeta, 0.8f);
+  }
+  t.tlu = fmaxf(10.f, t.tlu);
+  t.tlv = fmaxf(10.f, t.tlv);
+  t.tlw = fmaxf(30.f, t.tlw);
+}
+
+// src/windalign.f90:36-54
+__device__ __forceinline__ void windalign(float u, float v, float ffap, float ffcp,
+                                          float &ux, float &vy) {
+  float ffinv = 1.f / fmaxf(m_sqrt(u * u + v * v), 1.e-30f);
+  float sinphi = v * ffinv;
+  float vy1 = sinphi * ffap;
+  float cosphi = u * ffinv;
+  float ux1 = cosphi * ffap;
+  float ux2 = -sinphi * ffcp;
+  float vy2 = cosphi * ffcp;
+  ux = ux1 + ux2;
+  vy = vy1 + vy2;
+}
+
+// ------------------------------------------------- conformal map (poles) ----
+// Taylor's CMAPF transformations as used by FLEXPART poleward of +-75 deg
+// (src/cmapf_mod.f90: cspanf :494, cnllxy :310, cnxyll :367, cll2xy :295,
+// cxy2ll :526, cgszll :190).  Which sub-expressions run in double follows
+// the reference's declarations.
+constexpr float CM_REARTH = 6371.2f, CM_ALMST1 = .9999999f;
+constexpr float CM_PI = 3.14159265358979f;
+constexpr float CM_RADPDG = CM_PI / 180.f, CM_DGPRAD = 180.f / CM_PI;
+
+__device__ __forceinline__ float cspanf(float value, float begin, float end) {
+  float first = fminf(begin, end), last = fmaxf(begin, end);
+  float val = fmodf(value - first, last - first);
+  return (val <= 0.f) ? val + last : val + first;
+}
+
+__device__ void cnllxy(const float *sc, float xlat, float xlong, float &xi, float &eta) {
+  double gamma = sc[0];
+  double dlat = xlat;
+  double dlong = cspanf(xlong - sc[1], -180.f, 180.f);
+  dlong = dlong * CM_RADPDG;
+  float gdlong = (float)(gamma * dlong), sndgam, csdgam, rhog1;
+  if (fabsf(gdlong) < .01f) {
+    gdlong = gdlong * gdlong;
+    sndgam = (float)(dlong * (1.f - 1.f / 6.f * gdlong * (1.f - 1.f / 20.f * gdlong * (1.f - 1.f / 42.f * gdlong))));
+    csdgam = (float)(dlong * dlong * .5f * (1.f - 1.f / 12.f * gdlong * (1.f - 1.f / 30.f * gdlong * (1.f - 1.f / 56.f * gdlong))));
+  } else {
+    sndgam = (float)(m_sin(gdlong) / gamma);
+    csdgam = (float)((1.f - m_cos(gdlong)) / gamma / gamma);
+  }
+  double slat = sin(CM_RADPDG * dlat);
+  if ((slat >= CM_ALMST1) || (slat <= -CM_ALMST1)) {
+    eta = 1.f / sc[0];
+    xi = 0.f;
+    return;
+  }
+  double mercy = .5f * log((1.f + slat) / (1.f - slat));
+  double gmercy = gamma * mercy;
+  if (fabs(gmercy) < .001f)
+    rhog1 = (float)(mercy * (1.f - .5f * gmercy * (1.f - 1.f / 3.f * gmercy * (1.f - 1.f / 4.f * gmercy))));
+  else
+    rhog1 = (float)((1.f - exp(-gmercy)) / gamma);
+  eta = (float)(rhog1 + (1.f - gamma * rhog1) * gamma * csdgam);
+  xi = (float)((1.f - gamma * rhog1) * sndgam);
+}
+
+__device__ void cnxyll(const float *sc, double xi, double eta, float &xlat, float &xlong) {
+  double gamma = sc[0], temp, ymerc, along;
+  double arg2 = 2.f * eta - gamma * (xi * xi + eta * eta);
+  double arg1 = gamma * arg2;
+  if (fabs(arg1) < .01f) {
+    temp = (arg1 / (2.f - arg1)) * (arg1 / (2.f - arg1));
+    ymerc = arg2 / (2.f - arg1) * (1.f + temp * (1.f / 3.f + temp * (1.f / 5.f + temp * (1.f / 7.f))));
+  } else {
+    ymerc = -log(1.f - arg1) / 2.f / gamma;
+  }
+  temp = exp(-fabs(ymerc));
+  xlat = (float)copysign(atan2((1.f - temp) * (1.f + temp), 2.f * temp), ymerc);
+  double gxi = gamma * xi, cgeta = 1.f - gamma * eta;
+  if (fabs(gxi) < .01f * cgeta) {
+    temp = (gxi / cgeta) * (gxi / cgeta);
+    along = xi / cgeta * (1.f - temp * (1.f / 3.f - temp * (1.f / 5.f - temp * (1.f / 7.f))));
+  } else {
+    along = atan2(gxi, cgeta) / gamma;
+  }
+  xlong = (float)(sc[1] + CM_DGPRAD * along);
+  xlat = xlat * CM_DGPRAD;
+}
+
+__device__ void cll2xy(const float *sc, float xlat, float xlong, float &x, float &y) {
+  float xi, eta;
+  cnllxy(sc, xlat, xlong, xi, eta);
+  x = sc[2] + CM_REARTH / sc[6] * (xi * sc[4] + eta * sc[5]);
+  y = sc[3] + CM_REARTH / sc[6] * (eta * sc[4] - xi * sc[5]);
+}
+
+__device__ void cxy2ll(const float *sc, float x, float y, float &xlat, float &xlong) {
+  double xi0 = (x - sc[2]) * sc[6] / CM_REARTH;
+  double eta0 = (y - sc[3]) * sc[6] / CM_REARTH;
+  double xi = xi0 * sc[4] - eta0 * sc[5];
+  double eta = eta0 * sc[4] + xi0 * sc[5];
+  cnxyll(sc, xi, eta, xlat, xlong);
+  xlong = cspanf(xlong, -180.f, 180.f);
+}
+
+__device__ float cgszll(const float *sc, float xlat) {
+  double slat, ymerc, efact;
+  if (xlat > 89.985f) {
+    if (sc[0] > 0.9999f) return 2.f * sc[6];
+    efact = m_cos(CM_RADPDG * xlat);
+    if (efact <= 0.) return 0.f;
+    ymerc = -log(efact / (1.f + m_sin(CM_RADPDG * xlat)));
+  } else if (xlat < -89.985f) {
+    if (sc[0] < -0.9999f) return 2.f * sc[6];
+    efact = m_cos(CM_RADPDG * xlat);
+    if (efact <= 0.) return 0.f;
+    ymerc = log(efact / (1.f - m_sin(CM_RADPDG * xlat)));
+  } else {
+    slat = m_sin(CM_RADPDG * xlat);
+    ymerc = log((1.f + slat) / (1.f - slat)) / 2.f;
+  }
+  return (float)(sc[6] * m_cos(CM_RADPDG * xlat) * exp(sc[0] * ymerc));
+}
+
+// position update: src/advance.f90:750-778 (tfac = ldirect) and :923-951
+// (tfac = ldt*ldirect)
+__device__ __forceinline__ void move_horizontal(const DevCfg &c, int ngrid, double &xt,
+                                                double &yt, float dxm, float dym, float tfac) {
+  if (ngrid >= 0) {
+    float cosfact = (float)(c.dxconst / cos((yt * c.dy + c.ylat0) * PI180));
+    xt = xt + (double)(dxm * cosfact * tfac);
+    yt = yt + (double)(dym * c.dyconst * tfac);
+  } else {
+    const float *map = (ngrid == -1) ? c.northpolemap : c.southpolemap;
+    float xlon = (float)(c.xlon0 + xt * c.dx);
+    float ylat = (float)(c.ylat0 + yt * c.dy);
+    float xpol, ypol;
+    cll2xy(map, ylat, xlon, xpol, ypol);
+    float gridsize = 1000.f * cgszll(map, ylat);
+    dxm = dxm / gridsize;
+    dym = dym / gridsize;
+    xpol = xpol + dxm * tfac;
+    ypol = ypol + dym * tfac;
+    cxy2ll(map, xpol, ypol, ylat, xlon);
+    xt = (xlon - c.xlon0) / c.dx;
+    yt = (ylat - c.ylat0) / c.dy;
+  }
+}
+
+// cyclic boundary, pole crossing, domain exit: src/advance.f90:784-808
+__device__ __forceinline__ bool wrap_and_check(const DevCfg &c, double &xt, double &yt) {
+  const float eps = c.eps;
+  if (c.xglobal) {
+    if (xt >= (float)c.nxmin1) xt = xt - (float)c.nxmin1;
+    if (xt < 0.) xt = xt + (float)c.nxmin1;
+    if (xt <= eps) xt = eps;
+    if (fabs(xt - (float)c.nxmin1) <= eps) xt = (float)c.nxmin1 - eps;
+    if (yt < 0.) {
+      xt = d_modulo(xt * c.dx + 180.f, 360.f) / c.dx;
+      yt = -yt;
+    } else if (yt > (float)c.nymin1) {
+      xt = d_modulo(xt * c.dx + 180.f, 360.f) / c.dx;
+      yt = 2 * (float)c.nymin1 - yt;
+    }
+  }
+  return (xt < 0.) || (xt >= (float)c.nxmin1) || (yt < 0.) || (yt > (float)c.nymin1);
+}
+
+__device__ __forceinline__ int pole_grid(const DevCfg &c, double yt) {
+  if (c.nglobal && (yt > c.switchnorthg)) return -1;
+  if (c.sglobal && (yt < c.switchsouthg)) return -2;
+  return 0;
+}
+
+// ------------------------------------------------------------ settling ----
+// src/get_settling.f90:52-125 + dynamic_viscosity.f90; rho/tt from Fortran
+// slot 1 (literal in the reference)
+__device__ float get_settling(const DevCfg &c, const DevMetSlot &lit1, const float *sh,
+                              float xt, float yt, float zt, int nsp) {
+  const float ga = 9.81f;
+  int nix = f_int(xt), njy = f_int(yt);
+  int indz = find_indz(sh, c.nz, zt);
+  float dz = 1.f / (sh[indz] - sh[indz - 1]);
+  float dz1 = (zt - sh[indz - 1]) * dz;
+  float dz2 = (sh[indz] - zt) * dz;
+  int plane = c.nxd * c.nyd, o = nix + c.nxd * njy;
+  float4 A0 = __ldg(lit1.A + (indz - 1) * plane + o), A1 = __ldg(lit1.A + indz * plane + o);
+  float4 B0 = __ldg(lit1.B + (indz - 1) * plane + o), B1 = __ldg(lit1.B + indz * plane + o);
+  float temperature = dz2 * B0.y + dz1 * B1.y;
+  float airdens = dz2 * A0.w + dz1 * A1.w;
+  const float cc = 120.f, t_0 = 291.15f, eta_0 = 1.827e-5f;
+  float vis_dyn = eta_0 * (t_0 + cc) / (temperature + cc) * m_pow(temperature / t_0, 1.5f);
+  float vis_kin = vis_dyn / airdens;
+  float dq = c.dquer[nsp - 1], vsa = c.vsetaver[nsp - 1];
+  float reynolds = dq / 1.e6f * fabsf(vsa) / vis_kin;
+  float settling_old = vsa, settling = 0.f, c_d;
+  for (int i = 1; i <= 20; i++) {
+    if (reynolds < 1.917f) c_d = 24.f / reynolds;
+    else if (reynolds < 500.f) c_d = 18.5f / m_pow(reynolds, 0.6f);
+    else c_d = 0.44f;
+    settling = -1.f * m_sqrt(4.f * ga * dq / 1.e6f * c.density[nsp - 1] * c.cunningham[nsp - 1] /
+                             (3.f * c_d * airdens));
+    if (fabsf((settling - settling_old) / settling) < 0.01f) break;
+    reynolds = dq / 1.e6f * fabsf(settling) / vis_kin;
+    settling_old = settling;
+  }
+  return settling;
+}
+
+// species choice + call, src/advance.f90:518-531
+__device__ __forceinline__ float settling_term(const DevStepArgs &a, const float *sh,
+                                               int nrelpoint, double xt, double yt, float zt) {
+  const DevCfg &c = a.cfg;
+  if (c.mdomainfill != 0 || !c.lsettling) return 0.f;
+  int nsp;
+  for (nsp = 1; nsp <= c.nspec; nsp++)
+    if (__ldg(a.xmass + (nsp - 1) * c.numpoint + (nrelpoint - 1)) > EPS3) break;
+  if (nsp > c.nspec) nsp = c.nspec;
+  if (c.density[nsp - 1] > 0.f)
+    return get_settling(c, a.met_lit1, sh, (float)xt, (float)yt, zt, nsp);
+  return 0.f;
+}
+
+// ------------------------------------------------------------------ CBL ----
+#include "fpb_cbl.cuh"
+
+// --------------------------------------------------------- deposition ----
+// src/drydepokernel.f90:41-116 and drydepokernel_nest.f90
+__device__ __forceinline__ size_t didx(const DevCfg &c, int nxg, int nyg, int ix, int jy,
+                                       int ks, int kp, int nc, int na) {
+  size_t i = (size_t)(na - 1);
+  i = i * c.nclassunc + (nc - 1);
+  i = i * c.maxpointspec_act + (kp - 1);
+  i = i * c.nspec + (ks - 1);
+  i = i * nyg + jy;
+  i = i * nxg + ix;
+  return i;
+}
+
+__device__ void drydepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc,
+                                const float *deposit, float x, float y, int nage, int kp) {
+  const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
+  float xl, yl;
+  if (nest) {
+    xl = (x * c.dx + c.xoutshiftn) / c.dxoutn;
+    yl = (y * c.dy + c.youtshiftn) / c.dyoutn;
+  } else {
+    xl = (x * c.dx + c.xoutshift) / c.dxout;
+    yl = (y * c.dy + c.youtshift) / c.dyout;
+  }
+  int ix = f_int(xl), jy = f_int(yl), ixp, jyp;
+  float ddx = xl - (float)ix, ddy = yl - (float)jy, wx, wy;
+  if (ddx > 0.5f) { ixp = ix + 1; wx = 1.5f - ddx; } else { ixp = ix - 1; wx = 0.5f + ddx; }
+  if (ddy > 0.5f) { jyp = jy + 1; wy = 1.5f - ddy; } else { jyp = jy - 1; wy = 0.5f + ddy; }
+  const bool in00 = (ix >= 0) && (jy >= 0) && (ix <= nxg - 1) && (jy <= nyg - 1);
+  const bool in11 = (ixp >= 0) && (jyp >= 0) && (ixp <= nxg - 1) && (jyp <= nyg - 1);
+  const bool in10 = (ixp >= 0) && (jy >= 0) && (ixp <= nxg - 1) && (jy <= nyg - 1);
+  const bool in01 = (ix >= 0) && (jyp >= 0) && (ix <= nxg - 1) && (jyp <= nyg - 1);
+  for (int ks = 1; ks <= c.nspec; ks++) {
+    float dep = deposit[ks - 1];
+    if (!((fabsf(dep) > 0.f) && c.drydepspec[ks - 1])) continue;
+    if (!nest && !c.lusekerneloutput) {
+      if (in00) atomicAdd(grid + didx(c, nxg, nyg, ix, jy, ks, kp, nunc, nage), dep);
+      continue;
+    }
+    if (in00) atomicAdd(grid + didx(c, nxg, nyg, ix, jy, ks, kp, nunc, nage), dep * (wx * wy));
+    if (in11) atomicAdd(grid + didx(c, nxg, nyg, ixp, jyp, ks, kp, nunc, nage), dep * ((1.f - wx) * (1.f - wy)));
+    if (in10) atomicAdd(grid + didx(c, nxg, nyg, ixp, jy, ks, kp, nunc, nage), dep * ((1.f - wx) * wy));
+    if (in01) atomicAdd(grid + didx(c, nxg, nyg, ix, jyp, ks, kp, nunc, nage), dep * (wx * (1.f - wy)));
+  }
+}
+
+// =========================================================== step kernel ===
+struct PState { // the advance() in/out arguments of one particle
+  double xt, yt;
+  float zt, up, vp, wp, usigold, vsigold, wsigold;
+  int ldt, icbt;
+};
+
+// src/initialize.f90:66-217
+template <bool CBL>
+__device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, int nrand,
+                              PState &s) {
+  const DevCfg &c = a.cfg;
+  s.icbt = 1;
+  const int ngrid = pole_grid(c, s.yt); // "defined" behaviour, see DESIGN.md
+  int ix = d_int(s.xt), jy = d_int(s.yt), ixp = ix + 1, jyp = jy + 1;
+  if (jyp >= c.nymax) jyp = jyp - 1;
+  Hz z;
+  z.ngrid = ngrid;
+  make_weights(c, z, c.itime, (float)s.xt, (float)s.yt, ix, jy, ixp, jyp);
+  Turb t;
+  {
+    float h = __ldg(a.met[0].S + z.o00).x;
+    h = fmaxf(h, __ldg(a.met[0].S + z.o10).x);
+    h = fmaxf(h, __ldg(a.met[0].S + z.o01).x);
+    h = fmaxf(h, __ldg(a.met[0].S + z.o11).x);
+    h = fmaxf(h, __ldg(a.met[1].S + z.o00).x);
+    h = fmaxf(h, __ldg(a.met[1].S + z.o10).x);
+    h = fmaxf(h, __ldg(a.met[1].S + z.o01).x);
+    h = fmaxf(h, __ldg(a.met[1].S + z.o11).x);
+    t.h = h;
+  }
+  t.zeta = s.zt / t.h;
+  float usig, vsig, wsig;
+  if (t.zeta <= 1.f) {
+    interp_surface(a.met, z, t);
+    const int indz = find_indz(sh, c.nz, s.zt), indzp = indz + 1;
+    Lev lo, hi;
+    profile_level(c, a.met, z, indz, lo);
+    profile_level(c, a.met, z, indzp, hi);
+    // (u, v, w of initialize are dead: advance re-interpolates)
+    if (c.turbswitch) hanna(t, s.zt); else hanna1(t, s.zt);
+    if (nrand + 2 > c.maxrand) nrand = 1;
+    s.up = rng.get(nrand) * t.sigu;
+    s.vp = rng.get(nrand + 1) * t.sigv;
+    s.wp = rng.get(nrand + 2);
+    if (!c.turbswitch) {
+      s.wp = s.wp * t.sigw;
+    } else if (CBL && c.cblflag == 1) {
+      if (-t.h / t.ol > 5.f)
+        s.wp = cbl_initial_velocity(c, (float)(nrand - 1) / (float)(c.maxrand - 1),
+                                    rng.get(nrand + 3), s.zt, t.wst, t.h, t.sigw, t.ol);
+      else
+        s.wp = s.wp * t.sigw;
+    }
+    if (c.turbswitch) {
+      float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(s.wp * t.sigw), 1.e-5f));
+      q = fminf(q, 0.5f / fabsf(t.dsigwdz));
+      q = fminf(q, 600.f);
+      s.ldt = f_int(q * c.ctl);
+    } else {
+      float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(s.wp), 1.e-5f));
+      q = fminf(q, 600.f);
+      s.ldt = f_int(q * c.ctl);
+    }
+    s.ldt = max(s.ldt, c.mintime);
+    usig = (hi.usig + lo.usig) / 2.f;
+    vsig = (hi.vsig + lo.vsig) / 2.f;
+    wsig = (hi.wsig + lo.wsig) / 2.f;
+  } else {
+    float u, v, w;
+    interp_wind<true>(c, a.met, z, sh, s.zt, u, v, w, usig, vsig, wsig);
+    s.ldt = abs(c.lsynctime);
+    if (nrand + 1 > c.maxrand) nrand = 1;
+    s.up = rng.get(nrand) * 0.3f;
+    s.vp = rng.get(nrand + 1) * 0.3f;
+    nrand = nrand + 2;
+    s.wp = 0.f;
+  }
+  if (nrand + 2 > c.maxrand) nrand = 1;
+  s.usigold = rng.get(nrand) * usig;
+  s.vsigold = rng.get(nrand + 1) * vsig;
+  s.wsigold = rng.get(nrand + 2) * wsig;
+}
+
+struct AdvOut {
+  int nstop, nsub, pbl, pett, nan_cbl;
+};
+
+// src/advance.f90:133-985
+template <bool DRYDEP, bool CBL>
+__device__ void do_advance(const DevStepArgs &a, const float *sh, Rng &rng, int nrand,
+                           int nrelpoint, PState &s, float *prob, AdvOut &out) {
+  const DevCfg &c = a.cfg;
+  const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
+  const float eps = c.eps;
+  const float ztop = sh[nz - 1];
+  out.nstop = 0; out.nsub = 0; out.pbl = 0; out.pett = 0; out.nan_cbl = 0;
+
+  float vdepo[DRYDEP ? FPB_MAXSPEC : 1];
+  unsigned depo_todo = 0xffu;
+  if (DRYDEP) {
+#pragma unroll
+    for (int ks = 0; ks < FPB_MAXSPEC; ks++) { prob[ks] = 0.f; vdepo[ks] = 0.f; }
+  }
+
+  float dxsave = 0.f, dysave = 0.f, dawsave = 0.f, dcwsave = 0.f;
+  int itimec = itime;
+
+  const int ngrid = pole_grid(c, s.yt);
+  int ix = d_int(s.xt), jy = d_int(s.yt);
+  const int nix = d_nint(s.xt), njy = d_nint(s.yt);
+  int ixp = ix + 1, jyp = jy + 1;
+  if (jyp >= c.nymax) jyp = jyp - 1;
+
+  Hz z;
+  z.ngrid = ngrid;
+  make_weights(c, z, itime, (float)s.xt, (float)s.yt, ix, jy, ixp, jyp);
+
+  Turb t;
+  {
+    float h = 0.f; // advance.f90:236-252: max over 4 corners x 2 slots
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
+      float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
+      if (v0 > h) h = v0;
+      if (v1 > h) h = v1;
+      if (v2 > h) h = v2;
+      if (v3 > h) h = v3;
+    }
+    t.h = h;
+  }
+  const float tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal
+  t.zeta = s.zt / t.h;
+
+  float u = 0.f, v = 0.f, w = 0.f, usig = 0.f, vsig = 0.f, wsig = 0.f;
+  float ux = 0.f, vy = 0.f;
+  int ldt = s.ldt, icbt = s.icbt;
+  float zt = s.zt, up = s.up, vp = s.vp, wp = s.wp;
+  bool above = !(t.zeta <= 1.f);
+
+  if (!above) {
+    out.pbl = 1;
+    interp_surface(a.met, z, t);
+    int indz = 0, indzp = 0; // cached pair
+    Lev lo, hi;
+    int loop = 0;
+    for (;;) {
+      loop++;
+      out.nsub++;
+      if (c.method == 1) {
+        ldt = min(ldt, abs(c.lsynctime - itimec + itime));
+        itimec = itimec + ldt * c.ldirect;
+      } else {
+        ldt = abs(c.lsynctime);
+        itimec = itime + c.lsynctime;
+      }
+      const float dt = (float)ldt;
+      t.zeta = zt / t.h;
+
+      // level pair under the particle; reuse a cached level when possible
+      {
+        const int ni = find_indz(sh, nz, zt), nip = ni + 1;
+        if (loop == 1) {
+          profile_level(c, a.met, z, ni, lo);
+          profile_level(c, a.met, z, nip, hi);
+        } else if (ni != indz) {
+          if (ni == indzp) {
+            lo = hi;
+            profile_level(c, a.met, z, nip, hi);
+          } else if (nip == indz) {
+            hi = lo;
+            profile_level(c, a.met, z, ni, lo);
+          } else {
+            profile_level(c, a.met, z, ni, lo);
+            profile_level(c, a.met, z, nip, hi);
+          }
+        }
+        indz = ni;
+        indzp = nip;
+      }
+
+      // advance.f90:342-350
+      const float dz = 1.f / (sh[indzp - 1] - sh[indz - 1]);
+      const float dz1 = (zt - sh[indz - 1]) * dz;
+      const float dz2 = (sh[indzp - 1] - zt) * dz;
+      u = dz1 * hi.u + dz2 * lo.u;
+      v = dz1 * hi.v + dz2 * lo.v;
+      w = dz1 * hi.w + dz2 * lo.w;
+      const float rhoa = dz1 * hi.rho + dz2 * lo.rho;
+      const float rhograd = dz1 * hi.rhograd + dz2 * lo.rhograd;
+
+      if (c.turbswitch) hanna(t, zt); else hanna1(t, zt);
+
+      // horizontal turbulent velocities, advance.f90:371-384
+      if (nrand + 1 > maxrand) nrand = 1;
+      if (dt / t.tlu < .5f) {
+        up = (1.f - dt / t.tlu) * up + rng.get(nrand) * t.sigu * m_sqrt(2.f * dt / t.tlu);
+      } else {
+        float ru = m_exp(-dt / t.tlu);
+        up = ru * up + rng.get(nrand) * t.sigu * m_sqrt(1.f - ru * ru);
+      }
+      if (dt / t.tlv < .5f) {
+        vp = (1.f - dt / t.tlv) * vp + rng.get(nrand + 1) * t.sigv * m_sqrt(2.f * dt / t.tlv);
+      } else {
+        float rv = m_exp(-dt / t.tlv);
+        vp = rv * vp + rng.get(nrand + 1) * t.sigv * m_sqrt(1.f - rv * rv);
+      }
+      nrand = nrand + 2;
+
+      if (nrand + c.ifine > maxrand) nrand = 1;
+      const float rhoaux = rhograd / rhoa;
+      const float dtf = dt * c.fine;
+      const float dtftlw = dtf / t.tlw;
+
+      // vertical component in ifine short steps, advance.f90:396-498
+      for (int i = 1; i <= c.ifine; i++) {
+        float delz;
+        if (c.turbswitch) {
+          if (dtftlw < .5f) {
+            if (CBL && c.cblflag == 1) {
+              if (-t.h / t.ol > 5.f) {
+                int flagrein = 0;
+                nrand = nrand + 1;
+                float old_wp_buf = wp, ath, bth;
+                cbl_drift(c, wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol,
+                          ath, bth, flagrein);
+                wp = (wp + ath * dtf + bth * rng.get(nrand) * m_sqrt(dtf)) * (float)icbt;
+                delz = wp * dtf;
+                if (flagrein == 1) {
+                  cbl_reinitialize(c, rng, zt, t.wst, t.h, t.sigw, t.ol, old_wp_buf, nrand);
+                  wp = old_wp_buf;
+                  delz = wp * dtf;
+                  out.nan_cbl++;
+                }
+              } else {
+                nrand = nrand + 1;
+                float ath = -wp / t.tlw + t.sigw * t.dsigwdz + wp * wp / t.sigw * t.dsigwdz +
+                            t.sigw * t.sigw / rhoa * rhograd;
+                float bth = t.sigw * rng.get(nrand) * m_sqrt(2.f * dtftlw);
+                wp = (wp + ath * dtf + bth) * (float)icbt;
+                delz = wp * dtf;
+                float del_test = (1.f - wp) / wp;
+                if (isnan(wp) || isnan(del_test)) {
+                  nrand = nrand + 1;
+                  wp = t.sigw * rng.get(nrand);
+                  delz = wp * dtf;
+                  out.nan_cbl++;
+                }
+              }
+            } else {
+              wp = ((1.f - dtftlw) * wp + rng.get(nrand + i) * m_sqrt(2.f * dtftlw) +
+                    dtf * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
+              delz = wp * t.sigw * dtf;
+            }
+          } else {
+            float rw = m_exp(-dtftlw);
+            wp = (rw * wp + rng.get(nrand + i) * m_sqrt(1.f - rw * rw) +
+                  t.tlw * (1.f - rw) * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
+            delz = wp * t.sigw * dtf;
+          }
+        } else {
+          float rw = m_exp(-dtftlw);
+          wp = (rw * wp + rng.get(nrand + i) * m_sqrt(1.f - rw * rw) * t.sigw +
+                t.tlw * (1.f - rw) * (t.dsigw2dz + rhoaux * (t.sigw * t.sigw))) * (float)icbt;
+          delz = wp * dtf;
+        }
+        if (c.turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
+
+        if (fabsf(delz) > t.h) delz = fmodf(delz, t.h);
+        if (delz < -zt) {            // reflection at the ground
+          icbt = -1;
+          zt = -zt - delz;
+        } else if (delz > (t.h - zt)) { // reflection at h
+          icbt = -1;
+          zt = -zt - delz + 2.f * t.h;
+        } else {
+          icbt = 1;
+          zt = zt + delz;
+        }
+        if (i != c.ifine) {
+          t.zeta = zt / t.h;
+          hanna_short(t, zt);
+        }
+      }
+      if (!(CBL && c.cblflag == 1)) nrand = nrand + (c.ifine + 1);
+
+      // next time step, advance.f90:504-510
+      if (c.turbswitch) {
+        float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp * t.sigw), 1.e-5f));
+        q = fminf(q, 0.5f / fabsf(t.dsigwdz));
+        ldt = f_int(q * c.ctl);
+      } else {
+        float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp), 1.e-5f));
+        ldt = f_int(q * c.ctl);
+      }
+      ldt = max(ldt, c.mintime);
+
+      w = w + settling_term(a, sh, nrelpoint, s.xt, s.yt, zt);
+
+      dxsave = dxsave + u * dt;
+      dysave = dysave + v * dt;
+      dawsave = dawsave + up * dt;
+      dcwsave = dcwsave + vp * dt;
+      zt = zt + w * dt * (float)c.ldirect;
+
+      if (zt >= ztop) zt = ztop - 100.f * eps;
+
+      if (zt > t.h) {
+        if (itimec == itime + c.lsynctime) {
+          // "defined" behaviour for the stale-usig case
+          usig = 0.5f * (hi.usig + lo.usig);
+          vsig = 0.5f * (hi.vsig + lo.vsig);
+          wsig = 0.5f * (hi.wsig + lo.wsig);
+        } else {
+          above = true;
+        }
+        break;
+      }
+
+      // dry-deposition probability, advance.f90:582-599
+      if (DRYDEP && c.drydep && (zt < 2.f * HREF)) {
+#pragma unroll
+        for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
+          if (ks < c.nspec && c.drydepspec[ks]) {
+            if (depo_todo & (1u << ks)) { // interpol_vdep, src/interpol_vdep.f90:39-54
+              const int off = ks * (c.nxd * c.nyd);
+              float y0 = bil(z, __ldg(a.met[0].vdep + off + z.o00), __ldg(a.met[0].vdep + off + z.o10),
+                             __ldg(a.met[0].vdep + off + z.o01), __ldg(a.met[0].vdep + off + z.o11));
+              float y1 = bil(z, __ldg(a.met[1].vdep + off + z.o00), __ldg(a.met[1].vdep + off + z.o10),
+                             __ldg(a.met[1].vdep + off + z.o01), __ldg(a.met[1].vdep + off + z.o11));
+              vdepo[ks] = (y0 * z.dt2 + y1 * z.dt1) * z.dtt;
+              depo_todo &= ~(1u << ks);
+            }
+            prob[ks] = 1.f + (prob[ks] - 1.f) * m_exp(-vdepo[ks] * fabsf(dt) / (2.f * HREF));
+          }
+        }
+      }
+
+      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+
+      if (itimec == (itime + c.lsynctime)) {
+        usig = 0.5f * (hi.usig + lo.usig);
+        vsig = 0.5f * (hi.vsig + lo.vsig);
+        wsig = 0.5f * (hi.wsig + lo.wsig);
+        break;
+      }
+    }
+  }
+
+  if (above) { // label 700, advance.f90:629-708
+    interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
+    ldt = abs(c.lsynctime - itimec + itime);
+    const float dt = (float)ldt;
+    if (zt < tropop) {
+      float uxscale = m_sqrt(2.f * c.d_trop / dt);
+      if (nrand + 1 > maxrand) nrand = 1;
+      ux = rng.get(nrand) * uxscale;
+      vy = rng.get(nrand + 1) * uxscale;
+      nrand = nrand + 2;
+      wp = 0.f;
+    } else if (zt < tropop + 1000.f) {
+      float weight = (zt - tropop) / 1000.f;
+      float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
+      if (nrand + 2 > maxrand) nrand = 1;
+      ux = rng.get(nrand) * uxscale;
+      vy = rng.get(nrand + 1) * uxscale;
+      float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
+      wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
+      nrand = nrand + 3;
+    } else {
+      if (nrand > maxrand) nrand = 1;
+      ux = 0.f;
+      vy = 0.f;
+      float wpscale = m_sqrt(2.f * c.d_strat / dt);
+      wp = rng.get(nrand) * wpscale;
+      nrand = nrand + 1;
+    }
+    if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
+
+    w = w + settling_term(a, sh, nrelpoint, s.xt, s.yt, zt);
+
+    dxsave = dxsave + (u + ux) * dt;
+    dysave = dysave + (v + vy) * dt;
+    zt = zt + (w + wp) * dt * (float)c.ldirect;
+    if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+  }
+
+  // label 99: mesoscale fluctuations, advance.f90:728-739
+  {
+    float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
+    float rs = m_sqrt(1.f - r * r);
+    if (nrand + 2 > maxrand) nrand = 1;
+    s.usigold = r * s.usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
+    s.vsigold = r * s.vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
+    s.wsigold = r * s.wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
+    dxsave = dxsave + s.usigold * (float)c.lsynctime;
+    dysave = dysave + s.vsigold * (float)c.lsynctime;
+    zt = zt + s.wsigold * (float)c.lsynctime;
+    if (zt < 0.f) zt = -1.f * zt;
+  }
+
+  // advance.f90:747-778
+  windalign(dxsave, dysave, dawsave, dcwsave, ux, vy);
+  dxsave = dxsave + ux;
+  dysave = dysave + vy;
+  double xt = s.xt, yt = s.yt;
+  move_horizontal(c, ngrid, xt, yt, dxsave, dysave, (float)c.ldirect);
+
+  bool done = false;
+  if (wrap_and_check(c, xt, yt)) {
+    out.nstop = 3;
+    done = true;
+  }
+  if (!done) {
+    if (zt >= ztop) zt = ztop - 100.f * eps;
+    // Petterssen corrector, advance.f90:829-985
+    if (ldt != abs(c.lsynctime)) done = true;
+    else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
+    else if (pole_grid(c, yt) != ngrid) done = true;
+  }
+  if (!done) {
+    ix = d_int(xt);
+    jy = d_int(yt);
+    ixp = ix + 1;
+    jyp = jy + 1;
+    if (jyp >= c.nymax) jyp = jyp - 1;
+    const float uold = u, vold = v, wold = w;
+    make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    float d0, d1, d2;
+    interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
+    out.pett = 1;
+    w = w + settling_term(a, sh, nrelpoint, xt, yt, zt);
+    u = (u - uold) / 2.f;
+    v = (v - vold) / 2.f;
+    w = (w - wold) / 2.f;
+    zt = zt + w * (float)(ldt * c.ldirect);
+    if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+    move_horizontal(c, ngrid, xt, yt, u, v, (float)(ldt * c.ldirect));
+    if (wrap_and_check(c, xt, yt)) {
+      out.nstop = 3;
+    } else if (zt >= ztop) {
+      zt = ztop - 100.f * eps;
+    }
+  }
+
+  s.xt = xt; s.yt = yt; s.zt = zt;
+  s.up = up; s.vp = vp; s.wp = wp;
+  s.ldt = ldt; s.icbt = icbt;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
+  return (unsigned long long)__reduce_add_sync(0xffffffffu, v);
+}
+
+template <bool DRYDEP, bool CBL>
+__global__ void __launch_bounds__(128)
+fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int itime = c.itime;
+  unsigned n_act = 0, n_init = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
+
+  if (j < c.numpart && a.p.itra1[j] == itime) {
+    n_act = 1;
+    const int itramem = a.p.itramem[j];
+    const int npoint = a.p.npoint[j];
+    const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
+    const int itage = abs(itime - itramem);
+    int nage;
+    for (nage = 1; nage <= c.nageclass; nage++)
+      if (itage < c.lage[nage - 1]) break;
+
+    PState s;
+    s.xt = a.p.xtra1[j];
+    s.yt = a.p.ytra1[j];
+    s.zt = a.p.ztra1[j];
+    s.ldt = a.p.idt[j];
+    s.up = a.p.uap[j]; s.vp = a.p.ucp[j]; s.wp = a.p.uzp[j];
+    s.usigold = a.p.us[j]; s.vsigold = a.p.vs[j]; s.wsigold = a.p.ws[j];
+    s.icbt = a.p.cbt[j];
+
+    Rng rng;
+    rng.tab = a.rannumb;
+    rng.maxrand = c.maxrand;
+    rng.mode = c.rng_mode;
+    rng.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+    rng.pid = (uint32_t)(c.part_id_offset + c.part_id_stride * j);
+    rng.tstep = (uint32_t)itime;
+    rng.cblk = -1;
+
+    if ((itramem == itime) || (itime == 0)) {
+      int nrand;
+      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_init[j];
+      else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 4;
+      else nrand = f_int(rng.uniform(1u) * (float)(c.maxrand - 1)) + 1;
+      do_initialize<CBL>(a, sh, rng, nrand, s);
+      n_init = 1;
+    }
+
+    float prob[FPB_MAXSPEC];
+    AdvOut out;
+    {
+      int nrand;
+      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[j];
+      else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 64;
+      else nrand = f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
+      do_advance<DRYDEP, CBL>(a, sh, rng, nrand, npoint, s, prob, out);
+    }
+    n_pbl = out.pbl; n_sub = out.nsub; n_pett = out.pett; n_nan = out.nan_cbl;
+
+    // src/timemanager.f90:630-707
+    int itra1;
+    if (out.nstop > 1) {
+      itra1 = FPB_ITRA_DEAD;
+      n_term = 1;
+    } else {
+      itra1 = itime + c.lsynctime;
+      float xmassfract = 0.f;
+      float drydeposit[FPB_MAXSPEC];
+      for (int ks = 0; ks < c.nspec; ks++) {
+        float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
+        float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
+        drydeposit[ks] = 0.f;
+        if (c.drydepspec[ks]) {
+          const float pr = DRYDEP ? prob[ks] : 0.f;
+          drydeposit[ks] = xm1 * pr * decfact;
+          xm1 = xm1 * (1.f - pr) * decfact;
+          if (c.decay[ks] > 0.f)
+            drydeposit[ks] = drydeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
+        } else {
+          xm1 = xm1 * decfact;
+        }
+        a.p.xmass1[(size_t)ks * a.p.maxpart + j] = xm1;
+        if (c.mdomainfill == 0 && c.mquasilag == 0) {
+          float xm = __ldg(a.xmass + ks * c.numpoint + (npoint - 1));
+          if (xm > 0.f)
+            xmassfract = fmaxf(xmassfract, (float)__ldg(a.npart + npoint - 1) * xm1 / xm);
+        } else {
+          xmassfract = 1.0f;
+        }
+      }
+      if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; n_term = 1; }
+
+      if (DRYDEP && c.drydep && (c.ldirect == 1)) {
+        const int nclass = a.p.nclass[j];
+        drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)s.xt, (float)s.yt, nage, kp);
+        if (c.nested_output == 1)
+          drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)s.xt, (float)s.yt, nage, kp);
+      }
+      if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; n_term = 1; }
+    }
+
+    a.p.xtra1[j] = s.xt;
+    a.p.ytra1[j] = s.yt;
+    a.p.ztra1[j] = s.zt;
+    a.p.itra1[j] = itra1;
+    a.p.idt[j] = s.ldt;
+    a.p.uap[j] = s.up; a.p.ucp[j] = s.vp; a.p.uzp[j] = s.wp;
+    a.p.us[j] = s.usigold; a.p.vs[j] = s.vsigold; a.p.ws[j] = s.wsigold;
+    a.p.cbt[j] = (int16_t)s.icbt;
+  }
+
+  if (a.stats) {
+    unsigned long long v0 = warp_sum(n_act), v1 = warp_sum(n_init), v2 = warp_sum(n_term),
+                       v3 = warp_sum(n_pbl), v4 = warp_sum(n_sub), v5 = warp_sum(n_pett),
+                       v6 = warp_sum(n_nan);
+    if ((threadIdx.x & 31) == 0 && v0) {
+      atomicAdd(a.stats + 0, v0);
+      if (v1) atomicAdd(a.stats + 1, v1);
+      if (v2) atomicAdd(a.stats + 2, v2);
+      if (v3) atomicAdd(a.stats + 3, v3);
+      if (v4) atomicAdd(a.stats + 4, v4);
+      if (v5) atomicAdd(a.stats + 5, v5);
+      if (v6) atomicAdd(a.stats + 6, v6);
+    }
+  }
+}
+
+// ======================================================= conccalc kernel ===
+// A grid cell is named by a species-free key
+//   key = ix + nxg*(jy + nyg*((kz-1) + nzg*((kp-1) + mps*((nc-1) + ncu*(na-1)))))
+// and species ks lives at  inner + nxyz*((ks-1) + nspec*rest)  with
+// inner = key % nxyz, rest = key / nxyz  (reference index order,
+// src/outgrid_init.f90:192-193, packed to nspec).
+__device__ __forceinline__ unsigned cell_key(const DevCfg &c, int nxg, int nyg, int ix, int jy,
+                                             int kz, int kp, int nc, int na) {
+  unsigned i = (unsigned)(na - 1);
+  i = i * c.nclassunc + (nc - 1);
+  i = i * c.maxpointspec_act + (kp - 1);
+  i = i * c.numzgrid + (kz - 1);
+  i = i * nyg + jy;
+  i = i * nxg + ix;
+  return i;
+}
+
+struct AtomicSink { // red.global.add.f32 straight into the grid
+  float *grid[2];
+  __device__ void add(const DevCfg &c, int nest, int /*slot*/, int nxyz, unsigned key,
+                      const float *v) const {
+    const size_t inner = key % (unsigned)nxyz, rest = key / (unsigned)nxyz;
+    for (int ks = 0; ks < c.nspec; ks++)
+      atomicAdd(grid[nest] + inner + (size_t)nxyz * (ks + (size_t)c.nspec * rest), v[ks]);
+  }
+  __device__ void skip(int, int) const {}
+};
+
+struct RecordSink { // (key, value) records for the deterministic path
+  unsigned *keys; // [4*numpart], record id = 4*i + slot
+  float *vals;    // [nspec][4*numpart]
+  size_t nrec;
+  int i;
+  int nest_sel;
+  __device__ void add(const DevCfg &c, int nest, int slot, int /*nxyz*/, unsigned key,
+                      const float *v) const {
+    if (nest != nest_sel) return;
+    const size_t r = 4 * (size_t)i + slot;
+    keys[r] = key;
+    for (int ks = 0; ks < c.nspec; ks++) vals[(size_t)ks * nrec + r] = v[ks];
+  }
+};
+
+// src/conccalc.f90:50-444 for particle i
+template <class Sink>
+__device__ __forceinline__ void conc_particle(const DevConcArgs &a, const float *sh, int i,
+                                              const Sink &sink) {
+  const DevCfg &c = a.cfg;
+  const int itime = c.itime;
+  const float weight = c.weight;
+
+  const int itage = abs(itime - a.p.itramem[i]);
+  int nage;
+  for (nage = 1; nage <= c.nageclass; nage++)
+    if (itage < c.lage[nage - 1]) break;
+
+  const double xd = a.p.xtra1[i], yd = a.p.ytra1[i];
+  const float zt = a.p.ztra1[i];
+
+  float rhoi = 1.f;
+  if (c.ind_samp == -1) { // conccalc.f90:80-121, density of memind(2)
+    int ix = d_int(xd), jy = d_int(yd), ixp = ix + 1, jyp = jy + 1;
+    float ddx = (float)(xd - (float)ix), ddy = (float)(yd - (float)jy);
+    float rddx = 1.f - ddx, rddy = 1.f - ddy;
+    float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+    if (jyp >= c.nymax) jyp = jyp - 1;
+    const int indz = find_indz(sh, c.nz, zt);
+    const float dz1 = zt - sh[indz - 1], dz2 = sh[indz] - zt;
+    const float dz = 1.f / (dz1 + dz2);
+    const int plane = c.nxd * c.nyd;
+    float rp[2];
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      const float4 *A = a.met[1].A + (indz - 1 + n) * plane;
+      rp[n] = p1 * __ldg(A + ix + c.nxd * jy).w + p2 * __ldg(A + ixp + c.nxd * jy).w +
+              p3 * __ldg(A + ix + c.nxd * jyp).w + p4 * __ldg(A + ixp + c.nxd * jyp).w;
+    }
+    rhoi = (dz1 * rp[1] + dz2 * rp[0]) * dz;
+  }
+
+  const int nrelpointer =
+      ((c.ioutputforeachrelease == 0) || (c.mdomainfill == 1)) ? 1 : a.p.npoint[i];
+  int kz;
+  for (kz = 1; kz <= c.numzgrid; kz++)
+    if (c.outheight[kz - 1] > zt) break;
+  if (kz > c.numzgrid) return;
+
+  const int nclass = a.p.nclass[i];
+  const bool bk = c.drybkdep || c.wetbkdep;
+  float val[FPB_MAXSPEC], vw[FPB_MAXSPEC]; // xmass1/rhoi*weight [*max(xscav,0)]
+#pragma unroll
+  for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
+    val[ks] = 0.f;
+    if (ks < c.nspec) {
+      float xm = a.p.xmass1[(size_t)ks * a.p.maxpart + i];
+      val[ks] = xm / rhoi * weight;
+      if (bk) val[ks] = val[ks] * fmaxf(a.p.xscav_frac1[(size_t)ks * a.p.maxpart + i], 0.0f);
+    }
+  }
+
+  for (int nest = 0; nest <= (c.nested_output == 1 ? 1 : 0); nest++) {
+    const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
+    const int nxyz = nxg * nyg * c.numzgrid;
+    float xl, yl;
+    if (nest) {
+      xl = (float)((xd * c.dx + c.xoutshiftn) / c.dxoutn);
+      yl = (float)((yd * c.dy + c.youtshiftn) / c.dyoutn);
+    } else {
+      xl = (float)((xd * c.dx + c.xoutshift) / c.dxout);
+      yl = (float)((yd * c.dy + c.youtshift) / c.dyout);
+    }
+    int ix = f_int(xl);
+    if (xl < 0.f) ix = ix - 1;
+    int jy = f_int(yl);
+    if (yl < 0.f) jy = jy - 1;
+
+    if ((!c.lusekerneloutput) || (itage < 10800) || (xl < 0.5f) || (yl < 0.5f) ||
+        (xl > (float)(nxg - 1) - 0.5f) || (yl > (float)(nyg - 1) - 0.5f)) {
+      if ((ix >= 0) && (jy >= 0) && (ix <= nxg - 1) && (jy <= nyg - 1)) {
+        if (!bk && c.lparticlecountoutput) {
+#pragma unroll
+          for (int ks = 0; ks < FPB_MAXSPEC; ks++) vw[ks] = 1.f;
+          sink.add(c, nest, 0, nxyz, cell_key(c, nxg, nyg, ix, jy, kz, nrelpointer, nclass, nage), vw);
+        } else {
+          sink.add(c, nest, 0, nxyz, cell_key(c, nxg, nyg, ix, jy, kz, nrelpointer, nclass, nage), val);
+        }
+      }
+    } else {
+      float ddx = xl - (float)ix, ddy = yl - (float)jy, wx, wy;
+      int ixp, jyp;
+      if (ddx > 0.5f) { ixp = ix + 1; wx = 1.5f - ddx; } else { ixp = ix - 1; wx = 0.5f + ddx; }
+      if (ddy > 0.5f) { jyp = jy + 1; wy = 1.5f - ddy; } else { jyp = jy - 1; wy = 0.5f + ddy; }
+      const bool xin = (ix >= 0) && (ix <= nxg - 1), xpin = (ixp >= 0) && (ixp <= nxg - 1);
+      const bool yin = (jy >= 0) && (jy <= nyg - 1), ypin = (jyp >= 0) && (jyp <= nyg - 1);
+      // the four cells in the reference's order, conccalc.f90:225-283
+      if (xin && yin) {
+        const float w = wx * wy;
+#pragma unroll
+        for (int ks = 0; ks < FPB_MAXSPEC; ks++) vw[ks] = val[ks] * w;
+        sink.add(c, nest, 0, nxyz, cell_key(c, nxg, nyg, ix, jy, kz, nrelpointer, nclass, nage), vw);
+      }
+      if (xin && ypin) {
+        const float w = wx * (1.f - wy);
+#pragma unroll
+        for (int ks = 0; ks < FPB_MAXSPEC; ks++) vw[ks] = val[ks] * w;
+        sink.add(c, nest, 1, nxyz, cell_key(c, nxg, nyg, ix, jyp, kz, nrelpointer, nclass, nage), vw);
+      }
+      if (xpin && ypin) {
+        const float w = (1.f - wx) * (1.f - wy);
+#pragma unroll
+        for (int ks = 0; ks < FPB_MAXSPEC; ks++) vw[ks] = val[ks] * w;
+        sink.add(c, nest, 2, nxyz, cell_key(c, nxg, nyg, ixp, jyp, kz, nrelpointer, nclass, nage), vw);
+      }
+      if (xpin && yin) {
+        const float w = (1.f - wx) * wy;
+#pragma unroll
+        for (int ks = 0; ks < FPB_MAXSPEC; ks++) vw[ks] = val[ks] * w;
+        sink.add(c, nest, 3, nxyz, cell_key(c, nxg, nyg, ixp, jy, kz, nrelpointer, nclass, nage), vw);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fpb_conccalc_kernel(const __grid_constant__ DevConcArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.numpart) return;
+  if (a.p.itra1[i] != c.itime) return;
+  AtomicSink sink;
+  sink.grid[0] = a.gridunc;
+  sink.grid[1] = a.griduncn;
+  conc_particle(a, sh, i, sink);
+}
+
+// deterministic path, stage 1: one (key, value) record per touched cell.
+// keys must be pre-filled with 0xffffffff (= no record).
+__global__ void __launch_bounds__(256)
+fpb_conc_emit_kernel(const __grid_constant__ DevConcArgs a, int nest_sel, unsigned *keys,
+                     float *vals, size_t nrec) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.numpart) return;
+  if (a.p.itra1[i] != c.itime) return;
+  RecordSink sink;
+  sink.keys = keys;
+  sink.vals = vals;
+  sink.nrec = nrec;
+  sink.i = i;
+  sink.nest_sel = nest_sel;
+  conc_particle(a, sh, i, sink);
+}
+
+// src/conccalc.f90:451-498: each thread evaluates its particle against every
+// receptor; block partial sums go to crec_acc[n][ks] (= c(ks) of the reference).
+__global__ void __launch_bounds__(256)
+fpb_receptor_kernel(const __grid_constant__ DevConcArgs a) {
+  const DevCfg &c = a.cfg;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float factor = .596831f, hxmax = 6.0f, hymax = 4.0f, hzmax = 150.f;
+  bool act = (i < c.numpart) && (a.p.itra1[i] == c.itime);
+  double xd0 = 0., yd0 = 0.;
+  float zt = 0.f, hz = 1.f, hx = 1.f, hy = 1.f, zd = 2.f;
+  if (act) {
+    const int itage = abs(c.itime - a.p.itramem[i]);
+    xd0 = a.p.xtra1[i]; yd0 = a.p.ytra1[i]; zt = a.p.ztra1[i];
+    hz = fminf(50.f + 0.3f * m_sqrt((float)itage), hzmax);
+    zd = zt / hz;
+    hx = fminf((0.29f + 2.222e-3f * m_sqrt((float)itage)) * c.dx + (float)itage * 1.2e-5f, hxmax);
+    hy = fminf((0.18f + 1.389e-3f * m_sqrt((float)itage)) * c.dy + (float)itage * 7.5e-6f, hymax);
+    if (zd > 1.f) act = false;
+  }
+  for (int n = 0; n < c.numreceptor; n++) {
+    float kern = 0.f;
+    if (act) {
+      float xd = (float)((xd0 - c.xreceptor[n]) / hx);
+      float yd = (float)((yd0 - c.yreceptor[n]) / hy);
+      if (!(xd * xd > 1.f) && !(yd * yd > 1.f)) {
+        float h = hx * hy * hz;
+        float r2 = xd * xd + yd * yd + zd * zd;
+        if (r2 < 1.f) kern = factor * (1.f - r2) / h;
+      }
+    }
+    for (int ks = 0; ks < c.nspec; ks++) {
+      float v = (kern != 0.f) ? a.p.xmass1[(size_t)ks * a.p.maxpart + i] * kern : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(a.crec_acc + n * c.nspec + ks, v);
+    }
+  }
+}
+
+} // namespace
+
+#if FPB_STRICT
+#define FPB_SUF(name) name##_strict
+#else
+#define FPB_SUF(name) name##_fast
+#endif
+
+void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 127) / 128;
+  if (nb == 0) return;
+  const bool full = a.cfg.drydep || a.cfg.cblflag == 1;
+  if (full) fpb_step_kernel<true, true><<<nb, 128, 0, st>>>(a);
+  else fpb_step_kernel<false, false><<<nb, 128, 0, st>>>(a);
+}
+
+void FPB_SUF(fpbk_conccalc)(const DevConcArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb == 0) return;
+  fpb_conccalc_kernel<<<nb, 256, 0, st>>>(a);
+}
+
+void FPB_SUF(fpbk_conc_emit)(const DevConcArgs &a, int nest_sel, unsigned *keys, float *vals,
+                              size_t nrec, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb == 0) return;
+  fpb_conc_emit_kernel<<<nb, 256, 0, st>>>(a, nest_sel, keys, vals, nrec);
+}
+
+void FPB_SUF(fpbk_receptor)(const DevConcArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb == 0 || a.cfg.numreceptor == 0) return;
+  fpb_receptor_kernel<<<nb, 256, 0, st>>>(a);
+}

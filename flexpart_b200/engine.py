@@ -1,0 +1,141 @@
+"""Engine: Python handle on libfpb.so (include/fpb.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import FpbStepStats, FpbError, FpbhEngine, load_engine_lib
+
+_pf = C.POINTER(C.c_float)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_pf) if a is not None else None
+
+
+class Engine:
+    """One engine instance = one GPU's share of the particles + a met replica."""
+
+    def __init__(self, cb):
+        self.L = load_engine_lib()
+        self.cb = cb
+        self.h = C.c_void_p()
+        self._check(self.L.fpb_init(C.byref(cb.cfg), C.byref(self.h)))
+        c = cb.cfg
+        outer = c.maxspec * c.maxpointspec_act * c.nclassunc * c.maxageclass
+        self.shape_grid = (c.numxgrid, c.numygrid, c.numzgrid, c.maxspec, c.maxpointspec_act,
+                           c.nclassunc, c.maxageclass)
+        self.shape_dry = (c.numxgrid, c.numygrid, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
+        self.shape_gridn = (c.numxgridn, c.numygridn, c.numzgrid, c.maxspec, c.maxpointspec_act,
+                            c.nclassunc, c.maxageclass)
+        self.shape_dryn = (c.numxgridn, c.numygridn, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
+        self._outer = outer
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FpbError(self.L.fpb_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.fpb_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- RNG
+    def set_rannumb(self, table):
+        t = np.ascontiguousarray(table, np.float32)
+        self._check(self.L.fpb_set_rannumb(self.h, _fp(t), len(t)))
+
+    def fill_rannumb(self, maxrand=1000000, idummy=-320):
+        self._check(self.L.fpb_fill_rannumb(self.h, maxrand, idummy))
+
+    # --- met
+    def upload_met(self, slot, met):
+        self._check(self.L.fpb_upload_met(self.h, slot, C.byref(met.ptrs)))
+
+    def set_met_bracket(self, memind, memtime, lwindinterv=None):
+        mi = (C.c_int32 * 2)(*memind)
+        mt = (C.c_int32 * 2)(*memtime)
+        if lwindinterv is None:
+            lwindinterv = abs(memtime[1] - memtime[0])
+        self._check(self.L.fpb_set_met_bracket(self.h, mi, mt, lwindinterv))
+
+    # --- particles
+    def push_particles(self, parts, first=0, count=None):
+        count = parts.numpart - first if count is None else count
+        self._check(self.L.fpb_push_particles(self.h, first, count, C.byref(parts.ptrs)))
+
+    def pull_particles(self, parts, first=0, count=None):
+        count = parts.numpart - first if count is None else count
+        self._check(self.L.fpb_pull_particles(self.h, first, count, C.byref(parts.ptrs)))
+
+    def set_numpart(self, n):
+        self._check(self.L.fpb_set_numpart(self.h, n))
+
+    # --- hot path
+    def step(self, itime, ldeltat=0, stats=True):
+        st = FpbStepStats()
+        self._check(self.L.fpb_step(self.h, itime, ldeltat, C.byref(st) if stats else None))
+        return st.as_dict() if stats else None
+
+    def conccalc(self, itime, weight):
+        self._check(self.L.fpb_conccalc(self.h, itime, weight))
+
+    def fetch_grids(self, zero_conc=True):
+        c = self.cb.cfg
+        out = {"gridunc": np.zeros(self.shape_grid, np.float32, order="F"),
+               "drygridunc": np.zeros(self.shape_dry, np.float32, order="F"),
+               "creceptor": np.zeros((abi.MAXRECEPTOR, c.maxspec), np.float32, order="F")}
+        gn = dn = None
+        if c.nested_output == 1:
+            out["griduncn"] = np.zeros(self.shape_gridn, np.float32, order="F")
+            out["drygriduncn"] = np.zeros(self.shape_dryn, np.float32, order="F")
+            gn, dn = out["griduncn"], out["drygriduncn"]
+        self._check(self.L.fpb_fetch_grids(self.h, _fp(out["gridunc"]), _fp(gn), _fp(out["drygridunc"]),
+                                           _fp(dn), _fp(out["creceptor"]), 1 if zero_conc else 0))
+        return out
+
+    def scale_depgrids(self, factors):
+        f = np.ascontiguousarray(factors, np.float32)
+        self._check(self.L.fpb_scale_depgrids(self.h, _fp(f)))
+
+    def zero_conc_grids(self):
+        self._check(self.L.fpb_zero_conc_grids(self.h))
+
+    def sort_particles(self):
+        self._check(self.L.fpb_sort_particles(self.h))
+
+    def grid_device_ptr(self, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.fpb_grid_device_ptr(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    @property
+    def stream(self):
+        return self.L.fpb_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.L.fpb_launch_count(self.h))
+
+    def vtable(self):
+        """fpbh_engine table pointing at the library's own entry points."""
+        L, a = self.L, abi
+        v = FpbhEngine()
+        v.self = self.h
+        cast = lambda fn, T: C.cast(fn, T)
+        v.upload_met = cast(L.fpb_upload_met, a.UPLOAD_MET_FN)
+        v.set_met_bracket = cast(L.fpb_set_met_bracket, a.SET_BRACKET_FN)
+        v.push_particles = cast(L.fpb_push_particles, a.PUSH_FN)
+        v.pull_particles = cast(L.fpb_pull_particles, a.PUSH_FN)
+        v.set_numpart = cast(L.fpb_set_numpart, a.SET_NUMPART_FN)
+        v.step = cast(L.fpb_step, a.STEP_FN)
+        v.conccalc = cast(L.fpb_conccalc, a.CONC_FN)
+        v.fetch_grids = cast(L.fpb_fetch_grids, a.FETCH_FN)
+        v.scale_depgrids = cast(L.fpb_scale_depgrids, a.SCALE_FN)
+        return v

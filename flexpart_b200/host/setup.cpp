@@ -1,0 +1,125 @@
+// setup.cpp -- run-constant derivation on the host: what gridcheck_ecmwf,
+// readcommand and readoutgrid leave in com_mod / outg_mod for the hot path.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "fpbh_internal.h"
+
+static thread_local std::string g_err;
+int fpbh_fail(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+extern "C" const char *fpbh_last_error(void) { return g_err.c_str(); }
+
+// src/gridcheck_ecmwf.f90:300-366; par_mod: r_earth=6.371e6, pi=3.14159265,
+// switchnorth=75, switchsouth=-75 (src/par_mod.f90:63,123)
+extern "C" int fpbh_gridcheck(fpb_config *c) {
+  if (!c) return fpbh_fail("fpbh_gridcheck: null config");
+  if (c->nx < 2 || c->ny < 2 || c->nz < 2) return fpbh_fail("fpbh_gridcheck: grid too small");
+  if (c->nxmax < c->nx || c->nymax < c->ny || c->nzmax < c->nz)
+    return fpbh_fail("fpbh_gridcheck: padded extents smaller than the grid");
+  const float r_earth = 6.371e6f, pi = 3.14159265f;
+  const float switchnorth = 75.f, switchsouth = -75.f;
+  c->dxconst = 180.f / (c->dx * r_earth * pi);
+  c->dyconst = 180.f / (c->dy * r_earth * pi);
+  // cyclic if the last column repeats the first one (nx = nxfield+1)
+  const float xspan = c->dx * (float)(c->nx - 1);
+  c->xglobal = std::fabs(xspan - 360.f) < 0.001f ? 1 : 0;
+  c->nxmin1 = c->nx - 1;
+  c->nymin1 = c->ny - 1;
+  if (c->xlon0 > 180.f) c->xlon0 = c->xlon0 - 360.f;
+  const float yaux1 = c->ylat0, yaux2 = c->ylat0 + c->dy * (float)(c->ny - 1);
+  if (c->xglobal && std::fabs(yaux1 + 90.f) < 0.001f) {
+    c->sglobal = 1;
+    const float sizesouth = 6.f * (switchsouth + 90.f) / c->dy;
+    cmap::stlmbr(c->southpolemap, -90.f, 0.f);
+    cmap::stcm2p(c->southpolemap, 0.f, 0.f, switchsouth, 0.f, sizesouth, sizesouth, switchsouth, 180.f);
+    c->switchsouthg = (switchsouth - c->ylat0) / c->dy;
+  } else {
+    c->sglobal = 0;
+    c->switchsouthg = 999999.f;
+  }
+  if (c->xglobal && std::fabs(yaux2 - 90.f) < 0.001f) {
+    c->nglobal = 1;
+    const float sizenorth = 6.f * (90.f - switchnorth) / c->dy;
+    cmap::stlmbr(c->northpolemap, 90.f, 0.f);
+    cmap::stcm2p(c->northpolemap, 0.f, 0.f, switchnorth, 0.f, sizenorth, sizenorth, switchnorth, 180.f);
+    c->switchnorthg = (switchnorth - c->ylat0) / c->dy;
+  } else {
+    c->nglobal = 0;
+    c->switchnorthg = 999999.f;
+  }
+  c->eps = (float)c->nxmax / 3.e5f; // src/advance.f90:107
+  return 0;
+}
+
+// src/readcommand.f90:244-272 (turbulence switches), :377-383 (method),
+// :627-634 (backward runs); maxtl=1200 (src/com_mod.f90)
+extern "C" int fpbh_readcommand(fpb_config *c) {
+  if (!c) return fpbh_fail("fpbh_readcommand: null config");
+  if (c->ldirect != 1 && c->ldirect != -1)
+    return fpbh_fail("DIRECTION IN FILE \"COMMAND\" MUST BE EITHER -1 OR 1.");
+  if (c->lsynctime <= 0) return fpbh_fail("fpbh_readcommand: LSYNCTIME must be given positive");
+  if (c->ctl == 0.f) return fpbh_fail("fpbh_readcommand: CTL must not be 0");
+  const int maxtl = 1200;
+  c->ifine = c->ifine > 1 ? c->ifine : 1;
+  if (c->cblflag == 1) {
+    c->turbswitch = 1;
+    if (c->lsynctime > maxtl) c->lsynctime = maxtl;
+    if (c->ctl < 5.f) c->ctl = 5.f;
+    if ((float)c->ifine * c->ctl < 50.f) c->ifine = (int)(50.f / c->ctl) + 1;
+  } else if (c->ctl >= 0.1f) {
+    c->turbswitch = 1;
+  } else {
+    c->turbswitch = 0;
+    c->ifine = 1;
+  }
+  c->fine = 1.f / (float)c->ifine;
+  c->ctl = 1.f / c->ctl;
+  if (c->ldirect == -1) c->lsynctime = -c->lsynctime;
+  if (c->ctl > 0.f) {
+    c->method = 1;
+    c->mintime = 1; // par_mod minstep
+  } else {
+    c->method = 0;
+    c->mintime = c->lsynctime;
+  }
+  if (c->d_trop == 0.f) c->d_trop = 50.f;     // src/par_mod.f90:79
+  if (c->d_strat == 0.f) c->d_strat = 0.1f;
+  if (c->turbmesoscale == 0.f) c->turbmesoscale = 0.16f;
+  return 0;
+}
+
+// src/readoutgrid.f90:199-200
+extern "C" int fpbh_readoutgrid(fpb_config *c, float outlon0, float outlat0, int32_t numxgrid,
+                                int32_t numygrid, float dxout, float dyout, const float *outheights,
+                                int32_t numzgrid) {
+  if (!c || !outheights) return fpbh_fail("fpbh_readoutgrid: null argument");
+  if (numzgrid < 1 || numzgrid > FPB_MAXZGRID) return fpbh_fail("fpbh_readoutgrid: numzgrid out of range");
+  c->numxgrid = numxgrid; c->numygrid = numygrid; c->numzgrid = numzgrid;
+  c->dxout = dxout; c->dyout = dyout;
+  for (int k = 0; k < numzgrid; k++) c->outheight[k] = outheights[k];
+  c->xoutshift = c->xlon0 - outlon0;
+  c->youtshift = c->ylat0 - outlat0;
+  return 0;
+}
+
+// src/readoutgrid_nest.f90:111-112
+extern "C" int fpbh_readoutgrid_nest(fpb_config *c, float outlon0n, float outlat0n, int32_t numxgridn,
+                                     int32_t numygridn, float dxoutn, float dyoutn) {
+  if (!c) return fpbh_fail("fpbh_readoutgrid_nest: null argument");
+  c->numxgridn = numxgridn; c->numygridn = numygridn;
+  c->dxoutn = dxoutn; c->dyoutn = dyoutn;
+  c->xoutshiftn = c->xlon0 - outlon0n;
+  c->youtshiftn = c->ylat0 - outlat0n;
+  c->nested_output = 1;
+  return 0;
+}

@@ -1,0 +1,242 @@
+// synthmet.cpp -- synthetic "ECMWF-shaped" meteorology.
+//
+// Produces, for one time level, the arrays verttransform_ecmwf / calcpar
+// would leave in com_mod (src/com_mod.f90:355-371,410-427,451), in the same
+// padded Fortran layout: smooth analytic fields on a global lat-lon grid,
+// drhodz by the reference's finite differences
+// (src/verttransform_ecmwf.f90:392-398), uupol/vvpol by cc2gll poleward of the
+// switch latitudes and the pole-row treatment of :459-607, ww at the pole rows
+// replaced by the zonal mean of the neighbouring row.  Invariants the hot
+// path relies on are honoured: hmix in [100,4500] (src/calcpar.f90:165-166),
+// ustar >= 1e-8, rho > 0, heights strictly increasing with height(1)=0.
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "fpbh_internal.h"
+
+namespace {
+const double PI = 3.14159265358979323846;
+inline size_t i3(const fpb_config &c, int ix, int jy, int k) {
+  return (size_t)ix + (size_t)c.nxmax * ((size_t)jy + (size_t)c.nymax * (size_t)k);
+}
+inline size_t i2(const fpb_config &c, int ix, int jy) { return (size_t)ix + (size_t)c.nxmax * (size_t)jy; }
+
+template <class F>
+void parallel_levels(int nk, F f) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 32) nt = 32;
+  if ((int)nt > nk) nt = nk;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([=]() {
+      for (int k = (int)t; k < nk; k += (int)nt) f(k);
+    });
+  for (auto &x : th) x.join();
+}
+} // namespace
+
+extern "C" int fpbh_synth_heights(int32_t nz, float *height) {
+  if (nz < 2 || !height) return fpbh_fail("fpbh_synth_heights: bad argument");
+  // first layer 10 m, geometric stretching to ~80 km at 138 levels
+  const double top = 80000.0;
+  // solve 10*(r^(nz-1)-1)/(r-1) = top by bisection
+  double lo = 1.0001, hi = 2.0;
+  for (int it = 0; it < 200; it++) {
+    double r = 0.5 * (lo + hi);
+    double s = 10.0 * (std::pow(r, nz - 1) - 1.0) / (r - 1.0);
+    if (s > top) hi = r; else lo = r;
+  }
+  const double r = 0.5 * (lo + hi);
+  double z = 0.0, dz = 10.0;
+  height[0] = 0.f;
+  for (int k = 1; k < nz; k++) {
+    z += dz;
+    dz *= r;
+    height[k] = (float)z;
+  }
+  return 0;
+}
+
+extern "C" int fpbh_synth_met(const fpb_config *cp, const float *height, int32_t time_s,
+                              const fpb_met_ptrs *o) {
+  if (!cp || !height || !o) return fpbh_fail("fpbh_synth_met: null argument");
+  const fpb_config &c = *cp;
+  if (!o->uu || !o->vv || !o->ww || !o->rho || !o->drhodz || !o->hmix || !o->ustar || !o->wstar ||
+      !o->oli || !o->tropopause)
+    return fpbh_fail("fpbh_synth_met: mandatory output array is null");
+  const int nx = c.nx, ny = c.ny, nz = c.nz;
+  const double wt = 2.0 * PI * (double)time_s / 86400.0; // diurnal phase
+  float *uu = (float *)o->uu, *vv = (float *)o->vv, *ww = (float *)o->ww, *rho = (float *)o->rho;
+  float *drhodz = (float *)o->drhodz, *tt = (float *)o->tt;
+  float *uupol = (float *)o->uupol, *vvpol = (float *)o->vvpol;
+
+  std::vector<double> sl(nx), cl(nx), s2l(nx), s3l(nx), lam(nx);
+  for (int ix = 0; ix < nx; ix++) {
+    lam[ix] = ((double)c.xlon0 + (double)c.dx * ix) * PI / 180.0;
+    sl[ix] = std::sin(lam[ix]); cl[ix] = std::cos(lam[ix]);
+    s2l[ix] = std::sin(2 * lam[ix]); s3l[ix] = std::sin(3 * lam[ix]);
+  }
+  parallel_levels(nz, [&](int k) {
+    const double z = height[k];
+    const double rz = 1.225 * std::exp(-z / 8000.0);
+    const double tz = 288.0 - 6.5e-3 * std::fmin(z, 11000.0);
+    const double wz = 0.02 * std::sin(PI * z / 20000.0);
+    const double shear = 1.0 + z / 12000.0;
+    for (int jy = 0; jy < ny; jy++) {
+      const double phi = ((double)c.ylat0 + (double)c.dy * jy) * PI / 180.0;
+      const double cp_ = std::cos(phi), c2p = std::cos(2 * phi);
+      for (int ix = 0; ix < nx; ix++) {
+        const size_t i = i3(c, ix, jy, k);
+        uu[i] = (float)(15.0 * cp_ * shear + 5.0 * std::sin(3 * lam[ix] + 0.5 * wt) * c2p);
+        vv[i] = (float)(5.0 * std::sin(2 * lam[ix] + 0.3 * wt) * cp_);
+        ww[i] = (float)(wz * std::sin(lam[ix] + wt) * cp_);
+        // small horizontal density structure so that rho gathers matter
+        rho[i] = (float)(rz * (1.0 + 0.02 * sl[ix] * cp_));
+        if (tt) tt[i] = (float)(tz + 3.0 * cl[ix] * cp_);
+      }
+    }
+  });
+  // drhodz, src/verttransform_ecmwf.f90:392-398
+  parallel_levels(nz, [&](int k) {
+    for (int jy = 0; jy < ny; jy++)
+      for (int ix = 0; ix < nx; ix++) {
+        const size_t i = i3(c, ix, jy, k);
+        if (k == 0)
+          drhodz[i] = (rho[i3(c, ix, jy, 1)] - rho[i3(c, ix, jy, 0)]) / (height[1] - height[0]);
+        else if (k < nz - 1)
+          drhodz[i] = (rho[i3(c, ix, jy, k + 1)] - rho[i3(c, ix, jy, k - 1)]) / (height[k + 1] - height[k - 1]);
+      }
+  });
+  for (int jy = 0; jy < ny; jy++)
+    for (int ix = 0; ix < nx; ix++) drhodz[i3(c, ix, jy, nz - 1)] = drhodz[i3(c, ix, jy, nz - 2)];
+
+  // surface / PBL parameters
+  float *hmix = (float *)o->hmix, *ustar = (float *)o->ustar, *wstar = (float *)o->wstar;
+  float *oli = (float *)o->oli, *trop = (float *)o->tropopause;
+  for (int jy = 0; jy < ny; jy++) {
+    const double phi = ((double)c.ylat0 + (double)c.dy * jy) * PI / 180.0;
+    const double cp_ = std::cos(phi), sp = std::sin(phi);
+    for (int ix = 0; ix < nx; ix++) {
+      const size_t i = i2(c, ix, jy);
+      const double day = std::sin(lam[ix] + wt); // >0 "day side"
+      double h = 100.0 + 1400.0 * (1.0 + day) * cp_ * cp_;
+      hmix[i] = (float)std::fmin(4500.0, std::fmax(100.0, h));
+      ustar[i] = (float)(0.05 + 0.75 * 0.5 * (1.0 + std::sin(2 * lam[ix] + 0.7 * wt) * cp_));
+      wstar[i] = (float)(day > 0 ? 2.5 * day * cp_ : 0.0);
+      // 1/L: unstable (negative) by day, stable by night, |1/L| in [1e-3,0.1]
+      const double mag = 1e-3 + 0.099 * std::fabs(day) * cp_;
+      oli[i] = (float)(day > 0 ? -mag : mag);
+      trop[i] = (float)(16000.0 - 8000.0 * sp * sp);
+    }
+  }
+  if (o->vdep) {
+    float *vdep = (float *)o->vdep;
+    for (int ks = 0; ks < c.nspec; ks++)
+      for (int jy = 0; jy < ny; jy++) {
+        const double phi = ((double)c.ylat0 + (double)c.dy * jy) * PI / 180.0;
+        for (int ix = 0; ix < nx; ix++)
+          vdep[i3(c, ix, jy, ks)] =
+              (float)((1e-3 + 4.5e-3 * (1.0 + std::sin(lam[ix] + wt + ks) * std::cos(phi))) * (1.0 + 0.5 * ks));
+      }
+  }
+
+  // polar-stereographic winds, src/verttransform_ecmwf.f90:459-607
+  if (uupol && vvpol) {
+    const float pi_f = 3.14159265f;
+    if (c.nglobal) {
+      parallel_levels(nz, [&](int k) {
+        for (int jy = (int)c.switchnorthg - 2; jy <= c.nymin1; jy++) {
+          const float ylat = c.ylat0 + (float)jy * c.dy;
+          for (int ix = 0; ix <= c.nxmin1; ix++) {
+            const float xlon = c.xlon0 + (float)ix * c.dx;
+            const size_t i = i3(c, ix, jy, k);
+            cmap::cc2gll(c.northpolemap, ylat, xlon, uu[i], vv[i], uupol[i], vvpol[i]);
+          }
+        }
+        // pole row: wind of the central grid point rotated to 180 deg
+        const size_t ic = i3(c, nx / 2 - 1, c.nymin1, k);
+        float xlon = c.xlon0 + (float)(nx / 2 - 1) * c.dx;
+        float xlonr = xlon * pi_f / 180.f;
+        const float ffpol = std::sqrt(uu[ic] * uu[ic] + vv[ic] * vv[ic]);
+        float ddpol;
+        if (vv[ic] < 0.f) ddpol = std::atan(uu[ic] / vv[ic]) - xlonr;
+        else if (vv[ic] > 0.f) ddpol = pi_f + std::atan(uu[ic] / vv[ic]) - xlonr;
+        else ddpol = pi_f / 2 - xlonr;
+        if (ddpol < 0.f) ddpol = 2.0f * pi_f + ddpol;
+        if (ddpol > 2.0f * pi_f) ddpol = ddpol - 2.0f * pi_f;
+        xlon = 180.0f;
+        xlonr = xlon * pi_f / 180.f;
+        const float uuaux = -ffpol * std::sin(xlonr + ddpol), vvaux = -ffpol * std::cos(xlonr + ddpol);
+        float up, vp;
+        cmap::cc2gll(c.northpolemap, 90.0f, xlon, uuaux, vvaux, up, vp);
+        float wsum = 0.f;
+        for (int ix = 0; ix <= c.nxmin1; ix++) {
+          uupol[i3(c, ix, c.nymin1, k)] = up;
+          vvpol[i3(c, ix, c.nymin1, k)] = vp;
+          wsum += ww[i3(c, ix, ny - 2, k)];
+        }
+        wsum = wsum / (float)nx;
+        for (int ix = 0; ix <= c.nxmin1; ix++) ww[i3(c, ix, c.nymin1, k)] = wsum;
+      });
+    }
+    if (c.sglobal) {
+      parallel_levels(nz, [&](int k) {
+        for (int jy = 0; jy <= (int)c.switchsouthg + 3; jy++) {
+          const float ylat = c.ylat0 + (float)jy * c.dy;
+          for (int ix = 0; ix <= c.nxmin1; ix++) {
+            const float xlon = c.xlon0 + (float)ix * c.dx;
+            const size_t i = i3(c, ix, jy, k);
+            cmap::cc2gll(c.southpolemap, ylat, xlon, uu[i], vv[i], uupol[i], vvpol[i]);
+          }
+        }
+        const size_t ic = i3(c, nx / 2 - 1, 0, k);
+        float xlon = c.xlon0 + (float)(nx / 2 - 1) * c.dx;
+        float xlonr = xlon * pi_f / 180.f;
+        const float ffpol = std::sqrt(uu[ic] * uu[ic] + vv[ic] * vv[ic]);
+        float ddpol;
+        if (vv[ic] < 0.f) ddpol = std::atan(uu[ic] / vv[ic]) + xlonr;
+        else if (vv[ic] > 0.f) ddpol = pi_f + std::atan(uu[ic] / vv[ic]) + xlonr;
+        else ddpol = pi_f / 2 - xlonr;
+        if (ddpol < 0.f) ddpol = 2.0f * pi_f + ddpol;
+        if (ddpol > 2.0f * pi_f) ddpol = ddpol - 2.0f * pi_f;
+        xlon = 180.0f;
+        xlonr = xlon * pi_f / 180.f;
+        const float uuaux = +ffpol * std::sin(xlonr - ddpol), vvaux = -ffpol * std::cos(xlonr - ddpol);
+        float up, vp;
+        // (the reference passes northpolemap here, src/verttransform_ecmwf.f90:578)
+        cmap::cc2gll(c.northpolemap, -90.0f, xlon, uuaux, vvaux, up, vp);
+        float wsum = 0.f;
+        for (int ix = 0; ix <= c.nxmin1; ix++) {
+          uupol[i3(c, ix, 0, k)] = up;
+          vvpol[i3(c, ix, 0, k)] = vp;
+          wsum += ww[i3(c, ix, 1, k)];
+        }
+        wsum = wsum / (float)nx;
+        for (int ix = 0; ix <= c.nxmin1; ix++) ww[i3(c, ix, 0, k)] = wsum;
+      });
+    }
+  }
+  return 0;
+}
+
+// src/mpi_mod.f90:2940-2973 (set_fields_synthetic): homogeneous test fields
+extern "C" int fpbh_homogeneous_met(const fpb_config *cp, float u, float v, float w,
+                                    const fpb_met_ptrs *o) {
+  if (!cp || !o) return fpbh_fail("fpbh_homogeneous_met: null argument");
+  const fpb_config &c = *cp;
+  const size_t n3 = (size_t)c.nxmax * c.nymax * c.nzmax, n2 = (size_t)c.nxmax * c.nymax;
+  auto fill = [](const float *p, size_t n, float val) {
+    if (!p) return;
+    float *q = (float *)p;
+    for (size_t i = 0; i < n; i++) q[i] = val;
+  };
+  fill(o->uu, n3, u); fill(o->vv, n3, v); fill(o->ww, n3, w);
+  fill(o->uupol, n3, u); fill(o->vvpol, n3, v);
+  fill(o->rho, n3, 1.3f); fill(o->drhodz, n3, 0.f); fill(o->tt, n3, 300.f);
+  fill(o->hmix, n2, 10000.f); fill(o->tropopause, n2, 10000.f);
+  fill(o->ustar, n2, 1.f); fill(o->wstar, n2, 1.f); fill(o->oli, n2, 0.01f);
+  fill(o->vdep, n2 * c.maxspec, 0.f);
+  return 0;
+}

@@ -1,0 +1,234 @@
+// timemanager.cpp -- the reference's time loop (src/timemanager.f90:152-729)
+// with the engine in place of the per-particle loop and conccalc.
+//
+// Kept from the reference, in its order: getfields' two-slot rotation
+// (src/getfields.f90:96-176), particle release, decay of deposited mass at
+// loutnext, the sampling schedule with half weights at the window ends, the
+// output + second conccalc at loutend, the exit at ideltas, ldeltat, the
+// particle loop.  Left out (outside the hot-path scope):
+// wetdepo, OH, convmix, particle splitting, flux and trajectory output.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "fpbh_internal.h"
+
+namespace {
+struct MetStore { // com_mod met arrays, numwfmem = 2
+  std::vector<float> f3[2][8], f2[2][5], vd[2];
+  fpb_met_ptrs ptr[2];
+  void alloc(const fpb_config &c) {
+    const size_t n3 = (size_t)c.nxmax * c.nymax * c.nzmax, n2 = (size_t)c.nxmax * c.nymax;
+    for (int s = 0; s < 2; s++) {
+      for (auto &v : f3[s]) v.assign(n3, 0.f);
+      for (auto &v : f2[s]) v.assign(n2, 0.f);
+      vd[s].assign(n2 * c.maxspec, 0.f);
+      fpb_met_ptrs &m = ptr[s];
+      m.uu = f3[s][0].data(); m.vv = f3[s][1].data(); m.ww = f3[s][2].data(); m.rho = f3[s][3].data();
+      m.drhodz = f3[s][4].data(); m.tt = f3[s][5].data(); m.uupol = f3[s][6].data(); m.vvpol = f3[s][7].data();
+      m.hmix = f2[s][0].data(); m.ustar = f2[s][1].data(); m.wstar = f2[s][2].data();
+      m.oli = f2[s][3].data(); m.tropopause = f2[s][4].data();
+      m.vdep = vd[s].data();
+    }
+  }
+};
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const fpbh_releases *rel,
+                                const fpbh_run *run, const fpbh_engine *eng, fpbh_output_fn out,
+                                void *user, fpbh_run_result *res) {
+  if (!cp || !height || !rel || !run || !eng) return fpbh_fail("fpbh_timemanager: null argument");
+  const fpb_config &c = *cp;
+  if (c.lsynctime == 0) return fpbh_fail("fpbh_timemanager: lsynctime == 0");
+  if (run->met_interval <= 0) return fpbh_fail("fpbh_timemanager: met_interval <= 0");
+  const int ldirect = c.ldirect, lsynctime = c.lsynctime;
+
+  // host mirror of the particle arrays (com_mod.f90:675-695)
+  const size_t mp = (size_t)c.maxpart;
+  std::vector<double> xtra1(mp), ytra1(mp);
+  std::vector<float> ztra1(mp), uap(mp), ucp(mp), uzp(mp), us(mp), vs(mp), ws(mp);
+  std::vector<int32_t> itra1(mp, FPB_ITRA_DEAD), npoint(mp), nclass(mp), idt(mp), itramem(mp), itrasplit(mp);
+  std::vector<int16_t> cbt(mp);
+  std::vector<float> xmass1(mp * c.nspec), xscav(mp * c.nspec);
+  fpb_particle_ptrs P{};
+  P.xtra1 = xtra1.data(); P.ytra1 = ytra1.data(); P.ztra1 = ztra1.data();
+  P.itra1 = itra1.data(); P.npoint = npoint.data(); P.nclass = nclass.data(); P.idt = idt.data();
+  P.itramem = itramem.data(); P.itrasplit = itrasplit.data();
+  P.uap = uap.data(); P.ucp = ucp.data(); P.uzp = uzp.data();
+  P.us = us.data(); P.vs = vs.data(); P.ws = ws.data(); P.cbt = cbt.data();
+  P.xmass1 = xmass1.data(); P.xscav_frac1 = xscav.data(); P.ld = c.maxpart;
+  fpb_particle_ptrs Ponly_itra{};
+  Ponly_itra.itra1 = itra1.data();
+  Ponly_itra.ld = c.maxpart;
+  int32_t numpart = 0;
+
+  fpbh_release_state *rst = fpbh_release_state_new(rel->numpoint);
+  MetStore met;
+  met.alloc(c);
+
+  // grids handed to the output callback (reference layout, maxspec)
+  const size_t outer = (size_t)c.maxspec * c.maxpointspec_act * c.nclassunc * c.maxageclass;
+  std::vector<float> gridunc((size_t)c.numxgrid * c.numygrid * c.numzgrid * outer);
+  std::vector<float> drygridunc((size_t)c.numxgrid * c.numygrid * outer);
+  std::vector<float> griduncn, drygriduncn;
+  if (c.nested_output == 1) {
+    griduncn.resize((size_t)c.numxgridn * c.numygridn * c.numzgrid * outer);
+    drygriduncn.resize((size_t)c.numxgridn * c.numygridn * outer);
+  }
+  std::vector<float> creceptor((size_t)FPB_MAXRECEPTOR * c.maxspec);
+
+  fpbh_run_result R{};
+  int rc = 0;
+#define ENG(call)                                                    \
+  do {                                                               \
+    if ((call) != 0) {                                               \
+      rc = fpbh_fail("fpbh_timemanager: engine call failed: " #call); \
+      goto done;                                                     \
+    }                                                                \
+  } while (0)
+
+  {
+    // src/timemanager.f90:119-122
+    int loutnext = run->loutstep / 2;
+    float outnum = 0.f;
+    int loutstart = loutnext - run->loutaver / 2;
+    int loutend = loutnext + run->loutaver / 2;
+    const float outstep = (float)std::abs(run->loutstep);
+
+    int memind[2] = {1, 2};
+    int memtime[2] = {999999999, 999999999};
+    bool have_fields = false;
+    const bool DEP = c.drydep != 0;
+
+    for (int itime = 0; ldirect * itime <= ldirect * run->ideltas; itime += lsynctime) {
+      // ---- getfields, src/getfields.f90:96-176 (wind fields every
+      // met_interval seconds, times counted in the run's direction)
+      {
+        const int mi = run->met_interval;
+        auto synth = [&](int slot, int t) -> int {
+          if (run->met_homogeneous) {
+            if (fpbh_homogeneous_met(&c, run->met_u, run->met_v, run->met_w, &met.ptr[slot - 1])) return 1;
+          } else if (fpbh_synth_met(&c, height, t, &met.ptr[slot - 1])) {
+            return 1;
+          }
+          return eng->upload_met(eng->self, slot, &met.ptr[slot - 1]);
+        };
+        if (have_fields && ldirect * memtime[0] <= ldirect * itime && ldirect * memtime[1] > ldirect * itime) {
+          // fields in memory bracket itime
+        } else if (have_fields && ldirect * memtime[1] <= ldirect * itime) {
+          std::swap(memind[0], memind[1]);
+          memtime[0] = memtime[1];
+          // first field time strictly after itime (in run direction)
+          int k = (int)std::floor((double)(ldirect * itime) / mi) + 1;
+          memtime[1] = ldirect * k * mi;
+          ENG(synth(memind[1], memtime[1]));
+        } else {
+          int k = (int)std::floor((double)(ldirect * itime) / mi);
+          memind[0] = 1; memind[1] = 2;
+          memtime[0] = ldirect * k * mi;
+          memtime[1] = ldirect * (k + 1) * mi;
+          ENG(synth(1, memtime[0]));
+          ENG(synth(2, memtime[1]));
+          have_fields = true;
+        }
+        const int lwindinterv = std::abs(memtime[1] - memtime[0]);
+        ENG(eng->set_met_bracket(eng->self, memind, memtime, lwindinterv));
+      }
+
+      // ---- release particles, src/timemanager.f90:230-251
+      {
+        bool due = false;
+        for (int i = 0; i < rel->numpoint; i++)
+          if (itime >= rel->ireleasestart[i] && itime <= rel->ireleaseend[i]) due = true;
+        if (due) {
+          if (numpart > 0) ENG(eng->pull_particles(eng->self, 0, numpart, &Ponly_itra));
+          int32_t first = 0, n = 0;
+          if (fpbh_releaseparticles(&c, height, rel, rst, itime, &P, &numpart, &first, &n)) {
+            rc = 1;
+            goto done;
+          }
+          if (n > 0) ENG(eng->push_particles(eng->self, first, n, &P));
+          ENG(eng->set_numpart(eng->self, numpart));
+        }
+      }
+
+      // ---- decay of deposited mass, src/timemanager.f90:269-304
+      if (DEP && itime == loutnext && ldirect > 0) {
+        float f[FPB_MAXSPEC];
+        bool any = false;
+        for (int ks = 0; ks < c.nspec; ks++) {
+          f[ks] = 1.f;
+          if (c.decay[ks] > 0.f) {
+            f[ks] = (float)std::exp((double)(-1.f * outstep * c.decay[ks]));
+            any = true;
+          }
+        }
+        if (any) ENG(eng->scale_depgrids(eng->self, f));
+      }
+
+      // ---- sampling, src/timemanager.f90:350-365
+      if (ldirect * itime >= ldirect * loutstart && ldirect * itime <= ldirect * loutend) {
+        if ((itime - loutstart) % run->loutsample == 0) {
+          const float weight = (itime == loutstart || itime == loutend) ? 0.5f : 1.0f;
+          outnum += weight;
+          double t0 = now();
+          ENG(eng->conccalc(eng->self, itime, weight));
+          R.t_conc_s += now() - t0;
+        }
+        // ---- output, src/timemanager.f90:376-464
+        if (itime == loutend && outnum > 0.f) {
+          ENG(eng->fetch_grids(eng->self, gridunc.data(), griduncn.empty() ? nullptr : griduncn.data(),
+                               drygridunc.data(), drygriduncn.empty() ? nullptr : drygriduncn.data(),
+                               creceptor.data(), 1));
+          if (out && out(user, itime, outnum, gridunc.data(), griduncn.empty() ? nullptr : griduncn.data(),
+                         drygridunc.data(), drygriduncn.empty() ? nullptr : drygriduncn.data(),
+                         creceptor.data())) {
+            rc = fpbh_fail("fpbh_timemanager: output callback failed");
+            goto done;
+          }
+          R.outputs++;
+          outnum = 0.f;
+          loutnext = loutnext + run->loutstep;
+          loutstart = loutnext - run->loutaver / 2;
+          loutend = loutnext + run->loutaver / 2;
+          if (itime == loutstart) {
+            const float weight = 0.5f;
+            outnum += weight;
+            double t0 = now();
+            ENG(eng->conccalc(eng->self, itime, weight));
+            R.t_conc_s += now() - t0;
+          }
+        }
+      }
+
+      if (itime == run->ideltas) break; // src/timemanager.f90:509
+
+      // src/timemanager.f90:514-518
+      int ldeltat;
+      if (itime < loutnext) ldeltat = itime - (loutnext - run->loutstep);
+      else ldeltat = itime - loutnext;
+
+      // ---- the particle loop, src/timemanager.f90:531-712
+      {
+        fpb_step_stats st{};
+        double t0 = now();
+        ENG(eng->step(eng->self, itime, ldeltat, &st));
+        R.t_step_s += now() - t0;
+        R.particle_steps += st.n_active;
+        R.substeps += st.n_substeps;
+        R.syncs++;
+      }
+      if (run->max_steps > 0 && R.syncs >= run->max_steps) break;
+    }
+  }
+done:
+  R.numpart_final = numpart;
+  if (res) *res = R;
+  fpbh_release_state_free(rst);
+  return rc;
+#undef ENG
+}

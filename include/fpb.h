@@ -1,0 +1,249 @@
+/*
+ * fpb.h -- C ABI of the B200 particle-timestep engine (libfpb.so).
+ *
+ * This is the drop-in boundary for FLEXPART's per-particle hot path.  The
+ * reference (MeteoSwiss/flexpart, Fortran 90) has no FFI of its own; the seam
+ * is timemanager's particle loop and its conccalc calls.  Every entry point
+ * below names the reference lines it replaces (paths relative to the
+ * reference tree).  A Fortran ISO_C_BINDING interface module for these
+ * symbols is given as text in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success, non-zero on error,
+ *     and fpb_last_error() then holds a message (the reference convention is
+ *     banner + `stop 1`, e.g. src/timemanager.f90:205-208 -- the Fortran shim
+ *     does `if (ierr /= 0) stop 1`).
+ *   - all calls are synchronous on return.
+ *   - host arrays are Fortran column-major with the reference's padded extents
+ *     and stay owned by the caller; the library owns all device memory.
+ *   - particle slot indices and array offsets are 0-based here (Fortran slot
+ *     j is offset j-1); model times are FLEXPART's integer seconds.
+ *   - there is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef FPB_H
+#define FPB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPB_ABI_VERSION 1
+#define FPB_MAXSPEC 8      /* >= par_mod maxspec (5), src/par_mod.f90:210 */
+#define FPB_MAXAGECLASS 8  /* >= par_mod maxageclass */
+#define FPB_MAXZGRID 64    /* output-grid levels */
+#define FPB_MAXRECEPTOR 20 /* par_mod maxreceptor, src/par_mod.f90:204 */
+
+/* Values of itra1 for a terminated particle, src/timemanager.f90:632 */
+#define FPB_ITRA_DEAD (-999999999)
+
+/* fpb_config.rng_mode */
+enum {
+  FPB_RNG_REFERENCE = 0, /* ran3-indexed rannumb table, reference draw order
+                            (validation; src/advance.f90:153) */
+  FPB_RNG_PHILOX_INDEX = 1, /* Philox4x32-10 replaces ran3 as the table index */
+  FPB_RNG_PHILOX = 2     /* Philox4x32-10 + Box-Muller clipped to +-3, no table */
+};
+
+/* fpb_config.math_mode */
+enum {
+  FPB_MATH_FAST = 0,  /* FMA contraction on, float intrinsics */
+  FPB_MATH_STRICT = 1 /* no contraction, correctly rounded transcendentals:
+                         bit-comparable with the CPU oracle */
+};
+
+/* fpb_config.scatter_mode (conccalc / drydepokernel accumulation) */
+enum {
+  FPB_SCATTER_ATOMIC = 0,       /* red.global.add.f32 */
+  FPB_SCATTER_DETERMINISTIC = 1 /* sort by cell + ordered segmented sum */
+};
+
+/*
+ * Run constants: the subset of par_mod / com_mod / outg_mod / unc_mod /
+ * point_mod the hot path reads.  Copied by value in fpb_init.
+ */
+typedef struct fpb_config {
+  int32_t abi_version; /* FPB_ABI_VERSION */
+
+  /* --- meteorological grid, src/gridcheck_ecmwf.f90:300-366 ------------- */
+  int32_t nx, ny, nz;          /* used extents; nz = nuvz = levels+1 */
+  int32_t nxmax, nymax, nzmax; /* padded host extents, src/par_mod.f90:142-154 */
+  int32_t nxmin1, nymin1;
+  float dx, dy, xlon0, ylat0;
+  float dxconst, dyconst;      /* 180/(dx*r_earth*pi), src/gridcheck_ecmwf.f90 */
+  int32_t xglobal, nglobal, sglobal;
+  float switchnorthg, switchsouthg;
+  float northpolemap[9], southpolemap[9]; /* cmapf_mod stlmbr/stcm2p result */
+  float eps;                   /* nxmax/3.e5, src/advance.f90:107 */
+
+  /* --- COMMAND, src/readcommand.f90:244-272,377-383,622-634 ------------- */
+  int32_t ldirect;    /* +1 / -1 */
+  int32_t lsynctime;  /* negative for backward runs */
+  int32_t method, mintime, ifine;
+  int32_t turbswitch, cblflag, mdomainfill, mquasilag, lsettling;
+  float ctl;          /* already inverted: 1/CTL */
+  float fine;         /* 1/ifine */
+  float d_trop, d_strat, turbmesoscale; /* src/par_mod.f90:79 */
+  int32_t turboff;    /* com_mod turboff, src/com_mod.f90:778 */
+  int32_t ind_samp;   /* 0 or -1 */
+  int32_t ioutputforeachrelease, lusekerneloutput, lparticlecountoutput;
+  int32_t drydep, drybkdep, wetbkdep, nested_output;
+
+  /* --- species, src/readspecies.f90 / readreleases.f90:349-386 ---------- */
+  int32_t nspec;
+  float decay[FPB_MAXSPEC];
+  int32_t drydepspec[FPB_MAXSPEC];
+  float density[FPB_MAXSPEC], dquer[FPB_MAXSPEC], vsetaver[FPB_MAXSPEC],
+      cunningham[FPB_MAXSPEC];
+
+  /* --- age classes, src/readageclasses.f90 ------------------------------ */
+  int32_t nageclass;
+  int32_t lage[FPB_MAXAGECLASS];
+
+  /* --- output grids, src/readoutgrid.f90:199-200, outgrid_init.f90:192 -- */
+  int32_t numxgrid, numygrid, numzgrid;
+  float dxout, dyout, xoutshift, youtshift;
+  float outheight[FPB_MAXZGRID];
+  int32_t numxgridn, numygridn;
+  float dxoutn, dyoutn, xoutshiftn, youtshiftn;
+  int32_t maxpointspec_act, nclassunc, maxageclass;
+  int32_t maxspec; /* species extent of the host grid arrays (reference: 5) */
+
+  /* --- receptors, src/readreceptors.f90 --------------------------------- */
+  int32_t numreceptor;
+  float xreceptor[FPB_MAXRECEPTOR], yreceptor[FPB_MAXRECEPTOR],
+      receptorarea[FPB_MAXRECEPTOR];
+
+  /* --- releases, src/readreleases.f90 ----------------------------------- */
+  int32_t numpoint;
+  const int32_t *npart; /* [numpoint] */
+  const float *xmass;   /* (numpoint, maxspec) column-major: xmass[i + numpoint*k] */
+
+  /* --- vertical levels, src/verttransform_ecmwf.f90:153-168 ------------- */
+  const float *height; /* [nz], height[0] = 0 */
+
+  /* --- engine ----------------------------------------------------------- */
+  int32_t maxpart;      /* particle capacity on this device */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t rng_mode, math_mode, scatter_mode;
+  uint64_t seed;        /* Philox key */
+  int32_t part_id_stride, part_id_offset; /* global id = offset + stride*slot:
+                           multi-GPU partition, src/releaseparticles_mpi.f90:141 */
+  int32_t reserved[8];
+} fpb_config;
+
+/* One time level of the meteorological arrays the hot path gathers from
+ * (src/com_mod.f90:355-371,410-427,451).  3-D: (nxmax,nymax,nzmax); 2-D:
+ * (nxmax,nymax); vdep: (nxmax,nymax,maxspec).  uupol/vvpol may be NULL when
+ * neither pole is in the domain; tt may be NULL when lsettling == 0; vdep may
+ * be NULL when drydep == 0. */
+typedef struct fpb_met_ptrs {
+  const float *uu, *vv, *ww, *rho, *drhodz, *tt, *uupol, *vvpol;
+  const float *hmix, *ustar, *wstar, *oli, *tropopause;
+  const float *vdep;
+} fpb_met_ptrs;
+
+/* Particle arrays (src/com_mod.f90:675-695).  xmass1 / xscav_frac1 are
+ * (ld, nspec) column-major.  Any pointer may be NULL in fpb_pull_particles to
+ * skip that array; xscav_frac1 may be NULL unless drybkdep/wetbkdep. */
+typedef struct fpb_particle_ptrs {
+  double *xtra1, *ytra1;
+  float *ztra1;
+  int32_t *itra1, *npoint, *nclass, *idt, *itramem, *itrasplit;
+  float *uap, *ucp, *uzp, *us, *vs, *ws;
+  int16_t *cbt;
+  float *xmass1;
+  float *xscav_frac1;
+  int32_t ld;
+} fpb_particle_ptrs;
+
+typedef struct fpb_step_stats {
+  int64_t n_active;     /* particles with itra1 == itime on entry */
+  int64_t n_init;       /* of those, initialize() calls */
+  int64_t n_terminated; /* set to FPB_ITRA_DEAD in this step */
+  int64_t n_pbl;        /* took the PBL branch (zeta <= 1) on entry */
+  int64_t n_substeps;   /* label-100 loop iterations, summed */
+  int64_t n_petterssen; /* Petterssen corrector applied */
+  int64_t n_nan_cbl;    /* nan_count + nan_count2, src/advance.f90:421,439 */
+} fpb_step_stats;
+
+typedef struct fpb_handle fpb_handle;
+
+const char *fpb_last_error(void);
+int fpb_abi_version(void);
+size_t fpb_config_sizeof(void);
+
+/* after outgrid_init, before timemanager: src/FLEXPART.f90:342-453 */
+int fpb_init(const fpb_config *cfg, fpb_handle **out);
+/* src/timemanager.f90:760-774 */
+int fpb_finalize(fpb_handle *h);
+
+/* rannumb(maxrand) filled at src/FLEXPART.f90:56-59 */
+int fpb_set_rannumb(fpb_handle *h, const float *rannumb, int32_t n);
+/* Fill the table inside the library with the same ran3/gasdev1 recipe
+ * (src/random_mod.f90:70-139, src/FLEXPART.f90:47,56-59). */
+int fpb_fill_rannumb(fpb_handle *h, int32_t maxrand, int32_t idummy);
+
+/* after getfields returned a new field: src/timemanager.f90:200,
+ * src/getfields.f90:109-139.  slot is the Fortran slot index 1 or 2. */
+int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *met);
+/* memind(1:2), memtime(1:2), lwindinterv: src/getfields.f90:96-176 */
+int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2],
+                        const int32_t memtime[2], int32_t lwindinterv);
+
+/* after releaseparticles / init_domainfill / boundcond_domainfill / split:
+ * src/timemanager.f90:230-251,473-504.  Copies rows [first, first+count). */
+int fpb_push_particles(fpb_handle *h, int32_t first, int32_t count,
+                       const fpb_particle_ptrs *p);
+int fpb_set_numpart(fpb_handle *h, int32_t numpart);
+/* before partoutput / plumetraj / wetdepo / convmix: src/timemanager.f90:453 */
+int fpb_pull_particles(fpb_handle *h, int32_t first, int32_t count,
+                       const fpb_particle_ptrs *p);
+
+/* replaces the particle loop src/timemanager.f90:531-712 (initialize,
+ * advance, decay, dry-deposition split + drydepokernel, termination). */
+int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat,
+             fpb_step_stats *stats /* may be NULL */);
+
+/* replaces conccalc(itime,weight): src/timemanager.f90:364,463 */
+int fpb_conccalc(fpb_handle *h, int32_t itime, float weight);
+
+/* before concoutput*: src/timemanager.f90:376 (MPI build:
+ * mpif_tm_reduce_grid, src/timemanager_mpi.f90:468).  Copies the device
+ * grids into the caller's arrays in the reference layout
+ *   gridunc (numxgrid,numygrid,numzgrid,maxspec,maxpointspec_act,nclassunc,maxageclass)
+ *   drygridunc (numxgrid,numygrid,maxspec,maxpointspec_act,nclassunc,maxageclass)
+ *   creceptor (maxreceptor, maxspec)
+ * (src/outgrid_init.f90:192-201); NULL pointers are skipped.  With
+ * zero_conc != 0 gridunc/griduncn/creceptor are then zeroed on the device
+ * (src/concoutput.f90:719-720); deposition grids stay cumulative. */
+int fpb_fetch_grids(fpb_handle *h, float *gridunc, float *griduncn,
+                    float *drygridunc, float *drygriduncn, float *creceptor,
+                    int32_t zero_conc);
+/* decay of deposited mass: src/timemanager.f90:269-304;
+ * factor[ks] multiplies drygridunc(:,:,ks,...) (and the nested twin). */
+int fpb_scale_depgrids(fpb_handle *h, const float *factor_per_species);
+
+/* Device views for the host's collective (one NCCL reduce per output
+ * interval, the mpif_tm_reduce_grid slot src/mpi_mod.f90:2395-2579).
+ * which: 0 gridunc, 1 griduncn, 2 drygridunc, 3 drygriduncn, 4 creceptor.
+ * The device layout is packed to nspec species (not maxspec). */
+int fpb_grid_device_ptr(fpb_handle *h, int32_t which, void **dptr,
+                        size_t *nfloats);
+int fpb_zero_conc_grids(fpb_handle *h);
+
+/* Re-order the device-resident particles by met-grid cell for gather
+ * locality.  Slot identity seen through push/pull is preserved. */
+int fpb_sort_particles(fpb_handle *h);
+
+/* CUDA stream the engine launches on (for the caller's events), and the
+ * number of kernels the engine has launched so far. */
+void *fpb_stream(fpb_handle *h);
+int64_t fpb_launch_count(fpb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPB_H */

@@ -1,0 +1,139 @@
+/*
+ * fpb_host.h -- C ABI of the host-side companion library (libfpb_host.so).
+ *
+ * The reference's host is Fortran (no Fortran compiler exists in the build
+ * image), so the host pieces a run needs on top of the engine
+ * are provided in C++ with the reference's own names and semantics:
+ *   - run-constant derivation: gridcheck_ecmwf (global/pole flags, pole
+ *     maps), readcommand (CTL/IFINE/method switches), readoutgrid (shifts);
+ *   - a synthetic "ECMWF-shaped" met generator that fills the arrays
+ *     verttransform_ecmwf/calcpar would produce (incl. drhodz and uupol/vvpol);
+ *   - releaseparticles (release counts, slot search, ran1 position stream);
+ *   - timemanager: the reference's time loop driving an engine through a
+ *     table of function pointers with the fpb_* signatures.
+ * CPU only; needs no CUDA device.
+ */
+#ifndef FPB_HOST_H
+#define FPB_HOST_H
+
+#include "fpb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *fpbh_last_error(void);
+
+/* gridcheck_ecmwf: from nx,ny,nz,nxmax,nymax,nzmax,dx,dy,xlon0,ylat0 derive
+ * nxmin1,nymin1,xglobal,nglobal,sglobal,switchnorthg/southg,north/southpolemap,
+ * dxconst,dyconst,eps (src/gridcheck_ecmwf.f90:300-366, src/par_mod.f90:123,
+ * src/advance.f90:107). */
+int fpbh_gridcheck(fpb_config *cfg);
+
+/* readcommand derivations (src/readcommand.f90:244-272,377-383,622-634):
+ * in: ldirect, lsynctime (>0 as in COMMAND), ctl (as in COMMAND), ifine,
+ * cblflag; out: ifine, turbswitch, fine, ctl:=1/ctl, method, mintime,
+ * lsynctime sign, d_trop, d_strat, turbmesoscale defaults. */
+int fpbh_readcommand(fpb_config *cfg);
+
+/* readoutgrid (src/readoutgrid.f90:199-200): xoutshift=xlon0-outlon0 etc. */
+int fpbh_readoutgrid(fpb_config *cfg, float outlon0, float outlat0, int32_t numxgrid,
+                     int32_t numygrid, float dxout, float dyout, const float *outheights,
+                     int32_t numzgrid);
+int fpbh_readoutgrid_nest(fpb_config *cfg, float outlon0n, float outlat0n, int32_t numxgridn,
+                          int32_t numygridn, float dxoutn, float dyoutn);
+
+/* 137-layer-like level heights: height[0]=0, strictly increasing, ~80 km top
+ * (shape of src/verttransform_ecmwf.f90:153-168 output). */
+int fpbh_synth_heights(int32_t nz, float *height);
+
+/* Fill one time level of synthetic met into caller arrays with
+ * the padded Fortran layout; `time_s` moves the phase of the fields.
+ * All non-NULL pointers of `out` are written. */
+int fpbh_synth_met(const fpb_config *cfg, const float *height, int32_t time_s,
+                   const fpb_met_ptrs *out);
+/* homogeneous fields of mpi_mod's set_fields_synthetic (src/mpi_mod.f90:2940-2973) */
+int fpbh_homogeneous_met(const fpb_config *cfg, float u, float v, float w,
+                         const fpb_met_ptrs *out);
+
+/* conformal-map helpers (src/cmapf_mod.f90), exported for tests */
+void fpbh_stlmbr(float *strcmp, float tnglat, float xlong);
+void fpbh_stcm2p(float *strcmp, float x1, float y1, float xlat1, float xlong1, float x2,
+                 float y2, float xlat2, float xlong2);
+void fpbh_cc2gll(const float *strcmp, float xlat, float xlong, float ue, float vn, float *ug,
+                 float *vg);
+void fpbh_cll2xy(const float *strcmp, float xlat, float xlong, float *x, float *y);
+void fpbh_cxy2ll(const float *strcmp, float x, float y, float *xlat, float *xlong);
+
+/* RELEASES after coordtrafo: boxes in grid units (src/coordtrafo.f90:37-42),
+ * times relative to the simulation start and snapped to lsynctime
+ * (src/FLEXPART.f90:401-404). */
+typedef struct fpbh_releases {
+  int32_t numpoint;
+  const int32_t *ireleasestart, *ireleaseend;
+  const float *xpoint1, *ypoint1, *xpoint2, *ypoint2, *zpoint1, *zpoint2;
+  int32_t itsplit;
+} fpbh_releases;
+
+typedef struct fpbh_release_state fpbh_release_state;
+fpbh_release_state *fpbh_release_state_new(int32_t numpoint);
+void fpbh_release_state_free(fpbh_release_state *s);
+
+/* releaseparticles(itime), src/releaseparticles.f90:69-378 (zkind 1,
+ * EMISVAR factors 1).  Works on the host mirror `p` (itra1 must be current).
+ * On return first_changed and n_changed bound the rows that were written and
+ * *numpart is updated.  Returns 1 when maxpart is exceeded (label 996). */
+int fpbh_releaseparticles(const fpb_config *cfg, const float *height, const fpbh_releases *rel,
+                          fpbh_release_state *st, int32_t itime, const fpb_particle_ptrs *p,
+                          int32_t *numpart, int32_t *first_changed, int32_t *n_changed);
+
+/* engine seen by the time loop: the fpb_* entry points (or any
+ * implementation with the same contract), `self` passed as first argument */
+typedef struct fpbh_engine {
+  void *self;
+  int (*upload_met)(void *self, int32_t slot, const fpb_met_ptrs *met);
+  int (*set_met_bracket)(void *self, const int32_t memind[2], const int32_t memtime[2],
+                         int32_t lwindinterv);
+  int (*push_particles)(void *self, int32_t first, int32_t count, const fpb_particle_ptrs *p);
+  int (*pull_particles)(void *self, int32_t first, int32_t count, const fpb_particle_ptrs *p);
+  int (*set_numpart)(void *self, int32_t numpart);
+  int (*step)(void *self, int32_t itime, int32_t ldeltat, fpb_step_stats *stats);
+  int (*conccalc)(void *self, int32_t itime, float weight);
+  int (*fetch_grids)(void *self, float *gridunc, float *griduncn, float *drygridunc,
+                     float *drygriduncn, float *creceptor, int32_t zero_conc);
+  int (*scale_depgrids)(void *self, const float *factor);
+} fpbh_engine;
+
+/* one output interval handed to the caller (the concoutput slot,
+ * src/timemanager.f90:376-436); arrays are in the reference layout and are
+ * only valid during the call */
+typedef int (*fpbh_output_fn)(void *user, int32_t itime, float outnum, const float *gridunc,
+                              const float *griduncn, const float *drygridunc,
+                              const float *drygriduncn, const float *creceptor);
+
+typedef struct fpbh_run {
+  int32_t ideltas;                        /* signed run length (s) */
+  int32_t loutstep, loutaver, loutsample; /* signed like readcommand leaves them */
+  int32_t met_interval;                   /* s between synthetic wind fields */
+  int32_t met_homogeneous;                /* 1: set_fields_synthetic-style met */
+  float met_u, met_v, met_w;
+  int32_t max_steps;                      /* >0: stop after that many syncs */
+} fpbh_run;
+
+typedef struct fpbh_run_result {
+  int64_t particle_steps; /* sum over syncs of particles with itra1 == itime */
+  int64_t substeps;
+  int32_t syncs, outputs, numpart_final;
+  double t_step_s, t_conc_s; /* host wall time inside engine->step / conccalc */
+} fpbh_run_result;
+
+/* timemanager(metdata_format): src/timemanager.f90:152-729 with the engine
+ * in place of the particle loop and conccalc; met comes from fpbh_synth_met. */
+int fpbh_timemanager(const fpb_config *cfg, const float *height, const fpbh_releases *rel,
+                     const fpbh_run *run, const fpbh_engine *eng, fpbh_output_fn out, void *user,
+                     fpbh_run_result *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPB_HOST_H */

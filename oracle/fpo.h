@@ -1,0 +1,201 @@
+/*
+ * fpo.h -- CPU ORACLE for the FLEXPART per-particle timestep hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call it.
+ *
+ * It is a sequential, module-global-style restatement in plain C of the
+ * reference's Fortran algorithm (MeteoSwiss/flexpart, src/ *.f90); every
+ * function cites the file:line it follows.  It shares only the public type
+ * definitions of include/fpb.h (fpb_config, fpb_met_ptrs, fpb_particle_ptrs)
+ * so tests can hand one problem description to both sides.
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors or known-answer
+ * tests for this path and no Fortran compiler
+ * exists in the build image, so the oracle cannot be checked against outputs
+ * of the reference itself.  It is pinned instead by analytic known-answer
+ * cases, invariants and the Numerical-Recipes ran3 sequence (tests/).
+ *
+ * Arithmetic: default `real` = float, `real(dp)` = double, no contraction
+ * (build with -O2 -ffp-contract=off, mirroring src/makefile_meteoswiss:103-111).
+ * Transcendentals go through fpo_math.h: by default correctly rounded
+ * (double evaluation, rounded once to float); -DFPO_LIBM_FLOAT selects
+ * glibc's float routines, which is what gfortran would link.
+ */
+#ifndef FPO_H
+#define FPO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../include/fpb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fpo_state {
+  fpb_config c;   /* by-value copy; c.height/npart/xmass repointed to own copies */
+  float *height;  /* 1-based: height[1..nz] */
+  int32_t *npart; /* 1-based */
+  float *xmass;   /* xmass[(i-1) + numpoint*(k-1)] */
+
+  /* meteorology: Fortran slot 1..2 */
+  fpb_met_ptrs met[3];
+  int memind[3];
+  int memtime[3];
+  int lwindinterv;
+
+  /* rannumb(maxrand), 1-based */
+  float *rannumb;
+  int maxrand;
+
+  /* random_mod SAVEd state, src/random_mod.f90 */
+  int r3_inext, r3_inextp, r3_ma[56], r3_iff;
+  int r1_iv[33], r1_iy;
+  int gd_iset;
+  float gd_gset;
+  /* SAVEd `idummy` locals: src/advance.f90:120, src/initialize.f90:64,
+   * src/releaseparticles.f90 (idummy=-7) */
+  int idummy_advance, idummy_initialize, idummy_release;
+  float settling_saved; /* src/advance.f90:121 */
+
+  /* particles, 1-based arrays of maxpart+1 */
+  int maxpart, numpart;
+  double *xtra1, *ytra1;
+  float *ztra1;
+  int32_t *itra1, *npoint, *nclass, *idt, *itramem, *itrasplit;
+  float *uap, *ucp, *uzp, *us, *vs, *ws;
+  int16_t *cbt;
+  float *xmass1;      /* xmass1[j + (maxpart+1)*(k-1)] */
+  float *xscav_frac1; /* same layout */
+
+  /* interpol_mod, src/interpol_mod.f90 */
+  float *uprof, *vprof, *wprof, *usigprof, *vsigprof, *wsigprof, *rhoprof,
+      *rhogradprof; /* 1-based [nzmax+1] */
+  float u, v, w, usig, vsig, wsig;
+  float p1, p2, p3, p4, ddx, ddy, rddx, rddy, dtt, dt1, dt2;
+  int ix, jy, ixp, jyp, ngrid, indz, indzp;
+  int depoindicator[FPB_MAXSPEC + 1];
+  unsigned char *indzindicator; /* 1-based */
+
+  /* hanna_mod, src/hanna_mod.f90 */
+  float ust, wst, ol, h, zeta, sigu, sigv, tlu, tlv, tlw, sigw, dsigwdz,
+      dsigw2dz;
+
+  /* grids (reference layout, maxspec species extent) */
+  float *gridunc, *griduncn, *drygridunc, *drygriduncn, *creceptor;
+
+  /* behaviour switch ("cross-particle stale state"):
+   * 1 = reproduce the reference's leaks between calls,
+   * 0 = "defined" behaviour the device implements. */
+  int strict_reference;
+
+  /* validation hooks: per-call nrand injection (0 = draw from ran3) */
+  long n_ran3_draws;
+
+  /* counters */
+  long nan_count, nan_count2;
+  fpb_step_stats last;
+  /* per-particle trace of the last step (tests): branch + substeps */
+  int32_t *trace_nsub; /* 1-based, may be NULL */
+} fpo_state;
+
+/* lifecycle */
+fpo_state *fpo_create(const fpb_config *cfg, int strict_reference);
+void fpo_destroy(fpo_state *S);
+
+/* random_mod */
+float fpo_ran1(fpo_state *S, int *idum);
+float fpo_ran3(fpo_state *S, int *idum);
+float fpo_gasdev(fpo_state *S, int *idum);
+void fpo_gasdev1(fpo_state *S, int *idum, float *r1, float *r2);
+void fpo_fill_rannumb(fpo_state *S, int maxrand, int idummy);
+void fpo_set_rannumb(fpo_state *S, const float *tab, int n);
+const float *fpo_rannumb(fpo_state *S); /* 0-based view of the table */
+
+/* meteorology */
+void fpo_set_met(fpo_state *S, int slot, const fpb_met_ptrs *m);
+void fpo_set_met_bracket(fpo_state *S, const int memind[2],
+                         const int memtime[2], int lwindinterv);
+
+/* particles */
+void fpo_push_particles(fpo_state *S, int first, int count,
+                        const fpb_particle_ptrs *p);
+void fpo_pull_particles(fpo_state *S, int first, int count,
+                        const fpb_particle_ptrs *p);
+void fpo_set_numpart(fpo_state *S, int numpart);
+
+/* hot path */
+void fpo_initialize(fpo_state *S, int itime, int32_t *ldt, float *up, float *vp,
+                    float *wp, float *usigold, float *vsigold, float *wsigold,
+                    double xt, double yt, float zt, int16_t *icbt);
+void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt,
+                 float *up, float *vp, float *wp, float *usigold,
+                 float *vsigold, float *wsigold, int *nstop, double *xt,
+                 double *yt, float *zt, float *prob, int16_t *icbt);
+void fpo_step(fpo_state *S, int itime, int ldeltat, fpb_step_stats *stats);
+void fpo_conccalc(fpo_state *S, int itime, float weight);
+void fpo_drydepokernel(fpo_state *S, int nunc, const float *deposit, float x,
+                       float y, int nage, int kp);
+void fpo_drydepokernel_nest(fpo_state *S, int nunc, const float *deposit,
+                            float x, float y, int nage, int kp);
+void fpo_fetch_grids(fpo_state *S, float *gridunc, float *griduncn,
+                     float *drygridunc, float *drygriduncn, float *creceptor,
+                     int zero_conc);
+void fpo_scale_depgrids(fpo_state *S, const float *factor);
+
+/* pieces exported for unit tests */
+void fpo_hanna(fpo_state *S, float z);
+void fpo_hanna1(fpo_state *S, float z);
+void fpo_hanna_short(fpo_state *S, float z);
+void fpo_windalign(float u, float v, float ffap, float ffcp, float *ux,
+                   float *vy);
+void fpo_interpol_all(fpo_state *S, int itime, float xt, float yt, float zt);
+void fpo_interpol_misslev(fpo_state *S, int n);
+void fpo_interpol_wind(fpo_state *S, int itime, float xt, float yt, float zt);
+void fpo_interpol_wind_short(fpo_state *S, int itime, float xt, float yt,
+                             float zt);
+void fpo_interpol_vdep(fpo_state *S, int level, float *vdepo);
+void fpo_get_settling(fpo_state *S, int itime, float xt, float yt, float zt,
+                      int nsp, float *settling);
+void fpo_cbl(fpo_state *S, float wp, float zp, float ust, float wst, float h,
+             float rhoa, float rhograd, float sigmaw, float dsigmawdz,
+             float tlw, float *ptot, float *Q, float *phi, float *ath,
+             float *bth, float ol, int *flagrein);
+void fpo_re_initialize_particle(fpo_state *S, float zp, float ust, float wst,
+                                float h, float sigmaw, float *wp, int *nrand,
+                                float ol);
+void fpo_initialize_cbl_vel(fpo_state *S, int *idum, float zp, float ust,
+                            float wst, float h, float sigmaw, float *wp,
+                            float ol);
+
+void fpo_initialize_cbl_vel_defined(fpo_state *S, float dcas, float dcas1,
+                                    float zp, float wst, float h, float sigmaw,
+                                    float *wp, float ol);
+
+/* cmapf_mod */
+void fpo_stlmbr(float *strcmp, float tnglat, float xlong);
+void fpo_stcm2p(float *strcmp, float x1, float y1, float xlat1, float xlong1,
+                float x2, float y2, float xlat2, float xlong2);
+void fpo_cll2xy(const float *strcmp, float xlat, float xlong, float *x,
+                float *y);
+void fpo_cxy2ll(const float *strcmp, float x, float y, float *xlat,
+                float *xlong);
+float fpo_cgszll(const float *strcmp, float xlat, float xlong);
+void fpo_cc2gll(const float *strcmp, float xlat, float xlong, float ue,
+                float vn, float *ug, float *vg);
+
+/* releaseparticles (integer semantics + ran1 stream) */
+int fpo_releaseparticles(fpo_state *S, int itime, int numpoint,
+                         const int32_t *ireleasestart,
+                         const int32_t *ireleaseend, const float *xpoint1,
+                         const float *ypoint1, const float *xpoint2,
+                         const float *ypoint2, const float *zpoint1,
+                         const float *zpoint2, float *xmasssave, int itsplit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,47 @@
+/*
+ * fpo_vtable.c -- adapters that give the oracle the fpb_* call contract
+ * (int return, engine pointer first) so the tests can run the SAME host time
+ * loop (fpbh_timemanager) once on the oracle and once on the CUDA engine
+ * (test infrastructure).
+ */
+#include "fpo.h"
+
+int fpo_vt_upload_met(void *self, int32_t slot, const fpb_met_ptrs *met) {
+  fpo_set_met((fpo_state *)self, slot, met);
+  return 0;
+}
+int fpo_vt_set_met_bracket(void *self, const int32_t memind[2], const int32_t memtime[2],
+                           int32_t lwindinterv) {
+  int mi[2] = {memind[0], memind[1]}, mt[2] = {memtime[0], memtime[1]};
+  fpo_set_met_bracket((fpo_state *)self, mi, mt, lwindinterv);
+  return 0;
+}
+int fpo_vt_push_particles(void *self, int32_t first, int32_t count, const fpb_particle_ptrs *p) {
+  fpo_push_particles((fpo_state *)self, first, count, p);
+  return 0;
+}
+int fpo_vt_pull_particles(void *self, int32_t first, int32_t count, const fpb_particle_ptrs *p) {
+  fpo_pull_particles((fpo_state *)self, first, count, p);
+  return 0;
+}
+int fpo_vt_set_numpart(void *self, int32_t numpart) {
+  fpo_set_numpart((fpo_state *)self, numpart);
+  return 0;
+}
+int fpo_vt_step(void *self, int32_t itime, int32_t ldeltat, fpb_step_stats *stats) {
+  fpo_step((fpo_state *)self, itime, ldeltat, stats);
+  return 0;
+}
+int fpo_vt_conccalc(void *self, int32_t itime, float weight) {
+  fpo_conccalc((fpo_state *)self, itime, weight);
+  return 0;
+}
+int fpo_vt_fetch_grids(void *self, float *gridunc, float *griduncn, float *drygridunc,
+                       float *drygriduncn, float *creceptor, int32_t zero_conc) {
+  fpo_fetch_grids((fpo_state *)self, gridunc, griduncn, drygridunc, drygriduncn, creceptor, zero_conc);
+  return 0;
+}
+int fpo_vt_scale_depgrids(void *self, const float *factor) {
+  fpo_scale_depgrids((fpo_state *)self, factor);
+  return 0;
+}

@@ -1,0 +1,157 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  Test infrastructure:
+imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from flexpart_b200 import abi
+from flexpart_b200.abi import FpbConfig, FpbMetPtrs, FpbParticlePtrs, FpbStepStats, FpbhEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+_libs = {}
+
+
+def _fp(a):
+    return a.ctypes.data_as(_pf) if a is not None else None
+
+
+def load(libm_float=False):
+    name = "liboracle_libmf.so" if libm_float else "liboracle.so"
+    if name in _libs:
+        return _libs[name]
+    path = os.path.join(ORACLE_DIR, name)
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+    L = C.CDLL(path)
+    S = C.c_void_p
+    L.fpo_create.argtypes = [C.POINTER(FpbConfig), C.c_int]
+    L.fpo_create.restype = S
+    L.fpo_destroy.argtypes = [S]
+    L.fpo_ran1.argtypes = [S, _pi]; L.fpo_ran1.restype = C.c_float
+    L.fpo_ran3.argtypes = [S, _pi]; L.fpo_ran3.restype = C.c_float
+    L.fpo_fill_rannumb.argtypes = [S, C.c_int, C.c_int]
+    L.fpo_set_rannumb.argtypes = [S, _pf, C.c_int]
+    L.fpo_rannumb.argtypes = [S]; L.fpo_rannumb.restype = _pf
+    L.fpo_set_met.argtypes = [S, C.c_int, C.POINTER(FpbMetPtrs)]
+    L.fpo_set_met_bracket.argtypes = [S, _pi, _pi, C.c_int]
+    L.fpo_push_particles.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbParticlePtrs)]
+    L.fpo_pull_particles.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbParticlePtrs)]
+    L.fpo_set_numpart.argtypes = [S, C.c_int]
+    L.fpo_step.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbStepStats)]
+    L.fpo_conccalc.argtypes = [S, C.c_int, C.c_float]
+    L.fpo_fetch_grids.argtypes = [S, _pf, _pf, _pf, _pf, _pf, C.c_int]
+    L.fpo_scale_depgrids.argtypes = [S, _pf]
+    L.fpo_windalign.argtypes = [C.c_float] * 4 + [_pf, _pf]
+    L.fpo_stlmbr.argtypes = [_pf, C.c_float, C.c_float]
+    L.fpo_stcm2p.argtypes = [_pf] + [C.c_float] * 8
+    L.fpo_cll2xy.argtypes = [_pf, C.c_float, C.c_float, _pf, _pf]
+    L.fpo_cxy2ll.argtypes = [_pf, C.c_float, C.c_float, _pf, _pf]
+    L.fpo_cgszll.argtypes = [_pf, C.c_float, C.c_float]; L.fpo_cgszll.restype = C.c_float
+    L.fpo_cc2gll.argtypes = [_pf, C.c_float, C.c_float, C.c_float, C.c_float, _pf, _pf]
+    L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
+    L.fpo_releaseparticles.restype = C.c_int
+    L.fpo_mp_step.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float]
+    L.fpo_mp_step.restype = C.c_double
+    _libs[name] = L
+    return L
+
+
+class Oracle:
+    """Sequential CPU restatement of the hot path with the Engine's interface."""
+
+    def __init__(self, cb, strict_reference=False, libm_float=False):
+        self.L = load(libm_float)
+        self.cb = cb
+        self.S = C.c_void_p(self.L.fpo_create(C.byref(cb.cfg), 1 if strict_reference else 0))
+        self._keep = []
+
+    def close(self):
+        if self.S:
+            self.L.fpo_destroy(self.S)
+            self.S = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fill_rannumb(self, maxrand=1000000, idummy=-320):
+        self.L.fpo_fill_rannumb(self.S, maxrand, idummy)
+
+    def set_rannumb(self, table):
+        t = np.ascontiguousarray(table, np.float32)
+        self.L.fpo_set_rannumb(self.S, _fp(t), len(t))
+
+    def rannumb(self, n):
+        return np.ctypeslib.as_array(self.L.fpo_rannumb(self.S), shape=(n,)).copy()
+
+    def upload_met(self, slot, met):
+        self._keep.append(met)  # the oracle reads the host arrays in place
+        self._keep = self._keep[-4:]
+        self.L.fpo_set_met(self.S, slot, C.byref(met.ptrs))
+
+    def set_met_bracket(self, memind, memtime, lwindinterv=None):
+        if lwindinterv is None:
+            lwindinterv = abs(memtime[1] - memtime[0])
+        self.L.fpo_set_met_bracket(self.S, (C.c_int32 * 2)(*memind), (C.c_int32 * 2)(*memtime), lwindinterv)
+
+    def push_particles(self, parts, first=0, count=None):
+        count = parts.numpart - first if count is None else count
+        self.L.fpo_push_particles(self.S, first, count, C.byref(parts.ptrs))
+
+    def pull_particles(self, parts, first=0, count=None):
+        count = parts.numpart - first if count is None else count
+        self.L.fpo_pull_particles(self.S, first, count, C.byref(parts.ptrs))
+
+    def set_numpart(self, n):
+        self.L.fpo_set_numpart(self.S, n)
+
+    def step(self, itime, ldeltat=0, stats=True):
+        st = FpbStepStats()
+        self.L.fpo_step(self.S, itime, ldeltat, C.byref(st))
+        return st.as_dict()
+
+    def conccalc(self, itime, weight):
+        self.L.fpo_conccalc(self.S, itime, weight)
+
+    def fetch_grids(self, zero_conc=True):
+        c = self.cb.cfg
+        sg = (c.numxgrid, c.numygrid, c.numzgrid, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
+        sd = (c.numxgrid, c.numygrid, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
+        out = {"gridunc": np.zeros(sg, np.float32, order="F"), "drygridunc": np.zeros(sd, np.float32, order="F"),
+               "creceptor": np.zeros((abi.MAXRECEPTOR, c.maxspec), np.float32, order="F")}
+        gn = dn = None
+        if c.nested_output == 1:
+            sgn = (c.numxgridn, c.numygridn) + sg[2:]
+            sdn = (c.numxgridn, c.numygridn) + sd[2:]
+            out["griduncn"] = np.zeros(sgn, np.float32, order="F")
+            out["drygriduncn"] = np.zeros(sdn, np.float32, order="F")
+            gn, dn = out["griduncn"], out["drygriduncn"]
+        self.L.fpo_fetch_grids(self.S, _fp(out["gridunc"]), _fp(gn), _fp(out["drygridunc"]), _fp(dn),
+                               _fp(out["creceptor"]), 1 if zero_conc else 0)
+        return out
+
+    def scale_depgrids(self, factors):
+        f = np.ascontiguousarray(factors, np.float32)
+        self.L.fpo_scale_depgrids(self.S, _fp(f))
+
+    def vtable(self):
+        L, a = self.L, abi
+        v = FpbhEngine()
+        v.self = self.S
+        cast = lambda fn, T: C.cast(fn, T)
+        v.upload_met = cast(L.fpo_vt_upload_met, a.UPLOAD_MET_FN)
+        v.set_met_bracket = cast(L.fpo_vt_set_met_bracket, a.SET_BRACKET_FN)
+        v.push_particles = cast(L.fpo_vt_push_particles, a.PUSH_FN)
+        v.pull_particles = cast(L.fpo_vt_pull_particles, a.PUSH_FN)
+        v.set_numpart = cast(L.fpo_vt_set_numpart, a.SET_NUMPART_FN)
+        v.step = cast(L.fpo_vt_step, a.STEP_FN)
+        v.conccalc = cast(L.fpo_vt_conccalc, a.CONC_FN)
+        v.fetch_grids = cast(L.fpo_vt_fetch_grids, a.FETCH_FN)
+        v.scale_depgrids = cast(L.fpo_vt_scale_depgrids, a.SCALE_FN)
+        return v
