@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the FLEXPART per-particle hot path
+(fpb_conccalc + fpb_step) on B200, with the HBM-gather roofline and the CPU
+baseline beside it.
+
+Workload (BASELINE.json configs[1], "C2"): 1 M particles per GPU, global
+0.5 deg x 138-level synthetic ECMWF-shaped met, Hanna turbulence (CTL=5,
+IFINE=4 -> method 1), 100 box releases in the lowest 2 km, 900 s
+synchronisation interval, concentration sampling every step.  A "step" is one
+pass of the hot path over the whole batch: fpb_conccalc(itime, 1.0) +
+fpb_step(itime); the output-interval exchange (NCCL reduce of gridunc to rank
+0, then zeroing) runs every 4th step as in the reference (LOUTSTEP=3600).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload c2|c5slice] [--particles P]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every
+field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# algorithmic bytes per particle-step (SURVEY.md 8d / DESIGN.md): state
+# 74 B read + 58 B written, met gather 161 floats in the PBL (method 0 count)
+# or 105 floats above it; +76 B per conccalc sample.
+B_PBL, B_FT, B_CONC = 776, 552, 76
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
+    import flexpart_b200 as fb
+    import cases
+    npart_total = n_particles or args.particles
+    nrel = 100
+    if args.workload == "c5slice":
+        kw = dict(ctl=-5.0)            # method 0: one Langevin step per sync (HBM-bound regime)
+        zmax, lat = 12000.0, (-85.0, 85.0)
+    else:
+        kw = dict(ctl=5.0)             # Hanna, method 1
+        zmax, lat = 2000.0, (-60.0, 60.0)
+    each = max(1, npart_total // nrel)
+    cb = fb.make_config(nx=721, ny=361, nz=138, dx=0.5, dy=0.5, xlon0=-180.0, ylat0=-90.0,
+                        lsynctime=900, ifine=4, outlon0=-180.0, outlat0=-90.0, numxgrid=720,
+                        numygrid=360, dxout=0.5, dyout=0.5,
+                        outheights=(100.0, 250.0, 500.0, 1000.0, 2000.0, 3000.0, 5000.0, 8000.0, 12000.0, 50000.0),
+                        lage=(86400 * 20,), ioutputforeachrelease=0, npart=(each,) * nrel, nspec=1,
+                        maxpart=each * nrel, device=device, rng_mode=fb.RNG_PHILOX_INDEX,
+                        math_mode=fb.MATH_FAST, scatter_mode=fb.SCATTER_ATOMIC,
+                        part_id_stride=world, part_id_offset=rank, **kw)
+    rel = cases.releases_boxes(cb, seed=100 + rank, zmax=zmax, lat_range=lat, width=10.0)
+    return cb, rel
+
+
+def host_particles(cb, rel, pinned):
+    import flexpart_b200 as fb
+    parts = fb.Particles(cb.cfg.maxpart, cb.cfg.nspec, pinned=pinned)
+    st = fb.ReleaseState(cb.cfg.numpoint)
+    fb.release_particles(cb, rel, st, 0, parts)
+    return parts
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import flexpart_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; flexpart_b200 has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, args.warmup
+
+    t0 = time.time()
+    cb, rel = build_workload(args, rank, world, local)
+    c = cb.cfg
+    span = max(10800, (K * 3 + W + 2) * 900)
+    m0, m1 = fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(span)
+    log(f"[rank {rank}] met synthesised in {time.time() - t0:.1f}s")
+    eng = fb.Engine(cb)
+    eng.fill_rannumb()
+    eng.upload_met(1, m0)
+    eng.upload_met(2, m1)
+    eng.set_met_bracket((1, 2), (0, span))
+    parts = host_particles(cb, rel, pinned=True)
+    n = parts.numpart
+    eng.push_particles(parts)
+    ext = torch.cuda.ExternalStream(eng.stream, device=local)
+
+    gptr, gn = eng.grid_device_ptr(0)
+
+    class _Holder:  # zero-copy torch view of the device grid for NCCL
+        __cuda_array_interface__ = {"shape": (gn,), "typestr": "<f4", "data": (gptr, False), "version": 2}
+    grid_t = torch.as_tensor(_Holder(), device=f"cuda:{local}") if world > 1 else None
+
+    def exchange():
+        # the mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579): sum to rank 0, then zero
+        if world > 1:
+            dist.reduce(grid_t, dst=0, op=dist.ReduceOp.SUM)
+        eng.zero_conc_grids()
+
+    def one_step(k, stats):
+        itime = k * 900
+        eng.conccalc(itime, 1.0)
+        st = eng.step(itime, 0, stats=stats)
+        if (k + 1) % 4 == 0:
+            exchange()
+        return st
+
+    with torch.cuda.stream(ext):
+        k = 0
+        for _ in range(W):
+            one_step(k, False)
+            k += 1
+        # ---- device-timed region: K steps, inputs resident in HBM
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = eng.launch_count
+        ev0.record(ext)
+        psteps = nsub = npbl = 0
+        t_step_k = t_conc_k = 0.0
+        for _ in range(K):
+            st = one_step(k, True)
+            k += 1
+            psteps += st["n_active"]; nsub += st["n_substeps"]; npbl += st["n_pbl"]
+            a, b = eng.kernel_times()
+            t_step_k += a; t_conc_k += b
+        ev1.record(ext)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = eng.launch_count - l0
+        clocks = sampler.stop()
+
+        # ---- end-to-end: host buffers, particle arrays round-trip every step
+        hp = fb.Particles(c.maxpart, c.nspec, pinned=True)
+        hp.numpart = n
+        eng.pull_particles(hp)
+        bytes_row = 2 * 8 + 4 * 7 + 4 * 6 + 2 + 4 * c.nspec * 2
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_e0 = time.perf_counter()
+        e_steps = 0
+        KE = max(3, min(K, 6))
+        for _ in range(KE):
+            eng.push_particles(hp)              # H2D from pinned host memory
+            st = one_step(k, True)
+            k += 1
+            eng.pull_particles(hp)              # D2H of the step's result
+            e_steps += st["n_active"]
+        torch.cuda.synchronize()
+        t_e = time.perf_counter() - t_e0
+
+    tm = torch.tensor([ms, t_e * 1e3], device=f"cuda:{local}", dtype=torch.float64)
+    cnt = torch.tensor([psteps, e_steps, nsub, npbl, launches], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, e_ms_max = tm.tolist()
+    psteps_all, e_steps_all, nsub_all, npbl_all, launches_all = cnt.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = npbl * B_PBL + (psteps - npbl) * B_FT   # rank 0's kernel launches
+        achieved = alg_bytes / (t_step_k * 1e-3) / 1e9 if t_step_k > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload and tj.get("particles") == args.particles:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {
+            "metric": "particle-steps/s (advance+conccalc)",
+            "value": psteps_all / (ms_max * 1e-3),
+            "unit": "particle-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 positions)", "data": "synthetic",
+            "config": {
+                "workload": ("C2: 1M particles/GPU, global 0.5deg x 138 levels, Hanna CTL=5 IFINE=4, "
+                             "100 box releases 0-2 km, lsynctime 900 s, conccalc every step, "
+                             "grid exchange every 4 steps") if args.workload == "c2" else
+                            ("C5 slice: domain-spread particles/GPU, 0.5deg x 138 levels, CTL=-5 (method 0), "
+                             "conccalc every step"),
+                "particles_per_gpu": n, "grid": "721x361x138", "rng": "philox-indexed rannumb",
+                "math": "fast", "scatter": "atomic",
+                "l2": "no flush: each step streams the particle state (132 B/particle) and gathers "
+                      "from a 2.3 GB met replica, both larger than the 126 MB L2",
+                "parallelism": f"particle-partition x{world}",
+            },
+            "substeps_per_s": nsub_all / (ms_max * 1e-3),
+            "substeps_per_particle_step": nsub_all / max(psteps_all, 1),
+            "pbl_fraction": npbl_all / max(psteps_all, 1),
+            "clocks": clocks,
+            "gpu_launches": int(launches_all),
+            "e2e": {"value": e_steps_all / (e_ms_max * 1e-3), "unit": "particle-steps/s",
+                    "h2d_bytes_per_step": int(bytes_row * n), "d2h_bytes_per_step": int(bytes_row * n + 56),
+                    "steps": KE, "what": "fpb_push_particles(all rows, pinned host) + fpb_conccalc + "
+                                         "fpb_step(stats) + fpb_pull_particles(all rows) per step"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "fpb_step_kernel",
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / K,
+                         "kernel_ms_per_launch": t_step_k / K,
+                         "conccalc_ms_per_launch": t_conc_k / K,
+                         "note": "algorithmic bytes = 776 B per PBL particle-step, 552 B above the PBL "
+                                 "(state 132 B + 161/105 met floats); method-1 sub-steps make C2 "
+                                 "ALU/latency-bound, see substeps_per_particle_step"},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, threads=1, budget_s=args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, threads, budget_s, steps=None):
+    """Oracle (line-faithful CPU restatement of the reference path) timed on
+    the host cores on a bounded sample of the same workload."""
+    import flexpart_b200 as fb
+    from oracle_api import Oracle, load
+    import ctypes as C
+    t0 = time.time()
+    # calibrate on a tiny sample, then size the sample for ~budget_s of work
+    def make(nsample):
+        a2 = argparse.Namespace(**vars(args))
+        cb, rel = build_workload(a2, 0, 1, 0, n_particles=nsample)
+        return cb, rel
+    cb, rel = make(100 * 20)
+    span = 10800
+    m0, m1 = fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(span)
+
+    def run(nsample, nsteps):
+        per = max(1, nsample // threads)
+        states, keep = [], []
+        for t in range(threads):
+            cbt, relt = make(per)
+            o = Oracle(cbt)
+            o.fill_rannumb()
+            o.upload_met(1, m0); o.upload_met(2, m1)
+            o.set_met_bracket((1, 2), (0, span))
+            p = host_particles(cbt, relt, pinned=False)
+            o.push_particles(p)
+            states.append(o); keep.append((cbt, relt, p))
+        arr = (C.c_void_p * threads)(*[o.S for o in states])
+        L = load()
+        wall = 0.0
+        total = 0
+        for k in range(nsteps):
+            wall += L.fpo_mp_step(arr, threads, k * 900, 0, 1.0)
+            total += sum(kk[2].numpart for kk in keep)
+        for o in states:
+            o.close()
+        return total / wall, total, wall
+    rate, _, _ = run(2000 * threads, 2)
+    nsteps = steps or 4
+    nsample = int(max(2000 * threads, min(rate * budget_s / nsteps, 2_000_000)))
+    nsample = (nsample // (100 * threads)) * 100 * threads
+    rate, total, wall = run(nsample, nsteps)
+    return {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{nsample} particles x {nsteps} steps of the same workload "
+                      f"({total} particle-steps in {wall:.1f} s; oracle/ C restatement, gcc -O2, "
+                      f"{threads} thread(s); the Fortran reference cannot be built here)",
+            "setup_s": round(time.time() - t0 - wall, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    # each step is a bounded sample; keep the whole K+W run within a few minutes
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(K + W, 1)))
+    cb = cpu_baseline(args, threads=threads, budget_s=per_step_budget * K, steps=K)
+    line = {"impl": "reference", "metric": "particle-steps/s (advance+conccalc)", "value": cb["value"],
+            "unit": "particle-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
+            "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 positions)", "data": "synthetic",
+            "config": {"workload": "C2 sample (same releases, met and switches as the GPU arm)"
+                       if args.workload == "c2" else "C5 slice sample"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5slice"])
+    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    import __graft_entry__ as ge
+    ge.build(verbose=False)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

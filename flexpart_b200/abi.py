@@ -153,6 +153,8 @@ def load_engine_lib():
     L.fpb_stream.restype = C.c_void_p
     L.fpb_launch_count.argtypes = [H]
     L.fpb_launch_count.restype = C.c_int64
+    L.fpb_kernel_times.argtypes = [H, _pf, _pf]
+    L.fpb_get_rannumb.argtypes = [H, _pf, _i]
     if L.fpb_config_sizeof() != C.sizeof(FpbConfig):
         raise FpbError(f"fpb_config layout mismatch: C {L.fpb_config_sizeof()} vs ctypes {C.sizeof(FpbConfig)}")
     _engine = L

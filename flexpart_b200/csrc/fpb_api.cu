@@ -133,6 +133,8 @@ struct fpb_handle {
 
   unsigned long long *d_stats = nullptr;
   int64_t launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // step begin/end, conccalc begin/end
+  bool timed_step = false, timed_conc = false;
   ScatterWork scatter;
 };
 
@@ -283,6 +285,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
 
   CK(cudaSetDevice(h->device));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; k++) CK(cudaEventCreate(&h->ev[k]));
 
   const size_t n3 = (size_t)d.nxd * d.nyd * c.nz, n2 = (size_t)d.nxd * d.nyd;
   for (int s = 0; s < 2; s++) {
@@ -343,6 +346,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
   scatter_free(h->scatter);
+  for (int k = 0; k < 4; k++) cudaEventDestroy(h->ev[k]);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -571,8 +575,11 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.drygriduncn = h->drygriduncn;
   a.stats = stats ? h->d_stats : nullptr;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+  CK(cudaEventRecord(h->ev[0], h->stream));
   if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_step_strict(a, h->stream);
   else fpbk_step_fast(a, h->stream);
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  h->timed_step = true;
   h->launches++;
   CK(cudaGetLastError());
   if (stats) {
@@ -616,6 +623,7 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   a.griduncn = h->griduncn;
   a.crec_acc = h->crec_acc;
   const bool strict = h->cfg.math_mode == FPB_MATH_STRICT;
+  CK(cudaEventRecord(h->ev[2], h->stream));
   if (h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
     if (scatter_conccalc_deterministic(h->scatter, a, strict, h->stream, &h->launches)) return fail("%s", scatter_error());
   } else {
@@ -628,8 +636,38 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
                                                       h->cfg.nspec, weight, nullptr, a.cfg);
     h->launches += 2;
   }
+  CK(cudaEventRecord(h->ev[3], h->stream));
+  h->timed_conc = true;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int fpb_kernel_times(fpb_handle *h, float *step_ms, float *conccalc_ms) {
+  if (!h) return fail("fpb_kernel_times: null handle");
+  CK(cudaSetDevice(h->device));
+  if (step_ms) {
+    *step_ms = 0.f;
+    if (h->timed_step) {
+      CK(cudaEventSynchronize(h->ev[1]));
+      CK(cudaEventElapsedTime(step_ms, h->ev[0], h->ev[1]));
+    }
+  }
+  if (conccalc_ms) {
+    *conccalc_ms = 0.f;
+    if (h->timed_conc) {
+      CK(cudaEventSynchronize(h->ev[3]));
+      CK(cudaEventElapsedTime(conccalc_ms, h->ev[2], h->ev[3]));
+    }
+  }
+  return 0;
+}
+
+extern "C" int fpb_get_rannumb(fpb_handle *h, float *out, int32_t n) {
+  if (!h || !out) return fail("fpb_get_rannumb: null argument");
+  if (!h->d_rannumb || n > h->maxrand) return fail("fpb_get_rannumb: table has %d entries", h->maxrand);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->d_rannumb, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -115,6 +115,17 @@ class Engine:
         self._check(self.L.fpb_grid_device_ptr(self.h, which, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def kernel_times(self):
+        """(step_ms, conccalc_ms) of the most recent calls, device time."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self.L.fpb_kernel_times(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_rannumb(self, n):
+        out = np.zeros(n, np.float32)
+        self._check(self.L.fpb_get_rannumb(self.h, _fp(out), n))
+        return out
+
     @property
     def stream(self):
         return self.L.fpb_stream(self.h)

@@ -152,18 +152,31 @@ class Particles:
     F32 = ("ztra1", "uap", "ucp", "uzp", "us", "vs", "ws")
     I32 = ("itra1", "npoint", "nclass", "idt", "itramem", "itrasplit")
 
-    def __init__(self, maxpart, nspec):
+    def __init__(self, maxpart, nspec, pinned=False):
         self.maxpart, self.nspec = maxpart, nspec
-        self.xtra1 = np.zeros(maxpart, np.float64)
-        self.ytra1 = np.zeros(maxpart, np.float64)
+        self._pin = []
+        if pinned:  # page-locked host arrays (torch is the allocator, nothing more)
+            import torch
+
+            def zeros(shape, dt):
+                n = int(np.prod(shape))
+                t = torch.zeros(n, dtype=getattr(torch, np.dtype(dt).name), pin_memory=True)
+                self._pin.append(t)
+                return t.numpy().reshape(shape, order="F")
+        else:
+            def zeros(shape, dt):
+                return np.zeros(shape, dt, order="F")
+        self.xtra1 = zeros(maxpart, np.float64)
+        self.ytra1 = zeros(maxpart, np.float64)
         for n in self.F32:
-            setattr(self, n, np.zeros(maxpart, np.float32))
+            setattr(self, n, zeros(maxpart, np.float32))
         for n in self.I32:
-            setattr(self, n, np.zeros(maxpart, np.int32))
+            setattr(self, n, zeros(maxpart, np.int32))
         self.itra1[:] = abi.ITRA_DEAD
-        self.cbt = np.ones(maxpart, np.int16)
-        self.xmass1 = np.zeros((maxpart, nspec), np.float32, order="F")
-        self.xscav_frac1 = np.zeros((maxpart, nspec), np.float32, order="F")
+        self.cbt = zeros(maxpart, np.int16)
+        self.cbt[:] = 1
+        self.xmass1 = zeros((maxpart, nspec), np.float32)
+        self.xscav_frac1 = zeros((maxpart, nspec), np.float32)
         self.numpart = 0
         p = FpbParticlePtrs()
         p.xtra1 = self.xtra1.ctypes.data_as(C.POINTER(C.c_double))

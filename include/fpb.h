@@ -243,6 +243,14 @@ int fpb_sort_particles(fpb_handle *h);
 void *fpb_stream(fpb_handle *h);
 int64_t fpb_launch_count(fpb_handle *h);
 
+/* Device time (ms, CUDA events on the engine's stream) of the kernels of the
+ * most recent fpb_step / fpb_conccalc call; for the roofline report. */
+int fpb_kernel_times(fpb_handle *h, float *step_ms, float *conccalc_ms);
+
+/* Export the rannumb table the engine holds (validation: hand the same
+ * Gaussian stream to another implementation). */
+int fpb_get_rannumb(fpb_handle *h, float *out, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif
