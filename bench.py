@@ -107,7 +107,7 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
                         lage=(86400 * 20,), ioutputforeachrelease=0, npart=(each,) * nrel, nspec=1,
                         maxpart=each * nrel, device=device, rng_mode=fb.RNG_PHILOX_INDEX,
                         math_mode=fb.MATH_FAST, scatter_mode=fb.SCATTER_ATOMIC,
-                        part_id_stride=world, part_id_offset=rank, **kw)
+                        part_id_stride=world, part_id_offset=rank, sort_interval=args.sort_interval, **kw)
     rel = cases.releases_boxes(cb, seed=100 + rank, zmax=zmax, lat_range=lat, width=10.0)
     return cb, rel
 
@@ -255,7 +255,7 @@ def run_ours(args):
                             ("C5 slice: domain-spread particles/GPU, 0.5deg x 138 levels, CTL=-5 (method 0), "
                              "conccalc every step"),
                 "particles_per_gpu": n, "grid": "721x361x138", "rng": "philox-indexed rannumb",
-                "math": "fast", "scatter": "atomic",
+                "math": "fast", "scatter": "atomic", "sort_interval": args.sort_interval,
                 "l2": "no flush: each step streams the particle state (132 B/particle) and gathers "
                       "from a 2.3 GB met replica, both larger than the 126 MB L2",
                 "parallelism": f"particle-partition x{world}",
@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sort-interval", type=int, default=1)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -50,7 +50,7 @@ class FpbConfig(C.Structure):
         ("height", _pf),
         ("maxpart", _i), ("device", _i), ("rng_mode", _i), ("math_mode", _i), ("scatter_mode", _i),
         ("seed", C.c_uint64), ("part_id_stride", _i), ("part_id_offset", _i),
-        ("reserved", _i * 8),
+        ("sort_interval", _i), ("reserved", _i * 7),
     ]
 
 

@@ -17,6 +17,7 @@
 
 #include "fpb_device.cuh"
 #include "fpb_scatter.cuh"
+#include "fpb_sort.cuh"
 
 // ------------------------------------------------------------ error state --
 static thread_local std::string g_err;
@@ -114,8 +115,16 @@ struct fpb_handle {
   int memind[2] = {1, 2}, memtime[2] = {0, 0}, lwindinterv = 1;
   bool have_bracket = false;
 
-  DevParticles p{};
+  DevParticles p{};     // device rows
+  DevParticles p_alt{}; // second buffer: sort target / slot-ordered staging
+  int32_t *row_of_slot = nullptr;
+  bool permuted = false; // rows != slots
   int numpart = 0;
+  int active_rows = -1;  // live rows lead the arrays after a sort (-1: unknown)
+  int steps_since_sort = 1 << 30;
+  unsigned *d_nlive = nullptr;
+  std::vector<int32_t> h_slot;
+  DevCfg d_tmp;
 
   float *d_height = nullptr, *d_xmass = nullptr;
   int32_t *d_npart = nullptr;
@@ -135,6 +144,7 @@ struct fpb_handle {
   int64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // step begin/end, conccalc begin/end
   bool timed_step = false, timed_conc = false;
+  bool pending_init = true;
   ScatterWork scatter;
 };
 
@@ -293,14 +303,22 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
     DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
   }
   const size_t mp = (size_t)c.maxpart;
-  DA(h->p.xtra1, mp); DA(h->p.ytra1, mp); DA(h->p.ztra1, mp);
-  DA(h->p.itra1, mp); DA(h->p.npoint, mp); DA(h->p.nclass, mp); DA(h->p.idt, mp);
-  DA(h->p.itramem, mp); DA(h->p.itrasplit, mp);
-  DA(h->p.uap, mp); DA(h->p.ucp, mp); DA(h->p.uzp, mp);
-  DA(h->p.us, mp); DA(h->p.vs, mp); DA(h->p.ws, mp); DA(h->p.cbt, mp);
-  DA(h->p.xmass1, mp * c.nspec);
-  DA(h->p.xscav_frac1, mp * c.nspec);
-  h->p.maxpart = c.maxpart;
+  for (DevParticles *q : {&h->p, &h->p_alt}) {
+    DA(q->xtra1, mp); DA(q->ytra1, mp); DA(q->ztra1, mp);
+    DA(q->itra1, mp); DA(q->npoint, mp); DA(q->nclass, mp); DA(q->idt, mp);
+    DA(q->itramem, mp); DA(q->itrasplit, mp);
+    DA(q->uap, mp); DA(q->ucp, mp); DA(q->uzp, mp);
+    DA(q->us, mp); DA(q->vs, mp); DA(q->ws, mp); DA(q->cbt, mp);
+    DA(q->xmass1, mp * c.nspec);
+    DA(q->xscav_frac1, mp * c.nspec);
+    DA(q->slot, mp);
+    q->maxpart = c.maxpart;
+    sortk_iota(q->slot, c.maxpart, h->stream);
+  }
+  DA(h->row_of_slot, mp);
+  sortk_iota(h->row_of_slot, c.maxpart, h->stream);
+  DA(h->d_nlive, 1);
+  h->launches += 3;
   // itra1(:) = -999999999, src/FLEXPART.f90:315-317
   fill_i32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
   h->launches++;
@@ -336,11 +354,14 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(h->A[s]); cudaFree(h->B[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
   }
   cudaFree(h->stage);
-  cudaFree(h->p.xtra1); cudaFree(h->p.ytra1); cudaFree(h->p.ztra1); cudaFree(h->p.itra1);
-  cudaFree(h->p.npoint); cudaFree(h->p.nclass); cudaFree(h->p.idt); cudaFree(h->p.itramem);
-  cudaFree(h->p.itrasplit); cudaFree(h->p.uap); cudaFree(h->p.ucp); cudaFree(h->p.uzp);
-  cudaFree(h->p.us); cudaFree(h->p.vs); cudaFree(h->p.ws); cudaFree(h->p.cbt);
-  cudaFree(h->p.xmass1); cudaFree(h->p.xscav_frac1);
+  for (DevParticles *q : {&h->p, &h->p_alt}) {
+    cudaFree(q->xtra1); cudaFree(q->ytra1); cudaFree(q->ztra1); cudaFree(q->itra1);
+    cudaFree(q->npoint); cudaFree(q->nclass); cudaFree(q->idt); cudaFree(q->itramem);
+    cudaFree(q->itrasplit); cudaFree(q->uap); cudaFree(q->ucp); cudaFree(q->uzp);
+    cudaFree(q->us); cudaFree(q->vs); cudaFree(q->ws); cudaFree(q->cbt);
+    cudaFree(q->xmass1); cudaFree(q->xscav_frac1); cudaFree(q->slot);
+  }
+  cudaFree(h->row_of_slot); cudaFree(h->d_nlive);
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
@@ -425,6 +446,8 @@ extern "C" int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2], const
   return 0;
 }
 
+static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat);
+
 // -------------------------------------------------------------- particles --
 #define H2D(dst, src, T)                                                             \
   do {                                                                               \
@@ -439,32 +462,56 @@ extern "C" int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2], const
                          cudaMemcpyDeviceToHost, h->stream));                        \
   } while (0)
 
+static int copy_rows_h2d(fpb_handle *h, const DevParticles &d, int first, int count,
+                         const fpb_particle_ptrs *p) {
+  H2D(d.xtra1, p->xtra1, double); H2D(d.ytra1, p->ytra1, double); H2D(d.ztra1, p->ztra1, float);
+  H2D(d.itra1, p->itra1, int32_t); H2D(d.npoint, p->npoint, int32_t);
+  H2D(d.nclass, p->nclass, int32_t); H2D(d.idt, p->idt, int32_t);
+  H2D(d.itramem, p->itramem, int32_t);
+  if (p->itrasplit) H2D(d.itrasplit, p->itrasplit, int32_t);
+  H2D(d.uap, p->uap, float); H2D(d.ucp, p->ucp, float); H2D(d.uzp, p->uzp, float);
+  H2D(d.us, p->us, float); H2D(d.vs, p->vs, float); H2D(d.ws, p->ws, float);
+  H2D(d.cbt, p->cbt, int16_t);
+  if (!p->xmass1) return fail("fpb_push_particles: xmass1 is null");
+  for (int k = 0; k < h->cfg.nspec; k++) {
+    CK(cudaMemcpyAsync(d.xmass1 + (size_t)k * h->cfg.maxpart + first,
+                       p->xmass1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
+                       cudaMemcpyHostToDevice, h->stream));
+    if (p->xscav_frac1)
+      CK(cudaMemcpyAsync(d.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
+                         p->xscav_frac1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
+                         cudaMemcpyHostToDevice, h->stream));
+  }
+  return 0;
+}
+
 extern "C" int fpb_push_particles(fpb_handle *h, int32_t first, int32_t count, const fpb_particle_ptrs *p) {
   if (!h || !p) return fail("fpb_push_particles: null argument");
   if (count == 0) return 0;
   if (first < 0 || count < 0 || (int64_t)first + count > h->cfg.maxpart)
     return fail("fpb_push_particles: rows [%d,%d) outside capacity %d", first, first + count, h->cfg.maxpart);
   CK(cudaSetDevice(h->device));
-  H2D(h->p.xtra1, p->xtra1, double); H2D(h->p.ytra1, p->ytra1, double); H2D(h->p.ztra1, p->ztra1, float);
-  H2D(h->p.itra1, p->itra1, int32_t); H2D(h->p.npoint, p->npoint, int32_t);
-  H2D(h->p.nclass, p->nclass, int32_t); H2D(h->p.idt, p->idt, int32_t);
-  H2D(h->p.itramem, p->itramem, int32_t);
-  if (p->itrasplit) H2D(h->p.itrasplit, p->itrasplit, int32_t);
-  H2D(h->p.uap, p->uap, float); H2D(h->p.ucp, p->ucp, float); H2D(h->p.uzp, p->uzp, float);
-  H2D(h->p.us, p->us, float); H2D(h->p.vs, p->vs, float); H2D(h->p.ws, p->ws, float);
-  H2D(h->p.cbt, p->cbt, int16_t);
-  if (!p->xmass1) return fail("fpb_push_particles: xmass1 is null");
-  for (int k = 0; k < h->cfg.nspec; k++) {
-    CK(cudaMemcpyAsync(h->p.xmass1 + (size_t)k * h->cfg.maxpart + first,
-                       p->xmass1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
-                       cudaMemcpyHostToDevice, h->stream));
-    if (p->xscav_frac1)
-      CK(cudaMemcpyAsync(h->p.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
-                         p->xscav_frac1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
-                         cudaMemcpyHostToDevice, h->stream));
+  if (h->permuted && first == 0 && count >= h->numpart) {
+    // every row is replaced: drop the permutation
+    sortk_iota(h->p.slot, h->cfg.maxpart, h->stream);
+    sortk_iota(h->row_of_slot, h->cfg.maxpart, h->stream);
+    h->launches += 2;
+    h->permuted = false;
+  }
+  if (!h->permuted) {
+    if (copy_rows_h2d(h, h->p, first, count, p)) return 1;
+  } else {
+    // slot-ordered staging, then scatter to the rows the slots live in
+    if (copy_rows_h2d(h, h->p_alt, first, count, p)) return 1;
+    sortk_scatter_from_staging(h->p_alt, h->p, h->row_of_slot, first, count, h->cfg.nspec,
+                               p->itrasplit != nullptr, p->xscav_frac1 != nullptr, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(h->stream));
   if (first + count > h->numpart) h->numpart = first + count;
+  h->pending_init = true;
+  h->active_rows = -1;
   return 0;
 }
 
@@ -480,25 +527,67 @@ extern "C" int fpb_pull_particles(fpb_handle *h, int32_t first, int32_t count, c
   if (first < 0 || count < 0 || (int64_t)first + count > h->cfg.maxpart)
     return fail("fpb_pull_particles: rows [%d,%d) outside capacity %d", first, first + count, h->cfg.maxpart);
   CK(cudaSetDevice(h->device));
-  D2H(p->xtra1, h->p.xtra1, double); D2H(p->ytra1, h->p.ytra1, double); D2H(p->ztra1, h->p.ztra1, float);
-  D2H(p->itra1, h->p.itra1, int32_t); D2H(p->npoint, h->p.npoint, int32_t);
-  D2H(p->nclass, h->p.nclass, int32_t); D2H(p->idt, h->p.idt, int32_t);
-  D2H(p->itramem, h->p.itramem, int32_t); D2H(p->itrasplit, h->p.itrasplit, int32_t);
-  D2H(p->uap, h->p.uap, float); D2H(p->ucp, h->p.ucp, float); D2H(p->uzp, h->p.uzp, float);
-  D2H(p->us, h->p.us, float); D2H(p->vs, h->p.vs, float); D2H(p->ws, h->p.ws, float);
-  D2H(p->cbt, h->p.cbt, int16_t);
+  const DevParticles *src = &h->p;
+  if (h->permuted) {
+    sortk_gather_to_staging(h->p, h->p_alt, h->row_of_slot, first, count, h->cfg.nspec, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    src = &h->p_alt;
+  }
+  D2H(p->xtra1, src->xtra1, double); D2H(p->ytra1, src->ytra1, double); D2H(p->ztra1, src->ztra1, float);
+  D2H(p->itra1, src->itra1, int32_t); D2H(p->npoint, src->npoint, int32_t);
+  D2H(p->nclass, src->nclass, int32_t); D2H(p->idt, src->idt, int32_t);
+  D2H(p->itramem, src->itramem, int32_t); D2H(p->itrasplit, src->itrasplit, int32_t);
+  D2H(p->uap, src->uap, float); D2H(p->ucp, src->ucp, float); D2H(p->uzp, src->uzp, float);
+  D2H(p->us, src->us, float); D2H(p->vs, src->vs, float); D2H(p->ws, src->ws, float);
+  D2H(p->cbt, src->cbt, int16_t);
   for (int k = 0; k < h->cfg.nspec; k++) {
     if (p->xmass1)
       CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + first,
-                         h->p.xmass1 + (size_t)k * h->cfg.maxpart + first, (size_t)count * sizeof(float),
+                         src->xmass1 + (size_t)k * h->cfg.maxpart + first, (size_t)count * sizeof(float),
                          cudaMemcpyDeviceToHost, h->stream));
     if (p->xscav_frac1)
       CK(cudaMemcpyAsync(p->xscav_frac1 + (size_t)k * p->ld + first,
-                         h->p.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
+                         src->xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
                          (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+// ------------------------------------------------------------------- sort --
+static int do_sort(fpb_handle *h) {
+  const int n = h->numpart;
+  if (n <= 1) return 0;
+  if (scatter_reserve(h->scatter, (size_t)n, 1)) return fail("%s", scatter_error());
+  per_step_cfg(h, h->d_tmp, 0, 0);
+  sortk_build_keys(h->d_tmp, h->p, h->d_height, n, h->scatter.keys[0], h->scatter.ids[0], h->d_nlive, h->stream);
+  const unsigned long long ncell = (unsigned long long)h->d.nxd * h->d.nyd * h->cfg.nz;
+  int bits = 1;
+  while ((1ull << bits) < ncell + 1) bits++;
+  bits = ((bits + 7) / 8) * 8;
+  if (bits < 32) bits += 8; // dead rows carry all-ones keys and must sort last
+  if (bits > 32) bits = 32;
+  int cur = 0;
+  if (scatter_sort_pairs(h->scatter, (size_t)n, bits, h->stream, &h->launches, &cur)) return fail("%s", scatter_error());
+  sortk_permute(h->p, h->p_alt, h->scatter.ids[cur], n, h->cfg.nspec, h->stream);
+  std::swap(h->p, h->p_alt);
+  sortk_invert(h->p.slot, h->row_of_slot, n, h->stream);
+  h->launches += 3;
+  unsigned nlive = 0;
+  CK(cudaMemcpyAsync(&nlive, h->d_nlive, sizeof nlive, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->permuted = true;
+  h->active_rows = (int)nlive;
+  h->steps_since_sort = 0;
+  return 0;
+}
+
+extern "C" int fpb_sort_particles(fpb_handle *h) {
+  if (!h) return fail("fpb_sort_particles: null handle");
+  CK(cudaSetDevice(h->device));
+  return do_sort(h);
 }
 
 // ------------------------------------------------------------------- step --
@@ -526,17 +615,20 @@ static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
 // SAVEd idummy=-7, so the FIRST call of each re-seeds the shared generator.
 static int replay_ran3_indices(fpb_handle *h, int itime) {
   const int n = h->numpart;
-  h->h_itra1.resize(n); h->h_itramem.resize(n);
+  h->h_itra1.resize(n); h->h_itramem.resize(n); h->h_slot.resize(n);
   h->h_nrand_init.assign(n, 1); h->h_nrand_adv.assign(n, 1);
   CK(cudaMemcpyAsync(h->h_itra1.data(), h->p.itra1, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_itramem.data(), h->p.itramem, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (h->permuted)
+    CK(cudaMemcpyAsync(h->h_slot.data(), h->row_of_slot, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   const float scale = (float)(h->maxrand - 1);
-  for (int j = 0; j < n; j++) {
-    if (h->h_itra1[j] != itime) continue;
-    if (h->h_itramem[j] == itime || itime == 0)
-      h->h_nrand_init[j] = (int)(h->ran3.next(h->idummy_init) * scale) + 1;
-    h->h_nrand_adv[j] = (int)(h->ran3.next(h->idummy_adv) * scale) + 1;
+  for (int s = 0; s < n; s++) { // slot order = the reference's particle order
+    const int r = h->permuted ? h->h_slot[s] : s;
+    if (h->h_itra1[r] != itime) continue;
+    if (h->h_itramem[r] == itime || itime == 0)
+      h->h_nrand_init[s] = (int)(h->ran3.next(h->idummy_init) * scale) + 1;
+    h->h_nrand_adv[s] = (int)(h->ran3.next(h->idummy_adv) * scale) + 1;
   }
   CK(cudaMemcpyAsync(h->d_nrand_init, h->h_nrand_init.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_nrand_adv, h->h_nrand_adv.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -557,10 +649,15 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
     if (stats) memset(stats, 0, sizeof *stats);
     return 0;
   }
+  if (h->cfg.sort_interval > 0 && h->steps_since_sort >= h->cfg.sort_interval) {
+    if (do_sort(h)) return 1;
+  }
+  h->steps_since_sort++;
   if (h->cfg.rng_mode == FPB_RNG_REFERENCE && replay_ran3_indices(h, itime)) return 1;
 
   DevStepArgs a;
   per_step_cfg(h, a.cfg, itime, ldeltat);
+  if (h->active_rows >= 0) a.cfg.numpart = h->active_rows; // dead rows trail after a sort
   a.met[0] = slot_view(h, h->memind[0]);
   a.met[1] = slot_view(h, h->memind[1]);
   a.met_lit1 = slot_view(h, 1);
@@ -575,6 +672,13 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.drygriduncn = h->drygriduncn;
   a.stats = stats ? h->d_stats : nullptr;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+  // initialize() can only be due for rows pushed since the last step, or at itime 0
+  if (h->pending_init || itime == 0) {
+    if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_init_strict(a, h->stream);
+    else fpbk_init_fast(a, h->stream);
+    h->launches++;
+    h->pending_init = false;
+  }
   CK(cudaEventRecord(h->ev[0], h->stream));
   if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_step_strict(a, h->stream);
   else fpbk_step_fast(a, h->stream);
@@ -615,6 +719,7 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   DevConcArgs a;
   per_step_cfg(h, a.cfg, itime, 0);
   a.cfg.weight = weight;
+  const int nslots = h->numpart;
   a.met[0] = slot_view(h, h->memind[0]);
   a.met[1] = slot_view(h, h->memind[1]);
   a.p = h->p;
@@ -765,10 +870,6 @@ extern "C" int fpb_grid_device_ptr(fpb_handle *h, int32_t which, void **dptr, si
   return 0;
 }
 
-extern "C" int fpb_sort_particles(fpb_handle *h) {
-  if (!h) return fail("fpb_sort_particles: null handle");
-  return 0; // locality sort arrives with the sort kernels (fpb_scatter.cu)
-}
 
 extern "C" void *fpb_stream(fpb_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int64_t fpb_launch_count(fpb_handle *h) { return h ? h->launches : 0; }

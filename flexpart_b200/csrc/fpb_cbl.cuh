@@ -17,7 +17,7 @@ __device__ __forceinline__ float cbl_transition(float h, float ol) {
 
 // drift ath and diffusion bth of the CBL Langevin equation; sets flagrein
 // when the velocity is > 6 sigma from both modes.
-__device__ void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float h, float rhoa,
+__device__ __noinline__ void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float h, float rhoa,
                           float rhograd, float sigmaw, float dsigmawdz, float tlw, float ol,
                           float &ath, float &bth, int &flagrein) {
   const float usurad2 = 0.7071067812f, usurad2p = 0.3989422804f, C0 = 3.f,
@@ -112,7 +112,7 @@ __device__ void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float 
 }
 
 // moment closure shared by re_initialize_particle / initialize_cbl_vel
-__device__ void cbl_split(float zp, float wst, float h, float sigmaw, float ol, float &aluarw,
+__device__ __noinline__ void cbl_split(float zp, float wst, float h, float sigmaw, float ol, float &aluarw,
                           float &sigmawa, float &sigmawb, float &wa, float &wb) {
   const float costluar4 = 0.66667f, eps = 0.000001f;
   const float z = zp / h;
@@ -135,7 +135,7 @@ __device__ void cbl_split(float zp, float wst, float h, float sigmaw, float ol, 
 }
 
 // src/re_initialize_particle.f90:44-91 (draws continue in the rannumb stream)
-__device__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst, float h,
+__device__ __noinline__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst, float h,
                                  float sigmaw, float ol, float &wp, int &nrand) {
   float aluarw, sigmawa, sigmawb, wa, wb;
   nrand = nrand + 1;
@@ -166,7 +166,7 @@ __device__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst,
 // the global sequential stream here; the device ("defined" behaviour, shared
 // with oracle/ strict_reference=0) takes the mode selector from the uniform
 // that chose the table index and the normal from the next table entry.
-__device__ float cbl_initial_velocity(const DevCfg &c, float dcas, float dcas1, float zp,
+__device__ __noinline__ float cbl_initial_velocity(const DevCfg &c, float dcas, float dcas1, float zp,
                                       float wst, float h, float sigmaw, float ol) {
   float aluarw, sigmawa, sigmawb, wa, wb;
   const float timedir = (float)c.ldirect;

@@ -35,6 +35,7 @@ struct DevParticles {
   int16_t *cbt;
   float *xmass1;      // [nspec][maxpart]
   float *xscav_frac1; // [nspec][maxpart] or null
+  int32_t *slot;      // slot[row] = caller-visible slot index of device row `row`
   int32_t maxpart;
 };
 
@@ -115,6 +116,7 @@ struct DevConcArgs {
 
 // launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
+  void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \
   void fpbk_step_##SUF(const DevStepArgs &a, cudaStream_t st);                \
   void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \

@@ -29,6 +29,9 @@
 #ifndef FPB_STRICT
 #define FPB_STRICT 0
 #endif
+#ifndef FPB_STEP_MIN_BLOCKS
+#define FPB_STEP_MIN_BLOCKS 3 // resident 128-thread CTAs per SM the step kernel is tuned for
+#endif
 
 namespace {
 
@@ -41,9 +44,11 @@ __device__ __forceinline__ float m_sin(float x) { return (float)sin((double)x); 
 __device__ __forceinline__ float m_cos(float x) { return (float)cos((double)x); }
 __device__ __forceinline__ float m_erf(float x) { return (float)erf((double)x); }
 #else
-__device__ __forceinline__ float m_exp(float x) { return expf(x); }
-__device__ __forceinline__ float m_log(float x) { return logf(x); }
-__device__ __forceinline__ float m_pow(float a, float b) { return powf(a, b); }
+// production: MUFU-based exp / pow (a > 0 at every call site); relative error
+// ~1e-6, three orders of magnitude inside the 1e-5 position tolerance
+__device__ __forceinline__ float m_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float m_log(float x) { return __logf(x); }
+__device__ __forceinline__ float m_pow(float a, float b) { return exp2f(b * __log2f(a)); }
 __device__ __forceinline__ float m_sin(float x) { return sinf(x); }
 __device__ __forceinline__ float m_cos(float x) { return cosf(x); }
 __device__ __forceinline__ float m_erf(float x) { return erff(x); }
@@ -98,8 +103,11 @@ struct Rng {
     return u01(r.x);
   }
   // Fortran rannumb(i)
-  __device__ float get(int i) {
+  __device__ __forceinline__ float get(int i) {
     if (mode != FPB_RNG_PHILOX) return __ldg(tab + (i - 1));
+    return get_philox(i);
+  }
+  __device__ __noinline__ float get_philox(int i) {
     int blk = i >> 2;
     if (blk != cblk) {
       uint4 r = philox4x32_10(make_uint4(pid, tstep, 0x52414e44u, (uint32_t)blk), key);
@@ -458,7 +466,7 @@ __device__ __forceinline__ float cspanf(float value, float begin, float end) {
   return (val <= 0.f) ? val + last : val + first;
 }
 
-__device__ void cnllxy(const float *sc, float xlat, float xlong, float &xi, float &eta) {
+__device__ __noinline__ void cnllxy(const float *sc, float xlat, float xlong, float &xi, float &eta) {
   double gamma = sc[0];
   double dlat = xlat;
   double dlong = cspanf(xlong - sc[1], -180.f, 180.f);
@@ -488,7 +496,7 @@ __device__ void cnllxy(const float *sc, float xlat, float xlong, float &xi, floa
   xi = (float)((1.f - gamma * rhog1) * sndgam);
 }
 
-__device__ void cnxyll(const float *sc, double xi, double eta, float &xlat, float &xlong) {
+__device__ __noinline__ void cnxyll(const float *sc, double xi, double eta, float &xlat, float &xlong) {
   double gamma = sc[0], temp, ymerc, along;
   double arg2 = 2.f * eta - gamma * (xi * xi + eta * eta);
   double arg1 = gamma * arg2;
@@ -511,14 +519,14 @@ __device__ void cnxyll(const float *sc, double xi, double eta, float &xlat, floa
   xlat = xlat * CM_DGPRAD;
 }
 
-__device__ void cll2xy(const float *sc, float xlat, float xlong, float &x, float &y) {
+__device__ __noinline__ void cll2xy(const float *sc, float xlat, float xlong, float &x, float &y) {
   float xi, eta;
   cnllxy(sc, xlat, xlong, xi, eta);
   x = sc[2] + CM_REARTH / sc[6] * (xi * sc[4] + eta * sc[5]);
   y = sc[3] + CM_REARTH / sc[6] * (eta * sc[4] - xi * sc[5]);
 }
 
-__device__ void cxy2ll(const float *sc, float x, float y, float &xlat, float &xlong) {
+__device__ __noinline__ void cxy2ll(const float *sc, float x, float y, float &xlat, float &xlong) {
   double xi0 = (x - sc[2]) * sc[6] / CM_REARTH;
   double eta0 = (y - sc[3]) * sc[6] / CM_REARTH;
   double xi = xi0 * sc[4] - eta0 * sc[5];
@@ -527,7 +535,7 @@ __device__ void cxy2ll(const float *sc, float x, float y, float &xlat, float &xl
   xlong = cspanf(xlong, -180.f, 180.f);
 }
 
-__device__ float cgszll(const float *sc, float xlat) {
+__device__ __noinline__ float cgszll(const float *sc, float xlat) {
   double slat, ymerc, efact;
   if (xlat > 89.985f) {
     if (sc[0] > 0.9999f) return 2.f * sc[6];
@@ -599,7 +607,7 @@ __device__ __forceinline__ int pole_grid(const DevCfg &c, double yt) {
 // ------------------------------------------------------------ settling ----
 // src/get_settling.f90:52-125 + dynamic_viscosity.f90; rho/tt from Fortran
 // slot 1 (literal in the reference)
-__device__ float get_settling(const DevCfg &c, const DevMetSlot &lit1, const float *sh,
+__device__ __noinline__ float get_settling(const DevCfg &c, const DevMetSlot &lit1, const float *sh,
                               float xt, float yt, float zt, int nsp) {
   const float ga = 9.81f;
   int nix = f_int(xt), njy = f_int(yt);
@@ -661,7 +669,7 @@ __device__ __forceinline__ size_t didx(const DevCfg &c, int nxg, int nyg, int ix
   return i;
 }
 
-__device__ void drydepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc,
+__device__ __noinline__ void drydepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc,
                                 const float *deposit, float x, float y, int nage, int kp) {
   const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
   float xl, yl;
@@ -854,26 +862,33 @@ __device__ void do_advance(const DevStepArgs &a, const float *sh, Rng &rng, int 
       const float dt = (float)ldt;
       t.zeta = zt / t.h;
 
-      // level pair under the particle; reuse a cached level when possible
+      // level pair under the particle; reuse a cached level when possible.
+      // One call site for profile_level so that every lane of the warp that
+      // needs a level gathers it in the same (converged) pass.
       {
         const int ni = find_indz(sh, nz, zt), nip = ni + 1;
-        if (loop == 1) {
-          profile_level(c, a.met, z, ni, lo);
-          profile_level(c, a.met, z, nip, hi);
-        } else if (ni != indz) {
-          if (ni == indzp) {
+        bool need_lo = true, need_hi = true;
+        if (loop != 1) {
+          if (ni == indz) {
+            need_lo = need_hi = false;
+          } else if (ni == indzp) {
             lo = hi;
-            profile_level(c, a.met, z, nip, hi);
+            need_lo = false;
           } else if (nip == indz) {
             hi = lo;
-            profile_level(c, a.met, z, ni, lo);
-          } else {
-            profile_level(c, a.met, z, ni, lo);
-            profile_level(c, a.met, z, nip, hi);
+            need_hi = false;
           }
         }
         indz = ni;
         indzp = nip;
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+          if (q ? need_hi : need_lo) {
+            Lev t_;
+            profile_level(c, a.met, z, ni + q, t_);
+            if (q) hi = t_; else lo = t_;
+          }
+        }
       }
 
       // advance.f90:342-350
@@ -1149,8 +1164,56 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
   return (unsigned long long)__reduce_add_sync(0xffffffffu, v);
 }
 
-template <bool DRYDEP, bool CBL>
+__device__ __forceinline__ void make_rng(const DevCfg &c, const float *tab, int slot, Rng &rng) {
+  rng.tab = tab;
+  rng.maxrand = c.maxrand;
+  rng.mode = c.rng_mode;
+  rng.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+  rng.pid = (uint32_t)(c.part_id_offset + c.part_id_stride * slot);
+  rng.tstep = (uint32_t)c.itime;
+  rng.cblk = -1;
+}
+
+// initialize() for the particles released this step (src/timemanager.f90:553-555).
+// A separate launch keeps this once-per-lifetime code out of the step kernel.
+template <bool CBL>
 __global__ void __launch_bounds__(128)
+fpb_init_kernel(const __grid_constant__ DevStepArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int itime = c.itime;
+  unsigned n_init = 0;
+  if (j < c.numpart && a.p.itra1[j] == itime && ((a.p.itramem[j] == itime) || (itime == 0))) {
+    n_init = 1;
+    PState s;
+    s.xt = a.p.xtra1[j];
+    s.yt = a.p.ytra1[j];
+    s.zt = a.p.ztra1[j];
+    s.ldt = a.p.idt[j];
+    const int slot = a.p.slot[j];
+    Rng rng;
+    make_rng(c, a.rannumb, slot, rng);
+    int nrand;
+    if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_init[slot];
+    else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 4;
+    else nrand = f_int(rng.uniform(1u) * (float)(c.maxrand - 1)) + 1;
+    do_initialize<CBL>(a, sh, rng, nrand, s);
+    a.p.idt[j] = s.ldt;
+    a.p.uap[j] = s.up; a.p.ucp[j] = s.vp; a.p.uzp[j] = s.wp;
+    a.p.us[j] = s.usigold; a.p.vs[j] = s.vsigold; a.p.ws[j] = s.wsigold;
+    a.p.cbt[j] = (int16_t)s.icbt;
+  }
+  if (a.stats) {
+    unsigned long long v1 = warp_sum(n_init);
+    if ((threadIdx.x & 31) == 0 && v1) atomicAdd(a.stats + 1, v1);
+  }
+}
+
+template <bool DRYDEP, bool CBL>
+__global__ void __launch_bounds__(128, FPB_STEP_MIN_BLOCKS)
 fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
@@ -1159,7 +1222,7 @@ fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
 
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int itime = c.itime;
-  unsigned n_act = 0, n_init = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
+  unsigned n_act = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
 
   if (j < c.numpart && a.p.itra1[j] == itime) {
     n_act = 1;
@@ -1180,29 +1243,15 @@ fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
     s.usigold = a.p.us[j]; s.vsigold = a.p.vs[j]; s.wsigold = a.p.ws[j];
     s.icbt = a.p.cbt[j];
 
+    const int slot = a.p.slot[j];
     Rng rng;
-    rng.tab = a.rannumb;
-    rng.maxrand = c.maxrand;
-    rng.mode = c.rng_mode;
-    rng.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
-    rng.pid = (uint32_t)(c.part_id_offset + c.part_id_stride * j);
-    rng.tstep = (uint32_t)itime;
-    rng.cblk = -1;
-
-    if ((itramem == itime) || (itime == 0)) {
-      int nrand;
-      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_init[j];
-      else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 4;
-      else nrand = f_int(rng.uniform(1u) * (float)(c.maxrand - 1)) + 1;
-      do_initialize<CBL>(a, sh, rng, nrand, s);
-      n_init = 1;
-    }
+    make_rng(c, a.rannumb, slot, rng);
 
     float prob[FPB_MAXSPEC];
     AdvOut out;
     {
       int nrand;
-      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[j];
+      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[slot];
       else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 64;
       else nrand = f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
       do_advance<DRYDEP, CBL>(a, sh, rng, nrand, npoint, s, prob, out);
@@ -1262,12 +1311,11 @@ fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
   }
 
   if (a.stats) {
-    unsigned long long v0 = warp_sum(n_act), v1 = warp_sum(n_init), v2 = warp_sum(n_term),
+    unsigned long long v0 = warp_sum(n_act), v2 = warp_sum(n_term),
                        v3 = warp_sum(n_pbl), v4 = warp_sum(n_sub), v5 = warp_sum(n_pett),
                        v6 = warp_sum(n_nan);
     if ((threadIdx.x & 31) == 0 && v0) {
       atomicAdd(a.stats + 0, v0);
-      if (v1) atomicAdd(a.stats + 1, v1);
       if (v2) atomicAdd(a.stats + 2, v2);
       if (v3) atomicAdd(a.stats + 3, v3);
       if (v4) atomicAdd(a.stats + 4, v4);
@@ -1471,7 +1519,7 @@ fpb_conc_emit_kernel(const __grid_constant__ DevConcArgs a, int nest_sel, unsign
   sink.keys = keys;
   sink.vals = vals;
   sink.nrec = nrec;
-  sink.i = i;
+  sink.i = a.p.slot[i]; // record order = slot order = the reference's particle order
   sink.nest_sel = nest_sel;
   conc_particle(a, sh, i, sink);
 }
@@ -1522,6 +1570,13 @@ fpb_receptor_kernel(const __grid_constant__ DevConcArgs a) {
 #else
 #define FPB_SUF(name) name##_fast
 #endif
+
+void FPB_SUF(fpbk_init)(const DevStepArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 127) / 128;
+  if (nb == 0) return;
+  if (a.cfg.cblflag == 1) fpb_init_kernel<true><<<nb, 128, 0, st>>>(a);
+  else fpb_init_kernel<false><<<nb, 128, 0, st>>>(a);
+}
 
 void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   const int nb = (a.cfg.numpart + 127) / 128;

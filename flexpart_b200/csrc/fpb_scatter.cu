@@ -203,7 +203,7 @@ int scatter_sort_pairs(ScatterWork &w, size_t n, int bits, cudaStream_t st, int6
 int scatter_conccalc_deterministic(ScatterWork &w, const DevConcArgs &a, bool strict,
                                    cudaStream_t st, int64_t *launches) {
   const DevCfg &c = a.cfg;
-  const size_t nrec = 4 * (size_t)c.numpart;
+  const size_t nrec = 4 * (size_t)c.numpart; // record id = 4*slot + corner; slots < numpart
   if (nrec == 0) return 0;
   if (nrec >= 0xffffffffull) {
     s_err = "deterministic scatter: more than 2^32 records";

@@ -1,0 +1,23 @@
+// fpb_sort.cuh -- re-ordering of the device-resident particle rows by
+// meteorological grid cell (level-major: key = met array index of the cell
+// under the particle), for gather locality and warp convergence.
+// slot[row] / row_of_slot[slot] keep the caller's slot indices stable.
+#pragma once
+#include "fpb_device.cuh"
+#include "fpb_scatter.cuh"
+
+// build keys (dead rows sort last), returns the number of live rows via *d_nlive
+void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *height, int nrows,
+                      unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st);
+// dst row i := src row ids[i] for every particle array (incl. slot)
+void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
+                   int nrows, int nspec, cudaStream_t st);
+void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st);
+void sortk_iota(int32_t *a, int n, cudaStream_t st);
+// staging (slot order, rows [first,first+count)) <-> device rows
+void sortk_gather_to_staging(const DevParticles &rows, const DevParticles &stg,
+                             const int32_t *row_of_slot, int first, int count, int nspec,
+                             cudaStream_t st);
+void sortk_scatter_from_staging(const DevParticles &stg, const DevParticles &rows,
+                                const int32_t *row_of_slot, int first, int count, int nspec,
+                                bool have_split, bool have_scav, cudaStream_t st);

@@ -59,7 +59,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
                 npart=(10000,), xmass=None, maxspec=5, nclassunc=1, receptors=(),
                 maxpart=None, device=0, rng_mode=abi.RNG_REFERENCE, math_mode=abi.MATH_FAST,
                 scatter_mode=abi.SCATTER_ATOMIC, seed=0x5EEDF1E0, height=None,
-                part_id_stride=1, part_id_offset=0):
+                part_id_stride=1, part_id_offset=0, sort_interval=0):
     """Run constants for the engine, derived the way the reference's
     gridcheck_ecmwf / readcommand / readoutgrid / readreleases derive them."""
     L = load_host_lib()
@@ -116,6 +116,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
     c.maxpart = maxpart or int(npart_a.sum())
     c.device, c.rng_mode, c.math_mode, c.scatter_mode, c.seed = device, rng_mode, math_mode, scatter_mode, seed
     c.part_id_stride, c.part_id_offset = part_id_stride, part_id_offset
+    c.sort_interval = sort_interval
     h = np.ascontiguousarray(height, np.float32) if height is not None else synth_heights(nz)
     return ConfigBundle(c, h, npart_a, xmass_a)
 

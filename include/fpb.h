@@ -131,7 +131,9 @@ typedef struct fpb_config {
   uint64_t seed;        /* Philox key */
   int32_t part_id_stride, part_id_offset; /* global id = offset + stride*slot:
                            multi-GPU partition, src/releaseparticles_mpi.f90:141 */
-  int32_t reserved[8];
+  int32_t sort_interval; /* >0: fpb_step re-orders the device rows by met cell
+                            every that many steps (results do not depend on it) */
+  int32_t reserved[7];
 } fpb_config;
 
 /* One time level of the meteorological arrays the hot path gathers from
