@@ -1,0 +1,220 @@
+"""CPU tests of the drop-in boundary and the host logic: the C-ABI libraries
+load and export every symbol include/*.h declares, struct layouts match, the
+engine refuses to run without a CUDA device (no CPU fallback), and the host
+time loop (timemanager replay) keeps the reference's schedule."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import flexpart_b200 as fb
+from flexpart_b200 import abi
+import cases
+from oracle_api import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, prefix):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, txt)))
+
+
+def test_engine_library_exports_every_declared_symbol():
+    names = _declared("fpb.h", "fpb_")
+    assert len(names) >= 20
+    lib = C.CDLL(abi.ENGINE_LIB)  # loading needs no GPU
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_host_library_exports_every_declared_symbol():
+    names = _declared("fpb_host.h", "fpbh_")
+    assert len(names) >= 12
+    lib = C.CDLL(abi.HOST_LIB)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_the_headers():
+    L = fb.load_engine_lib()  # raises on a fpb_config size mismatch
+    assert L.fpb_abi_version() == abi.ABI_VERSION
+    # compile a probe against the real headers and compare every struct size
+    src = r'''
+#include <stdio.h>
+#include "fpb_host.h"
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fpb_config), sizeof(fpb_met_ptrs),
+ sizeof(fpb_particle_ptrs), sizeof(fpb_step_stats), sizeof(fpbh_releases), sizeof(fpbh_run),
+ sizeof(fpbh_run_result), sizeof(fpbh_engine)); return 0;}
+'''
+    exe = os.path.join(ROOT, "tests", "_abi_probe")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src.encode(), check=True)
+    out = subprocess.check_output([exe]).decode().split()
+    os.remove(exe)
+    expect = [C.sizeof(t) for t in (abi.FpbConfig, abi.FpbMetPtrs, abi.FpbParticlePtrs, abi.FpbStepStats,
+                                    abi.FpbhReleases, abi.FpbhRun, abi.FpbhRunResult, abi.FpbhEngine)]
+    assert [int(x) for x in out] == expect
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device fpb_init must fail
+    with a message, never silently compute elsewhere."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cb = cases.config_small()
+    with pytest.raises(fb.FpbError, match="no CUDA device"):
+        fb.Engine(cb)
+
+
+def test_bad_arguments_are_rejected():
+    L = fb.load_engine_lib()
+    h = C.c_void_p()
+    cb = cases.config_small()
+    bad = cb.clone(abi_version=99)
+    assert L.fpb_init(C.byref(bad.cfg), C.byref(h)) != 0
+    assert b"abi_version" in L.fpb_last_error()
+    bad = cb.clone(nz=1000)
+    assert L.fpb_init(C.byref(bad.cfg), C.byref(h)) != 0
+    assert b"nz" in L.fpb_last_error()
+    assert L.fpb_step(None, 0, 0, None) != 0
+    assert L.fpb_conccalc(None, 0, 1.0) != 0
+    assert L.fpb_upload_met(None, 1, None) != 0
+
+
+def test_readcommand_semantics():
+    """src/readcommand.f90:244-272,377-383,627-634."""
+    c = fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ctl=-5.0, ifine=4).cfg
+    assert (c.method, c.mintime, c.turbswitch, c.ifine) == (0, 900, 0, 1)
+    assert abs(c.ctl + 0.2) < 1e-7
+    c = fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ctl=5.0, ifine=4).cfg
+    assert (c.method, c.mintime, c.turbswitch, c.ifine) == (1, 1, 1, 4)
+    assert abs(c.ctl - 0.2) < 1e-7 and abs(c.fine - 0.25) < 1e-7
+    c = fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ctl=2.0, ifine=4,
+                       cblflag=1, lsynctime=1800).cfg
+    assert c.turbswitch == 1 and c.lsynctime == 1200 and abs(c.ctl - 0.2) < 1e-7 and c.ifine == 11
+    c = fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ldirect=-1).cfg
+    assert c.lsynctime == -900 and c.mintime == -900
+    with pytest.raises(fb.FpbError, match="EITHER -1 OR 1"):
+        fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ldirect=0)
+
+
+def test_gridcheck_semantics():
+    """src/gridcheck_ecmwf.f90:300-366."""
+    c = fb.make_config().cfg
+    assert (c.xglobal, c.nglobal, c.sglobal) == (1, 1, 1)
+    assert c.switchnorthg == 165.0 and c.switchsouthg == 15.0
+    assert c.nxmin1 == 360 and c.nymin1 == 180
+    assert abs(c.dxconst - 180.0 / (1.0 * 6.371e6 * 3.14159265)) < 1e-12
+    c = fb.make_config(nx=101, ny=81, nz=10, dx=0.25, dy=0.25, xlon0=0.0, ylat0=40.0,
+                       height=fb.synth_heights(10), outlon0=0.0, outlat0=40.0, numxgrid=10, numygrid=10).cfg
+    assert (c.xglobal, c.nglobal, c.sglobal) == (0, 0, 0)
+    assert c.switchnorthg == 999999.0 and c.switchsouthg == 999999.0
+
+
+def test_synthetic_met_invariants():
+    """What the hot path divides by or searches on."""
+    cb = cases.config_small()
+    c = cb.cfg
+    m = fb.MetFields(cb).synth(3600)
+    nx, ny, nz = c.nx, c.ny, c.nz
+    h = cb.height
+    assert h[0] == 0.0 and np.all(np.diff(h) > 0)
+    assert m.hmix[:nx, :ny].min() >= 100.0 and m.hmix[:nx, :ny].max() <= 4500.0
+    assert m.ustar[:nx, :ny].min() >= 1e-8 and m.rho[:nx, :ny, :nz].min() > 0
+    assert np.all(np.isfinite(m.oli)) and np.abs(m.oli[:nx, :ny]).min() >= 1e-3 - 1e-9
+    # cyclic column repeats the first one
+    for f in (m.uu, m.vv, m.rho, m.hmix):
+        np.testing.assert_allclose(f[0], f[nx - 1], rtol=0, atol=2e-4)
+    # drhodz by the reference's centred differences (verttransform_ecmwf.f90:392-398)
+    k = 5
+    ref = (m.rho[:nx, :ny, k + 1] - m.rho[:nx, :ny, k - 1]) / (h[k + 1] - h[k - 1])
+    np.testing.assert_allclose(m.drhodz[:nx, :ny, k], ref, rtol=1e-6)
+    np.testing.assert_array_equal(m.drhodz[:nx, :ny, nz - 1], m.drhodz[:nx, :ny, nz - 2])
+    # polar winds exist poleward of the switch rows and are constant on the pole rows
+    j0 = int(c.switchnorthg) - 2
+    assert np.abs(m.uupol[:nx, j0:ny, 0]).max() > 0
+    assert np.ptp(m.uupol[:nx, ny - 1, 3]) == 0 and np.ptp(m.vvpol[:nx, 0, 3]) == 0
+    assert np.ptp(m.ww[:nx, ny - 1, 7]) == 0
+
+
+def test_timemanager_schedule_matches_reference_loop():
+    """Sampling weights 0.5 at the window ends, output every LOUTSTEP with a
+    second half-weight sample when the next window starts at the same time
+    (src/timemanager.f90:350-365, 376-464), exit at ideltas (:509)."""
+    cb = cases.config_small(nrel=1, npart_each=50)
+    rel = cases.releases_boxes(cb)
+    calls = []
+
+    class Rec(Oracle):
+        pass
+    o = Rec(cb)
+    o.fill_rannumb(50000, -320)
+    v = o.vtable()
+    # (a struct field access returns a view of the slot: copy the raw addresses)
+    orig_conc = abi.CONC_FN(C.cast(v.conccalc, C.c_void_p).value)
+    orig_step = abi.STEP_FN(C.cast(v.step, C.c_void_p).value)
+
+    def conc(self_, itime, weight):
+        calls.append(("conc", itime, weight))
+        return orig_conc(self_, itime, weight)
+
+    def step(self_, itime, ldeltat, st):
+        calls.append(("step", itime, ldeltat))
+        return orig_step(self_, itime, ldeltat, st)
+    v.conccalc = abi.CONC_FN(conc)
+    v.step = abi.STEP_FN(step)
+    run = fb.RunSpec(ideltas=3 * 3600, loutstep=3600, loutaver=3600, loutsample=900)
+    res, outs = fb.timemanager(cb, rel, run, v)
+    assert res.syncs == 12 and res.outputs == 3
+    assert [o_["itime"] for o_ in outs] == [3600, 7200, 10800]
+    assert all(o_["outnum"] == 4.0 for o_ in outs)
+    conc_calls = [c_ for c_ in calls if c_[0] == "conc"]
+    w = {}
+    for _, t, wt in conc_calls:
+        w.setdefault(t, []).append(wt)
+    assert w[0] == [0.5] and w[900] == [1.0] and w[3600] == [0.5, 0.5] and w[10800] == [0.5, 0.5]
+    steps = [c_ for c_ in calls if c_[0] == "step"]
+    assert [t for _, t, _ in steps] == list(range(0, 10800, 900))
+    # ldeltat: time since the last deposition-decay reference (timemanager.f90:514-518)
+    ld = {t: l for _, t, l in steps}
+    assert ld[0] == 0 - (1800 - 3600) and ld[1800] == 0 and ld[2700] == 900 and ld[5400] == 0
+    # mass: every output holds outnum * total released mass
+    for o_ in outs:
+        assert abs(o_["gridunc"].sum() - 4.0 * 50 * (1.0 / 50)) < 1e-4
+
+
+def test_timemanager_backward_run_counts_down():
+    """LDIRECT=-1: lsynctime < 0, the loop counts down to a negative ideltas and
+    the met bracket is ordered in run direction (src/readcommand.f90:627-634)."""
+    cb = cases.config_small(nrel=1, npart_each=40, ldirect=-1, ctl=-5.0)
+    rel = cases.releases_boxes(cb, zmax=1000.0)
+    o = Oracle(cb)
+    o.fill_rannumb(50000, -320)
+    run = fb.RunSpec(ideltas=-4 * 900, ldirect=-1)
+    res, outs = fb.timemanager(cb, rel, run, o.vtable())
+    assert res.syncs == 4 and res.particle_steps == 160 and res.outputs == 1
+    assert outs[0]["itime"] == -3600
+    p = fb.Particles(cb.cfg.maxpart, 1)
+    p.numpart = 40
+    o.pull_particles(p)
+    assert np.all(p.itra1[:40] == -3600)
+
+
+def test_two_rank_partition_and_grid_reduce_gloo():
+    """Multi-GPU semantics on CPU: particles split round-robin over 2 ranks
+    (releaseparticles_mpi.f90:141-152), each with a full met replica; the only
+    collective is a sum-reduce of gridunc to rank 0 (mpi_mod.f90:2395-2579).
+    The reduced grid equals the single-rank grid."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", script],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout

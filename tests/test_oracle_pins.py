@@ -1,0 +1,378 @@
+"""CPU tests that pin the oracle (oracle/, a C restatement of the reference's
+Fortran): the reference ships no golden vectors for this path (SURVEY.md 4/8c,
+"parity unpinned"), so the pins are (1) analytic known-answer cases on
+set_fields_synthetic-style homogeneous met (src/mpi_mod.f90:2940-2973),
+(2) invariants the algorithm guarantees, (3) the defining recurrences of the
+Numerical-Recipes generators, (4) committed golden fixtures of the oracle's own
+output (tests/golden/, regression pins)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import flexpart_b200 as fb
+import cases
+from oracle_api import Oracle, load
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---------------------------------------------------------------- random_mod
+def test_ran3_is_knuth_subtractive():
+    """ran3 (src/random_mod.f90:93-139) is Knuth's subtractive lagged-Fibonacci
+    generator: x[n] = (x[n-55] - x[n-24]) mod 1e9 on the integer state."""
+    cb = cases.config_small()
+    o = Oracle(cb)
+    idum = C.c_int32(-1)
+    x = [o.L.fpo_ran3(o.S, C.byref(idum)) for _ in range(400)]
+    assert idum.value == 1
+    xs = np.array(x, dtype=np.float64)
+    assert 0.0 <= xs.min() and xs.max() < 1.0
+    # the float32 output keeps ~7 digits of the 9-digit integer state
+    rhs = (xs[:-55] - xs[31:-24]) % 1.0
+    err = np.abs(xs[55:] - rhs)
+    err = np.minimum(err, 1.0 - err)
+    assert err.max() < 3e-7
+
+
+def test_ran3_reseed_quirk_of_first_calls():
+    """initialize and advance each own a SAVEd idummy=-7 (src/advance.f90:120,
+    src/initialize.f90:64): the first call of each re-seeds the shared stream,
+    so both first draws are identical."""
+    cb = cases.config_small()
+    o = Oracle(cb)
+    a, b = C.c_int32(-7), C.c_int32(-7)
+    r1 = o.L.fpo_ran3(o.S, C.byref(a))
+    r2 = o.L.fpo_ran3(o.S, C.byref(b))
+    r3 = o.L.fpo_ran3(o.S, C.byref(a))
+    assert r1 == r2 and r3 != r1 and a.value == 1 and b.value == 1
+
+
+def test_ran1_is_park_miller():
+    """ran1 (src/random_mod.f90:12-42): Park-Miller minimal standard + Bays-Durham
+    shuffle; the underlying LCG satisfies idum' = 16807*idum mod (2^31-1)."""
+    cb = cases.config_small()
+    o = Oracle(cb)
+    idum = C.c_int32(-7)
+    vals, states = [], []
+    for _ in range(50):
+        vals.append(o.L.fpo_ran1(o.S, C.byref(idum)))
+        states.append(idum.value)
+    assert all(0.0 < v < 1.0 for v in vals)
+    for s0, s1 in zip(states[:-1], states[1:]):
+        assert s1 == (16807 * s0) % 2147483647
+
+
+def test_rannumb_table_statistics_and_tail():
+    """rannumb: N(0,1) clipped to +-3 (gasdev1, src/random_mod.f90:70-90); the
+    final gasdev1 call overwrites rannumb(maxrand) and rannumb(maxrand-1)
+    (src/FLEXPART.f90:59), so a shorter table shares all but its tail."""
+    cb = cases.config_small()
+    o = Oracle(cb)
+    n = 200000
+    o.fill_rannumb(n, -320)
+    t = o.rannumb(n)
+    assert t.min() >= -3.0 and t.max() <= 3.0
+    assert abs(t.mean()) < 0.01 and 0.99 < t.std() < 1.0  # N(0,1) winsorised at +-3: sd ~0.9986
+    o2 = Oracle(cb)
+    o2.fill_rannumb(n - 2, -320)
+    t2 = o2.rannumb(n - 2)
+    assert np.array_equal(t[:n - 4], t2[:n - 4])
+
+
+# ---------------------------------------------------------------- windalign
+def test_windalign_rotation():
+    L = load()
+    ux, vy = C.c_float(), C.c_float()
+    for (u, v) in [(10.0, 0.0), (0.0, 5.0), (-3.0, 4.0)]:
+        L.fpo_windalign(u, v, 2.0, 0.5, C.byref(ux), C.byref(vy))
+        ff = np.hypot(u, v)
+        c, s = u / ff, v / ff
+        assert abs(ux.value - (c * 2.0 - s * 0.5)) < 1e-5
+        assert abs(vy.value - (s * 2.0 + c * 0.5)) < 1e-5
+        assert abs(np.hypot(ux.value, vy.value) - np.hypot(2.0, 0.5)) < 1e-5
+
+
+# ---------------------------------------------------------------- cmapf
+def test_polar_map_round_trip_and_construction():
+    """cll2xy / cxy2ll invert each other on the polar-stereographic maps built
+    by gridcheck (stlmbr + stcm2p, src/gridcheck_ecmwf.f90:340-366); the
+    oracle's own stlmbr/stcm2p reproduce the host library's maps bit for bit."""
+    cb = cases.config_small(nx=361, ny=181, nz=10, height=fb.synth_heights(10))
+    c = cb.cfg
+    L = load()
+    nm = (C.c_float * 9)(*c.northpolemap)
+    x, y, lat, lon = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    for la, lo in [(76.0, 10.0), (85.0, -120.0), (89.5, 179.0), (80.0, 0.0)]:
+        L.fpo_cll2xy(nm, la, lo, C.byref(x), C.byref(y))
+        L.fpo_cxy2ll(nm, x.value, y.value, C.byref(lat), C.byref(lon))
+        assert abs(lat.value - la) < 2e-4
+        assert abs(((lon.value - lo + 180) % 360) - 180) < 2e-3
+    m = (C.c_float * 9)()
+    L.fpo_stlmbr(m, 90.0, 0.0)
+    sizenorth = float(np.float32(6.0) * (np.float32(90.0) - np.float32(75.0)) / np.float32(c.dy))
+    L.fpo_stcm2p(m, 0.0, 0.0, 75.0, 0.0, sizenorth, sizenorth, 75.0, 180.0)
+    assert list(m) == list(c.northpolemap)
+    ms = (C.c_float * 9)()
+    L.fpo_stlmbr(ms, -90.0, 0.0)
+    sizesouth = float(np.float32(6.0) * (np.float32(-75.0) + np.float32(90.0)) / np.float32(c.dy))
+    L.fpo_stcm2p(ms, 0.0, 0.0, -75.0, 0.0, sizesouth, sizesouth, -75.0, 180.0)
+    assert list(ms) == list(c.southpolemap)
+    # map scale: the 15 deg from the switch latitude to the pole span sizenorth/2 map
+    # units along each axis (stcm2p pins (0,0) and (size,size) 180 deg apart)
+    L.fpo_cll2xy(nm, 90.0, 0.0, C.byref(x), C.byref(y))
+    assert abs(x.value - sizenorth / 2) < 1e-2 and abs(y.value - sizenorth / 2) < 1e-2
+
+
+# ---------------------------------------------------------------- advance KATs
+def _homog(cb, u=10.0, v=0.0, w=0.0):
+    return fb.MetFields(cb).homogeneous(u, v, w), fb.MetFields(cb).homogeneous(u, v, w)
+
+
+def test_kat_uniform_zonal_wind_turbulence_off():
+    """Homogeneous u=10 m/s, turbulence off: dx = u*dt*dxconst/cos(lat) grid
+    units, dy = 0, the Petterssen correction vanishes, z unchanged."""
+    cb = cases.config_small(nrel=1, npart_each=64, turboff=1, ctl=-5.0)
+    c = cb.cfg
+    m0, m1 = _homog(cb, 10.0, 0.0, 0.0)
+    o = Oracle(cb)
+    o.fill_rannumb(20000, -320)
+    o.upload_met(1, m0); o.upload_met(2, m1)
+    o.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 64, lat_range=(-60.0, 60.0), zmax=12000.0)
+    x0, y0, z0 = p.xtra1.copy(), p.ytra1.copy(), p.ztra1.copy()
+    o.push_particles(p)
+    st = o.step(0)
+    assert st["n_active"] == 64 and st["n_init"] == 64 and st["n_petterssen"] == 64
+    o.pull_particles(p)
+    lat = np.deg2rad(y0[:64] * c.dy + c.ylat0)
+    expect = 10.0 * 900.0 * c.dxconst / np.cos(lat)
+    dx = (p.xtra1[:64] - x0[:64]) % c.nxmin1
+    assert np.abs(dx - expect).max() < 5e-6 * np.abs(expect).max() + 1e-9
+    assert np.abs(p.ytra1[:64] - y0[:64]).max() < 1e-12
+    assert np.abs(p.ztra1[:64] - z0[:64]).max() == 0.0
+    assert np.all(p.itra1[:64] == 900)
+
+
+def test_kat_cyclic_wrap():
+    """x wraps modulo nxmin1 under the cyclic boundary (src/advance.f90:784-788)."""
+    cb = cases.config_small(nrel=1, npart_each=4, turboff=1, ctl=-5.0)
+    c = cb.cfg
+    o = Oracle(cb)
+    o.fill_rannumb(20000, -320)
+    m0, m1 = _homog(cb, 40.0, 0.0, 0.0)
+    o.upload_met(1, m0); o.upload_met(2, m1)
+    o.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 4, zmax=5000.0)
+    p.xtra1[:4] = c.nxmin1 - 0.001
+    p.ytra1[:4] = [c.nymin1 / 2, c.nymin1 / 2 + 3, 8.0, 10.0]
+    o.push_particles(p)
+    o.step(0)
+    o.pull_particles(p)
+    assert np.all(p.xtra1[:4] >= 0) and np.all(p.xtra1[:4] < 1.0)
+    assert np.all(p.itra1[:4] == 900)
+
+
+def test_kat_meridional_wind_crosses_the_pole():
+    """v > 0 next to the north pole in the polar-stereographic branch: the
+    particle passes the pole and comes back down the opposite meridian
+    (src/advance.f90:754-765); it is never lost (nstop stays 0)."""
+    cb = cases.config_small(nrel=1, npart_each=2, turboff=1, ctl=-5.0)
+    c = cb.cfg
+    o = Oracle(cb)
+    o.fill_rannumb(20000, -320)
+    m0, m1 = fb.MetFields(cb), fb.MetFields(cb)
+    for m in (m0, m1):
+        m.homogeneous(0.0, 0.0, 0.0)
+        # uniform flow across the pole in map coordinates
+        m.uupol[...] = 0.0
+        m.vvpol[...] = 60.0
+    o.upload_met(1, m0); o.upload_met(2, m1)
+    o.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 2, zmax=5000.0)
+    p.xtra1[:2] = [c.nxmin1 / 2.0, c.nxmin1 / 2.0 + 1.0]
+    p.ytra1[:2] = c.nymin1 - 0.05  # 0.25 deg from the pole on the 5 deg grid
+    lon0 = p.xtra1[:2] * c.dx + c.xlon0
+    o.push_particles(p)
+    o.step(0)
+    o.pull_particles(p)
+    assert np.all(p.itra1[:2] == 900)
+    lon1 = p.xtra1[:2] * c.dx + c.xlon0
+    lat1 = p.ytra1[:2] * c.dy + c.ylat0
+    assert np.all(lat1 <= 90.0) and np.all(lat1 > 85.0)
+    moved = np.abs(((lon1 - lon0 + 180) % 360) - 180)
+    assert np.all(moved > 1.0)  # longitude swings as the particle rounds the pole
+
+
+def test_reflection_keeps_particles_above_ground():
+    """Langevin sub-steps reflect at the ground and at h (src/advance.f90:476-491):
+    z stays >= 0; mass and activity flags are untouched for a gas tracer."""
+    cb = cases.config_small(nrel=2, npart_each=256)
+    m0, m1 = cases.met_pair(cb)
+    o = Oracle(cb)
+    o.fill_rannumb()
+    o.upload_met(1, m0); o.upload_met(2, m1)
+    o.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 512, zmax=800.0)
+    o.push_particles(p)
+    tot = 0
+    for k in range(6):
+        st = o.step(k * 900)
+        tot += st["n_substeps"]
+        o.pull_particles(p)
+        assert p.ztra1[:512].min() >= 0.0
+        assert np.all(p.xmass1[:512, 0] == 1.0)
+        assert np.all(p.itra1[:512] == (k + 1) * 900)
+    assert tot > 6 * 512 * 2  # method 1 really sub-steps
+
+
+# ---------------------------------------------------------------- conccalc
+def test_conccalc_kernel_weights_and_mass():
+    """Direct attribution for young particles, 4-cell uniform kernel for old
+    ones (weights sum to 1, src/conccalc.f90:201-294): the grid receives exactly
+    weight * sum(xmass1) when every particle is inside the output grid."""
+    cb = cases.config_small(nrel=2, npart_each=1000, lage=(86400 * 30,))
+    n = 2000
+    p = cases.seeded_particles(cb, n, zmax=40000.0, lat_range=(-70.0, 70.0))
+    p.itramem[:1000] = -50000
+    p.xmass1[:n, 0] = np.linspace(0.5, 1.5, n, dtype=np.float32)
+    o = Oracle(cb)
+    o.push_particles(p)
+    o.conccalc(0, 0.5)
+    g = o.fetch_grids()["gridunc"]
+    assert abs(g.sum() - 0.5 * p.xmass1[:n, 0].sum()) < 1e-4 * n
+    assert g.min() >= 0.0
+    o2 = Oracle(cb)
+    q = cases.seeded_particles(cb, 1, zmax=50.0)
+    o2.push_particles(q)
+    o2.conccalc(0, 1.0)
+    assert (o2.fetch_grids()["gridunc"] > 0).sum() == 1
+    q.itramem[:1] = -20000
+    o3 = Oracle(cb)
+    o3.push_particles(q)
+    o3.conccalc(0, 1.0)
+    g3 = o3.fetch_grids()["gridunc"]
+    assert 1 <= (g3 > 0).sum() <= 4 and abs(g3.sum() - 1.0) < 1e-6
+
+
+def test_strict_vs_defined_oracle_modes_differ_rarely():
+    """The two oracle modes (the reference's stale module state vs the defined
+    behaviour the device implements) give the same trajectories
+    except for the listed rare events."""
+    cb = cases.config_small(nrel=4, npart_each=256)
+    m0, m1 = cases.met_pair(cb)
+    outs = []
+    for strict in (True, False):
+        o = Oracle(cb, strict_reference=strict)
+        o.fill_rannumb()
+        o.upload_met(1, m0); o.upload_met(2, m1)
+        o.set_met_bracket((1, 2), (0, 10800))
+        p = cases.seeded_particles(cb, 1024, zmax=2500.0, lat_range=(-70, 70))
+        o.push_particles(p)
+        for k in range(4):
+            o.step(k * 900)
+        o.pull_particles(p)
+        outs.append(p)
+    a, b = outs
+    differ = (a.xtra1[:1024] != b.xtra1[:1024]) | (a.ztra1[:1024] != b.ztra1[:1024])
+    assert differ.mean() < 0.05, differ.mean()
+
+
+def test_libm_float_vs_correctly_rounded_oracle():
+    """The oracle built on glibc's float libm (what gfortran links) and the
+    default correctly-rounded build agree to float rounding per step."""
+    cb = cases.config_small(nrel=4, npart_each=256)
+    m0, m1 = cases.met_pair(cb)
+    outs = []
+    for lf in (False, True):
+        o = Oracle(cb, libm_float=lf)
+        o.fill_rannumb()
+        o.upload_met(1, m0); o.upload_met(2, m1)
+        o.set_met_bracket((1, 2), (0, 10800))
+        p = cases.seeded_particles(cb, 1024, zmax=2500.0)
+        o.push_particles(p)
+        o.step(0)
+        o.pull_particles(p)
+        outs.append(p)
+    a, b = outs
+    same_sub = a.idt[:1024] == b.idt[:1024]
+    assert same_sub.mean() > 0.97
+    dx = np.abs(a.xtra1[:1024] - b.xtra1[:1024])[same_sub] / cb.cfg.nxmin1
+    assert np.median(dx) < 1e-7 and np.quantile(dx, 0.9) < 1e-5
+
+
+# ---------------------------------------------------------------- releases
+def test_releaseparticles_host_matches_oracle():
+    """Release counts, slot search and the ran1 position stream of the host
+    library equal the oracle's restatement bit for bit
+    (src/releaseparticles.f90:69-378)."""
+    cb = cases.config_small(nrel=3, npart_each=700, maxpart=2600)
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=3, start=0, end=3600)
+    o = Oracle(cb)
+    L = o.L
+    state = fb.ReleaseState(c.numpoint)
+    parts = fb.Particles(c.maxpart, 1)
+    xmasssave = np.zeros(c.numpoint, np.float32)
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+    def fp(a):
+        return a.ctypes.data_as(_pf)
+    total = 0
+    for itime in range(0, 4500, 900):
+        rc = L.fpo_releaseparticles(o.S, itime, c.numpoint, rel.start.ctypes.data_as(_pi),
+                                    rel.end.ctypes.data_as(_pi), fp(rel.xpoint1), fp(rel.ypoint1),
+                                    fp(rel.xpoint2), fp(rel.ypoint2), fp(rel.zpoint1), fp(rel.zpoint2),
+                                    fp(xmasssave), 99999999)
+        assert rc == 0
+        fb.release_particles(cb, rel, state, itime, parts)
+        q = fb.Particles(c.maxpart, 1)
+        q.numpart = parts.numpart
+        o.pull_particles(q)
+        k = parts.numpart
+        for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt"):
+            assert np.array_equal(getattr(parts, f)[:k], getattr(q, f)[:k]), (itime, f)
+        assert np.array_equal(parts.xmass1[:k], q.xmass1[:k])
+        total = k
+        # let the released particles "advance" so their slots stay occupied
+        parts.itra1[:k] = itime + 900
+        o.push_particles(parts, 0, k)
+    # half the rate at both ends of the interval: 700*900/3600 = 175 per step
+    assert total == 3 * (87 + 175 * 3 + 88)
+
+
+def test_releases_exceeding_maxpart_fail():
+    cb = cases.config_small(nrel=2, npart_each=100, maxpart=150)
+    rel = cases.releases_boxes(cb)
+    with pytest.raises(fb.FpbError, match="MAXIMUM ALLOWED NUMBER"):
+        fb.release_particles(cb, rel, fb.ReleaseState(2), 0, fb.Particles(150, 1))
+
+
+# ---------------------------------------------------------------- golden pins
+def _golden_case():
+    cb = cases.config_small(nrel=4, npart_each=64, lage=(86400 * 10,))
+    rel = cases.releases_boxes(cb, seed=11)
+    run = fb.RunSpec(ideltas=6 * 900)
+    o = Oracle(cb)
+    o.fill_rannumb()
+    res, outs = fb.timemanager(cb, rel, run, o.vtable())
+    p = fb.Particles(cb.cfg.maxpart, 1)
+    p.numpart = res.numpart_final
+    o.pull_particles(p)
+    return res, outs, p
+
+
+def test_golden_fixture_of_oracle_run():
+    """Regression pin: a committed fixture generated by tests/make_golden.py from
+    this oracle (NOT from the reference, which cannot be run here)."""
+    g = np.load(os.path.join(GOLD, "oracle_small_hanna.npz"))
+    res, outs, p = _golden_case()
+    n = res.numpart_final
+    assert n == int(g["numpart"]) and res.particle_steps == int(g["particle_steps"])
+    assert res.substeps == int(g["substeps"])
+    assert np.array_equal(p.itra1[:n], g["itra1"]) and np.array_equal(p.idt[:n], g["idt"])
+    np.testing.assert_array_equal(p.xtra1[:n], g["xtra1"])
+    np.testing.assert_array_equal(p.ytra1[:n], g["ytra1"])
+    np.testing.assert_array_equal(p.ztra1[:n], g["ztra1"])
+    np.testing.assert_array_equal(outs[-1]["gridunc"], g["gridunc_last"])
