@@ -190,3 +190,203 @@ def test_sort_is_transparent_philox():
     for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
         assert np.array_equal(getattr(qa, f)[:4096], getattr(qb, f)[:4096]), f
     assert rel_l2(ga, gb) < 1e-6
+
+
+# ----------------------------------------------------------------------------
+# feature coverage: every branch of the path, strict math (bit-exact) and fast
+# math (tolerance), oracle state re-injected every step
+# ----------------------------------------------------------------------------
+def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=True, exact=True,
+              dt=None, tol_h=1e-5):
+    c = cb.cfg
+    n = p.numpart
+    dt = dt or c.lsynctime
+    m0, m1 = mets or cases.met_pair(cb, bracket[0], bracket[1])
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    eng.fill_rannumb(); ora.fill_rannumb()
+    for e in (eng, ora):
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), bracket)
+    ora.push_particles(p)
+    tot = dict(n_active=0, n_pbl=0, n_petterssen=0, n_terminated=0, n_substeps=0, n_nan_cbl=0)
+    worst = 0.0
+    for k in range(nsteps):
+        itime = t0 + k * dt
+        po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
+        ora.pull_particles(po)
+        eng.push_particles(po)
+        for e in (eng, ora):
+            e.conccalc(itime, 1.0)
+        sg, so = eng.step(itime, 450), ora.step(itime, 450)
+        pg = fb.Particles(c.maxpart, c.nspec); pg.numpart = n
+        eng.pull_particles(pg); ora.pull_particles(po)
+        for key in tot:
+            tot[key] += so[key]
+        assert sg["n_active"] == so["n_active"] and sg["n_init"] == so["n_init"]
+        if exact:
+            assert sg == so, (k, sg, so)
+            for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+                assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (k, f)
+            assert np.array_equal(pg.xmass1[:n], po.xmass1[:n]), k
+        else:
+            assert np.array_equal(pg.itra1[:n], po.itra1[:n]), k
+            live = po.itra1[:n] != fb.ITRA_DEAD
+            dh, dz = pos_rel(pg, po, n, c)
+            # horizontal separation as a distance (longitude differences shrink
+            # with cos(lat): next to a pole a metre is many grid units of x)
+            coslat = np.cos(np.deg2rad(po.ytra1[:n] * c.dy + c.ylat0))
+            ddx = np.abs(pg.xtra1[:n] - po.xtra1[:n])
+            ddx = np.minimum(ddx, c.nxmin1 - ddx) if c.xglobal else ddx
+            dxy = np.hypot(ddx * coslat, pg.ytra1[:n] - po.ytra1[:n]) / c.nxmin1
+            worst = max(worst, dxy[live].max() if live.any() else 0.0)
+            # a sub-step landing on the other side of the 2*href deposition threshold changes one
+            # particle's mass slightly: bound the ensemble (L2) and the total mass
+            relm = np.abs(pg.xmass1[:n] - po.xmass1[:n]) / np.maximum(np.abs(po.xmass1[:n]), 1e-30)
+            assert (relm > 1e-5).mean() < 0.01, k       # integer-decision flips: rare, counted
+            assert abs(pg.xmass1[:n].sum() - po.xmass1[:n].sum()) < 1e-5 * po.xmass1[:n].sum(), k
+    if not exact:
+        assert worst < tol_h, worst
+    gg, go = eng.fetch_grids(), ora.fetch_grids()
+    if check_grids:
+        for name in go:
+            if go[name].size and np.abs(go[name]).sum() > 0:
+                # fast math: the few particles whose deposition threshold / sub-step count flips
+                # put 1e-3-level differences into single deposition cells
+                lim = 1e-5 if (exact or not name.startswith("dry")) else 2e-3
+                assert rel_l2(gg[name], go[name]) < lim, (name, rel_l2(gg[name], go[name]))
+                assert abs(gg[name].sum() - go[name].sum()) <= lim * abs(go[name].sum()), name
+    return tot, gg, go
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_polar_branches(exact):
+    """Particles poleward of +-75 deg use uupol/vvpol and the polar-stereographic
+    position update (src/advance.f90:161-175,754-778; cmapf_mod)."""
+    cb = cases.config_small(nrel=4, npart_each=512, math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    p = cases.seeded_particles(cb, 2048, zmax=9000.0, lat_range=(74.0, 89.9))
+    q = cases.seeded_particles(cb, 1024, zmax=9000.0, lat_range=(-89.9, -74.0), seed=9)
+    p.ytra1[1024:2048] = q.ytra1[:1024]
+    tot, _, _ = _per_step(cb, p, 5, exact=exact, tol_h=2e-5)
+    assert tot["n_active"] == 5 * 2048
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_backward_run(exact):
+    """LDIRECT=-1: negative lsynctime, dt1/dt2 both negative, positions stepped
+    with real(ldirect) (src/advance.f90:285,543,752)."""
+    cb = cases.config_small(nrel=4, npart_each=512, ldirect=-1,
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    assert cb.cfg.lsynctime == -900
+    p = cases.seeded_particles(cb, 2048, zmax=4000.0)
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    tot, _, _ = _per_step(cb, p, 5, mets=mets, bracket=(0, -10800), exact=exact)
+    assert tot["n_active"] == 5 * 2048 and tot["n_pbl"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_method0_hanna1_with_petterssen(exact):
+    """CTL<0: one Langevin step per lsynctime with hanna1, Petterssen corrector
+    on every step (src/advance.f90:829-985)."""
+    cb = cases.config_small(nrel=4, npart_each=512, ctl=-5.0,
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    p = cases.seeded_particles(cb, 2048, zmax=14000.0)
+    tot, _, _ = _per_step(cb, p, 6, exact=exact)
+    assert tot["n_petterssen"] > 0.9 * tot["n_active"]
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_drydep_decay_nested_output_two_species(exact):
+    """Dry-deposition probability + mass split + drydepokernel(_nest), radioactive
+    decay with the ldeltat back-correction, nested output grid, two species, two
+    age classes (src/advance.f90:582-599, src/timemanager.f90:642-707,
+    src/drydepokernel.f90, src/conccalc.f90:301-441)."""
+    cb = cases.config_small(nrel=3, npart_each=700, nspec=2, decay=[0.0, 1.0e-5], drydepspec=[1, 1],
+                            lage=(7200, 86400 * 10), nest=(-60.0, -30.0, 48, 24, 2.5, 2.5),
+                            ioutputforeachrelease=1,
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    assert cb.cfg.drydep == 1 and cb.cfg.nested_output == 1 and cb.cfg.maxpointspec_act == 3
+    p = cases.seeded_particles(cb, 2100, zmax=300.0, lat_range=(-40.0, 40.0))
+    p.itramem[:700] = -30000
+    p.xmass1[:2100, 1] = 0.5
+    tot, gg, go = _per_step(cb, p, 5, exact=exact)
+    assert go["drygridunc"].sum() > 0 and go["drygriduncn"].sum() > 0 and go["griduncn"].sum() > 0
+    assert gg["gridunc"].shape == (72, 36, 4, 5, 3, 1, 2)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_settling(exact):
+    """Gravitational settling for an aerosol species (src/get_settling.f90:52-125)."""
+    cb = cases.config_small(nrel=2, npart_each=512, lsettling=1, density=[2000.0], dquer=[5.0],
+                            vsetaver=[-1.5e-3], cunningham=[1.01],
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    p = cases.seeded_particles(cb, 1024, zmax=9000.0)
+    tot, _, _ = _per_step(cb, p, 4, exact=exact)
+    assert tot["n_active"] == 4 * 1024
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_cbl_skewed_turbulence(exact):
+    """CBLFLAG=1: bi-Gaussian drift/diffusion with re-initialisation
+    (src/cbl.f90, src/re_initialize_particle.f90, src/initialize_cbl_vel.f90)."""
+    cb = cases.config_small(nrel=2, npart_each=512, cblflag=1, ctl=5.0, ifine=4,
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    assert cb.cfg.ifine == 11 and cb.cfg.turbswitch == 1
+    p = cases.seeded_particles(cb, 1024, zmax=1200.0, lat_range=(-50.0, 50.0))
+    tot, _, _ = _per_step(cb, p, 3, exact=exact, tol_h=5e-5)
+    assert tot["n_pbl"] > 0
+
+
+def test_receptors_and_density_weighted_sampling():
+    """Receptor kernel (src/conccalc.f90:451-498) and ind_samp=-1 (xmass/rho,
+    src/conccalc.f90:80-125)."""
+    cb = cases.config_small(nrel=2, npart_each=1500, ind_samp=-1,
+                            receptors=[(36.0, 18.0, 1.0e9), (40.5, 20.2, 2.0e9)], math_mode=fb.MATH_STRICT)
+    p = cases.seeded_particles(cb, 3000, zmax=120.0, lat_range=(-5.0, 15.0))
+    p.xtra1[:3000] = np.random.RandomState(5).uniform(33.0, 43.0, 3000)
+    tot, gg, go = _per_step(cb, p, 3, exact=True)
+    assert go["creceptor"][:2, 0].min() > 0
+    np.testing.assert_allclose(gg["creceptor"], go["creceptor"], rtol=2e-5)
+
+
+def test_terminations_are_bit_exact():
+    """Domain exit on a limited-area grid (nstop=3), max age and minmass
+    terminate particles identically (src/advance.f90:804-808,
+    src/timemanager.f90:630-634,662-707)."""
+    cb = fb.make_config(nx=61, ny=41, nz=40, dx=0.5, dy=0.5, xlon0=0.0, ylat0=40.0,
+                        height=fb.synth_heights(138)[::3][:40], ctl=5.0, ifine=4,
+                        outlon0=0.0, outlat0=40.0, numxgrid=30, numygrid=20, dxout=1.0, dyout=1.0,
+                        lage=(2700,), npart=(800, 800), ioutputforeachrelease=0,
+                        decay=[4.0e-3], math_mode=fb.MATH_STRICT)
+    assert cb.cfg.xglobal == 0
+    p = cases.seeded_particles(cb, 1600, zmax=3000.0, lat_range=(40.5, 59.5))
+    p.xtra1[:1600] = np.random.RandomState(2).uniform(0.2, 59.8, 1600)
+    tot, _, _ = _per_step(cb, p, 4, exact=True, check_grids=False)
+    assert tot["n_terminated"] >= 1600  # everyone dies of age / mass / exit within the run
+
+
+def test_philox_modes_match_reference_statistics():
+    """Production RNG modes are statistically equivalent to the reference stream:
+    mean and spread of the displacement after 6 steps agree within sampling error."""
+    disp = {}
+    for mode in (fb.RNG_REFERENCE, fb.RNG_PHILOX_INDEX, fb.RNG_PHILOX):
+        cb = cases.config_small(nrel=8, npart_each=1024, rng_mode=mode)
+        m0, m1 = cases.met_pair(cb)
+        eng = fb.Engine(cb)
+        eng.fill_rannumb()
+        eng.upload_met(1, m0); eng.upload_met(2, m1)
+        eng.set_met_bracket((1, 2), (0, 10800))
+        p = cases.seeded_particles(cb, 8192, zmax=1500.0, lat_range=(-40.0, 40.0))
+        x0, z0 = p.xtra1[:8192].copy(), p.ztra1[:8192].copy()
+        eng.push_particles(p)
+        for k in range(6):
+            eng.step(k * 900)
+        eng.pull_particles(p)
+        w = cb.cfg.nxmin1
+        disp[mode] = (((p.xtra1[:8192] - x0 + w / 2) % w) - w / 2, p.ztra1[:8192] - z0)
+    rx, rz = disp[fb.RNG_REFERENCE]
+    for mode in (fb.RNG_PHILOX_INDEX, fb.RNG_PHILOX):
+        dx, dz = disp[mode]
+        assert abs(dx.mean() - rx.mean()) < 5 * rx.std() / np.sqrt(8192) + 1e-3
+        assert abs(dx.std() / rx.std() - 1.0) < 0.05
+        assert abs(dz.std() / rz.std() - 1.0) < 0.08
+        assert not np.array_equal(dx, rx)
