@@ -123,6 +123,7 @@ struct fpb_handle {
   int active_rows = -1;  // live rows lead the arrays after a sort (-1: unknown)
   int steps_since_sort = 1 << 30;
   unsigned *d_nlive = nullptr;
+  int *d_work = nullptr;
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
 
@@ -318,6 +319,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   DA(h->row_of_slot, mp);
   sortk_iota(h->row_of_slot, c.maxpart, h->stream);
   DA(h->d_nlive, 1);
+  DA(h->d_work, 1);
   h->launches += 3;
   // itra1(:) = -999999999, src/FLEXPART.f90:315-317
   fill_i32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
@@ -361,7 +363,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(q->us); cudaFree(q->vs); cudaFree(q->ws); cudaFree(q->cbt);
     cudaFree(q->xmass1); cudaFree(q->xscav_frac1); cudaFree(q->slot);
   }
-  cudaFree(h->row_of_slot); cudaFree(h->d_nlive);
+  cudaFree(h->row_of_slot); cudaFree(h->d_nlive); cudaFree(h->d_work);
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
@@ -671,6 +673,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.drygridunc = h->drygridunc;
   a.drygriduncn = h->drygriduncn;
   a.stats = stats ? h->d_stats : nullptr;
+  a.work_counter = h->d_work;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
   // initialize() can only be due for rows pushed since the last step, or at itime 0
   if (h->pending_init || itime == 0) {

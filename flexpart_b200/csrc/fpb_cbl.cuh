@@ -135,7 +135,7 @@ __device__ __noinline__ void cbl_split(float zp, float wst, float h, float sigma
 }
 
 // src/re_initialize_particle.f90:44-91 (draws continue in the rannumb stream)
-__device__ __noinline__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst, float h,
+__device__ __forceinline__ void cbl_reinitialize(const DevCfg &c, Rng &rng, float zp, float wst, float h,
                                  float sigmaw, float ol, float &wp, int &nrand) {
   float aluarw, sigmawa, sigmawb, wa, wb;
   nrand = nrand + 1;

@@ -103,6 +103,7 @@ struct DevStepArgs {
   const int32_t *nrand_adv;  //                      and for advance
   float *drygridunc, *drygriduncn;
   unsigned long long *stats; // 8 counters, fpb_step_stats order
+  int *work_counter;         // next unclaimed particle row (persistent step kernel)
 };
 
 struct DevConcArgs {

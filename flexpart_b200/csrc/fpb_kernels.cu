@@ -87,6 +87,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
+// 4 normals of one Philox block: Box-Muller, clipped to +-3 like gasdev1
+// (src/random_mod.f90:86-89).  Out of line and by value so that the caller's
+// generator state can stay in registers.
+__device__ __noinline__ float4 philox_normals4(uint32_t pid, uint32_t tstep, uint32_t blk, uint2 key) {
+  const uint4 r = philox4x32_10(make_uint4(pid, tstep, 0x52414e44u, blk), key);
+  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = u01(r.y);
+  const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u4 = u01(r.w);
+  const float ra = sqrtf(-2.f * __logf(u1)), rb = sqrtf(-2.f * __logf(u3));
+  float sa, ca, sb, cb;
+  __sincosf(6.28318530718f * u2, &sa, &ca);
+  __sincosf(6.28318530718f * u4, &sb, &cb);
+  return make_float4(fminf(fmaxf(ra * ca, -3.f), 3.f), fminf(fmaxf(ra * sa, -3.f), 3.f),
+                     fminf(fmaxf(rb * cb, -3.f), 3.f), fminf(fmaxf(rb * sb, -3.f), 3.f));
+}
+
 struct Rng {
   const float *tab; // rannumb, 0-based
   int maxrand;
@@ -95,39 +112,23 @@ struct Rng {
   uint32_t pid, tstep;
   // FPB_RNG_PHILOX: cache of the last generated block of 4 normals
   int cblk;
-  float cn[4];
+  float4 cn;
 
   // index stream: replaces ran3 (src/advance.f90:153, src/initialize.f90:68)
-  __device__ float uniform(uint32_t stream) const {
-    uint4 r = philox4x32_10(make_uint4(pid, tstep, stream, 0u), key);
+  __device__ __forceinline__ float uniform(uint32_t stream) const {
+    const uint4 r = philox4x32_10(make_uint4(pid, tstep, stream, 0u), key);
     return u01(r.x);
   }
   // Fortran rannumb(i)
   __device__ __forceinline__ float get(int i) {
     if (mode != FPB_RNG_PHILOX) return __ldg(tab + (i - 1));
-    return get_philox(i);
-  }
-  __device__ __noinline__ float get_philox(int i) {
-    int blk = i >> 2;
+    const int blk = i >> 2;
     if (blk != cblk) {
-      uint4 r = philox4x32_10(make_uint4(pid, tstep, 0x52414e44u, (uint32_t)blk), key);
-      // Box-Muller, clipped to +-3 like gasdev1 (src/random_mod.f90:86-89)
-      float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-      float u2 = u01(r.y);
-      float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
-      float u4 = u01(r.w);
-      float ra = sqrtf(-2.f * __logf(u1)), rb = sqrtf(-2.f * __logf(u3));
-      float sa, ca, sb, cb;
-      __sincosf(6.28318530718f * u2, &sa, &ca);
-      __sincosf(6.28318530718f * u4, &sb, &cb);
-      cn[0] = fminf(fmaxf(ra * ca, -3.f), 3.f);
-      cn[1] = fminf(fmaxf(ra * sa, -3.f), 3.f);
-      cn[2] = fminf(fmaxf(rb * cb, -3.f), 3.f);
-      cn[3] = fminf(fmaxf(rb * sb, -3.f), 3.f);
+      cn = philox_normals4(pid, tstep, (uint32_t)blk, key);
       cblk = blk;
     }
-    int k = i & 3;
-    return k == 0 ? cn[0] : k == 1 ? cn[1] : k == 2 ? cn[2] : cn[3];
+    const int k = i & 3;
+    return k == 0 ? cn.x : k == 1 ? cn.y : k == 2 ? cn.z : cn.w;
   }
 };
 
@@ -786,380 +787,6 @@ __device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, i
   s.wsigold = rng.get(nrand + 2) * wsig;
 }
 
-struct AdvOut {
-  int nstop, nsub, pbl, pett, nan_cbl;
-};
-
-// src/advance.f90:133-985
-template <bool DRYDEP, bool CBL>
-__device__ void do_advance(const DevStepArgs &a, const float *sh, Rng &rng, int nrand,
-                           int nrelpoint, PState &s, float *prob, AdvOut &out) {
-  const DevCfg &c = a.cfg;
-  const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
-  const float eps = c.eps;
-  const float ztop = sh[nz - 1];
-  out.nstop = 0; out.nsub = 0; out.pbl = 0; out.pett = 0; out.nan_cbl = 0;
-
-  float vdepo[DRYDEP ? FPB_MAXSPEC : 1];
-  unsigned depo_todo = 0xffu;
-  if (DRYDEP) {
-#pragma unroll
-    for (int ks = 0; ks < FPB_MAXSPEC; ks++) { prob[ks] = 0.f; vdepo[ks] = 0.f; }
-  }
-
-  float dxsave = 0.f, dysave = 0.f, dawsave = 0.f, dcwsave = 0.f;
-  int itimec = itime;
-
-  const int ngrid = pole_grid(c, s.yt);
-  int ix = d_int(s.xt), jy = d_int(s.yt);
-  const int nix = d_nint(s.xt), njy = d_nint(s.yt);
-  int ixp = ix + 1, jyp = jy + 1;
-  if (jyp >= c.nymax) jyp = jyp - 1;
-
-  Hz z;
-  z.ngrid = ngrid;
-  make_weights(c, z, itime, (float)s.xt, (float)s.yt, ix, jy, ixp, jyp);
-
-  Turb t;
-  {
-    float h = 0.f; // advance.f90:236-252: max over 4 corners x 2 slots
-#pragma unroll
-    for (int m = 0; m < 2; m++) {
-      float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
-      float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
-      if (v0 > h) h = v0;
-      if (v1 > h) h = v1;
-      if (v2 > h) h = v2;
-      if (v3 > h) h = v3;
-    }
-    t.h = h;
-  }
-  const float tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal
-  t.zeta = s.zt / t.h;
-
-  float u = 0.f, v = 0.f, w = 0.f, usig = 0.f, vsig = 0.f, wsig = 0.f;
-  float ux = 0.f, vy = 0.f;
-  int ldt = s.ldt, icbt = s.icbt;
-  float zt = s.zt, up = s.up, vp = s.vp, wp = s.wp;
-  bool above = !(t.zeta <= 1.f);
-
-  if (!above) {
-    out.pbl = 1;
-    interp_surface(a.met, z, t);
-    int indz = 0, indzp = 0; // cached pair
-    Lev lo, hi;
-    int loop = 0;
-    for (;;) {
-      loop++;
-      out.nsub++;
-      if (c.method == 1) {
-        ldt = min(ldt, abs(c.lsynctime - itimec + itime));
-        itimec = itimec + ldt * c.ldirect;
-      } else {
-        ldt = abs(c.lsynctime);
-        itimec = itime + c.lsynctime;
-      }
-      const float dt = (float)ldt;
-      t.zeta = zt / t.h;
-
-      // level pair under the particle; reuse a cached level when possible.
-      // One call site for profile_level so that every lane of the warp that
-      // needs a level gathers it in the same (converged) pass.
-      {
-        const int ni = find_indz(sh, nz, zt), nip = ni + 1;
-        bool need_lo = true, need_hi = true;
-        if (loop != 1) {
-          if (ni == indz) {
-            need_lo = need_hi = false;
-          } else if (ni == indzp) {
-            lo = hi;
-            need_lo = false;
-          } else if (nip == indz) {
-            hi = lo;
-            need_hi = false;
-          }
-        }
-        indz = ni;
-        indzp = nip;
-#pragma unroll 1
-        for (int q = 0; q < 2; q++) {
-          if (q ? need_hi : need_lo) {
-            Lev t_;
-            profile_level(c, a.met, z, ni + q, t_);
-            if (q) hi = t_; else lo = t_;
-          }
-        }
-      }
-
-      // advance.f90:342-350
-      const float dz = 1.f / (sh[indzp - 1] - sh[indz - 1]);
-      const float dz1 = (zt - sh[indz - 1]) * dz;
-      const float dz2 = (sh[indzp - 1] - zt) * dz;
-      u = dz1 * hi.u + dz2 * lo.u;
-      v = dz1 * hi.v + dz2 * lo.v;
-      w = dz1 * hi.w + dz2 * lo.w;
-      const float rhoa = dz1 * hi.rho + dz2 * lo.rho;
-      const float rhograd = dz1 * hi.rhograd + dz2 * lo.rhograd;
-
-      if (c.turbswitch) hanna(t, zt); else hanna1(t, zt);
-
-      // horizontal turbulent velocities, advance.f90:371-384
-      if (nrand + 1 > maxrand) nrand = 1;
-      if (dt / t.tlu < .5f) {
-        up = (1.f - dt / t.tlu) * up + rng.get(nrand) * t.sigu * m_sqrt(2.f * dt / t.tlu);
-      } else {
-        float ru = m_exp(-dt / t.tlu);
-        up = ru * up + rng.get(nrand) * t.sigu * m_sqrt(1.f - ru * ru);
-      }
-      if (dt / t.tlv < .5f) {
-        vp = (1.f - dt / t.tlv) * vp + rng.get(nrand + 1) * t.sigv * m_sqrt(2.f * dt / t.tlv);
-      } else {
-        float rv = m_exp(-dt / t.tlv);
-        vp = rv * vp + rng.get(nrand + 1) * t.sigv * m_sqrt(1.f - rv * rv);
-      }
-      nrand = nrand + 2;
-
-      if (nrand + c.ifine > maxrand) nrand = 1;
-      const float rhoaux = rhograd / rhoa;
-      const float dtf = dt * c.fine;
-      const float dtftlw = dtf / t.tlw;
-
-      // vertical component in ifine short steps, advance.f90:396-498
-      for (int i = 1; i <= c.ifine; i++) {
-        float delz;
-        if (c.turbswitch) {
-          if (dtftlw < .5f) {
-            if (CBL && c.cblflag == 1) {
-              if (-t.h / t.ol > 5.f) {
-                int flagrein = 0;
-                nrand = nrand + 1;
-                float old_wp_buf = wp, ath, bth;
-                cbl_drift(c, wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol,
-                          ath, bth, flagrein);
-                wp = (wp + ath * dtf + bth * rng.get(nrand) * m_sqrt(dtf)) * (float)icbt;
-                delz = wp * dtf;
-                if (flagrein == 1) {
-                  cbl_reinitialize(c, rng, zt, t.wst, t.h, t.sigw, t.ol, old_wp_buf, nrand);
-                  wp = old_wp_buf;
-                  delz = wp * dtf;
-                  out.nan_cbl++;
-                }
-              } else {
-                nrand = nrand + 1;
-                float ath = -wp / t.tlw + t.sigw * t.dsigwdz + wp * wp / t.sigw * t.dsigwdz +
-                            t.sigw * t.sigw / rhoa * rhograd;
-                float bth = t.sigw * rng.get(nrand) * m_sqrt(2.f * dtftlw);
-                wp = (wp + ath * dtf + bth) * (float)icbt;
-                delz = wp * dtf;
-                float del_test = (1.f - wp) / wp;
-                if (isnan(wp) || isnan(del_test)) {
-                  nrand = nrand + 1;
-                  wp = t.sigw * rng.get(nrand);
-                  delz = wp * dtf;
-                  out.nan_cbl++;
-                }
-              }
-            } else {
-              wp = ((1.f - dtftlw) * wp + rng.get(nrand + i) * m_sqrt(2.f * dtftlw) +
-                    dtf * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
-              delz = wp * t.sigw * dtf;
-            }
-          } else {
-            float rw = m_exp(-dtftlw);
-            wp = (rw * wp + rng.get(nrand + i) * m_sqrt(1.f - rw * rw) +
-                  t.tlw * (1.f - rw) * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
-            delz = wp * t.sigw * dtf;
-          }
-        } else {
-          float rw = m_exp(-dtftlw);
-          wp = (rw * wp + rng.get(nrand + i) * m_sqrt(1.f - rw * rw) * t.sigw +
-                t.tlw * (1.f - rw) * (t.dsigw2dz + rhoaux * (t.sigw * t.sigw))) * (float)icbt;
-          delz = wp * dtf;
-        }
-        if (c.turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
-
-        if (fabsf(delz) > t.h) delz = fmodf(delz, t.h);
-        if (delz < -zt) {            // reflection at the ground
-          icbt = -1;
-          zt = -zt - delz;
-        } else if (delz > (t.h - zt)) { // reflection at h
-          icbt = -1;
-          zt = -zt - delz + 2.f * t.h;
-        } else {
-          icbt = 1;
-          zt = zt + delz;
-        }
-        if (i != c.ifine) {
-          t.zeta = zt / t.h;
-          hanna_short(t, zt);
-        }
-      }
-      if (!(CBL && c.cblflag == 1)) nrand = nrand + (c.ifine + 1);
-
-      // next time step, advance.f90:504-510
-      if (c.turbswitch) {
-        float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp * t.sigw), 1.e-5f));
-        q = fminf(q, 0.5f / fabsf(t.dsigwdz));
-        ldt = f_int(q * c.ctl);
-      } else {
-        float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp), 1.e-5f));
-        ldt = f_int(q * c.ctl);
-      }
-      ldt = max(ldt, c.mintime);
-
-      w = w + settling_term(a, sh, nrelpoint, s.xt, s.yt, zt);
-
-      dxsave = dxsave + u * dt;
-      dysave = dysave + v * dt;
-      dawsave = dawsave + up * dt;
-      dcwsave = dcwsave + vp * dt;
-      zt = zt + w * dt * (float)c.ldirect;
-
-      if (zt >= ztop) zt = ztop - 100.f * eps;
-
-      if (zt > t.h) {
-        if (itimec == itime + c.lsynctime) {
-          // "defined" behaviour for the stale-usig case
-          usig = 0.5f * (hi.usig + lo.usig);
-          vsig = 0.5f * (hi.vsig + lo.vsig);
-          wsig = 0.5f * (hi.wsig + lo.wsig);
-        } else {
-          above = true;
-        }
-        break;
-      }
-
-      // dry-deposition probability, advance.f90:582-599
-      if (DRYDEP && c.drydep && (zt < 2.f * HREF)) {
-#pragma unroll
-        for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
-          if (ks < c.nspec && c.drydepspec[ks]) {
-            if (depo_todo & (1u << ks)) { // interpol_vdep, src/interpol_vdep.f90:39-54
-              const int off = ks * (c.nxd * c.nyd);
-              float y0 = bil(z, __ldg(a.met[0].vdep + off + z.o00), __ldg(a.met[0].vdep + off + z.o10),
-                             __ldg(a.met[0].vdep + off + z.o01), __ldg(a.met[0].vdep + off + z.o11));
-              float y1 = bil(z, __ldg(a.met[1].vdep + off + z.o00), __ldg(a.met[1].vdep + off + z.o10),
-                             __ldg(a.met[1].vdep + off + z.o01), __ldg(a.met[1].vdep + off + z.o11));
-              vdepo[ks] = (y0 * z.dt2 + y1 * z.dt1) * z.dtt;
-              depo_todo &= ~(1u << ks);
-            }
-            prob[ks] = 1.f + (prob[ks] - 1.f) * m_exp(-vdepo[ks] * fabsf(dt) / (2.f * HREF));
-          }
-        }
-      }
-
-      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
-
-      if (itimec == (itime + c.lsynctime)) {
-        usig = 0.5f * (hi.usig + lo.usig);
-        vsig = 0.5f * (hi.vsig + lo.vsig);
-        wsig = 0.5f * (hi.wsig + lo.wsig);
-        break;
-      }
-    }
-  }
-
-  if (above) { // label 700, advance.f90:629-708
-    interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
-    ldt = abs(c.lsynctime - itimec + itime);
-    const float dt = (float)ldt;
-    if (zt < tropop) {
-      float uxscale = m_sqrt(2.f * c.d_trop / dt);
-      if (nrand + 1 > maxrand) nrand = 1;
-      ux = rng.get(nrand) * uxscale;
-      vy = rng.get(nrand + 1) * uxscale;
-      nrand = nrand + 2;
-      wp = 0.f;
-    } else if (zt < tropop + 1000.f) {
-      float weight = (zt - tropop) / 1000.f;
-      float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
-      if (nrand + 2 > maxrand) nrand = 1;
-      ux = rng.get(nrand) * uxscale;
-      vy = rng.get(nrand + 1) * uxscale;
-      float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
-      wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
-      nrand = nrand + 3;
-    } else {
-      if (nrand > maxrand) nrand = 1;
-      ux = 0.f;
-      vy = 0.f;
-      float wpscale = m_sqrt(2.f * c.d_strat / dt);
-      wp = rng.get(nrand) * wpscale;
-      nrand = nrand + 1;
-    }
-    if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
-
-    w = w + settling_term(a, sh, nrelpoint, s.xt, s.yt, zt);
-
-    dxsave = dxsave + (u + ux) * dt;
-    dysave = dysave + (v + vy) * dt;
-    zt = zt + (w + wp) * dt * (float)c.ldirect;
-    if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
-  }
-
-  // label 99: mesoscale fluctuations, advance.f90:728-739
-  {
-    float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
-    float rs = m_sqrt(1.f - r * r);
-    if (nrand + 2 > maxrand) nrand = 1;
-    s.usigold = r * s.usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
-    s.vsigold = r * s.vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
-    s.wsigold = r * s.wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
-    dxsave = dxsave + s.usigold * (float)c.lsynctime;
-    dysave = dysave + s.vsigold * (float)c.lsynctime;
-    zt = zt + s.wsigold * (float)c.lsynctime;
-    if (zt < 0.f) zt = -1.f * zt;
-  }
-
-  // advance.f90:747-778
-  windalign(dxsave, dysave, dawsave, dcwsave, ux, vy);
-  dxsave = dxsave + ux;
-  dysave = dysave + vy;
-  double xt = s.xt, yt = s.yt;
-  move_horizontal(c, ngrid, xt, yt, dxsave, dysave, (float)c.ldirect);
-
-  bool done = false;
-  if (wrap_and_check(c, xt, yt)) {
-    out.nstop = 3;
-    done = true;
-  }
-  if (!done) {
-    if (zt >= ztop) zt = ztop - 100.f * eps;
-    // Petterssen corrector, advance.f90:829-985
-    if (ldt != abs(c.lsynctime)) done = true;
-    else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
-    else if (pole_grid(c, yt) != ngrid) done = true;
-  }
-  if (!done) {
-    ix = d_int(xt);
-    jy = d_int(yt);
-    ixp = ix + 1;
-    jyp = jy + 1;
-    if (jyp >= c.nymax) jyp = jyp - 1;
-    const float uold = u, vold = v, wold = w;
-    make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
-    float d0, d1, d2;
-    interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
-    out.pett = 1;
-    w = w + settling_term(a, sh, nrelpoint, xt, yt, zt);
-    u = (u - uold) / 2.f;
-    v = (v - vold) / 2.f;
-    w = (w - wold) / 2.f;
-    zt = zt + w * (float)(ldt * c.ldirect);
-    if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
-    move_horizontal(c, ngrid, xt, yt, u, v, (float)(ldt * c.ldirect));
-    if (wrap_and_check(c, xt, yt)) {
-      out.nstop = 3;
-    } else if (zt >= ztop) {
-      zt = ztop - 100.f * eps;
-    }
-  }
-
-  s.xt = xt; s.yt = yt; s.zt = zt;
-  s.up = up; s.vp = vp; s.wp = wp;
-  s.ldt = ldt; s.icbt = icbt;
-}
-
 __device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
   return (unsigned long long)__reduce_add_sync(0xffffffffu, v);
 }
@@ -1212,118 +839,7 @@ fpb_init_kernel(const __grid_constant__ DevStepArgs a) {
   }
 }
 
-template <bool DRYDEP, bool CBL>
-__global__ void __launch_bounds__(128, FPB_STEP_MIN_BLOCKS)
-fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
-  const DevCfg &c = a.cfg;
-  __shared__ float sh[FPB_MAXNZ];
-  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
-  __syncthreads();
-
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int itime = c.itime;
-  unsigned n_act = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
-
-  if (j < c.numpart && a.p.itra1[j] == itime) {
-    n_act = 1;
-    const int itramem = a.p.itramem[j];
-    const int npoint = a.p.npoint[j];
-    const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
-    const int itage = abs(itime - itramem);
-    int nage;
-    for (nage = 1; nage <= c.nageclass; nage++)
-      if (itage < c.lage[nage - 1]) break;
-
-    PState s;
-    s.xt = a.p.xtra1[j];
-    s.yt = a.p.ytra1[j];
-    s.zt = a.p.ztra1[j];
-    s.ldt = a.p.idt[j];
-    s.up = a.p.uap[j]; s.vp = a.p.ucp[j]; s.wp = a.p.uzp[j];
-    s.usigold = a.p.us[j]; s.vsigold = a.p.vs[j]; s.wsigold = a.p.ws[j];
-    s.icbt = a.p.cbt[j];
-
-    const int slot = a.p.slot[j];
-    Rng rng;
-    make_rng(c, a.rannumb, slot, rng);
-
-    float prob[FPB_MAXSPEC];
-    AdvOut out;
-    {
-      int nrand;
-      if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[slot];
-      else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 64;
-      else nrand = f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
-      do_advance<DRYDEP, CBL>(a, sh, rng, nrand, npoint, s, prob, out);
-    }
-    n_pbl = out.pbl; n_sub = out.nsub; n_pett = out.pett; n_nan = out.nan_cbl;
-
-    // src/timemanager.f90:630-707
-    int itra1;
-    if (out.nstop > 1) {
-      itra1 = FPB_ITRA_DEAD;
-      n_term = 1;
-    } else {
-      itra1 = itime + c.lsynctime;
-      float xmassfract = 0.f;
-      float drydeposit[FPB_MAXSPEC];
-      for (int ks = 0; ks < c.nspec; ks++) {
-        float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
-        float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
-        drydeposit[ks] = 0.f;
-        if (c.drydepspec[ks]) {
-          const float pr = DRYDEP ? prob[ks] : 0.f;
-          drydeposit[ks] = xm1 * pr * decfact;
-          xm1 = xm1 * (1.f - pr) * decfact;
-          if (c.decay[ks] > 0.f)
-            drydeposit[ks] = drydeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
-        } else {
-          xm1 = xm1 * decfact;
-        }
-        a.p.xmass1[(size_t)ks * a.p.maxpart + j] = xm1;
-        if (c.mdomainfill == 0 && c.mquasilag == 0) {
-          float xm = __ldg(a.xmass + ks * c.numpoint + (npoint - 1));
-          if (xm > 0.f)
-            xmassfract = fmaxf(xmassfract, (float)__ldg(a.npart + npoint - 1) * xm1 / xm);
-        } else {
-          xmassfract = 1.0f;
-        }
-      }
-      if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; n_term = 1; }
-
-      if (DRYDEP && c.drydep && (c.ldirect == 1)) {
-        const int nclass = a.p.nclass[j];
-        drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)s.xt, (float)s.yt, nage, kp);
-        if (c.nested_output == 1)
-          drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)s.xt, (float)s.yt, nage, kp);
-      }
-      if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; n_term = 1; }
-    }
-
-    a.p.xtra1[j] = s.xt;
-    a.p.ytra1[j] = s.yt;
-    a.p.ztra1[j] = s.zt;
-    a.p.itra1[j] = itra1;
-    a.p.idt[j] = s.ldt;
-    a.p.uap[j] = s.up; a.p.ucp[j] = s.vp; a.p.uzp[j] = s.wp;
-    a.p.us[j] = s.usigold; a.p.vs[j] = s.vsigold; a.p.ws[j] = s.wsigold;
-    a.p.cbt[j] = (int16_t)s.icbt;
-  }
-
-  if (a.stats) {
-    unsigned long long v0 = warp_sum(n_act), v2 = warp_sum(n_term),
-                       v3 = warp_sum(n_pbl), v4 = warp_sum(n_sub), v5 = warp_sum(n_pett),
-                       v6 = warp_sum(n_nan);
-    if ((threadIdx.x & 31) == 0 && v0) {
-      atomicAdd(a.stats + 0, v0);
-      if (v2) atomicAdd(a.stats + 2, v2);
-      if (v3) atomicAdd(a.stats + 3, v3);
-      if (v4) atomicAdd(a.stats + 4, v4);
-      if (v5) atomicAdd(a.stats + 5, v5);
-      if (v6) atomicAdd(a.stats + 6, v6);
-    }
-  }
-}
+#include "fpb_step.cuh"
 
 // ======================================================= conccalc kernel ===
 // A grid cell is named by a species-free key
@@ -1579,9 +1095,22 @@ void FPB_SUF(fpbk_init)(const DevStepArgs &a, cudaStream_t st) {
 }
 
 void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
-  const int nb = (a.cfg.numpart + 127) / 128;
-  if (nb == 0) return;
+  if (a.cfg.numpart <= 0) return;
   const bool full = a.cfg.drydep || a.cfg.cblflag == 1;
+  // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
+  static int resident[2] = {0, 0};
+  int &res = resident[full ? 1 : 0];
+  if (res == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_step_kernel<true, true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_step_kernel<false, false>, 128, 0);
+    res = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int want = (a.cfg.numpart + 127) / 128;
+  const int nb = want < res ? want : res;
+  cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
   if (full) fpb_step_kernel<true, true><<<nb, 128, 0, st>>>(a);
   else fpb_step_kernel<false, false><<<nb, 128, 0, st>>>(a);
 }

@@ -1,0 +1,573 @@
+// fpb_step.cuh -- advance() + the timemanager loop body as a per-lane state
+// machine.  Included inside the anonymous namespace of fpb_kernels.cu.
+//
+// The reference processes one particle start to finish (src/advance.f90:133-985
+// called from src/timemanager.f90:531-712).  The number of Langevin sub-steps
+// per call varies by an order of magnitude between particles (ldt follows the
+// local Lagrangian time scale), so "one thread = one particle, start to
+// finish" leaves most lanes of a warp idle.  Here a lane owns a particle only
+// while it has work, and the three pieces of advance() are separate phases
+// that a warp runs when enough of its lanes need them:
+//
+//   PROLOGUE  src/advance.f90:133-267 + :276 (first interpol_all pieces):
+//             load state, grid choice, weights, mixing height, branch choice
+//   SUBSTEP   one pass of the label-100 loop, src/advance.f90:282-609
+//   EPILOGUE  label 700 (above-PBL step), label 99 (mesoscale, windalign,
+//             position update, wrap/exit), Petterssen, then the rest of the
+//             timemanager loop body (src/timemanager.f90:630-707) and the store
+//
+// A lane that finishes its sub-steps parks in PENDING until enough lanes are
+// ready for the epilogue; idle lanes pull the next particle rows from a global
+// counter in batches.  Per-particle arithmetic and its order are unchanged, so
+// the strict build stays bit-identical to the oracle.
+
+enum : int { PH_IDLE = 0, PH_RUN = 1, PH_PENDING = 2 };
+
+template <bool DRYDEP, bool CBL>
+struct ParticleTask {
+  // --- identity / phase
+  int j, slot, phase;
+  // --- advance() arguments
+  double xt, yt;
+  float zt, up, vp, wp, usigold, vsigold, wsigold;
+  int ldt, icbt;
+  // --- advance() locals that live across sub-steps
+  int nrand, itimec, loop;
+  Hz z;
+  Turb t;
+  Lev lo, hi;
+  int indz, indzp;
+  float dxsave, dysave, dawsave, dcwsave;
+  float u, v, w, usig, vsig, wsig;
+  float tropop;
+  bool above;
+  int nsub, nan_cbl;
+  Rng rng;
+  float prob[DRYDEP ? FPB_MAXSPEC : 1];
+  float vdepo[DRYDEP ? FPB_MAXSPEC : 1];
+  unsigned depo_todo;
+
+  // ------------------------------------------------------------ PROLOGUE --
+  __device__ __forceinline__ void prologue(const DevStepArgs &a, const float *sh, int row) {
+    const DevCfg &c = a.cfg;
+    j = row;
+    slot = a.p.slot[row];
+    xt = a.p.xtra1[row];
+    yt = a.p.ytra1[row];
+    zt = a.p.ztra1[row];
+    ldt = a.p.idt[row];
+    up = a.p.uap[row]; vp = a.p.ucp[row]; wp = a.p.uzp[row];
+    usigold = a.p.us[row]; vsigold = a.p.vs[row]; wsigold = a.p.ws[row];
+    icbt = a.p.cbt[row];
+
+    make_rng(c, a.rannumb, slot, rng);
+    if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[slot];
+    else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 64;
+    else nrand = f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
+
+    if (DRYDEP) {
+#pragma unroll
+      for (int ks = 0; ks < FPB_MAXSPEC; ks++) { prob[ks] = 0.f; vdepo[ks] = 0.f; }
+    }
+    depo_todo = 0xffu;
+    dxsave = 0.f; dysave = 0.f; dawsave = 0.f; dcwsave = 0.f;
+    itimec = c.itime;
+    nsub = 0; nan_cbl = 0; loop = 0;
+    u = v = w = usig = vsig = wsig = 0.f;
+    indz = indzp = 0;
+
+    z.ngrid = pole_grid(c, yt);
+    const int ix = d_int(xt), jy = d_int(yt);
+    const int nix = d_nint(xt), njy = d_nint(yt);
+    int ixp = ix + 1, jyp = jy + 1;
+    if (jyp >= c.nymax) jyp = jyp - 1;
+    make_weights(c, z, c.itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
+
+    float h = 0.f; // advance.f90:236-252: max over 4 corners x 2 slots
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
+      const float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
+      if (v0 > h) h = v0;
+      if (v1 > h) h = v1;
+      if (v2 > h) h = v2;
+      if (v3 > h) h = v3;
+    }
+    t.h = h;
+    tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal, advance.f90:253
+    t.zeta = zt / t.h;
+    above = !(t.zeta <= 1.f);
+    if (!above) {
+      interp_surface(a.met, z, t);
+      phase = PH_RUN;
+    } else {
+      phase = PH_PENDING;
+    }
+  }
+
+  // ------------------------------------------------------------- SUBSTEP --
+  // one pass of the label-100 loop; leaves phase == PH_RUN to continue
+  __device__ __forceinline__ void substep(const DevStepArgs &a, const float *sh) {
+    const DevCfg &c = a.cfg;
+    const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
+    loop++;
+    nsub++;
+    if (c.method == 1) {
+      ldt = min(ldt, abs(c.lsynctime - itimec + itime));
+      itimec = itimec + ldt * c.ldirect;
+    } else {
+      ldt = abs(c.lsynctime);
+      itimec = itime + c.lsynctime;
+    }
+    const float dt = (float)ldt;
+    t.zeta = zt / t.h;
+
+    // level pair under the particle (src/advance.f90:310-331); a level computed
+    // again gives the same bits as the reference's cached one
+    {
+      int ni;
+      if (loop != 1 && sh[indz - 1] <= zt && sh[indzp - 1] > zt) ni = indz;  // still between the same levels
+      else ni = find_indz(sh, nz, zt);
+      const int nip = ni + 1;
+      bool need_lo = true, need_hi = true;
+      if (loop != 1) {
+        if (ni == indz) {
+          need_lo = need_hi = false;
+        } else if (ni == indzp) {
+          lo = hi;
+          need_lo = false;
+        } else if (nip == indz) {
+          hi = lo;
+          need_hi = false;
+        }
+      }
+      indz = ni;
+      indzp = nip;
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) {
+        if (q ? need_hi : need_lo) {
+          Lev t_;
+          profile_level(c, a.met, z, ni + q, t_);
+          if (q) hi = t_; else lo = t_;
+        }
+      }
+    }
+
+    // advance.f90:342-350
+    const float dz = 1.f / (sh[indzp - 1] - sh[indz - 1]);
+    const float dz1 = (zt - sh[indz - 1]) * dz;
+    const float dz2 = (sh[indzp - 1] - zt) * dz;
+    u = dz1 * hi.u + dz2 * lo.u;
+    v = dz1 * hi.v + dz2 * lo.v;
+    w = dz1 * hi.w + dz2 * lo.w;
+    const float rhoa = dz1 * hi.rho + dz2 * lo.rho;
+    const float rhograd = dz1 * hi.rhograd + dz2 * lo.rhograd;
+
+    if (c.turbswitch) hanna(t, zt); else hanna1(t, zt);
+
+    // horizontal turbulent velocities, advance.f90:371-384
+    if (nrand + 1 > maxrand) nrand = 1;
+    const float r_up = rng.get(nrand), r_vp = rng.get(nrand + 1);
+    nrand = nrand + 2;
+    if (nrand + c.ifine > maxrand) nrand = 1;
+    // first vertical normal requested early so its latency hides behind the u/v update
+    float r_w = (CBL && c.cblflag == 1) ? 0.f : rng.get(nrand + 1);
+    if (dt / t.tlu < .5f) {
+      up = (1.f - dt / t.tlu) * up + r_up * t.sigu * m_sqrt(2.f * dt / t.tlu);
+    } else {
+      const float ru = m_exp(-dt / t.tlu);
+      up = ru * up + r_up * t.sigu * m_sqrt(1.f - ru * ru);
+    }
+    if (dt / t.tlv < .5f) {
+      vp = (1.f - dt / t.tlv) * vp + r_vp * t.sigv * m_sqrt(2.f * dt / t.tlv);
+    } else {
+      const float rv = m_exp(-dt / t.tlv);
+      vp = rv * vp + r_vp * t.sigv * m_sqrt(1.f - rv * rv);
+    }
+
+    const float rhoaux = rhograd / rhoa;
+    const float dtf = dt * c.fine;
+    const float dtftlw = dtf / t.tlw;
+
+    // vertical component in ifine short steps, advance.f90:396-498
+    for (int i = 1; i <= c.ifine; i++) {
+      float delz;
+      // next iteration's normal (table modes: plain loads, harmless past the end)
+      const float r_w_next = (CBL && c.cblflag == 1) ? 0.f : rng.get(nrand + i + 1);
+      if (c.turbswitch) {
+        if (dtftlw < .5f) {
+          if (CBL && c.cblflag == 1) {
+            if (-t.h / t.ol > 5.f) {
+              int flagrein = 0;
+              nrand = nrand + 1;
+              float old_wp_buf = wp, ath, bth;
+              cbl_drift(c, wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol,
+                        ath, bth, flagrein);
+              wp = (wp + ath * dtf + bth * rng.get(nrand) * m_sqrt(dtf)) * (float)icbt;
+              delz = wp * dtf;
+              if (flagrein == 1) {
+                cbl_reinitialize(c, rng, zt, t.wst, t.h, t.sigw, t.ol, old_wp_buf, nrand);
+                wp = old_wp_buf;
+                delz = wp * dtf;
+                nan_cbl++;
+              }
+            } else {
+              nrand = nrand + 1;
+              const float ath = -wp / t.tlw + t.sigw * t.dsigwdz + wp * wp / t.sigw * t.dsigwdz +
+                                t.sigw * t.sigw / rhoa * rhograd;
+              const float bth = t.sigw * rng.get(nrand) * m_sqrt(2.f * dtftlw);
+              wp = (wp + ath * dtf + bth) * (float)icbt;
+              delz = wp * dtf;
+              const float del_test = (1.f - wp) / wp;
+              if (isnan(wp) || isnan(del_test)) {
+                nrand = nrand + 1;
+                wp = t.sigw * rng.get(nrand);
+                delz = wp * dtf;
+                nan_cbl++;
+              }
+            }
+          } else {
+            wp = ((1.f - dtftlw) * wp + r_w * m_sqrt(2.f * dtftlw) +
+                  dtf * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
+            delz = wp * t.sigw * dtf;
+          }
+        } else {
+          const float rw = m_exp(-dtftlw);
+          const float r_ = (CBL && c.cblflag == 1) ? rng.get(nrand + i) : r_w;
+          wp = (rw * wp + r_ * m_sqrt(1.f - rw * rw) +
+                t.tlw * (1.f - rw) * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
+          delz = wp * t.sigw * dtf;
+        }
+      } else {
+        const float rw = m_exp(-dtftlw);
+        wp = (rw * wp + r_w * m_sqrt(1.f - rw * rw) * t.sigw +
+              t.tlw * (1.f - rw) * (t.dsigw2dz + rhoaux * (t.sigw * t.sigw))) * (float)icbt;
+        delz = wp * dtf;
+      }
+      r_w = r_w_next;
+      if (c.turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
+
+      if (fabsf(delz) > t.h) delz = fmodf(delz, t.h);
+      if (delz < -zt) {               // reflection at the ground
+        icbt = -1;
+        zt = -zt - delz;
+      } else if (delz > (t.h - zt)) { // reflection at h
+        icbt = -1;
+        zt = -zt - delz + 2.f * t.h;
+      } else {
+        icbt = 1;
+        zt = zt + delz;
+      }
+      if (i != c.ifine) {
+        t.zeta = zt / t.h;
+        hanna_short(t, zt);
+      }
+    }
+    if (!(CBL && c.cblflag == 1)) nrand = nrand + (c.ifine + 1);
+
+    // next time step, advance.f90:504-510
+    if (c.turbswitch) {
+      float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp * t.sigw), 1.e-5f));
+      q = fminf(q, 0.5f / fabsf(t.dsigwdz));
+      ldt = f_int(q * c.ctl);
+    } else {
+      const float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp), 1.e-5f));
+      ldt = f_int(q * c.ctl);
+    }
+    ldt = max(ldt, c.mintime);
+
+    w = w + settling_term(a, sh, a.p.npoint[j], xt, yt, zt);
+
+    dxsave = dxsave + u * dt;
+    dysave = dysave + v * dt;
+    dawsave = dawsave + up * dt;
+    dcwsave = dcwsave + vp * dt;
+    zt = zt + w * dt * (float)c.ldirect;
+
+    const float ztop = sh[nz - 1];
+    if (zt >= ztop) zt = ztop - 100.f * c.eps;
+
+    if (zt > t.h) {
+      if (itimec == itime + c.lsynctime) {
+        // "defined" behaviour for the stale-usig case
+        usig = 0.5f * (hi.usig + lo.usig);
+        vsig = 0.5f * (hi.vsig + lo.vsig);
+        wsig = 0.5f * (hi.wsig + lo.wsig);
+      } else {
+        above = true;
+      }
+      phase = PH_PENDING;
+      return;
+    }
+
+    // dry-deposition probability, advance.f90:582-599
+    if (DRYDEP && c.drydep && (zt < 2.f * HREF)) {
+#pragma unroll
+      for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
+        if (ks < c.nspec && c.drydepspec[ks]) {
+          if (depo_todo & (1u << ks)) { // interpol_vdep, src/interpol_vdep.f90:39-54
+            const int off = ks * (c.nxd * c.nyd);
+            const float y0 = bil(z, __ldg(a.met[0].vdep + off + z.o00), __ldg(a.met[0].vdep + off + z.o10),
+                                 __ldg(a.met[0].vdep + off + z.o01), __ldg(a.met[0].vdep + off + z.o11));
+            const float y1 = bil(z, __ldg(a.met[1].vdep + off + z.o00), __ldg(a.met[1].vdep + off + z.o10),
+                                 __ldg(a.met[1].vdep + off + z.o01), __ldg(a.met[1].vdep + off + z.o11));
+            vdepo[ks] = (y0 * z.dt2 + y1 * z.dt1) * z.dtt;
+            depo_todo &= ~(1u << ks);
+          }
+          prob[ks] = 1.f + (prob[ks] - 1.f) * m_exp(-vdepo[ks] * fabsf(dt) / (2.f * HREF));
+        }
+      }
+    }
+
+    if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+
+    if (itimec == (itime + c.lsynctime)) {
+      usig = 0.5f * (hi.usig + lo.usig);
+      vsig = 0.5f * (hi.vsig + lo.vsig);
+      wsig = 0.5f * (hi.wsig + lo.wsig);
+      phase = PH_PENDING;
+    }
+  }
+
+  // ------------------------------------------------------------ EPILOGUE --
+  struct Counts { unsigned term, pett; };
+
+  __device__ __forceinline__ Counts epilogue(const DevStepArgs &a, const float *sh) {
+    const DevCfg &c = a.cfg;
+    const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
+    const float eps = c.eps;
+    const float ztop = sh[nz - 1];
+    const int npoint = a.p.npoint[j];
+    Counts cnt;
+    cnt.term = 0; cnt.pett = 0;
+    float ux = 0.f, vy = 0.f;
+    int nstop = 0;
+
+    if (above) { // label 700, advance.f90:629-708
+      interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
+      ldt = abs(c.lsynctime - itimec + itime);
+      const float dt = (float)ldt;
+      if (zt < tropop) {
+        const float uxscale = m_sqrt(2.f * c.d_trop / dt);
+        if (nrand + 1 > maxrand) nrand = 1;
+        ux = rng.get(nrand) * uxscale;
+        vy = rng.get(nrand + 1) * uxscale;
+        nrand = nrand + 2;
+        wp = 0.f;
+      } else if (zt < tropop + 1000.f) {
+        const float weight = (zt - tropop) / 1000.f;
+        const float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
+        if (nrand + 2 > maxrand) nrand = 1;
+        ux = rng.get(nrand) * uxscale;
+        vy = rng.get(nrand + 1) * uxscale;
+        const float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
+        wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
+        nrand = nrand + 3;
+      } else {
+        if (nrand > maxrand) nrand = 1;
+        ux = 0.f;
+        vy = 0.f;
+        const float wpscale = m_sqrt(2.f * c.d_strat / dt);
+        wp = rng.get(nrand) * wpscale;
+        nrand = nrand + 1;
+      }
+      if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
+
+      w = w + settling_term(a, sh, npoint, xt, yt, zt);
+
+      dxsave = dxsave + (u + ux) * dt;
+      dysave = dysave + (v + vy) * dt;
+      zt = zt + (w + wp) * dt * (float)c.ldirect;
+      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+    }
+
+    // label 99: mesoscale fluctuations, advance.f90:728-739
+    {
+      const float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
+      const float rs = m_sqrt(1.f - r * r);
+      if (nrand + 2 > maxrand) nrand = 1;
+      usigold = r * usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
+      vsigold = r * vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
+      wsigold = r * wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
+      dxsave = dxsave + usigold * (float)c.lsynctime;
+      dysave = dysave + vsigold * (float)c.lsynctime;
+      zt = zt + wsigold * (float)c.lsynctime;
+      if (zt < 0.f) zt = -1.f * zt;
+    }
+
+    // advance.f90:747-778
+    windalign(dxsave, dysave, dawsave, dcwsave, ux, vy);
+    dxsave = dxsave + ux;
+    dysave = dysave + vy;
+    const int ngrid = z.ngrid;
+    move_horizontal(c, ngrid, xt, yt, dxsave, dysave, (float)c.ldirect);
+
+    bool done = false;
+    if (wrap_and_check(c, xt, yt)) {
+      nstop = 3;
+      done = true;
+    }
+    if (!done) {
+      if (zt >= ztop) zt = ztop - 100.f * eps;
+      // Petterssen corrector, advance.f90:829-985
+      if (ldt != abs(c.lsynctime)) done = true;
+      else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
+      else if (pole_grid(c, yt) != ngrid) done = true;
+    }
+    if (!done) {
+      const int ix = d_int(xt), jy = d_int(yt);
+      const int ixp = ix + 1;
+      int jyp = jy + 1;
+      if (jyp >= c.nymax) jyp = jyp - 1;
+      const float uold = u, vold = v, wold = w;
+      make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
+      float d0, d1, d2;
+      interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
+      cnt.pett = 1;
+      w = w + settling_term(a, sh, npoint, xt, yt, zt);
+      u = (u - uold) / 2.f;
+      v = (v - vold) / 2.f;
+      w = (w - wold) / 2.f;
+      zt = zt + w * (float)(ldt * c.ldirect);
+      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
+      move_horizontal(c, ngrid, xt, yt, u, v, (float)(ldt * c.ldirect));
+      if (wrap_and_check(c, xt, yt)) {
+        nstop = 3;
+      } else if (zt >= ztop) {
+        zt = ztop - 100.f * eps;
+      }
+    }
+
+    // ---- rest of the timemanager loop body, src/timemanager.f90:630-707
+    const int itramem = a.p.itramem[j];
+    int itra1;
+    if (nstop > 1) {
+      itra1 = FPB_ITRA_DEAD;
+      cnt.term = 1;
+    } else {
+      itra1 = itime + c.lsynctime;
+      float xmassfract = 0.f;
+      float drydeposit[FPB_MAXSPEC];
+      for (int ks = 0; ks < c.nspec; ks++) {
+        float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
+        const float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
+        drydeposit[ks] = 0.f;
+        if (c.drydepspec[ks]) {
+          const float pr = DRYDEP ? prob[ks] : 0.f;
+          drydeposit[ks] = xm1 * pr * decfact;
+          xm1 = xm1 * (1.f - pr) * decfact;
+          if (c.decay[ks] > 0.f)
+            drydeposit[ks] = drydeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
+        } else {
+          xm1 = xm1 * decfact;
+        }
+        a.p.xmass1[(size_t)ks * a.p.maxpart + j] = xm1;
+        if (c.mdomainfill == 0 && c.mquasilag == 0) {
+          const float xm = __ldg(a.xmass + ks * c.numpoint + (npoint - 1));
+          if (xm > 0.f)
+            xmassfract = fmaxf(xmassfract, (float)__ldg(a.npart + npoint - 1) * xm1 / xm);
+        } else {
+          xmassfract = 1.0f;
+        }
+      }
+      if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; cnt.term = 1; }
+
+      if (DRYDEP && c.drydep && (c.ldirect == 1)) {
+        const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
+        const int itage = abs(itime - itramem);
+        int nage;
+        for (nage = 1; nage <= c.nageclass; nage++)
+          if (itage < c.lage[nage - 1]) break;
+        const int nclass = a.p.nclass[j];
+        drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+        if (c.nested_output == 1)
+          drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+      }
+      if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; cnt.term = 1; }
+    }
+
+    a.p.xtra1[j] = xt;
+    a.p.ytra1[j] = yt;
+    a.p.ztra1[j] = zt;
+    a.p.itra1[j] = itra1;
+    a.p.idt[j] = ldt;
+    a.p.uap[j] = up; a.p.ucp[j] = vp; a.p.uzp[j] = wp;
+    a.p.us[j] = usigold; a.p.vs[j] = vsigold; a.p.ws[j] = wsigold;
+    a.p.cbt[j] = (int16_t)icbt;
+    phase = PH_IDLE;
+    return cnt;
+  }
+};
+
+// Persistent kernel: every warp pulls batches of particle rows from
+// *a.work_counter and runs the three phases when enough lanes need them.
+template <bool DRYDEP, bool CBL>
+__global__ void __launch_bounds__(128, FPB_STEP_MIN_BLOCKS)
+fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+
+  constexpr unsigned FULL = 0xffffffffu;
+  // a phase runs when at least this many lanes wait for it (or nothing else can run)
+  constexpr int T_REFILL = 8, T_EPILOGUE = 8;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int itime = c.itime;
+  const int nrows = c.numpart;
+
+  ParticleTask<DRYDEP, CBL> task;
+  task.phase = PH_IDLE;
+  task.j = -1;
+  unsigned n_act = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
+  bool exhausted = false;
+
+  for (;;) {
+    const unsigned idle = __ballot_sync(FULL, task.phase == PH_IDLE);
+    const unsigned running = __ballot_sync(FULL, task.phase == PH_RUN);
+    const unsigned pending = __ballot_sync(FULL, task.phase == PH_PENDING);
+
+    if (idle && !exhausted && (__popc(idle) >= T_REFILL || running == 0)) {
+      const int n = __popc(idle), leader = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(a.work_counter, n);
+      base = __shfl_sync(FULL, base, leader);
+      if (task.phase == PH_IDLE) {
+        const int row = base + __popc(idle & lt_mask);
+        if (row < nrows && a.p.itra1[row] == itime) {
+          task.prologue(a, sh, row);
+          n_act++;
+          if (!task.above) n_pbl++;
+        }
+      }
+      if (base + n >= nrows) exhausted = true;
+      continue;
+    }
+    if (pending && (__popc(pending) >= T_EPILOGUE || running == 0)) {
+      if (task.phase == PH_PENDING) {
+        n_sub += task.nsub;
+        n_nan += task.nan_cbl;
+        const auto cnt = task.epilogue(a, sh);
+        n_term += cnt.term;
+        n_pett += cnt.pett;
+      }
+      continue;
+    }
+    if (running == 0) break; // nothing running, nothing pending, no rows left
+    if (task.phase == PH_RUN) task.substep(a, sh);
+  }
+
+  if (a.stats) {
+    const unsigned long long v0 = warp_sum(n_act), v2 = warp_sum(n_term), v3 = warp_sum(n_pbl),
+                             v4 = warp_sum(n_sub), v5 = warp_sum(n_pett), v6 = warp_sum(n_nan);
+    if (lane == 0 && v0) {
+      atomicAdd(a.stats + 0, v0);
+      if (v2) atomicAdd(a.stats + 2, v2);
+      if (v3) atomicAdd(a.stats + 3, v3);
+      if (v4) atomicAdd(a.stats + 4, v4);
+      if (v5) atomicAdd(a.stats + 5, v5);
+      if (v6) atomicAdd(a.stats + 6, v6);
+    }
+  }
+}
