@@ -124,6 +124,7 @@ struct fpb_handle {
   int steps_since_sort = 1 << 30;
   unsigned *d_nlive = nullptr;
   int *d_work = nullptr;
+  DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
 
@@ -320,6 +321,8 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   sortk_iota(h->row_of_slot, c.maxpart, h->stream);
   DA(h->d_nlive, 1);
   DA(h->d_work, 1);
+  DA(h->sc.flags, mp); DA(h->sc.s0, mp); DA(h->sc.s1, mp); DA(h->sc.s2, mp);
+  if (c.drydep) DA(h->sc.prob, mp * c.nspec);
   h->launches += 3;
   // itra1(:) = -999999999, src/FLEXPART.f90:315-317
   fill_i32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
@@ -364,6 +367,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(q->xmass1); cudaFree(q->xscav_frac1); cudaFree(q->slot);
   }
   cudaFree(h->row_of_slot); cudaFree(h->d_nlive); cudaFree(h->d_work);
+  cudaFree(h->sc.flags); cudaFree(h->sc.s0); cudaFree(h->sc.s1); cudaFree(h->sc.s2); cudaFree(h->sc.prob);
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
@@ -674,6 +678,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.drygriduncn = h->drygriduncn;
   a.stats = stats ? h->d_stats : nullptr;
   a.work_counter = h->d_work;
+  a.sc = h->sc;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
   // initialize() can only be due for rows pushed since the last step, or at itime 0
   if (h->pending_init || itime == 0) {
@@ -687,7 +692,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   else fpbk_step_fast(a, h->stream);
   CK(cudaEventRecord(h->ev[1], h->stream));
   h->timed_step = true;
-  h->launches++;
+  h->launches += 2; // fpb_pbl_kernel + fpb_finish_kernel
   CK(cudaGetLastError());
   if (stats) {
     unsigned long long hs[8];

@@ -90,6 +90,17 @@ struct DevCfg {
   float weight; // conccalc
 };
 
+// Hand-over between fpb_pbl_kernel and fpb_finish_kernel (fpb_step.cuh): what
+// the rest of advance() needs from the sub-step loop.  Rows with
+// itra1 == itime get `flags`; the float4 rows only when SC_PBL is set.
+struct DevScratch {
+  int32_t *flags;
+  float4 *s0; // dxsave, dysave, dawsave, dcwsave
+  float4 *s1; // u, v, w, usig
+  float4 *s2; // vsig, wsig, nrand (bits), itimec (bits)
+  float *prob; // [nspec][maxpart], dry-deposition probability (drydep runs only)
+};
+
 struct DevStepArgs {
   DevCfg cfg;
   DevMetSlot met[2];   // [0] = memind(1) (older field), [1] = memind(2)
@@ -103,7 +114,8 @@ struct DevStepArgs {
   const int32_t *nrand_adv;  //                      and for advance
   float *drygridunc, *drygriduncn;
   unsigned long long *stats; // 8 counters, fpb_step_stats order
-  int *work_counter;         // next unclaimed particle row (persistent step kernel)
+  int *work_counter;         // next unclaimed particle row (persistent sub-step kernel)
+  DevScratch sc;
 };
 
 struct DevConcArgs {

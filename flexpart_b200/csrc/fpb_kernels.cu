@@ -29,8 +29,8 @@
 #ifndef FPB_STRICT
 #define FPB_STRICT 0
 #endif
-#ifndef FPB_STEP_MIN_BLOCKS
-#define FPB_STEP_MIN_BLOCKS 3 // resident 128-thread CTAs per SM the step kernel is tuned for
+#ifndef FPB_PBL_MIN_BLOCKS
+#define FPB_PBL_MIN_BLOCKS 4 // resident 128-thread CTAs per SM the sub-step kernel is tuned for
 #endif
 
 namespace {
@@ -305,25 +305,36 @@ __device__ __forceinline__ void interp_surface(const DevMetSlot *met, const Hz &
 }
 
 // sigma_w, d(sigma_w)/dz and T_Lw of the unstable regime, shared by hanna and
-// hanna_short (src/hanna.f90:66-88, src/hanna_short.f90:59-77)
+// hanna_short (src/hanna.f90:66-88, src/hanna_short.f90:59-77).  The three
+// T_Lw candidates are evaluated by every lane and selected (same arithmetic
+// per candidate as the reference's if-chain, no divergent passes).
 __device__ __forceinline__ void hanna_unstable_w(Turb &t, float z) {
+#if FPB_STRICT
   const float z23 = m_pow(t.zeta, 0.66666f);
+  const float zm13 = m_pow(fmaxf(t.zeta, 1.e-3f), -.33333f);
+#else
+  const float lz = __log2f(t.zeta); // one MUFU.LG2 feeds both powers
+  const float z23 = exp2f(0.66666f * lz);
+  const float zm13 = exp2f(-.33333f * fmaxf(lz, -9.965784284662087f)); // log2(1e-3)
+#endif
   t.sigw = m_sqrt(1.2f * (t.wst * t.wst) * (1.f - .9f * t.zeta) * z23 +
                   (1.8f - 1.4f * t.zeta) * (t.ust * t.ust)) + 1.e-2f;
   t.dsigwdz = 0.5f / t.sigw / t.h *
-              (-1.4f * (t.ust * t.ust) +
-               (t.wst * t.wst) * (0.8f * m_pow(fmaxf(t.zeta, 1.e-3f), -.33333f) - 1.8f * z23));
-  if (z < fabsf(t.ol))
-    t.tlw = 0.1f * z / (t.sigw * (0.55f - 0.38f * fabsf(z / t.ol)));
-  else if (t.zeta < 0.1f)
-    t.tlw = 0.59f * z / t.sigw;
-  else
-    t.tlw = 0.15f * t.h / t.sigw * (1.f - m_exp(-5.f * t.zeta));
+              (-1.4f * (t.ust * t.ust) + (t.wst * t.wst) * (0.8f * zm13 - 1.8f * z23));
+  const float tl_a = 0.1f * z / (t.sigw * (0.55f - 0.38f * fabsf(z / t.ol)));
+  const float tl_b = 0.59f * z / t.sigw;
+  const float tl_c = 0.15f * t.h / t.sigw * (1.f - m_exp(-5.f * t.zeta));
+  t.tlw = (z < fabsf(t.ol)) ? tl_a : ((t.zeta < 0.1f) ? tl_b : tl_c);
 }
 
 // src/hanna.f90:42-106
-__device__ __forceinline__ void hanna(Turb &t, float z) {
-  if (t.h / fabsf(t.ol) < 1.f) {
+// regime: 0 = h/|ol| < 1, 1 = ol < 0, 2 = otherwise (fixed for one advance() call)
+__device__ __forceinline__ int hanna_regime(const Turb &t) {
+  return (t.h / fabsf(t.ol) < 1.f) ? 0 : ((t.ol < 0.f) ? 1 : 2);
+}
+
+__device__ __forceinline__ void hanna(Turb &t, float z, int regime) {
+  if (regime == 0) {
     t.ust = fmaxf(1.e-4f, t.ust);
     float corr = z / t.ust;
     t.sigu = 1.e-2f + 2.0f * t.ust * m_exp(-3.e-4f * corr);
@@ -334,7 +345,7 @@ __device__ __forceinline__ void hanna(Turb &t, float z) {
     t.tlu = 0.5f * z / t.sigw / (1.f + 1.5e-3f * corr);
     t.tlv = t.tlu;
     t.tlw = t.tlu;
-  } else if (t.ol < 0.f) {
+  } else if (regime == 1) {
     t.sigu = 1.e-2f + t.ust * m_pow(12.f - 0.5f * t.h / t.ol, 0.33333f);
     t.sigv = t.sigu;
     hanna_unstable_w(t, z);
@@ -356,14 +367,14 @@ __device__ __forceinline__ void hanna(Turb &t, float z) {
 }
 
 // src/hanna_short.f90:42-92
-__device__ __forceinline__ void hanna_short(Turb &t, float z) {
-  if (t.h / fabsf(t.ol) < 1.f) {
+__device__ __forceinline__ void hanna_short(Turb &t, float z, int regime) {
+  if (regime == 0) {
     t.ust = fmaxf(1.e-4f, t.ust);
     t.sigw = 1.3f * m_exp(-2.e-4f * z / t.ust);
     t.dsigwdz = -2.e-4f * t.sigw;
     t.sigw = t.sigw * t.ust + 1.e-2f;
     t.tlw = 0.5f * z / t.sigw / (1.f + 1.5e-3f * z / t.ust);
-  } else if (t.ol < 0.f) {
+  } else if (regime == 1) {
     hanna_unstable_w(t, z);
   } else {
     t.sigw = 1.e-2f + 1.3f * t.ust * (1.f - t.zeta);
@@ -377,8 +388,8 @@ __device__ __forceinline__ void hanna_short(Turb &t, float z) {
 }
 
 // src/hanna1.f90:42-128
-__device__ __forceinline__ void hanna1(Turb &t, float z) {
-  if (t.h / fabsf(t.ol) < 1.f) {
+__device__ __forceinline__ void hanna1(Turb &t, float z, int regime) {
+  if (regime == 0) {
     t.ust = fmaxf(1.e-4f, t.ust);
     t.sigu = 2.0f * t.ust * m_exp(-3.e-4f * z / t.ust);
     t.sigu = fmaxf(t.sigu, 1.e-5f);
@@ -389,7 +400,7 @@ __device__ __forceinline__ void hanna1(Turb &t, float z) {
     t.tlu = 0.5f * z / t.sigw / (1.f + 1.5e-3f * z / t.ust);
     t.tlv = t.tlu;
     t.tlw = t.tlu;
-  } else if (t.ol < 0.f) {
+  } else if (regime == 1) {
     t.sigu = t.ust * m_pow(12.f - 0.5f * t.h / t.ol, 0.33333f);
     t.sigu = fmaxf(t.sigu, 1.e-6f);
     t.sigv = t.sigu;
@@ -743,7 +754,7 @@ __device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, i
     profile_level(c, a.met, z, indz, lo);
     profile_level(c, a.met, z, indzp, hi);
     // (u, v, w of initialize are dead: advance re-interpolates)
-    if (c.turbswitch) hanna(t, s.zt); else hanna1(t, s.zt);
+    if (c.turbswitch) hanna(t, s.zt, hanna_regime(t)); else hanna1(t, s.zt, hanna_regime(t));
     if (nrand + 2 > c.maxrand) nrand = 1;
     s.up = rng.get(nrand) * t.sigu;
     s.vp = rng.get(nrand + 1) * t.sigv;
@@ -799,6 +810,16 @@ __device__ __forceinline__ void make_rng(const DevCfg &c, const float *tab, int 
   rng.pid = (uint32_t)(c.part_id_offset + c.part_id_stride * slot);
   rng.tstep = (uint32_t)c.itime;
   rng.cblk = -1;
+}
+
+// nrand at the top of advance(): the ran3 draw of src/advance.f90:153
+__device__ __forceinline__ int advance_nrand(const DevStepArgs &a, int slot) {
+  const DevCfg &c = a.cfg;
+  if (c.rng_mode == FPB_RNG_REFERENCE) return a.nrand_adv[slot];
+  if (c.rng_mode == FPB_RNG_PHILOX) return 64;
+  Rng rng;
+  make_rng(c, a.rannumb, slot, rng);
+  return f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
 }
 
 // initialize() for the particles released this step (src/timemanager.f90:553-555).
@@ -1096,7 +1117,9 @@ void FPB_SUF(fpbk_init)(const DevStepArgs &a, cudaStream_t st) {
 
 void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   if (a.cfg.numpart <= 0) return;
-  const bool full = a.cfg.drydep || a.cfg.cblflag == 1;
+  // lean variant: table RNG, no dry deposition, no settling, no CBL
+  const bool full = a.cfg.drydep || a.cfg.cblflag == 1 || a.cfg.lsettling ||
+                    a.cfg.rng_mode == FPB_RNG_PHILOX;
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
   static int resident[2] = {0, 0};
   int &res = resident[full ? 1 : 0];
@@ -1104,15 +1127,16 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_step_kernel<true, true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_step_kernel<false, false>, 128, 0);
+    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false>, 128, 0);
     res = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int want = (a.cfg.numpart + 127) / 128;
   const int nb = want < res ? want : res;
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
-  if (full) fpb_step_kernel<true, true><<<nb, 128, 0, st>>>(a);
-  else fpb_step_kernel<false, false><<<nb, 128, 0, st>>>(a);
+  if (full) fpb_pbl_kernel<true, true><<<nb, 128, 0, st>>>(a);
+  else fpb_pbl_kernel<false, false><<<nb, 128, 0, st>>>(a);
+  fpb_finish_kernel<<<want, 128, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_conccalc)(const DevConcArgs &a, cudaStream_t st) {

@@ -1,116 +1,158 @@
-// fpb_step.cuh -- advance() + the timemanager loop body as a per-lane state
-// machine.  Included inside the anonymous namespace of fpb_kernels.cu.
+// fpb_step.cuh -- advance() + the timemanager loop body as two kernels.
+// Included inside the anonymous namespace of fpb_kernels.cu.
 //
 // The reference processes one particle start to finish (src/advance.f90:133-985
 // called from src/timemanager.f90:531-712).  The number of Langevin sub-steps
 // per call varies by an order of magnitude between particles (ldt follows the
-// local Lagrangian time scale), so "one thread = one particle, start to
-// finish" leaves most lanes of a warp idle.  Here a lane owns a particle only
-// while it has work, and the three pieces of advance() are separate phases
-// that a warp runs when enough of its lanes need them:
+// local Lagrangian time scale) while everything after the sub-step loop runs
+// exactly once per particle, so the call is cut at label 99 / label 700:
 //
-//   PROLOGUE  src/advance.f90:133-267 + :276 (first interpol_all pieces):
-//             load state, grid choice, weights, mixing height, branch choice
-//   SUBSTEP   one pass of the label-100 loop, src/advance.f90:282-609
-//   EPILOGUE  label 700 (above-PBL step), label 99 (mesoscale, windalign,
-//             position update, wrap/exit), Petterssen, then the rest of the
-//             timemanager loop body (src/timemanager.f90:630-707) and the store
+//   fpb_pbl_kernel     persistent; a lane owns a particle only while it has
+//                      sub-steps to do.  REFILL = src/advance.f90:133-276 (load
+//                      state, grid choice, weights, mixing height, surface
+//                      parameters); SUBSTEP = one pass of the label-100 loop,
+//                      src/advance.f90:282-609.  A lane whose particle leaves
+//                      the loop writes the values the rest of advance() needs
+//                      to a scratch row and becomes idle; idle lanes pull the
+//                      next rows from a global counter in batches.
+//   fpb_finish_kernel  one thread per row, fully converged: label 700 (step
+//                      above the PBL), label 99 (mesoscale term, windalign,
+//                      position update, wrap/exit), Petterssen corrector, then
+//                      the rest of the timemanager loop body
+//                      (src/timemanager.f90:630-707) and the store.
 //
-// A lane that finishes its sub-steps parks in PENDING until enough lanes are
-// ready for the epilogue; idle lanes pull the next particle rows from a global
-// counter in batches.  Per-particle arithmetic and its order are unchanged, so
-// the strict build stays bit-identical to the oracle.
+// Per-particle arithmetic and its order are unchanged (floats pass through the
+// scratch row bit for bit), so the strict build stays bit-identical to the
+// oracle.
 
-enum : int { PH_IDLE = 0, PH_RUN = 1, PH_PENDING = 2 };
+enum : int { SC_PBL = 1, SC_ABOVE = 2 };
 
-template <bool DRYDEP, bool CBL>
-struct ParticleTask {
-  // --- identity / phase
-  int j, slot, phase;
-  // --- advance() arguments
-  double xt, yt;
-  float zt, up, vp, wp, usigold, vsigold, wsigold;
+// ----------------------------------------------------------- PBL kernel ----
+template <bool EXTRA, bool CBL>
+struct PblTask {
+  int j;
+  bool running, first;
+  int regime; // 0: h/|ol| < 1, 1: ol < 0, 2: stable  (hanna*.f90 branch, fixed for the call)
+  float zt, up, vp, wp;
   int ldt, icbt;
-  // --- advance() locals that live across sub-steps
-  int nrand, itimec, loop;
+  int nrand, itimec;
   Hz z;
-  Turb t;
+  float ust, wst, ol, h;
   Lev lo, hi;
-  int indz, indzp;
+  int indz;
   float dxsave, dysave, dawsave, dcwsave;
-  float u, v, w, usig, vsig, wsig;
-  float tropop;
-  bool above;
   int nsub, nan_cbl;
+  // EXTRA only
+  float xtf, ytf;
+  int npoint;
   Rng rng;
-  float prob[DRYDEP ? FPB_MAXSPEC : 1];
-  float vdepo[DRYDEP ? FPB_MAXSPEC : 1];
+  float prob[EXTRA ? FPB_MAXSPEC : 1];
+  float vdepo[EXTRA ? FPB_MAXSPEC : 1];
   unsigned depo_todo;
 
-  // ------------------------------------------------------------ PROLOGUE --
-  __device__ __forceinline__ void prologue(const DevStepArgs &a, const float *sh, int row) {
+  __device__ __forceinline__ float normal(const DevStepArgs &a, int i) {
+    if (EXTRA) return rng.get(i);
+    return __ldg(a.rannumb + (i - 1));
+  }
+
+  // src/advance.f90:133-276.  Returns true when the row is active.
+  __device__ __forceinline__ bool refill(const DevStepArgs &a, int row, bool &pbl) {
     const DevCfg &c = a.cfg;
+    pbl = false;
+    if (a.p.itra1[row] != c.itime) return false;
     j = row;
-    slot = a.p.slot[row];
-    xt = a.p.xtra1[row];
-    yt = a.p.ytra1[row];
+    const double xt = a.p.xtra1[row], yt = a.p.ytra1[row];
     zt = a.p.ztra1[row];
-    ldt = a.p.idt[row];
-    up = a.p.uap[row]; vp = a.p.ucp[row]; wp = a.p.uzp[row];
-    usigold = a.p.us[row]; vsigold = a.p.vs[row]; wsigold = a.p.ws[row];
-    icbt = a.p.cbt[row];
-
-    make_rng(c, a.rannumb, slot, rng);
-    if (c.rng_mode == FPB_RNG_REFERENCE) nrand = a.nrand_adv[slot];
-    else if (c.rng_mode == FPB_RNG_PHILOX) nrand = 64;
-    else nrand = f_int(rng.uniform(2u) * (float)(c.maxrand - 1)) + 1;
-
-    if (DRYDEP) {
-#pragma unroll
-      for (int ks = 0; ks < FPB_MAXSPEC; ks++) { prob[ks] = 0.f; vdepo[ks] = 0.f; }
-    }
-    depo_todo = 0xffu;
-    dxsave = 0.f; dysave = 0.f; dawsave = 0.f; dcwsave = 0.f;
-    itimec = c.itime;
-    nsub = 0; nan_cbl = 0; loop = 0;
-    u = v = w = usig = vsig = wsig = 0.f;
-    indz = indzp = 0;
 
     z.ngrid = pole_grid(c, yt);
     const int ix = d_int(xt), jy = d_int(yt);
-    const int nix = d_nint(xt), njy = d_nint(yt);
     int ixp = ix + 1, jyp = jy + 1;
     if (jyp >= c.nymax) jyp = jyp - 1;
     make_weights(c, z, c.itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
 
-    float h = 0.f; // advance.f90:236-252: max over 4 corners x 2 slots
+    // advance.f90:236-252 (max of hmix over 4 corners x 2 slots); the same
+    // words carry ustar, wstar, oli for interpol_all.f90:80-107
+    float4 s[2][4];
 #pragma unroll
     for (int m = 0; m < 2; m++) {
-      const float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
-      const float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
-      if (v0 > h) h = v0;
-      if (v1 > h) h = v1;
-      if (v2 > h) h = v2;
-      if (v3 > h) h = v3;
+      s[m][0] = __ldg(a.met[m].S + z.o00); s[m][1] = __ldg(a.met[m].S + z.o10);
+      s[m][2] = __ldg(a.met[m].S + z.o01); s[m][3] = __ldg(a.met[m].S + z.o11);
     }
-    t.h = h;
-    tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal, advance.f90:253
-    t.zeta = zt / t.h;
-    above = !(t.zeta <= 1.f);
-    if (!above) {
-      interp_surface(a.met, z, t);
-      phase = PH_RUN;
-    } else {
-      phase = PH_PENDING;
+    float hh = 0.f;
+#pragma unroll
+    for (int m = 0; m < 2; m++)
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (s[m][q].x > hh) hh = s[m][q].x;
+    h = hh;
+    const float zeta = zt / h;
+    if (!(zeta <= 1.f)) { // above the PBL for the whole step: nothing to do here
+      a.sc.flags[row] = SC_ABOVE;
+      running = false;
+      return true;
     }
+    pbl = true;
+    {
+      float us1[2], ws1[2], ol1[2];
+#pragma unroll
+      for (int m = 0; m < 2; m++) {
+        us1[m] = bil(z, s[m][0].y, s[m][1].y, s[m][2].y, s[m][3].y);
+        ws1[m] = bil(z, s[m][0].z, s[m][1].z, s[m][2].z, s[m][3].z);
+        ol1[m] = bil(z, s[m][0].w, s[m][1].w, s[m][2].w, s[m][3].w);
+      }
+      ust = (us1[0] * z.dt2 + us1[1] * z.dt1) * z.dtt;
+      wst = (ws1[0] * z.dt2 + ws1[1] * z.dt1) * z.dtt;
+      const float oliaux = (ol1[0] * z.dt2 + ol1[1] * z.dt1) * z.dtt;
+      ol = (oliaux != 0.f) ? 1.f / oliaux : 99999.f;
+    }
+    regime = (h / fabsf(ol) < 1.f) ? 0 : ((ol < 0.f) ? 1 : 2);
+
+    ldt = a.p.idt[row];
+    up = a.p.uap[row]; vp = a.p.ucp[row]; wp = a.p.uzp[row];
+    icbt = a.p.cbt[row];
+    const int slot = a.p.slot[row];
+    if (EXTRA) {
+      make_rng(c, a.rannumb, slot, rng);
+      xtf = (float)xt; ytf = (float)yt;
+      npoint = a.p.npoint[row];
+#pragma unroll
+      for (int ks = 0; ks < FPB_MAXSPEC; ks++) { prob[ks] = 0.f; vdepo[ks] = 0.f; }
+      depo_todo = 0xffu;
+    }
+    nrand = advance_nrand(a, slot);
+    dxsave = 0.f; dysave = 0.f; dawsave = 0.f; dcwsave = 0.f;
+    itimec = c.itime;
+    nsub = 0; nan_cbl = 0;
+    indz = 0;
+    first = true;
+    running = true;
+    return true;
   }
 
-  // ------------------------------------------------------------- SUBSTEP --
-  // one pass of the label-100 loop; leaves phase == PH_RUN to continue
+  // leave the sub-step loop: hand the rest of advance() to fpb_finish_kernel
+  __device__ __forceinline__ void finish(const DevStepArgs &a, bool above, float u, float v, float w,
+                                         float usig, float vsig, float wsig) {
+    const DevCfg &c = a.cfg;
+    a.p.ztra1[j] = zt;
+    a.p.uap[j] = up; a.p.ucp[j] = vp; a.p.uzp[j] = wp;
+    a.p.idt[j] = ldt;
+    a.p.cbt[j] = (int16_t)icbt;
+    a.sc.s0[j] = make_float4(dxsave, dysave, dawsave, dcwsave);
+    a.sc.s1[j] = make_float4(u, v, w, usig);
+    a.sc.s2[j] = make_float4(vsig, wsig, __int_as_float(nrand), __int_as_float(itimec));
+    a.sc.flags[j] = SC_PBL | (above ? SC_ABOVE : 0);
+    if (EXTRA && c.drydep) {
+#pragma unroll
+      for (int ks = 0; ks < FPB_MAXSPEC; ks++)
+        if (ks < c.nspec) a.sc.prob[(size_t)ks * a.p.maxpart + j] = prob[ks];
+    }
+    running = false;
+  }
+
+  // one pass of the label-100 loop, src/advance.f90:282-609
   __device__ __forceinline__ void substep(const DevStepArgs &a, const float *sh) {
     const DevCfg &c = a.cfg;
     const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
-    loop++;
     nsub++;
     if (c.method == 1) {
       ldt = min(ldt, abs(c.lsynctime - itimec + itime));
@@ -120,58 +162,68 @@ struct ParticleTask {
       itimec = itime + c.lsynctime;
     }
     const float dt = (float)ldt;
+    Turb t;
+    t.ust = ust; t.wst = wst; t.ol = ol; t.h = h;
     t.zeta = zt / t.h;
 
     // level pair under the particle (src/advance.f90:310-331); a level computed
     // again gives the same bits as the reference's cached one
     {
       int ni;
-      if (loop != 1 && sh[indz - 1] <= zt && sh[indzp - 1] > zt) ni = indz;  // still between the same levels
-      else ni = find_indz(sh, nz, zt);
-      const int nip = ni + 1;
+      if (first) {
+        ni = find_indz(sh, nz, zt);
+      } else if (sh[indz - 1] <= zt && sh[indz] > zt) {
+        ni = indz; // still between the same levels
+      } else if (indz + 1 < nz && sh[indz] <= zt && sh[indz + 1] > zt) {
+        ni = indz + 1;
+      } else if (indz >= 2 && sh[indz - 1] > zt && (indz == 2 || sh[indz - 2] <= zt)) {
+        ni = indz - 1;
+      } else {
+        ni = find_indz(sh, nz, zt);
+      }
       bool need_lo = true, need_hi = true;
-      if (loop != 1) {
+      if (!first) {
         if (ni == indz) {
           need_lo = need_hi = false;
-        } else if (ni == indzp) {
+        } else if (ni == indz + 1) {
           lo = hi;
           need_lo = false;
-        } else if (nip == indz) {
+        } else if (ni + 1 == indz) {
           hi = lo;
           need_hi = false;
         }
       }
       indz = ni;
-      indzp = nip;
+      first = false;
+      // one converged call site; a lane that needs both levels goes round twice
 #pragma unroll 1
-      for (int q = 0; q < 2; q++) {
-        if (q ? need_hi : need_lo) {
-          Lev t_;
-          profile_level(c, a.met, z, ni + q, t_);
-          if (q) hi = t_; else lo = t_;
-        }
+      while (need_lo || need_hi) {
+        const bool do_lo = need_lo;
+        Lev t_;
+        profile_level(c, a.met, z, ni + (do_lo ? 0 : 1), t_);
+        if (do_lo) { lo = t_; need_lo = false; } else { hi = t_; need_hi = false; }
       }
     }
 
     // advance.f90:342-350
-    const float dz = 1.f / (sh[indzp - 1] - sh[indz - 1]);
+    const float dz = 1.f / (sh[indz] - sh[indz - 1]);
     const float dz1 = (zt - sh[indz - 1]) * dz;
-    const float dz2 = (sh[indzp - 1] - zt) * dz;
-    u = dz1 * hi.u + dz2 * lo.u;
-    v = dz1 * hi.v + dz2 * lo.v;
-    w = dz1 * hi.w + dz2 * lo.w;
+    const float dz2 = (sh[indz] - zt) * dz;
+    const float u = dz1 * hi.u + dz2 * lo.u;
+    const float v = dz1 * hi.v + dz2 * lo.v;
+    float w = dz1 * hi.w + dz2 * lo.w;
     const float rhoa = dz1 * hi.rho + dz2 * lo.rho;
     const float rhograd = dz1 * hi.rhograd + dz2 * lo.rhograd;
 
-    if (c.turbswitch) hanna(t, zt); else hanna1(t, zt);
+    if (c.turbswitch) hanna(t, zt, regime); else hanna1(t, zt, regime);
 
     // horizontal turbulent velocities, advance.f90:371-384
     if (nrand + 1 > maxrand) nrand = 1;
-    const float r_up = rng.get(nrand), r_vp = rng.get(nrand + 1);
+    const float r_up = normal(a, nrand), r_vp = normal(a, nrand + 1);
     nrand = nrand + 2;
     if (nrand + c.ifine > maxrand) nrand = 1;
     // first vertical normal requested early so its latency hides behind the u/v update
-    float r_w = (CBL && c.cblflag == 1) ? 0.f : rng.get(nrand + 1);
+    float r_w = (CBL && c.cblflag == 1) ? 0.f : normal(a, nrand + 1);
     if (dt / t.tlu < .5f) {
       up = (1.f - dt / t.tlu) * up + r_up * t.sigu * m_sqrt(2.f * dt / t.tlu);
     } else {
@@ -190,10 +242,11 @@ struct ParticleTask {
     const float dtftlw = dtf / t.tlw;
 
     // vertical component in ifine short steps, advance.f90:396-498
+#pragma unroll 1
     for (int i = 1; i <= c.ifine; i++) {
       float delz;
       // next iteration's normal (table modes: plain loads, harmless past the end)
-      const float r_w_next = (CBL && c.cblflag == 1) ? 0.f : rng.get(nrand + i + 1);
+      const float r_w_next = (CBL && c.cblflag == 1) ? 0.f : normal(a, nrand + i + 1);
       if (c.turbswitch) {
         if (dtftlw < .5f) {
           if (CBL && c.cblflag == 1) {
@@ -203,7 +256,7 @@ struct ParticleTask {
               float old_wp_buf = wp, ath, bth;
               cbl_drift(c, wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol,
                         ath, bth, flagrein);
-              wp = (wp + ath * dtf + bth * rng.get(nrand) * m_sqrt(dtf)) * (float)icbt;
+              wp = (wp + ath * dtf + bth * normal(a, nrand) * m_sqrt(dtf)) * (float)icbt;
               delz = wp * dtf;
               if (flagrein == 1) {
                 cbl_reinitialize(c, rng, zt, t.wst, t.h, t.sigw, t.ol, old_wp_buf, nrand);
@@ -215,13 +268,13 @@ struct ParticleTask {
               nrand = nrand + 1;
               const float ath = -wp / t.tlw + t.sigw * t.dsigwdz + wp * wp / t.sigw * t.dsigwdz +
                                 t.sigw * t.sigw / rhoa * rhograd;
-              const float bth = t.sigw * rng.get(nrand) * m_sqrt(2.f * dtftlw);
+              const float bth = t.sigw * normal(a, nrand) * m_sqrt(2.f * dtftlw);
               wp = (wp + ath * dtf + bth) * (float)icbt;
               delz = wp * dtf;
               const float del_test = (1.f - wp) / wp;
               if (isnan(wp) || isnan(del_test)) {
                 nrand = nrand + 1;
-                wp = t.sigw * rng.get(nrand);
+                wp = t.sigw * normal(a, nrand);
                 delz = wp * dtf;
                 nan_cbl++;
               }
@@ -233,7 +286,7 @@ struct ParticleTask {
           }
         } else {
           const float rw = m_exp(-dtftlw);
-          const float r_ = (CBL && c.cblflag == 1) ? rng.get(nrand + i) : r_w;
+          const float r_ = (CBL && c.cblflag == 1) ? normal(a, nrand + i) : r_w;
           wp = (rw * wp + r_ * m_sqrt(1.f - rw * rw) +
                 t.tlw * (1.f - rw) * (t.dsigwdz + rhoaux * t.sigw)) * (float)icbt;
           delz = wp * t.sigw * dtf;
@@ -260,10 +313,11 @@ struct ParticleTask {
       }
       if (i != c.ifine) {
         t.zeta = zt / t.h;
-        hanna_short(t, zt);
+        hanna_short(t, zt, regime);
       }
     }
     if (!(CBL && c.cblflag == 1)) nrand = nrand + (c.ifine + 1);
+    ust = t.ust; // hanna* may raise ust to 1e-4 (idempotent)
 
     // next time step, advance.f90:504-510
     if (c.turbswitch) {
@@ -276,7 +330,7 @@ struct ParticleTask {
     }
     ldt = max(ldt, c.mintime);
 
-    w = w + settling_term(a, sh, a.p.npoint[j], xt, yt, zt);
+    if (EXTRA) w = w + settling_term(a, sh, npoint, xtf, ytf, zt);
 
     dxsave = dxsave + u * dt;
     dysave = dysave + v * dt;
@@ -290,18 +344,16 @@ struct ParticleTask {
     if (zt > t.h) {
       if (itimec == itime + c.lsynctime) {
         // "defined" behaviour for the stale-usig case
-        usig = 0.5f * (hi.usig + lo.usig);
-        vsig = 0.5f * (hi.vsig + lo.vsig);
-        wsig = 0.5f * (hi.wsig + lo.wsig);
+        finish(a, false, u, v, w, 0.5f * (hi.usig + lo.usig), 0.5f * (hi.vsig + lo.vsig),
+               0.5f * (hi.wsig + lo.wsig));
       } else {
-        above = true;
+        finish(a, true, u, v, w, 0.f, 0.f, 0.f);
       }
-      phase = PH_PENDING;
       return;
     }
 
     // dry-deposition probability, advance.f90:582-599
-    if (DRYDEP && c.drydep && (zt < 2.f * HREF)) {
+    if (EXTRA && c.drydep && (zt < 2.f * HREF)) {
 #pragma unroll
       for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
         if (ks < c.nspec && c.drydepspec[ks]) {
@@ -321,253 +373,303 @@ struct ParticleTask {
 
     if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
 
-    if (itimec == (itime + c.lsynctime)) {
-      usig = 0.5f * (hi.usig + lo.usig);
-      vsig = 0.5f * (hi.vsig + lo.vsig);
-      wsig = 0.5f * (hi.wsig + lo.wsig);
-      phase = PH_PENDING;
-    }
-  }
-
-  // ------------------------------------------------------------ EPILOGUE --
-  struct Counts { unsigned term, pett; };
-
-  __device__ __forceinline__ Counts epilogue(const DevStepArgs &a, const float *sh) {
-    const DevCfg &c = a.cfg;
-    const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
-    const float eps = c.eps;
-    const float ztop = sh[nz - 1];
-    const int npoint = a.p.npoint[j];
-    Counts cnt;
-    cnt.term = 0; cnt.pett = 0;
-    float ux = 0.f, vy = 0.f;
-    int nstop = 0;
-
-    if (above) { // label 700, advance.f90:629-708
-      interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
-      ldt = abs(c.lsynctime - itimec + itime);
-      const float dt = (float)ldt;
-      if (zt < tropop) {
-        const float uxscale = m_sqrt(2.f * c.d_trop / dt);
-        if (nrand + 1 > maxrand) nrand = 1;
-        ux = rng.get(nrand) * uxscale;
-        vy = rng.get(nrand + 1) * uxscale;
-        nrand = nrand + 2;
-        wp = 0.f;
-      } else if (zt < tropop + 1000.f) {
-        const float weight = (zt - tropop) / 1000.f;
-        const float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
-        if (nrand + 2 > maxrand) nrand = 1;
-        ux = rng.get(nrand) * uxscale;
-        vy = rng.get(nrand + 1) * uxscale;
-        const float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
-        wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
-        nrand = nrand + 3;
-      } else {
-        if (nrand > maxrand) nrand = 1;
-        ux = 0.f;
-        vy = 0.f;
-        const float wpscale = m_sqrt(2.f * c.d_strat / dt);
-        wp = rng.get(nrand) * wpscale;
-        nrand = nrand + 1;
-      }
-      if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
-
-      w = w + settling_term(a, sh, npoint, xt, yt, zt);
-
-      dxsave = dxsave + (u + ux) * dt;
-      dysave = dysave + (v + vy) * dt;
-      zt = zt + (w + wp) * dt * (float)c.ldirect;
-      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
-    }
-
-    // label 99: mesoscale fluctuations, advance.f90:728-739
-    {
-      const float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
-      const float rs = m_sqrt(1.f - r * r);
-      if (nrand + 2 > maxrand) nrand = 1;
-      usigold = r * usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
-      vsigold = r * vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
-      wsigold = r * wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
-      dxsave = dxsave + usigold * (float)c.lsynctime;
-      dysave = dysave + vsigold * (float)c.lsynctime;
-      zt = zt + wsigold * (float)c.lsynctime;
-      if (zt < 0.f) zt = -1.f * zt;
-    }
-
-    // advance.f90:747-778
-    windalign(dxsave, dysave, dawsave, dcwsave, ux, vy);
-    dxsave = dxsave + ux;
-    dysave = dysave + vy;
-    const int ngrid = z.ngrid;
-    move_horizontal(c, ngrid, xt, yt, dxsave, dysave, (float)c.ldirect);
-
-    bool done = false;
-    if (wrap_and_check(c, xt, yt)) {
-      nstop = 3;
-      done = true;
-    }
-    if (!done) {
-      if (zt >= ztop) zt = ztop - 100.f * eps;
-      // Petterssen corrector, advance.f90:829-985
-      if (ldt != abs(c.lsynctime)) done = true;
-      else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
-      else if (pole_grid(c, yt) != ngrid) done = true;
-    }
-    if (!done) {
-      const int ix = d_int(xt), jy = d_int(yt);
-      const int ixp = ix + 1;
-      int jyp = jy + 1;
-      if (jyp >= c.nymax) jyp = jyp - 1;
-      const float uold = u, vold = v, wold = w;
-      make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
-      float d0, d1, d2;
-      interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
-      cnt.pett = 1;
-      w = w + settling_term(a, sh, npoint, xt, yt, zt);
-      u = (u - uold) / 2.f;
-      v = (v - vold) / 2.f;
-      w = (w - wold) / 2.f;
-      zt = zt + w * (float)(ldt * c.ldirect);
-      if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
-      move_horizontal(c, ngrid, xt, yt, u, v, (float)(ldt * c.ldirect));
-      if (wrap_and_check(c, xt, yt)) {
-        nstop = 3;
-      } else if (zt >= ztop) {
-        zt = ztop - 100.f * eps;
-      }
-    }
-
-    // ---- rest of the timemanager loop body, src/timemanager.f90:630-707
-    const int itramem = a.p.itramem[j];
-    int itra1;
-    if (nstop > 1) {
-      itra1 = FPB_ITRA_DEAD;
-      cnt.term = 1;
-    } else {
-      itra1 = itime + c.lsynctime;
-      float xmassfract = 0.f;
-      float drydeposit[FPB_MAXSPEC];
-      for (int ks = 0; ks < c.nspec; ks++) {
-        float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
-        const float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
-        drydeposit[ks] = 0.f;
-        if (c.drydepspec[ks]) {
-          const float pr = DRYDEP ? prob[ks] : 0.f;
-          drydeposit[ks] = xm1 * pr * decfact;
-          xm1 = xm1 * (1.f - pr) * decfact;
-          if (c.decay[ks] > 0.f)
-            drydeposit[ks] = drydeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
-        } else {
-          xm1 = xm1 * decfact;
-        }
-        a.p.xmass1[(size_t)ks * a.p.maxpart + j] = xm1;
-        if (c.mdomainfill == 0 && c.mquasilag == 0) {
-          const float xm = __ldg(a.xmass + ks * c.numpoint + (npoint - 1));
-          if (xm > 0.f)
-            xmassfract = fmaxf(xmassfract, (float)__ldg(a.npart + npoint - 1) * xm1 / xm);
-        } else {
-          xmassfract = 1.0f;
-        }
-      }
-      if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; cnt.term = 1; }
-
-      if (DRYDEP && c.drydep && (c.ldirect == 1)) {
-        const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
-        const int itage = abs(itime - itramem);
-        int nage;
-        for (nage = 1; nage <= c.nageclass; nage++)
-          if (itage < c.lage[nage - 1]) break;
-        const int nclass = a.p.nclass[j];
-        drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
-        if (c.nested_output == 1)
-          drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
-      }
-      if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; cnt.term = 1; }
-    }
-
-    a.p.xtra1[j] = xt;
-    a.p.ytra1[j] = yt;
-    a.p.ztra1[j] = zt;
-    a.p.itra1[j] = itra1;
-    a.p.idt[j] = ldt;
-    a.p.uap[j] = up; a.p.ucp[j] = vp; a.p.uzp[j] = wp;
-    a.p.us[j] = usigold; a.p.vs[j] = vsigold; a.p.ws[j] = wsigold;
-    a.p.cbt[j] = (int16_t)icbt;
-    phase = PH_IDLE;
-    return cnt;
+    if (itimec == (itime + c.lsynctime))
+      finish(a, false, u, v, w, 0.5f * (hi.usig + lo.usig), 0.5f * (hi.vsig + lo.vsig),
+             0.5f * (hi.wsig + lo.wsig));
   }
 };
 
 // Persistent kernel: every warp pulls batches of particle rows from
-// *a.work_counter and runs the three phases when enough lanes need them.
-template <bool DRYDEP, bool CBL>
-__global__ void __launch_bounds__(128, FPB_STEP_MIN_BLOCKS)
-fpb_step_kernel(const __grid_constant__ DevStepArgs a) {
+// *a.work_counter; lanes run sub-steps until their particle leaves the loop.
+template <bool EXTRA, bool CBL>
+__global__ void __launch_bounds__(128, EXTRA ? 3 : FPB_PBL_MIN_BLOCKS)
+fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
   for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
   __syncthreads();
 
   constexpr unsigned FULL = 0xffffffffu;
-  // a phase runs when at least this many lanes wait for it (or nothing else can run)
-  constexpr int T_REFILL = 8, T_EPILOGUE = 8;
+  constexpr int T_REFILL = 8; // refill when at least this many lanes are idle
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int itime = c.itime;
   const int nrows = c.numpart;
 
-  ParticleTask<DRYDEP, CBL> task;
-  task.phase = PH_IDLE;
+  PblTask<EXTRA, CBL> task;
+  task.running = false;
   task.j = -1;
-  unsigned n_act = 0, n_term = 0, n_pbl = 0, n_sub = 0, n_pett = 0, n_nan = 0;
+  unsigned n_act = 0, n_pbl = 0, n_sub = 0, n_nan = 0;
   bool exhausted = false;
 
   for (;;) {
-    const unsigned idle = __ballot_sync(FULL, task.phase == PH_IDLE);
-    const unsigned running = __ballot_sync(FULL, task.phase == PH_RUN);
-    const unsigned pending = __ballot_sync(FULL, task.phase == PH_PENDING);
-
-    if (idle && !exhausted && (__popc(idle) >= T_REFILL || running == 0)) {
+    const unsigned idle = __ballot_sync(FULL, !task.running);
+    if (!exhausted && __popc(idle) >= T_REFILL) {
       const int n = __popc(idle), leader = __ffs(idle) - 1;
       int base = 0;
       if (lane == leader) base = atomicAdd(a.work_counter, n);
       base = __shfl_sync(FULL, base, leader);
-      if (task.phase == PH_IDLE) {
+      if (!task.running) {
         const int row = base + __popc(idle & lt_mask);
-        if (row < nrows && a.p.itra1[row] == itime) {
-          task.prologue(a, sh, row);
+        bool pbl = false;
+        if (row < nrows && task.refill(a, row, pbl)) {
           n_act++;
-          if (!task.above) n_pbl++;
+          if (pbl) n_pbl++;
         }
       }
       if (base + n >= nrows) exhausted = true;
       continue;
     }
-    if (pending && (__popc(pending) >= T_EPILOGUE || running == 0)) {
-      if (task.phase == PH_PENDING) {
+    if (idle == FULL) break; // no rows left and nothing running
+    if (task.running) {
+      task.substep(a, sh);
+      if (!task.running) {
         n_sub += task.nsub;
         n_nan += task.nan_cbl;
-        const auto cnt = task.epilogue(a, sh);
-        n_term += cnt.term;
-        n_pett += cnt.pett;
       }
-      continue;
     }
-    if (running == 0) break; // nothing running, nothing pending, no rows left
-    if (task.phase == PH_RUN) task.substep(a, sh);
   }
 
   if (a.stats) {
-    const unsigned long long v0 = warp_sum(n_act), v2 = warp_sum(n_term), v3 = warp_sum(n_pbl),
-                             v4 = warp_sum(n_sub), v5 = warp_sum(n_pett), v6 = warp_sum(n_nan);
+    const unsigned long long v0 = warp_sum(n_act), v3 = warp_sum(n_pbl), v4 = warp_sum(n_sub),
+                             v6 = warp_sum(n_nan);
     if (lane == 0 && v0) {
       atomicAdd(a.stats + 0, v0);
-      if (v2) atomicAdd(a.stats + 2, v2);
       if (v3) atomicAdd(a.stats + 3, v3);
       if (v4) atomicAdd(a.stats + 4, v4);
-      if (v5) atomicAdd(a.stats + 5, v5);
       if (v6) atomicAdd(a.stats + 6, v6);
+    }
+  }
+}
+
+// -------------------------------------------------------- finish kernel ----
+// label 700 + label 99 + Petterssen (src/advance.f90:629-985) and the rest of
+// the timemanager loop body (src/timemanager.f90:630-707) for row j.
+__device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh, int j,
+                                           unsigned &n_term, unsigned &n_pett) {
+  const DevCfg &c = a.cfg;
+  const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
+  const float eps = c.eps;
+  const float ztop = sh[nz - 1];
+  const int npoint = a.p.npoint[j];
+  const int slot = a.p.slot[j];
+  const int flags = a.sc.flags[j];
+
+  double xt = a.p.xtra1[j], yt = a.p.ytra1[j];
+  float zt = a.p.ztra1[j];
+  float wp = a.p.uzp[j];
+  float usigold = a.p.us[j], vsigold = a.p.vs[j], wsigold = a.p.ws[j];
+  int ldt = a.p.idt[j];
+
+  Rng rng;
+  make_rng(c, a.rannumb, slot, rng);
+
+  float dxsave = 0.f, dysave = 0.f, dawsave = 0.f, dcwsave = 0.f;
+  float u = 0.f, v = 0.f, w = 0.f, usig = 0.f, vsig = 0.f, wsig = 0.f;
+  int nrand, itimec = itime;
+  if (flags & SC_PBL) {
+    const float4 s0 = a.sc.s0[j], s1 = a.sc.s1[j], s2 = a.sc.s2[j];
+    dxsave = s0.x; dysave = s0.y; dawsave = s0.z; dcwsave = s0.w;
+    u = s1.x; v = s1.y; w = s1.z; usig = s1.w;
+    vsig = s2.x; wsig = s2.y;
+    nrand = __float_as_int(s2.z);
+    itimec = __float_as_int(s2.w);
+  } else {
+    nrand = advance_nrand(a, slot);
+  }
+
+  // advance.f90:199-253 at the position the call started from
+  Hz z;
+  z.ngrid = pole_grid(c, yt);
+  float h = 0.f, tropop;
+  {
+    const int ix = d_int(xt), jy = d_int(yt);
+    const int nix = d_nint(xt), njy = d_nint(yt);
+    int ixp = ix + 1, jyp = jy + 1;
+    if (jyp >= c.nymax) jyp = jyp - 1;
+    make_weights(c, z, itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
+      const float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
+      if (v0 > h) h = v0;
+      if (v1 > h) h = v1;
+      if (v2 > h) h = v2;
+      if (v3 > h) h = v3;
+    }
+    tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal, advance.f90:253
+  }
+
+  float ux = 0.f, vy = 0.f;
+  int nstop = 0;
+
+  if (flags & SC_ABOVE) { // label 700, advance.f90:629-708
+    interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
+    ldt = abs(c.lsynctime - itimec + itime);
+    const float dt = (float)ldt;
+    if (zt < tropop) {
+      const float uxscale = m_sqrt(2.f * c.d_trop / dt);
+      if (nrand + 1 > maxrand) nrand = 1;
+      ux = rng.get(nrand) * uxscale;
+      vy = rng.get(nrand + 1) * uxscale;
+      nrand = nrand + 2;
+      wp = 0.f;
+    } else if (zt < tropop + 1000.f) {
+      const float weight = (zt - tropop) / 1000.f;
+      const float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
+      if (nrand + 2 > maxrand) nrand = 1;
+      ux = rng.get(nrand) * uxscale;
+      vy = rng.get(nrand + 1) * uxscale;
+      const float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
+      wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
+      nrand = nrand + 3;
+    } else {
+      if (nrand > maxrand) nrand = 1;
+      ux = 0.f;
+      vy = 0.f;
+      const float wpscale = m_sqrt(2.f * c.d_strat / dt);
+      wp = rng.get(nrand) * wpscale;
+      nrand = nrand + 1;
+    }
+    if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
+
+    w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
+
+    dxsave = dxsave + (u + ux) * dt;
+    dysave = dysave + (v + vy) * dt;
+    zt = zt + (w + wp) * dt * (float)c.ldirect;
+    if (zt < 0.f) zt = fminf(h - EPS2, -1.f * zt);
+  }
+
+  // label 99: mesoscale fluctuations, advance.f90:728-739
+  {
+    const float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
+    const float rs = m_sqrt(1.f - r * r);
+    if (nrand + 2 > maxrand) nrand = 1;
+    usigold = r * usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
+    vsigold = r * vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
+    wsigold = r * wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
+    dxsave = dxsave + usigold * (float)c.lsynctime;
+    dysave = dysave + vsigold * (float)c.lsynctime;
+    zt = zt + wsigold * (float)c.lsynctime;
+    if (zt < 0.f) zt = -1.f * zt;
+  }
+
+  // advance.f90:747-778
+  windalign(dxsave, dysave, dawsave, dcwsave, ux, vy);
+  dxsave = dxsave + ux;
+  dysave = dysave + vy;
+  const int ngrid = z.ngrid;
+  move_horizontal(c, ngrid, xt, yt, dxsave, dysave, (float)c.ldirect);
+
+  bool done = false;
+  if (wrap_and_check(c, xt, yt)) {
+    nstop = 3;
+    done = true;
+  }
+  if (!done) {
+    if (zt >= ztop) zt = ztop - 100.f * eps;
+    // Petterssen corrector, advance.f90:829-985
+    if (ldt != abs(c.lsynctime)) done = true;
+    else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
+    else if (pole_grid(c, yt) != ngrid) done = true;
+  }
+  if (!done) {
+    const int ix = d_int(xt), jy = d_int(yt);
+    const int ixp = ix + 1;
+    int jyp = jy + 1;
+    if (jyp >= c.nymax) jyp = jyp - 1;
+    const float uold = u, vold = v, wold = w;
+    make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    float d0, d1, d2;
+    interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
+    n_pett++;
+    w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
+    u = (u - uold) / 2.f;
+    v = (v - vold) / 2.f;
+    w = (w - wold) / 2.f;
+    zt = zt + w * (float)(ldt * c.ldirect);
+    if (zt < 0.f) zt = fminf(h - EPS2, -1.f * zt);
+    move_horizontal(c, ngrid, xt, yt, u, v, (float)(ldt * c.ldirect));
+    if (wrap_and_check(c, xt, yt)) {
+      nstop = 3;
+    } else if (zt >= ztop) {
+      zt = ztop - 100.f * eps;
+    }
+  }
+
+  // ---- rest of the timemanager loop body, src/timemanager.f90:630-707
+  const int itramem = a.p.itramem[j];
+  int itra1;
+  if (nstop > 1) {
+    itra1 = FPB_ITRA_DEAD;
+    n_term++;
+  } else {
+    bool term = false;
+    itra1 = itime + c.lsynctime;
+    float xmassfract = 0.f;
+    float drydeposit[FPB_MAXSPEC];
+    for (int ks = 0; ks < c.nspec; ks++) {
+      float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
+      const float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
+      drydeposit[ks] = 0.f;
+      if (c.drydepspec[ks]) {
+        const float pr = (c.drydep && (flags & SC_PBL)) ? a.sc.prob[(size_t)ks * a.p.maxpart + j] : 0.f;
+        drydeposit[ks] = xm1 * pr * decfact;
+        xm1 = xm1 * (1.f - pr) * decfact;
+        if (c.decay[ks] > 0.f)
+          drydeposit[ks] = drydeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
+      } else {
+        xm1 = xm1 * decfact;
+      }
+      a.p.xmass1[(size_t)ks * a.p.maxpart + j] = xm1;
+      if (c.mdomainfill == 0 && c.mquasilag == 0) {
+        const float xm = __ldg(a.xmass + ks * c.numpoint + (npoint - 1));
+        if (xm > 0.f)
+          xmassfract = fmaxf(xmassfract, (float)__ldg(a.npart + npoint - 1) * xm1 / xm);
+      } else {
+        xmassfract = 1.0f;
+      }
+    }
+    if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; term = true; }
+
+    if (c.drydep && (c.ldirect == 1)) {
+      const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
+      const int itage = abs(itime - itramem);
+      int nage;
+      for (nage = 1; nage <= c.nageclass; nage++)
+        if (itage < c.lage[nage - 1]) break;
+      const int nclass = a.p.nclass[j];
+      drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+      if (c.nested_output == 1)
+        drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+    }
+    if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; term = true; }
+    if (term) n_term++;
+  }
+
+  a.p.xtra1[j] = xt;
+  a.p.ytra1[j] = yt;
+  a.p.ztra1[j] = zt;
+  a.p.itra1[j] = itra1;
+  a.p.idt[j] = ldt;
+  if (flags & SC_ABOVE) a.p.uzp[j] = wp; // uap, ucp, cbt: unchanged above the PBL
+  a.p.us[j] = usigold; a.p.vs[j] = vsigold; a.p.ws[j] = wsigold;
+}
+
+__global__ void __launch_bounds__(128)
+fpb_finish_kernel(const __grid_constant__ DevStepArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned n_term = 0, n_pett = 0;
+  if (j < c.numpart && a.p.itra1[j] == c.itime) finish_row(a, sh, j, n_term, n_pett);
+  if (a.stats) {
+    const unsigned long long v2 = warp_sum(n_term), v5 = warp_sum(n_pett);
+    if ((threadIdx.x & 31) == 0) {
+      if (v2) atomicAdd(a.stats + 2, v2);
+      if (v5) atomicAdd(a.stats + 5, v5);
     }
   }
 }
