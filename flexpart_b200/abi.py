@@ -114,7 +114,8 @@ class FpbhEngine(C.Structure):
                 ("conccalc", CONC_FN), ("fetch_grids", FETCH_FN), ("scale_depgrids", SCALE_FN)]
 
 
-ENGINE_LIB = os.path.join(_HERE, "libfpb.so")
+# FPB_ENGINE_LIB: load another build of the same library (kernel A/B experiments)
+ENGINE_LIB = os.environ.get("FPB_ENGINE_LIB") or os.path.join(_HERE, "libfpb.so")
 HOST_LIB = os.path.join(_HERE, "libfpb_host.so")
 _engine = None
 _host = None

@@ -562,17 +562,29 @@ extern "C" int fpb_pull_particles(fpb_handle *h, int32_t first, int32_t count, c
 }
 
 // ------------------------------------------------------------------- sort --
-static int do_sort(fpb_handle *h) {
+static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat);
+static DevMetSlot slot_view(const fpb_handle *h, int fslot);
+
+// itime_valid: the sort runs at the top of fpb_step(itime), so the key can carry
+// the turbulence regime of that step
+static int do_sort(fpb_handle *h, bool itime_valid, int itime) {
   const int n = h->numpart;
   if (n <= 1) return 0;
   if (scatter_reserve(h->scatter, (size_t)n, 1)) return fail("%s", scatter_error());
-  per_step_cfg(h, h->d_tmp, 0, 0);
-  sortk_build_keys(h->d_tmp, h->p, h->d_height, n, h->scatter.keys[0], h->scatter.ids[0], h->d_nlive, h->stream);
+  per_step_cfg(h, h->d_tmp, itime, 0);
   const unsigned long long ncell = (unsigned long long)h->d.nxd * h->d.nyd * h->cfg.nz;
-  int bits = 1;
-  while ((1ull << bits) < ncell + 1) bits++;
+  int cell_bits = 1;
+  while ((1ull << cell_bits) < ncell) cell_bits++;
+  const bool regime = itime_valid && h->have_bracket && cell_bits <= 29;
+  DevMetSlot met[2];
+  if (regime) {
+    met[0] = slot_view(h, h->memind[0]);
+    met[1] = slot_view(h, h->memind[1]);
+  }
+  sortk_build_keys(h->d_tmp, h->p, h->d_height, n, h->scatter.keys[0], h->scatter.ids[0], h->d_nlive,
+                   h->stream, regime ? met : nullptr, cell_bits);
+  int bits = cell_bits + (regime ? 2 : 0) + 1; // +1: dead rows carry all-ones keys and must sort last
   bits = ((bits + 7) / 8) * 8;
-  if (bits < 32) bits += 8; // dead rows carry all-ones keys and must sort last
   if (bits > 32) bits = 32;
   int cur = 0;
   if (scatter_sort_pairs(h->scatter, (size_t)n, bits, h->stream, &h->launches, &cur)) return fail("%s", scatter_error());
@@ -593,7 +605,7 @@ static int do_sort(fpb_handle *h) {
 extern "C" int fpb_sort_particles(fpb_handle *h) {
   if (!h) return fail("fpb_sort_particles: null handle");
   CK(cudaSetDevice(h->device));
-  return do_sort(h);
+  return do_sort(h, false, 0);
 }
 
 // ------------------------------------------------------------------- step --
@@ -656,7 +668,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
     return 0;
   }
   if (h->cfg.sort_interval > 0 && h->steps_since_sort >= h->cfg.sort_interval) {
-    if (do_sort(h)) return 1;
+    if (do_sort(h, true, itime)) return 1;
   }
   h->steps_since_sort++;
   if (h->cfg.rng_mode == FPB_RNG_REFERENCE && replay_ran3_indices(h, itime)) return 1;

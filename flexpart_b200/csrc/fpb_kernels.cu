@@ -184,7 +184,11 @@ __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot 
   const int base = (n - 1) * (c.nxd * c.nyd);
   float y1[2], y2[2], y3[2], r1[2], g1[2];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+#ifdef FPB_LEVEL_SLOT_LOOP
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int m = 0; m < 2; m++) {
     const float4 *A = met[m].A + base, *B = met[m].B + base;
     float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);

@@ -47,17 +47,20 @@ radix_hist_kernel(const unsigned *keys, size_t n, int shift, unsigned *hist, int
   for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = sh[d];
 }
 
-// pass 2: exclusive scan of hist (digit-major) in place; single block,
-// sequential over chunks -- the array is n/16 entries
-__global__ void __launch_bounds__(1024) scan_kernel(unsigned *hist, size_t m) {
-  __shared__ unsigned warp_tot[32];
+// pass 2: one block per digit scans that digit's row of per-block counts in
+// place (exclusive) and leaves the digit total in totals[digit]; the scatter
+// kernel turns the 256 totals into digit base offsets itself.
+__global__ void __launch_bounds__(256) digit_scan_kernel(unsigned *hist, int nblocks, unsigned *totals) {
+  __shared__ unsigned warp_tot[8];
   __shared__ unsigned carry;
+  unsigned *row = hist + (size_t)blockIdx.x * nblocks;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (size_t base = 0; base < m; base += 1024) {
-    size_t i = base + threadIdx.x;
-    unsigned v = (i < m) ? hist[i] : 0u, x = v;
+  for (int base = 0; base < nblocks; base += 256) {
+    const int i = base + threadIdx.x;
+    const unsigned v = (i < nblocks) ? row[i] : 0u;
+    unsigned x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       unsigned y = __shfl_up_sync(0xffffffffu, x, o);
@@ -65,22 +68,14 @@ __global__ void __launch_bounds__(1024) scan_kernel(unsigned *hist, size_t m) {
     }
     if (lane == 31) warp_tot[wid] = x;
     __syncthreads();
-    if (wid == 0) {
-      unsigned t = warp_tot[lane], s = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
-      }
-      warp_tot[lane] = s - t; // exclusive warp offsets
-    }
+    unsigned before = carry;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    if (i < nblocks) row[i] = before + (x - v);
     __syncthreads();
-    unsigned excl = carry + warp_tot[wid] + (x - v);
-    if (i < m) hist[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
+    if (threadIdx.x == 255) carry = before + x;
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
 // pass 3: stable scatter.  Element order inside a block is (round, thread);
@@ -88,11 +83,27 @@ __global__ void __launch_bounds__(1024) scan_kernel(unsigned *hist, size_t m) {
 // of this round + earlier lanes of this warp.
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const unsigned *keys, const unsigned *ids, unsigned *keys_out,
-                     unsigned *ids_out, size_t n, int shift, const unsigned *hist, int nblocks) {
+                     unsigned *ids_out, size_t n, int shift, const unsigned *hist, int nblocks,
+                     const unsigned *totals) {
   __shared__ unsigned run[RADIX];                // global offset + count so far
   __shared__ unsigned wcnt[SORT_WARPS][RADIX];   // this round's per-warp counts
+  __shared__ unsigned wsum[SORT_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) run[d] = hist[(size_t)d * nblocks + blockIdx.x];
+  static_assert(RADIX == SORT_THREADS, "one thread per digit in the base-offset scan");
+  { // digit base = exclusive scan of the digit totals
+    const unsigned v = totals[threadIdx.x];
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < wid; w++) before += wsum[w];
+    run[threadIdx.x] = before + (x - v) + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  }
   const size_t base = (size_t)blockIdx.x * SORT_TILE;
   for (int r = 0; r < SORT_ROUNDS; r++) {
     for (int d = threadIdx.x; d < RADIX * SORT_WARPS; d += SORT_THREADS) (&wcnt[0][0])[d] = 0;
@@ -175,10 +186,10 @@ int scatter_reserve(ScatterWork &w, size_t nrec, int nspec) {
     w.cap_vals = nrec * nspec;
   }
   size_t nblocks = (nrec + SORT_TILE - 1) / SORT_TILE;
-  if (nblocks * RADIX > w.cap_hist) {
+  if ((nblocks + 1) * RADIX > w.cap_hist) { // per-block counts + one row of digit totals
     cudaFree(w.hist);
-    SCK(cudaMalloc((void **)&w.hist, nblocks * RADIX * sizeof(unsigned)));
-    w.cap_hist = nblocks * RADIX;
+    SCK(cudaMalloc((void **)&w.hist, (nblocks + 1) * RADIX * sizeof(unsigned)));
+    w.cap_hist = (nblocks + 1) * RADIX;
   }
   return 0;
 }
@@ -189,9 +200,10 @@ int scatter_sort_pairs(ScatterWork &w, size_t n, int bits, cudaStream_t st, int6
   int cur = 0;
   for (int shift = 0; shift < bits; shift += RADIX_BITS) {
     radix_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(w.keys[cur], n, shift, w.hist, nblocks);
-    scan_kernel<<<1, 1024, 0, st>>>(w.hist, (size_t)nblocks * RADIX);
+    digit_scan_kernel<<<RADIX, 256, 0, st>>>(w.hist, nblocks, w.hist + (size_t)nblocks * RADIX);
     radix_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(w.keys[cur], w.ids[cur], w.keys[cur ^ 1],
-                                                           w.ids[cur ^ 1], n, shift, w.hist, nblocks);
+                                                           w.ids[cur ^ 1], n, shift, w.hist, nblocks,
+                                                           w.hist + (size_t)nblocks * RADIX);
     if (launches) *launches += 3;
     cur ^= 1;
   }

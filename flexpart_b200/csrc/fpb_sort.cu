@@ -3,9 +3,19 @@
 
 namespace {
 
+// Turbulence regime of the coming advance() call, as the top key bits: rows of
+// one regime become contiguous, so the lanes of a warp of fpb_pbl_kernel take
+// the same hanna*() branch.  0: h/|ol| < 1, 1: ol < 0, 2: stable, 3: above the
+// PBL (no sub-steps).  A grouping heuristic only -- results do not depend on
+// the row order -- so the interpolation here is the plain formula.
+struct RegimeMet {
+  const float4 *S0, *S1; // {hmix, ustar, wstar, oli} of memind(1), memind(2); null: no regime bits
+  float dt1, dt2;
+};
+
 __global__ void __launch_bounds__(256)
 build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsigned *keys,
-                  unsigned *ids, unsigned *nlive) {
+                  unsigned *ids, unsigned *nlive, RegimeMet rm, int cell_bits) {
   __shared__ float sh[FPB_MAXNZ];
   for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = height[i];
   __syncthreads();
@@ -15,7 +25,8 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
     unsigned key = 0xffffffffu;
     if (p.itra1[i] != FPB_ITRA_DEAD) {
       live = 1;
-      int ix = (int)p.xtra1[i], jy = (int)p.ytra1[i];
+      const double xd = p.xtra1[i], yd = p.ytra1[i];
+      int ix = (int)xd, jy = (int)yd;
       ix = min(max(ix, 0), c.nxd - 1);
       jy = min(max(jy, 0), c.nyd - 1);
       const float zt = p.ztra1[i];
@@ -25,6 +36,22 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
         if (sh[mid - 1] > zt) hi = mid; else lo = mid + 1;
       }
       key = (unsigned)(((lo - 2) * c.nyd + jy) * c.nxd + ix);
+      if (rm.S0) {
+        const int ixp = min(ix + 1, c.nxd - 1), jyp = min(jy + 1, c.nyd - 1);
+        const float ddx = (float)xd - (float)ix, ddy = (float)yd - (float)jy;
+        const float p1 = (1.f - ddx) * (1.f - ddy), p2 = ddx * (1.f - ddy), p3 = (1.f - ddx) * ddy, p4 = ddx * ddy;
+        const int o00 = ix + c.nxd * jy, o10 = ixp + c.nxd * jy, o01 = ix + c.nxd * jyp, o11 = ixp + c.nxd * jyp;
+        const float4 a0 = __ldg(rm.S0 + o00), b0 = __ldg(rm.S0 + o10), c0 = __ldg(rm.S0 + o01), d0 = __ldg(rm.S0 + o11);
+        const float4 a1 = __ldg(rm.S1 + o00), b1 = __ldg(rm.S1 + o10), c1 = __ldg(rm.S1 + o01), d1 = __ldg(rm.S1 + o11);
+        const float h = fmaxf(fmaxf(fmaxf(a0.x, b0.x), fmaxf(c0.x, d0.x)), fmaxf(fmaxf(a1.x, b1.x), fmaxf(c1.x, d1.x)));
+        const float oli = ((p1 * a0.w + p2 * b0.w + p3 * c0.w + p4 * d0.w) * rm.dt2 +
+                           (p1 * a1.w + p2 * b1.w + p3 * c1.w + p4 * d1.w) * rm.dt1);
+        unsigned regime;
+        if (!(zt <= h)) regime = 3u;
+        else if (h * fabsf(oli) < fabsf(rm.dt1 + rm.dt2)) regime = 0u;
+        else regime = ((oli < 0.f) != ((rm.dt1 + rm.dt2) < 0.f)) ? 1u : 2u;
+        key |= regime << cell_bits;
+      }
     }
     keys[i] = key;
     ids[i] = (unsigned)i;
@@ -103,9 +130,15 @@ inline unsigned nb(int n, int t) { return (unsigned)((n + t - 1) / t); }
 } // namespace
 
 void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *height, int nrows,
-                      unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st) {
+                      unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st,
+                      const DevMetSlot *met, int cell_bits) {
   cudaMemsetAsync(d_nlive, 0, sizeof(unsigned), st);
-  build_keys_kernel<<<nb(nrows, 256), 256, 0, st>>>(c, p, height, nrows, keys, ids, d_nlive);
+  RegimeMet rm;
+  rm.S0 = met ? met[0].S : nullptr;
+  rm.S1 = met ? met[1].S : nullptr;
+  rm.dt1 = (float)(c.itime - c.memtime[0]);
+  rm.dt2 = (float)(c.memtime[1] - c.itime);
+  build_keys_kernel<<<nb(nrows, 256), 256, 0, st>>>(c, p, height, nrows, keys, ids, d_nlive, rm, cell_bits);
 }
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
                    int nrows, int nspec, cudaStream_t st) {

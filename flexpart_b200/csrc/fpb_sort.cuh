@@ -1,14 +1,18 @@
 // fpb_sort.cuh -- re-ordering of the device-resident particle rows by
 // meteorological grid cell (level-major: key = met array index of the cell
-// under the particle), for gather locality and warp convergence.
+// under the particle, below the turbulence regime of the coming step), for
+// gather locality and warp convergence.
 // slot[row] / row_of_slot[slot] keep the caller's slot indices stable.
 #pragma once
 #include "fpb_device.cuh"
 #include "fpb_scatter.cuh"
 
-// build keys (dead rows sort last), returns the number of live rows via *d_nlive
+// build keys (dead rows sort last), returns the number of live rows via *d_nlive.
+// met != null: met[0..1] = the fields bracketing c.itime; the turbulence regime of
+// the coming step is put above the cell_bits cell bits of the key.
 void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *height, int nrows,
-                      unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st);
+                      unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st,
+                      const DevMetSlot *met, int cell_bits);
 // dst row i := src row ids[i] for every particle array (incl. slot)
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
                    int nrows, int nspec, cudaStream_t st);

@@ -38,7 +38,7 @@ struct PblTask {
   int nrand, itimec;
   Hz z;
   float ust, wst, ol, h;
-  Lev lo, hi;
+  Lev E, O; // cached profile levels: level n lives in O when n is odd, in E when even
   int indz;
   float dxsave, dysave, dawsave, dcwsave;
   int nsub, nan_cbl;
@@ -49,6 +49,16 @@ struct PblTask {
   float prob[EXTRA ? FPB_MAXSPEC : 1];
   float vdepo[EXTRA ? FPB_MAXSPEC : 1];
   unsigned depo_todo;
+
+  // usigprof/vsigprof/wsigprof of the upper (indz+1) and lower (indz) level
+  __device__ __forceinline__ float hi_sig(int k) const {
+    const Lev &L = (indz & 1) ? E : O;
+    return k == 0 ? L.usig : (k == 1 ? L.vsig : L.wsig);
+  }
+  __device__ __forceinline__ float lo_sig(int k) const {
+    const Lev &L = (indz & 1) ? O : E;
+    return k == 0 ? L.usig : (k == 1 ? L.vsig : L.wsig);
+  }
 
   __device__ __forceinline__ float normal(const DevStepArgs &a, int i) {
     if (EXTRA) return rng.get(i);
@@ -167,53 +177,45 @@ struct PblTask {
     t.zeta = zt / t.h;
 
     // level pair under the particle (src/advance.f90:310-331); a level computed
-    // again gives the same bits as the reference's cached one
+    // again gives the same bits as the reference's cached one.  The cache holds
+    // the pair (indz, indz+1) by parity, so moving one level up or down
+    // replaces exactly the register set that is no longer needed.
     {
       int ni;
       if (first) {
         ni = find_indz(sh, nz, zt);
-      } else if (sh[indz - 1] <= zt && sh[indz] > zt) {
-        ni = indz; // still between the same levels
-      } else if (indz + 1 < nz && sh[indz] <= zt && sh[indz + 1] > zt) {
-        ni = indz + 1;
-      } else if (indz >= 2 && sh[indz - 1] > zt && (indz == 2 || sh[indz - 2] <= zt)) {
-        ni = indz - 1;
-      } else {
-        ni = find_indz(sh, nz, zt);
+      } else { // walk from the previous level (same index as the reference's search from 2)
+        ni = indz;
+        while (ni + 1 < nz && sh[ni] <= zt) ni++;
+        while (ni > 1 && sh[ni - 1] > zt) ni--;
       }
-      bool need_lo = true, need_hi = true;
-      if (!first) {
-        if (ni == indz) {
-          need_lo = need_hi = false;
-        } else if (ni == indz + 1) {
-          lo = hi;
-          need_lo = false;
-        } else if (ni + 1 == indz) {
-          hi = lo;
-          need_hi = false;
-        }
-      }
+      bool need_lo = first || (ni != indz && ni != indz + 1);
+      bool need_hi = first || (ni + 1 != indz && ni != indz);
       indz = ni;
       first = false;
       // one converged call site; a lane that needs both levels goes round twice
 #pragma unroll 1
       while (need_lo || need_hi) {
         const bool do_lo = need_lo;
+        const int n = ni + (do_lo ? 0 : 1);
         Lev t_;
-        profile_level(c, a.met, z, ni + (do_lo ? 0 : 1), t_);
-        if (do_lo) { lo = t_; need_lo = false; } else { hi = t_; need_hi = false; }
+        profile_level(c, a.met, z, n, t_);
+        if (n & 1) O = t_; else E = t_;
+        if (do_lo) need_lo = false; else need_hi = false;
       }
     }
 
-    // advance.f90:342-350
+    // advance.f90:342-350; lower level = indz, upper = indz+1 (a sum of two
+    // products does not depend on their order)
     const float dz = 1.f / (sh[indz] - sh[indz - 1]);
     const float dz1 = (zt - sh[indz - 1]) * dz;
     const float dz2 = (sh[indz] - zt) * dz;
-    const float u = dz1 * hi.u + dz2 * lo.u;
-    const float v = dz1 * hi.v + dz2 * lo.v;
-    float w = dz1 * hi.w + dz2 * lo.w;
-    const float rhoa = dz1 * hi.rho + dz2 * lo.rho;
-    const float rhograd = dz1 * hi.rhograd + dz2 * lo.rhograd;
+    const float wE = (indz & 1) ? dz1 : dz2, wO = (indz & 1) ? dz2 : dz1;
+    const float u = wE * E.u + wO * O.u;
+    const float v = wE * E.v + wO * O.v;
+    float w = wE * E.w + wO * O.w;
+    const float rhoa = wE * E.rho + wO * O.rho;
+    const float rhograd = wE * E.rhograd + wO * O.rhograd;
 
     if (c.turbswitch) hanna(t, zt, regime); else hanna1(t, zt, regime);
 
@@ -344,8 +346,8 @@ struct PblTask {
     if (zt > t.h) {
       if (itimec == itime + c.lsynctime) {
         // "defined" behaviour for the stale-usig case
-        finish(a, false, u, v, w, 0.5f * (hi.usig + lo.usig), 0.5f * (hi.vsig + lo.vsig),
-               0.5f * (hi.wsig + lo.wsig));
+        finish(a, false, u, v, w, 0.5f * (hi_sig(0) + lo_sig(0)), 0.5f * (hi_sig(1) + lo_sig(1)),
+               0.5f * (hi_sig(2) + lo_sig(2)));
       } else {
         finish(a, true, u, v, w, 0.f, 0.f, 0.f);
       }
@@ -374,8 +376,8 @@ struct PblTask {
     if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
 
     if (itimec == (itime + c.lsynctime))
-      finish(a, false, u, v, w, 0.5f * (hi.usig + lo.usig), 0.5f * (hi.vsig + lo.vsig),
-             0.5f * (hi.wsig + lo.wsig));
+      finish(a, false, u, v, w, 0.5f * (hi_sig(0) + lo_sig(0)), 0.5f * (hi_sig(1) + lo_sig(1)),
+             0.5f * (hi_sig(2) + lo_sig(2)));
   }
 };
 
