@@ -108,7 +108,9 @@ struct fpb_handle {
   cudaStream_t stream = nullptr;
 
   // met: index = Fortran slot - 1
-  float4 *A[2] = {nullptr, nullptr}, *B[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
+  float4 *A[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
+  float *G[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
+  float2 *P[2] = {nullptr, nullptr};
   float *trop[2] = {nullptr, nullptr}, *vdep[2] = {nullptr, nullptr};
   float *stage = nullptr;
   size_t stage_n = 0;
@@ -301,7 +303,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
 
   const size_t n3 = (size_t)d.nxd * d.nyd * c.nz, n2 = (size_t)d.nxd * d.nyd;
   for (int s = 0; s < 2; s++) {
-    DA(h->A[s], n3); DA(h->B[s], n3); DA(h->S[s], n2);
+    DA(h->A[s], n3); DA(h->G[s], n3); DA(h->T[s], n3); DA(h->P[s], n3); DA(h->S[s], n2);
     DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
   }
   const size_t mp = (size_t)c.maxpart;
@@ -356,7 +358,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (int s = 0; s < 2; s++) {
-    cudaFree(h->A[s]); cudaFree(h->B[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
+    cudaFree(h->A[s]); cudaFree(h->G[s]); cudaFree(h->T[s]); cudaFree(h->P[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
   }
   cudaFree(h->stage);
   for (DevParticles *q : {&h->p, &h->p_alt}) {
@@ -417,15 +419,15 @@ extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m
   if (c.drydep && !m->vdep) return fail("fpb_upload_met: vdep required when drydep");
   CK(cudaSetDevice(h->device));
   const int s = slot - 1;
-  float *A = (float *)h->A[s], *B = (float *)h->B[s], *S = (float *)h->S[s];
+  float *A = (float *)h->A[s], *S = (float *)h->S[s];
   if (upload_component(h, A, 0, 4, m->uu, c.nz)) return 1;
   if (upload_component(h, A, 1, 4, m->vv, c.nz)) return 1;
   if (upload_component(h, A, 2, 4, m->ww, c.nz)) return 1;
   if (upload_component(h, A, 3, 4, m->rho, c.nz)) return 1;
-  if (upload_component(h, B, 0, 4, m->drhodz, c.nz)) return 1;
-  if (upload_component(h, B, 1, 4, m->tt, c.nz)) return 1;
-  if (upload_component(h, B, 2, 4, m->uupol, c.nz)) return 1;
-  if (upload_component(h, B, 3, 4, m->vvpol, c.nz)) return 1;
+  if (upload_component(h, h->G[s], 0, 1, m->drhodz, c.nz)) return 1;
+  if (upload_component(h, h->T[s], 0, 1, m->tt, c.nz)) return 1;
+  if (upload_component(h, (float *)h->P[s], 0, 2, m->uupol, c.nz)) return 1;
+  if (upload_component(h, (float *)h->P[s], 1, 2, m->vvpol, c.nz)) return 1;
   if (upload_component(h, S, 0, 4, m->hmix, 1)) return 1;
   if (upload_component(h, S, 1, 4, m->ustar, 1)) return 1;
   if (upload_component(h, S, 2, 4, m->wstar, 1)) return 1;
@@ -623,7 +625,7 @@ static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat) {
 static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
   DevMetSlot m;
   const int s = fslot - 1;
-  m.A = h->A[s]; m.B = h->B[s]; m.S = h->S[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
+  m.A = h->A[s]; m.G = h->G[s]; m.T = h->T[s]; m.P = h->P[s]; m.S = h->S[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
   return m;
 }
 

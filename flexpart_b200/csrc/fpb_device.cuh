@@ -2,7 +2,8 @@
 //
 // Data layout in HBM (DESIGN.md "Data layout"):
 //   met, per time slot:  A[k][jy][ix] = float4{uu,vv,ww,rho}
-//                        B[k][jy][ix] = float4{drhodz,tt,uupol,vvpol}
+//                        G[k][jy][ix] = drhodz, T[k][jy][ix] = tt,
+//                        P[k][jy][ix] = float2{uupol,vvpol}
 //                        S[jy][ix]    = float4{hmix,ustar,wstar,oli}
 //                        trop[jy][ix], vdep[ks][jy][ix]
 //     -> the 4 values a bilinear corner needs sit in one 16-B word and the
@@ -21,7 +22,9 @@
 
 struct DevMetSlot {
   const float4 *A;
-  const float4 *B;
+  const float *G;  // drhodz
+  const float *T;  // tt (settling only)
+  const float2 *P; // uupol, vvpol (poleward of the switch latitudes only)
   const float4 *S;
   const float *trop;
   const float *vdep;
@@ -96,8 +99,8 @@ struct DevCfg {
 struct DevScratch {
   int32_t *flags;
   float4 *s0; // dxsave, dysave, dawsave, dcwsave
-  float4 *s1; // u, v, w, usig
-  float4 *s2; // vsig, wsig, nrand (bits), itimec (bits)
+  float4 *s1; // u, v, w, indz of the last sub-step (bits)
+  int2 *s2;   // nrand, itimec
   float *prob; // [nspec][maxpart], dry-deposition probability (drydep runs only)
 };
 

@@ -30,7 +30,7 @@
 #define FPB_STRICT 0
 #endif
 #ifndef FPB_PBL_MIN_BLOCKS
-#define FPB_PBL_MIN_BLOCKS 4 // resident 128-thread CTAs per SM the sub-step kernel is tuned for
+#define FPB_PBL_MIN_BLOCKS 5 // resident 128-thread CTAs per SM the sub-step kernel is tuned for
 #endif
 
 namespace {
@@ -178,7 +178,11 @@ __device__ __forceinline__ int find_indz(const float *sh, int nz, float zt) {
   return lo - 1;
 }
 
-// one profile level: src/interpol_all.f90:135-238 == src/interpol_misslev.f90:56-157
+// one profile level: src/interpol_all.f90:135-238 == src/interpol_misslev.f90:56-157.
+// SIGMA=false leaves usigprof/vsigprof/wsigprof out (fpb_pbl_kernel: they are
+// only read once, after the sub-step loop, and fpb_finish_kernel recomputes
+// them for the final level pair with profile_sigma).
+template <bool SIGMA>
 __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot *met,
                                               const Hz &z, int n, Lev &L) {
   const int base = (n - 1) * (c.nxd * c.nyd);
@@ -190,40 +194,82 @@ __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot 
 #pragma unroll
 #endif
   for (int m = 0; m < 2; m++) {
-    const float4 *A = met[m].A + base, *B = met[m].B + base;
+    const float4 *A = met[m].A + base;
+    const float *G = met[m].G + base;
     float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
-    float4 Ba = __ldg(B + z.o00), Bb = __ldg(B + z.o10), Bc = __ldg(B + z.o01), Bd = __ldg(B + z.o11);
+    const float ga = __ldg(G + z.o00), gb = __ldg(G + z.o10), gc = __ldg(G + z.o01), gd = __ldg(G + z.o11);
     float ua, ub, uc, ud, va, vb, vc, vd;
     if (z.ngrid < 0) {
-      ua = Ba.z; ub = Bb.z; uc = Bc.z; ud = Bd.z;
-      va = Ba.w; vb = Bb.w; vc = Bc.w; vd = Bd.w;
+      const float2 *P = met[m].P + base;
+      const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
+      ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
+      va = Pa.y; vb = Pb.y; vc = Pc.y; vd = Pd.y;
     } else {
       ua = Aa.x; ub = Ab.x; uc = Ac.x; ud = Ad.x;
       va = Aa.y; vb = Ab.y; vc = Ac.y; vd = Ad.y;
     }
     y1[m] = bil(z, ua, ub, uc, ud);
     y2[m] = bil(z, va, vb, vc, vd);
-    usl = usl + ua + ub + uc + ud;
-    vsl = vsl + va + vb + vc + vd;
-    usq = usq + ua * ua + ub * ub + uc * uc + ud * ud;
-    vsq = vsq + va * va + vb * vb + vc * vc + vd * vd;
     y3[m] = bil(z, Aa.z, Ab.z, Ac.z, Ad.z);
-    g1[m] = bil(z, Ba.x, Bb.x, Bc.x, Bd.x);
+    g1[m] = bil(z, ga, gb, gc, gd);
     r1[m] = bil(z, Aa.w, Ab.w, Ac.w, Ad.w);
-    wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
-    wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
+    if (SIGMA) {
+      usl = usl + ua + ub + uc + ud;
+      vsl = vsl + va + vb + vc + vd;
+      usq = usq + ua * ua + ub * ub + uc * uc + ud * ud;
+      vsq = vsq + va * va + vb * vb + vc * vc + vd * vd;
+      wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
+      wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
+    }
   }
   L.u = (y1[0] * z.dt2 + y1[1] * z.dt1) * z.dtt;
   L.v = (y2[0] * z.dt2 + y2[1] * z.dt1) * z.dtt;
   L.w = (y3[0] * z.dt2 + y3[1] * z.dt1) * z.dtt;
   L.rho = (r1[0] * z.dt2 + r1[1] * z.dt1) * z.dtt;
   L.rhograd = (g1[0] * z.dt2 + g1[1] * z.dt1) * z.dtt;
+  if (SIGMA) {
+    float xaux = usq - usl * usl / 8.f;
+    L.usig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+    xaux = vsq - vsl * vsl / 8.f;
+    L.vsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+    xaux = wsq - wsl * wsl / 8.f;
+    L.wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  }
+}
+
+// usigprof(n), vsigprof(n), wsigprof(n) alone: the standard deviations over the
+// 8 surrounding values, src/interpol_all.f90:155-238 (same sums, same order)
+__device__ __forceinline__ void profile_sigma(const DevCfg &c, const DevMetSlot *met, const Hz &z,
+                                              int n, float &usig, float &vsig, float &wsig) {
+  const int base = (n - 1) * (c.nxd * c.nyd);
+  float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const float4 *A = met[m].A + base;
+    float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
+    float ua, ub, uc, ud, va, vb, vc, vd;
+    if (z.ngrid < 0) {
+      const float2 *P = met[m].P + base;
+      const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
+      ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
+      va = Pa.y; vb = Pb.y; vc = Pc.y; vd = Pd.y;
+    } else {
+      ua = Aa.x; ub = Ab.x; uc = Ac.x; ud = Ad.x;
+      va = Aa.y; vb = Ab.y; vc = Ac.y; vd = Ad.y;
+    }
+    usl = usl + ua + ub + uc + ud;
+    vsl = vsl + va + vb + vc + vd;
+    usq = usq + ua * ua + ub * ub + uc * uc + ud * ud;
+    vsq = vsq + va * va + vb * vb + vc * vc + vd * vd;
+    wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
+    wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
+  }
   float xaux = usq - usl * usl / 8.f;
-  L.usig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  usig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
   xaux = vsq - vsl * vsl / 8.f;
-  L.vsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  vsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
   xaux = wsq - wsl * wsl / 8.f;
-  L.wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
+  wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
 }
 
 // src/interpol_wind.f90:56-214 (SIGMA=true) / src/interpol_wind_short.f90:48-140
@@ -249,10 +295,10 @@ __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *m
       float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
       float ua, ub, uc, ud, va, vb, vc, vd;
       if (z.ngrid < 0) {
-        const float4 *B = met[m].B + base;
-        float4 Ba = __ldg(B + z.o00), Bb = __ldg(B + z.o10), Bc = __ldg(B + z.o01), Bd = __ldg(B + z.o11);
-        ua = Ba.z; ub = Bb.z; uc = Bc.z; ud = Bd.z;
-        va = Ba.w; vb = Bb.w; vc = Bc.w; vd = Bd.w;
+        const float2 *P = met[m].P + base;
+        const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
+        ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
+        va = Pa.y; vb = Pb.y; vc = Pc.y; vd = Pd.y;
       } else {
         ua = Aa.x; ub = Ab.x; uc = Ac.x; ud = Ad.x;
         va = Aa.y; vb = Ab.y; vc = Ac.y; vd = Ad.y;
@@ -633,8 +679,8 @@ __device__ __noinline__ float get_settling(const DevCfg &c, const DevMetSlot &li
   float dz2 = (sh[indz] - zt) * dz;
   int plane = c.nxd * c.nyd, o = nix + c.nxd * njy;
   float4 A0 = __ldg(lit1.A + (indz - 1) * plane + o), A1 = __ldg(lit1.A + indz * plane + o);
-  float4 B0 = __ldg(lit1.B + (indz - 1) * plane + o), B1 = __ldg(lit1.B + indz * plane + o);
-  float temperature = dz2 * B0.y + dz1 * B1.y;
+  const float t0 = __ldg(lit1.T + (indz - 1) * plane + o), t1 = __ldg(lit1.T + indz * plane + o);
+  float temperature = dz2 * t0 + dz1 * t1;
   float airdens = dz2 * A0.w + dz1 * A1.w;
   const float cc = 120.f, t_0 = 291.15f, eta_0 = 1.827e-5f;
   float vis_dyn = eta_0 * (t_0 + cc) / (temperature + cc) * m_pow(temperature / t_0, 1.5f);
@@ -755,8 +801,8 @@ __device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, i
     interp_surface(a.met, z, t);
     const int indz = find_indz(sh, c.nz, s.zt), indzp = indz + 1;
     Lev lo, hi;
-    profile_level(c, a.met, z, indz, lo);
-    profile_level(c, a.met, z, indzp, hi);
+    profile_level<true>(c, a.met, z, indz, lo);
+    profile_level<true>(c, a.met, z, indzp, hi);
     // (u, v, w of initialize are dead: advance re-interpolates)
     if (c.turbswitch) hanna(t, s.zt, hanna_regime(t)); else hanna1(t, s.zt, hanna_regime(t));
     if (nrand + 2 > c.maxrand) nrand = 1;

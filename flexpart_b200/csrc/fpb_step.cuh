@@ -28,17 +28,33 @@
 enum : int { SC_PBL = 1, SC_ABOVE = 2 };
 
 // ----------------------------------------------------------- PBL kernel ----
+// Per-lane shared-memory rows (word w of lane t lives at ls[w * PBL_THREADS],
+// ls = smem + t, so every access is conflict-free):
+//   LS_P1..LS_P4, LS_O00, LS_O01   horizontal weights / corner offsets of the call
+//   LS_TAG + e                     level held by cache entry e (0 = empty)
+//   LS_LEV + 5*e + f               field f of that level: u, v, w, rho, rhograd
+// The profile cache is direct-mapped by (level mod PBL_CACHE): it plays the
+// role of the reference's nzmax-long uprof.. arrays + indzindicator
+// (src/advance.f90:310-331) for the levels a particle visits during one call.
+constexpr int PBL_THREADS = 128;
+#ifndef FPB_PBL_CACHE
+#define FPB_PBL_CACHE 8
+#endif
+constexpr int PBL_CACHE = FPB_PBL_CACHE; // power of two
+constexpr int LEV_WORDS = 5; // u, v, w, rho, rhograd
+enum : int { LS_P1 = 0, LS_P2, LS_P3, LS_P4, LS_O00, LS_O01, LS_TAG, LS_LEV = LS_TAG + PBL_CACHE,
+             LS_WORDS = LS_LEV + LEV_WORDS * PBL_CACHE };
+
 template <bool EXTRA, bool CBL>
 struct PblTask {
   int j;
   bool running, first;
   int regime; // 0: h/|ol| < 1, 1: ol < 0, 2: stable  (hanna*.f90 branch, fixed for the call)
+  int ngrid;
   float zt, up, vp, wp;
   int ldt, icbt;
   int nrand, itimec;
-  Hz z;
   float ust, wst, ol, h;
-  Lev E, O; // cached profile levels: level n lives in O when n is odd, in E when even
   int indz;
   float dxsave, dysave, dawsave, dcwsave;
   int nsub, nan_cbl;
@@ -50,14 +66,20 @@ struct PblTask {
   float vdepo[EXTRA ? FPB_MAXSPEC : 1];
   unsigned depo_todo;
 
-  // usigprof/vsigprof/wsigprof of the upper (indz+1) and lower (indz) level
-  __device__ __forceinline__ float hi_sig(int k) const {
-    const Lev &L = (indz & 1) ? E : O;
-    return k == 0 ? L.usig : (k == 1 ? L.vsig : L.wsig);
+  __device__ __forceinline__ static float &lsf(float *ls, int w) { return ls[w * PBL_THREADS]; }
+  __device__ __forceinline__ static int &lsi(float *ls, int w) {
+    return reinterpret_cast<int *>(ls)[w * PBL_THREADS];
   }
-  __device__ __forceinline__ float lo_sig(int k) const {
-    const Lev &L = (indz & 1) ? O : E;
-    return k == 0 ? L.usig : (k == 1 ? L.vsig : L.wsig);
+
+  // interpol_mod weights of the call, rebuilt from the lane's shared row
+  __device__ __forceinline__ void load_weights(const DevCfg &c, float *ls, Hz &z) const {
+    z.p1 = lsf(ls, LS_P1); z.p2 = lsf(ls, LS_P2); z.p3 = lsf(ls, LS_P3); z.p4 = lsf(ls, LS_P4);
+    z.o00 = lsi(ls, LS_O00); z.o10 = z.o00 + 1;
+    z.o01 = lsi(ls, LS_O01); z.o11 = z.o01 + 1;
+    z.dt1 = (float)(c.itime - c.memtime[0]);
+    z.dt2 = (float)(c.memtime[1] - c.itime);
+    z.dtt = 1.f / (z.dt1 + z.dt2);
+    z.ngrid = ngrid;
   }
 
   __device__ __forceinline__ float normal(const DevStepArgs &a, int i) {
@@ -66,7 +88,7 @@ struct PblTask {
   }
 
   // src/advance.f90:133-276.  Returns true when the row is active.
-  __device__ __forceinline__ bool refill(const DevStepArgs &a, int row, bool &pbl) {
+  __device__ __forceinline__ bool refill(const DevStepArgs &a, float *ls, int row, bool &pbl) {
     const DevCfg &c = a.cfg;
     pbl = false;
     if (a.p.itra1[row] != c.itime) return false;
@@ -74,6 +96,7 @@ struct PblTask {
     const double xt = a.p.xtra1[row], yt = a.p.ytra1[row];
     zt = a.p.ztra1[row];
 
+    Hz z;
     z.ngrid = pole_grid(c, yt);
     const int ix = d_int(xt), jy = d_int(yt);
     int ixp = ix + 1, jyp = jy + 1;
@@ -102,6 +125,11 @@ struct PblTask {
       return true;
     }
     pbl = true;
+    ngrid = z.ngrid;
+    lsf(ls, LS_P1) = z.p1; lsf(ls, LS_P2) = z.p2; lsf(ls, LS_P3) = z.p3; lsf(ls, LS_P4) = z.p4;
+    lsi(ls, LS_O00) = z.o00; lsi(ls, LS_O01) = z.o01;
+#pragma unroll
+    for (int e = 0; e < PBL_CACHE; e++) lsi(ls, LS_TAG + e) = 0;
     {
       float us1[2], ws1[2], ol1[2];
 #pragma unroll
@@ -140,16 +168,15 @@ struct PblTask {
   }
 
   // leave the sub-step loop: hand the rest of advance() to fpb_finish_kernel
-  __device__ __forceinline__ void finish(const DevStepArgs &a, bool above, float u, float v, float w,
-                                         float usig, float vsig, float wsig) {
+  __device__ __forceinline__ void finish(const DevStepArgs &a, bool above, float u, float v, float w) {
     const DevCfg &c = a.cfg;
     a.p.ztra1[j] = zt;
     a.p.uap[j] = up; a.p.ucp[j] = vp; a.p.uzp[j] = wp;
     a.p.idt[j] = ldt;
     a.p.cbt[j] = (int16_t)icbt;
     a.sc.s0[j] = make_float4(dxsave, dysave, dawsave, dcwsave);
-    a.sc.s1[j] = make_float4(u, v, w, usig);
-    a.sc.s2[j] = make_float4(vsig, wsig, __int_as_float(nrand), __int_as_float(itimec));
+    a.sc.s1[j] = make_float4(u, v, w, __int_as_float(indz));
+    a.sc.s2[j] = make_int2(nrand, itimec);
     a.sc.flags[j] = SC_PBL | (above ? SC_ABOVE : 0);
     if (EXTRA && c.drydep) {
 #pragma unroll
@@ -160,7 +187,7 @@ struct PblTask {
   }
 
   // one pass of the label-100 loop, src/advance.f90:282-609
-  __device__ __forceinline__ void substep(const DevStepArgs &a, const float *sh) {
+  __device__ __forceinline__ void substep(const DevStepArgs &a, const float *sh, float *ls) {
     const DevCfg &c = a.cfg;
     const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
     nsub++;
@@ -176,46 +203,57 @@ struct PblTask {
     t.ust = ust; t.wst = wst; t.ol = ol; t.h = h;
     t.zeta = zt / t.h;
 
-    // level pair under the particle (src/advance.f90:310-331); a level computed
-    // again gives the same bits as the reference's cached one.  The cache holds
-    // the pair (indz, indz+1) by parity, so moving one level up or down
-    // replaces exactly the register set that is no longer needed.
+    // level pair under the particle (src/advance.f90:310-331): search, then
+    // compute the levels of the pair that this call has not computed yet
+    int e_lo, e_hi;
     {
       int ni;
       if (first) {
         ni = find_indz(sh, nz, zt);
+        first = false;
       } else { // walk from the previous level (same index as the reference's search from 2)
         ni = indz;
-        while (ni + 1 < nz && sh[ni] <= zt) ni++;
-        while (ni > 1 && sh[ni - 1] > zt) ni--;
+        if (ni + 1 < nz && sh[ni] <= zt) {
+          ni++;
+          while (ni + 1 < nz && sh[ni] <= zt) ni++;
+        } else if (ni > 1 && sh[ni - 1] > zt) {
+          ni--;
+          while (ni > 1 && sh[ni - 1] > zt) ni--;
+        }
       }
-      bool need_lo = first || (ni != indz && ni != indz + 1);
-      bool need_hi = first || (ni + 1 != indz && ni != indz);
       indz = ni;
-      first = false;
+      e_lo = ni & (PBL_CACHE - 1);
+      e_hi = (ni + 1) & (PBL_CACHE - 1);
+      bool need_lo = lsi(ls, LS_TAG + e_lo) != ni;
+      bool need_hi = lsi(ls, LS_TAG + e_hi) != ni + 1;
       // one converged call site; a lane that needs both levels goes round twice
 #pragma unroll 1
       while (need_lo || need_hi) {
         const bool do_lo = need_lo;
-        const int n = ni + (do_lo ? 0 : 1);
-        Lev t_;
-        profile_level(c, a.met, z, n, t_);
-        if (n & 1) O = t_; else E = t_;
+        const int n = ni + (do_lo ? 0 : 1), e = do_lo ? e_lo : e_hi;
+        Hz z;
+        load_weights(c, ls, z);
+        Lev L;
+        profile_level<false>(c, a.met, z, n, L);
+        float *q = ls + (LS_LEV + LEV_WORDS * e) * PBL_THREADS;
+        q[0 * PBL_THREADS] = L.u; q[1 * PBL_THREADS] = L.v; q[2 * PBL_THREADS] = L.w;
+        q[3 * PBL_THREADS] = L.rho; q[4 * PBL_THREADS] = L.rhograd;
+        lsi(ls, LS_TAG + e) = n;
         if (do_lo) need_lo = false; else need_hi = false;
       }
     }
+    const float *lo = ls + (LS_LEV + LEV_WORDS * e_lo) * PBL_THREADS,
+                *hi = ls + (LS_LEV + LEV_WORDS * e_hi) * PBL_THREADS;
 
-    // advance.f90:342-350; lower level = indz, upper = indz+1 (a sum of two
-    // products does not depend on their order)
+    // advance.f90:342-350
     const float dz = 1.f / (sh[indz] - sh[indz - 1]);
     const float dz1 = (zt - sh[indz - 1]) * dz;
     const float dz2 = (sh[indz] - zt) * dz;
-    const float wE = (indz & 1) ? dz1 : dz2, wO = (indz & 1) ? dz2 : dz1;
-    const float u = wE * E.u + wO * O.u;
-    const float v = wE * E.v + wO * O.v;
-    float w = wE * E.w + wO * O.w;
-    const float rhoa = wE * E.rho + wO * O.rho;
-    const float rhograd = wE * E.rhograd + wO * O.rhograd;
+    const float u = dz1 * hi[0 * PBL_THREADS] + dz2 * lo[0 * PBL_THREADS];
+    const float v = dz1 * hi[1 * PBL_THREADS] + dz2 * lo[1 * PBL_THREADS];
+    float w = dz1 * hi[2 * PBL_THREADS] + dz2 * lo[2 * PBL_THREADS];
+    const float rhoa = dz1 * hi[3 * PBL_THREADS] + dz2 * lo[3 * PBL_THREADS];
+    const float rhograd = dz1 * hi[4 * PBL_THREADS] + dz2 * lo[4 * PBL_THREADS];
 
     if (c.turbswitch) hanna(t, zt, regime); else hanna1(t, zt, regime);
 
@@ -346,10 +384,9 @@ struct PblTask {
     if (zt > t.h) {
       if (itimec == itime + c.lsynctime) {
         // "defined" behaviour for the stale-usig case
-        finish(a, false, u, v, w, 0.5f * (hi_sig(0) + lo_sig(0)), 0.5f * (hi_sig(1) + lo_sig(1)),
-               0.5f * (hi_sig(2) + lo_sig(2)));
+        finish(a, false, u, v, w);
       } else {
-        finish(a, true, u, v, w, 0.f, 0.f, 0.f);
+        finish(a, true, u, v, w);
       }
       return;
     }
@@ -360,6 +397,8 @@ struct PblTask {
       for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
         if (ks < c.nspec && c.drydepspec[ks]) {
           if (depo_todo & (1u << ks)) { // interpol_vdep, src/interpol_vdep.f90:39-54
+            Hz z;
+            load_weights(c, ls, z);
             const int off = ks * (c.nxd * c.nyd);
             const float y0 = bil(z, __ldg(a.met[0].vdep + off + z.o00), __ldg(a.met[0].vdep + off + z.o10),
                                  __ldg(a.met[0].vdep + off + z.o01), __ldg(a.met[0].vdep + off + z.o11));
@@ -375,21 +414,21 @@ struct PblTask {
 
     if (zt < 0.f) zt = fminf(t.h - EPS2, -1.f * zt);
 
-    if (itimec == (itime + c.lsynctime))
-      finish(a, false, u, v, w, 0.5f * (hi_sig(0) + lo_sig(0)), 0.5f * (hi_sig(1) + lo_sig(1)),
-             0.5f * (hi_sig(2) + lo_sig(2)));
+    if (itimec == (itime + c.lsynctime)) finish(a, false, u, v, w);
   }
 };
 
 // Persistent kernel: every warp pulls batches of particle rows from
 // *a.work_counter; lanes run sub-steps until their particle leaves the loop.
 template <bool EXTRA, bool CBL>
-__global__ void __launch_bounds__(128, EXTRA ? 3 : FPB_PBL_MIN_BLOCKS)
+__global__ void __launch_bounds__(PBL_THREADS, EXTRA ? 3 : FPB_PBL_MIN_BLOCKS)
 fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
+  __shared__ float lane_rows[LS_WORDS * PBL_THREADS];
   for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
   __syncthreads();
+  float *ls = lane_rows + threadIdx.x;
 
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int T_REFILL = 8; // refill when at least this many lanes are idle
@@ -413,7 +452,7 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
       if (!task.running) {
         const int row = base + __popc(idle & lt_mask);
         bool pbl = false;
-        if (row < nrows && task.refill(a, row, pbl)) {
+        if (row < nrows && task.refill(a, ls, row, pbl)) {
           n_act++;
           if (pbl) n_pbl++;
         }
@@ -423,7 +462,7 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
     }
     if (idle == FULL) break; // no rows left and nothing running
     if (task.running) {
-      task.substep(a, sh);
+      task.substep(a, sh, ls);
       if (!task.running) {
         n_sub += task.nsub;
         n_nan += task.nan_cbl;
@@ -467,14 +506,15 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 
   float dxsave = 0.f, dysave = 0.f, dawsave = 0.f, dcwsave = 0.f;
   float u = 0.f, v = 0.f, w = 0.f, usig = 0.f, vsig = 0.f, wsig = 0.f;
-  int nrand, itimec = itime;
+  int nrand, itimec = itime, indz_last = 1;
   if (flags & SC_PBL) {
-    const float4 s0 = a.sc.s0[j], s1 = a.sc.s1[j], s2 = a.sc.s2[j];
+    const float4 s0 = a.sc.s0[j], s1 = a.sc.s1[j];
+    const int2 s2 = a.sc.s2[j];
     dxsave = s0.x; dysave = s0.y; dawsave = s0.z; dcwsave = s0.w;
-    u = s1.x; v = s1.y; w = s1.z; usig = s1.w;
-    vsig = s2.x; wsig = s2.y;
-    nrand = __float_as_int(s2.z);
-    itimec = __float_as_int(s2.w);
+    u = s1.x; v = s1.y; w = s1.z;
+    indz_last = __float_as_int(s1.w);
+    nrand = s2.x;
+    itimec = s2.y;
   } else {
     nrand = advance_nrand(a, slot);
   }
@@ -503,6 +543,17 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 
   float ux = 0.f, vy = 0.f;
   int nstop = 0;
+
+  if ((flags & (SC_PBL | SC_ABOVE)) == SC_PBL) {
+    // usig = 0.5*(usigprof(indzp)+usigprof(indz)) etc. for the level pair of the last
+    // sub-step, advance.f90:604-606 (and the "defined" stale-usig case)
+    float a0, a1, a2, b0, b1, b2;
+    profile_sigma(c, a.met, z, indz_last, a0, a1, a2);
+    profile_sigma(c, a.met, z, indz_last + 1, b0, b1, b2);
+    usig = 0.5f * (b0 + a0);
+    vsig = 0.5f * (b1 + a1);
+    wsig = 0.5f * (b2 + a2);
+  }
 
   if (flags & SC_ABOVE) { // label 700, advance.f90:629-708
     interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
