@@ -144,6 +144,8 @@ def load_engine_lib():
     L.fpb_pull_particles.argtypes = [H, _i, _i, _ppart]
     L.fpb_set_numpart.argtypes = [H, _i]
     L.fpb_step.argtypes = [H, _i, _i, C.POINTER(FpbStepStats)]
+    L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
+                                C.POINTER(FpbStepStats)]
     L.fpb_conccalc.argtypes = [H, _i, _f]
     L.fpb_fetch_grids.argtypes = [H, _pf, _pf, _pf, _pf, _pf, _i]
     L.fpb_scale_depgrids.argtypes = [H, _pf]

@@ -150,6 +150,20 @@ struct fpb_handle {
   bool timed_step = false, timed_conc = false;
   bool pending_init = true;
   ScatterWork scatter;
+
+  // fpb_step_host pipeline lanes: chunk c runs on lane c % NLANES (own stream,
+  // sort work area and work counter), so the copies of one chunk overlap the
+  // kernels of another
+  struct Lane {
+    cudaStream_t st = nullptr;
+    ScatterWork sw;
+    int *d_work = nullptr;
+    unsigned *d_nlive = nullptr;
+  };
+  static constexpr int NLANES = 3;
+  Lane lanes[NLANES];
+  cudaEvent_t ev_ready = nullptr;
+  bool lanes_ready = false;
 };
 
 static void fill_devcfg(fpb_handle *h) {
@@ -375,6 +389,12 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
   scatter_free(h->scatter);
+  for (auto &L : h->lanes) {
+    if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
+    scatter_free(L.sw);
+    cudaFree(L.d_work); cudaFree(L.d_nlive);
+  }
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (int k = 0; k < 4; k++) cudaEventDestroy(h->ev[k]);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -461,7 +481,7 @@ static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat);
   do {                                                                               \
     if (!(src)) return fail("fpb_push_particles: array " #src " is null");          \
     CK(cudaMemcpyAsync((dst) + first, (src) + first, (size_t)count * sizeof(T),     \
-                       cudaMemcpyHostToDevice, h->stream));                          \
+                       cudaMemcpyHostToDevice, st));                                 \
   } while (0)
 #define D2H(dst, src, T)                                                             \
   do {                                                                               \
@@ -471,7 +491,7 @@ static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat);
   } while (0)
 
 static int copy_rows_h2d(fpb_handle *h, const DevParticles &d, int first, int count,
-                         const fpb_particle_ptrs *p) {
+                         const fpb_particle_ptrs *p, cudaStream_t st) {
   H2D(d.xtra1, p->xtra1, double); H2D(d.ytra1, p->ytra1, double); H2D(d.ztra1, p->ztra1, float);
   H2D(d.itra1, p->itra1, int32_t); H2D(d.npoint, p->npoint, int32_t);
   H2D(d.nclass, p->nclass, int32_t); H2D(d.idt, p->idt, int32_t);
@@ -484,11 +504,11 @@ static int copy_rows_h2d(fpb_handle *h, const DevParticles &d, int first, int co
   for (int k = 0; k < h->cfg.nspec; k++) {
     CK(cudaMemcpyAsync(d.xmass1 + (size_t)k * h->cfg.maxpart + first,
                        p->xmass1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
-                       cudaMemcpyHostToDevice, h->stream));
+                       cudaMemcpyHostToDevice, st));
     if (p->xscav_frac1)
       CK(cudaMemcpyAsync(d.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
                          p->xscav_frac1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
-                         cudaMemcpyHostToDevice, h->stream));
+                         cudaMemcpyHostToDevice, st));
   }
   return 0;
 }
@@ -507,10 +527,10 @@ extern "C" int fpb_push_particles(fpb_handle *h, int32_t first, int32_t count, c
     h->permuted = false;
   }
   if (!h->permuted) {
-    if (copy_rows_h2d(h, h->p, first, count, p)) return 1;
+    if (copy_rows_h2d(h, h->p, first, count, p, h->stream)) return 1;
   } else {
     // slot-ordered staging, then scatter to the rows the slots live in
-    if (copy_rows_h2d(h, h->p_alt, first, count, p)) return 1;
+    if (copy_rows_h2d(h, h->p_alt, first, count, p, h->stream)) return 1;
     sortk_scatter_from_staging(h->p_alt, h->p, h->row_of_slot, first, count, h->cfg.nspec,
                                p->itrasplit != nullptr, p->xscav_frac1 != nullptr, h->stream);
     h->launches++;
@@ -767,6 +787,196 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   h->timed_conc = true;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ------------------------------------------------------- host-buffer step --
+static DevParticles rows_view(const DevParticles &p, int c0) {
+  DevParticles v = p;
+  v.xtra1 += c0; v.ytra1 += c0; v.ztra1 += c0;
+  v.itra1 += c0; v.npoint += c0; v.nclass += c0; v.idt += c0; v.itramem += c0; v.itrasplit += c0;
+  v.uap += c0; v.ucp += c0; v.uzp += c0; v.us += c0; v.vs += c0; v.ws += c0;
+  v.cbt += c0;
+  v.xmass1 += c0;      // species stride stays maxpart
+  v.xscav_frac1 += c0;
+  v.slot += c0;
+  return v;
+}
+
+static DevScratch scratch_view(const DevScratch &s, int c0) {
+  DevScratch v = s;
+  v.flags += c0; v.s0 += c0; v.s1 += c0; v.s2 += c0;
+  if (v.prob) v.prob += c0;
+  return v;
+}
+
+static int ensure_lanes(fpb_handle *h) {
+  if (h->lanes_ready) return 0;
+  for (auto &L : h->lanes) {
+    CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    DA(L.d_work, 1);
+    DA(L.d_nlive, 1);
+  }
+  CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  h->lanes_ready = true;
+  return 0;
+}
+
+#define D2HS(dst, src, T)                                                                       \
+  CK(cudaMemcpyAsync((dst) + c0, (src) + c0, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, L.st))
+
+// One synchronisation interval for a host that keeps the particle arrays
+// (include/fpb.h).  Rows are cut into chunks; chunk c runs H2D -> sort ->
+// conccalc -> initialize -> particle loop -> D2H on lane c % NLANES, so the
+// PCIe copies of one chunk overlap the kernels of the others.  Particles are
+// independent within a step, so chunking changes nothing
+// but the order of the float atomics into the grids.
+extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,
+                             const fpb_particle_ptrs *p, float conc_weight, fpb_step_stats *stats) {
+  if (!h || !p) return fail("fpb_step_host: null argument");
+  if (!h->have_bracket) return fail("fpb_step_host: fpb_set_met_bracket has not been called");
+  if (numpart < 0 || numpart > h->cfg.maxpart) return fail("fpb_step_host: numpart %d outside capacity %d", numpart, h->cfg.maxpart);
+  if (conc_weight > 0.f && h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC)
+    return fail("fpb_step_host: the deterministic scatter needs resident particles "
+                "(fpb_push_particles + fpb_conccalc + fpb_step)");
+  if ((h->cfg.drybkdep || h->cfg.wetbkdep) && !p->xscav_frac1) return fail("fpb_step_host: xscav_frac1 is null");
+  CK(cudaSetDevice(h->device));
+  if (h->cfg.rng_mode != FPB_RNG_PHILOX && !h->d_rannumb) {
+    if (fpb_fill_rannumb(h, 1000000, -320)) return 1;
+  }
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (numpart == 0) return 0;
+  if (ensure_lanes(h)) return 1;
+  const fpb_config &c = h->cfg;
+  const bool strict = c.math_mode == FPB_MATH_STRICT;
+
+  // staging rows are in slot order
+  sortk_iota(h->p_alt.slot, numpart, h->stream);
+  h->launches++;
+  if (c.rng_mode == FPB_RNG_REFERENCE) {
+    // the reference's ran3 draws in particle order, from the host arrays (see replay_ran3_indices)
+    if (!p->itra1 || !p->itramem) return fail("fpb_step_host: itra1/itramem are null");
+    h->h_nrand_init.assign(numpart, 1); h->h_nrand_adv.assign(numpart, 1);
+    const float scale = (float)(h->maxrand - 1);
+    for (int s = 0; s < numpart; s++) {
+      if (p->itra1[s] != itime) continue;
+      if (p->itramem[s] == itime || itime == 0)
+        h->h_nrand_init[s] = (int)(h->ran3.next(h->idummy_init) * scale) + 1;
+      h->h_nrand_adv[s] = (int)(h->ran3.next(h->idummy_adv) * scale) + 1;
+    }
+    CK(cudaMemcpyAsync(h->d_nrand_init, h->h_nrand_init.data(), (size_t)numpart * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_nrand_adv, h->h_nrand_adv.data(), (size_t)numpart * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+  CK(cudaEventRecord(h->ev_ready, h->stream));
+
+  const unsigned long long ncell = (unsigned long long)h->d.nxd * h->d.nyd * c.nz;
+  int cell_bits = 1;
+  while ((1ull << cell_bits) < ncell) cell_bits++;
+  const bool regime = cell_bits <= 29;
+  int bits = cell_bits + (regime ? 2 : 0) + 1;
+  bits = ((bits + 7) / 8) * 8;
+  if (bits > 32) bits = 32;
+  DevMetSlot met[2] = {slot_view(h, h->memind[0]), slot_view(h, h->memind[1])};
+
+  // chunks of >= ~300k rows (each costs ~20 launches and a persistent-kernel tail;
+  // measured flat between 2 and 6 chunks at 1M rows), multiples of 128 rows
+  int nchunk = numpart / 300000;
+  nchunk = nchunk < 1 ? 1 : (nchunk > 6 ? 6 : nchunk);
+  if (const char *e = getenv("FPB_HOST_CHUNKS")) { // tuning knob
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) nchunk = v;
+  }
+  const int per = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
+
+  for (int ci = 0, c0 = 0; c0 < numpart; ci++, c0 += per) {
+    const int n = (numpart - c0 < per) ? numpart - c0 : per;
+    fpb_handle::Lane &L = h->lanes[ci % fpb_handle::NLANES];
+    if (scatter_reserve(L.sw, (size_t)per, 1)) return fail("%s", scatter_error());
+    CK(cudaStreamWaitEvent(L.st, h->ev_ready, 0));
+    if (copy_rows_h2d(h, h->p_alt, c0, n, p, L.st)) return 1;
+    const DevParticles stg = rows_view(h->p_alt, c0), rows = rows_view(h->p, c0);
+
+    DevStepArgs a;
+    per_step_cfg(h, a.cfg, itime, ldeltat);
+    a.cfg.numpart = n;
+    sortk_build_keys(a.cfg, stg, h->d_height, n, L.sw.keys[0], L.sw.ids[0], L.d_nlive, L.st,
+                     regime ? met : nullptr, cell_bits);
+    int cur = 0;
+    if (scatter_sort_pairs(L.sw, (size_t)n, bits, L.st, &h->launches, &cur)) return fail("%s", scatter_error());
+    sortk_permute(stg, rows, L.sw.ids[cur], n, c.nspec, L.st);
+    sortk_invert(rows.slot, h->row_of_slot, n, L.st, c0);
+    h->launches += 3;
+
+    if (conc_weight > 0.f) {
+      DevConcArgs q;
+      q.cfg = a.cfg;
+      q.cfg.weight = conc_weight;
+      q.met[0] = met[0]; q.met[1] = met[1];
+      q.p = rows;
+      q.height = h->d_height;
+      q.gridunc = h->gridunc; q.griduncn = h->griduncn; q.crec_acc = h->crec_acc;
+      if (strict) fpbk_conccalc_strict(q, L.st); else fpbk_conccalc_fast(q, L.st);
+      h->launches++;
+      if (c.numreceptor > 0) {
+        if (strict) fpbk_receptor_strict(q, L.st); else fpbk_receptor_fast(q, L.st);
+        h->launches++;
+      }
+    }
+
+    a.met[0] = met[0]; a.met[1] = met[1];
+    a.met_lit1 = slot_view(h, 1);
+    a.p = rows;
+    a.height = h->d_height;
+    a.rannumb = h->d_rannumb;
+    a.npart = h->d_npart;
+    a.xmass = h->d_xmass;
+    a.nrand_init = h->d_nrand_init; // indexed by (global) slot
+    a.nrand_adv = h->d_nrand_adv;
+    a.drygridunc = h->drygridunc;
+    a.drygriduncn = h->drygriduncn;
+    a.stats = h->d_stats;
+    a.work_counter = L.d_work;
+    a.sc = scratch_view(h->sc, c0);
+    if (strict) { fpbk_init_strict(a, L.st); fpbk_step_strict(a, L.st); }
+    else { fpbk_init_fast(a, L.st); fpbk_step_fast(a, L.st); }
+    h->launches += 3;
+
+    sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st);
+    h->launches++;
+    D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
+    D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
+    D2HS(p->idt, h->p_alt.idt, int32_t);
+    D2HS(p->uap, h->p_alt.uap, float); D2HS(p->ucp, h->p_alt.ucp, float); D2HS(p->uzp, h->p_alt.uzp, float);
+    D2HS(p->us, h->p_alt.us, float); D2HS(p->vs, h->p_alt.vs, float); D2HS(p->ws, h->p_alt.ws, float);
+    D2HS(p->cbt, h->p_alt.cbt, int16_t);
+    for (int k = 0; k < c.nspec; k++)
+      CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + c0, h->p_alt.xmass1 + (size_t)k * c.maxpart + c0,
+                         (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, L.st));
+    CK(cudaGetLastError());
+  }
+  for (auto &L : h->lanes) CK(cudaStreamSynchronize(L.st));
+  if (conc_weight > 0.f && c.numreceptor > 0) {
+    DevCfg d;
+    per_step_cfg(h, d, itime, ldeltat);
+    receptor_finalize_kernel<<<1, 256, 0, h->stream>>>(h->creceptor, h->crec_acc, c.numreceptor, c.nspec,
+                                                      conc_weight, nullptr, d);
+    h->launches++;
+  }
+  unsigned long long hs[8];
+  CK(cudaMemcpyAsync(hs, h->d_stats, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (stats) {
+    stats->n_active = (int64_t)hs[0]; stats->n_init = (int64_t)hs[1]; stats->n_terminated = (int64_t)hs[2];
+    stats->n_pbl = (int64_t)hs[3]; stats->n_substeps = (int64_t)hs[4]; stats->n_petterssen = (int64_t)hs[5];
+    stats->n_nan_cbl = (int64_t)hs[6];
+  }
+  // the device rows stay valid (sorted inside each chunk) for resident-mode calls
+  h->numpart = numpart;
+  h->permuted = true;
+  h->active_rows = -1;
+  h->pending_init = false;
+  h->steps_since_sort = 0;
   return 0;
 }
 

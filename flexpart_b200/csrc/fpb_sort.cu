@@ -78,9 +78,25 @@ permute_kernel(DevParticles s, DevParticles d, const unsigned *ids, int nrows, i
   }
 }
 
-__global__ void invert_kernel(const int32_t *slot, int32_t *row_of_slot, int nrows) {
+__global__ void invert_kernel(const int32_t *slot, int32_t *row_of_slot, int nrows, int base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nrows) row_of_slot[slot[i]] = i;
+  if (i < nrows) row_of_slot[slot[i]] = base + i;
+}
+
+// staging row slot[i] <- device row i, only the arrays the particle loop writes
+// (src/timemanager.f90:531-712: position, itra1, idt, turbulent velocities, cbt, masses)
+__global__ void __launch_bounds__(256)
+scatter_back_kernel(DevParticles rows, DevParticles stg, int count, int nspec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int s = rows.slot[i];
+  stg.xtra1[s] = rows.xtra1[i]; stg.ytra1[s] = rows.ytra1[i]; stg.ztra1[s] = rows.ztra1[i];
+  stg.itra1[s] = rows.itra1[i]; stg.idt[s] = rows.idt[i];
+  stg.uap[s] = rows.uap[i]; stg.ucp[s] = rows.ucp[i]; stg.uzp[s] = rows.uzp[i];
+  stg.us[s] = rows.us[i]; stg.vs[s] = rows.vs[i]; stg.ws[s] = rows.ws[i];
+  stg.cbt[s] = rows.cbt[i];
+  for (int k = 0; k < nspec; k++)
+    stg.xmass1[(size_t)k * stg.maxpart + s] = rows.xmass1[(size_t)k * rows.maxpart + i];
 }
 
 __global__ void iota_kernel(int32_t *a, int n) {
@@ -144,8 +160,12 @@ void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsig
                    int nrows, int nspec, cudaStream_t st) {
   permute_kernel<<<nb(nrows, 256), 256, 0, st>>>(src, dst, ids, nrows, nspec);
 }
-void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st) {
-  invert_kernel<<<nb(nrows, 256), 256, 0, st>>>(slot, row_of_slot, nrows);
+void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base) {
+  invert_kernel<<<nb(nrows, 256), 256, 0, st>>>(slot, row_of_slot, nrows, base);
+}
+void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
+                        cudaStream_t st) {
+  scatter_back_kernel<<<nb(count, 256), 256, 0, st>>>(rows, stg, count, nspec);
 }
 void sortk_iota(int32_t *a, int n, cudaStream_t st) {
   iota_kernel<<<nb(n, 256), 256, 0, st>>>(a, n);

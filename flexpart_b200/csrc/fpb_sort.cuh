@@ -16,7 +16,11 @@ void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *heigh
 // dst row i := src row ids[i] for every particle array (incl. slot)
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
                    int nrows, int nspec, cudaStream_t st);
-void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st);
+// row_of_slot[slot[i]] = base + i (slot = a view starting at device row `base`)
+void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base = 0);
+// staging row slot[i] <- row i of the view `rows` (arrays the particle loop writes only)
+void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
+                        cudaStream_t st);
 void sortk_iota(int32_t *a, int n, cudaStream_t st);
 // staging (slot order, rows [first,first+count)) <-> device rows
 void sortk_gather_to_staging(const DevParticles &rows, const DevParticles &stg,

@@ -431,7 +431,10 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   float *ls = lane_rows + threadIdx.x;
 
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int T_REFILL = 8; // refill when at least this many lanes are idle
+#ifndef FPB_T_REFILL
+#define FPB_T_REFILL 8
+#endif
+  constexpr int T_REFILL = FPB_T_REFILL; // refill when at least this many lanes are idle
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nrows = c.numpart;

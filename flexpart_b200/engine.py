@@ -83,6 +83,13 @@ class Engine:
         self._check(self.L.fpb_step(self.h, itime, ldeltat, C.byref(st) if stats else None))
         return st.as_dict() if stats else None
 
+    def step_host(self, parts, itime, ldeltat=0, conc_weight=0.0, stats=True):
+        """fpb_step_host: one interval on host-owned particle arrays (chunked, copies overlapped)."""
+        st = FpbStepStats()
+        self._check(self.L.fpb_step_host(self.h, itime, ldeltat, parts.numpart, C.byref(parts.ptrs),
+                                         conc_weight, C.byref(st) if stats else None))
+        return st.as_dict() if stats else None
+
     def conccalc(self, itime, weight):
         self._check(self.L.fpb_conccalc(self.h, itime, weight))
 

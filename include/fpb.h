@@ -212,6 +212,21 @@ int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat,
 /* replaces conccalc(itime,weight): src/timemanager.f90:364,463 */
 int fpb_conccalc(fpb_handle *h, int32_t itime, float weight);
 
+/* One whole synchronisation interval for a host that keeps the particle
+ * arrays (wetdepo / convmix / partoutput still on the CPU between steps):
+ * rows [0,numpart) of the caller's arrays go in, conccalc(itime,conc_weight)
+ * (skipped when conc_weight <= 0: outside the sampling window,
+ * src/timemanager.f90:340-364) and the particle loop src/timemanager.f90:531-712
+ * run, and the arrays the loop writes come back (xtra1, ytra1, ztra1, itra1,
+ * idt, uap, ucp, uzp, us, vs, ws, cbt, xmass1).  Equivalent to
+ * fpb_push_particles + fpb_conccalc + fpb_step + fpb_pull_particles, but cut
+ * into row chunks that run on separate streams so the host<->device copies of
+ * one chunk overlap the kernels of the others; give it page-locked arrays.
+ * Synchronous on return.  Not available with FPB_SCATTER_DETERMINISTIC. */
+int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,
+                  const fpb_particle_ptrs *p, float conc_weight,
+                  fpb_step_stats *stats /* may be NULL */);
+
 /* before concoutput*: src/timemanager.f90:376 (MPI build:
  * mpif_tm_reduce_grid, src/timemanager_mpi.f90:468).  Copies the device
  * grids into the caller's arrays in the reference layout

@@ -192,6 +192,62 @@ def test_sort_is_transparent_philox():
     assert rel_l2(ga, gb) < 1e-6
 
 
+def test_step_host_equals_resident_path():
+    """fpb_step_host (chunked, copies overlapped with kernels) returns exactly
+    what push + conccalc + step + pull return: particles bit for bit, grids up
+    to the order of the float atomics.  200k rows -> 3 chunks on 3 lanes."""
+    n = 200_000
+    out = []
+    for host_mode in (False, True):
+        cb = cases.config_small(nrel=8, npart_each=n // 8, rng_mode=fb.RNG_PHILOX_INDEX, sort_interval=1)
+        m0, m1 = cases.met_pair(cb)
+        eng = fb.Engine(cb)
+        eng.fill_rannumb()
+        eng.upload_met(1, m0); eng.upload_met(2, m1)
+        eng.set_met_bracket((1, 2), (0, 10800))
+        p = cases.seeded_particles(cb, n, zmax=2500.0)
+        stats = []
+        for k in range(4):
+            if host_mode:
+                stats.append(eng.step_host(p, k * 900, 0, conc_weight=1.0))
+            else:
+                eng.push_particles(p)
+                eng.conccalc(k * 900, 1.0)
+                stats.append(eng.step(k * 900))
+                eng.pull_particles(p)
+        out.append((p, eng.fetch_grids()["gridunc"], stats))
+        eng.close()
+    (pa, ga, sa), (pb, gb, sb) = out
+    assert sa == sb
+    for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+        assert np.array_equal(getattr(pa, f)[:n], getattr(pb, f)[:n]), f
+    assert np.array_equal(pa.xmass1[:n], pb.xmass1[:n])
+    assert rel_l2(ga, gb) < 1e-6 and ga.sum() > 0
+
+
+def test_step_host_strict_matches_oracle():
+    """strict math + reference RNG through fpb_step_host: bit-identical to the oracle."""
+    cb = cases.config_c1(npart=70_000, math_mode=fb.MATH_STRICT)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), (0, 10800))
+    pg = cases.seeded_particles(cb, 70_000, zmax=3000.0)
+    po = cases.seeded_particles(cb, 70_000, zmax=3000.0)
+    for k in range(3):
+        sg = eng.step_host(pg, k * 900, 0, conc_weight=1.0)
+        ora.push_particles(po)
+        ora.conccalc(k * 900, 1.0)
+        so = ora.step(k * 900)
+        ora.pull_particles(po)
+        assert sg == so
+        for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+            assert np.array_equal(getattr(pg, f)[:70_000], getattr(po, f)[:70_000]), (k, f)
+    assert rel_l2(eng.fetch_grids()["gridunc"], ora.fetch_grids()["gridunc"]) < 1e-5
+
+
 # ----------------------------------------------------------------------------
 # feature coverage: every branch of the path, strict math (bit-exact) and fast
 # math (tolerance), oracle state re-injected every step
