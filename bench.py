@@ -112,6 +112,22 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
     return cb, rel
 
 
+def workload_config(args, n, world):
+    """`config` of the JSON line: the same dict for the GPU arm and the reference arm."""
+    return {
+        "workload": ("C2: 1M particles/GPU, global 0.5deg x 138 levels, Hanna CTL=5 IFINE=4, "
+                     "100 box releases 0-2 km, lsynctime 900 s, conccalc every step, "
+                     "grid exchange every 4 steps") if args.workload == "c2" else
+                    ("C5 slice: domain-spread particles/GPU, 0.5deg x 138 levels, CTL=-5 (method 0), "
+                     "conccalc every step"),
+        "particles_per_gpu": n, "grid": "721x361x138", "rng": "philox-indexed rannumb",
+        "math": "fast", "scatter": "atomic", "sort_interval": args.sort_interval,
+        "l2": "no flush: each step streams the particle state (132 B/particle) and gathers "
+              "from a 2.9 GB met replica, both larger than the 126 MB L2",
+        "parallelism": f"particle-partition x{world}",
+    }
+
+
 def host_particles(cb, rel, pinned):
     import flexpart_b200 as fb
     parts = fb.Particles(cb.cfg.maxpart, cb.cfg.nspec, pinned=pinned)
@@ -256,18 +272,7 @@ def run_ours(args):
             "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (f64 positions)", "data": "synthetic",
-            "config": {
-                "workload": ("C2: 1M particles/GPU, global 0.5deg x 138 levels, Hanna CTL=5 IFINE=4, "
-                             "100 box releases 0-2 km, lsynctime 900 s, conccalc every step, "
-                             "grid exchange every 4 steps") if args.workload == "c2" else
-                            ("C5 slice: domain-spread particles/GPU, 0.5deg x 138 levels, CTL=-5 (method 0), "
-                             "conccalc every step"),
-                "particles_per_gpu": n, "grid": "721x361x138", "rng": "philox-indexed rannumb",
-                "math": "fast", "scatter": "atomic", "sort_interval": args.sort_interval,
-                "l2": "no flush: each step streams the particle state (132 B/particle) and gathers "
-                      "from a 2.3 GB met replica, both larger than the 126 MB L2",
-                "parallelism": f"particle-partition x{world}",
-            },
+            "config": workload_config(args, n, world),
             "substeps_per_s": nsub_all / (ms_max * 1e-3),
             "substeps_per_particle_step": nsub_all / max(psteps_all, 1),
             "pbl_fraction": npbl_all / max(psteps_all, 1),
@@ -362,8 +367,7 @@ def run_reference(args):
             "unit": "particle-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
             "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (f64 positions)", "data": "synthetic",
-            "config": {"workload": "C2 sample (same releases, met and switches as the GPU arm)"
-                       if args.workload == "c2" else "C5 slice sample"},
+            "config": workload_config(args, args.particles, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
