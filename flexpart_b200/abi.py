@@ -4,8 +4,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-MAXSPEC, MAXAGECLASS, MAXZGRID, MAXRECEPTOR = 8, 8, 64, 20
-ABI_VERSION = 1
+MAXSPEC, MAXAGECLASS, MAXZGRID, MAXRECEPTOR, MAXNESTS = 8, 8, 64, 20, 3
+ABI_VERSION = 2
 ITRA_DEAD = -999999999
 RNG_REFERENCE, RNG_PHILOX_INDEX, RNG_PHILOX = 0, 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
@@ -28,6 +28,9 @@ class FpbConfig(C.Structure):
         ("xglobal", _i), ("nglobal", _i), ("sglobal", _i),
         ("switchnorthg", _f), ("switchsouthg", _f),
         ("northpolemap", _f * 9), ("southpolemap", _f * 9), ("eps", _f),
+        ("numbnests", _i), ("nxn", _i * MAXNESTS), ("nyn", _i * MAXNESTS), ("nxmaxn", _i), ("nymaxn", _i),
+        ("xln", _f * MAXNESTS), ("yln", _f * MAXNESTS), ("xrn", _f * MAXNESTS), ("yrn", _f * MAXNESTS),
+        ("xresoln", _f * MAXNESTS), ("yresoln", _f * MAXNESTS),
         ("ldirect", _i), ("lsynctime", _i), ("method", _i), ("mintime", _i), ("ifine", _i),
         ("turbswitch", _i), ("cblflag", _i), ("mdomainfill", _i), ("mquasilag", _i), ("lsettling", _i),
         ("ctl", _f), ("fine", _f), ("d_trop", _f), ("d_strat", _f), ("turbmesoscale", _f),
@@ -139,6 +142,7 @@ def load_engine_lib():
     L.fpb_set_rannumb.argtypes = [H, _pf, _i]
     L.fpb_fill_rannumb.argtypes = [H, _i, _i]
     L.fpb_upload_met.argtypes = [H, _i, _pmet]
+    L.fpb_upload_met_nest.argtypes = [H, _i, _i, _pmet]
     L.fpb_set_met_bracket.argtypes = [H, _pi, _pi, _i]
     L.fpb_push_particles.argtypes = [H, _i, _i, _ppart]
     L.fpb_pull_particles.argtypes = [H, _i, _i, _ppart]
@@ -173,11 +177,13 @@ def load_host_lib():
     L = C.CDLL(HOST_LIB)
     L.fpbh_last_error.restype = C.c_char_p
     L.fpbh_gridcheck.argtypes = [C.POINTER(FpbConfig)]
+    L.fpbh_gridcheck_nest.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f]
     L.fpbh_readcommand.argtypes = [C.POINTER(FpbConfig)]
     L.fpbh_readoutgrid.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f, _pf, _i]
     L.fpbh_readoutgrid_nest.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f]
     L.fpbh_synth_heights.argtypes = [_i, _pf]
     L.fpbh_synth_met.argtypes = [C.POINTER(FpbConfig), _pf, _i, _pmet]
+    L.fpbh_synth_met_nest.argtypes = [C.POINTER(FpbConfig), _pf, _i, _i, _pmet]
     L.fpbh_homogeneous_met.argtypes = [C.POINTER(FpbConfig), _f, _f, _f, _pmet]
     L.fpbh_stlmbr.argtypes = [_pf, _f, _f]
     L.fpbh_stcm2p.argtypes = [_pf] + [_f] * 8

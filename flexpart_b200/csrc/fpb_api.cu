@@ -111,6 +111,9 @@ struct fpb_handle {
   float4 *A[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
   float *G[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
   float2 *P[2] = {nullptr, nullptr};
+  // nested input grids [nest][slot] (no polar twins, no tt: settling reads the mother grid)
+  float4 *An[FPB_MAXNESTS][2] = {}, *Sn[FPB_MAXNESTS][2] = {};
+  float *Gn[FPB_MAXNESTS][2] = {}, *tropn[FPB_MAXNESTS][2] = {}, *vdepn[FPB_MAXNESTS][2] = {};
   float *trop[2] = {nullptr, nullptr}, *vdep[2] = {nullptr, nullptr};
   float *stage = nullptr;
   size_t stage_n = 0;
@@ -182,6 +185,12 @@ static void fill_devcfg(fpb_handle *h) {
   memcpy(d.northpolemap, c.northpolemap, sizeof d.northpolemap);
   memcpy(d.southpolemap, c.southpolemap, sizeof d.southpolemap);
   d.eps = c.eps;
+  d.numbnests = c.numbnests;
+  for (int l = 0; l < FPB_MAXNESTS; l++) {
+    d.nxdn[l] = c.nxn[l]; d.nydn[l] = c.nyn[l];
+    d.xln[l] = c.xln[l]; d.yln[l] = c.yln[l]; d.xrn[l] = c.xrn[l]; d.yrn[l] = c.yrn[l];
+    d.xresoln[l] = c.xresoln[l]; d.yresoln[l] = c.yresoln[l];
+  }
   d.ldirect = c.ldirect; d.lsynctime = c.lsynctime; d.method = c.method;
   d.mintime = c.mintime; d.ifine = c.ifine;
   d.turbswitch = c.turbswitch; d.cblflag = c.cblflag; d.mdomainfill = c.mdomainfill;
@@ -251,24 +260,28 @@ __global__ void pack_component_kernel(float *dst, int comp, int ncomp, const flo
   dst[i * ncomp + comp] = src[((size_t)k * nymax + jy) * nxmax + ix];
 }
 
+static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk,
+                            int nxd, int nyd, int nxmax, int nymax);
 static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk) {
-  const fpb_config &c = h->cfg;
-  const DevCfg &d = h->d;
-  size_t nsrc = (size_t)c.nxmax * c.nymax * nk;
+  return upload_component(h, dst, comp, ncomp, src, nk, h->d.nxd, h->d.nyd, h->cfg.nxmax, h->cfg.nymax);
+}
+static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk,
+                            int nxd, int nyd, int nxmax, int nymax) {
+  size_t nsrc = (size_t)nxmax * nymax * nk;
   if (nsrc > h->stage_n) {
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
     CK(cudaMalloc((void **)&h->stage, nsrc * sizeof(float)));
     h->stage_n = nsrc;
   }
-  size_t n = (size_t)d.nxd * d.nyd * nk;
+  size_t n = (size_t)nxd * nyd * nk;
   if (src) {
     CK(cudaMemcpyAsync(h->stage, src, nsrc * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   } else {
     CK(cudaMemsetAsync(h->stage, 0, nsrc * sizeof(float), h->stream));
   }
   pack_component_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-      dst, comp, ncomp, h->stage, d.nxd, d.nyd, nk, c.nxmax, c.nymax);
+      dst, comp, ncomp, h->stage, nxd, nyd, nk, nxmax, nymax);
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream)); // the caller may reuse its array
@@ -286,6 +299,10 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   if (cfg->nageclass < 1 || cfg->nageclass > FPB_MAXAGECLASS) return fail("fpb_init: nageclass out of range");
   if (cfg->numzgrid < 1 || cfg->numzgrid > FPB_MAXZGRID) return fail("fpb_init: numzgrid out of range");
   if (cfg->numreceptor < 0 || cfg->numreceptor > FPB_MAXRECEPTOR) return fail("fpb_init: numreceptor out of range");
+  if (cfg->numbnests < 0 || cfg->numbnests > FPB_MAXNESTS) return fail("fpb_init: numbnests=%d out of range (max %d)", cfg->numbnests, FPB_MAXNESTS);
+  for (int l = 0; l < cfg->numbnests; l++)
+    if (cfg->nxn[l] < 2 || cfg->nyn[l] < 2 || cfg->nxn[l] > cfg->nxmaxn || cfg->nyn[l] > cfg->nymaxn)
+      return fail("fpb_init: nest %d extents %dx%d outside (2..nxmaxn=%d, 2..nymaxn=%d)", l + 1, cfg->nxn[l], cfg->nyn[l], cfg->nxmaxn, cfg->nymaxn);
   if (!cfg->height) return fail("fpb_init: height is null");
   if (cfg->maxpart < 1) return fail("fpb_init: maxpart < 1");
   if (cfg->numpoint < 1 || !cfg->npart || !cfg->xmass) return fail("fpb_init: releases (numpoint/npart/xmass) missing");
@@ -319,6 +336,13 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   for (int s = 0; s < 2; s++) {
     DA(h->A[s], n3); DA(h->G[s], n3); DA(h->T[s], n3); DA(h->P[s], n3); DA(h->S[s], n2);
     DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
+  }
+  for (int l = 0; l < c.numbnests; l++) {
+    const size_t m2 = (size_t)c.nxn[l] * c.nyn[l], m3 = m2 * c.nz;
+    for (int s = 0; s < 2; s++) {
+      DA(h->An[l][s], m3); DA(h->Gn[l][s], m3); DA(h->Sn[l][s], m2);
+      DA(h->tropn[l][s], m2); DA(h->vdepn[l][s], m2 * c.nspec);
+    }
   }
   const size_t mp = (size_t)c.maxpart;
   for (DevParticles *q : {&h->p, &h->p_alt}) {
@@ -374,6 +398,10 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   for (int s = 0; s < 2; s++) {
     cudaFree(h->A[s]); cudaFree(h->G[s]); cudaFree(h->T[s]); cudaFree(h->P[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
   }
+  for (int l = 0; l < FPB_MAXNESTS; l++)
+    for (int s = 0; s < 2; s++) {
+      cudaFree(h->An[l][s]); cudaFree(h->Gn[l][s]); cudaFree(h->Sn[l][s]); cudaFree(h->tropn[l][s]); cudaFree(h->vdepn[l][s]);
+    }
   cudaFree(h->stage);
   for (DevParticles *q : {&h->p, &h->p_alt}) {
     cudaFree(q->xtra1); cudaFree(q->ytra1); cudaFree(q->ztra1); cudaFree(q->itra1);
@@ -457,6 +485,33 @@ extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m
     // host vdep(nxmax,nymax,maxspec): species k is "level" k
     if (upload_component(h, h->vdep[s], 0, 1, m->vdep, c.nspec)) return 1;
   }
+  return 0;
+}
+
+extern "C" int fpb_upload_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_ptrs *m) {
+  if (!h || !m) return fail("fpb_upload_met_nest: null argument");
+  if (slot != 1 && slot != 2) return fail("fpb_upload_met_nest: slot must be 1 or 2 (got %d)", slot);
+  const fpb_config &c = h->cfg;
+  if (nest < 1 || nest > c.numbnests) return fail("fpb_upload_met_nest: nest %d outside 1..numbnests=%d", nest, c.numbnests);
+  if (!m->uu || !m->vv || !m->ww || !m->rho || !m->drhodz || !m->hmix || !m->ustar || !m->wstar ||
+      !m->oli || !m->tropopause)
+    return fail("fpb_upload_met_nest: a mandatory field pointer is null");
+  if (c.drydep && !m->vdep) return fail("fpb_upload_met_nest: vdep required when drydep");
+  CK(cudaSetDevice(h->device));
+  const int s = slot - 1, l = nest - 1;
+  const int nx = c.nxn[l], ny = c.nyn[l], mx = c.nxmaxn, my = c.nymaxn;
+  float *A = (float *)h->An[l][s], *S = (float *)h->Sn[l][s];
+  if (upload_component(h, A, 0, 4, m->uu, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_component(h, A, 1, 4, m->vv, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_component(h, A, 2, 4, m->ww, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_component(h, A, 3, 4, m->rho, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_component(h, h->Gn[l][s], 0, 1, m->drhodz, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_component(h, S, 0, 4, m->hmix, 1, nx, ny, mx, my)) return 1;
+  if (upload_component(h, S, 1, 4, m->ustar, 1, nx, ny, mx, my)) return 1;
+  if (upload_component(h, S, 2, 4, m->wstar, 1, nx, ny, mx, my)) return 1;
+  if (upload_component(h, S, 3, 4, m->oli, 1, nx, ny, mx, my)) return 1;
+  if (upload_component(h, h->tropn[l][s], 0, 1, m->tropopause, 1, nx, ny, mx, my)) return 1;
+  if (c.drydep && upload_component(h, h->vdepn[l][s], 0, 1, m->vdep, c.nspec, nx, ny, mx, my)) return 1;
   return 0;
 }
 
@@ -642,6 +697,18 @@ static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat) {
   d.numpart = h->numpart;
 }
 
+static void nest_views(const fpb_handle *h, DevStepArgs &a) {
+  for (int l = 0; l < FPB_MAXNESTS; l++) {
+    for (int m = 0; m < 2; m++) {
+      const int s = h->memind[m] - 1;
+      DevMetSlot v{};
+      v.A = h->An[l][s]; v.G = h->Gn[l][s]; v.S = h->Sn[l][s]; v.trop = h->tropn[l][s]; v.vdep = h->vdepn[l][s];
+      a.metn[l][m] = v;
+    }
+    a.tropn_lit1[l] = h->tropn[l][0];
+  }
+}
+
 static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
   DevMetSlot m;
   const int s = fslot - 1;
@@ -701,6 +768,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.met[0] = slot_view(h, h->memind[0]);
   a.met[1] = slot_view(h, h->memind[1]);
   a.met_lit1 = slot_view(h, 1);
+  nest_views(h, a);
   a.p = h->p;
   a.height = h->d_height;
   a.rannumb = h->d_rannumb;
@@ -926,6 +994,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
 
     a.met[0] = met[0]; a.met[1] = met[1];
     a.met_lit1 = slot_view(h, 1);
+  nest_views(h, a);
     a.p = rows;
     a.height = h->d_height;
     a.rannumb = h->d_rannumb;

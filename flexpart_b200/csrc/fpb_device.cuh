@@ -55,6 +55,11 @@ struct DevCfg {
   float switchnorthg, switchsouthg;
   float northpolemap[9], southpolemap[9];
   float eps;
+  // nested input grids (src/gridcheck_nests.f90:359-389); nxdn/nydn: device extents
+  int numbnests;
+  int nxdn[FPB_MAXNESTS], nydn[FPB_MAXNESTS];
+  float xln[FPB_MAXNESTS], yln[FPB_MAXNESTS], xrn[FPB_MAXNESTS], yrn[FPB_MAXNESTS];
+  float xresoln[FPB_MAXNESTS], yresoln[FPB_MAXNESTS];
   // command
   int ldirect, lsynctime, method, mintime, ifine;
   int turbswitch, cblflag, mdomainfill, mquasilag, lsettling, turboff;
@@ -108,6 +113,8 @@ struct DevStepArgs {
   DevCfg cfg;
   DevMetSlot met[2];   // [0] = memind(1) (older field), [1] = memind(2)
   DevMetSlot met_lit1; // Fortran slot 1, for the reference's literal-slot reads
+  DevMetSlot metn[FPB_MAXNESTS][2];         // nested input grids, ordered like met[]
+  const float *tropn_lit1[FPB_MAXNESTS];    // tropopausen(:,:,1,1,l), src/advance.f90:263
   DevParticles p;
   const float *height;   // [nz] 0-based (height[0] = level 1)
   const float *rannumb;  // 0-based table, rannumb[i-1] = Fortran rannumb(i)

@@ -140,12 +140,13 @@ struct Lev { // one cached profile level (uprof(n) ... wsigprof(n))
 struct Hz { // horizontal + temporal interpolation weights (interpol_mod)
   float p1, p2, p3, p4, dt1, dt2, dtt;
   int o00, o10, o01, o11; // 2-D offsets of the 4 corners
+  int plane;              // elements per level of the grid in use
   int ngrid;
 };
 
 __device__ __forceinline__ void make_weights(const DevCfg &c, Hz &z, int itime_eff,
                                              float xt, float yt, int ix, int jy,
-                                             int ixp, int jyp) {
+                                             int ixp, int jyp, int nxd, int nyd) {
   // src/interpol_all.f90:57-71 (identical in interpol_wind, interpol_wind_short)
   float ddx = xt - (float)ix, ddy = yt - (float)jy;
   float rddx = 1.f - ddx, rddy = 1.f - ddy;
@@ -156,10 +157,16 @@ __device__ __forceinline__ void make_weights(const DevCfg &c, Hz &z, int itime_e
   z.dt1 = (float)(itime_eff - c.memtime[0]);
   z.dt2 = (float)(c.memtime[1] - itime_eff);
   z.dtt = 1.f / (z.dt1 + z.dt2);
-  z.o00 = ix + c.nxd * jy;
-  z.o10 = ixp + c.nxd * jy;
-  z.o01 = ix + c.nxd * jyp;
-  z.o11 = ixp + c.nxd * jyp;
+  z.o00 = ix + nxd * jy;
+  z.o10 = ixp + nxd * jy;
+  z.o01 = ix + nxd * jyp;
+  z.o11 = ixp + nxd * jyp;
+  z.plane = nxd * nyd;
+}
+__device__ __forceinline__ void make_weights(const DevCfg &c, Hz &z, int itime_eff,
+                                             float xt, float yt, int ix, int jy,
+                                             int ixp, int jyp) {
+  make_weights(c, z, itime_eff, xt, yt, ix, jy, ixp, jyp, c.nxd, c.nyd);
 }
 
 __device__ __forceinline__ float bil(const Hz &z, float a, float b, float c, float d) {
@@ -185,7 +192,7 @@ __device__ __forceinline__ int find_indz(const float *sh, int nz, float zt) {
 template <bool SIGMA>
 __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot *met,
                                               const Hz &z, int n, Lev &L) {
-  const int base = (n - 1) * (c.nxd * c.nyd);
+  const int base = (n - 1) * z.plane;
   float y1[2], y2[2], y3[2], r1[2], g1[2];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #ifdef FPB_LEVEL_SLOT_LOOP
@@ -241,7 +248,7 @@ __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot 
 // 8 surrounding values, src/interpol_all.f90:155-238 (same sums, same order)
 __device__ __forceinline__ void profile_sigma(const DevCfg &c, const DevMetSlot *met, const Hz &z,
                                               int n, float &usig, float &vsig, float &wsig) {
-  const int base = (n - 1) * (c.nxd * c.nyd);
+  const int base = (n - 1) * z.plane;
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #pragma unroll
   for (int m = 0; m < 2; m++) {
@@ -282,7 +289,7 @@ __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *m
   const float dz = 1.f / (sh[indz] - sh[indz - 1]);
   const float dz1 = (zt - sh[indz - 1]) * dz;
   const float dz2 = (sh[indz] - zt) * dz;
-  const int plane = c.nxd * c.nyd;
+  const int plane = z.plane;
   float uh[2], vh[2], wh[2];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #pragma unroll
@@ -664,6 +671,59 @@ __device__ __forceinline__ int pole_grid(const DevCfg &c, double yt) {
   if (c.nglobal && (yt > c.switchnorthg)) return -1;
   if (c.sglobal && (yt < c.switchsouthg)) return -2;
   return 0;
+}
+
+// grid choice incl. the nesting level, src/advance.f90:161-175 (= :841-856)
+__device__ __forceinline__ int choose_grid(const DevCfg &c, double xt, double yt) {
+  const int ngrid = pole_grid(c, yt);
+  if (ngrid != 0) return ngrid;
+  for (int j = c.numbnests; j >= 1; j--)
+    if ((xt > c.xln[j - 1] + c.eps) && (xt < c.xrn[j - 1] - c.eps) &&
+        (yt > c.yln[j - 1] + c.eps) && (yt < c.yrn[j - 1] - c.eps))
+      return j;
+  return 0;
+}
+
+// The grid a call interpolates from: the mother grid, or nested grid ngrid
+// with the particle at xtn = (xt-xln)*xresoln, ytn = (yt-yln)*yresoln
+// (src/advance.f90:191-203).  The *_nests routines of the reference are the
+// mother-grid routines on the nest's arrays (src/interpol_all_nests.f90 etc.).
+struct GridSel {
+  const DevMetSlot *met;  // [2]: memind(1), memind(2)
+  const float *trop_lit1; // tropopause of Fortran slot 1 (literal in the reference)
+  int nxd, nyd;
+  float xf, yf;           // position in that grid's coordinates, real (f32)
+  int ix, jy, nix, njy;
+};
+
+__device__ __forceinline__ GridSel select_grid(const DevStepArgs &a, int ngrid, double xt, double yt) {
+  const DevCfg &c = a.cfg;
+  GridSel g;
+  if (ngrid > 0) {
+    const int l = ngrid - 1;
+    g.met = a.metn[l];
+    g.trop_lit1 = a.tropn_lit1[l];
+    g.nxd = c.nxdn[l];
+    g.nyd = c.nydn[l];
+    g.xf = (float)((xt - c.xln[l]) * c.xresoln[l]);
+    g.yf = (float)((yt - c.yln[l]) * c.yresoln[l]);
+    g.ix = f_int(g.xf);
+    g.jy = f_int(g.yf);
+    g.nix = (int)roundf(g.xf);
+    g.njy = (int)roundf(g.yf);
+  } else {
+    g.met = a.met;
+    g.trop_lit1 = a.met_lit1.trop;
+    g.nxd = c.nxd;
+    g.nyd = c.nyd;
+    g.xf = (float)xt;
+    g.yf = (float)yt;
+    g.ix = d_int(xt);
+    g.jy = d_int(yt);
+    g.nix = d_nint(xt);
+    g.njy = d_nint(yt);
+  }
+  return g;
 }
 
 // ------------------------------------------------------------ settling ----

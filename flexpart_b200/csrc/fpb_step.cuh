@@ -80,6 +80,11 @@ struct PblTask {
     z.dt2 = (float)(c.memtime[1] - c.itime);
     z.dtt = 1.f / (z.dt1 + z.dt2);
     z.ngrid = ngrid;
+    z.plane = (EXTRA && ngrid > 0) ? c.nxdn[ngrid - 1] * c.nydn[ngrid - 1] : c.nxd * c.nyd;
+  }
+  // time levels of the grid the call interpolates from (nests: EXTRA variant only)
+  __device__ __forceinline__ const DevMetSlot *grid_met(const DevStepArgs &a) const {
+    return (EXTRA && ngrid > 0) ? a.metn[ngrid - 1] : a.met;
   }
 
   __device__ __forceinline__ float normal(const DevStepArgs &a, int i) {
@@ -97,19 +102,29 @@ struct PblTask {
     zt = a.p.ztra1[row];
 
     Hz z;
-    z.ngrid = pole_grid(c, yt);
-    const int ix = d_int(xt), jy = d_int(yt);
-    int ixp = ix + 1, jyp = jy + 1;
-    if (jyp >= c.nymax) jyp = jyp - 1;
-    make_weights(c, z, c.itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    z.ngrid = EXTRA ? choose_grid(c, xt, yt) : pole_grid(c, yt);
+    ngrid = z.ngrid;
+    const DevMetSlot *met = a.met;
+    if (EXTRA && z.ngrid > 0) { // nested grid coordinates, advance.f90:191-203
+      const GridSel g = select_grid(a, z.ngrid, xt, yt);
+      int jyp = g.jy + 1;
+      if (jyp >= c.nymax) jyp = jyp - 1;
+      make_weights(c, z, c.itime, g.xf, g.yf, g.ix, g.jy, g.ix + 1, jyp, g.nxd, g.nyd);
+      met = g.met;
+    } else {
+      const int ix = d_int(xt), jy = d_int(yt);
+      int ixp = ix + 1, jyp = jy + 1;
+      if (jyp >= c.nymax) jyp = jyp - 1;
+      make_weights(c, z, c.itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    }
 
-    // advance.f90:236-252 (max of hmix over 4 corners x 2 slots); the same
+    // advance.f90:236-264 (max of hmix over 4 corners x 2 slots); the same
     // words carry ustar, wstar, oli for interpol_all.f90:80-107
     float4 s[2][4];
 #pragma unroll
     for (int m = 0; m < 2; m++) {
-      s[m][0] = __ldg(a.met[m].S + z.o00); s[m][1] = __ldg(a.met[m].S + z.o10);
-      s[m][2] = __ldg(a.met[m].S + z.o01); s[m][3] = __ldg(a.met[m].S + z.o11);
+      s[m][0] = __ldg(met[m].S + z.o00); s[m][1] = __ldg(met[m].S + z.o10);
+      s[m][2] = __ldg(met[m].S + z.o01); s[m][3] = __ldg(met[m].S + z.o11);
     }
     float hh = 0.f;
 #pragma unroll
@@ -125,7 +140,6 @@ struct PblTask {
       return true;
     }
     pbl = true;
-    ngrid = z.ngrid;
     lsf(ls, LS_P1) = z.p1; lsf(ls, LS_P2) = z.p2; lsf(ls, LS_P3) = z.p3; lsf(ls, LS_P4) = z.p4;
     lsi(ls, LS_O00) = z.o00; lsi(ls, LS_O01) = z.o01;
 #pragma unroll
@@ -234,7 +248,7 @@ struct PblTask {
         Hz z;
         load_weights(c, ls, z);
         Lev L;
-        profile_level<false>(c, a.met, z, n, L);
+        profile_level<false>(c, grid_met(a), z, n, L);
         float *q = ls + (LS_LEV + LEV_WORDS * e) * PBL_THREADS;
         q[0 * PBL_THREADS] = L.u; q[1 * PBL_THREADS] = L.v; q[2 * PBL_THREADS] = L.w;
         q[3 * PBL_THREADS] = L.rho; q[4 * PBL_THREADS] = L.rhograd;
@@ -399,11 +413,12 @@ struct PblTask {
           if (depo_todo & (1u << ks)) { // interpol_vdep, src/interpol_vdep.f90:39-54
             Hz z;
             load_weights(c, ls, z);
-            const int off = ks * (c.nxd * c.nyd);
-            const float y0 = bil(z, __ldg(a.met[0].vdep + off + z.o00), __ldg(a.met[0].vdep + off + z.o10),
-                                 __ldg(a.met[0].vdep + off + z.o01), __ldg(a.met[0].vdep + off + z.o11));
-            const float y1 = bil(z, __ldg(a.met[1].vdep + off + z.o00), __ldg(a.met[1].vdep + off + z.o10),
-                                 __ldg(a.met[1].vdep + off + z.o01), __ldg(a.met[1].vdep + off + z.o11));
+            const int off = ks * z.plane;
+            const DevMetSlot *met = grid_met(a);
+            const float y0 = bil(z, __ldg(met[0].vdep + off + z.o00), __ldg(met[0].vdep + off + z.o10),
+                                 __ldg(met[0].vdep + off + z.o01), __ldg(met[0].vdep + off + z.o11));
+            const float y1 = bil(z, __ldg(met[1].vdep + off + z.o00), __ldg(met[1].vdep + off + z.o10),
+                                 __ldg(met[1].vdep + off + z.o01), __ldg(met[1].vdep + off + z.o11));
             vdepo[ks] = (y0 * z.dt2 + y1 * z.dt1) * z.dtt;
             depo_todo &= ~(1u << ks);
           }
@@ -524,24 +539,25 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 
   // advance.f90:199-253 at the position the call started from
   Hz z;
-  z.ngrid = pole_grid(c, yt);
+  z.ngrid = choose_grid(c, xt, yt);
+  const DevMetSlot *met;
   float h = 0.f, tropop;
   {
-    const int ix = d_int(xt), jy = d_int(yt);
-    const int nix = d_nint(xt), njy = d_nint(yt);
-    int ixp = ix + 1, jyp = jy + 1;
+    const GridSel g = select_grid(a, z.ngrid, xt, yt);
+    met = g.met;
+    int jyp = g.jy + 1;
     if (jyp >= c.nymax) jyp = jyp - 1;
-    make_weights(c, z, itime, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    make_weights(c, z, itime, g.xf, g.yf, g.ix, g.jy, g.ix + 1, jyp, g.nxd, g.nyd);
 #pragma unroll
     for (int m = 0; m < 2; m++) {
-      const float v0 = __ldg(a.met[m].S + z.o00).x, v1 = __ldg(a.met[m].S + z.o10).x;
-      const float v2 = __ldg(a.met[m].S + z.o01).x, v3 = __ldg(a.met[m].S + z.o11).x;
+      const float v0 = __ldg(met[m].S + z.o00).x, v1 = __ldg(met[m].S + z.o10).x;
+      const float v2 = __ldg(met[m].S + z.o01).x, v3 = __ldg(met[m].S + z.o11).x;
       if (v0 > h) h = v0;
       if (v1 > h) h = v1;
       if (v2 > h) h = v2;
       if (v3 > h) h = v3;
     }
-    tropop = __ldg(a.met_lit1.trop + nix + c.nxd * njy); // slot 1 literal, advance.f90:253
+    tropop = __ldg(g.trop_lit1 + g.nix + g.nxd * g.njy); // slot 1 literal, advance.f90:253,263
   }
 
   float ux = 0.f, vy = 0.f;
@@ -551,15 +567,15 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     // usig = 0.5*(usigprof(indzp)+usigprof(indz)) etc. for the level pair of the last
     // sub-step, advance.f90:604-606 (and the "defined" stale-usig case)
     float a0, a1, a2, b0, b1, b2;
-    profile_sigma(c, a.met, z, indz_last, a0, a1, a2);
-    profile_sigma(c, a.met, z, indz_last + 1, b0, b1, b2);
+    profile_sigma(c, met, z, indz_last, a0, a1, a2);
+    profile_sigma(c, met, z, indz_last + 1, b0, b1, b2);
     usig = 0.5f * (b0 + a0);
     vsig = 0.5f * (b1 + a1);
     wsig = 0.5f * (b2 + a2);
   }
 
   if (flags & SC_ABOVE) { // label 700, advance.f90:629-708
-    interp_wind<true>(c, a.met, z, sh, zt, u, v, w, usig, vsig, wsig);
+    interp_wind<true>(c, met, z, sh, zt, u, v, w, usig, vsig, wsig);
     ldt = abs(c.lsynctime - itimec + itime);
     const float dt = (float)ldt;
     if (zt < tropop) {
@@ -627,17 +643,16 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     // Petterssen corrector, advance.f90:829-985
     if (ldt != abs(c.lsynctime)) done = true;
     else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
-    else if (pole_grid(c, yt) != ngrid) done = true;
+    else if (choose_grid(c, xt, yt) != ngrid) done = true;
   }
   if (!done) {
-    const int ix = d_int(xt), jy = d_int(yt);
-    const int ixp = ix + 1;
-    int jyp = jy + 1;
+    const GridSel g = select_grid(a, ngrid, xt, yt); // advance.f90:862-870
+    int jyp = g.jy + 1;
     if (jyp >= c.nymax) jyp = jyp - 1;
     const float uold = u, vold = v, wold = w;
-    make_weights(c, z, itime + ldt * c.ldirect, (float)xt, (float)yt, ix, jy, ixp, jyp);
+    make_weights(c, z, itime + ldt * c.ldirect, g.xf, g.yf, g.ix, g.jy, g.ix + 1, jyp, g.nxd, g.nyd);
     float d0, d1, d2;
-    interp_wind<false>(c, a.met, z, sh, zt, u, v, w, d0, d1, d2);
+    interp_wind<false>(c, met, z, sh, zt, u, v, w, d0, d1, d2);
     n_pett++;
     w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
     u = (u - uold) / 2.f;

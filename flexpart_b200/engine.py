@@ -58,6 +58,9 @@ class Engine:
     def upload_met(self, slot, met):
         self._check(self.L.fpb_upload_met(self.h, slot, C.byref(met.ptrs)))
 
+    def upload_met_nest(self, slot, nest, met):
+        self._check(self.L.fpb_upload_met_nest(self.h, slot, nest, C.byref(met.ptrs)))
+
     def set_met_bracket(self, memind, memtime, lwindinterv=None):
         mi = (C.c_int32 * 2)(*memind)
         mt = (C.c_int32 * 2)(*memtime)

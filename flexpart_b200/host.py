@@ -59,7 +59,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
                 npart=(10000,), xmass=None, maxspec=5, nclassunc=1, receptors=(),
                 maxpart=None, device=0, rng_mode=abi.RNG_REFERENCE, math_mode=abi.MATH_FAST,
                 scatter_mode=abi.SCATTER_ATOMIC, seed=0x5EEDF1E0, height=None,
-                part_id_stride=1, part_id_offset=0, sort_interval=0):
+                part_id_stride=1, part_id_offset=0, sort_interval=0, met_nests=()):
     """Run constants for the engine, derived the way the reference's
     gridcheck_ecmwf / readcommand / readoutgrid / readreleases derive them."""
     L = load_host_lib()
@@ -69,6 +69,8 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
     c.nxmax, c.nymax, c.nzmax = nxmax or nx, nymax or ny, nzmax or nz
     c.dx, c.dy, c.xlon0, c.ylat0 = dx, dy, xlon0, ylat0
     _hcheck(L.fpbh_gridcheck(C.byref(c)))
+    for (xlon0n, ylat0n, nxn, nyn, dxn, dyn) in met_nests:  # nested input grids, gridcheck_nests
+        _hcheck(L.fpbh_gridcheck_nest(C.byref(c), xlon0n, ylat0n, nxn, nyn, dxn, dyn))
     c.ldirect, c.lsynctime, c.ctl, c.ifine, c.cblflag = ldirect, lsynctime, ctl, ifine, cblflag
     _hcheck(L.fpbh_readcommand(C.byref(c)))
     c.turboff, c.mdomainfill, c.mquasilag, c.lsettling = turboff, mdomainfill, 0, lsettling
@@ -126,21 +128,27 @@ class MetFields:
     NAMES3 = ("uu", "vv", "ww", "rho", "drhodz", "tt", "uupol", "vvpol")
     NAMES2 = ("hmix", "ustar", "wstar", "oli", "tropopause")
 
-    def __init__(self, cb):
+    def __init__(self, cb, nest=0):
+        """nest = 0: mother grid; nest = l >= 1: nested input grid l (uun.. of com_mod)."""
         c = cb.cfg
-        self.cb = cb
+        self.cb, self.nest = cb, nest
+        nxm, nym = (c.nxmax, c.nymax) if nest == 0 else (c.nxmaxn, c.nymaxn)
         for n in self.NAMES3:
-            setattr(self, n, np.zeros((c.nxmax, c.nymax, c.nzmax), np.float32, order="F"))
+            setattr(self, n, np.zeros((nxm, nym, c.nzmax), np.float32, order="F"))
         for n in self.NAMES2:
-            setattr(self, n, np.zeros((c.nxmax, c.nymax), np.float32, order="F"))
-        self.vdep = np.zeros((c.nxmax, c.nymax, c.maxspec), np.float32, order="F")
+            setattr(self, n, np.zeros((nxm, nym), np.float32, order="F"))
+        self.vdep = np.zeros((nxm, nym, c.maxspec), np.float32, order="F")
         self.ptrs = FpbMetPtrs()
         for n in self.NAMES3 + self.NAMES2 + ("vdep",):
             setattr(self.ptrs, n, _fp(getattr(self, n)))
 
     def synth(self, time_s):
-        _hcheck(load_host_lib().fpbh_synth_met(C.byref(self.cb.cfg), _fp(self.cb.height), int(time_s),
-                                               C.byref(self.ptrs)))
+        L = load_host_lib()
+        if self.nest == 0:
+            _hcheck(L.fpbh_synth_met(C.byref(self.cb.cfg), _fp(self.cb.height), int(time_s), C.byref(self.ptrs)))
+        else:
+            _hcheck(L.fpbh_synth_met_nest(C.byref(self.cb.cfg), _fp(self.cb.height), int(time_s), self.nest,
+                                          C.byref(self.ptrs)))
         return self
 
     def homogeneous(self, u=10.0, v=0.0, w=0.0):

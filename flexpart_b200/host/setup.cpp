@@ -61,6 +61,32 @@ extern "C" int fpbh_gridcheck(fpb_config *c) {
   return 0;
 }
 
+// gridcheck_nests for nest l = c->numbnests+1 (src/gridcheck_nests.f90:359-389):
+// resolution ratios and the nest's borders in mother-grid coordinates
+extern "C" int fpbh_gridcheck_nest(fpb_config *c, float xlon0n, float ylat0n, int32_t nxn, int32_t nyn,
+                                   float dxn, float dyn) {
+  if (!c) return fpbh_fail("fpbh_gridcheck_nest: null config");
+  if (c->numbnests >= FPB_MAXNESTS) return fpbh_fail("fpbh_gridcheck_nest: more than FPB_MAXNESTS nests");
+  if (nxn < 2 || nyn < 2 || dxn <= 0.f || dyn <= 0.f) return fpbh_fail("fpbh_gridcheck_nest: bad nest grid");
+  const int l = c->numbnests;
+  c->xresoln[l] = c->dx / dxn;
+  c->yresoln[l] = c->dy / dyn;
+  const float xaux1 = xlon0n, xaux2 = xlon0n + (float)(nxn - 1) * dxn;
+  const float yaux1 = ylat0n, yaux2 = ylat0n + (float)(nyn - 1) * dyn;
+  c->xln[l] = (xaux1 - c->xlon0) / c->dx;
+  c->xrn[l] = (xaux2 - c->xlon0) / c->dx;
+  c->yln[l] = (yaux1 - c->ylat0) / c->dy;
+  c->yrn[l] = (yaux2 - c->ylat0) / c->dy;
+  if ((c->xln[l] < 0.f) || (c->yln[l] < 0.f) || (c->xrn[l] > (float)c->nxmin1) || (c->yrn[l] > (float)c->nymin1))
+    return fpbh_fail("Nested domain does not fit into mother domain");
+  c->nxn[l] = nxn;
+  c->nyn[l] = nyn;
+  if (nxn > c->nxmaxn) c->nxmaxn = nxn;
+  if (nyn > c->nymaxn) c->nymaxn = nyn;
+  c->numbnests = l + 1;
+  return 0;
+}
+
 // src/readcommand.f90:244-272 (turbulence switches), :377-383 (method),
 // :627-634 (backward runs); maxtl=1200 (src/com_mod.f90)
 extern "C" int fpbh_readcommand(fpb_config *c) {

@@ -221,6 +221,28 @@ extern "C" int fpbh_synth_met(const fpb_config *cp, const float *height, int32_t
   return 0;
 }
 
+// One time level of nested input grid `nest` (1-based): the same analytic
+// fields sampled on the nest's own, finer grid (what readwind_nests +
+// verttransform_nests + calcpar_nests leave in uun.. of src/com_mod.f90:501-529),
+// padded to (nxmaxn, nymaxn, nzmax).  No polar-stereographic twins on nests.
+extern "C" int fpbh_synth_met_nest(const fpb_config *cp, const float *height, int32_t time_s,
+                                   int32_t nest, const fpb_met_ptrs *o) {
+  if (!cp || !height || !o) return fpbh_fail("fpbh_synth_met_nest: null argument");
+  if (nest < 1 || nest > cp->numbnests) return fpbh_fail("fpbh_synth_met_nest: nest out of range");
+  fpb_config cn = *cp;
+  const int l = nest - 1;
+  cn.nx = cp->nxn[l]; cn.ny = cp->nyn[l];
+  cn.nxmax = cp->nxmaxn; cn.nymax = cp->nymaxn;
+  cn.dx = cp->dx / cp->xresoln[l]; cn.dy = cp->dy / cp->yresoln[l];
+  cn.xlon0 = cp->xlon0 + cp->xln[l] * cp->dx;
+  cn.ylat0 = cp->ylat0 + cp->yln[l] * cp->dy;
+  cn.nxmin1 = cn.nx - 1; cn.nymin1 = cn.ny - 1;
+  cn.nglobal = cn.sglobal = cn.xglobal = 0;
+  fpb_met_ptrs on = *o;
+  on.uupol = nullptr; on.vvpol = nullptr;
+  return fpbh_synth_met(&cn, height, time_s, &on);
+}
+
 // src/mpi_mod.f90:2940-2973 (set_fields_synthetic): homogeneous test fields
 extern "C" int fpbh_homogeneous_met(const fpb_config *cp, float u, float v, float w,
                                     const fpb_met_ptrs *o) {

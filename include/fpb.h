@@ -30,11 +30,13 @@
 extern "C" {
 #endif
 
-#define FPB_ABI_VERSION 1
+#define FPB_ABI_VERSION 2
 #define FPB_MAXSPEC 8      /* >= par_mod maxspec (5), src/par_mod.f90:210 */
 #define FPB_MAXAGECLASS 8  /* >= par_mod maxageclass */
 #define FPB_MAXZGRID 64    /* output-grid levels */
 #define FPB_MAXRECEPTOR 20 /* par_mod maxreceptor, src/par_mod.f90:204 */
+#define FPB_MAXNESTS 3     /* >= par_mod maxnests (0 shipped, 1 MeteoSwiss:
+                              src/par_mod.f90:152, src/par_mod_meteoswiss.f90:154) */
 
 /* Values of itra1 for a terminated particle, src/timemanager.f90:632 */
 #define FPB_ITRA_DEAD (-999999999)
@@ -77,6 +79,17 @@ typedef struct fpb_config {
   float switchnorthg, switchsouthg;
   float northpolemap[9], southpolemap[9]; /* cmapf_mod stlmbr/stcm2p result */
   float eps;                   /* nxmax/3.e5, src/advance.f90:107 */
+
+  /* --- nested meteorological input grids, src/gridcheck_nests.f90:340-385 --
+   * Nest l (1-based in the reference, index l-1 here) covers
+   * xln < x < xrn, yln < y < yrn in mother-grid units; a particle inside it
+   * (highest l first, src/advance.f90:166-173) is interpolated from the nest's
+   * arrays at xtn = (xt-xln)*xresoln, ytn = (yt-yln)*yresoln. */
+  int32_t numbnests;
+  int32_t nxn[FPB_MAXNESTS], nyn[FPB_MAXNESTS]; /* used extents */
+  int32_t nxmaxn, nymaxn;                       /* padded host extents, src/par_mod.f90:152 */
+  float xln[FPB_MAXNESTS], yln[FPB_MAXNESTS], xrn[FPB_MAXNESTS], yrn[FPB_MAXNESTS];
+  float xresoln[FPB_MAXNESTS], yresoln[FPB_MAXNESTS]; /* dx/dxn, dy/dyn */
 
   /* --- COMMAND, src/readcommand.f90:244-272,377-383,622-634 ------------- */
   int32_t ldirect;    /* +1 / -1 */
@@ -140,7 +153,9 @@ typedef struct fpb_config {
  * (src/com_mod.f90:355-371,410-427,451).  3-D: (nxmax,nymax,nzmax); 2-D:
  * (nxmax,nymax); vdep: (nxmax,nymax,maxspec).  uupol/vvpol may be NULL when
  * neither pole is in the domain; tt may be NULL when lsettling == 0; vdep may
- * be NULL when drydep == 0. */
+ * be NULL when drydep == 0.  For a nested grid (fpb_upload_met_nest) the
+ * extents are (nxmaxn,nymaxn,nzmax) / (nxmaxn,nymaxn) / (nxmaxn,nymaxn,maxspec)
+ * (src/com_mod.f90:501-529) and uupol/vvpol/tt are not read. */
 typedef struct fpb_met_ptrs {
   const float *uu, *vv, *ww, *rho, *drhodz, *tt, *uupol, *vvpol;
   const float *hmix, *ustar, *wstar, *oli, *tropopause;
@@ -191,6 +206,10 @@ int fpb_fill_rannumb(fpb_handle *h, int32_t maxrand, int32_t idummy);
 /* after getfields returned a new field: src/timemanager.f90:200,
  * src/getfields.f90:109-139.  slot is the Fortran slot index 1 or 2. */
 int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *met);
+/* the same for nested input grid `nest` (1..numbnests): the slices
+ * uun(:,:,:,slot,nest) .. of src/com_mod.f90:501-529, filled by
+ * readwind_nests / verttransform_nests / calcpar_nests (src/getfields.f90:141-170) */
+int fpb_upload_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_ptrs *met);
 /* memind(1:2), memtime(1:2), lwindinterv: src/getfields.f90:96-176 */
 int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2],
                         const int32_t memtime[2], int32_t lwindinterv);

@@ -29,6 +29,12 @@ const char *fpbh_last_error(void);
  * dxconst,dyconst,eps (src/gridcheck_ecmwf.f90:300-366, src/par_mod.f90:123,
  * src/advance.f90:107). */
 int fpbh_gridcheck(fpb_config *cfg);
+/* gridcheck_nests (src/gridcheck_nests.f90:359-389): appends one nested input
+ * grid (after fpbh_gridcheck): numbnests, nxn, nyn, nxmaxn, nymaxn, xresoln,
+ * yresoln, xln, xrn, yln, yrn; "Nested domain does not fit into mother domain"
+ * is an error as in the reference. */
+int fpbh_gridcheck_nest(fpb_config *cfg, float xlon0n, float ylat0n, int32_t nxn, int32_t nyn,
+                        float dxn, float dyn);
 
 /* readcommand derivations (src/readcommand.f90:244-272,377-383,622-634):
  * in: ldirect, lsynctime (>0 as in COMMAND), ctl (as in COMMAND), ifine,
@@ -52,6 +58,10 @@ int fpbh_synth_heights(int32_t nz, float *height);
  * All non-NULL pointers of `out` are written. */
 int fpbh_synth_met(const fpb_config *cfg, const float *height, int32_t time_s,
                    const fpb_met_ptrs *out);
+/* the same fields on nested input grid `nest` (1..numbnests), padded to
+ * (nxmaxn, nymaxn, nzmax) */
+int fpbh_synth_met_nest(const fpb_config *cfg, const float *height, int32_t time_s, int32_t nest,
+                        const fpb_met_ptrs *out);
 /* homogeneous fields of mpi_mod's set_fields_synthetic (src/mpi_mod.f90:2940-2973) */
 int fpbh_homogeneous_met(const fpb_config *cfg, float u, float v, float w,
                          const fpb_met_ptrs *out);

@@ -43,6 +43,8 @@ typedef struct fpo_state {
 
   /* meteorology: Fortran slot 1..2 */
   fpb_met_ptrs met[3];
+  /* nested input grids: metn[l][slot], l = 1..numbnests (uun.. of src/com_mod.f90:501-529) */
+  fpb_met_ptrs metn[FPB_MAXNESTS + 1][3];
   int memind[3];
   int memtime[3];
   int lwindinterv;
@@ -117,6 +119,7 @@ const float *fpo_rannumb(fpo_state *S); /* 0-based view of the table */
 
 /* meteorology */
 void fpo_set_met(fpo_state *S, int slot, const fpb_met_ptrs *m);
+void fpo_set_met_nest(fpo_state *S, int slot, int nest, const fpb_met_ptrs *m);
 void fpo_set_met_bracket(fpo_state *S, const int memind[2],
                          const int memtime[2], int lwindinterv);
 
@@ -152,6 +155,8 @@ void fpo_hanna1(fpo_state *S, float z);
 void fpo_hanna_short(fpo_state *S, float z);
 void fpo_windalign(float u, float v, float ffap, float ffcp, float *ux,
                    float *vy);
+/* the *_nests twins (src/interpol_all_nests.f90 etc.) are the same functions:
+ * with S->ngrid > 0 they read the nest's arrays and xt,yt are nest coordinates */
 void fpo_interpol_all(fpo_state *S, int itime, float xt, float yt, float zt);
 void fpo_interpol_misslev(fpo_state *S, int n);
 void fpo_interpol_wind(fpo_state *S, int itime, float xt, float yt, float zt);

@@ -30,11 +30,25 @@ static const float eps2 = 1.e-9f;
 #define eps3 1.17549435e-38f /* tiny(1.0) */
 
 #define IDX2(S, i, j) ((size_t)(i) + (size_t)(S)->c.nxmax * (size_t)(j))
+#define IDX2N(S, i, j) ((size_t)(i) + (size_t)(S)->c.nxmaxn * (size_t)(j))
 
 static int pole_grid(const fpo_state *S, double yt) {
   if (S->c.nglobal && (yt > S->c.switchnorthg)) return -1;
   if (S->c.sglobal && (yt < S->c.switchsouthg)) return -2;
-  return 0; /* numbnests = 0: no nested met input in this build */
+  return 0;
+}
+
+/* grid choice incl. the nesting level, src/advance.f90:161-175 (= :841-856) */
+static int choose_grid(const fpo_state *S, double xt, double yt) {
+  const fpb_config *c = &S->c;
+  const float eps = c->eps;
+  int ngrid = pole_grid(S, yt);
+  if (ngrid != 0) return ngrid;
+  for (int j = c->numbnests; j >= 1; j--)
+    if ((xt > c->xln[j - 1] + eps) && (xt < c->xrn[j - 1] - eps) &&
+        (yt > c->yln[j - 1] + eps) && (yt < c->yrn[j - 1] - eps))
+      return j;
+  return 0;
 }
 
 /* settling species choice, src/advance.f90:518-531 (and :686-699, :893-906) */
@@ -118,6 +132,9 @@ void fpo_initialize(fpo_state *S, int itime, int32_t *ldt, float *up, float *vp,
   nrand = fpo_int_f(fpo_ran3(S, &S->idummy_initialize) * (float)(maxrand - 1)) + 1;
 
   if (!S->strict_reference) S->ngrid = pole_grid(S, yt);
+  /* initialize() calls the mother-grid routines whatever ngrid a previous advance left:
+   * interpol_all only tests ngrid < 0 (src/initialize.f90:102, src/interpol_all.f90:144) */
+  if (S->ngrid > 0) S->ngrid = 0;
 
   S->ix = fpo_int_d(xt);
   S->jy = fpo_int_d(yt);
@@ -227,7 +244,7 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
   int ldt = *ldt_io;
   int icbt = *icbt_io;
 
-  float xts, yts, weight;
+  float xts, yts, xtn = 0.f, ytn = 0.f, weight;
   int itimec, i, nrand, loop, memindnext, ngr, nix, njy, ks;
   float dz, dz1, dz2;
   float ru, rv, rw, dt, ux = 0.f, vy = 0.f, tropop;
@@ -259,17 +276,27 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
   nrand = fpo_int_f(fpo_ran3(S, &S->idummy_advance) * (float)(maxrand - 1)) + 1;
 
   /* grid choice, :161-175 */
-  S->ngrid = pole_grid(S, yt);
+  S->ngrid = choose_grid(S, xt, yt);
 
   if (abs(itime - S->memtime[1]) < abs(itime - S->memtime[2]))
     memindnext = 1;
   else
     memindnext = 2;
 
-  S->ix = fpo_int_d(xt);
-  S->jy = fpo_int_d(yt);
-  nix = fpo_nint_d(xt);
-  njy = fpo_nint_d(yt);
+  /* nested grid coordinates, :191-203 */
+  if (S->ngrid > 0) {
+    xtn = (float)((xt - c->xln[S->ngrid - 1]) * c->xresoln[S->ngrid - 1]);
+    ytn = (float)((yt - c->yln[S->ngrid - 1]) * c->yresoln[S->ngrid - 1]);
+    S->ix = fpo_int_f(xtn);
+    S->jy = fpo_int_f(ytn);
+    nix = fpo_nint_f(xtn);
+    njy = fpo_nint_f(ytn);
+  } else {
+    S->ix = fpo_int_d(xt);
+    S->jy = fpo_int_d(yt);
+    nix = fpo_nint_d(xt);
+    njy = fpo_nint_d(yt);
+  }
   S->ixp = S->ix + 1;
   S->jyp = S->jy + 1;
 
@@ -282,15 +309,25 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
 
   if (S->jyp >= c->nymax) S->jyp = S->jyp - 1; /* :228-231 */
 
-  /* maximum mixing height around the particle, :236-253 */
+  /* maximum mixing height around the particle, :236-264 */
   S->h = 0.f;
-  for (int k = 1; k <= 2; k++) {
-    const float *hm = S->met[S->memind[k]].hmix;
-    for (int j = S->jy; j <= S->jyp; j++)
-      for (int ii = S->ix; ii <= S->ixp; ii++)
-        if (hm[IDX2(S, ii, j)] > S->h) S->h = hm[IDX2(S, ii, j)];
+  if (S->ngrid <= 0) {
+    for (int k = 1; k <= 2; k++) {
+      const float *hm = S->met[S->memind[k]].hmix;
+      for (int j = S->jy; j <= S->jyp; j++)
+        for (int ii = S->ix; ii <= S->ixp; ii++)
+          if (hm[IDX2(S, ii, j)] > S->h) S->h = hm[IDX2(S, ii, j)];
+    }
+    tropop = S->met[1].tropopause[IDX2(S, nix, njy)]; /* slot 1 literal, :253 */
+  } else {
+    for (int k = 1; k <= 2; k++) {
+      const float *hm = S->metn[S->ngrid][S->memind[k]].hmix;
+      for (int j = S->jy; j <= S->jyp; j++)
+        for (int ii = S->ix; ii <= S->ixp; ii++)
+          if (hm[IDX2N(S, ii, j)] > S->h) S->h = hm[IDX2N(S, ii, j)];
+    }
+    tropop = S->metn[S->ngrid][1].tropopause[IDX2N(S, nix, njy)]; /* :263 */
   }
-  tropop = S->met[1].tropopause[IDX2(S, nix, njy)]; /* slot 1 literal, :253 */
 
   S->zeta = zt / S->h;
 
@@ -313,9 +350,13 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
     S->zeta = zt / S->h;
 
     if (loop == 1) {
-      xts = (float)xt;
-      yts = (float)yt;
-      fpo_interpol_all(S, itime, xts, yts, zt);
+      if (S->ngrid <= 0) {
+        xts = (float)xt;
+        yts = (float)yt;
+        fpo_interpol_all(S, itime, xts, yts, zt);
+      } else { /* interpol_all_nests(itime,xtn,ytn,zt), :300-302 */
+        fpo_interpol_all(S, itime, xtn, ytn, zt);
+      }
     } else {
       for (i = 2; i <= nz; i++) {
         if (height[i] > zt) {
@@ -510,9 +551,13 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
 
   /* above the PBL: one step, :629-708 */
 L700:
-  xts = (float)xt;
-  yts = (float)yt;
-  fpo_interpol_wind(S, itime, xts, yts, zt);
+  if (S->ngrid <= 0) { /* :630-636 */
+    xts = (float)xt;
+    yts = (float)yt;
+    fpo_interpol_wind(S, itime, xts, yts, zt);
+  } else {
+    fpo_interpol_wind(S, itime, xtn, ytn, zt);
+  }
 
   ldt = abs(c->lsynctime - itimec + itime);
   dt = (float)ldt;
@@ -587,11 +632,18 @@ L99:
   if (ldt != abs(c->lsynctime)) goto Lout;
   if (abs(itime + ldt * c->ldirect) > abs(S->memtime[2])) goto Lout;
 
-  ngr = pole_grid(S, yt);
+  ngr = choose_grid(S, xt, yt); /* :841-857 */
   if (ngr != S->ngrid) goto Lout;
 
-  S->ix = fpo_int_d(xt);
-  S->jy = fpo_int_d(yt);
+  if (S->ngrid > 0) { /* :862-870 */
+    xtn = (float)((xt - c->xln[S->ngrid - 1]) * c->xresoln[S->ngrid - 1]);
+    ytn = (float)((yt - c->yln[S->ngrid - 1]) * c->yresoln[S->ngrid - 1]);
+    S->ix = fpo_int_f(xtn);
+    S->jy = fpo_int_f(ytn);
+  } else {
+    S->ix = fpo_int_d(xt);
+    S->jy = fpo_int_d(yt);
+  }
   S->ixp = S->ix + 1;
   S->jyp = S->jy + 1;
   if (!S->strict_reference && S->jyp >= c->nymax) S->jyp = S->jyp - 1;
@@ -600,9 +652,13 @@ L99:
   vold = S->v;
   wold = S->w;
 
-  xts = (float)xt;
-  yts = (float)yt;
-  fpo_interpol_wind_short(S, itime + ldt * c->ldirect, xts, yts, zt);
+  if (S->ngrid <= 0) { /* :885-891 */
+    xts = (float)xt;
+    yts = (float)yt;
+    fpo_interpol_wind_short(S, itime + ldt * c->ldirect, xts, yts, zt);
+  } else {
+    fpo_interpol_wind_short(S, itime + ldt * c->ldirect, xtn, ytn, zt);
+  }
   did_pett = 1;
 
   add_settling(S, itime + ldt, nrelpoint, xt, yt, zt);

@@ -7,9 +7,20 @@
 #include "fpo.h"
 #include "fpo_math.h"
 
-#define IDX3(S, i, j, k) \
-  ((size_t)(i) + (size_t)(S)->c.nxmax * ((size_t)(j) + (size_t)(S)->c.nymax * (size_t)((k)-1)))
-#define IDX2(S, i, j) ((size_t)(i) + (size_t)(S)->c.nxmax * (size_t)(j))
+/* Array extents and time level m of the grid in use: the mother grid
+ * (uu(0:nxmax-1,0:nymax-1,nzmax,slot)) or, when S->ngrid > 0, nested grid
+ * ngrid (uun(0:nxmaxn-1,0:nymaxn-1,nzmax,slot,ngrid)).  The *_nests routines
+ * of the reference (src/interpol_all_nests.f90:59-170,
+ * src/interpol_misslev_nests.f90, src/interpol_wind_nests.f90,
+ * src/interpol_wind_short_nests.f90, src/interpol_vdep_nests.f90) are the
+ * mother-grid routines with these arrays and without the polar branch. */
+#define LDX(S) ((size_t)((S)->ngrid > 0 ? (S)->c.nxmaxn : (S)->c.nxmax))
+#define LDY(S) ((size_t)((S)->ngrid > 0 ? (S)->c.nymaxn : (S)->c.nymax))
+#define IDX3(S, i, j, k) ((size_t)(i) + LDX(S) * ((size_t)(j) + LDY(S) * (size_t)((k)-1)))
+#define IDX2(S, i, j) ((size_t)(i) + LDX(S) * (size_t)(j))
+static inline const fpb_met_ptrs *grid_met(const fpo_state *S, int m) {
+  return (S->ngrid > 0) ? &S->metn[S->ngrid][S->memind[m]] : &S->met[S->memind[m]];
+}
 
 static const float EPS_SIG = 1.0e-30f;
 
@@ -39,7 +50,7 @@ static void profile_level(fpo_state *S, int n) {
   float y1[3], y2[3], y3[3], rho1[3], rhograd1[3];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f, xaux;
   for (int m = 1; m <= 2; m++) {
-    const fpb_met_ptrs *M = &S->met[S->memind[m]];
+    const fpb_met_ptrs *M = grid_met(S, m);
     size_t a = IDX3(S, S->ix, S->jy, n), b = IDX3(S, S->ixp, S->jy, n),
            c = IDX3(S, S->ix, S->jyp, n), d = IDX3(S, S->ixp, S->jyp, n);
     const float *fu = (S->ngrid < 0) ? M->uupol : M->uu;
@@ -79,7 +90,7 @@ void fpo_interpol_all(fpo_state *S, int itime, float xt, float yt, float zt) {
   weights(S, itime, xt, yt);
 
   for (int m = 1; m <= 2; m++) {
-    const fpb_met_ptrs *M = &S->met[S->memind[m]];
+    const fpb_met_ptrs *M = grid_met(S, m);
     size_t a = IDX2(S, S->ix, S->jy), b = IDX2(S, S->ixp, S->jy),
            c = IDX2(S, S->ix, S->jyp), d = IDX2(S, S->ixp, S->jyp);
     ust1[m] = bilin(S, M->ustar, a, b, c, d);
@@ -128,7 +139,7 @@ static void wind_common(fpo_state *S, int itime, float xt, float yt, float zt,
   dz2 = (S->height[S->indz + 1] - zt) * dz;
 
   for (int m = 1; m <= 2; m++) {
-    const fpb_met_ptrs *M = &S->met[S->memind[m]];
+    const fpb_met_ptrs *M = grid_met(S, m);
     const float *fu = (S->ngrid < 0) ? M->uupol : M->uu;
     const float *fv = (S->ngrid < 0) ? M->vvpol : M->vv;
     for (int n = 1; n <= 2; n++) {
@@ -180,7 +191,7 @@ void fpo_interpol_wind_short(fpo_state *S, int itime, float xt, float yt,
 void fpo_interpol_vdep(fpo_state *S, int level, float *vdepo) {
   float y[3];
   for (int m = 1; m <= 2; m++) {
-    const fpb_met_ptrs *M = &S->met[S->memind[m]];
+    const fpb_met_ptrs *M = grid_met(S, m);
     size_t a = IDX3(S, S->ix, S->jy, level), b = IDX3(S, S->ixp, S->jy, level),
            c = IDX3(S, S->ix, S->jyp, level),
            d = IDX3(S, S->ixp, S->jyp, level);

@@ -36,6 +36,7 @@ static inline float fpo_sqrtf(float x) { return sqrtf(x); }
 static inline int fpo_int_f(float x) { return (int)x; }
 static inline int fpo_int_d(double x) { return (int)x; }
 static inline int fpo_nint_d(double x) { return (int)lround(x); }
+static inline int fpo_nint_f(float x) { return (int)lroundf(x); }
 static inline float fpo_maxf(float a, float b) { return a > b ? a : b; }
 static inline float fpo_minf(float a, float b) { return a < b ? a : b; }
 /* Fortran modulo(a,p) for reals: result has the sign of p */

@@ -130,6 +130,9 @@ void fpo_destroy(fpo_state *S) {
 }
 
 void fpo_set_met(fpo_state *S, int slot, const fpb_met_ptrs *m) { S->met[slot] = *m; }
+void fpo_set_met_nest(fpo_state *S, int slot, int nest, const fpb_met_ptrs *m) {
+  if (nest >= 1 && nest <= FPB_MAXNESTS) S->metn[nest][slot] = *m;
+}
 
 void fpo_set_met_bracket(fpo_state *S, const int memind[2], const int memtime[2],
                          int lwindinterv) {

@@ -37,6 +37,7 @@ def load(libm_float=False):
     L.fpo_set_rannumb.argtypes = [S, _pf, C.c_int]
     L.fpo_rannumb.argtypes = [S]; L.fpo_rannumb.restype = _pf
     L.fpo_set_met.argtypes = [S, C.c_int, C.POINTER(FpbMetPtrs)]
+    L.fpo_set_met_nest.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbMetPtrs)]
     L.fpo_set_met_bracket.argtypes = [S, _pi, _pi, C.c_int]
     L.fpo_push_particles.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbParticlePtrs)]
     L.fpo_pull_particles.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbParticlePtrs)]
@@ -94,6 +95,11 @@ class Oracle:
         self._keep.append(met)  # the oracle reads the host arrays in place
         self._keep = self._keep[-4:]
         self.L.fpo_set_met(self.S, slot, C.byref(met.ptrs))
+
+    def upload_met_nest(self, slot, nest, met):
+        self._keep_n = getattr(self, "_keep_n", {})
+        self._keep_n[(slot, nest)] = met
+        self.L.fpo_set_met_nest(self.S, slot, nest, C.byref(met.ptrs))
 
     def set_met_bracket(self, memind, memtime, lwindinterv=None):
         if lwindinterv is None:

@@ -253,7 +253,7 @@ def test_step_host_strict_matches_oracle():
 # math (tolerance), oracle state re-injected every step
 # ----------------------------------------------------------------------------
 def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=True, exact=True,
-              dt=None, tol_h=1e-5):
+              dt=None, tol_h=1e-5, nest_mets=None):
     c = cb.cfg
     n = p.numpart
     dt = dt or c.lsynctime
@@ -262,6 +262,8 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
     eng.fill_rannumb(); ora.fill_rannumb()
     for e in (eng, ora):
         e.upload_met(1, m0); e.upload_met(2, m1)
+        for nest, (n0, n1) in enumerate(nest_mets or (), start=1):
+            e.upload_met_nest(1, nest, n0); e.upload_met_nest(2, nest, n1)
         e.set_met_bracket((1, 2), bracket)
     ora.push_particles(p)
     tot = dict(n_active=0, n_pbl=0, n_petterssen=0, n_terminated=0, n_substeps=0, n_nan_cbl=0)
@@ -324,6 +326,33 @@ def test_polar_branches(exact):
     p.ytra1[1024:2048] = q.ytra1[:1024]
     tot, _, _ = _per_step(cb, p, 5, exact=exact, tol_h=2e-5)
     assert tot["n_active"] == 5 * 2048
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_nested_input_grids(exact):
+    """Two nested met input grids (the MeteoSwiss build has maxnests=1,
+    src/par_mod_meteoswiss.f90:154): grid choice, nest coordinates, hmixn /
+    tropopausen, interpol_*_nests, vdepn and the same-grid test of the
+    Petterssen corrector (src/advance.f90:166-203,237-264,841-891).  The nests'
+    fields are biased so that reading the mother grid instead would show."""
+    nests = [(-40.0, 10.0, 161, 81, 0.5, 0.5), (-10.0, 20.0, 81, 61, 0.25, 0.25)]
+    cb = cases.config_small(nrel=4, npart_each=1024, met_nests=nests, nspec=2, drydepspec=(1, 0),
+                            xmass=np.ones((4, 2)), math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    assert cb.cfg.numbnests == 2
+    nm = []
+    for nest in (1, 2):
+        pair = (fb.MetFields(cb, nest=nest).synth(0), fb.MetFields(cb, nest=nest).synth(10800))
+        for m in pair:
+            m.uu += 3.0 * nest; m.vv -= 2.0 * nest; m.hmix *= (1.0 + 0.2 * nest)
+            m.tropopause -= 500.0 * nest; m.vdep *= (1.0 + nest)
+        nm.append(pair)
+    # most particles in and around the nests (lon -50..50, lat 0..60), the rest anywhere
+    p = cases.seeded_particles(cb, 4096, zmax=6000.0, lat_range=(0.0, 60.0), nspec=2)
+    r = np.random.RandomState(3)
+    p.xtra1[:3072] = (r.uniform(-50.0, 50.0, 3072) - cb.cfg.xlon0) / cb.cfg.dx
+    p.ztra1[:1024] = r.uniform(1.0, 40.0, 1024).astype(np.float32)  # around the 2*href deposition layer
+    tot, _, _ = _per_step(cb, p, 5, exact=exact, nest_mets=nm)
+    assert tot["n_active"] == 5 * 4096 and tot["n_pbl"] > 0 and tot["n_petterssen"] > 0
 
 
 @pytest.mark.parametrize("exact", [True, False])

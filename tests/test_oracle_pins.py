@@ -155,6 +155,62 @@ def test_kat_uniform_zonal_wind_turbulence_off():
     assert np.all(p.itra1[:64] == 900)
 
 
+def _homog_nest(cb, nest, u, v=0.0, w=0.0):
+    """mpi_mod's set_fields_synthetic values on a nested input grid."""
+    out = []
+    for _ in range(2):
+        m = fb.MetFields(cb, nest=nest)
+        m.uu[:] = u; m.vv[:] = v; m.ww[:] = w
+        m.rho[:] = 1.3; m.drhodz[:] = 0.0
+        m.hmix[:] = 10000.0; m.tropopause[:] = 10000.0
+        m.ustar[:] = 1.0; m.wstar[:] = 1.0; m.oli[:] = 0.01
+        out.append(m)
+    return out
+
+
+def test_kat_nested_input_grid_wind_is_used_inside_the_nest():
+    """Nested met input (src/advance.f90:166-173,191-203; interpol_*_nests): a
+    particle inside the nest is advected by the nest's wind, one outside by the
+    mother grid's; highest nest wins; at the border (eps margin) the mother
+    grid is used; leaving the nest skips the Petterssen corrector."""
+    nests = [(-20.0, 20.0, 81, 41, 0.5, 0.5), (-10.0, 25.0, 41, 21, 0.25, 0.25)]
+    cb = cases.config_small(nrel=1, npart_each=8, turboff=1, ctl=-5.0, met_nests=nests)
+    c = cb.cfg
+    assert c.numbnests == 2 and c.nxmaxn == 81 and c.nymaxn == 41
+    assert abs(c.xresoln[0] - 10.0) < 1e-6 and abs(c.xresoln[1] - 20.0) < 1e-5
+    o = Oracle(cb)
+    o.fill_rannumb(20000, -320)
+    m0, m1 = _homog(cb, 10.0)
+    o.upload_met(1, m0); o.upload_met(2, m1)
+    for nest, u in ((1, 20.0), (2, 40.0)):
+        a, b = _homog_nest(cb, nest, u)
+        o.upload_met_nest(1, nest, a); o.upload_met_nest(2, nest, b)
+    o.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 8, zmax=12000.0)
+    gx = lambda lon: (lon - c.xlon0) / c.dx
+    gy = lambda lat: (lat - c.ylat0) / c.dy
+    # 0: far outside; 1: inside nest 1 only; 2: inside nest 2 (and 1); 3: exactly on nest 1's
+    # left border (not inside: xt > xln + eps fails); 4: inside nest 1, leaves it eastwards
+    lon = np.array([-100.0, -15.0, -5.0, -20.0, 19.9, 60.0, 60.0, 60.0])
+    lat = np.array([30.0, 30.0, 27.0, 30.0, 30.0, 0.0, 0.0, 0.0])
+    p.xtra1[:8], p.ytra1[:8] = gx(lon), gy(lat)
+    x0, y0 = p.xtra1[:8].copy(), p.ytra1[:8].copy()
+    o.push_particles(p)
+    st = o.step(0)
+    o.pull_particles(p)
+    per_ms = 900.0 * c.dxconst / np.cos(np.deg2rad(lat))   # grid units per (m/s), first-order step
+    speed = (p.xtra1[:8] - x0) / per_ms
+    assert np.allclose(speed[[0, 3, 5, 6, 7]], 10.0, rtol=2e-5)
+    assert np.allclose(speed[1], 20.0, rtol=2e-5)
+    assert np.allclose(speed[2], 40.0, rtol=2e-5)
+    assert np.allclose(speed[4], 20.0, rtol=2e-5)       # nest wind, no corrector after leaving the nest
+    assert p.xtra1[4] > c.xrn[0]
+    # 3 enters nest 1 and 4 leaves it during the step: start and end point on different
+    # grids, so no corrector for them (src/advance.f90:841-857)
+    assert st["n_petterssen"] == 6
+    assert np.abs(p.ytra1[:8] - y0).max() < 1e-12
+
+
 def test_kat_cyclic_wrap():
     """x wraps modulo nxmin1 under the cyclic boundary (src/advance.f90:784-788)."""
     cb = cases.config_small(nrel=1, npart_each=4, turboff=1, ctl=-5.0)
