@@ -727,7 +727,10 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
   a.p.us[j] = usigold; a.p.vs[j] = vsigold; a.p.ws[j] = wsigold;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef FPB_FINISH_MIN_BLOCKS
+#define FPB_FINISH_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, FPB_FINISH_MIN_BLOCKS)
 fpb_finish_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
