@@ -40,6 +40,10 @@ class FpbConfig(C.Structure):
         ("nspec", _i), ("decay", _f * MAXSPEC), ("drydepspec", _i * MAXSPEC),
         ("density", _f * MAXSPEC), ("dquer", _f * MAXSPEC), ("vsetaver", _f * MAXSPEC),
         ("cunningham", _f * MAXSPEC),
+        ("wetdep", _i), ("wetdepspec", _i * MAXSPEC), ("weta_gas", _f * MAXSPEC), ("wetb_gas", _f * MAXSPEC),
+        ("crain_aero", _f * MAXSPEC), ("csnow_aero", _f * MAXSPEC), ("ccn_aero", _f * MAXSPEC),
+        ("in_aero", _f * MAXSPEC), ("henry", _f * MAXSPEC), ("readclouds", _i),
+        ("readclouds_nest", _i * MAXNESTS),
         ("nageclass", _i), ("lage", _i * MAXAGECLASS),
         ("numxgrid", _i), ("numygrid", _i), ("numzgrid", _i),
         ("dxout", _f), ("dyout", _f), ("xoutshift", _f), ("youtshift", _f),
@@ -59,7 +63,8 @@ class FpbConfig(C.Structure):
 
 class FpbMetPtrs(C.Structure):
     _fields_ = [(n, _pf) for n in ("uu", "vv", "ww", "rho", "drhodz", "tt", "uupol", "vvpol",
-                                   "hmix", "ustar", "wstar", "oli", "tropopause", "vdep")]
+                                   "hmix", "ustar", "wstar", "oli", "tropopause", "vdep",
+                                   "lsprec", "convprec", "tcc", "ctwc")] + [("clouds", C.POINTER(C.c_int8))]
 
 
 class FpbParticlePtrs(C.Structure):
@@ -107,6 +112,7 @@ STEP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, C.POINTER(FpbStepStats))
 CONC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _f)
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _pf, _pf, _pf, _pf, _pf, _i)
 SCALE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _pf)
+WETDEPO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _i)
 OUTPUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _f, _pf, _pf, _pf, _pf, _pf)
 
 
@@ -114,7 +120,8 @@ class FpbhEngine(C.Structure):
     _fields_ = [("self", C.c_void_p), ("upload_met", UPLOAD_MET_FN),
                 ("set_met_bracket", SET_BRACKET_FN), ("push_particles", PUSH_FN),
                 ("pull_particles", PUSH_FN), ("set_numpart", SET_NUMPART_FN), ("step", STEP_FN),
-                ("conccalc", CONC_FN), ("fetch_grids", FETCH_FN), ("scale_depgrids", SCALE_FN)]
+                ("conccalc", CONC_FN), ("fetch_grids", FETCH_FN), ("scale_depgrids", SCALE_FN),
+                ("wetdepo", WETDEPO_FN)]
 
 
 # FPB_ENGINE_LIB: load another build of the same library (kernel A/B experiments)
@@ -148,6 +155,8 @@ def load_engine_lib():
     L.fpb_pull_particles.argtypes = [H, _i, _i, _ppart]
     L.fpb_set_numpart.argtypes = [H, _i]
     L.fpb_step.argtypes = [H, _i, _i, C.POINTER(FpbStepStats)]
+    L.fpb_wetdepo.argtypes = [H, _i, _i, _i]
+    L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
                                 C.POINTER(FpbStepStats)]
     L.fpb_conccalc.argtypes = [H, _i, _f]

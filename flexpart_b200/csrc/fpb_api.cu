@@ -111,6 +111,14 @@ struct fpb_handle {
   float4 *A[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
   float *G[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
   float2 *P[2] = {nullptr, nullptr};
+  float4 *R[2] = {nullptr, nullptr};  // wet deposition: {lsprec, convprec, tcc, ctwc}
+  int8_t *Cl[2] = {nullptr, nullptr}; // wet deposition: clouds
+  float4 *Rn[FPB_MAXNESTS][2] = {};
+  int8_t *Cln[FPB_MAXNESTS][2] = {};
+  float *Tn[FPB_MAXNESTS][2] = {};
+  int8_t *stage8 = nullptr;
+  size_t stage8_n = 0;
+  float *wetgridunc = nullptr, *wetgriduncn = nullptr;
   // nested input grids [nest][slot] (no polar twins, no tt: settling reads the mother grid)
   float4 *An[FPB_MAXNESTS][2] = {}, *Sn[FPB_MAXNESTS][2] = {};
   float *Gn[FPB_MAXNESTS][2] = {}, *tropn[FPB_MAXNESTS][2] = {}, *vdepn[FPB_MAXNESTS][2] = {};
@@ -206,6 +214,13 @@ static void fill_devcfg(fpb_handle *h) {
     d.decay[k] = c.decay[k]; d.drydepspec[k] = c.drydepspec[k]; d.density[k] = c.density[k];
     d.dquer[k] = c.dquer[k]; d.vsetaver[k] = c.vsetaver[k]; d.cunningham[k] = c.cunningham[k];
   }
+  for (int k = 0; k < FPB_MAXSPEC; k++) {
+    d.wetdepspec[k] = c.wetdepspec[k]; d.weta_gas[k] = c.weta_gas[k]; d.wetb_gas[k] = c.wetb_gas[k];
+    d.crain_aero[k] = c.crain_aero[k]; d.csnow_aero[k] = c.csnow_aero[k]; d.ccn_aero[k] = c.ccn_aero[k];
+    d.in_aero[k] = c.in_aero[k]; d.henry[k] = c.henry[k];
+  }
+  d.readclouds = c.readclouds;
+  for (int l = 0; l < FPB_MAXNESTS; l++) d.readclouds_nest[l] = c.readclouds_nest[l];
   d.nageclass = c.nageclass;
   for (int k = 0; k < FPB_MAXAGECLASS; k++) d.lage[k] = c.lage[k];
   d.numxgrid = c.numxgrid; d.numygrid = c.numygrid; d.numzgrid = c.numzgrid;
@@ -258,6 +273,32 @@ __global__ void pack_component_kernel(float *dst, int comp, int ncomp, const flo
   size_t r = i / nxd;
   int jy = (int)(r % nyd), k = (int)(r / nyd);
   dst[i * ncomp + comp] = src[((size_t)k * nymax + jy) * nxmax + ix];
+}
+
+__global__ void pack_i8_kernel(int8_t *dst, const int8_t *src, int nxd, int nyd, int nk, int nxmax, int nymax) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)nxd * nyd * nk;
+  if (i >= n) return;
+  int ix = (int)(i % nxd);
+  size_t r = i / nxd;
+  int jy = (int)(r % nyd), k = (int)(r / nyd);
+  dst[i] = (jy < nymax) ? src[((size_t)k * nymax + jy) * nxmax + ix] : (int8_t)0;
+}
+
+static int upload_i8(fpb_handle *h, int8_t *dst, const int8_t *src, int nk, int nxd, int nyd, int nxmax, int nymax) {
+  const size_t nsrc = (size_t)nxmax * nymax * nk, n = (size_t)nxd * nyd * nk;
+  if (nsrc > h->stage8_n) {
+    if (h->stage8) cudaFree(h->stage8);
+    h->stage8 = nullptr;
+    CK(cudaMalloc((void **)&h->stage8, nsrc));
+    h->stage8_n = nsrc;
+  }
+  CK(cudaMemcpyAsync(h->stage8, src, nsrc, cudaMemcpyHostToDevice, h->stream));
+  pack_i8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dst, h->stage8, nxd, nyd, nk, nxmax, nymax);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk,
@@ -336,12 +377,14 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   for (int s = 0; s < 2; s++) {
     DA(h->A[s], n3); DA(h->G[s], n3); DA(h->T[s], n3); DA(h->P[s], n3); DA(h->S[s], n2);
     DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
+    if (c.wetdep) { DA(h->R[s], n2); DA(h->Cl[s], n3); }
   }
   for (int l = 0; l < c.numbnests; l++) {
     const size_t m2 = (size_t)c.nxn[l] * c.nyn[l], m3 = m2 * c.nz;
     for (int s = 0; s < 2; s++) {
       DA(h->An[l][s], m3); DA(h->Gn[l][s], m3); DA(h->Sn[l][s], m2);
       DA(h->tropn[l][s], m2); DA(h->vdepn[l][s], m2 * c.nspec);
+      if (c.wetdep) { DA(h->Rn[l][s], m2); DA(h->Cln[l][s], m3); DA(h->Tn[l][s], m3); }
     }
   }
   const size_t mp = (size_t)c.maxpart;
@@ -384,6 +427,10 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
     DA(h->griduncn, h->n_gridn); DA(h->drygriduncn, h->n_dryn);
   }
   h->n_rec = (size_t)FPB_MAXRECEPTOR * c.nspec;
+  if (c.wetdep) {
+    DA(h->wetgridunc, h->n_dry);
+    if (c.nested_output == 1) DA(h->wetgriduncn, h->n_dryn);
+  }
   DA(h->creceptor, h->n_rec); DA(h->crec_acc, h->n_rec);
   DA(h->d_stats, 8);
   CK(cudaStreamSynchronize(h->stream));
@@ -400,9 +447,11 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   }
   for (int l = 0; l < FPB_MAXNESTS; l++)
     for (int s = 0; s < 2; s++) {
+      cudaFree(h->Rn[l][s]); cudaFree(h->Cln[l][s]); cudaFree(h->Tn[l][s]);
       cudaFree(h->An[l][s]); cudaFree(h->Gn[l][s]); cudaFree(h->Sn[l][s]); cudaFree(h->tropn[l][s]); cudaFree(h->vdepn[l][s]);
     }
-  cudaFree(h->stage);
+  cudaFree(h->stage); cudaFree(h->stage8); cudaFree(h->wetgridunc); cudaFree(h->wetgriduncn);
+  for (int s = 0; s < 2; s++) { cudaFree(h->R[s]); cudaFree(h->Cl[s]); }
   for (DevParticles *q : {&h->p, &h->p_alt}) {
     cudaFree(q->xtra1); cudaFree(q->ytra1); cudaFree(q->ztra1); cudaFree(q->itra1);
     cudaFree(q->npoint); cudaFree(q->nclass); cudaFree(q->idt); cudaFree(q->itramem);
@@ -485,6 +534,17 @@ extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m
     // host vdep(nxmax,nymax,maxspec): species k is "level" k
     if (upload_component(h, h->vdep[s], 0, 1, m->vdep, c.nspec)) return 1;
   }
+  if (c.wetdep) {
+    if (!m->lsprec || !m->convprec || !m->tcc || !m->clouds || !m->tt)
+      return fail("fpb_upload_met: lsprec/convprec/tcc/clouds/tt required when wetdep");
+    if (c.readclouds && !m->ctwc) return fail("fpb_upload_met: ctwc required when readclouds");
+    float *R = (float *)h->R[s];
+    if (upload_component(h, R, 0, 4, m->lsprec, 1)) return 1;
+    if (upload_component(h, R, 1, 4, m->convprec, 1)) return 1;
+    if (upload_component(h, R, 2, 4, m->tcc, 1)) return 1;
+    if (upload_component(h, R, 3, 4, m->ctwc, 1)) return 1;
+    if (upload_i8(h, h->Cl[s], m->clouds, c.nz, h->d.nxd, h->d.nyd, c.nxmax, c.nymax)) return 1;
+  }
   return 0;
 }
 
@@ -512,6 +572,18 @@ extern "C" int fpb_upload_met_nest(fpb_handle *h, int32_t slot, int32_t nest, co
   if (upload_component(h, S, 3, 4, m->oli, 1, nx, ny, mx, my)) return 1;
   if (upload_component(h, h->tropn[l][s], 0, 1, m->tropopause, 1, nx, ny, mx, my)) return 1;
   if (c.drydep && upload_component(h, h->vdepn[l][s], 0, 1, m->vdep, c.nspec, nx, ny, mx, my)) return 1;
+  if (c.wetdep) {
+    if (!m->lsprec || !m->convprec || !m->tcc || !m->clouds || !m->tt)
+      return fail("fpb_upload_met_nest: lsprec/convprec/tcc/clouds/tt required when wetdep");
+    if (c.readclouds_nest[l] && !m->ctwc) return fail("fpb_upload_met_nest: ctwc required when readclouds_nest");
+    float *R = (float *)h->Rn[l][s];
+    if (upload_component(h, R, 0, 4, m->lsprec, 1, nx, ny, mx, my)) return 1;
+    if (upload_component(h, R, 1, 4, m->convprec, 1, nx, ny, mx, my)) return 1;
+    if (upload_component(h, R, 2, 4, m->tcc, 1, nx, ny, mx, my)) return 1;
+    if (upload_component(h, R, 3, 4, m->ctwc, 1, nx, ny, mx, my)) return 1;
+    if (upload_component(h, h->Tn[l][s], 0, 1, m->tt, c.nz, nx, ny, mx, my)) return 1;
+    if (upload_i8(h, h->Cln[l][s], m->clouds, c.nz, nx, ny, mx, my)) return 1;
+  }
   return 0;
 }
 
@@ -712,7 +784,7 @@ static void nest_views(const fpb_handle *h, DevStepArgs &a) {
 static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
   DevMetSlot m;
   const int s = fslot - 1;
-  m.A = h->A[s]; m.G = h->G[s]; m.T = h->T[s]; m.P = h->P[s]; m.S = h->S[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
+  m.A = h->A[s]; m.G = h->G[s]; m.T = h->T[s]; m.P = h->P[s]; m.S = h->S[s]; m.R = h->R[s]; m.C = h->Cl[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
   return m;
 }
 
@@ -1049,6 +1121,38 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
   return 0;
 }
 
+// ---------------------------------------------------------- wet deposition --
+extern "C" int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32_t ldeltat) {
+  if (!h) return fail("fpb_wetdepo: null handle");
+  if (!h->cfg.wetdep) return fail("fpb_wetdepo: the run was initialised without wet deposition (wetdep = 0)");
+  if (!h->have_bracket) return fail("fpb_wetdepo: fpb_set_met_bracket has not been called");
+  if (h->numpart == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  DevWetArgs a;
+  per_step_cfg(h, a.cfg, itime, ldeltat);
+  // time level closest to itime - ltsample/2, src/get_wetscav.f90:113-117
+  const int interp_time = (int)lroundf((float)itime - 0.5f * (float)ltsample);
+  int n = h->memind[1];
+  if (abs(h->memtime[0] - interp_time) < abs(h->memtime[1] - interp_time)) n = h->memind[0];
+  a.met = slot_view(h, n);
+  for (int l = 0; l < FPB_MAXNESTS; l++) {
+    DevMetSlot v{};
+    v.R = h->Rn[l][n - 1]; v.C = h->Cln[l][n - 1]; v.T = h->Tn[l][n - 1];
+    a.metn[l] = v;
+  }
+  a.p = h->p;
+  a.height = h->d_height;
+  a.wetgridunc = h->wetgridunc;
+  a.wetgriduncn = h->wetgriduncn;
+  a.ltsample = ltsample;
+  if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_wetdepo_strict(a, h->stream);
+  else fpbk_wetdepo_fast(a, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" int fpb_kernel_times(fpb_handle *h, float *step_ms, float *conccalc_ms) {
   if (!h) return fail("fpb_kernel_times: null handle");
   CK(cudaSetDevice(h->device));
@@ -1129,6 +1233,18 @@ extern "C" int fpb_fetch_grids(fpb_handle *h, float *gridunc, float *griduncn, f
   return 0;
 }
 
+extern "C" int fpb_fetch_wetgrids(fpb_handle *h, float *wetgridunc, float *wetgriduncn) {
+  if (!h) return fail("fpb_fetch_wetgrids: null handle");
+  const fpb_config &c = h->cfg;
+  if (!c.wetdep) return fail("fpb_fetch_wetgrids: the run was initialised without wet deposition");
+  CK(cudaSetDevice(h->device));
+  std::vector<float> tmp;
+  if (fetch_one(h, wetgridunc, h->wetgridunc, (size_t)c.numxgrid * c.numygrid, h->n_dry, tmp)) return 1;
+  if (c.nested_output == 1 && wetgriduncn)
+    if (fetch_one(h, wetgriduncn, h->wetgriduncn, (size_t)c.numxgridn * c.numygridn, h->n_dryn, tmp)) return 1;
+  return 0;
+}
+
 __global__ void scale_dep_kernel(float *g, size_t n, size_t inner, int nspec, DevCfg c, const float f0,
                                  const float f1, const float f2, const float f3, const float f4,
                                  const float f5, const float f6, const float f7) {
@@ -1151,6 +1267,16 @@ extern "C" int fpb_scale_depgrids(fpb_handle *h, const float *factor) {
   if (h->drygriduncn) {
     scale_dep_kernel<<<(unsigned)((h->n_dryn + 255) / 256), 256, 0, h->stream>>>(
         h->drygriduncn, h->n_dryn, (size_t)c.numxgridn * c.numygridn, c.nspec, h->d, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+    h->launches++;
+  }
+  if (h->wetgridunc) { // wetgridunc decays with drygridunc, src/timemanager.f90:276-282
+    scale_dep_kernel<<<(unsigned)((h->n_dry + 255) / 256), 256, 0, h->stream>>>(
+        h->wetgridunc, h->n_dry, (size_t)c.numxgrid * c.numygrid, c.nspec, h->d, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+    h->launches++;
+  }
+  if (h->wetgriduncn) {
+    scale_dep_kernel<<<(unsigned)((h->n_dryn + 255) / 256), 256, 0, h->stream>>>(
+        h->wetgriduncn, h->n_dryn, (size_t)c.numxgridn * c.numygridn, c.nspec, h->d, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
     h->launches++;
   }
   CK(cudaGetLastError());

@@ -28,6 +28,8 @@ struct DevMetSlot {
   const float4 *S;
   const float *trop;
   const float *vdep;
+  const float4 *R;   // {lsprec, convprec, tcc, ctwc}[jy][ix] (wet deposition only)
+  const int8_t *C;   // clouds[k][jy][ix] (wet deposition only)
 };
 
 struct DevParticles {
@@ -72,6 +74,10 @@ struct DevCfg {
   int drydepspec[FPB_MAXSPEC];
   float density[FPB_MAXSPEC], dquer[FPB_MAXSPEC], vsetaver[FPB_MAXSPEC],
       cunningham[FPB_MAXSPEC];
+  int wetdepspec[FPB_MAXSPEC];
+  float weta_gas[FPB_MAXSPEC], wetb_gas[FPB_MAXSPEC], crain_aero[FPB_MAXSPEC], csnow_aero[FPB_MAXSPEC],
+      ccn_aero[FPB_MAXSPEC], in_aero[FPB_MAXSPEC], henry[FPB_MAXSPEC];
+  int readclouds, readclouds_nest[FPB_MAXNESTS];
   int nageclass;
   int lage[FPB_MAXAGECLASS];
   // out grids
@@ -137,12 +143,25 @@ struct DevConcArgs {
   float *crec_acc; // [numreceptor][nspec] accumulators of c(ks)
 };
 
+// wetdepo (src/wetdepo.f90): one time level per grid, chosen on the host the way
+// get_wetscav does (src/get_wetscav.f90:113-117)
+struct DevWetArgs {
+  DevCfg cfg;
+  DevMetSlot met;                 // mother grid, time level n
+  DevMetSlot metn[FPB_MAXNESTS];  // nested grids, time level n
+  DevParticles p;
+  const float *height;
+  float *wetgridunc, *wetgriduncn;
+  int ltsample;
+};
+
 // launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
   void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \
   void fpbk_step_##SUF(const DevStepArgs &a, cudaStream_t st);                \
   void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
+  void fpbk_wetdepo_##SUF(const DevWetArgs &a, cudaStream_t st);              \
   void fpbk_conc_emit_##SUF(const DevConcArgs &a, int nest_sel, unsigned *keys, \
                             float *vals, size_t nrec, cudaStream_t st);
 FPB_DECL_LAUNCHERS(fast)

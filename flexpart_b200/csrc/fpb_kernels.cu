@@ -43,6 +43,7 @@ __device__ __forceinline__ float m_pow(float a, float b) { return (float)pow((do
 __device__ __forceinline__ float m_sin(float x) { return (float)sin((double)x); }
 __device__ __forceinline__ float m_cos(float x) { return (float)cos((double)x); }
 __device__ __forceinline__ float m_erf(float x) { return (float)erf((double)x); }
+__device__ __forceinline__ float m_log10(float x) { return (float)log10((double)x); }
 #else
 // production: MUFU-based exp / pow (a > 0 at every call site); relative error
 // ~1e-6, three orders of magnitude inside the 1e-5 position tolerance
@@ -52,6 +53,7 @@ __device__ __forceinline__ float m_pow(float a, float b) { return exp2f(b * __lo
 __device__ __forceinline__ float m_sin(float x) { return sinf(x); }
 __device__ __forceinline__ float m_cos(float x) { return cosf(x); }
 __device__ __forceinline__ float m_erf(float x) { return erff(x); }
+__device__ __forceinline__ float m_log10(float x) { return __log10f(x); }
 #endif
 __device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ int f_int(float x) { return (int)x; }   // Fortran int()
@@ -1210,6 +1212,227 @@ fpb_receptor_kernel(const __grid_constant__ DevConcArgs a) {
   }
 }
 
+
+// ======================================================== wet deposition ===
+// src/wetdepo.f90:70-147, src/get_wetscav.f90:78-314, src/interpol_rain.f90:77-127,
+// src/wetdepokernel.f90:38-108, src/wetdepokernel_nest.f90:38-105
+__device__ __forceinline__ float wet_powi(float x, int m) { // real**integer as libgcc's __powisf2
+  unsigned n = (unsigned)(m < 0 ? -m : m);
+  float y = (n % 2) ? x : 1.f;
+  while (n >>= 1) {
+    x = x * x;
+    if (n % 2) y = y * x;
+  }
+  return m < 0 ? 1.f / y : y;
+}
+
+// exponent of the Laakso / Kyro below-cloud polynomials (src/get_wetscav.f90:232-243):
+// terms of order 1e2..1e3 cancel to order 1, so the sum is evaluated with explicitly
+// rounded operations (no FMA contraction) in every math mode
+__device__ __forceinline__ float wet_poly(const float *b, float lg, float sqrt_prec) {
+  float e = __fadd_rn(b[0], __fmul_rn(b[1], wet_powi(lg, -4)));
+  e = __fadd_rn(e, __fmul_rn(b[2], wet_powi(lg, -3)));
+  e = __fadd_rn(e, __fmul_rn(b[3], wet_powi(lg, -2)));
+  e = __fadd_rn(e, __fmul_rn(b[4], wet_powi(lg, -1)));
+  e = __fadd_rn(e, __fmul_rn(b[5], sqrt_prec));
+  return e;
+}
+
+// returns wetscav; grfraction1 is written only when scavenging is evaluated
+__device__ float get_wetscav(const DevWetArgs &a, const float *sh, int i, int ks, float &grfraction1) {
+  const DevCfg &c = a.cfg;
+  const float lfr[5] = {0.5f, 0.65f, 0.8f, 0.9f, 0.95f};
+  const float cfr[5] = {0.4f, 0.55f, 0.7f, 0.8f, 0.9f};
+  const float bclr[6] = {274.35758f, 332839.59273f, 226656.57259f, 58005.91340f, 6588.38582f, 0.244984f};
+  const float bcls[6] = {22.7f, 0.0f, 0.0f, 1321.0f, 381.0f, 0.0f};
+  float wetscav = 0.f;
+  const double xd = a.p.xtra1[i], yd = a.p.ytra1[i];
+  int ngrid = 0;
+  for (int j = c.numbnests; j >= 1; j--) // no eps margin here, src/get_wetscav.f90:82-90
+    if ((xd > c.xln[j - 1]) && (xd < c.xrn[j - 1]) && (yd > c.yln[j - 1]) && (yd < c.yrn[j - 1])) {
+      ngrid = j;
+      break;
+    }
+  const DevMetSlot &M = (ngrid > 0) ? a.metn[ngrid - 1] : a.met;
+  const int nxd = (ngrid > 0) ? c.nxdn[ngrid - 1] : c.nxd, nyd = (ngrid > 0) ? c.nydn[ngrid - 1] : c.nyd;
+  const int nxu = (ngrid > 0) ? c.nxdn[ngrid - 1] : c.nx, nyu = (ngrid > 0) ? c.nydn[ngrid - 1] : c.ny;
+  float xt, yt;
+  int ix, jy;
+  bool clouds_read;
+  if (ngrid > 0) {
+    xt = (float)((xd - c.xln[ngrid - 1]) * c.xresoln[ngrid - 1]);
+    yt = (float)((yd - c.yln[ngrid - 1]) * c.yresoln[ngrid - 1]);
+    ix = f_int(xt);
+    jy = f_int(yt);
+    clouds_read = c.readclouds_nest[ngrid - 1] != 0;
+  } else {
+    xt = (float)xd;
+    yt = (float)yd;
+    ix = d_int(xd);
+    jy = d_int(yd);
+    clouds_read = c.readclouds != 0;
+  }
+  float lsp, convp, cc;
+  { // interpol_rain, level 1 of the chosen time level
+    if (xt >= (float)(nxu - 1)) xt = (float)(nxu - 1) - 0.00001f;
+    if (yt >= (float)(nyu - 1)) yt = (float)(nyu - 1) - 0.00001f;
+    const int jx = f_int(xt), jj = f_int(yt), jxp = jx + 1, jjp = jj + 1;
+    const float ddx = xt - (float)jx, ddy = yt - (float)jj, rddx = 1.f - ddx, rddy = 1.f - ddy;
+    const float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+    const float4 r1 = __ldg(M.R + jx + nxd * jj), r2 = __ldg(M.R + jxp + nxd * jj),
+                 r3 = __ldg(M.R + jx + nxd * jjp), r4 = __ldg(M.R + jxp + nxd * jjp);
+    lsp = p1 * r1.x + p2 * r2.x + p3 * r3.x + p4 * r4.x;
+    convp = p1 * r1.y + p2 * r2.y + p3 * r3.y + p4 * r4.y;
+    cc = p1 * r1.z + p2 * r2.z + p3 * r3.z + p4 * r4.z;
+  }
+  if ((lsp < 0.01f) && (convp < 0.01f)) return wetscav;
+
+  const int hz = find_indz(sh, c.nz, a.p.ztra1[i]);
+  const size_t i3 = (size_t)ix + (size_t)nxd * ((size_t)jy + (size_t)nyd * (size_t)(hz - 1));
+  const int clouds_v = __ldg(M.C + i3);
+  if (clouds_v <= 1) return wetscav;
+
+  int li, lj;
+  if (lsp > 20.f) li = 5; else if (lsp > 8.f) li = 4; else if (lsp > 3.f) li = 3; else if (lsp > 1.f) li = 2; else li = 1;
+  if (convp > 20.f) lj = 5; else if (convp > 8.f) lj = 4; else if (convp > 3.f) lj = 3; else if (convp > 1.f) lj = 2; else lj = 1;
+  grfraction1 = fmaxf(0.05f, cc * (lsp * lfr[li - 1] + convp * cfr[lj - 1]) / (lsp + convp));
+  const float prec1 = (lsp + convp) / grfraction1;
+  const float act_temp = __ldg(M.T + i3);
+
+  if (clouds_v >= 4) { // below-cloud scavenging
+    if ((c.dquer[ks] <= 0.f) && (c.weta_gas[ks] > 0.f || c.wetb_gas[ks] > 0.f)) {
+      wetscav = c.weta_gas[ks] * m_pow(prec1, c.wetb_gas[ks]);
+    } else if ((c.dquer[ks] > 0.f) && (c.crain_aero[ks] > 0.f || c.csnow_aero[ks] > 0.f)) {
+      const float dquer_m = fminf(10.f, c.dquer[ks]) / 1000000.f;
+      const float lg = m_log10(dquer_m);
+      if (act_temp >= 273.f && c.crain_aero[ks] > 0.f) {
+        wetscav = c.crain_aero[ks] * m_pow(10.f, wet_poly(bclr, lg, m_pow(prec1, 0.5f)));
+      } else if (act_temp < 273.f && c.csnow_aero[ks] > 0.f) {
+        wetscav = c.csnow_aero[ks] * m_pow(10.f, wet_poly(bcls, lg, m_pow(prec1, 0.5f)));
+      }
+    }
+  }
+  if (clouds_v < 4) { // in-cloud scavenging
+    float ccn = c.ccn_aero[ks], in = c.in_aero[ks];
+    if ((ccn > 0.f || in > 0.f) || (c.henry[ks] > 0.f && c.dquer[ks] <= 0.f)) {
+      if (ccn < 0.f) ccn = 0.f;
+      if (in < 0.f) in = 0.f;
+      float cl;
+      if (clouds_read) cl = __ldg(M.R + ix + nxd * jy).w * (grfraction1 / cc);
+      else cl = (1.e6f * 2.e-7f) * m_pow(prec1, 0.36f);
+      float liq_frac, ice_frac;
+      if (act_temp <= 253.f) {
+        liq_frac = 0.f; ice_frac = 1.f;
+      } else if (act_temp >= 273.f) {
+        liq_frac = 1.f; ice_frac = 0.f;
+      } else {
+        const float q = (act_temp - 273.f) / (273.f - 253.f);
+#if FPB_STRICT
+        ice_frac = (float)pow((double)q, 2.0);
+#else
+        ice_frac = q * q;
+#endif
+        liq_frac = fmaxf(0.f, 1.f - ice_frac);
+      }
+      const float frac_act = liq_frac * ccn + ice_frac * in;
+      float S_i;
+      if (c.dquer[ks] > 0.f) {
+        S_i = frac_act / cl;
+      } else {
+        const float cle = (1.f - cl) / (c.henry[ks] * (287.05f / 3500.f) * act_temp) + cl;
+        S_i = 1.f / cle;
+      }
+      wetscav = 6.2f * S_i * (prec1 / 3.6e6f); // incloud_ratio, src/par_mod.f90:82
+    }
+  }
+  return wetscav;
+}
+
+__device__ void wetdepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc, const float *deposit,
+                                float x, float y, int nage, int kp) {
+  const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
+  float xl, yl;
+  int ix, jy, ixp, jyp;
+  if (nest) { // floor(), src/wetdepokernel_nest.f90:43-44
+    xl = (x * c.dx + c.xoutshiftn) / c.dxoutn;
+    yl = (y * c.dy + c.youtshiftn) / c.dyoutn;
+    ix = (int)floorf(xl);
+    jy = (int)floorf(yl);
+  } else {
+    xl = (x * c.dx + c.xoutshift) / c.dxout;
+    yl = (y * c.dy + c.youtshift) / c.dyout;
+    ix = f_int(xl);
+    jy = f_int(yl);
+  }
+  const float ddx = xl - (float)ix, ddy = yl - (float)jy;
+  float wx, wy;
+  if (ddx > 0.5f) { ixp = ix + 1; wx = 1.5f - ddx; } else { ixp = ix - 1; wx = 0.5f + ddx; }
+  if (ddy > 0.5f) { jyp = jy + 1; wy = 1.5f - ddy; } else { jyp = jy - 1; wy = 0.5f + ddy; }
+  const bool in00 = (ix >= 0) && (jy >= 0) && (ix <= nxg - 1) && (jy <= nyg - 1);
+  const bool in11 = (ixp >= 0) && (jyp >= 0) && (ixp <= nxg - 1) && (jyp <= nyg - 1);
+  const bool in10 = (ixp >= 0) && (jy >= 0) && (ixp <= nxg - 1) && (jy <= nyg - 1);
+  const bool in01 = (ix >= 0) && (jyp >= 0) && (ix <= nxg - 1) && (jyp <= nyg - 1);
+  for (int ks = 1; ks <= c.nspec; ks++) {
+    const float dep = deposit[ks - 1];
+    if (dep == 0.f) continue; // adding 0 changes nothing
+    if (!nest && !c.lusekerneloutput) {
+      if (in00) atomicAdd(grid + didx(c, nxg, nyg, ix, jy, ks, kp, nunc, nage), dep);
+      continue;
+    }
+    if (in00) atomicAdd(grid + didx(c, nxg, nyg, ix, jy, ks, kp, nunc, nage), dep * (wx * wy));
+    if (in11) atomicAdd(grid + didx(c, nxg, nyg, ixp, jyp, ks, kp, nunc, nage), dep * ((1.f - wx) * (1.f - wy)));
+    if (in10) atomicAdd(grid + didx(c, nxg, nyg, ixp, jy, ks, kp, nunc, nage), dep * ((1.f - wx) * wy));
+    if (in01) atomicAdd(grid + didx(c, nxg, nyg, ix, jyp, ks, kp, nunc, nage), dep * (wx * (1.f - wy)));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fpb_wetdepo_kernel(const __grid_constant__ DevWetArgs a) {
+  const DevCfg &c = a.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.height[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.numpart) return;
+  const int itra1 = a.p.itra1[i];
+  if (itra1 == FPB_ITRA_DEAD) return;
+  if (c.ldirect == 1) {
+    if (itra1 > c.itime) return;
+  } else {
+    if (itra1 < c.itime) return;
+  }
+  const int itage = abs(itra1 - a.p.itramem[i]);
+  int nage;
+  for (nage = 1; nage <= c.nageclass; nage++)
+    if (itage < c.lage[nage - 1]) break;
+
+  float wetdeposit[FPB_MAXSPEC];
+  float grfraction1 = 0.f;
+  bool any = false;
+#pragma unroll
+  for (int ks = 0; ks < FPB_MAXSPEC; ks++) {
+    wetdeposit[ks] = 0.f;
+    if (ks < c.nspec && c.wetdepspec[ks]) {
+      const float wetscav = get_wetscav(a, sh, i, ks, grfraction1);
+      float *xm = a.p.xmass1 + (size_t)ks * a.p.maxpart + i;
+      const float xm0 = *xm;
+      if (wetscav > 0.f)
+        wetdeposit[ks] = xm0 * (1.f - m_exp(-wetscav * (float)abs(a.ltsample))) * grfraction1;
+      const float restmass = xm0 - wetdeposit[ks];
+      *xm = (restmass > EPS3) ? restmass : 0.f;
+      if (c.decay[ks] > 0.f) wetdeposit[ks] = wetdeposit[ks] * m_exp((float)abs(c.ldeltat) * c.decay[ks]);
+      any = any || (wetdeposit[ks] != 0.f);
+    }
+  }
+  if (c.ldirect == 1 && any) {
+    const int kp = (c.ioutputforeachrelease == 1) ? a.p.npoint[i] : 1;
+    const int nclass = a.p.nclass[i];
+    const float x = (float)a.p.xtra1[i], y = (float)a.p.ytra1[i];
+    wetdepo_scatter(c, a.wetgridunc, false, nclass, wetdeposit, x, y, nage, kp);
+    if (c.nested_output == 1) wetdepo_scatter(c, a.wetgriduncn, true, nclass, wetdeposit, x, y, nage, kp);
+  }
+}
+
 } // namespace
 
 #if FPB_STRICT
@@ -1227,9 +1450,9 @@ void FPB_SUF(fpbk_init)(const DevStepArgs &a, cudaStream_t st) {
 
 void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   if (a.cfg.numpart <= 0) return;
-  // lean variant: table RNG, no dry deposition, no settling, no CBL
+  // lean variant: table RNG, no dry deposition, no settling, no CBL, no nested input grids
   const bool full = a.cfg.drydep || a.cfg.cblflag == 1 || a.cfg.lsettling ||
-                    a.cfg.rng_mode == FPB_RNG_PHILOX;
+                    a.cfg.rng_mode == FPB_RNG_PHILOX || a.cfg.numbnests > 0;
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
   static int resident[2] = {0, 0};
   int &res = resident[full ? 1 : 0];
@@ -1260,6 +1483,12 @@ void FPB_SUF(fpbk_conc_emit)(const DevConcArgs &a, int nest_sel, unsigned *keys,
   const int nb = (a.cfg.numpart + 255) / 256;
   if (nb == 0) return;
   fpb_conc_emit_kernel<<<nb, 256, 0, st>>>(a, nest_sel, keys, vals, nrec);
+}
+
+void FPB_SUF(fpbk_wetdepo)(const DevWetArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb == 0) return;
+  fpb_wetdepo_kernel<<<nb, 256, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_receptor)(const DevConcArgs &a, cudaStream_t st) {

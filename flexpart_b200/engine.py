@@ -93,6 +93,20 @@ class Engine:
                                          conc_weight, C.byref(st) if stats else None))
         return st.as_dict() if stats else None
 
+    def wetdepo(self, itime, ltsample, ldeltat=0):
+        """wetdepo(itime, ltsample, loutnext) with ldeltat precomputed (src/wetdepo.f90:55-63)."""
+        self._check(self.L.fpb_wetdepo(self.h, itime, ltsample, ldeltat))
+
+    def fetch_wetgrids(self):
+        c = self.cb.cfg
+        out = {"wetgridunc": np.zeros(self.shape_dry, np.float32, order="F")}
+        wn = None
+        if c.nested_output == 1:
+            out["wetgriduncn"] = np.zeros(self.shape_dryn, np.float32, order="F")
+            wn = out["wetgriduncn"]
+        self._check(self.L.fpb_fetch_wetgrids(self.h, _fp(out["wetgridunc"]), _fp(wn)))
+        return out
+
     def conccalc(self, itime, weight):
         self._check(self.L.fpb_conccalc(self.h, itime, weight))
 
@@ -159,4 +173,5 @@ class Engine:
         v.conccalc = cast(L.fpb_conccalc, a.CONC_FN)
         v.fetch_grids = cast(L.fpb_fetch_grids, a.FETCH_FN)
         v.scale_depgrids = cast(L.fpb_scale_depgrids, a.SCALE_FN)
+        v.wetdepo = cast(L.fpb_wetdepo, a.WETDEPO_FN)
         return v

@@ -59,7 +59,9 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
                 npart=(10000,), xmass=None, maxspec=5, nclassunc=1, receptors=(),
                 maxpart=None, device=0, rng_mode=abi.RNG_REFERENCE, math_mode=abi.MATH_FAST,
                 scatter_mode=abi.SCATTER_ATOMIC, seed=0x5EEDF1E0, height=None,
-                part_id_stride=1, part_id_offset=0, sort_interval=0, met_nests=()):
+                part_id_stride=1, part_id_offset=0, sort_interval=0, met_nests=(),
+                wetdepspec=None, weta_gas=None, wetb_gas=None, crain_aero=None, csnow_aero=None,
+                ccn_aero=None, in_aero=None, henry=None, readclouds=0):
     """Run constants for the engine, derived the way the reference's
     gridcheck_ecmwf / readcommand / readoutgrid / readreleases derive them."""
     L = load_host_lib()
@@ -90,6 +92,19 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
     setarr("vsetaver", vsetaver, 0.0)
     setarr("cunningham", cunningham, 1.0)
     c.drydep = 1 if any(c.drydepspec[k] for k in range(nspec)) else 0
+    # wet deposition switches, readspecies / readreleases.f90:349-370 (negative = off)
+    setarr("wetdepspec", wetdepspec, 0)
+    setarr("weta_gas", weta_gas, -1.0)
+    setarr("wetb_gas", wetb_gas, -1.0)
+    setarr("crain_aero", crain_aero, -1.0)
+    setarr("csnow_aero", csnow_aero, -1.0)
+    setarr("ccn_aero", ccn_aero, -1.0)
+    setarr("in_aero", in_aero, -1.0)
+    setarr("henry", henry, 0.0)
+    c.wetdep = 1 if any(c.wetdepspec[k] for k in range(nspec)) else 0
+    c.readclouds = readclouds
+    for l in range(c.numbnests):
+        c.readclouds_nest[l] = readclouds
     c.nageclass = len(lage)
     for k, v in enumerate(lage):
         c.lage[k] = v
@@ -126,7 +141,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
 class MetFields:
     """One time level of the com_mod met arrays (padded, Fortran order)."""
     NAMES3 = ("uu", "vv", "ww", "rho", "drhodz", "tt", "uupol", "vvpol")
-    NAMES2 = ("hmix", "ustar", "wstar", "oli", "tropopause")
+    NAMES2 = ("hmix", "ustar", "wstar", "oli", "tropopause", "lsprec", "convprec", "tcc", "ctwc")
 
     def __init__(self, cb, nest=0):
         """nest = 0: mother grid; nest = l >= 1: nested input grid l (uun.. of com_mod)."""
@@ -138,9 +153,11 @@ class MetFields:
         for n in self.NAMES2:
             setattr(self, n, np.zeros((nxm, nym), np.float32, order="F"))
         self.vdep = np.zeros((nxm, nym, c.maxspec), np.float32, order="F")
+        self.clouds = np.zeros((nxm, nym, c.nzmax), np.int8, order="F")
         self.ptrs = FpbMetPtrs()
         for n in self.NAMES3 + self.NAMES2 + ("vdep",):
             setattr(self.ptrs, n, _fp(getattr(self, n)))
+        self.ptrs.clouds = self.clouds.ctypes.data_as(C.POINTER(C.c_int8))
 
     def synth(self, time_s):
         L = load_host_lib()

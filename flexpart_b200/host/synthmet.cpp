@@ -142,6 +142,42 @@ extern "C" int fpbh_synth_met(const fpb_config *cp, const float *height, int32_t
       }
   }
 
+  // precipitation / cloud fields for wet deposition: rain bands that move with
+  // the diurnal phase; clouds(ix,jy,k) carries verttransform_ecmwf's classes
+  // (src/verttransform_ecmwf.f90:640-700): 0 none, 1 cloud without precipitation,
+  // 2/3 in-cloud (convective / large-scale dominated), 4/5 below-cloud, 6 above
+  if (o->lsprec && o->convprec && o->tcc) {
+    float *lsprec = (float *)o->lsprec, *convprec = (float *)o->convprec, *tcc = (float *)o->tcc;
+    float *ctwc = (float *)o->ctwc;
+    int8_t *clouds = (int8_t *)o->clouds;
+    for (int jy = 0; jy < ny; jy++) {
+      const double phi = ((double)c.ylat0 + (double)c.dy * jy) * PI / 180.0;
+      const double cp_ = std::cos(phi);
+      for (int ix = 0; ix < nx; ix++) {
+        const size_t i = i2(c, ix, jy);
+        const double ls = 6.0 * std::sin(2 * lam[ix] + 0.4 * wt) * cp_ - 1.0;
+        const double cv = 30.0 * std::sin(3 * lam[ix] - 0.6 * wt) * cp_ * cp_ - 8.0;
+        lsprec[i] = (float)std::fmax(0.0, ls);
+        convprec[i] = (float)std::fmax(0.0, cv);
+        tcc[i] = (float)(0.25 + 0.7 * std::fabs(std::sin(lam[ix] + 0.2 * wt)));
+        if (ctwc) ctwc[i] = (float)(2.0e-4 * (1.0 + 0.8 * std::sin(2 * lam[ix] + wt)) * cp_ + 1.0e-5);
+        if (clouds) {
+          const bool rain = (lsprec[i] + convprec[i]) > 0.f;
+          const double base = 600.0 + 900.0 * (0.5 + 0.5 * std::sin(lam[ix])); // cloud base, m
+          const double top = base + 2500.0 + 3000.0 * cp_;
+          for (int k = 0; k < nz; k++) {
+            const double z = height[k];
+            int8_t v;
+            if (z > top) v = rain ? 6 : 0;
+            else if (z >= base) v = rain ? (convprec[i] > lsprec[i] ? 2 : 3) : 1;
+            else v = rain ? (convprec[i] > lsprec[i] ? 4 : 5) : 0;
+            clouds[i3(c, ix, jy, k)] = v;
+          }
+        }
+      }
+    }
+  }
+
   // polar-stereographic winds, src/verttransform_ecmwf.f90:459-607
   if (uupol && vvpol) {
     const float pi_f = 3.14159265f;

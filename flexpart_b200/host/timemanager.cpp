@@ -16,7 +16,8 @@
 
 namespace {
 struct MetStore { // com_mod met arrays, numwfmem = 2
-  std::vector<float> f3[2][8], f2[2][5], vd[2];
+  std::vector<float> f3[2][8], f2[2][5], vd[2], rain[2][4];
+  std::vector<int8_t> cl[2];
   fpb_met_ptrs ptr[2];
   void alloc(const fpb_config &c) {
     const size_t n3 = (size_t)c.nxmax * c.nymax * c.nzmax, n2 = (size_t)c.nxmax * c.nymax;
@@ -25,6 +26,13 @@ struct MetStore { // com_mod met arrays, numwfmem = 2
       for (auto &v : f2[s]) v.assign(n2, 0.f);
       vd[s].assign(n2 * c.maxspec, 0.f);
       fpb_met_ptrs &m = ptr[s];
+      m = fpb_met_ptrs{};
+      if (c.wetdep) { // lsprec, convprec, tcc, ctwc, clouds (src/com_mod.f90:376-395)
+        for (auto &v : rain[s]) v.assign(n2, 0.f);
+        cl[s].assign(n3, 0);
+        m.lsprec = rain[s][0].data(); m.convprec = rain[s][1].data(); m.tcc = rain[s][2].data();
+        m.ctwc = rain[s][3].data(); m.clouds = cl[s].data();
+      }
       m.uu = f3[s][0].data(); m.vv = f3[s][1].data(); m.ww = f3[s][2].data(); m.rho = f3[s][3].data();
       m.drhodz = f3[s][4].data(); m.tt = f3[s][5].data(); m.uupol = f3[s][6].data(); m.vvpol = f3[s][7].data();
       m.hmix = f2[s][0].data(); m.ustar = f2[s][1].data(); m.wstar = f2[s][2].data();
@@ -102,9 +110,16 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
     int memind[2] = {1, 2};
     int memtime[2] = {999999999, 999999999};
     bool have_fields = false;
-    const bool DEP = c.drydep != 0;
+    const bool DEP = c.drydep != 0 || c.wetdep != 0; // src/readreleases.f90:389
 
     for (int itime = 0; ldirect * itime <= ldirect * run->ideltas; itime += lsynctime) {
+      // ---- wet deposition, src/timemanager.f90:164-169: before new fields are read in,
+      // never at the very beginning; ldeltat as in src/wetdepo.f90:55-63
+      if (c.wetdep && itime != 0 && numpart > 0 && eng->wetdepo) {
+        const int ldw = (itime <= loutnext) ? itime - (loutnext - run->loutstep) : itime - loutnext;
+        ENG(eng->wetdepo(eng->self, itime, lsynctime, ldw));
+      }
+
       // ---- getfields, src/getfields.f90:96-176 (wind fields every
       // met_interval seconds, times counted in the run's direction)
       {

@@ -111,6 +111,16 @@ typedef struct fpb_config {
   float density[FPB_MAXSPEC], dquer[FPB_MAXSPEC], vsetaver[FPB_MAXSPEC],
       cunningham[FPB_MAXSPEC];
 
+  /* --- wet deposition, src/readspecies.f90 + src/readreleases.f90:349-370 -- */
+  int32_t wetdep;                     /* WETDEP */
+  int32_t wetdepspec[FPB_MAXSPEC];    /* WETDEPSPEC */
+  float weta_gas[FPB_MAXSPEC], wetb_gas[FPB_MAXSPEC];     /* below-cloud, gases */
+  float crain_aero[FPB_MAXSPEC], csnow_aero[FPB_MAXSPEC]; /* below-cloud, aerosols */
+  float ccn_aero[FPB_MAXSPEC], in_aero[FPB_MAXSPEC];      /* in-cloud, aerosols */
+  float henry[FPB_MAXSPEC];                               /* in-cloud, gases */
+  int32_t readclouds;                 /* ctwc holds cloud water read from the met input */
+  int32_t readclouds_nest[FPB_MAXNESTS];
+
   /* --- age classes, src/readageclasses.f90 ------------------------------ */
   int32_t nageclass;
   int32_t lage[FPB_MAXAGECLASS];
@@ -160,6 +170,13 @@ typedef struct fpb_met_ptrs {
   const float *uu, *vv, *ww, *rho, *drhodz, *tt, *uupol, *vvpol;
   const float *hmix, *ustar, *wstar, *oli, *tropopause;
   const float *vdep;
+  /* wet deposition only (wetdep != 0; may be NULL otherwise): lsprec, convprec,
+   * tcc (nxmax,nymax) [mm/h, mm/h, 0..1], ctwc (nxmax,nymax) total cloud water
+   * (read when readclouds), clouds (nxmax,nymax,nzmax) integer(kind=1) cloud /
+   * precipitation class of verttransform_ecmwf (src/com_mod.f90:376-395);
+   * tt is then required as well */
+  const float *lsprec, *convprec, *tcc, *ctwc;
+  const int8_t *clouds;
 } fpb_met_ptrs;
 
 /* Particle arrays (src/com_mod.f90:675-695).  xmass1 / xscav_frac1 are
@@ -245,6 +262,17 @@ int fpb_conccalc(fpb_handle *h, int32_t itime, float weight);
 int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,
                   const fpb_particle_ptrs *p, float conc_weight,
                   fpb_step_stats *stats /* may be NULL */);
+
+/* replaces wetdepo(itime,lsynctime,loutnext): src/timemanager.f90:164-169,
+ * src/wetdepo.f90:70-147 with get_wetscav, interpol_rain(_nests) and
+ * wetdepokernel(_nest).  ltsample = lsynctime; ldeltat as computed at
+ * src/wetdepo.f90:55-63.  Particles with itra1 <= itime (>= for backward
+ * runs) lose mass to wetgridunc/wetgriduncn.   */
+int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32_t ldeltat);
+/* wetgridunc(0:numxgrid-1,0:numygrid-1,maxspec,maxpointspec_act,nclassunc,
+ * maxageclass) and the nested twin (may be NULL): cumulative, never zeroed,
+ * decayed by fpb_scale_depgrids like drygridunc */
+int fpb_fetch_wetgrids(fpb_handle *h, float *wetgridunc, float *wetgriduncn);
 
 /* before concoutput*: src/timemanager.f90:376 (MPI build:
  * mpif_tm_reduce_grid, src/timemanager_mpi.f90:468).  Copies the device

@@ -112,6 +112,8 @@ typedef struct fpbh_engine {
   int (*fetch_grids)(void *self, float *gridunc, float *griduncn, float *drygridunc,
                      float *drygriduncn, float *creceptor, int32_t zero_conc);
   int (*scale_depgrids)(void *self, const float *factor);
+  /* may be NULL: wet deposition is then left to the caller (src/timemanager.f90:164-169) */
+  int (*wetdepo)(void *self, int32_t itime, int32_t ltsample, int32_t ldeltat);
 } fpbh_engine;
 
 /* one output interval handed to the caller (the concoutput slot,

@@ -88,6 +88,7 @@ typedef struct fpo_state {
 
   /* grids (reference layout, maxspec species extent) */
   float *gridunc, *griduncn, *drygridunc, *drygriduncn, *creceptor;
+  float *wetgridunc, *wetgriduncn; /* same layout as drygridunc(n) */
 
   /* behaviour switch ("cross-particle stale state"):
    * 1 = reproduce the reference's leaks between calls,
@@ -148,6 +149,9 @@ void fpo_fetch_grids(fpo_state *S, float *gridunc, float *griduncn,
                      float *drygridunc, float *drygriduncn, float *creceptor,
                      int zero_conc);
 void fpo_scale_depgrids(fpo_state *S, const float *factor);
+/* wetdepo(itime,ltsample,loutnext) with ldeltat precomputed (src/wetdepo.f90:55-63) */
+void fpo_wetdepo(fpo_state *S, int itime, int ltsample, int ldeltat);
+void fpo_fetch_wetgrids(fpo_state *S, float *wetgridunc, float *wetgriduncn);
 
 /* pieces exported for unit tests */
 void fpo_hanna(fpo_state *S, float z);

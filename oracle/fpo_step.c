@@ -105,9 +105,11 @@ fpo_state *fpo_create(const fpb_config *cfg, int strict_reference) {
   /* outgrid_init.f90:192-201, 305-338: allocate + zero */
   S->gridunc = (float *)calloc(gsize(c, c->numxgrid, c->numygrid) + 1, sizeof(float));
   S->drygridunc = (float *)calloc(dsize(c, c->numxgrid, c->numygrid) + 1, sizeof(float));
+  S->wetgridunc = (float *)calloc(dsize(c, c->numxgrid, c->numygrid) + 1, sizeof(float));
   if (c->nested_output == 1) {
     S->griduncn = (float *)calloc(gsize(c, c->numxgridn, c->numygridn) + 1, sizeof(float));
     S->drygriduncn = (float *)calloc(dsize(c, c->numxgridn, c->numygridn) + 1, sizeof(float));
+    S->wetgriduncn = (float *)calloc(dsize(c, c->numxgridn, c->numygridn) + 1, sizeof(float));
   }
   S->creceptor = (float *)calloc((size_t)MAXRECEPTOR * c->maxspec + 1, sizeof(float));
   return S;
@@ -126,6 +128,7 @@ void fpo_destroy(fpo_state *S) {
   free(S->indzindicator);
   free(S->gridunc); free(S->griduncn); free(S->drygridunc);
   free(S->drygriduncn); free(S->creceptor);
+  free(S->wetgridunc); free(S->wetgriduncn);
   free(S);
 }
 
@@ -585,12 +588,15 @@ void fpo_scale_depgrids(fpo_state *S, const float *factor) {
     const int nxg = nest ? c->numxgridn : c->numxgrid;
     const int nyg = nest ? c->numygridn : c->numygrid;
     float *grid = nest ? S->drygriduncn : S->drygridunc;
+    float *wgrid = nest ? S->wetgriduncn : S->wetgridunc;
     for (int ks = 1; ks <= c->nspec; ks++)
       for (int kp = 1; kp <= c->maxpointspec_act; kp++)
         for (int na = 1; na <= c->nageclass; na++)
           for (int l = 1; l <= c->nclassunc; l++)
             for (int jy = 0; jy < nyg; jy++)
-              for (int ix = 0; ix < nxg; ix++)
+              for (int ix = 0; ix < nxg; ix++) {
+                wgrid[didx(c, nxg, nyg, ix, jy, ks, kp, l, na)] *= factor[ks - 1];
                 grid[didx(c, nxg, nyg, ix, jy, ks, kp, l, na)] *= factor[ks - 1];
+              }
   }
 }

@@ -45,3 +45,7 @@ int fpo_vt_scale_depgrids(void *self, const float *factor) {
   fpo_scale_depgrids((fpo_state *)self, factor);
   return 0;
 }
+int fpo_vt_wetdepo(void *self, int32_t itime, int32_t ltsample, int32_t ldeltat) {
+  fpo_wetdepo((fpo_state *)self, itime, ltsample, ldeltat);
+  return 0;
+}

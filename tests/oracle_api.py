@@ -44,6 +44,8 @@ def load(libm_float=False):
     L.fpo_set_numpart.argtypes = [S, C.c_int]
     L.fpo_step.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbStepStats)]
     L.fpo_conccalc.argtypes = [S, C.c_int, C.c_float]
+    L.fpo_wetdepo.argtypes = [S, C.c_int, C.c_int, C.c_int]
+    L.fpo_fetch_wetgrids.argtypes = [S, _pf, _pf]
     L.fpo_fetch_grids.argtypes = [S, _pf, _pf, _pf, _pf, _pf, C.c_int]
     L.fpo_scale_depgrids.argtypes = [S, _pf]
     L.fpo_windalign.argtypes = [C.c_float] * 4 + [_pf, _pf]
@@ -125,6 +127,20 @@ class Oracle:
     def conccalc(self, itime, weight):
         self.L.fpo_conccalc(self.S, itime, weight)
 
+    def wetdepo(self, itime, ltsample, ldeltat=0):
+        self.L.fpo_wetdepo(self.S, itime, ltsample, ldeltat)
+
+    def fetch_wetgrids(self):
+        c = self.cb.cfg
+        sd = (c.numxgrid, c.numygrid, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
+        out = {"wetgridunc": np.zeros(sd, np.float32, order="F")}
+        wn = None
+        if c.nested_output == 1:
+            out["wetgriduncn"] = np.zeros((c.numxgridn, c.numygridn) + sd[2:], np.float32, order="F")
+            wn = out["wetgriduncn"]
+        self.L.fpo_fetch_wetgrids(self.S, _fp(out["wetgridunc"]), _fp(wn))
+        return out
+
     def fetch_grids(self, zero_conc=True):
         c = self.cb.cfg
         sg = (c.numxgrid, c.numygrid, c.numzgrid, c.maxspec, c.maxpointspec_act, c.nclassunc, c.maxageclass)
@@ -160,4 +176,5 @@ class Oracle:
         v.conccalc = cast(L.fpo_vt_conccalc, a.CONC_FN)
         v.fetch_grids = cast(L.fpo_vt_fetch_grids, a.FETCH_FN)
         v.scale_depgrids = cast(L.fpo_vt_scale_depgrids, a.SCALE_FN)
+        v.wetdepo = cast(L.fpo_vt_wetdepo, a.WETDEPO_FN)
         return v

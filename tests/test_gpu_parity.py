@@ -356,6 +356,73 @@ def test_nested_input_grids(exact):
 
 
 @pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("readclouds", [0, 1])
+def test_wet_deposition(exact, readclouds):
+    """wetdepo + get_wetscav + interpol_rain(_nests) + wetdepokernel(_nest)
+    (src/wetdepo.f90:70-147, src/get_wetscav.f90:78-314):
+    a gas (below-cloud A/B + Henry in-cloud) and an aerosol (rain/snow below-cloud
+    polynomials, CCN/IN in-cloud) with decay, on moving rain bands, one nested met
+    input grid, nested output grid, parameterised or read cloud water.  Interleaved
+    with the particle loop so that positions, ages and masses evolve."""
+    cb = cases.config_small(nrel=3, npart_each=1024, nspec=2, wetdepspec=(1, 1), weta_gas=(2.0e-5, -1.0),
+                            wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0), crain_aero=(-1.0, 1.0),
+                            csnow_aero=(-1.0, 1.0), ccn_aero=(-1.0, 0.9), in_aero=(-1.0, 0.1),
+                            dquer=(0.0, 0.6), density=(0.0, 0.0), decay=(0.0, 2.0e-6), readclouds=readclouds,
+                            met_nests=[(-60.0, -20.0, 121, 81, 1.0, 1.0)], nest=(-60.0, -30.0, 48, 24, 2.5, 2.5),
+                            ioutputforeachrelease=1, lage=(7200, 86400 * 10), xmass=np.ones((3, 2)),
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    c = cb.cfg
+    assert c.wetdep == 1 and c.numbnests == 1 and c.nested_output == 1
+    n = 3072
+    p = cases.seeded_particles(cb, n, zmax=9000.0, lat_range=(-70.0, 70.0), nspec=2)
+    p.itramem[:1024] = -30000
+    p.xmass1[:n, 1] = 0.5
+    mets = cases.met_pair(cb)
+    nmets = (fb.MetFields(cb, nest=1).synth(0), fb.MetFields(cb, nest=1).synth(10800))
+    for m in nmets:
+        m.lsprec *= 1.5; m.tt -= 5.0; m.ctwc *= 2.0
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, mets[0]); e.upload_met(2, mets[1])
+        e.upload_met_nest(1, 1, nmets[0]); e.upload_met_nest(2, 1, nmets[1])
+        e.set_met_bracket((1, 2), (0, 10800))
+    ora.push_particles(p)
+    for k in range(1, 6):
+        itime = k * 900
+        po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
+        ora.pull_particles(po)
+        if k == 1:
+            po.itra1[:n] = itime          # particles due at the first wetdepo call
+            ora.push_particles(po)
+        eng.push_particles(po)
+        for e in (eng, ora):
+            e.wetdepo(itime, 900, 450)     # timemanager.f90:164-169: before the particle loop
+            e.step(itime, 450)
+        pg = fb.Particles(c.maxpart, c.nspec); pg.numpart = n
+        eng.pull_particles(pg); ora.pull_particles(po)
+        if exact:
+            for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+                assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (k, f)
+            assert np.array_equal(pg.xmass1[:n], po.xmass1[:n]), k
+        else:
+            assert np.array_equal(pg.itra1[:n], po.itra1[:n]), k
+            relm = np.abs(pg.xmass1[:n] - po.xmass1[:n]) / np.maximum(np.abs(po.xmass1[:n]), 1e-30)
+            assert relm.max() < 2e-5, (k, relm.max())
+    wg, wo = eng.fetch_wetgrids(), ora.fetch_wetgrids()
+    for name in ("wetgridunc", "wetgriduncn"):
+        assert wo[name].sum() > 0
+        assert rel_l2(wg[name], wo[name]) < 1e-5, name
+        assert abs(wg[name].sum() - wo[name].sum()) <= 1e-5 * wo[name].sum(), name
+    # both scavenging regimes and both species were exercised
+    assert wo["wetgridunc"][:, :, 0].sum() > 0 and wo["wetgridunc"][:, :, 1].sum() > 0
+    # decay of the deposited mass at loutnext (timemanager.f90:269-304) hits wet and dry grids alike
+    f = np.exp(-3600.0 * np.array([c.decay[0], c.decay[1]], np.float32)).astype(np.float32)
+    eng.scale_depgrids(f); ora.scale_depgrids(f)
+    assert rel_l2(eng.fetch_wetgrids()["wetgridunc"], ora.fetch_wetgrids()["wetgridunc"]) < 1e-5
+
+
+@pytest.mark.parametrize("exact", [True, False])
 def test_backward_run(exact):
     """LDIRECT=-1: negative lsynctime, dt1/dt2 both negative, positions stepped
     with real(ldirect) (src/advance.f90:285,543,752)."""

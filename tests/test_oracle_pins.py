@@ -211,6 +211,83 @@ def test_kat_nested_input_grid_wind_is_used_inside_the_nest():
     assert np.abs(p.ytra1[:8] - y0).max() < 1e-12
 
 
+def _rain_met(cb, lsp, convp, tcc, cloud_class, temp):
+    """Homogeneous met with homogeneous precipitation / cloud class / temperature."""
+    out = []
+    for _ in range(2):
+        m = fb.MetFields(cb).homogeneous(0.0, 0.0, 0.0)
+        m.lsprec[:] = lsp; m.convprec[:] = convp; m.tcc[:] = tcc
+        m.clouds[:] = cloud_class; m.tt[:] = temp; m.ctwc[:] = 0.0
+        out.append(m)
+    return out
+
+
+def _wet_oracle(cb, mets):
+    o = Oracle(cb)
+    o.upload_met(1, mets[0]); o.upload_met(2, mets[1])
+    o.set_met_bracket((1, 2), (0, 10800))
+    return o
+
+
+def test_kat_wet_deposition_scavenging_coefficients():
+    """wetdepo / get_wetscav known answers (src/get_wetscav.f90:190-194,209-216,253-311,
+    src/wetdepo.f90:103-118) on homogeneous precipitation:
+      below cloud, gas:     wetscav = A * prec**B
+      in cloud, aerosol:    wetscav = 6.2 * (frac_act/cl) * prec/3.6e6, cl = 0.2*prec**0.36
+      deposited = m*(1-exp(-wetscav*ltsample))*grfraction; mass + grid sum conserved."""
+    n = 256
+    A, B = 2.0e-5, 0.62
+    kw = dict(nrel=1, npart_each=n, nspec=2, wetdepspec=(1, 1), weta_gas=(A, -1.0), wetb_gas=(B, -1.0),
+              ccn_aero=(-1.0, 0.9), in_aero=(-1.0, 0.1), dquer=(0.0, 0.6), xmass=np.ones((1, 2)),
+              outheights=(100.0, 1000.0, 5000.0, 50000.0))
+    cb = cases.config_small(**kw)
+    c = cb.cfg
+    assert c.wetdep == 1
+    lsp, tcc = 2.0, 0.8
+    grf = max(0.05, tcc * (lsp * 0.65) / lsp)          # lfr(2): 1 < lsp <= 3
+    prec = lsp / grf
+    # ---- below cloud (class 5): only the gas is scavenged (aerosol has no crain/csnow)
+    o = _wet_oracle(cb, _rain_met(cb, lsp, 0.0, tcc, 5, 280.0))
+    p = cases.seeded_particles(cb, n, zmax=3000.0, lat_range=(-60.0, 60.0), nspec=2)
+    p.xtra1[:n] = np.clip(p.xtra1[:n], 2.0, c.nxmin1 - 2.0)   # keep the 4-cell kernel inside the out-grid
+    p.itra1[:n] = 900
+    m0 = p.xmass1[:n].copy()
+    o.push_particles(p)
+    o.wetdepo(900, 900, 0)
+    o.pull_particles(p)
+    wetscav = A * prec ** B
+    dep = (1.0 - np.exp(-wetscav * 900.0)) * grf
+    assert np.allclose(p.xmass1[:n, 0], m0[:, 0] * (1.0 - dep), rtol=2e-6)
+    assert np.array_equal(p.xmass1[:n, 1], m0[:, 1])
+    g = o.fetch_wetgrids()["wetgridunc"]
+    assert abs(g[:, :, 0].sum() - (m0[:, 0] * dep).sum()) < 1e-5 * (m0[:, 0] * dep).sum()
+    assert g[:, :, 1:].sum() == 0.0
+    # ---- in cloud (class 3) at 263 K: ice_frac = 0.25, liq_frac = 0.75; gas has no henry -> untouched
+    o = _wet_oracle(cb, _rain_met(cb, lsp, 0.0, tcc, 3, 263.0))
+    p = cases.seeded_particles(cb, n, zmax=3000.0, lat_range=(-60.0, 60.0), nspec=2)
+    p.itra1[:n] = 900
+    o.push_particles(p)
+    o.wetdepo(900, 900, 0)
+    o.pull_particles(p)
+    frac_act = 0.75 * 0.9 + 0.25 * 0.1
+    cl = 0.2 * prec ** 0.36
+    wetscav = 6.2 * (frac_act / cl) * (prec / 3.6e6)
+    dep = (1.0 - np.exp(-wetscav * 900.0)) * grf
+    assert np.allclose(p.xmass1[:n, 1], m0[:, 1] * (1.0 - dep), rtol=5e-6)
+    assert np.array_equal(p.xmass1[:n, 0], m0[:, 0])
+    # ---- no precipitation / above the cloud (class <= 1) / not yet due (itra1 > itime): nothing happens
+    for mets, itra in ((_rain_met(cb, 0.005, 0.005, tcc, 5, 280.0), 900), (_rain_met(cb, lsp, 0.0, tcc, 1, 280.0), 900),
+                       (_rain_met(cb, lsp, 0.0, tcc, 5, 280.0), 1800)):
+        o = _wet_oracle(cb, mets)
+        p = cases.seeded_particles(cb, n, zmax=3000.0, nspec=2)
+        p.itra1[:n] = itra
+        o.push_particles(p)
+        o.wetdepo(900, 900, 0)
+        o.pull_particles(p)
+        assert np.array_equal(p.xmass1[:n], m0)
+        assert o.fetch_wetgrids()["wetgridunc"].sum() == 0.0
+
+
 def test_kat_cyclic_wrap():
     """x wraps modulo nxmin1 under the cyclic boundary (src/advance.f90:784-788)."""
     cb = cases.config_small(nrel=1, npart_each=4, turboff=1, ctl=-5.0)
