@@ -130,6 +130,7 @@ void fpo_push_particles(fpo_state *S, int first, int count,
 void fpo_pull_particles(fpo_state *S, int first, int count,
                         const fpb_particle_ptrs *p);
 void fpo_set_numpart(fpo_state *S, int numpart);
+const int32_t *fpo_trace_nsub(const fpo_state *S);
 
 /* hot path */
 void fpo_initialize(fpo_state *S, int itime, int32_t *ldt, float *up, float *vp,

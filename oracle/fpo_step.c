@@ -148,6 +148,9 @@ void fpo_set_met_bracket(fpo_state *S, const int memind[2], const int memtime[2]
 
 void fpo_set_numpart(fpo_state *S, int numpart) { S->numpart = numpart; }
 
+/* sub-steps each particle took in the last fpo_step (1-based like the particle arrays) */
+const int32_t *fpo_trace_nsub(const fpo_state *S) { return S->trace_nsub; }
+
 void fpo_push_particles(fpo_state *S, int first, int count,
                         const fpb_particle_ptrs *p) {
   for (int i = 0; i < count; i++) {
