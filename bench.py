@@ -298,10 +298,60 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, threads=1, budget_s=args.cpu_seconds)
-        print(json.dumps(line), flush=True)
     eng.close()
+    if rank == 0:
+        if world == 1 and args.workload == "c2" and not args.no_hbm_regime:
+            line["hbm_regime"] = hbm_regime(args, local, K=min(K, 12), W=3)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_regime(args, local, K, W):
+    """Secondary figure for the JSON line: the same path in its HBM-gather-bound
+    regime (CTL=-5 -> method 0, one Langevin step per particle and interval,
+    particles spread over the domain up to 12 km: the shipped options/COMMAND
+    setting, SURVEY.md 8d 'C5 slice').  Device-resident, kernels + sort."""
+    import torch
+    import flexpart_b200 as fb
+    a2 = argparse.Namespace(**vars(args))
+    a2.workload, a2.particles, a2.sort_interval = "c5slice", 8_000_000, 8
+    cb, rel = build_workload(a2, 0, 1, local)
+    span = max(10800, (K + W + 2) * 900)
+    eng = fb.Engine(cb)
+    eng.fill_rannumb()
+    eng.upload_met(1, fb.MetFields(cb).synth(0))
+    eng.upload_met(2, fb.MetFields(cb).synth(span))
+    eng.set_met_bracket((1, 2), (0, span))
+    parts = host_particles(cb, rel, pinned=False)
+    eng.push_particles(parts)
+    ext = torch.cuda.ExternalStream(eng.stream, device=local)
+    with torch.cuda.stream(ext):
+        for k in range(W):
+            eng.conccalc(k * 900, 1.0); eng.step(k * 900, 0, stats=False)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(ext)
+        ps = npbl = 0
+        tk = 0.0
+        for k in range(W, W + K):
+            eng.conccalc(k * 900, 1.0)
+            st = eng.step(k * 900, 0, stats=True)
+            ps += st["n_active"]; npbl += st["n_pbl"]
+            tk += eng.kernel_times()[0]
+        ev1.record(ext)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+    eng.close()
+    peak, _ = peaks()
+    alg = npbl * B_PBL + (ps - npbl) * B_FT
+    ach = alg / (tk * 1e-3) / 1e9
+    return {"workload": "C5 slice: 8M particles spread over the globe up to 12 km, CTL=-5 (method 0), "
+                        "conccalc every step, cell sort every 8th step",
+            "value": ps / (ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms / K,
+            "kernel_ms_per_launch": tk / K, "pbl_fraction": npbl / max(ps, 1),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "kernel": "fpb_pbl_kernel + fpb_finish_kernel"}}
 
 
 def cpu_baseline(args, threads, budget_s, steps=None):
@@ -384,6 +434,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-hbm-regime", action="store_true")
     ap.add_argument("--sort-interval", type=int, default=1)
     args = ap.parse_args()
     if args.warmup < 3:
