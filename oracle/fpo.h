@@ -11,11 +11,18 @@
  * definitions of include/fpb.h (fpb_config, fpb_met_ptrs, fpb_particle_ptrs)
  * so tests can hand one problem description to both sides.
  *
- * PARITY UNPINNED: the reference ships no golden vectors or known-answer
- * tests for this path and no Fortran compiler
- * exists in the build image, so the oracle cannot be checked against outputs
- * of the reference itself.  It is pinned instead by analytic known-answer
- * cases, invariants and the Numerical-Recipes ran3 sequence (tests/).
+ * PINNED AGAINST THE REFERENCE'S OWN SOURCES.  The reference ships no golden
+ * vectors for this path and is Fortran, with no Fortran compiler in the build
+ * image; oracle/f2c/f90toc.py therefore transpiles the reference's hot-path
+ * files (read where they lie under /root/reference/src, nothing copied) to C,
+ * oracle/f2c/Makefile compiles them into oracle/_ref/libflexref.so, and
+ * tests/test_ref_transpiled.py requires this oracle (strict_reference mode) to be
+ * bit-identical to that code call by call: random_mod, initialize, advance with
+ * every interpol / hanna / cbl / cmapf / settling branch, nested input grids,
+ * conccalc, drydepokernel(_nest), wetdepo.  What that cannot pin is the
+ * transcendental library (both sides call fpo_math.h) and gfortran's own code
+ * generation; see DESIGN.md section 2.  Analytic known-answer cases, invariants
+ * and the Numerical-Recipes generator recurrences pin it independently (tests/).
  *
  * Arithmetic: default `real` = float, `real(dp)` = double, no contraction
  * (build with -O2 -ffp-contract=off, mirroring src/makefile_meteoswiss:103-111).

@@ -1,0 +1,318 @@
+"""Pins the hand-written oracle against the REFERENCE'S OWN SOURCES.
+
+The reference is Fortran and this image has no Fortran compiler.  oracle/f2c/
+f90toc.py transpiles the reference's hot-path files (advance.f90, initialize.f90,
+interpol_*.f90 and their _nests twins, hanna*.f90, cbl.f90, windalign.f90,
+random_mod.f90, get_settling.f90, conccalc.f90, ...) statement by statement to C,
+from where they lie under /root/reference/src, and the result is compiled into
+oracle/_ref/libflexref.so (git-ignored, travels to the GPU box).  These tests run
+that code and the oracle on the same inputs, call by call in the reference's
+particle order, and require bit-identical results (oracle in strict_reference
+mode: the reference's module-state leaks between calls included).
+
+What the transpiled code does not fix is the transcendental library: both sides
+call oracle/fpo_math.h (correctly rounded exp/log/pow/sin/cos/erf), see DESIGN.md."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import flexpart_b200 as fb
+import cases
+import ref_api
+from oracle_api import Oracle, load
+
+pytestmark = pytest.mark.skipif(not ref_api.available(), reason="oracle/_ref/libflexref.so not built (no /root/reference)")
+
+MAXRAND = 20000
+
+
+def _pair(cb, mets, nest_mets=(), bracket=(0, 10800)):
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    ora = Oracle(cb, strict_reference=True)
+    ora.fill_rannumb(MAXRAND, -320)
+    tab = ref.fill_rannumb(-320)
+    # FLEXPART.f90:56-59 through the reference's gasdev1/ran3 == the oracle's table, bit for bit
+    assert np.array_equal(tab, ora.rannumb(MAXRAND))
+    for e in (ref, ora):
+        e.upload_met(1, mets[0]); e.upload_met(2, mets[1])
+        for nest, (n0, n1) in enumerate(nest_mets, start=1):
+            e.upload_met_nest(1, nest, n0); e.upload_met_nest(2, nest, n1)
+        e.set_met_bracket((1, 2), bracket)
+    return ref, ora
+
+
+def _oracle_calls(ora):
+    L = load()
+    S = ora.S
+    cf, ci = C.c_float, C.c_int32
+
+    def initialize(itime, ldt, xt, yt, zt):
+        ldt_c, up, vp, wp, us, vs, ws, icbt = ci(ldt), cf(), cf(), cf(), cf(), cf(), cf(), C.c_int16(0)
+        L.fpo_initialize(S, itime, C.byref(ldt_c), C.byref(up), C.byref(vp), C.byref(wp), C.byref(us), C.byref(vs),
+                         C.byref(ws), C.c_double(xt), C.c_double(yt), cf(zt), C.byref(icbt))
+        return ldt_c.value, up.value, vp.value, wp.value, us.value, vs.value, ws.value, icbt.value
+
+    def advance(itime, nrelpoint, ldt, up, vp, wp, us, vs, ws, xt, yt, zt, icbt, maxspec):
+        a = dict(ldt=ci(ldt), up=cf(up), vp=cf(vp), wp=cf(wp), us=cf(us), vs=cf(vs), ws=cf(ws), nstop=C.c_int(0),
+                 xt=C.c_double(xt), yt=C.c_double(yt), zt=cf(zt), icbt=C.c_int16(icbt))
+        prob = (cf * 8)()
+        L.fpo_advance(S, itime, nrelpoint, C.byref(a["ldt"]), C.byref(a["up"]), C.byref(a["vp"]), C.byref(a["wp"]),
+                      C.byref(a["us"]), C.byref(a["vs"]), C.byref(a["ws"]), C.byref(a["nstop"]), C.byref(a["xt"]),
+                      C.byref(a["yt"]), C.byref(a["zt"]), prob, C.byref(a["icbt"]))
+        out = {k: v.value for k, v in a.items()}
+        out["prob"] = np.array(prob[:maxspec], np.float32)
+        return out
+
+    L.fpo_initialize.argtypes = [C.c_void_p, C.c_int, C.POINTER(ci), C.POINTER(cf), C.POINTER(cf), C.POINTER(cf),
+                                 C.POINTER(cf), C.POINTER(cf), C.POINTER(cf), C.c_double, C.c_double, cf,
+                                 C.POINTER(C.c_int16)]
+    L.fpo_advance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ci)] + [C.POINTER(cf)] * 6 + \
+                             [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(cf),
+                              C.POINTER(cf), C.POINTER(C.c_int16)]
+    return initialize, advance
+
+
+def _bits(x):
+    return np.asarray(x, np.float32).view(np.uint32) if not isinstance(x, float) or True else x
+
+
+def _same(a, b):
+    """bitwise equality of python floats that carry float32 / float64 values, ints, arrays"""
+    if isinstance(a, np.ndarray):
+        return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if isinstance(a, float):
+        return np.float64(a).tobytes() == np.float64(b).tobytes() or (np.isnan(a) and np.isnan(b))
+    return a == b
+
+
+def _run_particle_loop(cb, ref, ora, p, nsteps, dt=None):
+    """The reference's particle loop order (src/timemanager.f90:531-611): initialize for new
+    particles, then advance, particle after particle, both implementations side by side."""
+    c = cb.cfg
+    o_init, o_adv = _oracle_calls(ora)
+    n = p.numpart
+    dt = dt or c.lsynctime
+    st = dict(xt=p.xtra1[:n].copy(), yt=p.ytra1[:n].copy(), zt=p.ztra1[:n].copy(), ldt=p.idt[:n].copy(),
+              up=np.zeros(n, np.float32), vp=np.zeros(n, np.float32), wp=np.zeros(n, np.float32),
+              us=np.zeros(n, np.float32), vs=np.zeros(n, np.float32), ws=np.zeros(n, np.float32),
+              icbt=np.ones(n, np.int16), alive=np.ones(n, bool))
+    counts = dict(calls=0, pbl_like=0, nstop=0)
+    for k in range(nsteps):
+        itime = k * dt
+        for j in range(n):
+            if not st["alive"][j]:
+                continue
+            if k == 0:
+                ri = ref.initialize(itime, int(st["ldt"][j]), st["xt"][j], st["yt"][j], float(st["zt"][j]))
+                oi = o_init(itime, int(st["ldt"][j]), st["xt"][j], st["yt"][j], float(st["zt"][j]))
+                assert all(_same(a, b) for a, b in zip(ri, oi)), ("initialize", j, ri, oi)
+                st["ldt"][j], st["up"][j], st["vp"][j], st["wp"][j], st["us"][j], st["vs"][j], st["ws"][j], st["icbt"][j] = ri
+            args = (itime, int(p.npoint[j]), int(st["ldt"][j]), float(st["up"][j]), float(st["vp"][j]), float(st["wp"][j]),
+                    float(st["us"][j]), float(st["vs"][j]), float(st["ws"][j]), float(st["xt"][j]), float(st["yt"][j]),
+                    float(st["zt"][j]), int(st["icbt"][j]))
+            ra = ref.advance(*args)
+            oa = o_adv(*args, c.maxspec)
+            for key in ra:
+                assert _same(ra[key], oa[key] if key != "prob" else oa[key][:len(ra[key])]), ("advance", k, j, key, ra[key], oa[key])
+            counts["calls"] += 1
+            if ra["nstop"] > 1:
+                st["alive"][j] = False
+                counts["nstop"] += 1
+                continue
+            for key, dst in (("ldt", "ldt"), ("up", "up"), ("vp", "vp"), ("wp", "wp"), ("us", "us"), ("vs", "vs"),
+                             ("ws", "ws"), ("xt", "xt"), ("yt", "yt"), ("zt", "zt"), ("icbt", "icbt")):
+                st[dst][j] = ra[key]
+    return counts, st
+
+
+def test_reference_random_mod_matches_oracle():
+    """ran1, ran3, gasdev (src/random_mod.f90) against the oracle's restatement, call by call."""
+    cb = cases.config_small(nrel=1, npart_each=8)
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    ora = Oracle(cb)
+    L, R = load(), ref.L
+    R.f_ran1.restype = R.f_ran3.restype = R.f_gasdev.restype = C.c_float
+    L.fpo_gasdev.restype = C.c_float
+    L.fpo_gasdev.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    for fn_r, fn_o, seed in ((R.f_ran1, L.fpo_ran1, -7), (R.f_ran3, L.fpo_ran3, -320), (R.f_ran3, L.fpo_ran3, -7),
+                             (R.f_gasdev, L.fpo_gasdev, -11)):
+        ir, io = C.c_int(seed), C.c_int32(seed)
+        for _ in range(3000):
+            a, b = fn_r(C.byref(ir)), fn_o(ora.S, C.byref(io))
+            assert np.float32(a).tobytes() == np.float32(b).tobytes() and ir.value == io.value
+
+
+@pytest.mark.parametrize("ctl,label", [(5.0, "hanna method 1"), (-5.0, "hanna1 method 0 + Petterssen")])
+def test_reference_advance_initialize_bit_identical(ctl, label):
+    """advance + initialize (with interpol_all/misslev/wind/wind_short, hanna/hanna1/hanna_short,
+    windalign, polar cmapf branch, reflection, Petterssen) on the synthetic global met:
+    every output of every call bit-identical, cross-particle module-state leaks included."""
+    cb = cases.config_small(nrel=4, npart_each=150, ctl=ctl)
+    n = 600
+    p = cases.seeded_particles(cb, n, zmax=7000.0, lat_range=(-89.0, 89.0))
+    p.ztra1[:200] = np.random.RandomState(1).uniform(1.0, 300.0, 200).astype(np.float32)
+    ref, ora = _pair(cb, cases.met_pair(cb))
+    counts, st = _run_particle_loop(cb, ref, ora, p, 4)
+    assert counts["calls"] >= 4 * n - 50
+
+
+def test_reference_nested_grids_and_drydep_bit_identical():
+    """nested met input (interpol_*_nests, nest choice, hmixn/tropopausen), dry-deposition
+    probability (interpol_vdep(_nests)) and settling (get_settling + viscosity)."""
+    nests = [(-40.0, 10.0, 81, 41, 1.0, 1.0)]
+    cb = cases.config_small(nrel=4, npart_each=128, met_nests=nests, nspec=2, drydepspec=(1, 0), xmass=np.ones((4, 2)),
+                            lsettling=1, density=(0.0, 2000.0), dquer=(0.0, 5.0), vsetaver=(0.0, -0.01),
+                            cunningham=(1.0, 1.1))
+    n = 512
+    p = cases.seeded_particles(cb, n, zmax=5000.0, lat_range=(0.0, 60.0), nspec=2)
+    r = np.random.RandomState(3)
+    p.xtra1[:384] = (r.uniform(-50.0, 50.0, 384) - cb.cfg.xlon0) / cb.cfg.dx
+    p.ztra1[:128] = r.uniform(1.0, 40.0, 128).astype(np.float32)
+    nm = (fb.MetFields(cb, nest=1).synth(0), fb.MetFields(cb, nest=1).synth(10800))
+    for m in nm:
+        m.uu += 3.0; m.hmix *= 1.2; m.vdep *= 2.0
+    ref, ora = _pair(cb, cases.met_pair(cb), nest_mets=[nm])
+    counts, st = _run_particle_loop(cb, ref, ora, p, 3)
+    assert counts["calls"] >= 3 * n - 50
+
+
+def test_reference_cbl_bit_identical():
+    """CBLFLAG=1: cbl, re_initialize_particle, initialize_cbl_vel (ran3 + gasdev from the global stream)."""
+    cb = cases.config_small(nrel=2, npart_each=150, cblflag=1, ctl=10.0, ifine=5)
+    n = 300
+    p = cases.seeded_particles(cb, n, zmax=1500.0, lat_range=(-50.0, 50.0))
+    ref, ora = _pair(cb, cases.met_pair(cb))
+    counts, st = _run_particle_loop(cb, ref, ora, p, 3)
+    assert counts["calls"] >= 3 * n - 20
+
+
+def test_reference_backward_run_bit_identical():
+    cb = cases.config_small(nrel=2, npart_each=128, ldirect=-1)
+    n = 256
+    p = cases.seeded_particles(cb, n, zmax=4000.0)
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    ref, ora = _pair(cb, mets, bracket=(0, -10800))
+    counts, st = _run_particle_loop(cb, ref, ora, p, 3, dt=-900)
+    assert counts["calls"] >= 3 * n - 20
+
+
+@pytest.mark.parametrize("ind_samp", [0, -1])
+def test_reference_conccalc_bit_identical(ind_samp):
+    """conccalc (mother + nested output grid, age classes, kernel / no-kernel branches,
+    density-weighted sampling, receptors): gridunc, griduncn, creceptor bit-identical
+    (same serial accumulation order)."""
+    cb = cases.config_small(nrel=3, npart_each=400, nspec=2, ind_samp=ind_samp, lage=(7200, 86400 * 10),
+                            nest=(-60.0, -30.0, 48, 24, 2.5, 2.5), ioutputforeachrelease=1, xmass=np.ones((3, 2)),
+                            receptors=((30.0, 20.0, 1.0e10), (40.5, 18.2, 2.0e10)))
+    c = cb.cfg
+    n = 1200
+    p = cases.seeded_particles(cb, n, zmax=6000.0, lat_range=(-70.0, 70.0), nspec=2)
+    p.itramem[:400] = -30000          # old enough for the kernel branch and the 2nd age class
+    p.xmass1[:n, 1] = 0.5
+    p.itra1[:n] = 900
+    r = np.random.RandomState(5)        # a cloud of low particles around the receptors
+    p.xtra1[400:500] = r.uniform(28.0, 42.0, 100); p.ytra1[400:500] = r.uniform(17.0, 21.0, 100)
+    p.ztra1[400:500] = r.uniform(1.0, 140.0, 100).astype(np.float32)
+    ref, ora = _pair(cb, cases.met_pair(cb))
+    ref.push_particles(p)
+    ora.push_particles(p)
+    for e in (ref, ora):
+        e.conccalc(900, 0.5)
+        e.conccalc(900, 1.0)
+    go = ora.fetch_grids(zero_conc=False)
+    assert go["gridunc"].sum() > 0 and go["griduncn"].sum() > 0 and go["creceptor"].sum() > 0
+    assert np.array_equal(ref.arr("gridunc").view(np.uint32), go["gridunc"].view(np.uint32))
+    assert np.array_equal(ref.arr("griduncn").view(np.uint32), go["griduncn"].view(np.uint32))
+    assert np.array_equal(ref.arr("creceptor")[:, :c.maxspec].view(np.uint32), go["creceptor"][:, :c.maxspec].view(np.uint32))
+
+
+@pytest.mark.parametrize("readclouds", [0, 1])
+def test_reference_wetdepo_bit_identical(readclouds):
+    """wetdepo + get_wetscav + interpol_rain(_nests) + wetdepokernel(_nest):
+    particle masses and wetgridunc / wetgriduncn bit-identical (serial accumulation order)."""
+    cb = cases.config_small(nrel=3, npart_each=512, nspec=2, wetdepspec=(1, 1), weta_gas=(2.0e-5, -1.0),
+                            wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0), crain_aero=(-1.0, 1.0),
+                            csnow_aero=(-1.0, 1.0), ccn_aero=(-1.0, 0.9), in_aero=(-1.0, 0.1),
+                            dquer=(0.0, 0.6), decay=(0.0, 2.0e-6), readclouds=readclouds,
+                            met_nests=[(-60.0, -20.0, 121, 81, 1.0, 1.0)], nest=(-60.0, -30.0, 48, 24, 2.5, 2.5),
+                            ioutputforeachrelease=1, lage=(7200, 86400 * 10), xmass=np.ones((3, 2)))
+    c = cb.cfg
+    n = 1536
+    p = cases.seeded_particles(cb, n, zmax=9000.0, lat_range=(-70.0, 70.0), nspec=2)
+    p.itramem[:512] = -30000
+    p.xmass1[:n, 1] = 0.5
+    p.itra1[:n] = 900
+    p.itra1[100:120] = 1800           # not yet due
+    p.itra1[120:130] = fb.ITRA_DEAD
+    mets = cases.met_pair(cb)
+    nm = (fb.MetFields(cb, nest=1).synth(0), fb.MetFields(cb, nest=1).synth(10800))
+    for m in nm:
+        m.lsprec *= 1.5; m.tt -= 5.0; m.ctwc *= 2.0
+    ref, ora = _pair(cb, mets, nest_mets=[nm])
+    for slot in (1, 2):
+        ref.upload_rain(slot, mets[slot - 1])
+        ref.upload_rain(slot, nm[slot - 1], nest=1)
+    ref.push_particles(p)
+    ora.push_particles(p)
+    # loutnext = 1800, loutstep = 3600: itime <= loutnext -> ldeltat = itime - (loutnext - loutstep)
+    ref.wetdepo(900, 900, 1800)
+    ora.wetdepo(900, 900, 900 - (1800 - 3600))
+    q = fb.Particles(c.maxpart, c.nspec); q.numpart = n
+    ora.pull_particles(q)
+    assert np.array_equal(ref.arr("xmass1")[:n, :2].view(np.uint32), q.xmass1[:n].view(np.uint32))
+    wo = ora.fetch_wetgrids()
+    assert wo["wetgridunc"][:, :, 0].sum() > 0 and wo["wetgridunc"][:, :, 1].sum() > 0 and wo["wetgriduncn"].sum() > 0
+    assert np.array_equal(ref.arr("wetgridunc").view(np.uint32), wo["wetgridunc"].view(np.uint32))
+    assert np.array_equal(ref.arr("wetgriduncn").view(np.uint32), wo["wetgriduncn"].view(np.uint32))
+
+
+def test_reference_drydepokernel_and_pieces_bit_identical():
+    """drydepokernel(_nest), windalign, hanna / hanna1 / hanna_short and the cmapf_mod
+    transformations called directly with random arguments."""
+    cb = cases.config_small(nrel=2, npart_each=8, nspec=2, drydepspec=(1, 1), xmass=np.ones((2, 2)),
+                            nest=(-60.0, -30.0, 48, 24, 2.5, 2.5), ioutputforeachrelease=1, lage=(7200, 86400 * 10))
+    c = cb.cfg
+    ref, ora = _pair(cb, cases.met_pair(cb))
+    L, R = load(), ref.L
+    r = np.random.RandomState(11)
+    cf, ci = C.c_float, C.c_int
+    # drydepokernel / _nest
+    L.fpo_drydepokernel.argtypes = L.fpo_drydepokernel_nest.argtypes = [C.c_void_p, ci, C.POINTER(cf), cf, cf, ci, ci]
+    for _ in range(400):
+        dep = (cf * 5)(*(r.uniform(0, 1, 5) * (r.uniform(0, 1, 5) > 0.3)))
+        x, y = float(np.float32(r.uniform(0, c.nxmin1))), float(np.float32(r.uniform(0, c.nymin1)))
+        nage, kp = int(r.randint(1, 3)), int(r.randint(1, 3))
+        for fr, fo in ((R.f_drydepokernel, L.fpo_drydepokernel), (R.f_drydepokernel_nest, L.fpo_drydepokernel_nest)):
+            fr(C.byref(ci(1)), dep, C.byref(cf(x)), C.byref(cf(y)), C.byref(ci(nage)), C.byref(ci(kp)))
+            fo(ora.S, 1, dep, x, y, nage, kp)
+    go = ora.fetch_grids(zero_conc=False)
+    assert go["drygridunc"].sum() > 0 and go["drygriduncn"].sum() > 0
+    assert np.array_equal(ref.arr("drygridunc").view(np.uint32), go["drygridunc"].view(np.uint32))
+    assert np.array_equal(ref.arr("drygriduncn").view(np.uint32), go["drygriduncn"].view(np.uint32))
+    # windalign
+    L.fpo_windalign.argtypes = [cf] * 4 + [C.POINTER(cf)] * 2
+    for _ in range(500):
+        a = [float(np.float32(v)) for v in r.normal(0, 5, 4)]
+        ux, vy, ox, oy = cf(), cf(), cf(), cf()
+        R.f_windalign(*[C.byref(cf(v)) for v in a], C.byref(ux), C.byref(vy))
+        L.fpo_windalign(*a, C.byref(ox), C.byref(oy))
+        assert (ux.value, vy.value) == (ox.value, oy.value)
+    # cmapf_mod: cll2xy, cxy2ll, cgszll on the run's polar maps
+    R.f_cgszll.restype = cf
+    L.fpo_cgszll.restype = cf
+    for mp in ("northpolemap", "southpolemap"):
+        mr = ref.arr(mp).ctypes.data_as(C.POINTER(cf))
+        mo = (cf * 9)(*getattr(c, mp))
+        for _ in range(500):
+            lat = float(np.float32(r.uniform(60, 90) * (1 if mp[0] == "n" else -1)))
+            lon = float(np.float32(r.uniform(-180, 180)))
+            x1, y1, x2, y2 = cf(), cf(), cf(), cf()
+            R.f_cll2xy(mr, C.byref(cf(lat)), C.byref(cf(lon)), C.byref(x1), C.byref(y1))
+            L.fpo_cll2xy(mo, lat, lon, C.byref(x2), C.byref(y2))
+            assert (x1.value, y1.value) == (x2.value, y2.value)
+            la1, lo1, la2, lo2 = cf(), cf(), cf(), cf()
+            R.f_cxy2ll(mr, C.byref(x1), C.byref(y1), C.byref(la1), C.byref(lo1))
+            L.fpo_cxy2ll(mo, x1.value, y1.value, C.byref(la2), C.byref(lo2))
+            assert (la1.value, lo1.value) == (la2.value, lo2.value)
+            assert R.f_cgszll(mr, C.byref(cf(lat)), C.byref(cf(lon))) == L.fpo_cgszll(mo, lat, lon)
