@@ -60,11 +60,19 @@ ALLOC_DIMS = {
     "vdepn": "0:nxmaxn-1,0:nymaxn-1,maxspec,numwfmem,maxnests",
     "cloudsn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "cloudshn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
     "ctwcn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
+    "zpoint1": "numpoint", "zpoint2": "numpoint", "xpoint1": "numpoint", "xpoint2": "numpoint",
+    "ypoint1": "numpoint", "ypoint2": "numpoint", "ireleasestart": "numpoint", "ireleaseend": "numpoint",
+    "kindz": "numpoint", "rho_rel": "numpoint", "xmasssave": "numpoint",
 }
 
 
 class F2CError(Exception):
     pass
+
+
+# calls inside extracted line ranges that belong to other subsystems and are guarded by
+# switches the tests leave off (ipout=3, iflux=1, linit_cond>=1, DRYBKDEP): reaching one aborts
+UNREACHED_CALLS = {"get_vdep_prob", "partpos_average", "calcfluxes", "initial_cond_calc"}
 
 
 # ----------------------------------------------------------------- lexer ----
@@ -249,6 +257,20 @@ class Program:
                 continue
             raise F2CError(f"{fname}: unexpected top-level statement: {s}")
 
+    def add_extract(self, text, parent, name, first, last, args):
+        """Synthetic subroutine `name(args)` = the declarations of subroutine `parent`
+        + its executable source lines first..last (1-based, inclusive)."""
+        if parent not in self.units:
+            raise F2CError(f"extract: {parent} not parsed")
+        decl = []
+        for lab, s in self.units[parent].lines:
+            if lab is None and (s.startswith("use ") or re.match(r"^(real|integer|logical|double\s*precision|character)\b", s)
+                                or s.startswith("implicit")):
+                decl.append((lab, s))
+        body = logical_lines("\n".join(text.splitlines()[first - 1:last]))
+        u = Unit("subroutine", name, list(args), decl + body)
+        self.units[name] = u
+
     # --------------------------------------------------------- declarations --
     DECL = re.compile(r"^(real|integer|logical|double\s*precision|character)\s*(\([^)]*\)|\*\s*\d+)?\s*((?:,\s*[a-z]+(?:\s*\([^()]*(?:\([^()]*\)[^()]*)*\))?\s*)*)(::)?\s*(.*)$")
 
@@ -284,7 +306,7 @@ class Program:
                 ftype = "real"
             elif ftype == "integer" and re.search(r"(kind=)?1\)", k):
                 ftype = "int8"
-            elif ftype == "integer" and re.search(r"(kind=)?2\)", k):
+            elif ftype == "integer" and (re.search(r"(kind=)?2\)", k) or re.fullmatch(r"\*2", k)):
                 ftype = "int16"
             elif ftype == "integer" and ("selected_int_kind(16)" in k or "8)" in k):
                 ftype = "int64"
@@ -902,6 +924,8 @@ class Gen:
             if name not in self.prog.units:
                 if name in ("flush", "mpif_mtime", "caldate"):
                     return res + [f"/* call {name} skipped */;"]
+                if name in UNREACHED_CALLS:
+                    return res + [f"f2c_stop(); /* call {name}: outside the path, must not be reached */"]
                 raise F2CError(f"{u.name}: call to unknown subroutine {name}")
             self.prog.called.add(name)
             al = [ctx.actual(ctx.cexpr(a)) for a in split_top(args, ",")] if args and args.strip() else []
@@ -1064,11 +1088,19 @@ def main(argv):
     ap.add_argument("--files", nargs="+", required=True)
     ap.add_argument("--units", nargs="+", required=True)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--extract", nargs="*", default=[],
+                    help="name:file:parent:first-last:arg,arg  (line range of a subroutine as its own unit)")
     args = ap.parse_args(argv)
     import os
     prog = Program()
     for f in args.files:
         prog.add_source(open(os.path.join(args.src, f), errors="replace").read(), f)
+    for spec in args.extract:
+        name, f, parent, rng, al = spec.split(":")
+        first, last = [int(x) for x in rng.split("-")]
+        prog.add_extract(open(os.path.join(args.src, f), errors="replace").read(), parent, name, first, last,
+                         [a for a in al.split(",") if a])
+        args.units.append(name)
     prog.collect_module_globals()
     runtime = {"nxmax", "nymax", "nuvzmax", "nwzmax", "nzmax", "maxnests", "nxmaxn", "nymaxn", "maxpart", "maxspec",
                "maxageclass", "nclassunc", "maxreceptor", "maxrand", "numwfmem", "nconvlevmax", "na", "maxpoint"}

@@ -86,6 +86,9 @@ class Ref:
         self.arr("drydepspec")[:c.nspec] = [c.drydepspec[k] for k in range(c.nspec)]
         if self.has("npart"):
             self.arr("npart")[:] = cb.npart
+        for k, v in dict(mquasilag=0, ipout=0, iflux=0, linit_cond=0, verbosity=0).items():
+            if self.has(k):
+                self.set(k, v)
         self.arr("xmass")[:, :] = cb.xmass[:, :c.maxspec]
         for nm in ("xreceptor", "yreceptor", "receptorarea"):
             self.arr(nm)[:c.numreceptor] = [getattr(c, nm)[k] for k in range(c.numreceptor)]
@@ -212,6 +215,28 @@ class Ref:
             self.arr(nm)[:n] = getattr(p, nm)[:n]
         self.arr("xmass1")[:n, :p.nspec] = p.xmass1[:n]
         self.arr("xscav_frac1")[:n, :p.nspec] = p.xscav_frac1[:n]
+
+    STATE = ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt", "uap", "ucp", "uzp",
+             "us", "vs", "ws", "cbt")
+
+    def push_state(self, p):
+        """every particle array of com_mod the loop reads (src/com_mod.f90:675-695)"""
+        n = p.numpart
+        self.set("numpart", n)
+        for nm in self.STATE:
+            self.arr(nm)[:n] = getattr(p, nm)[:n]
+        self.arr("xmass1")[:n, :p.nspec] = p.xmass1[:n]
+        self.arr("xscav_frac1")[:n, :p.nspec] = p.xscav_frac1[:n]
+
+    def pull_state(self, p):
+        n = p.numpart
+        for nm in self.STATE:
+            getattr(p, nm)[:n] = self.arr(nm)[:n]
+        p.xmass1[:n] = self.arr("xmass1")[:n, :p.nspec]
+
+    def particle_loop(self, itime, ldeltat):
+        """src/timemanager.f90:531-712"""
+        self.L.f_tm_particle_loop(C.byref(C.c_int(itime)), C.byref(C.c_int(ldeltat)))
 
     def wetdepo(self, itime, ltsample, loutnext):
         self.L.f_wetdepo(C.byref(C.c_int(itime)), C.byref(C.c_int(ltsample)), C.byref(C.c_int(loutnext)))

@@ -316,3 +316,109 @@ def test_reference_drydepokernel_and_pieces_bit_identical():
             L.fpo_cxy2ll(mo, x1.value, y1.value, C.byref(la2), C.byref(lo2))
             assert (la1.value, lo1.value) == (la2.value, lo2.value)
             assert R.f_cgszll(mr, C.byref(cf(lat)), C.byref(cf(lon))) == L.fpo_cgszll(mo, lat, lon)
+
+
+@pytest.mark.parametrize("ctl", [5.0, -5.0])
+def test_reference_timemanager_particle_loop_bit_identical(ctl):
+    """The particle loop of timemanager itself (src/timemanager.f90:531-712: age class,
+    initialize for new particles, advance, nstop, radioactive decay, dry-deposition split with
+    the ldeltat back-correction, xmassfract / age terminations, drydepokernel(_nest)) against
+    the oracle's fpo_step: every particle array and the deposition grids, 4 intervals."""
+    cb = cases.config_small(nrel=3, npart_each=300, nspec=2, decay=[0.0, 1.0e-5], drydepspec=[1, 1], ctl=ctl,
+                            lage=(3600, 86400 * 10), nest=(-60.0, -30.0, 48, 24, 2.5, 2.5), ioutputforeachrelease=1)
+    c = cb.cfg
+    n = 900
+    p = cases.seeded_particles(cb, n, zmax=400.0, lat_range=(-60.0, 60.0), nspec=2)
+    p.ztra1[300:600] = np.random.RandomState(2).uniform(500.0, 9000.0, 300).astype(np.float32)
+    p.itramem[:100] = -86400 * 10 + 1800      # reach lage(nageclass) during the run -> age termination
+    p.xmass1[:n, 1] = 0.5
+    p.xmass1[200:220, :] = 1.0e-9             # xmassfract < minmass -> mass termination
+    ref, ora = _pair(cb, cases.met_pair(cb))
+    ref.push_state(p)
+    ora.push_particles(p)
+    tot_term = 0
+    for k in range(4):
+        itime, ldeltat = k * 900, 450 + 900 * (k % 2)
+        ref.particle_loop(itime, ldeltat)
+        st = ora.step(itime, ldeltat)
+        tot_term += st["n_terminated"]
+        pr = fb.Particles(c.maxpart, c.nspec); pr.numpart = n
+        po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
+        ref.pull_state(pr); ora.pull_particles(po)
+        for f in ref.STATE:
+            a, b = getattr(pr, f)[:n], getattr(po, f)[:n]
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (k, f)
+        assert np.array_equal(pr.xmass1[:n].view(np.uint32), po.xmass1[:n].view(np.uint32)), k
+    assert tot_term >= 120
+    go = ora.fetch_grids(zero_conc=False)
+    assert go["drygridunc"].sum() > 0 and go["drygriduncn"].sum() > 0
+    assert np.array_equal(ref.arr("drygridunc").view(np.uint32), go["drygridunc"].view(np.uint32))
+    assert np.array_equal(ref.arr("drygriduncn").view(np.uint32), go["drygriduncn"].view(np.uint32))
+
+
+def test_reference_releaseparticles_bit_identical():
+    """releaseparticles (src/releaseparticles.f90:69-378): release counts per interval, the
+    free-slot search, the ran1 position stream and the particle masses, against the oracle's
+    restatement (which tests/test_oracle_pins.py in turn equates with the host library's)."""
+    cb = cases.config_small(nrel=3, npart_each=700, maxpart=2600)
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=3, start=0, end=3600)
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    o = Oracle(cb)
+    L = o.L
+    for nm in ("xpoint1", "xpoint2", "ypoint1", "ypoint2", "zpoint1", "zpoint2"):
+        ref.arr(nm)[:] = getattr(rel, nm)
+    ref.arr("ireleasestart")[:] = rel.start
+    ref.arr("ireleaseend")[:] = rel.end
+    ref.arr("kindz")[:] = 1
+    ref.arr("xmasssave")[:] = 0.0
+    for nm in ("area_hour", "point_hour", "area_dow", "point_dow"):
+        ref.arr(nm)[:] = 1.0              # no emission variation (readreleases default)
+    ref.set("ind_rel", 0); ref.set("itsplit", 99999999); ref.set("bdate", 2455197.5)
+    ref.set("numpart", 0); ref.set("numparticlecount", 0)
+    ref.arr("itra1")[:] = fb.ITRA_DEAD   # FLEXPART.f90:315-317
+    xmasssave = np.zeros(c.numpoint, np.float32)
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    fp = lambda a: a.ctypes.data_as(_pf)
+    for itime in range(0, 4500, 900):
+        rc = L.fpo_releaseparticles(o.S, itime, c.numpoint, rel.start.ctypes.data_as(_pi), rel.end.ctypes.data_as(_pi),
+                                    fp(rel.xpoint1), fp(rel.ypoint1), fp(rel.xpoint2), fp(rel.ypoint2),
+                                    fp(rel.zpoint1), fp(rel.zpoint2), fp(xmasssave), 99999999)
+        assert rc == 0
+        ref.L.f_releaseparticles(C.byref(C.c_int(itime)))
+        k = ref.get("numpart")
+        q = fb.Particles(c.maxpart, 1); q.numpart = k
+        o.pull_particles(q)
+        for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt"):
+            a, b = ref.arr(f)[:k], getattr(q, f)[:k]
+            assert np.array_equal(a.view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), (itime, f)
+        assert np.array_equal(ref.arr("xmass1")[:k, 0].view(np.uint32), q.xmass1[:k, 0].view(np.uint32))
+        # the released particles "advance": their slots stay occupied
+        ref.arr("itra1")[:k] = itime + 900
+        q.itra1[:k] = itime + 900
+        o.push_particles(q, 0, k)
+    assert k == 3 * (87 + 175 * 3 + 88)
+
+
+def test_reference_readcommand_derivations_match_host():
+    """fpbh_readcommand (turbulence switches, ifine, fine, ctl := 1/ctl, method, mintime) against
+    src/readcommand.f90:244-272,379-385 run from the reference's source."""
+    cb = cases.config_small(nrel=1, npart_each=8)
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    from flexpart_b200.abi import FpbConfig, load_host_lib
+    H = load_host_lib()
+    for ctl in (-5.0, -1.0, 0.05, 0.1, 1.0, 3.0, 5.0, 7.5, 40.0):
+        for ifine in (0, 1, 4, 5, 20):
+            for cbl in (0, 1):
+                for lsync in (300, 900, 3600):
+                    ref.set("ctl", ctl); ref.set("ifine", ifine); ref.set("cblflag", cbl); ref.set("lsynctime", lsync)
+                    ref.set("turbswitch", 0)
+                    ref.L.f_rc_turbulence_switches()
+                    ref.L.f_rc_method()
+                    c = FpbConfig()
+                    c.ldirect, c.lsynctime, c.ctl, c.ifine, c.cblflag = 1, lsync, ctl, ifine, cbl
+                    assert H.fpbh_readcommand(C.byref(c)) == 0
+                    got = (c.ifine, c.turbswitch, c.fine, c.ctl, c.method, c.mintime, c.lsynctime)
+                    exp = (ref.get("ifine"), ref.get("turbswitch"), ref.get("fine"), ref.get("ctl"), ref.get("method"),
+                           ref.get("mintime"), ref.get("lsynctime"))
+                    assert got == exp, (ctl, ifine, cbl, lsync, got, exp)
