@@ -297,7 +297,8 @@ def run_ours(args):
                                  "ALU/latency-bound, see substeps_per_particle_step"},
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args, threads=1, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = (cpu_baseline_reference(args, 1, args.cpu_seconds) if reference_available()
+                                    else cpu_baseline(args, threads=1, budget_s=args.cpu_seconds))
     eng.close()
     if rank == 0:
         if world == 1 and args.workload == "c2" and not args.no_hbm_regime:
@@ -404,6 +405,78 @@ def cpu_baseline(args, threads, budget_s, steps=None):
             "setup_s": round(time.time() - t0 - wall, 1)}
 
 
+# ---- the reference's own code (oracle/_ref/libflexref.so: the reference's Fortran sources
+# for the path transpiled to C at build time, oracle/f2c/) as the CPU baseline
+_REF_CTX = {}
+
+
+def _ref_worker(job):
+    """one process = one FLEXPART_MPI rank: its share of the particles, the whole met (the
+    arrays filled before the fork are shared copy-on-write)"""
+    w, nproc, nsteps = job
+    import flexpart_b200 as fb
+    ref, parts, cb = _REF_CTX["ref"], _REF_CTX["parts"], _REF_CTX["cb"]
+    idx = np.arange(w, parts.numpart, nproc)
+    sub = fb.Particles(cb.cfg.maxpart, cb.cfg.nspec)
+    for nm in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt", "uap", "ucp", "uzp",
+               "us", "vs", "ws", "cbt"):
+        getattr(sub, nm)[:len(idx)] = getattr(parts, nm)[idx]
+    sub.xmass1[:len(idx)] = parts.xmass1[idx]
+    sub.numpart = len(idx)
+    ref.push_state(sub)
+    total = 0
+    t0 = time.perf_counter()
+    for k in range(nsteps):
+        itime = k * 900
+        total += int(np.sum(ref.arr("itra1")[:len(idx)] == itime))
+        ref.conccalc(itime, 1.0)
+        ref.particle_loop(itime, 0)
+    return total, time.perf_counter() - t0
+
+
+def cpu_baseline_reference(args, threads, budget_s, steps=None):
+    """The reference's own particle loop (src/timemanager.f90:531-712 with initialize / advance
+    and everything below them) + conccalc, from oracle/_ref/libflexref.so, one process per
+    host core (the FLEXPART_MPI execution model, README_PARALLEL.md:60-73), bounded sample."""
+    import multiprocessing as mp
+    import flexpart_b200 as fb
+    import ref_api
+    t_setup = time.time()
+
+    def run(nsample, nsteps, nproc):
+        a2 = argparse.Namespace(**vars(args))
+        cb, rel = build_workload(a2, 0, 1, 0, n_particles=nsample)
+        ref = ref_api.Ref(cb, maxrand=100000)
+        ref.fill_rannumb()
+        ref.upload_met(1, fb.MetFields(cb).synth(0))
+        ref.upload_met(2, fb.MetFields(cb).synth(10800))
+        ref.set_met_bracket((1, 2), (0, 10800))
+        parts = host_particles(cb, rel, pinned=False)
+        _REF_CTX.update(ref=ref, parts=parts, cb=cb)
+        with mp.get_context("fork").Pool(nproc) as pool:
+            res = pool.map(_ref_worker, [(w, nproc, nsteps) for w in range(nproc)])
+        total, wall = sum(r[0] for r in res), max(r[1] for r in res)
+        return total / wall, total, wall
+    nsteps = steps or 4
+    rate, _, _ = run(2000 * threads, 2, threads)
+    nsample = int(max(2000 * threads, min(rate * budget_s / nsteps, 4_000_000)))
+    nsample = (nsample // (100 * threads)) * 100 * threads
+    rate, total, wall = run(nsample, nsteps, threads)
+    return {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
+            "sample": f"{nsample} particles x {nsteps} steps of the same workload ({total} particle-steps in "
+                      f"{wall:.1f} s; the reference's own Fortran sources for the path, transpiled to C "
+                      f"(oracle/f2c) and compiled gcc -O2, {threads} process(es) each with a share of the particles)",
+            "setup_s": round(time.time() - t_setup - wall, 1)}
+
+
+def reference_available():
+    try:
+        import ref_api
+        return ref_api.available()
+    except Exception:
+        return False
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -412,7 +485,10 @@ def run_reference(args):
     K, W = args.steps, args.warmup
     # each step is a bounded sample; keep the whole K+W run within a few minutes
     per_step_budget = max(2.0, min(20.0, 150.0 / max(K + W, 1)))
-    cb = cpu_baseline(args, threads=threads, budget_s=per_step_budget * K, steps=K)
+    if reference_available():
+        cb = cpu_baseline_reference(args, threads=threads, budget_s=per_step_budget * K, steps=K)
+    else:
+        cb = cpu_baseline(args, threads=threads, budget_s=per_step_budget * K, steps=K)
     line = {"impl": "reference", "metric": "particle-steps/s (advance+conccalc)", "value": cb["value"],
             "unit": "particle-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
             "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
