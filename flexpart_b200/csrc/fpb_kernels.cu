@@ -1454,21 +1454,26 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   const bool full = a.cfg.drydep || a.cfg.cblflag == 1 || a.cfg.lsettling ||
                     a.cfg.rng_mode == FPB_RNG_PHILOX || a.cfg.numbnests > 0;
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
-  static int resident[2] = {0, 0};
-  int &res = resident[full ? 1 : 0];
+  // lean + the usual switches (turbswitch, method 1, turbulence on) as compile-time constants
+  const bool spec = !full && a.cfg.turbswitch && a.cfg.method == 1 && !a.cfg.turboff;
+  static int resident[3] = {0, 0, 0};
+  const int variant = full ? 1 : (spec ? 2 : 0);
+  int &res = resident[variant];
   if (res == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false>, 128, 0);
+    if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true, false>, 128, 0);
+    else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, false>, 128, 0);
     res = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int want = (a.cfg.numpart + 127) / 128;
   const int nb = want < res ? want : res;
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
-  if (full) fpb_pbl_kernel<true, true><<<nb, 128, 0, st>>>(a);
-  else fpb_pbl_kernel<false, false><<<nb, 128, 0, st>>>(a);
+  if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, 128, 0, st>>>(a);
+  else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, 128, 0, st>>>(a);
+  else fpb_pbl_kernel<false, false, false><<<nb, 128, 0, st>>>(a);
   fpb_finish_kernel<<<want, 128, 0, st>>>(a);
 }
 

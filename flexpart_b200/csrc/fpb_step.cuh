@@ -45,7 +45,9 @@ constexpr int LEV_WORDS = 5; // u, v, w, rho, rhograd
 enum : int { LS_P1 = 0, LS_P2, LS_P3, LS_P4, LS_O00, LS_O01, LS_TAG, LS_LEV = LS_TAG + PBL_CACHE,
              LS_WORDS = LS_LEV + LEV_WORDS * PBL_CACHE };
 
-template <bool EXTRA, bool CBL>
+// SPEC = true: forward or backward Hanna run with turbswitch on, method 1, turbulence not
+// switched off -- the switches are compile-time constants (the launcher checks them).
+template <bool EXTRA, bool CBL, bool SPEC = false>
 struct PblTask {
   int j;
   bool running, first;
@@ -204,8 +206,10 @@ struct PblTask {
   __device__ __forceinline__ void substep(const DevStepArgs &a, const float *sh, float *ls) {
     const DevCfg &c = a.cfg;
     const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
+    const bool turbswitch = SPEC ? true : (c.turbswitch != 0), turboff = SPEC ? false : (c.turboff != 0);
+    const bool method1 = SPEC ? true : (c.method == 1);
     nsub++;
-    if (c.method == 1) {
+    if (method1) {
       ldt = min(ldt, abs(c.lsynctime - itimec + itime));
       itimec = itimec + ldt * c.ldirect;
     } else {
@@ -269,7 +273,7 @@ struct PblTask {
     const float rhoa = dz1 * hi[3 * PBL_THREADS] + dz2 * lo[3 * PBL_THREADS];
     const float rhograd = dz1 * hi[4 * PBL_THREADS] + dz2 * lo[4 * PBL_THREADS];
 
-    if (c.turbswitch) hanna(t, zt, regime); else hanna1(t, zt, regime);
+    if (turbswitch) hanna(t, zt, regime); else hanna1(t, zt, regime);
 
     // horizontal turbulent velocities, advance.f90:371-384
     if (nrand + 1 > maxrand) nrand = 1;
@@ -301,7 +305,7 @@ struct PblTask {
       float delz;
       // next iteration's normal (table modes: plain loads, harmless past the end)
       const float r_w_next = (CBL && c.cblflag == 1) ? 0.f : normal(a, nrand + i + 1);
-      if (c.turbswitch) {
+      if (turbswitch) {
         if (dtftlw < .5f) {
           if (CBL && c.cblflag == 1) {
             if (-t.h / t.ol > 5.f) {
@@ -352,7 +356,7 @@ struct PblTask {
         delz = wp * dtf;
       }
       r_w = r_w_next;
-      if (c.turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
+      if (turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
 
       if (fabsf(delz) > t.h) delz = fmodf(delz, t.h);
       if (delz < -zt) {               // reflection at the ground
@@ -374,7 +378,7 @@ struct PblTask {
     ust = t.ust; // hanna* may raise ust to 1e-4 (idempotent)
 
     // next time step, advance.f90:504-510
-    if (c.turbswitch) {
+    if (turbswitch) {
       float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(wp * t.sigw), 1.e-5f));
       q = fminf(q, 0.5f / fabsf(t.dsigwdz));
       ldt = f_int(q * c.ctl);
@@ -435,7 +439,7 @@ struct PblTask {
 
 // Persistent kernel: every warp pulls batches of particle rows from
 // *a.work_counter; lanes run sub-steps until their particle leaves the loop.
-template <bool EXTRA, bool CBL>
+template <bool EXTRA, bool CBL, bool SPEC>
 __global__ void __launch_bounds__(PBL_THREADS, EXTRA ? 3 : FPB_PBL_MIN_BLOCKS)
 fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
@@ -454,7 +458,7 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nrows = c.numpart;
 
-  PblTask<EXTRA, CBL> task;
+  PblTask<EXTRA, CBL, SPEC> task;
   task.running = false;
   task.j = -1;
   unsigned n_act = 0, n_pbl = 0, n_sub = 0, n_nan = 0;
