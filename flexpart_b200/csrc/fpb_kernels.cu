@@ -1454,8 +1454,8 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   const bool full = a.cfg.drydep || a.cfg.cblflag == 1 || a.cfg.lsettling ||
                     a.cfg.rng_mode == FPB_RNG_PHILOX || a.cfg.numbnests > 0;
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
-  // lean + the usual switches (turbswitch, method 1, turbulence on) as compile-time constants
-  const bool spec = !full && a.cfg.turbswitch && a.cfg.method == 1 && !a.cfg.turboff;
+  // lean + the usual switches (turbswitch, method 1, IFINE 4, turbulence on) as compile-time constants
+  const bool spec = !full && a.cfg.turbswitch && a.cfg.method == 1 && !a.cfg.turboff && a.cfg.ifine == 4;
   static int resident[3] = {0, 0, 0};
   const int variant = full ? 1 : (spec ? 2 : 0);
   int &res = resident[variant];

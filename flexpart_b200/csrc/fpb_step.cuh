@@ -45,8 +45,8 @@ constexpr int LEV_WORDS = 5; // u, v, w, rho, rhograd
 enum : int { LS_P1 = 0, LS_P2, LS_P3, LS_P4, LS_O00, LS_O01, LS_TAG, LS_LEV = LS_TAG + PBL_CACHE,
              LS_WORDS = LS_LEV + LEV_WORDS * PBL_CACHE };
 
-// SPEC = true: forward or backward Hanna run with turbswitch on, method 1, turbulence not
-// switched off -- the switches are compile-time constants (the launcher checks them).
+// SPEC = true: forward or backward Hanna run with turbswitch on, method 1, IFINE = 4, turbulence
+// not switched off -- the switches are compile-time constants (the launcher checks them).
 template <bool EXTRA, bool CBL, bool SPEC = false>
 struct PblTask {
   int j;
@@ -208,6 +208,7 @@ struct PblTask {
     const int itime = c.itime, nz = c.nz, maxrand = c.maxrand;
     const bool turbswitch = SPEC ? true : (c.turbswitch != 0), turboff = SPEC ? false : (c.turboff != 0);
     const bool method1 = SPEC ? true : (c.method == 1);
+    const int ifine = SPEC ? 4 : c.ifine; // IFINE = 4: the shipped options/COMMAND value
     nsub++;
     if (method1) {
       ldt = min(ldt, abs(c.lsynctime - itimec + itime));
@@ -279,7 +280,7 @@ struct PblTask {
     if (nrand + 1 > maxrand) nrand = 1;
     const float r_up = normal(a, nrand), r_vp = normal(a, nrand + 1);
     nrand = nrand + 2;
-    if (nrand + c.ifine > maxrand) nrand = 1;
+    if (nrand + ifine > maxrand) nrand = 1;
     // first vertical normal requested early so its latency hides behind the u/v update
     float r_w = (CBL && c.cblflag == 1) ? 0.f : normal(a, nrand + 1);
     if (dt / t.tlu < .5f) {
@@ -300,8 +301,8 @@ struct PblTask {
     const float dtftlw = dtf / t.tlw;
 
     // vertical component in ifine short steps, advance.f90:396-498
-#pragma unroll 1
-    for (int i = 1; i <= c.ifine; i++) {
+#pragma unroll
+    for (int i = 1; i <= ifine; i++) { // unrolled in the SPEC variant only (constant trip count)
       float delz;
       // next iteration's normal (table modes: plain loads, harmless past the end)
       const float r_w_next = (CBL && c.cblflag == 1) ? 0.f : normal(a, nrand + i + 1);
@@ -369,12 +370,12 @@ struct PblTask {
         icbt = 1;
         zt = zt + delz;
       }
-      if (i != c.ifine) {
+      if (i != ifine) {
         t.zeta = zt / t.h;
         hanna_short(t, zt, regime);
       }
     }
-    if (!(CBL && c.cblflag == 1)) nrand = nrand + (c.ifine + 1);
+    if (!(CBL && c.cblflag == 1)) nrand = nrand + (ifine + 1);
     ust = t.ust; // hanna* may raise ust to 1e-4 (idempotent)
 
     // next time step, advance.f90:504-510
