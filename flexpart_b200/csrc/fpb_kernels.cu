@@ -1474,7 +1474,11 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, 128, 0, st>>>(a);
   else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, 128, 0, st>>>(a);
   else fpb_pbl_kernel<false, false, false><<<nb, 128, 0, st>>>(a);
-  fpb_finish_kernel<<<want, 128, 0, st>>>(a);
+  // finish kernel: the variant without nests / settling / dry deposition / Philox-direct RNG when it applies
+  if (!a.cfg.drydep && !a.cfg.lsettling && a.cfg.numbnests == 0 && a.cfg.rng_mode != FPB_RNG_PHILOX)
+    fpb_finish_kernel<true><<<want, 128, 0, st>>>(a);
+  else
+    fpb_finish_kernel<false><<<want, 128, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_conccalc)(const DevConcArgs &a, cudaStream_t st) {

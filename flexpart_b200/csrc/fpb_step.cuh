@@ -508,6 +508,9 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
 // -------------------------------------------------------- finish kernel ----
 // label 700 + label 99 + Petterssen (src/advance.f90:629-985) and the rest of
 // the timemanager loop body (src/timemanager.f90:630-707) for row j.
+// SIMPLE = true: no nested input grids, no settling, no dry deposition, table RNG -- known at
+// compile time (the launcher checks); the general variant covers everything else.
+template <bool SIMPLE>
 __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh, int j,
                                            unsigned &n_term, unsigned &n_pett) {
   const DevCfg &c = a.cfg;
@@ -526,6 +529,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 
   Rng rng;
   make_rng(c, a.rannumb, slot, rng);
+  auto normal = [&](int i) -> float { return SIMPLE ? __ldg(a.rannumb + (i - 1)) : rng.get(i); };
 
   float dxsave = 0.f, dysave = 0.f, dawsave = 0.f, dcwsave = 0.f;
   float u = 0.f, v = 0.f, w = 0.f, usig = 0.f, vsig = 0.f, wsig = 0.f;
@@ -544,11 +548,11 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 
   // advance.f90:199-253 at the position the call started from
   Hz z;
-  z.ngrid = choose_grid(c, xt, yt);
+  z.ngrid = SIMPLE ? pole_grid(c, yt) : choose_grid(c, xt, yt);
   const DevMetSlot *met;
   float h = 0.f, tropop;
   {
-    const GridSel g = select_grid(a, z.ngrid, xt, yt);
+    const GridSel g = select_grid(a, SIMPLE ? min(z.ngrid, 0) : z.ngrid, xt, yt);
     met = g.met;
     int jyp = g.jy + 1;
     if (jyp >= c.nymax) jyp = jyp - 1;
@@ -586,30 +590,30 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     if (zt < tropop) {
       const float uxscale = m_sqrt(2.f * c.d_trop / dt);
       if (nrand + 1 > maxrand) nrand = 1;
-      ux = rng.get(nrand) * uxscale;
-      vy = rng.get(nrand + 1) * uxscale;
+      ux = normal(nrand) * uxscale;
+      vy = normal(nrand + 1) * uxscale;
       nrand = nrand + 2;
       wp = 0.f;
     } else if (zt < tropop + 1000.f) {
       const float weight = (zt - tropop) / 1000.f;
       const float uxscale = m_sqrt(2.f * c.d_trop / dt * (1.f - weight));
       if (nrand + 2 > maxrand) nrand = 1;
-      ux = rng.get(nrand) * uxscale;
-      vy = rng.get(nrand + 1) * uxscale;
+      ux = normal(nrand) * uxscale;
+      vy = normal(nrand + 1) * uxscale;
       const float wpscale = m_sqrt(2.f * c.d_strat / dt * weight);
-      wp = rng.get(nrand + 2) * wpscale + c.d_strat / 1000.f;
+      wp = normal(nrand + 2) * wpscale + c.d_strat / 1000.f;
       nrand = nrand + 3;
     } else {
       if (nrand > maxrand) nrand = 1;
       ux = 0.f;
       vy = 0.f;
       const float wpscale = m_sqrt(2.f * c.d_strat / dt);
-      wp = rng.get(nrand) * wpscale;
+      wp = normal(nrand) * wpscale;
       nrand = nrand + 1;
     }
     if (c.turboff) { ux = 0.f; vy = 0.f; wp = 0.f; }
 
-    w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
+    if (!SIMPLE) w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
 
     dxsave = dxsave + (u + ux) * dt;
     dysave = dysave + (v + vy) * dt;
@@ -622,9 +626,9 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     const float r = m_exp(-2.f * (float)abs(c.lsynctime) / (float)c.lwindinterv);
     const float rs = m_sqrt(1.f - r * r);
     if (nrand + 2 > maxrand) nrand = 1;
-    usigold = r * usigold + rs * rng.get(nrand) * usig * c.turbmesoscale;
-    vsigold = r * vsigold + rs * rng.get(nrand + 1) * vsig * c.turbmesoscale;
-    wsigold = r * wsigold + rs * rng.get(nrand + 2) * wsig * c.turbmesoscale;
+    usigold = r * usigold + rs * normal(nrand) * usig * c.turbmesoscale;
+    vsigold = r * vsigold + rs * normal(nrand + 1) * vsig * c.turbmesoscale;
+    wsigold = r * wsigold + rs * normal(nrand + 2) * wsig * c.turbmesoscale;
     dxsave = dxsave + usigold * (float)c.lsynctime;
     dysave = dysave + vsigold * (float)c.lsynctime;
     zt = zt + wsigold * (float)c.lsynctime;
@@ -648,10 +652,10 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     // Petterssen corrector, advance.f90:829-985
     if (ldt != abs(c.lsynctime)) done = true;
     else if (abs(itime + ldt * c.ldirect) > abs(c.memtime[1])) done = true;
-    else if (choose_grid(c, xt, yt) != ngrid) done = true;
+    else if ((SIMPLE ? pole_grid(c, yt) : choose_grid(c, xt, yt)) != ngrid) done = true;
   }
   if (!done) {
-    const GridSel g = select_grid(a, ngrid, xt, yt); // advance.f90:862-870
+    const GridSel g = select_grid(a, SIMPLE ? min(ngrid, 0) : ngrid, xt, yt); // advance.f90:862-870
     int jyp = g.jy + 1;
     if (jyp >= c.nymax) jyp = jyp - 1;
     const float uold = u, vold = v, wold = w;
@@ -659,7 +663,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     float d0, d1, d2;
     interp_wind<false>(c, met, z, sh, zt, u, v, w, d0, d1, d2);
     n_pett++;
-    w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
+    if (!SIMPLE) w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
     u = (u - uold) / 2.f;
     v = (v - vold) / 2.f;
     w = (w - wold) / 2.f;
@@ -688,7 +692,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
       float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
       const float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
       drydeposit[ks] = 0.f;
-      if (c.drydepspec[ks]) {
+      if (!SIMPLE && c.drydepspec[ks]) {
         const float pr = (c.drydep && (flags & SC_PBL)) ? a.sc.prob[(size_t)ks * a.p.maxpart + j] : 0.f;
         drydeposit[ks] = xm1 * pr * decfact;
         xm1 = xm1 * (1.f - pr) * decfact;
@@ -708,7 +712,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     }
     if (xmassfract < MINMASS) { itra1 = FPB_ITRA_DEAD; term = true; }
 
-    if (c.drydep && (c.ldirect == 1)) {
+    if (!SIMPLE && c.drydep && (c.ldirect == 1)) {
       const int kp = (c.ioutputforeachrelease == 1) ? npoint : 1;
       const int itage = abs(itime - itramem);
       int nage;
@@ -735,6 +739,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
 #ifndef FPB_FINISH_MIN_BLOCKS
 #define FPB_FINISH_MIN_BLOCKS 8
 #endif
+template <bool SIMPLE>
 __global__ void __launch_bounds__(128, FPB_FINISH_MIN_BLOCKS)
 fpb_finish_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
@@ -743,7 +748,7 @@ fpb_finish_kernel(const __grid_constant__ DevStepArgs a) {
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned n_term = 0, n_pett = 0;
-  if (j < c.numpart && a.p.itra1[j] == c.itime) finish_row(a, sh, j, n_term, n_pett);
+  if (j < c.numpart && a.p.itra1[j] == c.itime) finish_row<SIMPLE>(a, sh, j, n_term, n_pett);
   if (a.stats) {
     const unsigned long long v2 = warp_sum(n_term), v5 = warp_sum(n_pett);
     if ((threadIdx.x & 31) == 0) {
