@@ -27,6 +27,8 @@
 
 enum : int { SC_PBL = 1, SC_ABOVE = 2 };
 
+__device__ __noinline__ float rare_fmodf(float a, float b) { return fmodf(a, b); }
+
 // ----------------------------------------------------------- PBL kernel ----
 // Per-lane shared-memory rows (word w of lane t lives at ls[w * PBL_THREADS],
 // ls = smem + t, so every access is conflict-free):
@@ -359,7 +361,7 @@ struct PblTask {
       r_w = r_w_next;
       if (turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
 
-      if (fabsf(delz) > t.h) delz = fmodf(delz, t.h);
+      if (fabsf(delz) > t.h) delz = rare_fmodf(delz, t.h); // almost never taken: keep fmodf's body out of line
       if (delz < -zt) {               // reflection at the ground
         icbt = -1;
         zt = -zt - delz;
@@ -687,11 +689,11 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     bool term = false;
     itra1 = itime + c.lsynctime;
     float xmassfract = 0.f;
-    float drydeposit[FPB_MAXSPEC];
+    float drydeposit[SIMPLE ? 1 : FPB_MAXSPEC];
     for (int ks = 0; ks < c.nspec; ks++) {
       float xm1 = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
       const float decfact = (c.decay[ks] > 0.f) ? m_exp(-(float)abs(c.lsynctime) * c.decay[ks]) : 1.f;
-      drydeposit[ks] = 0.f;
+      if (!SIMPLE) drydeposit[ks] = 0.f;
       if (!SIMPLE && c.drydepspec[ks]) {
         const float pr = (c.drydep && (flags & SC_PBL)) ? a.sc.prob[(size_t)ks * a.p.maxpart + j] : 0.f;
         drydeposit[ks] = xm1 * pr * decfact;
