@@ -721,26 +721,21 @@ static int do_sort(fpb_handle *h, bool itime_valid, int itime) {
   if (n <= 1) return 0;
   if (scatter_reserve(h->scatter, (size_t)n, 1)) return fail("%s", scatter_error());
   per_step_cfg(h, h->d_tmp, itime, 0);
-  const unsigned long long ncell = (unsigned long long)h->d.nxd * h->d.nyd * h->cfg.nz;
-  int cell_bits = 1;
-  while ((1ull << cell_bits) < ncell) cell_bits++;
-  const bool regime = itime_valid && h->have_bracket && cell_bits <= 29;
+  const bool regime = itime_valid && h->have_bracket;
   DevMetSlot met[2];
   if (regime) {
     met[0] = slot_view(h, h->memind[0]);
     met[1] = slot_view(h, h->memind[1]);
   }
   sortk_build_keys(h->d_tmp, h->p, h->d_height, n, h->scatter.keys[0], h->scatter.ids[0], h->d_nlive,
-                   h->stream, regime ? met : nullptr, cell_bits);
-  int bits = cell_bits + (regime ? 2 : 0) + 1; // +1: dead rows carry all-ones keys and must sort last
-  bits = ((bits + 7) / 8) * 8;
+                   h->stream, regime ? met : nullptr);
+  int bits = ((sortk_key_bits(h->d_tmp, regime) + 7) / 8) * 8;
   if (bits > 32) bits = 32;
   int cur = 0;
   if (scatter_sort_pairs(h->scatter, (size_t)n, bits, h->stream, &h->launches, &cur)) return fail("%s", scatter_error());
-  sortk_permute(h->p, h->p_alt, h->scatter.ids[cur], n, h->cfg.nspec, h->stream);
+  sortk_permute(h->p, h->p_alt, h->scatter.ids[cur], n, h->cfg.nspec, h->stream, h->row_of_slot);
   std::swap(h->p, h->p_alt);
-  sortk_invert(h->p.slot, h->row_of_slot, n, h->stream);
-  h->launches += 3;
+  h->launches += 2;
   unsigned nlive = 0;
   CK(cudaMemcpyAsync(&nlive, h->d_nlive, sizeof nlive, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaGetLastError());
@@ -1010,12 +1005,8 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
   CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
   CK(cudaEventRecord(h->ev_ready, h->stream));
 
-  const unsigned long long ncell = (unsigned long long)h->d.nxd * h->d.nyd * c.nz;
-  int cell_bits = 1;
-  while ((1ull << cell_bits) < ncell) cell_bits++;
-  const bool regime = cell_bits <= 29;
-  int bits = cell_bits + (regime ? 2 : 0) + 1;
-  bits = ((bits + 7) / 8) * 8;
+  const bool regime = true;
+  int bits = ((sortk_key_bits(h->d, regime) + 7) / 8) * 8;
   if (bits > 32) bits = 32;
   DevMetSlot met[2] = {slot_view(h, h->memind[0]), slot_view(h, h->memind[1])};
 
@@ -1041,12 +1032,11 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     per_step_cfg(h, a.cfg, itime, ldeltat);
     a.cfg.numpart = n;
     sortk_build_keys(a.cfg, stg, h->d_height, n, L.sw.keys[0], L.sw.ids[0], L.d_nlive, L.st,
-                     regime ? met : nullptr, cell_bits);
+                     regime ? met : nullptr);
     int cur = 0;
     if (scatter_sort_pairs(L.sw, (size_t)n, bits, L.st, &h->launches, &cur)) return fail("%s", scatter_error());
-    sortk_permute(stg, rows, L.sw.ids[cur], n, c.nspec, L.st);
-    sortk_invert(rows.slot, h->row_of_slot, n, L.st, c0);
-    h->launches += 3;
+    sortk_permute(stg, rows, L.sw.ids[cur], n, c.nspec, L.st, h->row_of_slot, c0);
+    h->launches += 2;
 
     if (conc_weight > 0.f) {
       DevConcArgs q;

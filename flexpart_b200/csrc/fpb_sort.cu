@@ -13,9 +13,13 @@ struct RegimeMet {
   float dt1, dt2;
 };
 
+// key = (level, jy >> sy, ix >> sx) packed level-major into lb + yb + xb bits: the cell is
+// coarsened to a tile when the exact cell index would push the sort to a 4th radix pass
+struct KeyLayout { int sx, sy, xb, yb, cell_bits; };
+
 __global__ void __launch_bounds__(256)
 build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsigned *keys,
-                  unsigned *ids, unsigned *nlive, RegimeMet rm, int cell_bits) {
+                  unsigned *ids, unsigned *nlive, RegimeMet rm, KeyLayout kl) {
   __shared__ float sh[FPB_MAXNZ];
   for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = height[i];
   __syncthreads();
@@ -35,7 +39,7 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
         int mid = (lo + hi) >> 1;
         if (sh[mid - 1] > zt) hi = mid; else lo = mid + 1;
       }
-      key = (unsigned)(((lo - 2) * c.nyd + jy) * c.nxd + ix);
+      key = ((((unsigned)(lo - 2) << kl.yb) | (unsigned)(jy >> kl.sy)) << kl.xb) | (unsigned)(ix >> kl.sx);
       if (rm.S0) {
         const int ixp = min(ix + 1, c.nxd - 1), jyp = min(jy + 1, c.nyd - 1);
         const float ddx = (float)xd - (float)ix, ddy = (float)yd - (float)jy;
@@ -50,7 +54,7 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
         if (!(zt <= h)) regime = 3u;
         else if (h * fabsf(oli) < fabsf(rm.dt1 + rm.dt2)) regime = 0u;
         else regime = ((oli < 0.f) != ((rm.dt1 + rm.dt2) < 0.f)) ? 1u : 2u;
-        key |= regime << cell_bits;
+        key |= regime << kl.cell_bits;
       }
     }
     keys[i] = key;
@@ -61,7 +65,8 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
 }
 
 __global__ void __launch_bounds__(256)
-permute_kernel(DevParticles s, DevParticles d, const unsigned *ids, int nrows, int nspec) {
+permute_kernel(DevParticles s, DevParticles d, const unsigned *ids, int nrows, int nspec,
+               int32_t *row_of_slot, int base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   const unsigned j = ids[i];
@@ -71,7 +76,9 @@ permute_kernel(DevParticles s, DevParticles d, const unsigned *ids, int nrows, i
   d.uap[i] = s.uap[j]; d.ucp[i] = s.ucp[j]; d.uzp[i] = s.uzp[j];
   d.us[i] = s.us[j]; d.vs[i] = s.vs[j]; d.ws[i] = s.ws[j];
   d.cbt[i] = s.cbt[j];
-  d.slot[i] = s.slot[j];
+  const int32_t sl = s.slot[j];
+  d.slot[i] = sl;
+  row_of_slot[sl] = base + i; // the inverse map, kept in the same pass
   for (int k = 0; k < nspec; k++) {
     d.xmass1[(size_t)k * d.maxpart + i] = s.xmass1[(size_t)k * s.maxpart + j];
     d.xscav_frac1[(size_t)k * d.maxpart + i] = s.xscav_frac1[(size_t)k * s.maxpart + j];
@@ -145,20 +152,46 @@ scatter_kernel(DevParticles s, DevParticles d, const int32_t *row_of_slot, int f
 inline unsigned nb(int n, int t) { return (unsigned)((n + t - 1) / t); }
 } // namespace
 
+static int bits_for(int n) { // bits needed for values 0..n-1
+  int b = 1;
+  while ((1 << b) < n) b++;
+  return b;
+}
+
+int sortk_key_bits(const DevCfg &c, bool regime) {
+  // level bits + y bits + x bits (+2 regime) + 1 (dead rows = all ones, must sort last) <= 24 -> 3 passes
+  return sortk_key_layout_bits(c) + (regime ? 2 : 0) + 1;
+}
+
+static KeyLayout key_layout(const DevCfg &c) {
+  KeyLayout k;
+  const int lb = bits_for(c.nz > 1 ? c.nz - 1 : 1);
+  k.xb = bits_for(c.nxd); k.yb = bits_for(c.nyd); k.sx = k.sy = 0;
+  // method 1 (sub-stepping, sorted every step): tiles, 3 passes; method 0 (gather-bound, sorted
+  // rarely): exact cells, the locality is worth the 4th pass
+  while (c.method == 1 && lb + k.xb + k.yb > 21 && (k.xb > 1 || k.yb > 1)) { // drop low bits, x and y in turn
+    if (k.xb >= k.yb && k.xb > 1) { k.xb--; k.sx++; } else { k.yb--; k.sy++; }
+  }
+  k.cell_bits = lb + k.xb + k.yb;
+  return k;
+}
+
+int sortk_key_layout_bits(const DevCfg &c) { return key_layout(c).cell_bits; }
+
 void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *height, int nrows,
                       unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st,
-                      const DevMetSlot *met, int cell_bits) {
+                      const DevMetSlot *met) {
   cudaMemsetAsync(d_nlive, 0, sizeof(unsigned), st);
   RegimeMet rm;
   rm.S0 = met ? met[0].S : nullptr;
   rm.S1 = met ? met[1].S : nullptr;
   rm.dt1 = (float)(c.itime - c.memtime[0]);
   rm.dt2 = (float)(c.memtime[1] - c.itime);
-  build_keys_kernel<<<nb(nrows, 256), 256, 0, st>>>(c, p, height, nrows, keys, ids, d_nlive, rm, cell_bits);
+  build_keys_kernel<<<nb(nrows, 256), 256, 0, st>>>(c, p, height, nrows, keys, ids, d_nlive, rm, key_layout(c));
 }
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
-                   int nrows, int nspec, cudaStream_t st) {
-  permute_kernel<<<nb(nrows, 256), 256, 0, st>>>(src, dst, ids, nrows, nspec);
+                   int nrows, int nspec, cudaStream_t st, int32_t *row_of_slot, int base) {
+  permute_kernel<<<nb(nrows, 256), 256, 0, st>>>(src, dst, ids, nrows, nspec, row_of_slot, base);
 }
 void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base) {
   invert_kernel<<<nb(nrows, 256), 256, 0, st>>>(slot, row_of_slot, nrows, base);

@@ -9,14 +9,18 @@
 
 // build keys (dead rows sort last), returns the number of live rows via *d_nlive.
 // met != null: met[0..1] = the fields bracketing c.itime; the turbulence regime of
-// the coming step is put above the cell_bits cell bits of the key.
+// the coming step is put above the cell bits of the key.  The cell part is
+// (level, jy, ix) level-major, coarsened to tiles of 2^k cells when the exact index
+// would need a 4th 8-bit radix pass; sortk_key_bits() = number of key bits to sort.
 void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *height, int nrows,
                       unsigned *keys, unsigned *ids, unsigned *d_nlive, cudaStream_t st,
-                      const DevMetSlot *met, int cell_bits);
-// dst row i := src row ids[i] for every particle array (incl. slot)
+                      const DevMetSlot *met);
+int sortk_key_layout_bits(const DevCfg &c);
+int sortk_key_bits(const DevCfg &c, bool regime);
+// dst row i := src row ids[i] for every particle array (incl. slot);
+// row_of_slot[slot] := base + i
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
-                   int nrows, int nspec, cudaStream_t st);
-// row_of_slot[slot[i]] = base + i (slot = a view starting at device row `base`)
+                   int nrows, int nspec, cudaStream_t st, int32_t *row_of_slot, int base = 0);
 void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base = 0);
 // staging row slot[i] <- row i of the view `rows` (arrays the particle loop writes only)
 void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
