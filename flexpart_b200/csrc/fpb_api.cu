@@ -1010,22 +1010,44 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
   if (bits > 32) bits = 32;
   DevMetSlot met[2] = {slot_view(h, h->memind[0]), slot_view(h, h->memind[1])};
 
-  // chunks of >= ~300k rows (each costs ~20 launches and a persistent-kernel tail;
-  // measured flat between 2 and 6 chunks at 1M rows), multiples of 128 rows
-  int nchunk = numpart / 300000;
-  nchunk = nchunk < 1 ? 1 : (nchunk > 6 ? 6 : nchunk);
-  if (const char *e = getenv("FPB_HOST_CHUNKS")) { // tuning knob
-    const int v = atoi(e);
-    if (v >= 1 && v <= 64) nchunk = v;
+  // Equal row chunks of >= ~300k rows (multiples of 128 rows).  Each chunk costs ~20 launches and
+  // one tail of the persistent sub-step kernel (~0.18 ms, FPB_HOST_TIMING=1 shows the timeline), so
+  // there are few of them: measured flat between 2 and 4 chunks at 1M rows, worse beyond.
+  std::vector<int> bounds; // chunk c = rows [bounds[c], bounds[c+1])
+  {
+    int nchunk = numpart / 300000;
+    nchunk = nchunk < 1 ? 1 : (nchunk > 6 ? 6 : nchunk);
+    if (const char *e = getenv("FPB_HOST_CHUNKS")) { // tuning knob
+      const int v = atoi(e);
+      if (v >= 1 && v <= 64) nchunk = v;
+    }
+    const int per_eq = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
+    for (int c0 = 0; c0 < numpart; c0 += per_eq) bounds.push_back(c0);
+    bounds.push_back(numpart);
   }
-  const int per = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
+  // FPB_HOST_TIMING=1: per-chunk timeline (ms since the call started) on stderr
+  const bool timing = getenv("FPB_HOST_TIMING") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  mark(h->stream);
+  int per = 0; // largest chunk: size of the lanes' sort work areas
+  for (size_t k = 0; k + 1 < bounds.size(); k++) per = std::max(per, bounds[k + 1] - bounds[k]);
 
-  for (int ci = 0, c0 = 0; c0 < numpart; ci++, c0 += per) {
-    const int n = (numpart - c0 < per) ? numpart - c0 : per;
+  for (int ci = 0; ci + 1 < (int)bounds.size(); ci++) {
+    const int c0 = bounds[ci], n = bounds[ci + 1] - bounds[ci];
+    if (n <= 0) continue;
     fpb_handle::Lane &L = h->lanes[ci % fpb_handle::NLANES];
     if (scatter_reserve(L.sw, (size_t)per, 1)) return fail("%s", scatter_error());
     CK(cudaStreamWaitEvent(L.st, h->ev_ready, 0));
+    mark(L.st);
     if (copy_rows_h2d(h, h->p_alt, c0, n, p, L.st)) return 1;
+    mark(L.st);
     const DevParticles stg = rows_view(h->p_alt, c0), rows = rows_view(h->p, c0);
 
     DevStepArgs a;
@@ -1075,6 +1097,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
 
     sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st);
     h->launches++;
+    mark(L.st);
     D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
     D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
     D2HS(p->idt, h->p_alt.idt, int32_t);
@@ -1084,9 +1107,19 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     for (int k = 0; k < c.nspec; k++)
       CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + c0, h->p_alt.xmass1 + (size_t)k * c.maxpart + c0,
                          (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, L.st));
+    mark(L.st);
     CK(cudaGetLastError());
   }
   for (auto &L : h->lanes) CK(cudaStreamSynchronize(L.st));
+  if (timing) {
+    for (size_t k = 1; k + 3 < tev.size() + 1; k += 4) {
+      float t[4];
+      for (int q = 0; q < 4; q++) cudaEventElapsedTime(&t[q], tev[0], tev[k + q]);
+      fprintf(stderr, "fpb_step_host chunk %zu (%d rows): h2d %.3f-%.3f  kernels -%.3f  d2h -%.3f ms\n", (k - 1) / 4,
+              bounds[(k - 1) / 4 + 1] - bounds[(k - 1) / 4], t[0], t[1], t[2], t[3]);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   if (conc_weight > 0.f && c.numreceptor > 0) {
     DevCfg d;
     per_step_cfg(h, d, itime, ldeltat);

@@ -1469,7 +1469,7 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
     res = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int want = (a.cfg.numpart + 127) / 128;
-  const int nb = want < res ? want : res;
+  const int nb = want < res ? want : res; // persistent grid: one wave at most
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
   if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, 128, 0, st>>>(a);
   else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, 128, 0, st>>>(a);
