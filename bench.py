@@ -93,9 +93,17 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
     import cases
     npart_total = n_particles or args.particles
     nrel = 100
+    extra = {}
     if args.workload == "c5slice":
         kw = dict(ctl=-5.0)            # method 0: one Langevin step per sync (HBM-bound regime)
         zmax, lat = 12000.0, (-85.0, 85.0)
+    elif args.workload == "c3":
+        # BASELINE configs[2]: CBL skewed turbulence (forces ctl >= 5, ifine*ctl >= 50), two species with
+        # dry deposition, one of them wet-scavenged, nested output grid
+        kw = dict(ctl=10.0, cblflag=1)
+        extra = dict(nspec=2, drydepspec=(1, 1), wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0),
+                     henry=(1.0e-2, 0.0), nest=(-30.0, 20.0, 240, 160, 0.125, 0.125))
+        zmax, lat = 2000.0, (-60.0, 60.0)
     else:
         kw = dict(ctl=5.0)             # Hanna, method 1
         zmax, lat = 2000.0, (-60.0, 60.0)
@@ -104,7 +112,8 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
                         lsynctime=900, ifine=4, outlon0=-180.0, outlat0=-90.0, numxgrid=720,
                         numygrid=360, dxout=0.5, dyout=0.5,
                         outheights=(100.0, 250.0, 500.0, 1000.0, 2000.0, 3000.0, 5000.0, 8000.0, 12000.0, 50000.0),
-                        lage=(86400 * 20,), ioutputforeachrelease=0, npart=(each,) * nrel, nspec=1,
+                        lage=(86400 * 20,), ioutputforeachrelease=0, npart=(each,) * nrel,
+                        **({"nspec": 1} if "nspec" not in extra else {}), **extra,
                         maxpart=each * nrel, device=device, rng_mode=fb.RNG_PHILOX_INDEX,
                         math_mode=fb.MATH_FAST, scatter_mode=fb.SCATTER_ATOMIC,
                         part_id_stride=world, part_id_offset=rank, sort_interval=args.sort_interval, **kw)
@@ -118,6 +127,8 @@ def workload_config(args, n, world):
         "workload": ("C2: 1M particles/GPU, global 0.5deg x 138 levels, Hanna CTL=5 IFINE=4, "
                      "100 box releases 0-2 km, lsynctime 900 s, conccalc every step, "
                      "grid exchange every 4 steps") if args.workload == "c2" else
+                    ("C3: CBL skewed turbulence (CTL=10, IFINE=5), 2 species with dry deposition, wet deposition, "
+                     "nested output grid, 0.5deg x 138 levels") if args.workload == "c3" else
                     ("C5 slice: domain-spread particles/GPU, 0.5deg x 138 levels, CTL=-5 (method 0), "
                      "conccalc every step"),
         "particles_per_gpu": n, "grid": "721x361x138", "rng": "philox-indexed rannumb",
@@ -182,6 +193,8 @@ def run_ours(args):
 
     def one_step(k, stats):
         itime = k * 900
+        if c.wetdep and itime != 0:
+            eng.wetdepo(itime, 900, 450)
         eng.conccalc(itime, 1.0)
         st = eng.step(itime, 0, stats=stats)
         if (k + 1) % 4 == 0:
@@ -506,7 +519,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5slice"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5slice", "c3"])
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")

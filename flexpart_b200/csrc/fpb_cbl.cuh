@@ -9,6 +9,10 @@ __device__ __forceinline__ float cbl_cuberoot(float x) {
   return copysignf(m_pow(fabsf(x), 0.333333333f), x);
 }
 
+// x**2 of the reference; a multiplication in both math modes (pow(x, 2.) in
+// double rounds to the same float, and the fast exp2/log2 pow needs x > 0)
+__device__ __forceinline__ float cbl_sq(float x) { return x * x; }
+
 __device__ __forceinline__ float cbl_transition(float h, float ol) {
   float transition = 1.f;
   if (-h / ol < 15.f) transition = (m_sin((((-h / ol) + 10.f) / 10.f) * PI_F)) / 2.f + 0.5f;
@@ -45,7 +49,7 @@ __device__ __noinline__ void cbl_drift(const DevCfg &c, float wp, float zp, floa
   float dfluarw, rluarw, xluarw, drluarw, dxluarw;
   if (skew != 0.f) {
     const float a1 = 1.f + fluarw2, a3 = 3.f + fluarw2;
-    const float a3sq = m_pow(a3, 2.f), a1_15 = m_pow(a1, 1.5f);
+    const float a3sq = (a3 * a3), a1_15 = m_pow(a1, 1.5f);
     dfluarw = costluar4 * (1.f / 3.f) * cbl_cuberoot(m_pow(skew, -2.f)) * dskew;
     rluarw = m_pow(a1, 3.f) * skew2 / (a3sq * fluarw2);
     xluarw = a1_15 * skew / (a3 * fluarw);
@@ -90,8 +94,8 @@ __device__ __noinline__ void cbl_drift(const DevCfg &c, float wp, float zp, floa
   const float wold2 = wold * wold;
   const float sigmawa2 = sigmawa * sigmawa, sigmawb2 = sigmawb * sigmawb;
   if (fabsf(deltawa) > 6.f * sigmawa && fabsf(deltawb) > 6.f * sigmawb) flagrein = 1;
-  const float pa = (usurad2p * (1.f / sigmawa)) * (m_exp(-(0.5f * (m_pow(deltawa / sigmawa, 2.f)))));
-  const float pb = (usurad2p * (1.f / sigmawb)) * (m_exp(-(0.5f * (m_pow(deltawb / sigmawb, 2.f)))));
+  const float pa = (usurad2p * (1.f / sigmawa)) * (m_exp(-(0.5f * cbl_sq(deltawa / sigmawa))));
+  const float pb = (usurad2p * (1.f / sigmawb)) * (m_exp(-(0.5f * cbl_sq(deltawb / sigmawb))));
   const float ptot = dens * aluarw * pa + dens * bluarw * pb;
   const float aperfa = deltawa * usurad2 / sigmawa;
   const float aperfb = deltawb * usurad2 / sigmawb;
@@ -124,7 +128,7 @@ __device__ __noinline__ void cbl_split(float zp, float wst, float h, float sigma
   const float radw2 = m_sqrt(w2);
   const float fluarw = costluar4 * m_pow(skew, 0.333333333333333f);
   const float fluarw2 = fluarw * fluarw;
-  const float rluarw = m_pow(1.f + fluarw2, 3.f) * skew2 / (m_pow(3.f + fluarw2, 2.f) * fluarw2);
+  const float rluarw = m_pow(1.f + fluarw2, 3.f) * skew2 / (cbl_sq(3.f + fluarw2) * fluarw2);
   const float xluarw = m_pow(rluarw, 0.5f);
   aluarw = 0.5f * (1.f - xluarw / m_pow(4.f + rluarw, 0.5f));
   const float bluarw = 1.f - aluarw;

@@ -22,6 +22,7 @@
 // (indzindicator, src/advance.f90:310-331) becomes a two-entry cache of the
 // current level pair: a recomputed level gives the same bits because the
 // horizontal weights and the time weights are frozen for the whole call.
+#include <cstdio>
 #include <math.h>
 
 #include "fpb_device.cuh"

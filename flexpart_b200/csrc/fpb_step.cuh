@@ -317,6 +317,11 @@ struct PblTask {
               float old_wp_buf = wp, ath, bth;
               cbl_drift(c, wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol,
                         ath, bth, flagrein);
+#ifdef FPB_DEBUG_NAN
+              if (isnan(ath) || isnan(bth))
+                printf("cbl_drift nan: wp %g zt %g wst %g h %g rhoa %g rhograd %g sigw %g dsigwdz %g tlw %g ol %g -> ath %g bth %g flag %d\n",
+                       wp, zt, t.wst, t.h, rhoa, rhograd, t.sigw, t.dsigwdz, t.tlw, t.ol, ath, bth, flagrein);
+#endif
               wp = (wp + ath * dtf + bth * normal(a, nrand) * m_sqrt(dtf)) * (float)icbt;
               delz = wp * dtf;
               if (flagrein == 1) {
@@ -360,6 +365,11 @@ struct PblTask {
       }
       r_w = r_w_next;
       if (turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
+#ifdef FPB_DEBUG_NAN
+      if (isnan(delz) || isnan(up) || isnan(vp))
+        printf("substep nan: i %d wp %g up %g vp %g delz %g zt %g dt %g dtf %g tlw %g tlu %g sigu %g sigw %g dsigwdz %g h %g ol %g wst %g ust %g rhoa %g rhograd %g nrand %d\n",
+               i, wp, up, vp, delz, zt, dt, dtf, t.tlw, t.tlu, t.sigu, t.sigw, t.dsigwdz, t.h, t.ol, t.wst, t.ust, rhoa, rhograd, nrand);
+#endif
 
       if (fabsf(delz) > t.h) delz = rare_fmodf(delz, t.h); // almost never taken: keep fmodf's body out of line
       if (delz < -zt) {               // reflection at the ground

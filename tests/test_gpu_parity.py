@@ -319,7 +319,7 @@ def test_cuda_against_the_references_own_code(ctl):
 # math (tolerance), oracle state re-injected every step
 # ----------------------------------------------------------------------------
 def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=True, exact=True,
-              dt=None, tol_h=1e-5, nest_mets=None):
+              dt=None, tol_h=1e-5, nest_mets=None, tol_z=1e-5):
     c = cb.cfg
     n = p.numpart
     dt = dt or c.lsynctime
@@ -333,7 +333,7 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
         e.set_met_bracket((1, 2), bracket)
     ora.push_particles(p)
     tot = dict(n_active=0, n_pbl=0, n_petterssen=0, n_terminated=0, n_substeps=0, n_nan_cbl=0)
-    worst = 0.0
+    worst = worst_z = 0.0
     for k in range(nsteps):
         itime = t0 + k * dt
         po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
@@ -355,7 +355,15 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
         else:
             assert np.array_equal(pg.itra1[:n], po.itra1[:n]), k
             live = po.itra1[:n] != fb.ITRA_DEAD
-            dh, dz = pos_rel(pg, po, n, c)
+            for f in ("xtra1", "ytra1", "ztra1"):   # (max() below would swallow a NaN)
+                assert np.isfinite(getattr(pg, f)[:n]).all(), (k, f)
+            # vertical: relative to max(|z|, 1 m); a reflection or an extra sub-step decided the
+            # other way moves single particles, so bound percentiles: 99 % inside the 1e-5
+            # per-step tolerance, 99.9 % inside 10x that
+            dzr = np.abs(pg.ztra1[:n].astype(np.float64) - po.ztra1[:n]) / np.maximum(np.abs(po.ztra1[:n]), 1.0)
+            if live.any():
+                worst_z = max(worst_z, float(np.quantile(dzr[live], 0.99)),
+                              0.1 * float(np.quantile(dzr[live], 0.999)))
             # horizontal separation as a distance (longitude differences shrink
             # with cos(lat): next to a pole a metre is many grid units of x)
             coslat = np.cos(np.deg2rad(po.ytra1[:n] * c.dy + c.ylat0))
@@ -370,6 +378,7 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
             assert abs(pg.xmass1[:n].sum() - po.xmass1[:n].sum()) < 1e-5 * po.xmass1[:n].sum(), k
     if not exact:
         assert worst < tol_h, worst
+        assert worst_z < tol_z, worst_z
     gg, go = eng.fetch_grids(), ora.fetch_grids()
     if check_grids:
         for name in go:
@@ -550,6 +559,26 @@ def test_cbl_skewed_turbulence(exact):
                             math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
     assert cb.cfg.ifine == 11 and cb.cfg.turbswitch == 1
     p = cases.seeded_particles(cb, 1024, zmax=1200.0, lat_range=(-50.0, 50.0))
+    tot, _, _ = _per_step(cb, p, 3, exact=exact, tol_h=5e-5)
+    assert tot["n_pbl"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_cbl_drift_branch_strongly_unstable(exact):
+    """-h/L > 5 columns take the bi-Gaussian drift/diffusion of cbl.f90 itself
+    (src/advance.f90:417-435); its x**2 of a negative velocity difference must not
+    go through the fast exp2/log2 pow (regression: NaN positions in fast math)."""
+    cb = fb.make_config(nx=73, ny=37, nz=138, dx=5., dy=5., xlon0=-180.0, ylat0=-90.0, ifine=4, ctl=10.0,
+                        cblflag=1, outlon0=-180.0, outlat0=-90.0, numxgrid=72, numygrid=36, dxout=5.,
+                        dyout=5., lage=(86400 * 20,), ioutputforeachrelease=0, npart=(20,) * 100,
+                        maxpart=2000, math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    rel = cases.releases_boxes(cb, seed=100, zmax=2000.0, lat_range=(-60.0, 60.0), width=10.0)
+    p = fb.Particles(cb.cfg.maxpart, 1)
+    fb.release_particles(cb, rel, fb.ReleaseState(cb.cfg.numpoint), 0, p)
+    m0 = cases.met_pair(cb)[0]
+    ix, jy = p.xtra1[:p.numpart].astype(int), p.ytra1[:p.numpart].astype(int)
+    unstable = (-m0.hmix * m0.oli)[ix, jy] > 5.0
+    assert unstable.sum() > 200     # the branch is exercised
     tot, _, _ = _per_step(cb, p, 3, exact=exact, tol_h=5e-5)
     assert tot["n_pbl"] > 0
 
