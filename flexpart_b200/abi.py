@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 MAXSPEC, MAXAGECLASS, MAXZGRID, MAXRECEPTOR, MAXNESTS = 8, 8, 64, 20, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 ITRA_DEAD = -999999999
 RNG_REFERENCE, RNG_PHILOX_INDEX, RNG_PHILOX = 0, 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
@@ -79,7 +79,7 @@ class FpbParticlePtrs(C.Structure):
 
 class FpbStepStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_active", "n_init", "n_terminated", "n_pbl",
-                                         "n_substeps", "n_petterssen", "n_nan_cbl")]
+                                         "n_substeps", "n_petterssen", "n_nan_cbl", "n_nonfinite")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

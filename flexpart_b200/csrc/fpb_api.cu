@@ -870,6 +870,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
     stats->n_active = (int64_t)hs[0]; stats->n_init = (int64_t)hs[1]; stats->n_terminated = (int64_t)hs[2];
     stats->n_pbl = (int64_t)hs[3]; stats->n_substeps = (int64_t)hs[4]; stats->n_petterssen = (int64_t)hs[5];
     stats->n_nan_cbl = (int64_t)hs[6];
+    stats->n_nonfinite = (int64_t)hs[7];
   } else {
     CK(cudaStreamSynchronize(h->stream));
   }
@@ -1036,6 +1037,16 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     tev.push_back(e);
   };
   mark(h->stream);
+  // FPB_HOST_DEBUG=1: synchronise after every stage so that a device fault is attributed to it
+  const bool dbg = getenv("FPB_HOST_DEBUG") != nullptr;
+#define STAGE(name)                                                                              \
+  do {                                                                                           \
+    if (dbg) {                                                                                   \
+      cudaError_t e_ = cudaStreamSynchronize(L.st);                                              \
+      if (e_ != cudaSuccess) return fail("fpb_step_host: %s in stage %s of chunk %d (rows %d+%d)", \
+                                         cudaGetErrorString(e_), name, ci, c0, n);               \
+    }                                                                                            \
+  } while (0)
   int per = 0; // largest chunk: size of the lanes' sort work areas
   for (size_t k = 0; k + 1 < bounds.size(); k++) per = std::max(per, bounds[k + 1] - bounds[k]);
 
@@ -1048,6 +1059,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     mark(L.st);
     if (copy_rows_h2d(h, h->p_alt, c0, n, p, L.st)) return 1;
     mark(L.st);
+    STAGE("h2d");
     const DevParticles stg = rows_view(h->p_alt, c0), rows = rows_view(h->p, c0);
 
     DevStepArgs a;
@@ -1059,6 +1071,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     if (scatter_sort_pairs(L.sw, (size_t)n, bits, L.st, &h->launches, &cur)) return fail("%s", scatter_error());
     sortk_permute(stg, rows, L.sw.ids[cur], n, c.nspec, L.st, h->row_of_slot, c0);
     h->launches += 2;
+    STAGE("sort");
 
     if (conc_weight > 0.f) {
       DevConcArgs q;
@@ -1076,9 +1089,10 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
       }
     }
 
+    STAGE("conccalc");
     a.met[0] = met[0]; a.met[1] = met[1];
     a.met_lit1 = slot_view(h, 1);
-  nest_views(h, a);
+    nest_views(h, a);
     a.p = rows;
     a.height = h->d_height;
     a.rannumb = h->d_rannumb;
@@ -1091,12 +1105,15 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     a.stats = h->d_stats;
     a.work_counter = L.d_work;
     a.sc = scratch_view(h->sc, c0);
-    if (strict) { fpbk_init_strict(a, L.st); fpbk_step_strict(a, L.st); }
-    else { fpbk_init_fast(a, L.st); fpbk_step_fast(a, L.st); }
+    if (strict) fpbk_init_strict(a, L.st); else fpbk_init_fast(a, L.st);
+    STAGE("initialize");
+    if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
     h->launches += 3;
+    STAGE("step");
 
     sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st);
     h->launches++;
+    STAGE("scatter_back");
     mark(L.st);
     D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
     D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
@@ -1110,6 +1127,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     mark(L.st);
     CK(cudaGetLastError());
   }
+#undef STAGE
   for (auto &L : h->lanes) CK(cudaStreamSynchronize(L.st));
   if (timing) {
     for (size_t k = 1; k + 3 < tev.size() + 1; k += 4) {
@@ -1134,6 +1152,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     stats->n_active = (int64_t)hs[0]; stats->n_init = (int64_t)hs[1]; stats->n_terminated = (int64_t)hs[2];
     stats->n_pbl = (int64_t)hs[3]; stats->n_substeps = (int64_t)hs[4]; stats->n_petterssen = (int64_t)hs[5];
     stats->n_nan_cbl = (int64_t)hs[6];
+    stats->n_nonfinite = (int64_t)hs[7];
   }
   // the device rows stay valid (sorted inside each chunk) for resident-mode calls
   h->numpart = numpart;

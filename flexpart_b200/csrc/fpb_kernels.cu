@@ -880,6 +880,10 @@ __device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, i
                                     rng.get(nrand + 3), s.zt, t.wst, t.h, t.sigw, t.ol);
       else
         s.wp = s.wp * t.sigw;
+#ifdef FPB_DEBUG_NAN
+      if (isnan(s.wp))
+        printf("init nan: zt %g wst %g h %g sigw %g ol %g nrand %d r %g\n", s.zt, t.wst, t.h, t.sigw, t.ol, nrand, rng.get(nrand + 3));
+#endif
     }
     if (c.turbswitch) {
       float q = fminf(t.tlw, t.h / fmaxf(2.f * fabsf(s.wp * t.sigw), 1.e-5f));

@@ -366,7 +366,7 @@ struct PblTask {
       r_w = r_w_next;
       if (turboff) { up = 0.f; vp = 0.f; wp = 0.f; delz = 0.f; }
 #ifdef FPB_DEBUG_NAN
-      if (isnan(delz) || isnan(up) || isnan(vp))
+      if ((isnan(delz) || isnan(up) || isnan(vp)) && !isnan(zt) && !isnan(t.sigw))
         printf("substep nan: i %d wp %g up %g vp %g delz %g zt %g dt %g dtf %g tlw %g tlu %g sigu %g sigw %g dsigwdz %g h %g ol %g wst %g ust %g rhoa %g rhograd %g nrand %d\n",
                i, wp, up, vp, delz, zt, dt, dtf, t.tlw, t.tlu, t.sigu, t.sigw, t.dsigwdz, t.h, t.ol, t.wst, t.ust, rhoa, rhograd, nrand);
 #endif
@@ -687,6 +687,14 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     } else if (zt >= ztop) {
       zt = ztop - 100.f * eps;
     }
+  }
+
+  // A position that is not finite (the CBL closure is singular where its transition factor
+  // vanishes, src/initialize_cbl_vel.f90:50-63: the reference carries the NaN on) would index
+  // outside every grid downstream: the particle is terminated and counted instead.
+  if (!(isfinite(xt) && isfinite(yt) && isfinite(zt))) {
+    nstop = 4;
+    if (a.stats) atomicAdd(a.stats + 7, 1ull);
   }
 
   // ---- rest of the timemanager loop body, src/timemanager.f90:630-707

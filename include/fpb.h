@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPB_ABI_VERSION 2
+#define FPB_ABI_VERSION 3
 #define FPB_MAXSPEC 8      /* >= par_mod maxspec (5), src/par_mod.f90:210 */
 #define FPB_MAXAGECLASS 8  /* >= par_mod maxageclass */
 #define FPB_MAXZGRID 64    /* output-grid levels */
@@ -201,6 +201,8 @@ typedef struct fpb_step_stats {
   int64_t n_substeps;   /* label-100 loop iterations, summed */
   int64_t n_petterssen; /* Petterssen corrector applied */
   int64_t n_nan_cbl;    /* nan_count + nan_count2, src/advance.f90:421,439 */
+  int64_t n_nonfinite;  /* of n_terminated: position not finite after advance (the reference
+                           carries such a particle on and indexes out of bounds with it) */
 } fpb_step_stats;
 
 typedef struct fpb_handle fpb_handle;

@@ -316,6 +316,12 @@ void fpo_step(fpo_state *S, int itime, int ldeltat, fpb_step_stats *stats) {
                 &S->xtra1[j], &S->ytra1[j], &S->ztra1[j], prob, &S->cbt[j]);
     if (S->trace_nsub) S->trace_nsub[j] = (int32_t)(S->last.n_substeps - nsub0);
 
+    /* not in the reference (it carries a NaN particle on and indexes out of bounds with it):
+     * a position that is not finite terminates the particle, counted in n_nonfinite */
+    if (!(isfinite(S->xtra1[j]) && isfinite(S->ytra1[j]) && isfinite(S->ztra1[j]))) {
+      nstop = 4;
+      S->last.n_nonfinite++;
+    }
     if (nstop > 1) {
       S->itra1[j] = FPB_ITRA_DEAD;
       S->last.n_terminated++;

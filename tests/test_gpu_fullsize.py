@@ -122,3 +122,46 @@ def test_bookkeeping_integers(met):
         assert (q.idt[:N][q.itra1[:N] != fb.abi.ITRA_DEAD] >= 1).all()
         active = alive
     eng.close()
+
+
+def test_c3_features_at_full_size_stay_finite(met):
+    """configs[2]-like run at 1 M particles: CBL turbulence, two species with dry deposition, wet
+    deposition, nested output grid.  The CBL closure is singular in columns with -h/L just above 5
+    (src/initialize_cbl_vel.f90:50-63 gives NaN there, about one particle in a million): such a
+    particle is terminated and counted, every other one stays finite and inside the domain through
+    resident steps, wet deposition and a chunked host-buffer step."""
+    cb = c2_config(ctl=10.0, cblflag=1, nspec=2, drydepspec=(1, 1), wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0),
+                   wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0), nest=(-30.0, 20.0, 240, 160, 0.125, 0.125))
+    c = cb.cfg
+    eng = engine(cb, met)
+    p = released(cb)
+    eng.push_particles(p)
+    q = fb.Particles(c.maxpart, c.nspec); q.numpart = N
+    dead = nonfinite = 0
+    for k in range(4):
+        itime = k * 900
+        if itime:
+            eng.wetdepo(itime, 900, 450)
+        if k < 3:
+            eng.conccalc(itime, 1.0)
+            st = eng.step(itime, 0)
+            eng.pull_particles(q)
+        else:
+            st = eng.step_host(q, itime, 0, conc_weight=1.0)
+        dead += st["n_terminated"]; nonfinite += st["n_nonfinite"]
+        live = q.itra1[:N] != fb.ITRA_DEAD
+        assert int((~live).sum()) == dead
+        assert st["n_active"] == N - (dead - st["n_terminated"])
+        x, y, z = q.xtra1[:N][live], q.ytra1[:N][live], q.ztra1[:N][live]
+        assert np.isfinite(x).all() and np.isfinite(y).all() and np.isfinite(z).all()
+        assert x.min() >= 0 and x.max() <= c.nx - 1 and y.min() >= 0 and y.max() <= c.ny - 1
+        assert z.min() >= 0 and z.max() <= cb.height[c.nz - 1]
+        assert np.isfinite(q.xmass1[:N]).all()
+    assert dead == nonfinite and nonfinite < 50
+    g = eng.fetch_grids()
+    for name in ("gridunc", "griduncn", "drygridunc"):
+        assert np.isfinite(g[name]).all() and g[name].sum() > 0, name
+    w = eng.fetch_wetgrids()
+    for name in ("wetgridunc", "wetgriduncn"):
+        assert np.isfinite(w[name]).all(), name
+    assert w["wetgridunc"].sum() > 0        # (the synthetic rain bands may miss the small nest)

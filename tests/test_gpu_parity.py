@@ -563,6 +563,46 @@ def test_cbl_skewed_turbulence(exact):
     assert tot["n_pbl"] > 0
 
 
+def test_cbl_singular_closure_terminates_the_particle():
+    """-h/L just above 5: the transition factor is exactly 0, the skewness 0 and the closure of
+    initialize_cbl_vel 0/0 (src/initialize_cbl_vel.f90:50-63).  The reference carries the NaN
+    velocity on; here (and in the oracle) the particle is terminated and counted in n_nonfinite
+    instead of indexing out of bounds downstream."""
+    cb = cases.config_small(nrel=2, npart_each=256, cblflag=1, ctl=5.0, ifine=4, math_mode=fb.MATH_STRICT)
+    p = cases.seeded_particles(cb, 512, zmax=900.0, lat_range=(-50.0, 50.0))
+    mets = []
+    for t in (0, 10800):
+        m = fb.MetFields(cb).synth(t)
+        m.hmix[:] = 1000.0; m.oli[:] = -1.0 / 199.99; m.wstar[:] = 0.05; m.ustar[:] = 0.4
+        mets.append(m)
+    got = []
+    for e in (fb.Engine(cb), Oracle(cb)):
+        e.fill_rannumb()
+        e.upload_met(1, mets[0]); e.upload_met(2, mets[1]); e.set_met_bracket((1, 2), (0, 10800))
+        e.push_particles(p)
+        st = e.step(0, 450)
+        st.pop("n_substeps")      # (how long a NaN particle keeps sub-stepping is not defined)
+        q = fb.Particles(cb.cfg.maxpart, 1); q.numpart = 512
+        e.pull_particles(q)
+        got.append((st, q.itra1[:512].copy()))
+    assert got[0][0] == got[1][0] and got[0][0]["n_terminated"] == got[0][0]["n_nonfinite"] == 512
+    assert (got[0][1] == fb.ITRA_DEAD).all() and (got[1][1] == fb.ITRA_DEAD).all()
+    # fast math may or may not hit the exact zero; it must neither fault nor keep a NaN particle
+    cbf = cases.config_small(nrel=2, npart_each=256, cblflag=1, ctl=5.0, ifine=4, math_mode=fb.MATH_FAST)
+    eng = fb.Engine(cbf); eng.fill_rannumb()
+    eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1]); eng.set_met_bracket((1, 2), (0, 10800))
+    eng.push_particles(p)
+    eng.conccalc(0, 1.0)
+    st = eng.step(0, 450)
+    q = fb.Particles(cbf.cfg.maxpart, 1); q.numpart = 512
+    eng.pull_particles(q)
+    live = q.itra1[:512] != fb.ITRA_DEAD
+    assert st["n_terminated"] == st["n_nonfinite"] == int((~live).sum())
+    assert np.isfinite(q.ztra1[:512][live]).all() and np.isfinite(q.xtra1[:512][live]).all()
+    eng.conccalc(900, 1.0)
+    eng.step(900, 450)
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_cbl_drift_branch_strongly_unstable(exact):
     """-h/L > 5 columns take the bi-Gaussian drift/diffusion of cbl.f90 itself
