@@ -117,7 +117,9 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
                         maxpart=each * nrel, device=device, rng_mode=fb.RNG_PHILOX_INDEX,
                         math_mode=fb.MATH_FAST, scatter_mode=fb.SCATTER_ATOMIC,
                         part_id_stride=world, part_id_offset=rank, sort_interval=args.sort_interval, **kw)
-    rel = cases.releases_boxes(cb, seed=100 + rank, zmax=zmax, lat_range=lat, width=10.0)
+    # every rank releases its share of the same 100 boxes (round-robin partition of one global
+    # problem, src/releaseparticles_mpi.f90:141-152); the ranks differ by their ran1 seed offset
+    rel = cases.releases_boxes(cb, seed=100, zmax=zmax, lat_range=lat, width=10.0)
     return cb, rel
 
 
@@ -139,10 +141,10 @@ def workload_config(args, n, world):
     }
 
 
-def host_particles(cb, rel, pinned):
+def host_particles(cb, rel, pinned, mp_pid=0):
     import flexpart_b200 as fb
     parts = fb.Particles(cb.cfg.maxpart, cb.cfg.nspec, pinned=pinned)
-    st = fb.ReleaseState(cb.cfg.numpoint)
+    st = fb.ReleaseState(cb.cfg.numpoint, mp_pid=mp_pid)
     fb.release_particles(cb, rel, st, 0, parts)
     return parts
 
@@ -174,7 +176,7 @@ def run_ours(args):
     eng.upload_met(1, m0)
     eng.upload_met(2, m1)
     eng.set_met_bracket((1, 2), (0, span))
-    parts = host_particles(cb, rel, pinned=True)
+    parts = host_particles(cb, rel, pinned=True, mp_pid=rank)
     n = parts.numpart
     eng.push_particles(parts)
     ext = torch.cuda.ExternalStream(eng.stream, device=local)
@@ -185,10 +187,27 @@ def run_ours(args):
         __cuda_array_interface__ = {"shape": (gn,), "typestr": "<f4", "data": (gptr, False), "version": 2}
     grid_t = torch.as_tensor(_Holder(), device=f"cuda:{local}") if world > 1 else None
 
+    # Grid exchange off the critical path: the interval's grid is copied to a staging buffer on the
+    # engine's stream (10 MB device-to-device), zeroed, and the NCCL reduce of the staging buffer
+    # runs from a side stream while the next interval's steps compute.  Rank 0 reads the summed
+    # grid from the staging buffer (concoutput's input).
+    stage = torch.empty_like(grid_t) if world > 1 else None
+    side = torch.cuda.Stream(device=local) if world > 1 else None
+    pending = [None]
+
+    def exchange_wait():
+        if pending[0] is not None:
+            pending[0].wait()          # the current (engine) stream waits; the host does not
+            pending[0] = None
+
     def exchange():
         # the mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579): sum to rank 0, then zero
         if world > 1:
-            dist.reduce(grid_t, dst=0, op=dist.ReduceOp.SUM)
+            exchange_wait()            # the staging buffer is free again
+            stage.copy_(grid_t)
+            side.wait_stream(ext)
+            with torch.cuda.stream(side):
+                pending[0] = dist.reduce(stage, dst=0, op=dist.ReduceOp.SUM, async_op=True)
         eng.zero_conc_grids()
 
     def one_step(k, stats):
@@ -225,6 +244,7 @@ def run_ours(args):
             psteps += st["n_active"]; nsub += st["n_substeps"]; npbl += st["n_pbl"]
             a, b = eng.kernel_times()
             t_step_k += a; t_conc_k += b
+        exchange_wait()                # the last reduce is inside the timed region
         ev1.record(ext)
         torch.cuda.synchronize()
         if world > 1:
@@ -255,10 +275,13 @@ def run_ours(args):
                 exchange()
             k += 1
             e_steps += st["n_active"]
+        exchange_wait()
         torch.cuda.synchronize()
         t_e = time.perf_counter() - t_e0
         clocks = sampler.stop()
 
+    log(f"[rank {rank}] {ms / K:.3f} ms/step device-resident (step kernels {t_step_k / K:.3f}, conccalc {t_conc_k / K:.3f}), "
+        f"{t_e * 1e3 / KE:.3f} ms/step end to end")
     tm = torch.tensor([ms, t_e * 1e3], device=f"cuda:{local}", dtype=torch.float64)
     cnt = torch.tensor([psteps, e_steps, nsub, npbl, launches], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:

@@ -202,6 +202,8 @@ def load_host_lib():
     L.fpbh_release_state_new.argtypes = [_i]
     L.fpbh_release_state_new.restype = C.c_void_p
     L.fpbh_release_state_free.argtypes = [C.c_void_p]
+    L.fpbh_release_state_set_rank.argtypes = [C.c_void_p, _i]
+    L.fpbh_release_state_set_rank.restype = None
     L.fpbh_releaseparticles.argtypes = [C.POINTER(FpbConfig), _pf, C.POINTER(FpbhReleases),
                                         C.c_void_p, _i, _ppart, _pi, _pi, _pi]
     L.fpbh_timemanager.argtypes = [C.POINTER(FpbConfig), _pf, C.POINTER(FpbhReleases),

@@ -252,9 +252,11 @@ class Releases:
 
 
 class ReleaseState:
-    def __init__(self, numpoint):
+    def __init__(self, numpoint, mp_pid=0):
+        """mp_pid > 0: the rank's ran1 seed offset of the MPI build (src/mpi_mod.f90:331-335)."""
         self._L = load_host_lib()
         self.h = self._L.fpbh_release_state_new(numpoint)
+        self._L.fpbh_release_state_set_rank(self.h, mp_pid)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -46,6 +46,13 @@ extern "C" fpbh_release_state *fpbh_release_state_new(int32_t numpoint) {
   return s;
 }
 extern "C" void fpbh_release_state_free(fpbh_release_state *s) { delete s; }
+extern "C" void fpbh_release_state_set_rank(fpbh_release_state *s, int32_t mp_pid) {
+  if (!s || mp_pid <= 0) return;
+  const long long v = (244LL * 181LL) * ((long long)(mp_pid - 83) * 359LL); // Fortran mod: sign of the dividend
+  long long m = v % 104729LL;
+  if (m < 0) m = -m;
+  s->idum = s->idum + (int)(-m);
+}
 
 extern "C" int fpbh_releaseparticles(const fpb_config *cp, const float *height,
                                      const fpbh_releases *rel, fpbh_release_state *st, int32_t itime,

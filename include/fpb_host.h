@@ -88,6 +88,9 @@ typedef struct fpbh_releases {
 typedef struct fpbh_release_state fpbh_release_state;
 fpbh_release_state *fpbh_release_state_new(int32_t numpoint);
 void fpbh_release_state_free(fpbh_release_state *s);
+/* MPI build: rank mp_pid > 0 offsets the SAVEd idummy of releaseparticles by mp_seed
+ * (src/mpi_mod.f90:331-335, src/releaseparticles_mpi.f90:56-65).  Call before the first release. */
+void fpbh_release_state_set_rank(fpbh_release_state *s, int32_t mp_pid);
 
 /* releaseparticles(itime), src/releaseparticles.f90:69-378 (zkind 1,
  * EMISVAR factors 1).  Works on the host mirror `p` (itra1 must be current).
