@@ -172,6 +172,12 @@ __device__ __forceinline__ void make_weights(const DevCfg &c, Hz &z, int itime_e
   make_weights(c, z, itime_eff, xt, yt, ix, jy, ixp, jyp, c.nxd, c.nyd);
 }
 
+// warp-uniform test in front of the polar (uupol/vvpol) loads: ptxas predicates them otherwise
+// and every lane pays for loads only particles poleward of +-75 deg need
+__device__ __forceinline__ bool warp_any_polar(const Hz &z) {
+  return __any_sync(__activemask(), z.ngrid < 0);
+}
+
 __device__ __forceinline__ float bil(const Hz &z, float a, float b, float c, float d) {
   return z.p1 * a + z.p2 * b + z.p3 * c + z.p4 * d;
 }
@@ -188,6 +194,13 @@ __device__ __forceinline__ int find_indz(const float *sh, int nz, float zt) {
   return lo - 1;
 }
 
+// same index, starting from a hint (the level of the previous search of this particle):
+// one test when the particle is still between the same two levels
+__device__ __forceinline__ int find_indz_near(const float *sh, int nz, float zt, int hint) {
+  if (hint >= 1 && hint < nz && sh[hint] > zt && (hint == 1 || sh[hint - 1] <= zt)) return hint;
+  return find_indz(sh, nz, zt);
+}
+
 // one profile level: src/interpol_all.f90:135-238 == src/interpol_misslev.f90:56-157.
 // SIGMA=false leaves usigprof/vsigprof/wsigprof out (fpb_pbl_kernel: they are
 // only read once, after the sub-step loop, and fpb_finish_kernel recomputes
@@ -196,6 +209,7 @@ template <bool SIGMA>
 __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot *met,
                                               const Hz &z, int n, Lev &L) {
   const int base = (n - 1) * z.plane;
+  const bool polar_any = true; // (a vote inside the sub-step kernel's divergent gather loop costs 3 %)
   float y1[2], y2[2], y3[2], r1[2], g1[2];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #ifdef FPB_LEVEL_SLOT_LOOP
@@ -209,7 +223,7 @@ __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot 
     float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
     const float ga = __ldg(G + z.o00), gb = __ldg(G + z.o10), gc = __ldg(G + z.o01), gd = __ldg(G + z.o11);
     float ua, ub, uc, ud, va, vb, vc, vd;
-    if (z.ngrid < 0) {
+    if (polar_any && z.ngrid < 0) {
       const float2 *P = met[m].P + base;
       const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
       ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
@@ -252,13 +266,14 @@ __device__ __forceinline__ void profile_level(const DevCfg &c, const DevMetSlot 
 __device__ __forceinline__ void profile_sigma(const DevCfg &c, const DevMetSlot *met, const Hz &z,
                                               int n, float &usig, float &vsig, float &wsig) {
   const int base = (n - 1) * z.plane;
+  const bool polar_any = warp_any_polar(z);
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #pragma unroll
   for (int m = 0; m < 2; m++) {
     const float4 *A = met[m].A + base;
     float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
     float ua, ub, uc, ud, va, vb, vc, vd;
-    if (z.ngrid < 0) {
+    if (polar_any && z.ngrid < 0) {
       const float2 *P = met[m].P + base;
       const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
       ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
@@ -287,12 +302,14 @@ template <bool SIGMA>
 __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *met,
                                             const Hz &z, const float *sh, float zt,
                                             float &u, float &v, float &w, float &usig,
-                                            float &vsig, float &wsig) {
-  const int indz = find_indz(sh, c.nz, zt);
+                                            float &vsig, float &wsig, int &indz_io) {
+  // indz_io: in, a hint (0 = none); out, the level found
+  const int indz = indz_io = find_indz_near(sh, c.nz, zt, indz_io);
   const float dz = 1.f / (sh[indz] - sh[indz - 1]);
   const float dz1 = (zt - sh[indz - 1]) * dz;
   const float dz2 = (sh[indz] - zt) * dz;
   const int plane = z.plane;
+  const bool polar_any = warp_any_polar(z);
   float uh[2], vh[2], wh[2];
   float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
 #pragma unroll
@@ -304,7 +321,7 @@ __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *m
       const float4 *A = met[m].A + base;
       float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
       float ua, ub, uc, ud, va, vb, vc, vd;
-      if (z.ngrid < 0) {
+      if (polar_any && z.ngrid < 0) {
         const float2 *P = met[m].P + base;
         const float2 Pa = __ldg(P + z.o00), Pb = __ldg(P + z.o10), Pc = __ldg(P + z.o01), Pd = __ldg(P + z.o11);
         ua = Pa.x; ub = Pb.x; uc = Pc.x; ud = Pd.x;
@@ -631,7 +648,13 @@ __device__ __noinline__ float cgszll(const float *sc, float xlat) {
 __device__ __forceinline__ void move_horizontal(const DevCfg &c, int ngrid, double &xt,
                                                 double &yt, float dxm, float dym, float tfac) {
   if (ngrid >= 0) {
+#if FPB_STRICT
     float cosfact = (float)(c.dxconst / cos((yt * c.dy + c.ylat0) * PI180));
+#else
+    // fast: latitude formed in double, cosine in float (|lat| < 75 deg here: relative error < 5e-7
+    // of one step's displacement)
+    float cosfact = c.dxconst / cosf((float)((yt * c.dy + c.ylat0) * PI180));
+#endif
     xt = xt + (double)(dxm * cosfact * tfac);
     yt = yt + (double)(dym * c.dyconst * tfac);
   } else {
@@ -901,7 +924,8 @@ __device__ void do_initialize(const DevStepArgs &a, const float *sh, Rng &rng, i
     wsig = (hi.wsig + lo.wsig) / 2.f;
   } else {
     float u, v, w;
-    interp_wind<true>(c, a.met, z, sh, s.zt, u, v, w, usig, vsig, wsig);
+    int indz = 0;
+    interp_wind<true>(c, a.met, z, sh, s.zt, u, v, w, usig, vsig, wsig, indz);
     s.ldt = abs(c.lsynctime);
     if (nrand + 1 > c.maxrand) nrand = 1;
     s.up = rng.get(nrand) * 0.3f;

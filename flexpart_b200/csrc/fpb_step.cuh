@@ -603,7 +603,8 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
   }
 
   if (flags & SC_ABOVE) { // label 700, advance.f90:629-708
-    interp_wind<true>(c, met, z, sh, zt, u, v, w, usig, vsig, wsig);
+    indz_last = 0;
+    interp_wind<true>(c, met, z, sh, zt, u, v, w, usig, vsig, wsig, indz_last);
     ldt = abs(c.lsynctime - itimec + itime);
     const float dt = (float)ldt;
     if (zt < tropop) {
@@ -680,7 +681,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
     const float uold = u, vold = v, wold = w;
     make_weights(c, z, itime + ldt * c.ldirect, g.xf, g.yf, g.ix, g.jy, g.ix + 1, jyp, g.nxd, g.nyd);
     float d0, d1, d2;
-    interp_wind<false>(c, met, z, sh, zt, u, v, w, d0, d1, d2);
+    interp_wind<false>(c, met, z, sh, zt, u, v, w, d0, d1, d2, indz_last); // hint: the level before the move
     n_pett++;
     if (!SIMPLE) w = w + settling_term(a, sh, npoint, (float)xt, (float)yt, zt);
     u = (u - uold) / 2.f;
