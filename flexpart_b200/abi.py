@@ -91,6 +91,10 @@ class FpbhReleases(C.Structure):
                 ("zpoint1", _pf), ("zpoint2", _pf), ("itsplit", _i)]
 
 
+class FpbReleasePoints(C.Structure):
+    _fields_ = FpbhReleases._fields_ + [("mp_pid", _i)]
+
+
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
@@ -113,6 +117,8 @@ CONC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _f)
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _pf, _pf, _pf, _pf, _pf, _i)
 SCALE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _pf)
 WETDEPO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _i)
+SET_RELEASES_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+RELEASE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _pi, _pi)
 OUTPUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _f, _pf, _pf, _pf, _pf, _pf)
 
 
@@ -121,7 +127,7 @@ class FpbhEngine(C.Structure):
                 ("set_met_bracket", SET_BRACKET_FN), ("push_particles", PUSH_FN),
                 ("pull_particles", PUSH_FN), ("set_numpart", SET_NUMPART_FN), ("step", STEP_FN),
                 ("conccalc", CONC_FN), ("fetch_grids", FETCH_FN), ("scale_depgrids", SCALE_FN),
-                ("wetdepo", WETDEPO_FN)]
+                ("wetdepo", WETDEPO_FN), ("set_releases", SET_RELEASES_FN), ("releaseparticles", RELEASE_FN)]
 
 
 # FPB_ENGINE_LIB: load another build of the same library (kernel A/B experiments)
@@ -156,6 +162,8 @@ def load_engine_lib():
     L.fpb_set_numpart.argtypes = [H, _i]
     L.fpb_step.argtypes = [H, _i, _i, C.POINTER(FpbStepStats)]
     L.fpb_wetdepo.argtypes = [H, _i, _i, _i]
+    L.fpb_set_releases.argtypes = [H, C.POINTER(FpbReleasePoints)]
+    L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
                                 C.POINTER(FpbStepStats)]

@@ -137,6 +137,43 @@ struct fpb_handle {
   int steps_since_sort = 1 << 30;
   unsigned *d_nlive = nullptr;
   int *d_work = nullptr;
+  // device-side releaseparticles
+  struct Releases {
+    int numpoint = 0, itsplit = 0;
+    std::vector<int32_t> start, end;
+    std::vector<float> xmasssave;
+    float *d_pts[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // x1 y1 x2 y2 z1 z2
+    int32_t *d_offsets = nullptr;
+    float *d_uniforms = nullptr;
+    size_t uniforms_cap = 0;
+    unsigned *d_block_counts = nullptr;
+    int *d_out = nullptr;
+    // ran1 of releaseparticles (SAVEd idummy = -7, src/releaseparticles.f90:56)
+    int idum = -7, iv[32] = {0}, iy = 0;
+    float ran1() { // src/random_mod.f90:40-68 (Numerical Recipes ran1)
+      const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836, NTAB = 32;
+      const int NDIV = 1 + (IM - 1) / NTAB;
+      const float AM = 1.f / (float)IM, RNMX = 1.f - 1.2e-7f;
+      if (idum <= 0 || iy == 0) {
+        idum = (-idum > 1) ? -idum : 1;
+        for (int j = NTAB + 8; j >= 1; j--) {
+          const int k = idum / IQ;
+          idum = IA * (idum - k * IQ) - IR * k;
+          if (idum < 0) idum += IM;
+          if (j <= NTAB) iv[j - 1] = idum;
+        }
+        iy = iv[0];
+      }
+      const int k = idum / IQ;
+      idum = IA * (idum - k * IQ) - IR * k;
+      if (idum < 0) idum += IM;
+      const int j = iy / NDIV;
+      iy = iv[j];
+      iv[j] = idum;
+      const float t = AM * (float)iy;
+      return t < RNMX ? t : RNMX;
+    }
+  } rel;
   DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
@@ -462,6 +499,8 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->row_of_slot); cudaFree(h->d_nlive); cudaFree(h->d_work);
   cudaFree(h->sc.flags); cudaFree(h->sc.s0); cudaFree(h->sc.s1); cudaFree(h->sc.s2); cudaFree(h->sc.prob);
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
+  for (auto &q : h->rel.d_pts) cudaFree(q);
+  cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
@@ -923,6 +962,114 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   h->timed_conc = true;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------ releases --
+extern "C" int fpb_set_releases(fpb_handle *h, const fpb_release_points *r) {
+  if (!h || !r) return fail("fpb_set_releases: null argument");
+  if (r->numpoint != h->cfg.numpoint)
+    return fail("fpb_set_releases: numpoint %d differs from the configuration's %d", r->numpoint, h->cfg.numpoint);
+  const float *src[6] = {r->xpoint1, r->ypoint1, r->xpoint2, r->ypoint2, r->zpoint1, r->zpoint2};
+  for (auto q : src) if (!q) return fail("fpb_set_releases: a coordinate array is null");
+  if (!r->ireleasestart || !r->ireleaseend) return fail("fpb_set_releases: release times are null");
+  CK(cudaSetDevice(h->device));
+  auto &R = h->rel;
+  const int n = r->numpoint;
+  for (int k = 0; k < 6; k++) {
+    if (!R.d_pts[k]) DA(R.d_pts[k], n);
+    CK(cudaMemcpy(R.d_pts[k], src[k], (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!R.d_offsets) DA(R.d_offsets, n + 1);
+  if (!R.d_block_counts) DA(R.d_block_counts, (size_t)(h->cfg.maxpart + 1023) / 1024);
+  if (!R.d_out) DA(R.d_out, 2);
+  R.numpoint = n;
+  R.itsplit = r->itsplit;
+  R.start.assign(r->ireleasestart, r->ireleasestart + n);
+  R.end.assign(r->ireleaseend, r->ireleaseend + n);
+  R.xmasssave.assign(n, 0.f);
+  R.idum = -7; R.iy = 0;
+  if (r->mp_pid > 0) { // src/mpi_mod.f90:331-335, src/releaseparticles_mpi.f90:65
+    long long m = ((244LL * 181LL) * ((long long)(r->mp_pid - 83) * 359LL)) % 104729LL;
+    if (m < 0) m = -m;
+    R.idum += (int)(-m);
+  }
+  return 0;
+}
+
+extern "C" int fpb_releaseparticles(fpb_handle *h, int32_t itime, int32_t *numpart, int32_t *n_released) {
+  if (!h) return fail("fpb_releaseparticles: null handle");
+  auto &R = h->rel;
+  if (R.numpoint == 0) return fail("fpb_releaseparticles: fpb_set_releases has not been called");
+  const fpb_config &c = h->cfg;
+  if (numpart) *numpart = h->numpart;
+  if (n_released) *n_released = 0;
+  // release counts of this call, src/releaseparticles.f90:89-123
+  std::vector<int32_t> offsets(R.numpoint + 1, 0);
+  for (int i = 0; i < R.numpoint; i++) {
+    const int t0 = R.start[i], t1 = R.end[i];
+    int numrel = 0;
+    if (itime >= t0 && itime <= t1) {
+      if (t0 != t1) {
+        float rfraction = std::fabs((float)h->npart[i] * (float)c.lsynctime / (float)(t1 - t0));
+        if (itime == t0 || itime == t1) rfraction = rfraction / 2.f;
+        rfraction = rfraction * 1.f; // average_timecorrect (no EMISVAR files)
+        rfraction = rfraction + R.xmasssave[i];
+        numrel = (int)rfraction;
+        R.xmasssave[i] = rfraction - (float)numrel;
+      } else {
+        numrel = h->npart[i];
+      }
+    }
+    offsets[i + 1] = offsets[i] + numrel;
+  }
+  const int m = offsets[R.numpoint];
+  if (m == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  DevReleaseArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.p = h->p;
+  a.row_of_slot = h->row_of_slot;
+  a.permuted = h->permuted ? 1 : 0;
+  a.numpart_old = h->numpart;
+  a.numpoint = R.numpoint; a.n_new = m; a.itsplit = R.itsplit;
+  a.ztop = h->height[c.nz - 1];
+  a.xpoint1 = R.d_pts[0]; a.ypoint1 = R.d_pts[1]; a.xpoint2 = R.d_pts[2]; a.ypoint2 = R.d_pts[3];
+  a.zpoint1 = R.d_pts[4]; a.zpoint2 = R.d_pts[5];
+  a.offsets = R.d_offsets;
+  a.uniforms = nullptr;
+  a.xmass = h->d_xmass; a.npart = h->d_npart;
+  a.block_counts = R.d_block_counts;
+  a.out = R.d_out;
+  CK(cudaMemcpyAsync(R.d_offsets, offsets.data(), offsets.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  std::vector<float> u;
+  if (c.rng_mode == FPB_RNG_REFERENCE) { // the reference's ran1 stream: x, y, nclass, z per particle
+    u.resize((size_t)4 * m);
+    for (auto &v : u) v = R.ran1();
+    if (R.uniforms_cap < u.size()) {
+      cudaFree(R.d_uniforms); R.d_uniforms = nullptr;
+      DA(R.d_uniforms, u.size());
+      R.uniforms_cap = u.size();
+    }
+    CK(cudaMemcpyAsync(R.d_uniforms, u.data(), u.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    a.uniforms = R.d_uniforms;
+  }
+  const int out0[2] = {h->numpart, 0};
+  CK(cudaMemcpyAsync(R.d_out, out0, sizeof out0, cudaMemcpyHostToDevice, h->stream));
+  if (c.math_mode == FPB_MATH_STRICT) fpbk_release_strict(a, h->stream); else fpbk_release_fast(a, h->stream);
+  h->launches += 3;
+  int out[2];
+  CK(cudaMemcpyAsync(out, R.d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  if (out[1] < m)
+    return fail("RELEASEPARTICLES: TOTAL NUMBER OF PARTICLES REQUIRED (%d new, %d free slots) EXCEEDS THE "
+                "MAXIMUM ALLOWED NUMBER %d", m, out[1], c.maxpart);
+  h->numpart = out[0];
+  h->pending_init = true;
+  h->active_rows = -1;
+  if (numpart) *numpart = h->numpart;
+  if (n_released) *n_released = m;
   return 0;
 }
 

@@ -155,6 +155,24 @@ struct DevWetArgs {
   int ltsample;
 };
 
+// releaseparticles on the device (fpb_release.cuh)
+struct DevReleaseArgs {
+  DevCfg cfg;                 // cfg.itime = the release time
+  DevParticles p;
+  const int32_t *row_of_slot;
+  int permuted;               // rows != slots
+  int numpart_old;            // slots >= numpart_old have never been used
+  int numpoint, n_new, itsplit;
+  float ztop;                 // height(nz)
+  const float *xpoint1, *ypoint1, *xpoint2, *ypoint2, *zpoint1, *zpoint2;
+  const int32_t *offsets;     // [numpoint + 1] first new particle of each point
+  const float *uniforms;      // [4 * n_new] ran1 stream of the call, or null (Philox)
+  const float *xmass;         // [nspec][numpoint]
+  const int32_t *npart;
+  unsigned *block_counts;     // [ceil(maxpart / 1024)]
+  int *out;                   // [0] max(new slot) + 1 (atomicMax), [1] free slots
+};
+
 // launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
   void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \
@@ -162,6 +180,7 @@ struct DevWetArgs {
   void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_wetdepo_##SUF(const DevWetArgs &a, cudaStream_t st);              \
+  void fpbk_release_##SUF(const DevReleaseArgs &a, cudaStream_t st);          \
   void fpbk_conc_emit_##SUF(const DevConcArgs &a, int nest_sel, unsigned *keys, \
                             float *vals, size_t nrec, cudaStream_t st);
 FPB_DECL_LAUNCHERS(fast)

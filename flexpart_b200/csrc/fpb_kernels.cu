@@ -1002,6 +1002,7 @@ fpb_init_kernel(const __grid_constant__ DevStepArgs a) {
 }
 
 #include "fpb_step.cuh"
+#include "fpb_release.cuh"
 
 // ======================================================= conccalc kernel ===
 // A grid cell is named by a species-free key
@@ -1492,17 +1493,18 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true, false>, 128, 0);
-    else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, false>, 128, 0);
+    if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true, false>, PBL_THREADS, 0);
+    else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, true>, PBL_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, false>, PBL_THREADS, 0);
     res = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int want = (a.cfg.numpart + 127) / 128;
-  const int nb = want < res ? want : res; // persistent grid: one wave at most
+  const int want_pbl = (a.cfg.numpart + PBL_THREADS - 1) / PBL_THREADS;
+  const int nb = want_pbl < res ? want_pbl : res; // persistent grid: one wave at most
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
-  if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, 128, 0, st>>>(a);
-  else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, 128, 0, st>>>(a);
-  else fpb_pbl_kernel<false, false, false><<<nb, 128, 0, st>>>(a);
+  if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, PBL_THREADS, 0, st>>>(a);
+  else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, PBL_THREADS, 0, st>>>(a);
+  else fpb_pbl_kernel<false, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
   // finish kernel: the variant without nests / settling / dry deposition / Philox-direct RNG when it applies
   if (!a.cfg.drydep && !a.cfg.lsettling && a.cfg.numbnests == 0 && a.cfg.rng_mode != FPB_RNG_PHILOX)
     fpb_finish_kernel<true><<<want, 128, 0, st>>>(a);
@@ -1521,6 +1523,13 @@ void FPB_SUF(fpbk_conc_emit)(const DevConcArgs &a, int nest_sel, unsigned *keys,
   const int nb = (a.cfg.numpart + 255) / 256;
   if (nb == 0) return;
   fpb_conc_emit_kernel<<<nb, 256, 0, st>>>(a, nest_sel, keys, vals, nrec);
+}
+
+void FPB_SUF(fpbk_release)(const DevReleaseArgs &a, cudaStream_t st) {
+  const int nb = (a.p.maxpart + REL_BLOCK - 1) / REL_BLOCK;
+  release_count_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
+  release_scan_kernel<<<1, REL_BLOCK, 0, st>>>(a, nb);
+  release_assign_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_wetdepo)(const DevWetArgs &a, cudaStream_t st) {

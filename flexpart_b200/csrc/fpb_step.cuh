@@ -38,7 +38,10 @@ __device__ __noinline__ float rare_fmodf(float a, float b) { return fmodf(a, b);
 // The profile cache is direct-mapped by (level mod PBL_CACHE): it plays the
 // role of the reference's nzmax-long uprof.. arrays + indzindicator
 // (src/advance.f90:310-331) for the levels a particle visits during one call.
-constexpr int PBL_THREADS = 128;
+#ifndef FPB_PBL_THREADS
+#define FPB_PBL_THREADS 128
+#endif
+constexpr int PBL_THREADS = FPB_PBL_THREADS;
 #ifndef FPB_PBL_CACHE
 #define FPB_PBL_CACHE 8
 #endif
@@ -460,7 +463,7 @@ struct PblTask {
 // Persistent kernel: every warp pulls batches of particle rows from
 // *a.work_counter; lanes run sub-steps until their particle leaves the loop.
 template <bool EXTRA, bool CBL, bool SPEC>
-__global__ void __launch_bounds__(PBL_THREADS, EXTRA ? 3 : FPB_PBL_MIN_BLOCKS)
+__global__ void __launch_bounds__(PBL_THREADS, (EXTRA ? 3 : FPB_PBL_MIN_BLOCKS) * (128 / PBL_THREADS))
 fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
@@ -503,6 +506,12 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
       continue;
     }
     if (idle == FULL) break; // no rows left and nothing running
+#ifdef FPB_TAIL_STATS // tools/tail_stats.py: warp iterations / running lanes before and after the rows ran out
+    if (lane == 0) {
+      atomicAdd(a.stats + (exhausted ? 7 : 6), 1ull);
+      if (exhausted) atomicAdd(a.stats + 2, (unsigned long long)(32 - __popc(idle)));
+    }
+#endif
     if (task.running) {
       task.substep(a, sh, ls);
       if (!task.running) {

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import FpbStepStats, FpbError, FpbhEngine, load_engine_lib
+from .abi import FpbStepStats, FpbError, FpbhEngine, FpbReleasePoints, load_engine_lib
 
 _pf = C.POINTER(C.c_float)
 
@@ -93,6 +93,21 @@ class Engine:
                                          conc_weight, C.byref(st) if stats else None))
         return st.as_dict() if stats else None
 
+    def set_releases(self, rel, mp_pid=0):
+        """Release points for the device-side releaseparticles (host.Releases)."""
+        r = FpbReleasePoints()
+        for name, _ in FpbReleasePoints._fields_[:-1]:
+            setattr(r, name, getattr(rel.c_struct, name))
+        r.mp_pid = mp_pid
+        self._rel_keep = rel
+        self._check(self.L.fpb_set_releases(self.h, C.byref(r)))
+
+    def release_particles(self, itime):
+        """releaseparticles(itime) on the device; returns (numpart, particles created)."""
+        n, m = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.fpb_releaseparticles(self.h, itime, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
     def wetdepo(self, itime, ltsample, ldeltat=0):
         """wetdepo(itime, ltsample, loutnext) with ldeltat precomputed (src/wetdepo.f90:55-63)."""
         self._check(self.L.fpb_wetdepo(self.h, itime, ltsample, ldeltat))
@@ -158,8 +173,9 @@ class Engine:
     def launch_count(self):
         return int(self.L.fpb_launch_count(self.h))
 
-    def vtable(self):
-        """fpbh_engine table pointing at the library's own entry points."""
+    def vtable(self, device_release=False):
+        """fpbh_engine table pointing at the library's own entry points.
+        device_release: releaseparticles runs on the device (fpb_releaseparticles)."""
         L, a = self.L, abi
         v = FpbhEngine()
         v.self = self.h
@@ -174,4 +190,7 @@ class Engine:
         v.fetch_grids = cast(L.fpb_fetch_grids, a.FETCH_FN)
         v.scale_depgrids = cast(L.fpb_scale_depgrids, a.SCALE_FN)
         v.wetdepo = cast(L.fpb_wetdepo, a.WETDEPO_FN)
+        if device_release:
+            v.set_releases = cast(L.fpb_set_releases, a.SET_RELEASES_FN)
+            v.releaseparticles = cast(L.fpb_releaseparticles, a.RELEASE_FN)
         return v

@@ -73,6 +73,7 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
   Ponly_itra.itra1 = itra1.data();
   Ponly_itra.ld = c.maxpart;
   int32_t numpart = 0;
+  bool releases_set = false;
 
   fpbh_release_state *rst = fpbh_release_state_new(rel->numpoint);
   MetStore met;
@@ -159,14 +160,35 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
         bool due = false;
         for (int i = 0; i < rel->numpoint; i++)
           if (itime >= rel->ireleasestart[i] && itime <= rel->ireleaseend[i]) due = true;
-        if (due) {
+        if (due && eng->releaseparticles) { // particles are created where they live
+          if (!releases_set) {
+            fpb_release_points rp{};
+            rp.numpoint = rel->numpoint;
+            rp.ireleasestart = rel->ireleasestart; rp.ireleaseend = rel->ireleaseend;
+            rp.xpoint1 = rel->xpoint1; rp.ypoint1 = rel->ypoint1; rp.xpoint2 = rel->xpoint2;
+            rp.ypoint2 = rel->ypoint2; rp.zpoint1 = rel->zpoint1; rp.zpoint2 = rel->zpoint2;
+            rp.itsplit = rel->itsplit;
+            rp.mp_pid = 0;
+            ENG(eng->set_releases(eng->self, &rp));
+            releases_set = true;
+          }
+          ENG(eng->releaseparticles(eng->self, itime, &numpart, nullptr));
+        } else if (due) {
           if (numpart > 0) ENG(eng->pull_particles(eng->self, 0, numpart, &Ponly_itra));
           int32_t first = 0, n = 0;
           if (fpbh_releaseparticles(&c, height, rel, rst, itime, &P, &numpart, &first, &n)) {
             rc = 1;
             goto done;
           }
-          if (n > 0) ENG(eng->push_particles(eng->self, first, n, &P));
+          // push the new rows only: with re-used slots [first, first + n) also spans live
+          // particles, whose host copies are stale (only itra1 was refreshed above)
+          for (int j = first; j < first + n;) {
+            if (!(P.itra1[j] == itime && P.itramem[j] == itime)) { j++; continue; }
+            int k = j;
+            while (k < first + n && P.itra1[k] == itime && P.itramem[k] == itime) k++;
+            ENG(eng->push_particles(eng->self, j, k - j, &P));
+            j = k;
+          }
           ENG(eng->set_numpart(eng->self, numpart));
         }
       }

@@ -271,6 +271,30 @@ int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart
  * src/wetdepo.f90:55-63.  Particles with itra1 <= itime (>= for backward
  * runs) lose mass to wetgridunc/wetgriduncn.   */
 int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32_t ldeltat);
+
+/* Release points (src/point_mod.f90:15-26 after the conversions of src/readreleases.f90 and
+ * src/FLEXPART.f90:401-404): coordinates in grid units, heights in metres above ground
+ * (zkind 1), times in seconds relative to the start and snapped to lsynctime. */
+typedef struct fpb_release_points {
+  int32_t numpoint;
+  const int32_t *ireleasestart, *ireleaseend;
+  const float *xpoint1, *ypoint1, *xpoint2, *ypoint2, *zpoint1, *zpoint2;
+  int32_t itsplit;
+  int32_t mp_pid; /* MPI rank of the reference's seed offset (src/mpi_mod.f90:331-335); 0 = serial */
+} fpb_release_points;
+
+/* copies the release points to the device; resets the release state (xmasssave, ran1 seed) */
+int fpb_set_releases(fpb_handle *h, const fpb_release_points *rel);
+
+/* replaces `call releaseparticles(itime)` (src/timemanager.f90:230-233, src/releaseparticles.f90:69-378;
+ * EMISVAR factors 1, zkind 1, mass units): the new particles are created on the device, in the slots
+ * the reference's search finds (first slots whose itra1 differs from itime), so no particle row
+ * crosses the bus.  FPB_RNG_REFERENCE: positions from the reference's ran1 stream, bit-identical;
+ * Philox modes: four uniforms per particle from its counter stream.  *numpart returns the new
+ * numpart, *n_released the number of particles created.  Fails (label 996 of the reference) when
+ * fewer free slots than new particles are left.   */
+int fpb_releaseparticles(fpb_handle *h, int32_t itime, int32_t *numpart /* may be NULL */,
+                         int32_t *n_released /* may be NULL */);
 /* wetgridunc(0:numxgrid-1,0:numygrid-1,maxspec,maxpointspec_act,nclassunc,
  * maxageclass) and the nested twin (may be NULL): cumulative, never zeroed,
  * decayed by fpb_scale_depgrids like drygridunc */

@@ -117,6 +117,10 @@ typedef struct fpbh_engine {
   int (*scale_depgrids)(void *self, const float *factor);
   /* may be NULL: wet deposition is then left to the caller (src/timemanager.f90:164-169) */
   int (*wetdepo)(void *self, int32_t itime, int32_t ltsample, int32_t ldeltat);
+  /* may both be NULL: releaseparticles then runs on the host mirror (fpbh_releaseparticles) and the
+   * new rows are pushed; otherwise the engine creates the particles itself (fpb_releaseparticles) */
+  int (*set_releases)(void *self, const fpb_release_points *rel);
+  int (*releaseparticles)(void *self, int32_t itime, int32_t *numpart, int32_t *n_released);
 } fpbh_engine;
 
 /* one output interval handed to the caller (the concoutput slot,

@@ -218,3 +218,44 @@ def test_two_rank_partition_and_grid_reduce_gloo():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_timemanager_release_into_reused_slots_keeps_live_particles():
+    """Continuous releases with terminations by age: new particles take the dead slots between
+    live ones (src/releaseparticles.f90:139-160).  The time loop must hand the engine the new rows
+    only -- its host copies of the live rows in between are stale.  Checked against a loop that
+    works on the oracle's own state (fpo_releaseparticles + fpo_step, no host mirror)."""
+    cb = cases.config_small(nrel=3, npart_each=400, maxpart=1300, lage=(2700,))
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=11, start=0, end=3600)
+    nsteps = 4
+    ora = Oracle(cb); ora.fill_rannumb()
+    res, _ = fb.timemanager(cb, rel, fb.RunSpec(ideltas=nsteps * 900), ora.vtable())
+
+    ref = Oracle(cb); ref.fill_rannumb()
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    fp = lambda a: a.ctypes.data_as(_pf)
+    xmasssave = np.zeros(c.numpoint, np.float32)
+    for k in range(nsteps + 1):
+        itime = k * 900
+        if k % 12 == 0:   # the loop's 3-hourly synthetic fields (fpbh_timemanager)
+            ref.upload_met(1, fb.MetFields(cb).synth(itime)); ref.upload_met(2, fb.MetFields(cb).synth(itime + 10800))
+            ref.set_met_bracket((1, 2), (itime, itime + 10800))
+        assert ref.L.fpo_releaseparticles(ref.S, itime, c.numpoint, rel.start.ctypes.data_as(_pi),
+                                          rel.end.ctypes.data_as(_pi), fp(rel.xpoint1), fp(rel.ypoint1), fp(rel.xpoint2),
+                                          fp(rel.ypoint2), fp(rel.zpoint1), fp(rel.zpoint2), fp(xmasssave), 99999999) == 0
+        if k == nsteps:
+            break
+        ref.step(itime, 0)
+    n = res.numpart_final
+    a, b = fb.Particles(c.maxpart, 1), fb.Particles(c.maxpart, 1)
+    a.numpart = b.numpart = n
+    ora.pull_particles(a); ref.pull_particles(b)
+    assert np.array_equal(a.itra1[:n], b.itra1[:n])
+    live = b.itra1[:n] != fb.ITRA_DEAD
+    assert (~live).any() and (b.itramem[:n][live] < nsteps * 900).any()   # dead slots, and older particles still around
+    for f in ("xtra1", "ytra1", "ztra1", "idt", "npoint", "itramem"):
+        assert np.array_equal(getattr(a, f)[:n][live], getattr(b, f)[:n][live]), f
+    stepped = live & (b.itramem[:n] < nsteps * 900)   # (initialize sets the velocities of the newest ones)
+    for f in ("uap", "ucp", "uzp"):
+        assert np.array_equal(getattr(a, f)[:n][stepped], getattr(b, f)[:n][stepped]), f

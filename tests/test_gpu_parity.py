@@ -7,6 +7,8 @@ on the same seeded inputs.  Tolerances are BASELINE.json's north_star:
     conserved.
 In strict math mode the engine is expected to be bit-identical to the oracle,
 which is asserted where it holds (stronger than the stated tolerance)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -677,3 +679,124 @@ def test_philox_modes_match_reference_statistics():
         assert abs(dx.std() / rx.std() - 1.0) < 0.05
         assert abs(dz.std() / rz.std() - 1.0) < 0.08
         assert not np.array_equal(dx, rx)
+
+
+# ----------------------------------------------------------------------------
+# device-side releaseparticles
+# ----------------------------------------------------------------------------
+def _oracle_release(o, c, rel, itime, xmasssave):
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    fp = lambda a: a.ctypes.data_as(_pf)
+    rc = o.L.fpo_releaseparticles(o.S, itime, c.numpoint, rel.start.ctypes.data_as(_pi), rel.end.ctypes.data_as(_pi),
+                                  fp(rel.xpoint1), fp(rel.ypoint1), fp(rel.xpoint2), fp(rel.ypoint2),
+                                  fp(rel.zpoint1), fp(rel.zpoint2), fp(xmasssave), 99999999)
+    assert rc == 0
+
+
+@pytest.mark.parametrize("sort_interval", [0, 1])
+def test_device_release_matches_the_reference_stream(sort_interval):
+    """fpb_releaseparticles with the reference RNG: release counts, the slots chosen (terminated
+    slots are reused in ascending order, also when the device rows are cell-sorted), the ran1
+    positions, classes and masses equal the oracle's releaseparticles bit for bit
+    (src/releaseparticles.f90:69-378), and the steps in between stay bit-identical."""
+    cb = cases.config_small(nrel=3, npart_each=700, maxpart=2600, math_mode=fb.MATH_STRICT,
+                            sort_interval=sort_interval, lage=(2000,))
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=3, start=0, end=3600)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb(); e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+    eng.set_releases(rel)
+    xmasssave = np.zeros(c.numpoint, np.float32)
+    n_o = 0
+    reused = 0
+    for itime in range(0, 5400, 900):
+        _oracle_release(ora, c, rel, itime, xmasssave)
+        n_g, made = eng.release_particles(itime)
+        po = fb.Particles(c.maxpart, 1); po.numpart = c.maxpart
+        ora.pull_particles(po)
+        live = np.nonzero(po.itra1 == itime)[0]
+        n_o = max(n_o, int(live.max()) + 1 if live.size else 0)
+        assert n_g == n_o, (itime, n_g, n_o)
+        pg = fb.Particles(c.maxpart, 1); pg.numpart = n_g
+        eng.pull_particles(pg)
+        ora.set_numpart(n_g)
+        new = np.nonzero((po.itramem[:n_g] == itime) & (po.itra1[:n_g] == itime))[0]
+        assert made == new.size
+        reused += int((new < n_g - made).sum()) if itime else 0
+        for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt"):
+            assert np.array_equal(getattr(pg, f)[:n_g][new], getattr(po, f)[:n_g][new]), (itime, f)
+        assert np.array_equal(pg.xmass1[:n_g][new], po.xmass1[:n_g][new])
+        assert np.array_equal(pg.itra1[:n_g], po.itra1[:n_g]), itime
+        sg, so = eng.step(itime, 450), ora.step(itime, 450)
+        assert sg == so, (itime, sg, so)
+        eng.pull_particles(pg); po.numpart = n_g; ora.pull_particles(po)
+        for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+            assert np.array_equal(getattr(pg, f)[:n_g], getattr(po, f)[:n_g]), (itime, f)
+    assert reused > 0           # particles older than lage died and their slots were taken again
+    assert n_o < 3 * 700
+
+
+def test_device_release_philox_statistics():
+    """Philox modes: the same counts, slots, classes range and masses; positions uniform in
+    the release boxes, independent of the row order."""
+    cb = cases.config_small(nrel=4, npart_each=20000, maxpart=80000, rng_mode=fb.RNG_PHILOX_INDEX)
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=5)
+    eng = fb.Engine(cb)
+    eng.set_releases(rel)
+    n, made = eng.release_particles(0)
+    assert n == made == 80000
+    p = fb.Particles(c.maxpart, 1); p.numpart = n
+    eng.pull_particles(p)
+    assert (p.itra1[:n] == 0).all() and (p.idt[:n] == c.mintime).all()
+    assert np.array_equal(p.npoint[:n], np.repeat(np.arange(1, 5), 20000))
+    assert p.nclass[:n].min() >= 1 and p.nclass[:n].max() <= c.nclassunc
+    np.testing.assert_allclose(p.xmass1[:n, 0], cb.xmass[:, 0].repeat(20000) / 20000, rtol=1e-6)
+    for i in range(4):
+        m = p.npoint[:n] == i + 1
+        for arr, a, b in ((p.xtra1[:n][m], rel.xpoint1[i], rel.xpoint2[i]), (p.ytra1[:n][m], rel.ypoint1[i], rel.ypoint2[i]),
+                          (p.ztra1[:n][m], rel.zpoint1[i], rel.zpoint2[i])):
+            assert arr.min() >= min(a, b) - 1e-4 and arr.max() <= max(a, b) + 1e-4
+            u = (arr - a) / (b - a)
+            assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    # x, y, z are independent draws
+    u = np.stack([p.xtra1[:n], p.ytra1[:n], p.ztra1[:n]])
+    m = p.npoint[:n] == 1
+    assert np.abs(np.corrcoef(u[:, m])[np.triu_indices(3, 1)]).max() < 0.03
+
+
+def test_device_release_beyond_maxpart_fails():
+    cb = cases.config_small(nrel=2, npart_each=100, maxpart=150)
+    eng = fb.Engine(cb)
+    eng.set_releases(cases.releases_boxes(cb))
+    with pytest.raises(fb.FpbError, match="EXCEEDS THE MAXIMUM"):
+        eng.release_particles(0)
+
+
+def test_time_loop_with_device_release_is_bit_identical():
+    """The reference's time loop with releaseparticles on the device (continuous releases over
+    the first hour, terminations by age, cell sort every step) against the oracle fed by the
+    host-side releaseparticles: the same particles in the same slots, bit for bit."""
+    cb = cases.config_small(nrel=3, npart_each=800, maxpart=2600, math_mode=fb.MATH_STRICT,
+                            scatter_mode=fb.SCATTER_DETERMINISTIC, sort_interval=1, lage=(2700,))
+    rel = cases.releases_boxes(cb, seed=11, start=0, end=3600)
+    run = fb.RunSpec(ideltas=8 * 900)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    eng.fill_rannumb(); ora.fill_rannumb()
+    rg, og = fb.timemanager(cb, rel, run, eng.vtable(device_release=True))
+    ro, oo = fb.timemanager(cb, rel, run, ora.vtable())
+    n = ro.numpart_final
+    assert rg.numpart_final == n and rg.particle_steps == ro.particle_steps and rg.substeps == ro.substeps
+    pg, po = fb.Particles(cb.cfg.maxpart, 1), fb.Particles(cb.cfg.maxpart, 1)
+    pg.numpart = po.numpart = n
+    eng.pull_particles(pg); ora.pull_particles(po)
+    assert (po.itra1[:n] == fb.ITRA_DEAD).sum() > 0
+    for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+        live = po.itra1[:n] != fb.ITRA_DEAD
+        assert np.array_equal(getattr(pg, f)[:n][live], getattr(po, f)[:n][live]), f
+    assert np.array_equal(pg.itra1[:n], po.itra1[:n])
+    assert len(og) == len(oo) >= 1
+    for a, b in zip(og, oo):
+        assert np.array_equal(a["gridunc"], b["gridunc"])
