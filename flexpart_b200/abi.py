@@ -163,6 +163,8 @@ def load_engine_lib():
     L.fpb_step.argtypes = [H, _i, _i, C.POINTER(FpbStepStats)]
     L.fpb_wetdepo.argtypes = [H, _i, _i, _i]
     L.fpb_set_releases.argtypes = [H, C.POINTER(FpbReleasePoints)]
+    L.fpb_set_outgrid_geometry.argtypes = [H, _pf, _pf, _pf, _pf]
+    L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
@@ -212,6 +214,7 @@ def load_host_lib():
     L.fpbh_release_state_free.argtypes = [C.c_void_p]
     L.fpbh_release_state_set_rank.argtypes = [C.c_void_p, _i]
     L.fpbh_release_state_set_rank.restype = None
+    L.fpbh_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), _i, _f, _pf, _pf]
     L.fpbh_releaseparticles.argtypes = [C.POINTER(FpbConfig), _pf, C.POINTER(FpbhReleases),
                                         C.c_void_p, _i, _ppart, _pi, _pi, _pi]
     L.fpbh_timemanager.argtypes = [C.POINTER(FpbConfig), _pf, C.POINTER(FpbhReleases),

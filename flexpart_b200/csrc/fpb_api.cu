@@ -18,6 +18,7 @@
 #include "fpb_device.cuh"
 #include "fpb_scatter.cuh"
 #include "fpb_sort.cuh"
+#include "fpb_output.cuh"
 
 // ------------------------------------------------------------ error state --
 static thread_local std::string g_err;
@@ -137,6 +138,15 @@ struct fpb_handle {
   int steps_since_sort = 1 << 30;
   unsigned *d_nlive = nullptr;
   int *d_work = nullptr;
+  // concoutput on the device
+  struct Output {
+    float *area[2] = {nullptr, nullptr}, *volume[2] = {nullptr, nullptr}; // [0] mother, [1] nest
+    unsigned *block_counts = nullptr;
+    int32_t *d_i = nullptr;
+    float *d_r = nullptr;
+    int *d_counts = nullptr;
+    size_t cap = 0;
+  } outp;
   // device-side releaseparticles
   struct Releases {
     int numpoint = 0, itsplit = 0;
@@ -499,6 +509,8 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->row_of_slot); cudaFree(h->d_nlive); cudaFree(h->d_work);
   cudaFree(h->sc.flags); cudaFree(h->sc.s0); cudaFree(h->sc.s1); cudaFree(h->sc.s2); cudaFree(h->sc.prob);
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
+  for (int k = 0; k < 2; k++) { cudaFree(h->outp.area[k]); cudaFree(h->outp.volume[k]); }
+  cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r); cudaFree(h->outp.d_counts);
   for (auto &q : h->rel.d_pts) cudaFree(q);
   cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
@@ -961,6 +973,81 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   CK(cudaEventRecord(h->ev[3], h->stream));
   h->timed_conc = true;
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// -------------------------------------------------------------- output --
+extern "C" int fpb_set_outgrid_geometry(fpb_handle *h, const float *area, const float *volume,
+                                        const float *arean, const float *volumen) {
+  if (!h || !area || !volume) return fail("fpb_set_outgrid_geometry: null argument");
+  const fpb_config &c = h->cfg;
+  CK(cudaSetDevice(h->device));
+  auto up = [&](float *&d, const float *src, size_t n) -> int {
+    if (!d) DA(d, n);
+    CK(cudaMemcpy(d, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  const size_t n2 = (size_t)c.numxgrid * c.numygrid;
+  if (up(h->outp.area[0], area, n2) || up(h->outp.volume[0], volume, n2 * c.numzgrid)) return 1;
+  size_t cap = n2 * c.numzgrid;
+  if (c.nested_output == 1 && arean && volumen) {
+    const size_t m2 = (size_t)c.numxgridn * c.numygridn;
+    if (up(h->outp.area[1], arean, m2) || up(h->outp.volume[1], volumen, m2 * c.numzgrid)) return 1;
+    cap = std::max(cap, m2 * c.numzgrid);
+  }
+  if (cap > h->outp.cap) {
+    cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r);
+    h->outp.block_counts = nullptr; h->outp.d_i = nullptr; h->outp.d_r = nullptr;
+    DA(h->outp.block_counts, 2 * ((cap + 1023) / 1024));
+    DA(h->outp.d_i, cap); DA(h->outp.d_r, cap);
+    h->outp.cap = cap;
+  }
+  if (!h->outp.d_counts) DA(h->outp.d_counts, 2);
+  return 0;
+}
+
+extern "C" int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which, int32_t ks, int32_t kp,
+                                     int32_t nage, float outnum, float tot_mu, int32_t loutaver,
+                                     int32_t *sp_count_i, int32_t *sparse_dump_i, int32_t *sp_count_r,
+                                     float *sparse_dump_r) {
+  if (!h || !sp_count_i || !sparse_dump_i || !sp_count_r || !sparse_dump_r)
+    return fail("fpb_concoutput_sparse: null argument");
+  const fpb_config &c = h->cfg;
+  if (nest < 0 || nest > 1 || (nest == 1 && c.nested_output != 1)) return fail("fpb_concoutput_sparse: no such output grid %d", nest);
+  if (which < 0 || which > 2) return fail("fpb_concoutput_sparse: which = %d", which);
+  if (ks < 1 || ks > c.nspec || kp < 1 || kp > c.maxpointspec_act || nage < 1 || nage > c.nageclass)
+    return fail("fpb_concoutput_sparse: (ks, kp, nage) = (%d, %d, %d) out of range", ks, kp, nage);
+  if (!h->outp.area[nest] || !h->outp.volume[nest]) return fail("fpb_concoutput_sparse: fpb_set_outgrid_geometry has not been called");
+  if (which == 2 && !c.wetdep) return fail("fpb_concoutput_sparse: the run has no wet deposition");
+  CK(cudaSetDevice(h->device));
+  const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
+  const size_t n2 = (size_t)nxg * nyg;
+  SparseDumpArgs a;
+  a.which = which;
+  a.ncells = (int)(which == 0 ? n2 * c.numzgrid : n2);
+  const float *g = which == 0 ? (nest ? h->griduncn : h->gridunc)
+                 : which == 1 ? (nest ? h->drygriduncn : h->drygridunc) : (nest ? h->wetgriduncn : h->wetgridunc);
+  // device layout: [nage][class][kp][ks][cells]
+  const size_t inner = (size_t)a.ncells;
+  a.class_stride = (size_t)c.maxpointspec_act * c.nspec * inner;
+  a.grid = g + ((((size_t)(nage - 1) * c.nclassunc) * c.maxpointspec_act + (kp - 1)) * c.nspec + (ks - 1)) * inner;
+  a.nclassunc = c.nclassunc;
+  a.geom = which == 0 ? h->outp.volume[nest] : h->outp.area[nest];
+  a.ldirect = c.ldirect;
+  a.outnum = outnum; a.tot_mu = tot_mu; a.loutaver_abs = (float)std::abs(loutaver);
+  a.index_offset = which == 0 ? (int)n2 : 0; // kz is 1-based in ix+jy*numxgrid+kz*numxgrid*numygrid
+  a.block_counts = h->outp.block_counts;
+  a.out_i = h->outp.d_i; a.out_r = h->outp.d_r; a.counts = h->outp.d_counts;
+  fpb_sparse_dump(a, h->stream);
+  h->launches += 3;
+  int counts[2];
+  CK(cudaMemcpyAsync(counts, a.counts, sizeof counts, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  *sp_count_i = counts[0]; *sp_count_r = counts[1];
+  if (counts[0] > 0) CK(cudaMemcpyAsync(sparse_dump_i, a.out_i, (size_t)counts[0] * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (counts[1] > 0) CK(cudaMemcpyAsync(sparse_dump_r, a.out_r, (size_t)counts[1] * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

@@ -1,0 +1,121 @@
+// fpb_output.cu -- see fpb_output.cuh.  Compiled with --fmad=false: the sums of mean_sp and the
+// unit conversion keep the reference's operation order and rounding.
+//
+// The reference (src/concoutput.f90:287-475) walks the cells of one (ks, kp, nage) grid in
+// storage order.  A cell is written when its value exceeds tiny(0.0); the first cell of every run
+// of such cells also records its linear index, and the values of a run carry the sign
+// (-1)**(run number - 1): `sp_fact` flips at each run start.  Both lists are a stream compaction:
+// two block-level scans (non-zero cells, run starts) give every cell its place and its sign.
+#include "fpb_output.cuh"
+
+namespace {
+constexpr int OUT_BLOCK = 1024;
+constexpr float SMALLNUM = 1.17549435e-38f; // tiny(0.0), src/concoutput.f90:83
+
+// mean_sp over the uncertainty classes times nclassunc (src/mean_mod.f90:20-74,
+// src/concoutput.f90:326-331); the standard deviation is not part of the dump
+__device__ __forceinline__ float cell_total(const SparseDumpArgs &a, int i) {
+  float xl = 0.f;
+  for (int l = 0; l < a.nclassunc; l++) xl = xl + a.grid[(size_t)l * a.class_stride + i];
+  const float xm = xl / (float)a.nclassunc;
+  return xm * (float)a.nclassunc;
+}
+
+// magnitude written to sparse_dump_r (the sign is the run's)
+__device__ __forceinline__ float cell_value(const SparseDumpArgs &a, int i, float g) {
+  if (a.which == 0) { // src/concoutput.f90:225-235,451-454
+    const float factor3d = (a.ldirect == 1) ? 1.e12f / a.geom[i] / a.outnum : a.loutaver_abs / a.outnum;
+    return g * factor3d / a.tot_mu;
+  }
+  return 1.e12f * g / a.geom[i]; // :370-372, :402-405
+}
+
+// exclusive scan over a 1024-thread block of two counters at once
+__device__ __forceinline__ void block_scan2(unsigned va, unsigned vb, unsigned &ea, unsigned &eb,
+                                            unsigned &ta, unsigned &tb) {
+  __shared__ unsigned wa[32], wb[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned ia = va, ib = vb;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
+    if (lane >= d) { ia += xa; ib += xb; }
+  }
+  if (lane == 31) { wa[w] = ia; wb[w] = ib; }
+  __syncthreads();
+  if (w == 0) {
+    unsigned sa = wa[lane], sb = wb[lane], ja = sa, jb = sb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned xa = __shfl_up_sync(0xffffffffu, ja, d), xb = __shfl_up_sync(0xffffffffu, jb, d);
+      if (lane >= d) { ja += xa; jb += xb; }
+    }
+    wa[lane] = ja - sa; wb[lane] = jb - sb;
+  }
+  __syncthreads();
+  ea = wa[w] + ia - va;
+  eb = wb[w] + ib - vb;
+  __shared__ unsigned tot[2];
+  if (threadIdx.x == OUT_BLOCK - 1) { tot[0] = ea + va; tot[1] = eb + vb; }
+  __syncthreads();
+  ta = tot[0]; tb = tot[1];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cell_flags(const SparseDumpArgs &a, int i, float &g, unsigned &nz, unsigned &rs) {
+  nz = 0; rs = 0; g = 0.f;
+  if (i < a.ncells) {
+    g = cell_total(a, i);
+    nz = g > SMALLNUM;
+    if (nz) rs = (i == 0) || !(cell_total(a, i - 1) > SMALLNUM);
+  }
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) sparse_count_kernel(const SparseDumpArgs a) {
+  const int i = blockIdx.x * OUT_BLOCK + threadIdx.x;
+  float g;
+  unsigned nz, rs;
+  cell_flags(a, i, g, nz, rs);
+  const int cn = __syncthreads_count(nz), cr = __syncthreads_count(rs);
+  if (threadIdx.x == 0) { a.block_counts[2 * blockIdx.x] = cn; a.block_counts[2 * blockIdx.x + 1] = cr; }
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) sparse_scan_kernel(const SparseDumpArgs a, int nblocks) {
+  __shared__ unsigned run[2];
+  if (threadIdx.x == 0) { run[0] = 0; run[1] = 0; }
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += OUT_BLOCK) {
+    const int b = base + threadIdx.x;
+    const unsigned va = (b < nblocks) ? a.block_counts[2 * b] : 0u, vb = (b < nblocks) ? a.block_counts[2 * b + 1] : 0u;
+    unsigned ea, eb, ta, tb;
+    block_scan2(va, vb, ea, eb, ta, tb);
+    if (b < nblocks) { a.block_counts[2 * b] = run[0] + ea; a.block_counts[2 * b + 1] = run[1] + eb; }
+    __syncthreads();
+    if (threadIdx.x == 0) { run[0] += ta; run[1] += tb; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { a.counts[1] = (int)run[0]; a.counts[0] = (int)run[1]; }
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) sparse_write_kernel(const SparseDumpArgs a) {
+  const int i = blockIdx.x * OUT_BLOCK + threadIdx.x;
+  float g;
+  unsigned nz, rs;
+  cell_flags(a, i, g, nz, rs);
+  unsigned en, er, tn, tr;
+  block_scan2(nz, rs, en, er, tn, tr);
+  if (!nz) return;
+  const unsigned kn = a.block_counts[2 * blockIdx.x] + en;          // place in sparse_dump_r
+  const unsigned kr = a.block_counts[2 * blockIdx.x + 1] + er + rs; // number of this cell's run (1-based)
+  if (rs) a.out_i[kr - 1] = i + a.index_offset;
+  const float v = cell_value(a, i, g);
+  a.out_r[kn] = (kr & 1u) ? v : -v;
+}
+} // namespace
+
+void fpb_sparse_dump(const SparseDumpArgs &a, cudaStream_t st) {
+  const int nb = (a.ncells + OUT_BLOCK - 1) / OUT_BLOCK;
+  sparse_count_kernel<<<nb, OUT_BLOCK, 0, st>>>(a);
+  sparse_scan_kernel<<<1, OUT_BLOCK, 0, st>>>(a, nb);
+  sparse_write_kernel<<<nb, OUT_BLOCK, 0, st>>>(a);
+}

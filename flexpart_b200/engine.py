@@ -93,6 +93,22 @@ class Engine:
                                          conc_weight, C.byref(st) if stats else None))
         return st.as_dict() if stats else None
 
+    def set_outgrid_geometry(self, area, volume, arean=None, volumen=None):
+        """area/volume of outgrid_init (host.outgrid_geometry), Fortran order."""
+        keep = [np.asfortranarray(a, np.float32) if a is not None else None for a in (area, volume, arean, volumen)]
+        self._check(self.L.fpb_set_outgrid_geometry(self.h, *[_fp(a) if a is not None else None for a in keep]))
+
+    def concoutput_sparse(self, which, ks, kp, nage, outnum, tot_mu=1.0, loutaver=3600, nest=0):
+        """sparse dump of one (ks, kp, nage) grid: (sparse_dump_i, sparse_dump_r) of
+        src/concoutput.f90:352-475; which = 0 concentration, 1 dry, 2 wet deposition."""
+        c = self.cb.cfg
+        n = (c.numxgridn * c.numygridn if nest else c.numxgrid * c.numygrid) * (c.numzgrid if which == 0 else 1)
+        di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        ci, cr = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.fpb_concoutput_sparse(self.h, nest, which, ks, kp, nage, outnum, tot_mu, loutaver,
+                                                 C.byref(ci), di.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(cr), _fp(dr)))
+        return di[:ci.value].copy(), dr[:cr.value].copy()
+
     def set_releases(self, rel, mp_pid=0):
         """Release points for the device-side releaseparticles (host.Releases)."""
         r = FpbReleasePoints()

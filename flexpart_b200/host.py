@@ -251,6 +251,16 @@ class Releases:
         self.c_struct = r
 
 
+def outgrid_geometry(cb, outlat0, nest=0):
+    """area(numxgrid,numygrid), volume(numxgrid,numygrid,numzgrid) of outgrid_init (Fortran order)."""
+    c = cb.cfg
+    nx, ny = (c.numxgridn, c.numygridn) if nest else (c.numxgrid, c.numygrid)
+    area = np.zeros((nx, ny), np.float32, order="F")
+    volume = np.zeros((nx, ny, c.numzgrid), np.float32, order="F")
+    _hcheck(load_host_lib().fpbh_outgrid_geometry(C.byref(c), nest, outlat0, _fp(area), _fp(volume)))
+    return area, volume
+
+
 class ReleaseState:
     def __init__(self, numpoint, mp_pid=0):
         """mp_pid > 0: the rank's ran1 seed offset of the MPI build (src/mpi_mod.f90:331-335)."""

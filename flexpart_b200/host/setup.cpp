@@ -149,3 +149,34 @@ extern "C" int fpbh_readoutgrid_nest(fpb_config *c, float outlon0n, float outlat
   c->nested_output = 1;
   return 0;
 }
+
+// src/outgrid_init.f90:48-100 (area, volume; the wall areas are only used by the flux output)
+extern "C" int fpbh_outgrid_geometry(const fpb_config *cp, int32_t nest, float outlat0, float *area, float *volume) {
+  if (!cp || !area || !volume) return fpbh_fail("fpbh_outgrid_geometry: null argument");
+  const fpb_config &c = *cp;
+  if (nest && c.nested_output != 1) return fpbh_fail("fpbh_outgrid_geometry: no nested output grid");
+  const float r_earth = 6.371e6f, pi = 3.14159265f, pi180 = pi / 180.f; // src/par_mod.f90:59-60
+  const int nx = nest ? c.numxgridn : c.numxgrid, ny = nest ? c.numygridn : c.numygrid;
+  const float dyo = nest ? c.dyoutn : c.dyout, dxo = nest ? c.dxoutn : c.dxout;
+  for (int jy = 0; jy < ny; jy++) {
+    const float ylat = outlat0 + ((float)jy + 0.5f) * dyo;
+    const float ylatp = ylat + 0.5f * dyo, ylatm = ylat - 0.5f * dyo;
+    float hzone;
+    if (ylatm < 0.f && ylatp > 0.f) {
+      hzone = dyo * r_earth * pi180;
+    } else { // zone height between two latitude circles, M = 2*pi*R*h*dx/360
+      const float cp_ = std::cos(ylatp * pi180), cm_ = std::cos(ylatm * pi180);
+      hzone = (cp_ < cm_) ? std::sqrt(1.f - cp_ * cp_) - std::sqrt(1.f - cm_ * cm_)
+                          : std::sqrt(1.f - cm_ * cm_) - std::sqrt(1.f - cp_ * cp_);
+      hzone = hzone * r_earth;
+    }
+    const float gridarea = 2.f * pi * r_earth * hzone * dxo / 360.f;
+    for (int ix = 0; ix < nx; ix++) {
+      area[ix + (size_t)nx * jy] = gridarea;
+      volume[ix + (size_t)nx * jy] = gridarea * c.outheight[0];
+      for (int kz = 2; kz <= c.numzgrid; kz++)
+        volume[ix + (size_t)nx * (jy + (size_t)ny * (kz - 1))] = gridarea * (c.outheight[kz - 1] - c.outheight[kz - 2]);
+    }
+  }
+  return 0;
+}

@@ -272,6 +272,26 @@ int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart
  * runs) lose mass to wetgridunc/wetgriduncn.   */
 int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32_t ldeltat);
 
+/* Output-grid geometry of outgrid_init (src/outgrid_init.f90:48-100): area(numxgrid,numygrid) and
+ * volume(numxgrid,numygrid,numzgrid); the nested grid's (src/outgrid_init_nest.f90) may be NULL. */
+int fpb_set_outgrid_geometry(fpb_handle *h, const float *area, const float *volume,
+                             const float *arean, const float *volumen);
+
+/* The body of concoutput's loop over (ks, kp, nage) for the sparse binary output (iout = 1;
+ * src/concoutput.f90:287-475, concoutput_nest.f90 alike): mean over the uncertainty classes x
+ * nclassunc, conversion (1.e12/volume/outnum/tot_mu forward, abs(loutaver)/outnum/tot_mu backward;
+ * 1.e12/area for deposition) and the run-length dump -- the index of the first cell of every run of
+ * cells above tiny(0.0) and the values with the sign alternating from run to run -- built on the
+ * device, so only the compacted lists cross the bus.  which: 0 concentration, 1 dry deposition,
+ * 2 wet deposition; nest: 0 mother, 1 nested output grid; ks, kp, nage 1-based.  The buffers hold
+ * numxgrid*numygrid*numzgrid entries (numxgrid*numygrid for deposition).  The grid totals and
+ * their uncertainty (gridtotal, gridsigmatotal: diagnostics on stdout) are not computed.
+ *  */
+int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which, int32_t ks, int32_t kp,
+                          int32_t nage, float outnum, float tot_mu, int32_t loutaver,
+                          int32_t *sp_count_i, int32_t *sparse_dump_i, int32_t *sp_count_r,
+                          float *sparse_dump_r);
+
 /* Release points (src/point_mod.f90:15-26 after the conversions of src/readreleases.f90 and
  * src/FLEXPART.f90:401-404): coordinates in grid units, heights in metres above ground
  * (zkind 1), times in seconds relative to the start and snapped to lsynctime. */

@@ -85,6 +85,11 @@ typedef struct fpbh_releases {
   int32_t itsplit;
 } fpbh_releases;
 
+/* outgrid_init's cell areas and volumes (src/outgrid_init.f90:48-100; nest = 1:
+ * src/outgrid_init_nest.f90:84-117), the inputs of fpb_set_outgrid_geometry.
+ * outlat0: southern edge of the (nested) output grid in degrees. */
+int fpbh_outgrid_geometry(const fpb_config *cfg, int32_t nest, float outlat0, float *area, float *volume);
+
 typedef struct fpbh_release_state fpbh_release_state;
 fpbh_release_state *fpbh_release_state_new(int32_t numpoint);
 void fpbh_release_state_free(fpbh_release_state *s);

@@ -63,6 +63,13 @@ ALLOC_DIMS = {
     "zpoint1": "numpoint", "zpoint2": "numpoint", "xpoint1": "numpoint", "xpoint2": "numpoint",
     "ypoint1": "numpoint", "ypoint2": "numpoint", "ireleasestart": "numpoint", "ireleaseend": "numpoint",
     "kindz": "numpoint", "rho_rel": "numpoint", "xmasssave": "numpoint",
+    "area": "0:numxgrid-1,0:numygrid-1", "volume": "0:numxgrid-1,0:numygrid-1,numzgrid",
+    "areaeast": "0:numxgrid-1,0:numygrid-1,numzgrid", "areanorth": "0:numxgrid-1,0:numygrid-1,numzgrid",
+    "factor3d": "0:numxgrid-1,0:numygrid-1,numzgrid", "grid": "0:numxgrid-1,0:numygrid-1,numzgrid",
+    "gridsigma": "0:numxgrid-1,0:numygrid-1,numzgrid", "wetgrid": "0:numxgrid-1,0:numygrid-1",
+    "drygrid": "0:numxgrid-1,0:numygrid-1", "wetgridsigma": "0:numxgrid-1,0:numygrid-1",
+    "drygridsigma": "0:numxgrid-1,0:numygrid-1",
+    "sparse_dump_r": "numxgrid*numygrid*numzgrid", "sparse_dump_i": "numxgrid*numygrid*numzgrid",
 }
 
 
@@ -921,6 +928,8 @@ class Gen:
         m = re.match(r"^call\s+([a-z_][a-z0-9_]*)\s*(?:\((.*)\))?$", s)
         if m:
             name, args = m.groups()
+            if name == "mean":  # generic interface of mean_mod; dep_prec = sp selects mean_sp (src/par_mod.f90:33)
+                name = "mean_sp"
             if name not in self.prog.units:
                 if name in ("flush", "mpif_mtime", "caldate"):
                     return res + [f"/* call {name} skipped */;"]

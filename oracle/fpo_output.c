@@ -1,0 +1,123 @@
+/* fpo_output.c -- TEST INFRASTRUCTURE (see fpo.h).  Sequential restatement of
+ *   outgrid_init's cell areas and volumes   (src/outgrid_init.f90:48-100; nest: outgrid_init_nest.f90)
+ *   concoutput's loop body for one (ks, kp, nage): class mean (src/mean_mod.f90:20-74),
+ *   unit conversion and sparse dump          (src/concoutput.f90:225-235,287-475)
+ * on grids in the reference layout (as fpb_fetch_grids / fpo_fetch_grids return them). */
+#include <math.h>
+#include <stdlib.h>
+
+#include "fpo.h"
+#include "fpo_math.h"
+
+#define R_EARTH 6.371e6f
+#define PI_F 3.14159265f
+#define PI180 (PI_F / 180.f)
+
+/* src/outgrid_init.f90:52-99 */
+void fpo_outgrid_geometry(const fpb_config *c, int nest, float outlat0, float *area, float *volume) {
+  const int nx = nest ? c->numxgridn : c->numxgrid, ny = nest ? c->numygridn : c->numygrid;
+  const float lat0 = outlat0, dyo = nest ? c->dyoutn : c->dyout, dxo = nest ? c->dxoutn : c->dxout;
+  for (int jy = 0; jy < ny; jy++) {
+    float ylat = lat0 + ((float)jy + 0.5f) * dyo;
+    float ylatp = ylat + 0.5f * dyo;
+    float ylatm = ylat - 0.5f * dyo;
+    float hzone;
+    if ((ylatm < 0.f) && (ylatp > 0.f)) {
+      hzone = dyo * R_EARTH * PI180;
+    } else {
+      float cosfactp = fpo_cosf(ylatp * PI180);
+      float cosfactm = fpo_cosf(ylatm * PI180);
+      if (cosfactp < cosfactm) {
+        hzone = fpo_sqrtf(1.f - cosfactp * cosfactp) - fpo_sqrtf(1.f - cosfactm * cosfactm);
+        hzone = hzone * R_EARTH;
+      } else {
+        hzone = fpo_sqrtf(1.f - cosfactm * cosfactm) - fpo_sqrtf(1.f - cosfactp * cosfactp);
+        hzone = hzone * R_EARTH;
+      }
+    }
+    float gridarea = 2.f * PI_F * R_EARTH * hzone * dxo / 360.f;
+    for (int ix = 0; ix < nx; ix++) {
+      area[ix + nx * jy] = gridarea;
+      volume[ix + nx * jy] = area[ix + nx * jy] * c->outheight[0];
+      for (int kz = 2; kz <= c->numzgrid; kz++)
+        volume[ix + nx * (jy + (size_t)ny * (kz - 1))] =
+            area[ix + nx * jy] * (c->outheight[kz - 1] - c->outheight[kz - 2]);
+    }
+  }
+}
+
+/* mean_sp, src/mean_mod.f90:20-74 */
+static void mean_sp(const float *x, float *xm, float *xs, int number) {
+  const float eps = 1.0e-30f;
+  float xl = 0.f, xq = 0.f;
+  for (int i = 0; i < number; i++) {
+    xl = xl + x[i];
+    xq = xq + x[i] * x[i];
+  }
+  *xm = xl / (float)number;
+  float xaux = xq - xl * xl / (float)number;
+  if (xaux < eps) *xs = 0.f;
+  else *xs = fpo_sqrtf(xaux / (float)(number - 1));
+}
+
+/* which: 0 concentration (grid = gridunc, geom = volume), 1 dry / 2 wet deposition
+ * (grid = drygridunc / wetgridunc, geom = area) */
+void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float *grid_ref,
+                           const float *geom, int ks, int kp, int nage, float outnum, float tot_mu,
+                           int loutaver, int32_t *sp_count_i, int32_t *sparse_dump_i,
+                           int32_t *sp_count_r, float *sparse_dump_r) {
+  const int nx = nest ? c->numxgridn : c->numxgrid, ny = nest ? c->numygridn : c->numygrid;
+  const int nzg = which == 0 ? c->numzgrid : 1;
+  const float smallnum = 1.17549435e-38f; /* tiny(0.0) */
+  const size_t cells = (size_t)nx * ny * nzg;
+  float *grid = (float *)malloc(cells * sizeof(float));
+  float *aux = (float *)malloc((size_t)c->nclassunc * sizeof(float));
+  /* :287-340: mean over the classes, times the number of classes */
+  for (int jy = 0; jy < ny; jy++)
+    for (int ix = 0; ix < nx; ix++)
+      for (int kz = 1; kz <= nzg; kz++) {
+        const size_t cell = ix + (size_t)nx * (jy + (size_t)ny * (kz - 1));
+        for (int l = 1; l <= c->nclassunc; l++) {
+          size_t o = (size_t)(nage - 1);
+          o = o * c->nclassunc + (l - 1);
+          o = o * c->maxpointspec_act + (kp - 1);
+          o = o * c->maxspec + (ks - 1);
+          aux[l - 1] = grid_ref[o * cells + cell];
+        }
+        float xm, xs;
+        mean_sp(aux, &xm, &xs, c->nclassunc);
+        grid[cell] = xm * (float)c->nclassunc;
+      }
+  /* :352-475 */
+  int ci = 0, cr = 0;
+  float sp_fact = -1.f;
+  int sp_zer = 1;
+  for (int kz = 1; kz <= nzg; kz++)
+    for (int jy = 0; jy < ny; jy++)
+      for (int ix = 0; ix < nx; ix++) {
+        const size_t cell = ix + (size_t)nx * (jy + (size_t)ny * (kz - 1));
+        if (grid[cell] > smallnum) {
+          if (sp_zer) {
+            ci++;
+            sparse_dump_i[ci - 1] = which == 0 ? ix + jy * nx + kz * nx * ny : ix + jy * nx;
+            sp_zer = 0;
+            sp_fact = sp_fact * (-1.f);
+          }
+          cr++;
+          if (which == 0) {
+            /* factor3d, :225-235 */
+            float factor3d = (c->ldirect == 1) ? 1.e12f / geom[cell] / outnum
+                                               : (float)abs(loutaver) / outnum;
+            sparse_dump_r[cr - 1] = sp_fact * grid[cell] * factor3d / tot_mu;
+          } else {
+            sparse_dump_r[cr - 1] = sp_fact * 1.e12f * grid[cell] / geom[cell];
+          }
+        } else {
+          sp_zer = 1;
+        }
+      }
+  *sp_count_i = ci;
+  *sp_count_r = cr;
+  free(grid);
+  free(aux);
+}

@@ -800,3 +800,96 @@ def test_time_loop_with_device_release_is_bit_identical():
     assert len(og) == len(oo) >= 1
     for a, b in zip(og, oo):
         assert np.array_equal(a["gridunc"], b["gridunc"])
+
+
+# ----------------------------------------------------------------------------
+# concoutput's sparse dump on the device
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("ldirect", [1, -1])
+def test_sparse_output_dump_matches_the_reference_encoding(ldirect):
+    """fpb_concoutput_sparse against the sequential loop of src/concoutput.f90:287-475 run on the
+    fetched grids: same run starts, same values and signs, bit for bit -- concentration, dry and
+    wet deposition, mother and nested grid, 3 uncertainty classes, per-release grids, 2 age classes."""
+    from oracle_api import load
+    L = load()
+    kw = dict(nrel=3, npart_each=1500, nclassunc=3, ioutputforeachrelease=1, lage=(1800, 86400),
+              nest=(-30.0, 0.0, 40, 32, 1.25, 1.25), math_mode=fb.MATH_FAST)
+    if ldirect == 1:
+        kw.update(nspec=2, drydepspec=(1, 1), wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0),
+                  henry=(1.0e-2, 0.0))
+    cb = cases.config_small(ldirect=ldirect, **kw)
+    c = cb.cfg
+    p = cases.seeded_particles(cb, 4500, zmax=1500.0, lat_range=(-5.0, 35.0), nspec=c.nspec)
+    p.xtra1[:4500] = np.random.RandomState(5).uniform(26.0, 40.0, 4500)     # inside the nest too
+    p.nclass[:4500] = np.random.RandomState(6).randint(1, 4, 4500)
+    bracket = (0, 10800) if ldirect == 1 else (0, -10800)
+    m0, m1 = cases.met_pair(cb, bracket[0], bracket[1])
+    eng = fb.Engine(cb); eng.fill_rannumb()
+    eng.upload_met(1, m0); eng.upload_met(2, m1); eng.set_met_bracket((1, 2), bracket)
+    eng.push_particles(p)
+    outnum = 0.0
+    for k in range(4):
+        itime = ldirect * k * 900
+        if ldirect == 1 and k:
+            eng.wetdepo(itime, 900, 450)
+        eng.conccalc(itime, 1.0); outnum += 1.0
+        eng.step(itime, 450)
+    geo = [fb.outgrid_geometry(cb, c.ylat0 - c.youtshift), fb.outgrid_geometry(cb, c.ylat0 - c.youtshiftn, nest=1)]
+    eng.set_outgrid_geometry(geo[0][0], geo[0][1], geo[1][0], geo[1][1])
+    g = eng.fetch_grids(zero_conc=False)
+    w = eng.fetch_wetgrids() if c.wetdep else {}
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    checked = nonempty = 0
+    for nest in (0, 1):
+        nxy = (c.numxgridn * c.numygridn) if nest else (c.numxgrid * c.numygrid)
+        for which, name in ((0, "gridunc"), (1, "drygridunc"), (2, "wetgridunc")):
+            if (which == 1 and not c.drydep) or (which == 2 and not c.wetdep) or (which and ldirect != 1):
+                continue
+            arr = (w if which == 2 else g)[name + ("n" if nest else "")]
+            flat = np.ascontiguousarray(arr.reshape(-1, order="F"))
+            geom = geo[nest][1 if which == 0 else 0]
+            gflat = np.ascontiguousarray(geom.reshape(-1, order="F"))
+            n = nxy * (c.numzgrid if which == 0 else 1)
+            for ks in range(1, c.nspec + 1):
+                for kp in range(1, c.maxpointspec_act + 1):
+                    for nage in range(1, c.nageclass + 1):
+                        di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
+                        ci, cr = C.c_int32(), C.c_int32()
+                        tot_mu = float(cb.xmass[kp - 1, ks - 1])
+                        L.fpo_concoutput_sparse(C.byref(c), nest, which, flat.ctypes.data_as(_pf), gflat.ctypes.data_as(_pf),
+                                                ks, kp, nage, outnum, tot_mu, 3600, C.byref(ci), di.ctypes.data_as(_pi),
+                                                C.byref(cr), dr.ctypes.data_as(_pf))
+                        gi, gr = eng.concoutput_sparse(which, ks, kp, nage, outnum, tot_mu, 3600, nest=nest)
+                        assert np.array_equal(gi, di[:ci.value]), (nest, which, ks, kp, nage)
+                        assert np.array_equal(gr.view(np.uint32), dr[:cr.value].view(np.uint32)), (nest, which, ks, kp, nage)
+                        checked += 1; nonempty += ci.value > 0
+    assert checked >= 12 and nonempty >= checked // 2
+
+
+def test_sparse_output_dump_edge_cases():
+    """Empty grid, a full grid (one run), and runs that cross rows, levels and scan blocks."""
+    from oracle_api import load
+    L = load()
+    cb = cases.config_small(nrel=1, npart_each=3000)
+    c = cb.cfg
+    eng = fb.Engine(cb)
+    area, vol = fb.outgrid_geometry(cb, c.ylat0 - c.youtshift)
+    eng.set_outgrid_geometry(area, vol)
+    n = c.numxgrid * c.numygrid * c.numzgrid
+    gi, gr = eng.concoutput_sparse(0, 1, 1, 1, 1.0)
+    assert gi.size == 0 and gr.size == 0
+    # fill the device grid through conccalc: particles everywhere, big kernel overlap
+    p = cases.seeded_particles(cb, 3000, zmax=3000.0, lat_range=(-85.0, 85.0))
+    p.xtra1[:3000] = np.random.RandomState(2).uniform(0.5, c.nx - 1.5, 3000)
+    m0, m1 = cases.met_pair(cb)
+    eng.upload_met(1, m0); eng.upload_met(2, m1); eng.set_met_bracket((1, 2), (0, 10800))
+    eng.push_particles(p); eng.conccalc(0, 1.0)
+    g = eng.fetch_grids(zero_conc=False)["gridunc"]
+    flat = np.ascontiguousarray(g.reshape(-1, order="F")); gflat = np.ascontiguousarray(vol.reshape(-1, order="F"))
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32); ci, cr = C.c_int32(), C.c_int32()
+    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), gflat.ctypes.data_as(_pf), 1, 1, 1, 1.0, 1.0, 3600,
+                            C.byref(ci), di.ctypes.data_as(_pi), C.byref(cr), dr.ctypes.data_as(_pf))
+    gi, gr = eng.concoutput_sparse(0, 1, 1, 1, 1.0)
+    assert ci.value > 50 and cr.value > ci.value
+    assert np.array_equal(gi, di[:ci.value]) and np.array_equal(gr.view(np.uint32), dr[:cr.value].view(np.uint32))

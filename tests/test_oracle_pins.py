@@ -509,3 +509,38 @@ def test_golden_fixture_of_oracle_run():
     np.testing.assert_array_equal(p.ytra1[:n], g["ytra1"])
     np.testing.assert_array_equal(p.ztra1[:n], g["ztra1"])
     np.testing.assert_array_equal(outs[-1]["gridunc"], g["gridunc_last"])
+
+
+def test_outgrid_geometry_and_sparse_dump_known_answers():
+    """outgrid_init's cell areas (src/outgrid_init.f90:52-82) tile the sphere, the host library and
+    the oracle agree, and the sparse dump of concoutput (src/concoutput.f90:432-470) encodes runs
+    the way the reference's reader expects: index of each run start, sign flipping per run."""
+    from oracle_api import load
+    cb = fb.make_config(nx=73, ny=37, nz=40, dx=5., dy=5., xlon0=-180.0, ylat0=-90.0, outlon0=-180.0, outlat0=-90.0,
+                        numxgrid=72, numygrid=36, dxout=5.0, dyout=5.0, outheights=(100.0, 500.0, 1500.0), npart=(10,),
+                        height=fb.synth_heights(138)[::3][:40])
+    c = cb.cfg
+    L = load()
+    area = np.zeros((72, 36), np.float32, order="F"); vol = np.zeros((72, 36, 3), np.float32, order="F")
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    L.fpo_outgrid_geometry(C.byref(c), 0, -90.0, area.ctypes.data_as(_pf), vol.ctypes.data_as(_pf))
+    assert abs(area.sum() / (4 * np.pi * 6.371e6 ** 2) - 1) < 1e-5
+    np.testing.assert_allclose(vol[:, :, 1], area * 400.0, rtol=1e-6)
+    a2, v2 = fb.outgrid_geometry(cb, -90.0)
+    np.testing.assert_allclose(a2, area, rtol=2e-6); np.testing.assert_allclose(v2, vol, rtol=2e-6)
+    # hand-made grid: cells 3,4,5 | 10 | last cell of level 1 + first of level 2 (one run across the level)
+    g = np.zeros((72, 36, 3, c.maxspec, 1, 1, 1), np.float32, order="F")
+    flat = g.reshape(-1, order="F")
+    n2 = 72 * 36
+    for cell, v in ((3, 1.0), (4, 2.0), (5, 3.0), (10, 4.0), (n2 - 1, 5.0), (n2, 6.0), (2 * n2 + 7, 1e-39)):
+        flat[cell] = v
+    di = np.zeros(3 * n2, np.int32); dr = np.zeros(3 * n2, np.float32)
+    ci, cr = C.c_int32(), C.c_int32()
+    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), vol.ctypes.data_as(_pf), 1, 1, 1, 2.0, 1.0, 3600,
+                            C.byref(ci), di.ctypes.data_as(_pi), C.byref(cr), dr.ctypes.data_as(_pf))
+    assert (ci.value, cr.value) == (3, 6)                      # the denormal cell is not written
+    assert di[:3].tolist() == [3 + n2, 10 + n2, n2 - 1 + n2]   # kz is 1-based in the index
+    assert np.sign(dr[:6]).tolist() == [1, 1, 1, -1, 1, 1]
+    volf = vol.reshape(-1, order="F")
+    np.testing.assert_allclose(np.abs(dr[:6]), [v * 1e12 / volf[k] / 2.0 for k, v in
+                               ((3, 1.0), (4, 2.0), (5, 3.0), (10, 4.0), (n2 - 1, 5.0), (n2, 6.0))], rtol=1e-6)

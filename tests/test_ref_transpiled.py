@@ -422,3 +422,67 @@ def test_reference_readcommand_derivations_match_host():
                     exp = (ref.get("ifine"), ref.get("turbswitch"), ref.get("fine"), ref.get("ctl"), ref.get("method"),
                            ref.get("mintime"), ref.get("lsynctime"))
                     assert got == exp, (ctl, ifine, cbl, lsync, got, exp)
+
+
+def test_reference_outgrid_geometry_and_sparse_dump_bit_identical():
+    """outgrid_init's areas and volumes (src/outgrid_init.f90:51-99) and concoutput's work on one
+    (ks, kp, nage) grid -- factor3d (:214-225), the class mean (:275-335, mean_mod), and the three
+    sparse dumps (wet :353-381, dry :390-418, concentration :429-467) -- against the oracle's
+    restatement (oracle/fpo_output.c), which the GPU tests in turn equate with the device's."""
+    cb = cases.config_small(nrel=2, npart_each=10, nclassunc=3, ioutputforeachrelease=1, lage=(1800, 86400),
+                            nspec=2, drydepspec=(1, 1), wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0),
+                            wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0))
+    c = cb.cfg
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    o = Oracle(cb)
+    L = o.L
+    _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    outlat0 = np.float32(c.ylat0) - np.float32(c.youtshift)
+    ref.set("outlat0", float(outlat0))
+    ref.L.f_og_geometry()
+    area = np.zeros((c.numxgrid, c.numygrid), np.float32, order="F")
+    vol = np.zeros((c.numxgrid, c.numygrid, c.numzgrid), np.float32, order="F")
+    L.fpo_outgrid_geometry(C.byref(c), 0, float(outlat0), area.ctypes.data_as(_pf), vol.ctypes.data_as(_pf))
+    assert np.array_equal(ref.arr("area").view(np.uint32), area.view(np.uint32))
+    assert np.array_equal(ref.arr("volume").view(np.uint32), vol.view(np.uint32))
+
+    # random sparse grids with runs, gaps, denormals and exact zeros; classes differ
+    r = np.random.RandomState(4)
+    n2, n3 = c.numxgrid * c.numygrid, c.numxgrid * c.numygrid * c.numzgrid
+    for name in ("gridunc", "drygridunc", "wetgridunc"):
+        a = ref.arr(name)
+        v = r.uniform(0.0, 1.0, a.shape).astype(np.float32) * (r.uniform(size=a.shape) < 0.35)
+        v[r.uniform(size=a.shape) < 0.01] = 1e-39
+        blk = r.uniform(size=a.shape[:2]) < 0.5          # whole columns empty: longer gaps
+        v[blk] = 0.0
+        a[...] = v
+    ref.set("wetdep", 1)
+    outnum = np.float32(7.0)
+    ref.L.f_co_factor3d(C.byref(C.c_float(outnum)))
+    tot_mu = np.asfortranarray(r.uniform(0.5, 2.0, (c.maxspec, c.maxpointspec_act)).astype(np.float32))
+    volf = np.ascontiguousarray(vol.reshape(-1, order="F")); areaf = np.ascontiguousarray(area.reshape(-1, order="F"))
+    total = 0
+    for ks in (1, 2):
+        for kp in (1, 2):
+            for nage in (1, 2):
+                ref.L.f_co_mean(C.byref(C.c_int(ks)), C.byref(C.c_int(kp)), C.byref(C.c_int(nage)))
+                for which, fn, gname, geom, n in ((2, "f_co_wet", "wetgridunc", areaf, n2), (1, "f_co_dry", "drygridunc", areaf, n2),
+                                                  (0, "f_co_conc", "gridunc", volf, n3)):
+                    ci, cr = C.c_int(0), C.c_int(0)
+                    ref.arr("sparse_dump_i")[:] = -7; ref.arr("sparse_dump_r")[:] = np.nan
+                    if which == 0:
+                        getattr(ref.L, fn)(C.byref(C.c_int(ks)), C.byref(C.c_int(kp)), tot_mu.ctypes.data_as(_pf),
+                                           C.byref(ci), C.byref(cr))
+                    else:
+                        getattr(ref.L, fn)(C.byref(ci), C.byref(cr))
+                    flat = np.ascontiguousarray(ref.arr(gname).reshape(-1, order="F"))
+                    di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
+                    oi, orr = C.c_int32(), C.c_int32()
+                    L.fpo_concoutput_sparse(C.byref(c), 0, which, flat.ctypes.data_as(_pf), geom.ctypes.data_as(_pf), ks, kp, nage,
+                                            float(outnum), float(tot_mu[ks - 1, kp - 1]), 3600, C.byref(oi),
+                                            di.ctypes.data_as(_pi), C.byref(orr), dr.ctypes.data_as(_pf))
+                    assert (ci.value, cr.value) == (oi.value, orr.value), (ks, kp, nage, which)
+                    assert np.array_equal(ref.arr("sparse_dump_i")[:ci.value], di[:ci.value])
+                    assert np.array_equal(ref.arr("sparse_dump_r")[:cr.value].view(np.uint32), dr[:cr.value].view(np.uint32)), (ks, kp, nage, which)
+                    total += cr.value
+    assert total > 1000
