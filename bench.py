@@ -335,6 +335,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = (cpu_baseline_reference(args, 1, args.cpu_seconds) if reference_available()
                                     else cpu_baseline(args, threads=1, budget_s=args.cpu_seconds))
+    if rank == 0 and world == 1 and not args.no_hbm_regime:
+        line["next_rows"] = next_rows(eng, cb, rel, peaks()[0], k * 900)
     eng.close()
     if rank == 0:
         if world == 1 and args.workload == "c2" and not args.no_hbm_regime:
@@ -342,6 +344,50 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def next_rows(eng, cb, rel, peak, itime_now):
+    """The SURVEY 8f rows that run on the device, timed on the bench's own engine (wall clock
+    around the synchronous C-ABI calls, best of 5): releaseparticles for all particles at once,
+    concoutput's sparse dump of the concentration grid, wetdepo when the workload has it."""
+    import numpy as np
+    import flexpart_b200 as fb
+    c = cb.cfg
+    out = {}
+
+    def best(fn, n=5):
+        t = []
+        for _ in range(n):
+            t0 = time.perf_counter(); fn(); t.append(time.perf_counter() - t0)
+        return min(t)
+
+    # sparse dump of gridunc(:,:,:,1,1,:,1) as the steps left it
+    area, vol = fb.outgrid_geometry(cb, c.ylat0 - c.youtshift)
+    eng.set_outgrid_geometry(area, vol)
+    eng.conccalc(0, 1.0)
+    res = {}
+    t = best(lambda: res.update(d=eng.concoutput_sparse(0, 1, 1, 1, 4.0)))
+    cells = c.numxgrid * c.numygrid * c.numzgrid
+    nz = int(res["d"][1].size)
+    alg = 2 * cells * (4 * c.nclassunc + 4) + 8 * nz        # two passes over the cells + the lists
+    out["concoutput_sparse"] = {"ms": t * 1e3, "cells": cells, "nonzero": nz, "runs": int(res["d"][0].size),
+                                "d2h_bytes": 4 * (nz + int(res["d"][0].size)), "dense_d2h_bytes": 4 * cells,
+                                "alg_GBps": alg / t / 1e9, "frac_of_peak": alg / t / 1e9 / peak,
+                                "what": "fpb_concoutput_sparse incl. the D2H of the compacted lists"}
+    if c.wetdep:
+        t = best(lambda: eng.wetdepo(itime_now, 900, 450))
+        out["wetdepo"] = {"ms": t * 1e3, "particles_per_s": c.maxpart / t,
+                          "alg_GBps": c.maxpart * (28 + 64 + 5 + 8 * c.nspec) / t / 1e9,
+                          "what": "fpb_wetdepo over all particles (28 B state + 4 x 16 B rain words + cloud class + tt + masses)"}
+    # release of maxpart particles on a second engine (Philox positions): no particle row crosses PCIe
+    e2 = fb.Engine(cb)
+    e2.set_releases(rel)
+    t0 = time.perf_counter(); n, made = e2.release_particles(0); t = time.perf_counter() - t0
+    out["releaseparticles"] = {"ms": t * 1e3, "particles": made, "particles_per_s": made / t,
+                               "alg_GBps": made * 78 / t / 1e9,
+                               "what": "fpb_releaseparticles, all release points at once (first call: includes allocations)"}
+    e2.close() if hasattr(e2, "close") else None
+    return out
 
 
 def hbm_regime(args, local, K, W):
