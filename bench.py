@@ -49,19 +49,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML polled every 5 ms from a
+    thread (the same counters nvidia-smi prints); nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.mx, self.seen = [], [], set()
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = N.nvmlDeviceGetHandleByIndex(idx)
+            masks = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+            self.mx.append(float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)))
+
+            def poll():
+                while not self._stop.is_set():
+                    self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for n, m in masks.items():
+                        if r & m:
+                            self.seen.add(n)
+                    self._stop.wait(0.005)
+            self.nvml = threading.Thread(target=poll, daemon=True)
+            self.nvml.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,6 +102,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self._stop.set()
+            self.nvml.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(self.sm), "source": "nvml, 5 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,10 +116,9 @@ class ClockSampler:
             self.proc.kill()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
