@@ -164,6 +164,7 @@ def load_engine_lib():
     L.fpb_wetdepo.argtypes = [H, _i, _i, _i]
     L.fpb_set_releases.argtypes = [H, C.POINTER(FpbReleasePoints)]
     L.fpb_set_outgrid_geometry.argtypes = [H, _pf, _pf, _pf, _pf]
+    L.fpb_set_outgrid_origin.argtypes = [H, _f, _f, _f, _f]
     L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]

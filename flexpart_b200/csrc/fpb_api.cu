@@ -143,9 +143,11 @@ struct fpb_handle {
     float *area[2] = {nullptr, nullptr}, *volume[2] = {nullptr, nullptr}; // [0] mother, [1] nest
     unsigned *block_counts = nullptr;
     int32_t *d_i = nullptr;
-    float *d_r = nullptr;
+    float *d_r = nullptr, *d_density = nullptr;
     int *d_counts = nullptr;
     size_t cap = 0;
+    float lon0[2] = {0.f, 0.f}, lat0[2] = {0.f, 0.f};
+    bool have_origin = false;
   } outp;
   // device-side releaseparticles
   struct Releases {
@@ -511,6 +513,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->d_height); cudaFree(h->d_npart); cudaFree(h->d_xmass);
   for (int k = 0; k < 2; k++) { cudaFree(h->outp.area[k]); cudaFree(h->outp.volume[k]); }
   cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r); cudaFree(h->outp.d_counts);
+  cudaFree(h->outp.d_density);
   for (auto &q : h->rel.d_pts) cudaFree(q);
   cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
@@ -997,13 +1000,21 @@ extern "C" int fpb_set_outgrid_geometry(fpb_handle *h, const float *area, const 
     cap = std::max(cap, m2 * c.numzgrid);
   }
   if (cap > h->outp.cap) {
-    cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r);
-    h->outp.block_counts = nullptr; h->outp.d_i = nullptr; h->outp.d_r = nullptr;
+    cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r); cudaFree(h->outp.d_density);
+    h->outp.block_counts = nullptr; h->outp.d_i = nullptr; h->outp.d_r = nullptr; h->outp.d_density = nullptr;
     DA(h->outp.block_counts, 2 * ((cap + 1023) / 1024));
-    DA(h->outp.d_i, cap); DA(h->outp.d_r, cap);
+    DA(h->outp.d_i, cap); DA(h->outp.d_r, cap); DA(h->outp.d_density, cap);
     h->outp.cap = cap;
   }
   if (!h->outp.d_counts) DA(h->outp.d_counts, 2);
+  return 0;
+}
+
+extern "C" int fpb_set_outgrid_origin(fpb_handle *h, float outlon0, float outlat0, float outlon0n, float outlat0n) {
+  if (!h) return fail("fpb_set_outgrid_origin: null handle");
+  h->outp.lon0[0] = outlon0; h->outp.lat0[0] = outlat0;
+  h->outp.lon0[1] = outlon0n; h->outp.lat0[1] = outlat0n;
+  h->outp.have_origin = true;
   return 0;
 }
 
@@ -1015,7 +1026,9 @@ extern "C" int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which,
     return fail("fpb_concoutput_sparse: null argument");
   const fpb_config &c = h->cfg;
   if (nest < 0 || nest > 1 || (nest == 1 && c.nested_output != 1)) return fail("fpb_concoutput_sparse: no such output grid %d", nest);
-  if (which < 0 || which > 2) return fail("fpb_concoutput_sparse: which = %d", which);
+  if (which < 0 || which > 3) return fail("fpb_concoutput_sparse: which = %d", which);
+  if (which == 3 && (!h->outp.have_origin || !h->have_bracket))
+    return fail("fpb_concoutput_sparse: the mixing-ratio record needs fpb_set_outgrid_origin and a met bracket");
   if (ks < 1 || ks > c.nspec || kp < 1 || kp > c.maxpointspec_act || nage < 1 || nage > c.nageclass)
     return fail("fpb_concoutput_sparse: (ks, kp, nage) = (%d, %d, %d) out of range", ks, kp, nage);
   if (!h->outp.area[nest] || !h->outp.volume[nest]) return fail("fpb_concoutput_sparse: fpb_set_outgrid_geometry has not been called");
@@ -1025,18 +1038,45 @@ extern "C" int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which,
   const size_t n2 = (size_t)nxg * nyg;
   SparseDumpArgs a;
   a.which = which;
-  a.ncells = (int)(which == 0 ? n2 * c.numzgrid : n2);
-  const float *g = which == 0 ? (nest ? h->griduncn : h->gridunc)
+  const bool conc = which == 0 || which == 3;
+  a.ncells = (int)(conc ? n2 * c.numzgrid : n2);
+  const float *g = conc ? (nest ? h->griduncn : h->gridunc)
                  : which == 1 ? (nest ? h->drygriduncn : h->drygridunc) : (nest ? h->wetgriduncn : h->wetgridunc);
   // device layout: [nage][class][kp][ks][cells]
   const size_t inner = (size_t)a.ncells;
   a.class_stride = (size_t)c.maxpointspec_act * c.nspec * inner;
   a.grid = g + ((((size_t)(nage - 1) * c.nclassunc) * c.maxpointspec_act + (kp - 1)) * c.nspec + (ks - 1)) * inner;
   a.nclassunc = c.nclassunc;
-  a.geom = which == 0 ? h->outp.volume[nest] : h->outp.area[nest];
+  a.geom = conc ? h->outp.volume[nest] : h->outp.area[nest];
+  a.density = nullptr;
+  if (which == 3) { // densityoutgrid, src/concoutput.f90:164-190
+    if (c.numzgrid > 32) return fail("fpb_concoutput_sparse: numzgrid > 32");
+    DensityArgs d;
+    d.A = slot_view(h, h->memind[1]).A;
+    d.nxd = h->d.nxd; d.plane = h->d.nxd * h->d.nyd;
+    d.numx = nxg; d.numy = nyg; d.numz = c.numzgrid;
+    d.outlon0 = h->outp.lon0[nest]; d.outlat0 = h->outp.lat0[nest];
+    d.dxout = nest ? c.dxoutn : c.dxout; d.dyout = nest ? c.dyoutn : c.dyout;
+    d.xlon0 = c.xlon0; d.ylat0 = c.ylat0; d.dx = c.dx; d.dy = c.dy;
+    d.nxmin1 = c.nxmin1; d.nymin1 = c.nymin1;
+    for (int kz = 1; kz <= c.numzgrid; kz++) {
+      const float halfheight = (kz == 1) ? c.outheight[0] / 2.f : (c.outheight[kz - 1] + c.outheight[kz - 2]) / 2.f;
+      int kzz = 2;
+      for (; kzz <= c.nz; kzz++)
+        if (h->height[kzz - 2] < halfheight && h->height[kzz - 1] > halfheight) break;
+      kzz = std::max(std::min(kzz, (int)c.nz), 2);
+      d.kzz[kz - 1] = kzz;
+      d.dz1[kz - 1] = halfheight - h->height[kzz - 2];
+      d.dz2[kz - 1] = h->height[kzz - 1] - halfheight;
+    }
+    d.density = h->outp.d_density;
+    fpb_density_outgrid(d, h->stream);
+    h->launches++;
+    a.density = h->outp.d_density;
+  }
   a.ldirect = c.ldirect;
   a.outnum = outnum; a.tot_mu = tot_mu; a.loutaver_abs = (float)std::abs(loutaver);
-  a.index_offset = which == 0 ? (int)n2 : 0; // kz is 1-based in ix+jy*numxgrid+kz*numxgrid*numygrid
+  a.index_offset = conc ? (int)n2 : 0; // kz is 1-based in ix+jy*numxgrid+kz*numxgrid*numygrid
   a.block_counts = h->outp.block_counts;
   a.out_i = h->outp.d_i; a.out_r = h->outp.d_r; a.counts = h->outp.d_counts;
   fpb_sparse_dump(a, h->stream);

@@ -27,6 +27,8 @@ __device__ __forceinline__ float cell_value(const SparseDumpArgs &a, int i, floa
     const float factor3d = (a.ldirect == 1) ? 1.e12f / a.geom[i] / a.outnum : a.loutaver_abs / a.outnum;
     return g * factor3d / a.tot_mu;
   }
+  if (a.which == 3) // mixing ratio, :579-583 (tot_mu carries weightmolar(ks); weightair = 28.97)
+    return 1.e12f * g / a.geom[i] / a.outnum * 28.97f / a.tot_mu / a.density[i];
   return 1.e12f * g / a.geom[i]; // :370-372, :402-405
 }
 
@@ -111,7 +113,29 @@ __global__ void __launch_bounds__(OUT_BLOCK) sparse_write_kernel(const SparseDum
   const float v = cell_value(a, i, g);
   a.out_r[kn] = (kr & 1u) ? v : -v;
 }
+__global__ void __launch_bounds__(256) density_outgrid_kernel(const DensityArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n2 = a.numx * a.numy;
+  if (i >= n2 * a.numz) return;
+  const int kz = i / n2, jy = (i - kz * n2) / a.numx, ix = i - kz * n2 - jy * a.numx;
+  float xl = a.outlon0 + (float)ix * a.dxout;
+  float yl = a.outlat0 + (float)jy * a.dyout;
+  xl = (xl - a.xlon0) / a.dx;
+  yl = (yl - a.ylat0) / a.dy;
+  const int iix = max(min((int)roundf(xl), a.nxmin1), 0); // nint(): half away from zero
+  const int jjy = max(min((int)roundf(yl), a.nymin1), 0);
+  const int kzz = a.kzz[kz];
+  const float dz1 = a.dz1[kz], dz2 = a.dz2[kz], dz = dz1 + dz2;
+  const float r1 = a.A[(size_t)(kzz - 1) * a.plane + (size_t)jjy * a.nxd + iix].w;
+  const float r0 = a.A[(size_t)(kzz - 2) * a.plane + (size_t)jjy * a.nxd + iix].w;
+  a.density[i] = (r1 * dz1 + r0 * dz2) / dz;
+}
 } // namespace
+
+void fpb_density_outgrid(const DensityArgs &a, cudaStream_t st) {
+  const int n = a.numx * a.numy * a.numz;
+  density_outgrid_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+}
 
 void fpb_sparse_dump(const SparseDumpArgs &a, cudaStream_t st) {
   const int nb = (a.ncells + OUT_BLOCK - 1) / OUT_BLOCK;

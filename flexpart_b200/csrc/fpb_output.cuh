@@ -8,8 +8,9 @@ struct SparseDumpArgs {
   const float *grid;        // first class slice of (ks, kp, nage): [ncells]
   size_t class_stride;      // floats between the slices of consecutive uncertainty classes
   int nclassunc, ncells;
-  const float *geom;        // which = 0: volume[ncells]; 1, 2: area[ncells]
-  int which;                // 0 concentration, 1 dry deposition, 2 wet deposition
+  const float *geom;        // which = 0, 3: volume[ncells]; 1, 2: area[ncells]
+  const float *density;     // which = 3: densityoutgrid[ncells]
+  int which;                // 0 concentration, 1 dry deposition, 2 wet deposition, 3 mixing ratio
   int ldirect;
   float outnum, tot_mu, loutaver_abs;
   int index_offset;         // added to the linear cell index (numxgrid*numygrid for concentrations)
@@ -20,3 +21,17 @@ struct SparseDumpArgs {
 };
 
 void fpb_sparse_dump(const SparseDumpArgs &a, cudaStream_t st);
+
+// densityoutgrid of concoutput (src/concoutput.f90:164-190): rho of time level memind(2) at the
+// met cell nearest to each output cell, interpolated to the middle of the output layer
+struct DensityArgs {
+  const float4 *A;          // {uu, vv, ww, rho} of memind(2), [level][jy][ix], row stride nxd
+  int nxd, plane;
+  int numx, numy, numz;
+  float outlon0, outlat0, dxout, dyout, xlon0, ylat0, dx, dy;
+  int nxmin1, nymin1;
+  int kzz[32];              // per output layer: met level above its middle (Fortran index)
+  float dz1[32], dz2[32];
+  float *density;           // [numx * numy * numz]
+};
+void fpb_density_outgrid(const DensityArgs &a, cudaStream_t st);

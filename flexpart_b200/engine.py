@@ -98,11 +98,14 @@ class Engine:
         keep = [np.asfortranarray(a, np.float32) if a is not None else None for a in (area, volume, arean, volumen)]
         self._check(self.L.fpb_set_outgrid_geometry(self.h, *[_fp(a) if a is not None else None for a in keep]))
 
+    def set_outgrid_origin(self, outlon0, outlat0, outlon0n=0.0, outlat0n=0.0):
+        self._check(self.L.fpb_set_outgrid_origin(self.h, outlon0, outlat0, outlon0n, outlat0n))
+
     def concoutput_sparse(self, which, ks, kp, nage, outnum, tot_mu=1.0, loutaver=3600, nest=0):
         """sparse dump of one (ks, kp, nage) grid: (sparse_dump_i, sparse_dump_r) of
         src/concoutput.f90:352-475; which = 0 concentration, 1 dry, 2 wet deposition."""
         c = self.cb.cfg
-        n = (c.numxgridn * c.numygridn if nest else c.numxgrid * c.numygrid) * (c.numzgrid if which == 0 else 1)
+        n = (c.numxgridn * c.numygridn if nest else c.numxgrid * c.numygrid) * (c.numzgrid if which in (0, 3) else 1)
         di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
         ci, cr = C.c_int32(0), C.c_int32(0)
         self._check(self.L.fpb_concoutput_sparse(self.h, nest, which, ks, kp, nage, outnum, tot_mu, loutaver,

@@ -276,6 +276,9 @@ int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32_t ldeltat)
  * volume(numxgrid,numygrid,numzgrid); the nested grid's (src/outgrid_init_nest.f90) may be NULL. */
 int fpb_set_outgrid_geometry(fpb_handle *h, const float *area, const float *volume,
                              const float *arean, const float *volumen);
+/* lower left corners outlon0, outlat0 (and outlon0n, outlat0n) as read by readoutgrid(_nest): only
+ * needed for the mixing-ratio record (which = 3), whose densityoutgrid is looked up from them */
+int fpb_set_outgrid_origin(fpb_handle *h, float outlon0, float outlat0, float outlon0n, float outlat0n);
 
 /* The body of concoutput's loop over (ks, kp, nage) for the sparse binary output (iout = 1;
  * src/concoutput.f90:287-475, concoutput_nest.f90 alike): mean over the uncertainty classes x
@@ -283,7 +286,9 @@ int fpb_set_outgrid_geometry(fpb_handle *h, const float *area, const float *volu
  * 1.e12/area for deposition) and the run-length dump -- the index of the first cell of every run of
  * cells above tiny(0.0) and the values with the sign alternating from run to run -- built on the
  * device, so only the compacted lists cross the bus.  which: 0 concentration, 1 dry deposition,
- * 2 wet deposition; nest: 0 mother, 1 nested output grid; ks, kp, nage 1-based.  The buffers hold
+ * 2 wet deposition, 3 mixing ratio (iout = 2, 3; :563-593: 1.e12/volume/outnum*weightair/
+ * weightmolar(ks)/densityoutgrid with the air density of time level memind(2), :164-190 -- pass
+ * weightmolar(ks) in tot_mu); nest: 0 mother, 1 nested output grid; ks, kp, nage 1-based.  The buffers hold
  * numxgrid*numygrid*numzgrid entries (numxgrid*numygrid for deposition).  The grid totals and
  * their uncertainty (gridtotal, gridsigmatotal: diagnostics on stdout) are not computed.
  *  */

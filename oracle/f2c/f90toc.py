@@ -70,6 +70,7 @@ ALLOC_DIMS = {
     "drygrid": "0:numxgrid-1,0:numygrid-1", "wetgridsigma": "0:numxgrid-1,0:numygrid-1",
     "drygridsigma": "0:numxgrid-1,0:numygrid-1",
     "sparse_dump_r": "numxgrid*numygrid*numzgrid", "sparse_dump_i": "numxgrid*numygrid*numzgrid",
+    "densityoutgrid": "0:numxgrid-1,0:numygrid-1,numzgrid", "densitydrygrid": "0:numxgrid-1,0:numygrid-1,numzgrid",
 }
 
 

@@ -163,8 +163,10 @@ void fpo_fetch_wetgrids(fpo_state *S, float *wetgridunc, float *wetgriduncn);
 
 /* fpo_output.c: outgrid_init's cell geometry and concoutput's sparse dump of one (ks, kp, nage) */
 void fpo_outgrid_geometry(const fpb_config *c, int nest, float outlat0, float *area, float *volume);
+void fpo_density_outgrid(const fpb_config *c, const float *height, int nest, float outlon0, float outlat0,
+                         const float *rho, float *densityoutgrid);
 void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float *grid_ref,
-                           const float *geom, int ks, int kp, int nage, float outnum, float tot_mu,
+                           const float *geom, const float *density, int ks, int kp, int nage, float outnum, float tot_mu,
                            int loutaver, int32_t *sp_count_i, int32_t *sparse_dump_i,
                            int32_t *sp_count_r, float *sparse_dump_r);
 

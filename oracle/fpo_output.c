@@ -60,14 +60,50 @@ static void mean_sp(const float *x, float *xm, float *xs, int number) {
   else *xs = fpo_sqrtf(xaux / (float)(number - 1));
 }
 
+/* densityoutgrid, src/concoutput.f90:164-190: rho(0:nxmax-1,0:nymax-1,nzmax) of time level memind(2) */
+void fpo_density_outgrid(const fpb_config *c, const float *height, int nest, float outlon0, float outlat0,
+                         const float *rho, float *densityoutgrid) {
+  const int nx = nest ? c->numxgridn : c->numxgrid, ny = nest ? c->numygridn : c->numygrid;
+  const float dxo = nest ? c->dxoutn : c->dxout, dyo = nest ? c->dyoutn : c->dyout;
+  for (int kz = 1; kz <= c->numzgrid; kz++) {
+    float halfheight;
+    if (kz == 1) halfheight = c->outheight[0] / 2.f;
+    else halfheight = (c->outheight[kz - 1] + c->outheight[kz - 2]) / 2.f;
+    int kzz;
+    for (kzz = 2; kzz <= c->nz; kzz++)
+      if ((height[kzz - 2] < halfheight) && (height[kzz - 1] > halfheight)) break;
+    kzz = kzz < c->nz ? kzz : c->nz;
+    kzz = kzz > 2 ? kzz : 2;
+    float dz1 = halfheight - height[kzz - 2];
+    float dz2 = height[kzz - 1] - halfheight;
+    float dz = dz1 + dz2;
+    for (int jy = 0; jy < ny; jy++)
+      for (int ix = 0; ix < nx; ix++) {
+        float xl = outlon0 + (float)ix * dxo;
+        float yl = outlat0 + (float)jy * dyo;
+        xl = (xl - c->xlon0) / c->dx;
+        yl = (yl - c->ylat0) / c->dy;
+        int iix = fpo_nint_f(xl), jjy = fpo_nint_f(yl);
+        iix = iix < c->nxmin1 ? iix : c->nxmin1; iix = iix > 0 ? iix : 0;
+        jjy = jjy < c->nymin1 ? jjy : c->nymin1; jjy = jjy > 0 ? jjy : 0;
+        const size_t plane = (size_t)c->nxmax * c->nymax;
+        densityoutgrid[ix + (size_t)nx * (jy + (size_t)ny * (kz - 1))] =
+            (rho[iix + (size_t)c->nxmax * jjy + plane * (kzz - 1)] * dz1 +
+             rho[iix + (size_t)c->nxmax * jjy + plane * (kzz - 2)] * dz2) / dz;
+      }
+  }
+}
+
 /* which: 0 concentration (grid = gridunc, geom = volume), 1 dry / 2 wet deposition
- * (grid = drygridunc / wetgridunc, geom = area) */
+ * (grid = drygridunc / wetgridunc, geom = area), 3 mixing ratio (grid = gridunc, geom = volume,
+ * density = densityoutgrid, tot_mu = weightmolar(ks); src/concoutput.f90:563-593) */
 void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float *grid_ref,
-                           const float *geom, int ks, int kp, int nage, float outnum, float tot_mu,
+                           const float *geom, const float *density, int ks, int kp, int nage, float outnum, float tot_mu,
                            int loutaver, int32_t *sp_count_i, int32_t *sparse_dump_i,
                            int32_t *sp_count_r, float *sparse_dump_r) {
   const int nx = nest ? c->numxgridn : c->numxgrid, ny = nest ? c->numygridn : c->numygrid;
-  const int nzg = which == 0 ? c->numzgrid : 1;
+  const int conc = which == 0 || which == 3;
+  const int nzg = conc ? c->numzgrid : 1;
   const float smallnum = 1.17549435e-38f; /* tiny(0.0) */
   const size_t cells = (size_t)nx * ny * nzg;
   float *grid = (float *)malloc(cells * sizeof(float));
@@ -99,7 +135,7 @@ void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float
         if (grid[cell] > smallnum) {
           if (sp_zer) {
             ci++;
-            sparse_dump_i[ci - 1] = which == 0 ? ix + jy * nx + kz * nx * ny : ix + jy * nx;
+            sparse_dump_i[ci - 1] = conc ? ix + jy * nx + kz * nx * ny : ix + jy * nx;
             sp_zer = 0;
             sp_fact = sp_fact * (-1.f);
           }
@@ -109,6 +145,9 @@ void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float
             float factor3d = (c->ldirect == 1) ? 1.e12f / geom[cell] / outnum
                                                : (float)abs(loutaver) / outnum;
             sparse_dump_r[cr - 1] = sp_fact * grid[cell] * factor3d / tot_mu;
+          } else if (which == 3) {
+            const float weightair = 28.97f;
+            sparse_dump_r[cr - 1] = sp_fact * 1.e12f * grid[cell] / geom[cell] / outnum * weightair / tot_mu / density[cell];
           } else {
             sparse_dump_r[cr - 1] = sp_fact * 1.e12f * grid[cell] / geom[cell];
           }

@@ -58,7 +58,8 @@ def load(libm_float=False):
     L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
     L.fpo_releaseparticles.restype = C.c_int
     L.fpo_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_float, _pf, _pf]
-    L.fpo_concoutput_sparse.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_int, _pf, _pf, C.c_int, C.c_int, C.c_int,
+    L.fpo_density_outgrid.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, C.c_float, C.c_float, _pf, _pf]
+    L.fpo_concoutput_sparse.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_int, _pf, _pf, _pf, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_float, C.c_int, _pi, _pi, _pi, _pf]
     L.fpo_mp_step.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float]
     L.fpo_mp_step.restype = C.c_double

@@ -836,27 +836,35 @@ def test_sparse_output_dump_matches_the_reference_encoding(ldirect):
         eng.step(itime, 450)
     geo = [fb.outgrid_geometry(cb, c.ylat0 - c.youtshift), fb.outgrid_geometry(cb, c.ylat0 - c.youtshiftn, nest=1)]
     eng.set_outgrid_geometry(geo[0][0], geo[0][1], geo[1][0], geo[1][1])
+    eng.set_outgrid_origin(c.xlon0 - c.xoutshift, c.ylat0 - c.youtshift, c.xlon0 - c.xoutshiftn, c.ylat0 - c.youtshiftn)
     g = eng.fetch_grids(zero_conc=False)
     w = eng.fetch_wetgrids() if c.wetdep else {}
     _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
     checked = nonempty = 0
     for nest in (0, 1):
         nxy = (c.numxgridn * c.numygridn) if nest else (c.numxgrid * c.numygrid)
-        for which, name in ((0, "gridunc"), (1, "drygridunc"), (2, "wetgridunc")):
+        lon0 = c.xlon0 - (c.xoutshiftn if nest else c.xoutshift)
+        lat0 = c.ylat0 - (c.youtshiftn if nest else c.youtshift)
+        dens = np.zeros(nxy * c.numzgrid, np.float32)
+        rho2 = np.ascontiguousarray(m1.rho.reshape(-1, order="F"))       # memind(2) = slot 2
+        L.fpo_density_outgrid(C.byref(c), cb.height.ctypes.data_as(_pf), nest, lon0, lat0, rho2.ctypes.data_as(_pf),
+                              dens.ctypes.data_as(_pf))
+        for which, name in ((0, "gridunc"), (1, "drygridunc"), (2, "wetgridunc"), (3, "gridunc")):
             if (which == 1 and not c.drydep) or (which == 2 and not c.wetdep) or (which and ldirect != 1):
                 continue
             arr = (w if which == 2 else g)[name + ("n" if nest else "")]
             flat = np.ascontiguousarray(arr.reshape(-1, order="F"))
-            geom = geo[nest][1 if which == 0 else 0]
+            geom = geo[nest][1 if which in (0, 3) else 0]
             gflat = np.ascontiguousarray(geom.reshape(-1, order="F"))
-            n = nxy * (c.numzgrid if which == 0 else 1)
+            n = nxy * (c.numzgrid if which in (0, 3) else 1)
             for ks in range(1, c.nspec + 1):
                 for kp in range(1, c.maxpointspec_act + 1):
                     for nage in range(1, c.nageclass + 1):
                         di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
                         ci, cr = C.c_int32(), C.c_int32()
-                        tot_mu = float(cb.xmass[kp - 1, ks - 1])
+                        tot_mu = float(cb.xmass[kp - 1, ks - 1]) if which != 3 else 350.0 + ks   # weightmolar(ks)
                         L.fpo_concoutput_sparse(C.byref(c), nest, which, flat.ctypes.data_as(_pf), gflat.ctypes.data_as(_pf),
+                                                dens.ctypes.data_as(_pf) if which == 3 else None,
                                                 ks, kp, nage, outnum, tot_mu, 3600, C.byref(ci), di.ctypes.data_as(_pi),
                                                 C.byref(cr), dr.ctypes.data_as(_pf))
                         gi, gr = eng.concoutput_sparse(which, ks, kp, nage, outnum, tot_mu, 3600, nest=nest)
@@ -864,6 +872,7 @@ def test_sparse_output_dump_matches_the_reference_encoding(ldirect):
                         assert np.array_equal(gr.view(np.uint32), dr[:cr.value].view(np.uint32)), (nest, which, ks, kp, nage)
                         checked += 1; nonempty += ci.value > 0
     assert checked >= 12 and nonempty >= checked // 2
+    assert ldirect != 1 or checked >= 2 * 4 * 2 * 3 * 2 - 2 * 2 * 3 * 2   # incl. the mixing-ratio records
 
 
 def test_sparse_output_dump_edge_cases():
@@ -888,7 +897,7 @@ def test_sparse_output_dump_edge_cases():
     flat = np.ascontiguousarray(g.reshape(-1, order="F")); gflat = np.ascontiguousarray(vol.reshape(-1, order="F"))
     _pf, _pi = C.POINTER(C.c_float), C.POINTER(C.c_int32)
     di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32); ci, cr = C.c_int32(), C.c_int32()
-    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), gflat.ctypes.data_as(_pf), 1, 1, 1, 1.0, 1.0, 3600,
+    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), gflat.ctypes.data_as(_pf), None, 1, 1, 1, 1.0, 1.0, 3600,
                             C.byref(ci), di.ctypes.data_as(_pi), C.byref(cr), dr.ctypes.data_as(_pf))
     gi, gr = eng.concoutput_sparse(0, 1, 1, 1, 1.0)
     assert ci.value > 50 and cr.value > ci.value

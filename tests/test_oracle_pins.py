@@ -536,7 +536,7 @@ def test_outgrid_geometry_and_sparse_dump_known_answers():
         flat[cell] = v
     di = np.zeros(3 * n2, np.int32); dr = np.zeros(3 * n2, np.float32)
     ci, cr = C.c_int32(), C.c_int32()
-    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), vol.ctypes.data_as(_pf), 1, 1, 1, 2.0, 1.0, 3600,
+    L.fpo_concoutput_sparse(C.byref(c), 0, 0, flat.ctypes.data_as(_pf), vol.ctypes.data_as(_pf), None, 1, 1, 1, 2.0, 1.0, 3600,
                             C.byref(ci), di.ctypes.data_as(_pi), C.byref(cr), dr.ctypes.data_as(_pf))
     assert (ci.value, cr.value) == (3, 6)                      # the denormal cell is not written
     assert di[:3].tolist() == [3 + n2, 10 + n2, n2 - 1 + n2]   # kz is 1-based in the index

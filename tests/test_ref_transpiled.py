@@ -460,6 +460,17 @@ def test_reference_outgrid_geometry_and_sparse_dump_bit_identical():
     outnum = np.float32(7.0)
     ref.L.f_co_factor3d(C.byref(C.c_float(outnum)))
     tot_mu = np.asfortranarray(r.uniform(0.5, 2.0, (c.maxspec, c.maxpointspec_act)).astype(np.float32))
+    # densityoutgrid (:164-190) from a synthetic rho at memind(2)
+    m2 = fb.MetFields(cb).synth(10800)
+    ref.upload_met(2, m2); ref.set_met_bracket((1, 2), (0, 10800))
+    ref.set("outlon0", float(np.float32(c.xlon0) - np.float32(c.xoutshift)))
+    ref.arr("weightmolar")[:2] = (350.5, 28.0)
+    ref.L.f_co_density()
+    dens = np.zeros(n3, np.float32)
+    rho2 = np.ascontiguousarray(m2.rho.reshape(-1, order="F"))
+    L.fpo_density_outgrid(C.byref(c), cb.height.ctypes.data_as(_pf), 0, float(ref.get("outlon0")), float(outlat0),
+                          rho2.ctypes.data_as(_pf), dens.ctypes.data_as(_pf))
+    assert np.array_equal(ref.arr("densityoutgrid").reshape(-1, order="F").view(np.uint32), dens.view(np.uint32))
     volf = np.ascontiguousarray(vol.reshape(-1, order="F")); areaf = np.ascontiguousarray(area.reshape(-1, order="F"))
     total = 0
     for ks in (1, 2):
@@ -467,19 +478,23 @@ def test_reference_outgrid_geometry_and_sparse_dump_bit_identical():
             for nage in (1, 2):
                 ref.L.f_co_mean(C.byref(C.c_int(ks)), C.byref(C.c_int(kp)), C.byref(C.c_int(nage)))
                 for which, fn, gname, geom, n in ((2, "f_co_wet", "wetgridunc", areaf, n2), (1, "f_co_dry", "drygridunc", areaf, n2),
-                                                  (0, "f_co_conc", "gridunc", volf, n3)):
+                                                  (0, "f_co_conc", "gridunc", volf, n3), (3, "f_co_pptv", "gridunc", volf, n3)):
                     ci, cr = C.c_int(0), C.c_int(0)
                     ref.arr("sparse_dump_i")[:] = -7; ref.arr("sparse_dump_r")[:] = np.nan
                     if which == 0:
                         getattr(ref.L, fn)(C.byref(C.c_int(ks)), C.byref(C.c_int(kp)), tot_mu.ctypes.data_as(_pf),
                                            C.byref(ci), C.byref(cr))
+                    elif which == 3:
+                        getattr(ref.L, fn)(C.byref(C.c_int(ks)), C.byref(C.c_float(outnum)), C.byref(ci), C.byref(cr))
                     else:
                         getattr(ref.L, fn)(C.byref(ci), C.byref(cr))
                     flat = np.ascontiguousarray(ref.arr(gname).reshape(-1, order="F"))
                     di, dr = np.zeros(n, np.int32), np.zeros(n, np.float32)
                     oi, orr = C.c_int32(), C.c_int32()
-                    L.fpo_concoutput_sparse(C.byref(c), 0, which, flat.ctypes.data_as(_pf), geom.ctypes.data_as(_pf), ks, kp, nage,
-                                            float(outnum), float(tot_mu[ks - 1, kp - 1]), 3600, C.byref(oi),
+                    L.fpo_concoutput_sparse(C.byref(c), 0, which, flat.ctypes.data_as(_pf), geom.ctypes.data_as(_pf),
+                                            dens.ctypes.data_as(_pf) if which == 3 else None, ks, kp, nage,
+                                            float(outnum), float(tot_mu[ks - 1, kp - 1]) if which != 3 else float(ref.arr("weightmolar")[ks - 1]),
+                                            3600, C.byref(oi),
                                             di.ctypes.data_as(_pi), C.byref(orr), dr.ctypes.data_as(_pf))
                     assert (ci.value, cr.value) == (oi.value, orr.value), (ks, kp, nage, which)
                     assert np.array_equal(ref.arr("sparse_dump_i")[:ci.value], di[:ci.value])
