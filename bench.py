@@ -134,6 +134,8 @@ def build_workload(args, rank, world, device, cpu_only=False, n_particles=None):
         # BASELINE configs[2]: CBL skewed turbulence (forces ctl >= 5, ifine*ctl >= 50), two species with
         # dry deposition, one of them wet-scavenged, nested output grid
         kw = dict(ctl=10.0, cblflag=1)
+        if os.environ.get("FPB_BENCH_NOCBL"):     # experiment: the deposition features without CBL
+            kw = dict(ctl=5.0, cblflag=0)
         extra = dict(nspec=2, drydepspec=(1, 1), wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0),
                      henry=(1.0e-2, 0.0), nest=(-30.0, 20.0, 240, 160, 0.125, 0.125))
         zmax, lat = 2000.0, (-60.0, 60.0)

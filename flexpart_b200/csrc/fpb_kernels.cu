@@ -1486,14 +1486,20 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
   // lean + the usual switches (turbswitch, method 1, IFINE 4, turbulence on) as compile-time constants
   const bool spec = !full && a.cfg.turbswitch && a.cfg.method == 1 && !a.cfg.turboff && a.cfg.ifine == 4;
-  static int resident[3] = {0, 0, 0};
+  static int resident[4] = {0, 0, 0, 0};
+#ifdef FPB_NO_EXTRA_NOCBL
   const int variant = full ? 1 : (spec ? 2 : 0);
+#else
+  // 3: the full feature set without the CBL scheme (its drift routine costs registers in every path)
+  const int variant = full ? (a.cfg.cblflag == 1 ? 1 : 3) : (spec ? 2 : 0);
+#endif
   int &res = resident[variant];
   if (res == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, true, false>, PBL_THREADS, 0);
+    else if (variant == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<true, false, false>, PBL_THREADS, 0);
     else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, true>, PBL_THREADS, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, false>, PBL_THREADS, 0);
     res = sms * (per_sm > 0 ? per_sm : 1);
@@ -1503,6 +1509,7 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   const int nb = want_pbl < res ? want_pbl : res; // persistent grid: one wave at most
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
   if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, PBL_THREADS, 0, st>>>(a);
+  else if (variant == 3) fpb_pbl_kernel<true, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
   else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, PBL_THREADS, 0, st>>>(a);
   else fpb_pbl_kernel<false, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
   // finish kernel: the variant without nests / settling / dry deposition / Philox-direct RNG when it applies
