@@ -13,6 +13,22 @@ __device__ __forceinline__ float cbl_cuberoot(float x) {
 // double rounds to the same float, and the fast exp2/log2 pow needs x > 0)
 __device__ __forceinline__ float cbl_sq(float x) { return x * x; }
 
+// the closure's literal powers: strict math keeps the reference's x**p (correctly rounded pow);
+// fast math uses the algebraically equal root / product forms (one MUFU instead of two)
+#if FPB_STRICT
+__device__ __forceinline__ float cbl_p05(float x) { return m_pow(x, 0.5f); }
+__device__ __forceinline__ float cbl_pm05(float x) { return m_pow(x, -0.5f); }
+__device__ __forceinline__ float cbl_p15(float x) { return m_pow(x, 1.5f); }
+__device__ __forceinline__ float cbl_p3(float x) { return m_pow(x, 3.f); }
+__device__ __forceinline__ float cbl_pm2(float x) { return m_pow(x, -2.f); }
+#else
+__device__ __forceinline__ float cbl_p05(float x) { return sqrtf(x); }
+__device__ __forceinline__ float cbl_pm05(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float cbl_p15(float x) { return x * sqrtf(x); }
+__device__ __forceinline__ float cbl_p3(float x) { return x * x * x; }
+__device__ __forceinline__ float cbl_pm2(float x) { return 1.f / (x * x); }
+#endif
+
 __device__ __forceinline__ float cbl_transition(float h, float ol) {
   float transition = 1.f;
   if (-h / ol < 15.f) transition = (m_sin((((-h / ol) + 10.f) / 10.f) * PI_F)) / 2.f + 0.5f;
@@ -34,56 +50,56 @@ __device__ __noinline__ void cbl_drift(const DevCfg &c, float wp, float zp, floa
   const float dw2 = (2.f * sigmaw * dsigmawdz);
   const float alfa = 2.f * w2 / (C0 * tlw);
   const float wold = timedir * wp;
-  const float omz32 = m_pow(1.f - z, 3.f / 2.f);
+  const float omz32 = cbl_p15(1.f - z);
   const float w3 = ((1.2f * z * (omz32)) + eps) * (wst * wst * wst) * transition;
-  const float dw3 = (1.2f * ((omz32) + z * 1.5f * (m_pow(1.f - z, 1.f / 2.f)) * (-1.f))) *
+  const float dw3 = (1.2f * ((omz32) + z * 1.5f * (cbl_p05(1.f - z)) * (-1.f))) *
                     (wst * wst * wst) * (1.f / h) * transition;
-  const float w2_15 = m_pow(w2, 1.5f);
+  const float w2_15 = cbl_p15(w2);
   const float skew = w3 / (w2_15);
   const float skew2 = skew * skew;
-  const float dskew = (dw3 * w2_15 - w3 * 1.5f * m_pow(w2, 0.5f) * dw2) / (w2 * w2 * w2);
-  const float radw2 = m_pow(w2, 0.5f);
-  const float dradw2 = 0.5f * m_pow(w2, -0.5f) * dw2;
+  const float dskew = (dw3 * w2_15 - w3 * 1.5f * cbl_p05(w2) * dw2) / (w2 * w2 * w2);
+  const float radw2 = cbl_p05(w2);
+  const float dradw2 = 0.5f * cbl_pm05(w2) * dw2;
   const float fluarw = costluar4 * (cbl_cuberoot(skew));
   const float fluarw2 = fluarw * fluarw;
   float dfluarw, rluarw, xluarw, drluarw, dxluarw;
   if (skew != 0.f) {
     const float a1 = 1.f + fluarw2, a3 = 3.f + fluarw2;
-    const float a3sq = (a3 * a3), a1_15 = m_pow(a1, 1.5f);
-    dfluarw = costluar4 * (1.f / 3.f) * cbl_cuberoot(m_pow(skew, -2.f)) * dskew;
-    rluarw = m_pow(a1, 3.f) * skew2 / (a3sq * fluarw2);
+    const float a3sq = (a3 * a3), a1_15 = cbl_p15(a1);
+    dfluarw = costluar4 * (1.f / 3.f) * cbl_cuberoot(cbl_pm2(skew)) * dskew;
+    rluarw = cbl_p3(a1) * skew2 / (a3sq * fluarw2);
     xluarw = a1_15 * skew / (a3 * fluarw);
     drluarw = (((3.f * (a1 * a1) * (2.f * fluarw * dfluarw) * skew2) + (a1 * a1 * a1) * 2.f * skew * dskew) *
                    a3sq * fluarw2 -
                (a1 * a1 * a1) * skew2 *
                    ((2.f * a3 * (2.f * fluarw * dfluarw) * fluarw2) + (a3 * a3) * 2.f * fluarw * dfluarw)) /
               ((a3sq * fluarw2) * (a3sq * fluarw2));
-    dxluarw = (((1.5f * m_pow(a1, 0.5f) * (2.f * fluarw * dfluarw) * skew) + a1_15 * dskew) * a3 * fluarw -
+    dxluarw = (((1.5f * cbl_p05(a1) * (2.f * fluarw * dfluarw) * skew) + a1_15 * dskew) * a3 * fluarw -
                a1_15 * skew * (3.f * dfluarw + 3.f * fluarw2 * dfluarw)) /
               ((a3 * fluarw) * (a3 * fluarw));
   } else {
     dfluarw = 0.f; rluarw = 0.f; drluarw = 0.f; xluarw = 0.f; dxluarw = 0.f;
   }
-  const float r4 = m_pow(4.f + rluarw, 0.5f);
+  const float r4 = cbl_p05(4.f + rluarw);
   const float aluarw = 0.5f * (1.f - xluarw / r4);
   const float bluarw = 1.f - aluarw;
-  const float daluarw = -0.5f * ((dxluarw * r4) - (0.5f * xluarw * m_pow(4.f + rluarw, -0.5f) * drluarw)) /
+  const float daluarw = -0.5f * ((dxluarw * r4) - (0.5f * xluarw * cbl_pm05(4.f + rluarw) * drluarw)) /
                         (4.f + rluarw);
   const float dbluarw = -daluarw;
   const float ra = bluarw / (aluarw * (1.f + fluarw2));
   const float rb = aluarw / (bluarw * (1.f + fluarw2));
-  const float sra = m_pow(ra, 0.5f), srb = m_pow(rb, 0.5f);
+  const float sra = cbl_p05(ra), srb = cbl_p05(rb);
   const float sigmawa = radw2 * sra;
   const float sigmawb = radw2 * srb;
   const float dsigmawa =
       dradw2 * sra +
-      radw2 * ((0.5f * m_pow(ra, -0.5f)) *
+      radw2 * ((0.5f * cbl_pm05(ra)) *
                ((dbluarw * (aluarw * (1.f + fluarw2)) -
                  bluarw * (daluarw * (1.f + fluarw2) + aluarw * 2.f * fluarw * dfluarw)) /
                 ((aluarw * (1.f + fluarw2)) * (aluarw * (1.f + fluarw2)))));
   const float dsigmawb =
       dradw2 * srb +
-      radw2 * ((0.5f * m_pow(rb, -0.5f)) *
+      radw2 * ((0.5f * cbl_pm05(rb)) *
                ((daluarw * (bluarw * (1.f + fluarw2)) -
                  aluarw * (dbluarw * (1.f + fluarw2) + bluarw * 2.f * fluarw * dfluarw)) /
                 ((bluarw * (1.f + fluarw2)) * (bluarw * (1.f + fluarw2)))));
@@ -122,18 +138,18 @@ __device__ __noinline__ void cbl_split(float zp, float wst, float h, float sigma
   const float z = zp / h;
   const float transition = cbl_transition(h, ol);
   const float w2 = sigmaw * sigmaw;
-  const float w3 = (((1.2f * z * (m_pow(1.f - z, 3.f / 2.f))) + eps) * (wst * wst * wst)) * transition;
-  const float skew = w3 / (m_pow(w2, 1.5f));
+  const float w3 = (((1.2f * z * (cbl_p15(1.f - z))) + eps) * (wst * wst * wst)) * transition;
+  const float skew = w3 / (cbl_p15(w2));
   const float skew2 = skew * skew;
   const float radw2 = m_sqrt(w2);
   const float fluarw = costluar4 * m_pow(skew, 0.333333333333333f);
   const float fluarw2 = fluarw * fluarw;
-  const float rluarw = m_pow(1.f + fluarw2, 3.f) * skew2 / (cbl_sq(3.f + fluarw2) * fluarw2);
-  const float xluarw = m_pow(rluarw, 0.5f);
-  aluarw = 0.5f * (1.f - xluarw / m_pow(4.f + rluarw, 0.5f));
+  const float rluarw = cbl_p3(1.f + fluarw2) * skew2 / (cbl_sq(3.f + fluarw2) * fluarw2);
+  const float xluarw = cbl_p05(rluarw);
+  aluarw = 0.5f * (1.f - xluarw / cbl_p05(4.f + rluarw));
   const float bluarw = 1.f - aluarw;
-  sigmawa = radw2 * m_pow(bluarw / (aluarw * (1.f + fluarw2)), 0.5f);
-  sigmawb = radw2 * m_pow(aluarw / (bluarw * (1.f + fluarw2)), 0.5f);
+  sigmawa = radw2 * cbl_p05(bluarw / (aluarw * (1.f + fluarw2)));
+  sigmawb = radw2 * cbl_p05(aluarw / (bluarw * (1.f + fluarw2)));
   wa = (fluarw * sigmawa);
   wb = (fluarw * sigmawb);
 }
