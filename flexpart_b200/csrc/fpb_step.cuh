@@ -463,10 +463,13 @@ struct PblTask {
 // Persistent kernel: every warp pulls batches of particle rows from
 // *a.work_counter; lanes run sub-steps until their particle leaves the loop.
 template <bool EXTRA, bool CBL, bool SPEC>
+#ifndef FPB_CBL_BLOCKS
+#define FPB_CBL_BLOCKS 4
+#endif
 #ifndef FPB_EXTRA_NOCBL_BLOCKS
 #define FPB_EXTRA_NOCBL_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(PBL_THREADS, (EXTRA ? (CBL ? 3 : FPB_EXTRA_NOCBL_BLOCKS) : FPB_PBL_MIN_BLOCKS) * (128 / PBL_THREADS))
+__global__ void __launch_bounds__(PBL_THREADS, (EXTRA ? (CBL ? FPB_CBL_BLOCKS : FPB_EXTRA_NOCBL_BLOCKS) : FPB_PBL_MIN_BLOCKS) * (128 / PBL_THREADS))
 fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   const DevCfg &c = a.cfg;
   __shared__ float sh[FPB_MAXNZ];
