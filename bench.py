@@ -293,7 +293,8 @@ def run_ours(args):
         hp = fb.Particles(c.maxpart, c.nspec, pinned=True)
         hp.numpart = n
         eng.pull_particles(hp)
-        bytes_in = 2 * 8 + 4 * 7 + 4 * 6 + 2 + 4 * c.nspec * 2   # every array of fpb_particle_ptrs
+        # what fpb_step_host uploads: the arrays the loop reads (not itrasplit; xscav_frac1 only in backward deposition runs)
+        bytes_in = 2 * 8 + 4 + 4 * 5 + 4 * 6 + 2 + 4 * c.nspec * (2 if (c.drybkdep or c.wetbkdep) else 1)
         bytes_out = 2 * 8 + 4 * 3 + 4 * 6 + 2 + 4 * c.nspec      # xtra1..ztra1, itra1, idt, 6 velocities, cbt, xmass1
         for _ in range(3):                       # untimed: lane streams / sort work areas get created
             eng.step_host(hp, k * 900, 0, conc_weight=1.0)

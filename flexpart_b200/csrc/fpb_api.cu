@@ -222,6 +222,8 @@ struct fpb_handle {
   };
   static constexpr int NLANES = 3;
   Lane lanes[NLANES];
+  cudaStream_t st_in = nullptr;              // all host-to-device copies of fpb_step_host, in chunk order
+  cudaEvent_t ev_in[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_ready = nullptr;
   bool lanes_ready = false;
 };
@@ -671,13 +673,15 @@ static void per_step_cfg(fpb_handle *h, DevCfg &d, int itime, int ldeltat);
                          cudaMemcpyDeviceToHost, h->stream));                        \
   } while (0)
 
+// loop_only: just the arrays the particle loop and conccalc read (fpb_step_host): itrasplit is
+// not among them, xscav_frac1 only in backward deposition runs
 static int copy_rows_h2d(fpb_handle *h, const DevParticles &d, int first, int count,
-                         const fpb_particle_ptrs *p, cudaStream_t st) {
+                         const fpb_particle_ptrs *p, cudaStream_t st, bool loop_only = false) {
   H2D(d.xtra1, p->xtra1, double); H2D(d.ytra1, p->ytra1, double); H2D(d.ztra1, p->ztra1, float);
   H2D(d.itra1, p->itra1, int32_t); H2D(d.npoint, p->npoint, int32_t);
   H2D(d.nclass, p->nclass, int32_t); H2D(d.idt, p->idt, int32_t);
   H2D(d.itramem, p->itramem, int32_t);
-  if (p->itrasplit) H2D(d.itrasplit, p->itrasplit, int32_t);
+  if (p->itrasplit && !loop_only) H2D(d.itrasplit, p->itrasplit, int32_t);
   H2D(d.uap, p->uap, float); H2D(d.ucp, p->ucp, float); H2D(d.uzp, p->uzp, float);
   H2D(d.us, p->us, float); H2D(d.vs, p->vs, float); H2D(d.ws, p->ws, float);
   H2D(d.cbt, p->cbt, int16_t);
@@ -686,7 +690,7 @@ static int copy_rows_h2d(fpb_handle *h, const DevParticles &d, int first, int co
     CK(cudaMemcpyAsync(d.xmass1 + (size_t)k * h->cfg.maxpart + first,
                        p->xmass1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
                        cudaMemcpyHostToDevice, st));
-    if (p->xscav_frac1)
+    if (p->xscav_frac1 && (!loop_only || h->cfg.drybkdep || h->cfg.wetbkdep))
       CK(cudaMemcpyAsync(d.xscav_frac1 + (size_t)k * h->cfg.maxpart + first,
                          p->xscav_frac1 + (size_t)k * p->ld + first, (size_t)count * sizeof(float),
                          cudaMemcpyHostToDevice, st));
@@ -1228,6 +1232,8 @@ static int ensure_lanes(fpb_handle *h) {
     DA(L.d_nlive, 1);
   }
   CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+  for (auto &e : h->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->lanes_ready = true;
   return 0;
 }
@@ -1329,10 +1335,16 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     if (n <= 0) continue;
     fpb_handle::Lane &L = h->lanes[ci % fpb_handle::NLANES];
     if (scatter_reserve(L.sw, (size_t)per, 1)) return fail("%s", scatter_error());
+    // all uploads go through one stream, in chunk order: chunk 0 is complete (and its kernels
+    // start) after a third of the transfer instead of sharing the link with the later chunks
+    if (ci == 0) CK(cudaStreamWaitEvent(h->st_in, h->ev_ready, 0));
+    mark(h->st_in);
+    if (copy_rows_h2d(h, h->p_alt, c0, n, p, h->st_in, true)) return 1;
+    mark(h->st_in);
+    cudaEvent_t ev_in = h->ev_in[ci % 8];
+    CK(cudaEventRecord(ev_in, h->st_in));
     CK(cudaStreamWaitEvent(L.st, h->ev_ready, 0));
-    mark(L.st);
-    if (copy_rows_h2d(h, h->p_alt, c0, n, p, L.st)) return 1;
-    mark(L.st);
+    CK(cudaStreamWaitEvent(L.st, ev_in, 0));
     STAGE("h2d");
     const DevParticles stg = rows_view(h->p_alt, c0), rows = rows_view(h->p, c0);
 

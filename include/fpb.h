@@ -260,7 +260,9 @@ int fpb_conccalc(fpb_handle *h, int32_t itime, float weight);
  * fpb_push_particles + fpb_conccalc + fpb_step + fpb_pull_particles, but cut
  * into row chunks that run on separate streams so the host<->device copies of
  * one chunk overlap the kernels of the others; give it page-locked arrays.
- * Synchronous on return.  Not available with FPB_SCATTER_DETERMINISTIC. */
+ * Synchronous on return.  Not available with FPB_SCATTER_DETERMINISTIC.  Only the arrays the loop
+ * reads are uploaded (not itrasplit; xscav_frac1 only in backward deposition runs): the device copies
+ * of those two are undefined afterwards, push before pulling them. */
 int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,
                   const fpb_particle_ptrs *p, float conc_weight,
                   fpb_step_stats *stats /* may be NULL */);
