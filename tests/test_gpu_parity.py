@@ -902,3 +902,58 @@ def test_sparse_output_dump_edge_cases():
     gi, gr = eng.concoutput_sparse(0, 1, 1, 1, 1.0)
     assert ci.value > 50 and cr.value > ci.value
     assert np.array_equal(gi, di[:ci.value]) and np.array_equal(gr.view(np.uint32), dr[:cr.value].view(np.uint32))
+
+
+# ----------------------------------------------------------------------------
+# empty and ragged inputs
+# ----------------------------------------------------------------------------
+def test_empty_and_ragged_inputs():
+    """No particles, one particle, counts that are not a multiple of any block size, all particles
+    dead: every entry point returns cleanly and agrees with the oracle bit for bit."""
+    cb = cases.config_small(nrel=1, npart_each=1500, math_mode=fb.MATH_STRICT, wetdepspec=(1,),
+                            weta_gas=(2.0e-5,), wetb_gas=(0.62,), henry=(1.0e-2,), sort_interval=1)
+    c = cb.cfg
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb(); e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+    # nothing resident yet
+    z = eng.step(0, 0)
+    assert z["n_active"] == 0 and z["n_terminated"] == 0
+    eng.conccalc(0, 1.0); eng.wetdepo(0, 900, 0)
+    empty = fb.Particles(c.maxpart, 1)
+    assert eng.step_host(empty, 0, 0, conc_weight=1.0)["n_active"] == 0
+    assert np.abs(eng.fetch_grids(zero_conc=False)["gridunc"]).sum() == 0
+    for n in (1, 31, 129, 1025, 1499):
+        p = cases.seeded_particles(cb, n, zmax=2500.0, seed=n)
+        eng2, ora2 = fb.Engine(cb), Oracle(cb)
+        for e in (eng2, ora2):
+            e.fill_rannumb(); e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+            e.push_particles(p)
+        for k in range(2):
+            for e in (eng2, ora2):
+                if k:
+                    e.wetdepo(k * 900, 900, 450)
+                e.conccalc(k * 900, 1.0)
+            sg, so = eng2.step(k * 900, 450), ora2.step(k * 900, 450)
+            assert sg == so, (n, k, sg, so)
+        pg, po = fb.Particles(c.maxpart, 1), fb.Particles(c.maxpart, 1)
+        pg.numpart = po.numpart = n
+        eng2.pull_particles(pg); ora2.pull_particles(po)
+        for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+            assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (n, f)
+        assert np.array_equal(pg.xmass1[:n], po.xmass1[:n])
+        # the same rows through the host-buffer entry point (single ragged chunk)
+        q = cases.seeded_particles(cb, n, zmax=2500.0, seed=n)
+        eng3 = fb.Engine(cb); eng3.fill_rannumb(); eng3.upload_met(1, m0); eng3.upload_met(2, m1)
+        eng3.set_met_bracket((1, 2), (0, 10800))
+        st = eng3.step_host(q, 0, 450, conc_weight=1.0)
+        assert st["n_active"] == n
+    # all particles dead: the step does nothing, the sort copes with a key array of sentinels only
+    p = cases.seeded_particles(cb, 300, zmax=2500.0)
+    p.itra1[:300] = fb.ITRA_DEAD
+    eng.push_particles(p)
+    st = eng.step(0, 0)
+    assert st["n_active"] == 0
+    eng.sort_particles()
+    assert eng.step(900, 0)["n_active"] == 0
