@@ -95,6 +95,12 @@ class FpbReleasePoints(C.Structure):
     _fields_ = FpbhReleases._fields_ + [("mp_pid", _i)]
 
 
+class FpbPartoutPtrs(C.Structure):
+    _fields_ = [("npoint", _pi), ("xlon", _pf), ("ylat", _pf), ("ztra1", _pf), ("itramem", _pi), ("topo", _pf),
+                ("pvi", _pf), ("qvi", _pf), ("rhoi", _pf), ("hmixi", _pf), ("tri", _pf), ("tti", _pf),
+                ("xmass1", _pf), ("ld", _i)]
+
+
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
@@ -165,6 +171,9 @@ def load_engine_lib():
     L.fpb_set_releases.argtypes = [H, C.POINTER(FpbReleasePoints)]
     L.fpb_set_outgrid_geometry.argtypes = [H, _pf, _pf, _pf, _pf]
     L.fpb_set_outgrid_origin.argtypes = [H, _f, _f, _f, _f]
+    L.fpb_set_orography.argtypes = [H, _pf]
+    L.fpb_upload_pvqv.argtypes = [H, _i, _pf, _pf]
+    L.fpb_partoutput.argtypes = [H, _i, _pi, C.POINTER(FpbPartoutPtrs)]
     L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]

@@ -148,6 +148,15 @@ struct fpb_handle {
     size_t cap = 0;
     float lon0[2] = {0.f, 0.f}, lat0[2] = {0.f, 0.f};
     bool have_origin = false;
+    // partoutput
+    float2 *Q[2] = {nullptr, nullptr};  // {pv, qv} per Fortran slot
+    float *oro = nullptr;
+    bool have_q[2] = {false, false};
+    unsigned *po_counts = nullptr;
+    int *po_count = nullptr;
+    int32_t *po_i[2] = {nullptr, nullptr};
+    float *po_f[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *po_mass = nullptr;
   } outp;
   // device-side releaseparticles
   struct Releases {
@@ -516,6 +525,9 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   for (int k = 0; k < 2; k++) { cudaFree(h->outp.area[k]); cudaFree(h->outp.volume[k]); }
   cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r); cudaFree(h->outp.d_counts);
   cudaFree(h->outp.d_density);
+  cudaFree(h->outp.Q[0]); cudaFree(h->outp.Q[1]); cudaFree(h->outp.oro); cudaFree(h->outp.po_counts);
+  cudaFree(h->outp.po_count); cudaFree(h->outp.po_i[0]); cudaFree(h->outp.po_i[1]); cudaFree(h->outp.po_mass);
+  for (auto &q : h->outp.po_f) cudaFree(q);
   for (auto &q : h->rel.d_pts) cudaFree(q);
   cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
@@ -1092,6 +1104,83 @@ extern "C" int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which,
   *sp_count_i = counts[0]; *sp_count_r = counts[1];
   if (counts[0] > 0) CK(cudaMemcpyAsync(sparse_dump_i, a.out_i, (size_t)counts[0] * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (counts[1] > 0) CK(cudaMemcpyAsync(sparse_dump_r, a.out_r, (size_t)counts[1] * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------- partoutput --
+extern "C" int fpb_set_orography(fpb_handle *h, const float *oro) {
+  if (!h || !oro) return fail("fpb_set_orography: null argument");
+  CK(cudaSetDevice(h->device));
+  if (!h->outp.oro) DA(h->outp.oro, (size_t)h->d.nxd * h->d.nyd);
+  return upload_component(h, h->outp.oro, 0, 1, oro, 1);
+}
+
+extern "C" int fpb_upload_pvqv(fpb_handle *h, int32_t slot, const float *pv, const float *qv) {
+  if (!h || !pv || !qv) return fail("fpb_upload_pvqv: null argument");
+  if (slot < 1 || slot > 2) return fail("fpb_upload_pvqv: slot %d", slot);
+  CK(cudaSetDevice(h->device));
+  const int s = slot - 1;
+  if (!h->outp.Q[s]) DA(h->outp.Q[s], (size_t)h->d.nxd * h->d.nyd * h->cfg.nz);
+  if (upload_component(h, reinterpret_cast<float *>(h->outp.Q[s]), 0, 2, pv, h->cfg.nz)) return 1;
+  if (upload_component(h, reinterpret_cast<float *>(h->outp.Q[s]), 1, 2, qv, h->cfg.nz)) return 1;
+  h->outp.have_q[s] = true;
+  return 0;
+}
+
+extern "C" int fpb_partoutput(fpb_handle *h, int32_t itime, int32_t *nrecords, const fpb_partout_ptrs *out) {
+  if (!h || !nrecords || !out) return fail("fpb_partoutput: null argument");
+  if (!h->have_bracket) return fail("fpb_partoutput: fpb_set_met_bracket has not been called");
+  if (!h->outp.oro || !h->outp.have_q[h->memind[0] - 1] || !h->outp.have_q[h->memind[1] - 1])
+    return fail("fpb_partoutput: fpb_set_orography / fpb_upload_pvqv of both time levels are missing");
+  *nrecords = 0;
+  if (h->numpart == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  auto &O = h->outp;
+  const size_t mp = h->cfg.maxpart;
+  if (!O.po_count) {
+    DA(O.po_count, 1);
+    DA(O.po_counts, 2 * ((mp + 1023) / 1024));
+    DA(O.po_i[0], mp); DA(O.po_i[1], mp);
+    for (auto &q : O.po_f) DA(q, mp);
+    DA(O.po_mass, mp * h->cfg.nspec);
+  }
+  PartoutArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.met[0] = slot_view(h, h->memind[0]); a.met[1] = slot_view(h, h->memind[1]);
+  a.Q[0] = O.Q[h->memind[0] - 1]; a.Q[1] = O.Q[h->memind[1] - 1];
+  a.oro = O.oro;
+  a.height = h->d_height;
+  a.p = h->p;
+  a.row_of_slot = h->row_of_slot;
+  a.permuted = h->permuted ? 1 : 0;
+  a.numpart = h->numpart;
+  a.block_counts = O.po_counts; a.count = O.po_count;
+  a.npoint = O.po_i[0]; a.itramem = O.po_i[1];
+  a.xlon = O.po_f[0]; a.ylat = O.po_f[1]; a.ztra1 = O.po_f[2]; a.topo = O.po_f[3]; a.pvi = O.po_f[4];
+  a.qvi = O.po_f[5]; a.rhoi = O.po_f[6]; a.hmixi = O.po_f[7]; a.tri = O.po_f[8]; a.tti = O.po_f[9];
+  a.xmass1 = O.po_mass;
+  fpb_partoutput_launch(a, h->stream);
+  h->launches += 3;
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, O.po_count, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  *nrecords = n;
+  if (n == 0) return 0;
+  auto get = [&](void *dst, const void *src, size_t bytes) -> int {
+    if (dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+  };
+  const size_t nb = (size_t)n * 4;
+  if (get(out->npoint, a.npoint, nb) || get(out->itramem, a.itramem, nb) || get(out->xlon, a.xlon, nb) ||
+      get(out->ylat, a.ylat, nb) || get(out->ztra1, a.ztra1, nb) || get(out->topo, a.topo, nb) ||
+      get(out->pvi, a.pvi, nb) || get(out->qvi, a.qvi, nb) || get(out->rhoi, a.rhoi, nb) ||
+      get(out->hmixi, a.hmixi, nb) || get(out->tri, a.tri, nb) || get(out->tti, a.tti, nb))
+    return 1;
+  if (out->xmass1)
+    for (int ks = 0; ks < h->cfg.nspec; ks++)
+      if (get(out->xmass1 + (size_t)ks * out->ld, a.xmass1 + (size_t)ks * mp, nb)) return 1;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

@@ -130,7 +130,116 @@ __global__ void __launch_bounds__(256) density_outgrid_kernel(const DensityArgs 
   const float r0 = a.A[(size_t)(kzz - 2) * a.plane + (size_t)jjy * a.nxd + iix].w;
   a.density[i] = (r1 * dz1 + r0 * dz2) / dz;
 }
+// ---- partoutput
+__device__ __forceinline__ bool partout_active(const PartoutArgs &a, int s, int &row) {
+  if (s >= a.numpart) return false;
+  row = a.permuted ? a.row_of_slot[s] : s;
+  return a.p.itra1[row] == a.cfg.itime;
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) partout_count_kernel(const PartoutArgs a) {
+  int row;
+  const int n = __syncthreads_count(partout_active(a, blockIdx.x * OUT_BLOCK + threadIdx.x, row));
+  if (threadIdx.x == 0) { a.block_counts[2 * blockIdx.x] = n; a.block_counts[2 * blockIdx.x + 1] = 0; }
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) partout_scan_kernel(const PartoutArgs a, int nblocks) {
+  __shared__ unsigned run;
+  if (threadIdx.x == 0) run = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += OUT_BLOCK) {
+    const int b = base + threadIdx.x;
+    const unsigned v = (b < nblocks) ? a.block_counts[2 * b] : 0u;
+    unsigned ea, eb, ta, tb;
+    block_scan2(v, 0u, ea, eb, ta, tb);
+    if (b < nblocks) a.block_counts[2 * b] = run + ea;
+    __syncthreads();
+    if (threadIdx.x == 0) run += ta;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.count[0] = (int)run;
+}
+
+__global__ void __launch_bounds__(OUT_BLOCK) partout_write_kernel(const PartoutArgs a) {
+  const DevCfg &c = a.cfg;
+  const int s = blockIdx.x * OUT_BLOCK + threadIdx.x;
+  int row = 0;
+  const unsigned act = partout_active(a, s, row);
+  unsigned e, e2, t, t2;
+  block_scan2(act, 0u, e, e2, t, t2);
+  if (!act) return;
+  const unsigned k = a.block_counts[2 * blockIdx.x] + e;
+  const double xt = a.p.xtra1[row], yt = a.p.ytra1[row];
+  const float zt = a.p.ztra1[row];
+  a.xlon[k] = (float)(c.xlon0 + xt * c.dx);   // src/partoutput.f90:72-73
+  a.ylat[k] = (float)(c.ylat0 + yt * c.dy);
+  const int ix = (int)xt, jy = (int)yt;
+  const int ixp = ix + 1;
+  int jyp = jy + 1;
+  const float ddx = (float)(xt - (float)ix), ddy = (float)(yt - (float)jy);
+  const float rddx = 1.f - ddx, rddy = 1.f - ddy;
+  const float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+  if (jyp >= c.nymax) jyp = jyp - 1;
+  const int o00 = ix + c.nxd * jy, o10 = ixp + c.nxd * jy, o01 = ix + c.nxd * jyp, o11 = ixp + c.nxd * jyp;
+  a.topo[k] = p1 * a.oro[o00] + p2 * a.oro[o10] + p3 * a.oro[o01] + p4 * a.oro[o11];
+  int indz = c.nz - 1; // :105-112 (height is increasing: the first level above the particle)
+  for (int il = 2; il <= c.nz; il++)
+    if (a.height[il - 1] > zt) { indz = il - 1; break; }
+  const int indzp = indz + 1;
+  const float dz1 = zt - a.height[indz - 1], dz2 = a.height[indzp - 1] - zt;
+  const float dz = 1.f / (dz1 + dz2);
+  const float dt1 = (float)(c.itime - c.memtime[0]), dt2 = (float)(c.memtime[1] - c.itime);
+  const float dtt = 1.f / (dt1 + dt2);
+  const int plane = c.nxd * c.nyd;
+  float pvprof[2], qvprof[2], ttprof[2], rhoprof[2];
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const int base = (indz - 1 + n) * plane;
+    float pv1[2], qv1[2], tt1[2], rho1[2];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const float2 qa = a.Q[m][base + o00], qb = a.Q[m][base + o10], qc = a.Q[m][base + o01], qd = a.Q[m][base + o11];
+      pv1[m] = p1 * qa.x + p2 * qb.x + p3 * qc.x + p4 * qd.x;
+      qv1[m] = p1 * qa.y + p2 * qb.y + p3 * qc.y + p4 * qd.y;
+      const float *T = a.met[m].T + base;
+      tt1[m] = p1 * T[o00] + p2 * T[o10] + p3 * T[o01] + p4 * T[o11];
+      const float4 *A = a.met[m].A + base;
+      rho1[m] = p1 * A[o00].w + p2 * A[o10].w + p3 * A[o01].w + p4 * A[o11].w;
+    }
+    pvprof[n] = (pv1[0] * dt2 + pv1[1] * dt1) * dtt;
+    qvprof[n] = (qv1[0] * dt2 + qv1[1] * dt1) * dtt;
+    ttprof[n] = (tt1[0] * dt2 + tt1[1] * dt1) * dtt;
+    rhoprof[n] = (rho1[0] * dt2 + rho1[1] * dt1) * dtt;
+  }
+  a.pvi[k] = (dz1 * pvprof[1] + dz2 * pvprof[0]) * dz;
+  a.qvi[k] = (dz1 * qvprof[1] + dz2 * qvprof[0]) * dz;
+  a.tti[k] = (dz1 * ttprof[1] + dz2 * ttprof[0]) * dz;
+  a.rhoi[k] = (dz1 * rhoprof[1] + dz2 * rhoprof[0]) * dz;
+  float tr[2], hm[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const float *tp = a.met[m].trop;
+    tr[m] = p1 * tp[o00] + p2 * tp[o10] + p3 * tp[o01] + p4 * tp[o11];
+    const float4 *S = a.met[m].S;
+    hm[m] = p1 * S[o00].x + p2 * S[o10].x + p3 * S[o01].x + p4 * S[o11].x;
+  }
+  a.hmixi[k] = (hm[0] * dt2 + hm[1] * dt1) * dtt;
+  a.tri[k] = (tr[0] * dt2 + tr[1] * dt1) * dtt;
+  a.npoint[k] = a.p.npoint[row];
+  a.itramem[k] = a.p.itramem[row];
+  a.ztra1[k] = zt;
+  for (int ks = 0; ks < c.nspec; ks++)
+    a.xmass1[(size_t)ks * a.p.maxpart + k] = a.p.xmass1[(size_t)ks * a.p.maxpart + row];
+}
 } // namespace
+
+void fpb_partoutput_launch(const PartoutArgs &a, cudaStream_t st) {
+  const int nb = (a.numpart + OUT_BLOCK - 1) / OUT_BLOCK;
+  if (nb == 0) return;
+  partout_count_kernel<<<nb, OUT_BLOCK, 0, st>>>(a);
+  partout_scan_kernel<<<1, OUT_BLOCK, 0, st>>>(a, nb);
+  partout_write_kernel<<<nb, OUT_BLOCK, 0, st>>>(a);
+}
 
 void fpb_density_outgrid(const DensityArgs &a, cudaStream_t st) {
   const int n = a.numx * a.numy * a.numz;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "fpb_device.cuh"
+
 struct SparseDumpArgs {
   const float *grid;        // first class slice of (ks, kp, nage): [ncells]
   size_t class_stride;      // floats between the slices of consecutive uncertainty classes
@@ -35,3 +37,23 @@ struct DensityArgs {
   float *density;           // [numx * numy * numz]
 };
 void fpb_density_outgrid(const DensityArgs &a, cudaStream_t st);
+
+// partoutput (src/partoutput.f90:66-192): one record per particle with itra1 == itime, in slot
+// order; the fields of the two time levels interpolated to the particle
+struct PartoutArgs {
+  DevCfg cfg;               // cfg.itime, cfg.memtime set
+  DevMetSlot met[2];        // memind(1), memind(2)
+  const float2 *Q[2];       // {pv, qv} of the same time levels
+  const float *oro;         // [nyd][nxd]
+  const float *height;
+  DevParticles p;
+  const int32_t *row_of_slot;
+  int permuted, numpart;
+  unsigned *block_counts;
+  int *count;               // records written
+  // outputs, compacted in slot order
+  int32_t *npoint, *itramem;
+  float *xlon, *ylat, *ztra1, *topo, *pvi, *qvi, *rhoi, *hmixi, *tri, *tti;
+  float *xmass1;            // [nspec][maxpart]
+};
+void fpb_partoutput_launch(const PartoutArgs &a, cudaStream_t st);

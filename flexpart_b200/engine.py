@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import FpbStepStats, FpbError, FpbhEngine, FpbReleasePoints, load_engine_lib
+from .abi import FpbStepStats, FpbError, FpbhEngine, FpbReleasePoints, FpbPartoutPtrs, load_engine_lib
 
 _pf = C.POINTER(C.c_float)
 
@@ -97,6 +97,28 @@ class Engine:
         """area/volume of outgrid_init (host.outgrid_geometry), Fortran order."""
         keep = [np.asfortranarray(a, np.float32) if a is not None else None for a in (area, volume, arean, volumen)]
         self._check(self.L.fpb_set_outgrid_geometry(self.h, *[_fp(a) if a is not None else None for a in keep]))
+
+    def set_orography(self, oro):
+        self._check(self.L.fpb_set_orography(self.h, _fp(np.asfortranarray(oro, np.float32))))
+
+    def upload_pvqv(self, slot, pv, qv):
+        pv, qv = np.asfortranarray(pv, np.float32), np.asfortranarray(qv, np.float32)
+        self._check(self.L.fpb_upload_pvqv(self.h, slot, _fp(pv), _fp(qv)))
+
+    def partoutput(self, itime):
+        """records of partoutput(itime): dict of arrays, one entry per particle with itra1 == itime."""
+        c = self.cb.cfg
+        mp = c.maxpart
+        out = {k: np.zeros(mp, np.int32) for k in ("npoint", "itramem")}
+        out.update({k: np.zeros(mp, np.float32) for k in ("xlon", "ylat", "ztra1", "topo", "pvi", "qvi", "rhoi", "hmixi", "tri", "tti")})
+        out["xmass1"] = np.zeros((mp, c.nspec), np.float32, order="F")
+        r = FpbPartoutPtrs()
+        for k, a in out.items():
+            setattr(r, k, a.ctypes.data_as(C.POINTER(C.c_int32 if a.dtype == np.int32 else C.c_float)))
+        r.ld = mp
+        n = C.c_int32(0)
+        self._check(self.L.fpb_partoutput(self.h, itime, C.byref(n), C.byref(r)))
+        return {k: a[:n.value].copy() for k, a in out.items()}
 
     def set_outgrid_origin(self, outlon0, outlat0, outlon0n=0.0, outlat0n=0.0):
         self._check(self.L.fpb_set_outgrid_origin(self.h, outlon0, outlat0, outlon0n, outlat0n))

@@ -299,6 +299,23 @@ int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which, int32_t ks
                           int32_t *sp_count_i, int32_t *sparse_dump_i, int32_t *sp_count_r,
                           float *sparse_dump_r);
 
+/* partoutput (src/partoutput.f90:66-192): the particle dump's
+ * records -- position in degrees, height, release point and time, and topography, potential
+ * vorticity, humidity, density, mixing height, tropopause and temperature interpolated to the
+ * particle -- built on the device for the particles with itra1 == itime, in slot order.  Needs
+ * the orography (once) and pv, qv of both time levels (after each fpb_upload_met of a slot). */
+int fpb_set_orography(fpb_handle *h, const float *oro /* (nxmax,nymax) */);
+int fpb_upload_pvqv(fpb_handle *h, int32_t slot, const float *pv, const float *qv /* (nxmax,nymax,nzmax) */);
+typedef struct fpb_partout_ptrs { /* each [>= number of active particles]; xmass1 (ld, nspec) column-major */
+  int32_t *npoint;
+  float *xlon, *ylat, *ztra1;
+  int32_t *itramem;
+  float *topo, *pvi, *qvi, *rhoi, *hmixi, *tri, *tti;
+  float *xmass1;
+  int32_t ld;
+} fpb_partout_ptrs;
+int fpb_partoutput(fpb_handle *h, int32_t itime, int32_t *nrecords, const fpb_partout_ptrs *out);
+
 /* Release points (src/point_mod.f90:15-26 after the conversions of src/readreleases.f90 and
  * src/FLEXPART.f90:401-404): coordinates in grid units, heights in metres above ground
  * (zkind 1), times in seconds relative to the start and snapped to lsynctime. */

@@ -163,6 +163,10 @@ void fpo_fetch_wetgrids(fpo_state *S, float *wetgridunc, float *wetgriduncn);
 
 /* fpo_output.c: outgrid_init's cell geometry and concoutput's sparse dump of one (ks, kp, nage) */
 void fpo_outgrid_geometry(const fpb_config *c, int nest, float outlat0, float *area, float *volume);
+void fpo_partoutput_record(const fpb_config *c, const float *height, int itime, const int32_t memtime[2],
+                           double xtra1, double ytra1, float ztra1, const float *oro,
+                           const float *pv[2], const float *qv[2], const float *tt[2], const float *rho[2],
+                           const float *hmix[2], const float *tropopause[2], float out[9]);
 void fpo_density_outgrid(const fpb_config *c, const float *height, int nest, float outlon0, float outlat0,
                          const float *rho, float *densityoutgrid);
 void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float *grid_ref,

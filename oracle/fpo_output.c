@@ -160,3 +160,61 @@ void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float
   free(grid);
   free(aux);
 }
+
+/* partoutput's record of one particle, src/partoutput.f90:70-183.  Field arrays in the com_mod
+ * layout (0:nxmax-1,0:nymax-1,nzmax) of the time levels memind(1), memind(2). */
+void fpo_partoutput_record(const fpb_config *c, const float *height, int itime, const int32_t memtime[2],
+                           double xtra1, double ytra1, float ztra1, const float *oro,
+                           const float *pv[2], const float *qv[2], const float *tt[2], const float *rho[2],
+                           const float *hmix[2], const float *tropopause[2], float out[9]) {
+  const size_t nxm = c->nxmax, plane = (size_t)c->nxmax * c->nymax;
+  float dt1 = (float)(itime - memtime[0]), dt2 = (float)(memtime[1] - itime);
+  float dtt = 1.f / (dt1 + dt2);
+  float xlon = (float)(c->xlon0 + xtra1 * c->dx);
+  float ylat = (float)(c->ylat0 + ytra1 * c->dy);
+  int ix = (int)xtra1, jy = (int)ytra1;
+  int ixp = ix + 1, jyp = jy + 1;
+  float ddx = (float)(xtra1 - (float)ix), ddy = (float)(ytra1 - (float)jy);
+  float rddx = 1.f - ddx, rddy = 1.f - ddy;
+  float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+  if (jyp >= c->nymax) jyp = jyp - 1;
+#define F2(f) (p1 * (f)[ix + nxm * jy] + p2 * (f)[ixp + nxm * jy] + p3 * (f)[ix + nxm * jyp] + p4 * (f)[ixp + nxm * jyp])
+#define F3(f, k) (p1 * (f)[ix + nxm * jy + plane * ((k)-1)] + p2 * (f)[ixp + nxm * jy + plane * ((k)-1)] + \
+                  p3 * (f)[ix + nxm * jyp + plane * ((k)-1)] + p4 * (f)[ixp + nxm * jyp + plane * ((k)-1)])
+  float topo = F2(oro);
+  int indz = c->nz - 1, indzp;
+  for (int il = 2; il <= c->nz; il++)
+    if (height[il - 1] > ztra1) { indz = il - 1; break; }
+  indzp = indz + 1;
+  float dz1 = ztra1 - height[indz - 1], dz2 = height[indzp - 1] - ztra1;
+  float dz = 1.f / (dz1 + dz2);
+  float pvprof[2], qvprof[2], ttprof[2], rhoprof[2];
+  for (int ind = indz; ind <= indzp; ind++) {
+    float pv1[2], qv1[2], tt1[2], rho1[2];
+    for (int m = 0; m < 2; m++) {
+      pv1[m] = F3(pv[m], ind);
+      qv1[m] = F3(qv[m], ind);
+      tt1[m] = F3(tt[m], ind);
+      rho1[m] = F3(rho[m], ind);
+    }
+    pvprof[ind - indz] = (pv1[0] * dt2 + pv1[1] * dt1) * dtt;
+    qvprof[ind - indz] = (qv1[0] * dt2 + qv1[1] * dt1) * dtt;
+    ttprof[ind - indz] = (tt1[0] * dt2 + tt1[1] * dt1) * dtt;
+    rhoprof[ind - indz] = (rho1[0] * dt2 + rho1[1] * dt1) * dtt;
+  }
+  float pvi = (dz1 * pvprof[1] + dz2 * pvprof[0]) * dz;
+  float qvi = (dz1 * qvprof[1] + dz2 * qvprof[0]) * dz;
+  float tti = (dz1 * ttprof[1] + dz2 * ttprof[0]) * dz;
+  float rhoi = (dz1 * rhoprof[1] + dz2 * rhoprof[0]) * dz;
+  float tr[2], hm[2];
+  for (int m = 0; m < 2; m++) {
+    tr[m] = F2(tropopause[m]);
+    hm[m] = F2(hmix[m]);
+  }
+  float hmixi = (hm[0] * dt2 + hm[1] * dt1) * dtt;
+  float tri = (tr[0] * dt2 + tr[1] * dt1) * dtt;
+#undef F2
+#undef F3
+  out[0] = xlon; out[1] = ylat; out[2] = topo; out[3] = pvi; out[4] = qvi; out[5] = rhoi;
+  out[6] = hmixi; out[7] = tri; out[8] = tti;
+}

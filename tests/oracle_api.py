@@ -58,6 +58,8 @@ def load(libm_float=False):
     L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
     L.fpo_releaseparticles.restype = C.c_int
     L.fpo_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_float, _pf, _pf]
+    L.fpo_partoutput_record.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, _pi, C.c_double, C.c_double, C.c_float, _pf] + \
+        [C.POINTER(_pf)] * 6 + [_pf]
     L.fpo_density_outgrid.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, C.c_float, C.c_float, _pf, _pf]
     L.fpo_concoutput_sparse.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_int, _pf, _pf, _pf, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_float, C.c_int, _pi, _pi, _pi, _pf]

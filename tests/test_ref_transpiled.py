@@ -501,3 +501,41 @@ def test_reference_outgrid_geometry_and_sparse_dump_bit_identical():
                     assert np.array_equal(ref.arr("sparse_dump_r")[:cr.value].view(np.uint32), dr[:cr.value].view(np.uint32)), (ks, kp, nage, which)
                     total += cr.value
     assert total > 1000
+
+
+def test_reference_partoutput_record_bit_identical():
+    """The per-particle interpolation of partoutput (src/partoutput.f90:48-50,73-179) against the
+    oracle's restatement (oracle/fpo_output.c), which the GPU tests equate with the device's."""
+    cb = cases.config_small(nrel=1, npart_each=400)
+    c = cb.cfg
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    L = Oracle(cb).L
+    m = [fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(10800)]
+    ref.upload_met(1, m[0]); ref.upload_met(2, m[1]); ref.set_met_bracket((1, 2), (0, 10800))
+    r = np.random.RandomState(3)
+    shp3, shp2 = m[0].uu.shape, m[0].hmix.shape
+    pv = [np.asfortranarray(r.normal(0, 2e-6, shp3).astype(np.float32)) for _ in range(2)]
+    qv = [np.asfortranarray(r.uniform(0, 0.02, shp3).astype(np.float32)) for _ in range(2)]
+    oro = np.asfortranarray(r.uniform(0, 3000.0, shp2).astype(np.float32))
+    ref.arr("oro")[...] = oro
+    for s in (0, 1):
+        ref.arr("pv")[:, :, :, s] = pv[s]; ref.arr("qv")[:, :, :, s] = qv[s]
+    p = cases.seeded_particles(cb, 400, zmax=12000.0, lat_range=(-89.0, 89.0))
+    ref.push_particles(p)
+    itime = 2700
+    f = lambda: C.c_float(0.0)
+    dt1, dt2, dtt = f(), f(), f()
+    ref.L.f_pp_dt(C.byref(C.c_int(itime)), C.byref(dt1), C.byref(dt2), C.byref(dtt))
+    _pf = C.POINTER(C.c_float)
+    pair = lambda a, b: (_pf * 2)(a.ctypes.data_as(_pf), b.ctypes.data_as(_pf))
+    args = [pair(pv[0], pv[1]), pair(qv[0], qv[1]), pair(m[0].tt, m[1].tt), pair(m[0].rho, m[1].rho),
+            pair(m[0].hmix, m[1].hmix), pair(m[0].tropopause, m[1].tropopause)]
+    memtime = (C.c_int32 * 2)(0, 10800)
+    out = np.zeros(9, np.float32)
+    for i in range(400):
+        v = [f() for _ in range(9)]
+        ref.L.f_pp_record(C.byref(C.c_int(i + 1)), C.byref(dt1), C.byref(dt2), C.byref(dtt), *[C.byref(x) for x in v])
+        L.fpo_partoutput_record(C.byref(c), cb.height.ctypes.data_as(_pf), itime, memtime, float(p.xtra1[i]), float(p.ytra1[i]),
+                                float(p.ztra1[i]), oro.ctypes.data_as(_pf), *args, out.ctypes.data_as(_pf))
+        got = np.array([x.value for x in v], np.float32)
+        assert np.array_equal(got.view(np.uint32), out.view(np.uint32)), (i, got, out)
