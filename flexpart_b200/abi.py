@@ -176,6 +176,7 @@ def load_engine_lib():
     L.fpb_partoutput.argtypes = [H, _i, _pi, C.POINTER(FpbPartoutPtrs)]
     L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
+    L.fpb_split_particles.argtypes = [H, _i, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
                                 C.POINTER(FpbStepStats)]

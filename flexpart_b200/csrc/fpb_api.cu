@@ -1293,6 +1293,35 @@ extern "C" int fpb_releaseparticles(fpb_handle *h, int32_t itime, int32_t *numpa
   return 0;
 }
 
+extern "C" int fpb_split_particles(fpb_handle *h, int32_t itime, int32_t *numpart) {
+  if (!h) return fail("fpb_split_particles: null handle");
+  if (numpart) *numpart = h->numpart;
+  if (h->numpart == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  auto &R = h->rel;
+  if (!R.d_block_counts) DA(R.d_block_counts, (size_t)(h->cfg.maxpart + 1023) / 1024);
+  if (!R.d_out) DA(R.d_out, 2);
+  DevSplitArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.p = h->p;
+  a.row_of_slot = h->row_of_slot;
+  a.permuted = h->permuted ? 1 : 0;
+  a.numpart_old = h->numpart;
+  a.block_counts = R.d_block_counts;
+  a.total = R.d_out;
+  if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_split_strict(a, h->stream); else fpbk_split_fast(a, h->stream);
+  h->launches += 3;
+  int total = 0;
+  CK(cudaMemcpyAsync(&total, R.d_out, sizeof total, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  const int room = h->cfg.maxpart - h->numpart;
+  h->numpart += total < room ? total : room;
+  h->active_rows = -1;
+  if (numpart) *numpart = h->numpart;
+  return 0;
+}
+
 // ------------------------------------------------------- host-buffer step --
 static DevParticles rows_view(const DevParticles &p, int c0) {
   DevParticles v = p;

@@ -173,6 +173,16 @@ struct DevReleaseArgs {
   int *out;                   // [0] max(new slot) + 1 (atomicMax), [1] free slots
 };
 
+// particle splitting (fpb_release.cuh)
+struct DevSplitArgs {
+  DevCfg cfg;                 // cfg.itime
+  DevParticles p;
+  const int32_t *row_of_slot;
+  int permuted, numpart_old;
+  unsigned *block_counts;
+  int *total;                 // candidates found
+};
+
 // launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
   void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \
@@ -181,6 +191,7 @@ struct DevReleaseArgs {
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_wetdepo_##SUF(const DevWetArgs &a, cudaStream_t st);              \
   void fpbk_release_##SUF(const DevReleaseArgs &a, cudaStream_t st);          \
+  void fpbk_split_##SUF(const DevSplitArgs &a, cudaStream_t st);              \
   void fpbk_conc_emit_##SUF(const DevConcArgs &a, int nest_sel, unsigned *keys, \
                             float *vals, size_t nrec, cudaStream_t st);
 FPB_DECL_LAUNCHERS(fast)

@@ -1535,8 +1535,16 @@ void FPB_SUF(fpbk_conc_emit)(const DevConcArgs &a, int nest_sel, unsigned *keys,
 void FPB_SUF(fpbk_release)(const DevReleaseArgs &a, cudaStream_t st) {
   const int nb = (a.p.maxpart + REL_BLOCK - 1) / REL_BLOCK;
   release_count_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
-  release_scan_kernel<<<1, REL_BLOCK, 0, st>>>(a, nb);
+  release_scan_kernel<<<1, REL_BLOCK, 0, st>>>(a.block_counts, a.out + 1, nb);
   release_assign_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
+}
+
+void FPB_SUF(fpbk_split)(const DevSplitArgs &a, cudaStream_t st) {
+  const int nb = (a.numpart_old + REL_BLOCK - 1) / REL_BLOCK;
+  if (nb == 0) return;
+  split_count_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
+  release_scan_kernel<<<1, REL_BLOCK, 0, st>>>(a.block_counts, a.total, nb);
+  split_assign_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_wetdepo)(const DevWetArgs &a, cudaStream_t st) {

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(REL_BLOCK) release_count_kernel(const DevRelea
 }
 
 // exclusive scan of the block counts (one block; the list is maxpart / 1024 long)
-__global__ void __launch_bounds__(REL_BLOCK) release_scan_kernel(const DevReleaseArgs a, int nblocks) {
+__global__ void __launch_bounds__(REL_BLOCK) release_scan_kernel(unsigned *block_counts, int *total, int nblocks) {
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned running;
   if (threadIdx.x == 0) running = 0;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(REL_BLOCK) release_scan_kernel(const DevReleas
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int base = 0; base < nblocks; base += REL_BLOCK) {
     const int i = base + threadIdx.x;
-    const unsigned v = (i < nblocks) ? a.block_counts[i] : 0u;
+    const unsigned v = (i < nblocks) ? block_counts[i] : 0u;
     unsigned inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -53,12 +53,12 @@ __global__ void __launch_bounds__(REL_BLOCK) release_scan_kernel(const DevReleas
     }
     __syncthreads();
     const unsigned excl = running + warp_tot[w] + inc - v;
-    if (i < nblocks) a.block_counts[i] = excl;
+    if (i < nblocks) block_counts[i] = excl;
     __syncthreads();
     if (threadIdx.x == REL_BLOCK - 1) running = excl + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) a.out[1] = (int)running; // free slots in total
+  if (threadIdx.x == 0) *total = (int)running;
 }
 
 __global__ void __launch_bounds__(REL_BLOCK) release_assign_kernel(const DevReleaseArgs a) {
@@ -134,4 +134,59 @@ __global__ void __launch_bounds__(REL_BLOCK) release_assign_kernel(const DevRele
   a.p.cbt[row] = 1;
   a.p.slot[row] = s;
   atomicMax(a.out, s + 1);
+}
+
+// ---- particle splitting, src/timemanager.f90:472-503: every particle (slot j <= numpart) whose
+// itrasplit has been reached is duplicated into slot numpart + (its rank among such particles), both
+// halves carry half the mass; candidates beyond maxpart stay untouched.
+__device__ __forceinline__ bool split_candidate(const DevSplitArgs &a, int s, int &row) {
+  if (s >= a.numpart_old) return false;
+  row = a.permuted ? a.row_of_slot[s] : s;
+  return a.cfg.ldirect * a.cfg.itime >= a.cfg.ldirect * a.p.itrasplit[row];
+}
+
+__global__ void __launch_bounds__(REL_BLOCK) split_count_kernel(const DevSplitArgs a) {
+  int row;
+  const int n = __syncthreads_count(split_candidate(a, blockIdx.x * REL_BLOCK + threadIdx.x, row));
+  if (threadIdx.x == 0) a.block_counts[blockIdx.x] = (unsigned)n;
+}
+
+__global__ void __launch_bounds__(REL_BLOCK) split_assign_kernel(const DevSplitArgs a) {
+  __shared__ unsigned warp_cnt[32];
+  const int s = blockIdx.x * REL_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int j = 0;
+  const bool cand = split_candidate(a, s, j);
+  const unsigned bal = __ballot_sync(0xffffffffu, cand);
+  if (lane == 0) warp_cnt[w] = __popc(bal);
+  __syncthreads();
+  if (w == 0) {
+    unsigned t = warp_cnt[lane], ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += u;
+    }
+    warp_cnt[lane] = ti - t;
+  }
+  __syncthreads();
+  if (!cand) return;
+  const int r = (int)(a.block_counts[blockIdx.x] + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u)));
+  const int n = a.numpart_old + r; // 0-based new slot = row (fresh rows are never permuted)
+  if (n >= a.p.maxpart) return;
+  const DevParticles &p = a.p;
+  const int split = 2 * (p.itrasplit[j] - p.itramem[j]) + p.itramem[j];
+  p.itrasplit[j] = split; p.itrasplit[n] = split;
+  p.itramem[n] = p.itramem[j]; p.itra1[n] = p.itra1[j]; p.idt[n] = p.idt[j];
+  p.npoint[n] = p.npoint[j]; p.nclass[n] = p.nclass[j];
+  p.xtra1[n] = p.xtra1[j]; p.ytra1[n] = p.ytra1[j]; p.ztra1[n] = p.ztra1[j];
+  p.uap[n] = p.uap[j]; p.ucp[n] = p.ucp[j]; p.uzp[n] = p.uzp[j];
+  p.us[n] = p.us[j]; p.vs[n] = p.vs[j]; p.ws[n] = p.ws[j];
+  p.cbt[n] = p.cbt[j];
+  p.slot[n] = n;
+  for (int ks = 0; ks < a.cfg.nspec; ks++) {
+    const float m = p.xmass1[(size_t)ks * p.maxpart + j] / 2.f;
+    p.xmass1[(size_t)ks * p.maxpart + j] = m;
+    p.xmass1[(size_t)ks * p.maxpart + n] = m;
+  }
 }

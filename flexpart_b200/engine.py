@@ -149,6 +149,12 @@ class Engine:
         self._check(self.L.fpb_releaseparticles(self.h, itime, C.byref(n), C.byref(m)))
         return n.value, m.value
 
+    def split_particles(self, itime):
+        """particle splitting of timemanager (src/timemanager.f90:472-503); returns the new numpart."""
+        n = C.c_int32(0)
+        self._check(self.L.fpb_split_particles(self.h, itime, C.byref(n)))
+        return n.value
+
     def wetdepo(self, itime, ltsample, ldeltat=0):
         """wetdepo(itime, ltsample, loutnext) with ldeltat precomputed (src/wetdepo.f90:55-63)."""
         self._check(self.L.fpb_wetdepo(self.h, itime, ltsample, ldeltat))

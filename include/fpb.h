@@ -299,6 +299,14 @@ int fpb_concoutput_sparse(fpb_handle *h, int32_t nest, int32_t which, int32_t ks
                           int32_t *sp_count_i, int32_t *sparse_dump_i, int32_t *sp_count_r,
                           float *sparse_dump_r);
 
+/* replaces the particle-splitting block of timemanager (src/timemanager.f90:472-503): every
+ * particle (dead ones included, as in the reference) whose itrasplit has been reached is duplicated
+ * into the slot numpart + its rank among such particles, both halves with half the mass and
+ * itrasplit doubled; candidates that would exceed maxpart stay untouched.  The caller keeps the
+ * outer test `ldirect*itime >= ldirect*itsplit`.  Needs fpb_set_releases (for the block-scan scratch)
+ * or any earlier fpb_releaseparticles.  *numpart returns the new numpart. */
+int fpb_split_particles(fpb_handle *h, int32_t itime, int32_t *numpart);
+
 /* partoutput (src/partoutput.f90:66-192): the particle dump's
  * records -- position in degrees, height, release point and time, and topography, potential
  * vorticity, humidity, density, mixing height, tropopause and temperature interpolated to the

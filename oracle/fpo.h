@@ -137,6 +137,7 @@ void fpo_push_particles(fpo_state *S, int first, int count,
 void fpo_pull_particles(fpo_state *S, int first, int count,
                         const fpb_particle_ptrs *p);
 void fpo_set_numpart(fpo_state *S, int numpart);
+int fpo_numpart(const fpo_state *S);
 const int32_t *fpo_trace_nsub(const fpo_state *S);
 
 /* hot path */
@@ -218,6 +219,7 @@ void fpo_cc2gll(const float *strcmp, float xlat, float xlong, float ue,
                 float vn, float *ug, float *vg);
 
 /* releaseparticles (integer semantics + ran1 stream) */
+void fpo_split_particles(fpo_state *S, int itime);
 int fpo_releaseparticles(fpo_state *S, int itime, int numpoint,
                          const int32_t *ireleasestart,
                          const int32_t *ireleaseend, const float *xpoint1,

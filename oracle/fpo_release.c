@@ -87,3 +87,38 @@ int fpo_releaseparticles(fpo_state *S, int itime, int numpoint,
   }
   return 0;
 }
+
+/* particle splitting, src/timemanager.f90:472-503 (the caller keeps the outer itsplit test) */
+void fpo_split_particles(fpo_state *S, int itime) {
+  const fpb_config *c = &S->c;
+  int n = S->numpart;
+  for (int j = 1; j <= S->numpart; j++) {
+    if (c->ldirect * itime >= c->ldirect * S->itrasplit[j]) {
+      if (n < c->maxpart) {
+        n = n + 1;
+        S->itrasplit[j] = 2 * (S->itrasplit[j] - S->itramem[j]) + S->itramem[j];
+        S->itrasplit[n] = S->itrasplit[j];
+        S->itramem[n] = S->itramem[j];
+        S->itra1[n] = S->itra1[j];
+        S->idt[n] = S->idt[j];
+        S->npoint[n] = S->npoint[j];
+        S->nclass[n] = S->nclass[j];
+        S->xtra1[n] = S->xtra1[j];
+        S->ytra1[n] = S->ytra1[j];
+        S->ztra1[n] = S->ztra1[j];
+        S->uap[n] = S->uap[j];
+        S->ucp[n] = S->ucp[j];
+        S->uzp[n] = S->uzp[j];
+        S->us[n] = S->us[j];
+        S->vs[n] = S->vs[j];
+        S->ws[n] = S->ws[j];
+        S->cbt[n] = S->cbt[j];
+        for (int ks = 1; ks <= c->nspec; ks++) {
+          XM1(S, j, ks) = XM1(S, j, ks) / 2.f;
+          XM1(S, n, ks) = XM1(S, j, ks);
+        }
+      }
+    }
+  }
+  S->numpart = n;
+}

@@ -147,6 +147,7 @@ void fpo_set_met_bracket(fpo_state *S, const int memind[2], const int memtime[2]
 }
 
 void fpo_set_numpart(fpo_state *S, int numpart) { S->numpart = numpart; }
+int fpo_numpart(const fpo_state *S) { return S->numpart; }
 
 /* sub-steps each particle took in the last fpo_step (1-based like the particle arrays) */
 const int32_t *fpo_trace_nsub(const fpo_state *S) { return S->trace_nsub; }

@@ -57,6 +57,8 @@ def load(libm_float=False):
     L.fpo_cc2gll.argtypes = [_pf, C.c_float, C.c_float, C.c_float, C.c_float, _pf, _pf]
     L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
     L.fpo_releaseparticles.restype = C.c_int
+    L.fpo_split_particles.argtypes = [S, C.c_int]
+    L.fpo_numpart.argtypes = [S]; L.fpo_numpart.restype = C.c_int
     L.fpo_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_float, _pf, _pf]
     L.fpo_partoutput_record.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, _pi, C.c_double, C.c_double, C.c_float, _pf] + \
         [C.POINTER(_pf)] * 6 + [_pf]

@@ -1011,3 +1011,43 @@ def test_partoutput_records_match_the_reference_interpolation(sort_interval):
                                 float(q.ztra1[s]), oro.ctypes.data_as(_pf), *args, out.ctypes.data_as(_pf))
         got = np.array([rec[k][j] for k in names], np.float32)
         assert np.array_equal(got.view(np.uint32), out.view(np.uint32)), (s, dict(zip(names, zip(got, out))))
+
+
+# ----------------------------------------------------------------------------
+# particle splitting on the device
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("sort_interval,maxpart", [(0, 4000), (1, 4000), (1, 1700)])
+def test_particle_splitting_matches_the_reference_loop(sort_interval, maxpart):
+    """fpb_split_particles against the sequential loop of src/timemanager.f90:472-503: the same
+    particles split (dead ones included), copies appended in particle order, half the mass each,
+    itrasplit doubled; with maxpart = 1700 only the first candidates find room."""
+    cb = cases.config_small(nrel=2, npart_each=600, maxpart=maxpart, nspec=2, math_mode=fb.MATH_STRICT,
+                            sort_interval=sort_interval, lage=(3000,))
+    c = cb.cfg
+    n = 1200
+    p = cases.seeded_particles(cb, n, zmax=3000.0, nspec=2)
+    r = np.random.RandomState(8)
+    p.itrasplit[:n] = r.choice([900, 1800, 2700, 99999999], n)
+    p.itramem[:n] = r.choice([0, -900], n)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb(); e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+        e.push_particles(p)
+    np_o = n
+    for k in range(4):
+        itime = k * 900
+        sg, so = eng.step(itime, 0), ora.step(itime, 0)
+        assert sg == so
+        ng = eng.split_particles(itime + 900)
+        ora.L.fpo_split_particles(ora.S, itime + 900)
+        np_o = ora.L.fpo_numpart(ora.S)
+        assert ng == np_o, (k, ng, np_o)
+        pg, po = fb.Particles(c.maxpart, 2), fb.Particles(c.maxpart, 2)
+        pg.numpart = po.numpart = ng
+        eng.pull_particles(pg); ora.pull_particles(po)
+        for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1", "itrasplit"):
+            assert np.array_equal(getattr(pg, f)[:ng], getattr(po, f)[:ng]), (k, f)
+        assert np.array_equal(pg.xmass1[:ng], po.xmass1[:ng]), k
+    assert np_o > n and (maxpart > 2000 or np_o == maxpart)
+    assert (po.itra1[:np_o] == fb.ITRA_DEAD).any()

@@ -539,3 +539,38 @@ def test_reference_partoutput_record_bit_identical():
                                 float(p.ztra1[i]), oro.ctypes.data_as(_pf), *args, out.ctypes.data_as(_pf))
         got = np.array([x.value for x in v], np.float32)
         assert np.array_equal(got.view(np.uint32), out.view(np.uint32)), (i, got, out)
+
+
+def test_reference_particle_splitting_bit_identical():
+    """The splitting block of timemanager (src/timemanager.f90:473-504) against the oracle's loop:
+    same candidates, same slots, halved masses, doubled itrasplit, saturation at maxpart."""
+    cb = cases.config_small(nrel=2, npart_each=300, maxpart=800, nspec=2)
+    c = cb.cfg
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    o = Oracle(cb)
+    n = 600
+    p = cases.seeded_particles(cb, n, zmax=3000.0, nspec=2)
+    r = np.random.RandomState(8)
+    p.itrasplit[:n] = r.choice([900, 1800, 99999999], n)
+    p.itramem[:n] = r.choice([0, -900], n)
+    p.itra1[:n:7] = fb.ITRA_DEAD
+    for nm in ("uap", "ucp", "uzp", "us", "vs", "ws"):
+        getattr(p, nm)[:n] = r.normal(size=n).astype(np.float32)
+    p.idt[:n] = r.randint(1, 900, n)
+    o.push_particles(p)
+    ref.push_particles(p); ref.push_state(p)
+    ref.arr("itrasplit")[:n] = p.itrasplit[:n]
+    ref.set("itsplit", 900)
+    for itime in (900, 1800):
+        ref.L.f_tm_split(C.byref(C.c_int(itime)))
+        o.L.fpo_split_particles(o.S, itime)
+        k = ref.get("numpart")
+        assert k == o.L.fpo_numpart(o.S)
+        q = fb.Particles(c.maxpart, 2); q.numpart = k
+        o.pull_particles(q)
+        for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "itrasplit", "npoint", "nclass", "idt", "uap", "ucp",
+                  "uzp", "us", "vs", "ws", "cbt"):
+            a, b = ref.arr(f)[:k], getattr(q, f)[:k]
+            assert np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), (itime, f)
+        assert np.array_equal(ref.arr("xmass1")[:k, :2].view(np.uint32), q.xmass1[:k, :2].view(np.uint32))
+    assert k == c.maxpart          # the second round ran out of slots
