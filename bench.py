@@ -197,6 +197,16 @@ def run_ours(args):
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        # one process per GPU: run on the cores next to that GPU, so that the pinned particle arrays
+        # of the end-to-end leg are allocated on its NUMA node (torchrun does not bind ranks)
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+            N.nvmlDeviceSetCpuAffinity(N.nvmlDeviceGetHandleByIndex(idx))
+        except Exception as e:
+            log(f"[rank {rank}] no CPU affinity set ({e})")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, args.warmup
 
