@@ -1051,3 +1051,55 @@ def test_particle_splitting_matches_the_reference_loop(sort_interval, maxpart):
         assert np.array_equal(pg.xmass1[:ng], po.xmass1[:ng]), k
     assert np_o > n and (maxpart > 2000 or np_o == maxpart)
     assert (po.itra1[:np_o] == fb.ITRA_DEAD).any()
+
+
+def test_mixed_entry_points_keep_one_consistent_state():
+    """Device release -> host-buffer step -> device release into re-used slots -> resident step,
+    alternating, against the oracle doing the same sequence: the entry points share one particle
+    state (row order, slot map, numpart) and must leave it consistent for each other."""
+    cb = cases.config_small(nrel=3, npart_each=600, maxpart=2600, math_mode=fb.MATH_STRICT, sort_interval=1,
+                            lage=(1800,))
+    c = cb.cfg
+    rel = cases.releases_boxes(cb, seed=3, start=0, end=2700)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb(); e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+    eng.set_releases(rel)
+    xmasssave = np.zeros(c.numpoint, np.float32)
+
+    def compare(tag, n):
+        pg, po = fb.Particles(c.maxpart, 1), fb.Particles(c.maxpart, 1)
+        pg.numpart = po.numpart = n
+        eng.pull_particles(pg); ora.pull_particles(po)
+        live = po.itra1[:n] != fb.ITRA_DEAD
+        assert np.array_equal(pg.itra1[:n], po.itra1[:n]), tag
+        for f in ("xtra1", "ytra1", "ztra1", "itramem", "npoint", "nclass", "idt"):
+            assert np.array_equal(getattr(pg, f)[:n][live], getattr(po, f)[:n][live]), (tag, f)
+        old = live & (po.itramem[:n] != po.itra1[:n])   # (initialize sets the velocities of the newest ones)
+        for f in ("uap", "ucp", "uzp", "us", "vs", "ws"):
+            assert np.array_equal(getattr(pg, f)[:n][old], getattr(po, f)[:n][old]), (tag, f)
+        assert np.array_equal(pg.xmass1[:n][live], po.xmass1[:n][live]), tag
+        return pg
+
+    for k in range(5):
+        itime = k * 900
+        _oracle_release(ora, c, rel, itime, xmasssave)
+        n, _ = eng.release_particles(itime)
+        assert n == ora.L.fpo_numpart(ora.S)
+        host = compare(("release", k), n)
+        so = ora.step(itime, 450)
+        if k % 2 == 0:      # the host keeps the arrays for this interval
+            host.itrasplit[:n] = 99999999
+            sg = eng.step_host(host, itime, 450)
+            assert sg == so, (k, sg, so)
+            po = fb.Particles(c.maxpart, 1); po.numpart = n
+            ora.pull_particles(po)
+            live = po.itra1[:n] != fb.ITRA_DEAD
+            assert np.array_equal(host.itra1[:n], po.itra1[:n])
+            assert np.array_equal(host.xtra1[:n][live], po.xtra1[:n][live]) and np.array_equal(host.ztra1[:n][live], po.ztra1[:n][live])
+        else:
+            sg = eng.step(itime, 450)
+            assert sg == so, (k, sg, so)
+        compare(("step", k), n)
+    assert (host.itra1[:n] == fb.ITRA_DEAD).any()
