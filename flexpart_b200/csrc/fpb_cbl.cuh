@@ -9,6 +9,10 @@ __device__ __forceinline__ float cbl_cuberoot(float x) {
   return copysignf(m_pow(fabsf(x), 0.333333333f), x);
 }
 
+#ifndef FPB_CBL_DRIFT_INLINE
+#define FPB_CBL_DRIFT_INLINE __forceinline__ // measured: -6 % on the C3 workload against a call
+#endif
+
 // x**2 of the reference; a multiplication in both math modes (pow(x, 2.) in
 // double rounds to the same float, and the fast exp2/log2 pow needs x > 0)
 __device__ __forceinline__ float cbl_sq(float x) { return x * x; }
@@ -37,7 +41,7 @@ __device__ __forceinline__ float cbl_transition(float h, float ol) {
 
 // drift ath and diffusion bth of the CBL Langevin equation; sets flagrein
 // when the velocity is > 6 sigma from both modes.
-__device__ __noinline__ void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float h, float rhoa,
+__device__ FPB_CBL_DRIFT_INLINE void cbl_drift(const DevCfg &c, float wp, float zp, float wst, float h, float rhoa,
                           float rhograd, float sigmaw, float dsigmawdz, float tlw, float ol,
                           float &ath, float &bth, int &flagrein) {
   const float usurad2 = 0.7071067812f, usurad2p = 0.3989422804f, C0 = 3.f,
