@@ -407,6 +407,9 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   if (!cfg->height) return fail("fpb_init: height is null");
   if (cfg->maxpart < 1) return fail("fpb_init: maxpart < 1");
   if (cfg->numpoint < 1 || !cfg->npart || !cfg->xmass) return fail("fpb_init: releases (numpoint/npart/xmass) missing");
+  if (cfg->ldirect != 1 && cfg->ldirect != -1) return fail("fpb_init: ldirect must be 1 or -1 (got %d)", cfg->ldirect);
+  if ((cfg->drybkdep || cfg->wetbkdep) && cfg->ldirect != -1)
+    return fail("fpb_init: drybkdep/wetbkdep (IND_RECEPTOR 3/4) are backward-run options (src/readcommand.f90:320-339)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)

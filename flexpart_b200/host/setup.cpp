@@ -110,7 +110,8 @@ extern "C" int fpbh_readcommand(fpb_config *c) {
   }
   c->fine = 1.f / (float)c->ifine;
   c->ctl = 1.f / c->ctl;
-  if (c->ldirect == -1) c->lsynctime = -c->lsynctime;
+  // method / mintime are derived while lsynctime is still positive (src/readcommand.f90:377-383);
+  // the sign flip of a backward run comes later (:627-634), so mintime stays +|lsynctime|
   if (c->ctl > 0.f) {
     c->method = 1;
     c->mintime = 1; // par_mod minstep
@@ -118,6 +119,7 @@ extern "C" int fpbh_readcommand(fpb_config *c) {
     c->method = 0;
     c->mintime = c->lsynctime;
   }
+  if (c->ldirect == -1) c->lsynctime = -c->lsynctime;
   if (c->d_trop == 0.f) c->d_trop = 50.f;     // src/par_mod.f90:79
   if (c->d_strat == 0.f) c->d_strat = 0.1f;
   if (c->turbmesoscale == 0.f) c->turbmesoscale = 0.16f;

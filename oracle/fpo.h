@@ -102,8 +102,13 @@ typedef struct fpo_state {
    * 0 = "defined" behaviour the device implements. */
   int strict_reference;
 
-  /* validation hooks: per-call nrand injection (0 = draw from ran3) */
+  /* validation hooks */
   long n_ran3_draws;
+  /* when set, the uniform behind `nrand=int(ran3(idummy)*real(maxrand-1))+1` (src/advance.f90:153,
+   * src/initialize.f90:68) is popped from this queue instead of ran3: lets a test hand the oracle the
+   * engine's counter-based (Philox) index stream, so that the production RNG mode can be compared */
+  float *index_queue;
+  long index_queue_n, index_queue_pos;
 
   /* counters */
   long nan_count, nan_count2;
@@ -124,6 +129,8 @@ void fpo_gasdev1(fpo_state *S, int *idum, float *r1, float *r2);
 void fpo_fill_rannumb(fpo_state *S, int maxrand, int idummy);
 void fpo_set_rannumb(fpo_state *S, const float *tab, int n);
 const float *fpo_rannumb(fpo_state *S); /* 0-based view of the table */
+float fpo_index_uniform(fpo_state *S, int *idum);
+void fpo_set_index_uniforms(fpo_state *S, const float *u, long n);
 
 /* meteorology */
 void fpo_set_met(fpo_state *S, int slot, const fpb_met_ptrs *m);

@@ -129,7 +129,7 @@ void fpo_initialize(fpo_state *S, int itime, int32_t *ldt, float *up, float *vp,
   const int maxrand = S->maxrand;
 
   *icbt = 1;
-  nrand = fpo_int_f(fpo_ran3(S, &S->idummy_initialize) * (float)(maxrand - 1)) + 1;
+  nrand = fpo_int_f(fpo_index_uniform(S, &S->idummy_initialize) * (float)(maxrand - 1)) + 1;
 
   if (!S->strict_reference) S->ngrid = pole_grid(S, yt);
   /* initialize() calls the mother-grid routines whatever ngrid a previous advance left:
@@ -273,7 +273,7 @@ void fpo_advance(fpo_state *S, int itime, int nrelpoint, int32_t *ldt_io,
 
   itimec = itime;
 
-  nrand = fpo_int_f(fpo_ran3(S, &S->idummy_advance) * (float)(maxrand - 1)) + 1;
+  nrand = fpo_int_f(fpo_index_uniform(S, &S->idummy_advance) * (float)(maxrand - 1)) + 1;
 
   /* grid choice, :161-175 */
   S->ngrid = choose_grid(S, xt, yt);

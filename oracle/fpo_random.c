@@ -75,6 +75,23 @@ float fpo_ran3(fpo_state *S, int *idum) {
   return (float)mj * fac;
 }
 
+/* the uniform that picks the rannumb index of an initialize / advance call: ran3, or the next
+ * entry of the injected queue (validation hook, fpo.h) */
+float fpo_index_uniform(fpo_state *S, int *idum) {
+  if (S->index_queue && S->index_queue_pos < S->index_queue_n) return S->index_queue[S->index_queue_pos++];
+  return fpo_ran3(S, idum);
+}
+
+void fpo_set_index_uniforms(fpo_state *S, const float *u, long n) {
+  free(S->index_queue);
+  S->index_queue = NULL;
+  S->index_queue_n = S->index_queue_pos = 0;
+  if (!u || n <= 0) return;
+  S->index_queue = (float *)malloc((size_t)n * sizeof(float));
+  memcpy(S->index_queue, u, (size_t)n * sizeof(float));
+  S->index_queue_n = n;
+}
+
 /* src/random_mod.f90:45-67 */
 float fpo_gasdev(fpo_state *S, int *idum) {
   if (S->gd_iset == 0) {

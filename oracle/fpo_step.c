@@ -129,6 +129,7 @@ void fpo_destroy(fpo_state *S) {
   free(S->gridunc); free(S->griduncn); free(S->drygridunc);
   free(S->drygriduncn); free(S->creceptor);
   free(S->wetgridunc); free(S->wetgriduncn);
+  free(S->index_queue);
   free(S);
 }
 

@@ -36,6 +36,7 @@ def load(libm_float=False):
     L.fpo_fill_rannumb.argtypes = [S, C.c_int, C.c_int]
     L.fpo_set_rannumb.argtypes = [S, _pf, C.c_int]
     L.fpo_rannumb.argtypes = [S]; L.fpo_rannumb.restype = _pf
+    L.fpo_set_index_uniforms.argtypes = [S, _pf, C.c_long]
     L.fpo_set_met.argtypes = [S, C.c_int, C.POINTER(FpbMetPtrs)]
     L.fpo_set_met_nest.argtypes = [S, C.c_int, C.c_int, C.POINTER(FpbMetPtrs)]
     L.fpo_set_met_bracket.argtypes = [S, _pi, _pi, C.c_int]
@@ -97,6 +98,14 @@ class Oracle:
     def set_rannumb(self, table):
         t = np.ascontiguousarray(table, np.float32)
         self.L.fpo_set_rannumb(self.S, _fp(t), len(t))
+
+    def set_index_uniforms(self, u):
+        """validation hook: the uniforms behind the next nrand draws (tests/philox_ref.py)"""
+        if u is None:
+            self.L.fpo_set_index_uniforms(self.S, None, 0)
+        else:
+            u = np.ascontiguousarray(u, np.float32)
+            self.L.fpo_set_index_uniforms(self.S, _fp(u), len(u))
 
     def rannumb(self, n):
         return np.ctypeslib.as_array(self.L.fpo_rannumb(self.S), shape=(n,)).copy()

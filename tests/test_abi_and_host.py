@@ -100,7 +100,7 @@ def test_readcommand_semantics():
                        cblflag=1, lsynctime=1800).cfg
     assert c.turbswitch == 1 and c.lsynctime == 1200 and abs(c.ctl - 0.2) < 1e-7 and c.ifine == 11
     c = fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ldirect=-1).cfg
-    assert c.lsynctime == -900 and c.mintime == -900
+    assert c.lsynctime == -900 and c.mintime == 900   # mintime is set before the sign flip, readcommand.f90:384 vs :631
     with pytest.raises(fb.FpbError, match="EITHER -1 OR 1"):
         fb.make_config(nx=73, ny=37, nz=10, dx=5.0, dy=5.0, height=fb.synth_heights(10), ldirect=0)
 

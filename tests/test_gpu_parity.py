@@ -321,7 +321,10 @@ def test_cuda_against_the_references_own_code(ctl):
 # math (tolerance), oracle state re-injected every step
 # ----------------------------------------------------------------------------
 def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=True, exact=True,
-              dt=None, tol_h=1e-5, nest_mets=None, tol_z=1e-5):
+              dt=None, tol_h=1e-5, nest_mets=None, tol_z=1e-5, philox=False, wet=False, report=None):
+    """philox: the engine runs a production RNG mode (Philox-indexed rannumb); the oracle is handed
+    the same index uniforms (tests/philox_ref.py).  wet: fpb_wetdepo before every step but the first
+    (src/timemanager.f90:164-169).  report: dict that receives the measured worst deviations."""
     c = cb.cfg
     n = p.numpart
     dt = dt or c.lsynctime
@@ -341,7 +344,13 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
         po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
         ora.pull_particles(po)
         eng.push_particles(po)
+        if philox:
+            import philox_ref
+            assert c.rng_mode == fb.RNG_PHILOX_INDEX
+            ora.set_index_uniforms(philox_ref.index_queue(c, po, itime))
         for e in (eng, ora):
+            if wet and k:
+                e.wetdepo(itime, abs(dt), abs(dt) // 2)
             e.conccalc(itime, 1.0)
         sg, so = eng.step(itime, 450), ora.step(itime, 450)
         pg = fb.Particles(c.maxpart, c.nspec); pg.numpart = n
@@ -378,6 +387,8 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
             relm = np.abs(pg.xmass1[:n] - po.xmass1[:n]) / np.maximum(np.abs(po.xmass1[:n]), 1e-30)
             assert (relm > 1e-5).mean() < 0.01, k       # integer-decision flips: rare, counted
             assert abs(pg.xmass1[:n].sum() - po.xmass1[:n].sum()) < 1e-5 * po.xmass1[:n].sum(), k
+    if report is not None:
+        report.update(worst_h=float(worst), worst_z=float(worst_z))
     if not exact:
         assert worst < tol_h, worst
         assert worst_z < tol_z, worst_z
@@ -388,8 +399,17 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
                 # fast math: the few particles whose deposition threshold / sub-step count flips
                 # put 1e-3-level differences into single deposition cells
                 lim = 1e-5 if (exact or not name.startswith("dry")) else 2e-3
+                if report is not None:
+                    report["grid_" + name] = float(rel_l2(gg[name], go[name]))
                 assert rel_l2(gg[name], go[name]) < lim, (name, rel_l2(gg[name], go[name]))
                 assert abs(gg[name].sum() - go[name].sum()) <= lim * abs(go[name].sum()), name
+    if wet:
+        wg, wo = eng.fetch_wetgrids(), ora.fetch_wetgrids()
+        for name in wo:
+            if wo[name] is not None and wo[name].size and np.abs(wo[name]).sum() > 0:
+                if report is not None:
+                    report["grid_" + name] = float(rel_l2(wg[name], wo[name]))
+                assert rel_l2(wg[name], wo[name]) < (1e-5 if exact else 2e-3), name
     return tot, gg, go
 
 
@@ -510,6 +530,19 @@ def test_backward_run(exact):
     mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
     tot, _, _ = _per_step(cb, p, 5, mets=mets, bracket=(0, -10800), exact=exact)
     assert tot["n_active"] == 5 * 2048 and tot["n_pbl"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_backward_method0_keeps_mintime_positive(exact):
+    """LDIRECT=-1 with CTL<0: mintime = +|lsynctime| (src/readcommand.f90:384 runs before the sign
+    flip at :631), so ldt=max(ldt,mintime) stays positive and the Petterssen corrector runs."""
+    cb = cases.config_small(nrel=4, npart_each=512, ldirect=-1, ctl=-5.0,
+                            math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST)
+    assert cb.cfg.lsynctime == -900 and cb.cfg.mintime == 900 and cb.cfg.method == 0
+    p = cases.seeded_particles(cb, 2048, zmax=9000.0)
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    tot, _, _ = _per_step(cb, p, 5, mets=mets, bracket=(0, -10800), exact=exact)
+    assert tot["n_petterssen"] > 0.9 * tot["n_active"]
 
 
 @pytest.mark.parametrize("exact", [True, False])
@@ -635,6 +668,20 @@ def test_receptors_and_density_weighted_sampling():
     tot, gg, go = _per_step(cb, p, 3, exact=True)
     assert go["creceptor"][:2, 0].min() > 0
     np.testing.assert_allclose(gg["creceptor"], go["creceptor"], rtol=2e-5)
+
+
+def test_particle_count_output():
+    """par_mod's lparticlecountoutput: conccalc adds 1 per particle instead of its mass in the
+    no-kernel branch (src/conccalc.f90:171-183) -- young particles (itage < 10800) take it, old ones
+    keep the mass-weighted 4-cell kernel."""
+    cb = cases.config_small(nrel=2, npart_each=1500, lparticlecountoutput=1, math_mode=fb.MATH_STRICT,
+                            scatter_mode=fb.SCATTER_DETERMINISTIC)
+    p = cases.seeded_particles(cb, 3000, zmax=4000.0, lat_range=(-60.0, 60.0))
+    p.xmass1[:3000, 0] = 0.25
+    tot, gg, go = _per_step(cb, p, 2, exact=True)
+    assert np.array_equal(gg["gridunc"], go["gridunc"])
+    # every sampled particle counts 1 (weight 1, two samples), whatever its mass
+    assert abs(float(go["gridunc"].sum()) - 2.0 * 3000) < 1e-2
 
 
 def test_terminations_are_bit_exact():

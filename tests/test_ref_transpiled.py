@@ -187,8 +187,13 @@ def test_reference_cbl_bit_identical():
     assert counts["calls"] >= 3 * n - 20
 
 
-def test_reference_backward_run_bit_identical():
-    cb = cases.config_small(nrel=2, npart_each=128, ldirect=-1)
+@pytest.mark.parametrize("ctl", [5.0, -5.0])
+def test_reference_backward_run_bit_identical(ctl):
+    """LDIRECT=-1, method 1 and method 0 (CTL<0: mintime must stay +|lsynctime|, src/readcommand.f90:384
+    vs :631, or ldt=max(ldt,mintime) (src/advance.f90:510) goes negative and the Petterssen corrector
+    (src/advance.f90:829) is skipped)."""
+    cb = cases.config_small(nrel=2, npart_each=128, ldirect=-1, ctl=ctl)
+    assert cb.cfg.mintime == (1 if ctl > 0 else 900) and cb.cfg.lsynctime == -900
     n = 256
     p = cases.seeded_particles(cb, n, zmax=4000.0)
     mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
@@ -422,6 +427,13 @@ def test_reference_readcommand_derivations_match_host():
                     exp = (ref.get("ifine"), ref.get("turbswitch"), ref.get("fine"), ref.get("ctl"), ref.get("method"),
                            ref.get("mintime"), ref.get("lsynctime"))
                     assert got == exp, (ctl, ifine, cbl, lsync, got, exp)
+                    # backward run: only lsynctime changes sign, after method/mintime were derived
+                    # (src/readcommand.f90:627-634)
+                    b = FpbConfig()
+                    b.ldirect, b.lsynctime, b.ctl, b.ifine, b.cblflag = -1, lsync, ctl, ifine, cbl
+                    assert H.fpbh_readcommand(C.byref(b)) == 0
+                    assert (b.ifine, b.turbswitch, b.fine, b.ctl, b.method, b.mintime, b.lsynctime) == \
+                        exp[:6] + (-exp[6],), (ctl, ifine, cbl, lsync)
 
 
 def test_reference_outgrid_geometry_and_sparse_dump_bit_identical():
