@@ -384,12 +384,173 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_hbm_regime:
         line["next_rows"] = next_rows(eng, cb, rel, peaks()[0], k * 900)
     eng.close()
+    del hp, parts
+    if args.workload == "c2" and not args.no_c5:
+        # every rank takes part (strong scaling over the same process group)
+        c5 = c5_strong(args, rank, world, local, (m0, m1), span, K=min(K, 12), W=3)
+        if rank == 0:
+            line["c5_strong"] = c5
+            log(f"[rank 0] c5_strong: {c5['value']:.3e} particle-steps/s, {c5['ms_per_step']:.3f} ms/step, "
+                f"frac {c5['roofline']['frac']:.3f}, mass ratio {c5['mass_check']['ratio']:.6f}")
     if rank == 0:
         if world == 1 and args.workload == "c2" and not args.no_hbm_regime:
             line["hbm_regime"] = hbm_regime(args, local, K=min(K, 12), W=3)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def c5_config(n_rank, device, rank, world, sort_interval=8):
+    """BASELINE configs[4]: global domain-filling run, 0.5 deg x 138 levels, the shipped CTL=-5 /
+    IFINE=4 (method 0: one Langevin step per particle and interval), one species (air-mass tracer)."""
+    import flexpart_b200 as fb
+    return fb.make_config(nx=721, ny=361, nz=138, dx=0.5, dy=0.5, xlon0=-180.0, ylat0=-90.0,
+                          lsynctime=900, ctl=-5.0, ifine=4, mdomainfill=1, outlon0=-180.0, outlat0=-90.0,
+                          numxgrid=720, numygrid=360, dxout=0.5, dyout=0.5,
+                          outheights=(100.0, 250.0, 500.0, 1000.0, 2000.0, 3000.0, 5000.0, 8000.0, 12000.0, 100000.0),
+                          lage=(86400 * 20,), ioutputforeachrelease=0, npart=(C5_TOTAL,), nspec=1,
+                          maxpart=n_rank, device=device, rng_mode=fb.RNG_PHILOX_INDEX, math_mode=fb.MATH_FAST,
+                          scatter_mode=fb.SCATTER_ATOMIC, part_id_stride=world, part_id_offset=rank,
+                          sort_interval=sort_interval)
+
+
+C5_TOTAL = 100_000_000
+
+
+def c5_strong(args, rank, world, local, mets, span, K, W):
+    """BASELINE configs[4] / north_star target: 100 M domain-filling particles in total, STRONG
+    scaling (100 M / N per GPU, created on the device by fpb_init_domainfill, every N-th particle of
+    the one global set per rank), device-resident steps (conccalc + particle loop, cell sort every
+    8th step), grid exchange every 4th step.  Returns the extra key of the JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    import flexpart_b200 as fb
+    total = int(os.environ.get("FPB_C5_TOTAL", C5_TOTAL))
+    n_rank = (total + world - 1) // world + 1024
+    cb = c5_config(n_rank, local, rank, world)
+    cb.cfg.npart[0] = total
+    cb.npart[0] = total
+    c = cb.cfg
+    eng = fb.Engine(cb)
+    eng.fill_rannumb()
+    t0 = time.perf_counter()
+    eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1])
+    t_met = time.perf_counter() - t0
+    eng.set_met_bracket((1, 2), (0, span))
+    t0 = time.perf_counter()
+    n, info = eng.init_domainfill((0.0, 0.0, float(c.nx - 1), float(c.ny - 1)))
+    t_fill = time.perf_counter() - t0
+    ext = torch.cuda.ExternalStream(eng.stream, device=local)
+    comm = GridExchange(eng, local, world, ext)
+
+    def one_step(k, stats):
+        itime = k * 900
+        eng.conccalc(itime, 1.0)
+        st = eng.step(itime, 0, stats=stats)
+        if (k + 1) % 4 == 0:
+            comm.exchange()
+        return st
+
+    with torch.cuda.stream(ext):
+        k = 0
+        for _ in range(W):
+            one_step(k, False); k += 1
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0.record(ext)
+        ps = npbl = 0
+        tk = tc = 0.0
+        for _ in range(K):
+            st = one_step(k, True); k += 1
+            ps += st["n_active"]; npbl += st["n_pbl"]
+            a, b = eng.kernel_times()
+            tk += a; tc += b
+        comm.wait()
+        ev1.record(ext)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        # mass check of the reduced grid: one sample of every particle, summed over the ranks, must
+        # hold the air mass the particles were created with (kernel weights sum to 1, the grid is
+        # global and reaches above the model top)
+        comm.wait()
+        eng.zero_conc_grids()
+        eng.conccalc(k * 900, 1.0)
+        gsum = comm.reduced_sum()
+    tm = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+    cnt = torch.tensor([ps, npbl, n], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    eng.close()
+    if rank != 0:
+        return None
+    ms_max = tm.item()
+    ps_all, npbl_all, n_all = cnt.tolist()
+    peak, _ = peaks()
+    alg = npbl * B_PBL + (ps - npbl) * B_FT
+    ach = alg / (tk * 1e-3) / 1e9 if tk > 0 else 0.0
+    mass_ratio = gsum / info["colmasstotal"]
+    return {"workload": f"C5: global domain-fill, {total} particles in total over {world} GPU(s) (strong scaling), "
+                        "0.5deg x 138 levels, shipped CTL=-5 IFINE=4 (method 0), conccalc every step, "
+                        "cell sort every 8th step, grid exchange every 4th step",
+            "scaling": "strong", "value": ps_all / (ms_max * 1e-3), "unit": "particle-steps/s",
+            "n_gpus": world, "particles_total": int(n_all), "particles_rank0": int(n), "steps": K,
+            "ms_per_step": ms_max / K, "kernel_ms_per_launch": tk / K, "conccalc_ms_per_launch": tc / K,
+            "pbl_fraction": npbl_all / max(ps_all, 1),
+            "init_domainfill_ms": t_fill * 1e3, "met_upload_ms_per_slot": t_met * 1e3 / 2,
+            "mass_check": {"grid_sum_over_ranks": gsum, "colmasstotal": info["colmasstotal"], "ratio": mass_ratio,
+                           "ok": bool(abs(mass_ratio - 1.0) < 2e-3)},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "kernel": "fpb_pbl_kernel + fpb_finish_kernel (rank 0)",
+                         "algorithmic_bytes_per_launch": alg / K}}
+
+
+class GridExchange:
+    """The mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579, src/timemanager_mpi.f90:468-485):
+    sum of gridunc over the ranks to rank 0, then zero.  The interval's grid is copied to a staging
+    buffer on the engine's stream, zeroed, and the NCCL reduce of the staging buffer runs from a side
+    stream while the next interval's steps compute."""
+
+    def __init__(self, eng, local, world, ext):
+        import torch
+        self.eng, self.world, self.ext, self.local = eng, world, ext, local
+        gptr, gn = eng.grid_device_ptr(0)
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (gn,), "typestr": "<f4", "data": (gptr, False), "version": 2}
+        self.grid = torch.as_tensor(_Holder(), device=f"cuda:{local}")
+        self.stage = torch.empty_like(self.grid) if world > 1 else None
+        self.side = torch.cuda.Stream(device=local) if world > 1 else None
+        self.pending = None
+
+    def wait(self):
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
+
+    def exchange(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            self.wait()
+            self.stage.copy_(self.grid)
+            self.side.wait_stream(self.ext)
+            with torch.cuda.stream(self.side):
+                self.pending = dist.reduce(self.stage, dst=0, op=dist.ReduceOp.SUM, async_op=True)
+        self.eng.zero_conc_grids()
+
+    def reduced_sum(self):
+        """sum over all cells of the grid summed over the ranks (float64), valid on rank 0"""
+        import torch
+        import torch.distributed as dist
+        g = self.grid.clone()
+        if self.world > 1:
+            dist.reduce(g, dst=0, op=dist.ReduceOp.SUM)
+        return float(g.double().sum().item())
 
 
 def next_rows(eng, cb, rel, peak, itime_now):
@@ -639,6 +800,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hbm-regime", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 strong-scaling leg (extra key c5_strong)")
     ap.add_argument("--sort-interval", type=int, default=1)
     args = ap.parse_args()
     if args.warmup < 3:

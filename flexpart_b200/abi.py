@@ -101,6 +101,11 @@ class FpbPartoutPtrs(C.Structure):
                 ("xmass1", _pf), ("ld", _i)]
 
 
+class FpbDomainfillInfo(C.Structure):
+    _fields_ = [("nx_we", _i * 2), ("ny_sn", _i * 2), ("gdomainfill", _i), ("numcolumn", _i),
+                ("numparttot", _i), ("colmasstotal", _f), ("xmassperparticle", _f)]
+
+
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
@@ -178,6 +183,8 @@ def load_engine_lib():
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_split_particles.argtypes = [H, _i, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
+    L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
+    L.fpb_boundcond_domainfill.argtypes = [H, _i, _i]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
                                 C.POINTER(FpbStepStats)]
     L.fpb_conccalc.argtypes = [H, _i, _f]

@@ -19,6 +19,7 @@
 #include "fpb_scatter.cuh"
 #include "fpb_sort.cuh"
 #include "fpb_output.cuh"
+#include "fpb_domainfill.cuh"
 
 // ------------------------------------------------------------ error state --
 static thread_local std::string g_err;
@@ -195,6 +196,36 @@ struct fpb_handle {
       return t < RNMX ? t : RNMX;
     }
   } rel;
+  // init_domainfill: ran1 with its own SAVEd idummy = -11 (src/init_domainfill.f90:47)
+  struct Domainfill {
+    bool done = false;
+    int gdomainfill = 0;
+    int nx_we[2] = {0, 0}, ny_sn[2] = {0, 0};
+    int idum = -11, iv[32] = {0}, iy = 0;
+    float ran1() { // src/random_mod.f90:40-68
+      const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836, NTAB = 32;
+      const int NDIV = 1 + (IM - 1) / NTAB;
+      const float AM = 1.f / (float)IM, RNMX = 1.f - 1.2e-7f;
+      if (idum <= 0 || iy == 0) {
+        idum = (-idum > 1) ? -idum : 1;
+        for (int j = NTAB + 8; j >= 1; j--) {
+          const int k = idum / IQ;
+          idum = IA * (idum - k * IQ) - IR * k;
+          if (idum < 0) idum += IM;
+          if (j <= NTAB) iv[j - 1] = idum;
+        }
+        iy = iv[0];
+      }
+      const int k = idum / IQ;
+      idum = IA * (idum - k * IQ) - IR * k;
+      if (idum < 0) idum += IM;
+      const int j = iy / NDIV;
+      iy = iv[j];
+      iv[j] = idum;
+      const float t = AM * (float)iy;
+      return t < RNMX ? t : RNMX;
+    }
+  } dfill;
   DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
@@ -311,6 +342,9 @@ static int dalloc(T **p, size_t n) {
   if (n == 0) n = 1;
   CK(cudaMalloc((void **)p, n * sizeof(T)));
   CK(cudaMemset(*p, 0, n * sizeof(T)));
+  // the memset runs on the legacy default stream, which the engine's non-blocking streams do not
+  // order against: without this a later cudaMemcpyAsync into the new buffer can be overtaken by it
+  CK(cudaStreamSynchronize(cudaStreamLegacy));
   return 0;
 }
 #define DA(ptr, n)                      \
@@ -1323,6 +1357,163 @@ extern "C" int fpb_split_particles(fpb_handle *h, int32_t itime, int32_t *numpar
   h->active_rows = -1;
   if (numpart) *numpart = h->numpart;
   return 0;
+}
+
+// ------------------------------------------------------------ domain fill --
+// gridarea(jy) of src/init_domainfill.f90:81-130 (cos evaluated in double and rounded once: the
+// convention of the strict kernels and of the oracle)
+static void domainfill_gridarea(const fpb_config &c, const int ny_sn[2], std::vector<float> &ga) {
+  const float pi = 3.14159265f, r_earth = 6.371e6f, pih = pi / 180.f;
+  auto cosf_cr = [](float x) { return (float)cos((double)x); };
+  auto zone = [&](float cp, float cm) {
+    return (cp < cm) ? sqrtf(r_earth * r_earth - cp * cp) - sqrtf(r_earth * r_earth - cm * cm)
+                     : sqrtf(r_earth * r_earth - cm * cm) - sqrtf(r_earth * r_earth - cp * cp);
+  };
+  for (int jy = ny_sn[0]; jy <= ny_sn[1]; jy++) {
+    const float ylat = c.ylat0 + (float)jy * c.dy, ylatp = ylat + 0.5f * c.dy, ylatm = ylat - 0.5f * c.dy;
+    float hzone;
+    if ((ylatm < 0.f) && (ylatp > 0.f)) hzone = 1.f / c.dyconst;
+    else hzone = zone(cosf_cr(ylatp * pih) * r_earth, cosf_cr(ylatm * pih) * r_earth);
+    ga[jy] = 2.f * pi * r_earth * hzone * c.dx / 360.f;
+  }
+  if (c.sglobal) {
+    const float cp = cosf_cr((c.ylat0 + 0.5f * c.dy) * pih) * r_earth;
+    ga[0] = 2.f * pi * r_earth * (sqrtf(r_earth * r_earth - 0.f * 0.f) - sqrtf(r_earth * r_earth - cp * cp)) * c.dx / 360.f;
+  }
+  if (c.nglobal) {
+    const float ylat = c.ylat0 + (float)c.nymin1 * c.dy;
+    const float cm = cosf_cr((ylat - 0.5f * c.dy) * pih) * r_earth;
+    ga[c.nymin1] = 2.f * pi * r_earth * (sqrtf(r_earth * r_earth - 0.f * 0.f) - sqrtf(r_earth * r_earth - cm * cm)) * c.dx / 360.f;
+  }
+}
+
+extern "C" int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
+                                   int32_t itsplit, int32_t *numpart, fpb_domainfill_info *info) {
+  if (!h) return fail("fpb_init_domainfill: null handle");
+  const fpb_config &c = h->cfg;
+  if (c.mdomainfill != 1)
+    return fail("fpb_init_domainfill: mdomainfill = %d; only the air-mass tracer (MDOMAINFILL = 1) is built "
+                "(2 = stratospheric ozone needs the PV test of src/init_domainfill.f90:236-251)", c.mdomainfill);
+  if (h->numpart != 0) return fail("fpb_init_domainfill: the particle set is not empty (ipin = 1 restarts are host-side)");
+  CK(cudaSetDevice(h->device));
+  auto &D = h->dfill;
+  // :55-76
+  D.nx_we[0] = std::max((int)xpoint1, 0);
+  D.nx_we[1] = std::min((int)xpoint2 + 1, (int)c.nxmin1);
+  D.ny_sn[0] = std::max((int)ypoint1, 0);
+  D.ny_sn[1] = std::min((int)ypoint2 + 1, (int)c.nymin1);
+  D.gdomainfill = 0;
+  if (c.xglobal && c.sglobal && c.nglobal)
+    D.gdomainfill = (D.nx_we[0] == 0 && D.nx_we[1] == c.nxmin1 && D.ny_sn[0] == 0 && D.ny_sn[1] == c.nymin1) ? 1 : 0;
+  if (c.xglobal) D.nx_we[1] = std::min(D.nx_we[1], (int)c.nx - 2);
+  if (D.nx_we[1] < D.nx_we[0] || D.ny_sn[1] < D.ny_sn[0]) return fail("fpb_init_domainfill: empty domain box");
+
+  DomainfillArgs a;
+  per_step_cfg(h, a.cfg, 0, 0);
+  a.p = h->p;
+  a.A1 = h->A[0]; a.T1 = h->T[0];
+  a.height = h->d_height;
+  a.nx0 = D.nx_we[0]; a.nx1 = D.nx_we[1]; a.ny0 = D.ny_sn[0]; a.ny1 = D.ny_sn[1];
+  a.ncolx = a.nx1 - a.nx0 + 1;
+  a.ncols = a.ncolx * (a.ny1 - a.ny0 + 1);
+  if (a.ncols > 1024 * 1024) return fail("fpb_init_domainfill: more than 2^20 columns");
+  a.npart1 = (float)h->npart[0];
+  a.itsplit = itsplit;
+  a.id_stride = h->d.part_id_stride; a.id_offset = h->d.part_id_offset;
+  a.uniforms = nullptr; a.u_off = nullptr;
+  std::vector<float> ga(c.ny + 1, 0.f);
+  domainfill_gridarea(c, D.ny_sn, ga);
+  float *d_ga = nullptr, *d_colmass = nullptr, *d_total = nullptr, *d_uniforms = nullptr;
+  int32_t *d_ncolumn = nullptr;
+  unsigned *d_colstart = nullptr, *d_bsums = nullptr;
+  unsigned long long *d_uoff = nullptr;
+  int *d_out = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_ga); cudaFree(d_colmass); cudaFree(d_total); cudaFree(d_uniforms); cudaFree(d_ncolumn);
+    cudaFree(d_colstart); cudaFree(d_bsums); cudaFree(d_uoff); cudaFree(d_out);
+  };
+#define DFA(ptr, n) do { if (dalloc(&(ptr), (n))) { cleanup(); return 1; } } while (0)
+#define DFK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+    return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+  DFA(d_ga, ga.size()); DFA(d_colmass, (size_t)a.ncols); DFA(d_total, 1); DFA(d_ncolumn, (size_t)a.ncols);
+  DFA(d_colstart, (size_t)a.ncols); DFA(d_bsums, (size_t)(a.ncols + 1023) / 1024 + 1); DFA(d_out, 4);
+  DFK(cudaMemcpyAsync(d_ga, ga.data(), ga.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  a.gridarea = d_ga; a.colmass = d_colmass; a.total = d_total; a.ncolumn = d_ncolumn; a.colstart = d_colstart;
+  a.block_sums = d_bsums; a.out = d_out;
+  // a fresh, unpermuted particle set
+  sortk_iota(h->p.slot, c.maxpart, h->stream);
+  sortk_iota(h->row_of_slot, c.maxpart, h->stream);
+  fill_i32_kernel<<<(unsigned)((c.maxpart + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
+  h->launches += 3;
+  h->permuted = false;
+  fpb_domainfill_launch(a, h->stream, &h->launches, 0);
+  int out[4] = {0, 0, 0, 0};
+  float total = 0.f;
+  DFK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  DFK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, h->stream));
+  DFK(cudaGetLastError());
+  DFK(cudaStreamSynchronize(h->stream));
+  const long long numparttot = out[0];
+  const long long mine = numparttot > a.id_offset ? (numparttot - a.id_offset + a.id_stride - 1) / a.id_stride : 0;
+  if (mine > c.maxpart) {
+    cleanup();
+    return fail("fpb_init_domainfill: %lld particles for this rank exceed maxpart = %d "
+                "(numpart too large: src/init_domainfill.f90:254-257)", mine, c.maxpart);
+  }
+  if (c.rng_mode == FPB_RNG_REFERENCE) {
+    // the reference's ran1 stream in its draw order: columns jy-major, particles in order, per
+    // particle [pnew when ncolumn <= 20] x [x again at ix = 0] [x again at ix = nxmin1] y class
+    std::vector<int32_t> ncol((size_t)a.ncols);
+    DFK(cudaMemcpy(ncol.data(), d_ncolumn, ncol.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> uoff((size_t)a.ncols);
+    unsigned long long pos = 0;
+    for (int col = 0; col < a.ncols; col++) {
+      const int ix = a.nx0 + col % a.ncolx;
+      const int dpp = (ncol[col] > 20 ? 0 : 1) + 3 + (ix == 0 ? 1 : 0) + (ix == c.nxmin1 ? 1 : 0);
+      uoff[col] = pos;
+      pos += (unsigned long long)ncol[col] * dpp;
+    }
+    std::vector<float> u((size_t)pos);
+    for (auto &v : u) v = D.ran1();
+    DFA(d_uniforms, u.size()); DFA(d_uoff, uoff.size());
+    DFK(cudaMemcpy(d_uniforms, u.data(), u.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DFK(cudaMemcpy(d_uoff, uoff.data(), uoff.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    a.uniforms = d_uniforms; a.u_off = d_uoff;
+  }
+  fpb_domainfill_launch(a, h->stream, &h->launches, 1);
+  DFK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  DFK(cudaGetLastError());
+  DFK(cudaStreamSynchronize(h->stream));
+#undef DFA
+#undef DFK
+  cleanup();
+  if (c.rng_mode == FPB_RNG_REFERENCE && out[3] != 0)
+    return fail("fpb_init_domainfill: %d particles found no or several pressure layers (non-monotonic rho*tt "
+                "profile); the reference's ran1 draw order cannot be replayed for them", out[3]);
+  h->numpart = out[2]; // :391-397: dead particles at the end of the arrays are dropped
+  h->pending_init = true;
+  h->active_rows = -1;
+  D.done = true;
+  if (numpart) *numpart = h->numpart;
+  if (info) {
+    info->nx_we[0] = D.nx_we[0]; info->nx_we[1] = D.nx_we[1];
+    info->ny_sn[0] = D.ny_sn[0]; info->ny_sn[1] = D.ny_sn[1];
+    info->gdomainfill = D.gdomainfill;
+    info->numcolumn = out[1];
+    info->numparttot = (int32_t)numparttot;
+    info->colmasstotal = total;
+    info->xmassperparticle = numparttot > 0 ? total / (float)numparttot : 0.f;
+  }
+  return 0;
+}
+
+extern "C" int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend) {
+  (void)itime; (void)loutend;
+  if (!h) return fail("fpb_boundcond_domainfill: null handle");
+  if (!h->dfill.done) return fail("fpb_boundcond_domainfill: fpb_init_domainfill has not been called");
+  if (h->dfill.gdomainfill) return 0; // src/boundcond_domainfill.f90:54: nothing to do for a global domain
+  return fail("fpb_boundcond_domainfill: the inflow boundary of a limited domain "
+              "(src/boundcond_domainfill.f90:59-580) is not built; only global domain-filling runs on the device");
 }
 
 // ------------------------------------------------------- host-buffer step --

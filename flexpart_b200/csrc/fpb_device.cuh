@@ -183,6 +183,23 @@ struct DevSplitArgs {
   int *total;                 // candidates found
 };
 
+#ifdef __CUDACC__
+// Philox4x32-10 (Salmon et al. 2011), counter = (particle id, time, stream, block)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+#endif
+
 // launchers (one set per math mode; defined in fpb_kernels.cu compiled twice)
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
   void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \

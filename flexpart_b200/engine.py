@@ -149,6 +149,20 @@ class Engine:
         self._check(self.L.fpb_releaseparticles(self.h, itime, C.byref(n), C.byref(m)))
         return n.value, m.value
 
+    def init_domainfill(self, box, itsplit=99999999):
+        """init_domainfill (src/init_domainfill.f90:55-283) over the box (xpoint1, ypoint1, xpoint2,
+        ypoint2) in grid units, on the device; returns (numpart, info dict)."""
+        from .abi import FpbDomainfillInfo
+        n, info = C.c_int32(0), FpbDomainfillInfo()
+        self._check(self.L.fpb_init_domainfill(self.h, box[0], box[1], box[2], box[3], itsplit, C.byref(n),
+                                               C.byref(info)))
+        return n.value, dict(nx_we=tuple(info.nx_we), ny_sn=tuple(info.ny_sn), gdomainfill=info.gdomainfill,
+                             numcolumn=info.numcolumn, numparttot=info.numparttot,
+                             colmasstotal=info.colmasstotal, xmassperparticle=info.xmassperparticle)
+
+    def boundcond_domainfill(self, itime, loutend=0):
+        self._check(self.L.fpb_boundcond_domainfill(self.h, itime, loutend))
+
     def split_particles(self, itime):
         """particle splitting of timemanager (src/timemanager.f90:472-503); returns the new numpart."""
         n = C.c_int32(0)

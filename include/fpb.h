@@ -347,6 +347,35 @@ int fpb_set_releases(fpb_handle *h, const fpb_release_points *rel);
  * fewer free slots than new particles are left.   */
 int fpb_releaseparticles(fpb_handle *h, int32_t itime, int32_t *numpart /* may be NULL */,
                          int32_t *n_released /* may be NULL */);
+/* Domain-filling runs (MDOMAINFILL = 1; BASELINE configs[4]).  fpb_init_domainfill replaces `call
+ * init_domainfill` (src/timemanager.f90:230-235, src/init_domainfill.f90:55-283): the box of release
+ * point 1 (grid units) is filled with npart(1) particles, each column holding a number proportional
+ * to its air mass ((p(1)-p(nz))/g*area from rho*r_air*tt of time slot 1, so fpb_upload_met(1, ..)
+ * with tt must have happened), at pressure-equidistant heights (random ones in columns of <= 20
+ * particles), every particle carrying its share of the column mass in species 1.  The particles are
+ * created on the device, in the reference's order (columns south to north, west to east):
+ * FPB_RNG_REFERENCE replays the reference's ran1 stream bit for bit, the Philox modes draw from the
+ * particle's counter stream.  With part_id_stride = N, part_id_offset = r the call keeps every N-th
+ * particle (global index g with g mod N = r, in slot g / N): the round-robin distribution of
+ * src/init_domainfill_mpi.f90:86-104 without the root process or any exchange.  Needs an empty
+ * particle set (ipin = 0).  Not built: MDOMAINFILL = 2 (stratospheric ozone, :236-251) and the
+ * second half of the routine (:287-398, inflow columns of a limited domain).
+ * fpb_boundcond_domainfill replaces `call boundcond_domainfill(itime,loutend)`
+ * (src/timemanager.f90:240): for a global domain (gdomainfill) the reference returns at once
+ * (src/boundcond_domainfill.f90:54) and so does this; a limited domain is refused. */
+typedef struct fpb_domainfill_info {
+  int32_t nx_we[2], ny_sn[2]; /* domain box in met-grid indices, src/com_mod.f90:245 */
+  int32_t gdomainfill;        /* 1: global domain filling, no boundary conditions */
+  int32_t numcolumn;          /* largest number of particles in one column */
+  int32_t numparttot;         /* particles created over all ranks */
+  float colmasstotal;         /* air mass of the box [kg] */
+  float xmassperparticle;     /* colmasstotal / numparttot */
+} fpb_domainfill_info;
+int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
+                        int32_t itsplit, int32_t *numpart /* may be NULL */,
+                        fpb_domainfill_info *info /* may be NULL */);
+int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend);
+
 /* wetgridunc(0:numxgrid-1,0:numygrid-1,maxspec,maxpointspec_act,nclassunc,
  * maxageclass) and the nested twin (may be NULL): cumulative, never zeroed,
  * decayed by fpb_scale_depgrids like drygridunc */

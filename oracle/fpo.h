@@ -68,6 +68,8 @@ typedef struct fpo_state {
   /* SAVEd `idummy` locals: src/advance.f90:120, src/initialize.f90:64,
    * src/releaseparticles.f90 (idummy=-7) */
   int idummy_advance, idummy_initialize, idummy_release;
+  int idummy_domainfill;  /* src/init_domainfill.f90:47 (idummy = -11) */
+  int numparticlecount;   /* src/com_mod.f90:676 */
   float settling_saved; /* src/advance.f90:121 */
 
   /* particles, 1-based arrays of maxpart+1 */
@@ -224,6 +226,11 @@ void fpo_cxy2ll(const float *strcmp, float x, float y, float *xlat,
 float fpo_cgszll(const float *strcmp, float xlat, float xlong);
 void fpo_cc2gll(const float *strcmp, float xlat, float xlong, float ue,
                 float vn, float *ug, float *vg);
+
+/* init_domainfill (fpo_domainfill.c) */
+void fpo_domainfill_gridarea(const fpb_config *c, const int ny_sn[2], float *gridarea);
+int fpo_init_domainfill(fpo_state *S, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
+                        int itsplit, int32_t *out, float *fout);
 
 /* releaseparticles (integer semantics + ran1 stream) */
 void fpo_split_particles(fpo_state *S, int itime);

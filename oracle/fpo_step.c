@@ -70,6 +70,7 @@ fpo_state *fpo_create(const fpb_config *cfg, int strict_reference) {
   S->idummy_advance = -7;
   S->idummy_initialize = -7;
   S->idummy_release = -7;
+  S->idummy_domainfill = -11;
   S->maxpart = c->maxpart;
   size_t n = (size_t)c->maxpart + 1;
   S->xtra1 = (double *)calloc(n, sizeof(double));

@@ -59,6 +59,8 @@ def load(libm_float=False):
     L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
     L.fpo_releaseparticles.restype = C.c_int
     L.fpo_split_particles.argtypes = [S, C.c_int]
+    L.fpo_init_domainfill.argtypes = [S, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _pi, _pf]
+    L.fpo_init_domainfill.restype = C.c_int
     L.fpo_numpart.argtypes = [S]; L.fpo_numpart.restype = C.c_int
     L.fpo_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_float, _pf, _pf]
     L.fpo_partoutput_record.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, _pi, C.c_double, C.c_double, C.c_float, _pf] + \
@@ -98,6 +100,18 @@ class Oracle:
     def set_rannumb(self, table):
         t = np.ascontiguousarray(table, np.float32)
         self.L.fpo_set_rannumb(self.S, _fp(t), len(t))
+
+    def init_domainfill(self, box, itsplit=99999999):
+        """init_domainfill over the box (xpoint1, ypoint1, xpoint2, ypoint2) in grid units;
+        returns (numpart, info) like Engine.init_domainfill"""
+        out, fout = np.zeros(8, np.int32), np.zeros(2, np.float32)
+        rc = self.L.fpo_init_domainfill(self.S, box[0], box[1], box[2], box[3], itsplit,
+                                        out.ctypes.data_as(_pi), _fp(fout))
+        if rc:
+            raise RuntimeError("init_domainfill: numpart exceeds maxpart")
+        return self.L.fpo_numpart(self.S), dict(nx_we=(int(out[0]), int(out[1])), ny_sn=(int(out[2]), int(out[3])),
+                                                gdomainfill=int(out[4]), numcolumn=int(out[5]), numparttot=int(out[6]),
+                                                colmasstotal=float(fout[0]), xmassperparticle=float(fout[1]))
 
     def set_index_uniforms(self, u):
         """validation hook: the uniforms behind the next nrand draws (tests/philox_ref.py)"""

@@ -405,6 +405,46 @@ def test_reference_releaseparticles_bit_identical():
     assert k == 3 * (87 + 175 * 3 + 88)
 
 
+@pytest.mark.parametrize("box,npart1", [((-180.0, -90.0, 180.0, 90.0), 30000),    # global: gdomainfill
+                                        ((-180.0, -90.0, 180.0, 90.0), 2500),     # sparse: ncolumn <= 20 -> random heights
+                                        ((-40.0, 10.0, 65.0, 72.5), 12000)])      # limited domain
+def test_reference_init_domainfill_bit_identical(box, npart1):
+    """init_domainfill (src/init_domainfill.f90:55-283, MDOMAINFILL = 1): the domain box, column air
+    masses, particles per column, the pressure-equidistant (or, for thin columns, random) heights,
+    the ran1 positions, masses and the out-of-domain termination against the oracle's restatement."""
+    cb = cases.config_small(nrel=1, npart_each=npart1, maxpart=npart1 + 2000, mdomainfill=1, nclassunc=3)
+    c = cb.cfg
+    m0, m1 = cases.met_pair(cb)
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    o = Oracle(cb)
+    for e in (ref, o):
+        e.upload_met(1, m0); e.upload_met(2, m1)
+    pts = [(box[0] - c.xlon0) / c.dx, (box[1] - c.ylat0) / c.dy, (box[2] - c.xlon0) / c.dx, (box[3] - c.ylat0) / c.dy]
+    pts = [float(np.float32(v)) for v in pts]
+    for nm, v in zip(("xpoint1", "ypoint1", "xpoint2", "ypoint2"), pts):
+        ref.arr(nm)[0] = v
+    ref.set("ipin", 0); ref.set("itsplit", 99999999); ref.set("numpart", 0); ref.set("numparticlecount", 0)
+    ref.set("gdomainfill", 0)
+    ref.arr("itra1")[:] = fb.ITRA_DEAD
+    ref.L.f_init_domainfill()
+    n, info = o.init_domainfill(pts)
+    assert n == ref.get("numpart") and n > 0.9 * npart1
+    assert info["nx_we"] == tuple(ref.arr("nx_we")) and info["ny_sn"] == tuple(ref.arr("ny_sn"))
+    assert info["gdomainfill"] == ref.get("gdomainfill") == (1 if box[0] == -180.0 else 0)
+    assert info["numcolumn"] == ref.get("numcolumn")
+    assert np.float32(info["xmassperparticle"]).tobytes() == np.float32(ref.get("xmassperparticle")).tobytes()
+    q = fb.Particles(c.maxpart, 1); q.numpart = n
+    o.pull_particles(q)
+    for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt", "itrasplit"):
+        a, b = ref.arr(f)[:n], getattr(q, f)[:n]
+        assert np.array_equal(a.view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), f
+    assert np.array_equal(ref.arr("xmass1")[:n, 0].view(np.uint32), q.xmass1[:n, 0].view(np.uint32))
+    assert len(np.unique(q.nclass[:n])) == 3
+    # every particle carries its column's share: the masses add up to the air mass of the box
+    # (thin columns round to 0 or 1 particle: only the dense cases close to better than a per cent)
+    assert abs(q.xmass1[:n, 0].astype(np.float64).sum() / info["colmasstotal"] - 1.0) < (2e-3 if npart1 >= 10000 else 0.1)
+
+
 def test_reference_readcommand_derivations_match_host():
     """fpbh_readcommand (turbulence switches, ifine, fine, ctl := 1/ctl, method, mintime) against
     src/readcommand.f90:244-272,379-385 run from the reference's source."""
