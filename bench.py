@@ -226,34 +226,12 @@ def run_ours(args):
     eng.push_particles(parts)
     ext = torch.cuda.ExternalStream(eng.stream, device=local)
 
-    gptr, gn = eng.grid_device_ptr(0)
-
-    class _Holder:  # zero-copy torch view of the device grid for NCCL
-        __cuda_array_interface__ = {"shape": (gn,), "typestr": "<f4", "data": (gptr, False), "version": 2}
-    grid_t = torch.as_tensor(_Holder(), device=f"cuda:{local}") if world > 1 else None
-
-    # Grid exchange off the critical path: the interval's grid is copied to a staging buffer on the
-    # engine's stream (10 MB device-to-device), zeroed, and the NCCL reduce of the staging buffer
-    # runs from a side stream while the next interval's steps compute.  Rank 0 reads the summed
-    # grid from the staging buffer (concoutput's input).
-    stage = torch.empty_like(grid_t) if world > 1 else None
-    side = torch.cuda.Stream(device=local) if world > 1 else None
-    pending = [None]
-
-    def exchange_wait():
-        if pending[0] is not None:
-            pending[0].wait()          # the current (engine) stream waits; the host does not
-            pending[0] = None
-
-    def exchange():
-        # the mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579): sum to rank 0, then zero
-        if world > 1:
-            exchange_wait()            # the staging buffer is free again
-            stage.copy_(grid_t)
-            side.wait_stream(ext)
-            with torch.cuda.stream(side):
-                pending[0] = dist.reduce(stage, dst=0, op=dist.ReduceOp.SUM, async_op=True)
-        eng.zero_conc_grids()
+    # Grid exchange off the critical path, behind the C ABI (fpb_reduce_grids_begin/_end): the
+    # interval's grids are copied to staging buffers and zeroed on the engine's stream, and ONE NCCL
+    # reduce group sums the staging buffers to rank 0 from a high-priority side stream while the next
+    # interval's steps compute.  Rank 0 reads the sums from the staging buffers (concoutput's input).
+    comm = GridExchange(eng, rank, world, local)
+    exchange, exchange_wait = comm.exchange, comm.wait
 
     def one_step(k, stats):
         itime = k * 900
@@ -296,6 +274,26 @@ def run_ours(args):
             dist.barrier()
         ms = ev0.elapsed_time(ev1)
         launches = eng.launch_count - l0
+
+        # ---- result check of the exchange (untimed): one sample of every active particle on every
+        # rank, summed to rank 0, must hold weight * sum(mass) of all ranks' particles (the kernel
+        # weights of conccalc sum to 1 and the output grid is global)
+        eng.zero_conc_grids()
+        eng.conccalc(k * 900, 1.0)
+        gsum = comm.reduced_sum()
+        hchk = fb.Particles(c.maxpart, c.nspec)
+        hchk.numpart = n
+        eng.pull_particles(hchk)
+        msum = float(hchk.xmass1[:n][hchk.itra1[:n] == k * 900].astype(np.float64).sum())
+        mt = torch.tensor([msum], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.SUM)
+        msum_all = mt.item()
+        if rank == 0:
+            log(f"[rank 0] exchange check: sum(reduced gridunc) / sum(mass over {world} rank(s)) = {gsum / msum_all:.7f}; "
+                f"reduce {np.mean(comm.ms) if comm.ms else 0.0:.3f} ms per exchange on rank 0")
+            assert abs(gsum / msum_all - 1.0) < 5e-5, (gsum, msum_all)
+        del hchk
 
         # ---- end-to-end: host buffers through the C ABI's host-buffer entry point;
         # every step copies the particle arrays in from pinned memory and the
@@ -360,6 +358,10 @@ def run_ours(args):
             "pbl_fraction": npbl_all / max(psteps_all, 1),
             "clocks": clocks,
             "gpu_launches": int(launches_all),
+            "exchange": {"what": "fpb_reduce_grids_begin/_end: staging copy + zero on the engine stream, one NCCL "
+                                 "reduce group (sum to rank 0) on a high-priority side stream; every 4th step",
+                         "reduce_ms_rank0": float(np.mean(comm.ms)) if comm.ms else 0.0,
+                         "mass_check_ratio": gsum / msum_all},
             "e2e": {"value": e_steps_all / (e_ms_max * 1e-3), "unit": "particle-steps/s",
                     "h2d_bytes_per_step": int(bytes_in * n), "d2h_bytes_per_step": int(bytes_out * n + 64),
                     "steps": KE, "what": "fpb_step_host per step: all particle arrays H2D from pinned host "
@@ -441,7 +443,7 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
     n, info = eng.init_domainfill((0.0, 0.0, float(c.nx - 1), float(c.ny - 1)))
     t_fill = time.perf_counter() - t0
     ext = torch.cuda.ExternalStream(eng.stream, device=local)
-    comm = GridExchange(eng, local, world, ext)
+    comm = GridExchange(eng, rank, world, local)
 
     def one_step(k, stats):
         itime = k * 900
@@ -510,46 +512,42 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
 
 
 class GridExchange:
-    """The mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579, src/timemanager_mpi.f90:468-485):
-    sum of gridunc over the ranks to rank 0, then zero.  The interval's grid is copied to a staging
-    buffer on the engine's stream, zeroed, and the NCCL reduce of the staging buffer runs from a side
-    stream while the next interval's steps compute."""
+    """The mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579, src/timemanager_mpi.f90:468-485)
+    through the C ABI: fpb_comm_init joins the NCCL communicator (the 128-byte id travels over the
+    host's own channel: here torch.distributed, MPI_Bcast in the Fortran host), and
+    fpb_reduce_grids_begin/_end do the staged, overlapped sum to rank 0."""
 
-    def __init__(self, eng, local, world, ext):
-        import torch
-        self.eng, self.world, self.ext, self.local = eng, world, ext, local
-        gptr, gn = eng.grid_device_ptr(0)
-
-        class _Holder:
-            __cuda_array_interface__ = {"shape": (gn,), "typestr": "<f4", "data": (gptr, False), "version": 2}
-        self.grid = torch.as_tensor(_Holder(), device=f"cuda:{local}")
-        self.stage = torch.empty_like(self.grid) if world > 1 else None
-        self.side = torch.cuda.Stream(device=local) if world > 1 else None
-        self.pending = None
+    def __init__(self, eng, rank, world, local):
+        import flexpart_b200 as fb
+        self.eng, self.rank, self.world, self.local = eng, rank, world, local
+        self.ms, self.pending = [], False
+        uid = [fb.Engine.comm_unique_id() if (rank == 0 and world > 1) else bytes(128)]
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
 
     def wait(self):
-        if self.pending is not None:
-            self.pending.wait()
-            self.pending = None
+        if self.pending:
+            _, _, ms = self.eng.reduce_grids_device(0)   # host waits for the reduce
+            self.ms.append(ms)
+            self.pending = False
 
     def exchange(self):
-        import torch
-        import torch.distributed as dist
-        if self.world > 1:
-            self.wait()
-            self.stage.copy_(self.grid)
-            self.side.wait_stream(self.ext)
-            with torch.cuda.stream(self.side):
-                self.pending = dist.reduce(self.stage, dst=0, op=dist.ReduceOp.SUM, async_op=True)
-        self.eng.zero_conc_grids()
+        self.wait()
+        self.eng.reduce_grids_begin()
+        self.pending = True
 
     def reduced_sum(self):
-        """sum over all cells of the grid summed over the ranks (float64), valid on rank 0"""
+        """exchange now; sum over all cells of the summed grid (float64), valid on rank 0"""
         import torch
-        import torch.distributed as dist
-        g = self.grid.clone()
-        if self.world > 1:
-            dist.reduce(g, dst=0, op=dist.ReduceOp.SUM)
+        self.wait()
+        self.eng.reduce_grids_begin()
+        ptr, n, ms = self.eng.reduce_grids_device(0)
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        g = torch.as_tensor(_Holder(), device=f"cuda:{self.local}")
         return float(g.double().sum().item())
 
 

@@ -183,6 +183,12 @@ def load_engine_lib():
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_split_particles.argtypes = [H, _i, _pi]
     L.fpb_fetch_wetgrids.argtypes = [H, _pf, _pf]
+    L.fpb_comm_unique_id.argtypes = [C.c_void_p]
+    L.fpb_comm_init.argtypes = [H, C.c_void_p, _i, _i]
+    L.fpb_reduce_grids_begin.argtypes = [H]
+    L.fpb_reduce_grids_end.argtypes = [H, _pf, _pf, _pf, _pf, _pf, _pf, _pf]
+    L.fpb_reduce_grids_device.argtypes = [H, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _pf]
+    L.fpb_comm_finalize.argtypes = [H]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
     L.fpb_boundcond_domainfill.argtypes = [H, _i, _i]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,

@@ -5,6 +5,7 @@
 // ran3 draw order in validation mode and launches the kernels of
 // fpb_kernels.cu / fpb_scatter.cu on one CUDA stream.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -226,6 +227,16 @@ struct fpb_handle {
       return t < RNMX ? t : RNMX;
     }
   } dfill;
+  // grid exchange over NCCL (fpb_comm_init / fpb_reduce_grids_begin / _end)
+  struct Comm {
+    void *nccl = nullptr;       // ncclComm_t
+    int rank = 0, nranks = 1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_t0 = nullptr, ev_done = nullptr;
+    float *stage[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_n[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool in_flight = false, timed = false;
+  } comm;
   DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
@@ -535,6 +546,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   return 0;
 }
 
+extern "C" int fpb_comm_finalize(fpb_handle *h);
 extern "C" int fpb_finalize(fpb_handle *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
@@ -577,6 +589,9 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(L.d_work); cudaFree(L.d_nlive);
   }
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->st_in) { cudaStreamSynchronize(h->st_in); cudaStreamDestroy(h->st_in); }
+  for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
+  fpb_comm_finalize(h);
   for (int k = 0; k < 4; k++) cudaEventDestroy(h->ev[k]);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -1940,3 +1955,185 @@ extern "C" int fpb_grid_device_ptr(fpb_handle *h, int32_t which, void **dptr, si
 
 extern "C" void *fpb_stream(fpb_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int64_t fpb_launch_count(fpb_handle *h) { return h ? h->launches : 0; }
+
+
+// ------------------------------------------------------------ collective --
+// The one collective of the path: the sum of the accumulation grids over the ranks at each output
+// interval (mpif_tm_reduce_grid, src/mpi_mod.f90:2395-2579, called at src/timemanager_mpi.f90:468-485),
+// as an NCCL reduce over NVLink.  NCCL is bound at run time (dlopen of libnccl.so.2, or the copy the
+// host process has already loaded), so libfpb.so has no link-time dependency on it and single-GPU
+// hosts need no NCCL at all.
+namespace {
+struct NcclUid { char b[128]; }; // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int *) = nullptr;
+  bool ok = false;
+} g_nccl;
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0; // ncclFloat32, ncclSum (nccl.h)
+
+int nccl_load() {
+  if (g_nccl.ok) return 0;
+  void *lib = nullptr;
+  if (dlsym(RTLD_DEFAULT, "ncclCommInitRank")) lib = dlopen(nullptr, RTLD_NOW); // already in the process
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail("fpb_comm: libnccl.so.2 not found (%s); the multi-GPU grid reduce needs NCCL", dlerror());
+  g_nccl.lib = lib;
+#define NSYM(field, name)                                                          \
+  *(void **)(&g_nccl.field) = dlsym(lib, name);                                    \
+  if (!g_nccl.field) return fail("fpb_comm: symbol %s missing in the NCCL library", name);
+  NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank") NSYM(CommDestroy, "ncclCommDestroy")
+  NSYM(Reduce, "ncclReduce") NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd")
+  NSYM(GetErrorString, "ncclGetErrorString") NSYM(GetVersion, "ncclGetVersion")
+#undef NSYM
+  g_nccl.ok = true;
+  return 0;
+}
+#define NK(call)                                                                              \
+  do {                                                                                        \
+    int r_ = (call);                                                                          \
+    if (r_ != 0) return fail("%s failed: %s", #call, g_nccl.GetErrorString(r_));              \
+  } while (0)
+} // namespace
+
+extern "C" int fpb_comm_unique_id(void *id128) {
+  if (!id128) return fail("fpb_comm_unique_id: null argument");
+  if (nccl_load()) return 1;
+  NK(g_nccl.GetUniqueId(id128));
+  return 0;
+}
+
+extern "C" int fpb_comm_init(fpb_handle *h, const void *id128, int32_t rank, int32_t nranks) {
+  if (!h || !id128) return fail("fpb_comm_init: null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("fpb_comm_init: rank %d of %d", rank, nranks);
+  if (h->comm.nccl) return fail("fpb_comm_init: the handle already has a communicator");
+  CK(cudaSetDevice(h->device));
+  auto &Q = h->comm;
+  Q.rank = rank; Q.nranks = nranks;
+  if (nranks > 1) {
+    if (nccl_load()) return 1;
+    NcclUid uid;
+    memcpy(uid.b, id128, sizeof uid.b);
+    NK(g_nccl.CommInitRank(&Q.nccl, nranks, uid, rank));
+  }
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CK(cudaStreamCreateWithPriority(&Q.side, cudaStreamNonBlocking, hi)); // ahead of the step kernels
+  CK(cudaEventCreateWithFlags(&Q.ev_staged, cudaEventDisableTiming));
+  CK(cudaEventCreate(&Q.ev_t0));
+  CK(cudaEventCreate(&Q.ev_done));
+  // staging copies of the grids: the interval's sums leave through them while the next interval
+  // accumulates into the (zeroed) grids
+  const float *src[7] = {h->gridunc, h->griduncn, h->drygridunc, h->drygriduncn, h->wetgridunc, h->wetgriduncn,
+                         h->cfg.numreceptor > 0 ? h->creceptor : nullptr};
+  const size_t n[7] = {h->n_grid, h->n_gridn, h->n_dry, h->n_dryn, h->n_dry, h->n_dryn, h->n_rec};
+  for (int k = 0; k < 7; k++) {
+    Q.stage_n[k] = src[k] ? n[k] : 0;
+    if (Q.stage_n[k]) DA(Q.stage[k], Q.stage_n[k]);
+  }
+  return 0;
+}
+
+// Start the exchange of the interval that just ended: copy the grids to the staging buffers and
+// zero the concentration grids (src/concoutput.f90:719-720) on the engine's stream, then sum the
+// staging buffers to rank 0 on a high-priority side stream.  Returns at once; the engine may step on.
+extern "C" int fpb_reduce_grids_begin(fpb_handle *h) {
+  if (!h) return fail("fpb_reduce_grids_begin: null handle");
+  auto &Q = h->comm;
+  if (!Q.side) return fail("fpb_reduce_grids_begin: fpb_comm_init has not been called");
+  CK(cudaSetDevice(h->device));
+  if (Q.in_flight) CK(cudaStreamWaitEvent(h->stream, Q.ev_done, 0)); // the staging buffers are free again
+  const float *src[7] = {h->gridunc, h->griduncn, h->drygridunc, h->drygriduncn, h->wetgridunc, h->wetgriduncn,
+                         h->creceptor};
+  for (int k = 0; k < 7; k++)
+    if (Q.stage_n[k])
+      CK(cudaMemcpyAsync(Q.stage[k], src[k], Q.stage_n[k] * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(h->gridunc, 0, h->n_grid * sizeof(float), h->stream));
+  if (h->griduncn) CK(cudaMemsetAsync(h->griduncn, 0, h->n_gridn * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->creceptor, 0, h->n_rec * sizeof(float), h->stream));
+  CK(cudaEventRecord(Q.ev_staged, h->stream));
+  CK(cudaStreamWaitEvent(Q.side, Q.ev_staged, 0));
+  CK(cudaEventRecord(Q.ev_t0, Q.side));
+  if (Q.nranks > 1) {
+    NK(g_nccl.GroupStart());
+    for (int k = 0; k < 7; k++)
+      if (Q.stage_n[k])
+        NK(g_nccl.Reduce(Q.stage[k], Q.stage[k], Q.stage_n[k], NCCL_FLOAT32, NCCL_SUM, 0, Q.nccl, Q.side));
+    NK(g_nccl.GroupEnd());
+    h->launches++;
+  }
+  CK(cudaEventRecord(Q.ev_done, Q.side));
+  Q.in_flight = true;
+  Q.timed = true;
+  return 0;
+}
+
+// Finish the exchange: wait for the sums; on rank 0 copy them into the caller's arrays (reference
+// layout, like fpb_fetch_grids / fpb_fetch_wetgrids; NULL pointers are skipped).  Other ranks pass NULLs.
+extern "C" int fpb_reduce_grids_end(fpb_handle *h, float *gridunc, float *griduncn, float *drygridunc,
+                                    float *drygriduncn, float *wetgridunc, float *wetgriduncn, float *creceptor) {
+  if (!h) return fail("fpb_reduce_grids_end: null handle");
+  auto &Q = h->comm;
+  if (!Q.in_flight) return fail("fpb_reduce_grids_end: no exchange in flight");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(Q.ev_done));
+  Q.in_flight = false;
+  if (Q.rank != 0) return 0;
+  const fpb_config &c = h->cfg;
+  std::vector<float> tmp;
+  float *dst[6] = {gridunc, griduncn, drygridunc, drygriduncn, wetgridunc, wetgriduncn};
+  const size_t inner[6] = {(size_t)c.numxgrid * c.numygrid * c.numzgrid, (size_t)c.numxgridn * c.numygridn * c.numzgrid,
+                           (size_t)c.numxgrid * c.numygrid, (size_t)c.numxgridn * c.numygridn,
+                           (size_t)c.numxgrid * c.numygrid, (size_t)c.numxgridn * c.numygridn};
+  for (int k = 0; k < 6; k++)
+    if (dst[k] && Q.stage_n[k] && fetch_one(h, dst[k], Q.stage[k], inner[k], Q.stage_n[k], tmp)) return 1;
+  if (creceptor && Q.stage_n[6]) { // (maxreceptor, maxspec), species beyond nspec zero
+    tmp.resize(h->n_rec);
+    CK(cudaMemcpyAsync(tmp.data(), Q.stage[6], h->n_rec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(creceptor, 0, (size_t)FPB_MAXRECEPTOR * c.maxspec * sizeof(float));
+    memcpy(creceptor, tmp.data(), h->n_rec * sizeof(float));
+  }
+  return 0;
+}
+
+// device view of a reduced staging buffer (valid on rank 0 between _begin and the next _begin, after
+// the engine's stream or the host has waited for the exchange) and the duration of the last reduce
+extern "C" int fpb_reduce_grids_device(fpb_handle *h, int32_t which, void **dptr, size_t *nfloats, float *reduce_ms) {
+  if (!h) return fail("fpb_reduce_grids_device: null handle");
+  auto &Q = h->comm;
+  if (which < 0 || which > 6) return fail("fpb_reduce_grids_device: which=%d", which);
+  if (!Q.side) return fail("fpb_reduce_grids_device: fpb_comm_init has not been called");
+  CK(cudaSetDevice(h->device));
+  if (Q.in_flight) CK(cudaEventSynchronize(Q.ev_done));
+  if (dptr) *dptr = Q.stage[which];
+  if (nfloats) *nfloats = Q.stage_n[which];
+  if (reduce_ms) {
+    *reduce_ms = 0.f;
+    if (Q.timed) CK(cudaEventElapsedTime(reduce_ms, Q.ev_t0, Q.ev_done));
+  }
+  return 0;
+}
+
+extern "C" int fpb_comm_finalize(fpb_handle *h) {
+  if (!h) return 0;
+  auto &Q = h->comm;
+  cudaSetDevice(h->device);
+  if (Q.side) { cudaStreamSynchronize(Q.side); }
+  if (Q.nccl) { g_nccl.CommDestroy(Q.nccl); Q.nccl = nullptr; }
+  for (auto &p : Q.stage) { cudaFree(p); p = nullptr; }
+  if (Q.ev_staged) cudaEventDestroy(Q.ev_staged);
+  if (Q.ev_t0) cudaEventDestroy(Q.ev_t0);
+  if (Q.ev_done) cudaEventDestroy(Q.ev_done);
+  if (Q.side) cudaStreamDestroy(Q.side);
+  Q = fpb_handle::Comm();
+  return 0;
+}

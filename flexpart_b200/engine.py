@@ -149,6 +149,50 @@ class Engine:
         self._check(self.L.fpb_releaseparticles(self.h, itime, C.byref(n), C.byref(m)))
         return n.value, m.value
 
+    # ---- the grid exchange of a multi-GPU run (mpif_tm_reduce_grid slot), NCCL behind the C ABI
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id, created on rank 0 and broadcast by the host"""
+        buf = C.create_string_buffer(128)
+        L = load_engine_lib()
+        if L.fpb_comm_unique_id(buf):
+            raise FpbError(L.fpb_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.L.fpb_comm_init(self.h, buf, rank, nranks))
+
+    def reduce_grids_begin(self):
+        self._check(self.L.fpb_reduce_grids_begin(self.h))
+
+    def reduce_grids_end(self, fetch=True):
+        """waits for the exchange; with fetch=True rank 0 gets the summed grids (reference layout)"""
+        c = self.cb.cfg
+        out = {}
+        if fetch:
+            out["gridunc"] = np.zeros(self.shape_grid, np.float32, order="F")
+            out["drygridunc"] = np.zeros(self.shape_dry, np.float32, order="F")
+            if c.nested_output == 1:
+                out["griduncn"] = np.zeros(self.shape_gridn, np.float32, order="F")
+                out["drygriduncn"] = np.zeros(self.shape_dryn, np.float32, order="F")
+            if c.wetdep:
+                out["wetgridunc"] = np.zeros(self.shape_dry, np.float32, order="F")
+                if c.nested_output == 1:
+                    out["wetgriduncn"] = np.zeros(self.shape_dryn, np.float32, order="F")
+            if c.numreceptor > 0:
+                out["creceptor"] = np.zeros((abi.MAXRECEPTOR, c.maxspec), np.float32, order="F")
+        g = lambda k: _fp(out[k]) if k in out else None
+        self._check(self.L.fpb_reduce_grids_end(self.h, g("gridunc"), g("griduncn"), g("drygridunc"),
+                                                g("drygriduncn"), g("wetgridunc"), g("wetgriduncn"), g("creceptor")))
+        return out
+
+    def reduce_grids_device(self, which=0):
+        """(device pointer, floats, ms of the last reduce) of a summed staging buffer; waits for the exchange"""
+        p, n, ms = C.c_void_p(), C.c_size_t(), C.c_float()
+        self._check(self.L.fpb_reduce_grids_device(self.h, which, C.byref(p), C.byref(n), C.byref(ms)))
+        return p.value, n.value, ms.value
+
     def init_domainfill(self, box, itsplit=99999999):
         """init_domainfill (src/init_domainfill.f90:55-283) over the box (xpoint1, ypoint1, xpoint2,
         ypoint2) in grid units, on the device; returns (numpart, info dict)."""

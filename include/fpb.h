@@ -405,6 +405,32 @@ int fpb_grid_device_ptr(fpb_handle *h, int32_t which, void **dptr,
                         size_t *nfloats);
 int fpb_zero_conc_grids(fpb_handle *h);
 
+/* The grid exchange of a multi-GPU run: one process per GPU, particles partitioned, full met replica
+ * and private grids per GPU; at each output interval the grids are summed to rank 0 -- the slot of
+ * mpif_tm_reduce_grid(_nest) (src/mpi_mod.f90:2395-2579, called at src/timemanager_mpi.f90:468-485)
+ * -- as ONE NCCL reduce group over NVLink, on a high-priority side stream so that the next interval's
+ * steps proceed meanwhile.  NCCL is bound at run time (dlopen), libfpb.so does not link against it.
+ *   fpb_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host broadcasts it (MPI_Bcast in
+ *                        the Fortran host, src/mpi_mod.f90:162 mpif_init is where the ranks meet)
+ *   fpb_comm_init        every rank, after fpb_init: joins the communicator (nranks = 1: no NCCL)
+ *   fpb_reduce_grids_begin  gridunc, griduncn, drygridunc(n), wetgridunc(n) are copied to staging
+ *                        buffers (creceptor too) and gridunc/griduncn/creceptor zeroed (src/concoutput.f90:719-720) on the
+ *                        engine's stream; the staging buffers are summed to rank 0.  Returns at once.
+ *   fpb_reduce_grids_end waits; on rank 0 the sums are written to the caller's arrays in the
+ *                        reference layout (see fpb_fetch_grids; NULL = skip).  Deposition grids stay
+ *                        cumulative per rank, rank 0 receives their sum (the drygridunc0 of the reference).
+ *   fpb_reduce_grids_device  device pointer of a summed staging buffer (which: 0 gridunc, 1 griduncn,
+ *                        2 drygridunc, 3 drygriduncn, 4 wetgridunc, 5 wetgriduncn, 6 creceptor; nspec-packed) and
+ *                        the device time of the last reduce [ms], for a host that post-processes on
+ *                        the GPU (fpb_concoutput_sparse) or reports the exchange cost. */
+int fpb_comm_unique_id(void *id128);
+int fpb_comm_init(fpb_handle *h, const void *id128, int32_t rank, int32_t nranks);
+int fpb_reduce_grids_begin(fpb_handle *h);
+int fpb_reduce_grids_end(fpb_handle *h, float *gridunc, float *griduncn, float *drygridunc,
+                         float *drygriduncn, float *wetgridunc, float *wetgriduncn, float *creceptor);
+int fpb_reduce_grids_device(fpb_handle *h, int32_t which, void **dptr, size_t *nfloats, float *reduce_ms);
+int fpb_comm_finalize(fpb_handle *h);
+
 /* Re-order the device-resident particles by met-grid cell for gather
  * locality.  Slot identity seen through push/pull is preserved. */
 int fpb_sort_particles(fpb_handle *h);
