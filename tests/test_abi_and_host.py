@@ -259,3 +259,73 @@ def test_timemanager_release_into_reused_slots_keeps_live_particles():
     stepped = live & (b.itramem[:n] < nsteps * 900)   # (initialize sets the velocities of the newest ones)
     for f in ("uap", "ucp", "uzp"):
         assert np.array_equal(getattr(a, f)[:n][stepped], getattr(b, f)[:n][stepped]), f
+
+
+# ---------------------------------------------------------------------------------------------
+# include/fpb_mod.f90 (the ISO_C_BINDING module of INTEGRATION.md) against include/fpb.h
+# ---------------------------------------------------------------------------------------------
+_F_KIND = {"integer(c_int32_t)": 4, "integer(c_int64_t)": 8, "integer(c_int16_t)": 2, "integer(c_int8_t)": 1,
+           "integer(c_int)": 4, "integer(c_size_t)": 8, "real(c_float)": 4, "real(c_double)": 8, "type(c_ptr)": 8}
+
+
+def _fortran_module():
+    """parse include/fpb_mod.f90 on its own: parameters, derived types (field, kind, extent), interfaces"""
+    txt = open(os.path.join(ROOT, "include", "fpb_mod.f90")).read()
+    txt = re.sub(r"&\s*\n\s*", " ", txt)
+    params = {m.group(1): int(m.group(2)) for m in re.finditer(r"parameter\s*::\s*(\w+)\s*=\s*(-?\d+)", txt)}
+    types = {}
+    for m in re.finditer(r"type, bind\(C\) :: (\w+)\n(.*?)end type", txt, flags=re.S):
+        fields = []
+        for line in m.group(2).strip().splitlines():
+            mm = re.match(r"\s*(\S+(?:\(\w+\))?)\s*::\s*(\w+)(?:\((\w+)\))?\s*$", line)
+            assert mm, line
+            ext = mm.group(3)
+            fields.append((mm.group(2), mm.group(1), (params[ext] if ext in params else int(ext)) if ext else 1))
+        types[m.group(1)] = fields
+    funcs = set(re.findall(r"function (fpb_\w+)\(", txt))
+    return params, types, funcs
+
+
+def test_fortran_module_is_generated_from_the_header():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_fortran_module as g
+    assert open(g.OUT).read() == g.generate(), "include/fpb_mod.f90 is stale: python tools/gen_fortran_module.py"
+
+
+def test_fortran_module_layout_matches_the_c_compiler():
+    """Field order, kinds and array extents of every derived type, laid out by the C rules a bind(C)
+    type follows, against gcc's own offsetof/sizeof of the header's structs; the parameters against
+    the header's constants; an interface for every exported symbol."""
+    params, types, funcs = _fortran_module()
+    assert set(types) == {"fpb_config", "fpb_met_ptrs", "fpb_particle_ptrs", "fpb_step_stats", "fpb_partout_ptrs",
+                          "fpb_release_points", "fpb_domainfill_info"}
+    lines = []
+    for t, fields in types.items():
+        for f, _, _ in fields:
+            lines.append(f'printf("{t}.{f} %zu\\n", offsetof({t}, {f}));')
+        lines.append(f'printf("{t} %zu\\n", sizeof({t}));')
+    for k in params:
+        lines.append(f'printf("{k} %d\\n", (int){k});')
+    src = "#include <stdio.h>\n#include <stddef.h>\n#include \"fpb.h\"\nint main(void){\n" + "\n".join(lines) + "\nreturn 0;}\n"
+    exe = os.path.join(ROOT, "tests", "_fmod_probe")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    got = dict(l.split() for l in subprocess.check_output([exe]).decode().splitlines())
+    os.remove(exe)
+    for k, v in params.items():
+        assert int(got[k]) == v, k
+    for t, fields in types.items():
+        off, align = 0, 1
+        for f, kind, n in fields:
+            sz = _F_KIND[kind]
+            off = (off + sz - 1) // sz * sz
+            assert int(got[f"{t}.{f}"]) == off, (t, f, got[f"{t}.{f}"], off)
+            off += sz * n
+            align = max(align, sz)
+        assert int(got[t]) == (off + align - 1) // align * align, t
+    # every field of the C structs is there (the probe above would not notice a field missing at the end)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_fortran_module as g
+    _, structs, _ = g.parse()
+    for name, cf in structs:
+        assert [f[2] for f in cf] == [f[0] for f in types[name]], name
+    assert funcs == set(_declared("fpb.h", "fpb_")), funcs ^ set(_declared("fpb.h", "fpb_"))
