@@ -511,6 +511,21 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
                          "algorithmic_bytes_per_launch": alg / K}}
 
 
+class _stdout_to_stderr:
+    """fd-level redirect: keeps native libraries' banners (NCCL) off the one-JSON-line stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class GridExchange:
     """The mpif_tm_reduce_grid slot (src/mpi_mod.f90:2395-2579, src/timemanager_mpi.f90:468-485)
     through the C ABI: fpb_comm_init joins the NCCL communicator (the 128-byte id travels over the
@@ -521,11 +536,15 @@ class GridExchange:
         import flexpart_b200 as fb
         self.eng, self.rank, self.world, self.local = eng, rank, world, local
         self.ms, self.pending = [], False
-        uid = [fb.Engine.comm_unique_id() if (rank == 0 and world > 1) else bytes(128)]
-        if world > 1:
-            import torch.distributed as dist
-            dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(uid[0], rank, world)
+        with _stdout_to_stderr():            # NCCL prints its version banner on stdout
+            uid = [fb.Engine.comm_unique_id() if (rank == 0 and world > 1) else bytes(128)]
+            if world > 1:
+                import torch.distributed as dist
+                dist.broadcast_object_list(uid, src=0)
+            eng.comm_init(uid[0], rank, world)
+            # the first collective of a communicator sets up its NVLink channels (~1 s): not part of any step
+            eng.reduce_grids_begin()
+            eng.reduce_grids_device(0)
 
     def wait(self):
         if self.pending:

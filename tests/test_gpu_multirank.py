@@ -63,7 +63,8 @@ def test_one_rank_exchange_is_fetch_grids():
     res = []
     for use_comm in (False, True):
         cb = cases.config_small(nrel=4, npart_each=1024, rng_mode=fb.RNG_PHILOX_INDEX, nspec=2, drydepspec=(1, 0),
-                                receptors=[(36.0, 18.0, 1.0e9)], nest=(-60.0, -30.0, 48, 24, 2.5, 2.5))
+                                receptors=[(36.0, 18.0, 1.0e9)], nest=(-60.0, -30.0, 48, 24, 2.5, 2.5),
+                                scatter_mode=fb.SCATTER_DETERMINISTIC)
         eng = fb.Engine(cb)
         eng.fill_rannumb()
         m0, m1 = cases.met_pair(cb)
@@ -87,4 +88,8 @@ def test_one_rank_exchange_is_fetch_grids():
         eng.close()
     for a, b in zip(*res):
         for k in ("gridunc", "griduncn", "drygridunc", "drygriduncn", "creceptor"):
-            assert np.array_equal(a[k], b[k]) and (np.abs(a[k]).sum() > 0 or k == "creceptor"), k
+            assert np.abs(a[k]).sum() > 0 or k == "creceptor", k
+            if k.startswith("grid"):    # the deterministic scatter is bit-reproducible from run to run
+                assert np.array_equal(a[k], b[k]), k
+            else:                       # deposition / receptor sums are float atomics
+                np.testing.assert_allclose(a[k], b[k], rtol=1e-5, atol=1e-30)
