@@ -455,6 +455,8 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   if (cfg->ldirect != 1 && cfg->ldirect != -1) return fail("fpb_init: ldirect must be 1 or -1 (got %d)", cfg->ldirect);
   if ((cfg->drybkdep || cfg->wetbkdep) && cfg->ldirect != -1)
     return fail("fpb_init: drybkdep/wetbkdep (IND_RECEPTOR 3/4) are backward-run options (src/readcommand.f90:320-339)");
+  if (cfg->drybkdep && !cfg->drydep) return fail("fpb_init: drybkdep needs drydep (a species with dry deposition)");
+  if (cfg->wetbkdep && !cfg->wetdep) return fail("fpb_init: wetbkdep needs wetdep (a species with wet deposition)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -931,6 +933,42 @@ static int replay_ran3_indices(fpb_handle *h, int itime) {
   return 0;
 }
 
+// RECEPTOR block of the particle loop (src/timemanager.f90:563-598) for the rows in `rows`
+static int launch_bkdep(fpb_handle *h, const DevCfg &cfg, const DevParticles &rows, cudaStream_t st) {
+  const fpb_config &c = h->cfg;
+  if (!c.drybkdep && !c.wetbkdep) return 0;
+  if (c.wetbkdep && h->rel.numpoint == 0)
+    return fail("fpb_step: wetbkdep needs the release heights (fpb_set_releases) for xscav_frac1 = wetscav * "
+                "(zpoint2 - zpoint1) * grfraction, src/timemanager.f90:590-591");
+  DevBkdepArgs a;
+  a.w.cfg = cfg;
+  // time level closest to itime - lsynctime/2, src/get_wetscav.f90:113-117 (ltsample = lsynctime)
+  const int interp_time = (int)lroundf((float)cfg.itime - 0.5f * (float)c.lsynctime);
+  int n = h->memind[1];
+  if (abs(h->memtime[0] - interp_time) < abs(h->memtime[1] - interp_time)) n = h->memind[0];
+  a.w.met = slot_view(h, n);
+  for (int l = 0; l < FPB_MAXNESTS; l++) {
+    DevMetSlot v{};
+    v.R = h->Rn[l][n - 1]; v.C = h->Cln[l][n - 1]; v.T = h->Tn[l][n - 1];
+    a.w.metn[l] = v;
+    for (int m = 0; m < 2; m++) {
+      DevMetSlot q{};
+      q.vdep = h->vdepn[l][h->memind[m] - 1];
+      a.vmetn[l][m] = q;
+    }
+  }
+  a.w.p = rows;
+  a.w.height = h->d_height;
+  a.w.wetgridunc = nullptr; a.w.wetgriduncn = nullptr;
+  a.w.ltsample = c.lsynctime;
+  a.vmet[0] = slot_view(h, h->memind[0]);
+  a.vmet[1] = slot_view(h, h->memind[1]);
+  a.zpoint1 = h->rel.d_pts[4]; a.zpoint2 = h->rel.d_pts[5];
+  if (c.math_mode == FPB_MATH_STRICT) fpbk_bkdep_strict(a, st); else fpbk_bkdep_fast(a, st);
+  h->launches++;
+  return 0;
+}
+
 extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_stats *stats) {
   if (!h) return fail("fpb_step: null handle");
   if (!h->have_bracket) return fail("fpb_step: fpb_set_met_bracket has not been called");
@@ -978,6 +1016,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
     h->launches++;
     h->pending_init = false;
   }
+  if (launch_bkdep(h, a.cfg, a.p, h->stream)) return 1;
   CK(cudaEventRecord(h->ev[0], h->stream));
   if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_step_strict(a, h->stream);
   else fpbk_step_fast(a, h->stream);
@@ -1719,12 +1758,13 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     a.work_counter = L.d_work;
     a.sc = scratch_view(h->sc, c0);
     if (strict) fpbk_init_strict(a, L.st); else fpbk_init_fast(a, L.st);
+    if (launch_bkdep(h, a.cfg, rows, L.st)) return 1;
     STAGE("initialize");
     if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
     h->launches += 3;
     STAGE("step");
 
-    sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st);
+    sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st, c.drybkdep || c.wetbkdep);
     h->launches++;
     STAGE("scatter_back");
     mark(L.st);
@@ -1734,9 +1774,13 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     D2HS(p->uap, h->p_alt.uap, float); D2HS(p->ucp, h->p_alt.ucp, float); D2HS(p->uzp, h->p_alt.uzp, float);
     D2HS(p->us, h->p_alt.us, float); D2HS(p->vs, h->p_alt.vs, float); D2HS(p->ws, h->p_alt.ws, float);
     D2HS(p->cbt, h->p_alt.cbt, int16_t);
-    for (int k = 0; k < c.nspec; k++)
+    for (int k = 0; k < c.nspec; k++) {
       CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + c0, h->p_alt.xmass1 + (size_t)k * c.maxpart + c0,
                          (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, L.st));
+      if (c.drybkdep || c.wetbkdep) // set once after the release by the receptor block of the loop
+        CK(cudaMemcpyAsync(p->xscav_frac1 + (size_t)k * p->ld + c0, h->p_alt.xscav_frac1 + (size_t)k * c.maxpart + c0,
+                           (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, L.st));
+    }
     mark(L.st);
     CK(cudaGetLastError());
   }

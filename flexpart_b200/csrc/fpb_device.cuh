@@ -155,6 +155,14 @@ struct DevWetArgs {
   int ltsample;
 };
 
+// backward-run receptor scavenging of the particle loop (src/timemanager.f90:563-598)
+struct DevBkdepArgs {
+  DevWetArgs w;                        // cfg, particles, height; met / metn = the time level get_wetscav picks
+  DevMetSlot vmet[2];                  // memind(1), memind(2): vdep for get_vdep_prob
+  DevMetSlot vmetn[FPB_MAXNESTS][2];
+  const float *zpoint1, *zpoint2;      // [numpoint] release heights (wet scavenging)
+};
+
 // releaseparticles on the device (fpb_release.cuh)
 struct DevReleaseArgs {
   DevCfg cfg;                 // cfg.itime = the release time
@@ -207,6 +215,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0
   void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_wetdepo_##SUF(const DevWetArgs &a, cudaStream_t st);              \
+  void fpbk_bkdep_##SUF(const DevBkdepArgs &a, cudaStream_t st);              \
   void fpbk_release_##SUF(const DevReleaseArgs &a, cudaStream_t st);          \
   void fpbk_split_##SUF(const DevSplitArgs &a, cudaStream_t st);              \
   void fpbk_conc_emit_##SUF(const DevConcArgs &a, int nest_sel, unsigned *keys, \

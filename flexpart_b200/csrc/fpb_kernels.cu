@@ -1450,6 +1450,80 @@ fpb_wetdepo_kernel(const __grid_constant__ DevWetArgs a) {
   }
 }
 
+// ----------------------------------------------------------------------------
+// RECEPTOR: dry/wet depovel (src/timemanager.f90:563-598): in a backward deposition run
+// (IND_RECEPTOR 3 / 4) the scavenged fraction xscav_frac1 is determined once, right after the
+// release (it was initialised negative) and before the particle moves: the deposition velocity at
+// the particle (get_vdep_prob, src/get_vdep_prob.f90:41-124) or wetscav * release depth *
+// grfraction (get_wetscav); a species that is not deposited loses its mass.
+__global__ void __launch_bounds__(256)
+fpb_bkdep_kernel(const __grid_constant__ DevBkdepArgs a) {
+  const DevCfg &c = a.w.cfg;
+  __shared__ float sh[FPB_MAXNZ];
+  for (int i = threadIdx.x; i < c.nz; i += blockDim.x) sh[i] = a.w.height[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.numpart) return;
+  const DevParticles &p = a.w.p;
+  if (p.itra1[i] != c.itime) return;
+  if (c.drybkdep) {
+    bool todo = false;
+    for (int ks = 0; ks < c.nspec; ks++) todo = todo || (p.xscav_frac1[(size_t)ks * p.maxpart + i] < 0.f);
+    if (todo) {
+      const double xt = p.xtra1[i], yt = p.ytra1[i];
+      const float zt = p.ztra1[i];
+      const int ngrid = choose_grid(c, xt, yt);
+      Hz z;
+      z.ngrid = ngrid;
+      const DevMetSlot *met = a.vmet;
+      if (ngrid > 0) { // the weights of the grid the velocities are read from ("defined")
+        const int l = ngrid - 1;
+        const float xf = (float)((xt - c.xln[l]) * c.xresoln[l]), yf = (float)((yt - c.yln[l]) * c.yresoln[l]);
+        const int ix = f_int(xf), jy = f_int(yf);
+        make_weights(c, z, c.itime, xf, yf, ix, jy, ix + 1, min(jy + 1, c.nydn[l] - 1), c.nxdn[l], c.nydn[l]);
+        met = a.vmetn[l];
+      } else {
+        const int ix = d_int(xt), jy = d_int(yt);
+        make_weights(c, z, c.itime, (float)xt, (float)yt, ix, jy, ix + 1, min(jy + 1, c.nyd - 1));
+      }
+      for (int ks = 0; ks < c.nspec; ks++) {
+        float *xs = p.xscav_frac1 + (size_t)ks * p.maxpart + i;
+        if (!(*xs < 0.f)) continue;
+        if (c.drydepspec[ks]) {
+          float prob = 0.f;
+          if (c.drydep && (zt < 2.f * HREF)) { // interpol_vdep, src/interpol_vdep.f90:39-54
+            const int off = ks * z.plane;
+            const float y0 = bil(z, __ldg(met[0].vdep + off + z.o00), __ldg(met[0].vdep + off + z.o10),
+                                 __ldg(met[0].vdep + off + z.o01), __ldg(met[0].vdep + off + z.o11));
+            const float y1 = bil(z, __ldg(met[1].vdep + off + z.o00), __ldg(met[1].vdep + off + z.o10),
+                                 __ldg(met[1].vdep + off + z.o01), __ldg(met[1].vdep + off + z.o11));
+            prob = (y0 * z.dt2 + y1 * z.dt1) * z.dtt;
+          }
+          *xs = prob;
+        } else {
+          p.xmass1[(size_t)ks * p.maxpart + i] = 0.f;
+          *xs = 0.f;
+        }
+      }
+    }
+  }
+  if (c.wetbkdep) {
+    for (int ks = 0; ks < c.nspec; ks++) {
+      float *xs = p.xscav_frac1 + (size_t)ks * p.maxpart + i;
+      if (!(*xs < 0.f)) continue;
+      float grfraction1 = 0.f;
+      const float wetscav = get_wetscav(a.w, sh, i, ks, grfraction1);
+      if (wetscav > 0.f) {
+        const int np = p.npoint[i] - 1;
+        *xs = wetscav * (a.zpoint2[np] - a.zpoint1[np]) * grfraction1;
+      } else {
+        p.xmass1[(size_t)ks * p.maxpart + i] = 0.f;
+        *xs = 0.f;
+      }
+    }
+  }
+}
+
 } // namespace
 
 #if FPB_STRICT
@@ -1532,6 +1606,12 @@ void FPB_SUF(fpbk_split)(const DevSplitArgs &a, cudaStream_t st) {
   split_count_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
   release_scan_kernel<<<1, REL_BLOCK, 0, st>>>(a.block_counts, a.total, nb);
   split_assign_kernel<<<nb, REL_BLOCK, 0, st>>>(a);
+}
+
+void FPB_SUF(fpbk_bkdep)(const DevBkdepArgs &a, cudaStream_t st) {
+  const int nb = (a.w.cfg.numpart + 255) / 256;
+  if (nb == 0) return;
+  fpb_bkdep_kernel<<<nb, 256, 0, st>>>(a);
 }
 
 void FPB_SUF(fpbk_wetdepo)(const DevWetArgs &a, cudaStream_t st) {

@@ -1,6 +1,4 @@
 // fpb_sort.cu -- see fpb_sort.cuh.  Integer / data-movement kernels only.
-#include <stdlib.h>
-
 #include "fpb_sort.cuh"
 
 namespace {
@@ -17,8 +15,7 @@ struct RegimeMet {
 
 // key = (level, jy >> sy, ix >> sx) packed level-major into lb + yb + xb bits: the cell is
 // coarsened to a tile when the exact cell index would push the sort to a 4th radix pass
-// len_bits > 0: a chain-length class above the regime bits (longest first), see key_layout()
-struct KeyLayout { int sx, sy, xb, yb, cell_bits, len_bits, len_t; };
+struct KeyLayout { int sx, sy, xb, yb, cell_bits; };
 
 __global__ void __launch_bounds__(256)
 build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsigned *keys,
@@ -58,18 +55,6 @@ build_keys_kernel(DevCfg c, DevParticles p, const float *height, int nrows, unsi
         else if (h * fabsf(oli) < fabsf(rm.dt1 + rm.dt2)) regime = 0u;
         else regime = ((oli < 0.f) != ((rm.dt1 + rm.dt2) < 0.f)) ? 1u : 2u;
         key |= regime << kl.cell_bits;
-        if (kl.len_bits) {
-          // predicted number of Langevin sub-steps of the coming call: lsynctime / ldt (r = 0.84 on C2);
-          // class 0 = longest, handed out first, so that the kernel's tail consists of short chains
-          const unsigned top = (1u << kl.len_bits) - 1u;
-          unsigned cls = top;
-          if (regime != 3u) {
-            const int nsub = abs(c.lsynctime) / max(p.idt[i], 1);
-            cls = 0u;
-            for (int t = kl.len_t; cls < top && nsub < t; t >>= 1) cls++;
-          }
-          key |= cls << (kl.cell_bits + 2);
-        }
       }
     }
     keys[i] = key;
@@ -108,7 +93,7 @@ __global__ void invert_kernel(const int32_t *slot, int32_t *row_of_slot, int nro
 // staging row slot[i] <- device row i, only the arrays the particle loop writes
 // (src/timemanager.f90:531-712: position, itra1, idt, turbulent velocities, cbt, masses)
 __global__ void __launch_bounds__(256)
-scatter_back_kernel(DevParticles rows, DevParticles stg, int count, int nspec) {
+scatter_back_kernel(DevParticles rows, DevParticles stg, int count, int nspec, bool scav) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int s = rows.slot[i];
@@ -117,8 +102,10 @@ scatter_back_kernel(DevParticles rows, DevParticles stg, int count, int nspec) {
   stg.uap[s] = rows.uap[i]; stg.ucp[s] = rows.ucp[i]; stg.uzp[s] = rows.uzp[i];
   stg.us[s] = rows.us[i]; stg.vs[s] = rows.vs[i]; stg.ws[s] = rows.ws[i];
   stg.cbt[s] = rows.cbt[i];
-  for (int k = 0; k < nspec; k++)
+  for (int k = 0; k < nspec; k++) {
     stg.xmass1[(size_t)k * stg.maxpart + s] = rows.xmass1[(size_t)k * rows.maxpart + i];
+    if (scav) stg.xscav_frac1[(size_t)k * stg.maxpart + s] = rows.xscav_frac1[(size_t)k * rows.maxpart + i];
+  }
 }
 
 __global__ void iota_kernel(int32_t *a, int n) {
@@ -173,33 +160,18 @@ static int bits_for(int n) { // bits needed for values 0..n-1
   return b;
 }
 
-static KeyLayout key_layout(const DevCfg &c);
 int sortk_key_bits(const DevCfg &c, bool regime) {
-  // level bits + y bits + x bits (+2 regime + chain-length class) + 1 (dead rows = all ones, must
-  // sort last) <= 24 -> 3 passes
-  return sortk_key_layout_bits(c) + (regime ? 2 + key_layout(c).len_bits : 0) + 1;
+  // level bits + y bits + x bits (+2 regime) + 1 (dead rows = all ones, must sort last) <= 24 -> 3 passes
+  return sortk_key_layout_bits(c) + (regime ? 2 : 0) + 1;
 }
 
 static KeyLayout key_layout(const DevCfg &c) {
   KeyLayout k;
   const int lb = bits_for(c.nz > 1 ? c.nz - 1 : 1);
   k.xb = bits_for(c.nxd); k.yb = bits_for(c.nyd); k.sx = k.sy = 0;
-  // Chain-length class (method 1 only): longest-processing-time-first hand-out.  The persistent
-  // sub-step kernel ends with a drain whose length is the longest chain still running when the row
-  // counter runs out (up to ~160 sequential sub-steps on C2, 0.17 ms of a 1.0 ms launch at 1 M rows);
-  // with the long chains handed out first the last rows are short ones.  FPB_LEN_BITS / FPB_LEN_T: knobs.
-  static int len_bits = -1, len_t = 48;
-  if (len_bits < 0) {
-    const char *e = getenv("FPB_LEN_BITS"), *t = getenv("FPB_LEN_T");
-    len_bits = e ? atoi(e) : 2;
-    if (len_bits < 0 || len_bits > 3) len_bits = 2;
-    if (t && atoi(t) > 0) len_t = atoi(t);
-  }
-  k.len_bits = (c.method == 1) ? len_bits : 0;
-  k.len_t = len_t;
   // method 1 (sub-stepping, sorted every step): tiles, 3 passes; method 0 (gather-bound, sorted
   // rarely): exact cells, the locality is worth the 4th pass
-  while (c.method == 1 && lb + k.xb + k.yb > 21 - k.len_bits && (k.xb > 1 || k.yb > 1)) { // drop low bits, x and y in turn
+  while (c.method == 1 && lb + k.xb + k.yb > 21 && (k.xb > 1 || k.yb > 1)) { // drop low bits, x and y in turn
     if (k.xb >= k.yb && k.xb > 1) { k.xb--; k.sx++; } else { k.yb--; k.sy++; }
   }
   k.cell_bits = lb + k.xb + k.yb;
@@ -227,8 +199,8 @@ void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStre
   invert_kernel<<<nb(nrows, 256), 256, 0, st>>>(slot, row_of_slot, nrows, base);
 }
 void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
-                        cudaStream_t st) {
-  scatter_back_kernel<<<nb(count, 256), 256, 0, st>>>(rows, stg, count, nspec);
+                        cudaStream_t st, bool scav) {
+  scatter_back_kernel<<<nb(count, 256), 256, 0, st>>>(rows, stg, count, nspec, scav);
 }
 void sortk_iota(int32_t *a, int n, cudaStream_t st) {
   iota_kernel<<<nb(n, 256), 256, 0, st>>>(a, n);

@@ -24,7 +24,7 @@ void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsig
 void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base = 0);
 // staging row slot[i] <- row i of the view `rows` (arrays the particle loop writes only)
 void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
-                        cudaStream_t st);
+                        cudaStream_t st, bool scav = false);
 void sortk_iota(int32_t *a, int n, cudaStream_t st);
 // staging (slot order, rows [first,first+count)) <-> device rows
 void sortk_gather_to_staging(const DevParticles &rows, const DevParticles &stg,

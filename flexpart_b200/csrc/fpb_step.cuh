@@ -38,9 +38,6 @@ __device__ __noinline__ float rare_fmodf(float a, float b) { return fmodf(a, b);
 // The profile cache is direct-mapped by (level mod PBL_CACHE): it plays the
 // role of the reference's nzmax-long uprof.. arrays + indzindicator
 // (src/advance.f90:310-331) for the levels a particle visits during one call.
-#ifndef FPB_PREFETCH_RN
-#define FPB_PREFETCH_RN 1
-#endif
 #ifndef FPB_PBL_THREADS
 #define FPB_PBL_THREADS 128
 #endif
@@ -402,17 +399,6 @@ struct PblTask {
     }
     if (!(CBL && c.cblflag == 1)) nrand = nrand + (ifine + 1);
     ust = t.ust; // hanna* may raise ust to 1e-4 (idempotent)
-#if FPB_PREFETCH_RN
-    // The next sub-step reads rannumb(nrand .. nrand+ifine+2): 7 consecutive table entries at a
-    // random place of a 4 MB table, i.e. L2 round trips that the ~1.3 eligible warps per scheduler do
-    // not hide (long-scoreboard is the first stall reason of this kernel).  Their address is known
-    // now, a whole sub-step ahead: pull the two 32-byte sectors into L1 (no register cost).
-    if (!EXTRA) {
-      const float *q = a.rannumb + (nrand - 1);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 7));
-    }
-#endif
 
     // next time step, advance.f90:504-510
     if (turbswitch) {

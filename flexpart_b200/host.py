@@ -61,7 +61,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
                 scatter_mode=abi.SCATTER_ATOMIC, seed=0x5EEDF1E0, height=None,
                 part_id_stride=1, part_id_offset=0, sort_interval=0, met_nests=(),
                 wetdepspec=None, weta_gas=None, wetb_gas=None, crain_aero=None, csnow_aero=None,
-                ccn_aero=None, in_aero=None, henry=None, readclouds=0):
+                ccn_aero=None, in_aero=None, henry=None, readclouds=0, ind_receptor=1):
     """Run constants for the engine, derived the way the reference's
     gridcheck_ecmwf / readcommand / readoutgrid / readreleases derive them."""
     L = load_host_lib()
@@ -102,6 +102,9 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
     setarr("in_aero", in_aero, -1.0)
     setarr("henry", henry, 0.0)
     c.wetdep = 1 if any(c.wetdepspec[k] for k in range(nspec)) else 0
+    # backward runs, src/readcommand.f90:320-339: IND_RECEPTOR 3 = wet, 4 = dry deposition at the receptor
+    c.wetbkdep = 1 if (ldirect == -1 and ind_receptor == 3) else 0
+    c.drybkdep = 1 if (ldirect == -1 and ind_receptor == 4) else 0
     c.readclouds = readclouds
     for l in range(c.numbnests):
         c.readclouds_nest[l] = readclouds

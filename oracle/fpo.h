@@ -70,6 +70,7 @@ typedef struct fpo_state {
   int idummy_advance, idummy_initialize, idummy_release;
   int idummy_domainfill;  /* src/init_domainfill.f90:47 (idummy = -11) */
   int numparticlecount;   /* src/com_mod.f90:676 */
+  float *zpoint1, *zpoint2; /* 1-based release heights (point_mod), backward wet scavenging only */
   float settling_saved; /* src/advance.f90:121 */
 
   /* particles, 1-based arrays of maxpart+1 */
@@ -226,6 +227,12 @@ void fpo_cxy2ll(const float *strcmp, float x, float y, float *xlat,
 float fpo_cgszll(const float *strcmp, float xlat, float xlong);
 void fpo_cc2gll(const float *strcmp, float xlat, float xlong, float ue,
                 float vn, float *ug, float *vg);
+
+/* backward-run receptor scavenging of the particle loop (src/timemanager.f90:571-598) */
+void fpo_set_release_heights(fpo_state *S, const float *zpoint1, const float *zpoint2, int numpoint);
+void fpo_get_vdep_prob(fpo_state *S, int itime, double xt, double yt, float zt, float *prob);
+float fpo_get_wetscav(fpo_state *S, int itime, int ltsample, int jpart, int ks, float *grfraction1);
+void fpo_interpol_weights(fpo_state *S, int itime, float xt, float yt);
 
 /* init_domainfill (fpo_domainfill.c) */
 void fpo_domainfill_gridarea(const fpb_config *c, const int ny_sn[2], float *gridarea);

@@ -51,6 +51,47 @@ static int choose_grid(const fpo_state *S, double xt, double yt) {
   return 0;
 }
 
+/* src/get_vdep_prob.f90:41-124: the deposition velocity at a receptor particle's position (backward
+ * dry-deposition runs, called once per particle right after its release, src/timemanager.f90:571-583).
+ * The reference's interpol_vdep reuses the weights p1..p4, dt1, dt2, dtt the previous interpol_* call
+ * left in interpol_mod -- the particle's own initialize() call on the mother grid; strict_reference
+ * keeps that, the "defined" mode (the device) computes the weights of the grid it reads from. */
+void fpo_get_vdep_prob(fpo_state *S, int itime, double xt, double yt, float zt, float *prob) {
+  const fpb_config *c = &S->c;
+  const float href = 15.f;
+  float xf, yf, vdepo[FPB_MAXSPEC + 1];
+  if (c->drydep)
+    for (int ks = 1; ks <= c->nspec; ks++) {
+      S->depoindicator[ks] = 1;
+      prob[ks - 1] = 0.f;
+    }
+  S->ngrid = choose_grid(S, xt, yt);
+  if (S->ngrid > 0) {
+    xf = (float)((xt - c->xln[S->ngrid - 1]) * c->xresoln[S->ngrid - 1]);
+    yf = (float)((yt - c->yln[S->ngrid - 1]) * c->yresoln[S->ngrid - 1]);
+    S->ix = fpo_int_f(xf);
+    S->jy = fpo_int_f(yf);
+  } else {
+    xf = (float)xt;
+    yf = (float)yt;
+    S->ix = fpo_int_d(xt);
+    S->jy = fpo_int_d(yt);
+  }
+  S->ixp = S->ix + 1;
+  S->jyp = S->jy + 1;
+  if (!S->strict_reference) { /* (row ny exists in neither array: its weight is 0 there) */
+    const int nyd = S->ngrid > 0 ? c->nyn[S->ngrid - 1] : ((c->ny < c->nymax) ? c->ny + 1 : c->ny);
+    if (S->jyp > nyd - 1) S->jyp = nyd - 1;
+    fpo_interpol_weights(S, itime, xf, yf);
+  }
+  if (c->drydep && (zt < 2.f * href))
+    for (int ks = 1; ks <= c->nspec; ks++)
+      if (c->drydepspec[ks - 1]) {
+        if (S->depoindicator[ks]) fpo_interpol_vdep(S, ks, &vdepo[ks]);
+        prob[ks - 1] = vdepo[ks];
+      }
+}
+
 /* settling species choice, src/advance.f90:518-531 (and :686-699, :893-906) */
 static void add_settling(fpo_state *S, int itime, int nrelpoint, double xt,
                          double yt, float zt) {

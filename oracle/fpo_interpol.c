@@ -39,6 +39,8 @@ static void weights(fpo_state *S, int itime, float xt, float yt) {
   S->dtt = 1.f / (S->dt1 + S->dt2);
 }
 
+void fpo_interpol_weights(fpo_state *S, int itime, float xt, float yt) { weights(S, itime, xt, yt); }
+
 static inline float bilin(const fpo_state *S, const float *f, size_t a,
                           size_t b, size_t c, size_t d) {
   return S->p1 * f[a] + S->p2 * f[b] + S->p3 * f[c] + S->p4 * f[d];

@@ -130,8 +130,18 @@ void fpo_destroy(fpo_state *S) {
   free(S->gridunc); free(S->griduncn); free(S->drygridunc);
   free(S->drygriduncn); free(S->creceptor);
   free(S->wetgridunc); free(S->wetgriduncn);
-  free(S->index_queue);
+  free(S->index_queue); free(S->zpoint1); free(S->zpoint2);
   free(S);
+}
+
+void fpo_set_release_heights(fpo_state *S, const float *zpoint1, const float *zpoint2, int numpoint) {
+  free(S->zpoint1); free(S->zpoint2);
+  S->zpoint1 = (float *)calloc((size_t)numpoint + 1, sizeof(float));
+  S->zpoint2 = (float *)calloc((size_t)numpoint + 1, sizeof(float));
+  for (int i = 0; i < numpoint; i++) {
+    S->zpoint1[i + 1] = zpoint1[i];
+    S->zpoint2[i + 1] = zpoint2[i];
+  }
 }
 
 void fpo_set_met(fpo_state *S, int slot, const fpb_met_ptrs *m) { S->met[slot] = *m; }
@@ -310,8 +320,35 @@ void fpo_step(fpo_state *S, int itime, int ldeltat, fpb_step_stats *stats) {
       S->last.n_init++;
     }
 
-    /* backward-run receptor scavenging (get_vdep_prob / get_wetscav,
-     * src/timemanager.f90:571-598) is outside the hot-path scope */
+    /* RECEPTOR: dry/wet depovel, src/timemanager.f90:563-598 -- once after release (xscav_frac1 was
+     * initialised negative), before the particle is moved */
+    if (c->drybkdep) {
+      for (int ks = 1; ks <= c->nspec; ks++)
+        if (XSC(S, j, ks) < 0.f) {
+          float prob_rec[FPB_MAXSPEC];
+          fpo_get_vdep_prob(S, itime, S->xtra1[j], S->ytra1[j], S->ztra1[j], prob_rec);
+          if (c->drydepspec[ks - 1]) {
+            XSC(S, j, ks) = prob_rec[ks - 1];
+          } else {
+            XM1(S, j, ks) = 0.f;
+            XSC(S, j, ks) = 0.f;
+          }
+        }
+    }
+    if (c->wetbkdep) {
+      for (int ks = 1; ks <= c->nspec; ks++)
+        if (XSC(S, j, ks) < 0.f) {
+          float grfraction1 = 0.f;
+          const float wetscav = fpo_get_wetscav(S, itime, c->lsynctime, j, ks, &grfraction1);
+          if (wetscav > 0.f) {
+            const int np = S->npoint[j];
+            XSC(S, j, ks) = wetscav * (S->zpoint2[np] - S->zpoint1[np]) * grfraction1;
+          } else {
+            XM1(S, j, ks) = 0.f;
+            XSC(S, j, ks) = 0.f;
+          }
+        }
+    }
 
     long nsub0 = S->last.n_substeps;
     fpo_advance(S, itime, S->npoint[j], &S->idt[j], &S->uap[j], &S->ucp[j],

@@ -57,6 +57,11 @@ static void interpol_rain(const fpb_met_ptrs *M, size_t ldx, int nx, int ny, flo
   *yint3 = p1 * M->tcc[a] + p2 * M->tcc[b] + p3 * M->tcc[c] + p4 * M->tcc[d];
 }
 
+static float get_wetscav(fpo_state *S, int itime, int ltsample, int jpart, int ks, float *grfraction1);
+float fpo_get_wetscav(fpo_state *S, int itime, int ltsample, int jpart, int ks, float *grfraction1) {
+  return get_wetscav(S, itime, ltsample, jpart, ks, grfraction1);
+}
+
 /* src/get_wetscav.f90:78-314.  Returns wetscav; grfraction1 is only written
  * when scavenging is evaluated (as in the reference). */
 static float get_wetscav(fpo_state *S, int itime, int ltsample, int jpart, int ks,

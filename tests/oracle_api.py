@@ -59,6 +59,7 @@ def load(libm_float=False):
     L.fpo_releaseparticles.argtypes = [S, C.c_int, C.c_int, _pi, _pi] + [_pf] * 6 + [_pf, C.c_int]
     L.fpo_releaseparticles.restype = C.c_int
     L.fpo_split_particles.argtypes = [S, C.c_int]
+    L.fpo_set_release_heights.argtypes = [S, _pf, _pf, C.c_int]
     L.fpo_init_domainfill.argtypes = [S, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _pi, _pf]
     L.fpo_init_domainfill.restype = C.c_int
     L.fpo_numpart.argtypes = [S]; L.fpo_numpart.restype = C.c_int
@@ -100,6 +101,10 @@ class Oracle:
     def set_rannumb(self, table):
         t = np.ascontiguousarray(table, np.float32)
         self.L.fpo_set_rannumb(self.S, _fp(t), len(t))
+
+    def set_releases(self, rel, mp_pid=0):
+        """the release heights the backward wet-scavenging block needs (src/timemanager.f90:590-591)"""
+        self.L.fpo_set_release_heights(self.S, _fp(rel.zpoint1), _fp(rel.zpoint2), len(rel.zpoint1))
 
     def init_domainfill(self, box, itsplit=99999999):
         """init_domainfill over the box (xpoint1, ypoint1, xpoint2, ypoint2) in grid units;

@@ -131,7 +131,7 @@ def test_full_size_fill_conserves_the_air_mass():
     n = 4_000_000
     cb = fb.make_config(nx=721, ny=361, nz=138, dx=0.5, dy=0.5, xlon0=-180.0, ylat0=-90.0, lsynctime=900, ctl=-5.0,
                         ifine=4, outlon0=-180.0, outlat0=-90.0, numxgrid=720, numygrid=360, dxout=0.5, dyout=0.5,
-                        outheights=(100.0, 1000.0, 5000.0, 50000.0), lage=(86400 * 20,), ioutputforeachrelease=0,
+                        outheights=(100.0, 1000.0, 5000.0, 100000.0), lage=(86400 * 20,), ioutputforeachrelease=0,
                         npart=(n,), nspec=1, maxpart=n + 200000, mdomainfill=1, rng_mode=fb.RNG_PHILOX_INDEX,
                         sort_interval=1)
     c = cb.cfg

@@ -321,7 +321,7 @@ def test_cuda_against_the_references_own_code(ctl):
 # math (tolerance), oracle state re-injected every step
 # ----------------------------------------------------------------------------
 def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=True, exact=True,
-              dt=None, tol_h=1e-5, nest_mets=None, tol_z=1e-5, philox=False, wet=False, report=None):
+              dt=None, tol_h=1e-5, nest_mets=None, tol_z=1e-5, philox=False, wet=False, report=None, rel=None):
     """philox: the engine runs a production RNG mode (Philox-indexed rannumb); the oracle is handed
     the same index uniforms (tests/philox_ref.py).  wet: fpb_wetdepo before every step but the first
     (src/timemanager.f90:164-169).  report: dict that receives the measured worst deviations."""
@@ -336,6 +336,8 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
         for nest, (n0, n1) in enumerate(nest_mets or (), start=1):
             e.upload_met_nest(1, nest, n0); e.upload_met_nest(2, nest, n1)
         e.set_met_bracket((1, 2), bracket)
+        if rel is not None:
+            e.set_releases(rel)
     ora.push_particles(p)
     tot = dict(n_active=0, n_pbl=0, n_petterssen=0, n_terminated=0, n_substeps=0, n_nan_cbl=0)
     worst = worst_z = 0.0
@@ -363,8 +365,12 @@ def _per_step(cb, p, nsteps, mets=None, bracket=(0, 10800), t0=0, check_grids=Tr
             for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
                 assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (k, f)
             assert np.array_equal(pg.xmass1[:n], po.xmass1[:n]), k
+            if c.drybkdep or c.wetbkdep:
+                assert np.array_equal(pg.xscav_frac1[:n], po.xscav_frac1[:n]), k
         else:
             assert np.array_equal(pg.itra1[:n], po.itra1[:n]), k
+            if c.drybkdep or c.wetbkdep:
+                np.testing.assert_allclose(pg.xscav_frac1[:n], po.xscav_frac1[:n], rtol=2e-5, atol=1e-12)
             live = po.itra1[:n] != fb.ITRA_DEAD
             for f in ("xtra1", "ytra1", "ztra1"):   # (max() below would swallow a NaN)
                 assert np.isfinite(getattr(pg, f)[:n]).all(), (k, f)
@@ -530,6 +536,47 @@ def test_backward_run(exact):
     mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
     tot, _, _ = _per_step(cb, p, 5, mets=mets, bracket=(0, -10800), exact=exact)
     assert tot["n_active"] == 5 * 2048 and tot["n_pbl"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("kind", ["dry", "wet"])
+def test_backward_receptor_scavenging(kind, exact):
+    """IND_RECEPTOR 4 / 3 (DRYBKDEP / WETBKDEP): the receptor block of the particle loop
+    (src/timemanager.f90:563-598) sets xscav_frac1 once after the release -- get_vdep_prob or
+    get_wetscav * release depth * grfraction -- and conccalc weights every sample with it
+    (src/conccalc.f90:181); resident steps and one host-buffer step."""
+    kw = dict(nrel=3, npart_each=1000, ldirect=-1, nspec=2, lage=(86400 * 10,), ioutputforeachrelease=1,
+              xmass=np.ones((3, 2)), math_mode=fb.MATH_STRICT if exact else fb.MATH_FAST,
+              met_nests=[(-60.0, -20.0, 121, 81, 1.0, 1.0)])
+    if kind == "dry":
+        kw.update(ind_receptor=4, drydepspec=(1, 0))
+    else:
+        kw.update(ind_receptor=3, wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0))
+    cb = cases.config_small(**kw)
+    c = cb.cfg
+    n = 3000
+    p = cases.seeded_particles(cb, n, zmax=60.0 if kind == "dry" else 9000.0, lat_range=(-70.0, 70.0), nspec=2)
+    p.xscav_frac1[:n] = -1.0
+    p.xmass1[:n, 1] = 0.5
+    rel = cases.releases_boxes(cb, seed=5, zmax=1500.0)
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    nm = [(fb.MetFields(cb, nest=1).synth(0), fb.MetFields(cb, nest=1).synth(-10800))]
+    for m in nm[0]:
+        m.vdep *= 2.0; m.lsprec *= 1.5
+    tot, gg, go = _per_step(cb, p, 3, mets=mets, bracket=(0, -10800), exact=exact, nest_mets=nm, rel=rel)
+    assert go["gridunc"][:, :, :, 0].sum() > 0 and go["gridunc"][:, :, :, 1].sum() == 0
+    # the same through fpb_step_host: xscav_frac1 comes back with the arrays the loop writes
+    eng = fb.Engine(cb)
+    eng.fill_rannumb()
+    eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1])
+    eng.upload_met_nest(1, 1, nm[0][0]); eng.upload_met_nest(2, 1, nm[0][1])
+    eng.set_met_bracket((1, 2), (0, -10800)); eng.set_releases(rel)
+    q = cases.seeded_particles(cb, n, zmax=60.0 if kind == "dry" else 9000.0, lat_range=(-70.0, 70.0), nspec=2)
+    q.xscav_frac1[:n] = -1.0
+    eng.step_host(q, 0, 450, conc_weight=1.0)
+    assert (q.xscav_frac1[:n] >= 0).all() and (q.xscav_frac1[:n, 0] > 0).sum() > 100
+    assert (q.xmass1[:n, 1] == 0).all()
+    eng.close()
 
 
 @pytest.mark.parametrize("exact", [True, False])

@@ -361,6 +361,54 @@ def test_reference_timemanager_particle_loop_bit_identical(ctl):
     assert np.array_equal(ref.arr("drygriduncn").view(np.uint32), go["drygriduncn"].view(np.uint32))
 
 
+@pytest.mark.parametrize("kind", ["dry", "wet"])
+def test_reference_backward_receptor_scavenging_bit_identical(kind):
+    """The RECEPTOR block of the particle loop (src/timemanager.f90:563-598) in a backward deposition
+    run: xscav_frac1 is set once after the release from get_vdep_prob (IND_RECEPTOR = 4) or
+    get_wetscav * release depth * grfraction (IND_RECEPTOR = 3); the species that is not deposited
+    loses its mass.  Particle loop of the reference against fpo_step, two intervals."""
+    kw = dict(nrel=3, npart_each=300, ldirect=-1, nspec=2, lage=(86400 * 10,), ioutputforeachrelease=1,
+              xmass=np.ones((3, 2)))
+    if kind == "dry":
+        kw.update(ind_receptor=4, drydepspec=(1, 0))
+    else:
+        kw.update(ind_receptor=3, wetdepspec=(1, 0), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0))
+    cb = cases.config_small(**kw)
+    c = cb.cfg
+    assert (c.drybkdep, c.wetbkdep) == ((1, 0) if kind == "dry" else (0, 1))
+    n = 900
+    p = cases.seeded_particles(cb, n, zmax=60.0 if kind == "dry" else 9000.0, lat_range=(-70.0, 70.0), nspec=2)
+    p.xscav_frac1[:n] = -1.0                       # releaseparticles.f90:171
+    p.xmass1[:n, 1] = 0.5
+    rel = cases.releases_boxes(cb, seed=5, zmax=1500.0)
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    ref, ora = _pair(cb, mets, bracket=(0, -10800))
+    if kind == "wet":
+        for slot in (1, 2):
+            ref.upload_rain(slot, mets[slot - 1])
+    ref.arr("zpoint1")[:] = rel.zpoint1; ref.arr("zpoint2")[:] = rel.zpoint2
+    ora.set_releases(rel)
+    ref.push_state(p)
+    ora.push_particles(p)
+    for k in range(2):
+        itime = -k * 900
+        ref.particle_loop(itime, 450)
+        ora.step(itime, 450)
+        pr = fb.Particles(c.maxpart, c.nspec); pr.numpart = n
+        po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
+        ref.pull_state(pr); ora.pull_particles(po)
+        for f in ref.STATE:
+            a, b = getattr(pr, f)[:n], getattr(po, f)[:n]
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (k, f)
+        assert np.array_equal(pr.xmass1[:n].view(np.uint32), po.xmass1[:n].view(np.uint32)), k
+        xs = ref.arr("xscav_frac1")[:n, :2]
+        assert np.array_equal(xs.view(np.uint32), po.xscav_frac1[:n].view(np.uint32)), k
+        assert (xs >= 0).all() and (xs[:, 0] > 0).sum() > 50 and (xs[:, 1] == 0).all()
+        assert (po.xmass1[:n, 1] == 0).all()      # the species without deposition contributes nothing
+        if kind == "wet":
+            assert ((xs[:, 0] == 0) & (po.xmass1[:n, 0] == 0)).sum() > 50   # particles outside the rain
+
+
 def test_reference_releaseparticles_bit_identical():
     """releaseparticles (src/releaseparticles.f90:69-378): release counts per interval, the
     free-slot search, the ran1 position stream and the particle masses, against the oracle's
