@@ -167,6 +167,10 @@ def load_engine_lib():
     L.fpb_fill_rannumb.argtypes = [H, _i, _i]
     L.fpb_upload_met.argtypes = [H, _i, _pmet]
     L.fpb_upload_met_nest.argtypes = [H, _i, _i, _pmet]
+    L.fpb_upload_met_begin.argtypes = [H, _i, _pmet]
+    L.fpb_upload_met_end.argtypes = [H, _pf]
+    L.fpb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.fpb_host_unregister.argtypes = [C.c_void_p]
     L.fpb_set_met_bracket.argtypes = [H, _pi, _pi, _i]
     L.fpb_push_particles.argtypes = [H, _i, _i, _ppart]
     L.fpb_pull_particles.argtypes = [H, _i, _i, _ppart]

@@ -111,21 +111,29 @@ struct fpb_handle {
   cudaStream_t stream = nullptr;
 
   // met: index = Fortran slot - 1
-  float4 *A[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
-  float *G[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
-  float2 *P[2] = {nullptr, nullptr};
-  float4 *R[2] = {nullptr, nullptr};  // wet deposition: {lsprec, convprec, tcc, ctwc}
-  int8_t *Cl[2] = {nullptr, nullptr}; // wet deposition: clouds
-  float4 *Rn[FPB_MAXNESTS][2] = {};
-  int8_t *Cln[FPB_MAXNESTS][2] = {};
-  float *Tn[FPB_MAXNESTS][2] = {};
+  // FPB_NSLOTS time levels: 1, 2 = the reference's memind slots; 3 = read-ahead slot, allocated on its
+  // first upload (numwfmem = 3 of the reference's MPI build with a dedicated reader, src/par_mod.f90:226-227)
+  float4 *A[FPB_NSLOTS] = {}, *S[FPB_NSLOTS] = {};
+  float *G[FPB_NSLOTS] = {}, *T[FPB_NSLOTS] = {};
+  float2 *P[FPB_NSLOTS] = {};
+  float4 *R[FPB_NSLOTS] = {};  // wet deposition: {lsprec, convprec, tcc, ctwc}
+  int8_t *Cl[FPB_NSLOTS] = {}; // wet deposition: clouds
+  float4 *Rn[FPB_MAXNESTS][FPB_NSLOTS] = {};
+  int8_t *Cln[FPB_MAXNESTS][FPB_NSLOTS] = {};
+  float *Tn[FPB_MAXNESTS][FPB_NSLOTS] = {};
+  bool slot_ready[FPB_NSLOTS] = {};
+  cudaStream_t st_met = nullptr;   // uploads run here, next to the steps on `stream`
+  cudaEvent_t ev_met = nullptr;
+  bool met_in_flight = false;
+  float met_upload_ms = 0.f;
+  cudaEvent_t ev_met0 = nullptr;
   int8_t *stage8 = nullptr;
   size_t stage8_n = 0;
   float *wetgridunc = nullptr, *wetgriduncn = nullptr;
   // nested input grids [nest][slot] (no polar twins, no tt: settling reads the mother grid)
-  float4 *An[FPB_MAXNESTS][2] = {}, *Sn[FPB_MAXNESTS][2] = {};
-  float *Gn[FPB_MAXNESTS][2] = {}, *tropn[FPB_MAXNESTS][2] = {}, *vdepn[FPB_MAXNESTS][2] = {};
-  float *trop[2] = {nullptr, nullptr}, *vdep[2] = {nullptr, nullptr};
+  float4 *An[FPB_MAXNESTS][FPB_NSLOTS] = {}, *Sn[FPB_MAXNESTS][FPB_NSLOTS] = {};
+  float *Gn[FPB_MAXNESTS][FPB_NSLOTS] = {}, *tropn[FPB_MAXNESTS][FPB_NSLOTS] = {}, *vdepn[FPB_MAXNESTS][FPB_NSLOTS] = {};
+  float *trop[FPB_NSLOTS] = {}, *vdep[FPB_NSLOTS] = {};
   float *stage = nullptr;
   size_t stage_n = 0;
   int memind[2] = {1, 2}, memtime[2] = {0, 0}, lwindinterv = 1;
@@ -151,9 +159,9 @@ struct fpb_handle {
     float lon0[2] = {0.f, 0.f}, lat0[2] = {0.f, 0.f};
     bool have_origin = false;
     // partoutput
-    float2 *Q[2] = {nullptr, nullptr};  // {pv, qv} per Fortran slot
+    float2 *Q[FPB_NSLOTS] = {};  // {pv, qv} per Fortran slot
     float *oro = nullptr;
-    bool have_q[2] = {false, false};
+    bool have_q[FPB_NSLOTS] = {};
     unsigned *po_counts = nullptr;
     int *po_count = nullptr;
     int32_t *po_i[2] = {nullptr, nullptr};
@@ -368,16 +376,26 @@ __global__ void fill_i32_kernel(int32_t *p, int32_t v, int n) {
   if (i < n) p[i] = v;
 }
 
-// dst[(k*nyd + jy)*nxd + ix].comp = src[(k*nymax + jy)*nxmax + ix]
-__global__ void pack_component_kernel(float *dst, int comp, int ncomp, const float *src,
-                                      int nxd, int nyd, int nk, int nxmax, int nymax) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n = (size_t)nxd * nyd * nk;
+// Fortran-layout host arrays -> device layout.  Up to four arrays that end up interleaved in one
+// device word ({uu,vv,ww,rho}, {hmix,ustar,wstar,oli}, ...) are copied into the staging buffer back
+// to back (one H2D copy each, no host synchronisation in between) and ONE kernel then writes whole
+// words:  dst[(k*nyd + jy)*nxd + ix] = {src_c[(k*nymax + jy)*nxmax + ix], c = 0..NC-1}.
+template <int NC>
+__global__ void __launch_bounds__(256)
+pack_group_kernel(float *dst, const float *stage, size_t comp_stride, int nxd, int nyd, int nk, int nxmax, int nymax) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)nxd * nyd * nk;
   if (i >= n) return;
-  int ix = (int)(i % nxd);
-  size_t r = i / nxd;
-  int jy = (int)(r % nyd), k = (int)(r / nyd);
-  dst[i * ncomp + comp] = src[((size_t)k * nymax + jy) * nxmax + ix];
+  const int ix = (int)(i % nxd);
+  const size_t r = i / nxd;
+  const int jy = (int)(r % nyd), k = (int)(r / nyd);
+  const size_t o = ((size_t)k * nymax + jy) * nxmax + ix;
+  float v[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) v[c] = (jy < nymax) ? stage[c * comp_stride + o] : 0.f;
+  if (NC == 4) reinterpret_cast<float4 *>(dst)[i] = make_float4(v[0], v[1 % NC], v[2 % NC], v[3 % NC]);
+  else if (NC == 2) reinterpret_cast<float2 *>(dst)[i] = make_float2(v[0], v[1 % NC]);
+  else dst[i] = v[0];
 }
 
 __global__ void pack_i8_kernel(int8_t *dst, const int8_t *src, int nxd, int nyd, int nk, int nxmax, int nymax) {
@@ -390,47 +408,67 @@ __global__ void pack_i8_kernel(int8_t *dst, const int8_t *src, int nxd, int nyd,
   dst[i] = (jy < nymax) ? src[((size_t)k * nymax + jy) * nxmax + ix] : (int8_t)0;
 }
 
-static int upload_i8(fpb_handle *h, int8_t *dst, const int8_t *src, int nk, int nxd, int nyd, int nxmax, int nymax) {
+// stream-ordered, no host synchronisation (pageable sources make cudaMemcpyAsync block by themselves)
+static int upload_i8(fpb_handle *h, cudaStream_t st, int8_t *dst, const int8_t *src, int nk, int nxd, int nyd,
+                     int nxmax, int nymax) {
   const size_t nsrc = (size_t)nxmax * nymax * nk, n = (size_t)nxd * nyd * nk;
   if (nsrc > h->stage8_n) {
+    CK(cudaStreamSynchronize(st));
     if (h->stage8) cudaFree(h->stage8);
     h->stage8 = nullptr;
     CK(cudaMalloc((void **)&h->stage8, nsrc));
     h->stage8_n = nsrc;
   }
-  CK(cudaMemcpyAsync(h->stage8, src, nsrc, cudaMemcpyHostToDevice, h->stream));
-  pack_i8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dst, h->stage8, nxd, nyd, nk, nxmax, nymax);
+  CK(cudaMemcpyAsync(h->stage8, src, nsrc, cudaMemcpyHostToDevice, st));
+  pack_i8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, h->stage8, nxd, nyd, nk, nxmax, nymax);
   h->launches++;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
-static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk,
-                            int nxd, int nyd, int nxmax, int nymax);
-static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk) {
-  return upload_component(h, dst, comp, ncomp, src, nk, h->d.nxd, h->d.nyd, h->cfg.nxmax, h->cfg.nymax);
-}
-static int upload_component(fpb_handle *h, float *dst, int comp, int ncomp, const float *src, int nk,
-                            int nxd, int nyd, int nxmax, int nymax) {
-  size_t nsrc = (size_t)nxmax * nymax * nk;
-  if (nsrc > h->stage_n) {
+static int upload_group(fpb_handle *h, cudaStream_t st, float *dst, int ncomp, const float *const *src, int nk,
+                        int nxd, int nyd, int nxmax, int nymax) {
+  const size_t nsrc = (size_t)nxmax * nymax * nk;
+  if (nsrc * ncomp > h->stage_n) {
+    CK(cudaStreamSynchronize(st));
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
-    CK(cudaMalloc((void **)&h->stage, nsrc * sizeof(float)));
-    h->stage_n = nsrc;
+    CK(cudaMalloc((void **)&h->stage, nsrc * ncomp * sizeof(float)));
+    h->stage_n = nsrc * ncomp;
   }
-  size_t n = (size_t)nxd * nyd * nk;
-  if (src) {
-    CK(cudaMemcpyAsync(h->stage, src, nsrc * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  } else {
-    CK(cudaMemsetAsync(h->stage, 0, nsrc * sizeof(float), h->stream));
+  for (int c = 0; c < ncomp; c++) {
+    if (src[c]) CK(cudaMemcpyAsync(h->stage + c * nsrc, src[c], nsrc * sizeof(float), cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(h->stage + c * nsrc, 0, nsrc * sizeof(float), st));
   }
-  pack_component_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-      dst, comp, ncomp, h->stage, nxd, nyd, nk, nxmax, nymax);
+  const size_t n = (size_t)nxd * nyd * nk;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (ncomp == 4) pack_group_kernel<4><<<nb, 256, 0, st>>>(dst, h->stage, nsrc, nxd, nyd, nk, nxmax, nymax);
+  else if (ncomp == 2) pack_group_kernel<2><<<nb, 256, 0, st>>>(dst, h->stage, nsrc, nxd, nyd, nk, nxmax, nymax);
+  else if (ncomp == 1) pack_group_kernel<1><<<nb, 256, 0, st>>>(dst, h->stage, nsrc, nxd, nyd, nk, nxmax, nymax);
+  else return fail("upload_group: ncomp = %d", ncomp);
   h->launches++;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(h->stream)); // the caller may reuse its array
+  return 0;
+}
+static int upload_group(fpb_handle *h, cudaStream_t st, float *dst, int ncomp, const float *const *src, int nk) {
+  return upload_group(h, st, dst, ncomp, src, nk, h->d.nxd, h->d.nyd, h->cfg.nxmax, h->cfg.nymax);
+}
+
+// device arrays of one time level (slot index s = Fortran slot - 1)
+static int alloc_met_slot(fpb_handle *h, int s) {
+  if (h->A[s]) return 0;
+  const DevCfg &d = h->d;
+  const fpb_config &c = h->cfg;
+  const size_t n3 = (size_t)d.nxd * d.nyd * c.nz, n2 = (size_t)d.nxd * d.nyd;
+  DA(h->A[s], n3); DA(h->G[s], n3); DA(h->T[s], n3); DA(h->P[s], n3); DA(h->S[s], n2);
+  DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
+  if (c.wetdep) { DA(h->R[s], n2); DA(h->Cl[s], n3); }
+  for (int l = 0; l < c.numbnests; l++) {
+    const size_t m2 = (size_t)c.nxn[l] * c.nyn[l], m3 = m2 * c.nz;
+    DA(h->An[l][s], m3); DA(h->Gn[l][s], m3); DA(h->Sn[l][s], m2);
+    DA(h->tropn[l][s], m2); DA(h->vdepn[l][s], m2 * c.nspec);
+    if (c.wetdep) { DA(h->Rn[l][s], m2); DA(h->Cln[l][s], m3); DA(h->Tn[l][s], m3); }
+  }
   return 0;
 }
 
@@ -483,20 +521,11 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&h->ev[k]));
 
-  const size_t n3 = (size_t)d.nxd * d.nyd * c.nz, n2 = (size_t)d.nxd * d.nyd;
-  for (int s = 0; s < 2; s++) {
-    DA(h->A[s], n3); DA(h->G[s], n3); DA(h->T[s], n3); DA(h->P[s], n3); DA(h->S[s], n2);
-    DA(h->trop[s], n2); DA(h->vdep[s], n2 * c.nspec);
-    if (c.wetdep) { DA(h->R[s], n2); DA(h->Cl[s], n3); }
-  }
-  for (int l = 0; l < c.numbnests; l++) {
-    const size_t m2 = (size_t)c.nxn[l] * c.nyn[l], m3 = m2 * c.nz;
-    for (int s = 0; s < 2; s++) {
-      DA(h->An[l][s], m3); DA(h->Gn[l][s], m3); DA(h->Sn[l][s], m2);
-      DA(h->tropn[l][s], m2); DA(h->vdepn[l][s], m2 * c.nspec);
-      if (c.wetdep) { DA(h->Rn[l][s], m2); DA(h->Cln[l][s], m3); DA(h->Tn[l][s], m3); }
-    }
-  }
+  CK(cudaStreamCreateWithFlags(&h->st_met, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_met, cudaEventDisableTiming));
+  CK(cudaEventCreate(&h->ev_met0));
+  for (int s = 0; s < 2; s++)
+    if (alloc_met_slot(h, s)) return 1;
   const size_t mp = (size_t)c.maxpart;
   for (DevParticles *q : {&h->p, &h->p_alt}) {
     DA(q->xtra1, mp); DA(q->ytra1, mp); DA(q->ztra1, mp);
@@ -553,16 +582,19 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (int s = 0; s < 2; s++) {
+  if (h->st_met) { cudaStreamSynchronize(h->st_met); cudaStreamDestroy(h->st_met); }
+  if (h->ev_met) cudaEventDestroy(h->ev_met);
+  if (h->ev_met0) cudaEventDestroy(h->ev_met0);
+  for (int s = 0; s < FPB_NSLOTS; s++) {
     cudaFree(h->A[s]); cudaFree(h->G[s]); cudaFree(h->T[s]); cudaFree(h->P[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
   }
   for (int l = 0; l < FPB_MAXNESTS; l++)
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < FPB_NSLOTS; s++) {
       cudaFree(h->Rn[l][s]); cudaFree(h->Cln[l][s]); cudaFree(h->Tn[l][s]);
       cudaFree(h->An[l][s]); cudaFree(h->Gn[l][s]); cudaFree(h->Sn[l][s]); cudaFree(h->tropn[l][s]); cudaFree(h->vdepn[l][s]);
     }
   cudaFree(h->stage); cudaFree(h->stage8); cudaFree(h->wetgridunc); cudaFree(h->wetgriduncn);
-  for (int s = 0; s < 2; s++) { cudaFree(h->R[s]); cudaFree(h->Cl[s]); }
+  for (int s = 0; s < FPB_NSLOTS; s++) { cudaFree(h->R[s]); cudaFree(h->Cl[s]); }
   for (DevParticles *q : {&h->p, &h->p_alt}) {
     cudaFree(q->xtra1); cudaFree(q->ytra1); cudaFree(q->ztra1); cudaFree(q->itra1);
     cudaFree(q->npoint); cudaFree(q->nclass); cudaFree(q->idt); cudaFree(q->itramem);
@@ -576,7 +608,8 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   for (int k = 0; k < 2; k++) { cudaFree(h->outp.area[k]); cudaFree(h->outp.volume[k]); }
   cudaFree(h->outp.block_counts); cudaFree(h->outp.d_i); cudaFree(h->outp.d_r); cudaFree(h->outp.d_counts);
   cudaFree(h->outp.d_density);
-  cudaFree(h->outp.Q[0]); cudaFree(h->outp.Q[1]); cudaFree(h->outp.oro); cudaFree(h->outp.po_counts);
+  for (auto &q : h->outp.Q) cudaFree(q);
+  cudaFree(h->outp.oro); cudaFree(h->outp.po_counts);
   cudaFree(h->outp.po_count); cudaFree(h->outp.po_i[0]); cudaFree(h->outp.po_i[1]); cudaFree(h->outp.po_mass);
   for (auto &q : h->outp.po_f) cudaFree(q);
   for (auto &q : h->rel.d_pts) cudaFree(q);
@@ -625,9 +658,41 @@ extern "C" int fpb_fill_rannumb(fpb_handle *h, int32_t maxrand, int32_t idummy) 
 }
 
 // -------------------------------------------------------------------- met --
-extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m) {
+static int finish_met_upload(fpb_handle *h) {
+  if (!h->met_in_flight) return 0;
+  CK(cudaEventSynchronize(h->ev_met));
+  CK(cudaEventElapsedTime(&h->met_upload_ms, h->ev_met0, h->ev_met));
+  h->met_in_flight = false;
+  return 0;
+}
+
+// One time level: 7 copies-and-packs instead of one per field; everything on the upload stream.
+static int enqueue_met(fpb_handle *h, int s, const fpb_met_ptrs *m) {
+  const fpb_config &c = h->cfg;
+  cudaStream_t st = h->st_met;
+  const float *a4[4] = {m->uu, m->vv, m->ww, m->rho}, *g1[1] = {m->drhodz}, *t1[1] = {m->tt};
+  const float *p2[2] = {m->uupol, m->vvpol}, *s4[4] = {m->hmix, m->ustar, m->wstar, m->oli}, *tr[1] = {m->tropopause};
+  if (upload_group(h, st, (float *)h->A[s], 4, a4, c.nz)) return 1;
+  if (upload_group(h, st, h->G[s], 1, g1, c.nz)) return 1;
+  if (upload_group(h, st, h->T[s], 1, t1, c.nz)) return 1;
+  if (upload_group(h, st, (float *)h->P[s], 2, p2, c.nz)) return 1;
+  if (upload_group(h, st, (float *)h->S[s], 4, s4, 1)) return 1;
+  if (upload_group(h, st, h->trop[s], 1, tr, 1)) return 1;
+  if (c.drydep) { // host vdep(nxmax,nymax,maxspec): species k is "level" k
+    const float *vd[1] = {m->vdep};
+    if (upload_group(h, st, h->vdep[s], 1, vd, c.nspec)) return 1;
+  }
+  if (c.wetdep) {
+    const float *r4[4] = {m->lsprec, m->convprec, m->tcc, m->ctwc};
+    if (upload_group(h, st, (float *)h->R[s], 4, r4, 1)) return 1;
+    if (upload_i8(h, st, h->Cl[s], m->clouds, c.nz, h->d.nxd, h->d.nyd, c.nxmax, c.nymax)) return 1;
+  }
+  return 0;
+}
+
+extern "C" int fpb_upload_met_begin(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m) {
   if (!h || !m) return fail("fpb_upload_met: null argument");
-  if (slot != 1 && slot != 2) return fail("fpb_upload_met: slot must be 1 or 2 (got %d)", slot);
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_met: slot must be 1..%d (got %d)", FPB_NSLOTS, slot);
   if (!m->uu || !m->vv || !m->ww || !m->rho || !m->drhodz || !m->hmix || !m->ustar || !m->wstar ||
       !m->oli || !m->tropopause)
     return fail("fpb_upload_met: a mandatory field pointer is null");
@@ -635,85 +700,100 @@ extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m
   if ((c.nglobal || c.sglobal) && (!m->uupol || !m->vvpol))
     return fail("fpb_upload_met: uupol/vvpol required when a pole is in the domain");
   if (c.lsettling && !m->tt) return fail("fpb_upload_met: tt required when lsettling");
+  if (c.mdomainfill && !m->tt) return fail("fpb_upload_met: tt required for domain-filling runs (column air mass)");
   if (c.drydep && !m->vdep) return fail("fpb_upload_met: vdep required when drydep");
-  CK(cudaSetDevice(h->device));
-  const int s = slot - 1;
-  float *A = (float *)h->A[s], *S = (float *)h->S[s];
-  if (upload_component(h, A, 0, 4, m->uu, c.nz)) return 1;
-  if (upload_component(h, A, 1, 4, m->vv, c.nz)) return 1;
-  if (upload_component(h, A, 2, 4, m->ww, c.nz)) return 1;
-  if (upload_component(h, A, 3, 4, m->rho, c.nz)) return 1;
-  if (upload_component(h, h->G[s], 0, 1, m->drhodz, c.nz)) return 1;
-  if (upload_component(h, h->T[s], 0, 1, m->tt, c.nz)) return 1;
-  if (upload_component(h, (float *)h->P[s], 0, 2, m->uupol, c.nz)) return 1;
-  if (upload_component(h, (float *)h->P[s], 1, 2, m->vvpol, c.nz)) return 1;
-  if (upload_component(h, S, 0, 4, m->hmix, 1)) return 1;
-  if (upload_component(h, S, 1, 4, m->ustar, 1)) return 1;
-  if (upload_component(h, S, 2, 4, m->wstar, 1)) return 1;
-  if (upload_component(h, S, 3, 4, m->oli, 1)) return 1;
-  if (upload_component(h, h->trop[s], 0, 1, m->tropopause, 1)) return 1;
-  if (c.drydep) {
-    // host vdep(nxmax,nymax,maxspec): species k is "level" k
-    if (upload_component(h, h->vdep[s], 0, 1, m->vdep, c.nspec)) return 1;
-  }
   if (c.wetdep) {
     if (!m->lsprec || !m->convprec || !m->tcc || !m->clouds || !m->tt)
       return fail("fpb_upload_met: lsprec/convprec/tcc/clouds/tt required when wetdep");
     if (c.readclouds && !m->ctwc) return fail("fpb_upload_met: ctwc required when readclouds");
-    float *R = (float *)h->R[s];
-    if (upload_component(h, R, 0, 4, m->lsprec, 1)) return 1;
-    if (upload_component(h, R, 1, 4, m->convprec, 1)) return 1;
-    if (upload_component(h, R, 2, 4, m->tcc, 1)) return 1;
-    if (upload_component(h, R, 3, 4, m->ctwc, 1)) return 1;
-    if (upload_i8(h, h->Cl[s], m->clouds, c.nz, h->d.nxd, h->d.nyd, c.nxmax, c.nymax)) return 1;
   }
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const int s = slot - 1;
+  if (alloc_met_slot(h, s)) return 1;
+  CK(cudaEventRecord(h->ev_met0, h->st_met));
+  if (enqueue_met(h, s, m)) return 1;
+  CK(cudaEventRecord(h->ev_met, h->st_met));
+  h->met_in_flight = true;
+  h->slot_ready[s] = true;
   return 0;
+}
+
+extern "C" int fpb_upload_met_end(fpb_handle *h, float *upload_ms) {
+  if (!h) return fail("fpb_upload_met_end: null handle");
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  if (upload_ms) *upload_ms = h->met_upload_ms;
+  return 0;
+}
+
+extern "C" int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *m) {
+  if (fpb_upload_met_begin(h, slot, m)) return 1;
+  return fpb_upload_met_end(h, nullptr); // the caller may reuse its arrays
 }
 
 extern "C" int fpb_upload_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_ptrs *m) {
   if (!h || !m) return fail("fpb_upload_met_nest: null argument");
-  if (slot != 1 && slot != 2) return fail("fpb_upload_met_nest: slot must be 1 or 2 (got %d)", slot);
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_met_nest: slot must be 1..%d (got %d)", FPB_NSLOTS, slot);
   const fpb_config &c = h->cfg;
   if (nest < 1 || nest > c.numbnests) return fail("fpb_upload_met_nest: nest %d outside 1..numbnests=%d", nest, c.numbnests);
   if (!m->uu || !m->vv || !m->ww || !m->rho || !m->drhodz || !m->hmix || !m->ustar || !m->wstar ||
       !m->oli || !m->tropopause)
     return fail("fpb_upload_met_nest: a mandatory field pointer is null");
   if (c.drydep && !m->vdep) return fail("fpb_upload_met_nest: vdep required when drydep");
-  CK(cudaSetDevice(h->device));
-  const int s = slot - 1, l = nest - 1;
-  const int nx = c.nxn[l], ny = c.nyn[l], mx = c.nxmaxn, my = c.nymaxn;
-  float *A = (float *)h->An[l][s], *S = (float *)h->Sn[l][s];
-  if (upload_component(h, A, 0, 4, m->uu, c.nz, nx, ny, mx, my)) return 1;
-  if (upload_component(h, A, 1, 4, m->vv, c.nz, nx, ny, mx, my)) return 1;
-  if (upload_component(h, A, 2, 4, m->ww, c.nz, nx, ny, mx, my)) return 1;
-  if (upload_component(h, A, 3, 4, m->rho, c.nz, nx, ny, mx, my)) return 1;
-  if (upload_component(h, h->Gn[l][s], 0, 1, m->drhodz, c.nz, nx, ny, mx, my)) return 1;
-  if (upload_component(h, S, 0, 4, m->hmix, 1, nx, ny, mx, my)) return 1;
-  if (upload_component(h, S, 1, 4, m->ustar, 1, nx, ny, mx, my)) return 1;
-  if (upload_component(h, S, 2, 4, m->wstar, 1, nx, ny, mx, my)) return 1;
-  if (upload_component(h, S, 3, 4, m->oli, 1, nx, ny, mx, my)) return 1;
-  if (upload_component(h, h->tropn[l][s], 0, 1, m->tropopause, 1, nx, ny, mx, my)) return 1;
-  if (c.drydep && upload_component(h, h->vdepn[l][s], 0, 1, m->vdep, c.nspec, nx, ny, mx, my)) return 1;
   if (c.wetdep) {
     if (!m->lsprec || !m->convprec || !m->tcc || !m->clouds || !m->tt)
       return fail("fpb_upload_met_nest: lsprec/convprec/tcc/clouds/tt required when wetdep");
-    if (c.readclouds_nest[l] && !m->ctwc) return fail("fpb_upload_met_nest: ctwc required when readclouds_nest");
-    float *R = (float *)h->Rn[l][s];
-    if (upload_component(h, R, 0, 4, m->lsprec, 1, nx, ny, mx, my)) return 1;
-    if (upload_component(h, R, 1, 4, m->convprec, 1, nx, ny, mx, my)) return 1;
-    if (upload_component(h, R, 2, 4, m->tcc, 1, nx, ny, mx, my)) return 1;
-    if (upload_component(h, R, 3, 4, m->ctwc, 1, nx, ny, mx, my)) return 1;
-    if (upload_component(h, h->Tn[l][s], 0, 1, m->tt, c.nz, nx, ny, mx, my)) return 1;
-    if (upload_i8(h, h->Cln[l][s], m->clouds, c.nz, nx, ny, mx, my)) return 1;
+    if (c.readclouds_nest[nest - 1] && !m->ctwc) return fail("fpb_upload_met_nest: ctwc required when readclouds_nest");
   }
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const int s = slot - 1, l = nest - 1;
+  if (alloc_met_slot(h, s)) return 1;
+  const int nx = c.nxn[l], ny = c.nyn[l], mx = c.nxmaxn, my = c.nymaxn;
+  cudaStream_t st = h->st_met;
+  const float *a4[4] = {m->uu, m->vv, m->ww, m->rho}, *g1[1] = {m->drhodz};
+  const float *s4[4] = {m->hmix, m->ustar, m->wstar, m->oli}, *tr[1] = {m->tropopause};
+  if (upload_group(h, st, (float *)h->An[l][s], 4, a4, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_group(h, st, h->Gn[l][s], 1, g1, c.nz, nx, ny, mx, my)) return 1;
+  if (upload_group(h, st, (float *)h->Sn[l][s], 4, s4, 1, nx, ny, mx, my)) return 1;
+  if (upload_group(h, st, h->tropn[l][s], 1, tr, 1, nx, ny, mx, my)) return 1;
+  if (c.drydep) {
+    const float *vd[1] = {m->vdep};
+    if (upload_group(h, st, h->vdepn[l][s], 1, vd, c.nspec, nx, ny, mx, my)) return 1;
+  }
+  if (c.wetdep) {
+    const float *r4[4] = {m->lsprec, m->convprec, m->tcc, m->ctwc}, *t1[1] = {m->tt};
+    if (upload_group(h, st, (float *)h->Rn[l][s], 4, r4, 1, nx, ny, mx, my)) return 1;
+    if (upload_group(h, st, h->Tn[l][s], 1, t1, c.nz, nx, ny, mx, my)) return 1;
+    if (upload_i8(h, st, h->Cln[l][s], m->clouds, c.nz, nx, ny, mx, my)) return 1;
+  }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// page-lock the host's met / particle arrays so that fpb_upload_met_begin and fpb_step_host copy
+// asynchronously at full PCIe rate (a Fortran host need not link the CUDA runtime for this)
+extern "C" int fpb_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return fail("fpb_host_register: null argument");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int fpb_host_unregister(void *p) {
+  if (!p) return fail("fpb_host_unregister: null argument");
+  CK(cudaHostUnregister(p));
   return 0;
 }
 
 extern "C" int fpb_set_met_bracket(fpb_handle *h, const int32_t memind[2], const int32_t memtime[2],
                                    int32_t lwindinterv) {
   if (!h || !memind || !memtime) return fail("fpb_set_met_bracket: null argument");
-  if (!((memind[0] == 1 && memind[1] == 2) || (memind[0] == 2 && memind[1] == 1)))
-    return fail("fpb_set_met_bracket: memind must be a permutation of (1,2)");
+  if (memind[0] < 1 || memind[0] > FPB_NSLOTS || memind[1] < 1 || memind[1] > FPB_NSLOTS || memind[0] == memind[1])
+    return fail("fpb_set_met_bracket: memind must be two different slots of 1..%d", FPB_NSLOTS);
+  if (!h->slot_ready[memind[0] - 1] || !h->slot_ready[memind[1] - 1])
+    return fail("fpb_set_met_bracket: slot %d or %d has not been uploaded", memind[0], memind[1]);
+  cudaSetDevice(h->device);
+  if (finish_met_upload(h)) return 1; // a read-ahead upload into one of these slots must have landed
   if (memtime[0] == memtime[1]) return fail("fpb_set_met_bracket: memtime(1) == memtime(2)");
   if (lwindinterv == 0) return fail("fpb_set_met_bracket: lwindinterv == 0");
   h->memind[0] = memind[0]; h->memind[1] = memind[1];
@@ -1204,17 +1284,23 @@ extern "C" int fpb_set_orography(fpb_handle *h, const float *oro) {
   if (!h || !oro) return fail("fpb_set_orography: null argument");
   CK(cudaSetDevice(h->device));
   if (!h->outp.oro) DA(h->outp.oro, (size_t)h->d.nxd * h->d.nyd);
-  return upload_component(h, h->outp.oro, 0, 1, oro, 1);
+  if (finish_met_upload(h)) return 1;
+  const float *o1[1] = {oro};
+  if (upload_group(h, h->st_met, h->outp.oro, 1, o1, 1)) return 1;
+  CK(cudaStreamSynchronize(h->st_met));
+  return 0;
 }
 
 extern "C" int fpb_upload_pvqv(fpb_handle *h, int32_t slot, const float *pv, const float *qv) {
   if (!h || !pv || !qv) return fail("fpb_upload_pvqv: null argument");
-  if (slot < 1 || slot > 2) return fail("fpb_upload_pvqv: slot %d", slot);
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_pvqv: slot %d", slot);
   CK(cudaSetDevice(h->device));
   const int s = slot - 1;
   if (!h->outp.Q[s]) DA(h->outp.Q[s], (size_t)h->d.nxd * h->d.nyd * h->cfg.nz);
-  if (upload_component(h, reinterpret_cast<float *>(h->outp.Q[s]), 0, 2, pv, h->cfg.nz)) return 1;
-  if (upload_component(h, reinterpret_cast<float *>(h->outp.Q[s]), 1, 2, qv, h->cfg.nz)) return 1;
+  if (finish_met_upload(h)) return 1;
+  const float *q2[2] = {pv, qv};
+  if (upload_group(h, h->st_met, reinterpret_cast<float *>(h->outp.Q[s]), 2, q2, h->cfg.nz)) return 1;
+  CK(cudaStreamSynchronize(h->st_met));
   h->outp.have_q[s] = true;
   return 0;
 }

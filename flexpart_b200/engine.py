@@ -58,6 +58,26 @@ class Engine:
     def upload_met(self, slot, met):
         self._check(self.L.fpb_upload_met(self.h, slot, C.byref(met.ptrs)))
 
+    def upload_met_begin(self, slot, met):
+        """read-ahead upload (slot 1..3): returns once the copies are enqueued; keep `met` alive and
+        untouched until upload_met_end()"""
+        self._met_keep = met
+        self._check(self.L.fpb_upload_met_begin(self.h, slot, C.byref(met.ptrs)))
+
+    def upload_met_end(self):
+        ms = C.c_float(0.0)
+        self._check(self.L.fpb_upload_met_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def host_register(self, *arrays):
+        """page-lock numpy arrays (cudaHostRegister) for asynchronous copies"""
+        for a in arrays:
+            self._check(self.L.fpb_host_register(a.ctypes.data, a.nbytes))
+
+    def host_unregister(self, *arrays):
+        for a in arrays:
+            self._check(self.L.fpb_host_unregister(a.ctypes.data))
+
     def upload_met_nest(self, slot, nest, met):
         self._check(self.L.fpb_upload_met_nest(self.h, slot, nest, C.byref(met.ptrs)))
 

@@ -35,6 +35,8 @@ extern "C" {
 #define FPB_MAXAGECLASS 8  /* >= par_mod maxageclass */
 #define FPB_MAXZGRID 64    /* output-grid levels */
 #define FPB_MAXRECEPTOR 20 /* par_mod maxreceptor, src/par_mod.f90:204 */
+#define FPB_NSLOTS 3       /* met time levels on the device: memind slots 1, 2 + a read-ahead slot
+                              (numwfmem = 3 of the reference's MPI build, src/par_mod.f90:226-227) */
 #define FPB_MAXNESTS 3     /* >= par_mod maxnests (0 shipped, 1 MeteoSwiss:
                               src/par_mod.f90:152, src/par_mod_meteoswiss.f90:154) */
 
@@ -223,8 +225,22 @@ int fpb_set_rannumb(fpb_handle *h, const float *rannumb, int32_t n);
 int fpb_fill_rannumb(fpb_handle *h, int32_t maxrand, int32_t idummy);
 
 /* after getfields returned a new field: src/timemanager.f90:200,
- * src/getfields.f90:109-139.  slot is the Fortran slot index 1 or 2. */
+ * src/getfields.f90:109-139.  slot is the Fortran slot index 1 or 2 (3: read-ahead, below). */
 int fpb_upload_met(fpb_handle *h, int32_t slot, const fpb_met_ptrs *met);
+/* The same in two halves, for reading ahead: _begin enqueues the copies and the re-packing of one
+ * time level on the engine's upload stream and returns (with page-locked source arrays -- see
+ * fpb_host_register -- at once; the arrays must stay untouched until _end), the steps of the
+ * current bracket go on meanwhile; _end waits and reports the device time of the upload [ms].
+ * A third slot exists for this (FPB_NSLOTS = 3; the numwfmem = 3 of the reference's MPI build with
+ * a dedicated reader process, src/par_mod.f90:226-227, src/getfields_mpi.f90): the field after next
+ * goes to the slot that is not in the bracket, and fpb_set_met_bracket(memind) then names any two
+ * of the three.  fpb_set_met_bracket waits for an upload in flight. */
+int fpb_upload_met_begin(fpb_handle *h, int32_t slot, const fpb_met_ptrs *met);
+int fpb_upload_met_end(fpb_handle *h, float *upload_ms /* may be NULL */);
+/* cudaHostRegister / cudaHostUnregister for a host that does not link the CUDA runtime: page-locks
+ * the met arrays (asynchronous uploads) or the particle arrays (fpb_step_host) */
+int fpb_host_register(void *p, size_t bytes);
+int fpb_host_unregister(void *p);
 /* the same for nested input grid `nest` (1..numbnests): the slices
  * uun(:,:,:,slot,nest) .. of src/com_mod.f90:501-529, filled by
  * readwind_nests / verttransform_nests / calcpar_nests (src/getfields.f90:141-170) */

@@ -1197,3 +1197,65 @@ def test_mixed_entry_points_keep_one_consistent_state():
             assert sg == so, (k, sg, so)
         compare(("step", k), n)
     assert (host.itra1[:n] == fb.ITRA_DEAD).any()
+
+
+def test_read_ahead_met_slot_and_bracket_rotation():
+    """fpb_upload_met_begin/_end into the third slot while steps of the current bracket run, then the
+    bracket rotates (1,2) -> (2,3) -> (3,1): the reference's numwfmem = 3 read-ahead
+    (src/par_mod.f90:226-227).  Same particles as an engine that uploads synchronously into the
+    two classic slots, bit for bit; page-locked and pageable sources."""
+    cb = cases.config_small(nrel=4, npart_each=1024, rng_mode=fb.RNG_PHILOX_INDEX, sort_interval=1)
+    times = (0, 3600, 7200, 10800)
+    mets = [fb.MetFields(cb).synth(t) for t in times]
+    p0 = cases.seeded_particles(cb, 4096, zmax=2500.0)
+
+    def run(read_ahead, pinned):
+        eng = fb.Engine(cb)
+        eng.fill_rannumb()
+        eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1])
+        slots = [1, 2]                                  # slots of (older, newer)
+        eng.set_met_bracket(slots, (times[0], times[1]))
+        if pinned:
+            for m in mets[2:]:
+                eng.host_register(*[getattr(m, n) for n in fb.MetFields.NAMES3 + fb.MetFields.NAMES2])
+        eng.push_particles(p0)
+        nxt = 2
+        ms = []
+        for k in range(12):
+            itime = k * 900
+            if itime >= times[nxt - 1] and nxt < len(times):           # the bracket moves on
+                if read_ahead:
+                    free = ({1, 2, 3} - set(slots)).pop()
+                    ms.append(eng.upload_met_end())                    # the field after next has landed in `free`
+                    slots = [slots[1], free]
+                else:
+                    eng.upload_met(slots[0], mets[nxt])                # classic: overwrite the older slot
+                    slots = [slots[1], slots[0]]
+                eng.set_met_bracket(slots, (times[nxt - 1], times[nxt]))
+                nxt += 1
+            if read_ahead and nxt < len(times) and itime == times[nxt - 2]:   # start reading ahead at the start of a bracket
+                eng.upload_met_begin(({1, 2, 3} - set(slots)).pop(), mets[nxt])
+            eng.conccalc(itime, 1.0)
+            eng.step(itime)
+        q = fb.Particles(cb.cfg.maxpart, 1); q.numpart = 4096
+        eng.pull_particles(q)
+        g = eng.fetch_grids()["gridunc"]
+        if pinned:
+            for m in mets[2:]:
+                eng.host_unregister(*[getattr(m, n) for n in fb.MetFields.NAMES3 + fb.MetFields.NAMES2])
+        eng.close()
+        return q, g, ms
+
+    qa, ga, _ = run(False, False)
+    for pinned in (False, True):
+        qb, gb, ms = run(True, pinned)
+        assert len(ms) == 2 and all(m > 0 for m in ms)
+        for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+            assert np.array_equal(getattr(qa, f)[:4096], getattr(qb, f)[:4096]), (pinned, f)
+        assert rel_l2(gb, ga) < 1e-6
+    # a slot that was never uploaded cannot enter the bracket
+    eng = fb.Engine(cb)
+    eng.upload_met(1, mets[0])
+    with pytest.raises(fb.FpbError, match="has not been uploaded"):
+        eng.set_met_bracket((1, 3), (0, 3600))
+    eng.close()
