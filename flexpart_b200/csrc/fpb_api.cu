@@ -522,7 +522,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&h->ev[k]));
 
   CK(cudaStreamCreateWithFlags(&h->st_met, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&h->ev_met, cudaEventDisableTiming));
+  CK(cudaEventCreate(&h->ev_met));
   CK(cudaEventCreate(&h->ev_met0));
   for (int s = 0; s < 2; s++)
     if (alloc_met_slot(h, s)) return 1;
