@@ -283,6 +283,7 @@ struct fpb_handle {
   Lane lanes[NLANES];
   cudaStream_t st_in = nullptr;              // all host-to-device copies of fpb_step_host, in chunk order
   cudaEvent_t ev_in[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_det[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_ready = nullptr;
   bool lanes_ready = false;
 };
@@ -626,6 +627,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->st_in) { cudaStreamSynchronize(h->st_in); cudaStreamDestroy(h->st_in); }
   for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
+  for (auto &e : h->ev_det) if (e) cudaEventDestroy(e);
   fpb_comm_finalize(h);
   for (int k = 0; k < 4; k++) cudaEventDestroy(h->ev[k]);
   cudaStreamDestroy(h->stream);
@@ -1146,6 +1148,7 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   a.gridunc = h->gridunc;
   a.griduncn = h->griduncn;
   a.crec_acc = h->crec_acc;
+  a.slot_base = 0;
   const bool strict = h->cfg.math_mode == FPB_MATH_STRICT;
   CK(cudaEventRecord(h->ev[2], h->stream));
   if (h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
@@ -1686,6 +1689,7 @@ static int ensure_lanes(fpb_handle *h) {
   CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
   for (auto &e : h->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : h->ev_det) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->lanes_ready = true;
   return 0;
 }
@@ -1704,9 +1708,6 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
   if (!h || !p) return fail("fpb_step_host: null argument");
   if (!h->have_bracket) return fail("fpb_step_host: fpb_set_met_bracket has not been called");
   if (numpart < 0 || numpart > h->cfg.maxpart) return fail("fpb_step_host: numpart %d outside capacity %d", numpart, h->cfg.maxpart);
-  if (conc_weight > 0.f && h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC)
-    return fail("fpb_step_host: the deterministic scatter needs resident particles "
-                "(fpb_push_particles + fpb_conccalc + fpb_step)");
   if ((h->cfg.drybkdep || h->cfg.wetbkdep) && !p->xscav_frac1) return fail("fpb_step_host: xscav_frac1 is null");
   CK(cudaSetDevice(h->device));
   if (h->cfg.rng_mode != FPB_RNG_PHILOX && !h->d_rannumb) {
@@ -1819,8 +1820,17 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
       q.p = rows;
       q.height = h->d_height;
       q.gridunc = h->gridunc; q.griduncn = h->griduncn; q.crec_acc = h->crec_acc;
-      if (strict) fpbk_conccalc_strict(q, L.st); else fpbk_conccalc_fast(q, L.st);
-      h->launches++;
+      q.slot_base = c0;
+      if (c.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
+        // every cell must receive its contributions in slot order: the chunks hold ascending slot
+        // ranges, so chunk ci adds after chunk ci-1 has (an event chain across the lanes)
+        if (ci > 0) CK(cudaStreamWaitEvent(L.st, h->ev_det[(ci - 1) % 8], 0));
+        if (scatter_conccalc_deterministic(L.sw, q, strict, L.st, &h->launches)) return fail("%s", scatter_error());
+        CK(cudaEventRecord(h->ev_det[ci % 8], L.st));
+      } else {
+        if (strict) fpbk_conccalc_strict(q, L.st); else fpbk_conccalc_fast(q, L.st);
+        h->launches++;
+      }
       if (c.numreceptor > 0) {
         if (strict) fpbk_receptor_strict(q, L.st); else fpbk_receptor_fast(q, L.st);
         h->launches++;

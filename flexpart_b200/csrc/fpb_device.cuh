@@ -141,6 +141,7 @@ struct DevConcArgs {
   const float *height;
   float *gridunc, *griduncn;
   float *crec_acc; // [numreceptor][nspec] accumulators of c(ks)
+  int slot_base;   // deterministic path on a row chunk (fpb_step_host): record id = 4*(slot - slot_base) + corner
 };
 
 // wetdepo (src/wetdepo.f90): one time level per grid, chosen on the host the way

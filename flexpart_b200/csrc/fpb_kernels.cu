@@ -6,22 +6,22 @@
 //                               once, transcendentals evaluated in double and
 //                               rounded once -> bit-comparable with oracle/.
 //
-// One thread owns one particle for the whole synchronisation interval:
-//   fpb_step_kernel      = timemanager particle-loop body  (src/timemanager.f90:531-712)
-//                          + initialize                    (src/initialize.f90:66-217)
-//                          + advance                       (src/advance.f90:133-985)
-//                          with interpol_all/misslev/wind/wind_short/vdep,
-//                          hanna/hanna1/hanna_short, cbl, windalign, the
-//                          polar-stereographic update (cmapf_mod), settling,
-//                          and drydepokernel(_nest).
-//   fpb_conccalc_kernel  = conccalc mother + nested grid    (src/conccalc.f90:50-444)
-//   fpb_receptor_kernel  = conccalc receptor loop           (src/conccalc.f90:451-498)
+// Kernels (fpb_step.cuh, fpb_release.cuh, fpb_cbl.cuh are included below):
+//   fpb_init_kernel      initialize() for new particles           (src/initialize.f90:66-217)
+//   fpb_bkdep_kernel     receptor scavenging of backward runs      (src/timemanager.f90:563-598)
+//   fpb_pbl_kernel       persistent; the Langevin sub-step loop    (src/advance.f90:133-609) with
+//                        interpol_all/misslev/vdep, hanna/hanna_short/hanna1, cbl, settling
+//   fpb_finish_kernel    rest of advance() + rest of the loop body (src/advance.f90:629-985,
+//                        src/timemanager.f90:630-707): interpol_wind(_short), windalign, cmapf,
+//                        Petterssen, decay, dry-deposition split + drydepokernel(_nest), terminations
+//   fpb_conccalc_kernel / fpb_conc_emit_kernel / fpb_receptor_kernel   (src/conccalc.f90:50-498)
+//   fpb_wetdepo_kernel   wetdepo + get_wetscav + wetdepokernel(_nest)  (src/wetdepo.f90:70-147)
+//   release_* / split_*  releaseparticles, particle splitting      (src/releaseparticles.f90:69-378)
 //
-// The reference keeps its scratch in module globals (interpol_mod,
-// hanna_mod); here it is per-thread registers.  The nzmax-long profile cache
-// (indzindicator, src/advance.f90:310-331) becomes a two-entry cache of the
-// current level pair: a recomputed level gives the same bits because the
-// horizontal weights and the time weights are frozen for the whole call.
+// The reference keeps its scratch in module globals (interpol_mod, hanna_mod); here it is
+// per-thread registers plus a per-lane shared-memory row: the nzmax-long profile cache
+// (indzindicator, src/advance.f90:310-331) becomes a direct-mapped cache of 8 levels; a recomputed
+// level gives the same bits because the horizontal and time weights are frozen for the whole call.
 #include <cstdio>
 #include <math.h>
 
@@ -29,6 +29,9 @@
 
 #ifndef FPB_STRICT
 #define FPB_STRICT 0
+#endif
+#ifndef FPB_WARP_AGGREGATE
+#define FPB_WARP_AGGREGATE 1
 #endif
 #ifndef FPB_PBL_MIN_BLOCKS
 #define FPB_PBL_MIN_BLOCKS 5 // resident 128-thread CTAs per SM the sub-step kernel is tuned for
@@ -1008,13 +1011,27 @@ __device__ __forceinline__ unsigned cell_key(const DevCfg &c, int nxg, int nyg, 
   return i;
 }
 
-struct AtomicSink { // red.global.add.f32 straight into the grid
+// red.global.add.f32 into the grid, warp-aggregated: the rows are cell-sorted, so most lanes of a
+// warp hit the same output cell; the lanes with the same cell key (match.any) add up their
+// contributions by shuffles and the first of them issues ONE atomic per species.
+struct AtomicSink {
   float *grid[2];
   __device__ void add(const DevCfg &c, int nest, int /*slot*/, int nxyz, unsigned key,
                       const float *v) const {
     const size_t inner = key % (unsigned)nxyz, rest = key / (unsigned)nxyz;
+#if FPB_WARP_AGGREGATE
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int lane = threadIdx.x & 31;
+    const bool leader = (__ffs(peers) - 1) == lane;
+    for (int ks = 0; ks < c.nspec; ks++) {
+      float sum = 0.f;
+      for (unsigned m = peers; m; m &= m - 1) sum += __shfl_sync(peers, v[ks], __ffs(m) - 1);
+      if (leader) atomicAdd(grid[nest] + inner + (size_t)nxyz * (ks + (size_t)c.nspec * rest), sum);
+    }
+#else
     for (int ks = 0; ks < c.nspec; ks++)
       atomicAdd(grid[nest] + inner + (size_t)nxyz * (ks + (size_t)c.nspec * rest), v[ks]);
+#endif
   }
   __device__ void skip(int, int) const {}
 };
@@ -1185,7 +1202,7 @@ fpb_conc_emit_kernel(const __grid_constant__ DevConcArgs a, int nest_sel, unsign
   sink.keys = keys;
   sink.vals = vals;
   sink.nrec = nrec;
-  sink.i = a.p.slot[i]; // record order = slot order = the reference's particle order
+  sink.i = a.p.slot[i] - a.slot_base; // record order = slot order = the reference's particle order
   sink.nest_sel = nest_sel;
   conc_particle(a, sh, i, sink);
 }
@@ -1547,14 +1564,17 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   // persistent grid: as many CTAs as can be resident (one wave), never more than the rows need
   // lean + the usual switches (turbswitch, method 1, IFINE 4, turbulence on) as compile-time constants
   const bool spec = !full && a.cfg.turbswitch && a.cfg.method == 1 && !a.cfg.turboff && a.cfg.ifine == 4;
-  static int resident[4] = {0, 0, 0, 0};
+  static int resident[16][4] = {}; // resident CTAs per kernel variant, per device of this process
 #ifdef FPB_NO_EXTRA_NOCBL
   const int variant = full ? 1 : (spec ? 2 : 0);
 #else
   // 3: the full feature set without the CBL scheme (its drift routine costs registers in every path)
   const int variant = full ? (a.cfg.cblflag == 1 ? 1 : 3) : (spec ? 2 : 0);
 #endif
-  int &res = resident[variant];
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  int uncached = 0;
+  int &res = (dev_now >= 0 && dev_now < 16) ? resident[dev_now][variant] : uncached;
   if (res == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);

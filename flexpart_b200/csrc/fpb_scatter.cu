@@ -21,7 +21,10 @@ namespace {
 
 constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256, SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ROUNDS = 16;                       // elements per thread
+#ifndef FPB_SORT_ROUNDS
+#define FPB_SORT_ROUNDS 16
+#endif
+constexpr int SORT_ROUNDS = FPB_SORT_ROUNDS;          // elements per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS; // elements per block
 
 __global__ void iota_fill_kernel(unsigned *keys, unsigned *ids, size_t n) {

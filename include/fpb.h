@@ -276,7 +276,8 @@ int fpb_conccalc(fpb_handle *h, int32_t itime, float weight);
  * fpb_push_particles + fpb_conccalc + fpb_step + fpb_pull_particles, but cut
  * into row chunks that run on separate streams so the host<->device copies of
  * one chunk overlap the kernels of the others; give it page-locked arrays.
- * Synchronous on return.  Not available with FPB_SCATTER_DETERMINISTIC.  Only the arrays the loop
+ * Synchronous on return.  With FPB_SCATTER_DETERMINISTIC the chunks add to the grids in slot order
+ * (bit-identical to the resident path and to the serial loop).  Only the arrays the loop
  * reads are uploaded (not itrasplit; xscav_frac1 only in backward deposition runs): the device copies
  * of those two are undefined afterwards, push before pulling them. */
 int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,

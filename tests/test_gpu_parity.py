@@ -227,6 +227,37 @@ def test_step_host_equals_resident_path():
     assert rel_l2(ga, gb) < 1e-6 and ga.sum() > 0
 
 
+def test_step_host_deterministic_scatter_in_chunks(monkeypatch):
+    """FPB_SCATTER_DETERMINISTIC through fpb_step_host: the row chunks (3 lanes, 5 chunks here) add to
+    the grid in slot order, so gridunc is bit-identical to the oracle's serial accumulation."""
+    monkeypatch.setenv("FPB_HOST_CHUNKS", "5")
+    cb = cases.config_c1(npart=70_000, math_mode=fb.MATH_STRICT, scatter_mode=fb.SCATTER_DETERMINISTIC,
+                         lage=(86400 * 20,), ioutputforeachrelease=0)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), (0, 10800))
+    pg = cases.seeded_particles(cb, 70_000, zmax=3000.0, lat_range=(12.0, 70.0))
+    pg.xtra1[:70_000] = np.random.RandomState(11).uniform(160.0, 235.0, 70_000)    # inside the 85 x 65 output grid
+    pg.itramem[:35_000] = -20000                                                  # half of them use the 4-cell kernel
+    po = fb.Particles(cb.cfg.maxpart, 1)
+    for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+        getattr(po, f)[:] = getattr(pg, f)
+    po.xmass1[:] = pg.xmass1; po.numpart = pg.numpart
+    for k in range(3):
+        sg = eng.step_host(pg, k * 900, 0, conc_weight=1.0)
+        ora.push_particles(po)
+        ora.conccalc(k * 900, 1.0)
+        so = ora.step(k * 900)
+        ora.pull_particles(po)
+        assert sg == so
+        assert np.array_equal(pg.xtra1[:70_000], po.xtra1[:70_000]) and np.array_equal(pg.ztra1[:70_000], po.ztra1[:70_000])
+    gg, go = eng.fetch_grids()["gridunc"], ora.fetch_grids()["gridunc"]
+    assert go.sum() > 0 and np.array_equal(gg, go)
+
+
 def test_step_host_strict_matches_oracle():
     """strict math + reference RNG through fpb_step_host: bit-identical to the oracle."""
     cb = cases.config_c1(npart=70_000, math_mode=fb.MATH_STRICT)
