@@ -30,9 +30,6 @@
 #ifndef FPB_STRICT
 #define FPB_STRICT 0
 #endif
-#ifndef FPB_WARP_AGGREGATE
-#define FPB_WARP_AGGREGATE 1
-#endif
 #ifndef FPB_PBL_MIN_BLOCKS
 #define FPB_PBL_MIN_BLOCKS 5 // resident 128-thread CTAs per SM the sub-step kernel is tuned for
 #endif
@@ -1011,27 +1008,18 @@ __device__ __forceinline__ unsigned cell_key(const DevCfg &c, int nxg, int nyg, 
   return i;
 }
 
-// red.global.add.f32 into the grid, warp-aggregated: the rows are cell-sorted, so most lanes of a
-// warp hit the same output cell; the lanes with the same cell key (match.any) add up their
-// contributions by shuffles and the first of them issues ONE atomic per species.
+// red.global.add.f32 straight into the grid.  (Measured and rejected, round 2: aggregating the lanes
+// that hit the same cell with match.any + shuffles before ONE atomic per group -- the rows are
+// cell-sorted, so most of a warp shares its output cell -- is SLOWER on B200: conccalc 0.052 vs
+// 0.034 ms at 1 M particles, 3.47 vs 2.13 ms at 100 M; the LSU already merges same-address reds of
+// a warp.)
 struct AtomicSink {
   float *grid[2];
   __device__ void add(const DevCfg &c, int nest, int /*slot*/, int nxyz, unsigned key,
                       const float *v) const {
     const size_t inner = key % (unsigned)nxyz, rest = key / (unsigned)nxyz;
-#if FPB_WARP_AGGREGATE
-    const unsigned peers = __match_any_sync(__activemask(), key);
-    const int lane = threadIdx.x & 31;
-    const bool leader = (__ffs(peers) - 1) == lane;
-    for (int ks = 0; ks < c.nspec; ks++) {
-      float sum = 0.f;
-      for (unsigned m = peers; m; m &= m - 1) sum += __shfl_sync(peers, v[ks], __ffs(m) - 1);
-      if (leader) atomicAdd(grid[nest] + inner + (size_t)nxyz * (ks + (size_t)c.nspec * rest), sum);
-    }
-#else
     for (int ks = 0; ks < c.nspec; ks++)
       atomicAdd(grid[nest] + inner + (size_t)nxyz * (ks + (size_t)c.nspec * rest), v[ks]);
-#endif
   }
   __device__ void skip(int, int) const {}
 };
