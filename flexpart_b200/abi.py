@@ -106,6 +106,10 @@ class FpbDomainfillInfo(C.Structure):
                 ("numparttot", _i), ("colmasstotal", _f), ("xmassperparticle", _f)]
 
 
+class FpbConvPtrs(C.Structure):
+    _fields_ = [(n, _pf) for n in ("ps", "tt2", "td2", "tth", "qvh")]
+
+
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
@@ -193,6 +197,9 @@ def load_engine_lib():
     L.fpb_reduce_grids_end.argtypes = [H, _pf, _pf, _pf, _pf, _pf, _pf, _pf]
     L.fpb_reduce_grids_device.argtypes = [H, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _pf]
     L.fpb_comm_finalize.argtypes = [H]
+    L.fpb_set_convection.argtypes = [H, _i, _i, _i, _pf, _pf, _pf, _pf]
+    L.fpb_upload_convmet.argtypes = [H, _i, C.POINTER(FpbConvPtrs)]
+    L.fpb_convmix.argtypes = [H, _i, _pi, _pi]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
     L.fpb_boundcond_domainfill.argtypes = [H, _i, _i]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,

@@ -21,6 +21,7 @@
 #include "fpb_sort.cuh"
 #include "fpb_output.cuh"
 #include "fpb_domainfill.cuh"
+#include "fpb_convmix.cuh"
 
 // ------------------------------------------------------------ error state --
 static thread_local std::string g_err;
@@ -245,6 +246,25 @@ struct fpb_handle {
     size_t stage_n[7] = {0, 0, 0, 0, 0, 0, 0};
     bool in_flight = false, timed = false;
   } comm;
+  // convective mixing (fpb_set_convection / fpb_upload_convmet / fpb_convmix)
+  struct Conv {
+    int nuvz = 0, nuvzmax = 0, nconvlev = 0;
+    float *d_ab = nullptr;                 // akz, bkz, akm, bkm: 4 x (nuvz + 1), 1-based
+    float2 *CT[FPB_NSLOTS] = {};
+    float4 *CS[FPB_NSLOTS] = {};
+    bool have[FPB_NSLOTS] = {};
+    float *cbaseflux = nullptr, *cbase_bak = nullptr;
+    float *pool = nullptr;
+    int pool_cols = 0;
+    ScatterWork sw;
+    unsigned *block_counts = nullptr, *col_key = nullptr;
+    int32_t *colidx = nullptr, *col_start = nullptr, *col_lconv = nullptr, *key_by_slot = nullptr;
+    int *d_total = nullptr;
+    uint8_t *draws = nullptr;
+    float *rn_by_slot = nullptr;
+    size_t cap_rows = 0, cap_cols = 0;
+    int iseed = -88;                       // SAVEd iseed of redist, src/redist.f90:58
+  } conv;
   DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
@@ -615,6 +635,15 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   for (auto &q : h->outp.po_f) cudaFree(q);
   for (auto &q : h->rel.d_pts) cudaFree(q);
   cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
+  {
+    auto &V = h->conv;
+    cudaFree(V.d_ab); cudaFree(V.cbaseflux); cudaFree(V.cbase_bak); cudaFree(V.pool); cudaFree(V.block_counts);
+    cudaFree(V.col_key); cudaFree(V.colidx); cudaFree(V.col_start); cudaFree(V.col_lconv); cudaFree(V.key_by_slot);
+    cudaFree(V.d_total); cudaFree(V.draws); cudaFree(V.rn_by_slot);
+    for (auto &q : V.CT) cudaFree(q);
+    for (auto &q : V.CS) cudaFree(q);
+    scatter_free(V.sw);
+  }
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
@@ -1657,6 +1686,214 @@ extern "C" int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t lo
   if (h->dfill.gdomainfill) return 0; // src/boundcond_domainfill.f90:54: nothing to do for a global domain
   return fail("fpb_boundcond_domainfill: the inflow boundary of a limited domain "
               "(src/boundcond_domainfill.f90:59-580) is not built; only global domain-filling runs on the device");
+}
+
+// ----------------------------------------------------------- convection --
+extern "C" int fpb_set_convection(fpb_handle *h, int32_t nuvz, int32_t nuvzmax, int32_t nconvlev, const float *akz,
+                                  const float *bkz, const float *akm, const float *bkm) {
+  if (!h || !akz || !bkz || !akm || !bkm) return fail("fpb_set_convection: null argument");
+  if (nuvz < 4 || nuvz > nuvzmax || nconvlev < 2 || nconvlev > nuvz - 2)
+    return fail("fpb_set_convection: nuvz = %d (max %d), nconvlev = %d out of range", nuvz, nuvzmax, nconvlev);
+  if (h->cfg.numbnests > 0)
+    return fail("fpb_set_convection: nested input grids are not built for convmix (src/convmix.f90:198-281)");
+  CK(cudaSetDevice(h->device));
+  auto &V = h->conv;
+  V.nuvz = nuvz; V.nuvzmax = nuvzmax; V.nconvlev = nconvlev;
+  cudaFree(V.d_ab); V.d_ab = nullptr;
+  const size_t n1 = (size_t)nuvz + 1;
+  DA(V.d_ab, 4 * n1);
+  std::vector<float> ab(4 * n1, 0.f);
+  const float *src[4] = {akz, bkz, akm, bkm};
+  for (int q = 0; q < 4; q++)
+    for (int k = 0; k < nuvz; k++) ab[q * n1 + k + 1] = src[q][k];
+  CK(cudaMemcpy(V.d_ab, ab.data(), ab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!V.cbaseflux) DA(V.cbaseflux, (size_t)h->d.nxd * h->d.nyd); // cbaseflux = 0 at the start
+  return 0;
+}
+
+extern "C" int fpb_upload_convmet(fpb_handle *h, int32_t slot, const fpb_conv_ptrs *m) {
+  if (!h || !m) return fail("fpb_upload_convmet: null argument");
+  auto &V = h->conv;
+  if (V.nuvz == 0) return fail("fpb_upload_convmet: fpb_set_convection has not been called");
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_convmet: slot %d", slot);
+  if (!m->ps || !m->tt2 || !m->td2 || !m->tth || !m->qvh) return fail("fpb_upload_convmet: a field pointer is null");
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const int s = slot - 1;
+  const size_t n2 = (size_t)h->d.nxd * h->d.nyd;
+  if (!V.CT[s]) { DA(V.CT[s], n2 * V.nuvz); DA(V.CS[s], n2); }
+  const fpb_config &c = h->cfg;
+  // tth, qvh: (nxmax, nymax, nuvzmax) -> {tth, qvh}[k][jy][ix]
+  const float *q2[2] = {m->tth, m->qvh}, *s4[4] = {m->ps, m->tt2, m->td2, nullptr};
+  // (upload_group packs `nk` levels of an array whose level stride is nxmax*nymax: nuvz of nuvzmax)
+  if (upload_group(h, h->st_met, (float *)V.CT[s], 2, q2, V.nuvz)) return 1;
+  if (upload_group(h, h->st_met, (float *)V.CS[s], 4, s4, 1)) return 1;
+  CK(cudaStreamSynchronize(h->st_met));
+  V.have[s] = true;
+  (void)c;
+  return 0;
+}
+
+// the reference's sort2 (src/sort2.f90, Numerical Recipes' quicksort of arr with brr alongside): the
+// order in which the particles of a column -- and the columns -- are visited decides which particle
+// gets which ran3 uniform, so the replay of the reference stream needs this very permutation
+static void sort2_reference(int n, int32_t *arr, int32_t *brr) {
+  const int M = 7, NSTACK = 50;
+  int istack[NSTACK + 1];
+  int jstack = 0, l = 1, ir = n, i, j, k;
+  int32_t a, b;
+  arr--; brr--; // 1-based
+  for (;;) {
+    if (ir - l < M) {
+      for (j = l + 1; j <= ir; j++) {
+        a = arr[j]; b = brr[j];
+        for (i = j - 1; i >= 1; i--) {
+          if (arr[i] <= a) break;
+          arr[i + 1] = arr[i]; brr[i + 1] = brr[i];
+        }
+        arr[i + 1] = a; brr[i + 1] = b;
+      }
+      if (jstack == 0) return;
+      ir = istack[jstack]; l = istack[jstack - 1]; jstack -= 2;
+    } else {
+      k = (l + ir) / 2;
+      std::swap(arr[k], arr[l + 1]); std::swap(brr[k], brr[l + 1]);
+      if (arr[l + 1] > arr[ir]) { std::swap(arr[l + 1], arr[ir]); std::swap(brr[l + 1], brr[ir]); }
+      if (arr[l] > arr[ir]) { std::swap(arr[l], arr[ir]); std::swap(brr[l], brr[ir]); }
+      if (arr[l + 1] > arr[l]) { std::swap(arr[l + 1], arr[l]); std::swap(brr[l + 1], brr[l]); }
+      i = l + 1; j = ir;
+      a = arr[l]; b = brr[l];
+      for (;;) {
+        do i++; while (arr[i] < a);
+        do j--; while (arr[j] > a);
+        if (j < i) break;
+        std::swap(arr[i], arr[j]); std::swap(brr[i], brr[j]);
+      }
+      arr[l] = arr[j]; arr[j] = a;
+      brr[l] = brr[j]; brr[j] = b;
+      jstack += 2;
+      if (jstack > NSTACK) return; // ('nstack too small in sort2': 2^25 elements and more)
+      if (ir - i + 1 >= j - l) {
+        istack[jstack] = ir; istack[jstack - 1] = i; ir = j - 1;
+      } else {
+        istack[jstack] = j - 1; istack[jstack - 1] = l; l = i;
+      }
+    }
+  }
+}
+
+extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int32_t *nconvecting) {
+  if (!h) return fail("fpb_convmix: null handle");
+  auto &V = h->conv;
+  if (ncolumns) *ncolumns = 0;
+  if (nconvecting) *nconvecting = 0;
+  if (V.nuvz == 0) return fail("fpb_convmix: fpb_set_convection has not been called");
+  if (!h->have_bracket) return fail("fpb_convmix: fpb_set_met_bracket has not been called");
+  if (!V.have[h->memind[0] - 1] || !V.have[h->memind[1] - 1])
+    return fail("fpb_convmix: fpb_upload_convmet of both time levels of the bracket is missing");
+  if (h->numpart <= 0) return 0; // src/convmix.f90:75
+  CK(cudaSetDevice(h->device));
+  const fpb_config &c = h->cfg;
+  const int n = h->active_rows >= 0 ? h->active_rows : h->numpart;
+  if (n <= 0) return 0;
+  const bool refrng = c.rng_mode == FPB_RNG_REFERENCE;
+  const int CONV_BATCH = 4096;
+  const size_t pf = fpb_convmix_pool_floats(V.nuvz, V.nconvlev);
+  if (!V.pool) { DA(V.pool, pf * CONV_BATCH); V.pool_cols = CONV_BATCH; }
+  if ((size_t)n > V.cap_rows) {
+    cudaFree(V.block_counts); cudaFree(V.colidx); cudaFree(V.col_key); cudaFree(V.col_start); cudaFree(V.col_lconv);
+    V.block_counts = nullptr; V.colidx = nullptr; V.col_key = nullptr; V.col_start = nullptr; V.col_lconv = nullptr;
+    DA(V.block_counts, (size_t)(n + 1023) / 1024 + 1); DA(V.colidx, (size_t)n);
+    DA(V.col_key, (size_t)n + 1); DA(V.col_start, (size_t)n + 2); DA(V.col_lconv, (size_t)n + 1);
+    V.cap_rows = n;
+  }
+  if (!V.d_total) DA(V.d_total, 1);
+  const size_t nb2 = (size_t)h->d.nxd * h->d.nyd;
+  if (refrng && !V.key_by_slot) {
+    DA(V.key_by_slot, (size_t)c.maxpart); DA(V.draws, (size_t)c.maxpart); DA(V.rn_by_slot, (size_t)c.maxpart);
+    DA(V.cbase_bak, nb2);
+  }
+  if (scatter_reserve(V.sw, (size_t)n, 1)) return fail("%s", scatter_error());
+
+  ConvmixArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.p = h->p;
+  a.nrows = n;
+  a.nuvz = V.nuvz; a.nconvlev = V.nconvlev;
+  const size_t n1 = (size_t)V.nuvz + 1;
+  a.akz = V.d_ab; a.bkz = V.d_ab + n1; a.akm = V.d_ab + 2 * n1; a.bkm = V.d_ab + 3 * n1;
+  for (int m = 0; m < 2; m++) { a.CT[m] = V.CT[h->memind[m] - 1]; a.CS[m] = V.CS[h->memind[m] - 1]; }
+  a.cbaseflux = V.cbaseflux;
+  a.ztop = h->height[c.nz - 1];
+  a.keys = V.sw.keys[0]; a.ids = V.sw.ids[0];
+  a.key_by_slot = refrng ? V.key_by_slot : nullptr;
+  a.block_counts = V.block_counts; a.colidx = V.colidx; a.col_key = V.col_key; a.col_start = V.col_start;
+  a.col_lconv = V.col_lconv; a.pool = V.pool;
+  a.draws = V.draws; a.rn_by_slot = nullptr; a.sorted_ids = nullptr;
+  if (refrng) CK(cudaMemsetAsync(V.key_by_slot, 0xff, (size_t)h->numpart * sizeof(int32_t), h->stream)); // -1
+  fpb_convmix_keys(a, h->stream);
+  int bits = 1;
+  while ((1ll << bits) < (long long)c.nx * c.ny + 1) bits++;
+  bits = ((bits + 1 + 7) / 8) * 8; // + the all-ones key of the rows that are not due
+  if (bits > 32) bits = 32;
+  int cur = 0;
+  if (scatter_sort_pairs(V.sw, (size_t)n, bits, h->stream, &h->launches, &cur)) return fail("%s", scatter_error());
+  a.sorted_ids = V.sw.ids[cur];
+  fpb_convmix_heads(a, V.sw.keys[cur], V.d_total, h->stream);
+  h->launches += 4;
+  int ncols = 0;
+  CK(cudaMemcpyAsync(&ncols, V.d_total, sizeof ncols, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  if (ncolumns) *ncolumns = ncols;
+  if (ncols == 0) return 0;
+  std::vector<int32_t> col_start((size_t)ncols + 1);
+  CK(cudaMemcpy(col_start.data(), V.col_start, col_start.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+
+  // reference RNG: which particles draw is only known once their column's matrix exists, and the
+  // uniforms must be handed out in the reference's visiting order: pass 0 marks, the host replays
+  // ran3 in sort2 order, pass 1 moves.  Philox: one pass.
+  for (int pass = refrng ? 0 : 1; pass <= 1; pass++) {
+    if (pass == 1 && refrng) {
+      const int np = h->numpart;
+      std::vector<int32_t> igrid(np), ipoint(np);
+      std::vector<uint8_t> draws(np);
+      std::vector<float> rn(np, 0.f);
+      CK(cudaMemcpy(igrid.data(), V.key_by_slot, (size_t)np * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(draws.data(), V.draws, (size_t)np, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < np; i++) ipoint[i] = i;
+      sort2_reference(np, igrid.data(), ipoint.data());
+      for (int kq = 0; kq < np; kq++) {
+        if (igrid[kq] == -1) continue;
+        const int ip = ipoint[kq];
+        if (draws[ip]) rn[ip] = h->ran3.next(V.iseed);
+      }
+      CK(cudaMemcpy(V.rn_by_slot, rn.data(), (size_t)np * sizeof(float), cudaMemcpyHostToDevice));
+      a.rn_by_slot = V.rn_by_slot;
+      // the columns are computed once more below: cbaseflux must not be advanced twice
+      CK(cudaMemcpyAsync(V.cbaseflux, V.cbase_bak, nb2 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (pass == 0) {
+      CK(cudaMemsetAsync(V.draws, 0, (size_t)h->numpart, h->stream));
+      CK(cudaMemcpyAsync(V.cbase_bak, V.cbaseflux, nb2 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    for (int c0 = 0; c0 < ncols; c0 += V.pool_cols) {
+      const int c1 = std::min(ncols, c0 + V.pool_cols);
+      fpb_convmix_columns(a, c0, c1, h->stream);
+      fpb_convmix_redist(a, c0, col_start[c0], col_start[c1], pass, h->stream);
+      h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (nconvecting) {
+    std::vector<int32_t> lc((size_t)ncols);
+    CK(cudaMemcpy(lc.data(), V.col_lconv, lc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int v : lc) k += v > 0;
+    *nconvecting = k;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------- host-buffer step --

@@ -1,0 +1,200 @@
+// fpb_convect.cu -- convmix on the device (src/convmix.f90:60-196, mother grid).
+//
+// The reference sorts the particles by grid column (sort2), walks the sorted list and, whenever a new
+// column starts, interpolates the column's sounding in time and calls calcmatrix (-> the Emanuel
+// scheme); every particle of a convecting column is then moved by redist.  Here:
+//   conv_keys_kernel     column key of every active row (igrid = nint(y)*nx + nint(x), :96-134)
+//   [stable LSD radix sort of (key, row), fpb_scatter.cu]
+//   conv_heads_* kernels run heads -> column index of every sorted position, first position and
+//                        key of every column (block scan)
+//   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + convect
+//                        (fpb_convect.cuh) on the column's slice of a work pool, cbaseflux in/out,
+//                        heights of the eta half levels when the column convects
+//   conv_redist_kernel   one thread per particle of the batch's columns: redist
+// Columns are processed in batches (the work pool holds CONV_BATCH columns, ~200 KB each at 138
+// levels).  Compiled with --fmad=false; the column arithmetic is bit-comparable with the
+// reference's routines in every math mode (see fpb_convect.cuh).
+#include "fpb_convect.cuh"
+#include "fpb_convmix.cuh"
+
+namespace {
+using namespace fpbconv;
+
+constexpr int CB = 1024;
+
+__global__ void __launch_bounds__(256) conv_keys_kernel(const ConvmixArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nrows) return;
+  unsigned key = 0xffffffffu;
+  if (a.p.itra1[i] == a.cfg.itime) {
+    const float x = (float)a.p.xtra1[i], y = (float)a.p.ytra1[i]; // x = xtra1(ipart): real
+    const int ix = (int)roundf(x), jy = (int)roundf(y);           // nint
+    key = (unsigned)(jy * a.cfg.nx + ix);
+  }
+  a.keys[i] = key;
+  a.ids[i] = (unsigned)i;
+  if (a.key_by_slot) a.key_by_slot[a.p.slot[i]] = (key == 0xffffffffu) ? -1 : (int)key + 1; // igrid(ipart)
+}
+
+// heads of the runs of equal keys among the sorted keys
+__global__ void __launch_bounds__(CB) conv_heads_count_kernel(const ConvmixArgs a, const unsigned *keys) {
+  const int i = blockIdx.x * CB + threadIdx.x;
+  const bool head = i < a.nrows && keys[i] != 0xffffffffu && (i == 0 || keys[i - 1] != keys[i]);
+  const int n = __syncthreads_count(head);
+  if (threadIdx.x == 0) a.block_counts[blockIdx.x] = (unsigned)n;
+}
+
+__global__ void __launch_bounds__(CB) conv_scan_blocks_kernel(unsigned *v, int n, int *total) {
+  __shared__ unsigned wtot[32];
+  __shared__ unsigned running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += CB) {
+    const int i = base + threadIdx.x;
+    const unsigned x = (i < n) ? v[i] : 0u;
+    unsigned inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      unsigned t = wtot[lane], ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, ti, d);
+        if (lane >= d) ti += u;
+      }
+      wtot[lane] = ti - t;
+    }
+    __syncthreads();
+    const unsigned excl = running + wtot[w] + inc - x;
+    if (i < n) v[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == CB - 1) running = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = (int)running;
+}
+
+__global__ void __launch_bounds__(CB) conv_heads_assign_kernel(const ConvmixArgs a, const unsigned *keys) {
+  __shared__ unsigned wcnt[32];
+  const int i = blockIdx.x * CB + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool live = i < a.nrows && keys[i] != 0xffffffffu;
+  const bool head = live && (i == 0 || keys[i - 1] != keys[i]);
+  const unsigned bal = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) wcnt[w] = __popc(bal);
+  __syncthreads();
+  if (w == 0) {
+    unsigned t = wcnt[lane], ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += u;
+    }
+    wcnt[lane] = ti - t;
+  }
+  __syncthreads();
+  if (!live) return;
+  // heads up to and including this position
+  const int incl = (int)(a.block_counts[blockIdx.x] + wcnt[w] + __popc(bal & ((2u << lane) - 1u)));
+  const int c = incl - 1;
+  a.colidx[i] = c;
+  if (head) {
+    a.col_key[c] = keys[i];
+    a.col_start[c] = i;
+  }
+  if (i + 1 == a.nrows || keys[i + 1] == 0xffffffffu) a.col_start[incl] = i + 1; // end of the last column
+}
+
+__global__ void __launch_bounds__(64) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  const DevCfg &cf = a.cfg;
+  const int nuvz = a.nuvz;
+  const size_t nfl = conv_pool_floats(nuvz, a.nconvlev);
+  float *pool = a.pool + (size_t)(c - c0) * nfl;
+  const size_t nvec = (size_t)(CONV_NVEC + 1) * (nuvz + 4);
+  for (size_t k = 0; k < nvec; k++) pool[k] = 0.f; // (the reference's zero-initialised locals)
+  ConvWork w;
+  conv_carve(w, pool, nuvz, a.nconvlev);
+  w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
+  const unsigned key = a.col_key[c];
+  const int jy = (int)(key / (unsigned)cf.nx), ix = (int)(key - (unsigned)jy * cf.nx);
+  // src/convmix.f90:62-65,163-171
+  const float dt1 = (float)(cf.itime - cf.memtime[0]), dt2 = (float)(cf.memtime[1] - cf.itime);
+  const float dtt = 1.f / (dt1 + dt2);
+  const size_t o2 = (size_t)jy * cf.nxd + ix, plane = (size_t)cf.nxd * cf.nyd;
+  const float4 s1 = a.CS[0][o2], s2 = a.CS[1][o2];
+  w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
+  w.tt2conv = (s1.y * dt2 + s2.y * dt1) * dtt;
+  w.td2conv = (s1.z * dt2 + s2.z * dt1) * dtt;
+  for (int kz = 1; kz <= nuvz - 1; kz++) {
+    const float2 q1 = a.CT[0][(size_t)kz * plane + o2], q2 = a.CT[1][(size_t)kz * plane + o2]; // level kz+1
+    w.tconv[kz] = (q1.x * dt2 + q2.x * dt1) * dtt;
+    w.qconv[kz] = (q1.y * dt2 + q2.y * dt1) * dtt;
+  }
+  float cbmf = a.cbaseflux[o2];
+  const bool lconv = conv_calcmatrix(w, (float)abs(cf.lsynctime), cbmf);
+  a.cbaseflux[o2] = cbmf;
+  a.col_lconv[c] = lconv ? w.nconvtop : 0;
+  if (lconv) conv_uvzlev(w);
+}
+
+// mode 0: mark the particles that will draw a uniform (reference RNG replay); 1: redistribute
+__global__ void __launch_bounds__(128) conv_redist_kernel(const ConvmixArgs a, int c0, int i0, int i1, int mode) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  const DevCfg &cf = a.cfg;
+  const int c = a.colidx[i];
+  const int nconvtop = a.col_lconv[c];
+  if (nconvtop == 0) return; // the column does not convect
+  ConvWork w;
+  conv_carve(w, a.pool + (size_t)(c - c0) * conv_pool_floats(a.nuvz, a.nconvlev), a.nuvz, a.nconvlev);
+  w.nconvtop = nconvtop;
+  const int row = (int)a.sorted_ids[i];
+  const int slot = a.p.slot[row];
+  float z = a.p.ztra1[row];
+  const int levold = conv_levold(w, z);
+  if (mode == 0) {
+    a.draws[slot] = levold > 0 ? 1 : 0;
+    return;
+  }
+  if (levold > 0) {
+    float rn;
+    if (a.rn_by_slot) {
+      rn = a.rn_by_slot[slot];
+    } else { // counter stream of the particle (stream 48), src/redist.f90:140 `rn = ran3(iseed)`
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)(cf.part_id_offset + cf.part_id_stride * slot),
+                                               (uint32_t)cf.itime, 48u, 0u),
+                                    make_uint2((uint32_t)cf.seed, (uint32_t)(cf.seed >> 32)));
+      rn = u01(r.x);
+    }
+    z = conv_redist(w, z, levold, rn, cf.ldirect, cf.lsynctime);
+  }
+  if (z > a.ztop - 0.5f) z = a.ztop - 0.5f; // label 90
+  a.p.ztra1[row] = z;
+}
+
+} // namespace
+
+void fpb_convmix_keys(const ConvmixArgs &a, cudaStream_t st) {
+  conv_keys_kernel<<<(a.nrows + 255) / 256, 256, 0, st>>>(a);
+}
+void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *total, cudaStream_t st) {
+  const int nb = (a.nrows + CB - 1) / CB;
+  conv_heads_count_kernel<<<nb, CB, 0, st>>>(a, sorted_keys);
+  conv_scan_blocks_kernel<<<1, CB, 0, st>>>(a.block_counts, nb, total);
+  conv_heads_assign_kernel<<<nb, CB, 0, st>>>(a, sorted_keys);
+}
+void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) {
+  conv_column_kernel<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(a, c0, c1);
+}
+void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st) {
+  if (i1 > i0) conv_redist_kernel<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(a, c0, i0, i1, mode);
+}
+size_t fpb_convmix_pool_floats(int nuvz, int nconvlev) { return fpbconv::conv_pool_floats(nuvz, nconvlev); }

@@ -1,0 +1,697 @@
+// fpb_convect.cuh -- the column part of FLEXPART's convective mixing, one grid column per thread:
+//   conv_calcmatrix   src/calcmatrix.f90:45-135   pressures, saturation humidity, the call of the
+//                                                 Emanuel scheme, the redistribution matrix fmassfrac
+//   conv_convect      src/convect43c.f90:11-972   Emanuel (2002) convection scheme 4.3c as FLEXPART
+//                                                 carries it: saturated up/downdraft mass fluxes
+//                                                 between all level pairs (FMASS) and the
+//                                                 compensating subsidence (SUB)
+//   conv_tlift        src/convect43c.f90:974-1090 lifted-parcel temperature / condensate
+//   conv_qvsat, conv_ew   src/qvsat.f90, src/ew.f90
+//   conv_uvzlev       src/redist.f90:63-118       heights of the eta half levels of the column
+//   conv_redist       src/redist.f90:120-237      new height of one particle: destination level drawn
+//                                                 from the matrix row (column for backward runs),
+//                                                 or displacement by the compensating subsidence
+// The reference keeps the column in module conv_mod and convect's work arrays on the stack; here
+// both live in a per-column slice of a global-memory pool (ConvWork).  All arithmetic is the
+// reference's, statement by statement, evaluated like the validation build of the other kernels
+// (no FMA contraction, exp/log/pow evaluated in double and rounded once), so the result is
+// bit-comparable with the reference's own routine (oracle/_ref).  Written for nvcc and, for the
+// CPU-side cross-check of tests/test_convection.py only, for g++ (FPB_CONV_HOST).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FPB_HD __host__ __device__
+#else
+#define FPB_HD
+#endif
+
+namespace fpbconv {
+
+FPB_HD inline float c_exp(float x) { return (float)exp((double)x); }
+FPB_HD inline float c_log(float x) { return (float)log((double)x); }
+FPB_HD inline float c_pow(float a, float b) { return (float)pow((double)a, (double)b); }
+FPB_HD inline float c_sqrt(float x) { return sqrtf(x); }
+FPB_HD inline float c_max(float a, float b) { return a > b ? a : b; }
+FPB_HD inline float c_min(float a, float b) { return a < b ? a : b; }
+FPB_HD inline float c_powi(float x, int m) { // real**integer as libgcc's __powisf2 (what gfortran emits)
+  unsigned n = (unsigned)(m < 0 ? -m : m);
+  float y = (n % 2) ? x : 1.f;
+  while (n >>= 1) {
+    x = x * x;
+    if (n % 2) y = y * x;
+  }
+  return m < 0 ? 1.f / y : y;
+}
+
+// One column: conv_mod's arrays + convect's work arrays.  Vectors are 1-based (element i at [i]),
+// matrices Fortran-ordered: (i,j) at [i + ld*j].
+struct ConvWork {
+  int nuvz, nconvlev, ld;
+  const float *akz, *bkz, *akm, *bkm; // 1-based hybrid coefficients (src/com_mod.f90, akz(nuvz) ...)
+  // conv_mod
+  float *pconv, *phconv, *dpr, *pconv_hpa, *phconv_hpa, *tconv, *qconv, *qsconv, *ft, *fq, *sub;
+  float *fmass; // after conv_calcmatrix: fmassfrac (fmassfrac(k,kk) = delt*fmass(k,kk) + diagonal)
+  float psconv, tt2conv, td2conv;
+  int nconvtop;
+  // convect locals
+  float *fup, *fdown, *m, *mp, *tvp, *tv, *water, *qp, *ep, *th, *wt, *evap, *clw, *sigp, *tp, *cpn, *lv, *lvcp,
+      *h, *hp, *gz, *hm, *uvzlev;
+  int *nent;
+  float *ment, *qent, *elij, *sij;
+};
+
+constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more vector)
+
+FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
+  const size_t lv = (size_t)nuvz + 4, ld = (size_t)nconvlev + 3;
+  return (CONV_NVEC + 1) * lv + 5 * ld * ld;
+}
+
+// carve the column's slice of the pool
+FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev) {
+  const size_t lv = (size_t)nuvz + 4;
+  w.nuvz = nuvz; w.nconvlev = nconvlev; w.ld = nconvlev + 3;
+  float **vec[CONV_NVEC] = {&w.pconv, &w.phconv, &w.dpr, &w.pconv_hpa, &w.phconv_hpa, &w.tconv, &w.qconv, &w.qsconv,
+                            &w.ft, &w.fq, &w.sub, &w.fup, &w.fdown, &w.m, &w.mp, &w.tvp, &w.tv, &w.water, &w.qp,
+                            &w.ep, &w.th, &w.wt, &w.evap, &w.clw, &w.sigp, &w.tp, &w.cpn, &w.lv, &w.lvcp, &w.h,
+                            &w.hp, &w.gz, &w.hm, &w.uvzlev, nullptr};
+  float *p = pool;
+  for (int k = 0; k < CONV_NVEC - 1; k++) { *vec[k] = p; p += lv; }
+  w.nent = reinterpret_cast<int *>(p); p += lv;
+  p += lv; // (spare)
+  const size_t ld2 = (size_t)w.ld * w.ld;
+  w.fmass = p; p += ld2;
+  w.ment = p; p += ld2;
+  w.qent = p; p += ld2;
+  w.elij = p; p += ld2;
+  w.sij = p;
+}
+
+#define CV(a, i) w.a[(i)]
+#define CM(a, i, j) w.a[(i) + w.ld * (j)]
+
+// src/ew.f90: saturation vapour pressure over water [Pa] (Goff-Gratch)
+FPB_HD inline float conv_ew(float x) {
+  float y = 373.16f / x;
+  float a = -7.90298f * (y - 1.f);
+  a = a + (5.02808f * 0.43429f * c_log(y));
+  float c = (1.f - (1.f / y)) * 11.344f;
+  c = -1.f + c_pow(10.f, c);
+  c = -1.3816f * c / c_powi(10.f, 7);
+  float d = (1.f - y) * 3.49149f;
+  d = -1.f + c_pow(10.f, d);
+  d = 8.1328f * d / c_powi(10.f, 3);
+  y = a + c + d;
+  return 101324.6f * c_pow(10.f, y);
+}
+
+// src/qvsat.f90: f_qvsat with f_esl / f_esi
+FPB_HD inline float conv_qvsat(float p, float t) {
+  const float rddrv = 287.0f / 461.0f;
+  float fespt;
+  if (t >= 253.15f) {
+    const float f = 1.0007f + 3.46e-8f * p;
+    fespt = f * 611.21f * c_exp(17.502f * (t - 273.15f) / (t - 32.18f));
+  } else {
+    const float f = 1.0003f + 4.18e-8f * p;
+    fespt = f * 611.15f * c_exp(22.452f * (t - 273.15f) / (t - 0.6f));
+  }
+  if (p - (1.0f - rddrv) * fespt == 0.f) return 1.f;
+  return rddrv * fespt / (p - (1.0f - rddrv) * fespt);
+}
+
+namespace k { // thermodynamic constants of convect / tlift, src/convect43c.f90:262-275
+constexpr float CPD = 1005.7f, CPV = 1870.0f, CL = 2500.0f, RV = 461.5f, RD = 287.04f, LV0 = 2.501e6f, G = 9.81f,
+                ROWL = 1000.0f, CPVMCL = CL - CPV, EPS0 = RD / RV, EPSI = 1.f / EPS0, GINV = 1.0f / G, EPSILON = 1.e-20f;
+}
+
+// src/convect43c.f90:974-1090
+FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
+  using namespace k;
+  const float qnk = CV(qconv, nk), tnk = CV(tconv, nk);
+  const float ah0 = (CPD * (1.f - qnk) + CL * qnk) * tnk + qnk * (LV0 - CPVMCL * (tnk - 273.15f)) + CV(gz, nk);
+  const float cpp = CPD * (1.f - qnk) + qnk * CPV;
+  const float cpinv = 1.f / cpp;
+  if (kk == 1) {
+    for (int i = 1; i <= icb - 1; i++) CV(clw, i) = 0.0f;
+    for (int i = nk; i <= icb - 1; i++) {
+      CV(tp, i) = tnk - (CV(gz, i) - CV(gz, nk)) * cpinv;
+      CV(tvp, i) = CV(tp, i) * (1.f + qnk * EPSI);
+    }
+  }
+  int nst = icb, nsb = icb;
+  if (kk == 2) {
+    nst = nl;
+    nsb = icb + 1;
+  }
+  for (int i = nsb; i <= nst; i++) {
+    float tg = CV(tconv, i), qg = CV(qsconv, i);
+    float alv = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
+    for (int j = 1; j <= 2; j++) {
+      float s = CPD + alv * alv * qg / (RV * CV(tconv, i) * CV(tconv, i));
+      s = 1.f / s;
+      const float ahg = CPD * tg + (CL - CPD) * qnk * CV(tconv, i) + alv * qg + CV(gz, i);
+      tg = tg + s * (ah0 - ahg);
+      tg = c_max(tg, 35.0f);
+      const float tc = tg - 273.15f;
+      const float denom = 243.5f + tc;
+      float es;
+      if (tc >= 0.0f) es = 6.112f * c_exp(17.67f * tc / denom);
+      else es = c_exp(23.33086f - 6111.72784f / tg + 0.15215f * c_log(tg));
+      qg = EPS0 * es / (CV(pconv_hpa, i) - es * (1.f - EPS0));
+    }
+    alv = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
+    CV(tp, i) = (ah0 - (CL - CPD) * qnk * CV(tconv, i) - CV(gz, i) - alv * qg) / CPD;
+    CV(clw, i) = qnk - qg;
+    CV(clw, i) = c_max(0.0f, CV(clw, i));
+    const float rg = qg / (1.f - qnk);
+    CV(tvp, i) = CV(tp, i) * (1.f + rg * EPSI);
+  }
+}
+
+// src/convect43c.f90:11-972.  nl = nconvlev; cbmf in/out; returns iflag.
+FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
+  using namespace k;
+  const int MINORIG = 1;
+  const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, SIGD = 0.05f, SIGS = 0.12f, OMTRAIN = 50.0f,
+              OMTSNOW = 5.5f, COEFFR = 1.0f, COEFFS = 0.8f, BETA = 10.0f, DTMAX = 0.9f, ALPHA = 0.025f, DAMP = 0.1f;
+  int iflag;
+  const float delti = 1.0f / delt;
+  (void)BETA;
+
+  for (int i = 1; i <= nl + 1; i++) {
+    CV(ft, i) = 0.0f; CV(fq, i) = 0.0f; CV(fdown, i) = 0.0f; CV(sub, i) = 0.0f; CV(fup, i) = 0.0f;
+    CV(m, i) = 0.0f; CV(mp, i) = 0.0f;
+    for (int j = 1; j <= nl + 1; j++) {
+      CM(fmass, i, j) = 0.0f;
+      CM(ment, i, j) = 0.0f;
+    }
+  }
+  for (int i = 1; i <= nl + 1; i++) {
+    const float q = CV(qconv, i);
+    const float rdcp = (RD * (1.f - q) + q * RV) / (CPD * (1.f - q) + q * CPV);
+    CV(th, i) = CV(tconv, i) * c_pow(1000.0f / CV(pconv_hpa, i), rdcp);
+  }
+  float precip = 0.0f;
+  iflag = 0;
+
+  // geopotential, heat capacity, static energies (:413-437)
+  CV(gz, 1) = 0.0f;
+  CV(cpn, 1) = CPD * (1.f - CV(qconv, 1)) + CV(qconv, 1) * CPV;
+  CV(h, 1) = CV(tconv, 1) * CV(cpn, 1);
+  CV(lv, 1) = LV0 - CPVMCL * (CV(tconv, 1) - 273.15f);
+  CV(hm, 1) = CV(lv, 1) * CV(qconv, 1);
+  CV(tv, 1) = CV(tconv, 1) * (1.f + CV(qconv, 1) * EPSI - CV(qconv, 1));
+  float ahmin = 1.0e12f;
+  int ihmin = nl;
+  for (int i = 2; i <= nl + 1; i++) {
+    const float tvx = CV(tconv, i) * (1.f + CV(qconv, i) * EPSI - CV(qconv, i));
+    const float tvy = CV(tconv, i - 1) * (1.f + CV(qconv, i - 1) * EPSI - CV(qconv, i - 1));
+    CV(gz, i) = CV(gz, i - 1) + 0.5f * RD * (tvx + tvy) * (CV(pconv_hpa, i - 1) - CV(pconv_hpa, i)) / CV(phconv_hpa, i);
+    CV(cpn, i) = CPD * (1.f - CV(qconv, i)) + CPV * CV(qconv, i);
+    CV(h, i) = CV(tconv, i) * CV(cpn, i) + CV(gz, i);
+    CV(lv, i) = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
+    CV(hm, i) = (CPD * (1.f - CV(qconv, i)) + CL * CV(qconv, i)) * (CV(tconv, i) - CV(tconv, 1)) +
+                CV(lv, i) * CV(qconv, i) + CV(gz, i);
+    CV(tv, i) = CV(tconv, i) * (1.f + CV(qconv, i) * EPSI - CV(qconv, i));
+    if (i >= MINORIG && CV(hm, i) < ahmin && CV(hm, i) < CV(hm, i - 1)) {
+      ahmin = CV(hm, i);
+      ihmin = i;
+    }
+  }
+  ihmin = ihmin < nl - 1 ? ihmin : nl - 1;
+  float ahmax = 0.0f;
+  int nk = MINORIG;
+  for (int i = MINORIG; i <= ihmin; i++)
+    if (CV(hm, i) > ahmax) {
+      nk = i;
+      ahmax = CV(hm, i);
+    }
+  if (CV(tconv, nk) < 250.0f || CV(qconv, nk) <= 0.0f || ihmin == (nl - 1)) {
+    cbmf = 0.0f;
+    return 0;
+  }
+  // lifted condensation level (:464-471)
+  const float rh = CV(qconv, nk) / CV(qsconv, nk);
+  const float chi = CV(tconv, nk) / (1669.0f - 122.0f * rh - CV(tconv, nk));
+  const float plcl = CV(pconv_hpa, nk) * c_pow(rh, chi);
+  if (plcl < 200.0f || plcl >= 2000.0f) {
+    cbmf = 0.0f;
+    return 2;
+  }
+  int icb = nl - 1;
+  for (int i = nk + 1; i <= nl; i++)
+    if (CV(pconv_hpa, i) < plcl) icb = icb < i ? icb : i;
+  if (icb >= (nl - 1)) {
+    cbmf = 0.0f;
+    return 3;
+  }
+  conv_tlift(w, icb, nk, nl, 1);
+  for (int i = nk; i <= icb; i++) CV(tvp, i) = CV(tvp, i) - CV(tp, i) * CV(qconv, nk);
+  if (cbmf == 0.0f && CV(tvp, icb) <= (CV(tv, icb) - DTMAX)) return 0;
+  if (iflag != 4) iflag = 1;
+  conv_tlift(w, icb, nk, nl, 2);
+  // precipitation efficiencies (:503-520)
+  for (int i = 1; i <= nk; i++) {
+    CV(ep, i) = 0.0f;
+    CV(sigp, i) = SIGS;
+  }
+  for (int i = nk + 1; i <= nl; i++) {
+    const float tca = CV(tp, i) - 273.15f;
+    float elacrit;
+    if (tca >= 0.0f) elacrit = ELCRIT;
+    else elacrit = ELCRIT * (1.0f - tca / TLCRIT);
+    elacrit = c_max(elacrit, 0.0f);
+    const float epmax = 0.999f;
+    CV(ep, i) = epmax * (1.0f - elacrit / c_max(CV(clw, i), 1.0e-8f));
+    CV(ep, i) = c_max(CV(ep, i), 0.0f);
+    CV(ep, i) = c_min(CV(ep, i), epmax);
+    CV(sigp, i) = SIGS;
+  }
+  for (int i = icb + 1; i <= nl; i++) CV(tvp, i) = CV(tvp, i) - CV(tp, i) * CV(qconv, nk);
+  CV(tvp, nl + 1) = CV(tvp, nl) - (CV(gz, nl + 1) - CV(gz, nl)) / CPD;
+  // initialise the work arrays (:529-545)
+  for (int i = 1; i <= nl + 1; i++) {
+    CV(hp, i) = CV(h, i);
+    CV(nent, i) = 0;
+    CV(water, i) = 0.0f;
+    CV(evap, i) = 0.0f;
+    CV(wt, i) = OMTSNOW;
+    CV(lvcp, i) = CV(lv, i) / CV(cpn, i);
+    for (int j = 1; j <= nl + 1; j++) {
+      CM(qent, i, j) = CV(qconv, j);
+      CM(elij, i, j) = 0.0f;
+      CM(sij, i, j) = 0.0f;
+    }
+  }
+  CV(qp, 1) = CV(qconv, 1);
+  for (int i = 2; i <= nl + 1; i++) CV(qp, i) = CV(qconv, i - 1);
+  // level of neutral buoyancy (:549-573)
+  float cape = 0.0f, capem = 0.0f, byp = 0.0f;
+  int inb = icb + 1, inb1 = inb;
+  for (int i = icb + 1; i <= nl - 1; i++) {
+    const float by = (CV(tvp, i) - CV(tv, i)) * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) / CV(pconv_hpa, i);
+    cape = cape + by;
+    if (by >= 0.0f) inb1 = i + 1;
+    if (cape > 0.0f) {
+      inb = i + 1;
+      byp = (CV(tvp, i + 1) - CV(tv, i + 1)) * (CV(phconv_hpa, i + 1) - CV(phconv_hpa, i + 2)) / CV(pconv_hpa, i + 1);
+      capem = cape;
+    }
+  }
+  inb = inb > inb1 ? inb : inb1;
+  cape = capem + byp;
+  float defrac = capem - cape;
+  defrac = c_max(defrac, 0.001f);
+  float frac = -cape / defrac;
+  frac = c_min(frac, 1.0f);
+  frac = c_max(frac, 0.0f);
+  for (int i = icb; i <= inb; i++)
+    CV(hp, i) = CV(h, nk) + (CV(lv, i) + (CPD - CPV) * CV(tconv, i)) * CV(ep, i) * CV(clw, i);
+  // cloud base mass flux (:583-611)
+  float dbosum = 0.0f;
+  const float tvpplcl = CV(tvp, icb - 1) - RD * CV(tvp, icb - 1) * (CV(pconv_hpa, icb - 1) - plcl) /
+                                               (CV(cpn, icb - 1) * CV(pconv_hpa, icb - 1));
+  const float tvaplcl = CV(tv, icb) + (CV(tvp, icb) - CV(tvp, icb + 1)) * (plcl - CV(pconv_hpa, icb)) /
+                                          (CV(pconv_hpa, icb) - CV(pconv_hpa, icb + 1));
+  float dtpbl = 0.0f;
+  for (int i = nk; i <= icb - 1; i++)
+    dtpbl = dtpbl + (CV(tvp, i) - CV(tv, i)) * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1));
+  dtpbl = dtpbl / (CV(phconv_hpa, nk) - CV(phconv_hpa, icb));
+  const float dtmin = tvpplcl - tvaplcl + DTMAX + dtpbl;
+  const float dtma = dtmin;
+  const float cbmfold = cbmf;
+  const float delt0 = delt / 3.f;
+  const float damps = DAMP * delt / delt0;
+  cbmf = (1.f - damps) * cbmf + 0.1f * ALPHA * dtma;
+  cbmf = c_max(cbmf, 0.0f);
+  if (cbmf == 0.0f && cbmfold == 0.0f) return iflag;
+  // rates of mixing (:621-631)
+  CV(m, icb) = 0.0f;
+  for (int i = icb + 1; i <= inb; i++) {
+    const int kq = i < inb1 ? i : inb1;
+    const float dbo = fabsf(CV(tv, kq) - CV(tvp, kq)) + ENTP * 0.02f * (CV(phconv_hpa, kq) - CV(phconv_hpa, kq + 1));
+    dbosum = dbosum + dbo;
+    CV(m, i) = cbmf * dbo;
+  }
+  for (int i = icb + 1; i <= inb; i++) CV(m, i) = CV(m, i) / dbosum;
+  // entrained air mass flux, mixing fractions (:636-682)
+  for (int i = icb + 1; i <= inb; i++) {
+    const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+    for (int j = icb; j <= inb; j++) {
+      const float bf2 = 1.f + CV(lv, j) * CV(lv, j) * CV(qsconv, j) / (RV * CV(tconv, j) * CV(tconv, j) * CPD);
+      float anum = CV(h, j) - CV(hp, i) + (CPV - CPD) * CV(tconv, j) * (qti - CV(qconv, j));
+      float denom = CV(h, i) - CV(hp, i) + (CPD - CPV) * (CV(qconv, i) - qti) * CV(tconv, j);
+      float dei = denom;
+      if (fabsf(dei) < 0.01f) dei = 0.01f;
+      CM(sij, i, j) = anum / dei;
+      CM(sij, i, i) = 1.0f;
+      float altem = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti - CV(qsconv, j);
+      altem = altem / bf2;
+      const float cwat = CV(clw, j) * (1.f - CV(ep, j));
+      const float stemp = CM(sij, i, j);
+      if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
+        anum = anum - CV(lv, j) * (qti - CV(qsconv, j) - cwat * bf2);
+        denom = denom + CV(lv, j) * (CV(qconv, i) - qti);
+        if (fabsf(denom) < 0.01f) denom = 0.01f;
+        CM(sij, i, j) = anum / denom;
+        altem = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti - CV(qsconv, j);
+        altem = altem - (bf2 - 1.f) * cwat;
+      }
+      if (CM(sij, i, j) > 0.0f && CM(sij, i, j) < 0.9f) {
+        CM(qent, i, j) = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti;
+        CM(elij, i, j) = altem;
+        CM(elij, i, j) = c_max(0.0f, CM(elij, i, j));
+        CM(ment, i, j) = CV(m, i) / (1.f - CM(sij, i, j));
+        CV(nent, i) = CV(nent, i) + 1;
+      }
+      CM(sij, i, j) = c_max(0.0f, CM(sij, i, j));
+      CM(sij, i, j) = c_min(1.0f, CM(sij, i, j));
+    }
+    if (CV(nent, i) == 0) {
+      CM(ment, i, i) = CV(m, i);
+      CM(qent, i, i) = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+      CM(elij, i, i) = CV(clw, i);
+      CM(sij, i, i) = 1.0f;
+    }
+  }
+  CM(sij, inb, inb) = 1.0f;
+  // normalise the entrained fluxes (:686-746)
+  for (int i = icb + 1; i <= inb; i++) {
+    if (CV(nent, i) != 0) {
+      const float qp1 = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+      const float anum = CV(h, i) - CV(hp, i) - CV(lv, i) * (qp1 - CV(qsconv, i));
+      float denom = CV(h, i) - CV(hp, i) + CV(lv, i) * (CV(qconv, i) - qp1);
+      if (fabsf(denom) < 0.01f) denom = 0.01f;
+      float scrit = anum / denom;
+      const float alt = qp1 - CV(qsconv, i) + scrit * (CV(qconv, i) - qp1);
+      if (alt < 0.0f) scrit = 1.0f;
+      scrit = c_max(scrit, 0.0f);
+      float asij = 0.0f, smin = 1.0f;
+      for (int j = icb; j <= inb; j++) {
+        if (CM(sij, i, j) > 0.0f && CM(sij, i, j) < 0.9f) {
+          float smid, sjmax, sjmin;
+          if (j > i) {
+            smid = c_min(CM(sij, i, j), scrit);
+            sjmax = smid;
+            sjmin = smid;
+            if (smid < smin && CM(sij, i, j + 1) < smid) {
+              smin = smid;
+              sjmax = c_min(c_min(CM(sij, i, j + 1), CM(sij, i, j)), scrit);
+              sjmin = c_max(CM(sij, i, j - 1), CM(sij, i, j));
+              sjmin = c_min(sjmin, scrit);
+            }
+          } else {
+            sjmax = c_max(CM(sij, i, j + 1), scrit);
+            smid = c_max(CM(sij, i, j), scrit);
+            sjmin = 0.0f;
+            if (j > 1) sjmin = CM(sij, i, j - 1);
+            sjmin = c_max(sjmin, scrit);
+          }
+          const float delp = fabsf(sjmax - smid);
+          const float delm = fabsf(sjmin - smid);
+          asij = asij + (delp + delm) * (CV(phconv_hpa, j) - CV(phconv_hpa, j + 1));
+          CM(ment, i, j) = CM(ment, i, j) * (delp + delm) * (CV(phconv_hpa, j) - CV(phconv_hpa, j + 1));
+        }
+      }
+      asij = c_max(1.0e-21f, asij);
+      asij = 1.0f / asij;
+      for (int j = icb; j <= inb; j++) CM(ment, i, j) = CM(ment, i, j) * asij;
+      float bsum = 0.0f;
+      for (int j = icb; j <= inb; j++) bsum = bsum + CM(ment, i, j);
+      if (bsum < 1.0e-18f) {
+        CV(nent, i) = 0;
+        CM(ment, i, i) = CV(m, i);
+        CM(qent, i, i) = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+        CM(elij, i, i) = CV(clw, i);
+        CM(sij, i, i) = 1.0f;
+      }
+    }
+  }
+  // precipitating downdraft (:750-842)
+  if (!(CV(ep, inb) < 0.0001f)) {
+    int jtt = 2;
+    for (int i = inb; i >= 1; i--) {
+      float wdtrain = G * CV(ep, i) * CV(m, i) * CV(clw, i);
+      if (i > 1) {
+        for (int j = 1; j <= i - 1; j++) {
+          float awat = CM(elij, j, i) - (1.f - CV(ep, i)) * CV(clw, i);
+          awat = c_max(0.0f, awat);
+          wdtrain = wdtrain + G * awat * CM(ment, j, i);
+        }
+      }
+      float coeff = COEFFS;
+      CV(wt, i) = OMTSNOW;
+      if (CV(tconv, i) > 273.0f) {
+        coeff = COEFFR;
+        CV(wt, i) = OMTRAIN;
+      }
+      const float qsm = 0.5f * (CV(qconv, i) + CV(qp, i + 1));
+      float afac = coeff * CV(phconv_hpa, i) * (CV(qsconv, i) - qsm) / (1.0e4f + 2.0e3f * CV(phconv_hpa, i) * CV(qsconv, i));
+      afac = c_max(afac, 0.0f);
+      float sigt = CV(sigp, i);
+      sigt = c_max(0.0f, sigt);
+      sigt = c_min(1.0f, sigt);
+      const float b6 = 100.f * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) * sigt * afac / CV(wt, i);
+      const float c6 = (CV(water, i + 1) * CV(wt, i + 1) + wdtrain / SIGD) / CV(wt, i);
+      const float revap = 0.5f * (-b6 + c_sqrt(b6 * b6 + 4.f * c6));
+      CV(evap, i) = sigt * afac * revap;
+      CV(water, i) = revap * revap;
+      if (i != 1) {
+        float dhdp = (CV(h, i) - CV(h, i - 1)) / (CV(pconv_hpa, i - 1) - CV(pconv_hpa, i));
+        dhdp = c_max(dhdp, 10.0f);
+        CV(mp, i) = 100.f * GINV * CV(lv, i) * SIGD * CV(evap, i) / dhdp;
+        CV(mp, i) = c_max(CV(mp, i), 0.0f);
+        const float fac = 20.0f / (CV(phconv_hpa, i - 1) - CV(phconv_hpa, i));
+        CV(mp, i) = (fac * CV(mp, i + 1) + CV(mp, i)) / (1.f + fac);
+        if (CV(pconv_hpa, i) > (0.949f * CV(pconv_hpa, 1))) {
+          jtt = jtt > i ? jtt : i;
+          CV(mp, i) = CV(mp, jtt) * (CV(pconv_hpa, 1) - CV(pconv_hpa, i)) / (CV(pconv_hpa, 1) - CV(pconv_hpa, jtt));
+        }
+      }
+      if (i == inb) continue; // label 400
+      float qstm;
+      if (i == 1) qstm = CV(qsconv, 1);
+      else qstm = CV(qsconv, i - 1);
+      if (CV(mp, i) > CV(mp, i + 1)) {
+        const float rat = CV(mp, i + 1) / CV(mp, i);
+        CV(qp, i) = CV(qp, i + 1) * rat + CV(qconv, i) * (1.0f - rat) +
+                    100.f * GINV * SIGD * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) * (CV(evap, i) / CV(mp, i));
+      } else {
+        if (CV(mp, i + 1) > 0.0f)
+          CV(qp, i) = (CV(gz, i + 1) - CV(gz, i) + CV(qp, i + 1) * (CV(lv, i + 1) + CV(tconv, i + 1) * (CL - CPD)) +
+                       CPD * (CV(tconv, i + 1) - CV(tconv, i))) /
+                      (CV(lv, i) + CV(tconv, i) * (CL - CPD));
+      }
+      CV(qp, i) = c_min(CV(qp, i), qstm);
+      CV(qp, i) = c_max(CV(qp, i), 0.0f);
+    }
+    precip = precip + CV(wt, 1) * SIGD * CV(water, 1) * 3600.f * 24000.f / (ROWL * G);
+  }
+  (void)precip;
+  // tendencies of the lowest level (:855-872)   (wd, tprime, qprime are not used by FLEXPART)
+  float dpinv = 0.01f / (CV(phconv_hpa, 1) - CV(phconv_hpa, 2));
+  float am = 0.0f;
+  if (nk == 1)
+    for (int kq = 2; kq <= inb; kq++) am = am + CV(m, kq);
+  CV(fup, 1) = am;
+  if ((2.f * G * dpinv * am) >= delti) iflag = 4;
+  CV(ft, 1) = CV(ft, 1) + G * dpinv * am * (CV(tconv, 2) - CV(tconv, 1) + (CV(gz, 2) - CV(gz, 1)) / CV(cpn, 1));
+  CV(ft, 1) = CV(ft, 1) - CV(lvcp, 1) * SIGD * CV(evap, 1);
+  CV(ft, 1) = CV(ft, 1) + SIGD * CV(wt, 2) * (CL - CPD) * CV(water, 2) * (CV(tconv, 2) - CV(tconv, 1)) * dpinv / CV(cpn, 1);
+  CV(fq, 1) = CV(fq, 1) + G * CV(mp, 2) * (CV(qp, 2) - CV(qconv, 1)) * dpinv + SIGD * CV(evap, 1);
+  CV(fq, 1) = CV(fq, 1) + G * am * (CV(qconv, 2) - CV(qconv, 1)) * dpinv;
+  for (int j = 2; j <= inb; j++) CV(fq, 1) = CV(fq, 1) + G * dpinv * CM(ment, j, 1) * (CM(qent, j, 1) - CV(qconv, 1));
+  // levels above (:877-930): net saturated up- and downdraft mass fluxes through each level
+  for (int i = 2; i <= inb; i++) {
+    dpinv = 0.01f / (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1));
+    const float cpinv = 1.0f / CV(cpn, i);
+    float amp1 = 0.0f, ad = 0.0f;
+    if (i >= nk)
+      for (int kq = i + 1; kq <= inb + 1; kq++) amp1 = amp1 + CV(m, kq);
+    for (int kq = 1; kq <= i; kq++)
+      for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + CM(ment, kq, j);
+    CV(fup, i) = amp1;
+    if ((2.f * G * dpinv * amp1) >= delti) iflag = 4;
+    for (int kq = 1; kq <= i - 1; kq++)
+      for (int j = i; j <= inb; j++) ad = ad + CM(ment, j, kq);
+    CV(fdown, i) = ad;
+    CV(ft, i) = CV(ft, i) +
+                G * dpinv * (amp1 * (CV(tconv, i + 1) - CV(tconv, i) + (CV(gz, i + 1) - CV(gz, i)) * cpinv) -
+                             ad * (CV(tconv, i) - CV(tconv, i - 1) + (CV(gz, i) - CV(gz, i - 1)) * cpinv)) -
+                SIGD * CV(lvcp, i) * CV(evap, i);
+    CV(ft, i) = CV(ft, i) + G * dpinv * CM(ment, i, i) *
+                                (CV(hp, i) - CV(h, i) + CV(tconv, i) * (CPV - CPD) * (CV(qconv, i) - CM(qent, i, i))) * cpinv;
+    CV(ft, i) = CV(ft, i) + SIGD * CV(wt, i + 1) * (CL - CPD) * CV(water, i + 1) * (CV(tconv, i + 1) - CV(tconv, i)) * dpinv * cpinv;
+    CV(fq, i) = CV(fq, i) + G * dpinv * (amp1 * (CV(qconv, i + 1) - CV(qconv, i)) - ad * (CV(qconv, i) - CV(qconv, i - 1)));
+    for (int kq = 1; kq <= i - 1; kq++) {
+      float awat = CM(elij, kq, i) - (1.f - CV(ep, i)) * CV(clw, i);
+      awat = c_max(awat, 0.0f);
+      CV(fq, i) = CV(fq, i) + G * dpinv * CM(ment, kq, i) * (CM(qent, kq, i) - awat - CV(qconv, i));
+    }
+    for (int kq = i; kq <= inb; kq++) CV(fq, i) = CV(fq, i) + G * dpinv * CM(ment, kq, i) * (CM(qent, kq, i) - CV(qconv, i));
+    CV(fq, i) = CV(fq, i) + SIGD * CV(evap, i) +
+                G * (CV(mp, i + 1) * (CV(qp, i + 1) - CV(qconv, i)) - CV(mp, i) * (CV(qp, i) - CV(qconv, i - 1))) * dpinv;
+  }
+  // (the adjustments of ft / fq at the top of the convection layer and the enthalpy correction,
+  //  :934-956, only change FT and FQ, which FLEXPART does not read: left out)
+  (void)frac;
+  // mass displacement matrix and compensating subsidence (:972-989)
+  CV(sub, 1) = 0.f;
+  int nconvtop = 1;
+  for (int i = 1; i <= inb + 1; i++) {
+    for (int j = 1; j <= inb + 1; j++) {
+      if (j == nk) CM(fmass, j, i) = CM(fmass, j, i) + CV(m, i);
+      CM(fmass, j, i) = CM(fmass, j, i) + CM(ment, j, i);
+      if (CM(fmass, j, i) > EPSILON) {
+        nconvtop = nconvtop > i ? nconvtop : i;
+        nconvtop = nconvtop > j ? nconvtop : j;
+      }
+    }
+    if (i > 1) CV(sub, i) = CV(fup, i - 1) - CV(fdown, i);
+  }
+  w.nconvtop = nconvtop + 1;
+  return iflag;
+}
+
+// src/calcmatrix.f90:45-135 (ECMWF branch).  cbmf = cbaseflux(ix,jy), in/out.  Returns lconv.
+// tconv(1..nuvz-1), qconv(1..nuvz-1) and psconv must be set.
+FPB_HD inline bool conv_calcmatrix(ConvWork &w, float delt, float &cbmf) {
+  const float ga = 9.81f;
+  const int nuvz = w.nuvz, nconvlev = w.nconvlev;
+  CV(phconv, 1) = w.psconv;
+  for (int kuvz = 2; kuvz <= nuvz; kuvz++) {
+    const int kq = kuvz - 1;
+    CV(pconv, kq) = (w.akz[kuvz] + w.bkz[kuvz] * w.psconv);
+    CV(phconv, kuvz) = (w.akm[kuvz] + w.bkm[kuvz] * w.psconv);
+    CV(dpr, kq) = CV(phconv, kq) - CV(phconv, kuvz);
+    CV(qsconv, kq) = conv_qvsat(CV(pconv, kq), CV(tconv, kq));
+  }
+  const float cbmfold = cbmf;
+  for (int kq = 1; kq <= nconvlev + 1; kq++) {
+    CV(pconv_hpa, kq) = CV(pconv, kq) / 100.f;
+    CV(phconv_hpa, kq) = CV(phconv, kq) / 100.f;
+  }
+  CV(phconv_hpa, nconvlev + 1) = CV(phconv, nconvlev + 1) / 100.f;
+  w.nconvtop = 0;
+  const int iflag = conv_convect(w, nconvlev, delt, cbmf);
+  if (iflag != 1 && iflag != 4) {
+    cbmf = cbmfold;
+    return false;
+  }
+  if (cbmf <= 0.f && cbmfold <= 0.f) {
+    cbmf = cbmfold;
+    return false;
+  }
+  // fmassfrac(k,kk) = delt*fmass(k,kk) (+ what stays in the level on the diagonal), in place
+  for (int kq = 1; kq <= w.nconvtop; kq++) {
+    const float rlevmass = CV(dpr, kq) / ga;
+    float summe = 0.f;
+    for (int kk = 1; kk <= w.nconvtop; kk++) {
+      CM(fmass, kq, kk) = delt * CM(fmass, kq, kk);
+      summe = summe + CM(fmass, kq, kk);
+    }
+    CM(fmass, kq, kq) = CM(fmass, kq, kq) + rlevmass - summe;
+  }
+  return true;
+}
+
+// src/redist.f90:63-118: heights above ground of the eta half levels of the column
+FPB_HD inline void conv_uvzlev(ConvWork &w) {
+  const float cnst = 287.05f / 9.81f; // r_air/ga
+  float tvold = w.tt2conv * (1.f + 0.378f * conv_ew(w.td2conv) / w.psconv);
+  float pold = w.psconv;
+  CV(uvzlev, 1) = 0.f;
+  float pint = CV(phconv, 2);
+  float tv1 = CV(tconv, 1) * (1.f + 0.608f * CV(qconv, 1));
+  float tv2 = CV(tconv, 2) * (1.f + 0.608f * CV(qconv, 2));
+  float tv = tv1 + (tv2 - tv1) * (CV(pconv, 1) - CV(phconv, 2)) / (CV(pconv, 1) - CV(pconv, 2));
+  if (fabsf(tv - tvold) > 0.2f) CV(uvzlev, 2) = CV(uvzlev, 1) + cnst * c_log(pold / pint) * (tv - tvold) / c_log(tv / tvold);
+  else CV(uvzlev, 2) = CV(uvzlev, 1) + cnst * c_log(pold / pint) * tv;
+  tvold = tv;
+  tv1 = tv2;
+  pold = pint;
+  for (int kz = 3; kz <= w.nconvtop + 1; kz++) {
+    pint = CV(phconv, kz);
+    tv2 = CV(tconv, kz) * (1.f + 0.608f * CV(qconv, kz));
+    tv = tv1 + (tv2 - tv1) * (CV(pconv, kz - 1) - CV(phconv, kz)) / (CV(pconv, kz - 1) - CV(pconv, kz));
+    if (fabsf(tv - tvold) > 0.2f)
+      CV(uvzlev, kz) = CV(uvzlev, kz - 1) + cnst * c_log(pold / pint) * (tv - tvold) / c_log(tv / tvold);
+    else
+      CV(uvzlev, kz) = CV(uvzlev, kz - 1) + cnst * c_log(pold / pint) * tv;
+    tvold = tv;
+    tv1 = tv2;
+    pold = pint;
+  }
+}
+
+// level of the particle in the column, src/redist.f90:122-131; 0: above the convective domain
+FPB_HD inline int conv_levold(const ConvWork &w, float ztold) {
+  for (int kz = 2; kz <= w.nconvtop; kz++)
+    if (CV(uvzlev, kz) >= ztold) return kz - 1;
+  return 0;
+}
+
+// src/redist.f90:120-237 for one particle (levold > 0): rn = the uniform of `ran3(iseed)`
+FPB_HD inline float conv_redist(const ConvWork &w, float ztold, int levold, float rn, int ldirect, int lsynctime) {
+  const float ga = 9.81f, r_air = 287.05f;
+  float z = ztold, dlevfrac = 0.5f;
+  int levnew = levold;
+  float ffraction = 0.f;
+  const float totlevmass = CV(dpr, levold) / ga;
+  for (int kq = 1; kq <= w.nconvtop; kq++) {
+    const float f = (ldirect == 1) ? CM(fmass, levold, kq) : CM(fmass, kq, levold);
+    ffraction = ffraction + f / totlevmass;
+    if (rn <= ffraction) {
+      levnew = kq;
+      if (ffraction > 1.e-20f) dlevfrac = (ffraction - rn) / f * totlevmass;
+      else dlevfrac = 0.5f;
+      break;
+    }
+  }
+  if (levnew <= w.nconvtop) {
+    if (levnew == levold) {
+      z = ztold;
+    } else {
+      const float dlogp = (1.f - dlevfrac) * (c_log(CV(phconv, levnew + 1)) - c_log(CV(phconv, levnew)));
+      const float pint = c_log(CV(phconv, levnew)) + dlogp;
+      const float dz1 = pint - c_log(CV(phconv, levnew));
+      const float dz2 = c_log(CV(phconv, levnew + 1)) - pint;
+      const float dz = dz1 + dz2;
+      z = (CV(uvzlev, levnew) * dz2 + CV(uvzlev, levnew + 1) * dz1) / dz;
+      if (z < 0.f) z = -1.f * z;
+    }
+  }
+  if (levnew <= w.nconvtop && levnew == levold) { // compensating subsidence
+    const float zo = z;
+    float wsub_lo, wsub_hi;
+    if (levold > 1) {
+      const float temp_levold = CV(tconv, levold - 1) + (CV(tconv, levold) - CV(tconv, levold - 1)) *
+                                                            (CV(pconv, levold - 1) - CV(phconv, levold)) /
+                                                            (CV(pconv, levold - 1) - CV(pconv, levold));
+      const float sub_levold = CV(sub, levold) / (1.f - CV(sub, levold) / CV(dpr, levold) * ga);
+      wsub_lo = -1.f * sub_levold * r_air * temp_levold / (CV(phconv, levold));
+    } else {
+      wsub_lo = 0.f;
+    }
+    const float temp_levold1 = CV(tconv, levold) + (CV(tconv, levold + 1) - CV(tconv, levold)) *
+                                                       (CV(pconv, levold) - CV(phconv, levold + 1)) /
+                                                       (CV(pconv, levold) - CV(pconv, levold + 1));
+    const float sub_levold1 = CV(sub, levold + 1) / (1.f - CV(sub, levold + 1) / CV(dpr, levold + 1) * ga);
+    wsub_hi = -1.f * sub_levold1 * r_air * temp_levold1 / (CV(phconv, levold + 1));
+    const float dz1 = zo - CV(uvzlev, levold);
+    const float dz2 = CV(uvzlev, levold + 1) - zo;
+    const float dz = dz1 + dz2;
+    const float wsubpart = (dz2 * wsub_lo + dz1 * wsub_hi) / dz;
+    z = zo + wsubpart * (float)lsynctime;
+    if (z < 0.f) z = -1.f * z;
+  }
+  return z;
+}
+
+#undef CV
+#undef CM
+
+} // namespace fpbconv

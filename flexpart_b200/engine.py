@@ -213,6 +213,26 @@ class Engine:
         self._check(self.L.fpb_reduce_grids_device(self.h, which, C.byref(p), C.byref(n), C.byref(ms)))
         return p.value, n.value, ms.value
 
+    # ---- convective mixing (convmix / calcmatrix / convect / redist on the device)
+    def set_convection(self, nuvz, nuvzmax, nconvlev, akz, bkz, akm, bkm):
+        """akz.. are the Fortran arrays (1:nuvz) as numpy arrays of length >= nuvz (0-based)"""
+        arrs = [np.ascontiguousarray(a[:nuvz], np.float32) for a in (akz, bkz, akm, bkm)]
+        self._check(self.L.fpb_set_convection(self.h, nuvz, nuvzmax, nconvlev, *[_fp(a) for a in arrs]))
+
+    def upload_convmet(self, slot, ps, tt2, td2, tth, qvh):
+        """ps, tt2, td2 (nxmax,nymax) and tth, qvh (nxmax,nymax,nuvzmax), Fortran order, float32"""
+        from .abi import FpbConvPtrs
+        m = FpbConvPtrs()
+        keep = [np.asfortranarray(a, np.float32) for a in (ps, tt2, td2, tth, qvh)]
+        m.ps, m.tt2, m.td2, m.tth, m.qvh = [_fp(a) for a in keep]
+        self._check(self.L.fpb_upload_convmet(self.h, slot, C.byref(m)))
+
+    def convmix(self, itime):
+        """convmix(itime); returns (occupied columns, convecting columns)"""
+        nc, nv = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.fpb_convmix(self.h, itime, C.byref(nc), C.byref(nv)))
+        return nc.value, nv.value
+
     def init_domainfill(self, box, itsplit=99999999):
         """init_domainfill (src/init_domainfill.f90:55-283) over the box (xpoint1, ypoint1, xpoint2,
         ypoint2) in grid units, on the device; returns (numpart, info dict)."""

@@ -393,6 +393,33 @@ int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoin
                         fpb_domainfill_info *info /* may be NULL */);
 int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend);
 
+/* Convective mixing (LCONVECTION = 1, the shipped default).
+ * fpb_convmix replaces `call convmix(itime,metdata_format)` (src/timemanager.f90:183-193,258-263;
+ * src/convmix.f90:60-196): the active particles are grouped by grid column, every occupied column's
+ * sounding is interpolated in time and run through calcmatrix / the Emanuel scheme
+ * (src/calcmatrix.f90, src/convect43c.f90; one thread per column), and the particles of the
+ * convecting columns get their new height from redist (src/redist.f90) -- all on the device, the
+ * particles stay resident.  The cloud base mass flux of every column (cbaseflux) is kept on the
+ * device between calls.  The column arithmetic is the reference's statement by statement and is
+ * evaluated without contraction in every math mode.  FPB_RNG_REFERENCE replays the reference's
+ * ran3 stream in its sort2 visiting order (bit-identical heights); the Philox modes draw the
+ * uniform from the particle's counter stream.
+ *   fpb_set_convection  once: nuvz, the padded level extent of tth/qvh (nuvzmax), nconvlev
+ *                       (src/gridcheck_ecmwf.f90:553-566) and akz, bkz, akm, bkm (1:nuvz)
+ *   fpb_upload_convmet  next to every fpb_upload_met: ps, tt2, td2 (nxmax,nymax) and tth, qvh
+ *                       (nxmax,nymax,nuvzmax) of the time level (src/com_mod.f90:372-417)
+ * ECMWF fields (metdata_format = GRIBFILE_CENTRE_ECMWF) on the mother grid; nested input grids
+ * (src/convmix.f90:198-281) and the flux diagnostics (calcfluxes, iflux = 1) are not built. */
+typedef struct fpb_conv_ptrs {
+  const float *ps, *tt2, *td2;
+  const float *tth, *qvh;
+} fpb_conv_ptrs;
+int fpb_set_convection(fpb_handle *h, int32_t nuvz, int32_t nuvzmax, int32_t nconvlev, const float *akz,
+                       const float *bkz, const float *akm, const float *bkm);
+int fpb_upload_convmet(fpb_handle *h, int32_t slot, const fpb_conv_ptrs *met);
+int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns /* occupied columns, may be NULL */,
+                int32_t *nconvecting /* of those, columns with convection, may be NULL */);
+
 /* wetgridunc(0:numxgrid-1,0:numygrid-1,maxspec,maxpointspec_act,nclassunc,
  * maxageclass) and the nested twin (may be NULL): cumulative, never zeroed,
  * decayed by fpb_scale_depgrids like drygridunc */

@@ -60,6 +60,7 @@ ALLOC_DIMS = {
     "vdepn": "0:nxmaxn-1,0:nymaxn-1,maxspec,numwfmem,maxnests",
     "cloudsn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "cloudshn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
     "ctwcn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
+    "tthn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests", "qvhn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests",
     "zpoint1": "numpoint", "zpoint2": "numpoint", "xpoint1": "numpoint", "xpoint2": "numpoint",
     "ypoint1": "numpoint", "ypoint2": "numpoint", "ireleasestart": "numpoint", "ireleaseend": "numpoint",
     "kindz": "numpoint", "rho_rel": "numpoint", "xmasssave": "numpoint",
@@ -200,7 +201,7 @@ INTRINSICS = {"abs", "sqrt", "exp", "log", "log10", "sin", "cos", "tan", "atan",
               "amax1", "amin1", "mod", "modulo", "int", "nint", "real", "dble", "float", "sign", "floor", "tiny",
               "erf", "sngl", "ifix", "aint", "anint", "iabs", "dabs", "dsqrt", "dexp", "dlog", "dsin", "dcos", "datan2",
               "datan", "ceiling", "huge", "epsilon", "kind", "selected_real_kind", "selected_int_kind", "maxval", "minval",
-              "isnan"}
+              "isnan", "alog", "alog10"}
 
 
 class Unit:
@@ -712,7 +713,7 @@ class Ctx:
         if name in ("abs", "iabs", "dabs"):
             return f"F_ABS({a[0]})"
         one = {"sqrt": "F_SQRT", "dsqrt": "F_SQRT", "exp": "F_EXP", "dexp": "F_EXP", "log": "F_LOG", "dlog": "F_LOG",
-               "log10": "F_LOG10", "sin": "F_SIN", "dsin": "F_SIN", "cos": "F_COS", "dcos": "F_COS", "tan": "F_TAN",
+               "alog": "F_LOG", "alog10": "F_LOG10", "log10": "F_LOG10", "sin": "F_SIN", "dsin": "F_SIN", "cos": "F_COS", "dcos": "F_COS", "tan": "F_TAN",
                "atan": "F_ATAN", "datan": "F_ATAN", "asin": "F_ASIN", "acos": "F_ACOS", "erf": "F_ERF",
                "nint": "F_NINT", "floor": "F_FLOOR", "ceiling": "F_CEILING", "aint": "F_AINT", "anint": "F_ANINT"}
         if name in one:
@@ -841,7 +842,11 @@ class Gen:
                 if static:
                     n_const = try_const(size, u, ctx)
                     if n_const is None:
-                        raise F2CError(f"{u.name}: SAVEd array {nm} with non-constant size")
+                        # extent from a par_mod parameter (run-time value here): allocated at the first call
+                        if sym.init is not None:
+                            raise F2CError(f"{u.name}: initialised SAVEd array {nm} with non-constant size")
+                        out.append(f"  static {ct} *f_{nm} = NULL; if (!f_{nm}) f_{nm} = ({ct} *)calloc((size_t)({size}), sizeof({ct}));")
+                        continue
                     init = ""
                     if sym.init is not None:
                         vals = array_ctor(sym.init, ctx, n_const)
@@ -1104,7 +1109,9 @@ def main(argv):
     import os
     prog = Program()
     for f in args.files:
-        prog.add_source(open(os.path.join(args.src, f), errors="replace").read(), f)
+        # (a path with a directory part is taken as it is: the stub modules under oracle/f2c/stubs)
+        path = f if os.sep in f else os.path.join(args.src, f)
+        prog.add_source(open(path, errors="replace").read(), os.path.basename(f))
     for spec in args.extract:
         name, f, parent, rng, al = spec.split(":")
         first, last = [int(x) for x in rng.split("-")]

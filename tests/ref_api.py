@@ -51,6 +51,9 @@ class Ref:
                          maxnests=max(c.numbnests, 1), nxmaxn=max(c.nxmaxn, 1), nymaxn=max(c.nymaxn, 1),
                          maxageclass=c.maxageclass, nclassunc=c.nclassunc, maxrand=maxrand, numwfmem=2).items():
             self.set(k, v)
+        for k, v in dict(nuvzmax=c.nzmax, nwzmax=c.nzmax, nconvlevmax=c.nzmax - 1, na=c.nzmax).items():
+            if self.has(k):     # convection (conv_mod extents)
+                self.set(k, v)
         # extents of the allocatable arrays
         for k in ("numxgrid", "numygrid", "numzgrid", "maxpointspec_act", "numpoint", "numreceptor"):
             self.set(k, getattr(c, k))
