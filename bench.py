@@ -624,6 +624,23 @@ def next_rows(eng, cb, rel, peak, itime_now):
         out["wetdepo"] = {"ms": t * 1e3, "particles_per_s": c.maxpart / t,
                           "alg_GBps": c.maxpart * (28 + 64 + 5 + 8 * c.nspec) / t / 1e9,
                           "what": "fpb_wetdepo over all particles (28 B state + 4 x 16 B rain words + cloud class + tt + masses)"}
+    # convective mixing (LCONVECTION = 1, the shipped default) for the bench's own particles: occupied
+    # columns -> Emanuel scheme per column -> redist, all on the device
+    try:
+        import conv_cases
+        akm, bkm, akz, bkz, nconvlev = conv_cases.hybrid_levels(c.nz)
+        f0 = conv_cases.conv_fields(cb, akz, bkz, c.nz, 1)
+        eng.set_convection(c.nz, c.nzmax, nconvlev, akz[1:], bkz[1:], akm[1:], bkm[1:])
+        eng.upload_convmet(1, *f0); eng.upload_convmet(2, *f0)
+        eng.upload_convmet(3, *f0)
+        res = {}
+        t = best(lambda: res.update(n=eng.convmix(itime_now)), n=3)
+        out["convmix"] = {"ms": t * 1e3, "occupied_columns": res["n"][0], "convecting_columns": res["n"][1],
+                          "particles": c.maxpart, "nconvlev": nconvlev,
+                          "what": "fpb_convmix: column sort, calcmatrix + Emanuel scheme (one thread per occupied "
+                                  "column), redist; synthetic soundings (tests/conv_cases.py)"}
+    except Exception as e:  # (the convection leg must not take the bench line down)
+        out["convmix"] = {"error": str(e)}
     # release of maxpart particles on a second engine (Philox positions): no particle row crosses PCIe
     e2 = fb.Engine(cb)
     e2.set_releases(rel)
