@@ -207,8 +207,27 @@ def run_ours(args):
             N.nvmlDeviceSetCpuAffinity(N.nvmlDeviceGetHandleByIndex(idx))
         except Exception as e:
             log(f"[rank {rank}] no CPU affinity set ({e})")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with _stdout_to_stderr():            # (NCCL prints its version banner on stdout)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     K, W = args.steps, args.warmup
+
+    if args.workload == "c5":
+        # the C5 leg alone (profiling): the line's headline fields are the c5_strong ones
+        cbm = c5_config(1024, local, rank, world)
+        span = max(10800, (K + W + 6) * 900)
+        mets = (fb.MetFields(cbm).synth(0), fb.MetFields(cbm).synth(span))
+        c5 = c5_strong(args, rank, world, local, mets, span, K=K, W=W)
+        if rank == 0:
+            line = {"metric": "particle-steps/s (advance+conccalc)", "value": c5["value"], "unit": "particle-steps/s",
+                    "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": c5["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 positions)", "data": "synthetic",
+                    "config": {"workload": c5["workload"]}, "roofline": c5["roofline"], "c5_strong": c5,
+                    "gpu_launches": c5.get("gpu_launches")}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     t0 = time.time()
     cb, rel = build_workload(args, rank, world, local)
@@ -483,6 +502,7 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
         if world > 1:
             dist.barrier()
         ev0.record(ext)
+        l0 = eng.launch_count
         ps = npbl = 0
         tk = tc = 0.0
         for _ in range(K):
@@ -493,6 +513,7 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
         comm.wait()
         ev1.record(ext)
         torch.cuda.synchronize()
+        launches = eng.launch_count - l0
         if world > 1:
             dist.barrier()
         ms = ev0.elapsed_time(ev1)
@@ -523,7 +544,8 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
             "scaling": "strong", "value": ps_all / (ms_max * 1e-3), "unit": "particle-steps/s",
             "n_gpus": world, "particles_total": int(n_all), "particles_rank0": int(n), "steps": K,
             "ms_per_step": ms_max / K, "kernel_ms_per_launch": tk / K, "conccalc_ms_per_launch": tc / K,
-            "pbl_fraction": npbl_all / max(ps_all, 1),
+            "pbl_fraction": npbl_all / max(ps_all, 1), "gpu_launches": int(launches),
+            "exchange_reduce_ms_rank0": float(np.mean(comm.ms)) if comm.ms else 0.0,
             "init_domainfill_ms": t_fill * 1e3, "met_upload_ms_per_slot": t_met * 1e3 / 2,
             "mass_check": {"grid_sum_over_ranks": gsum, "colmasstotal": info["colmasstotal"], "ratio": mass_ratio,
                            "ok": bool(abs(mass_ratio - 1.0) < 2e-3)},
@@ -850,7 +872,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5slice", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5slice", "c3", "c5"])
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -13,7 +13,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fpb_device.cuh"
@@ -245,6 +248,15 @@ struct fpb_handle {
     float *stage[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_n[7] = {0, 0, 0, 0, 0, 0, 0};
     bool in_flight = false, timed = false;
+    // The NCCL enqueue (group start .. end, tens of microseconds of host time) runs on a worker
+    // thread: every engine call is synchronous for the host, so host time between two calls is idle
+    // GPU time; fpb_reduce_grids_begin only posts the job.
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool job = false, job_done = true, quit = false;
+    int job_rc = 0;
+    std::string job_err;
   } comm;
   // convective mixing (fpb_set_convection / fpb_upload_convmet / fpb_convmix)
   struct Conv {
@@ -2381,6 +2393,46 @@ int nccl_load() {
   } while (0)
 } // namespace
 
+// worker: records the start event, enqueues the reduce group on the side stream, records the end event
+static void comm_worker(fpb_handle *h) {
+  auto &Q = h->comm;
+  cudaSetDevice(h->device);
+  for (;;) {
+    std::unique_lock<std::mutex> lk(Q.mu);
+    Q.cv.wait(lk, [&] { return Q.job || Q.quit; });
+    if (Q.quit) return;
+    Q.job = false;
+    lk.unlock();
+    int rc = 0;
+    std::string err;
+    auto nk = [&](int r, const char *what) {
+      if (r != 0 && rc == 0) { rc = 1; err = std::string(what) + " failed: " + g_nccl.GetErrorString(r); }
+    };
+    if (cudaEventRecord(Q.ev_t0, Q.side) != cudaSuccess) { rc = 1; err = "cudaEventRecord failed"; }
+    nk(g_nccl.GroupStart(), "ncclGroupStart");
+    for (int k = 0; k < 7; k++)
+      if (Q.stage_n[k])
+        nk(g_nccl.Reduce(Q.stage[k], Q.stage[k], Q.stage_n[k], NCCL_FLOAT32, NCCL_SUM, 0, Q.nccl, Q.side), "ncclReduce");
+    nk(g_nccl.GroupEnd(), "ncclGroupEnd");
+    if (cudaEventRecord(Q.ev_done, Q.side) != cudaSuccess && rc == 0) { rc = 1; err = "cudaEventRecord failed"; }
+    lk.lock();
+    Q.job_rc = rc; Q.job_err = err; Q.job_done = true;
+    lk.unlock();
+    Q.cv.notify_all();
+  }
+}
+// the posted job has been enqueued (its events are recorded); returns its status
+static int comm_wait_enqueued(fpb_handle *h) {
+  auto &Q = h->comm;
+  std::unique_lock<std::mutex> lk(Q.mu);
+  Q.cv.wait(lk, [&] { return Q.job_done; });
+  if (Q.job_rc) {
+    Q.job_rc = 0;
+    return fail("fpb_reduce_grids: %s", Q.job_err.c_str());
+  }
+  return 0;
+}
+
 extern "C" int fpb_comm_unique_id(void *id128) {
   if (!id128) return fail("fpb_comm_unique_id: null argument");
   if (nccl_load()) return 1;
@@ -2400,6 +2452,7 @@ extern "C" int fpb_comm_init(fpb_handle *h, const void *id128, int32_t rank, int
     NcclUid uid;
     memcpy(uid.b, id128, sizeof uid.b);
     NK(g_nccl.CommInitRank(&Q.nccl, nranks, uid, rank));
+    Q.worker = std::thread(comm_worker, h);
   }
   int lo = 0, hi = 0;
   CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -2411,7 +2464,8 @@ extern "C" int fpb_comm_init(fpb_handle *h, const void *id128, int32_t rank, int
   // accumulates into the (zeroed) grids
   const float *src[7] = {h->gridunc, h->griduncn, h->drygridunc, h->drygriduncn, h->wetgridunc, h->wetgriduncn,
                          h->cfg.numreceptor > 0 ? h->creceptor : nullptr};
-  const size_t n[7] = {h->n_grid, h->n_gridn, h->n_dry, h->n_dryn, h->n_dry, h->n_dryn, h->n_rec};
+  const size_t n[7] = {h->n_grid, h->n_gridn, h->cfg.drydep ? h->n_dry : 0, h->cfg.drydep ? h->n_dryn : 0,
+                       h->n_dry, h->n_dryn, h->n_rec};  // (grids nothing is ever added to stay at home)
   for (int k = 0; k < 7; k++) {
     Q.stage_n[k] = src[k] ? n[k] : 0;
     if (Q.stage_n[k]) DA(Q.stage[k], Q.stage_n[k]);
@@ -2427,6 +2481,7 @@ extern "C" int fpb_reduce_grids_begin(fpb_handle *h) {
   auto &Q = h->comm;
   if (!Q.side) return fail("fpb_reduce_grids_begin: fpb_comm_init has not been called");
   CK(cudaSetDevice(h->device));
+  if (comm_wait_enqueued(h)) return 1;
   if (Q.in_flight) CK(cudaStreamWaitEvent(h->stream, Q.ev_done, 0)); // the staging buffers are free again
   const float *src[7] = {h->gridunc, h->griduncn, h->drygridunc, h->drygriduncn, h->wetgridunc, h->wetgriduncn,
                          h->creceptor};
@@ -2438,16 +2493,18 @@ extern "C" int fpb_reduce_grids_begin(fpb_handle *h) {
   CK(cudaMemsetAsync(h->creceptor, 0, h->n_rec * sizeof(float), h->stream));
   CK(cudaEventRecord(Q.ev_staged, h->stream));
   CK(cudaStreamWaitEvent(Q.side, Q.ev_staged, 0));
-  CK(cudaEventRecord(Q.ev_t0, Q.side));
   if (Q.nranks > 1) {
-    NK(g_nccl.GroupStart());
-    for (int k = 0; k < 7; k++)
-      if (Q.stage_n[k])
-        NK(g_nccl.Reduce(Q.stage[k], Q.stage[k], Q.stage_n[k], NCCL_FLOAT32, NCCL_SUM, 0, Q.nccl, Q.side));
-    NK(g_nccl.GroupEnd());
+    { // post the enqueue of the reduce group to the worker
+      std::lock_guard<std::mutex> lk(Q.mu);
+      Q.job = true;
+      Q.job_done = false;
+    }
+    Q.cv.notify_all();
     h->launches++;
+  } else {
+    CK(cudaEventRecord(Q.ev_t0, Q.side));
+    CK(cudaEventRecord(Q.ev_done, Q.side));
   }
-  CK(cudaEventRecord(Q.ev_done, Q.side));
   Q.in_flight = true;
   Q.timed = true;
   return 0;
@@ -2461,6 +2518,7 @@ extern "C" int fpb_reduce_grids_end(fpb_handle *h, float *gridunc, float *gridun
   auto &Q = h->comm;
   if (!Q.in_flight) return fail("fpb_reduce_grids_end: no exchange in flight");
   CK(cudaSetDevice(h->device));
+  if (comm_wait_enqueued(h)) return 1;
   CK(cudaEventSynchronize(Q.ev_done));
   Q.in_flight = false;
   if (Q.rank != 0) return 0;
@@ -2490,6 +2548,7 @@ extern "C" int fpb_reduce_grids_device(fpb_handle *h, int32_t which, void **dptr
   if (which < 0 || which > 6) return fail("fpb_reduce_grids_device: which=%d", which);
   if (!Q.side) return fail("fpb_reduce_grids_device: fpb_comm_init has not been called");
   CK(cudaSetDevice(h->device));
+  if (comm_wait_enqueued(h)) return 1;
   if (Q.in_flight) CK(cudaEventSynchronize(Q.ev_done));
   if (dptr) *dptr = Q.stage[which];
   if (nfloats) *nfloats = Q.stage_n[which];
@@ -2504,6 +2563,12 @@ extern "C" int fpb_comm_finalize(fpb_handle *h) {
   if (!h) return 0;
   auto &Q = h->comm;
   cudaSetDevice(h->device);
+  if (Q.worker.joinable()) {
+    comm_wait_enqueued(h);
+    { std::lock_guard<std::mutex> lk(Q.mu); Q.quit = true; }
+    Q.cv.notify_all();
+    Q.worker.join();
+  }
   if (Q.side) { cudaStreamSynchronize(Q.side); }
   if (Q.nccl) { g_nccl.CommDestroy(Q.nccl); Q.nccl = nullptr; }
   for (auto &p : Q.stage) { cudaFree(p); p = nullptr; }
@@ -2511,6 +2576,8 @@ extern "C" int fpb_comm_finalize(fpb_handle *h) {
   if (Q.ev_t0) cudaEventDestroy(Q.ev_t0);
   if (Q.ev_done) cudaEventDestroy(Q.ev_done);
   if (Q.side) cudaStreamDestroy(Q.side);
-  Q = fpb_handle::Comm();
+  Q.side = nullptr; Q.ev_staged = Q.ev_t0 = Q.ev_done = nullptr;
+  Q.in_flight = Q.timed = false; Q.quit = false; Q.job = false; Q.job_done = true;
+  for (auto &v : Q.stage_n) v = 0;
   return 0;
 }
