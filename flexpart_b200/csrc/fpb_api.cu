@@ -1809,9 +1809,17 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   const int n = h->active_rows >= 0 ? h->active_rows : h->numpart;
   if (n <= 0) return 0;
   const bool refrng = c.rng_mode == FPB_RNG_REFERENCE;
-  const int CONV_BATCH = 4096;
+  // the column kernel is latency-bound (one thread per column walking its own work slice): as many
+  // columns at once as a quarter of the free device memory holds, at most 32768
   const size_t pf = fpb_convmix_pool_floats(V.nuvz, V.nconvlev);
-  if (!V.pool) { DA(V.pool, pf * CONV_BATCH); V.pool_cols = CONV_BATCH; }
+  if (!V.pool) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t cols = (free_b / 4) / (pf * sizeof(float));
+    cols = std::max<size_t>(256, std::min<size_t>(cols, 32768));
+    DA(V.pool, pf * cols);
+    V.pool_cols = (int)cols;
+  }
   if ((size_t)n > V.cap_rows) {
     cudaFree(V.block_counts); cudaFree(V.colidx); cudaFree(V.col_key); cudaFree(V.col_start); cudaFree(V.col_lconv);
     V.block_counts = nullptr; V.colidx = nullptr; V.col_key = nullptr; V.col_start = nullptr; V.col_lconv = nullptr;

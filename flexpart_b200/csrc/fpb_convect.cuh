@@ -27,6 +27,13 @@
 #define FPB_HD
 #endif
 
+#ifdef __CUDA_ARCH__
+#define FPB_PRAGMA(x) _Pragma(#x)
+#define FPB_UNROLL(n) FPB_PRAGMA(unroll n)
+#else
+#define FPB_UNROLL(n)
+#endif
+
 namespace fpbconv {
 
 FPB_HD inline float c_exp(float x) { return (float)exp((double)x); }
@@ -436,6 +443,7 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     for (int i = inb; i >= 1; i--) {
       float wdtrain = G * CV(ep, i) * CV(m, i) * CV(clw, i);
       if (i > 1) {
+FPB_UNROLL(4)
         for (int j = 1; j <= i - 1; j++) {
           float awat = CM(elij, j, i) - (1.f - CV(ep, i)) * CV(clw, i);
           awat = c_max(0.0f, awat);
@@ -491,52 +499,36 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     precip = precip + CV(wt, 1) * SIGD * CV(water, 1) * 3600.f * 24000.f / (ROWL * G);
   }
   (void)precip;
-  // tendencies of the lowest level (:855-872)   (wd, tprime, qprime are not used by FLEXPART)
+  // net saturated up- and downdraft mass fluxes through each level (:855-913).  The temperature and
+  // humidity tendencies FT, FQ that the scheme also forms there (:867-872,914-934) are not read by
+  // FLEXPART (only FMASS and SUB are) and are left out; IFLAG = 4 (CFL condition on the subsidence)
+  // is kept.  The inner loops are unrolled so that several of the (independent) matrix loads are in
+  // flight at once; the additions keep the reference's order.
   float dpinv = 0.01f / (CV(phconv_hpa, 1) - CV(phconv_hpa, 2));
   float am = 0.0f;
   if (nk == 1)
     for (int kq = 2; kq <= inb; kq++) am = am + CV(m, kq);
   CV(fup, 1) = am;
   if ((2.f * G * dpinv * am) >= delti) iflag = 4;
-  CV(ft, 1) = CV(ft, 1) + G * dpinv * am * (CV(tconv, 2) - CV(tconv, 1) + (CV(gz, 2) - CV(gz, 1)) / CV(cpn, 1));
-  CV(ft, 1) = CV(ft, 1) - CV(lvcp, 1) * SIGD * CV(evap, 1);
-  CV(ft, 1) = CV(ft, 1) + SIGD * CV(wt, 2) * (CL - CPD) * CV(water, 2) * (CV(tconv, 2) - CV(tconv, 1)) * dpinv / CV(cpn, 1);
-  CV(fq, 1) = CV(fq, 1) + G * CV(mp, 2) * (CV(qp, 2) - CV(qconv, 1)) * dpinv + SIGD * CV(evap, 1);
-  CV(fq, 1) = CV(fq, 1) + G * am * (CV(qconv, 2) - CV(qconv, 1)) * dpinv;
-  for (int j = 2; j <= inb; j++) CV(fq, 1) = CV(fq, 1) + G * dpinv * CM(ment, j, 1) * (CM(qent, j, 1) - CV(qconv, 1));
-  // levels above (:877-930): net saturated up- and downdraft mass fluxes through each level
   for (int i = 2; i <= inb; i++) {
     dpinv = 0.01f / (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1));
-    const float cpinv = 1.0f / CV(cpn, i);
     float amp1 = 0.0f, ad = 0.0f;
     if (i >= nk)
       for (int kq = i + 1; kq <= inb + 1; kq++) amp1 = amp1 + CV(m, kq);
-    for (int kq = 1; kq <= i; kq++)
+    for (int kq = 1; kq <= i; kq++) {
+FPB_UNROLL(8)
       for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + CM(ment, kq, j);
+    }
     CV(fup, i) = amp1;
     if ((2.f * G * dpinv * amp1) >= delti) iflag = 4;
-    for (int kq = 1; kq <= i - 1; kq++)
-      for (int j = i; j <= inb; j++) ad = ad + CM(ment, j, kq);
-    CV(fdown, i) = ad;
-    CV(ft, i) = CV(ft, i) +
-                G * dpinv * (amp1 * (CV(tconv, i + 1) - CV(tconv, i) + (CV(gz, i + 1) - CV(gz, i)) * cpinv) -
-                             ad * (CV(tconv, i) - CV(tconv, i - 1) + (CV(gz, i) - CV(gz, i - 1)) * cpinv)) -
-                SIGD * CV(lvcp, i) * CV(evap, i);
-    CV(ft, i) = CV(ft, i) + G * dpinv * CM(ment, i, i) *
-                                (CV(hp, i) - CV(h, i) + CV(tconv, i) * (CPV - CPD) * (CV(qconv, i) - CM(qent, i, i))) * cpinv;
-    CV(ft, i) = CV(ft, i) + SIGD * CV(wt, i + 1) * (CL - CPD) * CV(water, i + 1) * (CV(tconv, i + 1) - CV(tconv, i)) * dpinv * cpinv;
-    CV(fq, i) = CV(fq, i) + G * dpinv * (amp1 * (CV(qconv, i + 1) - CV(qconv, i)) - ad * (CV(qconv, i) - CV(qconv, i - 1)));
     for (int kq = 1; kq <= i - 1; kq++) {
-      float awat = CM(elij, kq, i) - (1.f - CV(ep, i)) * CV(clw, i);
-      awat = c_max(awat, 0.0f);
-      CV(fq, i) = CV(fq, i) + G * dpinv * CM(ment, kq, i) * (CM(qent, kq, i) - awat - CV(qconv, i));
+FPB_UNROLL(8)
+      for (int j = i; j <= inb; j++) ad = ad + CM(ment, j, kq);
     }
-    for (int kq = i; kq <= inb; kq++) CV(fq, i) = CV(fq, i) + G * dpinv * CM(ment, kq, i) * (CM(qent, kq, i) - CV(qconv, i));
-    CV(fq, i) = CV(fq, i) + SIGD * CV(evap, i) +
-                G * (CV(mp, i + 1) * (CV(qp, i + 1) - CV(qconv, i)) - CV(mp, i) * (CV(qp, i) - CV(qconv, i - 1))) * dpinv;
+    CV(fdown, i) = ad;
   }
-  // (the adjustments of ft / fq at the top of the convection layer and the enthalpy correction,
-  //  :934-956, only change FT and FQ, which FLEXPART does not read: left out)
+  // (likewise the adjustments of ft / fq at the top of the convection layer and the enthalpy
+  //  correction, :934-956)
   (void)frac;
   // mass displacement matrix and compensating subsidence (:972-989)
   CV(sub, 1) = 0.f;

@@ -108,3 +108,45 @@ if "hbm_regime" in bench:
 print("cpu_baseline", bench.get("cpu_baseline"))
 print(f"reference arm {ref['value']:.3e} on {ref['cpu_baseline']['cores']} cores")
 print(f"C3 device-resident {c3['value']:.3e} ({c3['ms_per_step']:.3f} ms/step), e2e {c3['e2e']['value']:.3e}, substeps/particle-step {c3['substeps_per_particle_step']:.1f}")
+
+# ---- the other workloads' captures (round 2+): C3 (full-feature instantiation) and C5 (HBM-gather regime)
+for tag, label in (("c3", "C3: CBL + deposition + nested output, 1 M particles"), ("c5", "C5: 100 M domain-filling particles, method 0")):
+    rawp = os.path.join(G, f"ncu_full_{R}_{tag}_raw.csv")
+    if not os.path.exists(rawp):
+        continue
+    for suffix in (f"ncu_full_{R}_{tag}_raw.csv", f"ncu_full_{R}_{tag}_details.txt", f"launches_{R}_{tag}.csv"):
+        if os.path.exists(os.path.join(G, suffix)):
+            shutil.copy(os.path.join(G, suffix), os.path.join(P, suffix))
+    if os.path.exists(os.path.join(G, f"bench_{R}_{tag}.json")):
+        shutil.copy(os.path.join(G, f"bench_{R}_{tag}.json"), os.path.join(P, f"bench_{R}_{tag}.json"))
+    FF = [r for r in rows(rawp) if r.get("Kernel Name")]
+    uu = rows(rawp)[0]
+    print(f"\n### {label} (ncu --set full, one launch each)\n")
+    print("| Kernel | time (ms) | DRAM read (MB) | DRAM write (MB) | DRAM throughput | L2 hit | issue slots busy | threads / instruction | regs | occupancy |\n|---|---|---|---|---|---|---|---|---|---|")
+    for r in FF:
+        def sc(col):
+            v, u = num(r, col), uu.get(col, "")
+            return None if v is None else v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1}.get(u, 1)
+        t, tu = num(r, "gpu__time_duration.sum"), uu.get("gpu__time_duration.sum", "ns")
+        tms = t * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6}.get(tu, 1e-6)
+        rd, wr = sc("dram__bytes_read.sum") or 0, sc("dram__bytes_write.sum") or 0
+        print(f"| `{short(r['Kernel Name'])}` | {tms:.3f} | {rd / 1e6:.0f} | {wr / 1e6:.0f} | "
+              f"{(rd + wr) / (tms * 1e-3) / 1e9:.0f} GB/s | {num(r, 'lts__t_sector_hit_rate.pct') or 0:.0f} % | "
+              f"{(num(r, 'sm__inst_issued.avg.pct_of_peak_sustained_active') or num(r, 'smsp__issue_active.avg.pct') or 0):.0f} % | "
+              f"{num(r, 'smsp__thread_inst_executed_per_inst_executed.ratio') or 0:.1f} | {num(r, 'launch__registers_per_thread') or 0:.0f} | "
+              f"{num(r, 'sm__warps_active.avg.pct_of_peak_sustained_active') or 0:.0f} % |")
+    lp = os.path.join(G, f"launches_{R}_{tag}.csv")
+    if os.path.exists(lp):
+        LL = rows(lp)
+        nm = [short(r["Kernel Name"]) for r in LL]
+        tt = [float(r["Metric Value"]) for r in LL]
+        cc = [i for i, n in enumerate(nm) if n.startswith("fpb_conccalc_kernel")]
+        if len(cc) >= 3:
+            a2, b2 = cc[-2], cc[-1]
+            ag = OrderedDict()
+            for n, t in zip(nm[a2:b2], tt[a2:b2]):
+                c = ag.setdefault(n, [0, 0.0]); c[0] += 1; c[1] += t
+            tot2 = sum(v[1] for v in ag.values())
+            print(f"\nOne step of that workload (launch list, cold-cache serialised):\n\n| Kernel | launches | µs | share |\n|---|---|---|---|")
+            for n, (k, t) in sorted(ag.items(), key=lambda kv: -kv[1][1]):
+                print(f"| `{n}` | {k} | {t / 1e3:.1f} | {100 * t / tot2:.1f} % |")
