@@ -1816,7 +1816,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t cols = (free_b / 4) / (pf * sizeof(float));
-    cols = std::max<size_t>(256, std::min<size_t>(cols, 32768));
+    cols = std::max<size_t>(256, std::min<size_t>(cols, 65536)) / 32 * 32; // whole blocks of 32 interleaved slices
     DA(V.pool, pf * cols);
     V.pool_cols = (int)cols;
   }

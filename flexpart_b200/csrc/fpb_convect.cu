@@ -9,9 +9,12 @@
 //                        key of every column (block scan)
 //   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + convect
 //                        (fpb_convect.cuh) on the column's slice of a work pool, cbaseflux in/out,
-//                        heights of the eta half levels when the column convects
+//                        heights of the eta half levels when the column convects.  The 32 columns of
+//                        a warp interleave their slices element by element (stride 32): the lanes run
+//                        the same loops, so a warp-wide access to "element e of my column" is one
+//                        128-byte line instead of 32 scattered sectors.
 //   conv_redist_kernel   one thread per particle of the batch's columns: redist
-// Columns are processed in batches (the work pool holds CONV_BATCH columns, ~200 KB each at 138
+// Columns are processed in batches (the work pool holds up to 65536 columns, 150-270 KB each at 138
 // levels).  Compiled with --fmad=false; the column arithmetic is bit-comparable with the
 // reference's routines in every math mode (see fpb_convect.cuh).
 #include "fpb_convect.cuh"
@@ -111,17 +114,19 @@ __global__ void __launch_bounds__(CB) conv_heads_assign_kernel(const ConvmixArgs
   if (i + 1 == a.nrows || keys[i + 1] == 0xffffffffu) a.col_start[incl] = i + 1; // end of the last column
 }
 
-__global__ void __launch_bounds__(64) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
+__global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1) return;
   const DevCfg &cf = a.cfg;
   const int nuvz = a.nuvz;
   const size_t nfl = conv_pool_floats(nuvz, a.nconvlev);
-  float *pool = a.pool + (size_t)(c - c0) * nfl;
+  // slice of column q = c - c0: block of 32 slices (q / 32), lane q % 32, elements interleaved
+  const int q = c - c0;
+  float *pool = a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32);
   const size_t nvec = (size_t)(CONV_NVEC + 1) * (nuvz + 4);
-  for (size_t k = 0; k < nvec; k++) pool[k] = 0.f; // (the reference's zero-initialised locals)
+  for (size_t k = 0; k < nvec; k++) pool[k * 32] = 0.f; // (the reference's zero-initialised locals)
   ConvWork w;
-  conv_carve(w, pool, nuvz, a.nconvlev);
+  conv_carve(w, pool, nuvz, a.nconvlev, 32);
   w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
   const unsigned key = a.col_key[c];
   const int jy = (int)(key / (unsigned)cf.nx), ix = (int)(key - (unsigned)jy * cf.nx);
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(64) conv_column_kernel(const ConvmixArgs a, in
   w.td2conv = (s1.z * dt2 + s2.z * dt1) * dtt;
   for (int kz = 1; kz <= nuvz - 1; kz++) {
     const float2 q1 = a.CT[0][(size_t)kz * plane + o2], q2 = a.CT[1][(size_t)kz * plane + o2]; // level kz+1
-    w.tconv[kz] = (q1.x * dt2 + q2.x * dt1) * dtt;
-    w.qconv[kz] = (q1.y * dt2 + q2.y * dt1) * dtt;
+    w.tconv[(size_t)kz * w.stride] = (q1.x * dt2 + q2.x * dt1) * dtt;
+    w.qconv[(size_t)kz * w.stride] = (q1.y * dt2 + q2.y * dt1) * dtt;
   }
   float cbmf = a.cbaseflux[o2];
   const bool lconv = conv_calcmatrix(w, (float)abs(cf.lsynctime), cbmf);
@@ -154,7 +159,8 @@ __global__ void __launch_bounds__(128) conv_redist_kernel(const ConvmixArgs a, i
   const int nconvtop = a.col_lconv[c];
   if (nconvtop == 0) return; // the column does not convect
   ConvWork w;
-  conv_carve(w, a.pool + (size_t)(c - c0) * conv_pool_floats(a.nuvz, a.nconvlev), a.nuvz, a.nconvlev);
+  const int q = c - c0;
+  conv_carve(w, a.pool + (size_t)(q / 32) * 32 * conv_pool_floats(a.nuvz, a.nconvlev) + (q % 32), a.nuvz, a.nconvlev, 32);
   w.nconvtop = nconvtop;
   const int row = (int)a.sorted_ids[i];
   const int slot = a.p.slot[row];
@@ -192,7 +198,7 @@ void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *t
   conv_heads_assign_kernel<<<nb, CB, 0, st>>>(a, sorted_keys);
 }
 void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) {
-  conv_column_kernel<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(a, c0, c1);
+  conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
 }
 void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st) {
   if (i1 > i0) conv_redist_kernel<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(a, c0, i0, i1, mode);

@@ -52,10 +52,12 @@ FPB_HD inline float c_powi(float x, int m) { // real**integer as libgcc's __powi
   return m < 0 ? 1.f / y : y;
 }
 
-// One column: conv_mod's arrays + convect's work arrays.  Vectors are 1-based (element i at [i]),
-// matrices Fortran-ordered: (i,j) at [i + ld*j].
+// One column: conv_mod's arrays + convect's work arrays.  Vectors are 1-based (element i at
+// [i*stride]), matrices Fortran-ordered: (i,j) at [(i + ld*j)*stride].  stride = 32 on the device: the
+// 32 columns of a warp interleave their work slices, so that lanes touching the same element of
+// their own column -- the normal case, the lanes run the same loops -- share cache lines.
 struct ConvWork {
-  int nuvz, nconvlev, ld;
+  int nuvz, nconvlev, ld, stride;
   const float *akz, *bkz, *akm, *bkm; // 1-based hybrid coefficients (src/com_mod.f90, akz(nuvz) ...)
   // conv_mod
   float *pconv, *phconv, *dpr, *pconv_hpa, *phconv_hpa, *tconv, *qconv, *qsconv, *ft, *fq, *sub;
@@ -66,20 +68,22 @@ struct ConvWork {
   float *fup, *fdown, *m, *mp, *tvp, *tv, *water, *qp, *ep, *th, *wt, *evap, *clw, *sigp, *tp, *cpn, *lv, *lvcp,
       *h, *hp, *gz, *hm, *uvzlev;
   int *nent;
-  float *ment, *qent, *elij, *sij;
+  float *ment, *elij, *sij;
 };
 
 constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more vector)
 
+// floats of one column's slice
 FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
   const size_t lv = (size_t)nuvz + 4, ld = (size_t)nconvlev + 3;
-  return (CONV_NVEC + 1) * lv + 5 * ld * ld;
+  return (CONV_NVEC + 1) * lv + 4 * ld * ld;
 }
 
-// carve the column's slice of the pool
-FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev) {
-  const size_t lv = (size_t)nuvz + 4;
-  w.nuvz = nuvz; w.nconvlev = nconvlev; w.ld = nconvlev + 3;
+// carve the column's slice: `pool` = first float of the slice (for stride 32: of the warp's block of
+// 32 slices, plus the lane)
+FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, int stride = 1) {
+  const size_t lv = ((size_t)nuvz + 4) * stride;
+  w.nuvz = nuvz; w.nconvlev = nconvlev; w.ld = nconvlev + 3; w.stride = stride;
   float **vec[CONV_NVEC] = {&w.pconv, &w.phconv, &w.dpr, &w.pconv_hpa, &w.phconv_hpa, &w.tconv, &w.qconv, &w.qsconv,
                             &w.ft, &w.fq, &w.sub, &w.fup, &w.fdown, &w.m, &w.mp, &w.tvp, &w.tv, &w.water, &w.qp,
                             &w.ep, &w.th, &w.wt, &w.evap, &w.clw, &w.sigp, &w.tp, &w.cpn, &w.lv, &w.lvcp, &w.h,
@@ -88,16 +92,15 @@ FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev) 
   for (int k = 0; k < CONV_NVEC - 1; k++) { *vec[k] = p; p += lv; }
   w.nent = reinterpret_cast<int *>(p); p += lv;
   p += lv; // (spare)
-  const size_t ld2 = (size_t)w.ld * w.ld;
+  const size_t ld2 = (size_t)w.ld * w.ld * stride;
   w.fmass = p; p += ld2;
   w.ment = p; p += ld2;
-  w.qent = p; p += ld2;
   w.elij = p; p += ld2;
   w.sij = p;
 }
 
-#define CV(a, i) w.a[(i)]
-#define CM(a, i, j) w.a[(i) + w.ld * (j)]
+#define CV(a, i) w.a[(size_t)(i) * w.stride]
+#define CM(a, i, j) w.a[(size_t)((i) + w.ld * (j)) * w.stride]
 
 // src/ew.f90: saturation vapour pressure over water [Pa] (Goff-Gratch)
 FPB_HD inline float conv_ew(float x) {
@@ -191,11 +194,9 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
   for (int i = 1; i <= nl + 1; i++) {
     CV(ft, i) = 0.0f; CV(fq, i) = 0.0f; CV(fdown, i) = 0.0f; CV(sub, i) = 0.0f; CV(fup, i) = 0.0f;
     CV(m, i) = 0.0f; CV(mp, i) = 0.0f;
-    for (int j = 1; j <= nl + 1; j++) {
-      CM(fmass, i, j) = 0.0f;
-      CM(ment, i, j) = 0.0f;
-    }
   }
+  // (FMASS, MENT, ELIJ, SIJ: the reference zeroes them over (NL+1)^2 here and at :529-545; they are
+  //  only ever read inside [1, INB+2]^2, so they are zeroed there, below, once INB is known)
   for (int i = 1; i <= nl + 1; i++) {
     const float q = CV(qconv, i);
     const float rdcp = (RD * (1.f - q) + q * RV) / (CPD * (1.f - q) + q * CPV);
@@ -287,11 +288,6 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     CV(evap, i) = 0.0f;
     CV(wt, i) = OMTSNOW;
     CV(lvcp, i) = CV(lv, i) / CV(cpn, i);
-    for (int j = 1; j <= nl + 1; j++) {
-      CM(qent, i, j) = CV(qconv, j);
-      CM(elij, i, j) = 0.0f;
-      CM(sij, i, j) = 0.0f;
-    }
   }
   CV(qp, 1) = CV(qconv, 1);
   for (int i = 2; i <= nl + 1; i++) CV(qp, i) = CV(qconv, i - 1);
@@ -309,6 +305,16 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     }
   }
   inb = inb > inb1 ? inb : inb1;
+  { // the matrices, over the part of them that is ever read (calcmatrix / redist go up to nconvtop <= INB+2)
+    const int nz0 = (inb + 2) < (nl + 1) ? (inb + 2) : (nl + 1);
+    for (int j = 1; j <= nz0; j++)
+      for (int i = 1; i <= nz0; i++) {
+        CM(fmass, i, j) = 0.0f;
+        CM(ment, i, j) = 0.0f;
+        CM(elij, i, j) = 0.0f;
+        CM(sij, i, j) = 0.0f;
+      }
+  }
   cape = capem + byp;
   float defrac = capem - cape;
   defrac = c_max(defrac, 0.001f);
@@ -368,7 +374,6 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
         altem = altem - (bf2 - 1.f) * cwat;
       }
       if (CM(sij, i, j) > 0.0f && CM(sij, i, j) < 0.9f) {
-        CM(qent, i, j) = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti;
         CM(elij, i, j) = altem;
         CM(elij, i, j) = c_max(0.0f, CM(elij, i, j));
         CM(ment, i, j) = CV(m, i) / (1.f - CM(sij, i, j));
@@ -379,7 +384,6 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     }
     if (CV(nent, i) == 0) {
       CM(ment, i, i) = CV(m, i);
-      CM(qent, i, i) = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
       CM(elij, i, i) = CV(clw, i);
       CM(sij, i, i) = 1.0f;
     }
@@ -431,7 +435,6 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
       if (bsum < 1.0e-18f) {
         CV(nent, i) = 0;
         CM(ment, i, i) = CV(m, i);
-        CM(qent, i, i) = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
         CM(elij, i, i) = CV(clw, i);
         CM(sij, i, i) = 1.0f;
       }
@@ -515,15 +518,16 @@ FPB_UNROLL(4)
     float amp1 = 0.0f, ad = 0.0f;
     if (i >= nk)
       for (int kq = i + 1; kq <= inb + 1; kq++) amp1 = amp1 + CV(m, kq);
-    for (int kq = 1; kq <= i; kq++) {
+    // (rows 1..ICB of MENT are zero -- only rows ICB+1..INB are ever set -- and x + 0.0 == x)
+    for (int kq = icb + 1; kq <= i; kq++) {
 FPB_UNROLL(8)
       for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + CM(ment, kq, j);
     }
     CV(fup, i) = amp1;
     if ((2.f * G * dpinv * amp1) >= delti) iflag = 4;
-    for (int kq = 1; kq <= i - 1; kq++) {
+    for (int kq = icb; kq <= i - 1; kq++) { // (columns 1..ICB-1 of MENT are zero)
 FPB_UNROLL(8)
-      for (int j = i; j <= inb; j++) ad = ad + CM(ment, j, kq);
+      for (int j = (i > icb + 1 ? i : icb + 1); j <= inb; j++) ad = ad + CM(ment, j, kq);
     }
     CV(fdown, i) = ad;
   }

@@ -34,7 +34,7 @@ extern "C" int conv_check_column(int nuvz, int nconvlev, const float *akz, const
       const int levold = conv_levold(w, z[i]);
       if (levold > 0) z[i] = conv_redist(w, z[i], levold, rn[used++], ldirect, lsynctime);
     }
-    memcpy(fmassfrac, w.fmass, sizeof(float) * w.ld * w.ld);
+    memcpy(fmassfrac, w.fmass, sizeof(float) * w.ld * w.ld); // (stride 1 on the host)
     memcpy(sub, w.sub, sizeof(float) * (nuvz + 2));
     memcpy(uvzlev, w.uvzlev, sizeof(float) * (nuvz + 2));
   }
