@@ -199,6 +199,7 @@ def load_engine_lib():
     L.fpb_comm_finalize.argtypes = [H]
     L.fpb_set_convection.argtypes = [H, _i, _i, _i, _pf, _pf, _pf, _pf]
     L.fpb_upload_convmet.argtypes = [H, _i, C.POINTER(FpbConvPtrs)]
+    L.fpb_upload_convmet_nest.argtypes = [H, _i, _i, C.POINTER(FpbConvPtrs)]
     L.fpb_convmix.argtypes = [H, _i, _pi, _pi]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
     L.fpb_boundcond_domainfill.argtypes = [H, _i, _i]

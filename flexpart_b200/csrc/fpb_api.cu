@@ -262,10 +262,10 @@ struct fpb_handle {
   struct Conv {
     int nuvz = 0, nuvzmax = 0, nconvlev = 0;
     float *d_ab = nullptr;                 // akz, bkz, akm, bkm: 4 x (nuvz + 1), 1-based
-    float2 *CT[FPB_NSLOTS] = {};
-    float4 *CS[FPB_NSLOTS] = {};
-    bool have[FPB_NSLOTS] = {};
-    float *cbaseflux = nullptr, *cbase_bak = nullptr;
+    float2 *CT[FPB_MAXNESTS + 1][FPB_NSLOTS] = {};   // [0]: mother grid, [l]: nested input grid l
+    float4 *CS[FPB_MAXNESTS + 1][FPB_NSLOTS] = {};
+    bool have[FPB_MAXNESTS + 1][FPB_NSLOTS] = {};
+    float *cbaseflux[FPB_MAXNESTS + 1] = {}, *cbase_bak[FPB_MAXNESTS + 1] = {};
     float *pool = nullptr;
     int pool_cols = 0;
     ScatterWork sw;
@@ -649,11 +649,13 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->rel.d_offsets); cudaFree(h->rel.d_uniforms); cudaFree(h->rel.d_block_counts); cudaFree(h->rel.d_out);
   {
     auto &V = h->conv;
-    cudaFree(V.d_ab); cudaFree(V.cbaseflux); cudaFree(V.cbase_bak); cudaFree(V.pool); cudaFree(V.block_counts);
+    cudaFree(V.d_ab); cudaFree(V.pool); cudaFree(V.block_counts);
+    for (auto &q : V.cbaseflux) cudaFree(q);
+    for (auto &q : V.cbase_bak) cudaFree(q);
     cudaFree(V.col_key); cudaFree(V.colidx); cudaFree(V.col_start); cudaFree(V.col_lconv); cudaFree(V.key_by_slot);
     cudaFree(V.d_total); cudaFree(V.draws); cudaFree(V.rn_by_slot);
-    for (auto &q : V.CT) cudaFree(q);
-    for (auto &q : V.CS) cudaFree(q);
+    for (auto &g : V.CT) for (auto &q : g) cudaFree(q);
+    for (auto &g : V.CS) for (auto &q : g) cudaFree(q);
     scatter_free(V.sw);
   }
   cudaFree(h->d_rannumb); cudaFree(h->d_nrand_init); cudaFree(h->d_nrand_adv);
@@ -1706,8 +1708,6 @@ extern "C" int fpb_set_convection(fpb_handle *h, int32_t nuvz, int32_t nuvzmax, 
   if (!h || !akz || !bkz || !akm || !bkm) return fail("fpb_set_convection: null argument");
   if (nuvz < 4 || nuvz > nuvzmax || nconvlev < 2 || nconvlev > nuvz - 2)
     return fail("fpb_set_convection: nuvz = %d (max %d), nconvlev = %d out of range", nuvz, nuvzmax, nconvlev);
-  if (h->cfg.numbnests > 0)
-    return fail("fpb_set_convection: nested input grids are not built for convmix (src/convmix.f90:198-281)");
   CK(cudaSetDevice(h->device));
   auto &V = h->conv;
   V.nuvz = nuvz; V.nuvzmax = nuvzmax; V.nconvlev = nconvlev;
@@ -1719,31 +1719,42 @@ extern "C" int fpb_set_convection(fpb_handle *h, int32_t nuvz, int32_t nuvzmax, 
   for (int q = 0; q < 4; q++)
     for (int k = 0; k < nuvz; k++) ab[q * n1 + k + 1] = src[q][k];
   CK(cudaMemcpy(V.d_ab, ab.data(), ab.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (!V.cbaseflux) DA(V.cbaseflux, (size_t)h->d.nxd * h->d.nyd); // cbaseflux = 0 at the start
+  for (int g = 0; g <= h->cfg.numbnests; g++) { // cbaseflux(n) = 0 at the start
+    const size_t n2 = g ? (size_t)h->cfg.nxn[g - 1] * h->cfg.nyn[g - 1] : (size_t)h->d.nxd * h->d.nyd;
+    if (!V.cbaseflux[g]) { DA(V.cbaseflux[g], n2); DA(V.cbase_bak[g], n2); }
+  }
   return 0;
 }
 
-extern "C" int fpb_upload_convmet(fpb_handle *h, int32_t slot, const fpb_conv_ptrs *m) {
+static int upload_convmet(fpb_handle *h, int32_t slot, int32_t nest, const fpb_conv_ptrs *m) {
   if (!h || !m) return fail("fpb_upload_convmet: null argument");
   auto &V = h->conv;
+  const fpb_config &c = h->cfg;
   if (V.nuvz == 0) return fail("fpb_upload_convmet: fpb_set_convection has not been called");
   if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_convmet: slot %d", slot);
+  if (nest < 0 || nest > c.numbnests) return fail("fpb_upload_convmet: nest %d outside 0..numbnests=%d", nest, c.numbnests);
   if (!m->ps || !m->tt2 || !m->td2 || !m->tth || !m->qvh) return fail("fpb_upload_convmet: a field pointer is null");
   CK(cudaSetDevice(h->device));
   if (finish_met_upload(h)) return 1;
   const int s = slot - 1;
-  const size_t n2 = (size_t)h->d.nxd * h->d.nyd;
-  if (!V.CT[s]) { DA(V.CT[s], n2 * V.nuvz); DA(V.CS[s], n2); }
-  const fpb_config &c = h->cfg;
-  // tth, qvh: (nxmax, nymax, nuvzmax) -> {tth, qvh}[k][jy][ix]
+  const int nxd = nest ? c.nxn[nest - 1] : h->d.nxd, nyd = nest ? c.nyn[nest - 1] : h->d.nyd;
+  const int mx = nest ? c.nxmaxn : c.nxmax, my = nest ? c.nymaxn : c.nymax;
+  const size_t n2 = (size_t)nxd * nyd;
+  if (!V.CT[nest][s]) { DA(V.CT[nest][s], n2 * V.nuvz); DA(V.CS[nest][s], n2); }
+  // tth, qvh: (nxmax, nymax, nuvzmax) -> {tth, qvh}[k][jy][ix]: the first nuvz of the nuvzmax levels
   const float *q2[2] = {m->tth, m->qvh}, *s4[4] = {m->ps, m->tt2, m->td2, nullptr};
-  // (upload_group packs `nk` levels of an array whose level stride is nxmax*nymax: nuvz of nuvzmax)
-  if (upload_group(h, h->st_met, (float *)V.CT[s], 2, q2, V.nuvz)) return 1;
-  if (upload_group(h, h->st_met, (float *)V.CS[s], 4, s4, 1)) return 1;
+  if (upload_group(h, h->st_met, (float *)V.CT[nest][s], 2, q2, V.nuvz, nxd, nyd, mx, my)) return 1;
+  if (upload_group(h, h->st_met, (float *)V.CS[nest][s], 4, s4, 1, nxd, nyd, mx, my)) return 1;
   CK(cudaStreamSynchronize(h->st_met));
-  V.have[s] = true;
-  (void)c;
+  V.have[nest][s] = true;
   return 0;
+}
+extern "C" int fpb_upload_convmet(fpb_handle *h, int32_t slot, const fpb_conv_ptrs *m) {
+  return upload_convmet(h, slot, 0, m);
+}
+extern "C" int fpb_upload_convmet_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_conv_ptrs *m) {
+  if (nest < 1) return fail("fpb_upload_convmet_nest: nest %d", nest);
+  return upload_convmet(h, slot, nest, m);
 }
 
 // the reference's sort2 (src/sort2.f90, Numerical Recipes' quicksort of arr with brr alongside): the
@@ -1801,8 +1812,9 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   if (nconvecting) *nconvecting = 0;
   if (V.nuvz == 0) return fail("fpb_convmix: fpb_set_convection has not been called");
   if (!h->have_bracket) return fail("fpb_convmix: fpb_set_met_bracket has not been called");
-  if (!V.have[h->memind[0] - 1] || !V.have[h->memind[1] - 1])
-    return fail("fpb_convmix: fpb_upload_convmet of both time levels of the bracket is missing");
+  for (int g = 0; g <= h->cfg.numbnests; g++)
+    if (!V.have[g][h->memind[0] - 1] || !V.have[g][h->memind[1] - 1])
+      return fail("fpb_convmix: fpb_upload_convmet%s of both time levels of the bracket is missing (grid %d)", g ? "_nest" : "", g);
   if (h->numpart <= 0) return 0; // src/convmix.f90:75
   CK(cudaSetDevice(h->device));
   const fpb_config &c = h->cfg;
@@ -1828,10 +1840,8 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
     V.cap_rows = n;
   }
   if (!V.d_total) DA(V.d_total, 1);
-  const size_t nb2 = (size_t)h->d.nxd * h->d.nyd;
   if (refrng && !V.key_by_slot) {
     DA(V.key_by_slot, (size_t)c.maxpart); DA(V.draws, (size_t)c.maxpart); DA(V.rn_by_slot, (size_t)c.maxpart);
-    DA(V.cbase_bak, nb2);
   }
   if (scatter_reserve(V.sw, (size_t)n, 1)) return fail("%s", scatter_error());
 
@@ -1842,8 +1852,18 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   a.nuvz = V.nuvz; a.nconvlev = V.nconvlev;
   const size_t n1 = (size_t)V.nuvz + 1;
   a.akz = V.d_ab; a.bkz = V.d_ab + n1; a.akm = V.d_ab + 2 * n1; a.bkm = V.d_ab + 3 * n1;
-  for (int m = 0; m < 2; m++) { a.CT[m] = V.CT[h->memind[m] - 1]; a.CS[m] = V.CS[h->memind[m] - 1]; }
-  a.cbaseflux = V.cbaseflux;
+  long long maxcol = (long long)c.nx * c.ny;
+  for (int g = 0; g <= FPB_MAXNESTS; g++) {
+    for (int m = 0; m < 2; m++) { a.CT[g][m] = V.CT[g][h->memind[m] - 1]; a.CS[g][m] = V.CS[g][h->memind[m] - 1]; }
+    a.cbaseflux[g] = V.cbaseflux[g];
+    a.gnx[g] = g ? c.nxn[g - 1] : c.nx;
+    a.gnxd[g] = g ? c.nxn[g - 1] : h->d.nxd;
+    a.gnyd[g] = g ? c.nyn[g - 1] : h->d.nyd;
+    if (g >= 1 && g <= c.numbnests) maxcol = std::max(maxcol, (long long)c.nxn[g - 1] * c.nyn[g - 1]);
+  }
+  a.col_bits = 1;
+  while ((1ll << a.col_bits) < maxcol + 1) a.col_bits++;
+  a.ecmwf_eps = 1;
   a.ztop = h->height[c.nz - 1];
   a.keys = V.sw.keys[0]; a.ids = V.sw.ids[0];
   a.key_by_slot = refrng ? V.key_by_slot : nullptr;
@@ -1852,9 +1872,9 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   a.draws = V.draws; a.rn_by_slot = nullptr; a.sorted_ids = nullptr;
   if (refrng) CK(cudaMemsetAsync(V.key_by_slot, 0xff, (size_t)h->numpart * sizeof(int32_t), h->stream)); // -1
   fpb_convmix_keys(a, h->stream);
-  int bits = 1;
-  while ((1ll << bits) < (long long)c.nx * c.ny + 1) bits++;
-  bits = ((bits + 1 + 7) / 8) * 8; // + the all-ones key of the rows that are not due
+  int gbits = 0;
+  while ((1 << gbits) < c.numbnests + 1) gbits++;
+  int bits = ((a.col_bits + gbits + 1 + 7) / 8) * 8; // + the all-ones key of the rows that are not due
   if (bits > 32) bits = 32;
   int cur = 0;
   if (scatter_sort_pairs(V.sw, (size_t)n, bits, h->stream, &h->launches, &cur)) return fail("%s", scatter_error());
@@ -1881,21 +1901,33 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
       std::vector<float> rn(np, 0.f);
       CK(cudaMemcpy(igrid.data(), V.key_by_slot, (size_t)np * sizeof(int32_t), cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(draws.data(), V.draws, (size_t)np, cudaMemcpyDeviceToHost));
-      for (int i = 0; i < np; i++) ipoint[i] = i;
-      sort2_reference(np, igrid.data(), ipoint.data());
-      for (int kq = 0; kq < np; kq++) {
-        if (igrid[kq] == -1) continue;
-        const int ip = ipoint[kq];
-        if (draws[ip]) rn[ip] = h->ran3.next(V.iseed);
+      // the mother grid first, then every nest with its own sort2 (src/convmix.f90:150-196,203-281)
+      std::vector<int32_t> ig(np);
+      for (int g = 0; g <= c.numbnests; g++) {
+        for (int i = 0; i < np; i++) {
+          ipoint[i] = i;
+          const int32_t kk = igrid[i];
+          ig[i] = (kk != -1 && (kk >> a.col_bits) == g) ? (kk & ((1 << a.col_bits) - 1)) + 1 : -1;
+        }
+        sort2_reference(np, ig.data(), ipoint.data());
+        for (int kq = 0; kq < np; kq++) {
+          if (ig[kq] == -1) continue;
+          const int ip = ipoint[kq];
+          if (draws[ip]) rn[ip] = h->ran3.next(V.iseed);
+        }
       }
       CK(cudaMemcpy(V.rn_by_slot, rn.data(), (size_t)np * sizeof(float), cudaMemcpyHostToDevice));
       a.rn_by_slot = V.rn_by_slot;
       // the columns are computed once more below: cbaseflux must not be advanced twice
-      CK(cudaMemcpyAsync(V.cbaseflux, V.cbase_bak, nb2 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      for (int g = 0; g <= c.numbnests; g++)
+        CK(cudaMemcpyAsync(V.cbaseflux[g], V.cbase_bak[g], (size_t)a.gnxd[g] * a.gnyd[g] * sizeof(float),
+                           cudaMemcpyDeviceToDevice, h->stream));
     }
     if (pass == 0) {
       CK(cudaMemsetAsync(V.draws, 0, (size_t)h->numpart, h->stream));
-      CK(cudaMemcpyAsync(V.cbase_bak, V.cbaseflux, nb2 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      for (int g = 0; g <= c.numbnests; g++)
+        CK(cudaMemcpyAsync(V.cbase_bak[g], V.cbaseflux[g], (size_t)a.gnxd[g] * a.gnyd[g] * sizeof(float),
+                           cudaMemcpyDeviceToDevice, h->stream));
     }
     for (int c0 = 0; c0 < ncols; c0 += V.pool_cols) {
       const int c1 = std::min(ncols, c0 + V.pool_cols);

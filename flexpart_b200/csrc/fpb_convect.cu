@@ -28,15 +28,29 @@ constexpr int CB = 1024;
 __global__ void __launch_bounds__(256) conv_keys_kernel(const ConvmixArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nrows) return;
+  const DevCfg &c = a.cfg;
   unsigned key = 0xffffffffu;
-  if (a.p.itra1[i] == a.cfg.itime) {
+  if (a.p.itra1[i] == c.itime) {
     const float x = (float)a.p.xtra1[i], y = (float)a.p.ytra1[i]; // x = xtra1(ipart): real
-    const int ix = (int)roundf(x), jy = (int)roundf(y);           // nint
-    key = (unsigned)(jy * a.cfg.nx + ix);
+    int ngrid = 0; // innermost nest the particle is in, src/convmix.f90:100-118
+    const float eps = a.ecmwf_eps ? c.eps : 0.f;
+    for (int j = c.numbnests; j >= 1; j--)
+      if (x > c.xln[j - 1] + eps && x < c.xrn[j - 1] - eps && y > c.yln[j - 1] + eps && y < c.yrn[j - 1] - eps) {
+        ngrid = j;
+        break;
+      }
+    int ix, jy;
+    if (ngrid > 0) {
+      const float xtn = (x - c.xln[ngrid - 1]) * c.xresoln[ngrid - 1], ytn = (y - c.yln[ngrid - 1]) * c.yresoln[ngrid - 1];
+      ix = (int)roundf(xtn); jy = (int)roundf(ytn); // nint
+    } else {
+      ix = (int)roundf(x); jy = (int)roundf(y);
+    }
+    key = ((unsigned)ngrid << a.col_bits) | (unsigned)(jy * a.gnx[ngrid] + ix);
   }
   a.keys[i] = key;
   a.ids[i] = (unsigned)i;
-  if (a.key_by_slot) a.key_by_slot[a.p.slot[i]] = (key == 0xffffffffu) ? -1 : (int)key + 1; // igrid(ipart)
+  if (a.key_by_slot) a.key_by_slot[a.p.slot[i]] = (int)key; // (grid, igrid - 1) of the particle, -1: not due
 }
 
 // heads of the runs of equal keys among the sorted keys
@@ -129,23 +143,25 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   conv_carve(w, pool, nuvz, a.nconvlev, 32);
   w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
   const unsigned key = a.col_key[c];
-  const int jy = (int)(key / (unsigned)cf.nx), ix = (int)(key - (unsigned)jy * cf.nx);
-  // src/convmix.f90:62-65,163-171
+  const int g = (int)(key >> a.col_bits);
+  const unsigned col = key & ((1u << a.col_bits) - 1u);
+  const int jy = (int)(col / (unsigned)a.gnx[g]), ix = (int)(col - (unsigned)jy * a.gnx[g]);
+  // src/convmix.f90:62-65,163-171 (nests: :221-233)
   const float dt1 = (float)(cf.itime - cf.memtime[0]), dt2 = (float)(cf.memtime[1] - cf.itime);
   const float dtt = 1.f / (dt1 + dt2);
-  const size_t o2 = (size_t)jy * cf.nxd + ix, plane = (size_t)cf.nxd * cf.nyd;
-  const float4 s1 = a.CS[0][o2], s2 = a.CS[1][o2];
+  const size_t o2 = (size_t)jy * a.gnxd[g] + ix, plane = (size_t)a.gnxd[g] * a.gnyd[g];
+  const float4 s1 = a.CS[g][0][o2], s2 = a.CS[g][1][o2];
   w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
   w.tt2conv = (s1.y * dt2 + s2.y * dt1) * dtt;
   w.td2conv = (s1.z * dt2 + s2.z * dt1) * dtt;
   for (int kz = 1; kz <= nuvz - 1; kz++) {
-    const float2 q1 = a.CT[0][(size_t)kz * plane + o2], q2 = a.CT[1][(size_t)kz * plane + o2]; // level kz+1
+    const float2 q1 = a.CT[g][0][(size_t)kz * plane + o2], q2 = a.CT[g][1][(size_t)kz * plane + o2]; // level kz+1
     w.tconv[(size_t)kz * w.stride] = (q1.x * dt2 + q2.x * dt1) * dtt;
     w.qconv[(size_t)kz * w.stride] = (q1.y * dt2 + q2.y * dt1) * dtt;
   }
-  float cbmf = a.cbaseflux[o2];
+  float cbmf = a.cbaseflux[g][o2];
   const bool lconv = conv_calcmatrix(w, (float)abs(cf.lsynctime), cbmf);
-  a.cbaseflux[o2] = cbmf;
+  a.cbaseflux[g][o2] = cbmf;
   a.col_lconv[c] = lconv ? w.nconvtop : 0;
   if (lconv) conv_uvzlev(w);
 }

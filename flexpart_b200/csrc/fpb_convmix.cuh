@@ -11,9 +11,13 @@ struct ConvmixArgs {
   int nrows;                  // rows to look at (live rows lead the arrays after a cell sort)
   int nuvz, nconvlev;
   const float *akz, *bkz, *akm, *bkm; // device, 1-based (element k at [k])
-  const float2 *CT[2];        // {tth, qvh}[k][jy][ix] of memind(1), memind(2), k = 0..nuvz-1 (Fortran level k+1)
-  const float4 *CS[2];        // {ps, tt2, td2, -}[jy][ix]
-  float *cbaseflux;           // [nyd*nxd] cloud base mass flux of every column, kept between calls
+  // grid g = 0: mother grid, g = l: nested input grid l (src/convmix.f90:198-281)
+  const float2 *CT[FPB_MAXNESTS + 1][2]; // {tth, qvh}[k][jy][ix] of memind(1), memind(2), k = 0..nuvz-1 (Fortran level k+1)
+  const float4 *CS[FPB_MAXNESTS + 1][2]; // {ps, tt2, td2, -}[jy][ix]
+  float *cbaseflux[FPB_MAXNESTS + 1];    // cloud base mass flux of every column, kept between calls
+  int gnx[FPB_MAXNESTS + 1], gnxd[FPB_MAXNESTS + 1], gnyd[FPB_MAXNESTS + 1]; // nx of igrid = 1 + jy*nx + ix; device extents
+  int col_bits;               // key = (grid << col_bits) | (jy*nx + ix)
+  int ecmwf_eps;              // nest test with the eps margin (metdata_format = ECMWF, src/convmix.f90:104-110)
   float ztop;                 // height(nz)
   unsigned *keys, *ids;       // column key / row of every row (sort input)
   const unsigned *sorted_ids; // rows in column order

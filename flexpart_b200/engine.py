@@ -219,13 +219,17 @@ class Engine:
         arrs = [np.ascontiguousarray(a[:nuvz], np.float32) for a in (akz, bkz, akm, bkm)]
         self._check(self.L.fpb_set_convection(self.h, nuvz, nuvzmax, nconvlev, *[_fp(a) for a in arrs]))
 
-    def upload_convmet(self, slot, ps, tt2, td2, tth, qvh):
-        """ps, tt2, td2 (nxmax,nymax) and tth, qvh (nxmax,nymax,nuvzmax), Fortran order, float32"""
+    def upload_convmet(self, slot, ps, tt2, td2, tth, qvh, nest=0):
+        """ps, tt2, td2 (nxmax,nymax) and tth, qvh (nxmax,nymax,nuvzmax), Fortran order, float32;
+        nest >= 1: the fields of that nested input grid (nxmaxn, nymaxn extents)"""
         from .abi import FpbConvPtrs
         m = FpbConvPtrs()
         keep = [np.asfortranarray(a, np.float32) for a in (ps, tt2, td2, tth, qvh)]
         m.ps, m.tt2, m.td2, m.tth, m.qvh = [_fp(a) for a in keep]
-        self._check(self.L.fpb_upload_convmet(self.h, slot, C.byref(m)))
+        if nest:
+            self._check(self.L.fpb_upload_convmet_nest(self.h, slot, nest, C.byref(m)))
+        else:
+            self._check(self.L.fpb_upload_convmet(self.h, slot, C.byref(m)))
 
     def convmix(self, itime):
         """convmix(itime); returns (occupied columns, convecting columns)"""

@@ -408,8 +408,12 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend);
  *                       (src/gridcheck_ecmwf.f90:553-566) and akz, bkz, akm, bkm (1:nuvz)
  *   fpb_upload_convmet  next to every fpb_upload_met: ps, tt2, td2 (nxmax,nymax) and tth, qvh
  *                       (nxmax,nymax,nuvzmax) of the time level (src/com_mod.f90:372-417)
- * ECMWF fields (metdata_format = GRIBFILE_CENTRE_ECMWF) on the mother grid; nested input grids
- * (src/convmix.f90:198-281) and the flux diagnostics (calcfluxes, iflux = 1) are not built. */
+ *   fpb_upload_convmet_nest  the same fields of nested input grid `nest` (psn, tt2n, td2n (nxmaxn,
+ *                       nymaxn); tthn, qvhn (nxmaxn,nymaxn,nuvzmax)): a particle inside a nest takes
+ *                       part in the nest's columns only (the innermost one, src/convmix.f90:100-134,
+ *                       198-281), with the nest's own cbasefluxn
+ * ECMWF fields (metdata_format = GRIBFILE_CENTRE_ECMWF); the flux diagnostics (calcfluxes, iflux = 1)
+ * are not built. */
 typedef struct fpb_conv_ptrs {
   const float *ps, *tt2, *td2;
   const float *tth, *qvh;
@@ -417,6 +421,7 @@ typedef struct fpb_conv_ptrs {
 int fpb_set_convection(fpb_handle *h, int32_t nuvz, int32_t nuvzmax, int32_t nconvlev, const float *akz,
                        const float *bkz, const float *akm, const float *bkm);
 int fpb_upload_convmet(fpb_handle *h, int32_t slot, const fpb_conv_ptrs *met);
+int fpb_upload_convmet_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_conv_ptrs *met);
 int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns /* occupied columns, may be NULL */,
                 int32_t *nconvecting /* of those, columns with convection, may be NULL */);
 

@@ -45,14 +45,23 @@ def sounding(rs, akz, bkz, nuvz):
     return tconv, qconv, ps, tt2, td2
 
 
-def conv_fields(cb, akz, bkz, nuvz, seed, tshift=0.0):
+def conv_fields(cb, akz, bkz, nuvz, seed, tshift=0.0, nest=0):
     """ps, tt2, td2 (nxmax,nymax) and tth, qvh (nxmax,nymax,nuvzmax = nzmax) of one time level: a smooth
-    field of soundings (warm and moist in the tropics so that part of the columns convects)"""
+    field of soundings (warm and moist in the tropics so that part of the columns convects); nest >= 1:
+    the same on nested input grid `nest` ((nxmaxn,nymaxn) extents, its own coordinates)"""
     c = cb.cfg
     rs = np.random.RandomState(seed)
-    nxm, nym, nzm = c.nxmax, c.nymax, c.nzmax
-    lon = np.arange(nxm)[:, None] * c.dx + c.xlon0
-    lat = np.arange(nym)[None, :] * c.dy + c.ylat0
+    nzm = c.nzmax
+    if nest:
+        l = nest - 1
+        nxm, nym = c.nxmaxn, c.nymaxn
+        lon = (c.xln[l] + np.arange(nxm)[:, None] / c.xresoln[l]) * c.dx + c.xlon0
+        lat = (c.yln[l] + np.arange(nym)[None, :] / c.yresoln[l]) * c.dy + c.ylat0
+        tshift = tshift + 0.7 * nest          # (a nest that differs from the mother grid shows a wrong pick)
+    else:
+        nxm, nym = c.nxmax, c.nymax
+        lon = np.arange(nxm)[:, None] * c.dx + c.xlon0
+        lat = np.arange(nym)[None, :] * c.dy + c.ylat0
     ps = (100000.0 + 1500.0 * np.sin(np.deg2rad(2 * lon)) * np.cos(np.deg2rad(lat))).astype(np.float32)
     t0 = 272.0 + 32.0 * np.cos(np.deg2rad(lat)) ** 2 + 2.0 * np.sin(np.deg2rad(3 * lon)) + tshift
     rh0 = np.clip(0.55 + 0.42 * np.cos(np.deg2rad(lat)) ** 2 + 0.1 * np.sin(np.deg2rad(5 * lon)), 0.2, 0.98)

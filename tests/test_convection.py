@@ -107,11 +107,12 @@ def test_column_code_is_bit_identical_to_the_reference_routines(hostlib, ldirect
 # ------------------------------------------------------------------------------------------
 # GPU: fpb_convmix against the reference's convmix
 # ------------------------------------------------------------------------------------------
-def _conv_setup(rng_mode, ldirect=1, n=6000, sort_interval=0):
+def _conv_setup(rng_mode, ldirect=1, n=6000, sort_interval=0, met_nests=()):
     nuvz = 138
     akm, bkm, akz, bkz, nconvlev = conv_cases.hybrid_levels(nuvz)
     cb = cases.config_small(nrel=4, npart_each=n // 4, nz=nuvz, height=fb.synth_heights(nuvz), ldirect=ldirect,
-                            rng_mode=rng_mode, math_mode=fb.MATH_STRICT, sort_interval=sort_interval)
+                            rng_mode=rng_mode, math_mode=fb.MATH_STRICT, sort_interval=sort_interval,
+                            met_nests=met_nests)
     sign = 1 if ldirect == 1 else -1
     f0 = conv_cases.conv_fields(cb, akz, bkz, nuvz, 1)
     f1 = conv_cases.conv_fields(cb, akz, bkz, nuvz, 2, tshift=1.5)
@@ -191,4 +192,60 @@ def test_convmix_philox_moves_only_convecting_columns():
     assert not moved[n - 200:].any()
     # a second engine gives the same result (counter-based stream), also through a step in between
     eng.conccalc(0, 1.0); eng.step(0)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_convmix_nested_input_grids_bit_identical():
+    """Two nested input grids (src/convmix.f90:100-134,198-281): a particle takes part in the columns of the
+    innermost nest it is in, with the nest's own soundings and cbasefluxn; the reference visits the mother
+    grid first, then nest by nest, each with its own sort2 -- the replayed ran3 stream follows that."""
+    if not ref_api.available():
+        pytest.skip("oracle/_ref/libflexref.so not built")
+    nests = [(-40.0, -10.0, 81, 41, 1.0, 1.0), (-10.0, 0.0, 81, 61, 0.25, 0.25)]
+    cb, (akm, bkm, akz, bkz, nconvlev, nuvz), (f0, f1), p, sign = _conv_setup(fb.RNG_REFERENCE, 1, 8000, 1, nests)
+    c, n = cb.cfg, p.numpart
+    assert c.numbnests == 2
+    r = np.random.RandomState(3)
+    p.xtra1[:5000] = (r.uniform(-50.0, 50.0, 5000) - c.xlon0) / c.dx      # most particles in and around the nests
+    p.ytra1[:5000] = (r.uniform(-20.0, 40.0, 5000) - c.ylat0) / c.dy
+    fn = {l: (conv_cases.conv_fields(cb, akz, bkz, nuvz, 1, nest=l), conv_cases.conv_fields(cb, akz, bkz, nuvz, 2, 1.5, nest=l))
+          for l in (1, 2)}
+    ref = ref_api.Ref(cb, maxrand=2000)
+    ref.set("nuvz", nuvz); ref.set("nconvlev", nconvlev)
+    for nm, a in (("akm", akm), ("bkm", bkm), ("akz", akz), ("bkz", bkz)):
+        ref.arr(nm)[:nuvz] = a[1:nuvz + 1]
+    for slot, f in ((1, f0), (2, f1)):
+        for nm, a in zip(("ps", "tt2", "td2"), f[:3]):
+            ref.arr(nm)[:, :, 0, slot - 1] = a
+        ref.arr("tth")[:, :, :, slot - 1] = f[3]; ref.arr("qvh")[:, :, :, slot - 1] = f[4]
+        for l in (1, 2):
+            g = fn[l][slot - 1]
+            for nm, a in zip(("psn", "tt2n", "td2n"), g[:3]):
+                ref.arr(nm)[:, :, 0, slot - 1, l - 1] = a
+            ref.arr("tthn")[:, :, :, slot - 1, l - 1] = g[3]; ref.arr("qvhn")[:, :, :, slot - 1, l - 1] = g[4]
+    ref.set_met_bracket((1, 2), (0, 10800))
+    ref.arr("cbaseflux")[:] = 0.0; ref.arr("cbasefluxn")[:] = 0.0
+    ref.push_state(p)
+    eng = fb.Engine(cb)
+    m0, m1 = fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(10800)
+    eng.upload_met(1, m0); eng.upload_met(2, m1)
+    for l in (1, 2):
+        eng.upload_met_nest(1, l, fb.MetFields(cb, nest=l).synth(0)); eng.upload_met_nest(2, l, fb.MetFields(cb, nest=l).synth(10800))
+    eng.set_met_bracket((1, 2), (0, 10800))
+    eng.set_convection(nuvz, c.nzmax, nconvlev, akz[1:], bkz[1:], akm[1:], bkm[1:])
+    eng.upload_convmet(1, *f0); eng.upload_convmet(2, *f1)
+    for l in (1, 2):
+        eng.upload_convmet(1, *fn[l][0], nest=l); eng.upload_convmet(2, *fn[l][1], nest=l)
+    eng.push_particles(p)
+    eng.sort_particles()
+    for k in range(2):
+        ref.L.f_convmix(C.byref(C.c_int(0)), C.byref(C.c_int(2)))
+        ncol, nconv = eng.convmix(0)
+        q = fb.Particles(c.maxpart, 1); q.numpart = n
+        eng.pull_particles(q)
+        zr = ref.arr("ztra1")[:n]
+        assert nconv > 20
+        assert np.array_equal(zr.view(np.uint32), q.ztra1[:n].view(np.uint32)), (k, np.abs(zr - q.ztra1[:n]).max())
+    assert (ref.arr("cbasefluxn")[:, :, 0] > 0).sum() > 5 and (ref.arr("cbasefluxn")[:, :, 1] > 0).sum() > 5
     eng.close()
