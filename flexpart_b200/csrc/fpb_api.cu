@@ -301,6 +301,14 @@ struct fpb_handle {
   bool timed_step = false, timed_conc = false;
   bool pending_init = true;
   ScatterWork scatter;
+  // deterministic deposition / receptor records (FPB_SCATTER_DETERMINISTIC), grown on demand
+  struct DepStore {
+    unsigned *keys[2] = {nullptr, nullptr};
+    float *vals[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    float *rec = nullptr; // receptor contributions [numreceptor*nspec][nslots]
+    size_t cap_rec = 0;
+  } depstore;
 
   // fpb_step_host pipeline lanes: chunk c runs on lane c % NLANES (own stream,
   // sort work area and work counter), so the copies of one chunk overlap the
@@ -308,6 +316,7 @@ struct fpb_handle {
   struct Lane {
     cudaStream_t st = nullptr;
     ScatterWork sw;
+    DepStore dep;
     int *d_work = nullptr;
     unsigned *d_nlive = nullptr;
   };
@@ -316,9 +325,69 @@ struct fpb_handle {
   cudaStream_t st_in = nullptr;              // all host-to-device copies of fpb_step_host, in chunk order
   cudaEvent_t ev_in[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_det[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_dep[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_ready = nullptr;
   bool lanes_ready = false;
 };
+
+// ---- deterministic deposition records -----------------------------------------------------------
+static void dep_free(fpb_handle::DepStore &s) {
+  for (int g = 0; g < 2; g++) { cudaFree(s.keys[g]); cudaFree(s.vals[g]); s.keys[g] = nullptr; s.vals[g] = nullptr; }
+  cudaFree(s.rec);
+  s.rec = nullptr;
+  s.cap = s.cap_rec = 0;
+}
+// record area for nslots particle slots starting at slot_base; keys cleared to "no record"
+static int dep_begin(fpb_handle *h, fpb_handle::DepStore &s, int nslots, int slot_base, cudaStream_t st,
+                     DevDepRecords &out) {
+  const size_t nrec = 4 * (size_t)nslots;
+  const int ngrids = h->cfg.nested_output == 1 ? 2 : 1;
+  if (nrec > s.cap) {
+    CK(cudaStreamSynchronize(st));
+    for (int g = 0; g < 2; g++) { cudaFree(s.keys[g]); cudaFree(s.vals[g]); s.keys[g] = nullptr; s.vals[g] = nullptr; }
+    for (int g = 0; g < ngrids; g++) {
+      CK(cudaMalloc((void **)&s.keys[g], nrec * sizeof(unsigned)));
+      CK(cudaMalloc((void **)&s.vals[g], nrec * h->cfg.nspec * sizeof(float)));
+    }
+    s.cap = nrec;
+  }
+  for (int g = 0; g < 2; g++) {
+    out.keys[g] = g < ngrids ? s.keys[g] : nullptr;
+    out.vals[g] = g < ngrids ? s.vals[g] : nullptr;
+    if (g < ngrids) CK(cudaMemsetAsync(s.keys[g], 0xff, nrec * sizeof(unsigned), st));
+  }
+  out.nrec = nrec;
+  out.slot_base = slot_base;
+  return 0;
+}
+// add the records to the (dry or wet) deposition grids, every cell in slot order
+static int dep_apply(fpb_handle *h, ScatterWork &sw, const DevDepRecords &r, float *grid, float *gridn, cudaStream_t st) {
+  const fpb_config &c = h->cfg;
+  const unsigned long long per = (unsigned long long)c.maxpointspec_act * c.nclassunc * c.maxageclass;
+  if (scatter_records_deterministic(sw, r.keys[0], r.vals[0], r.nrec, c.nspec, grid, c.numxgrid * c.numygrid,
+                                    per * c.numxgrid * c.numygrid, st, &h->launches))
+    return fail("%s", scatter_error());
+  if (c.nested_output == 1 &&
+      scatter_records_deterministic(sw, r.keys[1], r.vals[1], r.nrec, c.nspec, gridn, c.numxgridn * c.numygridn,
+                                    per * c.numxgridn * c.numygridn, st, &h->launches))
+    return fail("%s", scatter_error());
+  return 0;
+}
+// receptor contribution area [numreceptor*nspec][nslots], zeroed
+static int rec_begin(fpb_handle *h, fpb_handle::DepStore &s, int nslots, cudaStream_t st, DevConcArgs &a) {
+  const size_t n = (size_t)h->cfg.numreceptor * h->cfg.nspec * nslots;
+  if (n > s.cap_rec) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(s.rec);
+    s.rec = nullptr;
+    CK(cudaMalloc((void **)&s.rec, n * sizeof(float)));
+    s.cap_rec = n;
+  }
+  CK(cudaMemsetAsync(s.rec, 0, n * sizeof(float), st));
+  a.rec_vals = s.rec;
+  a.rec_nslots = nslots;
+  return 0;
+}
 
 static void fill_devcfg(fpb_handle *h) {
   const fpb_config &c = h->cfg;
@@ -662,15 +731,18 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->gridunc); cudaFree(h->griduncn); cudaFree(h->drygridunc); cudaFree(h->drygriduncn);
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
   scatter_free(h->scatter);
+  dep_free(h->depstore);
   for (auto &L : h->lanes) {
     if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
     scatter_free(L.sw);
+    dep_free(L.dep);
     cudaFree(L.d_work); cudaFree(L.d_nlive);
   }
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->st_in) { cudaStreamSynchronize(h->st_in); cudaStreamDestroy(h->st_in); }
   for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
   for (auto &e : h->ev_det) if (e) cudaEventDestroy(e);
+  for (auto &e : h->ev_dep) if (e) cudaEventDestroy(e);
   fpb_comm_finalize(h);
   for (int k = 0; k < 4; k++) cudaEventDestroy(h->ev[k]);
   cudaStreamDestroy(h->stream);
@@ -1085,6 +1157,7 @@ static int launch_bkdep(fpb_handle *h, const DevCfg &cfg, const DevParticles &ro
   a.w.p = rows;
   a.w.height = h->d_height;
   a.w.wetgridunc = nullptr; a.w.wetgriduncn = nullptr;
+  a.w.dep = DevDepRecords{};
   a.w.ltsample = c.lsynctime;
   a.vmet[0] = slot_view(h, h->memind[0]);
   a.vmet[1] = slot_view(h, h->memind[1]);
@@ -1133,6 +1206,9 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.stats = stats ? h->d_stats : nullptr;
   a.work_counter = h->d_work;
   a.sc = h->sc;
+  a.dep = DevDepRecords{};
+  const bool det_dry = h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC && h->cfg.drydep;
+  if (det_dry && dep_begin(h, h->depstore, h->numpart, 0, h->stream, a.dep)) return 1;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
   // initialize() can only be due for rows pushed since the last step, or at itime 0
   if (h->pending_init || itime == 0) {
@@ -1148,6 +1224,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   CK(cudaEventRecord(h->ev[1], h->stream));
   h->timed_step = true;
   h->launches += 2; // fpb_pbl_kernel + fpb_finish_kernel
+  if (det_dry && dep_apply(h, h->scatter, a.dep, h->drygridunc, h->drygriduncn, h->stream)) return 1;
   CK(cudaGetLastError());
   if (stats) {
     unsigned long long hs[8];
@@ -1192,7 +1269,10 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   a.griduncn = h->griduncn;
   a.crec_acc = h->crec_acc;
   a.slot_base = 0;
+  a.rec_vals = nullptr; a.rec_nslots = 0;
   const bool strict = h->cfg.math_mode == FPB_MATH_STRICT;
+  const bool det_rec = h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC && h->cfg.numreceptor > 0;
+  if (det_rec && rec_begin(h, h->depstore, nslots, h->stream, a)) return 1;
   CK(cudaEventRecord(h->ev[2], h->stream));
   if (h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
     if (scatter_conccalc_deterministic(h->scatter, a, strict, h->stream, &h->launches)) return fail("%s", scatter_error());
@@ -1202,6 +1282,11 @@ extern "C" int fpb_conccalc(fpb_handle *h, int32_t itime, float weight) {
   }
   if (h->cfg.numreceptor > 0) {
     if (strict) fpbk_receptor_strict(a, h->stream); else fpbk_receptor_fast(a, h->stream);
+    if (det_rec) {
+      if (scatter_receptor_ordered(a.rec_vals, h->cfg.numreceptor * h->cfg.nspec, nslots, h->crec_acc, h->stream))
+        return fail("%s", scatter_error());
+      h->launches++;
+    }
     receptor_finalize_kernel<<<1, 256, 0, h->stream>>>(h->creceptor, h->crec_acc, h->cfg.numreceptor,
                                                       h->cfg.nspec, weight, nullptr, a.cfg);
     h->launches += 2;
@@ -1979,6 +2064,7 @@ static int ensure_lanes(fpb_handle *h) {
   CK(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
   for (auto &e : h->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : h->ev_det) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : h->ev_dep) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->lanes_ready = true;
   return 0;
 }
@@ -2110,20 +2196,28 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
       q.height = h->d_height;
       q.gridunc = h->gridunc; q.griduncn = h->griduncn; q.crec_acc = h->crec_acc;
       q.slot_base = c0;
-      if (c.scatter_mode == FPB_SCATTER_DETERMINISTIC) {
+      q.rec_vals = nullptr; q.rec_nslots = 0;
+      const bool det = c.scatter_mode == FPB_SCATTER_DETERMINISTIC;
+      if (det) {
         // every cell must receive its contributions in slot order: the chunks hold ascending slot
         // ranges, so chunk ci adds after chunk ci-1 has (an event chain across the lanes)
         if (ci > 0) CK(cudaStreamWaitEvent(L.st, h->ev_det[(ci - 1) % 8], 0));
         if (scatter_conccalc_deterministic(L.sw, q, strict, L.st, &h->launches)) return fail("%s", scatter_error());
-        CK(cudaEventRecord(h->ev_det[ci % 8], L.st));
       } else {
         if (strict) fpbk_conccalc_strict(q, L.st); else fpbk_conccalc_fast(q, L.st);
         h->launches++;
       }
       if (c.numreceptor > 0) {
+        if (det && rec_begin(h, L.dep, n, L.st, q)) return 1;
         if (strict) fpbk_receptor_strict(q, L.st); else fpbk_receptor_fast(q, L.st);
         h->launches++;
+        if (det) { // the running sums continue from the previous chunk's
+          if (scatter_receptor_ordered(q.rec_vals, c.numreceptor * c.nspec, n, h->crec_acc, L.st))
+            return fail("%s", scatter_error());
+          h->launches++;
+        }
       }
+      if (det) CK(cudaEventRecord(h->ev_det[ci % 8], L.st));
     }
 
     STAGE("conccalc");
@@ -2142,12 +2236,21 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     a.stats = h->d_stats;
     a.work_counter = L.d_work;
     a.sc = scratch_view(h->sc, c0);
+    a.dep = DevDepRecords{};
+    const bool det_dry = c.scatter_mode == FPB_SCATTER_DETERMINISTIC && c.drydep;
+    if (det_dry && dep_begin(h, L.dep, n, c0, L.st, a.dep)) return 1;
     if (strict) fpbk_init_strict(a, L.st); else fpbk_init_fast(a, L.st);
     if (launch_bkdep(h, a.cfg, rows, L.st)) return 1;
     STAGE("initialize");
     if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
     h->launches += 3;
     STAGE("step");
+    if (det_dry) { // deposition in slot order across the chunks, like the concentration grid
+      if (ci > 0) CK(cudaStreamWaitEvent(L.st, h->ev_dep[(ci - 1) % 8], 0));
+      if (dep_apply(h, L.sw, a.dep, h->drygridunc, h->drygriduncn, L.st)) return 1;
+      CK(cudaEventRecord(h->ev_dep[ci % 8], L.st));
+      STAGE("drydep records");
+    }
 
     sortk_scatter_back(rows, h->p_alt, n, c.nspec, L.st, c.drybkdep || c.wetbkdep);
     h->launches++;
@@ -2229,9 +2332,13 @@ extern "C" int fpb_wetdepo(fpb_handle *h, int32_t itime, int32_t ltsample, int32
   a.wetgridunc = h->wetgridunc;
   a.wetgriduncn = h->wetgriduncn;
   a.ltsample = ltsample;
+  a.dep = DevDepRecords{};
+  const bool det = h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC;
+  if (det && dep_begin(h, h->depstore, h->numpart, 0, h->stream, a.dep)) return 1;
   if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_wetdepo_strict(a, h->stream);
   else fpbk_wetdepo_fast(a, h->stream);
   h->launches++;
+  if (det && dep_apply(h, h->scatter, a.dep, h->wetgridunc, h->wetgriduncn, h->stream)) return 1;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return 0;

@@ -115,6 +115,17 @@ struct DevScratch {
   float *prob; // [nspec][maxpart], dry-deposition probability (drydep runs only)
 };
 
+// Deterministic deposition (FPB_SCATTER_DETERMINISTIC): instead of atomics the kernels write one
+// (cell key, values) record per touched cell -- record id = 4*(slot - slot_base) + corner -- and the
+// records are then sorted by key and added run by run in record (= particle) order, like conccalc's
+// (fpb_scatter.cu).  grid 0 = mother output grid, 1 = nested.  keys == null: atomics.
+struct DevDepRecords {
+  unsigned *keys[2]; // [nrec], pre-filled with 0xffffffff
+  float *vals[2];    // [nspec][nrec]
+  size_t nrec;
+  int slot_base;
+};
+
 struct DevStepArgs {
   DevCfg cfg;
   DevMetSlot met[2];   // [0] = memind(1) (older field), [1] = memind(2)
@@ -132,6 +143,7 @@ struct DevStepArgs {
   unsigned long long *stats; // 8 counters, fpb_step_stats order
   int *work_counter;         // next unclaimed particle row (persistent sub-step kernel)
   DevScratch sc;
+  DevDepRecords dep;         // dry deposition records (deterministic mode), else keys = null
 };
 
 struct DevConcArgs {
@@ -142,6 +154,8 @@ struct DevConcArgs {
   float *gridunc, *griduncn;
   float *crec_acc; // [numreceptor][nspec] accumulators of c(ks)
   int slot_base;   // deterministic path on a row chunk (fpb_step_host): record id = 4*(slot - slot_base) + corner
+  float *rec_vals; // deterministic receptors: [numreceptor*nspec][nslots] xmass1*kernel of every particle, or null
+  int rec_nslots;
 };
 
 // wetdepo (src/wetdepo.f90): one time level per grid, chosen on the host the way
@@ -154,6 +168,7 @@ struct DevWetArgs {
   const float *height;
   float *wetgridunc, *wetgriduncn;
   int ltsample;
+  DevDepRecords dep; // wet deposition records (deterministic mode), else keys = null
 };
 
 // backward-run receptor scavenging of the particle loop (src/timemanager.f90:563-598)

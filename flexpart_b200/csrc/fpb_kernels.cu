@@ -804,8 +804,27 @@ __device__ __forceinline__ size_t didx(const DevCfg &c, int nxg, int nyg, int ix
   return i;
 }
 
+// species-free cell key of a deposition grid: like cell_key() without the level
+__device__ __forceinline__ unsigned dep_key(const DevCfg &c, int nxg, int nyg, int ix, int jy, int kp, int nc, int na) {
+  unsigned i = (unsigned)(na - 1);
+  i = i * c.nclassunc + (nc - 1);
+  i = i * c.maxpointspec_act + (kp - 1);
+  i = i * nyg + jy;
+  i = i * nxg + ix;
+  return i;
+}
+// one record of the deterministic path: the nspec values of corner `corner` of record slot `rslot`
+__device__ __forceinline__ void dep_record(const DevCfg &c, const DevDepRecords &r, int g, int rslot, int corner,
+                                           unsigned key, const float *deposit, float w, const int *specmask) {
+  const size_t id = 4 * (size_t)rslot + corner;
+  r.keys[g][id] = key;
+  for (int ks = 0; ks < c.nspec; ks++)
+    r.vals[g][(size_t)ks * r.nrec + id] = (specmask == nullptr || specmask[ks]) ? deposit[ks] * w : 0.f;
+}
+
 __device__ __noinline__ void drydepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc,
-                                const float *deposit, float x, float y, int nage, int kp) {
+                                const float *deposit, float x, float y, int nage, int kp,
+                                const DevDepRecords &rec, int rslot) {
   const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
   float xl, yl;
   if (nest) {
@@ -823,6 +842,25 @@ __device__ __noinline__ void drydepo_scatter(const DevCfg &c, float *grid, bool 
   const bool in11 = (ixp >= 0) && (jyp >= 0) && (ixp <= nxg - 1) && (jyp <= nyg - 1);
   const bool in10 = (ixp >= 0) && (jy >= 0) && (ixp <= nxg - 1) && (jy <= nyg - 1);
   const bool in01 = (ix >= 0) && (jyp >= 0) && (ix <= nxg - 1) && (jyp <= nyg - 1);
+  if (rec.keys[0]) { // deterministic: records, added in particle order after the kernel
+    const int g = nest ? 1 : 0;
+    float dep[FPB_MAXSPEC];
+    bool any = false;
+    for (int ks = 0; ks < c.nspec; ks++) {
+      dep[ks] = ((fabsf(deposit[ks]) > 0.f) && c.drydepspec[ks]) ? deposit[ks] : 0.f;
+      any = any || dep[ks] != 0.f;
+    }
+    if (!any) return;
+    if (!nest && !c.lusekerneloutput) {
+      if (in00) dep_record(c, rec, g, rslot, 0, dep_key(c, nxg, nyg, ix, jy, kp, nunc, nage), dep, 1.f, nullptr);
+      return;
+    }
+    if (in00) dep_record(c, rec, g, rslot, 0, dep_key(c, nxg, nyg, ix, jy, kp, nunc, nage), dep, wx * wy, nullptr);
+    if (in11) dep_record(c, rec, g, rslot, 1, dep_key(c, nxg, nyg, ixp, jyp, kp, nunc, nage), dep, (1.f - wx) * (1.f - wy), nullptr);
+    if (in10) dep_record(c, rec, g, rslot, 2, dep_key(c, nxg, nyg, ixp, jy, kp, nunc, nage), dep, (1.f - wx) * wy, nullptr);
+    if (in01) dep_record(c, rec, g, rslot, 3, dep_key(c, nxg, nyg, ix, jyp, kp, nunc, nage), dep, wx * (1.f - wy), nullptr);
+    return;
+  }
   for (int ks = 1; ks <= c.nspec; ks++) {
     float dep = deposit[ks - 1];
     if (!((fabsf(dep) > 0.f) && c.drydepspec[ks - 1])) continue;
@@ -1225,6 +1263,15 @@ fpb_receptor_kernel(const __grid_constant__ DevConcArgs a) {
         if (r2 < 1.f) kern = factor * (1.f - r2) / h;
       }
     }
+    if (a.rec_vals) { // deterministic: the contributions are summed in particle order afterwards
+      if (i < c.numpart && a.p.itra1[i] == c.itime) {
+        const int sl = a.p.slot[i] - a.slot_base;
+        for (int ks = 0; ks < c.nspec; ks++)
+          a.rec_vals[(size_t)(n * c.nspec + ks) * a.rec_nslots + sl] =
+              (kern != 0.f) ? a.p.xmass1[(size_t)ks * a.p.maxpart + i] * kern : 0.f;
+      }
+      continue;
+    }
     for (int ks = 0; ks < c.nspec; ks++) {
       float v = (kern != 0.f) ? a.p.xmass1[(size_t)ks * a.p.maxpart + i] * kern : 0.f;
 #pragma unroll
@@ -1371,7 +1418,7 @@ __device__ float get_wetscav(const DevWetArgs &a, const float *sh, int i, int ks
 }
 
 __device__ void wetdepo_scatter(const DevCfg &c, float *grid, bool nest, int nunc, const float *deposit,
-                                float x, float y, int nage, int kp) {
+                                float x, float y, int nage, int kp, const DevDepRecords &rec, int rslot) {
   const int nxg = nest ? c.numxgridn : c.numxgrid, nyg = nest ? c.numygridn : c.numygrid;
   float xl, yl;
   int ix, jy, ixp, jyp;
@@ -1394,6 +1441,18 @@ __device__ void wetdepo_scatter(const DevCfg &c, float *grid, bool nest, int nun
   const bool in11 = (ixp >= 0) && (jyp >= 0) && (ixp <= nxg - 1) && (jyp <= nyg - 1);
   const bool in10 = (ixp >= 0) && (jy >= 0) && (ixp <= nxg - 1) && (jy <= nyg - 1);
   const bool in01 = (ix >= 0) && (jyp >= 0) && (ix <= nxg - 1) && (jyp <= nyg - 1);
+  if (rec.keys[0]) { // deterministic: records
+    const int g = nest ? 1 : 0;
+    if (!nest && !c.lusekerneloutput) {
+      if (in00) dep_record(c, rec, g, rslot, 0, dep_key(c, nxg, nyg, ix, jy, kp, nunc, nage), deposit, 1.f, nullptr);
+      return;
+    }
+    if (in00) dep_record(c, rec, g, rslot, 0, dep_key(c, nxg, nyg, ix, jy, kp, nunc, nage), deposit, wx * wy, nullptr);
+    if (in11) dep_record(c, rec, g, rslot, 1, dep_key(c, nxg, nyg, ixp, jyp, kp, nunc, nage), deposit, (1.f - wx) * (1.f - wy), nullptr);
+    if (in10) dep_record(c, rec, g, rslot, 2, dep_key(c, nxg, nyg, ixp, jy, kp, nunc, nage), deposit, (1.f - wx) * wy, nullptr);
+    if (in01) dep_record(c, rec, g, rslot, 3, dep_key(c, nxg, nyg, ix, jyp, kp, nunc, nage), deposit, wx * (1.f - wy), nullptr);
+    return;
+  }
   for (int ks = 1; ks <= c.nspec; ks++) {
     const float dep = deposit[ks - 1];
     if (dep == 0.f) continue; // adding 0 changes nothing
@@ -1450,8 +1509,9 @@ fpb_wetdepo_kernel(const __grid_constant__ DevWetArgs a) {
     const int kp = (c.ioutputforeachrelease == 1) ? a.p.npoint[i] : 1;
     const int nclass = a.p.nclass[i];
     const float x = (float)a.p.xtra1[i], y = (float)a.p.ytra1[i];
-    wetdepo_scatter(c, a.wetgridunc, false, nclass, wetdeposit, x, y, nage, kp);
-    if (c.nested_output == 1) wetdepo_scatter(c, a.wetgriduncn, true, nclass, wetdeposit, x, y, nage, kp);
+    const int rslot = a.p.slot[i] - a.dep.slot_base;
+    wetdepo_scatter(c, a.wetgridunc, false, nclass, wetdeposit, x, y, nage, kp, a.dep, rslot);
+    if (c.nested_output == 1) wetdepo_scatter(c, a.wetgriduncn, true, nclass, wetdeposit, x, y, nage, kp, a.dep, rslot);
   }
 }
 

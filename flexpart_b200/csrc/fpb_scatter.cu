@@ -215,6 +215,56 @@ int scatter_sort_pairs(ScatterWork &w, size_t n, int bits, cudaStream_t st, int6
   return 0;
 }
 
+namespace {
+__global__ void iota_ids_kernel(unsigned *ids, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = (unsigned)i;
+}
+// creceptor's c(ks) of one (receptor, species): the particles' contributions added in slot order
+// (src/conccalc.f90:476-492) by one warp -- every lane ends with the same sequential sum
+__global__ void __launch_bounds__(32) receptor_seqsum_kernel(const float *vals, int nslots, float *acc) {
+  const float *v = vals + (size_t)blockIdx.x * nslots;
+  const int lane = threadIdx.x;
+  float sum = acc[blockIdx.x];
+  for (int base = 0; base < nslots; base += 32) {
+    const float x = (base + lane < nslots) ? v[base + lane] : 0.f;
+    const int n = min(32, nslots - base);
+    for (int k = 0; k < n; k++) sum = sum + __shfl_sync(0xffffffffu, x, k);
+  }
+  if (lane == 0) acc[blockIdx.x] = sum;
+}
+} // namespace
+
+// records (keys[nrec], vals[nspec][nrec]) written by a kernel -> grid, every cell in record order
+int scatter_records_deterministic(ScatterWork &w, const unsigned *keys, const float *vals, size_t nrec, int nspec,
+                                  float *grid, int nxyz, unsigned long long ncell, cudaStream_t st, int64_t *launches) {
+  if (nrec == 0) return 0;
+  if (ncell >= 0xffffffffull || nrec >= 0xffffffffull) {
+    s_err = "deterministic scatter: more than 2^32 cells or records";
+    return 1;
+  }
+  if (scatter_reserve(w, nrec, 1)) return 1;
+  int bits = 1;
+  while ((1ull << bits) < ncell + 1) bits++;
+  bits = ((bits + RADIX_BITS - 1) / RADIX_BITS) * RADIX_BITS;
+  if (bits < 32) bits = (bits + RADIX_BITS <= 32) ? bits + RADIX_BITS : 32; // the all-ones keys sort last
+  SCK(cudaMemcpyAsync(w.keys[0], keys, nrec * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+  iota_ids_kernel<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(w.ids[0], nrec);
+  int cur = 0;
+  if (scatter_sort_pairs(w, nrec, bits, st, launches, &cur)) return 1;
+  segsum_kernel<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(w.keys[cur], w.ids[cur], vals, nrec, grid, nxyz, nspec);
+  if (launches) *launches += 2;
+  SCK(cudaGetLastError());
+  return 0;
+}
+
+int scatter_receptor_ordered(const float *vals, int nsums, int nslots, float *acc, cudaStream_t st) {
+  if (nsums <= 0 || nslots <= 0) return 0;
+  receptor_seqsum_kernel<<<nsums, 32, 0, st>>>(vals, nslots, acc);
+  SCK(cudaGetLastError());
+  return 0;
+}
+
 int scatter_conccalc_deterministic(ScatterWork &w, const DevConcArgs &a, bool strict,
                                    cudaStream_t st, int64_t *launches) {
   const DevCfg &c = a.cfg;

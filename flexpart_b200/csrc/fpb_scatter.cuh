@@ -20,6 +20,11 @@ struct ScatterWork {
 
 int scatter_conccalc_deterministic(ScatterWork &w, const DevConcArgs &a, bool strict,
                                    cudaStream_t st, int64_t *launches);
+// deposition records written by fpb_finish_kernel / fpb_wetdepo_kernel (DevDepRecords) -> grid
+int scatter_records_deterministic(ScatterWork &w, const unsigned *keys, const float *vals, size_t nrec, int nspec,
+                                  float *grid, int nxyz, unsigned long long ncell, cudaStream_t st, int64_t *launches);
+// receptor sums in particle order: vals[nsums][nslots] -> acc[nsums] += sequential sum
+int scatter_receptor_ordered(const float *vals, int nsums, int nslots, float *acc, cudaStream_t st);
 // stable sort of n (key, id) pairs on keys' low `bits` bits; result in
 // w.keys[*out] / w.ids[*out]
 int scatter_sort_pairs(ScatterWork &w, size_t n, int bits, cudaStream_t st, int64_t *launches,

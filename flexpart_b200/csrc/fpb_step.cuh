@@ -762,9 +762,10 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
       for (nage = 1; nage <= c.nageclass; nage++)
         if (itage < c.lage[nage - 1]) break;
       const int nclass = a.p.nclass[j];
-      drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+      const int rslot = slot - a.dep.slot_base;
+      drydepo_scatter(c, a.drygridunc, false, nclass, drydeposit, (float)xt, (float)yt, nage, kp, a.dep, rslot);
       if (c.nested_output == 1)
-        drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp);
+        drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp, a.dep, rslot);
     }
     if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; term = true; }
     if (term) n_term++;

@@ -61,7 +61,8 @@ enum {
 /* fpb_config.scatter_mode (conccalc / drydepokernel accumulation) */
 enum {
   FPB_SCATTER_ATOMIC = 0,       /* red.global.add.f32 */
-  FPB_SCATTER_DETERMINISTIC = 1 /* sort by cell + ordered segmented sum */
+  FPB_SCATTER_DETERMINISTIC = 1 /* sort by cell + ordered segmented sum: the concentration grids, the dry and wet
+                                 * deposition grids and the receptor sums are bit-identical to the serial loops */
 };
 
 /*

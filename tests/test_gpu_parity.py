@@ -748,6 +748,75 @@ def test_receptors_and_density_weighted_sampling():
     np.testing.assert_allclose(gg["creceptor"], go["creceptor"], rtol=2e-5)
 
 
+def test_deterministic_deposition_and_receptors_bit_exact():
+    """FPB_SCATTER_DETERMINISTIC covers every accumulator of the path: the dry and wet deposition
+    grids (drydepokernel / wetdepokernel and the _nest twins) and the receptor sums are added in
+    particle order as the reference's loops do (src/drydepokernel.f90:80-114,
+    src/wetdepokernel.f90:63-105, src/conccalc.f90:476-496): bit-identical to the oracle, not
+    merely within a tolerance."""
+    cb = cases.config_small(nrel=3, npart_each=1024, nspec=2, drydepspec=[1, 1], decay=[0.0, 1.0e-5],
+                            wetdepspec=(1, 1), weta_gas=(2.0e-5, -1.0), wetb_gas=(0.62, -1.0), henry=(1.0e-2, 0.0),
+                            crain_aero=(-1.0, 1.0), csnow_aero=(-1.0, 1.0), ccn_aero=(-1.0, 0.9),
+                            in_aero=(-1.0, 0.1), dquer=(0.0, 0.6), density=(0.0, 0.0),
+                            nest=(-60.0, -30.0, 48, 24, 2.5, 2.5), ioutputforeachrelease=1,
+                            lage=(7200, 86400 * 10), xmass=np.ones((3, 2)),
+                            receptors=[(36.0, 18.0, 1.0e9), (40.5, 20.2, 2.0e9)],
+                            math_mode=fb.MATH_STRICT, scatter_mode=fb.SCATTER_DETERMINISTIC)
+    c = cb.cfg
+    assert c.drydep == 1 and c.wetdep == 1 and c.nested_output == 1 and c.numreceptor == 2
+    n = 3072
+    p = cases.seeded_particles(cb, n, zmax=400.0, lat_range=(-40.0, 40.0), nspec=2)
+    r = np.random.RandomState(11)
+    p.xtra1[:1024] = r.uniform(33.0, 43.0, 1024)      # a cloud around the receptors
+    p.ytra1[:1024] = r.uniform(15.0, 23.0, 1024)
+    p.ztra1[:1024] = r.uniform(1.0, 120.0, 1024).astype(np.float32)
+    p.itramem[:1024] = -30000
+    p.xmass1[:n, 1] = 0.5
+    tot, gg, go = _per_step(cb, p, 5, exact=True, wet=True, check_grids=False)
+    for name in ("gridunc", "griduncn", "drygridunc", "drygriduncn", "creceptor"):
+        assert np.abs(go[name]).sum() > 0, name
+        assert np.array_equal(gg[name], go[name]), (name, rel_l2(gg[name], go[name]))
+
+
+def test_deterministic_deposition_through_step_host(monkeypatch):
+    """The same guarantee through fpb_step_host: dry deposition records and receptor sums of the row
+    chunks are added chunk after chunk (event chain across the lanes)."""
+    monkeypatch.setenv("FPB_HOST_CHUNKS", "5")
+    cb = cases.config_small(nrel=3, npart_each=7000, nspec=2, drydepspec=[1, 1], decay=[0.0, 1.0e-5],
+                            nest=(-60.0, -30.0, 48, 24, 2.5, 2.5), ioutputforeachrelease=1,
+                            lage=(7200, 86400 * 10), xmass=np.ones((3, 2)),
+                            receptors=[(36.0, 18.0, 1.0e9), (40.5, 20.2, 2.0e9)],
+                            math_mode=fb.MATH_STRICT, scatter_mode=fb.SCATTER_DETERMINISTIC)
+    c = cb.cfg
+    n = 21000
+    p = cases.seeded_particles(cb, n, zmax=300.0, lat_range=(-40.0, 40.0), nspec=2)
+    r = np.random.RandomState(12)
+    p.xtra1[:7000] = r.uniform(33.0, 43.0, 7000)
+    p.ytra1[:7000] = r.uniform(15.0, 23.0, 7000)
+    p.ztra1[:7000] = r.uniform(1.0, 120.0, 7000).astype(np.float32)
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), (0, 10800))
+    ora.push_particles(p)
+    for k in range(3):
+        itime = k * c.lsynctime
+        po = fb.Particles(c.maxpart, c.nspec); po.numpart = n
+        ora.pull_particles(po)
+        ora.conccalc(itime, 1.0)
+        ora.step(itime, 450)
+        eng.step_host(po, itime, 450, conc_weight=1.0)
+        pq = fb.Particles(c.maxpart, c.nspec); pq.numpart = n
+        ora.pull_particles(pq)
+        assert np.array_equal(po.xtra1[:n], pq.xtra1[:n]) and np.array_equal(po.xmass1[:n], pq.xmass1[:n]), k
+    gg, go = eng.fetch_grids(), ora.fetch_grids()
+    for name in ("gridunc", "griduncn", "drygridunc", "drygriduncn", "creceptor"):
+        assert np.abs(go[name]).sum() > 0, name
+        assert np.array_equal(gg[name], go[name]), (name, rel_l2(gg[name], go[name]))
+
+
 def test_particle_count_output():
     """par_mod's lparticlecountoutput: conccalc adds 1 per particle instead of its mass in the
     no-kernel branch (src/conccalc.f90:171-183) -- young particles (itage < 10800) take it, old ones
