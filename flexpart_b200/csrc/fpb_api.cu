@@ -1207,6 +1207,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   a.work_counter = h->d_work;
   a.sc = h->sc;
   a.dep = DevDepRecords{};
+  a.grid_frac = 0.f;
   const bool det_dry = h->cfg.scatter_mode == FPB_SCATTER_DETERMINISTIC && h->cfg.drydep;
   if (det_dry && dep_begin(h, h->depstore, h->numpart, 0, h->stream, a.dep)) return 1;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
@@ -2119,12 +2120,12 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
   if (bits > 32) bits = 32;
   DevMetSlot met[2] = {slot_view(h, h->memind[0]), slot_view(h, h->memind[1])};
 
-  // Equal row chunks of >= ~300k rows (multiples of 128 rows).  Each chunk costs ~20 launches and
+  // Equal row chunks of >= ~250k rows (multiples of 128 rows).  Each chunk costs ~20 launches and
   // one tail of the persistent sub-step kernel (~0.18 ms, FPB_HOST_TIMING=1 shows the timeline), so
-  // there are few of them: measured flat between 2 and 4 chunks at 1M rows, worse beyond.
+  // there are few of them: 4 at 1M rows, worse beyond 6.
   std::vector<int> bounds; // chunk c = rows [bounds[c], bounds[c+1])
   {
-    int nchunk = numpart / 300000;
+    int nchunk = numpart / 250000;
     nchunk = nchunk < 1 ? 1 : (nchunk > 6 ? 6 : nchunk);
     if (const char *e = getenv("FPB_HOST_CHUNKS")) { // tuning knob
       const int v = atoi(e);
@@ -2134,6 +2135,11 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     for (int c0 = 0; c0 < numpart; c0 += per_eq) bounds.push_back(c0);
     bounds.push_back(numpart);
   }
+  // The persistent sub-step grid of a chunk takes 0.6 of a resident wave, so that the next chunk's
+  // kernels start under its draining tail (measured at 1 M rows, gpurun_out/ab_host.txt:
+  // 3 chunks x full grid 3.17 ms, 4 x 0.6: 2.95 ms, 4 x 0.4: 2.97, 6 x 0.6: 3.03, 8 x 0.6: 3.21)
+  float host_grid_frac = bounds.size() > 2 ? 0.6f : 0.f;
+  if (const char *e = getenv("FPB_HOST_GRID_FRAC")) host_grid_frac = (float)atof(e); // tuning knob
   // FPB_HOST_TIMING=1: per-chunk timeline (ms since the call started) on stderr
   const bool timing = getenv("FPB_HOST_TIMING") != nullptr;
   std::vector<cudaEvent_t> tev;
@@ -2237,6 +2243,7 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     a.work_counter = L.d_work;
     a.sc = scratch_view(h->sc, c0);
     a.dep = DevDepRecords{};
+    a.grid_frac = host_grid_frac;
     const bool det_dry = c.scatter_mode == FPB_SCATTER_DETERMINISTIC && c.drydep;
     if (det_dry && dep_begin(h, L.dep, n, c0, L.st, a.dep)) return 1;
     if (strict) fpbk_init_strict(a, L.st); else fpbk_init_fast(a, L.st);

@@ -144,6 +144,7 @@ struct DevStepArgs {
   int *work_counter;         // next unclaimed particle row (persistent sub-step kernel)
   DevScratch sc;
   DevDepRecords dep;         // dry deposition records (deterministic mode), else keys = null
+  float grid_frac;           // persistent sub-step grid as a fraction of one resident wave (0 = 1: all of it)
 };
 
 struct DevConcArgs {

@@ -1635,7 +1635,12 @@ void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   }
   const int want = (a.cfg.numpart + 127) / 128;
   const int want_pbl = (a.cfg.numpart + PBL_THREADS - 1) / PBL_THREADS;
-  const int nb = want_pbl < res ? want_pbl : res; // persistent grid: one wave at most
+  int cap = res; // persistent grid: one wave at most
+  if (a.grid_frac > 0.f && a.grid_frac < 1.f) { // (fpb_step_host: the chunks' grids share the SMs)
+    cap = (int)((float)res * a.grid_frac);
+    if (cap < 1) cap = 1;
+  }
+  const int nb = want_pbl < cap ? want_pbl : cap;
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
   if (variant == 1) fpb_pbl_kernel<true, true, false><<<nb, PBL_THREADS, 0, st>>>(a);
   else if (variant == 3) fpb_pbl_kernel<true, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
