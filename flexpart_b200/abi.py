@@ -202,7 +202,7 @@ def load_engine_lib():
     L.fpb_upload_convmet_nest.argtypes = [H, _i, _i, C.POINTER(FpbConvPtrs)]
     L.fpb_convmix.argtypes = [H, _i, _pi, _pi]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
-    L.fpb_boundcond_domainfill.argtypes = [H, _i, _i]
+    L.fpb_boundcond_domainfill.argtypes = [H, _i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
                                 C.POINTER(FpbStepStats)]
     L.fpb_conccalc.argtypes = [H, _i, _f]

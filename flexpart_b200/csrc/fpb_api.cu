@@ -215,7 +215,20 @@ struct fpb_handle {
     int gdomainfill = 0;
     int nx_we[2] = {0, 0}, ny_sn[2] = {0, 0};
     int idum = -11, iv[32] = {0}, iy = 0;
-    float ran1() { // src/random_mod.f90:40-68
+    int idum_bc = -11;        // boundcond_domainfill's own SAVEd idummy (src/boundcond_domainfill.f90:49)
+    int itsplit = 0, numparticlecount = 0;
+    float xmassperparticle = 0.f;
+    // inflow boundary of a limited box (fpb_boundcond_domainfill)
+    int nloc = 0;
+    std::vector<uint8_t> loc_draws; // ran1 draws per particle of each location (2 or 3)
+    BcLoc *d_loc = nullptr;
+    float *d_acc = nullptr;
+    int32_t *d_mmass = nullptr, *d_first = nullptr, *d_uoff = nullptr;
+    unsigned *d_blocks = nullptr;
+    int *d_out = nullptr;
+    float *d_uniforms = nullptr;
+    size_t uniforms_cap = 0;
+    float ran1(int &idum) { // src/random_mod.f90:40-68 (iv, iy are SAVEd in ran1, idum is the caller's)
       const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836, NTAB = 32;
       const int NDIV = 1 + (IM - 1) / NTAB;
       const float AM = 1.f / (float)IM, RNMX = 1.f - 1.2e-7f;
@@ -238,6 +251,7 @@ struct fpb_handle {
       const float t = AM * (float)iy;
       return t < RNMX ? t : RNMX;
     }
+    float ran1() { return ran1(idum); }
   } dfill;
   // grid exchange over NCCL (fpb_comm_init / fpb_reduce_grids_begin / _end)
   struct Comm {
@@ -732,6 +746,11 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
   scatter_free(h->scatter);
   dep_free(h->depstore);
+  {
+    auto &D = h->dfill;
+    cudaFree(D.d_loc); cudaFree(D.d_acc); cudaFree(D.d_mmass); cudaFree(D.d_first); cudaFree(D.d_uoff);
+    cudaFree(D.d_blocks); cudaFree(D.d_out); cudaFree(D.d_uniforms);
+  }
   for (auto &L : h->lanes) {
     if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
     scatter_free(L.sw);
@@ -1659,6 +1678,123 @@ static void domainfill_gridarea(const fpb_config &c, const int ny_sn[2], std::ve
   }
 }
 
+// Second half of init_domainfill (src/init_domainfill.f90:287-389) for a limited box: fewer release
+// heights per boundary column ("on the order of nz"), memorised for boundcond_domainfill.  A few
+// thousand columns, once per run: the pressure profiles come from the device, the sequential
+// pnew recurrence and everything that stays constant per release location are worked out here.
+static int domainfill_boundary_setup(fpb_handle *h, const DomainfillArgs &a, const float *d_colmass, float colmasstotal,
+                                     int numcolumn) {
+  const fpb_config &c = h->cfg;
+  auto &D = h->dfill;
+  const int nz = c.nz, nx0 = a.nx0, nx1 = a.nx1, ny0 = a.ny0, ny1 = a.ny1;
+  const int MAXCOLUMN = 3000; // par_mod
+  std::vector<float> colmass((size_t)a.ncols);
+  CK(cudaMemcpy(colmass.data(), d_colmass, colmass.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  float fractus = (float)numcolumn / (float)nz;
+  fractus = sqrtf(fractus > 1.f ? fractus : 1.f) / 2.f;
+  std::vector<int2> cols;
+  for (int jy = ny0; jy <= ny1; jy++)
+    for (int ix = nx0; ix <= nx1; ix++)
+      if (ix == nx0 || ix == nx1 || jy == ny0 || jy == ny1) cols.push_back(make_int2(ix, jy));
+  int2 *d_cols = nullptr;
+  float *d_pp = nullptr;
+  std::vector<float> pps(cols.size() * nz);
+  if (dalloc(&d_pp, pps.size())) return 1;
+  if (cudaMalloc((void **)&d_cols, cols.size() * sizeof(int2)) != cudaSuccess) { cudaFree(d_pp); return fail("cudaMalloc failed"); }
+  cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream);
+  fpb_domainfill_profiles(a, d_cols, (int)cols.size(), d_pp, h->stream);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(pps.data(), d_pp, pps.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_cols); cudaFree(d_pp);
+  if (e != cudaSuccess) return fail("fpb_init_domainfill: boundary profiles: %s", cudaGetErrorString(e));
+
+  // zcolumn_we(k, jy, :) / zcolumn_sn(k, ix, :) with element 0 and the element after the last = 0
+  std::vector<std::vector<float>> zwe[2], zsn[2];
+  for (int k = 0; k < 2; k++) { zwe[k].assign(c.ny + 1, {}); zsn[k].assign(c.nx + 1, {}); }
+  for (size_t q = 0; q < cols.size(); q++) {
+    const int ix = cols[q].x, jy = cols[q].y;
+    const float cm = colmass[(size_t)(jy - ny0) * a.ncolx + (ix - nx0)];
+    const int ncolumn = (int)roundf(0.999f / fractus * (float)h->npart[0] * cm / colmasstotal); // nint()
+    if (ncolumn > MAXCOLUMN) return fail("fpb_init_domainfill: maxcolumn too small (%d release heights in a boundary column)", ncolumn);
+    if (ncolumn == 0) continue;
+    const float *pp = pps.data() + q * nz - 1; // pp[1..nz]
+    std::vector<float> z((size_t)ncolumn + 2, 0.f);
+    const float deltacol = (pp[1] - pp[nz]) / (float)ncolumn;
+    float pnew = pp[1] + deltacol / 2.f;
+    for (int j = 1; j <= ncolumn; j++) {
+      pnew = pnew - deltacol;
+      for (int kz = 1; kz <= nz - 1; kz++)
+        if ((pp[kz] >= pnew) && (pp[kz + 1] < pnew)) {
+          const float dz1 = pp[kz] - pnew, dz2 = pnew - pp[kz + 1];
+          const float dz = 1.f / (dz1 + dz2);
+          float zposition = (h->height[kz - 1] * dz2 + h->height[kz] * dz1) * dz;
+          if (zposition > h->height[nz - 1] - 0.5f) zposition = h->height[nz - 1] - 0.5f;
+          z[j] = zposition;
+        }
+    }
+    if (ix == nx0) zwe[0][jy] = z;
+    if (ix == nx1) zwe[1][jy] = z;
+    if (jy == ny0) zsn[0][ix] = z;
+    if (jy == ny1) zsn[1][ix] = z;
+  }
+
+  // the release locations in the order boundcond_domainfill visits them
+  std::vector<BcLoc> loc;
+  D.loc_draws.clear();
+  const float ztop = h->height[nz - 1];
+  auto add_column = [&](bool we, int k /*0,1*/, int idx, const std::vector<float> &Z, float cosfact) {
+    const int ncol = (int)Z.size() - 2;
+    for (int j = 1; j <= ncol; j++) {
+      BcLoc q;
+      float deltaz;
+      if (j == 1) deltaz = (Z[2] + Z[1]) / 2.f;
+      else if (j == ncol) deltaz = (Z[j] - Z[j - 2]) / 2.f;
+      else deltaz = (Z[j + 1] - Z[j - 1]) / 2.f;
+      const bool low = we ? idx == ny0 : idx == nx0, high = we ? idx == ny1 : idx == nx1;
+      if (we) q.boundarea = (low || high) ? deltaz * 111198.5f / 2.f * c.dy : deltaz * 111198.5f * c.dy;
+      else q.boundarea = (low || high) ? deltaz * 111198.5f / 2.f * cosfact * c.dx : deltaz * 111198.5f * cosfact * c.dx;
+      int indz = 1;
+      for (int i = 2; i <= nz; i++)
+        if (h->height[i - 1] > Z[j]) { indz = i - 1; break; }
+      q.indz = indz;
+      q.dz1 = Z[j] - h->height[indz - 1];
+      q.dz2 = h->height[indz] - Z[j];
+      q.dz = 1.f / (q.dz1 + q.dz2);
+      q.flags = (we ? BC_WE : 0) | (k ? BC_K2 : 0) | (low ? BC_EDGE_LOW : (high ? BC_EDGE_HIGH : 0));
+      q.zb = 0.f;
+      if (j == 1) q.za = Z[1] + (Z[2] - Z[1]) / 4.f;
+      else if (j == ncol) q.za = (2.f * Z[j] + Z[j - 1] + ztop) / 4.f;
+      else { q.za = Z[j - 1]; q.zb = Z[j + 1] - Z[j - 1]; q.flags |= BC_ZDRAW; }
+      q.idx = idx;
+      q.gx = we ? (k ? nx1 : nx0) : idx;
+      q.gy = we ? idx : (k ? ny1 : ny0);
+      loc.push_back(q);
+      D.loc_draws.push_back((q.flags & BC_ZDRAW) ? 3 : 2);
+    }
+  };
+  for (int jy = ny0; jy <= ny1; jy++)
+    for (int k = 0; k < 2; k++)
+      if (zwe[k][jy].size() > 2) add_column(true, k, jy, zwe[k][jy], 0.f);
+  for (int ix = nx0; ix <= nx1; ix++)
+    for (int k = 0; k < 2; k++) {
+      const float ylat = c.ylat0 + (float)(k ? ny1 : ny0) * c.dy;
+      const float cosfact = (float)cos((double)(ylat * (3.14159265f / 180.f)));
+      if (zsn[k][ix].size() > 2) add_column(false, k, ix, zsn[k][ix], cosfact);
+    }
+  D.nloc = (int)loc.size();
+  cudaFree(D.d_loc); cudaFree(D.d_acc); cudaFree(D.d_mmass); cudaFree(D.d_first); cudaFree(D.d_uoff);
+  cudaFree(D.d_blocks); cudaFree(D.d_out);
+  D.d_loc = nullptr; D.d_acc = nullptr; D.d_mmass = nullptr; D.d_first = nullptr; D.d_uoff = nullptr;
+  D.d_blocks = nullptr; D.d_out = nullptr;
+  const size_t n = loc.size() ? loc.size() : 1;
+  CK(cudaMalloc((void **)&D.d_loc, n * sizeof(BcLoc)));
+  DA(D.d_acc, n); DA(D.d_mmass, n); DA(D.d_first, n + 1); DA(D.d_uoff, n);
+  DA(D.d_blocks, (size_t)(c.maxpart + 1023) / 1024 + 1); DA(D.d_out, 2);
+  if (!loc.empty()) CK(cudaMemcpy(D.d_loc, loc.data(), loc.size() * sizeof(BcLoc), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
                                    int32_t itsplit, int32_t *numpart, fpb_domainfill_info *info) {
   if (!h) return fail("fpb_init_domainfill: null handle");
@@ -1756,6 +1892,10 @@ extern "C" int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, 
   DFK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
   DFK(cudaGetLastError());
   DFK(cudaStreamSynchronize(h->stream));
+  D.itsplit = itsplit;
+  D.numparticlecount = (int)numparttot;
+  D.xmassperparticle = numparttot > 0 ? total / (float)numparttot : 0.f;
+  if (!D.gdomainfill && domainfill_boundary_setup(h, a, d_colmass, total, out[1])) { cleanup(); return 1; }
 #undef DFA
 #undef DFK
   cleanup();
@@ -1779,13 +1919,92 @@ extern "C" int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, 
   return 0;
 }
 
-extern "C" int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend) {
-  (void)itime; (void)loutend;
+extern "C" int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int32_t *numpart,
+                                        int32_t *n_created) {
+  (void)loutend; // (the dump of the accumulated masses to boundcond.bin at loutend stays with the caller)
   if (!h) return fail("fpb_boundcond_domainfill: null handle");
-  if (!h->dfill.done) return fail("fpb_boundcond_domainfill: fpb_init_domainfill has not been called");
-  if (h->dfill.gdomainfill) return 0; // src/boundcond_domainfill.f90:54: nothing to do for a global domain
-  return fail("fpb_boundcond_domainfill: the inflow boundary of a limited domain "
-              "(src/boundcond_domainfill.f90:59-580) is not built; only global domain-filling runs on the device");
+  auto &D = h->dfill;
+  if (!D.done) return fail("fpb_boundcond_domainfill: fpb_init_domainfill has not been called");
+  if (numpart) *numpart = h->numpart;
+  if (n_created) *n_created = 0;
+  if (D.gdomainfill) return 0; // src/boundcond_domainfill.f90:54: nothing to do for a global domain
+  if (!h->have_bracket) return fail("fpb_boundcond_domainfill: fpb_set_met_bracket has not been called");
+  const fpb_config &c = h->cfg;
+  CK(cudaSetDevice(h->device));
+  BoundcondArgs a;
+  per_step_cfg(h, a.cfg, itime, 0);
+  a.p = h->p;
+  a.row_of_slot = h->row_of_slot;
+  a.permuted = h->permuted ? 1 : 0;
+  a.numpart_old = h->numpart;
+  a.A[0] = slot_view(h, h->memind[0]).A;
+  a.A[1] = slot_view(h, h->memind[1]).A;
+  a.dt1 = (float)(itime - h->memtime[0]);
+  a.dt2 = (float)(h->memtime[1] - itime);
+  a.dtt = 1.f / (a.dt1 + a.dt2);
+  a.nx0 = D.nx_we[0]; a.nx1 = D.nx_we[1]; a.ny0 = D.ny_sn[0]; a.ny1 = D.ny_sn[1];
+  a.check_x = (!c.xglobal || D.nx_we[1] != c.nx - 2) ? 1 : 0;
+  a.loc = D.d_loc; a.nloc = D.nloc;
+  a.acc_mass = D.d_acc; a.mmass = D.d_mmass; a.first = D.d_first;
+  a.uniforms = nullptr; a.u_off = D.d_uoff;
+  a.n_new = 0; a.n_mine = 0; a.r0 = 0;
+  a.numparticlecount = D.numparticlecount;
+  a.xmassperparticle = D.xmassperparticle;
+  a.itsplit = D.itsplit;
+  a.id_stride = h->d.part_id_stride;
+  a.block_counts = D.d_blocks; a.out = D.d_out;
+  fpb_boundcond_launch(a, h->stream, &h->launches, 0);
+  std::vector<int32_t> mmass((size_t)D.nloc), first((size_t)D.nloc + 1, 0), uoff((size_t)D.nloc, 0);
+  CK(cudaMemcpyAsync(mmass.data(), D.d_mmass, mmass.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  long long ndraws = 0;
+  for (int l = 0; l < D.nloc; l++) {
+    first[l + 1] = first[l] + mmass[l];
+    uoff[l] = (int32_t)ndraws;
+    ndraws += (long long)mmass[l] * D.loc_draws[l];
+  }
+  const int n_new = first[D.nloc];
+  if (n_new == 0) return 0;
+  const int stride = h->d.part_id_stride, offset = h->d.part_id_offset;
+  a.n_new = n_new;
+  a.r0 = (int)((((long long)offset - D.numparticlecount) % stride + stride) % stride);
+  a.n_mine = n_new > a.r0 ? (n_new - a.r0 + stride - 1) / stride : 0;
+  CK(cudaMemcpyAsync(D.d_first, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  std::vector<float> u;
+  if (c.rng_mode == FPB_RNG_REFERENCE) { // the reference's ran1 stream of the call: [along] [height] class
+    u.resize((size_t)ndraws);
+    for (auto &v : u) v = D.ran1(D.idum_bc);
+    if (D.uniforms_cap < u.size()) {
+      cudaFree(D.d_uniforms); D.d_uniforms = nullptr;
+      DA(D.d_uniforms, u.size());
+      D.uniforms_cap = u.size();
+    }
+    CK(cudaMemcpyAsync(D.d_uniforms, u.data(), u.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(D.d_uoff, uoff.data(), uoff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    a.uniforms = D.d_uniforms;
+  }
+  D.numparticlecount += n_new;
+  if (a.n_mine > 0) {
+    const int out0[2] = {h->numpart, 0};
+    CK(cudaMemcpyAsync(D.d_out, out0, sizeof out0, cudaMemcpyHostToDevice, h->stream));
+    fpb_boundcond_launch(a, h->stream, &h->launches, 1);
+    int out[2];
+    CK(cudaMemcpyAsync(out, D.d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if (out[1] < a.n_mine)
+      return fail("boundcond_domainfill: too many particles required (%d new, %d free slots, maxpart %d)", a.n_mine,
+                  out[1], c.maxpart);
+    h->numpart = out[0];
+    h->pending_init = true;
+    h->active_rows = -1;
+  } else {
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (numpart) *numpart = h->numpart;
+  if (n_created) *n_created = a.n_mine;
+  return 0;
 }
 
 // ----------------------------------------------------------- convection --

@@ -251,7 +251,196 @@ __global__ void __launch_bounds__(32 * FILL_WARPS) df_fill_kernel(const Domainfi
   }
 }
 
+__global__ void __launch_bounds__(256) df_profiles_kernel(const DomainfillArgs a, const int2 *cols, int n, float *out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * a.cfg.nz) return;
+  const int col = t / a.cfg.nz, kz = t % a.cfg.nz + 1;
+  out[t] = level_pressure(a, cols[col].x, cols[col].y, kz);
+}
+
+// ------------------------------------------------------------------ boundcond_domainfill ----
+// :59-72: particles that left the box are terminated
+__global__ void __launch_bounds__(256) bc_terminate_kernel(const BoundcondArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.numpart_old) return;
+  if (a.p.itra1[i] != a.cfg.itime) return;
+  const double x = a.p.xtra1[i], y = a.p.ytra1[i];
+  bool out = (y > (double)(float)a.ny1) || (y < (double)(float)a.ny0);
+  if (a.check_x && ((x < (double)(float)a.nx0) || (x > (double)(float)a.nx1))) out = true;
+  if (out) a.p.itra1[i] = FPB_ITRA_DEAD;
+}
+
+// :104-197 / :343-439: mass flux through one boundary location, accumulated mass, particles due
+__global__ void __launch_bounds__(256) bc_flux_kernel(const BoundcondArgs a) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= a.nloc) return;
+  const BcLoc q = a.loc[l];
+  const DevCfg &c = a.cfg;
+  const size_t plane = (size_t)c.nxd * c.nyd;
+  const size_t o = (size_t)(q.indz - 1) * plane + (size_t)q.gy * c.nxd + q.gx;
+  float windhl[2], rhohl[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const float4 lo = __ldg(a.A[m] + o), hi = __ldg(a.A[m] + o + plane);
+    const float w1 = (q.flags & BC_WE) ? lo.x : lo.y, w2 = (q.flags & BC_WE) ? hi.x : hi.y;
+    windhl[m] = __fmul_rn(__fadd_rn(__fmul_rn(q.dz2, w1), __fmul_rn(q.dz1, w2)), q.dz);
+    rhohl[m] = __fmul_rn(__fadd_rn(__fmul_rn(q.dz2, lo.w), __fmul_rn(q.dz1, hi.w)), q.dz);
+  }
+  const float windx = __fmul_rn(__fadd_rn(__fmul_rn(windhl[0], a.dt2), __fmul_rn(windhl[1], a.dt1)), a.dtt);
+  const float rhox = __fmul_rn(__fadd_rn(__fmul_rn(rhohl[0], a.dt2), __fmul_rn(rhohl[1], a.dt1)), a.dtt);
+  const float flux = __fmul_rn(__fmul_rn(__fmul_rn(windx, rhox), q.boundarea), (float)c.lsynctime);
+  float acc = a.acc_mass[l];
+  if (!(q.flags & BC_K2)) acc = (flux >= 0.f) ? __fadd_rn(acc, flux) : 0.f;
+  else acc = (flux <= 0.f) ? __fadd_rn(acc, fabsf(flux)) : 0.f;
+  const float xm = a.xmassperparticle, half = __fdiv_rn(xm, 2.f);
+  int mmass = 0;
+  if (acc >= half) {
+    mmass = (int)__fdiv_rn(__fadd_rn(acc, half), xm);
+    acc = __fsub_rn(acc, __fmul_rn((float)mmass, xm));
+  }
+  a.acc_mass[l] = acc;
+  a.mmass[l] = mmass;
+}
+
+__device__ __forceinline__ bool bc_slot_free(const BoundcondArgs &a, int s, int &row) {
+  row = a.permuted ? a.row_of_slot[s] : s;
+  return s >= a.numpart_old || a.p.itra1[row] != a.cfg.itime;
+}
+
+__global__ void __launch_bounds__(DF_BLOCK) bc_count_free_kernel(const BoundcondArgs a) {
+  const int s = blockIdx.x * DF_BLOCK + threadIdx.x;
+  int row;
+  const int free_here = (s < a.p.maxpart) && bc_slot_free(a, s, row);
+  const int n = __syncthreads_count(free_here);
+  if (threadIdx.x == 0) a.block_counts[blockIdx.x] = (unsigned)n;
+}
+
+// exclusive scan of any number of block counts by one block; total -> *total
+__global__ void __launch_bounds__(DF_BLOCK) bc_scan_kernel(unsigned *v, int n, int *total) {
+  __shared__ unsigned wtot[32];
+  __shared__ unsigned running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += DF_BLOCK) {
+    const int i = base + threadIdx.x;
+    const unsigned x = (i < n) ? v[i] : 0u;
+    unsigned inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      unsigned t = wtot[lane], ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, ti, d);
+        if (lane >= d) ti += u;
+      }
+      wtot[lane] = ti - t;
+    }
+    __syncthreads();
+    const unsigned excl = running + wtot[w] + inc - x;
+    if (i < n) v[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == DF_BLOCK - 1) running = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = (int)running;
+}
+
+// :199-313 / :441-541: the m-th particle this rank creates goes to its m-th free slot (the reference's
+// minpart search: first slot whose itra1 differs from itime, minpart only grows)
+__global__ void __launch_bounds__(DF_BLOCK) bc_create_kernel(const BoundcondArgs a) {
+  __shared__ unsigned warp_cnt[32];
+  const DevCfg &c = a.cfg;
+  const int s = blockIdx.x * DF_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int row = 0;
+  const bool free_here = (s < a.p.maxpart) && bc_slot_free(a, s, row);
+  const unsigned bal = __ballot_sync(0xffffffffu, free_here);
+  if (lane == 0) warp_cnt[w] = __popc(bal);
+  __syncthreads();
+  if (w == 0) {
+    unsigned t = warp_cnt[lane], ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += u;
+    }
+    warp_cnt[lane] = ti - t;
+  }
+  __syncthreads();
+  if (!free_here) return;
+  const int m = (int)(a.block_counts[blockIdx.x] + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u)));
+  if (m >= a.n_mine) return;
+  const int r = a.r0 + m * a.id_stride; // particle of the call, in the reference's creation order
+  int lo = 0, hi = a.nloc - 1;          // its location: first[l] <= r < first[l + 1]
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.first[mid] <= r) lo = mid; else hi = mid - 1;
+  }
+  const BcLoc q = a.loc[lo];
+  const int g = a.numparticlecount + r; // numparticlecount - 1 of this particle
+  float u_h, u_z = 0.f, u_c;
+  if (a.uniforms) {
+    const int dpp = (q.flags & BC_ZDRAW) ? 3 : 2;
+    const float *u = a.uniforms + a.u_off[lo] + (size_t)(r - a.first[lo]) * dpp;
+    int k = 0;
+    u_h = u[k++];
+    if (q.flags & BC_ZDRAW) u_z = u[k++];
+    u_c = u[k++];
+  } else {
+    const uint2 key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+    const uint4 v = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)c.itime, 34u, 0u), key);
+    u_h = u01(v.x); u_z = u01(v.y); u_c = u01(v.z);
+  }
+  // position along the boundary: half a cell at the two ends of the boundary, a whole cell else
+  float along;
+  if (q.flags & BC_EDGE_LOW) along = __fadd_rn((float)q.idx, __fmul_rn(0.5f, u_h));
+  else if (q.flags & BC_EDGE_HIGH) along = __fsub_rn((float)q.idx, __fmul_rn(0.5f, u_h));
+  else along = __fadd_rn((float)q.idx, __fsub_rn(u_h, .5f));
+  const DevParticles &p = a.p;
+  if (q.flags & BC_WE) { p.xtra1[row] = (double)(float)q.gx; p.ytra1[row] = (double)along; }
+  else { p.ytra1[row] = (double)(float)q.gy; p.xtra1[row] = (double)along; }
+  p.ztra1[row] = (q.flags & BC_ZDRAW) ? __fadd_rn(q.za, __fmul_rn(u_z, q.zb)) : q.za;
+  const int nc = (int)__fmul_rn(u_c, (float)c.nclassunc) + 1;
+  p.nclass[row] = min(nc, c.nclassunc);
+  p.npoint[row] = g + 1;
+  p.idt[row] = c.mintime;
+  p.itra1[row] = c.itime;
+  p.itramem[row] = c.itime;
+  p.itrasplit[row] = c.itime + c.ldirect * a.itsplit;
+  p.xmass1[row] = a.xmassperparticle;
+  // (the reference leaves the other species and the velocity memory of the slot's last owner;
+  //  initialize() sets the velocities and the CBL flag at the particle's first step)
+  p.slot[row] = s;
+  atomicMax(a.out, s + 1);
+}
+
 } // namespace
+
+void fpb_domainfill_profiles(const DomainfillArgs &a, const int2 *cols, int n, float *out, cudaStream_t st) {
+  if (n <= 0) return;
+  df_profiles_kernel<<<(n * a.cfg.nz + 255) / 256, 256, 0, st>>>(a, cols, n, out);
+}
+
+void fpb_boundcond_launch(const BoundcondArgs &a, cudaStream_t st, int64_t *launches, int phase) {
+  if (phase == 0) {
+    if (a.numpart_old > 0) bc_terminate_kernel<<<(a.numpart_old + 255) / 256, 256, 0, st>>>(a);
+    if (a.nloc > 0) bc_flux_kernel<<<(a.nloc + 255) / 256, 256, 0, st>>>(a);
+    *launches += 2;
+  } else {
+    const int nb = (a.p.maxpart + DF_BLOCK - 1) / DF_BLOCK;
+    bc_count_free_kernel<<<nb, DF_BLOCK, 0, st>>>(a);
+    bc_scan_kernel<<<1, DF_BLOCK, 0, st>>>(a.block_counts, nb, a.out + 1);
+    bc_create_kernel<<<nb, DF_BLOCK, 0, st>>>(a);
+    *launches += 3;
+  }
+}
 
 void fpb_domainfill_launch(const DomainfillArgs &a, cudaStream_t st, int64_t *launches, int phase) {
   const int nb = (a.ncols + DF_BLOCK - 1) / DF_BLOCK;

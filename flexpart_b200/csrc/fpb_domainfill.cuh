@@ -32,3 +32,45 @@ struct DomainfillArgs {
 };
 
 void fpb_domainfill_launch(const DomainfillArgs &a, cudaStream_t st, int64_t *launches, int phase);
+// pressure profiles pp(kz) = rho*r_air*tt of the listed columns (init_domainfill.f90:322-324), out[n][nz]
+void fpb_domainfill_profiles(const DomainfillArgs &a, const int2 *cols, int n, float *out, cudaStream_t st);
+
+// ---- boundcond_domainfill (src/boundcond_domainfill.f90:54-560): inflow boundary of a limited box
+// One release location of the boundary: what does not change during the run is worked out once by
+// the host from the heights memorised by init_domainfill (:104-143, :343-381).
+struct BcLoc {
+  int gx, gy;        // grid point whose wind and density give the mass flux
+  int indz;          // 1-based model level below the release height
+  float dz1, dz2, dz;
+  float boundarea;
+  float za, zb;      // height of a new particle: za (+ u * zb at an interior height)
+  int idx;           // jy (west/east boundary) or ix (south/north)
+  int flags;         // see BC_* below
+};
+enum { BC_WE = 1, BC_K2 = 2, BC_EDGE_LOW = 4, BC_EDGE_HIGH = 8, BC_ZDRAW = 16 };
+
+struct BoundcondArgs {
+  DevCfg cfg;                  // cfg.itime = the call's itime
+  DevParticles p;
+  const int32_t *row_of_slot;
+  int permuted, numpart_old;
+  const float4 *A[2];          // {uu,vv,ww,rho} of memind(1), memind(2)
+  float dt1, dt2, dtt;
+  int nx0, nx1, ny0, ny1, check_x;
+  const BcLoc *loc;
+  int nloc;
+  float *acc_mass;             // [nloc]
+  int32_t *mmass;              // [nloc] particles each location releases in this call
+  const int32_t *first;        // [nloc + 1] exclusive prefix of mmass
+  const float *uniforms;       // reference RNG: the call's ran1 stream in the reference's draw order
+  const int32_t *u_off;        // [nloc] first stream entry of each location
+  int n_new;                   // particles of the call over all ranks
+  int n_mine, r0;              // this rank creates r = r0, r0 + stride, ... (n_mine of them)
+  int numparticlecount;        // before the call
+  float xmassperparticle;
+  int itsplit, id_stride;
+  unsigned *block_counts;      // [ceil(maxpart / 1024) + 1]
+  int *out;                    // [0] max(new slot) + 1, [1] free slots
+};
+// phase 0: terminate + fluxes -> mmass; phase 1: create the particles
+void fpb_boundcond_launch(const BoundcondArgs &a, cudaStream_t st, int64_t *launches, int phase);

@@ -249,7 +249,11 @@ class Engine:
                              colmasstotal=info.colmasstotal, xmassperparticle=info.xmassperparticle)
 
     def boundcond_domainfill(self, itime, loutend=0):
-        self._check(self.L.fpb_boundcond_domainfill(self.h, itime, loutend))
+        """boundcond_domainfill(itime, loutend) (src/boundcond_domainfill.f90:54-560); returns
+        (numpart, particles created by this rank)."""
+        n, m = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.fpb_boundcond_domainfill(self.h, itime, loutend, C.byref(n), C.byref(m)))
+        return n.value, m.value
 
     def split_particles(self, itime):
         """particle splitting of timemanager (src/timemanager.f90:472-503); returns the new numpart."""

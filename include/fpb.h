@@ -376,11 +376,21 @@ int fpb_releaseparticles(fpb_handle *h, int32_t itime, int32_t *numpart /* may b
  * particle's counter stream.  With part_id_stride = N, part_id_offset = r the call keeps every N-th
  * particle (global index g with g mod N = r, in slot g / N): the round-robin distribution of
  * src/init_domainfill_mpi.f90:86-104 without the root process or any exchange.  Needs an empty
- * particle set (ipin = 0).  Not built: MDOMAINFILL = 2 (stratospheric ozone, :236-251) and the
- * second half of the routine (:287-398, inflow columns of a limited domain).
+ * particle set (ipin = 0).  For a box that is not the whole globe the second half of the routine
+ * (:287-389) memorises the release heights of the four inflow boundaries.  Not built:
+ * MDOMAINFILL = 2 (stratospheric ozone, :236-251) and restarts (ipin = 1, boundcond.bin).
  * fpb_boundcond_domainfill replaces `call boundcond_domainfill(itime,loutend)`
- * (src/timemanager.f90:240): for a global domain (gdomainfill) the reference returns at once
- * (src/boundcond_domainfill.f90:54) and so does this; a limited domain is refused. */
+ * (src/timemanager.f90:240, src/boundcond_domainfill.f90:54-560): for a global domain (gdomainfill)
+ * the reference returns at once and so does this.  For a limited box the particles of the current
+ * step that left the box are terminated, the air-mass flux through every boundary release location
+ * (wind and density of the met bracket at itime, so fpb_set_met_bracket must have been called) is
+ * accumulated, and wherever half a particle mass has accumulated new particles are created in the
+ * slots the reference's search finds -- all on the device; per call one int per release location
+ * comes back to the host.  FPB_RNG_REFERENCE replays the routine's own ran1 stream (bit-identical),
+ * the Philox modes draw from the new particle's counter stream.  With part_id_stride = N every rank
+ * accumulates the same fluxes and keeps every N-th new particle.  *numpart returns the new numpart,
+ * *n_created the particles this rank created.  A boundary column with exactly two release heights
+ * reads element 0 of a 1-based array in the reference (:115); that element is 0 here. */
 typedef struct fpb_domainfill_info {
   int32_t nx_we[2], ny_sn[2]; /* domain box in met-grid indices, src/com_mod.f90:245 */
   int32_t gdomainfill;        /* 1: global domain filling, no boundary conditions */
@@ -392,7 +402,8 @@ typedef struct fpb_domainfill_info {
 int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
                         int32_t itsplit, int32_t *numpart /* may be NULL */,
                         fpb_domainfill_info *info /* may be NULL */);
-int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend);
+int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int32_t *numpart /* may be NULL */,
+                             int32_t *n_created /* may be NULL */);
 
 /* Convective mixing (LCONVECTION = 1, the shipped default).
  * fpb_convmix replaces `call convmix(itime,metdata_format)` (src/timemanager.f90:183-193,258-263;

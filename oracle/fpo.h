@@ -70,6 +70,15 @@ typedef struct fpo_state {
   int idummy_advance, idummy_initialize, idummy_release;
   int idummy_domainfill;  /* src/init_domainfill.f90:47 (idummy = -11) */
   int numparticlecount;   /* src/com_mod.f90:676 */
+  /* inflow boundary of a limited domain-filling box (src/com_mod.f90:244-253), set by fpo_init_domainfill */
+  struct {
+    int nx_we[2], ny_sn[2], gdomainfill;
+    float xmassperparticle;
+    int32_t *numcolumn_we, *numcolumn_sn;        /* (2, 0:nymax-1) / (2, 0:nxmax-1) */
+    float *zcolumn_we, *zcolumn_sn;              /* (2, 0:n-1, 0:maxcolumn+1): third index 0 holds 0 */
+    float *acc_mass_we, *acc_mass_sn;
+    int idummy;                                  /* src/boundcond_domainfill.f90:49 */
+  } bc;
   float *zpoint1, *zpoint2; /* 1-based release heights (point_mod), backward wet scavenging only */
   float settling_saved; /* src/advance.f90:121 */
 
@@ -238,6 +247,11 @@ void fpo_interpol_weights(fpo_state *S, int itime, float xt, float yt);
 void fpo_domainfill_gridarea(const fpb_config *c, const int ny_sn[2], float *gridarea);
 int fpo_init_domainfill(fpo_state *S, float xpoint1, float ypoint1, float xpoint2, float ypoint2,
                         int itsplit, int32_t *out, float *fout);
+/* boundcond_domainfill(itime): returns the number of particles created, -1 when maxpart is exceeded */
+int fpo_boundcond_domainfill(fpo_state *S, int itime, int itsplit);
+/* total number of boundary release locations and the sum of the accumulated masses (diagnostics) */
+int fpo_boundcond_locations(fpo_state *S, double *accmass_sum);
+int fpo_numparticlecount(const fpo_state *S);
 
 /* releaseparticles (integer semantics + ran1 stream) */
 void fpo_split_particles(fpo_state *S, int itime);

@@ -71,6 +71,7 @@ fpo_state *fpo_create(const fpb_config *cfg, int strict_reference) {
   S->idummy_initialize = -7;
   S->idummy_release = -7;
   S->idummy_domainfill = -11;
+  S->bc.idummy = -11;
   S->maxpart = c->maxpart;
   size_t n = (size_t)c->maxpart + 1;
   S->xtra1 = (double *)calloc(n, sizeof(double));
@@ -131,6 +132,8 @@ void fpo_destroy(fpo_state *S) {
   free(S->drygriduncn); free(S->creceptor);
   free(S->wetgridunc); free(S->wetgriduncn);
   free(S->index_queue); free(S->zpoint1); free(S->zpoint2);
+  free(S->bc.numcolumn_we); free(S->bc.numcolumn_sn); free(S->bc.zcolumn_we); free(S->bc.zcolumn_sn);
+  free(S->bc.acc_mass_we); free(S->bc.acc_mass_sn);
   free(S);
 }
 
@@ -160,6 +163,7 @@ void fpo_set_met_bracket(fpo_state *S, const int memind[2], const int memtime[2]
 
 void fpo_set_numpart(fpo_state *S, int numpart) { S->numpart = numpart; }
 int fpo_numpart(const fpo_state *S) { return S->numpart; }
+int fpo_numparticlecount(const fpo_state *S) { return S->numparticlecount; }
 
 /* sub-steps each particle took in the last fpo_step (1-based like the particle arrays) */
 const int32_t *fpo_trace_nsub(const fpo_state *S) { return S->trace_nsub; }

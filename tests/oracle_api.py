@@ -62,7 +62,12 @@ def load(libm_float=False):
     L.fpo_set_release_heights.argtypes = [S, _pf, _pf, C.c_int]
     L.fpo_init_domainfill.argtypes = [S, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _pi, _pf]
     L.fpo_init_domainfill.restype = C.c_int
+    L.fpo_boundcond_domainfill.argtypes = [S, C.c_int, C.c_int]
+    L.fpo_boundcond_domainfill.restype = C.c_int
+    L.fpo_boundcond_locations.argtypes = [S, C.POINTER(C.c_double)]
+    L.fpo_boundcond_locations.restype = C.c_int
     L.fpo_numpart.argtypes = [S]; L.fpo_numpart.restype = C.c_int
+    L.fpo_numparticlecount.argtypes = [S]; L.fpo_numparticlecount.restype = C.c_int
     L.fpo_outgrid_geometry.argtypes = [C.POINTER(FpbConfig), C.c_int, C.c_float, _pf, _pf]
     L.fpo_partoutput_record.argtypes = [C.POINTER(FpbConfig), _pf, C.c_int, _pi, C.c_double, C.c_double, C.c_float, _pf] + \
         [C.POINTER(_pf)] * 6 + [_pf]
@@ -117,6 +122,24 @@ class Oracle:
         return self.L.fpo_numpart(self.S), dict(nx_we=(int(out[0]), int(out[1])), ny_sn=(int(out[2]), int(out[3])),
                                                 gdomainfill=int(out[4]), numcolumn=int(out[5]), numparttot=int(out[6]),
                                                 colmasstotal=float(fout[0]), xmassperparticle=float(fout[1]))
+
+    def boundcond_domainfill(self, itime, itsplit=99999999):
+        """boundcond_domainfill(itime); returns the number of particles created"""
+        n = self.L.fpo_boundcond_domainfill(self.S, itime, itsplit)
+        if n < 0:
+            raise RuntimeError("boundcond_domainfill: too many particles required")
+        return n
+
+    def numpart(self):
+        return self.L.fpo_numpart(self.S)
+
+    def numparticlecount(self):
+        return self.L.fpo_numparticlecount(self.S)
+
+    def boundcond_locations(self):
+        acc = C.c_double(0.0)
+        n = self.L.fpo_boundcond_locations(self.S, C.byref(acc))
+        return n, acc.value
 
     def set_index_uniforms(self, u):
         """validation hook: the uniforms behind the next nrand draws (tests/philox_ref.py)"""

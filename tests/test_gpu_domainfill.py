@@ -44,13 +44,9 @@ def test_reference_stream_is_bit_identical_to_the_oracle(box, npart1, math_mode)
     for f in FIELDS:
         assert np.array_equal(getattr(pg, f)[:no], getattr(po, f)[:no]), f
     assert np.array_equal(pg.xmass1[:no], po.xmass1[:no])
-    # global domain: boundcond_domainfill returns at once (src/boundcond_domainfill.f90:54);
-    # the inflow boundary of a limited domain is refused, not silently skipped
+    # global domain: boundcond_domainfill returns at once (src/boundcond_domainfill.f90:54)
     if io["gdomainfill"]:
-        eng.boundcond_domainfill(900)
-    else:
-        with pytest.raises(fb.FpbError, match="limited domain"):
-            eng.boundcond_domainfill(900)
+        assert eng.boundcond_domainfill(900) == (no, 0)
     # the created particles step like any others (initialize runs for them: itramem == itime == 0)
     fill = lambda e: e.fill_rannumb()
     fill(eng); fill(ora)
@@ -63,6 +59,106 @@ def test_reference_stream_is_bit_identical_to_the_oracle(box, npart1, math_mode)
         for f in FIELDS + ("uap", "ucp", "uzp", "us", "vs", "ws"):
             assert np.array_equal(getattr(pg, f)[:no], getattr(po, f)[:no]), f
     eng.close()
+
+
+@pytest.mark.parametrize("math_mode", [fb.MATH_STRICT, fb.MATH_FAST])
+def test_boundcond_domainfill_limited_box_bit_identical(math_mode):
+    """boundcond_domainfill on the device (src/boundcond_domainfill.f90:54-560) interleaved with the
+    particle loop and the cell sort: terminations, accumulated boundary masses, the slots the new
+    particles take and their ran1 positions are those of the oracle (pinned against the reference's
+    routine in tests/test_ref_transpiled.py), call after call."""
+    npart1 = 150000
+    cb = cases.config_small(nrel=1, npart_each=npart1, maxpart=npart1 + 30000, mdomainfill=1, nclassunc=3,
+                            math_mode=math_mode, sort_interval=1)
+    c = cb.cfg
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, m0); e.upload_met(2, m1); e.set_met_bracket((1, 2), (0, 10800))
+    pts = _box(c, -60.0, -30.0, 70.0, 45.0)
+    no, io = ora.init_domainfill(pts)
+    ng, ig = eng.init_domainfill(pts)
+    assert ng == no and ig["gdomainfill"] == 0
+    created = terminated = 0
+    exact = math_mode == fb.MATH_STRICT
+    for k in range(6):
+        itime = k * c.lsynctime
+        if not exact and k:     # fast math: re-inject the oracle's particle state before every call
+            q = fb.Particles(c.maxpart, 1); q.numpart = ora.numpart()
+            ora.pull_particles(q)
+            eng.push_particles(q)
+        po0 = fb.Particles(c.maxpart, 1); po0.numpart = ora.numpart()
+        ora.pull_particles(po0)
+        mo = ora.boundcond_domainfill(itime)
+        n, mg = eng.boundcond_domainfill(itime)
+        assert mg == mo and n == ora.numpart(), (k, mg, mo, n, ora.numpart())
+        created += mo
+        pg, po = fb.Particles(c.maxpart, 1), fb.Particles(c.maxpart, 1)
+        pg.numpart = po.numpart = n
+        eng.pull_particles(pg); ora.pull_particles(po)
+        terminated += int(((po0.itra1[:po0.numpart] == itime) & (po.itra1[:po0.numpart] == fb.ITRA_DEAD)).sum())
+        for f in FIELDS:
+            assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (k, f)
+        assert np.array_equal(pg.xmass1[:n], po.xmass1[:n]), k
+        sg, so = eng.step(itime), ora.step(itime)
+        assert sg["n_active"] == so["n_active"] and sg["n_init"] == so["n_init"], k
+        if exact:
+            eng.pull_particles(pg); ora.pull_particles(po)
+            for f in FIELDS + ("uap", "ucp", "uzp", "us", "vs", "ws"):
+                assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), (k, f)
+    assert created > 300 and terminated > 100, (created, terminated)
+    eng.close()
+
+
+def test_boundcond_domainfill_philox_rank_partition():
+    """Production RNG: every rank accumulates the same boundary fluxes and keeps every N-th new
+    particle; the union over the ranks is the one-rank result (particles keyed by their global
+    count), and the new particles sit on the boundary they entered through."""
+    npart1 = 300000
+    base = dict(nrel=1, npart_each=npart1, maxpart=npart1 + 30000, mdomainfill=1, rng_mode=fb.RNG_PHILOX_INDEX)
+    m0 = m1 = None
+
+    def run(cb):
+        nonlocal m0, m1
+        if m0 is None:
+            m0, m1 = cases.met_pair(cb)
+        c = cb.cfg
+        eng = fb.Engine(cb)
+        eng.upload_met(1, m0); eng.upload_met(2, m1); eng.set_met_bracket((1, 2), (0, 10800))
+        n, info = eng.init_domainfill(_box(c, -60.0, -30.0, 70.0, 45.0))
+        new = {}
+        for k in range(4):
+            itime = k * c.lsynctime
+            n, m = eng.boundcond_domainfill(itime)
+            p = fb.Particles(c.maxpart, 1); p.numpart = n
+            eng.pull_particles(p)
+            sel = np.nonzero((p.itramem[:n] == itime) & (p.itra1[:n] == itime) & (p.npoint[:n] > info["numparttot"]))[0] \
+                if k else np.nonzero((p.itra1[:n] == 0) & (p.npoint[:n] > info["numparttot"]))[0]
+            assert len(sel) == m, (k, len(sel), m)
+            for s in sel:
+                new[int(p.npoint[s])] = (float(p.xtra1[s]), float(p.ytra1[s]), float(p.ztra1[s]), int(p.nclass[s]),
+                                         float(p.xmass1[s, 0]), itime)
+            live = p.itra1[:n] == itime          # the particle loop would move the clock on
+            p.itra1[:n][live] = itime + c.lsynctime
+            eng.push_particles(p)
+        eng.close()
+        return info, new
+
+    info, one = run(cases.config_small(**base))
+    assert len(one) > 500
+    nx_we, ny_sn = info["nx_we"], info["ny_sn"]
+    for x, y, z, nc, xm, _ in one.values():
+        assert x in (float(nx_we[0]), float(nx_we[1])) or y in (float(ny_sn[0]), float(ny_sn[1]))
+        assert nx_we[0] - 0.5 <= x <= nx_we[1] + 0.5 and ny_sn[0] - 0.5 <= y <= ny_sn[1] + 0.5 and z > 0.0
+        assert np.float32(xm) == np.float32(info["xmassperparticle"])
+    union = {}
+    for r in range(3):
+        _, part = run(cases.config_small(**dict(base, part_id_stride=3, part_id_offset=r)))
+        assert not (set(part) & set(union))
+        assert all((g - 1) % 3 == r for g in part)
+        union.update(part)
+    assert union == one
 
 
 def test_philox_fill_properties_and_rank_partition():

@@ -493,6 +493,70 @@ def test_reference_init_domainfill_bit_identical(box, npart1):
     assert abs(q.xmass1[:n, 0].astype(np.float64).sum() / info["colmasstotal"] - 1.0) < (2e-3 if npart1 >= 10000 else 0.1)
 
 
+def test_reference_boundcond_domainfill_bit_identical():
+    """boundcond_domainfill (src/boundcond_domainfill.f90:54-560) on a limited domain-filling box:
+    the boundary release heights memorised by init_domainfill (:287-389), then per call the
+    termination of particles outside the box, the mass flux through every boundary location, the
+    accumulated masses and the particles created from them (slots, positions, ran1 stream)."""
+    npart1 = 60000
+    cb = cases.config_small(nrel=1, npart_each=npart1, maxpart=npart1 + 20000, mdomainfill=1, nclassunc=3)
+    c = cb.cfg
+    m0, m1 = cases.met_pair(cb)
+    ref = ref_api.Ref(cb, maxrand=MAXRAND)
+    o = Oracle(cb)
+    for e in (ref, o):
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), (0, 10800))
+    box = (-60.0, -30.0, 70.0, 45.0)
+    pts = [(box[0] - c.xlon0) / c.dx, (box[1] - c.ylat0) / c.dy, (box[2] - c.xlon0) / c.dx, (box[3] - c.ylat0) / c.dy]
+    pts = [float(np.float32(v)) for v in pts]
+    for nm, v in zip(("xpoint1", "ypoint1", "xpoint2", "ypoint2"), pts):
+        ref.arr(nm)[0] = v
+    ref.set("ipin", 0); ref.set("itsplit", 99999999); ref.set("numpart", 0); ref.set("numparticlecount", 0)
+    ref.set("gdomainfill", 0); ref.set("ipout", 0)
+    ref.arr("itra1")[:] = fb.ITRA_DEAD
+    ref.L.f_init_domainfill()
+    n, info = o.init_domainfill(pts)
+    assert info["gdomainfill"] == 0 and n == ref.get("numpart")
+    nloc, _ = o.boundcond_locations()
+    assert nloc == int(ref.arr("numcolumn_we").sum() + ref.arr("numcolumn_sn").sum()) and nloc > 1000
+    assert ref.arr("numcolumn_we").max() >= 3
+    rs = np.random.RandomState(4)
+    created_total = 0
+    for k in range(10):
+        itime = k * c.lsynctime
+        q = fb.Particles(c.maxpart, 1); q.numpart = o.numpart()
+        o.pull_particles(q)
+        npt = q.numpart
+        if k:   # the particle loop moved the particles on: here a random walk, some of them out of the box
+            mv = q.itra1[:npt] == itime
+            q.xtra1[:npt][mv] += rs.normal(0.0, 0.8, mv.sum())
+            q.ytra1[:npt][mv] += rs.normal(0.0, 0.8, mv.sum())
+            o.push_particles(q)
+            ref.arr("xtra1")[:npt] = q.xtra1[:npt]; ref.arr("ytra1")[:npt] = q.ytra1[:npt]
+        itime_c = C.c_int(itime); lout = C.c_int(10 ** 9)
+        ref.L.f_boundcond_domainfill(C.byref(itime_c), C.byref(lout))
+        created = o.boundcond_domainfill(itime)
+        created_total += created
+        n = o.numpart()
+        assert n == ref.get("numpart"), k
+        q = fb.Particles(c.maxpart, 1); q.numpart = n
+        o.pull_particles(q)
+        for f in ("xtra1", "ytra1", "ztra1", "itra1", "itramem", "npoint", "nclass", "idt", "itrasplit"):
+            a, b = ref.arr(f)[:n], getattr(q, f)[:n]
+            assert np.array_equal(a.view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), (k, f)
+        assert np.array_equal(ref.arr("xmass1")[:n, 0].view(np.uint32), q.xmass1[:n, 0].view(np.uint32)), k
+        assert o.numparticlecount() == ref.get("numparticlecount")
+        # advance the clock of the live particles as the particle loop would
+        live = q.itra1[:n] == itime
+        q.itra1[:n][live] = itime + c.lsynctime
+        o.push_particles(q)
+        ref.arr("itra1")[:n] = q.itra1[:n]
+    assert created_total > 80
+    acc_ref = float(ref.arr("acc_mass_we").astype(np.float64).sum() + ref.arr("acc_mass_sn").astype(np.float64).sum())
+    assert abs(o.boundcond_locations()[1] - acc_ref) <= 1e-9 * abs(acc_ref)
+
+
 def test_reference_readcommand_derivations_match_host():
     """fpbh_readcommand (turbulence switches, ifine, fine, ctl := 1/ctl, method, mintime) against
     src/readcommand.f90:244-272,379-385 run from the reference's source."""
