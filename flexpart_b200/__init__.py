@@ -10,13 +10,14 @@ from .abi import (FpbConfig, FpbMetPtrs, FpbParticlePtrs, FpbStepStats, load_eng
                   load_host_lib, FpbError, RNG_REFERENCE, RNG_PHILOX_INDEX, RNG_PHILOX,
                   MATH_FAST, MATH_STRICT, SCATTER_ATOMIC, SCATTER_DETERMINISTIC, ITRA_DEAD)
 from .host import (make_config, MetFields, Particles, synth_heights, Releases, RunSpec,
-                   timemanager, release_particles, ReleaseState, outgrid_geometry)
+                   timemanager, release_particles, ReleaseState, outgrid_geometry,
+                   verttransform_heights)
 from .engine import Engine
 
 __all__ = [
     "FpbConfig", "FpbMetPtrs", "FpbParticlePtrs", "FpbStepStats", "FpbError", "Engine",
     "make_config", "MetFields", "Particles", "synth_heights", "Releases", "RunSpec",
-    "timemanager", "release_particles", "ReleaseState", "outgrid_geometry", "load_engine_lib", "load_host_lib",
+    "timemanager", "release_particles", "ReleaseState", "outgrid_geometry", "verttransform_heights", "load_engine_lib", "load_host_lib",
     "RNG_REFERENCE", "RNG_PHILOX_INDEX", "RNG_PHILOX", "MATH_FAST", "MATH_STRICT",
     "SCATTER_ATOMIC", "SCATTER_DETERMINISTIC", "ITRA_DEAD",
 ]

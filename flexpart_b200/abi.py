@@ -110,6 +110,16 @@ class FpbConvPtrs(C.Structure):
     _fields_ = [(n, _pf) for n in ("ps", "tt2", "td2", "tth", "qvh")]
 
 
+class FpbRawmetPtrs(C.Structure):
+    _fields_ = [(n, _pf) for n in ("uuh", "vvh", "tth", "qvh", "pvh", "wwh", "ps", "tt2", "td2", "sshf", "surfstr",
+                                   "lsprec", "convprec", "tcc", "excessoro")]
+
+
+class FpbMetOutPtrs(C.Structure):
+    _fields_ = [(n, _pf) for n in ("uu", "vv", "ww", "rho", "drhodz", "tt", "qv", "pv", "uupol", "vvpol", "hmix",
+                                   "ustar", "wstar", "oli", "tropopause")] + [("clouds", C.POINTER(C.c_int8))]
+
+
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
@@ -201,6 +211,10 @@ def load_engine_lib():
     L.fpb_upload_convmet.argtypes = [H, _i, C.POINTER(FpbConvPtrs)]
     L.fpb_upload_convmet_nest.argtypes = [H, _i, _i, C.POINTER(FpbConvPtrs)]
     L.fpb_convmix.argtypes = [H, _i, _pi, _pi]
+    L.fpb_set_vertical.argtypes = [H, _i, _i, _i, _i, _pf, _pf, _pf, _pf]
+    L.fpb_calcpar_verttransform.argtypes = [H, _i, C.POINTER(FpbRawmetPtrs), _i, _pf]
+    L.fpb_upload_vdep.argtypes = [H, _i, _pf]
+    L.fpb_fetch_met.argtypes = [H, _i, C.POINTER(FpbMetOutPtrs)]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
     L.fpb_boundcond_domainfill.argtypes = [H, _i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,
@@ -237,6 +251,7 @@ def load_host_lib():
     L.fpbh_readoutgrid.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f, _pf, _i]
     L.fpbh_readoutgrid_nest.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f]
     L.fpbh_synth_heights.argtypes = [_i, _pf]
+    L.fpbh_verttransform_heights.argtypes = [C.POINTER(FpbConfig), _i, _pf, _pf, _pf, _pf, _pf, _pf, _pf, _pf, _pi, _pi]
     L.fpbh_synth_met.argtypes = [C.POINTER(FpbConfig), _pf, _i, _pmet]
     L.fpbh_synth_met_nest.argtypes = [C.POINTER(FpbConfig), _pf, _i, _i, _pmet]
     L.fpbh_homogeneous_met.argtypes = [C.POINTER(FpbConfig), _f, _f, _f, _pmet]

@@ -24,6 +24,7 @@
 #include "fpb_sort.cuh"
 #include "fpb_output.cuh"
 #include "fpb_domainfill.cuh"
+#include "fpb_metproc.cuh"
 #include "fpb_convmix.cuh"
 
 // ------------------------------------------------------------ error state --
@@ -291,6 +292,16 @@ struct fpb_handle {
     size_t cap_rows = 0, cap_cols = 0;
     int iseed = -88;                       // SAVEd iseed of redist, src/redist.f90:58
   } conv;
+  // calcpar + verttransform on the device (fpb_set_vertical / fpb_calcpar_verttransform)
+  struct MetProc {
+    int nuvz = 0, nwz = 0, nuvzmax = 0, nwzmax = 0;
+    float *d_ab = nullptr;   // akz, bkz, akm, bkm: 4 x (nuvz + 1), 1-based
+    float *d_cosf = nullptr; // [ny]
+    float2 *UV = nullptr;
+    float *W = nullptr, *PV = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
+    float4 *SF2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
+  } metproc;
   DevScratch sc{}; // fpb_pbl_kernel -> fpb_finish_kernel hand-over rows
   std::vector<int32_t> h_slot;
   DevCfg d_tmp;
@@ -746,6 +757,14 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->creceptor); cudaFree(h->crec_acc); cudaFree(h->d_stats);
   scatter_free(h->scatter);
   dep_free(h->depstore);
+  {
+    auto &M = h->metproc;
+    cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.excessoro);
+    cudaFree(M.uvzlev); cudaFree(M.SF2);
+    if (M.ev0) cudaEventDestroy(M.ev0);
+    if (M.ev1) cudaEventDestroy(M.ev1);
+    if (M.evk) cudaEventDestroy(M.evk);
+  }
   {
     auto &D = h->dfill;
     cudaFree(D.d_loc); cudaFree(D.d_acc); cudaFree(D.d_mmass); cudaFree(D.d_first); cudaFree(D.d_uoff);
@@ -2004,6 +2023,165 @@ extern "C" int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t lo
   }
   if (numpart) *numpart = h->numpart;
   if (n_created) *n_created = a.n_mine;
+  return 0;
+}
+
+// ------------------------------------------------- calcpar + verttransform --
+void fpb_metproc_launch(const fpbmet::MetGrid &g, cudaStream_t st, int64_t *launches); // fpb_metproc.cu
+
+extern "C" int fpb_set_vertical(fpb_handle *h, int32_t nuvz, int32_t nwz, int32_t nuvzmax, int32_t nwzmax,
+                                const float *akm, const float *bkm, const float *akz, const float *bkz) {
+  if (!h || !akm || !bkm || !akz || !bkz) return fail("fpb_set_vertical: null argument");
+  const fpb_config &c = h->cfg;
+  if (nuvz != c.nz || nwz != nuvz)
+    return fail("fpb_set_vertical: nuvz = %d, nwz = %d, nz = %d: only the ECMWF layout nz = nuvz = nwz "
+                "(src/gridcheck_ecmwf.f90:434-436,516-526) is built", nuvz, nwz, c.nz);
+  if (nuvzmax < nuvz || nwzmax < nwz) return fail("fpb_set_vertical: nuvzmax/nwzmax smaller than nuvz/nwz");
+  CK(cudaSetDevice(h->device));
+  auto &M = h->metproc;
+  M.nuvz = nuvz; M.nwz = nwz; M.nuvzmax = nuvzmax; M.nwzmax = nwzmax;
+  cudaFree(M.d_ab); M.d_ab = nullptr;
+  cudaFree(M.d_cosf); M.d_cosf = nullptr;
+  const size_t n1 = (size_t)nuvz + 1;
+  DA(M.d_ab, 4 * n1);
+  std::vector<float> ab(4 * n1, 0.f);
+  const float *src[4] = {akz, bkz, akm, bkm};
+  for (int q = 0; q < 4; q++)
+    for (int k = 0; k < nuvz; k++) ab[q * n1 + k + 1] = src[q][k];
+  CK(cudaMemcpy(M.d_ab, ab.data(), ab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // cosf(jy) = 1./cos((real(jy)*dy+ylat0)*pi180), src/verttransform_ecmwf.f90:406-408
+  std::vector<float> cosf((size_t)c.ny, 0.f);
+  const float pi180 = 3.14159265f / 180.f;
+  for (int jy = 0; jy < c.ny; jy++) cosf[jy] = 1.f / (float)cos((double)(((float)jy * c.dy + c.ylat0) * pi180));
+  DA(M.d_cosf, cosf.size());
+  CK(cudaMemcpy(M.d_cosf, cosf.data(), cosf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!M.ev0) { CK(cudaEventCreate(&M.ev0)); CK(cudaEventCreate(&M.ev1)); CK(cudaEventCreate(&M.evk)); }
+  return 0;
+}
+
+extern "C" int fpb_upload_vdep(fpb_handle *h, int32_t slot, const float *vdep) {
+  if (!h || !vdep) return fail("fpb_upload_vdep: null argument");
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_upload_vdep: slot %d", slot);
+  if (!h->cfg.drydep) return fail("fpb_upload_vdep: the run has no dry deposition (drydep = 0)");
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  if (alloc_met_slot(h, slot - 1)) return 1;
+  const float *vd[1] = {vdep};
+  if (upload_group(h, h->st_met, h->vdep[slot - 1], 1, vd, h->cfg.nspec)) return 1;
+  CK(cudaStreamSynchronize(h->st_met));
+  return 0;
+}
+
+extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_rawmet_ptrs *m, int32_t lsubgrid,
+                                         float *device_ms) {
+  if (!h || !m) return fail("fpb_calcpar_verttransform: null argument");
+  auto &M = h->metproc;
+  auto &V = h->conv;
+  const fpb_config &c = h->cfg;
+  if (M.nuvz == 0) return fail("fpb_calcpar_verttransform: fpb_set_vertical has not been called");
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_calcpar_verttransform: slot %d", slot);
+  if (!m->uuh || !m->vvh || !m->tth || !m->qvh || !m->wwh || !m->ps || !m->tt2 || !m->td2 || !m->sshf || !m->surfstr)
+    return fail("fpb_calcpar_verttransform: a mandatory field pointer is null");
+  if (c.wetdep && (!m->lsprec || !m->convprec || !m->tcc))
+    return fail("fpb_calcpar_verttransform: lsprec/convprec/tcc required when wetdep");
+  if (c.wetdep && c.readclouds)
+    return fail("fpb_calcpar_verttransform: cloud water read from the input (readclouds) is not built");
+  if (c.numbnests > 0) return fail("fpb_calcpar_verttransform: nested input grids (calcpar_nests / verttransform_nests) are not built");
+  if (lsubgrid == 1 && !m->excessoro) return fail("fpb_calcpar_verttransform: excessoro required when lsubgrid = 1");
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const int s = slot - 1;
+  if (alloc_met_slot(h, s)) return 1;
+  const int nxd = h->d.nxd, nyd = h->d.nyd, nuvz = M.nuvz;
+  const size_t n2 = (size_t)nxd * nyd, n3 = n2 * nuvz;
+  if (!M.UV) { DA(M.UV, n3); DA(M.W, n3); DA(M.uvzlev, n3); DA(M.SF2, n2); }
+  if (m->pvh && !M.PV) DA(M.PV, n3);
+  if (lsubgrid == 1 && !M.excessoro) DA(M.excessoro, n2);
+  if (!V.CT[0][s]) { DA(V.CT[0][s], n3); DA(V.CS[0][s], n2); }
+  if (!h->outp.Q[s]) DA(h->outp.Q[s], n3);
+  cudaStream_t st = h->st_met;
+  CK(cudaEventRecord(M.ev0, st));
+  {
+    const float *uv[2] = {m->uuh, m->vvh}, *w1[1] = {m->wwh}, *tq[2] = {m->tth, m->qvh}, *pv[1] = {m->pvh};
+    const float *s1[4] = {m->ps, m->tt2, m->td2, m->sshf}, *s2[4] = {m->surfstr, m->lsprec, m->convprec, m->tcc};
+    const float *ex[1] = {m->excessoro};
+    if (upload_group(h, st, (float *)M.UV, 2, uv, nuvz)) return 1;
+    if (upload_group(h, st, M.W, 1, w1, M.nwz)) return 1;
+    if (upload_group(h, st, (float *)V.CT[0][s], 2, tq, nuvz)) return 1;
+    if (m->pvh && upload_group(h, st, M.PV, 1, pv, nuvz)) return 1;
+    if (upload_group(h, st, (float *)V.CS[0][s], 4, s1, 1)) return 1;
+    if (upload_group(h, st, (float *)M.SF2, 4, s2, 1)) return 1;
+    if (lsubgrid == 1 && upload_group(h, st, M.excessoro, 1, ex, 1)) return 1;
+  }
+  fpbmet::MetGrid g{};
+  g.nx = c.nx; g.ny = c.ny; g.nz = c.nz; g.nuvz = nuvz; g.nwz = M.nwz;
+  g.nxd = nxd; g.nyd = nyd;
+  g.dx = c.dx; g.dy = c.dy; g.xlon0 = c.xlon0; g.ylat0 = c.ylat0; g.dxconst = c.dxconst; g.dyconst = c.dyconst;
+  g.nglobal = c.nglobal; g.sglobal = c.sglobal;
+  g.switchnorthg = c.switchnorthg; g.switchsouthg = c.switchsouthg;
+  for (int k = 0; k < 9; k++) { g.northpolemap[k] = c.northpolemap[k]; g.southpolemap[k] = c.southpolemap[k]; }
+  g.lsubgrid = lsubgrid; g.readclouds = 0;
+  const size_t n1 = (size_t)nuvz + 1;
+  g.akz = M.d_ab; g.bkz = M.d_ab + n1; g.akm = M.d_ab + 2 * n1; g.bkm = M.d_ab + 3 * n1;
+  g.height = h->d_height; g.cosf = M.d_cosf;
+  g.UV = M.UV; g.W = M.W; g.TQ = V.CT[0][s]; g.PV = m->pvh ? M.PV : nullptr;
+  g.SF1 = V.CS[0][s]; g.SF2 = M.SF2; g.excessoro = M.excessoro; g.uvzlev = M.uvzlev;
+  g.A = h->A[s]; g.G = h->G[s]; g.T = h->T[s]; g.P = h->P[s]; g.S = h->S[s]; g.trop = h->trop[s];
+  g.R = c.wetdep ? h->R[s] : nullptr; g.Cl = c.wetdep ? h->Cl[s] : nullptr; g.Q = h->outp.Q[s];
+  CK(cudaEventRecord(M.evk, st));
+  fpb_metproc_launch(g, st, &h->launches);
+  CK(cudaEventRecord(M.ev1, st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (device_ms) {
+    CK(cudaEventElapsedTime(device_ms, M.ev0, M.ev1));
+    CK(cudaEventElapsedTime(device_ms + 1, M.evk, M.ev1));
+  }
+  h->slot_ready[s] = true;
+  V.have[0][s] = (V.nuvz == nuvz);
+  return 0;
+}
+
+extern "C" int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs *o) {
+  if (!h || !o) return fail("fpb_fetch_met: null argument");
+  if (slot < 1 || slot > FPB_NSLOTS || !h->slot_ready[slot - 1]) return fail("fpb_fetch_met: slot %d holds no field", slot);
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const fpb_config &c = h->cfg;
+  const int s = slot - 1, nxd = h->d.nxd, nyd = h->d.nyd, nz = c.nz;
+  const size_t n2 = (size_t)nxd * nyd, n3 = n2 * nz;
+  std::vector<float> buf;
+  // device [k][jy][ix][ncomp] -> host (nxmax, nymax, nk) of component `comp`
+  auto fetch = [&](const void *dev, int ncomp, int nk, float *const *dst) -> int {
+    if (!dev) return 0;
+    bool any = false;
+    for (int q = 0; q < ncomp; q++) any = any || dst[q];
+    if (!any) return 0;
+    buf.resize((size_t)nxd * nyd * nk * ncomp);
+    CK(cudaMemcpy(buf.data(), dev, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < ncomp; q++) {
+      if (!dst[q]) continue;
+      for (int k = 0; k < nk; k++)
+        for (int jy = 0; jy < c.ny; jy++)
+          for (int ix = 0; ix < c.nx; ix++)
+            dst[q][(size_t)ix + (size_t)c.nxmax * ((size_t)jy + (size_t)c.nymax * k)] =
+                buf[(((size_t)k * nyd + jy) * nxd + ix) * ncomp + q];
+    }
+    return 0;
+  };
+  float *a4[4] = {o->uu, o->vv, o->ww, o->rho}, *g1[1] = {o->drhodz}, *t1[1] = {o->tt}, *p2[2] = {o->uupol, o->vvpol};
+  float *q2[2] = {o->pv, o->qv}, *s4[4] = {o->hmix, o->ustar, o->wstar, o->oli}, *tr[1] = {o->tropopause};
+  if (fetch(h->A[s], 4, nz, a4) || fetch(h->G[s], 1, nz, g1) || fetch(h->T[s], 1, nz, t1) || fetch(h->P[s], 2, nz, p2) ||
+      fetch(h->outp.Q[s], 2, nz, q2) || fetch(h->S[s], 4, 1, s4) || fetch(h->trop[s], 1, 1, tr))
+    return 1;
+  if (o->clouds && h->Cl[s]) {
+    std::vector<int8_t> cb(n3);
+    CK(cudaMemcpy(cb.data(), h->Cl[s], n3, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < nz; k++)
+      for (int jy = 0; jy < c.ny; jy++)
+        for (int ix = 0; ix < c.nx; ix++)
+          o->clouds[(size_t)ix + (size_t)c.nxmax * ((size_t)jy + (size_t)c.nymax * k)] = cb[((size_t)k * nyd + jy) * nxd + ix];
+  }
   return 0;
 }
 

@@ -237,6 +237,56 @@ class Engine:
         self._check(self.L.fpb_convmix(self.h, itime, C.byref(nc), C.byref(nv)))
         return nc.value, nv.value
 
+    # ---- calcpar + verttransform_ecmwf on the device
+    def set_vertical(self, nuvz, akm, bkm, akz, bkz, nwz=None, nuvzmax=None, nwzmax=None):
+        """akm.. are the Fortran arrays (1:nuvz) as numpy arrays of length >= nuvz (0-based)"""
+        c = self.cb.cfg
+        arrs = [np.ascontiguousarray(a[:nuvz], np.float32) for a in (akm, bkm, akz, bkz)]
+        self._check(self.L.fpb_set_vertical(self.h, nuvz, nwz or nuvz, nuvzmax or c.nzmax, nwzmax or c.nzmax,
+                                            *[_fp(a) for a in arrs]))
+
+    def calcpar_verttransform(self, slot, raw, lsubgrid=0):
+        """raw: dict of Fortran-ordered float32 arrays (uuh, vvh, wwh, tth, qvh, [pvh,] ps, tt2, td2, sshf,
+        surfstr, [lsprec, convprec, tcc, excessoro]) with the reference's padded extents; the met slot is
+        built on the device.  Returns the device time (upload + kernels) in ms; the kernels' share is
+        left in self.metproc_kernel_ms."""
+        from .abi import FpbRawmetPtrs
+        m = FpbRawmetPtrs()
+        keep = {}
+        for name, _ in FpbRawmetPtrs._fields_:
+            a = raw.get(name)
+            if a is not None:
+                keep[name] = np.asfortranarray(a, np.float32)
+                setattr(m, name, _fp(keep[name]))
+        ms = (C.c_float * 2)()
+        self._check(self.L.fpb_calcpar_verttransform(self.h, slot, C.byref(m), lsubgrid, ms))
+        self.metproc_kernel_ms = ms[1]
+        return ms[0]
+
+    def upload_vdep(self, slot, vdep):
+        a = np.asfortranarray(vdep, np.float32)
+        self._check(self.L.fpb_upload_vdep(self.h, slot, _fp(a)))
+
+    def fetch_met(self, slot, fields=None):
+        """the transformed fields of a slot in the reference's padded layout (Fortran order)"""
+        from .abi import FpbMetOutPtrs
+        c = self.cb.cfg
+        o, out = FpbMetOutPtrs(), {}
+        for name, _ in FpbMetOutPtrs._fields_:
+            if fields is not None and name not in fields:
+                continue
+            if name == "clouds":
+                if not c.wetdep:
+                    continue
+                out[name] = np.zeros((c.nxmax, c.nymax, c.nzmax), np.int8, order="F")
+                o.clouds = out[name].ctypes.data_as(C.POINTER(C.c_int8))
+                continue
+            shape = (c.nxmax, c.nymax) if name in ("hmix", "ustar", "wstar", "oli", "tropopause") else (c.nxmax, c.nymax, c.nzmax)
+            out[name] = np.zeros(shape, np.float32, order="F")
+            setattr(o, name, _fp(out[name]))
+        self._check(self.L.fpb_fetch_met(self.h, slot, C.byref(o)))
+        return out
+
     def init_domainfill(self, box, itsplit=99999999):
         """init_domainfill (src/init_domainfill.f90:55-283) over the box (xpoint1, ypoint1, xpoint2,
         ypoint2) in grid units, on the device; returns (numpart, info dict)."""

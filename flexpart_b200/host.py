@@ -254,6 +254,19 @@ class Releases:
         self.c_struct = r
 
 
+def verttransform_heights(cb, nuvz, akz, bkz, raw):
+    """height(1:nuvz) of verttransform_ecmwf's first call (src/verttransform_ecmwf.f90:131-163) from a raw
+    wind field (dict with ps, tt2, td2, tth, qvh, Fortran order); akz, bkz 0-based (1:nuvz).
+    Returns (height, (ixm, jym))."""
+    h = np.zeros(nuvz, np.float32)
+    keep = [np.ascontiguousarray(akz[:nuvz], np.float32), np.ascontiguousarray(bkz[:nuvz], np.float32)] + \
+           [np.asfortranarray(raw[n], np.float32) for n in ("ps", "tt2", "td2", "tth", "qvh")]
+    ix, jy = C.c_int32(0), C.c_int32(0)
+    _hcheck(load_host_lib().fpbh_verttransform_heights(C.byref(cb.cfg), nuvz, *[_fp(a) for a in keep], _fp(h),
+                                                       C.byref(ix), C.byref(jy)))
+    return h, (ix.value, jy.value)
+
+
 def outgrid_geometry(cb, outlat0, nest=0):
     """area(numxgrid,numygrid), volume(numxgrid,numygrid,numzgrid) of outgrid_init (Fortran order)."""
     c = cb.cfg

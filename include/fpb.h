@@ -405,6 +405,45 @@ int fpb_init_domainfill(fpb_handle *h, float xpoint1, float ypoint1, float xpoin
 int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int32_t *numpart /* may be NULL */,
                              int32_t *n_created /* may be NULL */);
 
+/* calcpar + verttransform_ecmwf on the device.
+ * fpb_calcpar_verttransform replaces the pair `call calcpar(n,uuh,vvh,pvh,metdata_format)` /
+ * `call verttransform_ecmwf(n,uuh,vvh,wwh,pvh)` of getfields (src/getfields.f90:126-129,161-164,
+ * 177-180): the wind field as readwind_ecmwf leaves it is copied to the device once and becomes
+ * met slot `slot` there -- friction velocity, Obukhov length, mixing height, convective velocity
+ * scale and thermal tropopause (src/calcpar.f90:78-258, scalev.f90, obukhov.f90, richardson.f90),
+ * u, v, T, q, PV, density and density gradient on the height levels, the vertical wind in m/s with
+ * the slope term of the eta surfaces, polar-stereographic winds and pole rows, the parameterised
+ * cloud / precipitation classes (src/verttransform_ecmwf.f90:198-607,683-724) -- so the transformed
+ * fields never exist on the host.  The same arithmetic in the same order as the reference (no
+ * contraction, transcendentals evaluated in double): bit-identical fields.  The slot is then what
+ * fpb_upload_met would have produced; when fpb_set_convection has been called with the same nuvz
+ * the convection fields of the slot (fpb_upload_convmet) are set as well.
+ * Needs fpb_set_vertical first.  ECMWF layout only: nz = nuvz = nwz.  `height` of fpb_config must be
+ * what verttransform_ecmwf's first call derives (fpbh_verttransform_heights in fpb_host.h).
+ * Not built: dry-deposition velocities (getvdep: land-use inventory; upload vdep with
+ * fpb_upload_vdep), calcpv (pvh is an input; may be NULL = 0), cloud water read from the input
+ * (readclouds), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
+ * fpb_fetch_met copies a slot back in the reference's padded layout (any pointer may be NULL): for
+ * the parts of a host model that still read the transformed fields, and for the tests. */
+typedef struct fpb_rawmet_ptrs {
+  const float *uuh, *vvh, *tth, *qvh; /* (nxmax, nymax, nuvzmax) */
+  const float *pvh;                   /* (nxmax, nymax, nuvzmax) or NULL */
+  const float *wwh;                   /* (nxmax, nymax, nwzmax) */
+  const float *ps, *tt2, *td2, *sshf, *surfstr, *lsprec, *convprec, *tcc; /* (nxmax, nymax) */
+  const float *excessoro;             /* (nxmax, nymax), lsubgrid = 1 only */
+} fpb_rawmet_ptrs;
+typedef struct fpb_met_out_ptrs {
+  float *uu, *vv, *ww, *rho, *drhodz, *tt, *qv, *pv, *uupol, *vvpol; /* (nxmax, nymax, nzmax) */
+  float *hmix, *ustar, *wstar, *oli, *tropopause;                    /* (nxmax, nymax) */
+  int8_t *clouds;                                                     /* (nxmax, nymax, nzmax) */
+} fpb_met_out_ptrs;
+int fpb_set_vertical(fpb_handle *h, int32_t nuvz, int32_t nwz, int32_t nuvzmax, int32_t nwzmax, const float *akm,
+                     const float *bkm, const float *akz, const float *bkz);
+int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_rawmet_ptrs *raw, int32_t lsubgrid,
+                              float *device_ms /* may be NULL; [0] upload + kernels, [1] kernels only (ms) */);
+int fpb_upload_vdep(fpb_handle *h, int32_t slot, const float *vdep /* (nxmax, nymax, maxspec) */);
+int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs *out);
+
 /* Convective mixing (LCONVECTION = 1, the shipped default).
  * fpb_convmix replaces `call convmix(itime,metdata_format)` (src/timemanager.f90:183-193,258-263;
  * src/convmix.f90:60-196): the active particles are grouped by grid column, every occupied column's

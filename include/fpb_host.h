@@ -53,6 +53,15 @@ int fpbh_readoutgrid_nest(fpb_config *cfg, float outlon0n, float outlat0n, int32
  * (shape of src/verttransform_ecmwf.f90:153-168 output). */
 int fpbh_synth_heights(int32_t nz, float *height);
 
+/* height(1:nuvz) as the first call of verttransform_ecmwf derives it (src/verttransform_ecmwf.f90:
+ * 131-163): heights of the eta levels of the first grid point (south to north, west to east) whose
+ * surface pressure exceeds 1000 hPa.  For callers that leave calcpar + verttransform to the device
+ * (fpb_calcpar_verttransform): fpb_config::height must be this array.  akz, bkz: the Fortran arrays
+ * (1:nuvz); ps, tt2, td2 (nxmax,nymax); tth, qvh (nxmax,nymax,nuvzmax); *ixm, *jym may be NULL. */
+int fpbh_verttransform_heights(const fpb_config *cfg, int32_t nuvz, const float *akz, const float *bkz,
+                               const float *ps, const float *tt2, const float *td2, const float *tth,
+                               const float *qvh, float *height, int32_t *ixm, int32_t *jym);
+
 /* Fill one time level of synthetic met into caller arrays with
  * the padded Fortran layout; `time_s` moves the phase of the fields.
  * All non-NULL pointers of `out` are written. */

@@ -305,7 +305,16 @@ class Program:
         if base != "character" and not rest.strip():
             return False
         if base == "character":
-            return True  # strings are only used for messages
+            # strings are only used for messages and file names: remember the names so that
+            # assignments to them can be dropped
+            if unit is not None:
+                names = getattr(unit, "char_vars", set())
+                for ent in split_top(rest, ","):
+                    mm = re.match(r"^\s*([a-z_][a-z0-9_]*)", ent)
+                    if mm:
+                        names.add(mm.group(1))
+                unit.char_vars = names
+            return True
         ftype = "double" if base.startswith("double") else base
         if kind:
             k = kind.replace(" ", "")
@@ -853,7 +862,16 @@ class Gen:
                         init = " = {" + ", ".join(vals) + "}"
                     out.append(f"  static {ct} f_{nm}[{n_const}]{init};")
                 else:
-                    out.append(f"  {ct} f_{nm}[{size}]; memset(f_{nm}, 0, sizeof f_{nm});")
+                    n_const = try_const(size, u, ctx)
+                    if n_const is not None and n_const <= 16384:
+                        out.append(f"  {ct} f_{nm}[{size}]; memset(f_{nm}, 0, sizeof f_{nm});")
+                    else:
+                        # automatic array of run-time (or large) extent: kept on the heap between calls,
+                        # zeroed at every entry (-finit-local-zero, src/makefile_meteoswiss:89)
+                        out.append(f"  static {ct} *f_{nm} = NULL; static size_t f_{nm}_n = 0; "
+                                   f"if (f_{nm}_n != (size_t)({size})) {{ free(f_{nm}); f_{nm}_n = (size_t)({size}); "
+                                   f"f_{nm} = ({ct} *)malloc(f_{nm}_n * sizeof({ct})); }} "
+                                   f"memset(f_{nm}, 0, f_{nm}_n * sizeof({ct}));")
             else:
                 init = f" = {ctx.cexpr(sym.init)}" if sym.init is not None else " = 0"
                 out.append(f"  {static}{ct} f_{nm}{init};")
@@ -863,6 +881,7 @@ class Gen:
         # pass 2: executable statements
         self.indent = 1
         self.do_stack = []
+        self.where_stack = []
         for lab, s in stmts:
             for line in self.stmt(ctx, u, lab, s):
                 out.append("  " * self.indent_for(line) + line)
@@ -902,6 +921,14 @@ class Gen:
             return res + ["} else {"]
         if re.match(r"^end\s*if$", s):
             return res + ["}"]
+        # named do construct: `name: do ...`, left through `exit name` (a goto past its end)
+        m = re.match(r"^([a-z_][a-z0-9_]*)\s*:\s*(do\b.*)$", s)
+        do_name = None
+        if m:
+            do_name, s = m.group(1), m.group(2)
+        if re.match(r"^do\b", s):
+            self.do_count = getattr(self, "do_count", 0) + 1
+            self.do_stack.append((do_name, self.do_count))
         m = re.match(r"^do\s+([a-z_][a-z0-9_]*)\s*=\s*(.*)$", s)
         if m:
             var, rng = m.groups()
@@ -914,8 +941,18 @@ class Gen:
             return res + [f"{{ const int _b = {b}; for ({v} = {a}; {v} <= _b; {v}++) {{"]
         if s == "do":
             return res + ["{ for (;;) {"]
-        if re.match(r"^end\s*do$", s):
+        m = re.match(r"^end\s*do(?:\s+([a-z_][a-z0-9_]*))?$", s)
+        if m:
+            nm, cnt = self.do_stack.pop() if self.do_stack else (None, 0)
+            if nm is not None:
+                return res + ["} }", f"Lx_{nm}_{cnt}: ;"]
             return res + ["} }"]
+        m = re.match(r"^exit\s+([a-z_][a-z0-9_]*)$", s)
+        if m:
+            for nm, cnt in reversed(self.do_stack):
+                if nm == m.group(1):
+                    return res + [f"goto Lx_{nm}_{cnt};"]
+            raise F2CError(f"{u.name}: exit {m.group(1)}: no such construct")
         m = re.match(r"^go\s*to\s*(\d+)$", s)
         if m:
             return res + [f"goto L{m.group(1)};"]
@@ -945,10 +982,35 @@ class Gen:
             self.prog.called.add(name)
             al = [ctx.actual(ctx.cexpr(a)) for a in split_top(args, ",")] if args and args.strip() else []
             return res + [f"f_{name}({', '.join(al)});"]
+        # WHERE construct: the assignments of its body become masked element loops
+        m = re.match(r"^where\s*\(", s)
+        if m:
+            mask, rest = take_paren(s[s.index("("):])
+            rest = rest.strip()
+            if rest:
+                self.where_stack.append(mask)
+                try:
+                    inner = self.stmt(ctx, u, None, rest)
+                finally:
+                    self.where_stack.pop()
+                return res + inner
+            self.where_stack.append(mask)
+            return res
+        if re.match(r"^else\s*where$", s):
+            if not self.where_stack:
+                raise F2CError(f"{u.name}: elsewhere outside where")
+            self.where_stack[-1] = ".not.(" + self.where_stack[-1] + ")"
+            return res
+        if re.match(r"^end\s*where$", s):
+            self.where_stack.pop()
+            return res
         # assignment
         lhs, rhs = split_assign(s)
         if lhs is None:
             raise F2CError(f"{u.name}: cannot translate statement: {s}")
+        el = self.elementalize(ctx, u, lhs, rhs, self.where_stack[-1] if self.where_stack else None)
+        if el is not None:
+            return res + el
         lm = re.match(r"^([a-z_][a-z0-9_]*)\s*(\((.*)\))?$", lhs.strip())
         if not lm:
             raise F2CError(f"{u.name}: bad assignment target {lhs}")
@@ -956,6 +1018,8 @@ class Gen:
         sym = ctx.lookup(name)
         if u.kind == "function" and name == u.result and lm.group(2) is None:
             return res + [f"f_{name}_result = {ctx.cexpr(rhs)};"]
+        if sym is None and name in getattr(u, "char_vars", set()):
+            return res + ["/* character assignment skipped */;"]
         if sym is None:
             raise F2CError(f"{u.name}: assignment to undeclared {name}")
         if sym.param is not None:
@@ -981,6 +1045,113 @@ class Gen:
                 return res + [f"{{ long _n = {size}; for (long _k = 0; _k < _n; _k++) f_{name}[_k] = {ctx.cexpr(rhs)}; }}"]
             raise F2CError(f"{u.name}: array section assignment not supported: {s}")
         return res + [f"{ctx.cexpr(lhs)} = {ctx.cexpr(rhs)};"]
+
+
+    # ---- array syntax -> element loops -----------------------------------------------------------
+    def elementalize(self, ctx, u, lhs, rhs, mask):
+        """`A(sections) = expr` (or whole-array `A = expr` with an array-valued expr, or any assignment
+        under a WHERE mask) as nested element loops; None when the statement is scalar."""
+        lm = re.match(r"^([a-z_][a-z0-9_]*)\s*(\((.*)\))?$", lhs.strip())
+        if not lm:
+            return None
+        name = lm.group(1)
+        sym = ctx.lookup(name)
+        if sym is None or sym.dims is None:
+            if mask is not None:
+                raise F2CError(f"{u.name}: scalar assignment inside where: {lhs} = {rhs}")
+            return None
+        secs = []   # (lo, hi) Fortran text of every sectioned dimension of the target, in order
+
+        def rewrite_ref(sym_r, args_text, target=False):
+            """subscript list of one array reference with its sections replaced by loop indices;
+            returns (new text or None when the reference has no section, number of sections)"""
+            if args_text is None:
+                subs = [":"] * len(sym_r.dims)
+            else:
+                subs = [x.strip() for x in split_top(args_text, ",")]
+            if len(subs) != len(sym_r.dims):
+                raise F2CError(f"{u.name}: {sym_r.name}: rank {len(sym_r.dims)} but {len(subs)} subscripts")
+            out, k = [], 0
+            for (dlo, dhi), sub in zip(sym_r.dims, subs):
+                parts = split_top(sub, ":")
+                if len(parts) == 1:
+                    out.append(rewrite_expr(sub))
+                    continue
+                if len(parts) > 2:
+                    raise F2CError(f"{u.name}: strided section {sub}")
+                lo = parts[0].strip() or dlo
+                hi = parts[1].strip() or dhi
+                out.append(f"(({lo})+isec{k}_)")
+                if target:
+                    secs.append((lo, hi))
+                k += 1
+            return ",".join(out), k
+
+        def rewrite_expr(text):
+            """array references with sections / whole arrays in an expression -> element references"""
+            toks = lex(text)
+            out, i = [], 0
+            while i < len(toks):
+                kind, val = toks[i]
+                if kind == "id":
+                    sy = ctx.lookup(val)
+                    is_arr = sy is not None and sy.dims is not None
+                    if i + 1 < len(toks) and toks[i + 1][1] == "(":
+                        depth, j = 0, i + 1
+                        while True:
+                            if toks[j][1] == "(":
+                                depth += 1
+                            elif toks[j][1] == ")":
+                                depth -= 1
+                                if depth == 0:
+                                    break
+                            j += 1
+                        inner = " ".join(t[1] for t in toks[i + 2:j])
+                        if is_arr:
+                            new, k = rewrite_ref(sy, inner)
+                            if k and k != nsec[0]:
+                                raise F2CError(f"{u.name}: non-conforming section of {val} in {lhs} = {rhs}")
+                            out.append(f"{val}({new})")
+                        else:
+                            args = [rewrite_expr(a) for a in split_top(inner, ",")] if inner.strip() else []
+                            out.append(f"{val}({','.join(args)})")
+                        i = j + 1
+                        continue
+                    if is_arr and sy.param is None:
+                        if len(sy.dims) != nsec[0]:
+                            raise F2CError(f"{u.name}: whole array {val} (rank {len(sy.dims)}) in {lhs} = {rhs}")
+                        new, _ = rewrite_ref(sy, None)
+                        out.append(f"{val}({new})")
+                        i += 1
+                        continue
+                out.append(val)
+                i += 1
+            return " ".join(out)
+
+        nsec = [0]
+        new_lhs_args, n = rewrite_ref(sym, lm.group(3), target=True)
+        if n == 0:
+            if mask is not None:
+                raise F2CError(f"{u.name}: element assignment inside where: {lhs} = {rhs}")
+            return None
+        nsec[0] = n
+        # a scalar right-hand side without any array keeps the fast whole-array path of the caller
+        new_rhs = rewrite_expr(rhs)
+        cond = rewrite_expr(mask) if mask is not None else None
+        if cond is not None and re.search(rf"\b{name}\b", mask):
+            raise F2CError(f"{u.name}: where mask depends on its target {name}")
+        lines = []
+        for k in range(n - 1, -1, -1):
+            u.syms.setdefault(f"isec{k}_", Sym(f"isec{k}_", "integer"))
+            lo, hi = secs[k]
+            lines.append(f"{{ int f_isec{k}_; const int _n{k} = ({ctx.cexpr(hi)}) - ({ctx.cexpr(lo)}); "
+                         f"for (f_isec{k}_ = 0; f_isec{k}_ <= _n{k}; f_isec{k}_++) {{")
+        body = f"{ctx.cexpr(name + '(' + new_lhs_args + ')')} = {ctx.cexpr(new_rhs)};"
+        if cond is not None:
+            body = f"if ({ctx.cexpr(cond)}) {body}"
+        lines.append(body)
+        lines += ["} }"] * n
+        return lines
 
 
 def take_paren(s):

@@ -1,0 +1,68 @@
+"""Shared pieces of tests/test_metproc.py (CPU) and tests/test_gpu_metproc.py: running the reference's
+calcpar + verttransform_ecmwf (oracle/_ref) on a synthetic wind field and comparing a set of
+transformed fields with its arrays.  Test infrastructure."""
+import ctypes as C
+
+import numpy as np
+
+import ref_api
+
+def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None):
+    """calcpar + verttransform_ecmwf of the reference on time slot 1; returns (ref, height)"""
+    c = cb.cfg
+    ref = ref_api.Ref(cb, maxrand=1000)
+    for k, v in dict(nuvz=nuvz, nwz=nuvz, nz=nuvz, nmixz=0, lsubgrid=lsubgrid, readclouds=0, sumclouds=0).items():
+        ref.set(k, v)
+    for nm, a in (("akz", akz), ("bkz", bkz), ("akm", akm), ("bkm", bkm), ("aknew", akz), ("bknew", bkz)):
+        ref.arr(nm)[:nuvz] = a[1:nuvz + 1]
+    for nm in ("ps", "tt2", "td2", "sshf", "surfstr", "lsprec", "convprec", "tcc"):
+        ref.arr(nm)[:, :, 0, 0] = raw[nm]
+    ref.arr("tth")[:, :, :, 0] = raw["tth"]
+    ref.arr("qvh")[:, :, :, 0] = raw["qvh"]
+    if excessoro is not None:
+        ref.arr("excessoro")[:, :] = excessoro
+    n, fmt = C.c_int(1), C.c_int(2)   # GRIBFILE_CENTRE_ECMWF
+    pvh = np.zeros_like(raw["uuh"])
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    ref.L.f_calcpar(C.byref(n), P(raw["uuh"]), P(raw["vvh"]), P(pvh), C.byref(fmt))
+    ref.L.f_verttransform_ecmwf(C.byref(n), P(raw["uuh"]), P(raw["vvh"]), P(raw["wwh"]), P(pvh))
+    return ref, ref.arr("height")[:nuvz].copy(), pvh
+
+
+
+def compare_fields(cb, ref, got, nuvz, exact=True, tol=0.0):
+    """got: dict name -> array [k][jy][ix] (or [jy][ix]) over the used grid; against the reference's
+    slot-1 arrays.  Returns the fields that differ."""
+    c = cb.cfg
+    nx, ny = c.nx, c.ny
+    r3 = lambda nm: np.transpose(ref.arr(nm)[:nx, :ny, :nuvz, 0], (2, 1, 0))
+    r2 = lambda nm: ref.arr(nm)[:nx, :ny, 0, 0].T
+    bad = {}
+    for nm, a in got.items():
+        if nm in ("uupol", "vvpol"):
+            continue
+        b = r3(nm) if a.ndim == 3 else r2(nm)
+        if nm == "clouds":
+            if not np.array_equal(a, b):
+                bad[nm] = int((a != b).sum())
+            continue
+        assert np.isfinite(b).all(), nm
+        if exact:
+            if not np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32)):
+                bad[nm] = (int((a != b).sum()), float(np.abs(a - b).max()))
+        else:
+            d = np.abs(a - b) / np.maximum(np.abs(b), 1e-20)
+            if d.max() > tol:
+                bad[nm] = float(d.max())
+    # polar stereographic winds: only defined poleward of the switch latitudes; cc2gll works in double
+    # (sin / cos of the device's and glibc's libm agree to an ulp of double: a float ulp at most)
+    jn, js = int(c.switchnorthg) - 2, int(c.switchsouthg) + 3
+    for nm in ("uupol", "vvpol"):
+        if nm not in got:
+            continue
+        b = r3(nm)
+        a = got[nm]
+        for sl in (slice(jn, ny), slice(0, js + 1)):
+            if not np.allclose(a[:, sl], b[:, sl], rtol=2e-6, atol=1e-6):
+                bad[nm] = float(np.abs(a[:, sl] - b[:, sl]).max())
+    return bad
