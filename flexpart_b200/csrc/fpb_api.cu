@@ -298,7 +298,7 @@ struct fpb_handle {
     float *d_ab = nullptr;   // akz, bkz, akm, bkm: 4 x (nuvz + 1), 1-based
     float *d_cosf = nullptr; // [ny]
     float2 *UV = nullptr;
-    float *W = nullptr, *PV = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
+    float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
     float4 *SF2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
   } metproc;
@@ -759,7 +759,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   dep_free(h->depstore);
   {
     auto &M = h->metproc;
-    cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.excessoro);
+    cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro);
     cudaFree(M.uvzlev); cudaFree(M.SF2);
     if (M.ev0) cudaEventDestroy(M.ev0);
     if (M.ev1) cudaEventDestroy(M.ev1);
@@ -2095,7 +2095,8 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   const int nxd = h->d.nxd, nyd = h->d.nyd, nuvz = M.nuvz;
   const size_t n2 = (size_t)nxd * nyd, n3 = n2 * nuvz;
   if (!M.UV) { DA(M.UV, n3); DA(M.W, n3); DA(M.uvzlev, n3); DA(M.SF2, n2); }
-  if (m->pvh && !M.PV) DA(M.PV, n3);
+  if (!M.PV) DA(M.PV, n3);
+  if (!m->pvh && !M.theta) DA(M.theta, n3); // calcpv on the device
   if (lsubgrid == 1 && !M.excessoro) DA(M.excessoro, n2);
   if (!V.CT[0][s]) { DA(V.CT[0][s], n3); DA(V.CS[0][s], n2); }
   if (!h->outp.Q[s]) DA(h->outp.Q[s], n3);
@@ -2117,14 +2118,14 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   g.nx = c.nx; g.ny = c.ny; g.nz = c.nz; g.nuvz = nuvz; g.nwz = M.nwz;
   g.nxd = nxd; g.nyd = nyd;
   g.dx = c.dx; g.dy = c.dy; g.xlon0 = c.xlon0; g.ylat0 = c.ylat0; g.dxconst = c.dxconst; g.dyconst = c.dyconst;
-  g.nglobal = c.nglobal; g.sglobal = c.sglobal;
+  g.nglobal = c.nglobal; g.sglobal = c.sglobal; g.xglobal = c.xglobal;
   g.switchnorthg = c.switchnorthg; g.switchsouthg = c.switchsouthg;
   for (int k = 0; k < 9; k++) { g.northpolemap[k] = c.northpolemap[k]; g.southpolemap[k] = c.southpolemap[k]; }
   g.lsubgrid = lsubgrid; g.readclouds = 0;
   const size_t n1 = (size_t)nuvz + 1;
   g.akz = M.d_ab; g.bkz = M.d_ab + n1; g.akm = M.d_ab + 2 * n1; g.bkm = M.d_ab + 3 * n1;
   g.height = h->d_height; g.cosf = M.d_cosf;
-  g.UV = M.UV; g.W = M.W; g.TQ = V.CT[0][s]; g.PV = m->pvh ? M.PV : nullptr;
+  g.UV = M.UV; g.W = M.W; g.TQ = V.CT[0][s]; g.PV = M.PV; g.theta = m->pvh ? nullptr : M.theta;
   g.SF1 = V.CS[0][s]; g.SF2 = M.SF2; g.excessoro = M.excessoro; g.uvzlev = M.uvzlev;
   g.A = h->A[s]; g.G = h->G[s]; g.T = h->T[s]; g.P = h->P[s]; g.S = h->S[s]; g.trop = h->trop[s];
   g.R = c.wetdep ? h->R[s] : nullptr; g.Cl = c.wetdep ? h->Cl[s] : nullptr; g.Q = h->outp.Q[s];

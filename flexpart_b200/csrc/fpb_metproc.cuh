@@ -10,6 +10,8 @@
 //   met_calcpar_column  src/calcpar.f90:78-258 with scalev.f90, obukhov.f90, richardson.f90:
 //                       friction velocity, Obukhov length, mixing height, convective velocity scale,
 //                       thermal tropopause
+//   met_theta_column, met_calcpv_column, met_pv_pole_level   src/calcpv.f90:42-315: potential
+//                       vorticity on the eta levels (isentropic differences of u and v)
 // Arithmetic is the reference's, statement by statement, evaluated like the validation build of the
 // other kernels (no FMA contraction; exp/log/pow/sin/cos/atan in double, rounded once), so the
 // fields are bit-comparable with the reference's own routines (oracle/_ref).  Written for nvcc and,
@@ -43,7 +45,7 @@ struct MetGrid {
   int nx, ny, nz, nuvz, nwz; // grid points used (nx = nxmin1 + 1, ny = nymin1 + 1); nz = nuvz levels
   int nxd, nyd;              // row length / rows of the device arrays
   float dx, dy, xlon0, ylat0, dxconst, dyconst;
-  int nglobal, sglobal;
+  int nglobal, sglobal, xglobal;
   float switchnorthg, switchsouthg;
   float northpolemap[9], southpolemap[9];
   int lsubgrid;
@@ -55,7 +57,8 @@ struct MetGrid {
   const float2 *UV;          // {uuh, vvh}, nuvz levels
   const float *W;            // wwh, nwz levels
   const float2 *TQ;          // {tth, qvh}
-  const float *PV;           // pvh or null
+  float *PV;                 // pvh: given by the caller or computed by met_calcpv_column (null: pv = 0)
+  float *theta;              // work (calcpv): potential temperature on the eta levels, or null
   const float4 *SF1;         // {ps, tt2, td2, sshf}
   const float4 *SF2;         // {surfstr, lsprec, convprec, tcc}
   const float *excessoro;    // lsubgrid = 1 only
@@ -462,6 +465,138 @@ FPB_HD inline void met_calcpar_column(const MetGrid &g, int ix, int jy) {
     if (done) break;
   }
   (void)cnst;
+}
+
+// ---- calcpv, src/calcpv.f90 ---------------------------------------------------------------------
+FPB_HD inline void met_theta_column(const MetGrid &g, int ix, int jy) { // :57-66 (theta = tth * ppmk)
+  const float kappa = 0.286f;
+  const float ps = g.SF1[m_o2(g, ix, jy)].x;
+  for (int kl = 1; kl <= g.nuvz; kl++) {
+    const float ppml = g.akz[kl] + g.bkz[kl] * ps;
+    const float ppmk = c_pow(100000.f / ppml, kappa);
+    g.theta[m_o3(g, ix, jy, kl)] = g.TQ[m_o3(g, ix, jy, kl)].x * ppmk;
+  }
+}
+
+// the level pair of column (cx, cy) that brackets `theta`, searched alternately upwards and
+// downwards from klpt, at most nlck pairs (:118-166); the wind component interpolated to theta
+template <bool U>
+FPB_HD inline bool met_isentropic(const MetGrid &g, int cx, int cy, float theta, int klpt, int nlck, float &val) {
+  const float eps = 1.e-5f;
+  int kup = klpt - 1, kdn = klpt, kch = 0;
+  for (;;) {
+    kup = kup + 1;
+    if (kch >= nlck) return false;
+    for (int pass = 0; pass < 2; pass++) {
+      int k;
+      if (pass == 0) {
+        if (kup >= g.nuvz) continue;
+        kch = kch + 1;
+        k = kup;
+      } else {
+        kdn = kdn - 1;
+        if (kdn < 1) break;
+        kch = kch + 1;
+        k = kdn;
+      }
+      const float thdn = g.theta[m_o3(g, cx, cy, k)], thup = g.theta[m_o3(g, cx, cy, k + 1)];
+      if (((thdn >= theta) && (thup <= theta)) || ((thdn <= theta) && (thup >= theta))) {
+        float dt1 = fabsf(theta - thdn), dt2 = fabsf(theta - thup), dt = dt1 + dt2;
+        if (dt < eps) { dt1 = 0.5f; dt2 = 0.5f; dt = 1.0f; }
+        const float2 a = g.UV[m_o3(g, cx, cy, k)], b = g.UV[m_o3(g, cx, cy, k + 1)];
+        val = U ? (a.x * dt2 + b.x * dt1) / dt : (a.y * dt2 + b.y * dt1) / dt;
+        return true;
+      }
+    }
+  }
+}
+
+FPB_HD inline void met_calcpv_column(const MetGrid &g, int ix, int jy) {
+  if (g.sglobal && jy == 0) return;           // pole rows: met_pv_pole_level
+  if (g.nglobal && jy == g.ny - 1) return;
+  const int nuvz = g.nuvz, nx = g.nx, nxmin1 = g.nx - 1, nymin1 = g.ny - 1, nlck = nuvz / 3;
+  const float pi = M_PI_F, r_earth = 6.371e6f;
+  const float phi = (g.ylat0 + (float)jy * g.dy) * pi / 180.f;
+  const float f = 0.00014585f * m_sin(phi);
+  const float tanphi = (float)tan((double)phi), cosphi = m_cos(phi);
+  int jyvp = jy + 1, jyvm = jy - 1;
+  if (jy == 0) jyvm = 0;
+  if (jy == nymin1) jyvp = nymin1;
+  int jumpy = 2;
+  if (jy == 0 || jy == nymin1) jumpy = 1;
+  if (g.sglobal && jy == 1) { jyvm = 1; jumpy = 1; }
+  if (g.nglobal && jy == g.ny - 2) { jyvp = g.ny - 2; jumpy = 1; }
+  int ixvp = ix + 1, ixvm = ix - 1, jumpx = 2, ivrp, ivrm;
+  if (g.xglobal) {
+    ivrp = ixvp; ivrm = ixvm;
+    if (ixvm < 0) ivrm = ixvm + nxmin1;
+    if (ixvp >= nx) ivrp = ixvp - nx + 1;
+  } else {
+    if (ix == 0) ixvm = 0;
+    if (ix == nxmin1) ixvp = nxmin1;
+    ivrp = ixvp; ivrm = ixvm;
+    if (ix == 0 || ix == nxmin1) jumpx = 1;
+  }
+  const float ps = g.SF1[m_o2(g, ix, jy)].x;
+  for (int kl = 1; kl <= nuvz; kl++) {
+    const float theta = g.theta[m_o3(g, ix, jy, kl)];
+    int klvrp = kl + 1, klvrm = kl - 1;
+    if (klvrp > nuvz) klvrp = nuvz;
+    if (klvrm < 1) klvrm = 1;
+    const float thetap = g.theta[m_o3(g, ix, jy, klvrp)], thetam = g.theta[m_o3(g, ix, jy, klvrm)];
+    const float dthetadp = (thetap - thetam) / ((g.akz[klvrp] + g.bkz[klvrp] * ps) - (g.akz[klvrm] + g.bkz[klvrm] * ps));
+    const float2 uv0 = g.UV[m_o3(g, ix, jy, kl)];
+    // v on the isentropic surface at the x neighbours, :105-176
+    int jux = jumpx, ii = 0;
+    float vx[2] = {0.f, 0.f};
+    for (int i = ixvm; i <= ixvp; i += jumpx) {
+      int ivr = i;
+      if (g.xglobal) {
+        if (i < 0) ivr = ivr + nxmin1;
+        if (i >= nx) ivr = ivr - nx + 1;
+      }
+      float v;
+      if (!met_isentropic<false>(g, ivr, jy, theta, kl, nlck, v)) { v = uv0.y; jux = jux - 1; }
+      if (ii < 2) vx[ii] = v;
+      ii++;
+    }
+    float dvdx;
+    if (jux > 0) {
+      dvdx = (vx[1] - vx[0]) / (float)jux / (g.dx * pi / 180.f);
+    } else {
+      dvdx = g.UV[m_o3(g, ivrp, jy, kl)].y - g.UV[m_o3(g, ivrm, jy, kl)].y;
+      dvdx = dvdx / (float)jumpx / (g.dx * pi / 180.f);
+    }
+    // u at the y neighbours, :183-252
+    int juy = jumpy, jj = 0;
+    float uy[2] = {0.f, 0.f};
+    for (int j = jyvm; j <= jyvp; j += jumpy) {
+      float u;
+      if (!met_isentropic<true>(g, ix, j, theta, kl, nlck, u)) { u = uv0.x; juy = juy - 1; }
+      if (jj < 2) uy[jj] = u;
+      jj++;
+    }
+    float dudy;
+    if (juy > 0) {
+      dudy = (uy[1] - uy[0]) / (float)juy / (g.dy * pi / 180.f);
+    } else {
+      dudy = g.UV[m_o3(g, ix, jyvp, kl)].x - g.UV[m_o3(g, ix, jyvm, kl)].x;
+      dudy = dudy / (float)jumpy / (g.dy * pi / 180.f);
+    }
+    g.PV[m_o3(g, ix, jy, kl)] = dthetadp * (f + (dvdx / cosphi - dudy + uv0.x * tanphi) / r_earth) * (-1.e6f) * 9.81f;
+  }
+}
+
+// the pole rows take the zonal mean of the neighbouring row, :277-313
+FPB_HD inline void met_pv_pole_level(const MetGrid &g, int kl) {
+  for (int south = 0; south < 2; south++) {
+    if (south ? !g.sglobal : !g.nglobal) continue;
+    const int jyp = south ? 0 : g.ny - 1, jyn = south ? 1 : g.ny - 2;
+    float pvavr = 0.f;
+    for (int ix = 0; ix < g.nx; ix++) pvavr = pvavr + g.PV[m_o3(g, ix, jyn, kl)];
+    pvavr = pvavr / (float)g.nx;
+    for (int ix = 0; ix < g.nx; ix++) g.PV[m_o3(g, ix, jyp, kl)] = pvavr;
+  }
 }
 
 } // namespace fpbmet

@@ -411,6 +411,7 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int3
  * 177-180): the wind field as readwind_ecmwf leaves it is copied to the device once and becomes
  * met slot `slot` there -- friction velocity, Obukhov length, mixing height, convective velocity
  * scale and thermal tropopause (src/calcpar.f90:78-258, scalev.f90, obukhov.f90, richardson.f90),
+ * potential vorticity on the eta levels (src/calcpv.f90),
  * u, v, T, q, PV, density and density gradient on the height levels, the vertical wind in m/s with
  * the slope term of the eta surfaces, polar-stereographic winds and pole rows, the parameterised
  * cloud / precipitation classes (src/verttransform_ecmwf.f90:198-607,683-724) -- so the transformed
@@ -421,13 +422,12 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int3
  * Needs fpb_set_vertical first.  ECMWF layout only: nz = nuvz = nwz.  `height` of fpb_config must be
  * what verttransform_ecmwf's first call derives (fpbh_verttransform_heights in fpb_host.h).
  * Not built: dry-deposition velocities (getvdep: land-use inventory; upload vdep with
- * fpb_upload_vdep), calcpv (pvh is an input; may be NULL = 0), cloud water read from the input
- * (readclouds), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
+ * fpb_upload_vdep), cloud water read from the input (readclouds), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
  * fpb_fetch_met copies a slot back in the reference's padded layout (any pointer may be NULL): for
  * the parts of a host model that still read the transformed fields, and for the tests. */
 typedef struct fpb_rawmet_ptrs {
   const float *uuh, *vvh, *tth, *qvh; /* (nxmax, nymax, nuvzmax) */
-  const float *pvh;                   /* (nxmax, nymax, nuvzmax) or NULL */
+  const float *pvh;                   /* (nxmax, nymax, nuvzmax); NULL: calcpv runs on the device */
   const float *wwh;                   /* (nxmax, nymax, nwzmax) */
   const float *ps, *tt2, *td2, *sshf, *surfstr, *lsprec, *convprec, *tcc; /* (nxmax, nymax) */
   const float *excessoro;             /* (nxmax, nymax), lsubgrid = 1 only */

@@ -17,6 +17,14 @@ extern "C" void met_check_run(const MetGrid *g) {
     for (int ix = 0; ix < g->nx; ix++) met_levels_column(*g, ix, jy);
   for (int jy = 0; jy < g->ny; jy++)
     for (int ix = 0; ix < g->nx; ix++) met_calcpar_column(*g, ix, jy);
+  if (g->theta) {
+    for (int jy = 0; jy < g->ny; jy++)
+      for (int ix = 0; ix < g->nx; ix++) met_theta_column(*g, ix, jy);
+    for (int jy = 0; jy < g->ny; jy++)
+      for (int ix = 0; ix < g->nx; ix++) met_calcpv_column(*g, ix, jy);
+    if (g->nglobal || g->sglobal)
+      for (int kl = 1; kl <= g->nuvz; kl++) met_pv_pole_level(*g, kl);
+  }
   for (int jy = 0; jy < g->ny; jy++)
     for (int ix = 0; ix < g->nx; ix++) met_interp_column(*g, ix, jy);
   if (g->nglobal || g->sglobal)

@@ -28,11 +28,11 @@ class MetGrid(C.Structure):
                 ("nxd", C.c_int), ("nyd", C.c_int),
                 ("dx", C.c_float), ("dy", C.c_float), ("xlon0", C.c_float), ("ylat0", C.c_float),
                 ("dxconst", C.c_float), ("dyconst", C.c_float),
-                ("nglobal", C.c_int), ("sglobal", C.c_int),
+                ("nglobal", C.c_int), ("sglobal", C.c_int), ("xglobal", C.c_int),
                 ("switchnorthg", C.c_float), ("switchsouthg", C.c_float),
                 ("northpolemap", C.c_float * 9), ("southpolemap", C.c_float * 9),
                 ("lsubgrid", C.c_int), ("readclouds", C.c_int)] + \
-               [(n, C.c_void_p) for n in ("akz", "bkz", "akm", "bkm", "height", "cosf", "UV", "W", "TQ", "PV", "SF1",
+               [(n, C.c_void_p) for n in ("akz", "bkz", "akm", "bkm", "height", "cosf", "UV", "W", "TQ", "PV", "theta", "SF1",
                                           "SF2", "excessoro", "uvzlev", "A", "G", "T", "P", "S", "trop", "R", "Cl", "Q")]
 
 
@@ -61,7 +61,8 @@ def device_layout_inputs(cb, raw, pvh, akm, bkm, akz, bkz, nuvz, height):
     k["UV"] = np.ascontiguousarray(np.stack([lev(raw["uuh"], nuvz), lev(raw["vvh"], nuvz)], axis=-1))
     k["W"] = lev(raw["wwh"], nuvz)
     k["TQ"] = np.ascontiguousarray(np.stack([lev(raw["tth"], nuvz), lev(raw["qvh"], nuvz)], axis=-1))
-    k["PV"] = lev(pvh, nuvz)
+    k["PV"] = np.zeros_like(k["W"])                      # computed by the calcpv pass
+    k["theta"] = np.zeros_like(k["W"])
     s2 = lambda a: np.ascontiguousarray(a[:nx, :ny].T)
     k["SF1"] = np.ascontiguousarray(np.stack([s2(raw[n]) for n in ("ps", "tt2", "td2", "sshf")], axis=-1))
     k["SF2"] = np.ascontiguousarray(np.stack([s2(raw[n]) for n in ("surfstr", "lsprec", "convprec", "tcc")], axis=-1))
@@ -78,7 +79,8 @@ def make_grid(cb, k, nuvz, lsubgrid=0):
     nx, ny = c.nx, c.ny
     g = MetGrid()
     g.nx, g.ny, g.nz, g.nuvz, g.nwz, g.nxd, g.nyd = nx, ny, nuvz, nuvz, nuvz, nx, ny
-    for f in ("dx", "dy", "xlon0", "ylat0", "dxconst", "dyconst", "nglobal", "sglobal", "switchnorthg", "switchsouthg"):
+    for f in ("dx", "dy", "xlon0", "ylat0", "dxconst", "dyconst", "nglobal", "sglobal", "xglobal", "switchnorthg",
+              "switchsouthg"):
         setattr(g, f, getattr(c, f))
     g.northpolemap[:] = list(c.northpolemap); g.southpolemap[:] = list(c.southpolemap)
     g.lsubgrid, g.readclouds = lsubgrid, 0
@@ -117,6 +119,11 @@ def test_calcpar_verttransform_host_build_matches_reference(seed):
     _host_lib().met_check_run(C.byref(g))
     bad = compare(cb, ref, out, nuvz)
     assert not bad, bad
+    # calcpv: the potential vorticity on the eta levels (the reference's pvh after calcpar)
+    pv_ref = np.transpose(pvh[:c.nx, :c.ny, :nuvz], (2, 1, 0))
+    assert np.abs(pv_ref).max() > 0.1
+    assert np.array_equal(k["PV"].view(np.uint32), np.ascontiguousarray(pv_ref).view(np.uint32)), \
+        (int((k["PV"] != pv_ref).sum()), float(np.abs(k["PV"] - pv_ref).max()))
     # the case exercises what it should: all cloud classes, both stabilities, columns whose top lies
     # below the reference column's, a tropopause everywhere
     cl = out["Cl"]
