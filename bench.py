@@ -424,7 +424,7 @@ def run_ours(args):
             line["cpu_baseline"] = (cpu_baseline_reference(args, 1, args.cpu_seconds) if reference_available()
                                     else cpu_baseline(args, threads=1, budget_s=args.cpu_seconds))
     if rank == 0 and world == 1 and not args.no_hbm_regime:
-        line["next_rows"] = next_rows(eng, cb, rel, peaks()[0], k * 900)
+        line["next_rows"] = next_rows(eng, cb, rel, peaks()[0], k * 900, cpu=not args.no_cpu)
     eng.close()
     del hp, parts
     if args.workload == "c2" and not args.no_c5:
@@ -613,7 +613,7 @@ class GridExchange:
         return float(g.double().sum().item())
 
 
-def next_rows(eng, cb, rel, peak, itime_now):
+def next_rows(eng, cb, rel, peak, itime_now, cpu=True):
     """The SURVEY 8f rows that run on the device, timed on the bench's own engine (wall clock
     around the synchronous C-ABI calls, best of 5): releaseparticles for all particles at once,
     concoutput's sparse dump of the concentration grid, wetdepo when the workload has it."""
@@ -663,6 +663,44 @@ def next_rows(eng, cb, rel, peak, itime_now):
                                   "column), redist; synthetic soundings (tests/conv_cases.py)"}
     except Exception as e:  # (the convection leg must not take the bench line down)
         out["convmix"] = {"error": str(e)}
+    # calcpar + verttransform_ecmwf on the device (what getfields does to every new wind field): the raw
+    # model-level field goes up once, the met slot is built there (slot 3, the read-ahead slot)
+    try:
+        import met_cases
+        akm, bkm, akz, bkz, _ = conv_cases.hybrid_levels(c.nz)
+        raw = met_cases.raw_fields(cb, akz, bkz, c.nz, seed=1)
+        eng.set_vertical(c.nz, akm[1:], bkm[1:], akz[1:], bkz[1:])
+        eng.calcpar_verttransform(3, raw)
+        ms, kms = [], []
+        for _ in range(3):
+            ms.append(eng.calcpar_verttransform(3, raw)); kms.append(eng.metproc_kernel_ms)
+        raw_bytes = sum(int(a[:c.nx, :c.ny].size) * 4 for k, a in raw.items())
+        n3 = c.nx * c.ny * c.nz
+        alg = 4 * n3 * (6 + 12)      # 6 raw 3-D fields read, 12 transformed 3-D values written per grid point
+        out["getfields"] = {"ms": min(ms), "kernels_ms": min(kms), "grid": f"{c.nx}x{c.ny}x{c.nz}",
+                            "raw_field_bytes": raw_bytes, "upload_GBps": raw_bytes / ((min(ms) - min(kms)) * 1e-3) / 1e9,
+                            "kernels_alg_GBps": alg / (min(kms) * 1e-3) / 1e9,
+                            "kernels_frac_of_peak": alg / (min(kms) * 1e-3) / 1e9 / peak,
+                            "what": "fpb_calcpar_verttransform: pageable raw wind field (uuh, vvh, wwh, tth, qvh, 2-D "
+                                    "fields) H2D + calcpar, calcpv, verttransform_ecmwf kernels (device time)"}
+        if cpu:     # the reference's own routines (oracle/_ref) on a bounded sample: 1 deg x same levels
+            try:
+                import flexpart_b200 as fb2
+                import cases as _cases
+                from metproc_common import reference_run
+                cbs = _cases.config_small(nrel=1, npart_each=8, nx=361, ny=181, nz=c.nz, height=fb2.synth_heights(c.nz))
+                raws = met_cases.raw_fields(cbs, akz, bkz, c.nz, seed=1)
+                tm = {}
+                reference_run(cbs, raws, akm, bkm, akz, bkz, c.nz, timing=tm)
+                out["getfields"]["cpu_reference"] = {
+                    "grid": f"361x181x{c.nz}", "calcpar_s": tm["calcpar_s"], "verttransform_s": tm["verttransform_s"],
+                    "cores": 1, "kind": "reference",
+                    "what": "src/calcpar.f90 + src/verttransform_ecmwf.f90 from the reference's sources "
+                            "(oracle/f2c, gcc -O2), one core, a quarter of the bench grid's columns"}
+            except Exception as e:
+                out["getfields"]["cpu_reference"] = {"error": str(e)}
+    except Exception as e:
+        out["getfields"] = {"error": str(e)}
     # release of maxpart particles on a second engine (Philox positions): no particle row crosses PCIe
     e2 = fb.Engine(cb)
     e2.set_releases(rel)

@@ -7,7 +7,7 @@ import numpy as np
 
 import ref_api
 
-def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None):
+def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None, timing=None):
     """calcpar + verttransform_ecmwf of the reference on time slot 1; returns (ref, height)"""
     c = cb.cfg
     ref = ref_api.Ref(cb, maxrand=1000)
@@ -24,8 +24,13 @@ def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None)
     n, fmt = C.c_int(1), C.c_int(2)   # GRIBFILE_CENTRE_ECMWF
     pvh = np.zeros_like(raw["uuh"])
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    import time
+    t0 = time.perf_counter()
     ref.L.f_calcpar(C.byref(n), P(raw["uuh"]), P(raw["vvh"]), P(pvh), C.byref(fmt))
+    t1 = time.perf_counter()
     ref.L.f_verttransform_ecmwf(C.byref(n), P(raw["uuh"]), P(raw["vvh"]), P(raw["wwh"]), P(pvh))
+    if timing is not None:
+        timing.update(calcpar_s=t1 - t0, verttransform_s=time.perf_counter() - t1)
     return ref, ref.arr("height")[:nuvz].copy(), pvh
 
 
