@@ -11,13 +11,13 @@ from .abi import (FpbConfig, FpbMetPtrs, FpbParticlePtrs, FpbStepStats, load_eng
                   MATH_FAST, MATH_STRICT, SCATTER_ATOMIC, SCATTER_DETERMINISTIC, ITRA_DEAD)
 from .host import (make_config, MetFields, Particles, synth_heights, Releases, RunSpec,
                    timemanager, release_particles, ReleaseState, outgrid_geometry,
-                   verttransform_heights)
+                   verttransform_heights, synth_hybrid_levels, synth_rawmet)
 from .engine import Engine
 
 __all__ = [
     "FpbConfig", "FpbMetPtrs", "FpbParticlePtrs", "FpbStepStats", "FpbError", "Engine",
     "make_config", "MetFields", "Particles", "synth_heights", "Releases", "RunSpec",
-    "timemanager", "release_particles", "ReleaseState", "outgrid_geometry", "verttransform_heights", "load_engine_lib", "load_host_lib",
+    "timemanager", "release_particles", "ReleaseState", "outgrid_geometry", "verttransform_heights", "synth_hybrid_levels", "synth_rawmet", "load_engine_lib", "load_host_lib",
     "RNG_REFERENCE", "RNG_PHILOX_INDEX", "RNG_PHILOX", "MATH_FAST", "MATH_STRICT",
     "SCATTER_ATOMIC", "SCATTER_DETERMINISTIC", "ITRA_DEAD",
 ]

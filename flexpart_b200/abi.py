@@ -123,13 +123,14 @@ class FpbMetOutPtrs(C.Structure):
 class FpbhRun(C.Structure):
     _fields_ = [("ideltas", _i), ("loutstep", _i), ("loutaver", _i), ("loutsample", _i),
                 ("met_interval", _i), ("met_homogeneous", _i),
-                ("met_u", _f), ("met_v", _f), ("met_w", _f), ("max_steps", _i)]
+                ("met_u", _f), ("met_v", _f), ("met_w", _f), ("max_steps", _i), ("met_raw", _i), ("lconvection", _i)]
 
 
 class FpbhRunResult(C.Structure):
     _fields_ = [("particle_steps", C.c_int64), ("substeps", C.c_int64), ("syncs", _i),
                 ("outputs", _i), ("numpart_final", _i), ("t_step_s", C.c_double),
-                ("t_conc_s", C.c_double)]
+                ("t_conc_s", C.c_double), ("convmix_calls", _i), ("convecting_columns", _i),
+                ("boundary_particles", _i), ("split_calls", _i)]
 
 
 _pmet, _ppart = C.POINTER(FpbMetPtrs), C.POINTER(FpbParticlePtrs)
@@ -144,6 +145,13 @@ SCALE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _pf)
 WETDEPO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _i)
 SET_RELEASES_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 RELEASE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _pi, _pi)
+INIT_DF_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _f, _f, _f, _f, _i, _pi, C.c_void_p)
+BOUNDCOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _pi, _pi)
+SPLIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _pi)
+SET_VERTICAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _i, _i, _pf, _pf, _pf, _pf)
+CALCPAR_VT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, C.c_void_p, _i, _pf)
+SET_CONV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _i, _i, _pf, _pf, _pf, _pf)
+CONVMIX_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _pi, _pi)
 OUTPUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _i, _f, _pf, _pf, _pf, _pf, _pf)
 
 
@@ -152,7 +160,10 @@ class FpbhEngine(C.Structure):
                 ("set_met_bracket", SET_BRACKET_FN), ("push_particles", PUSH_FN),
                 ("pull_particles", PUSH_FN), ("set_numpart", SET_NUMPART_FN), ("step", STEP_FN),
                 ("conccalc", CONC_FN), ("fetch_grids", FETCH_FN), ("scale_depgrids", SCALE_FN),
-                ("wetdepo", WETDEPO_FN), ("set_releases", SET_RELEASES_FN), ("releaseparticles", RELEASE_FN)]
+                ("wetdepo", WETDEPO_FN), ("set_releases", SET_RELEASES_FN), ("releaseparticles", RELEASE_FN),
+                ("init_domainfill", INIT_DF_FN), ("boundcond_domainfill", BOUNDCOND_FN),
+                ("split_particles", SPLIT_FN), ("set_vertical", SET_VERTICAL_FN),
+                ("calcpar_verttransform", CALCPAR_VT_FN), ("set_convection", SET_CONV_FN), ("convmix", CONVMIX_FN)]
 
 
 # FPB_ENGINE_LIB: load another build of the same library (kernel A/B experiments)
@@ -251,6 +262,8 @@ def load_host_lib():
     L.fpbh_readoutgrid.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f, _pf, _i]
     L.fpbh_readoutgrid_nest.argtypes = [C.POINTER(FpbConfig), _f, _f, _i, _i, _f, _f]
     L.fpbh_synth_heights.argtypes = [_i, _pf]
+    L.fpbh_synth_hybrid_levels.argtypes = [_i, _pf, _pf, _pf, _pf, _pi]
+    L.fpbh_synth_rawmet.argtypes = [C.POINTER(FpbConfig), _i, _pf, _pf, _i, C.POINTER(FpbRawmetPtrs)]
     L.fpbh_verttransform_heights.argtypes = [C.POINTER(FpbConfig), _i, _pf, _pf, _pf, _pf, _pf, _pf, _pf, _pf, _pi, _pi]
     L.fpbh_synth_met.argtypes = [C.POINTER(FpbConfig), _pf, _i, _pmet]
     L.fpbh_synth_met_nest.argtypes = [C.POINTER(FpbConfig), _pf, _i, _i, _pmet]

@@ -396,4 +396,13 @@ class Engine:
         if device_release:
             v.set_releases = cast(L.fpb_set_releases, a.SET_RELEASES_FN)
             v.releaseparticles = cast(L.fpb_releaseparticles, a.RELEASE_FN)
+        # domain filling, splitting, calcpar + verttransform, convective mixing
+        v.init_domainfill = cast(L.fpb_init_domainfill, a.INIT_DF_FN)
+        v.boundcond_domainfill = cast(L.fpb_boundcond_domainfill, a.BOUNDCOND_FN)
+        if device_release:
+            v.split_particles = cast(L.fpb_split_particles, a.SPLIT_FN)
+        v.set_vertical = cast(L.fpb_set_vertical, a.SET_VERTICAL_FN)
+        v.calcpar_verttransform = cast(L.fpb_calcpar_verttransform, a.CALCPAR_VT_FN)
+        v.set_convection = cast(L.fpb_set_convection, a.SET_CONV_FN)
+        v.convmix = cast(L.fpb_convmix, a.CONVMIX_FN)
         return v

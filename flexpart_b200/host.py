@@ -254,6 +254,32 @@ class Releases:
         self.c_struct = r
 
 
+def synth_hybrid_levels(nuvz):
+    """(akm, bkm, akz, bkz, nconvlev): the synthetic vertical structure of fpbh_timemanager's met_raw runs
+    (arrays (1:nuvz), 0-based)"""
+    arrs = [np.zeros(nuvz, np.float32) for _ in range(4)]
+    n = C.c_int32(0)
+    _hcheck(load_host_lib().fpbh_synth_hybrid_levels(nuvz, *[_fp(a) for a in arrs], C.byref(n)))
+    return (*arrs, n.value)
+
+
+def synth_rawmet(cb, nuvz, akz, bkz, time_s):
+    """one time level of fpbh_synth_rawmet as a dict of Fortran-ordered arrays (the `raw` argument of
+    Engine.calcpar_verttransform)"""
+    from .abi import FpbRawmetPtrs
+    c = cb.cfg
+    raw, m = {}, FpbRawmetPtrs()
+    for n in ("uuh", "vvh", "tth", "qvh", "wwh"):
+        raw[n] = np.zeros((c.nxmax, c.nymax, c.nzmax), np.float32, order="F")
+    for n in ("ps", "tt2", "td2", "sshf", "surfstr", "lsprec", "convprec", "tcc"):
+        raw[n] = np.zeros((c.nxmax, c.nymax), np.float32, order="F")
+    for n, a in raw.items():
+        setattr(m, n, _fp(a))
+    keep = [np.ascontiguousarray(akz[:nuvz], np.float32), np.ascontiguousarray(bkz[:nuvz], np.float32)]
+    _hcheck(load_host_lib().fpbh_synth_rawmet(C.byref(c), nuvz, _fp(keep[0]), _fp(keep[1]), int(time_s), C.byref(m)))
+    return raw
+
+
 def verttransform_heights(cb, nuvz, akz, bkz, raw):
     """height(1:nuvz) of verttransform_ecmwf's first call (src/verttransform_ecmwf.f90:131-163) from a raw
     wind field (dict with ps, tt2, td2, tth, qvh, Fortran order); akz, bkz 0-based (1:nuvz).
@@ -303,7 +329,7 @@ def release_particles(cb, rel, state, itime, parts):
 
 class RunSpec:
     def __init__(self, ideltas, loutstep=3600, loutaver=3600, loutsample=900, met_interval=10800,
-                 homogeneous=None, max_steps=0, ldirect=1):
+                 homogeneous=None, max_steps=0, ldirect=1, met_raw=False, lconvection=False):
         r = FpbhRun()
         s = -1 if ldirect < 0 else 1
         r.ideltas = ideltas
@@ -313,6 +339,7 @@ class RunSpec:
             r.met_homogeneous = 1
             r.met_u, r.met_v, r.met_w = homogeneous
         r.max_steps = max_steps
+        r.met_raw, r.lconvection = int(met_raw), int(lconvection)
         self.c_struct = r
 
 

@@ -298,3 +298,98 @@ extern "C" int fpbh_homogeneous_met(const fpb_config *cp, float u, float v, floa
   fill(o->vdep, n2 * c.maxspec, 0.f);
   return 0;
 }
+
+// ---- model-level ("raw") fields: what readwind_ecmwf would leave for calcpar + verttransform -------
+// L137-like hybrid coefficients as FLEXPART holds them (src/gridcheck_ecmwf.f90:470-566): akm, bkm
+// on the half levels (index 1 = surface), akz, bkz on the layer centres (akz(1) = 0, bkz(1) = 1: the
+// surface itself); all arrays (1:nuvz), 0-based here.  nconvlev as derived at :553-566.
+extern "C" int fpbh_synth_hybrid_levels(int32_t nuvz, float *akm, float *bkm, float *akz, float *bkz, int32_t *nconvlev) {
+  if (nuvz < 4 || !akm || !bkm || !akz || !bkz) return fpbh_fail("fpbh_synth_hybrid_levels: bad argument");
+  for (int k = 1; k <= nuvz; k++) {
+    const double eta = std::pow((double)(nuvz - k) / (nuvz - 1.0), 1.35);
+    const double b = std::pow(eta, 2.2);
+    akm[k - 1] = (float)(101325.0 * (eta - b) + 1.0 * (1.0 - eta)); // ~1 Pa at the top
+    bkm[k - 1] = (float)b;
+  }
+  akz[0] = 0.f; bkz[0] = 1.f;
+  for (int k = 2; k <= nuvz; k++) {
+    akz[k - 1] = 0.5f * (akm[k - 2] + akm[k - 1]);
+    bkz[k - 1] = 0.5f * (bkm[k - 2] + bkm[k - 1]);
+  }
+  if (nconvlev) {
+    int n = nuvz - 2;
+    for (int i = 1; i <= nuvz - 2; i++)
+      if (akz[i - 1] + bkz[i - 1] * 101325.f < 5000.f) { n = i; break; }
+    *nconvlev = n < nuvz - 2 ? n : nuvz - 2;
+  }
+  return 0;
+}
+
+// One time level of synthetic model-level fields in the reference's padded layout: a warm, moist
+// tropical belt (part of the columns convect, part of them rain), jets aloft, two mountain massifs
+// (surface pressure down to ~720 hPa), day/night surface heat flux.  `time_s` moves the phases.
+extern "C" int fpbh_synth_rawmet(const fpb_config *cp, int32_t nuvz, const float *akz, const float *bkz, int32_t time_s,
+                                 const fpb_rawmet_ptrs *o) {
+  if (!cp || !akz || !bkz || !o) return fpbh_fail("fpbh_synth_rawmet: null argument");
+  if (!o->uuh || !o->vvh || !o->tth || !o->qvh || !o->wwh || !o->ps || !o->tt2 || !o->td2 || !o->sshf || !o->surfstr)
+    return fpbh_fail("fpbh_synth_rawmet: mandatory output array is null");
+  const fpb_config &c = *cp;
+  const int nx = c.nx, ny = c.ny;
+  const double wt = 2.0 * PI * (double)time_s / 86400.0;
+  float *uuh = (float *)o->uuh, *vvh = (float *)o->vvh, *tth = (float *)o->tth, *qvh = (float *)o->qvh, *wwh = (float *)o->wwh;
+  float *ps = (float *)o->ps, *tt2 = (float *)o->tt2, *td2 = (float *)o->td2, *sshf = (float *)o->sshf;
+  float *surfstr = (float *)o->surfstr, *lsprec = (float *)o->lsprec, *convprec = (float *)o->convprec, *tcc = (float *)o->tcc;
+  std::vector<double> t0((size_t)nx * ny), rh0((size_t)nx * ny);
+  for (int jy = 0; jy < ny; jy++) {
+    const double lat = (double)c.ylat0 + (double)c.dy * jy, cphi = std::cos(lat * PI / 180.0);
+    for (int ix = 0; ix < nx; ix++) {
+      const double lon = (double)c.xlon0 + (double)c.dx * ix, lam = lon * PI / 180.0;
+      const size_t i = i2(c, ix, jy), q = (size_t)ix + (size_t)nx * jy;
+      const double bump = 28000.0 * std::exp(-(std::pow((lon - 85.0) / 25.0, 2) + std::pow((lat - 33.0) / 12.0, 2))) +
+                          20000.0 * std::exp(-(std::pow((lon + 70.0) / 12.0, 2) + std::pow((lat + 20.0) / 25.0, 2)));
+      ps[i] = (float)(100000.0 + 1500.0 * std::sin(2 * lam + 0.2 * wt) * cphi - bump);
+      t0[q] = 272.0 + 32.0 * cphi * cphi + 2.0 * std::sin(3 * lam + 0.5 * wt);
+      rh0[q] = std::fmin(0.98, std::fmax(0.2, 0.55 + 0.42 * cphi * cphi + 0.1 * std::sin(5 * lam + wt)));
+      tt2[i] = (float)(t0[q] + 0.5);
+      td2[i] = (float)(t0[q] + 0.5 - 2.0 - 4.0 * (1.0 - rh0[q]));
+      const double day = std::sin(lam + wt);
+      sshf[i] = (float)(-160.0 * cphi * day + 15.0); // upward (negative) by day
+      surfstr[i] = (float)(0.02 + 0.25 * std::fabs(std::sin(2 * lam + 0.7 * wt) * cphi));
+      if (lsprec) lsprec[i] = (float)std::fmax(0.0, 2.5 * std::sin(3 * lam + 0.35 + 0.3 * wt) * std::sin(2 * lat * PI / 180.0 + 0.17) - 0.8);
+      if (convprec) convprec[i] = (float)std::fmax(0.0, 3.0 * std::pow(cphi, 6) * std::sin(5 * lam + 0.4 * wt) - 0.6);
+      if (tcc) tcc[i] = (float)std::fmin(1.0, std::fmax(0.0, 0.5 + 0.5 * std::sin(2 * lam) * std::cos(3 * lat * PI / 180.0)));
+    }
+  }
+  parallel_levels(nuvz, [&](int k0) {
+    const int k = k0 + 1; // Fortran level
+    const double eta = k > 1 ? ((double)akz[k - 1] + (double)bkz[k - 1] * 101325.0) / 101325.0 : 1.0;
+    for (int jy = 0; jy < ny; jy++) {
+      const double lat = (double)c.ylat0 + (double)c.dy * jy, phi = lat * PI / 180.0, cphi = std::cos(phi);
+      const double ttrop = 205.0 + 8.0 * cphi * cphi;
+      for (int ix = 0; ix < nx; ix++) {
+        const double lon = (double)c.xlon0 + (double)c.dx * ix, lam = lon * PI / 180.0;
+        const size_t i = i3(c, ix, jy, k0), q = (size_t)ix + (size_t)nx * jy;
+        const double psd = ps[i2(c, ix, jy)];
+        const double p = k > 1 ? (double)akz[k - 1] + (double)bkz[k - 1] * psd : psd;
+        const double t = std::fmax(t0[q] * std::pow(p / psd, 0.19), ttrop) + 0.2 * std::sin(0.37 * k + lam);
+        const double es = 611.2 * std::exp(17.67 * (t - 273.15) / (t - 29.65));
+        const double qs = 0.622 * es / std::fmax(p - 0.378 * es, 1.0);
+        const double rh = std::fmin(1.0, std::fmax(0.02, rh0[q] * std::pow(p / psd, 1.2)));
+        tth[i] = (float)t;
+        qvh[i] = (float)std::fmin(0.03, std::fmax(1e-7, rh * qs));
+        const double jet = 35.0 * std::pow(1.0 - eta, 0.7) * cphi * cphi;
+        uuh[i] = (float)(4.0 + jet * (1.0 + 0.3 * std::sin(3 * lam + 0.5 * wt)) + 2.0 * std::sin(0.21 * k + lam));
+        vvh[i] = (float)(6.0 * std::sin(2 * lam + 0.7 * eta + 0.3 * wt) * cphi + 1.5 * std::cos(0.17 * k));
+        wwh[i] = (float)(1.6 * eta * (1.0 - eta) * std::sin(4 * lam + wt) * std::sin(3 * phi) + 0.02 * std::sin(0.5 * k + phi));
+      }
+    }
+  });
+  // level 1 carries the 10 m wind and repeats the lowest layer's temperature and humidity
+  for (int jy = 0; jy < ny; jy++)
+    for (int ix = 0; ix < nx; ix++) {
+      const size_t a = i3(c, ix, jy, 0), b = i3(c, ix, jy, 1);
+      uuh[a] = 0.6f * uuh[b]; vvh[a] = 0.6f * vvh[b];
+      tth[a] = tth[b]; qvh[a] = qvh[b];
+    }
+  return 0;
+}

@@ -5,8 +5,9 @@
 // (src/getfields.f90:96-176), particle release, decay of deposited mass at
 // loutnext, the sampling schedule with half weights at the window ends, the
 // output + second conccalc at loutend, the exit at ideltas, ldeltat, the
-// particle loop.  Left out (outside the hot-path scope):
-// wetdepo, OH, convmix, particle splitting, flux and trajectory output.
+// particle loop; wet deposition, domain filling (init_domainfill / boundcond_domainfill),
+// convective mixing and particle splitting where the run asks for them.  Left out (outside the
+// hot-path scope): OH reaction, flux and trajectory output, particle dumps.
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -39,6 +40,20 @@ struct MetStore { // com_mod met arrays, numwfmem = 2
       m.oli = f2[s][3].data(); m.tropopause = f2[s][4].data();
       m.vdep = vd[s].data();
     }
+  }
+};
+struct RawStore { // one time level of model-level fields (readwind_ecmwf's uuh.. and com_mod's tth, ps, ..)
+  std::vector<float> f3[5], f2[8];
+  fpb_rawmet_ptrs ptr{};
+  void alloc(const fpb_config &c) {
+    const size_t n3 = (size_t)c.nxmax * c.nymax * c.nzmax, n2 = (size_t)c.nxmax * c.nymax;
+    for (auto &v : f3) v.assign(n3, 0.f);
+    for (auto &v : f2) v.assign(n2, 0.f);
+    ptr.uuh = f3[0].data(); ptr.vvh = f3[1].data(); ptr.tth = f3[2].data(); ptr.qvh = f3[3].data(); ptr.wwh = f3[4].data();
+    ptr.pvh = nullptr;
+    ptr.ps = f2[0].data(); ptr.tt2 = f2[1].data(); ptr.td2 = f2[2].data(); ptr.sshf = f2[3].data();
+    ptr.surfstr = f2[4].data(); ptr.lsprec = f2[5].data(); ptr.convprec = f2[6].data(); ptr.tcc = f2[7].data();
+    ptr.excessoro = nullptr;
   }
 };
 double now() {
@@ -77,7 +92,20 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
 
   fpbh_release_state *rst = fpbh_release_state_new(rel->numpoint);
   MetStore met;
-  met.alloc(c);
+  RawStore raw;
+  std::vector<float> akm, bkm, akz, bkz;
+  if (run->met_raw) {
+    if (!eng->set_vertical || !eng->calcpar_verttransform)
+    { fpbh_release_state_free(rst); return fpbh_fail("fpbh_timemanager: met_raw needs set_vertical / calcpar_verttransform in the engine table"); }
+    raw.alloc(c);
+    akm.resize(c.nz); bkm.resize(c.nz); akz.resize(c.nz); bkz.resize(c.nz);
+  } else {
+    met.alloc(c);
+  }
+  if (run->lconvection && (!run->met_raw || !eng->set_convection || !eng->convmix))
+  { fpbh_release_state_free(rst); return fpbh_fail("fpbh_timemanager: lconvection needs met_raw and set_convection / convmix in the engine table"); }
+  if (c.mdomainfill >= 1 && (!eng->init_domainfill || !eng->boundcond_domainfill))
+  { fpbh_release_state_free(rst); return fpbh_fail("fpbh_timemanager: mdomainfill needs init_domainfill / boundcond_domainfill in the engine table"); }
 
   // grids handed to the output callback (reference layout, maxspec)
   const size_t outer = (size_t)c.maxspec * c.maxpointspec_act * c.nclassunc * c.maxageclass;
@@ -112,6 +140,20 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
     int memtime[2] = {999999999, 999999999};
     bool have_fields = false;
     const bool DEP = c.drydep != 0 || c.wetdep != 0; // src/readreleases.f90:389
+    if (run->met_raw) { // gridcheck's vertical structure, then the engine's copies of it
+      int32_t nconvlev = 0;
+      if (fpbh_synth_hybrid_levels(c.nz, akm.data(), bkm.data(), akz.data(), bkz.data(), &nconvlev)) { rc = 1; goto done; }
+      ENG(eng->set_vertical(eng->self, c.nz, c.nz, c.nzmax, c.nzmax, akm.data(), bkm.data(), akz.data(), bkz.data()));
+      if (run->lconvection)
+        ENG(eng->set_convection(eng->self, c.nz, c.nzmax, nconvlev, akz.data(), bkz.data(), akm.data(), bkm.data()));
+    }
+    auto do_convmix = [&](int itime) -> int {
+      int32_t ncol = 0, nconv = 0;
+      if (eng->convmix(eng->self, itime, &ncol, &nconv)) return 1;
+      R.convmix_calls++;
+      R.convecting_columns += nconv;
+      return 0;
+    };
 
     for (int itime = 0; ldirect * itime <= ldirect * run->ideltas; itime += lsynctime) {
       // ---- wet deposition, src/timemanager.f90:164-169: before new fields are read in,
@@ -121,11 +163,18 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
         ENG(eng->wetdepo(eng->self, itime, lsynctime, ldw));
       }
 
+      // ---- convection for backward runs, src/timemanager.f90:183-193: before the next field is read
+      if (ldirect == -1 && run->lconvection && itime < 0) ENG(do_convmix(itime));
+
       // ---- getfields, src/getfields.f90:96-176 (wind fields every
       // met_interval seconds, times counted in the run's direction)
       {
         const int mi = run->met_interval;
         auto synth = [&](int slot, int t) -> int {
+          if (run->met_raw) { // readwind -> calcpar -> verttransform, the last two on the device
+            if (fpbh_synth_rawmet(&c, c.nz, akz.data(), bkz.data(), t, &raw.ptr)) return 1;
+            return eng->calcpar_verttransform(eng->self, slot, &raw.ptr, 0, nullptr);
+          }
           if (run->met_homogeneous) {
             if (fpbh_homogeneous_met(&c, run->met_u, run->met_v, run->met_w, &met.ptr[slot - 1])) return 1;
           } else if (fpbh_synth_met(&c, height, t, &met.ptr[slot - 1])) {
@@ -156,7 +205,16 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
       }
 
       // ---- release particles, src/timemanager.f90:230-251
-      {
+      if (c.mdomainfill >= 1) {
+        if (itime == 0) {
+          ENG(eng->init_domainfill(eng->self, rel->xpoint1[0], rel->ypoint1[0], rel->xpoint2[0], rel->ypoint2[0],
+                                   rel->itsplit, &numpart, nullptr));
+        } else {
+          int32_t created = 0;
+          ENG(eng->boundcond_domainfill(eng->self, itime, loutend, &numpart, &created));
+          R.boundary_particles += created;
+        }
+      } else {
         bool due = false;
         for (int i = 0; i < rel->numpoint; i++)
           if (itime >= rel->ireleasestart[i] && itime <= rel->ireleaseend[i]) due = true;
@@ -192,6 +250,9 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
           ENG(eng->set_numpart(eng->self, numpart));
         }
       }
+
+      // ---- convective mixing for forward runs, src/timemanager.f90:258-263
+      if (ldirect == 1 && run->lconvection) ENG(do_convmix(itime));
 
       // ---- decay of deposited mass, src/timemanager.f90:269-304
       if (DEP && itime == loutnext && ldirect > 0) {
@@ -238,6 +299,22 @@ extern "C" int fpbh_timemanager(const fpb_config *cp, const float *height, const
             double t0 = now();
             ENG(eng->conccalc(eng->self, itime, weight));
             R.t_conc_s += now() - t0;
+          }
+          // ---- particle splitting, src/timemanager.f90:472-503
+          if (eng->split_particles && ldirect * itime >= ldirect * rel->itsplit) {
+            if (!releases_set && eng->set_releases) { // (the engine's block-scan scratch)
+              fpb_release_points rp{};
+              rp.numpoint = rel->numpoint;
+              rp.ireleasestart = rel->ireleasestart; rp.ireleaseend = rel->ireleaseend;
+              rp.xpoint1 = rel->xpoint1; rp.ypoint1 = rel->ypoint1; rp.xpoint2 = rel->xpoint2;
+              rp.ypoint2 = rel->ypoint2; rp.zpoint1 = rel->zpoint1; rp.zpoint2 = rel->zpoint2;
+              rp.itsplit = rel->itsplit;
+              rp.mp_pid = 0;
+              ENG(eng->set_releases(eng->self, &rp));
+              releases_set = true;
+            }
+            ENG(eng->split_particles(eng->self, itime, &numpart));
+            R.split_calls++;
           }
         }
       }

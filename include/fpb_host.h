@@ -62,6 +62,15 @@ int fpbh_verttransform_heights(const fpb_config *cfg, int32_t nuvz, const float 
                                const float *ps, const float *tt2, const float *td2, const float *tth,
                                const float *qvh, float *height, int32_t *ixm, int32_t *jym);
 
+/* Synthetic hybrid coefficients (L137-like; akm, bkm half levels, akz, bkz layer centres with level 1
+ * the surface, src/gridcheck_ecmwf.f90:470-566) and one time level of synthetic model-level fields
+ * (uuh, vvh, wwh, tth, qvh, ps, tt2, td2, sshf, surfstr, [lsprec, convprec, tcc]) in the reference's
+ * padded layout: the input of fpb_calcpar_verttransform when the run has no GRIB files.  Arrays of
+ * the coefficients are the Fortran (1:nuvz), 0-based. */
+int fpbh_synth_hybrid_levels(int32_t nuvz, float *akm, float *bkm, float *akz, float *bkz, int32_t *nconvlev);
+int fpbh_synth_rawmet(const fpb_config *cfg, int32_t nuvz, const float *akz, const float *bkz, int32_t time_s,
+                      const fpb_rawmet_ptrs *out);
+
 /* Fill one time level of synthetic met into caller arrays with
  * the padded Fortran layout; `time_s` moves the phase of the fields.
  * All non-NULL pointers of `out` are written. */
@@ -135,6 +144,21 @@ typedef struct fpbh_engine {
    * new rows are pushed; otherwise the engine creates the particles itself (fpb_releaseparticles) */
   int (*set_releases)(void *self, const fpb_release_points *rel);
   int (*releaseparticles)(void *self, int32_t itime, int32_t *numpart, int32_t *n_released);
+  /* domain-filling runs (cfg->mdomainfill >= 1, src/timemanager.f90:230-241): both required then */
+  int (*init_domainfill)(void *self, float xpoint1, float ypoint1, float xpoint2, float ypoint2, int32_t itsplit,
+                         int32_t *numpart, fpb_domainfill_info *info);
+  int (*boundcond_domainfill)(void *self, int32_t itime, int32_t loutend, int32_t *numpart, int32_t *n_created);
+  /* may be NULL: no particle splitting (src/timemanager.f90:472-503) */
+  int (*split_particles)(void *self, int32_t itime, int32_t *numpart);
+  /* fpbh_run::met_raw: the wind fields are model-level fields and the engine does calcpar +
+   * verttransform (src/getfields.f90:126-129) */
+  int (*set_vertical)(void *self, int32_t nuvz, int32_t nwz, int32_t nuvzmax, int32_t nwzmax, const float *akm,
+                      const float *bkm, const float *akz, const float *bkz);
+  int (*calcpar_verttransform)(void *self, int32_t slot, const fpb_rawmet_ptrs *raw, int32_t lsubgrid, float *device_ms);
+  /* fpbh_run::lconvection (needs met_raw: the convection scheme reads the model-level fields) */
+  int (*set_convection)(void *self, int32_t nuvz, int32_t nuvzmax, int32_t nconvlev, const float *akz, const float *bkz,
+                        const float *akm, const float *bkm);
+  int (*convmix)(void *self, int32_t itime, int32_t *ncolumns, int32_t *nconvecting);
 } fpbh_engine;
 
 /* one output interval handed to the caller (the concoutput slot,
@@ -151,6 +175,10 @@ typedef struct fpbh_run {
   int32_t met_homogeneous;                /* 1: set_fields_synthetic-style met */
   float met_u, met_v, met_w;
   int32_t max_steps;                      /* >0: stop after that many syncs */
+  int32_t met_raw;                        /* 1: synthetic model-level fields (fpbh_synth_rawmet) through the
+                                           * engine's calcpar_verttransform; fpb_config::height must then be
+                                           * fpbh_verttransform_heights of the field at time 0 */
+  int32_t lconvection;                    /* 1: convmix every step (COMMAND LCONVECTION), needs met_raw */
 } fpbh_run;
 
 typedef struct fpbh_run_result {
@@ -158,10 +186,16 @@ typedef struct fpbh_run_result {
   int64_t substeps;
   int32_t syncs, outputs, numpart_final;
   double t_step_s, t_conc_s; /* host wall time inside engine->step / conccalc */
+  int32_t convmix_calls, convecting_columns; /* lconvection: calls made, columns that convected (summed) */
+  int32_t boundary_particles, split_calls;   /* domain filling: particles created at the boundaries */
 } fpbh_run_result;
 
 /* timemanager(metdata_format): src/timemanager.f90:152-729 with the engine
- * in place of the particle loop and conccalc; met comes from fpbh_synth_met. */
+ * in place of the particle loop and conccalc; met comes from fpbh_synth_met, or -- fpbh_run::met_raw --
+ * as model-level fields from fpbh_synth_rawmet that the engine transforms itself.  Domain-filling
+ * runs (init_domainfill / boundcond_domainfill), convective mixing (forward: after the release,
+ * backward: before the new fields, :183-193,258-263) and particle splitting (:472-503) are part of
+ * the loop when the configuration asks for them and the engine table has the entry points. */
 int fpbh_timemanager(const fpb_config *cfg, const float *height, const fpbh_releases *rel,
                      const fpbh_run *run, const fpbh_engine *eng, fpbh_output_fn out, void *user,
                      fpbh_run_result *result);

@@ -49,3 +49,35 @@ int fpo_vt_wetdepo(void *self, int32_t itime, int32_t ltsample, int32_t ldeltat)
   fpo_wetdepo((fpo_state *)self, itime, ltsample, ldeltat);
   return 0;
 }
+
+/* domain filling and splitting: the oracle keeps the itsplit of init_domainfill for boundcond */
+static int vt_itsplit = 99999999;
+
+int fpo_vt_init_domainfill(void *self, float xpoint1, float ypoint1, float xpoint2, float ypoint2, int32_t itsplit,
+                           int32_t *numpart, void *info) {
+  fpo_state *S = (fpo_state *)self;
+  int32_t out[8];
+  float fout[2];
+  (void)info;
+  vt_itsplit = itsplit;
+  if (fpo_init_domainfill(S, xpoint1, ypoint1, xpoint2, ypoint2, itsplit, out, fout)) return 1;
+  if (numpart) *numpart = S->numpart;
+  return 0;
+}
+
+int fpo_vt_boundcond_domainfill(void *self, int32_t itime, int32_t loutend, int32_t *numpart, int32_t *n_created) {
+  fpo_state *S = (fpo_state *)self;
+  (void)loutend;
+  const int n = fpo_boundcond_domainfill(S, itime, vt_itsplit);
+  if (n < 0) return 1;
+  if (numpart) *numpart = S->numpart;
+  if (n_created) *n_created = n;
+  return 0;
+}
+
+int fpo_vt_split_particles(void *self, int32_t itime, int32_t *numpart) {
+  fpo_state *S = (fpo_state *)self;
+  fpo_split_particles(S, itime);
+  if (numpart) *numpart = S->numpart;
+  return 0;
+}

@@ -236,4 +236,7 @@ class Oracle:
         v.fetch_grids = cast(L.fpo_vt_fetch_grids, a.FETCH_FN)
         v.scale_depgrids = cast(L.fpo_vt_scale_depgrids, a.SCALE_FN)
         v.wetdepo = cast(L.fpo_vt_wetdepo, a.WETDEPO_FN)
+        v.init_domainfill = cast(L.fpo_vt_init_domainfill, a.INIT_DF_FN)
+        v.boundcond_domainfill = cast(L.fpo_vt_boundcond_domainfill, a.BOUNDCOND_FN)
+        v.split_particles = cast(L.fpo_vt_split_particles, a.SPLIT_FN)
         return v
