@@ -286,6 +286,41 @@ def _fortran_module():
     return params, types, funcs
 
 
+def test_timemanager_domainfill_boundary_and_splitting_on_the_oracle():
+    """mdomainfill = 1 in the host loop (src/timemanager.f90:230-241,472-503): init_domainfill at itime 0,
+    boundcond_domainfill afterwards, splitting at loutend once itsplit is reached -- here with the oracle
+    behind the engine table (tests/test_gpu_timeloop.py runs the CUDA engine through the same loop)."""
+    from oracle_api import Oracle
+    cb = cases.config_small(nrel=1, npart_each=20000, maxpart=60000, mdomainfill=1, nclassunc=2)
+    rel = fb.Releases(cb, lon1=[-60.0], lon2=[70.0], lat1=[-30.0], lat2=[45.0], z1=[0.0], z2=[100.0], start=[0],
+                      end=[0], itsplit=5400)
+    ora = Oracle(cb)
+    ora.fill_rannumb()
+    r, outs = fb.timemanager(cb, rel, fb.RunSpec(ideltas=10 * 900), ora.vtable())
+    assert r.syncs == 10 and len(outs) == 2 and r.split_calls == 1 and r.boundary_particles > 0
+    n0 = 19984                      # init_domainfill: nint(0.999 * npart * share) summed over the columns
+    assert abs(r.numpart_final - 2 * n0) < 200
+    p = fb.Particles(cb.cfg.maxpart, 1); p.numpart = r.numpart_final
+    ora.pull_particles(p)
+    live = p.itra1[:p.numpart] != fb.ITRA_DEAD
+    # the halves of a split particle carry half the mass each: the air mass of the box stays what
+    # init_domainfill distributed (up to what left and entered through the boundaries in 10 steps)
+    o2 = Oracle(cb)
+    m0, m1 = cases.met_pair(cb)
+    o2.upload_met(1, m0); o2.upload_met(2, m1)
+    c = cb.cfg
+    pts = [float(np.float32(v)) for v in ((-60.0 - c.xlon0) / c.dx, (-30.0 - c.ylat0) / c.dy, (70.0 - c.xlon0) / c.dx,
+                                          (45.0 - c.ylat0) / c.dy)]
+    _, info = o2.init_domainfill(pts)
+    m = p.xmass1[:p.numpart, 0][live].astype(np.float64).sum()
+    assert live.sum() > 30000 and abs(m / info["colmasstotal"] - 1.0) < 0.1, m / info["colmasstotal"]
+    # a run without the domain-filling entry points in the table is refused, not silently different
+    v = ora.vtable()
+    v.init_domainfill = abi.INIT_DF_FN()
+    with pytest.raises(fb.FpbError, match="init_domainfill"):
+        fb.timemanager(cb, rel, fb.RunSpec(ideltas=900), v)
+
+
 def test_fortran_module_is_generated_from_the_header():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_fortran_module as g
