@@ -469,7 +469,7 @@ def c5_strong(args, rank, world, local, mets, span, K, W):
     import flexpart_b200 as fb
     total = int(os.environ.get("FPB_C5_TOTAL", C5_TOTAL))
     n_rank = (total + world - 1) // world + 1024
-    cb = c5_config(n_rank, local, rank, world)
+    cb = c5_config(n_rank, local, rank, world, sort_interval=int(os.environ.get("FPB_C5_SORT", "8")))
     cb.cfg.npart[0] = total
     cb.npart[0] = total
     c = cb.cfg

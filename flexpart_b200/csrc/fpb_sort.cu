@@ -85,6 +85,72 @@ permute_kernel(DevParticles s, DevParticles d, const unsigned *ids, int nrows, i
   }
 }
 
+// ---- packed permute: a random-row gather of 18 separate 2/4/8-byte arrays fetches a 32-byte sector per
+// value (8x the useful bytes for the 4-byte fields).  For large row counts the rows are first packed
+// into array-of-structures records (coalesced reads, records written back to back), then every
+// destination row reads ITS source record -- 3 to 4 whole sectors -- and writes the arrays coalesced.
+// Record: [xtra1 ytra1 | ztra1 itra1 npoint nclass] [idt itramem itrasplit uap ucp uzp us vs]
+//         [ws slot cbt+pad xmass1(1:nspec) xscav_frac1(1:nspec)], padded to 16 bytes.
+template <int NSPEC> struct PackedRow {
+  static constexpr int WORDS = ((76 + 8 * NSPEC + 15) / 16) * 4;
+};
+
+template <int NSPEC>
+__global__ void __launch_bounds__(256) pack_rows_kernel(DevParticles s, uint4 *rec, int nrows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  constexpr int W = PackedRow<NSPEC>::WORDS;
+  unsigned w[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) w[k] = 0u;
+  const unsigned long long x = (unsigned long long)__double_as_longlong(s.xtra1[i]);
+  const unsigned long long y = (unsigned long long)__double_as_longlong(s.ytra1[i]);
+  w[0] = (unsigned)x; w[1] = (unsigned)(x >> 32); w[2] = (unsigned)y; w[3] = (unsigned)(y >> 32);
+  w[4] = __float_as_uint(s.ztra1[i]); w[5] = (unsigned)s.itra1[i]; w[6] = (unsigned)s.npoint[i]; w[7] = (unsigned)s.nclass[i];
+  w[8] = (unsigned)s.idt[i]; w[9] = (unsigned)s.itramem[i]; w[10] = (unsigned)s.itrasplit[i];
+  w[11] = __float_as_uint(s.uap[i]); w[12] = __float_as_uint(s.ucp[i]); w[13] = __float_as_uint(s.uzp[i]);
+  w[14] = __float_as_uint(s.us[i]); w[15] = __float_as_uint(s.vs[i]);
+  w[16] = __float_as_uint(s.ws[i]); w[17] = (unsigned)s.slot[i]; w[18] = (unsigned)(unsigned short)s.cbt[i];
+#pragma unroll
+  for (int k = 0; k < NSPEC; k++) {
+    w[19 + k] = __float_as_uint(s.xmass1[(size_t)k * s.maxpart + i]);
+    w[19 + NSPEC + k] = __float_as_uint(s.xscav_frac1[(size_t)k * s.maxpart + i]);
+  }
+  uint4 *r = rec + (size_t)i * (W / 4);
+#pragma unroll
+  for (int k = 0; k < W / 4; k++) r[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
+template <int NSPEC>
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const uint4 *rec, DevParticles d, const unsigned *ids, int nrows,
+                                                          int32_t *row_of_slot, int base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  constexpr int W = PackedRow<NSPEC>::WORDS;
+  const uint4 *r = rec + (size_t)ids[i] * (W / 4);
+  unsigned w[W];
+#pragma unroll
+  for (int k = 0; k < W / 4; k++) {
+    const uint4 v = __ldg(r + k);
+    w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+  }
+  d.xtra1[i] = __longlong_as_double((long long)((unsigned long long)w[0] | ((unsigned long long)w[1] << 32)));
+  d.ytra1[i] = __longlong_as_double((long long)((unsigned long long)w[2] | ((unsigned long long)w[3] << 32)));
+  d.ztra1[i] = __uint_as_float(w[4]); d.itra1[i] = (int)w[5]; d.npoint[i] = (int)w[6]; d.nclass[i] = (int)w[7];
+  d.idt[i] = (int)w[8]; d.itramem[i] = (int)w[9]; d.itrasplit[i] = (int)w[10];
+  d.uap[i] = __uint_as_float(w[11]); d.ucp[i] = __uint_as_float(w[12]); d.uzp[i] = __uint_as_float(w[13]);
+  d.us[i] = __uint_as_float(w[14]); d.vs[i] = __uint_as_float(w[15]); d.ws[i] = __uint_as_float(w[16]);
+  const int32_t sl = (int32_t)w[17];
+  d.slot[i] = sl;
+  d.cbt[i] = (int16_t)(unsigned short)w[18];
+  row_of_slot[sl] = base + i;
+#pragma unroll
+  for (int k = 0; k < NSPEC; k++) {
+    d.xmass1[(size_t)k * d.maxpart + i] = __uint_as_float(w[19 + k]);
+    d.xscav_frac1[(size_t)k * d.maxpart + i] = __uint_as_float(w[19 + NSPEC + k]);
+  }
+}
+
 __global__ void invert_kernel(const int32_t *slot, int32_t *row_of_slot, int nrows, int base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nrows) row_of_slot[slot[i]] = base + i;
@@ -194,6 +260,21 @@ void sortk_build_keys(const DevCfg &c, const DevParticles &p, const float *heigh
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
                    int nrows, int nspec, cudaStream_t st, int32_t *row_of_slot, int base) {
   permute_kernel<<<nb(nrows, 256), 256, 0, st>>>(src, dst, ids, nrows, nspec, row_of_slot, base);
+}
+size_t sortk_packed_bytes(int nrows, int nspec) {
+  if (nspec < 1 || nspec > 4) return 0; // (more species: the plain gather)
+  return (size_t)nrows * (((76 + 8 * nspec + 15) / 16) * 16);
+}
+void sortk_permute_packed(const DevParticles &src, const DevParticles &dst, const unsigned *ids, int nrows, int nspec,
+                          cudaStream_t st, int32_t *row_of_slot, void *records, int base) {
+  uint4 *rec = reinterpret_cast<uint4 *>(records);
+  const unsigned g = nb(nrows, 256);
+  switch (nspec) {
+    case 1: pack_rows_kernel<1><<<g, 256, 0, st>>>(src, rec, nrows); unpack_rows_kernel<1><<<g, 256, 0, st>>>(rec, dst, ids, nrows, row_of_slot, base); break;
+    case 2: pack_rows_kernel<2><<<g, 256, 0, st>>>(src, rec, nrows); unpack_rows_kernel<2><<<g, 256, 0, st>>>(rec, dst, ids, nrows, row_of_slot, base); break;
+    case 3: pack_rows_kernel<3><<<g, 256, 0, st>>>(src, rec, nrows); unpack_rows_kernel<3><<<g, 256, 0, st>>>(rec, dst, ids, nrows, row_of_slot, base); break;
+    default: pack_rows_kernel<4><<<g, 256, 0, st>>>(src, rec, nrows); unpack_rows_kernel<4><<<g, 256, 0, st>>>(rec, dst, ids, nrows, row_of_slot, base); break;
+  }
 }
 void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base) {
   invert_kernel<<<nb(nrows, 256), 256, 0, st>>>(slot, row_of_slot, nrows, base);

@@ -21,6 +21,11 @@ int sortk_key_bits(const DevCfg &c, bool regime);
 // row_of_slot[slot] := base + i
 void sortk_permute(const DevParticles &src, const DevParticles &dst, const unsigned *ids,
                    int nrows, int nspec, cudaStream_t st, int32_t *row_of_slot, int base = 0);
+// the same through packed records (`records`: sortk_packed_bytes() bytes of scratch; 0 = not available for
+// this nspec): two coalesced passes instead of one gather that fetches a sector per value
+size_t sortk_packed_bytes(int nrows, int nspec);
+void sortk_permute_packed(const DevParticles &src, const DevParticles &dst, const unsigned *ids, int nrows, int nspec,
+                          cudaStream_t st, int32_t *row_of_slot, void *records, int base = 0);
 void sortk_invert(const int32_t *slot, int32_t *row_of_slot, int nrows, cudaStream_t st, int base = 0);
 // staging row slot[i] <- row i of the view `rows` (arrays the particle loop writes only)
 void sortk_scatter_back(const DevParticles &rows, const DevParticles &stg, int count, int nspec,
