@@ -119,6 +119,8 @@ struct fpb_handle {
   // FPB_NSLOTS time levels: 1, 2 = the reference's memind slots; 3 = read-ahead slot, allocated on its
   // first upload (numwfmem = 3 of the reference's MPI build with a dedicated reader, src/par_mod.f90:226-227)
   float4 *A[FPB_NSLOTS] = {}, *S[FPB_NSLOTS] = {};
+  MetPair *AP[FPB_NSLOTS] = {}; // x-neighbour pairs of A (interp_wind's 256-bit loads), or null
+  bool use_pairs = false;
   float *G[FPB_NSLOTS] = {}, *T[FPB_NSLOTS] = {};
   float2 *P[FPB_NSLOTS] = {};
   float4 *R[FPB_NSLOTS] = {};  // wet deposition: {lsprec, convprec, tcc, ctwc}
@@ -583,6 +585,30 @@ static int upload_group(fpb_handle *h, cudaStream_t st, float *dst, int ncomp, c
   return upload_group(h, st, dst, ncomp, src, nk, h->d.nxd, h->d.nyd, h->cfg.nxmax, h->cfg.nymax);
 }
 
+__global__ void __launch_bounds__(256) pair_kernel(const float4 *A, MetPair *AP, int nxd, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  MetPair q;
+  q.a = A[i];
+  q.b = ((int)(i % (size_t)nxd) < nxd - 1) ? A[i + 1] : q.a;
+  AP[i] = q;
+}
+// after A of slot s has been written on stream st
+static int build_pairs(fpb_handle *h, int s, cudaStream_t st) {
+  if (!h->use_pairs) return 0;
+  const size_t n3 = (size_t)h->d.nxd * h->d.nyd * h->cfg.nz;
+  if (!h->AP[s] && cudaMalloc((void **)&h->AP[s], n3 * sizeof(MetPair)) != cudaSuccess) {
+    cudaGetLastError();
+    h->use_pairs = false; // (no room: the plain loads)
+    for (auto &q : h->AP) { cudaFree(q); q = nullptr; }
+    return 0;
+  }
+  pair_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(h->A[s], h->AP[s], h->d.nxd, n3);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // device arrays of one time level (slot index s = Fortran slot - 1)
 static int alloc_met_slot(fpb_handle *h, int s) {
   if (h->A[s]) return 0;
@@ -643,6 +669,7 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
       h->xmass[(size_t)k * cfg->numpoint + i] = cfg->xmass[i + (size_t)cfg->numpoint * k];
   h->cfg.height = nullptr; h->cfg.npart = nullptr; h->cfg.xmass = nullptr;
   fill_devcfg(h);
+  if (const char *e = getenv("FPB_MET_PAIRS")) h->use_pairs = atoi(e) != 0; // (experiment knob)
   const DevCfg &d = h->d;
   const fpb_config &c = h->cfg;
 
@@ -715,6 +742,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   if (h->ev_met) cudaEventDestroy(h->ev_met);
   if (h->ev_met0) cudaEventDestroy(h->ev_met0);
   for (int s = 0; s < FPB_NSLOTS; s++) {
+    cudaFree(h->AP[s]);
     cudaFree(h->A[s]); cudaFree(h->G[s]); cudaFree(h->T[s]); cudaFree(h->P[s]); cudaFree(h->S[s]); cudaFree(h->trop[s]); cudaFree(h->vdep[s]);
   }
   for (int l = 0; l < FPB_MAXNESTS; l++)
@@ -871,6 +899,7 @@ extern "C" int fpb_upload_met_begin(fpb_handle *h, int32_t slot, const fpb_met_p
   if (alloc_met_slot(h, s)) return 1;
   CK(cudaEventRecord(h->ev_met0, h->st_met));
   if (enqueue_met(h, s, m)) return 1;
+  if (build_pairs(h, s, h->st_met)) return 1;
   CK(cudaEventRecord(h->ev_met, h->st_met));
   h->met_in_flight = true;
   h->slot_ready[s] = true;
@@ -1153,7 +1182,7 @@ static void nest_views(const fpb_handle *h, DevStepArgs &a) {
     for (int m = 0; m < 2; m++) {
       const int s = h->memind[m] - 1;
       DevMetSlot v{};
-      v.A = h->An[l][s]; v.G = h->Gn[l][s]; v.S = h->Sn[l][s]; v.trop = h->tropn[l][s]; v.vdep = h->vdepn[l][s];
+      v.A = h->An[l][s]; v.AP = nullptr; v.G = h->Gn[l][s]; v.S = h->Sn[l][s]; v.trop = h->tropn[l][s]; v.vdep = h->vdepn[l][s];
       a.metn[l][m] = v;
     }
     a.tropn_lit1[l] = h->tropn[l][0];
@@ -1163,7 +1192,7 @@ static void nest_views(const fpb_handle *h, DevStepArgs &a) {
 static DevMetSlot slot_view(const fpb_handle *h, int fslot) {
   DevMetSlot m;
   const int s = fslot - 1;
-  m.A = h->A[s]; m.G = h->G[s]; m.T = h->T[s]; m.P = h->P[s]; m.S = h->S[s]; m.R = h->R[s]; m.C = h->Cl[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
+  m.A = h->A[s]; m.AP = h->AP[s]; m.G = h->G[s]; m.T = h->T[s]; m.P = h->P[s]; m.S = h->S[s]; m.R = h->R[s]; m.C = h->Cl[s]; m.trop = h->trop[s]; m.vdep = h->vdep[s];
   return m;
 }
 
@@ -2156,6 +2185,7 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   g.R = c.wetdep ? h->R[s] : nullptr; g.Cl = c.wetdep ? h->Cl[s] : nullptr; g.Q = h->outp.Q[s];
   CK(cudaEventRecord(M.evk, st));
   fpb_metproc_launch(g, st, &h->launches);
+  if (build_pairs(h, s, st)) return 1;
   CK(cudaEventRecord(M.ev1, st));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));

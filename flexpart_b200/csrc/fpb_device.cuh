@@ -20,8 +20,13 @@
 
 #define FPB_MAXNZ 160
 
+// two x-neighbours of the wind/density word in one aligned 32-byte sector: AP[i] = {A[i], A[i+1]}
+// (the same values a second time; one 256-bit load per corner pair in interp_wind)
+struct __align__(32) MetPair { float4 a, b; };
+
 struct DevMetSlot {
   const float4 *A;
+  const MetPair *AP; // or null
   const float *G;  // drhodz
   const float *T;  // tt (settling only)
   const float2 *P; // uupol, vvpol (poleward of the switch latitudes only)

@@ -284,6 +284,23 @@ __device__ __forceinline__ void profile_sigma(const DevCfg &c, const DevMetSlot 
   wsig = (xaux < EPS_SIG) ? 0.f : m_sqrt(xaux / 7.f);
 }
 
+#ifndef FPB_PREFETCH_WIND
+#define FPB_PREFETCH_WIND 0 // 0: off (measured: the 16 prefetches cost more LSU issue than the latency they hide, +15 % on the C5 finish kernel); 1: into L1, 2: into L2
+#endif
+__device__ __forceinline__ void prefetch_gl(const void *p) {
+#if FPB_PREFETCH_WIND == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
+__device__ __forceinline__ void ldg_pair(const MetPair *p, float4 &a, float4 &b) { // LDG.E.256
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 // src/interpol_wind.f90:56-214 (SIGMA=true) / src/interpol_wind_short.f90:48-140
 template <bool SIGMA>
 __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *met,
@@ -297,16 +314,63 @@ __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *m
   const float dz2 = (sh[indz] - zt) * dz;
   const int plane = z.plane;
   const bool polar_any = warp_any_polar(z);
-  float uh[2], vh[2], wh[2];
-  float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+  // x-neighbour pairs in one aligned 32-byte word (MetPair, FPB_MET_PAIRS=1): measured SLOWER than the
+  // two 16-byte loads (C5 finish kernel +5 %: twice the L2 footprint for the same sectors), so the pair
+  // arrays are not built by default.  The two-way branch itself stays: with it ptxas issues the four loads
+  // of one (time, level) pair back to back and consumes them before the next four, which is 3-4 % faster
+  // than the fully hoisted schedule it picks for the branch-free loop (gpurun_out/ab_np.txt; compiler
+  // barriers or `#pragma unroll 1` do not reproduce it: ab_b.txt, ab_u.txt).
+#ifndef FPB_MET_PAIRS_CODE
+#define FPB_MET_PAIRS_CODE 1
+#endif
+#ifndef FPB_WIND_BARRIER
+#define FPB_WIND_BARRIER 0
+#endif
+#ifndef FPB_WIND_UNROLL
+#define FPB_WIND_UNROLL 0
+#endif
+#if FPB_MET_PAIRS_CODE
+  const bool pairs = met[0].AP != nullptr && z.o10 == z.o00 + 1 && z.o11 == z.o01 + 1;
+#else
+  constexpr bool pairs = false;
+#endif
+#if FPB_PREFETCH_WIND
+  // The 16 corner words are independent, but at 64 registers the compiler keeps only four float4 loads in
+  // flight: four dependent rounds of DRAM latency.  Prefetches need no destination register, so all 16
+  // go out at once and the loads below find their sectors on the way (or in the cache).
 #pragma unroll
   for (int m = 0; m < 2; m++) {
-    float u1[2], v1[2], w1[2];
 #pragma unroll
+    for (int n = 0; n < 2; n++) {
+      const float4 *A = met[m].A + (indz - 1 + n) * plane;
+      prefetch_gl(A + z.o00); prefetch_gl(A + z.o10); prefetch_gl(A + z.o01); prefetch_gl(A + z.o11);
+    }
+  }
+#endif
+  float uh[2], vh[2], wh[2];
+  float usl = 0.f, vsl = 0.f, wsl = 0.f, usq = 0.f, vsq = 0.f, wsq = 0.f;
+#if FPB_WIND_UNROLL == 1
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+  for (int m = 0; m < 2; m++) {
+    float u1[2], v1[2], w1[2];
+#if FPB_WIND_UNROLL == 2
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
     for (int n = 0; n < 2; n++) {
       const int base = (indz - 1 + n) * plane;
       const float4 *A = met[m].A + base;
-      float4 Aa = __ldg(A + z.o00), Ab = __ldg(A + z.o10), Ac = __ldg(A + z.o01), Ad = __ldg(A + z.o11);
+      float4 Aa, Ab, Ac, Ad;
+      if (pairs) { // x-neighbours in one aligned 32-byte word: half the load instructions and sector requests
+        ldg_pair(met[m].AP + base + z.o00, Aa, Ab);
+        ldg_pair(met[m].AP + base + z.o01, Ac, Ad);
+      } else {
+        Aa = __ldg(A + z.o00); Ab = __ldg(A + z.o10); Ac = __ldg(A + z.o01); Ad = __ldg(A + z.o11);
+      }
       float ua, ub, uc, ud, va, vb, vc, vd;
       if (polar_any && z.ngrid < 0) {
         const float2 *P = met[m].P + base;
@@ -328,7 +392,13 @@ __device__ __forceinline__ void interp_wind(const DevCfg &c, const DevMetSlot *m
         wsl = wsl + Aa.z + Ab.z + Ac.z + Ad.z;
         wsq = wsq + Aa.z * Aa.z + Ab.z * Ab.z + Ac.z * Ac.z + Ad.z * Ad.z;
       }
+#if FPB_WIND_BARRIER == 1
+      asm volatile("" ::: "memory");
+#endif
     }
+#if FPB_WIND_BARRIER == 2
+    asm volatile("" ::: "memory");
+#endif
     uh[m] = dz2 * u1[0] + dz1 * u1[1];
     vh[m] = dz2 * v1[0] + dz1 * v1[1];
     wh[m] = dz2 * w1[0] + dz1 * w1[1];
