@@ -33,5 +33,9 @@ ncu --set full --clock-control none --import-source on -k 'regex:fpb_(pbl|finish
     --launch-skip 9 --launch-count 3 -f -o $O/full_${R}_c5 $B5 > $O/ncu_f5.log 2>&1
 ncu -i $O/full_${R}_c5.ncu-rep --page raw --csv > $O/ncu_full_${R}_c5_raw.csv 2>> $O/ncu_f5.log
 ncu -i $O/full_${R}_c5.ncu-rep --page details > $O/ncu_full_${R}_c5_details.txt 2>> $O/ncu_f5.log
+# ---- calcpar + verttransform_ecmwf on the device: launch list of the met_* kernels
+python tools/metproc_profile.py > $O/metproc_${R}.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:(met_|pack_group|pair_)' \
+    -c 60 --csv --log-file $O/launches_${R}_metproc.csv python tools/metproc_profile.py > $O/ncu_lm.log 2>&1
 rm -f $O/full_${R}*.ncu-rep   # (the exports above are what is tracked; the reports exceed the 64 MiB merge limit)
 tail -2 $O/ncu_f.log $O/ncu_f3.log $O/ncu_f5.log
