@@ -327,6 +327,8 @@ struct fpb_handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // step begin/end, conccalc begin/end
   bool timed_step = false, timed_conc = false;
   bool pending_init = true;
+  bool have_init_until = false; // fpb_push_particles: latest itramem pushed (times ldirect)
+  long long init_until = 0;
   ScatterWork scatter;
   void *sort_rec = nullptr; // packed records of the cell sort (sortk_permute_packed)
   size_t sort_rec_cap = 0;
@@ -1057,6 +1059,15 @@ extern "C" int fpb_push_particles(fpb_handle *h, int32_t first, int32_t count, c
   CK(cudaStreamSynchronize(h->stream));
   if (first + count > h->numpart) h->numpart = first + count;
   h->pending_init = true;
+  // rows staged ahead of their release (itramem later than the next step, in the run's direction) get
+  // their initialize() at that later step: remember until when the init kernel has to be launched
+  if (p->itramem) {
+    const int ld = h->cfg.ldirect;
+    for (int32_t i = first; i < first + count; i++) {
+      const long long t = (long long)ld * p->itramem[i];
+      if (!h->have_init_until || t > h->init_until) { h->init_until = t; h->have_init_until = true; }
+    }
+  }
   h->active_rows = -1;
   return 0;
 }
@@ -1304,7 +1315,7 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
   if (det_dry && dep_begin(h, h->depstore, h->numpart, 0, h->stream, a.dep)) return 1;
   if (stats) CK(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), h->stream));
   // initialize() can only be due for rows pushed since the last step, or at itime 0
-  if (h->pending_init || itime == 0) {
+  if (h->pending_init || itime == 0 || (h->have_init_until && (long long)h->cfg.ldirect * itime <= h->init_until)) {
     if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_init_strict(a, h->stream);
     else fpbk_init_fast(a, h->stream);
     h->launches++;
@@ -2532,8 +2543,24 @@ static int ensure_lanes(fpb_handle *h) {
 // PCIe copies of one chunk overlap the kernels of the others.  Particles are
 // independent within a step, so chunking changes nothing
 // but the order of the float atomics into the grids.
+static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart, const fpb_particle_ptrs *p,
+                          float conc_weight, fpb_step_stats *stats);
 extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart,
                              const fpb_particle_ptrs *p, float conc_weight, fpb_step_stats *stats) {
+  const int rc = step_host_impl(h, itime, ldeltat, numpart, p, conc_weight, stats);
+  if (rc && h && h->lanes_ready) {
+    // an error in the middle of the chunk loop leaves copies into the caller's arrays in flight on the
+    // lanes: let them land before the caller may touch (or free) its buffers
+    cudaSetDevice(h->device);
+    for (auto &L : h->lanes) if (L.st) cudaStreamSynchronize(L.st);
+    if (h->st_in) cudaStreamSynchronize(h->st_in);
+    cudaStreamSynchronize(h->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart, const fpb_particle_ptrs *p,
+                          float conc_weight, fpb_step_stats *stats) {
   if (!h || !p) return fail("fpb_step_host: null argument");
   if (!h->have_bracket) return fail("fpb_step_host: fpb_set_met_bracket has not been called");
   if (numpart < 0 || numpart > h->cfg.maxpart) return fail("fpb_step_host: numpart %d outside capacity %d", numpart, h->cfg.maxpart);

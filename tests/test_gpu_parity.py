@@ -817,6 +817,35 @@ def test_deterministic_deposition_through_step_host(monkeypatch):
         assert np.array_equal(gg[name], go[name]), (name, rel_l2(gg[name], go[name]))
 
 
+def test_rows_staged_ahead_of_their_release_are_initialized():
+    """fpb_push_particles may stage rows whose release time lies ahead (itra1 = itramem = a later
+    itime): initialize() is due at THAT step, not at the push (a round-1 advisor finding: the init
+    kernel was only launched right after a push or at itime 0)."""
+    cb = cases.config_small(nrel=2, npart_each=1500, math_mode=fb.MATH_STRICT)
+    c = cb.cfg
+    n = 3000
+    p = cases.seeded_particles(cb, n, zmax=2500.0)
+    p.itra1[1000:n] = 1800; p.itramem[1000:n] = 1800      # two thirds start two steps later
+    m0, m1 = cases.met_pair(cb)
+    eng, ora = fb.Engine(cb), Oracle(cb)
+    for e in (eng, ora):
+        e.fill_rannumb()
+        e.upload_met(1, m0); e.upload_met(2, m1)
+        e.set_met_bracket((1, 2), (0, 10800))
+        e.push_particles(p)
+    n_init = []
+    for k in range(4):
+        sg, so = eng.step(k * 900, 450), ora.step(k * 900, 450)
+        assert sg == so, (k, sg, so)
+        n_init.append(so["n_init"])
+    assert n_init == [1000, 0, 2000, 0]
+    pg, po = fb.Particles(c.maxpart, 1), fb.Particles(c.maxpart, 1)
+    pg.numpart = po.numpart = n
+    eng.pull_particles(pg); ora.pull_particles(po)
+    for f in INT_FIELDS + FLOAT_FIELDS + ("xtra1", "ytra1"):
+        assert np.array_equal(getattr(pg, f)[:n], getattr(po, f)[:n]), f
+
+
 def test_particle_count_output():
     """par_mod's lparticlecountoutput: conccalc adds 1 per particle instead of its mass in the
     no-kernel branch (src/conccalc.f90:171-183) -- young particles (itage < 10800) take it, old ones
