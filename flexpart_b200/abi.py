@@ -112,12 +112,12 @@ class FpbConvPtrs(C.Structure):
 
 class FpbRawmetPtrs(C.Structure):
     _fields_ = [(n, _pf) for n in ("uuh", "vvh", "tth", "qvh", "pvh", "wwh", "ps", "tt2", "td2", "sshf", "surfstr",
-                                   "lsprec", "convprec", "tcc", "excessoro")]
+                                   "lsprec", "convprec", "tcc", "excessoro", "clwch", "ciwch")]
 
 
 class FpbMetOutPtrs(C.Structure):
     _fields_ = [(n, _pf) for n in ("uu", "vv", "ww", "rho", "drhodz", "tt", "qv", "pv", "uupol", "vvpol", "hmix",
-                                   "ustar", "wstar", "oli", "tropopause")] + [("clouds", C.POINTER(C.c_int8))]
+                                   "ustar", "wstar", "oli", "tropopause")] + [("clouds", C.POINTER(C.c_int8)), ("ctwc", _pf)]
 
 
 class FpbhRun(C.Structure):

@@ -301,6 +301,7 @@ struct fpb_handle {
     float *d_cosf = nullptr; // [ny]
     float2 *UV = nullptr;
     float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
+    float *CLW = nullptr, *CIW = nullptr, *clw = nullptr; // readclouds
     float4 *SF2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
   } metproc;
@@ -792,7 +793,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   dep_free(h->depstore);
   {
     auto &M = h->metproc;
-    cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro);
+    cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro); cudaFree(M.CLW); cudaFree(M.CIW); cudaFree(M.clw);
     cudaFree(M.uvzlev); cudaFree(M.SF2);
     if (M.ev0) cudaEventDestroy(M.ev0);
     if (M.ev1) cudaEventDestroy(M.ev1);
@@ -2149,8 +2150,8 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
     return fail("fpb_calcpar_verttransform: a mandatory field pointer is null");
   if (c.wetdep && (!m->lsprec || !m->convprec || !m->tcc))
     return fail("fpb_calcpar_verttransform: lsprec/convprec/tcc required when wetdep");
-  if (c.wetdep && c.readclouds)
-    return fail("fpb_calcpar_verttransform: cloud water read from the input (readclouds) is not built");
+  const bool rdcl = c.wetdep && c.readclouds;
+  if (rdcl && !m->clwch) return fail("fpb_calcpar_verttransform: clwch required when readclouds");
   if (c.numbnests > 0) return fail("fpb_calcpar_verttransform: nested input grids (calcpar_nests / verttransform_nests) are not built");
   if (lsubgrid == 1 && !m->excessoro) return fail("fpb_calcpar_verttransform: excessoro required when lsubgrid = 1");
   CK(cudaSetDevice(h->device));
@@ -2163,6 +2164,8 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   if (!M.PV) DA(M.PV, n3);
   if (!m->pvh && !M.theta) DA(M.theta, n3); // calcpv on the device
   if (lsubgrid == 1 && !M.excessoro) DA(M.excessoro, n2);
+  if (rdcl && !M.CLW) { DA(M.CLW, n3); DA(M.clw, n3); }
+  if (rdcl && m->ciwch && !M.CIW) DA(M.CIW, n3);
   if (!V.CT[0][s]) { DA(V.CT[0][s], n3); DA(V.CS[0][s], n2); }
   if (!h->outp.Q[s]) DA(h->outp.Q[s], n3);
   cudaStream_t st = h->st_met;
@@ -2178,6 +2181,9 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
     if (upload_group(h, st, (float *)V.CS[0][s], 4, s1, 1)) return 1;
     if (upload_group(h, st, (float *)M.SF2, 4, s2, 1)) return 1;
     if (lsubgrid == 1 && upload_group(h, st, M.excessoro, 1, ex, 1)) return 1;
+    const float *cw[1] = {m->clwch}, *ci[1] = {m->ciwch};
+    if (rdcl && upload_group(h, st, M.CLW, 1, cw, nuvz)) return 1;
+    if (rdcl && m->ciwch && upload_group(h, st, M.CIW, 1, ci, nuvz)) return 1;
   }
   fpbmet::MetGrid g{};
   g.nx = c.nx; g.ny = c.ny; g.nz = c.nz; g.nuvz = nuvz; g.nwz = M.nwz;
@@ -2186,7 +2192,8 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   g.nglobal = c.nglobal; g.sglobal = c.sglobal; g.xglobal = c.xglobal;
   g.switchnorthg = c.switchnorthg; g.switchsouthg = c.switchsouthg;
   for (int k = 0; k < 9; k++) { g.northpolemap[k] = c.northpolemap[k]; g.southpolemap[k] = c.southpolemap[k]; }
-  g.lsubgrid = lsubgrid; g.readclouds = 0;
+  g.lsubgrid = lsubgrid; g.readclouds = rdcl ? 1 : 0;
+  g.CLW = rdcl ? M.CLW : nullptr; g.CIW = (rdcl && m->ciwch) ? M.CIW : nullptr; g.clw = rdcl ? M.clw : nullptr;
   const size_t n1 = (size_t)nuvz + 1;
   g.akz = M.d_ab; g.bkz = M.d_ab + n1; g.akm = M.d_ab + 2 * n1; g.bkm = M.d_ab + 3 * n1;
   g.height = h->d_height; g.cosf = M.d_cosf;
@@ -2241,6 +2248,10 @@ extern "C" int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs
   if (fetch(h->A[s], 4, nz, a4) || fetch(h->G[s], 1, nz, g1) || fetch(h->T[s], 1, nz, t1) || fetch(h->P[s], 2, nz, p2) ||
       fetch(h->outp.Q[s], 2, nz, q2) || fetch(h->S[s], 4, 1, s4) || fetch(h->trop[s], 1, 1, tr))
     return 1;
+  if (o->ctwc && h->R[s]) {
+    float *r4[4] = {nullptr, nullptr, nullptr, o->ctwc};
+    if (fetch(h->R[s], 4, 1, r4)) return 1;
+  }
   if (o->clouds && h->Cl[s]) {
     std::vector<int8_t> cb(n3);
     CK(cudaMemcpy(cb.data(), h->Cl[s], n3, cudaMemcpyDeviceToHost));

@@ -1,11 +1,12 @@
 // fpb_metproc.cuh -- what getfields does to a freshly read wind field before the particle loop may
 // use it (src/getfields.f90:126-129), one grid column per thread:
 //   met_levels_column   src/verttransform_ecmwf.f90:198-231   heights of the eta levels (uvzlev)
-//   met_interp_column   src/verttransform_ecmwf.f90:233-472,:530-542,:683-724
+//   met_interp_column   src/verttransform_ecmwf.f90:233-472,:530-542,:610-724
 //                       u, v, T, q, PV, density on the terrain-following height levels, the vertical
 //                       wind (eta-dot -> m/s, plus the slope term of the eta surfaces), the density
 //                       gradient, polar-stereographic winds poleward of the switch latitudes, and
-//                       the parameterised cloud / precipitation classes
+//                       the cloud / precipitation classes (parameterised from the humidity, or from the
+//                       cloud water of the input: readclouds)
 //   met_pole_level      src/verttransform_ecmwf.f90:474-527,:544-607   the pole rows
 //   met_calcpar_column  src/calcpar.f90:78-258 with scalev.f90, obukhov.f90, richardson.f90:
 //                       friction velocity, Obukhov length, mixing height, convective velocity scale,
@@ -62,6 +63,8 @@ struct MetGrid {
   const float4 *SF1;         // {ps, tt2, td2, sshf}
   const float4 *SF2;         // {surfstr, lsprec, convprec, tcc}
   const float *excessoro;    // lsubgrid = 1 only
+  const float *CLW, *CIW;    // readclouds: clwch (and ciwch unless the input holds their sum), nuvz levels
+  float *clw;                // readclouds work: cloud water of the column's layers, nz levels
   float *uvzlev;             // work: nuvz levels
   // the met slot the particle loop reads
   float4 *A;                 // {uu, vv, ww, rho}
@@ -249,6 +252,67 @@ FPB_HD inline void met_interp_column(const MetGrid &g, int ix, int jy) {
     float4 r = g.R[m_o2(g, ix, jy)];
     r.x = s2.y; r.y = s2.z; r.z = s2.w;
     g.R[m_o2(g, ix, jy)] = r;
+  }
+  if (g.Cl && g.readclouds) {
+    // cloud water from the input (:610-681).  `cloudh_min` is a scalar the reference carries from column to
+    // column; a column reads it only after setting it when it holds any cloud water -- here it starts
+    // at 0 in every column (a precipitating column WITHOUT cloud water gets no below-cloud class).
+    const float lsp = s2.y, convp = s2.z;
+    float ctwc = 0.f, cloudh_min = 0.f;
+    // clwc on the height levels: interpolated like qv (:270-272,:283-286,:297-301,:339-344), ice added (:620-622)
+    {
+      int idxc = 2;
+      for (int iz = 1; iz <= nz; iz++) {
+        const float hz = g.height[iz - 1];
+        float cw;
+        auto at = [&](int kz) {
+          const size_t o = m_o3(g, ix, jy, kz);
+          return g.CLW[o];
+        };
+        auto ice = [&](int kz) { return g.CIW ? g.CIW[m_o3(g, ix, jy, kz)] : 0.f; };
+        float ci;
+        if (iz == 1) { cw = at(1); ci = ice(1); }
+        else if (iz == nz || hz > uvztop) { cw = at(nuvz); ci = ice(nuvz); }
+        else {
+          for (int kz = idxc; kz <= nuvz; kz++)
+            if (idxc <= kz && hz > c.uvz(kz - 1) && hz <= c.uvz(kz)) { idxc = kz; break; }
+          const int kz = idxc;
+          const float dz1 = hz - c.uvz(kz - 1), dz2 = c.uvz(kz) - hz, dz = dz1 + dz2;
+          cw = (at(kz - 1) * dz2 + at(kz) * dz1) / dz;
+          ci = g.CIW ? (ice(kz - 1) * dz2 + ice(kz) * dz1) / dz : 0.f;
+        }
+        if (g.CIW) cw = cw + ci;
+        g.clw[m_o3(g, ix, jy, iz)] = cw; // (clwc for now)
+      }
+    }
+    for (int kz = 1; kz <= nz - 1; kz++) {
+      const size_t o = m_o3(g, ix, jy, kz);
+      const float clwc = g.clw[o];
+      float w = 0.f;
+      if (clwc > 0.f) {
+        w = (clwc * g.A[o].w) * (g.height[kz] - g.height[kz - 1]);
+        ctwc = ctwc + w;
+        cloudh_min = c_min(g.height[kz], g.height[kz - 1]);
+      }
+      g.clw[o] = w;
+    }
+    g.clw[m_o3(g, ix, jy, nz)] = 0.f;
+    for (int kz = 1; kz <= nz; kz++) g.Cl[m_o3(g, ix, jy, kz)] = 0;
+    if ((lsp > 0.01f) || (convp > 0.01f)) {
+      for (int kz = nz; kz >= 2; kz--) {
+        const size_t o = m_o3(g, ix, jy, kz);
+        int cl = 0;
+        if (g.clw[o] > 0.f) cl = (lsp >= convp) ? 3 : 2;
+        else if (cloudh_min >= g.height[kz - 1]) cl = (lsp >= convp) ? 5 : 4;
+        if (g.height[kz - 1] >= 19000.f) cl = 0;
+        g.Cl[o] = (int8_t)cl;
+      }
+    }
+    if (g.R) {
+      float4 r = g.R[m_o2(g, ix, jy)];
+      r.w = ctwc;
+      g.R[m_o2(g, ix, jy)] = r;
+    }
   }
   if (g.Cl && !g.readclouds) {
     const float lsp = s2.y, convp = s2.z;

@@ -281,7 +281,9 @@ class Engine:
                 out[name] = np.zeros((c.nxmax, c.nymax, c.nzmax), np.int8, order="F")
                 o.clouds = out[name].ctypes.data_as(C.POINTER(C.c_int8))
                 continue
-            shape = (c.nxmax, c.nymax) if name in ("hmix", "ustar", "wstar", "oli", "tropopause") else (c.nxmax, c.nymax, c.nzmax)
+            if name == "ctwc" and not c.wetdep:
+                continue
+            shape = (c.nxmax, c.nymax) if name in ("hmix", "ustar", "wstar", "oli", "tropopause", "ctwc") else (c.nxmax, c.nymax, c.nzmax)
             out[name] = np.zeros(shape, np.float32, order="F")
             setattr(o, name, _fp(out[name]))
         self._check(self.L.fpb_fetch_met(self.h, slot, C.byref(o)))

@@ -413,8 +413,10 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int3
  * scale and thermal tropopause (src/calcpar.f90:78-258, scalev.f90, obukhov.f90, richardson.f90),
  * potential vorticity on the eta levels (src/calcpv.f90),
  * u, v, T, q, PV, density and density gradient on the height levels, the vertical wind in m/s with
- * the slope term of the eta surfaces, polar-stereographic winds and pole rows, the parameterised
- * cloud / precipitation classes (src/verttransform_ecmwf.f90:198-607,683-724) -- so the transformed
+ * the slope term of the eta surfaces, polar-stereographic winds and pole rows, the cloud /
+ * precipitation classes -- parameterised from the humidity or, with readclouds, from the input's cloud
+ * water, with the column total ctwc (src/verttransform_ecmwf.f90:198-724; readclouds: the scalar
+ * cloudh_min the reference carries from column to column starts at 0 in every column here) -- so the transformed
  * fields never exist on the host.  The same arithmetic in the same order as the reference (no
  * contraction, transcendentals evaluated in double): bit-identical fields.  The slot is then what
  * fpb_upload_met would have produced; when fpb_set_convection has been called with the same nuvz
@@ -422,7 +424,7 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int3
  * Needs fpb_set_vertical first.  ECMWF layout only: nz = nuvz = nwz.  `height` of fpb_config must be
  * what verttransform_ecmwf's first call derives (fpbh_verttransform_heights in fpb_host.h).
  * Not built: dry-deposition velocities (getvdep: land-use inventory; upload vdep with
- * fpb_upload_vdep), cloud water read from the input (readclouds), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
+ * fpb_upload_vdep), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
  * fpb_fetch_met copies a slot back in the reference's padded layout (any pointer may be NULL): for
  * the parts of a host model that still read the transformed fields, and for the tests. */
 typedef struct fpb_rawmet_ptrs {
@@ -431,11 +433,14 @@ typedef struct fpb_rawmet_ptrs {
   const float *wwh;                   /* (nxmax, nymax, nwzmax) */
   const float *ps, *tt2, *td2, *sshf, *surfstr, *lsprec, *convprec, *tcc; /* (nxmax, nymax) */
   const float *excessoro;             /* (nxmax, nymax), lsubgrid = 1 only */
+  const float *clwch, *ciwch;         /* (nxmax, nymax, nuvzmax), readclouds only: cloud liquid (+ ice: ciwch NULL when
+                                       * the input holds their sum, `sumclouds`) water content */
 } fpb_rawmet_ptrs;
 typedef struct fpb_met_out_ptrs {
   float *uu, *vv, *ww, *rho, *drhodz, *tt, *qv, *pv, *uupol, *vvpol; /* (nxmax, nymax, nzmax) */
   float *hmix, *ustar, *wstar, *oli, *tropopause;                    /* (nxmax, nymax) */
   int8_t *clouds;                                                     /* (nxmax, nymax, nzmax) */
+  float *ctwc;                                                        /* (nxmax, nymax), wet deposition only */
 } fpb_met_out_ptrs;
 int fpb_set_vertical(fpb_handle *h, int32_t nuvz, int32_t nwz, int32_t nuvzmax, int32_t nwzmax, const float *akm,
                      const float *bkm, const float *akz, const float *bkz);

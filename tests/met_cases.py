@@ -53,9 +53,21 @@ def raw_fields(cb, akz, bkz, nuvz, seed=1, tshift=0.0, mountain=True):
     lsprec = np.clip(2.5 * np.sin(np.deg2rad(3 * lon + 20.0)) * np.sin(np.deg2rad(2 * lat + 10.0)) - 0.8, 0.0, None)
     convprec = np.clip(3.0 * np.cos(np.deg2rad(lat)) ** 6 * np.sin(np.deg2rad(5 * lon)) - 0.6, 0.0, None)
     tcc = np.clip(0.5 + 0.5 * np.sin(np.deg2rad(2 * lon)) * np.cos(np.deg2rad(3 * lat)), 0.0, 1.0)
+    # cloud liquid / ice water (readclouds): decks between 800 and 400 hPa over two thirds of the globe, ice above
+    # 500 hPa; every precipitating column holds cloud water (the reference's below-cloud test reads a scalar
+    # that only a column with cloud water sets, src/verttransform_ecmwf.f90:634-665)
+    clwch = np.zeros((nxm, nym, nzm), np.float32, order="F")
+    ciwch = np.zeros((nxm, nym, nzm), np.float32, order="F")
+    cloudy = (np.sin(np.deg2rad(2.5 * lon + 20.0)) * np.cos(np.deg2rad(2.0 * lat)) > -0.4) | (lsprec + convprec > 0.0)
+    for k in range(2, nuvz + 1):
+        eta = (akz[k] + bkz[k] * 101325.0) / 101325.0
+        if 0.4 < eta < 0.8:
+            clwch[:, :, k - 1] = np.where(cloudy, 2.0e-4 * np.sin(np.pi * (eta - 0.4) / 0.4) * (1.0 + 0.5 * np.sin(np.deg2rad(4 * lon))), 0.0)
+        if 0.25 < eta < 0.5:
+            ciwch[:, :, k - 1] = np.where(cloudy, 5.0e-5 * np.sin(np.pi * (eta - 0.25) / 0.25), 0.0)
     del rs
     F = lambda a: np.asfortranarray(np.broadcast_to(a, (nxm, nym)).astype(np.float32))
-    return dict(uuh=uuh, vvh=vvh, wwh=wwh, tth=tth, qvh=qvh, ps=ps, tt2=tt2, td2=td2, sshf=F(sshf),
+    return dict(clwch=clwch, ciwch=ciwch, uuh=uuh, vvh=vvh, wwh=wwh, tth=tth, qvh=qvh, ps=ps, tt2=tt2, td2=td2, sshf=F(sshf),
                 surfstr=F(surfstr), lsprec=F(lsprec), convprec=F(convprec), tcc=F(tcc))
 
 

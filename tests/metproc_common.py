@@ -7,11 +7,11 @@ import numpy as np
 
 import ref_api
 
-def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None, timing=None):
+def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None, timing=None, readclouds=0, sumclouds=0):
     """calcpar + verttransform_ecmwf of the reference on time slot 1; returns (ref, height)"""
     c = cb.cfg
     ref = ref_api.Ref(cb, maxrand=1000)
-    for k, v in dict(nuvz=nuvz, nwz=nuvz, nz=nuvz, nmixz=0, lsubgrid=lsubgrid, readclouds=0, sumclouds=0).items():
+    for k, v in dict(nuvz=nuvz, nwz=nuvz, nz=nuvz, nmixz=0, lsubgrid=lsubgrid, readclouds=readclouds, sumclouds=sumclouds).items():
         ref.set(k, v)
     for nm, a in (("akz", akz), ("bkz", bkz), ("akm", akm), ("bkm", bkm), ("aknew", akz), ("bknew", bkz)):
         ref.arr(nm)[:nuvz] = a[1:nuvz + 1]
@@ -19,6 +19,10 @@ def reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, lsubgrid=0, excessoro=None,
         ref.arr(nm)[:, :, 0, 0] = raw[nm]
     ref.arr("tth")[:, :, :, 0] = raw["tth"]
     ref.arr("qvh")[:, :, :, 0] = raw["qvh"]
+    if readclouds:
+        ref.arr("clwch")[:, :, :, 0] = raw["clwch"] + (raw["ciwch"] if sumclouds else 0.0)
+        if not sumclouds:
+            ref.arr("ciwch")[:, :, :, 0] = raw["ciwch"]
     if excessoro is not None:
         ref.arr("excessoro")[:, :] = excessoro
     n, fmt = C.c_int(1), C.c_int(2)   # GRIBFILE_CENTRE_ECMWF
@@ -45,6 +49,11 @@ def compare_fields(cb, ref, got, nuvz, exact=True, tol=0.0):
     bad = {}
     for nm, a in got.items():
         if nm in ("uupol", "vvpol"):
+            continue
+        if nm == "ctwc":
+            b = ref.arr("ctwc")[:nx, :ny, 0].T
+            if not np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32)):
+                bad[nm] = (int((a != b).sum()), float(np.abs(a - b).max()))
             continue
         b = r3(nm) if a.ndim == 3 else r2(nm)
         if nm == "clouds":

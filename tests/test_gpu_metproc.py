@@ -52,6 +52,32 @@ def test_device_slot_is_bit_identical_to_the_reference_routines(nx, ny, nuvz, se
     eng.close()
 
 
+@pytest.mark.parametrize("sumclouds", [0, 1])
+def test_readclouds_slot_is_bit_identical_to_the_reference_routines(sumclouds):
+    """cloud water read from the input (src/verttransform_ecmwf.f90:610-681): classes and column total ctwc"""
+    nuvz = 40
+    kw = dict(nrel=1, npart_each=8, nz=nuvz, wetdepspec=(1,), weta_gas=(2.0e-5,), wetb_gas=(0.62,), readclouds=1)
+    cb0 = cases.config_small(**kw, height=fb.synth_heights(nuvz))
+    akm, bkm, akz, bkz, _ = conv_cases.hybrid_levels(nuvz)
+    raw = met_cases.raw_fields(cb0, akz, bkz, nuvz, seed=3)
+    ref, height, pvh = reference_run(cb0, raw, akm, bkm, akz, bkz, nuvz, readclouds=1, sumclouds=sumclouds)
+    cb = cases.config_small(**kw, height=height)
+    c = cb.cfg
+    eng = fb.Engine(cb)
+    eng.set_vertical(nuvz, akm[1:], bkm[1:], akz[1:], bkz[1:])
+    dev_raw = dict(raw)
+    if sumclouds:
+        dev_raw["clwch"] = raw["clwch"] + raw["ciwch"]
+        dev_raw["ciwch"] = None
+    eng.calcpar_verttransform(1, dev_raw)
+    got, f = _device_fields(cb, eng, nuvz)
+    got["ctwc"] = np.ascontiguousarray(f["ctwc"][:c.nx, :c.ny].T)
+    bad = compare_fields(cb, ref, got, nuvz)
+    assert not bad, bad
+    assert set(np.unique(got["clouds"])) == {0, 2, 3, 4, 5} and (got["ctwc"] > 0).mean() > 0.5
+    eng.close()
+
+
 def test_particles_step_alike_on_device_built_and_uploaded_slots():
     """The slot fpb_calcpar_verttransform builds is what fpb_upload_met makes of the same fields: the
     particle loop, wet deposition and conccalc give bit-identical results on both, and the oracle on

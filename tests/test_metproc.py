@@ -33,7 +33,7 @@ class MetGrid(C.Structure):
                 ("northpolemap", C.c_float * 9), ("southpolemap", C.c_float * 9),
                 ("lsubgrid", C.c_int), ("readclouds", C.c_int)] + \
                [(n, C.c_void_p) for n in ("akz", "bkz", "akm", "bkm", "height", "cosf", "UV", "W", "TQ", "PV", "theta", "SF1",
-                                          "SF2", "excessoro", "uvzlev", "A", "G", "T", "P", "S", "trop", "R", "Cl", "Q")]
+                                          "SF2", "excessoro", "CLW", "CIW", "clw", "uvzlev", "A", "G", "T", "P", "S", "trop", "R", "Cl", "Q")]
 
 
 def _host_lib():
@@ -74,7 +74,7 @@ def device_layout_inputs(cb, raw, pvh, akm, bkm, akz, bkz, nuvz, height):
     return k
 
 
-def make_grid(cb, k, nuvz, lsubgrid=0):
+def make_grid(cb, k, nuvz, lsubgrid=0, readclouds=0):
     c = cb.cfg
     nx, ny = c.nx, c.ny
     g = MetGrid()
@@ -83,7 +83,7 @@ def make_grid(cb, k, nuvz, lsubgrid=0):
               "switchsouthg"):
         setattr(g, f, getattr(c, f))
     g.northpolemap[:] = list(c.northpolemap); g.southpolemap[:] = list(c.southpolemap)
-    g.lsubgrid, g.readclouds = lsubgrid, 0
+    g.lsubgrid, g.readclouds = lsubgrid, readclouds
     out = dict(uvzlev=np.zeros((nuvz, ny, nx), np.float32), A=np.zeros((nuvz, ny, nx, 4), np.float32),
                G=np.zeros((nuvz, ny, nx), np.float32), T=np.zeros((nuvz, ny, nx), np.float32),
                P=np.zeros((nuvz, ny, nx, 2), np.float32), S=np.zeros((ny, nx, 4), np.float32),
@@ -100,6 +100,31 @@ def compare(cb, ref, out, nuvz):
            "hmix": out["S"][..., 0], "ustar": out["S"][..., 1], "wstar": out["S"][..., 2], "oli": out["S"][..., 3],
            "tropopause": out["trop"], "clouds": out["Cl"], "uupol": out["P"][..., 0], "vvpol": out["P"][..., 1]}
     return compare_fields(cb, ref, got, nuvz)
+
+
+@pytest.mark.parametrize("sumclouds", [0, 1])
+def test_readclouds_branch_matches_reference(sumclouds):
+    """cloud water from the input (src/verttransform_ecmwf.f90:610-681): clwc (+ ciwc) on the height levels,
+    the column total ctwc and the in-cloud / below-cloud classes"""
+    nuvz = 40
+    cb = cases.config_small(nrel=1, npart_each=8, nz=nuvz, wetdepspec=(1,), weta_gas=(2.0e-5,), wetb_gas=(0.62,),
+                            readclouds=1)
+    c = cb.cfg
+    akm, bkm, akz, bkz, _ = conv_cases.hybrid_levels(nuvz)
+    raw = met_cases.raw_fields(cb, akz, bkz, nuvz, seed=3)
+    ref, height, pvh = reference_run(cb, raw, akm, bkm, akz, bkz, nuvz, readclouds=1, sumclouds=sumclouds)
+    k = device_layout_inputs(cb, raw, pvh, akm, bkm, akz, bkz, nuvz, height)
+    lev = lambda a: np.ascontiguousarray(np.transpose(a[:c.nx, :c.ny, :nuvz], (2, 1, 0)))
+    k["CLW"] = lev(raw["clwch"] + (raw["ciwch"] if sumclouds else 0.0))
+    if not sumclouds:
+        k["CIW"] = lev(raw["ciwch"])
+    k["clw"] = np.zeros_like(k["W"])
+    g, out = make_grid(cb, k, nuvz, readclouds=1)
+    _host_lib().met_check_run(C.byref(g))
+    got = {"clouds": out["Cl"], "ctwc": out["R"][..., 3], "rho": out["A"][..., 3], "qv": out["Q"][..., 1]}
+    bad = compare_fields(cb, ref, got, nuvz)
+    assert not bad, bad
+    assert set(np.unique(out["Cl"])) == {0, 2, 3, 4, 5} and (out["R"][..., 3] > 0).mean() > 0.5
 
 
 @pytest.mark.parametrize("seed", [1, 2])
