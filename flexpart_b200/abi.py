@@ -57,7 +57,7 @@ class FpbConfig(C.Structure):
         ("height", _pf),
         ("maxpart", _i), ("device", _i), ("rng_mode", _i), ("math_mode", _i), ("scatter_mode", _i),
         ("seed", C.c_uint64), ("part_id_stride", _i), ("part_id_offset", _i),
-        ("sort_interval", _i), ("reserved", _i * 7),
+        ("sort_interval", _i), ("iflux", _i), ("ipout", _i), ("reserved", _i * 5),
     ]
 
 
@@ -99,6 +99,11 @@ class FpbPartoutPtrs(C.Structure):
     _fields_ = [("npoint", _pi), ("xlon", _pf), ("ylat", _pf), ("ztra1", _pf), ("itramem", _pi), ("topo", _pf),
                 ("pvi", _pf), ("qvi", _pf), ("rhoi", _pf), ("hmixi", _pf), ("tri", _pf), ("tti", _pf),
                 ("xmass1", _pf), ("ld", _i)]
+
+
+class FpbPartavPtrs(C.Structure):
+    _fields_ = [("npart_av", _pi)] + [(n, _pf) for n in ("cartx", "carty", "cartz", "z", "topo", "pv", "qv", "tt", "uu", "vv",
+                                                          "rho", "tro", "hmix", "energy")]
 
 
 class FpbDomainfillInfo(C.Structure):
@@ -208,6 +213,8 @@ def load_engine_lib():
     L.fpb_set_orography.argtypes = [H, _pf]
     L.fpb_upload_pvqv.argtypes = [H, _i, _pf, _pf]
     L.fpb_partoutput.argtypes = [H, _i, _pi, C.POINTER(FpbPartoutPtrs)]
+    L.fpb_fetch_fluxes.argtypes = [H, _pf, _i]
+    L.fpb_fetch_partpos_average.argtypes = [H, _i, C.POINTER(FpbPartavPtrs), _i]
     L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]
     L.fpb_split_particles.argtypes = [H, _i, _pi]

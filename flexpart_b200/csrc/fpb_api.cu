@@ -176,6 +176,13 @@ struct fpb_handle {
     float *po_f[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float *po_mass = nullptr;
   } outp;
+  // the optional hooks of the particle loop: calcfluxes / partpos_average (fpb_output.cuh)
+  struct Hooks {
+    uint8_t *adv = nullptr;
+    float *old = nullptr, *flux = nullptr, *av = nullptr;
+    int32_t *npart_av = nullptr;
+    size_t nflux = 0;
+  } hooks;
   // device-side releaseparticles
   struct Releases {
     int numpoint = 0, itsplit = 0;
@@ -741,6 +748,13 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   DA(h->d_work, 1);
   DA(h->sc.flags, mp); DA(h->sc.s0, mp); DA(h->sc.s1, mp); DA(h->sc.s2, mp);
   if (c.drydep) DA(h->sc.prob, mp * c.nspec);
+  if (c.iflux == 1 || c.ipout == 3) DA(h->hooks.adv, mp);
+  if (c.iflux == 1) {
+    h->hooks.nflux = (size_t)6 * c.numxgrid * c.numygrid * c.numzgrid * c.nspec * c.maxpointspec_act * c.nageclass;
+    DA(h->hooks.flux, h->hooks.nflux);
+    DA(h->hooks.old, mp * (3 + (size_t)c.nspec));
+  }
+  if (c.ipout == 3) { DA(h->hooks.npart_av, mp); DA(h->hooks.av, mp * 14); }
   h->launches += 3;
   // itra1(:) = -999999999, src/FLEXPART.f90:315-317
   fill_i32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, h->stream>>>(h->p.itra1, FPB_ITRA_DEAD, c.maxpart);
@@ -828,6 +842,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   scatter_free(h->scatter);
   cudaFree(h->sort_rec);
   dep_free(h->depstore);
+  cudaFree(h->hooks.adv); cudaFree(h->hooks.old); cudaFree(h->hooks.flux); cudaFree(h->hooks.av); cudaFree(h->hooks.npart_av);
   {
     auto &M = h->metproc;
     cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro); cudaFree(M.CLW); cudaFree(M.CIW); cudaFree(M.clw);
@@ -1312,6 +1327,32 @@ static int launch_bkdep(fpb_handle *h, const DevCfg &cfg, const DevParticles &ro
   return 0;
 }
 
+// calcfluxes / partpos_average around the step kernels (src/timemanager.f90:614-623); rows = the view the step
+// kernels work on, row0 = its first row in the engine's arrays
+static bool hooks_on(const fpb_handle *h) { return h->cfg.iflux == 1 || h->cfg.ipout == 3; }
+static int hooks_args(fpb_handle *h, HookArgs &k, const DevCfg &cfg, const DevParticles &rows, int row0) {
+  const fpb_config &c = h->cfg;
+  if (c.ipout == 3 && (!h->outp.oro || !h->outp.have_q[h->memind[0] - 1] || !h->outp.have_q[h->memind[1] - 1]))
+    return fail("ipout = 3 (partpos_average): fpb_set_orography / fpb_upload_pvqv of both time levels are missing");
+  if (c.ipout == 3 && (!h->T[h->memind[0] - 1] || !h->T[h->memind[1] - 1]))
+    return fail("ipout = 3 (partpos_average): tt of both time levels is missing (fpb_upload_met)");
+  k.cfg = cfg;
+  k.met[0] = slot_view(h, h->memind[0]); k.met[1] = slot_view(h, h->memind[1]);
+  k.Q[0] = h->outp.Q[h->memind[0] - 1]; k.Q[1] = h->outp.Q[h->memind[1] - 1];
+  k.oro = h->outp.oro;
+  k.height = h->d_height;
+  k.p = rows;
+  k.iflux = c.iflux == 1; k.ipout3 = c.ipout == 3;
+  k.adv = h->hooks.adv + row0;
+  k.old = h->hooks.old ? h->hooks.old + row0 : nullptr;
+  k.old_stride = (size_t)c.maxpart;
+  k.flux = h->hooks.flux;
+  k.npart_av = h->hooks.npart_av;
+  k.av = h->hooks.av;
+  k.av_stride = (size_t)c.maxpart;
+  return 0;
+}
+
 extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_stats *stats) {
   if (!h) return fail("fpb_step: null handle");
   if (!h->have_bracket) return fail("fpb_step: fpb_set_met_bracket has not been called");
@@ -1364,10 +1405,20 @@ extern "C" int fpb_step(fpb_handle *h, int32_t itime, int32_t ldeltat, fpb_step_
     h->pending_init = false;
   }
   if (launch_bkdep(h, a.cfg, a.p, h->stream)) return 1;
+  HookArgs hk;
+  if (hooks_on(h)) {
+    if (hooks_args(h, hk, a.cfg, a.p, 0)) return 1;
+    fpb_hooks_pre(hk, h->stream);
+    h->launches++;
+  }
   CK(cudaEventRecord(h->ev[0], h->stream));
   if (h->cfg.math_mode == FPB_MATH_STRICT) fpbk_step_strict(a, h->stream);
   else fpbk_step_fast(a, h->stream);
   CK(cudaEventRecord(h->ev[1], h->stream));
+  if (hooks_on(h)) {
+    fpb_hooks_post(hk, h->stream);
+    h->launches++;
+  }
   h->timed_step = true;
   h->launches += 2; // fpb_pbl_kernel + fpb_finish_kernel
   if (det_dry && dep_apply(h, h->scatter, a.dep, h->drygridunc, h->drygriduncn, h->stream)) return 1;
@@ -1579,6 +1630,37 @@ extern "C" int fpb_upload_pvqv(fpb_handle *h, int32_t slot, const float *pv, con
   if (upload_group(h, h->st_met, reinterpret_cast<float *>(h->outp.Q[s]), 2, q2, h->cfg.nz)) return 1;
   CK(cudaStreamSynchronize(h->st_met));
   h->outp.have_q[s] = true;
+  return 0;
+}
+
+extern "C" int fpb_fetch_fluxes(fpb_handle *h, float *flux, int32_t zero) {
+  if (!h) return fail("fpb_fetch_fluxes: null handle");
+  if (h->cfg.iflux != 1) return fail("fpb_fetch_fluxes: the engine was created with iflux = %d (no flux calculation)", h->cfg.iflux);
+  CK(cudaSetDevice(h->device));
+  if (flux) CK(cudaMemcpyAsync(flux, h->hooks.flux, h->hooks.nflux * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (zero) CK(cudaMemsetAsync(h->hooks.flux, 0, h->hooks.nflux * sizeof(float), h->stream)); // src/fluxoutput.f90:288-303
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int fpb_fetch_partpos_average(fpb_handle *h, int32_t numpart, const fpb_partav_ptrs *out, int32_t zero) {
+  if (!h || !out) return fail("fpb_fetch_partpos_average: null argument");
+  if (h->cfg.ipout != 3) return fail("fpb_fetch_partpos_average: the engine was created with ipout = %d", h->cfg.ipout);
+  if (numpart < 0 || numpart > h->cfg.maxpart) return fail("fpb_fetch_partpos_average: numpart %d outside capacity", numpart);
+  CK(cudaSetDevice(h->device));
+  const size_t mp = (size_t)h->cfg.maxpart, nb = (size_t)numpart * sizeof(float);
+  float *dst[14] = {out->cartx, out->carty, out->cartz, out->z, out->topo, out->pv, out->qv, out->tt, out->uu, out->vv,
+                    out->rho, out->tro, out->hmix, out->energy};
+  if (numpart > 0) {
+    if (out->npart_av) CK(cudaMemcpyAsync(out->npart_av, h->hooks.npart_av, nb, cudaMemcpyDeviceToHost, h->stream));
+    for (int q = 0; q < 14; q++)
+      if (dst[q]) CK(cudaMemcpyAsync(dst[q], h->hooks.av + q * mp, nb, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (zero) { // src/partoutput_average.f90:171-187
+    CK(cudaMemsetAsync(h->hooks.npart_av, 0, mp * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->hooks.av, 0, mp * 14 * sizeof(float), h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -2681,7 +2763,7 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
   // Deterministic dry deposition keeps the chunk-by-chunk path in any case (its record areas live in the lanes).
   const bool dbg = getenv("FPB_HOST_DEBUG") != nullptr;
   bool streamed = !dbg && getenv("FPB_HOST_STREAM") && atoi(getenv("FPB_HOST_STREAM")) != 0 &&
-                  !(c.scatter_mode == FPB_SCATTER_DETERMINISTIC && c.drydep);
+                  !(c.scatter_mode == FPB_SCATTER_DETERMINISTIC && c.drydep) && !hooks_on(h);
   std::vector<int> bounds; // chunk c = rows [bounds[c], bounds[c+1])
   int per_eq = 0;
   {
@@ -2921,7 +3003,16 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
       if (strict) fpbk_finish_strict(a, post); else fpbk_finish_fast(a, post);
       h->launches += 4;
     } else {
+      HookArgs hk;
+      if (hooks_on(h)) {
+        if (hooks_args(h, hk, a.cfg, rows, c0)) return 1;
+        fpb_hooks_pre(hk, L.st);
+      }
       if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
+      if (hooks_on(h)) {
+        fpb_hooks_post(hk, L.st);
+        h->launches += 2;
+      }
       h->launches += 3;
     }
     STAGE("step");

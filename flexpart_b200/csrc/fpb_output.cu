@@ -231,7 +231,193 @@ __global__ void __launch_bounds__(OUT_BLOCK) partout_write_kernel(const PartoutA
   for (int ks = 0; ks < c.nspec; ks++)
     a.xmass1[(size_t)ks * a.p.maxpart + k] = a.p.xmass1[(size_t)ks * a.p.maxpart + row];
 }
+
+// ---- loop hooks: calcfluxes / partpos_average
+__global__ void __launch_bounds__(256) hooks_pre_kernel(const HookArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.cfg.numpart) return;
+  const bool adv = a.p.itra1[j] == a.cfg.itime;
+  a.adv[j] = adv ? 1 : 0;
+  if (!adv || !a.iflux) return;
+  // src/timemanager.f90:559-561: xold, yold, zold are default reals
+  a.old[j] = (float)a.p.xtra1[j];
+  a.old[a.old_stride + j] = (float)a.p.ytra1[j];
+  a.old[2 * a.old_stride + j] = a.p.ztra1[j];
+  for (int ks = 0; ks < a.cfg.nspec; ks++)
+    a.old[(3 + (size_t)ks) * a.old_stride + j] = a.p.xmass1[(size_t)ks * a.p.maxpart + j];
+}
+
+// src/calcfluxes.f90:49-166 for row j (nage: src/timemanager.f90:544-547)
+__device__ __forceinline__ void flux_row(const HookArgs &a, int j) {
+  const DevCfg &c = a.cfg;
+  const float xold = a.old[j], yold = a.old[a.old_stride + j], zold = a.old[2 * a.old_stride + j];
+  const double xt = a.p.xtra1[j], yt = a.p.ytra1[j];
+  const float zt = a.p.ztra1[j];
+  const int itage = abs(c.itime - a.p.itramem[j]);
+  int nage;
+  for (nage = 1; nage <= c.nageclass; nage++)
+    if (itage < c.lage[nage - 1]) break;
+  if (nage > c.nageclass) return; // (the reference would index past the array)
+  const int kp = (c.ioutputforeachrelease == 1 && c.mdomainfill == 0) ? a.p.npoint[j] : 1;
+  const float xmean = (float)(((double)xold + xt) / 2.0);
+  const float ymean = (float)(((double)yold + yt) / 2.0);
+  const int ixave = (int)((xmean * c.dx + c.xoutshift) / c.dxout);
+  const int jyave = (int)((ymean * c.dy + c.youtshift) / c.dyout);
+  int kzave;
+  for (kzave = 1; kzave <= c.numzgrid; kzave++)
+    if (c.outheight[kzave - 1] > zt) break;
+  const size_t n1 = 6, nxg = c.numxgrid, nyg = c.numygrid, nzg = c.numzgrid;
+  auto add = [&](int i, int ix, int jy, int kz, int k) { // flux(i, ix, jy, kz, k, kp, nage) += xmass1(jpart, k)
+    const size_t o = (i - 1) + n1 * (ix + nxg * (jy + nyg * ((kz - 1) + nzg * ((k - 1) + (size_t)c.nspec *
+                     ((kp - 1) + (size_t)c.maxpointspec_act * (nage - 1))))));
+    atomicAdd(a.flux + o, a.old[(3 + (size_t)(k - 1)) * a.old_stride + j]);
+  };
+  auto half = [&](int kz) { // outheighthalf, src/readoutgrid.f90:194-197
+    return kz == 1 ? c.outheight[0] / 2.f : (c.outheight[kz - 2] + c.outheight[kz - 1]) / 2.f;
+  };
+  // vertical fluxes
+  if (ixave >= 0 && jyave >= 0 && ixave <= c.numxgrid - 1 && jyave <= c.numygrid - 1) {
+    int kz;
+    for (kz = 1; kz <= c.numzgrid; kz++)
+      if (half(kz) > zold) break;
+    const int k1 = min(c.numzgrid, kz);
+    for (kz = 1; kz <= c.numzgrid; kz++)
+      if (half(kz) > zt) break;
+    const int k2 = min(c.numzgrid, kz);
+    for (int k = 1; k <= c.nspec; k++) {
+      for (kz = k1; kz <= k2 - 1; kz++) add(5, ixave, jyave, kz, k);
+      for (kz = k2; kz <= k1 - 1; kz++) add(6, ixave, jyave, kz, k);
+    }
+  }
+  // west-east fluxes
+  if (kzave <= c.numzgrid && jyave >= 0 && jyave <= c.numygrid - 1) {
+    if (fabs((double)xold - xt) < (double)((float)c.nx / 2.f)) {
+      const int ix1 = (int)((xold * c.dx + c.xoutshift) / c.dxout + 0.5f);
+      const int ix2 = (int)((xt * (double)c.dx + (double)c.xoutshift) / (double)c.dxout + 0.5);
+      for (int k = 1; k <= c.nspec; k++) {
+        for (int ix = ix1; ix <= ix2 - 1; ix++)
+          if (ix >= 0 && ix <= c.numxgrid - 1) add(1, ix, jyave, kzave, k);
+        for (int ix = ix2; ix <= ix1 - 1; ix++)
+          if (ix >= 0 && ix <= c.numxgrid - 1) add(2, ix, jyave, kzave, k);
+      }
+    } else { // the particle crossed the date line of a global domain
+      const int ixs = (int)((((float)c.nxmin1 - 1.0e5f) * c.dx + c.xoutshift) / c.dxout);
+      if (ixs >= 0 && ixs <= c.numxgrid - 1) {
+        const int i = ((double)xold > xt) ? 1 : 2;
+        for (int k = 1; k <= c.nspec; k++) add(i, ixs, jyave, kzave, k);
+      }
+    }
+  }
+  // south-north fluxes
+  if (kzave <= c.numzgrid && ixave >= 0 && ixave <= c.numxgrid - 1) {
+    const int jy1 = (int)((yold * c.dy + c.youtshift) / c.dyout + 0.5f);
+    const int jy2 = (int)((yt * (double)c.dy + (double)c.youtshift) / (double)c.dyout + 0.5);
+    for (int k = 1; k <= c.nspec; k++) {
+      for (int jy = jy1; jy <= jy2 - 1; jy++)
+        if (jy >= 0 && jy <= c.numygrid - 1) add(3, ixave, jy, kzave, k);
+      for (int jy = jy2; jy <= jy1 - 1; jy++)
+        if (jy >= 0 && jy <= c.numygrid - 1) add(4, ixave, jy, kzave, k);
+    }
+  }
+}
+
+// src/partpos_average.f90:47-186 for row j
+__device__ __forceinline__ void average_row(const HookArgs &a, int j) {
+  const DevCfg &c = a.cfg;
+  const double xt = a.p.xtra1[j], yt = a.p.ytra1[j];
+  const float zt = a.p.ztra1[j];
+  float xlon = (float)((double)c.xlon0 + xt * (double)c.dx), ylat = (float)((double)c.ylat0 + yt * (double)c.dy);
+  const int ix = (int)xt, jy = (int)yt;
+  const int ixp = ix + 1;
+  int jyp = jy + 1;
+  const float ddx = (float)(xt - (double)(float)ix), ddy = (float)(yt - (double)(float)jy);
+  const float rddx = 1.f - ddx, rddy = 1.f - ddy;
+  const float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+  if (jyp >= c.nymax) jyp = jyp - 1;
+  const int o00 = ix + c.nxd * jy, o10 = ixp + c.nxd * jy, o01 = ix + c.nxd * jyp, o11 = ixp + c.nxd * jyp;
+  const float topo = p1 * a.oro[o00] + p2 * a.oro[o10] + p3 * a.oro[o01] + p4 * a.oro[o11];
+  int indz = c.nz - 1;
+  for (int il = 2; il <= c.nz; il++)
+    if (a.height[il - 1] > zt) { indz = il - 1; break; }
+  const int indzp = indz + 1;
+  const float dz1 = zt - a.height[indz - 1], dz2 = a.height[indzp - 1] - zt;
+  const float dz = 1.f / (dz1 + dz2);
+  const float dt1 = (float)(c.itime - c.memtime[0]), dt2 = (float)(c.memtime[1] - c.itime);
+  const float dtt = 1.f / (dt1 + dt2);
+  const int plane = c.nxd * c.nyd;
+  float pvprof[2], qvprof[2], ttprof[2], uuprof[2], vvprof[2], rhoprof[2];
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const int base = (indz - 1 + n) * plane;
+    float pv1[2], qv1[2], tt1[2], uu1[2], vv1[2], rho1[2];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const float2 qa = a.Q[m][base + o00], qb = a.Q[m][base + o10], qc = a.Q[m][base + o01], qd = a.Q[m][base + o11];
+      pv1[m] = p1 * qa.x + p2 * qb.x + p3 * qc.x + p4 * qd.x;
+      qv1[m] = p1 * qa.y + p2 * qb.y + p3 * qc.y + p4 * qd.y;
+      const float *T = a.met[m].T + base;
+      tt1[m] = p1 * T[o00] + p2 * T[o10] + p3 * T[o01] + p4 * T[o11];
+      const float4 *A = a.met[m].A + base;
+      const float4 wa = A[o00], wb = A[o10], wc = A[o01], wd = A[o11];
+      uu1[m] = p1 * wa.x + p2 * wb.x + p3 * wc.x + p4 * wd.x;
+      vv1[m] = p1 * wa.y + p2 * wb.y + p3 * wc.y + p4 * wd.y;
+      rho1[m] = p1 * wa.w + p2 * wb.w + p3 * wc.w + p4 * wd.w;
+    }
+    pvprof[n] = (pv1[0] * dt2 + pv1[1] * dt1) * dtt;
+    qvprof[n] = (qv1[0] * dt2 + qv1[1] * dt1) * dtt;
+    ttprof[n] = (tt1[0] * dt2 + tt1[1] * dt1) * dtt;
+    uuprof[n] = (uu1[0] * dt2 + uu1[1] * dt1) * dtt;
+    vvprof[n] = (vv1[0] * dt2 + vv1[1] * dt1) * dtt;
+    rhoprof[n] = (rho1[0] * dt2 + rho1[1] * dt1) * dtt;
+  }
+  const float pvi = (dz1 * pvprof[1] + dz2 * pvprof[0]) * dz;
+  const float qvi = (dz1 * qvprof[1] + dz2 * qvprof[0]) * dz;
+  const float tti = (dz1 * ttprof[1] + dz2 * ttprof[0]) * dz;
+  const float uui = (dz1 * uuprof[1] + dz2 * uuprof[0]) * dz;
+  const float vvi = (dz1 * vvprof[1] + dz2 * vvprof[0]) * dz;
+  const float rhoi = (dz1 * rhoprof[1] + dz2 * rhoprof[0]) * dz;
+  float tr[2], hm[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const float *tp = a.met[m].trop;
+    tr[m] = p1 * tp[o00] + p2 * tp[o10] + p3 * tp[o01] + p4 * tp[o11];
+    const float4 *S = a.met[m].S;
+    hm[m] = p1 * S[o00].x + p2 * S[o10].x + p3 * S[o01].x + p4 * S[o11].x;
+  }
+  const float hmixi = (hm[0] * dt2 + hm[1] * dt1) * dtt;
+  const float tri = (tr[0] * dt2 + tr[1] * dt1) * dtt;
+  const float energy = ((tti * 1004.6f + (zt + topo) * 9.81f) + qvi * 2501000.f) + (uui * uui + vvi * vvi) / 2.f;
+  const float pi180 = 3.14159265f / 180.f;
+  xlon = xlon * pi180;
+  ylat = ylat * pi180;
+  const float cy = (float)cos((double)ylat), sy = (float)sin((double)ylat);
+  const float cx = (float)cos((double)xlon), sx = (float)sin((double)xlon);
+  const float x = cy * sx, y = -((1.0f * cy) * cx), z = sy;
+  const int s = a.p.slot[j];
+  a.npart_av[s] = a.npart_av[s] + 1;
+  const float v[14] = {x, y, z, zt, topo, pvi, qvi, tti, uui, vvi, rhoi, tri, hmixi, energy};
+#pragma unroll
+  for (int q = 0; q < 14; q++) a.av[q * a.av_stride + s] = a.av[q * a.av_stride + s] + v[q];
+}
+
+__global__ void __launch_bounds__(256) hooks_post_kernel(const HookArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.cfg.numpart || !a.adv[j]) return;
+  if (a.iflux) flux_row(a, j);
+  // (the reference also averages a particle that the step has just terminated -- at a position that may lie
+  // outside the fields; such a particle is never written by partoutput_average, so it is left out)
+  if (a.ipout3 && a.p.itra1[j] != FPB_ITRA_DEAD) average_row(a, j);
+}
 } // namespace
+
+void fpb_hooks_pre(const HookArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb) hooks_pre_kernel<<<nb, 256, 0, st>>>(a);
+}
+void fpb_hooks_post(const HookArgs &a, cudaStream_t st) {
+  const int nb = (a.cfg.numpart + 255) / 256;
+  if (nb) hooks_post_kernel<<<nb, 256, 0, st>>>(a);
+}
 
 void fpb_partoutput_launch(const PartoutArgs &a, cudaStream_t st) {
   const int nb = (a.numpart + OUT_BLOCK - 1) / OUT_BLOCK;

@@ -57,3 +57,31 @@ struct PartoutArgs {
   float *xmass1;            // [nspec][maxpart]
 };
 void fpb_partoutput_launch(const PartoutArgs &a, cudaStream_t st);
+
+// The two optional hooks of the particle loop (src/timemanager.f90:614-623), run by fpb_step /
+// fpb_step_host around the step kernels when fpb_config.iflux == 1 / ipout == 3:
+//   calcfluxes       (src/calcfluxes.f90)       gross mass fluxes through the faces of the output grid
+//                    cells a particle crosses during the step, flux(6, numxgrid, numygrid, numzgrid,
+//                    nspec, maxpointspec_act, nageclass): needs the position and the masses from BEFORE
+//                    the step (advance moves the particle; decay and deposition change the masses after
+//                    the hook), which fpb_hooks_pre memorises per row
+//   partpos_average  (src/partpos_average.f90)  running sums of position (Cartesian), height, topography,
+//                    pv, qv, tt, uu, vv, rho, tropopause, hmix and energy per particle (= slot)
+struct HookArgs {
+  DevCfg cfg;               // cfg.itime, cfg.memtime set; cfg.numpart = rows of the view
+  DevMetSlot met[2];        // memind(1), memind(2)
+  const float2 *Q[2];       // {pv, qv} of the same time levels (averages only)
+  const float *oro;         // [nyd][nxd] (averages only)
+  const float *height;
+  DevParticles p;           // row view
+  int iflux, ipout3;
+  uint8_t *adv;             // [rows] 1 = the row is advanced by this step (itra1 == itime before it)
+  float *old;               // [3 + nspec][old_stride]: xold, yold, zold, xmass1(ks) of the row before the step
+  size_t old_stride;
+  float *flux;
+  int32_t *npart_av;        // [maxpart] by slot
+  float *av;                // [14][av_stride] by slot: cartx, carty, cartz, z, topo, pv, qv, tt, uu, vv, rho, tro, hmix, energy
+  size_t av_stride;
+};
+void fpb_hooks_pre(const HookArgs &a, cudaStream_t st);
+void fpb_hooks_post(const HookArgs &a, cudaStream_t st);

@@ -140,6 +140,25 @@ class Engine:
         self._check(self.L.fpb_partoutput(self.h, itime, C.byref(n), C.byref(r)))
         return {k: a[:n.value].copy() for k, a in out.items()}
 
+    def fetch_fluxes(self, zero=False):
+        """flux(6, numxgrid, numygrid, numzgrid, nspec, maxpointspec_act, nageclass) of calcfluxes (iflux = 1)"""
+        c = self.cb.cfg
+        f = np.zeros((6, c.numxgrid, c.numygrid, c.numzgrid, c.nspec, c.maxpointspec_act, c.nageclass), np.float32, order="F")
+        self._check(self.L.fpb_fetch_fluxes(self.h, _fp(f), 1 if zero else 0))
+        return f
+
+    def fetch_partpos_average(self, numpart, zero=False):
+        """npart_av and the part_av_* sums of partpos_average (ipout = 3) for the first numpart slots"""
+        from .abi import FpbPartavPtrs
+        r = FpbPartavPtrs()
+        out = {"npart_av": np.zeros(numpart, np.int32)}
+        r.npart_av = out["npart_av"].ctypes.data_as(C.POINTER(C.c_int32))
+        for name, _ in FpbPartavPtrs._fields_[1:]:
+            out[name] = np.zeros(numpart, np.float32)
+            setattr(r, name, _fp(out[name]))
+        self._check(self.L.fpb_fetch_partpos_average(self.h, numpart, C.byref(r), 1 if zero else 0))
+        return out
+
     def set_outgrid_origin(self, outlon0, outlat0, outlon0n=0.0, outlat0n=0.0):
         self._check(self.L.fpb_set_outgrid_origin(self.h, outlon0, outlat0, outlon0n, outlat0n))
 

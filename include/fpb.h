@@ -159,7 +159,11 @@ typedef struct fpb_config {
                            multi-GPU partition, src/releaseparticles_mpi.f90:141 */
   int32_t sort_interval; /* >0: fpb_step re-orders the device rows by met cell
                             every that many steps (results do not depend on it) */
-  int32_t reserved[7];
+  /* --- optional hooks of the particle loop, src/timemanager.f90:614-623 -- */
+  int32_t iflux;         /* 1: calcfluxes after every advance (src/calcfluxes.f90); fpb_fetch_fluxes */
+  int32_t ipout;         /* 3: partpos_average after every advance (src/partpos_average.f90);
+                            fpb_fetch_partpos_average.  Other values: nothing happens in the loop */
+  int32_t reserved[5];
 } fpb_config;
 
 /* One time level of the meteorological arrays the hot path gathers from
@@ -341,6 +345,27 @@ typedef struct fpb_partout_ptrs { /* each [>= number of active particles]; xmass
   int32_t ld;
 } fpb_partout_ptrs;
 int fpb_partoutput(fpb_handle *h, int32_t itime, int32_t *nrecords, const fpb_partout_ptrs *out);
+
+/* The two optional hooks of the particle loop (src/timemanager.f90:614-623) run inside fpb_step / fpb_step_host
+ * when the configuration asks for them:
+ *   iflux = 1  calcfluxes (src/calcfluxes.f90): every advanced particle adds its masses (from before the step's
+ *              decay / deposition, as the reference's call order has it) to the faces of the output-grid cells
+ *              it crossed.  fpb_fetch_fluxes copies flux(6, 0:numxgrid-1, 0:numygrid-1, numzgrid, nspec,
+ *              maxpointspec_act, nageclass) out (NULL: no copy) and, with zero != 0, clears it the way
+ *              fluxoutput does after writing (src/fluxoutput.f90:288-303).  The calcfluxes call inside convmix
+ *              (src/convmix.f90) is not built.
+ *   ipout = 3  partpos_average (src/partpos_average.f90): per-particle running sums for partoutput_average;
+ *              needs fpb_set_orography and fpb_upload_pvqv like fpb_partoutput.  fpb_fetch_partpos_average
+ *              copies the first numpart slots of npart_av / part_av_* (any pointer may be NULL) and, with
+ *              zero != 0, clears them (src/partoutput_average.f90:171-187).  A particle the step has just
+ *              terminated is left out (the reference averages it at a position that may lie outside the
+ *              fields; it is never written). */
+typedef struct fpb_partav_ptrs {
+  int32_t *npart_av;
+  float *cartx, *carty, *cartz, *z, *topo, *pv, *qv, *tt, *uu, *vv, *rho, *tro, *hmix, *energy;
+} fpb_partav_ptrs;
+int fpb_fetch_fluxes(fpb_handle *h, float *flux, int32_t zero);
+int fpb_fetch_partpos_average(fpb_handle *h, int32_t numpart, const fpb_partav_ptrs *out, int32_t zero);
 
 /* Release points (src/point_mod.f90:15-26 after the conversions of src/readreleases.f90 and
  * src/FLEXPART.f90:401-404): coordinates in grid units, heights in metres above ground

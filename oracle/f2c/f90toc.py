@@ -50,6 +50,11 @@ ALLOC_DIMS = {
     "wetgridunc": "0:numxgrid-1,0:numygrid-1,maxspec,maxpointspec_act,nclassunc,maxageclass",
     "wetgriduncn": "0:numxgridn-1,0:numygridn-1,maxspec,maxpointspec_act,nclassunc,maxageclass",
     "outheight": "numzgrid", "outheighthalf": "numzgrid",
+    "flux": "6,0:numxgrid-1,0:numygrid-1,numzgrid,nspec,maxpointspec_act,nageclass",
+    "npart_av": "maxpart", "part_av_cartx": "maxpart", "part_av_carty": "maxpart", "part_av_cartz": "maxpart",
+    "part_av_z": "maxpart", "part_av_topo": "maxpart", "part_av_pv": "maxpart", "part_av_qv": "maxpart",
+    "part_av_tt": "maxpart", "part_av_rho": "maxpart", "part_av_tro": "maxpart", "part_av_hmix": "maxpart",
+    "part_av_uu": "maxpart", "part_av_vv": "maxpart", "part_av_energy": "maxpart",
     "xmass": "numpoint,maxspec", "npart": "numpoint",
     "uun": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "vvn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests",
     "wwn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "ttn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests",

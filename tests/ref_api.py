@@ -57,6 +57,8 @@ class Ref:
         # extents of the allocatable arrays
         for k in ("numxgrid", "numygrid", "numzgrid", "maxpointspec_act", "numpoint", "numreceptor"):
             self.set(k, getattr(c, k))
+        for k in ("nspec", "nageclass"):          # extents of flux_mod's flux
+            self.set(k, getattr(c, k))
         self.set("numxgridn", max(c.numxgridn, 1)); self.set("numygridn", max(c.numygridn, 1))
         L.ref_alloc()
         self.set("numxgridn", c.numxgridn); self.set("numygridn", c.numygridn)

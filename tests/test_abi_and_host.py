@@ -333,7 +333,7 @@ def test_fortran_module_layout_matches_the_c_compiler():
     the header's constants; an interface for every exported symbol."""
     params, types, funcs = _fortran_module()
     assert set(types) == {"fpb_config", "fpb_met_ptrs", "fpb_particle_ptrs", "fpb_step_stats", "fpb_partout_ptrs",
-                          "fpb_release_points", "fpb_domainfill_info", "fpb_conv_ptrs", "fpb_rawmet_ptrs",
+                          "fpb_release_points", "fpb_domainfill_info", "fpb_conv_ptrs", "fpb_rawmet_ptrs", "fpb_partav_ptrs",
                           "fpb_met_out_ptrs"}
     lines = []
     for t, fields in types.items():
