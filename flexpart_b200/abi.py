@@ -233,6 +233,8 @@ def load_engine_lib():
     L.fpb_calcpar_verttransform.argtypes = [H, _i, C.POINTER(FpbRawmetPtrs), _i, _pf]
     L.fpb_upload_vdep.argtypes = [H, _i, _pf]
     L.fpb_fetch_met.argtypes = [H, _i, C.POINTER(FpbMetOutPtrs)]
+    L.fpb_calcpar_verttransform_nest.argtypes = [H, _i, _i, C.POINTER(FpbRawmetPtrs), _i, _f, _f, _f, _f, _pf]
+    L.fpb_fetch_met_nest.argtypes = [H, _i, _i, C.POINTER(FpbMetOutPtrs)]
     L.fpb_init_domainfill.argtypes = [H, _f, _f, _f, _f, _i, _pi, C.POINTER(FpbDomainfillInfo)]
     L.fpb_boundcond_domainfill.argtypes = [H, _i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.fpb_step_host.argtypes = [H, _i, _i, _i, C.POINTER(FpbParticlePtrs), C.c_float,

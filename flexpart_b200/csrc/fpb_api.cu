@@ -310,6 +310,11 @@ struct fpb_handle {
     float2 *UV = nullptr;
     float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
     float *CLW = nullptr, *CIW = nullptr, *clw = nullptr; // readclouds
+    struct NestWork { // calcpar_nests / verttransform_nests: work arrays in the nest's extents
+      float2 *UV = nullptr;
+      float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr, *T = nullptr, *cosf = nullptr;
+      float4 *SF2 = nullptr;
+    } nw[FPB_MAXNESTS];
     float4 *SF2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
   } metproc;
@@ -847,6 +852,10 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     auto &M = h->metproc;
     cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro); cudaFree(M.CLW); cudaFree(M.CIW); cudaFree(M.clw);
     cudaFree(M.uvzlev); cudaFree(M.SF2);
+    for (auto &w : M.nw) {
+      cudaFree(w.UV); cudaFree(w.W); cudaFree(w.PV); cudaFree(w.theta); cudaFree(w.excessoro); cudaFree(w.uvzlev);
+      cudaFree(w.T); cudaFree(w.cosf); cudaFree(w.SF2);
+    }
     if (M.ev0) cudaEventDestroy(M.ev0);
     if (M.ev1) cudaEventDestroy(M.ev1);
     if (M.evk) cudaEventDestroy(M.evk);
@@ -2275,7 +2284,6 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
     return fail("fpb_calcpar_verttransform: lsprec/convprec/tcc required when wetdep");
   const bool rdcl = c.wetdep && c.readclouds;
   if (rdcl && !m->clwch) return fail("fpb_calcpar_verttransform: clwch required when readclouds");
-  if (c.numbnests > 0) return fail("fpb_calcpar_verttransform: nested input grids (calcpar_nests / verttransform_nests) are not built");
   if (lsubgrid == 1 && !m->excessoro) return fail("fpb_calcpar_verttransform: excessoro required when lsubgrid = 1");
   CK(cudaSetDevice(h->device));
   if (finish_met_upload(h)) return 1;
@@ -2339,13 +2347,96 @@ extern "C" int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_
   return 0;
 }
 
-extern "C" int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs *o) {
-  if (!h || !o) return fail("fpb_fetch_met: null argument");
-  if (slot < 1 || slot > FPB_NSLOTS || !h->slot_ready[slot - 1]) return fail("fpb_fetch_met: slot %d holds no field", slot);
+// calcpar_nests + verttransform_nests (+ calcpv_nests) for nested input grid `nest` (src/getfields.f90:131-134):
+// the same column code as the mother grid with the nest's geometry, no pole rows, no wrap in x
+extern "C" int fpb_calcpar_verttransform_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_rawmet_ptrs *m,
+                                              int32_t lsubgrid, float dxn, float dyn, float xlon0n, float ylat0n,
+                                              float *device_ms) {
+  if (!h || !m) return fail("fpb_calcpar_verttransform_nest: null argument");
+  auto &M = h->metproc;
+  auto &V = h->conv;
+  const fpb_config &c = h->cfg;
+  if (M.nuvz == 0) return fail("fpb_calcpar_verttransform_nest: fpb_set_vertical has not been called");
+  if (slot < 1 || slot > FPB_NSLOTS) return fail("fpb_calcpar_verttransform_nest: slot %d", slot);
+  if (nest < 1 || nest > c.numbnests) return fail("fpb_calcpar_verttransform_nest: nest %d outside 1..numbnests=%d", nest, c.numbnests);
+  if (!m->uuh || !m->vvh || !m->tth || !m->qvh || !m->wwh || !m->ps || !m->tt2 || !m->td2 || !m->sshf || !m->surfstr)
+    return fail("fpb_calcpar_verttransform_nest: a mandatory field pointer is null");
+  if (c.wetdep && (!m->lsprec || !m->convprec || !m->tcc))
+    return fail("fpb_calcpar_verttransform_nest: lsprec/convprec/tcc required when wetdep");
+  if (c.wetdep && c.readclouds_nest[nest - 1])
+    return fail("fpb_calcpar_verttransform_nest: cloud water from the input (readclouds_nest) is not built");
+  if (lsubgrid == 1 && !m->excessoro) return fail("fpb_calcpar_verttransform_nest: excessoro required when lsubgrid = 1");
+  if (!(dxn > 0.f) || !(dyn > 0.f)) return fail("fpb_calcpar_verttransform_nest: dxn, dyn must be positive");
   CK(cudaSetDevice(h->device));
   if (finish_met_upload(h)) return 1;
+  const int s = slot - 1, l = nest - 1;
+  if (alloc_met_slot(h, s)) return 1;
+  const int nxd = c.nxn[l], nyd = c.nyn[l], mx = c.nxmaxn, my = c.nymaxn, nuvz = M.nuvz;
+  const size_t n2 = (size_t)nxd * nyd, n3 = n2 * nuvz;
+  auto &W = M.nw[l];
+  if (!W.UV) {
+    DA(W.UV, n3); DA(W.W, n3); DA(W.uvzlev, n3); DA(W.SF2, n2); DA(W.PV, n3);
+    // cosf(jy) = 1./cos((real(jy)*dyn(l)+ylat0n(l))*pi180), src/verttransform_nests.f90:283-286
+    std::vector<float> cosf((size_t)nyd, 0.f);
+    const float pi180 = 3.14159265f / 180.f;
+    for (int jy = 0; jy < nyd; jy++) cosf[jy] = 1.f / (float)cos((double)(((float)jy * dyn + ylat0n) * pi180));
+    DA(W.cosf, cosf.size());
+    CK(cudaMemcpy(W.cosf, cosf.data(), cosf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!m->pvh && !W.theta) DA(W.theta, n3);
+  if (lsubgrid == 1 && !W.excessoro) DA(W.excessoro, n2);
+  if (!c.wetdep && !W.T) DA(W.T, n3); // (ttn is kept only for wet deposition, src/com_mod.f90:501-529)
+  if (!V.CT[nest][s]) { DA(V.CT[nest][s], n3); DA(V.CS[nest][s], n2); }
+  cudaStream_t st = h->st_met;
+  CK(cudaEventRecord(M.ev0, st));
+  {
+    const float *uv[2] = {m->uuh, m->vvh}, *w1[1] = {m->wwh}, *tq[2] = {m->tth, m->qvh}, *pv[1] = {m->pvh};
+    const float *s1[4] = {m->ps, m->tt2, m->td2, m->sshf}, *s2[4] = {m->surfstr, m->lsprec, m->convprec, m->tcc};
+    const float *ex[1] = {m->excessoro};
+    if (upload_group(h, st, (float *)W.UV, 2, uv, nuvz, nxd, nyd, mx, my)) return 1;
+    if (upload_group(h, st, W.W, 1, w1, M.nwz, nxd, nyd, mx, my)) return 1;
+    if (upload_group(h, st, (float *)V.CT[nest][s], 2, tq, nuvz, nxd, nyd, mx, my)) return 1;
+    if (m->pvh && upload_group(h, st, W.PV, 1, pv, nuvz, nxd, nyd, mx, my)) return 1;
+    if (upload_group(h, st, (float *)V.CS[nest][s], 4, s1, 1, nxd, nyd, mx, my)) return 1;
+    if (upload_group(h, st, (float *)W.SF2, 4, s2, 1, nxd, nyd, mx, my)) return 1;
+    if (lsubgrid == 1 && upload_group(h, st, W.excessoro, 1, ex, 1, nxd, nyd, mx, my)) return 1;
+  }
+  fpbmet::MetGrid g{};
+  g.nx = nxd; g.ny = nyd; g.nz = c.nz; g.nuvz = nuvz; g.nwz = M.nwz;
+  g.nxd = nxd; g.nyd = nyd;
+  g.dx = dxn; g.dy = dyn; g.xlon0 = xlon0n; g.ylat0 = ylat0n; g.dxconst = c.dxconst; g.dyconst = c.dyconst;
+  g.nest = 1; g.xresol = c.xresoln[l]; g.yresol = c.yresoln[l];
+  g.lsubgrid = lsubgrid;
+  const size_t n1 = (size_t)nuvz + 1;
+  g.akz = M.d_ab; g.bkz = M.d_ab + n1; g.akm = M.d_ab + 2 * n1; g.bkm = M.d_ab + 3 * n1;
+  g.height = h->d_height; g.cosf = W.cosf;
+  g.UV = W.UV; g.W = W.W; g.TQ = V.CT[nest][s]; g.PV = W.PV; g.theta = m->pvh ? nullptr : W.theta;
+  g.SF1 = V.CS[nest][s]; g.SF2 = W.SF2; g.excessoro = W.excessoro; g.uvzlev = W.uvzlev;
+  g.A = h->An[l][s]; g.G = h->Gn[l][s]; g.T = c.wetdep ? h->Tn[l][s] : W.T; g.S = h->Sn[l][s]; g.trop = h->tropn[l][s];
+  g.R = c.wetdep ? h->Rn[l][s] : nullptr; g.Cl = c.wetdep ? h->Cln[l][s] : nullptr;
+  CK(cudaEventRecord(M.evk, st));
+  fpb_metproc_launch(g, st, &h->launches);
+  CK(cudaEventRecord(M.ev1, st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (device_ms) {
+    CK(cudaEventElapsedTime(device_ms, M.ev0, M.ev1));
+    CK(cudaEventElapsedTime(device_ms + 1, M.evk, M.ev1));
+  }
+  V.have[nest][s] = (V.nuvz == nuvz);
+  return 0;
+}
+
+static int fetch_met_impl(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_out_ptrs *o) {
+  if (!h || !o) return fail("fpb_fetch_met: null argument");
+  if (slot < 1 || slot > FPB_NSLOTS || !h->slot_ready[slot - 1]) return fail("fpb_fetch_met: slot %d holds no field", slot);
   const fpb_config &c = h->cfg;
-  const int s = slot - 1, nxd = h->d.nxd, nyd = h->d.nyd, nz = c.nz;
+  if (nest < 0 || nest > c.numbnests) return fail("fpb_fetch_met_nest: nest %d outside 1..numbnests=%d", nest, c.numbnests);
+  CK(cudaSetDevice(h->device));
+  if (finish_met_upload(h)) return 1;
+  const int s = slot - 1, l = nest - 1, nz = c.nz;
+  const int nxd = nest ? c.nxn[l] : h->d.nxd, nyd = nest ? c.nyn[l] : h->d.nyd;
+  const int nxu = nest ? c.nxn[l] : c.nx, nyu = nest ? c.nyn[l] : c.ny, mx = nest ? c.nxmaxn : c.nxmax, my = nest ? c.nymaxn : c.nymax;
   const size_t n2 = (size_t)nxd * nyd, n3 = n2 * nz;
   std::vector<float> buf;
   // device [k][jy][ix][ncomp] -> host (nxmax, nymax, nk) of component `comp`
@@ -2359,31 +2450,44 @@ extern "C" int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs
     for (int q = 0; q < ncomp; q++) {
       if (!dst[q]) continue;
       for (int k = 0; k < nk; k++)
-        for (int jy = 0; jy < c.ny; jy++)
-          for (int ix = 0; ix < c.nx; ix++)
-            dst[q][(size_t)ix + (size_t)c.nxmax * ((size_t)jy + (size_t)c.nymax * k)] =
+        for (int jy = 0; jy < nyu; jy++)
+          for (int ix = 0; ix < nxu; ix++)
+            dst[q][(size_t)ix + (size_t)mx * ((size_t)jy + (size_t)my * k)] =
                 buf[(((size_t)k * nyd + jy) * nxd + ix) * ncomp + q];
     }
     return 0;
   };
   float *a4[4] = {o->uu, o->vv, o->ww, o->rho}, *g1[1] = {o->drhodz}, *t1[1] = {o->tt}, *p2[2] = {o->uupol, o->vvpol};
   float *q2[2] = {o->pv, o->qv}, *s4[4] = {o->hmix, o->ustar, o->wstar, o->oli}, *tr[1] = {o->tropopause};
-  if (fetch(h->A[s], 4, nz, a4) || fetch(h->G[s], 1, nz, g1) || fetch(h->T[s], 1, nz, t1) || fetch(h->P[s], 2, nz, p2) ||
-      fetch(h->outp.Q[s], 2, nz, q2) || fetch(h->S[s], 4, 1, s4) || fetch(h->trop[s], 1, 1, tr))
-    return 1;
-  if (o->ctwc && h->R[s]) {
-    float *r4[4] = {nullptr, nullptr, nullptr, o->ctwc};
-    if (fetch(h->R[s], 4, 1, r4)) return 1;
+  float *r4[4] = {nullptr, nullptr, nullptr, o->ctwc};
+  const int8_t *Cl;
+  if (nest) {
+    if (fetch(h->An[l][s], 4, nz, a4) || fetch(h->Gn[l][s], 1, nz, g1) || fetch(h->Tn[l][s], 1, nz, t1) ||
+        fetch(h->Sn[l][s], 4, 1, s4) || fetch(h->tropn[l][s], 1, 1, tr))
+      return 1;
+    if (o->ctwc && h->Rn[l][s] && fetch(h->Rn[l][s], 4, 1, r4)) return 1;
+    Cl = h->Cln[l][s];
+  } else {
+    if (fetch(h->A[s], 4, nz, a4) || fetch(h->G[s], 1, nz, g1) || fetch(h->T[s], 1, nz, t1) || fetch(h->P[s], 2, nz, p2) ||
+        fetch(h->outp.Q[s], 2, nz, q2) || fetch(h->S[s], 4, 1, s4) || fetch(h->trop[s], 1, 1, tr))
+      return 1;
+    if (o->ctwc && h->R[s] && fetch(h->R[s], 4, 1, r4)) return 1;
+    Cl = h->Cl[s];
   }
-  if (o->clouds && h->Cl[s]) {
+  if (o->clouds && Cl) {
     std::vector<int8_t> cb(n3);
-    CK(cudaMemcpy(cb.data(), h->Cl[s], n3, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cb.data(), Cl, n3, cudaMemcpyDeviceToHost));
     for (int k = 0; k < nz; k++)
-      for (int jy = 0; jy < c.ny; jy++)
-        for (int ix = 0; ix < c.nx; ix++)
-          o->clouds[(size_t)ix + (size_t)c.nxmax * ((size_t)jy + (size_t)c.nymax * k)] = cb[((size_t)k * nyd + jy) * nxd + ix];
+      for (int jy = 0; jy < nyu; jy++)
+        for (int ix = 0; ix < nxu; ix++)
+          o->clouds[(size_t)ix + (size_t)mx * ((size_t)jy + (size_t)my * k)] = cb[((size_t)k * nyd + jy) * nxd + ix];
   }
   return 0;
+}
+extern "C" int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs *o) { return fetch_met_impl(h, slot, 0, o); }
+extern "C" int fpb_fetch_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_out_ptrs *o) {
+  if (nest < 1) return fail("fpb_fetch_met_nest: nest %d", nest);
+  return fetch_met_impl(h, slot, nest, o);
 }
 
 // ----------------------------------------------------------- convection --

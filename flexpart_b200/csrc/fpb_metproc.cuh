@@ -51,6 +51,9 @@ struct MetGrid {
   float northpolemap[9], southpolemap[9];
   int lsubgrid;
   int readclouds;            // (0: parameterised clouds)
+  int nest;                  // 1: a nested input grid (calcpar_nests / verttransform_nests / calcpv_nests): the same
+                             // column arithmetic with the nest's geometry, no poles, no wrap
+  float xresol, yresol;      // nest: xresoln(l), yresoln(l) of the slope term (src/verttransform_nests.f90:322-323)
   const float *akz, *bkz, *akm, *bkm; // 1-based, [nuvz + 1]
   const float *height;       // height(k) = height[k - 1]
   const float *cosf;         // [ny] 1 / cos(latitude of row jy), rows 1 .. ny-2 (:406-408)
@@ -221,7 +224,8 @@ FPB_HD inline void met_interp_column(const MetGrid &g, int ix, int jy) {
       const float dzdy1 = (g.uvzlev[m_o3(g, ix, jy + 1, kz - 1)] - g.uvzlev[m_o3(g, ix, jy - 1, kz - 1)]) / 2.f;
       const float dzdy2 = (g.uvzlev[m_o3(g, ix, jy + 1, kz)] - g.uvzlev[m_o3(g, ix, jy - 1, kz)]) / 2.f;
       const float dzdy = (dzdy1 * dz2 + dzdy2 * dz1) / dz;
-      ww = ww + (dzdx * uu * g.dxconst * g.cosf[jy] + dzdy * vv * g.dyconst);
+      if (g.nest) ww = ww + (dzdx * uu * g.dxconst * g.xresol * g.cosf[jy] + dzdy * vv * g.dyconst * g.yresol);
+      else ww = ww + (dzdx * uu * g.dxconst * g.cosf[jy] + dzdy * vv * g.dyconst);
     }
     const size_t o = m_o3(g, ix, jy, iz);
     g.A[o] = make_float4(uu, vv, ww, rho);

@@ -282,14 +282,34 @@ class Engine:
         self.metproc_kernel_ms = ms[1]
         return ms[0]
 
+    def calcpar_verttransform_nest(self, slot, nest, raw, dxn, dyn, xlon0n, ylat0n, lsubgrid=0):
+        """the same for nested input grid `nest` (arrays with the nest's padded extents)"""
+        from .abi import FpbRawmetPtrs
+        m = FpbRawmetPtrs()
+        keep = {}
+        for name, _ in FpbRawmetPtrs._fields_:
+            a = raw.get(name)
+            if a is not None:
+                keep[name] = np.asfortranarray(a, np.float32)
+                setattr(m, name, _fp(keep[name]))
+        ms = (C.c_float * 2)()
+        self._check(self.L.fpb_calcpar_verttransform_nest(self.h, slot, nest, C.byref(m), lsubgrid, dxn, dyn, xlon0n, ylat0n, ms))
+        return ms[0]
+
     def upload_vdep(self, slot, vdep):
         a = np.asfortranarray(vdep, np.float32)
         self._check(self.L.fpb_upload_vdep(self.h, slot, _fp(a)))
 
-    def fetch_met(self, slot, fields=None):
-        """the transformed fields of a slot in the reference's padded layout (Fortran order)"""
+    def fetch_met(self, slot, fields=None, nest=0):
+        """the transformed fields of a slot (of nested input grid `nest`) in the reference's padded layout"""
         from .abi import FpbMetOutPtrs
         c = self.cb.cfg
+        if nest:
+            class _N:   # the nest's padded extents
+                nxmax, nymax, nzmax, wetdep = c.nxmaxn, c.nymaxn, c.nzmax, c.wetdep
+            c = _N
+            skip = ("uupol", "vvpol", "pv", "qv") + (() if c.wetdep else ("tt",))
+            fields = [n for n, _ in FpbMetOutPtrs._fields_ if n not in skip and (fields is None or n in fields)]
         o, out = FpbMetOutPtrs(), {}
         for name, _ in FpbMetOutPtrs._fields_:
             if fields is not None and name not in fields:
@@ -305,7 +325,10 @@ class Engine:
             shape = (c.nxmax, c.nymax) if name in ("hmix", "ustar", "wstar", "oli", "tropopause", "ctwc") else (c.nxmax, c.nymax, c.nzmax)
             out[name] = np.zeros(shape, np.float32, order="F")
             setattr(o, name, _fp(out[name]))
-        self._check(self.L.fpb_fetch_met(self.h, slot, C.byref(o)))
+        if nest:
+            self._check(self.L.fpb_fetch_met_nest(self.h, slot, nest, C.byref(o)))
+        else:
+            self._check(self.L.fpb_fetch_met(self.h, slot, C.byref(o)))
         return out
 
     def init_domainfill(self, box, itsplit=99999999):

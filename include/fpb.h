@@ -449,7 +449,7 @@ int fpb_boundcond_domainfill(fpb_handle *h, int32_t itime, int32_t loutend, int3
  * Needs fpb_set_vertical first.  ECMWF layout only: nz = nuvz = nwz.  `height` of fpb_config must be
  * what verttransform_ecmwf's first call derives (fpbh_verttransform_heights in fpb_host.h).
  * Not built: dry-deposition velocities (getvdep: land-use inventory; upload vdep with
- * fpb_upload_vdep), nested input grids (calcpar_nests / verttransform_nests), the NCEP/GFS variant.
+ * fpb_upload_vdep), the NCEP/GFS variant.
  * fpb_fetch_met copies a slot back in the reference's padded layout (any pointer may be NULL): for
  * the parts of a host model that still read the transformed fields, and for the tests. */
 typedef struct fpb_rawmet_ptrs {
@@ -473,6 +473,19 @@ int fpb_calcpar_verttransform(fpb_handle *h, int32_t slot, const fpb_rawmet_ptrs
                               float *device_ms /* may be NULL; [0] upload + kernels, [1] kernels only (ms) */);
 int fpb_upload_vdep(fpb_handle *h, int32_t slot, const float *vdep /* (nxmax, nymax, maxspec) */);
 int fpb_fetch_met(fpb_handle *h, int32_t slot, const fpb_met_out_ptrs *out);
+/* The same for nested input grid `nest` (1-based), replacing the calcpar_nests / verttransform_nests pair of
+ * getfields (src/getfields.f90:131-134; src/calcpar_nests.f90, src/verttransform_nests.f90, src/calcpv_nests.f90):
+ * the raw arrays have the nest's padded extents (nxmaxn, nymaxn, ..); dxn, dyn, xlon0n, ylat0n are the nest's
+ * own grid constants as gridcheck_nests read them (src/gridcheck_nests.f90: they enter cosf, the latitude
+ * dependent tropopause search and calcpv); bit-identical fields, as for the mother grid.  The nest's slot is
+ * then what fpb_upload_met_nest would have produced (and fpb_upload_convmet_nest, when fpb_set_convection was
+ * called with the same nuvz).  Not built: readclouds_nest, getvdep_nests (upload vdepn: fpb_upload_met_nest
+ * is still the way to hand over deposition velocities).  fpb_fetch_met_nest: uupol / vvpol / pv / qv do not
+ * exist for nests (left untouched); tt only when the run has wet deposition. */
+int fpb_calcpar_verttransform_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_rawmet_ptrs *raw,
+                                   int32_t lsubgrid, float dxn, float dyn, float xlon0n, float ylat0n,
+                                   float *device_ms /* may be NULL */);
+int fpb_fetch_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_out_ptrs *out);
 
 /* Convective mixing (LCONVECTION = 1, the shipped default).
  * fpb_convmix replaces `call convmix(itime,metdata_format)` (src/timemanager.f90:183-193,258-263;

@@ -66,6 +66,10 @@ ALLOC_DIMS = {
     "cloudsn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "cloudshn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
     "ctwcn": "0:nxmaxn-1,0:nymaxn-1,numwfmem,maxnests",
     "tthn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests", "qvhn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests",
+    "qvn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "pvn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests",
+    "clwcn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests", "ciwcn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests",
+    "clwn": "0:nxmaxn-1,0:nymaxn-1,nzmax,numwfmem,maxnests",
+    "clwchn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests", "ciwchn": "0:nxmaxn-1,0:nymaxn-1,nuvzmax,numwfmem,maxnests",
     "zpoint1": "numpoint", "zpoint2": "numpoint", "xpoint1": "numpoint", "xpoint2": "numpoint",
     "ypoint1": "numpoint", "ypoint2": "numpoint", "ireleasestart": "numpoint", "ireleaseend": "numpoint",
     "kindz": "numpoint", "rho_rel": "numpoint", "xmasssave": "numpoint",

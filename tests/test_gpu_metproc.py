@@ -78,6 +78,50 @@ def test_readclouds_slot_is_bit_identical_to_the_reference_routines(sumclouds):
     eng.close()
 
 
+@pytest.mark.parametrize("wet", [True, False])
+def test_nested_grid_slot_is_bit_identical_to_the_reference_routines(wet):
+    """fpb_calcpar_verttransform_nest against calcpar_nests + verttransform_nests + calcpv_nests run from their
+    sources (src/getfields.f90:131-134), and a particle step through the nest on the slots built that way"""
+    from metproc_common import nest_configs, reference_run_nest, compare_fields_nest, NEST
+    nuvz = 40
+    kw = dict(nrel=1, npart_each=512, nz=nuvz, math_mode=fb.MATH_STRICT)
+    if wet:
+        kw.update(wetdepspec=(1,), weta_gas=(2.0e-5,), wetb_gas=(0.62,))
+    cb0, _ = nest_configs(**kw, height=fb.synth_heights(nuvz))
+    akm, bkm, akz, bkz, _ = conv_cases.hybrid_levels(nuvz)
+    raw = met_cases.raw_fields(cb0, akz, bkz, nuvz, seed=1)
+    ref, height, _ = reference_run(cb0, raw, akm, bkm, akz, bkz, nuvz)
+    cb, cbn = nest_configs(**kw, height=height)
+    rawn = met_cases.raw_fields(cbn, akz, bkz, nuvz, seed=4)
+    reference_run_nest(ref, cb, rawn, nuvz)
+    g = NEST
+    eng = fb.Engine(cb)
+    eng.set_vertical(nuvz, akm[1:], bkm[1:], akz[1:], bkz[1:])
+    for slot in (1, 2):
+        eng.calcpar_verttransform(slot, raw)
+        ms = eng.calcpar_verttransform_nest(slot, 1, rawn, g["dxn"], g["dyn"], g["xlon0n"], g["ylat0n"])
+        assert ms > 0.0
+    f = eng.fetch_met(1, nest=1)
+    names3 = ("uu", "vv", "ww", "rho", "drhodz") + (("tt", "clouds") if wet else ())
+    got = {nm: np.ascontiguousarray(np.transpose(f[nm][:g["nxn"], :g["nyn"], :nuvz], (2, 1, 0))) for nm in names3}
+    for nm in FIELDS2:
+        got[nm] = np.ascontiguousarray(f[nm][:g["nxn"], :g["nyn"]].T)
+    bad = compare_fields_nest(ref, got, nuvz)
+    assert not bad, bad
+    # particles inside the nest step on the device-built nest slots without leaving the fields
+    eng.fill_rannumb()
+    eng.set_met_bracket((1, 2), (0, 10800))
+    p = cases.seeded_particles(cb, 512, zmax=3000.0, lat_range=(g["ylat0n"] + 3.0, g["ylat0n"] + g["nyn"] - 4.0))
+    p.xtra1[:512] = (np.random.RandomState(3).uniform(g["xlon0n"] + 3.0, g["xlon0n"] + g["nxn"] - 4.0, 512) - cb.cfg.xlon0) / cb.cfg.dx
+    eng.push_particles(p)
+    st = eng.step(0, 450)
+    assert st["n_active"] == 512 and st["n_nonfinite"] == 0
+    q = fb.Particles(cb.cfg.maxpart, 1); q.numpart = 512
+    eng.pull_particles(q)
+    assert np.isfinite(q.xtra1[:512]).all() and np.isfinite(q.ztra1[:512]).all() and (q.itra1[:512] == 900).all()
+    eng.close()
+
+
 def test_particles_step_alike_on_device_built_and_uploaded_slots():
     """The slot fpb_calcpar_verttransform builds is what fpb_upload_met makes of the same fields: the
     particle loop, wet deposition and conccalc give bit-identical results on both, and the oracle on

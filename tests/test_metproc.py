@@ -31,7 +31,7 @@ class MetGrid(C.Structure):
                 ("nglobal", C.c_int), ("sglobal", C.c_int), ("xglobal", C.c_int),
                 ("switchnorthg", C.c_float), ("switchsouthg", C.c_float),
                 ("northpolemap", C.c_float * 9), ("southpolemap", C.c_float * 9),
-                ("lsubgrid", C.c_int), ("readclouds", C.c_int)] + \
+                ("lsubgrid", C.c_int), ("readclouds", C.c_int), ("nest", C.c_int), ("xresol", C.c_float), ("yresol", C.c_float)] + \
                [(n, C.c_void_p) for n in ("akz", "bkz", "akm", "bkm", "height", "cosf", "UV", "W", "TQ", "PV", "theta", "SF1",
                                           "SF2", "excessoro", "CLW", "CIW", "clw", "uvzlev", "A", "G", "T", "P", "S", "trop", "R", "Cl", "Q")]
 
@@ -100,6 +100,34 @@ def compare(cb, ref, out, nuvz):
            "hmix": out["S"][..., 0], "ustar": out["S"][..., 1], "wstar": out["S"][..., 2], "oli": out["S"][..., 3],
            "tropopause": out["trop"], "clouds": out["Cl"], "uupol": out["P"][..., 0], "vvpol": out["P"][..., 1]}
     return compare_fields(cb, ref, got, nuvz)
+
+
+def test_nested_grid_host_build_matches_reference():
+    """calcpar_nests + verttransform_nests + calcpv_nests (src/getfields.f90:131-134): the column code with the
+    nest's geometry, no poles, no wrap, xresoln / yresoln in the slope term"""
+    from metproc_common import nest_configs, reference_run_nest, compare_fields_nest, NEST
+    nuvz = 40
+    kw = dict(nrel=1, npart_each=8, nz=nuvz, wetdepspec=(1,), weta_gas=(2.0e-5,), wetb_gas=(0.62,))
+    cb0, _ = nest_configs(**kw, height=fb.synth_heights(nuvz))
+    akm, bkm, akz, bkz, _ = conv_cases.hybrid_levels(nuvz)
+    raw = met_cases.raw_fields(cb0, akz, bkz, nuvz, seed=1)
+    ref, height, _ = reference_run(cb0, raw, akm, bkm, akz, bkz, nuvz)
+    cb, cbn = nest_configs(**kw, height=height)
+    rawn = met_cases.raw_fields(cbn, akz, bkz, nuvz, seed=4)
+    pvhn = reference_run_nest(ref, cb, rawn, nuvz)
+    k = device_layout_inputs(cbn, rawn, pvhn, akm, bkm, akz, bkz, nuvz, height)
+    g, out = make_grid(cbn, k, nuvz)
+    g.nglobal = g.sglobal = g.xglobal = 0
+    g.nest, g.xresol, g.yresol = 1, cb.cfg.xresoln[0], cb.cfg.yresoln[0]
+    g.dxconst, g.dyconst = cb.cfg.dxconst, cb.cfg.dyconst       # the mother grid's (src/verttransform_nests.f90:322)
+    _host_lib().met_check_run(C.byref(g))
+    got = {"uu": out["A"][..., 0], "vv": out["A"][..., 1], "ww": out["A"][..., 2], "rho": out["A"][..., 3],
+           "drhodz": out["G"], "tt": out["T"], "hmix": out["S"][..., 0], "ustar": out["S"][..., 1],
+           "wstar": out["S"][..., 2], "oli": out["S"][..., 3], "tropopause": out["trop"], "clouds": out["Cl"],
+           "pv": out["Q"][..., 0], "qv": out["Q"][..., 1]}
+    bad = compare_fields_nest(ref, got, nuvz)
+    assert not bad, bad
+    assert len(set(np.unique(out["Cl"]))) >= 4 and np.abs(out["A"][..., 2]).max() > 0.01
 
 
 @pytest.mark.parametrize("sumclouds", [0, 1])
