@@ -2658,6 +2658,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   a.block_counts = V.block_counts; a.colidx = V.colidx; a.col_key = V.col_key; a.col_start = V.col_start;
   a.col_lconv = V.col_lconv; a.pool = V.pool;
   a.draws = V.draws; a.rn_by_slot = nullptr; a.sorted_ids = nullptr;
+  a.flux = (c.iflux == 1) ? h->hooks.flux : nullptr;
   if (refrng) CK(cudaMemsetAsync(V.key_by_slot, 0xff, (size_t)h->numpart * sizeof(int32_t), h->stream)); // -1
   fpb_convmix_keys(a, h->stream);
   int gbits = 0;

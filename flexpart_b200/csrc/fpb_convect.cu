@@ -19,6 +19,7 @@
 // reference's routines in every math mode (see fpb_convect.cuh).
 #include "fpb_convect.cuh"
 #include "fpb_convmix.cuh"
+#include "fpb_output.cuh"
 
 namespace {
 using namespace fpbconv;
@@ -199,7 +200,20 @@ __global__ void __launch_bounds__(128) conv_redist_kernel(const ConvmixArgs a, i
     z = conv_redist(w, z, levold, rn, cf.ldirect, cf.lsynctime);
   }
   if (z > a.ztop - 0.5f) z = a.ztop - 0.5f; // label 90
+  const float ztold = a.p.ztra1[row];
   a.p.ztra1[row] = z;
+  if (a.flux) { // gross fluxes of the convective displacement, src/convmix.f90:205-218
+    const int itage = abs(a.p.itra1[row] - a.p.itramem[row]);
+    int nage;
+    for (nage = 1; nage <= cf.nageclass; nage++)
+      if (itage < cf.lage[nage - 1]) break;
+    if (nage <= cf.nageclass) {
+      const double xt = a.p.xtra1[row], yt = a.p.ytra1[row];
+      const int kp = (cf.ioutputforeachrelease == 1 && cf.mdomainfill == 0) ? a.p.npoint[row] : 1;
+      fpb_flux_particle(cf, a.flux, nage, kp, (float)xt, (float)yt, ztold, xt, yt, z,
+                        [&](int k) { return a.p.xmass1[(size_t)(k - 1) * a.p.maxpart + row]; });
+    }
+  }
 }
 
 } // namespace

@@ -30,6 +30,7 @@ struct ConvmixArgs {
   float *pool;                // work pool: CONV_BATCH columns x conv_pool_floats()
   uint8_t *draws;             // reference RNG: [slot] the particle draws a uniform
   const float *rn_by_slot;    // reference RNG: the uniforms, by slot; null: Philox
+  float *flux;                // iflux = 1: calcfluxes after redist (src/convmix.f90:205-218), else null
 };
 
 void fpb_convmix_keys(const ConvmixArgs &a, cudaStream_t st);

@@ -251,74 +251,14 @@ __global__ void __launch_bounds__(256) hooks_pre_kernel(const HookArgs a) {
 __device__ __forceinline__ void flux_row(const HookArgs &a, int j) {
   const DevCfg &c = a.cfg;
   const float xold = a.old[j], yold = a.old[a.old_stride + j], zold = a.old[2 * a.old_stride + j];
-  const double xt = a.p.xtra1[j], yt = a.p.ytra1[j];
-  const float zt = a.p.ztra1[j];
   const int itage = abs(c.itime - a.p.itramem[j]);
   int nage;
   for (nage = 1; nage <= c.nageclass; nage++)
     if (itage < c.lage[nage - 1]) break;
   if (nage > c.nageclass) return; // (the reference would index past the array)
   const int kp = (c.ioutputforeachrelease == 1 && c.mdomainfill == 0) ? a.p.npoint[j] : 1;
-  const float xmean = (float)(((double)xold + xt) / 2.0);
-  const float ymean = (float)(((double)yold + yt) / 2.0);
-  const int ixave = (int)((xmean * c.dx + c.xoutshift) / c.dxout);
-  const int jyave = (int)((ymean * c.dy + c.youtshift) / c.dyout);
-  int kzave;
-  for (kzave = 1; kzave <= c.numzgrid; kzave++)
-    if (c.outheight[kzave - 1] > zt) break;
-  const size_t n1 = 6, nxg = c.numxgrid, nyg = c.numygrid, nzg = c.numzgrid;
-  auto add = [&](int i, int ix, int jy, int kz, int k) { // flux(i, ix, jy, kz, k, kp, nage) += xmass1(jpart, k)
-    const size_t o = (i - 1) + n1 * (ix + nxg * (jy + nyg * ((kz - 1) + nzg * ((k - 1) + (size_t)c.nspec *
-                     ((kp - 1) + (size_t)c.maxpointspec_act * (nage - 1))))));
-    atomicAdd(a.flux + o, a.old[(3 + (size_t)(k - 1)) * a.old_stride + j]);
-  };
-  auto half = [&](int kz) { // outheighthalf, src/readoutgrid.f90:194-197
-    return kz == 1 ? c.outheight[0] / 2.f : (c.outheight[kz - 2] + c.outheight[kz - 1]) / 2.f;
-  };
-  // vertical fluxes
-  if (ixave >= 0 && jyave >= 0 && ixave <= c.numxgrid - 1 && jyave <= c.numygrid - 1) {
-    int kz;
-    for (kz = 1; kz <= c.numzgrid; kz++)
-      if (half(kz) > zold) break;
-    const int k1 = min(c.numzgrid, kz);
-    for (kz = 1; kz <= c.numzgrid; kz++)
-      if (half(kz) > zt) break;
-    const int k2 = min(c.numzgrid, kz);
-    for (int k = 1; k <= c.nspec; k++) {
-      for (kz = k1; kz <= k2 - 1; kz++) add(5, ixave, jyave, kz, k);
-      for (kz = k2; kz <= k1 - 1; kz++) add(6, ixave, jyave, kz, k);
-    }
-  }
-  // west-east fluxes
-  if (kzave <= c.numzgrid && jyave >= 0 && jyave <= c.numygrid - 1) {
-    if (fabs((double)xold - xt) < (double)((float)c.nx / 2.f)) {
-      const int ix1 = (int)((xold * c.dx + c.xoutshift) / c.dxout + 0.5f);
-      const int ix2 = (int)((xt * (double)c.dx + (double)c.xoutshift) / (double)c.dxout + 0.5);
-      for (int k = 1; k <= c.nspec; k++) {
-        for (int ix = ix1; ix <= ix2 - 1; ix++)
-          if (ix >= 0 && ix <= c.numxgrid - 1) add(1, ix, jyave, kzave, k);
-        for (int ix = ix2; ix <= ix1 - 1; ix++)
-          if (ix >= 0 && ix <= c.numxgrid - 1) add(2, ix, jyave, kzave, k);
-      }
-    } else { // the particle crossed the date line of a global domain
-      const int ixs = (int)((((float)c.nxmin1 - 1.0e5f) * c.dx + c.xoutshift) / c.dxout);
-      if (ixs >= 0 && ixs <= c.numxgrid - 1) {
-        const int i = ((double)xold > xt) ? 1 : 2;
-        for (int k = 1; k <= c.nspec; k++) add(i, ixs, jyave, kzave, k);
-      }
-    }
-  }
-  // south-north fluxes
-  if (kzave <= c.numzgrid && ixave >= 0 && ixave <= c.numxgrid - 1) {
-    const int jy1 = (int)((yold * c.dy + c.youtshift) / c.dyout + 0.5f);
-    const int jy2 = (int)((yt * (double)c.dy + (double)c.youtshift) / (double)c.dyout + 0.5);
-    for (int k = 1; k <= c.nspec; k++) {
-      for (int jy = jy1; jy <= jy2 - 1; jy++)
-        if (jy >= 0 && jy <= c.numygrid - 1) add(3, ixave, jy, kzave, k);
-      for (int jy = jy2; jy <= jy1 - 1; jy++)
-        if (jy >= 0 && jy <= c.numygrid - 1) add(4, ixave, jy, kzave, k);
-    }
-  }
+  fpb_flux_particle(c, a.flux, nage, kp, xold, yold, zold, a.p.xtra1[j], a.p.ytra1[j], a.p.ztra1[j],
+                    [&](int k) { return a.old[(3 + (size_t)(k - 1)) * a.old_stride + j]; });
 }
 
 // src/partpos_average.f90:47-186 for row j

@@ -85,3 +85,73 @@ struct HookArgs {
 };
 void fpb_hooks_pre(const HookArgs &a, cudaStream_t st);
 void fpb_hooks_post(const HookArgs &a, cudaStream_t st);
+
+#ifdef __CUDACC__
+// src/calcfluxes.f90:55-166 for one particle: old position (default reals) -> new position; mass(k) = xmass1(jpart, k).
+// The caller has worked out the age class (1..nageclass) and kp.  Used by the loop hook (fpb_output.cu) and by
+// convmix's own call after redist (src/convmix.f90:205-218, fpb_convect.cu); compile without contraction.
+template <class MassFn>
+__device__ __forceinline__ void fpb_flux_particle(const DevCfg &c, float *flux, int nage, int kp, float xold, float yold,
+                                                  float zold, double xt, double yt, float zt, MassFn mass) {
+  const float xmean = (float)(((double)xold + xt) / 2.0);
+  const float ymean = (float)(((double)yold + yt) / 2.0);
+  const int ixave = (int)((xmean * c.dx + c.xoutshift) / c.dxout);
+  const int jyave = (int)((ymean * c.dy + c.youtshift) / c.dyout);
+  int kzave;
+  for (kzave = 1; kzave <= c.numzgrid; kzave++)
+    if (c.outheight[kzave - 1] > zt) break;
+  const size_t n1 = 6, nxg = c.numxgrid, nyg = c.numygrid, nzg = c.numzgrid;
+  auto add = [&](int i, int ix, int jy, int kz, int k) { // flux(i, ix, jy, kz, k, kp, nage) += xmass1(jpart, k)
+    const size_t o = (i - 1) + n1 * (ix + nxg * (jy + nyg * ((kz - 1) + nzg * ((k - 1) + (size_t)c.nspec *
+                     ((kp - 1) + (size_t)c.maxpointspec_act * (nage - 1))))));
+    atomicAdd(flux + o, mass(k));
+  };
+  auto half = [&](int kz) { // outheighthalf, src/readoutgrid.f90:194-197
+    return kz == 1 ? c.outheight[0] / 2.f : (c.outheight[kz - 2] + c.outheight[kz - 1]) / 2.f;
+  };
+  // vertical fluxes
+  if (ixave >= 0 && jyave >= 0 && ixave <= c.numxgrid - 1 && jyave <= c.numygrid - 1) {
+    int kz;
+    for (kz = 1; kz <= c.numzgrid; kz++)
+      if (half(kz) > zold) break;
+    const int k1 = min(c.numzgrid, kz);
+    for (kz = 1; kz <= c.numzgrid; kz++)
+      if (half(kz) > zt) break;
+    const int k2 = min(c.numzgrid, kz);
+    for (int k = 1; k <= c.nspec; k++) {
+      for (kz = k1; kz <= k2 - 1; kz++) add(5, ixave, jyave, kz, k);
+      for (kz = k2; kz <= k1 - 1; kz++) add(6, ixave, jyave, kz, k);
+    }
+  }
+  // west-east fluxes
+  if (kzave <= c.numzgrid && jyave >= 0 && jyave <= c.numygrid - 1) {
+    if (fabs((double)xold - xt) < (double)((float)c.nx / 2.f)) {
+      const int ix1 = (int)((xold * c.dx + c.xoutshift) / c.dxout + 0.5f);
+      const int ix2 = (int)((xt * (double)c.dx + (double)c.xoutshift) / (double)c.dxout + 0.5);
+      for (int k = 1; k <= c.nspec; k++) {
+        for (int ix = ix1; ix <= ix2 - 1; ix++)
+          if (ix >= 0 && ix <= c.numxgrid - 1) add(1, ix, jyave, kzave, k);
+        for (int ix = ix2; ix <= ix1 - 1; ix++)
+          if (ix >= 0 && ix <= c.numxgrid - 1) add(2, ix, jyave, kzave, k);
+      }
+    } else { // the particle crossed the date line of a global domain
+      const int ixs = (int)((((float)c.nxmin1 - 1.0e5f) * c.dx + c.xoutshift) / c.dxout);
+      if (ixs >= 0 && ixs <= c.numxgrid - 1) {
+        const int i = ((double)xold > xt) ? 1 : 2;
+        for (int k = 1; k <= c.nspec; k++) add(i, ixs, jyave, kzave, k);
+      }
+    }
+  }
+  // south-north fluxes
+  if (kzave <= c.numzgrid && ixave >= 0 && ixave <= c.numxgrid - 1) {
+    const int jy1 = (int)((yold * c.dy + c.youtshift) / c.dyout + 0.5f);
+    const int jy2 = (int)((yt * (double)c.dy + (double)c.youtshift) / (double)c.dyout + 0.5);
+    for (int k = 1; k <= c.nspec; k++) {
+      for (int jy = jy1; jy <= jy2 - 1; jy++)
+        if (jy >= 0 && jy <= c.numygrid - 1) add(3, ixave, jy, kzave, k);
+      for (int jy = jy2; jy <= jy1 - 1; jy++)
+        if (jy >= 0 && jy <= c.numygrid - 1) add(4, ixave, jy, kzave, k);
+    }
+  }
+}
+#endif

@@ -352,8 +352,8 @@ int fpb_partoutput(fpb_handle *h, int32_t itime, int32_t *nrecords, const fpb_pa
  *              decay / deposition, as the reference's call order has it) to the faces of the output-grid cells
  *              it crossed.  fpb_fetch_fluxes copies flux(6, 0:numxgrid-1, 0:numygrid-1, numzgrid, nspec,
  *              maxpointspec_act, nageclass) out (NULL: no copy) and, with zero != 0, clears it the way
- *              fluxoutput does after writing (src/fluxoutput.f90:288-303).  The calcfluxes call inside convmix
- *              (src/convmix.f90) is not built.
+ *              fluxoutput does after writing (src/fluxoutput.f90:288-303).  fpb_convmix adds the fluxes of its
+ *              vertical displacements the same way (src/convmix.f90:205-218).
  *   ipout = 3  partpos_average (src/partpos_average.f90): per-particle running sums for partoutput_average;
  *              needs fpb_set_orography and fpb_upload_pvqv like fpb_partoutput.  fpb_fetch_partpos_average
  *              copies the first numpart slots of npart_av / part_av_* (any pointer may be NULL) and, with
@@ -506,8 +506,8 @@ int fpb_fetch_met_nest(fpb_handle *h, int32_t slot, int32_t nest, const fpb_met_
  *                       nymaxn); tthn, qvhn (nxmaxn,nymaxn,nuvzmax)): a particle inside a nest takes
  *                       part in the nest's columns only (the innermost one, src/convmix.f90:100-134,
  *                       198-281), with the nest's own cbasefluxn
- * ECMWF fields (metdata_format = GRIBFILE_CENTRE_ECMWF); the flux diagnostics (calcfluxes, iflux = 1)
- * are not built. */
+ * ECMWF fields (metdata_format = GRIBFILE_CENTRE_ECMWF).  With iflux = 1 every displaced particle's
+ * calcfluxes call (src/convmix.f90:205-218) adds to the flux array fpb_fetch_fluxes returns. */
 typedef struct fpb_conv_ptrs {
   const float *ps, *tt2, *td2;
   const float *tth, *qvh;

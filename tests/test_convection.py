@@ -107,12 +107,12 @@ def test_column_code_is_bit_identical_to_the_reference_routines(hostlib, ldirect
 # ------------------------------------------------------------------------------------------
 # GPU: fpb_convmix against the reference's convmix
 # ------------------------------------------------------------------------------------------
-def _conv_setup(rng_mode, ldirect=1, n=6000, sort_interval=0, met_nests=()):
+def _conv_setup(rng_mode, ldirect=1, n=6000, sort_interval=0, met_nests=(), iflux=0):
     nuvz = 138
     akm, bkm, akz, bkz, nconvlev = conv_cases.hybrid_levels(nuvz)
     cb = cases.config_small(nrel=4, npart_each=n // 4, nz=nuvz, height=fb.synth_heights(nuvz), ldirect=ldirect,
                             rng_mode=rng_mode, math_mode=fb.MATH_STRICT, sort_interval=sort_interval,
-                            met_nests=met_nests)
+                            met_nests=met_nests, iflux=iflux)
     sign = 1 if ldirect == 1 else -1
     f0 = conv_cases.conv_fields(cb, akz, bkz, nuvz, 1)
     f1 = conv_cases.conv_fields(cb, akz, bkz, nuvz, 2, tshift=1.5)
@@ -123,15 +123,16 @@ def _conv_setup(rng_mode, ldirect=1, n=6000, sort_interval=0, met_nests=()):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ldirect", [1, -1])
-@pytest.mark.parametrize("sort_interval", [0, 1])
-def test_convmix_reference_stream_is_bit_identical(ldirect, sort_interval):
+@pytest.mark.parametrize("sort_interval,iflux", [(0, 0), (1, 1)])
+def test_convmix_reference_stream_is_bit_identical(ldirect, sort_interval, iflux):
     """convmix on the device, the reference's ran3 stream replayed in its sort2 visiting order, against
     the reference's own convmix (oracle/_ref): every particle height bit-identical over three calls
-    (cbaseflux carried from call to call), forward and backward, rows cell-sorted or not."""
+    (cbaseflux carried from call to call), forward and backward, rows cell-sorted or not.  iflux = 1: the
+    gross fluxes of the convective displacements (calcfluxes, src/convmix.f90:205-218) as well."""
     if not ref_api.available():
         pytest.skip("oracle/_ref/libflexref.so not built")
     cb, (akm, bkm, akz, bkz, nconvlev, nuvz), (f0, f1), p, sign = _conv_setup(fb.RNG_REFERENCE, ldirect, 6000,
-                                                                                  sort_interval)
+                                                                                  sort_interval, iflux=iflux)
     c, n = cb.cfg, p.numpart
     mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(10800 * sign))
     ref = ref_api.Ref(cb, maxrand=2000)
@@ -145,6 +146,12 @@ def test_convmix_reference_stream_is_bit_identical(ldirect, sort_interval):
     ref.set_met_bracket((1, 2), (0, 10800 * sign))
     ref.arr("cbaseflux")[:] = 0.0
     ref.push_state(p)
+    if iflux:
+        ref.set("iflux", 1)
+        oh = np.array([cb.cfg.outheight[k] for k in range(cb.cfg.numzgrid)], np.float32)
+        half = ref.arr("outheighthalf")          # src/readoutgrid.f90:194-197
+        half[0] = oh[0] / np.float32(2.0)
+        half[1:] = (oh[:-1] + oh[1:]) / np.float32(2.0)
     eng = fb.Engine(cb)
     eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1]); eng.set_met_bracket((1, 2), (0, 10800 * sign))
     eng.set_convection(nuvz, c.nzmax, nconvlev, akz[1:], bkz[1:], akm[1:], bkm[1:])
@@ -166,7 +173,10 @@ def test_convmix_reference_stream_is_bit_identical(ldirect, sort_interval):
         assert np.array_equal(q.ztra1[n - 200:n], p.ztra1[n - 200:n])
         moved += int((zr != z_before).sum())
     assert moved > 500
-    # the cloud base mass fluxes carried on the device equal the reference's
+    if iflux:   # unit masses: the sums are exact whatever the order of the atomics
+        fg, fr = eng.fetch_fluxes(), ref.arr("flux")
+        assert fg.shape == fr.shape and fg[4].sum() > 100 and fg[5].sum() > 100 and np.array_equal(fg, fr)
+        assert not fg[:4].any()     # a vertical displacement crosses no lateral face
     eng.close()
 
 
