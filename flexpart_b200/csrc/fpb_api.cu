@@ -311,7 +311,7 @@ struct fpb_handle {
     float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr;
     float *CLW = nullptr, *CIW = nullptr, *clw = nullptr; // readclouds
     struct NestWork { // calcpar_nests / verttransform_nests: work arrays in the nest's extents
-      float2 *UV = nullptr;
+      float2 *UV = nullptr, *Q = nullptr;
       float *W = nullptr, *PV = nullptr, *theta = nullptr, *excessoro = nullptr, *uvzlev = nullptr, *T = nullptr, *cosf = nullptr;
       float4 *SF2 = nullptr;
     } nw[FPB_MAXNESTS];
@@ -854,7 +854,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(M.uvzlev); cudaFree(M.SF2);
     for (auto &w : M.nw) {
       cudaFree(w.UV); cudaFree(w.W); cudaFree(w.PV); cudaFree(w.theta); cudaFree(w.excessoro); cudaFree(w.uvzlev);
-      cudaFree(w.T); cudaFree(w.cosf); cudaFree(w.SF2);
+      cudaFree(w.T); cudaFree(w.cosf); cudaFree(w.SF2); cudaFree(w.Q);
     }
     if (M.ev0) cudaEventDestroy(M.ev0);
     if (M.ev1) cudaEventDestroy(M.ev1);
@@ -2386,6 +2386,7 @@ extern "C" int fpb_calcpar_verttransform_nest(fpb_handle *h, int32_t slot, int32
   if (!m->pvh && !W.theta) DA(W.theta, n3);
   if (lsubgrid == 1 && !W.excessoro) DA(W.excessoro, n2);
   if (!c.wetdep && !W.T) DA(W.T, n3); // (ttn is kept only for wet deposition, src/com_mod.f90:501-529)
+  if (c.wetdep && !W.Q) DA(W.Q, n3);  // (qvn: read by the cloud classes)
   if (!V.CT[nest][s]) { DA(V.CT[nest][s], n3); DA(V.CS[nest][s], n2); }
   cudaStream_t st = h->st_met;
   CK(cudaEventRecord(M.ev0, st));
@@ -2413,7 +2414,7 @@ extern "C" int fpb_calcpar_verttransform_nest(fpb_handle *h, int32_t slot, int32
   g.UV = W.UV; g.W = W.W; g.TQ = V.CT[nest][s]; g.PV = W.PV; g.theta = m->pvh ? nullptr : W.theta;
   g.SF1 = V.CS[nest][s]; g.SF2 = W.SF2; g.excessoro = W.excessoro; g.uvzlev = W.uvzlev;
   g.A = h->An[l][s]; g.G = h->Gn[l][s]; g.T = c.wetdep ? h->Tn[l][s] : W.T; g.S = h->Sn[l][s]; g.trop = h->tropn[l][s];
-  g.R = c.wetdep ? h->Rn[l][s] : nullptr; g.Cl = c.wetdep ? h->Cln[l][s] : nullptr;
+  g.R = c.wetdep ? h->Rn[l][s] : nullptr; g.Cl = c.wetdep ? h->Cln[l][s] : nullptr; g.Q = c.wetdep ? W.Q : nullptr;
   CK(cudaEventRecord(M.evk, st));
   fpb_metproc_launch(g, st, &h->launches);
   CK(cudaEventRecord(M.ev1, st));

