@@ -2882,7 +2882,7 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
     }
     per_eq = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
     const char *plan = getenv("FPB_HOST_PLAN"); // tuning knob: chunk sizes as fractions, e.g. "0.1,0.3,0.3,0.2,0.1"
-    if (streamed && !getenv("FPB_HOST_CHUNKS") && (plan || numpart >= 400000)) {
+    if (plan || (streamed && !getenv("FPB_HOST_CHUNKS") && numpart >= 400000)) {
       // streamed and large: a small first chunk (the kernels start early), large ones in the middle (copy
       // efficiency), small ones at the end (what is left to do when the last copy has landed is short)
       std::vector<double> fr = {0.06, 0.14, 0.22, 0.22, 0.18, 0.10, 0.05, 0.03};
