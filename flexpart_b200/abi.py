@@ -57,7 +57,7 @@ class FpbConfig(C.Structure):
         ("height", _pf),
         ("maxpart", _i), ("device", _i), ("rng_mode", _i), ("math_mode", _i), ("scatter_mode", _i),
         ("seed", C.c_uint64), ("part_id_stride", _i), ("part_id_offset", _i),
-        ("sort_interval", _i), ("iflux", _i), ("ipout", _i), ("reserved", _i * 5),
+        ("sort_interval", _i), ("iflux", _i), ("ipout", _i), ("linit_cond", _i), ("reserved", _i * 4),
     ]
 
 
@@ -214,6 +214,8 @@ def load_engine_lib():
     L.fpb_upload_pvqv.argtypes = [H, _i, _pf, _pf]
     L.fpb_partoutput.argtypes = [H, _i, _pi, C.POINTER(FpbPartoutPtrs)]
     L.fpb_fetch_fluxes.argtypes = [H, _pf, _i]
+    L.fpb_fetch_init_cond.argtypes = [H, _pf, _i]
+    L.fpb_initial_cond_final.argtypes = [H, _i]
     L.fpb_fetch_partpos_average.argtypes = [H, _i, C.POINTER(FpbPartavPtrs), _i]
     L.fpb_concoutput_sparse.argtypes = [H, _i, _i, _i, _i, _i, _f, _f, _i, _pi, _pi, _pi, _pf]
     L.fpb_releaseparticles.argtypes = [H, _i, _pi, _pi]

@@ -179,9 +179,9 @@ struct fpb_handle {
   // the optional hooks of the particle loop: calcfluxes / partpos_average (fpb_output.cuh)
   struct Hooks {
     uint8_t *adv = nullptr;
-    float *old = nullptr, *flux = nullptr, *av = nullptr;
+    float *old = nullptr, *flux = nullptr, *av = nullptr, *init_cond = nullptr;
     int32_t *npart_av = nullptr;
-    size_t nflux = 0;
+    size_t nflux = 0, ninit = 0;
   } hooks;
   // device-side releaseparticles
   struct Releases {
@@ -377,6 +377,7 @@ struct fpb_handle {
   static constexpr int MAXCHUNKS = 32;
   cudaStream_t st_pbl = nullptr, st_post[NLANES] = {};
   cudaEvent_t ev_rdy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_out[MAXCHUNKS] = {};
   int *d_stream_ctl = nullptr; // [2 + MAXCHUNKS]
   bool stream_live = false;    // a streamed sub-step kernel may be waiting for rows
 };
@@ -502,6 +503,7 @@ static void fill_devcfg(fpb_handle *h) {
   d.lusekerneloutput = c.lusekerneloutput; d.lparticlecountoutput = c.lparticlecountoutput;
   d.drydep = c.drydep; d.drybkdep = c.drybkdep; d.wetbkdep = c.wetbkdep;
   d.nested_output = c.nested_output;
+  d.linit_cond = c.linit_cond;
   d.nspec = c.nspec;
   for (int k = 0; k < FPB_MAXSPEC; k++) {
     d.decay[k] = c.decay[k]; d.drydepspec[k] = c.drydepspec[k]; d.density[k] = c.density[k];
@@ -700,6 +702,8 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   if (cfg->ldirect != 1 && cfg->ldirect != -1) return fail("fpb_init: ldirect must be 1 or -1 (got %d)", cfg->ldirect);
   if ((cfg->drybkdep || cfg->wetbkdep) && cfg->ldirect != -1)
     return fail("fpb_init: drybkdep/wetbkdep (IND_RECEPTOR 3/4) are backward-run options (src/readcommand.f90:320-339)");
+  if (cfg->linit_cond < 0 || cfg->linit_cond > 2) return fail("fpb_init: linit_cond must be 0, 1 or 2 (got %d)", cfg->linit_cond);
+  if (cfg->linit_cond > 0 && cfg->ldirect == 1) return fail("fpb_init: linit_cond is a backward-run option (src/readcommand.f90:349)");
   if (cfg->drybkdep && !cfg->drydep) return fail("fpb_init: drybkdep needs drydep (a species with dry deposition)");
   if (cfg->wetbkdep && !cfg->wetdep) return fail("fpb_init: wetbkdep needs wetdep (a species with wet deposition)");
   int ndev = 0;
@@ -753,11 +757,15 @@ extern "C" int fpb_init(const fpb_config *cfg, fpb_handle **out) {
   DA(h->d_work, 1);
   DA(h->sc.flags, mp); DA(h->sc.s0, mp); DA(h->sc.s1, mp); DA(h->sc.s2, mp);
   if (c.drydep) DA(h->sc.prob, mp * c.nspec);
-  if (c.iflux == 1 || c.ipout == 3) DA(h->hooks.adv, mp);
+  if (c.iflux == 1 || c.ipout == 3 || c.linit_cond > 0) DA(h->hooks.adv, mp);
+  if (c.iflux == 1 || c.linit_cond > 0) DA(h->hooks.old, mp * (3 + (size_t)c.nspec));
   if (c.iflux == 1) {
     h->hooks.nflux = (size_t)6 * c.numxgrid * c.numygrid * c.numzgrid * c.nspec * c.maxpointspec_act * c.nageclass;
     DA(h->hooks.flux, h->hooks.nflux);
-    DA(h->hooks.old, mp * (3 + (size_t)c.nspec));
+  }
+  if (c.linit_cond > 0) {
+    h->hooks.ninit = (size_t)c.numxgrid * c.numygrid * c.numzgrid * c.maxspec * c.maxpointspec_act;
+    DA(h->hooks.init_cond, h->hooks.ninit);
   }
   if (c.ipout == 3) { DA(h->hooks.npart_av, mp); DA(h->hooks.av, mp * 14); }
   h->launches += 3;
@@ -848,6 +856,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   cudaFree(h->sort_rec);
   dep_free(h->depstore);
   cudaFree(h->hooks.adv); cudaFree(h->hooks.old); cudaFree(h->hooks.flux); cudaFree(h->hooks.av); cudaFree(h->hooks.npart_av);
+  cudaFree(h->hooks.init_cond);
   {
     auto &M = h->metproc;
     cudaFree(M.d_ab); cudaFree(M.d_cosf); cudaFree(M.UV); cudaFree(M.W); cudaFree(M.PV); cudaFree(M.theta); cudaFree(M.excessoro); cudaFree(M.CLW); cudaFree(M.CIW); cudaFree(M.clw);
@@ -875,6 +884,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
   if (h->st_pbl) { cudaStreamSynchronize(h->st_pbl); cudaStreamDestroy(h->st_pbl); }
   for (auto &q : h->st_post) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
   for (auto &e : h->ev_rdy) if (e) cudaEventDestroy(e);
+  for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
   cudaFree(h->d_stream_ctl);
   if (h->st_in) { cudaStreamSynchronize(h->st_in); cudaStreamDestroy(h->st_in); }
   for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
@@ -1338,7 +1348,7 @@ static int launch_bkdep(fpb_handle *h, const DevCfg &cfg, const DevParticles &ro
 
 // calcfluxes / partpos_average around the step kernels (src/timemanager.f90:614-623); rows = the view the step
 // kernels work on, row0 = its first row in the engine's arrays
-static bool hooks_on(const fpb_handle *h) { return h->cfg.iflux == 1 || h->cfg.ipout == 3; }
+static bool hooks_on(const fpb_handle *h) { return h->cfg.iflux == 1 || h->cfg.ipout == 3 || h->cfg.linit_cond > 0; }
 static int hooks_args(fpb_handle *h, HookArgs &k, const DevCfg &cfg, const DevParticles &rows, int row0) {
   const fpb_config &c = h->cfg;
   if (c.ipout == 3 && (!h->outp.oro || !h->outp.have_q[h->memind[0] - 1] || !h->outp.have_q[h->memind[1] - 1]))
@@ -1351,7 +1361,11 @@ static int hooks_args(fpb_handle *h, HookArgs &k, const DevCfg &cfg, const DevPa
   k.oro = h->outp.oro;
   k.height = h->d_height;
   k.p = rows;
-  k.iflux = c.iflux == 1; k.ipout3 = c.ipout == 3;
+  k.iflux = c.iflux == 1; k.ipout3 = c.ipout == 3; k.linit = c.linit_cond;
+  k.flags = h->sc.flags + row0;
+  k.init_cond = h->hooks.init_cond;
+  k.maxspec = c.maxspec;
+  k.final_pass = 0;
   k.adv = h->hooks.adv + row0;
   k.old = h->hooks.old ? h->hooks.old + row0 : nullptr;
   k.old_stride = (size_t)c.maxpart;
@@ -1648,6 +1662,40 @@ extern "C" int fpb_fetch_fluxes(fpb_handle *h, float *flux, int32_t zero) {
   CK(cudaSetDevice(h->device));
   if (flux) CK(cudaMemcpyAsync(flux, h->hooks.flux, h->hooks.nflux * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   if (zero) CK(cudaMemsetAsync(h->hooks.flux, 0, h->hooks.nflux * sizeof(float), h->stream)); // src/fluxoutput.f90:288-303
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int fpb_fetch_init_cond(fpb_handle *h, float *init_cond, int32_t zero) {
+  if (!h) return fail("fpb_fetch_init_cond: null handle");
+  if (h->cfg.linit_cond <= 0) return fail("fpb_fetch_init_cond: the engine was created with linit_cond = 0");
+  CK(cudaSetDevice(h->device));
+  if (init_cond) CK(cudaMemcpyAsync(init_cond, h->hooks.init_cond, h->hooks.ninit * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (zero) CK(cudaMemsetAsync(h->hooks.init_cond, 0, h->hooks.ninit * sizeof(float), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// src/timemanager.f90:733-737: initial_cond_calc for every particle still active at the end of the run
+extern "C" int fpb_initial_cond_final(fpb_handle *h, int32_t itime) {
+  if (!h) return fail("fpb_initial_cond_final: null handle");
+  if (h->cfg.linit_cond <= 0) return fail("fpb_initial_cond_final: the engine was created with linit_cond = 0");
+  if (h->cfg.linit_cond == 1 && !h->have_bracket) return fail("fpb_initial_cond_final: fpb_set_met_bracket has not been called");
+  if (h->numpart == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  HookArgs k;
+  DevCfg cfg;
+  per_step_cfg(h, cfg, itime, 0);
+  if (h->active_rows >= 0) cfg.numpart = h->active_rows;
+  const int ipout = h->cfg.ipout;
+  h->cfg.ipout = 0; // (no average fields needed here)
+  const int rc = hooks_args(h, k, cfg, h->p, 0);
+  h->cfg.ipout = ipout;
+  if (rc) return 1;
+  k.iflux = 0; k.ipout3 = 0; k.final_pass = 1;
+  fpb_hooks_post(k, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -2773,6 +2821,7 @@ static int ensure_lanes(fpb_handle *h) {
   CK(cudaStreamCreateWithFlags(&h->st_pbl, cudaStreamNonBlocking));
   for (auto &q : h->st_post) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
   for (auto &e : h->ev_rdy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : h->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   DA(h->d_stream_ctl, 4 + 2 * fpb_handle::MAXCHUNKS);
   // (loaded here, not under a running sub-step kernel; see step_host_impl)
   CK(cudaMemsetAsync(h->d_stream_ctl, 0, (2 + fpb_handle::MAXCHUNKS) * sizeof(int), h->st_pbl));
@@ -2963,6 +3012,26 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
   int per = 0; // largest chunk: size of the lanes' sort work areas
   for (size_t k = 0; k + 1 < bounds.size(); k++) per = std::max(per, bounds[k + 1] - bounds[k]);
 
+  // FPB_HOST_DEFER_D2H=1 (tuning knob): every chunk's copy back to the host waits for the LAST chunk's upload, on one
+  // stream of its own -- the two directions then do not share the link while the uploads (the critical path) run
+  const bool defer_d2h = !streamed && !dbg && !timing && bounds.size() > 2 && getenv("FPB_HOST_DEFER_D2H") &&
+                         atoi(getenv("FPB_HOST_DEFER_D2H")) != 0;
+  auto d2h_rows = [&](int c0, int n, cudaStream_t post) -> int {
+    D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
+    D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
+    D2HS(p->idt, h->p_alt.idt, int32_t);
+    D2HS(p->uap, h->p_alt.uap, float); D2HS(p->ucp, h->p_alt.ucp, float); D2HS(p->uzp, h->p_alt.uzp, float);
+    D2HS(p->us, h->p_alt.us, float); D2HS(p->vs, h->p_alt.vs, float); D2HS(p->ws, h->p_alt.ws, float);
+    D2HS(p->cbt, h->p_alt.cbt, int16_t);
+    for (int k = 0; k < c.nspec; k++) {
+      CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + c0, h->p_alt.xmass1 + (size_t)k * c.maxpart + c0,
+                         (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, post));
+      if (c.drybkdep || c.wetbkdep) // set once after the release by the receptor block of the loop
+        CK(cudaMemcpyAsync(p->xscav_frac1 + (size_t)k * p->ld + c0, h->p_alt.xscav_frac1 + (size_t)k * c.maxpart + c0,
+                           (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, post));
+    }
+    return 0;
+  };
   auto fill_step_args = [&](DevStepArgs &a, int c0, int n) {
     per_step_cfg(h, a.cfg, itime, ldeltat);
     a.cfg.numpart = n;
@@ -3132,24 +3201,26 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
     sortk_scatter_back(rows, h->p_alt, n, c.nspec, post, c.drybkdep || c.wetbkdep);
     h->launches++;
     STAGE("scatter_back");
-    mark(post);
-    D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
-    D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
-    D2HS(p->idt, h->p_alt.idt, int32_t);
-    D2HS(p->uap, h->p_alt.uap, float); D2HS(p->ucp, h->p_alt.ucp, float); D2HS(p->uzp, h->p_alt.uzp, float);
-    D2HS(p->us, h->p_alt.us, float); D2HS(p->vs, h->p_alt.vs, float); D2HS(p->ws, h->p_alt.ws, float);
-    D2HS(p->cbt, h->p_alt.cbt, int16_t);
-    for (int k = 0; k < c.nspec; k++) {
-      CK(cudaMemcpyAsync(p->xmass1 + (size_t)k * p->ld + c0, h->p_alt.xmass1 + (size_t)k * c.maxpart + c0,
-                         (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, post));
-      if (c.drybkdep || c.wetbkdep) // set once after the release by the receptor block of the loop
-        CK(cudaMemcpyAsync(p->xscav_frac1 + (size_t)k * p->ld + c0, h->p_alt.xscav_frac1 + (size_t)k * c.maxpart + c0,
-                           (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, post));
+    if (defer_d2h) { // (copied out after the last upload, below)
+      CK(cudaEventRecord(h->ev_out[ci], post));
+      CK(cudaGetLastError());
+      continue;
     }
+    mark(post);
+    if (d2h_rows(c0, n, post)) return 1;
     mark(post);
     CK(cudaGetLastError());
   }
 #undef STAGE
+  if (defer_d2h) {
+    const int nch = (int)bounds.size() - 1;
+    CK(cudaStreamWaitEvent(h->st_pbl, h->ev_in[(nch - 1) % 8], 0)); // (st_pbl is idle in this mode: the copy-out stream)
+    for (int ci = 0; ci < nch; ci++) {
+      CK(cudaStreamWaitEvent(h->st_pbl, h->ev_out[ci], 0));
+      if (d2h_rows(bounds[ci], bounds[ci + 1] - bounds[ci], h->st_pbl)) return 1;
+    }
+    CK(cudaStreamSynchronize(h->st_pbl));
+  }
   const double host_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   for (auto &L : h->lanes) CK(cudaStreamSynchronize(L.st));
   if (streamed) {

@@ -73,6 +73,7 @@ struct DevCfg {
   float ctl, fine, d_trop, d_strat, turbmesoscale;
   int ind_samp, ioutputforeachrelease, lusekerneloutput, lparticlecountoutput;
   int drydep, drybkdep, wetbkdep, nested_output;
+  int linit_cond;
   // species
   int nspec;
   float decay[FPB_MAXSPEC];
@@ -113,7 +114,7 @@ struct DevCfg {
 // the rest of advance() needs from the sub-step loop.  Rows with
 // itra1 == itime get `flags`; the float4 rows only when SC_PBL is set.
 struct DevScratch {
-  int32_t *flags;
+  int32_t *flags; // SC_* bits (fpb_step.cuh)
   float4 *s0; // dxsave, dysave, dawsave, dcwsave
   float4 *s1; // u, v, w, indz of the last sub-step (bits)
   int2 *s2;   // nrand, itimec

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) hooks_pre_kernel(const HookArgs a) {
   if (j >= a.cfg.numpart) return;
   const bool adv = a.p.itra1[j] == a.cfg.itime;
   a.adv[j] = adv ? 1 : 0;
-  if (!adv || !a.iflux) return;
+  if (!adv || !(a.iflux || a.linit)) return;
   // src/timemanager.f90:559-561: xold, yold, zold are default reals
   a.old[j] = (float)a.p.xtra1[j];
   a.old[a.old_stride + j] = (float)a.p.ytra1[j];
@@ -340,9 +340,98 @@ __device__ __forceinline__ void average_row(const HookArgs &a, int j) {
   for (int q = 0; q < 14; q++) a.av[q * a.av_stride + s] = a.av[q * a.av_stride + s] + v[q];
 }
 
+// src/initial_cond_calc.f90:49-204 for row j; old_mass: the masses from before the step (termination by nstop)
+__device__ __forceinline__ void init_cond_row(const HookArgs &a, int j, bool old_mass) {
+  const DevCfg &c = a.cfg;
+  const double xt = a.p.xtra1[j], yt = a.p.ytra1[j];
+  const float zt = a.p.ztra1[j];
+  float rhoi = 1.f;
+  if (a.linit == 1) { // mass unit: rho of memind(2) at the particle
+    int ix = (int)xt, jy = (int)yt;
+    const float ddx = (float)(xt - (double)(float)ix), ddy = (float)(yt - (double)(float)jy);
+    const float rddx = 1.f - ddx, rddy = 1.f - ddy;
+    const float p1 = rddx * rddy, p2 = ddx * rddy, p3 = rddx * ddy, p4 = ddx * ddy;
+    // (a particle that has left the domain: the reference reads past its arrays; nearest grid point here)
+    ix = max(0, min(ix, c.nxd - 1)); jy = max(0, min(jy, c.nyd - 1));
+    const int ixp = min(ix + 1, c.nxd - 1), jyp = min(jy + 1, c.nyd - 1);
+    int indz = c.nz - 1;
+    for (int il = 2; il <= c.nz; il++)
+      if (a.height[il - 1] > zt) { indz = il - 1; break; }
+    const int indzp = indz + 1;
+    const float dz1 = zt - a.height[indz - 1], dz2 = a.height[indzp - 1] - zt;
+    const float dz = 1.f / (dz1 + dz2);
+    const int plane = c.nxd * c.nyd;
+    float rhoprof[2];
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      const float4 *A = a.met[1].A + (indz - 1 + n) * plane;
+      rhoprof[n] = p1 * A[ix + c.nxd * jy].w + p2 * A[ixp + c.nxd * jy].w + p3 * A[ix + c.nxd * jyp].w + p4 * A[ixp + c.nxd * jyp].w;
+    }
+    rhoi = (dz1 * rhoprof[1] + dz2 * rhoprof[0]) * dz;
+  }
+  const int nrelpointer = ((c.ioutputforeachrelease == 0) || (c.mdomainfill == 1)) ? 1 : a.p.npoint[j];
+  int kz;
+  for (kz = 1; kz <= c.numzgrid; kz++)
+    if (c.outheight[kz - 1] > zt) break;
+  if (kz > c.numzgrid) return;
+  const float xl = (float)((xt * (double)c.dx + (double)c.xoutshift) / (double)c.dxout);
+  const float yl = (float)((yt * (double)c.dy + (double)c.youtshift) / (double)c.dyout);
+  int ix = (int)xl;
+  if (xl < 0.f) ix = ix - 1;
+  int jy = (int)yl;
+  if (yl < 0.f) jy = jy - 1;
+  const size_t nxg = c.numxgrid, nyg = c.numygrid, nzg = c.numzgrid;
+  auto mass = [&](int ks) {
+    return old_mass ? a.old[(3 + (size_t)(ks - 1)) * a.old_stride + j] : a.p.xmass1[(size_t)(ks - 1) * a.p.maxpart + j];
+  };
+  auto add = [&](int cx, int cy, int ks, float v) { // init_cond(cx, cy, kz, ks, nrelpointer) += v
+    atomicAdd(a.init_cond + cx + nxg * (cy + nyg * ((kz - 1) + nzg * ((ks - 1) + (size_t)a.maxspec * (nrelpointer - 1)))), v);
+  };
+  if ((xl < 0.5f) || (yl < 0.5f) || (xl > (float)(c.numxgrid - 1) - 0.5f) || (yl > (float)(c.numygrid - 1) - 0.5f)) {
+    if ((ix >= 0) && (jy >= 0) && (ix <= c.numxgrid - 1) && (jy <= c.numygrid - 1))
+      for (int ks = 1; ks <= c.nspec; ks++) add(ix, jy, ks, mass(ks) / rhoi);
+  } else {
+    const float ddx = xl - (float)ix, ddy = yl - (float)jy;
+    float wx, wy;
+    int ixp, jyp;
+    if (ddx > 0.5f) { ixp = ix + 1; wx = 1.5f - ddx; } else { ixp = ix - 1; wx = 0.5f + ddx; }
+    if (ddy > 0.5f) { jyp = jy + 1; wy = 1.5f - ddy; } else { jyp = jy - 1; wy = 0.5f + ddy; }
+    if ((ix >= 0) && (ix <= c.numxgrid - 1)) {
+      if ((jy >= 0) && (jy <= c.numygrid - 1)) {
+        const float w = wx * wy;
+        for (int ks = 1; ks <= c.nspec; ks++) add(ix, jy, ks, mass(ks) / rhoi * w);
+      }
+      if ((jyp >= 0) && (jyp <= c.numygrid - 1)) {
+        const float w = wx * (1.f - wy);
+        for (int ks = 1; ks <= c.nspec; ks++) add(ix, jyp, ks, mass(ks) / rhoi * w);
+      }
+    }
+    if ((ixp >= 0) && (ixp <= c.numxgrid - 1)) {
+      if ((jyp >= 0) && (jyp <= c.numygrid - 1)) {
+        const float w = (1.f - wx) * (1.f - wy);
+        for (int ks = 1; ks <= c.nspec; ks++) add(ixp, jyp, ks, mass(ks) / rhoi * w);
+      }
+      if ((jy >= 0) && (jy <= c.numygrid - 1)) {
+        const float w = (1.f - wx) * wy;
+        for (int ks = 1; ks <= c.nspec; ks++) add(ixp, jy, ks, mass(ks) / rhoi * w);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) hooks_post_kernel(const HookArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.cfg.numpart || !a.adv[j]) return;
+  if (j >= a.cfg.numpart) return;
+  if (a.final_pass) { // src/timemanager.f90:733-737
+    if (a.p.itra1[j] == a.cfg.itime) init_cond_row(a, j, false);
+    return;
+  }
+  if (!a.adv[j]) return;
+  if (a.linit) {
+    const int f = a.flags[j];
+    if (f & 4) init_cond_row(a, j, true);        // SC_TERM_NSTOP, src/timemanager.f90:631
+    else if (f & 8) init_cond_row(a, j, false);  // SC_TERM_AGE, :702
+  }
   if (a.iflux) flux_row(a, j);
   // (the reference also averages a particle that the step has just terminated -- at a position that may lie
   // outside the fields; such a particle is never written by partoutput_average, so it is left out)

@@ -75,6 +75,11 @@ struct HookArgs {
   const float *height;
   DevParticles p;           // row view
   int iflux, ipout3;
+  int linit;                // linit_cond: initial_cond_calc for the rows the step terminated (0: off)
+  int final_pass;           // 1: fpb_initial_cond_final -- every row with itra1 == itime, nothing else
+  const int32_t *flags;     // the step's scratch flags (SC_TERM_*)
+  float *init_cond;         // (numxgrid, numygrid, numzgrid, maxspec, maxpointspec_act)
+  int maxspec;
   uint8_t *adv;             // [rows] 1 = the row is advanced by this step (itra1 == itime before it)
   float *old;               // [3 + nspec][old_stride]: xold, yold, zold, xmass1(ks) of the row before the step
   size_t old_stride;

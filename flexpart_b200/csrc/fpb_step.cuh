@@ -25,7 +25,8 @@
 // scratch row bit for bit), so the strict build stays bit-identical to the
 // oracle.
 
-enum : int { SC_PBL = 1, SC_ABOVE = 2 };
+// SC_TERM_*: why the step terminated the particle (written only when linit_cond asks for initial_cond_calc)
+enum : int { SC_PBL = 1, SC_ABOVE = 2, SC_TERM_NSTOP = 4, SC_TERM_AGE = 8 };
 
 __device__ __noinline__ float rare_fmodf(float a, float b) { return fmodf(a, b); }
 
@@ -802,6 +803,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
   if (nstop > 1) {
     itra1 = FPB_ITRA_DEAD;
     n_term++;
+    if (c.linit_cond) a.sc.flags[j] = flags | SC_TERM_NSTOP; // src/timemanager.f90:631
   } else {
     bool term = false;
     itra1 = itime + c.lsynctime;
@@ -843,7 +845,11 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
       if (c.nested_output == 1)
         drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp, a.dep, rslot);
     }
-    if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) { itra1 = FPB_ITRA_DEAD; term = true; }
+    if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) {
+      if (c.linit_cond && itra1 != FPB_ITRA_DEAD) a.sc.flags[j] = flags | SC_TERM_AGE; // :702
+      itra1 = FPB_ITRA_DEAD;
+      term = true;
+    }
     if (term) n_term++;
   }
 

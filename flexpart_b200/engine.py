@@ -147,6 +147,16 @@ class Engine:
         self._check(self.L.fpb_fetch_fluxes(self.h, _fp(f), 1 if zero else 0))
         return f
 
+    def fetch_init_cond(self, zero=False):
+        """init_cond(numxgrid, numygrid, numzgrid, maxspec, maxpointspec_act) of initial_cond_calc (linit_cond > 0)"""
+        c = self.cb.cfg
+        f = np.zeros((c.numxgrid, c.numygrid, c.numzgrid, c.maxspec, c.maxpointspec_act), np.float32, order="F")
+        self._check(self.L.fpb_fetch_init_cond(self.h, _fp(f), 1 if zero else 0))
+        return f
+
+    def initial_cond_final(self, itime):
+        self._check(self.L.fpb_initial_cond_final(self.h, itime))
+
     def fetch_partpos_average(self, numpart, zero=False):
         """npart_av and the part_av_* sums of partpos_average (ipout = 3) for the first numpart slots"""
         from .abi import FpbPartavPtrs

@@ -61,7 +61,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
                 scatter_mode=abi.SCATTER_ATOMIC, seed=0x5EEDF1E0, height=None,
                 part_id_stride=1, part_id_offset=0, sort_interval=0, met_nests=(),
                 wetdepspec=None, weta_gas=None, wetb_gas=None, crain_aero=None, csnow_aero=None,
-                ccn_aero=None, in_aero=None, henry=None, readclouds=0, ind_receptor=1, iflux=0, ipout=0):
+                ccn_aero=None, in_aero=None, henry=None, readclouds=0, ind_receptor=1, iflux=0, ipout=0, linit_cond=0):
     """Run constants for the engine, derived the way the reference's
     gridcheck_ecmwf / readcommand / readoutgrid / readreleases derive them."""
     L = load_host_lib()
@@ -137,7 +137,7 @@ def make_config(nx=361, ny=181, nz=138, dx=1.0, dy=1.0, xlon0=-180.0, ylat0=-90.
     c.device, c.rng_mode, c.math_mode, c.scatter_mode, c.seed = device, rng_mode, math_mode, scatter_mode, seed
     c.part_id_stride, c.part_id_offset = part_id_stride, part_id_offset
     c.sort_interval = sort_interval
-    c.iflux, c.ipout = iflux, ipout
+    c.iflux, c.ipout, c.linit_cond = iflux, ipout, linit_cond
     h = np.ascontiguousarray(height, np.float32) if height is not None else synth_heights(nz)
     return ConfigBundle(c, h, npart_a, xmass_a)
 

@@ -163,7 +163,9 @@ typedef struct fpb_config {
   int32_t iflux;         /* 1: calcfluxes after every advance (src/calcfluxes.f90); fpb_fetch_fluxes */
   int32_t ipout;         /* 3: partpos_average after every advance (src/partpos_average.f90);
                             fpb_fetch_partpos_average.  Other values: nothing happens in the loop */
-  int32_t reserved[5];
+  int32_t linit_cond;    /* 1 (mass units) / 2 (mass mixing ratio): initial_cond_calc for every particle the loop
+                            terminates (src/initial_cond_calc.f90; backward runs); fpb_fetch_init_cond */
+  int32_t reserved[4];
 } fpb_config;
 
 /* One time level of the meteorological arrays the hot path gathers from
@@ -365,6 +367,17 @@ typedef struct fpb_partav_ptrs {
   float *cartx, *carty, *cartz, *z, *topo, *pv, *qv, *tt, *uu, *vv, *rho, *tro, *hmix, *energy;
 } fpb_partav_ptrs;
 int fpb_fetch_fluxes(fpb_handle *h, float *flux, int32_t zero);
+/*   linit_cond = 1, 2  initial_cond_calc (src/initial_cond_calc.f90, backward runs): a particle that leaves the
+ *              domain (src/timemanager.f90:631; its masses from before the step) or reaches the maximum age
+ *              (:702; its masses after decay and deposition) adds xmass1 / rho (1) or xmass1 (2) to the
+ *              sensitivity-to-initial-conditions grid through the output kernel.  fpb_initial_cond_final does the
+ *              same for every particle still active at the end of the run (:733-737; call it with the final itime
+ *              in place of that loop); fpb_fetch_init_cond copies init_cond(0:numxgrid-1, 0:numygrid-1, numzgrid,
+ *              maxspec, maxpointspec_act) out and, with zero != 0, clears it.  linit_cond = 1 reads rho of memind(2)
+ *              at the particle: for a particle outside the domain the reference reads past its arrays there, the
+ *              engine takes the nearest grid point. */
+int fpb_initial_cond_final(fpb_handle *h, int32_t itime);
+int fpb_fetch_init_cond(fpb_handle *h, float *init_cond, int32_t zero);
 int fpb_fetch_partpos_average(fpb_handle *h, int32_t numpart, const fpb_partav_ptrs *out, int32_t zero);
 
 /* Release points (src/point_mod.f90:15-26 after the conversions of src/readreleases.f90 and

@@ -51,6 +51,7 @@ ALLOC_DIMS = {
     "wetgriduncn": "0:numxgridn-1,0:numygridn-1,maxspec,maxpointspec_act,nclassunc,maxageclass",
     "outheight": "numzgrid", "outheighthalf": "numzgrid",
     "flux": "6,0:numxgrid-1,0:numygrid-1,numzgrid,nspec,maxpointspec_act,nageclass",
+    "init_cond": "0:numxgrid-1,0:numygrid-1,numzgrid,maxspec,maxpointspec_act",
     "npart_av": "maxpart", "part_av_cartx": "maxpart", "part_av_carty": "maxpart", "part_av_cartz": "maxpart",
     "part_av_z": "maxpart", "part_av_topo": "maxpart", "part_av_pv": "maxpart", "part_av_qv": "maxpart",
     "part_av_tt": "maxpart", "part_av_rho": "maxpart", "part_av_tro": "maxpart", "part_av_hmix": "maxpart",

@@ -138,3 +138,85 @@ def test_hooks_need_their_fields():
     with pytest.raises(fb.FpbError, match="iflux"):
         eng.fetch_fluxes()
     eng.close()
+
+
+@pytest.mark.parametrize("linit_cond,regional", [(2, True), (1, False)])
+def test_initial_cond_calc_matches_the_reference_routine(linit_cond, regional):
+    """LINIT_COND (backward runs): initial_cond_calc for the particles the loop terminates -- leaving a regional
+    domain (src/timemanager.f90:631, masses from before the step) or reaching the maximum age (:702) -- and, at the
+    end, for every particle still active (:733-737), against src/initial_cond_calc.f90 called for the same
+    particles on the engine's own positions.  linit_cond = 1 (division by rho at the particle) runs on the global
+    grid: outside the domain the reference reads past its arrays."""
+    kw = dict(nrel=4, npart_each=512, nspec=2, lage=(2700,), ioutputforeachrelease=1, ldirect=-1, linit_cond=linit_cond,
+              math_mode=fb.MATH_FAST, rng_mode=fb.RNG_PHILOX_INDEX, sort_interval=1)
+    if regional:   # 144 x 72 degrees: particles near the edges leave with the wind (nstop = 3)
+        kw.update(dx=2.0, dy=2.0, xlon0=-60.0, ylat0=5.0, outlon0=-60.0, outlat0=5.0, numxgrid=70, numygrid=35,
+                  dxout=2.0, dyout=2.0)
+    cb = cases.config_small(**kw)
+    c = cb.cfg
+    assert c.lsynctime == -900 and bool(c.xglobal) == (not regional)
+    n = 2048
+    lat = (c.ylat0 + 2.0, c.ylat0 + (c.ny - 1) * c.dy - 2.0) if regional else (-70.0, 70.0)
+    p = cases.seeded_particles(cb, n, zmax=6000.0, lat_range=lat, nspec=2)
+    r = np.random.RandomState(12)
+    if regional:
+        p.xtra1[:n] = r.uniform(0.05, c.nx - 1.05, n)
+        p.xtra1[:300] = r.uniform(0.001, 0.02, 300)                 # right at the western / eastern edge
+        p.xtra1[300:600] = r.uniform(c.nx - 1.02, c.nx - 1.001, 300)
+    p.xmass1[:n, 0] = 1.0
+    p.xmass1[:n, 1] = 0.5
+    p.itramem[:n:4] = 900              # a quarter reaches the maximum age two steps earlier
+    mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
+    eng = fb.Engine(cb)
+    eng.fill_rannumb()
+    eng.upload_met(1, mets[0]); eng.upload_met(2, mets[1]); eng.set_met_bracket((1, 2), (0, -10800))
+    ref = ref_api.Ref(cb, maxrand=1000)
+    ref.upload_met(1, mets[0]); ref.upload_met(2, mets[1]); ref.set_met_bracket((1, 2), (0, -10800))
+    ref.set("linit_cond", linit_cond)
+    ref.arr("init_cond")[...] = 0.0
+    eng.push_particles(p)
+    n_stop = n_age = 0
+
+    def ref_calc(post, mass, rows, it):
+        q = fb.Particles(c.maxpart, c.nspec); q.numpart = n
+        for f in ref.STATE:
+            getattr(q, f)[:n] = getattr(post, f)[:n]
+        q.xmass1[:n] = mass[:n]
+        q.itra1[:n] = fb.ITRA_DEAD
+        q.itra1[rows] = it
+        ref.push_state(q)
+        for j in rows:
+            ref.L.f_initial_cond_calc(C.byref(C.c_int(it)), C.byref(C.c_int(int(j) + 1)))
+
+    for k in range(4):
+        itime = -900 * k
+        pre = fb.Particles(c.maxpart, c.nspec); pre.numpart = n
+        eng.pull_particles(pre)
+        eng.step(itime, 450)
+        post = fb.Particles(c.maxpart, c.nspec); post.numpart = n
+        eng.pull_particles(post)
+        died = (pre.itra1[:n] == itime) & (post.itra1[:n] == fb.ITRA_DEAD)
+        x, y = post.xtra1[:n], post.ytra1[:n]
+        outside = (x < 0.0) | (x >= np.float32(c.nxmin1)) | (y < 0.0) | (y > np.float32(c.nymin1))
+        stop = np.nonzero(died & outside)[0]
+        age = np.nonzero(died & ~outside)[0]
+        assert (np.abs(itime - 900 - post.itramem[age]) >= 2700).all()
+        n_stop += stop.size; n_age += age.size
+        ref_calc(post, pre.xmass1, stop, itime)
+        ref_calc(post, post.xmass1, age, itime - 900)
+    got, want = eng.fetch_init_cond(), ref.arr("init_cond")
+    assert got.shape == want.shape and want.sum() > 0
+    assert np.array_equal(got > 0, want > 0) and np.allclose(got, want, rtol=3e-6, atol=0.0)
+    assert n_age > 400 and (n_stop > 50) == regional, (n_stop, n_age)
+    # the end of the run: everything still active
+    itime = -3600
+    post = fb.Particles(c.maxpart, c.nspec); post.numpart = n
+    eng.pull_particles(post)
+    alive = np.nonzero(post.itra1[:n] == itime)[0]
+    assert alive.size > 100
+    eng.initial_cond_final(itime)
+    ref_calc(post, post.xmass1, alive, itime)
+    got, want = eng.fetch_init_cond(zero=True), ref.arr("init_cond")
+    assert np.array_equal(got > 0, want > 0) and np.allclose(got, want, rtol=3e-6, atol=0.0)
+    assert not eng.fetch_init_cond().any()
+    eng.close()

@@ -14,3 +14,7 @@ for plan in ${PLANS:-0.3,0.3,0.25,0.15 0.3,0.3,0.25,0.1,0.05 0.35,0.35,0.2,0.07,
   run FPB_HOST_PLAN=$plan
 done
 for fr in 0.6 1.0; do run FPB_HOST_PLAN=0.3,0.3,0.25,0.1,0.05 FPB_HOST_GRID_FRAC=$fr; done
+run FPB_HOST_DEFER_D2H=1
+for plan in 0.3,0.3,0.25,0.15 0.3,0.3,0.25,0.1,0.05 0.4,0.3,0.2,0.1; do
+  run FPB_HOST_DEFER_D2H=1 FPB_HOST_PLAN=$plan
+done
