@@ -187,6 +187,17 @@ void fpo_partoutput_record(const fpb_config *c, const float *height, int itime, 
                            double xtra1, double ytra1, float ztra1, const float *oro,
                            const float *pv[2], const float *qv[2], const float *tt[2], const float *rho[2],
                            const float *hmix[2], const float *tropopause[2], float out[9]);
+
+/* the optional hooks of the particle loop (fpo_hooks.c): src/calcfluxes.f90, src/partpos_average.f90,
+ * src/initial_cond_calc.f90 */
+void fpo_calcfluxes(const fpb_config *c, float *flux, int nage, int npoint, float xold, float yold, float zold,
+                    double xtra1, double ytra1, float ztra1, const float *mass);
+void fpo_partpos_average(const fpb_config *c, const float *height, int itime, const int32_t memtime[2], double xtra1,
+                         double ytra1, float ztra1, const float *oro, const float *pv[2], const float *qv[2],
+                         const float *tt[2], const float *uu[2], const float *vv[2], const float *rho[2],
+                         const float *hmix[2], const float *tropopause[2], float out[14]);
+void fpo_initial_cond_calc(const fpb_config *c, const float *height, float *init_cond, int linit_cond, double xtra1,
+                           double ytra1, float ztra1, int npoint, const float *rho2, const float *mass);
 void fpo_density_outgrid(const fpb_config *c, const float *height, int nest, float outlon0, float outlat0,
                          const float *rho, float *densityoutgrid);
 void fpo_concoutput_sparse(const fpb_config *c, int nest, int which, const float *grid_ref,
