@@ -166,6 +166,7 @@ def test_initial_cond_calc_matches_the_reference_routine(linit_cond, regional):
     p.xmass1[:n, 0] = 1.0
     p.xmass1[:n, 1] = 0.5
     p.itramem[:n:4] = 900              # a quarter reaches the maximum age two steps earlier
+    p.itramem[1:n:4] = -1800           # a quarter is young enough to be active at the end
     mets = (fb.MetFields(cb).synth(0), fb.MetFields(cb).synth(-10800))
     eng = fb.Engine(cb)
     eng.fill_rannumb()
