@@ -373,44 +373,10 @@ struct fpb_handle {
   cudaEvent_t ev_dep[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_ready = nullptr;
   bool lanes_ready = false;
-  // fpb_step_host, streamed: one persistent sub-step launch for all chunks (DevStepArgs::stream_ctl)
   static constexpr int MAXCHUNKS = 32;
-  cudaStream_t st_pbl = nullptr, st_post[NLANES] = {};
-  cudaEvent_t ev_rdy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t st_out = nullptr;      // FPB_HOST_DEFER_D2H: the copy-out stream
   cudaEvent_t ev_out[MAXCHUNKS] = {};
-  int *d_stream_ctl = nullptr; // [2 + MAXCHUNKS]
-  bool stream_live = false;    // a streamed sub-step kernel may be waiting for rows
 };
-
-// cuStreamWaitValue32 through the runtime's driver entry point (libcuda is not linked)
-typedef int (*wait_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
-static wait_value32_fn driver_wait_value32() {
-  static wait_value32_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (wait_value32_fn)p;
-    cudaGetLastError();
-  }
-  return fn;
-}
-struct StreamBounds { int b[fpb_handle::MAXCHUNKS + 1]; };
-__global__ void stream_set_bounds_kernel(int *dst, StreamBounds v, int n) {
-  for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = v.b[k];
-}
-__global__ void stream_set_ready_kernel(int *ctl, int rows) {
-  __threadfence();
-  atomicExch(ctl, rows);
-}
-__global__ void stream_wait_done_kernel(const int *word, int n) { // fallback without the driver call
-  const volatile int *w = word;
-  while (*w < n) __nanosleep(500);
-  __threadfence();
-}
 
 // ---- deterministic deposition records -----------------------------------------------------------
 static void dep_free(fpb_handle::DepStore &s) {
@@ -881,11 +847,8 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     cudaFree(L.d_work); cudaFree(L.d_nlive);
   }
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-  if (h->st_pbl) { cudaStreamSynchronize(h->st_pbl); cudaStreamDestroy(h->st_pbl); }
-  for (auto &q : h->st_post) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
-  for (auto &e : h->ev_rdy) if (e) cudaEventDestroy(e);
+  if (h->st_out) { cudaStreamSynchronize(h->st_out); cudaStreamDestroy(h->st_out); }
   for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
-  cudaFree(h->d_stream_ctl);
   if (h->st_in) { cudaStreamSynchronize(h->st_in); cudaStreamDestroy(h->st_in); }
   for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
   for (auto &e : h->ev_det) if (e) cudaEventDestroy(e);
@@ -2818,17 +2781,8 @@ static int ensure_lanes(fpb_handle *h) {
   for (auto &e : h->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : h->ev_det) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : h->ev_dep) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CK(cudaStreamCreateWithFlags(&h->st_pbl, cudaStreamNonBlocking));
-  for (auto &q : h->st_post) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
-  for (auto &e : h->ev_rdy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
   for (auto &e : h->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  DA(h->d_stream_ctl, 4 + 2 * fpb_handle::MAXCHUNKS);
-  // (loaded here, not under a running sub-step kernel; see step_host_impl)
-  CK(cudaMemsetAsync(h->d_stream_ctl, 0, (2 + fpb_handle::MAXCHUNKS) * sizeof(int), h->st_pbl));
-  stream_set_ready_kernel<<<1, 1, 0, h->st_pbl>>>(h->d_stream_ctl, 0);
-  stream_wait_done_kernel<<<1, 1, 0, h->st_pbl>>>(h->d_stream_ctl, 0);
-  stream_set_bounds_kernel<<<1, 32, 0, h->st_pbl>>>(h->d_stream_ctl + 2, StreamBounds{}, 1);
-  CK(cudaStreamSynchronize(h->st_pbl));
   h->lanes_ready = true;
   return 0;
 }
@@ -2851,16 +2805,12 @@ extern "C" int fpb_step_host(fpb_handle *h, int32_t itime, int32_t ldeltat, int3
     // an error in the middle of the chunk loop leaves copies into the caller's arrays in flight on the
     // lanes: let them land before the caller may touch (or free) its buffers
     cudaSetDevice(h->device);
-    if (h->stream_live) // let a streamed sub-step kernel (and the chunks waiting for it) go: all counters large
-      cudaMemsetAsync(h->d_stream_ctl, 0x7f, (2 + fpb_handle::MAXCHUNKS) * sizeof(int), h->st_in);
     for (auto &L : h->lanes) if (L.st) cudaStreamSynchronize(L.st);
     if (h->st_in) cudaStreamSynchronize(h->st_in);
-    if (h->st_pbl) cudaStreamSynchronize(h->st_pbl);
-    for (auto &q : h->st_post) if (q) cudaStreamSynchronize(q);
+    if (h->st_out) cudaStreamSynchronize(h->st_out);
     cudaStreamSynchronize(h->stream);
     cudaGetLastError();
   }
-  if (h) h->stream_live = false;
   return rc;
 }
 static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t numpart, const fpb_particle_ptrs *p,
@@ -2907,45 +2857,31 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
   // Equal row chunks of >= ~250k rows (multiples of 128 rows).  Each chunk costs ~20 launches and
   // one tail of the persistent sub-step kernel (~0.18 ms, FPB_HOST_TIMING=1 shows the timeline), so
   // there are few of them: 4 at 1M rows, worse beyond 6.
-  // Streamed (FPB_HOST_STREAM=1; built, measured, NOT the default): ONE persistent sub-step launch consumes the
-  // chunks as their copies and preparation kernels land (DevStepArgs::stream_ctl) -- one tail of that kernel
-  // instead of one per chunk; the chunk's finish kernel, scatter-back and D2H wait on a second stream for the
-  // kernel's per-chunk count.  Measured on C2 (1 M rows, profiles/ab_r02_stream.txt): 3.4-3.9 ms per step against
-  // 2.96 chunk by chunk, whatever the chunk plan or grid fraction: what a chunk costs after its copy has landed
-  // is not the kernel's tail but the chain of its slowest particle (up to 160 sequential Langevin sub-steps,
-  // ~0.6 ms), and chunk-by-chunk launches already overlap those chains across chunks with MORE lanes in flight
-  // (two 0.6-wave grids) than one grid that must leave room for the preparation kernels it waits for.
-  // Deterministic dry deposition keeps the chunk-by-chunk path in any case (its record areas live in the lanes).
+  // (Round 2, built, measured and removed again -- commit cd7639e has it, DESIGN.md section 5: ONE persistent sub-step
+  // launch that consumes the chunks as their copies land.  3.4-3.9 ms per step against 2.96 chunk by chunk: what a
+  // chunk costs after its copy has landed is the chain of its slowest particle, not the kernel's tail.)
   const bool dbg = getenv("FPB_HOST_DEBUG") != nullptr;
-  bool streamed = !dbg && getenv("FPB_HOST_STREAM") && atoi(getenv("FPB_HOST_STREAM")) != 0 &&
-                  !(c.scatter_mode == FPB_SCATTER_DETERMINISTIC && c.drydep) && !hooks_on(h);
   std::vector<int> bounds; // chunk c = rows [bounds[c], bounds[c+1])
-  int per_eq = 0;
   {
-    int nchunk = streamed ? numpart / 125000 : numpart / 250000;
-    const int most = streamed ? 16 : 6;
-    nchunk = nchunk < 1 ? 1 : (nchunk > most ? most : nchunk);
+    int nchunk = numpart / 250000;
+    nchunk = nchunk < 1 ? 1 : (nchunk > 6 ? 6 : nchunk);
     if (const char *e = getenv("FPB_HOST_CHUNKS")) { // tuning knob
       const int v = atoi(e);
       if (v >= 1 && v <= fpb_handle::MAXCHUNKS) nchunk = v;
     }
-    per_eq = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
-    const char *plan = getenv("FPB_HOST_PLAN"); // tuning knob: chunk sizes as fractions, e.g. "0.1,0.3,0.3,0.2,0.1"
-    if (plan || (streamed && !getenv("FPB_HOST_CHUNKS") && numpart >= 400000)) {
-      // streamed and large: a small first chunk (the kernels start early), large ones in the middle (copy
-      // efficiency), small ones at the end (what is left to do when the last copy has landed is short)
-      std::vector<double> fr = {0.06, 0.14, 0.22, 0.22, 0.18, 0.10, 0.05, 0.03};
-      if (plan) {
-        fr.clear();
-        for (const char *q = plan; *q;) {
-          char *end = nullptr;
-          const double v = strtod(q, &end);
-          if (end == q) break;
-          if (v > 0.) fr.push_back(v);
-          q = (*end == ',') ? end + 1 : end;
-        }
-        if (fr.empty() || (int)fr.size() > fpb_handle::MAXCHUNKS) fr = {0.5, 0.5};
+    const int per_eq = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
+    // FPB_HOST_PLAN (tuning knob): chunk sizes as fractions, e.g. "0.3,0.3,0.25,0.15" -- a smaller last chunk shortens
+    // what is left to do when the last copy has landed (measured: -2 %, profiles/ab_r02_hostplan.txt)
+    if (const char *plan = getenv("FPB_HOST_PLAN")) {
+      std::vector<double> fr;
+      for (const char *q = plan; *q;) {
+        char *end = nullptr;
+        const double v = strtod(q, &end);
+        if (end == q) break;
+        if (v > 0.) fr.push_back(v);
+        q = (*end == ',') ? end + 1 : end;
       }
+      if (fr.empty() || (int)fr.size() > fpb_handle::MAXCHUNKS) fr = {0.5, 0.5};
       double tot = 0., acc = 0.;
       for (double v : fr) tot += v;
       bounds.push_back(0);
@@ -2960,37 +2896,14 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
       bounds.push_back(numpart);
     }
   }
-  if (bounds.size() <= 2) streamed = false;
-  if (streamed) {
-    // CUDA loads a kernel at its first launch and that may wait for the device -- which would be waiting, in
-    // the sub-step kernel, for the very chunk whose kernel is being loaded.  So the first call of a process
-    // with a given set of kernel variants runs chunk by chunk (it launches everything the streamed path does).
-    unsigned long long sig = 1;
-    const int parts[] = {strict, c.scatter_mode, conc_weight > 0.f, c.numreceptor > 0, c.drybkdep || c.wetbkdep, c.drydep,
-                         c.cblflag, c.lsettling, c.rng_mode, c.numbnests > 0, c.turbswitch, c.method, h->d.turboff, c.ifine == 4,
-                         c.nested_output, c.ind_samp, h->device};
-    for (int v : parts) sig = sig * 1000003ull + (unsigned long long)(v + 7);
-    static std::mutex mu;
-    static std::vector<unsigned long long> warmed;
-    std::lock_guard<std::mutex> lk(mu);
-    if (std::find(warmed.begin(), warmed.end(), sig) == warmed.end()) {
-      warmed.push_back(sig);
-      streamed = false;
-    }
-  }
-  const wait_value32_fn wait_value = (streamed && !getenv("FPB_HOST_WAIT_KERNEL")) ? driver_wait_value32() : nullptr;
   // The persistent sub-step grid of a chunk takes 0.6 of a resident wave, so that the next chunk's
   // kernels start under its draining tail (measured at 1 M rows, gpurun_out/ab_host.txt:
   // 3 chunks x full grid 3.17 ms, 4 x 0.6: 2.95 ms, 4 x 0.4: 2.97, 6 x 0.6: 3.03, 8 x 0.6: 3.21)
   float host_grid_frac = bounds.size() > 2 ? 0.6f : 0.f;
   if (const char *e = getenv("FPB_HOST_GRID_FRAC")) host_grid_frac = (float)atof(e); // tuning knob
-  // (streamed: the one sub-step grid must leave room for the chunks' preparation kernels it waits for)
-  if (streamed && !(host_grid_frac > 0.f && host_grid_frac <= 0.85f)) host_grid_frac = 0.6f;
   // FPB_HOST_TIMING=1: per-chunk timeline (ms since the call started) on stderr
   const bool timing = getenv("FPB_HOST_TIMING") != nullptr;
   std::vector<cudaEvent_t> tev;
-  cudaEvent_t tev_pbl[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> tev_rdy;
   const auto t_host0 = std::chrono::steady_clock::now();
   auto mark = [&](cudaStream_t st) {
     if (!timing) return;
@@ -3014,7 +2927,7 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
 
   // FPB_HOST_DEFER_D2H=1 (tuning knob): every chunk's copy back to the host waits for the LAST chunk's upload, on one
   // stream of its own -- the two directions then do not share the link while the uploads (the critical path) run
-  const bool defer_d2h = !streamed && !dbg && !timing && bounds.size() > 2 && getenv("FPB_HOST_DEFER_D2H") &&
+  const bool defer_d2h = !dbg && !timing && bounds.size() > 2 && getenv("FPB_HOST_DEFER_D2H") &&
                          atoi(getenv("FPB_HOST_DEFER_D2H")) != 0;
   auto d2h_rows = [&](int c0, int n, cudaStream_t post) -> int {
     D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
@@ -3052,42 +2965,6 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
     a.dep = DevDepRecords{};
     a.grid_frac = host_grid_frac;
   };
-  if (streamed) {
-    const int nchunks = (int)bounds.size() - 1;
-    // every work area the chunks need is sized BEFORE the sub-step kernel starts: a device allocation (or a
-    // cudaFree) waits for the device, which waits for rows that would never be submitted
-    {
-      const bool det = c.scatter_mode == FPB_SCATTER_DETERMINISTIC && conc_weight > 0.f;
-      for (int k = 0; k < fpb_handle::NLANES && k < nchunks; k++) {
-        fpb_handle::Lane &L = h->lanes[k];
-        if (scatter_reserve(L.sw, det ? 4 * (size_t)per : (size_t)per, det ? c.nspec : 1)) return fail("%s", scatter_error());
-        if (det && c.numreceptor > 0) {
-          DevConcArgs q;
-          if (rec_begin(h, L.dep, per, L.st, q)) return 1;
-        }
-      }
-    }
-    CK(cudaMemsetAsync(h->d_stream_ctl, 0, (2 + fpb_handle::MAXCHUNKS) * sizeof(int), h->stream));
-    {
-      StreamBounds sb{};
-      for (int k = 0; k <= nchunks; k++) sb.b[k] = bounds[k];
-      stream_set_bounds_kernel<<<1, 32, 0, h->stream>>>(h->d_stream_ctl + 2 + nchunks, sb, nchunks + 1);
-    }
-    CK(cudaEventRecord(h->ev_ready, h->stream)); // (re-recorded: the lanes wait for the cleared counters, too)
-    CK(cudaStreamWaitEvent(h->st_pbl, h->ev_ready, 0));
-    DevStepArgs g;
-    fill_step_args(g, 0, numpart);
-    g.work_counter = h->d_work;
-    g.stream_ctl = h->d_stream_ctl;
-    g.nchunks = nchunks;
-    h->stream_live = true;
-    if (timing) { cudaEventCreate(&tev_pbl[0]); cudaEventCreate(&tev_pbl[1]); cudaEventRecord(tev_pbl[0], h->st_pbl); }
-    if (strict) fpbk_pbl_strict(g, h->st_pbl); else fpbk_pbl_fast(g, h->st_pbl);
-    if (timing) cudaEventRecord(tev_pbl[1], h->st_pbl);
-    h->launches++;
-    for (auto &q : h->st_post) CK(cudaStreamWaitEvent(q, h->ev_ready, 0));
-  }
-
   for (int ci = 0; ci + 1 < (int)bounds.size(); ci++) {
     const int c0 = bounds[ci], n = bounds[ci + 1] - bounds[ci];
     if (n <= 0) continue;
@@ -3159,37 +3036,17 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
     if (launch_bkdep(h, a.cfg, rows, L.st)) return 1;
     STAGE("initialize");
     cudaStream_t post = L.st; // the stream the rest of the chunk runs on
-    if (streamed) {
-      // the rows are ready for the sub-step kernel: publish them in chunk order; the rest of the chunk waits
-      // on its own stream for the kernel's count, so that this lane can go on preparing chunk ci + NLANES
-      if (ci > 0) CK(cudaStreamWaitEvent(L.st, h->ev_rdy[(ci - 1) % 8], 0));
-      stream_set_ready_kernel<<<1, 1, 0, L.st>>>(h->d_stream_ctl, bounds[ci + 1]);
-      CK(cudaEventRecord(h->ev_rdy[ci % 8], L.st));
-      if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, L.st); tev_rdy.push_back(e); }
-      post = h->st_post[ci % fpb_handle::NLANES];
-      CK(cudaStreamWaitEvent(post, h->ev_rdy[ci % 8], 0));
-      int *word = h->d_stream_ctl + 2 + ci;
-      if (wait_value) {
-        if (wait_value(post, (unsigned long long)(uintptr_t)word, (unsigned)n, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
-          return fail("fpb_step_host: cuStreamWaitValue32 failed");
-      } else {
-        stream_wait_done_kernel<<<1, 1, 0, post>>>(word, n);
-      }
-      if (strict) fpbk_finish_strict(a, post); else fpbk_finish_fast(a, post);
-      h->launches += 4;
-    } else {
-      HookArgs hk;
-      if (hooks_on(h)) {
-        if (hooks_args(h, hk, a.cfg, rows, c0)) return 1;
-        fpb_hooks_pre(hk, L.st);
-      }
-      if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
-      if (hooks_on(h)) {
-        fpb_hooks_post(hk, L.st);
-        h->launches += 2;
-      }
-      h->launches += 3;
+    HookArgs hk;
+    if (hooks_on(h)) {
+      if (hooks_args(h, hk, a.cfg, rows, c0)) return 1;
+      fpb_hooks_pre(hk, L.st);
     }
+    if (strict) fpbk_step_strict(a, L.st); else fpbk_step_fast(a, L.st);
+    if (hooks_on(h)) {
+      fpb_hooks_post(hk, L.st);
+      h->launches += 2;
+    }
+    h->launches += 3;
     STAGE("step");
     if (det_dry) { // deposition in slot order across the chunks, like the concentration grid
       if (ci > 0) CK(cudaStreamWaitEvent(L.st, h->ev_dep[(ci - 1) % 8], 0));
@@ -3214,46 +3071,21 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
 #undef STAGE
   if (defer_d2h) {
     const int nch = (int)bounds.size() - 1;
-    CK(cudaStreamWaitEvent(h->st_pbl, h->ev_in[(nch - 1) % 8], 0)); // (st_pbl is idle in this mode: the copy-out stream)
+    CK(cudaStreamWaitEvent(h->st_out, h->ev_in[(nch - 1) % 8], 0));
     for (int ci = 0; ci < nch; ci++) {
-      CK(cudaStreamWaitEvent(h->st_pbl, h->ev_out[ci], 0));
-      if (d2h_rows(bounds[ci], bounds[ci + 1] - bounds[ci], h->st_pbl)) return 1;
+      CK(cudaStreamWaitEvent(h->st_out, h->ev_out[ci], 0));
+      if (d2h_rows(bounds[ci], bounds[ci + 1] - bounds[ci], h->st_out)) return 1;
     }
-    CK(cudaStreamSynchronize(h->st_pbl));
+    CK(cudaStreamSynchronize(h->st_out));
   }
   const double host_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   for (auto &L : h->lanes) CK(cudaStreamSynchronize(L.st));
-  if (streamed) {
-    for (auto &q : h->st_post) CK(cudaStreamSynchronize(q));
-    CK(cudaStreamSynchronize(h->st_pbl));
-    h->stream_live = false;
-    int ctl2[2] = {0, 0}, claimed = 0;
-    CK(cudaMemcpy(ctl2, h->d_stream_ctl, sizeof ctl2, cudaMemcpyDeviceToHost));
-    if (ctl2[1]) {
-      cudaMemcpy(&claimed, h->d_work, sizeof(int), cudaMemcpyDeviceToHost);
-      return fail("fpb_step_host: the streamed sub-step kernel gave up waiting for its rows (%d of %d ready, %d claimed)",
-                  ctl2[0], numpart, claimed);
-    }
-  }
   if (timing) {
     for (size_t k = 1; k + 3 < tev.size() + 1; k += 4) {
       float t[4];
       for (int q = 0; q < 4; q++) cudaEventElapsedTime(&t[q], tev[0], tev[k + q]);
       fprintf(stderr, "fpb_step_host chunk %zu (%d rows): h2d %.3f-%.3f  kernels -%.3f  d2h -%.3f ms\n", (k - 1) / 4,
               bounds[(k - 1) / 4 + 1] - bounds[(k - 1) / 4], t[0], t[1], t[2], t[3]);
-    }
-    for (size_t k = 0; k < tev_rdy.size(); k++) {
-      float t = 0.f;
-      cudaEventElapsedTime(&t, tev[0], tev_rdy[k]);
-      fprintf(stderr, "fpb_step_host chunk %zu ready for the sub-step kernel at %.3f ms\n", k, t);
-      cudaEventDestroy(tev_rdy[k]);
-    }
-    if (tev_pbl[0]) {
-      float t0 = 0.f, t1 = 0.f;
-      cudaEventElapsedTime(&t0, tev[0], tev_pbl[0]);
-      cudaEventElapsedTime(&t1, tev[0], tev_pbl[1]);
-      fprintf(stderr, "fpb_step_host streamed sub-step kernel: %.3f-%.3f ms\n", t0, t1);
-      cudaEventDestroy(tev_pbl[0]); cudaEventDestroy(tev_pbl[1]);
     }
     fprintf(stderr, "fpb_step_host: all chunks submitted after %.3f ms of host time\n", host_submit_ms);
     for (auto e : tev) cudaEventDestroy(e);

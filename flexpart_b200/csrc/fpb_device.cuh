@@ -151,13 +151,6 @@ struct DevStepArgs {
   DevScratch sc;
   DevDepRecords dep;         // dry deposition records (deterministic mode), else keys = null
   float grid_frac;           // persistent sub-step grid as a fraction of one resident wave (0 = 1: all of it)
-  // fpb_step_host, streamed: ONE persistent sub-step launch consumes the row chunks as their copies and
-  // preparation kernels land.  ctl[0] = rows ready so far (written in stream order after a chunk's
-  // preparation), ctl[1] = error flag (the wait gave up), ctl[2 + k] = rows of chunk k the kernel is done
-  // with (the chunk's finish kernel waits for it), ctl[2 + nchunks + k] = first row of chunk k (k = 0..nchunks).
-  // Null: every row is ready at launch.
-  int *stream_ctl = nullptr;
-  int nchunks = 0;
 };
 
 struct DevConcArgs {
@@ -242,8 +235,6 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0
 #define FPB_DECL_LAUNCHERS(SUF)                                               \
   void fpbk_init_##SUF(const DevStepArgs &a, cudaStream_t st);                \
   void fpbk_step_##SUF(const DevStepArgs &a, cudaStream_t st);                \
-  void fpbk_pbl_##SUF(const DevStepArgs &a, cudaStream_t st);                 \
-  void fpbk_finish_##SUF(const DevStepArgs &a, cudaStream_t st);              \
   void fpbk_conccalc_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_receptor_##SUF(const DevConcArgs &a, cudaStream_t st);            \
   void fpbk_wetdepo_##SUF(const DevWetArgs &a, cudaStream_t st);              \

@@ -1674,8 +1674,7 @@ void FPB_SUF(fpbk_init)(const DevStepArgs &a, cudaStream_t st) {
   else fpb_init_kernel<false><<<nb, 128, 0, st>>>(a);
 }
 
-// the persistent sub-step kernel alone (fpb_step_host, streamed, launches it once for all chunks)
-void FPB_SUF(fpbk_pbl)(const DevStepArgs &a, cudaStream_t st) {
+void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
   if (a.cfg.numpart <= 0) return;
   // lean variant: table RNG, no dry deposition, no settling, no CBL, no nested input grids
   const bool full = a.cfg.drydep || a.cfg.cblflag == 1 || a.cfg.lsettling ||
@@ -1704,6 +1703,7 @@ void FPB_SUF(fpbk_pbl)(const DevStepArgs &a, cudaStream_t st) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpb_pbl_kernel<false, false, false>, PBL_THREADS, 0);
     res = sms * (per_sm > 0 ? per_sm : 1);
   }
+  const int want = (a.cfg.numpart + 127) / 128;
   const int want_pbl = (a.cfg.numpart + PBL_THREADS - 1) / PBL_THREADS;
   int cap = res; // persistent grid: one wave at most
   if (a.grid_frac > 0.f && a.grid_frac < 1.f) { // (fpb_step_host: the chunks' grids share the SMs)
@@ -1716,21 +1716,11 @@ void FPB_SUF(fpbk_pbl)(const DevStepArgs &a, cudaStream_t st) {
   else if (variant == 3) fpb_pbl_kernel<true, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
   else if (variant == 2) fpb_pbl_kernel<false, false, true><<<nb, PBL_THREADS, 0, st>>>(a);
   else fpb_pbl_kernel<false, false, false><<<nb, PBL_THREADS, 0, st>>>(a);
-}
-
-void FPB_SUF(fpbk_finish)(const DevStepArgs &a, cudaStream_t st) {
-  if (a.cfg.numpart <= 0) return;
-  const int want = (a.cfg.numpart + 127) / 128;
   // finish kernel: the variant without nests / settling / dry deposition / Philox-direct RNG when it applies
-  if (!a.cfg.drydep && !a.cfg.lsettling && a.cfg.numbnests == 0 && a.cfg.rng_mode != FPB_RNG_PHILOX)
+  if (!a.cfg.drydep && !a.cfg.lsettling && a.cfg.numbnests == 0 && a.cfg.rng_mode != FPB_RNG_PHILOX && !a.cfg.linit_cond)
     fpb_finish_kernel<true><<<want, 128, 0, st>>>(a);
   else
     fpb_finish_kernel<false><<<want, 128, 0, st>>>(a);
-}
-
-void FPB_SUF(fpbk_step)(const DevStepArgs &a, cudaStream_t st) {
-  FPB_SUF(fpbk_pbl)(a, st);
-  FPB_SUF(fpbk_finish)(a, st);
 }
 
 void FPB_SUF(fpbk_conccalc)(const DevConcArgs &a, cudaStream_t st) {

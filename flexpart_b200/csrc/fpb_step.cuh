@@ -493,102 +493,30 @@ fpb_pbl_kernel(const __grid_constant__ DevStepArgs a) {
   task.j = -1;
   unsigned n_act = 0, n_pbl = 0, n_sub = 0, n_nan = 0;
   bool exhausted = false;
-  int poll_skip = 0;
 
-  int *const ctl = a.stream_ctl; // fpb_step_host, streamed (see DevStepArgs); warp-uniform
-  // streamed: task.j >= 0 on an idle lane = a row the lane is done with and has not counted yet;
-  // task.j <= -2 = row (-2 - j) is claimed, its copies / preparation kernels have not landed yet
+  // (Round 2, built, measured and removed again -- commit cd7639e has it: a variant of this loop that polls a
+  // "rows ready" word and counts finished rows per chunk, so that ONE launch serves all chunks of fpb_step_host.
+  // The host step got slower, DESIGN.md section 5, and the extra warp-uniform tests in this loop cost the
+  // resident C2 step 3.6 %, profiles/ab_r02_pblloop.txt.)
   for (;;) {
     const unsigned idle = __ballot_sync(FULL, !task.running);
-    unsigned waiting = 0;
-    int load_row = -1;
-    bool loading = false; // warp-uniform
-    if (ctl) {
-      // rows this warp is done with, counted per chunk (the chunk's finish kernel waits for the sum): when
-      // the warp is about to take new rows anyway, and at once when the rows have run out
-      const bool pend = !task.running && task.j >= 0;
-      unsigned todo = __ballot_sync(FULL, pend);
-      if (todo && (exhausted || __popc(idle) >= T_REFILL)) {
-        int ck = -1;
-        if (pend) {
-          ck = 0;
-          while (ck + 1 < a.nchunks && task.j >= ctl[2 + a.nchunks + ck + 1]) ck++; // chunk k = rows [b[k], b[k+1])
-          __threadfence(); // the scratch row before the count
-        }
-        __syncwarp();
-        while (todo) {
-          const int ld = __ffs(todo) - 1;
-          const int ckl = __shfl_sync(FULL, ck, ld);
-          const unsigned grp = __ballot_sync(FULL, pend && ck == ckl);
-          if (lane == ld) {
-            __threadfence();
-            atomicAdd(ctl + 2 + ckl, __popc(grp));
-          }
-          todo &= ~grp;
-        }
-        if (pend) task.j = -1;
-      }
-      // claimed rows: load them once they are ready; until then the running lanes go on (a chunk's count must
-      // not depend on a LATER chunk's arrival), and a warp with nothing else to do sleeps on the flag
-      const bool wt = !task.running && task.j <= -2;
-      waiting = __ballot_sync(FULL, wt);
-      if (waiting && (idle == FULL || --poll_skip < 0)) {
-        poll_skip = 3; // (with lanes running: look at the flag every 4th sub-step)
-        const int myrow = wt ? -2 - task.j : 0x7fffffff;
-        const int first = __reduce_min_sync(FULL, myrow); // (a batch may straddle two chunks: lane by lane)
-        const volatile int *rdy = ctl;
-        int r = *rdy;
-        if (r <= first && idle == FULL) {
-          unsigned long long t0 = 0, t1 = 0;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-          bool dead = false;
-          while ((r = *rdy) <= first) {
-            __nanosleep(200);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) { // 4 s: the host side died; let every waiter go
-              if (lane == 0) {
-                atomicExch(ctl + 1, 1);
-                for (int k = 0; k < a.nchunks; k++) atomicExch(ctl + 2 + k, 0x3fffffff);
-              }
-              dead = true;
-              break;
-            }
-          }
-          if (dead) break;
-        }
-        if (r > first) {
-          __threadfence(); // acquire side of the ready flag
-          if (myrow < r) load_row = myrow;
-          loading = true;
-        }
-      }
-    }
-    if (!loading && !exhausted && !waiting && __popc(idle) >= T_REFILL) {
+    if (!exhausted && __popc(idle) >= T_REFILL) {
       const int n = __popc(idle), leader = __ffs(idle) - 1;
       int base = 0;
       if (lane == leader) base = atomicAdd(a.work_counter, n);
       base = __shfl_sync(FULL, base, leader);
       if (!task.running) {
         const int row = base + __popc(idle & lt_mask);
-        if (ctl) task.j = row < nrows ? -2 - row : -1;
-        else if (row < nrows) load_row = row;
-      }
-      if (base + n >= nrows) exhausted = true;
-      if (ctl) continue; // (the next pass looks at the ready flag)
-      loading = true;
-    }
-    if (loading) {
-      if (load_row >= 0) {
-        if (ctl) task.j = load_row; // (inactive rows count as done, too)
         bool pbl = false;
-        if (task.refill(a, ls, load_row, pbl)) {
+        if (row < nrows && task.refill(a, ls, row, pbl)) {
           n_act++;
           if (pbl) n_pbl++;
         }
       }
+      if (base + n >= nrows) exhausted = true;
       continue;
     }
-    if (idle == FULL && !waiting) break; // no rows left and nothing running
+    if (idle == FULL) break; // no rows left and nothing running
 #ifdef FPB_TAIL_STATS // tools/tail_stats.py: warp iterations / running lanes before and after the rows ran out
     if (lane == 0) {
       atomicAdd(a.stats + (exhausted ? 7 : 6), 1ull);
@@ -803,7 +731,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
   if (nstop > 1) {
     itra1 = FPB_ITRA_DEAD;
     n_term++;
-    if (c.linit_cond) a.sc.flags[j] = flags | SC_TERM_NSTOP; // src/timemanager.f90:631
+    if (!SIMPLE && c.linit_cond) a.sc.flags[j] = flags | SC_TERM_NSTOP; // src/timemanager.f90:631 (launcher: general variant)
   } else {
     bool term = false;
     itra1 = itime + c.lsynctime;
@@ -846,7 +774,7 @@ __device__ __forceinline__ void finish_row(const DevStepArgs &a, const float *sh
         drydepo_scatter(c, a.drygriduncn, true, nclass, drydeposit, (float)xt, (float)yt, nage, kp, a.dep, rslot);
     }
     if (abs(itra1 - itramem) >= c.lage[c.nageclass - 1]) {
-      if (c.linit_cond && itra1 != FPB_ITRA_DEAD) a.sc.flags[j] = flags | SC_TERM_AGE; // :702
+      if (!SIMPLE && c.linit_cond && itra1 != FPB_ITRA_DEAD) a.sc.flags[j] = flags | SC_TERM_AGE; // :702
       itra1 = FPB_ITRA_DEAD;
       term = true;
     }

@@ -194,15 +194,14 @@ def test_sort_is_transparent_philox():
     assert rel_l2(ga, gb) < 1e-6
 
 
-@pytest.mark.parametrize("streamed", [0, 1])
-def test_step_host_equals_resident_path(monkeypatch, streamed):
+@pytest.mark.parametrize("knobs", [{}, {"FPB_HOST_PLAN": "0.4,0.3,0.2,0.1", "FPB_HOST_DEFER_D2H": "1"}])
+def test_step_host_equals_resident_path(monkeypatch, knobs):
     """fpb_step_host (chunked, copies overlapped with kernels) returns exactly
     what push + conccalc + step + pull return: particles bit for bit, grids up
-    to the order of the float atomics.  200k rows -> 3 chunks on 3 lanes.
-    streamed: the opt-in variant with ONE persistent sub-step launch fed chunk by chunk (5 chunks)."""
-    if streamed:
-        monkeypatch.setenv("FPB_HOST_STREAM", "1")
-        monkeypatch.setenv("FPB_HOST_CHUNKS", "5")
+    to the order of the float atomics.  200k rows -> 3 chunks on 3 lanes; also with the tuning knobs
+    (unequal chunks, copy-out deferred behind the last upload)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
     n = 200_000
     out = []
     for host_mode in (False, True):
@@ -232,13 +231,10 @@ def test_step_host_equals_resident_path(monkeypatch, streamed):
     assert rel_l2(ga, gb) < 1e-6 and ga.sum() > 0
 
 
-@pytest.mark.parametrize("streamed", [0, 1])
-def test_step_host_deterministic_scatter_in_chunks(monkeypatch, streamed):
+def test_step_host_deterministic_scatter_in_chunks(monkeypatch):
     """FPB_SCATTER_DETERMINISTIC through fpb_step_host: the row chunks (3 lanes, 5 chunks here) add to
     the grid in slot order, so gridunc is bit-identical to the oracle's serial accumulation."""
     monkeypatch.setenv("FPB_HOST_CHUNKS", "5")
-    if streamed:
-        monkeypatch.setenv("FPB_HOST_STREAM", "1")
     cb = cases.config_c1(npart=70_000, math_mode=fb.MATH_STRICT, scatter_mode=fb.SCATTER_DETERMINISTIC,
                          lage=(86400 * 20,), ioutputforeachrelease=0)
     m0, m1 = cases.met_pair(cb)
