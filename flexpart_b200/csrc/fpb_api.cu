@@ -2870,16 +2870,26 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
       if (v >= 1 && v <= fpb_handle::MAXCHUNKS) nchunk = v;
     }
     const int per_eq = (((numpart + nchunk - 1) / nchunk) + 127) / 128 * 128;
-    // FPB_HOST_PLAN (tuning knob): chunk sizes as fractions, e.g. "0.3,0.3,0.25,0.15" -- a smaller last chunk shortens
-    // what is left to do when the last copy has landed (measured: -2 %, profiles/ab_r02_hostplan.txt)
-    if (const char *plan = getenv("FPB_HOST_PLAN")) {
+    // From four chunks on the first ones are larger and the last one holds 0.6 of an equal share: what is left to do when the last copy has landed
+    // is shorter (with the copy-out deferred behind the last upload, below: -2.8 %, profiles/ab_r02_hostplan.txt).
+    // FPB_HOST_PLAN (tuning knob): chunk sizes as fractions, e.g. "0.3,0.3,0.25,0.15"; "equal": equal chunks.
+    const char *plan = getenv("FPB_HOST_PLAN");
+    if (plan && !strcmp(plan, "equal")) plan = nullptr;
+    else if (!plan && !getenv("FPB_HOST_CHUNKS") && nchunk >= 4) plan = "auto";
+    if (plan) {
       std::vector<double> fr;
-      for (const char *q = plan; *q;) {
-        char *end = nullptr;
-        const double v = strtod(q, &end);
-        if (end == q) break;
-        if (v > 0.) fr.push_back(v);
-        q = (*end == ',') ? end + 1 : end;
+      if (!strcmp(plan, "auto")) {
+        fr.assign((size_t)nchunk, 1.0); // 4 chunks: 0.30, 0.30, 0.25, 0.15
+        for (int k = 0; k < nchunk / 2; k++) fr[k] = 1.2;
+        fr.back() = 0.6;
+      } else {
+        for (const char *q = plan; *q;) {
+          char *end = nullptr;
+          const double v = strtod(q, &end);
+          if (end == q) break;
+          if (v > 0.) fr.push_back(v);
+          q = (*end == ',') ? end + 1 : end;
+        }
       }
       if (fr.empty() || (int)fr.size() > fpb_handle::MAXCHUNKS) fr = {0.5, 0.5};
       double tot = 0., acc = 0.;
@@ -2925,10 +2935,11 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
   int per = 0; // largest chunk: size of the lanes' sort work areas
   for (size_t k = 0; k + 1 < bounds.size(); k++) per = std::max(per, bounds[k + 1] - bounds[k]);
 
-  // FPB_HOST_DEFER_D2H=1 (tuning knob): every chunk's copy back to the host waits for the LAST chunk's upload, on one
-  // stream of its own -- the two directions then do not share the link while the uploads (the critical path) run
-  const bool defer_d2h = !dbg && !timing && bounds.size() > 2 && getenv("FPB_HOST_DEFER_D2H") &&
-                         atoi(getenv("FPB_HOST_DEFER_D2H")) != 0;
+  // Every chunk's copy back to the host waits for the LAST chunk's upload, on one stream of its own: the two directions
+  // then do not share the link while the uploads (the critical path) run.  FPB_HOST_DEFER_D2H=0 (tuning knob): each
+  // chunk copies out as soon as it is done.
+  const bool defer_d2h = !dbg && !timing && bounds.size() > 2 &&
+                         !(getenv("FPB_HOST_DEFER_D2H") && atoi(getenv("FPB_HOST_DEFER_D2H")) == 0);
   auto d2h_rows = [&](int c0, int n, cudaStream_t post) -> int {
     D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
     D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);

@@ -194,12 +194,12 @@ def test_sort_is_transparent_philox():
     assert rel_l2(ga, gb) < 1e-6
 
 
-@pytest.mark.parametrize("knobs", [{}, {"FPB_HOST_PLAN": "0.4,0.3,0.2,0.1", "FPB_HOST_DEFER_D2H": "1"}])
+@pytest.mark.parametrize("knobs", [{}, {"FPB_HOST_PLAN": "0.4,0.3,0.2,0.1"}, {"FPB_HOST_PLAN": "equal", "FPB_HOST_DEFER_D2H": "0"}])
 def test_step_host_equals_resident_path(monkeypatch, knobs):
     """fpb_step_host (chunked, copies overlapped with kernels) returns exactly
     what push + conccalc + step + pull return: particles bit for bit, grids up
-    to the order of the float atomics.  200k rows -> 3 chunks on 3 lanes; also with the tuning knobs
-    (unequal chunks, copy-out deferred behind the last upload)."""
+    to the order of the float atomics.  200k rows -> 3 chunks on 3 lanes (copy-out deferred behind the last
+    upload); also with the tuning knobs (unequal chunks; equal chunks that copy out at once)."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     n = 200_000
