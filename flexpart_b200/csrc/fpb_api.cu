@@ -2938,8 +2938,11 @@ static int step_host_impl(fpb_handle *h, int32_t itime, int32_t ldeltat, int32_t
   // Every chunk's copy back to the host waits for the LAST chunk's upload, on one stream of its own: the two directions
   // then do not share the link while the uploads (the critical path) run.  FPB_HOST_DEFER_D2H=0 (tuning knob): each
   // chunk copies out as soon as it is done.
+  // (Not with several ranks on one host: their copies share the host's PCIe root ports and memory anyway, and bunching
+  // the copy-out at the end of the step makes that worse -- 7.5 against 6.6-7.0 ms per step and rank at 8 ranks.)
+  const char *defer_env = getenv("FPB_HOST_DEFER_D2H");
   const bool defer_d2h = !dbg && !timing && bounds.size() > 2 &&
-                         !(getenv("FPB_HOST_DEFER_D2H") && atoi(getenv("FPB_HOST_DEFER_D2H")) == 0);
+                         (defer_env ? atoi(defer_env) != 0 : h->comm.nranks <= 1);
   auto d2h_rows = [&](int c0, int n, cudaStream_t post) -> int {
     D2HS(p->xtra1, h->p_alt.xtra1, double); D2HS(p->ytra1, h->p_alt.ytra1, double);
     D2HS(p->ztra1, h->p_alt.ztra1, float); D2HS(p->itra1, h->p_alt.itra1, int32_t);
