@@ -361,7 +361,9 @@ int fpb_partoutput(fpb_handle *h, int32_t itime, int32_t *nrecords, const fpb_pa
  *              copies the first numpart slots of npart_av / part_av_* (any pointer may be NULL) and, with
  *              zero != 0, clears them (src/partoutput_average.f90:171-187).  A particle the step has just
  *              terminated is left out (the reference averages it at a position that may lie outside the
- *              fields; it is never written). */
+ *              fields; it is never written).
+ * flux and init_cond are accumulated with float atomics in every scatter_mode (the order of the additions is not
+ * the particle order; sums of exactly representable masses are exact, others agree to 1e-6 relative). */
 typedef struct fpb_partav_ptrs {
   int32_t *npart_av;
   float *cartx, *carty, *cartz, *z, *topo, *pv, *qv, *tt, *uu, *vv, *rho, *tro, *hmix, *energy;
