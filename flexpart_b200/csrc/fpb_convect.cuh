@@ -350,40 +350,53 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     CV(m, i) = cbmf * dbo;
   }
   for (int i = icb + 1; i <= inb; i++) CV(m, i) = CV(m, i) / dbosum;
-  // entrained air mass flux, mixing fractions (:636-682)
+  // entrained air mass flux, mixing fractions (:636-682).  What depends on j alone -- bf2 and cwat of the reference's
+  // inner loop -- is worked out once per level (into the unused ft / fq vectors: the same expressions, so the same
+  // bits), and sij(i,j) is carried in a register while its statements run instead of being re-read after every store
+  // (the stores stay where the reference has them: sij(i,i) = 1 inside the j loop is read back when j == i).
+  for (int j = icb; j <= inb; j++) {
+    CV(ft, j) = 1.f + CV(lv, j) * CV(lv, j) * CV(qsconv, j) / (RV * CV(tconv, j) * CV(tconv, j) * CPD);
+    CV(fq, j) = CV(clw, j) * (1.f - CV(ep, j));
+  }
   for (int i = icb + 1; i <= inb; i++) {
     const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+    const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
+    int nent_i = CV(nent, i);
     for (int j = icb; j <= inb; j++) {
-      const float bf2 = 1.f + CV(lv, j) * CV(lv, j) * CV(qsconv, j) / (RV * CV(tconv, j) * CV(tconv, j) * CPD);
-      float anum = CV(h, j) - CV(hp, i) + (CPV - CPD) * CV(tconv, j) * (qti - CV(qconv, j));
-      float denom = CV(h, i) - CV(hp, i) + (CPD - CPV) * (CV(qconv, i) - qti) * CV(tconv, j);
+      const float bf2 = CV(ft, j);
+      const float t_j = CV(tconv, j), qs_j = CV(qsconv, j);
+      float anum = CV(h, j) - hp_i + (CPV - CPD) * t_j * (qti - CV(qconv, j));
+      float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
       float dei = denom;
       if (fabsf(dei) < 0.01f) dei = 0.01f;
-      CM(sij, i, j) = anum / dei;
+      float s = anum / dei;
       CM(sij, i, i) = 1.0f;
-      float altem = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti - CV(qsconv, j);
+      if (j == i) s = 1.0f;
+      float altem = s * q_i + (1.f - s) * qti - qs_j;
       altem = altem / bf2;
-      const float cwat = CV(clw, j) * (1.f - CV(ep, j));
-      const float stemp = CM(sij, i, j);
+      const float cwat = CV(fq, j);
+      const float stemp = s;
       if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
-        anum = anum - CV(lv, j) * (qti - CV(qsconv, j) - cwat * bf2);
-        denom = denom + CV(lv, j) * (CV(qconv, i) - qti);
+        const float lv_j = CV(lv, j);
+        anum = anum - lv_j * (qti - qs_j - cwat * bf2);
+        denom = denom + lv_j * (q_i - qti);
         if (fabsf(denom) < 0.01f) denom = 0.01f;
-        CM(sij, i, j) = anum / denom;
-        altem = CM(sij, i, j) * CV(qconv, i) + (1.f - CM(sij, i, j)) * qti - CV(qsconv, j);
+        s = anum / denom;
+        altem = s * q_i + (1.f - s) * qti - qs_j;
         altem = altem - (bf2 - 1.f) * cwat;
       }
-      if (CM(sij, i, j) > 0.0f && CM(sij, i, j) < 0.9f) {
-        CM(elij, i, j) = altem;
-        CM(elij, i, j) = c_max(0.0f, CM(elij, i, j));
-        CM(ment, i, j) = CV(m, i) / (1.f - CM(sij, i, j));
-        CV(nent, i) = CV(nent, i) + 1;
+      if (s > 0.0f && s < 0.9f) {
+        CM(elij, i, j) = c_max(0.0f, altem);
+        CM(ment, i, j) = m_i / (1.f - s);
+        nent_i = nent_i + 1;
       }
-      CM(sij, i, j) = c_max(0.0f, CM(sij, i, j));
-      CM(sij, i, j) = c_min(1.0f, CM(sij, i, j));
+      s = c_max(0.0f, s);
+      s = c_min(1.0f, s);
+      CM(sij, i, j) = s;
     }
-    if (CV(nent, i) == 0) {
-      CM(ment, i, i) = CV(m, i);
+    CV(nent, i) = nent_i;
+    if (nent_i == 0) {
+      CM(ment, i, i) = m_i;
       CM(elij, i, i) = CV(clw, i);
       CM(sij, i, i) = 1.0f;
     }
@@ -401,37 +414,48 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
       if (alt < 0.0f) scrit = 1.0f;
       scrit = c_max(scrit, 0.0f);
       float asij = 0.0f, smin = 1.0f;
+      // (row i of sij is read through a sliding window s_m1, s_0, s_p1 = sij(i, j-1 .. j+1): it is not written here)
+      float s_m1 = icb > 1 ? CM(sij, i, icb - 1) : 0.0f, s_0 = CM(sij, i, icb), s_p1 = CM(sij, i, icb + 1);
+      float ph_j = CV(phconv_hpa, icb);
       for (int j = icb; j <= inb; j++) {
-        if (CM(sij, i, j) > 0.0f && CM(sij, i, j) < 0.9f) {
+        const float ph_j1 = CV(phconv_hpa, j + 1);
+        if (s_0 > 0.0f && s_0 < 0.9f) {
           float smid, sjmax, sjmin;
           if (j > i) {
-            smid = c_min(CM(sij, i, j), scrit);
+            smid = c_min(s_0, scrit);
             sjmax = smid;
             sjmin = smid;
-            if (smid < smin && CM(sij, i, j + 1) < smid) {
+            if (smid < smin && s_p1 < smid) {
               smin = smid;
-              sjmax = c_min(c_min(CM(sij, i, j + 1), CM(sij, i, j)), scrit);
-              sjmin = c_max(CM(sij, i, j - 1), CM(sij, i, j));
+              sjmax = c_min(c_min(s_p1, s_0), scrit);
+              sjmin = c_max(s_m1, s_0);
               sjmin = c_min(sjmin, scrit);
             }
           } else {
-            sjmax = c_max(CM(sij, i, j + 1), scrit);
-            smid = c_max(CM(sij, i, j), scrit);
+            sjmax = c_max(s_p1, scrit);
+            smid = c_max(s_0, scrit);
             sjmin = 0.0f;
-            if (j > 1) sjmin = CM(sij, i, j - 1);
+            if (j > 1) sjmin = s_m1;
             sjmin = c_max(sjmin, scrit);
           }
           const float delp = fabsf(sjmax - smid);
           const float delm = fabsf(sjmin - smid);
-          asij = asij + (delp + delm) * (CV(phconv_hpa, j) - CV(phconv_hpa, j + 1));
-          CM(ment, i, j) = CM(ment, i, j) * (delp + delm) * (CV(phconv_hpa, j) - CV(phconv_hpa, j + 1));
+          asij = asij + (delp + delm) * (ph_j - ph_j1);
+          CM(ment, i, j) = CM(ment, i, j) * (delp + delm) * (ph_j - ph_j1);
         }
+        s_m1 = s_0;
+        s_0 = s_p1;
+        s_p1 = CM(sij, i, j + 2);
+        ph_j = ph_j1;
       }
       asij = c_max(1.0e-21f, asij);
       asij = 1.0f / asij;
-      for (int j = icb; j <= inb; j++) CM(ment, i, j) = CM(ment, i, j) * asij;
-      float bsum = 0.0f;
-      for (int j = icb; j <= inb; j++) bsum = bsum + CM(ment, i, j);
+      float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
+      for (int j = icb; j <= inb; j++) {
+        const float v = CM(ment, i, j) * asij;
+        CM(ment, i, j) = v;
+        bsum = bsum + v;
+      }
       if (bsum < 1.0e-18f) {
         CV(nent, i) = 0;
         CM(ment, i, i) = CV(m, i);
