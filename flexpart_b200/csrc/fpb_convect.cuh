@@ -362,37 +362,52 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
     const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
     int nent_i = CV(nent, i);
-    for (int j = icb; j <= inb; j++) {
-      const float bf2 = CV(ft, j);
-      const float t_j = CV(tconv, j), qs_j = CV(qsconv, j);
-      float anum = CV(h, j) - hp_i + (CPV - CPD) * t_j * (qti - CV(qconv, j));
-      float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
-      float dei = denom;
-      if (fabsf(dei) < 0.01f) dei = 0.01f;
-      float s = anum / dei;
-      CM(sij, i, i) = 1.0f;
-      if (j == i) s = 1.0f;
-      float altem = s * q_i + (1.f - s) * qti - qs_j;
-      altem = altem / bf2;
-      const float cwat = CV(fq, j);
-      const float stemp = s;
-      if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
-        const float lv_j = CV(lv, j);
-        anum = anum - lv_j * (qti - qs_j - cwat * bf2);
-        denom = denom + lv_j * (q_i - qti);
-        if (fabsf(denom) < 0.01f) denom = 0.01f;
-        s = anum / denom;
-        altem = s * q_i + (1.f - s) * qti - qs_j;
-        altem = altem - (bf2 - 1.f) * cwat;
+    // four levels at a time: their vector elements are requested together (the loop is bound by the latency of
+    // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
+    for (int j0 = icb; j0 <= inb; j0 += 4) {
+      float bf2_[4], t_[4], qs_[4], hj_[4], qj_[4], cw_[4], lv_[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u <= inb ? j0 + u : inb;
+        bf2_[u] = CV(ft, j); t_[u] = CV(tconv, j); qs_[u] = CV(qsconv, j); hj_[u] = CV(h, j); qj_[u] = CV(qconv, j);
+        cw_[u] = CV(fq, j); lv_[u] = CV(lv, j);
       }
-      if (s > 0.0f && s < 0.9f) {
-        CM(elij, i, j) = c_max(0.0f, altem);
-        CM(ment, i, j) = m_i / (1.f - s);
-        nent_i = nent_i + 1;
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u;
+        if (j <= inb) {
+          const float bf2 = bf2_[u];
+          const float t_j = t_[u], qs_j = qs_[u];
+          float anum = hj_[u] - hp_i + (CPV - CPD) * t_j * (qti - qj_[u]);
+          float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
+          float dei = denom;
+          if (fabsf(dei) < 0.01f) dei = 0.01f;
+          float s = anum / dei;
+          CM(sij, i, i) = 1.0f;
+          if (j == i) s = 1.0f;
+          float altem = s * q_i + (1.f - s) * qti - qs_j;
+          altem = altem / bf2;
+          const float cwat = cw_[u];
+          const float stemp = s;
+          if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
+            const float lv_j = lv_[u];
+            anum = anum - lv_j * (qti - qs_j - cwat * bf2);
+            denom = denom + lv_j * (q_i - qti);
+            if (fabsf(denom) < 0.01f) denom = 0.01f;
+            s = anum / denom;
+            altem = s * q_i + (1.f - s) * qti - qs_j;
+            altem = altem - (bf2 - 1.f) * cwat;
+          }
+          if (s > 0.0f && s < 0.9f) {
+            CM(elij, i, j) = c_max(0.0f, altem);
+            CM(ment, i, j) = m_i / (1.f - s);
+            nent_i = nent_i + 1;
+          }
+          s = c_max(0.0f, s);
+          s = c_min(1.0f, s);
+          CM(sij, i, j) = s;
+        }
       }
-      s = c_max(0.0f, s);
-      s = c_min(1.0f, s);
-      CM(sij, i, j) = s;
     }
     CV(nent, i) = nent_i;
     if (nent_i == 0) {
