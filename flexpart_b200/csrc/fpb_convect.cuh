@@ -429,47 +429,64 @@ FPB_UNROLL(4)
       if (alt < 0.0f) scrit = 1.0f;
       scrit = c_max(scrit, 0.0f);
       float asij = 0.0f, smin = 1.0f;
-      // (row i of sij is read through a sliding window s_m1, s_0, s_p1 = sij(i, j-1 .. j+1): it is not written here)
-      float s_m1 = icb > 1 ? CM(sij, i, icb - 1) : 0.0f, s_0 = CM(sij, i, icb), s_p1 = CM(sij, i, icb + 1);
-      float ph_j = CV(phconv_hpa, icb);
-      for (int j = icb; j <= inb; j++) {
-        const float ph_j1 = CV(phconv_hpa, j + 1);
-        if (s_0 > 0.0f && s_0 < 0.9f) {
-          float smid, sjmax, sjmin;
-          if (j > i) {
-            smid = c_min(s_0, scrit);
-            sjmax = smid;
-            sjmin = smid;
-            if (smid < smin && s_p1 < smid) {
-              smin = smid;
-              sjmax = c_min(c_min(s_p1, s_0), scrit);
-              sjmin = c_max(s_m1, s_0);
-              sjmin = c_min(sjmin, scrit);
-            }
-          } else {
-            sjmax = c_max(s_p1, scrit);
-            smid = c_max(s_0, scrit);
-            sjmin = 0.0f;
-            if (j > 1) sjmin = s_m1;
-            sjmin = c_max(sjmin, scrit);
-          }
-          const float delp = fabsf(sjmax - smid);
-          const float delm = fabsf(sjmin - smid);
-          asij = asij + (delp + delm) * (ph_j - ph_j1);
-          CM(ment, i, j) = CM(ment, i, j) * (delp + delm) * (ph_j - ph_j1);
+      // (four levels at a time, their row elements requested together: row i of sij is not written here)
+      for (int j0 = icb; j0 <= inb; j0 += 4) {
+        float sv[6], mv[4], ph[5];
+FPB_UNROLL(6)
+        for (int u = 0; u < 6; u++) {
+          const int jj = j0 - 1 + u;
+          sv[u] = (jj >= 1 && jj <= inb + 1) ? CM(sij, i, jj) : 0.0f;
         }
-        s_m1 = s_0;
-        s_0 = s_p1;
-        s_p1 = CM(sij, i, j + 2);
-        ph_j = ph_j1;
+FPB_UNROLL(4)
+        for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
+FPB_UNROLL(5)
+        for (int u = 0; u < 5; u++) ph[u] = CV(phconv_hpa, (j0 + u <= inb + 1 ? j0 + u : inb + 1));
+FPB_UNROLL(4)
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u;
+          const float s_m1 = sv[u], s_0 = sv[u + 1], s_p1 = sv[u + 2];
+          if (j <= inb && s_0 > 0.0f && s_0 < 0.9f) {
+            float smid, sjmax, sjmin;
+            if (j > i) {
+              smid = c_min(s_0, scrit);
+              sjmax = smid;
+              sjmin = smid;
+              if (smid < smin && s_p1 < smid) {
+                smin = smid;
+                sjmax = c_min(c_min(s_p1, s_0), scrit);
+                sjmin = c_max(s_m1, s_0);
+                sjmin = c_min(sjmin, scrit);
+              }
+            } else {
+              sjmax = c_max(s_p1, scrit);
+              smid = c_max(s_0, scrit);
+              sjmin = 0.0f;
+              if (j > 1) sjmin = s_m1;
+              sjmin = c_max(sjmin, scrit);
+            }
+            const float delp = fabsf(sjmax - smid);
+            const float delm = fabsf(sjmin - smid);
+            asij = asij + (delp + delm) * (ph[u] - ph[u + 1]);
+            CM(ment, i, j) = mv[u] * (delp + delm) * (ph[u] - ph[u + 1]);
+          }
+        }
       }
       asij = c_max(1.0e-21f, asij);
       asij = 1.0f / asij;
       float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
-      for (int j = icb; j <= inb; j++) {
-        const float v = CM(ment, i, j) * asij;
-        CM(ment, i, j) = v;
-        bsum = bsum + v;
+      for (int j0 = icb; j0 <= inb; j0 += 4) {
+        float mv[4];
+FPB_UNROLL(4)
+        for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
+FPB_UNROLL(4)
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u;
+          if (j <= inb) {
+            const float v = mv[u] * asij;
+            CM(ment, i, j) = v;
+            bsum = bsum + v;
+          }
+        }
       }
       if (bsum < 1.0e-18f) {
         CV(nent, i) = 0;
