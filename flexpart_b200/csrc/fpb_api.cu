@@ -291,7 +291,8 @@ struct fpb_handle {
     float4 *CS[FPB_MAXNESTS + 1][FPB_NSLOTS] = {};
     bool have[FPB_MAXNESTS + 1][FPB_NSLOTS] = {};
     float *cbaseflux[FPB_MAXNESTS + 1] = {}, *cbase_bak[FPB_MAXNESTS + 1] = {};
-    float *pool = nullptr;
+    float *pool = nullptr, *pool2 = nullptr;
+    uint8_t *col_state = nullptr;
     int pool_cols = 0;
     ScatterWork sw;
     unsigned *block_counts = nullptr, *col_key = nullptr;
@@ -810,6 +811,7 @@ extern "C" int fpb_finalize(fpb_handle *h) {
     for (auto &q : V.cbaseflux) cudaFree(q);
     for (auto &q : V.cbase_bak) cudaFree(q);
     cudaFree(V.col_key); cudaFree(V.colidx); cudaFree(V.col_start); cudaFree(V.col_lconv); cudaFree(V.key_by_slot);
+    cudaFree(V.pool2); cudaFree(V.col_state);
     cudaFree(V.d_total); cudaFree(V.draws); cudaFree(V.rn_by_slot);
     for (auto &g : V.CT) for (auto &q : g) cudaFree(q);
     for (auto &g : V.CS) for (auto &q : g) cudaFree(q);
@@ -2627,16 +2629,21 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   if (!V.pool) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t cols = (free_b / 4) / (pf * sizeof(float));
+    const size_t ld2 = (size_t)(V.nconvlev + 3) * (V.nconvlev + 3); // + the contiguous MENT of the flux assembly
+    size_t cols = (free_b / 4) / ((pf + ld2) * sizeof(float));
     cols = std::max<size_t>(256, std::min<size_t>(cols, 65536)) / 32 * 32; // whole blocks of 32 interleaved slices
     DA(V.pool, pf * cols);
+    DA(V.pool2, ld2 * cols);
     V.pool_cols = (int)cols;
   }
   if ((size_t)n > V.cap_rows) {
     cudaFree(V.block_counts); cudaFree(V.colidx); cudaFree(V.col_key); cudaFree(V.col_start); cudaFree(V.col_lconv);
+    cudaFree(V.col_state);
     V.block_counts = nullptr; V.colidx = nullptr; V.col_key = nullptr; V.col_start = nullptr; V.col_lconv = nullptr;
+    V.col_state = nullptr;
     DA(V.block_counts, (size_t)(n + 1023) / 1024 + 1); DA(V.colidx, (size_t)n);
     DA(V.col_key, (size_t)n + 1); DA(V.col_start, (size_t)n + 2); DA(V.col_lconv, (size_t)n + 1);
+    DA(V.col_state, ((size_t)n + 1) * fpb_convmix_state_bytes());
     V.cap_rows = n;
   }
   if (!V.d_total) DA(V.d_total, 1);
@@ -2668,7 +2675,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   a.keys = V.sw.keys[0]; a.ids = V.sw.ids[0];
   a.key_by_slot = refrng ? V.key_by_slot : nullptr;
   a.block_counts = V.block_counts; a.colidx = V.colidx; a.col_key = V.col_key; a.col_start = V.col_start;
-  a.col_lconv = V.col_lconv; a.pool = V.pool;
+  a.col_lconv = V.col_lconv; a.pool = V.pool; a.pool2 = V.pool2; a.col_state = V.col_state;
   a.draws = V.draws; a.rn_by_slot = nullptr; a.sorted_ids = nullptr;
   a.flux = (c.iflux == 1) ? h->hooks.flux : nullptr;
   if (refrng) CK(cudaMemsetAsync(V.key_by_slot, 0xff, (size_t)h->numpart * sizeof(int32_t), h->stream)); // -1
@@ -2734,7 +2741,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
       const int c1 = std::min(ncols, c0 + V.pool_cols);
       fpb_convmix_columns(a, c0, c1, h->stream);
       fpb_convmix_redist(a, c0, col_start[c0], col_start[c1], pass, h->stream);
-      h->launches += 2;
+      h->launches += 4;
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));

@@ -129,28 +129,39 @@ __global__ void __launch_bounds__(CB) conv_heads_assign_kernel(const ConvmixArgs
   if (i + 1 == a.nrows || keys[i + 1] == 0xffffffffu) a.col_start[incl] = i + 1; // end of the last column
 }
 
+// the column's slice of the work pool: block of 32 slices (q / 32), lane q % 32, elements interleaved
+__device__ __forceinline__ void conv_column_work(const ConvmixArgs &a, int q, ConvWork &w) {
+  const size_t nfl = conv_pool_floats(a.nuvz, a.nconvlev);
+  conv_carve(w, a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32), a.nuvz, a.nconvlev, 32);
+  w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
+  w.mentc = a.pool2 + (size_t)q * w.ld * w.ld;
+}
+__device__ __forceinline__ void conv_column_place(const ConvmixArgs &a, int c, int &g, size_t &o2, size_t &plane) {
+  const unsigned key = a.col_key[c];
+  g = (int)(key >> a.col_bits);
+  const unsigned col = key & ((1u << a.col_bits) - 1u);
+  const int jy = (int)(col / (unsigned)a.gnx[g]), ix = (int)(col - (unsigned)jy * a.gnx[g]);
+  o2 = (size_t)jy * a.gnxd[g] + ix;
+  plane = (size_t)a.gnxd[g] * a.gnyd[g];
+}
+
+// first half: sounding, calcmatrix and the Emanuel scheme up to the flux assembly, one thread per column
 __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1) return;
   const DevCfg &cf = a.cfg;
   const int nuvz = a.nuvz;
-  const size_t nfl = conv_pool_floats(nuvz, a.nconvlev);
-  // slice of column q = c - c0: block of 32 slices (q / 32), lane q % 32, elements interleaved
   const int q = c - c0;
-  float *pool = a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32);
-  const size_t nvec = (size_t)(CONV_NVEC + 1) * (nuvz + 4);
-  for (size_t k = 0; k < nvec; k++) pool[k * 32] = 0.f; // (the reference's zero-initialised locals)
   ConvWork w;
-  conv_carve(w, pool, nuvz, a.nconvlev, 32);
-  w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
-  const unsigned key = a.col_key[c];
-  const int g = (int)(key >> a.col_bits);
-  const unsigned col = key & ((1u << a.col_bits) - 1u);
-  const int jy = (int)(col / (unsigned)a.gnx[g]), ix = (int)(col - (unsigned)jy * a.gnx[g]);
+  conv_column_work(a, q, w);
+  const size_t nvec = (size_t)(CONV_NVEC + 1) * (nuvz + 4);
+  for (size_t k = 0; k < nvec; k++) w.pconv[k * 32] = 0.f; // (the reference's zero-initialised locals; pconv = first vector)
+  int g;
+  size_t o2, plane;
+  conv_column_place(a, c, g, o2, plane);
   // src/convmix.f90:62-65,163-171 (nests: :221-233)
   const float dt1 = (float)(cf.itime - cf.memtime[0]), dt2 = (float)(cf.memtime[1] - cf.itime);
   const float dtt = 1.f / (dt1 + dt2);
-  const size_t o2 = (size_t)jy * a.gnxd[g] + ix, plane = (size_t)a.gnxd[g] * a.gnyd[g];
   const float4 s1 = a.CS[g][0][o2], s2 = a.CS[g][1][o2];
   w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
   w.tt2conv = (s1.y * dt2 + s2.y * dt1) * dtt;
@@ -161,7 +172,91 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
     w.qconv[(size_t)kz * w.stride] = (q1.y * dt2 + q2.y * dt1) * dtt;
   }
   float cbmf = a.cbaseflux[g][o2];
-  const bool lconv = conv_calcmatrix(w, (float)abs(cf.lsynctime), cbmf);
+  ConvState st;
+  conv_calcmatrix_a(w, (float)abs(cf.lsynctime), cbmf, st);
+  static_cast<ConvState *>(a.col_state)[c] = st;
+}
+
+// the flux assembly (src/convect43c.f90:855-913; conv_flux_assembly is its definition) with ONE BLOCK PER COLUMN:
+// thread t owns level i = 2 + t and runs that level's two sums in the reference's order, on the column's MENT in
+// shared memory (the one-thread-per-column walk re-read the matrix from DRAM once per level: two thirds of
+// fpb_convmix, profiles/convmix_column_r02.txt)
+constexpr int ASM_THREADS = 128;
+#define WV(a, i) w.a[(size_t)(i) * w.stride]
+__global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const ConvmixArgs a, int c0, int c1) {
+  extern __shared__ float smem[];
+  const int c = c0 + blockIdx.x;
+  ConvState *stp = static_cast<ConvState *>(a.col_state) + c;
+  if (!stp->go) return; // block-uniform
+  const int inb = stp->inb, icb = stp->icb, nk = stp->nk;
+  const float delti = stp->delti;
+  ConvWork w;
+  conv_column_work(a, c - c0, w);
+  const int ld = w.ld;
+  float *T = smem;                       // MENT, (i,j) at [i + ld*j], rows / columns icb .. inb+1
+  float *mv = smem + (size_t)ld * ld;    // m(1 .. inb+1)
+  float *ph = mv + ld;                   // phconv_hpa(1 .. inb+2)
+  for (int e = threadIdx.x; e < ld * ld; e += ASM_THREADS) {
+    const int i = e % ld, j = e / ld;
+    T[e] = (i >= icb + 1 && i <= inb && j >= icb && j <= inb) ? w.mentc[e] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < ld; i += ASM_THREADS) {
+    mv[i] = (i >= 1 && i <= inb + 1) ? WV(m, i) : 0.0f;
+    ph[i] = (i >= 1 && i <= inb + 2 && i < ld) ? WV(phconv_hpa, i) : 0.0f;
+  }
+  __syncthreads();
+  using namespace k;
+  int flag4 = 0;
+  if (threadIdx.x == 0) { // level 1 (:855-866)
+    const float dpinv = 0.01f / (ph[1] - ph[2]);
+    float am = 0.0f;
+    if (nk == 1)
+      for (int kq = 2; kq <= inb; kq++) am = am + mv[kq];
+    WV(fup, 1) = am;
+    if ((2.f * G * dpinv * am) >= delti) flag4 = 1;
+  }
+  for (int i = 2 + threadIdx.x; i <= inb; i += ASM_THREADS) {
+    const float dpinv = 0.01f / (ph[i] - ph[i + 1]);
+    float amp1 = 0.0f, ad = 0.0f;
+    if (i >= nk)
+      for (int kq = i + 1; kq <= inb + 1; kq++) amp1 = amp1 + mv[kq];
+    for (int kq = icb + 1; kq <= i; kq++) {
+#pragma unroll 8
+      for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + T[kq + ld * j];
+    }
+    WV(fup, i) = amp1;
+    if ((2.f * G * dpinv * amp1) >= delti) flag4 = 1;
+    for (int kq = icb; kq <= i - 1; kq++) {
+#pragma unroll 8
+      for (int j = (i > icb + 1 ? i : icb + 1); j <= inb; j++) ad = ad + T[j + ld * kq];
+    }
+    WV(fdown, i) = ad;
+  }
+  if (flag4) stp->iflag = 4; // (every writer writes the same value)
+}
+#undef WV
+
+// second half: mass displacement matrix, subsidence, the redistribution matrix, heights of the half levels
+__global__ void __launch_bounds__(32) conv_column_tail_kernel(const ConvmixArgs a, int c0, int c1) {
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  const DevCfg &cf = a.cfg;
+  ConvWork w;
+  conv_column_work(a, c - c0, w);
+  int g;
+  size_t o2, plane;
+  conv_column_place(a, c, g, o2, plane);
+  // (psconv, tt2conv, td2conv of the first half: conv_uvzlev reads them)
+  const float dt1 = (float)(cf.itime - cf.memtime[0]), dt2 = (float)(cf.memtime[1] - cf.itime);
+  const float dtt = 1.f / (dt1 + dt2);
+  const float4 s1 = a.CS[g][0][o2], s2 = a.CS[g][1][o2];
+  w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
+  w.tt2conv = (s1.y * dt2 + s2.y * dt1) * dtt;
+  w.td2conv = (s1.z * dt2 + s2.z * dt1) * dtt;
+  const ConvState st = static_cast<const ConvState *>(a.col_state)[c];
+  w.nconvtop = 0;
+  float cbmf = st.cbmf;
+  const bool lconv = conv_calcmatrix_b(w, (float)abs(cf.lsynctime), cbmf, st);
   a.cbaseflux[g][o2] = cbmf;
   a.col_lconv[c] = lconv ? w.nconvtop : 0;
   if (lconv) conv_uvzlev(w);
@@ -228,8 +323,19 @@ void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *t
   conv_heads_assign_kernel<<<nb, CB, 0, st>>>(a, sorted_keys);
 }
 void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) {
+  if (c1 <= c0) return;
+  const int ld = a.nconvlev + 3;
+  const size_t smem = ((size_t)ld * ld + 2 * (size_t)ld) * sizeof(float);
+  static bool attr_set = false; // (64 KB of dynamic shared memory: above the default limit)
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_assembly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
   conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
+  conv_assembly_kernel<<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
+  conv_column_tail_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
 }
+size_t fpb_convmix_state_bytes() { return sizeof(fpbconv::ConvState); }
 void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st) {
   if (i1 > i0) conv_redist_kernel<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(a, c0, i0, i1, mode);
 }

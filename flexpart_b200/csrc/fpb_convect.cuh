@@ -69,6 +69,15 @@ struct ConvWork {
       *h, *hp, *gz, *hm, *uvzlev;
   int *nent;
   float *ment, *elij, *sij;
+  float *mentc; // device: the column's final MENT once more, contiguous (element (i,j) at [i + ld*j]), for the
+                // warp-per-column flux assembly (conv_assembly_kernel); null: not wanted
+};
+
+// what the two halves of conv_convect / conv_calcmatrix hand over around the flux assembly
+struct ConvState {
+  int go;     // 1: the scheme got as far as the flux assembly (iflag so far in `iflag`), 0: `iflag` is final
+  int iflag, inb, icb, nk;
+  float delti, cbmf, cbmfold;
 };
 
 constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more vector)
@@ -84,6 +93,7 @@ FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
 FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, int stride = 1) {
   const size_t lv = ((size_t)nuvz + 4) * stride;
   w.nuvz = nuvz; w.nconvlev = nconvlev; w.ld = nconvlev + 3; w.stride = stride;
+  w.mentc = nullptr;
   float **vec[CONV_NVEC] = {&w.pconv, &w.phconv, &w.dpr, &w.pconv_hpa, &w.phconv_hpa, &w.tconv, &w.qconv, &w.qsconv,
                             &w.ft, &w.fq, &w.sub, &w.fup, &w.fdown, &w.m, &w.mp, &w.tvp, &w.tv, &w.water, &w.qp,
                             &w.ep, &w.th, &w.wt, &w.evap, &w.clw, &w.sigp, &w.tp, &w.cpn, &w.lv, &w.lvcp, &w.h,
@@ -181,8 +191,10 @@ FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
   }
 }
 
-// src/convect43c.f90:11-972.  nl = nconvlev; cbmf in/out; returns iflag.
-FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
+// src/convect43c.f90:11-972 in two halves around the flux assembly (:855-913), so that the device can run that
+// O(n^3) part with a warp per column (fpb_convect.cu).  nl = nconvlev; cbmf in/out.
+// conv_convect_a: everything up to the flux assembly.  false: the scheme is over, st.iflag is its result.
+FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   using namespace k;
   const int MINORIG = 1;
   const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, SIGD = 0.05f, SIGS = 0.12f, OMTRAIN = 50.0f,
@@ -239,7 +251,7 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
     }
   if (CV(tconv, nk) < 250.0f || CV(qconv, nk) <= 0.0f || ihmin == (nl - 1)) {
     cbmf = 0.0f;
-    return 0;
+    st.iflag = 0; return false;
   }
   // lifted condensation level (:464-471)
   const float rh = CV(qconv, nk) / CV(qsconv, nk);
@@ -247,18 +259,18 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
   const float plcl = CV(pconv_hpa, nk) * c_pow(rh, chi);
   if (plcl < 200.0f || plcl >= 2000.0f) {
     cbmf = 0.0f;
-    return 2;
+    st.iflag = 2; return false;
   }
   int icb = nl - 1;
   for (int i = nk + 1; i <= nl; i++)
     if (CV(pconv_hpa, i) < plcl) icb = icb < i ? icb : i;
   if (icb >= (nl - 1)) {
     cbmf = 0.0f;
-    return 3;
+    st.iflag = 3; return false;
   }
   conv_tlift(w, icb, nk, nl, 1);
   for (int i = nk; i <= icb; i++) CV(tvp, i) = CV(tvp, i) - CV(tp, i) * CV(qconv, nk);
-  if (cbmf == 0.0f && CV(tvp, icb) <= (CV(tv, icb) - DTMAX)) return 0;
+  if (cbmf == 0.0f && CV(tvp, icb) <= (CV(tv, icb) - DTMAX)) { st.iflag = 0; return false; }
   if (iflag != 4) iflag = 1;
   conv_tlift(w, icb, nk, nl, 2);
   // precipitation efficiencies (:503-520)
@@ -340,7 +352,7 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
   const float damps = DAMP * delt / delt0;
   cbmf = (1.f - damps) * cbmf + 0.1f * ALPHA * dtma;
   cbmf = c_max(cbmf, 0.0f);
-  if (cbmf == 0.0f && cbmfold == 0.0f) return iflag;
+  if (cbmf == 0.0f && cbmfold == 0.0f) { st.iflag = iflag; return false; }
   // rates of mixing (:621-631)
   CV(m, icb) = 0.0f;
   for (int i = icb + 1; i <= inb; i++) {
@@ -563,6 +575,22 @@ FPB_UNROLL(4)
   // FLEXPART (only FMASS and SUB are) and are left out; IFLAG = 4 (CFL condition on the subsidence)
   // is kept.  The inner loops are unrolled so that several of the (independent) matrix loads are in
   // flight at once; the additions keep the reference's order.
+  if (w.mentc) { // (device) the final MENT of the rows that were set, contiguous, for the warp-per-column assembly
+    for (int j = icb; j <= inb; j++)
+      for (int i = icb + 1; i <= inb; i++) w.mentc[i + w.ld * j] = CM(ment, i, j);
+  }
+  (void)frac;
+  st.go = 1; st.iflag = iflag; st.inb = inb; st.icb = icb; st.nk = nk; st.delti = delti;
+  return true;
+}
+
+// the flux assembly in the reference's order (the definition of what conv_assembly_kernel computes; the host
+// build and the sequential path run it as it stands)
+FPB_HD inline void conv_flux_assembly(ConvWork &w, ConvState &st) {
+  using namespace k;
+  const int inb = st.inb, icb = st.icb, nk = st.nk;
+  const float delti = st.delti;
+  int iflag = st.iflag;
   float dpinv = 0.01f / (CV(phconv_hpa, 1) - CV(phconv_hpa, 2));
   float am = 0.0f;
   if (nk == 1)
@@ -587,9 +615,14 @@ FPB_UNROLL(8)
     }
     CV(fdown, i) = ad;
   }
-  // (likewise the adjustments of ft / fq at the top of the convection layer and the enthalpy
-  //  correction, :934-956)
-  (void)frac;
+  st.iflag = iflag;
+}
+
+// conv_convect_b: mass displacement matrix and compensating subsidence (:972-989); returns iflag
+FPB_HD inline int conv_convect_b(ConvWork &w, const ConvState &st) {
+  using namespace k;
+  const int inb = st.inb, nk = st.nk;
+  const int iflag = st.iflag;
   // mass displacement matrix and compensating subsidence (:972-989)
   CV(sub, 1) = 0.f;
   int nconvtop = 1;
@@ -608,10 +641,19 @@ FPB_UNROLL(8)
   return iflag;
 }
 
-// src/calcmatrix.f90:45-135 (ECMWF branch).  cbmf = cbaseflux(ix,jy), in/out.  Returns lconv.
-// tconv(1..nuvz-1), qconv(1..nuvz-1) and psconv must be set.
-FPB_HD inline bool conv_calcmatrix(ConvWork &w, float delt, float &cbmf) {
-  const float ga = 9.81f;
+// the whole scheme, sequentially; returns iflag
+FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
+  ConvState st;
+  st.go = 0;
+  if (!conv_convect_a(w, nl, delt, cbmf, st)) return st.iflag;
+  conv_flux_assembly(w, st);
+  return conv_convect_b(w, st);
+}
+
+// src/calcmatrix.f90:45-135 (ECMWF branch), like conv_convect in two halves around the flux assembly.
+// cbmf = cbaseflux(ix,jy), in/out.  tconv(1..nuvz-1), qconv(1..nuvz-1) and psconv must be set.
+// conv_calcmatrix_a: pressures, saturation humidity, the scheme up to the flux assembly (st.go: it is due)
+FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvState &st) {
   const int nuvz = w.nuvz, nconvlev = w.nconvlev;
   CV(phconv, 1) = w.psconv;
   for (int kuvz = 2; kuvz <= nuvz; kuvz++) {
@@ -621,14 +663,26 @@ FPB_HD inline bool conv_calcmatrix(ConvWork &w, float delt, float &cbmf) {
     CV(dpr, kq) = CV(phconv, kq) - CV(phconv, kuvz);
     CV(qsconv, kq) = conv_qvsat(CV(pconv, kq), CV(tconv, kq));
   }
-  const float cbmfold = cbmf;
+  st.cbmfold = cbmf;
   for (int kq = 1; kq <= nconvlev + 1; kq++) {
     CV(pconv_hpa, kq) = CV(pconv, kq) / 100.f;
     CV(phconv_hpa, kq) = CV(phconv, kq) / 100.f;
   }
   CV(phconv_hpa, nconvlev + 1) = CV(phconv, nconvlev + 1) / 100.f;
   w.nconvtop = 0;
-  const int iflag = conv_convect(w, nconvlev, delt, cbmf);
+  st.go = 0;
+  st.inb = st.icb = st.nk = 0;
+  st.delti = 0.f;
+  if (conv_convect_a(w, nconvlev, delt, cbmf, st)) st.go = 1;
+  st.cbmf = cbmf;
+}
+
+// conv_calcmatrix_b: the rest of the scheme (when the assembly ran) and the redistribution matrix.  Returns lconv.
+FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const ConvState &st) {
+  const float ga = 9.81f;
+  const float cbmfold = st.cbmfold;
+  cbmf = st.cbmf;
+  const int iflag = st.go ? conv_convect_b(w, st) : st.iflag;
   if (iflag != 1 && iflag != 4) {
     cbmf = cbmfold;
     return false;
@@ -648,6 +702,14 @@ FPB_HD inline bool conv_calcmatrix(ConvWork &w, float delt, float &cbmf) {
     CM(fmass, kq, kq) = CM(fmass, kq, kq) + rlevmass - summe;
   }
   return true;
+}
+
+// the whole routine, sequentially
+FPB_HD inline bool conv_calcmatrix(ConvWork &w, float delt, float &cbmf) {
+  ConvState st;
+  conv_calcmatrix_a(w, delt, cbmf, st);
+  if (st.go) conv_flux_assembly(w, st);
+  return conv_calcmatrix_b(w, delt, cbmf, st);
 }
 
 // src/redist.f90:63-118: heights above ground of the eta half levels of the column
