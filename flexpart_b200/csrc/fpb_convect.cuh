@@ -627,12 +627,28 @@ FPB_HD inline int conv_convect_b(ConvWork &w, const ConvState &st) {
   CV(sub, 1) = 0.f;
   int nconvtop = 1;
   for (int i = 1; i <= inb + 1; i++) {
-    for (int j = 1; j <= inb + 1; j++) {
-      if (j == nk) CM(fmass, j, i) = CM(fmass, j, i) + CV(m, i);
-      CM(fmass, j, i) = CM(fmass, j, i) + CM(ment, j, i);
-      if (CM(fmass, j, i) > EPSILON) {
-        nconvtop = nconvtop > i ? nconvtop : i;
-        nconvtop = nconvtop > j ? nconvtop : j;
+    const float m_i = CV(m, i);
+    for (int j0 = 1; j0 <= inb + 1; j0 += 4) { // (four elements requested together, then in order)
+      float fv[4], mv[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u <= inb + 1 ? j0 + u : inb + 1;
+        fv[u] = CM(fmass, j, i);
+        mv[u] = CM(ment, j, i);
+      }
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u;
+        if (j <= inb + 1) {
+          float f = fv[u];
+          if (j == nk) f = f + m_i;
+          f = f + mv[u];
+          CM(fmass, j, i) = f;
+          if (f > EPSILON) {
+            nconvtop = nconvtop > i ? nconvtop : i;
+            nconvtop = nconvtop > j ? nconvtop : j;
+          }
+        }
       }
     }
     if (i > 1) CV(sub, i) = CV(fup, i - 1) - CV(fdown, i);
@@ -695,9 +711,19 @@ FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const
   for (int kq = 1; kq <= w.nconvtop; kq++) {
     const float rlevmass = CV(dpr, kq) / ga;
     float summe = 0.f;
-    for (int kk = 1; kk <= w.nconvtop; kk++) {
-      CM(fmass, kq, kk) = delt * CM(fmass, kq, kk);
-      summe = summe + CM(fmass, kq, kk);
+    for (int kk0 = 1; kk0 <= w.nconvtop; kk0 += 4) {
+      float fv[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) fv[u] = CM(fmass, kq, (kk0 + u <= w.nconvtop ? kk0 + u : w.nconvtop));
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int kk = kk0 + u;
+        if (kk <= w.nconvtop) {
+          const float v = delt * fv[u];
+          CM(fmass, kq, kk) = v;
+          summe = summe + v;
+        }
+      }
     }
     CM(fmass, kq, kq) = CM(fmass, kq, kq) + rlevmass - summe;
   }
