@@ -374,18 +374,18 @@ FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, 
     const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
     const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
     int nent_i = CV(nent, i);
-    // four levels at a time: their vector elements are requested together (the loop is bound by the latency of
+    // eight levels at a time: their vector elements are requested together (the loop is bound by the latency of
     // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
-    for (int j0 = icb; j0 <= inb; j0 += 4) {
-      float bf2_[4], t_[4], qs_[4], hj_[4], qj_[4], cw_[4], lv_[4];
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
+    for (int j0 = icb; j0 <= inb; j0 += 8) {
+      float bf2_[8], t_[8], qs_[8], hj_[8], qj_[8], cw_[8], lv_[8];
+FPB_UNROLL(8)
+      for (int u = 0; u < 8; u++) {
         const int j = j0 + u <= inb ? j0 + u : inb;
         bf2_[u] = CV(ft, j); t_[u] = CV(tconv, j); qs_[u] = CV(qsconv, j); hj_[u] = CV(h, j); qj_[u] = CV(qconv, j);
         cw_[u] = CV(fq, j); lv_[u] = CV(lv, j);
       }
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
+FPB_UNROLL(8)
+      for (int u = 0; u < 8; u++) {
         const int j = j0 + u;
         if (j <= inb) {
           const float bf2 = bf2_[u];
