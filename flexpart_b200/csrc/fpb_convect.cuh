@@ -577,7 +577,14 @@ FPB_UNROLL(4)
   // flight at once; the additions keep the reference's order.
   if (w.mentc) { // (device) the final MENT of the rows that were set, contiguous, for the warp-per-column assembly
     for (int j = icb; j <= inb; j++)
-      for (int i = icb + 1; i <= inb; i++) w.mentc[i + w.ld * j] = CM(ment, i, j);
+      for (int i0 = icb + 1; i0 <= inb; i0 += 8) { // (eight loads in flight)
+        float v[8];
+FPB_UNROLL(8)
+        for (int u = 0; u < 8; u++) v[u] = CM(ment, (i0 + u <= inb ? i0 + u : inb), j);
+FPB_UNROLL(8)
+        for (int u = 0; u < 8; u++)
+          if (i0 + u <= inb) w.mentc[i0 + u + w.ld * j] = v[u];
+      }
   }
   (void)frac;
   st.go = 1; st.iflag = iflag; st.inb = inb; st.icb = icb; st.nk = nk; st.delti = delti;
