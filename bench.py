@@ -659,7 +659,8 @@ def next_rows(eng, cb, rel, peak, itime_now, cpu=True):
         t = best(lambda: res.update(n=eng.convmix(itime_now)), n=3)
         out["convmix"] = {"ms": t * 1e3, "occupied_columns": res["n"][0], "convecting_columns": res["n"][1],
                           "particles": c.maxpart, "nconvlev": nconvlev,
-                          "what": "fpb_convmix: column sort, calcmatrix + Emanuel scheme (one thread per occupied "
+                          "what": "fpb_convmix: column sort, calcmatrix + Emanuel scheme (one thread per occupied column, the flux "
+                                  "assembly one block per "
                                   "column), redist; synthetic soundings (tests/conv_cases.py)"}
     except Exception as e:  # (the convection leg must not take the bench line down)
         out["convmix"] = {"error": str(e)}

@@ -8,11 +8,17 @@
 //   conv_heads_* kernels run heads -> column index of every sorted position, first position and
 //                        key of every column (block scan)
 //   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + convect
-//                        (fpb_convect.cuh) on the column's slice of a work pool, cbaseflux in/out,
-//                        heights of the eta half levels when the column convects.  The 32 columns of
-//                        a warp interleave their slices element by element (stride 32): the lanes run
-//                        the same loops, so a warp-wide access to "element e of my column" is one
-//                        128-byte line instead of 32 scattered sectors.
+//                        (fpb_convect.cuh) up to the flux assembly, on the column's slice of a work pool.
+//                        The 32 columns of a warp interleave their slices element by element (stride
+//                        32): the lanes run the same loops, so a warp-wide access to "element e of my
+//                        column" is one 128-byte line instead of 32 scattered sectors.  The kernel is
+//                        bound by the latency of those loads (every warp walks 32 columns, all warps
+//                        are resident at once), so its inner loops request 4-8 elements together
+//                        before working through them in the reference's order.
+//   conv_assembly_kernel ONE BLOCK PER COLUMN: the O(n^3) sums of the flux assembly on the column's
+//                        MENT in shared memory, thread t = level t + 2, each sum in the reference's order
+//   conv_column_tail_kernel  one thread per column again: mass displacement matrix, subsidence,
+//                        redistribution matrix, cbaseflux out, heights of the eta half levels
 //   conv_redist_kernel   one thread per particle of the batch's columns: redist
 // Columns are processed in batches (the work pool holds up to 65536 columns, 150-270 KB each at 138
 // levels).  Compiled with --fmad=false; the column arithmetic is bit-comparable with the
