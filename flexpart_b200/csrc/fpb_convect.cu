@@ -179,8 +179,36 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   }
   float cbmf = a.cbaseflux[g][o2];
   ConvState st;
-  conv_calcmatrix_a(w, (float)abs(cf.lsynctime), cbmf, st);
+  conv_calcmatrix_a(w, (float)abs(cf.lsynctime), cbmf, st, true);
   static_cast<ConvState *>(a.col_state)[c] = st;
+}
+
+// the loops over level pairs of the scheme (zeroing, mixing fractions, normalisation: conv_zero_rows, conv_mix_row,
+// conv_norm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
+// still reads "element e of 32 columns" as one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every
+// column.  The rows are independent, so the bits are the sequential loop's; what changes is that a column's chain is
+// 1 / MIX_ROWS as long and MIX_ROWS times as many warps are there to hide the loads.  After a block barrier the same
+// threads write the contiguous copy of MENT, matrix column by matrix column.
+constexpr int MIX_ROWS = 8;
+__global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const ConvmixArgs a, int c0, int c1) {
+  const int c = c0 + blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
+  ConvState st;
+  st.go = 0;
+  if (c < c1) st = static_cast<const ConvState *>(a.col_state)[c];
+  ConvWork w;
+  conv_column_work(a, c < c1 ? c - c0 : 0, w);
+  if (st.go) {
+    int r0 = (st.icb + 1 + y) % MIX_ROWS; // the rows of this thread, from the first one of the matrix on
+    if (r0 == 0) r0 = MIX_ROWS;
+    conv_zero_rows(w, st, r0, MIX_ROWS);
+    for (int i = st.icb + 1 + y; i <= st.inb; i += MIX_ROWS) {
+      conv_mix_row(w, st, i);
+      conv_norm_row(w, st, i);
+    }
+  }
+  __syncthreads();
+  if (st.go) conv_mentc_copy(w, st, st.icb + y, MIX_ROWS);
 }
 
 // the flux assembly (src/convect43c.f90:855-913; conv_flux_assembly is its definition) with ONE BLOCK PER COLUMN:
@@ -338,6 +366,7 @@ void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) 
     attr_set = true;
   }
   conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
+  conv_mix_kernel<<<(c1 - c0 + 31) / 32, dim3(32, MIX_ROWS), 0, st>>>(a, c0, c1);
   conv_assembly_kernel<<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
   conv_column_tail_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
 }

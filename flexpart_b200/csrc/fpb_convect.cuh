@@ -194,14 +194,15 @@ FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
 // src/convect43c.f90:11-972 in two halves around the flux assembly (:855-913), so that the device can run that
 // O(n^3) part with a warp per column (fpb_convect.cu).  nl = nconvlev; cbmf in/out.
 // conv_convect_a: everything up to the flux assembly.  false: the scheme is over, st.iflag is its result.
-FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
+// conv_convect_head: everything in front of the loops over level pairs (:277-631): the O(n) part, one column after
+// the other in every build.  false: the scheme is over, st.iflag is its result; true: st.{iflag,icb,inb,nk,delti} set.
+FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   using namespace k;
   const int MINORIG = 1;
-  const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, SIGD = 0.05f, SIGS = 0.12f, OMTRAIN = 50.0f,
-              OMTSNOW = 5.5f, COEFFR = 1.0f, COEFFS = 0.8f, BETA = 10.0f, DTMAX = 0.9f, ALPHA = 0.025f, DAMP = 0.1f;
+  const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, SIGS = 0.12f,
+              OMTSNOW = 5.5f, DTMAX = 0.9f, ALPHA = 0.025f, DAMP = 0.1f;
   int iflag;
   const float delti = 1.0f / delt;
-  (void)BETA;
 
   for (int i = 1; i <= nl + 1; i++) {
     CV(ft, i) = 0.0f; CV(fq, i) = 0.0f; CV(fdown, i) = 0.0f; CV(sub, i) = 0.0f; CV(fup, i) = 0.0f;
@@ -214,7 +215,6 @@ FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, 
     const float rdcp = (RD * (1.f - q) + q * RV) / (CPD * (1.f - q) + q * CPV);
     CV(th, i) = CV(tconv, i) * c_pow(1000.0f / CV(pconv_hpa, i), rdcp);
   }
-  float precip = 0.0f;
   iflag = 0;
 
   // geopotential, heat capacity, static energies (:413-437)
@@ -317,16 +317,6 @@ FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, 
     }
   }
   inb = inb > inb1 ? inb : inb1;
-  { // the matrices, over the part of them that is ever read (calcmatrix / redist go up to nconvtop <= INB+2)
-    const int nz0 = (inb + 2) < (nl + 1) ? (inb + 2) : (nl + 1);
-    for (int j = 1; j <= nz0; j++)
-      for (int i = 1; i <= nz0; i++) {
-        CM(fmass, i, j) = 0.0f;
-        CM(ment, i, j) = 0.0f;
-        CM(elij, i, j) = 0.0f;
-        CM(sij, i, j) = 0.0f;
-      }
-  }
   cape = capem + byp;
   float defrac = capem - cape;
   defrac = c_max(defrac, 0.001f);
@@ -362,232 +352,206 @@ FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, 
     CV(m, i) = cbmf * dbo;
   }
   for (int i = icb + 1; i <= inb; i++) CV(m, i) = CV(m, i) / dbosum;
-  // entrained air mass flux, mixing fractions (:636-682).  What depends on j alone -- bf2 and cwat of the reference's
-  // inner loop -- is worked out once per level (into the unused ft / fq vectors: the same expressions, so the same
-  // bits), and sij(i,j) is carried in a register while its statements run instead of being re-read after every store
-  // (the stores stay where the reference has them: sij(i,i) = 1 inside the j loop is read back when j == i).
+  // what depends on j alone in the loop over level pairs below -- bf2 and cwat of the reference's inner loop -- is
+  // worked out once per level (into the unused ft / fq vectors: the same expressions, so the same bits)
   for (int j = icb; j <= inb; j++) {
     CV(ft, j) = 1.f + CV(lv, j) * CV(lv, j) * CV(qsconv, j) / (RV * CV(tconv, j) * CV(tconv, j) * CPD);
     CV(fq, j) = CV(clw, j) * (1.f - CV(ep, j));
   }
-  for (int i = icb + 1; i <= inb; i++) {
-    const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
-    const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
-    int nent_i = CV(nent, i);
-    // eight levels at a time: their vector elements are requested together (the loop is bound by the latency of
-    // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
-    for (int j0 = icb; j0 <= inb; j0 += 8) {
-      float bf2_[8], t_[8], qs_[8], hj_[8], qj_[8], cw_[8], lv_[8];
+  (void)frac;
+  st.iflag = iflag; st.inb = inb; st.icb = icb; st.nk = nk; st.delti = delti;
+  return true;
+}
+
+// The loops over level pairs (:529-545 zeroing, :636-682 mixing fractions, :686-746 normalisation) row by row: row i of
+// SIJ / MENT / ELIJ and NENT(i) depend on the column's vectors and on row i alone, so the rows can be worked in any
+// order -- or by different threads (conv_mix_kernel) -- with the reference's bits.
+// conv_zero_rows: FMASS, MENT, ELIJ, SIJ over the part of them that is ever read (calcmatrix / redist go up to
+// nconvtop <= INB+2), rows r0, r0+step, ...  (the reference zeroes (NL+1)^2)
+FPB_HD inline void conv_zero_rows(ConvWork &w, const ConvState &st, int r0, int step) {
+  const int nl = w.nconvlev;
+  const int nz0 = (st.inb + 2) < (nl + 1) ? (st.inb + 2) : (nl + 1);
+  for (int i = r0; i <= nz0; i += step)
+    for (int j = 1; j <= nz0; j++) {
+      CM(fmass, i, j) = 0.0f;
+      CM(ment, i, j) = 0.0f;
+      CM(elij, i, j) = 0.0f;
+      CM(sij, i, j) = 0.0f;
+    }
+}
+
+// entrained air mass flux, mixing fractions of row i (:636-682); sij(i,j) is carried in a register while its
+// statements run instead of being re-read after every store (the stores stay where the reference has them:
+// sij(i,i) = 1 inside the j loop is read back when j == i)
+FPB_HD inline void conv_mix_row(ConvWork &w, const ConvState &st, int i) {
+  using namespace k;
+  const int icb = st.icb, inb = st.inb, nk = st.nk;
+  const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+  const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
+  int nent_i = CV(nent, i);
+  // eight levels at a time: their vector elements are requested together (the loop is bound by the latency of
+  // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
+  for (int j0 = icb; j0 <= inb; j0 += 8) {
+    float bf2_[8], t_[8], qs_[8], hj_[8], qj_[8], cw_[8], lv_[8];
 FPB_UNROLL(8)
-      for (int u = 0; u < 8; u++) {
-        const int j = j0 + u <= inb ? j0 + u : inb;
-        bf2_[u] = CV(ft, j); t_[u] = CV(tconv, j); qs_[u] = CV(qsconv, j); hj_[u] = CV(h, j); qj_[u] = CV(qconv, j);
-        cw_[u] = CV(fq, j); lv_[u] = CV(lv, j);
+    for (int u = 0; u < 8; u++) {
+      const int j = j0 + u <= inb ? j0 + u : inb;
+      bf2_[u] = CV(ft, j); t_[u] = CV(tconv, j); qs_[u] = CV(qsconv, j); hj_[u] = CV(h, j); qj_[u] = CV(qconv, j);
+      cw_[u] = CV(fq, j); lv_[u] = CV(lv, j);
+    }
+FPB_UNROLL(8)
+    for (int u = 0; u < 8; u++) {
+      const int j = j0 + u;
+      if (j <= inb) {
+        const float bf2 = bf2_[u];
+        const float t_j = t_[u], qs_j = qs_[u];
+        float anum = hj_[u] - hp_i + (CPV - CPD) * t_j * (qti - qj_[u]);
+        float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
+        float dei = denom;
+        if (fabsf(dei) < 0.01f) dei = 0.01f;
+        float s = anum / dei;
+        CM(sij, i, i) = 1.0f;
+        if (j == i) s = 1.0f;
+        float altem = s * q_i + (1.f - s) * qti - qs_j;
+        altem = altem / bf2;
+        const float cwat = cw_[u];
+        const float stemp = s;
+        if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
+          const float lv_j = lv_[u];
+          anum = anum - lv_j * (qti - qs_j - cwat * bf2);
+          denom = denom + lv_j * (q_i - qti);
+          if (fabsf(denom) < 0.01f) denom = 0.01f;
+          s = anum / denom;
+          altem = s * q_i + (1.f - s) * qti - qs_j;
+          altem = altem - (bf2 - 1.f) * cwat;
+        }
+        if (s > 0.0f && s < 0.9f) {
+          CM(elij, i, j) = c_max(0.0f, altem);
+          CM(ment, i, j) = m_i / (1.f - s);
+          nent_i = nent_i + 1;
+        }
+        s = c_max(0.0f, s);
+        s = c_min(1.0f, s);
+        CM(sij, i, j) = s;
       }
-FPB_UNROLL(8)
-      for (int u = 0; u < 8; u++) {
+    }
+  }
+  CV(nent, i) = nent_i;
+  if (nent_i == 0) {
+    CM(ment, i, i) = m_i;
+    CM(elij, i, i) = CV(clw, i);
+    CM(sij, i, i) = 1.0f;
+  }
+  if (i == inb) CM(sij, inb, inb) = 1.0f; // (:683, after the loop over i in the reference: row inb is complete here)
+}
+
+// normalise the entrained fluxes of row i (:686-746)
+FPB_HD inline void conv_norm_row(ConvWork &w, const ConvState &st, int i) {
+  const int icb = st.icb, inb = st.inb, nk = st.nk;
+  if (CV(nent, i) != 0) {
+    const float qp1 = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
+    const float anum = CV(h, i) - CV(hp, i) - CV(lv, i) * (qp1 - CV(qsconv, i));
+    float denom = CV(h, i) - CV(hp, i) + CV(lv, i) * (CV(qconv, i) - qp1);
+    if (fabsf(denom) < 0.01f) denom = 0.01f;
+    float scrit = anum / denom;
+    const float alt = qp1 - CV(qsconv, i) + scrit * (CV(qconv, i) - qp1);
+    if (alt < 0.0f) scrit = 1.0f;
+    scrit = c_max(scrit, 0.0f);
+    float asij = 0.0f, smin = 1.0f;
+    // (four levels at a time, their row elements requested together: row i of sij is not written here)
+    for (int j0 = icb; j0 <= inb; j0 += 4) {
+      float sv[6], mv[4], ph[5];
+FPB_UNROLL(6)
+      for (int u = 0; u < 6; u++) {
+        const int jj = j0 - 1 + u;
+        sv[u] = (jj >= 1 && jj <= inb + 1) ? CM(sij, i, jj) : 0.0f;
+      }
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
+FPB_UNROLL(5)
+      for (int u = 0; u < 5; u++) ph[u] = CV(phconv_hpa, (j0 + u <= inb + 1 ? j0 + u : inb + 1));
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
         const int j = j0 + u;
-        if (j <= inb) {
-          const float bf2 = bf2_[u];
-          const float t_j = t_[u], qs_j = qs_[u];
-          float anum = hj_[u] - hp_i + (CPV - CPD) * t_j * (qti - qj_[u]);
-          float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
-          float dei = denom;
-          if (fabsf(dei) < 0.01f) dei = 0.01f;
-          float s = anum / dei;
-          CM(sij, i, i) = 1.0f;
-          if (j == i) s = 1.0f;
-          float altem = s * q_i + (1.f - s) * qti - qs_j;
-          altem = altem / bf2;
-          const float cwat = cw_[u];
-          const float stemp = s;
-          if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
-            const float lv_j = lv_[u];
-            anum = anum - lv_j * (qti - qs_j - cwat * bf2);
-            denom = denom + lv_j * (q_i - qti);
-            if (fabsf(denom) < 0.01f) denom = 0.01f;
-            s = anum / denom;
-            altem = s * q_i + (1.f - s) * qti - qs_j;
-            altem = altem - (bf2 - 1.f) * cwat;
+        const float s_m1 = sv[u], s_0 = sv[u + 1], s_p1 = sv[u + 2];
+        if (j <= inb && s_0 > 0.0f && s_0 < 0.9f) {
+          float smid, sjmax, sjmin;
+          if (j > i) {
+            smid = c_min(s_0, scrit);
+            sjmax = smid;
+            sjmin = smid;
+            if (smid < smin && s_p1 < smid) {
+              smin = smid;
+              sjmax = c_min(c_min(s_p1, s_0), scrit);
+              sjmin = c_max(s_m1, s_0);
+              sjmin = c_min(sjmin, scrit);
+            }
+          } else {
+            sjmax = c_max(s_p1, scrit);
+            smid = c_max(s_0, scrit);
+            sjmin = 0.0f;
+            if (j > 1) sjmin = s_m1;
+            sjmin = c_max(sjmin, scrit);
           }
-          if (s > 0.0f && s < 0.9f) {
-            CM(elij, i, j) = c_max(0.0f, altem);
-            CM(ment, i, j) = m_i / (1.f - s);
-            nent_i = nent_i + 1;
-          }
-          s = c_max(0.0f, s);
-          s = c_min(1.0f, s);
-          CM(sij, i, j) = s;
+          const float delp = fabsf(sjmax - smid);
+          const float delm = fabsf(sjmin - smid);
+          asij = asij + (delp + delm) * (ph[u] - ph[u + 1]);
+          CM(ment, i, j) = mv[u] * (delp + delm) * (ph[u] - ph[u + 1]);
         }
       }
     }
-    CV(nent, i) = nent_i;
-    if (nent_i == 0) {
-      CM(ment, i, i) = m_i;
+    asij = c_max(1.0e-21f, asij);
+    asij = 1.0f / asij;
+    float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
+    for (int j0 = icb; j0 <= inb; j0 += 4) {
+      float mv[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u;
+        if (j <= inb) {
+          const float v = mv[u] * asij;
+          CM(ment, i, j) = v;
+          bsum = bsum + v;
+        }
+      }
+    }
+    if (bsum < 1.0e-18f) {
+      CV(nent, i) = 0;
+      CM(ment, i, i) = CV(m, i);
       CM(elij, i, i) = CV(clw, i);
       CM(sij, i, i) = 1.0f;
     }
   }
-  CM(sij, inb, inb) = 1.0f;
-  // normalise the entrained fluxes (:686-746)
-  for (int i = icb + 1; i <= inb; i++) {
-    if (CV(nent, i) != 0) {
-      const float qp1 = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
-      const float anum = CV(h, i) - CV(hp, i) - CV(lv, i) * (qp1 - CV(qsconv, i));
-      float denom = CV(h, i) - CV(hp, i) + CV(lv, i) * (CV(qconv, i) - qp1);
-      if (fabsf(denom) < 0.01f) denom = 0.01f;
-      float scrit = anum / denom;
-      const float alt = qp1 - CV(qsconv, i) + scrit * (CV(qconv, i) - qp1);
-      if (alt < 0.0f) scrit = 1.0f;
-      scrit = c_max(scrit, 0.0f);
-      float asij = 0.0f, smin = 1.0f;
-      // (four levels at a time, their row elements requested together: row i of sij is not written here)
-      for (int j0 = icb; j0 <= inb; j0 += 4) {
-        float sv[6], mv[4], ph[5];
-FPB_UNROLL(6)
-        for (int u = 0; u < 6; u++) {
-          const int jj = j0 - 1 + u;
-          sv[u] = (jj >= 1 && jj <= inb + 1) ? CM(sij, i, jj) : 0.0f;
-        }
-FPB_UNROLL(4)
-        for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
-FPB_UNROLL(5)
-        for (int u = 0; u < 5; u++) ph[u] = CV(phconv_hpa, (j0 + u <= inb + 1 ? j0 + u : inb + 1));
-FPB_UNROLL(4)
-        for (int u = 0; u < 4; u++) {
-          const int j = j0 + u;
-          const float s_m1 = sv[u], s_0 = sv[u + 1], s_p1 = sv[u + 2];
-          if (j <= inb && s_0 > 0.0f && s_0 < 0.9f) {
-            float smid, sjmax, sjmin;
-            if (j > i) {
-              smid = c_min(s_0, scrit);
-              sjmax = smid;
-              sjmin = smid;
-              if (smid < smin && s_p1 < smid) {
-                smin = smid;
-                sjmax = c_min(c_min(s_p1, s_0), scrit);
-                sjmin = c_max(s_m1, s_0);
-                sjmin = c_min(sjmin, scrit);
-              }
-            } else {
-              sjmax = c_max(s_p1, scrit);
-              smid = c_max(s_0, scrit);
-              sjmin = 0.0f;
-              if (j > 1) sjmin = s_m1;
-              sjmin = c_max(sjmin, scrit);
-            }
-            const float delp = fabsf(sjmax - smid);
-            const float delm = fabsf(sjmin - smid);
-            asij = asij + (delp + delm) * (ph[u] - ph[u + 1]);
-            CM(ment, i, j) = mv[u] * (delp + delm) * (ph[u] - ph[u + 1]);
-          }
-        }
-      }
-      asij = c_max(1.0e-21f, asij);
-      asij = 1.0f / asij;
-      float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
-      for (int j0 = icb; j0 <= inb; j0 += 4) {
-        float mv[4];
-FPB_UNROLL(4)
-        for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
-FPB_UNROLL(4)
-        for (int u = 0; u < 4; u++) {
-          const int j = j0 + u;
-          if (j <= inb) {
-            const float v = mv[u] * asij;
-            CM(ment, i, j) = v;
-            bsum = bsum + v;
-          }
-        }
-      }
-      if (bsum < 1.0e-18f) {
-        CV(nent, i) = 0;
-        CM(ment, i, i) = CV(m, i);
-        CM(elij, i, i) = CV(clw, i);
-        CM(sij, i, i) = 1.0f;
-      }
-    }
-  }
-  // precipitating downdraft (:750-842)
-  if (!(CV(ep, inb) < 0.0001f)) {
-    int jtt = 2;
-    for (int i = inb; i >= 1; i--) {
-      float wdtrain = G * CV(ep, i) * CV(m, i) * CV(clw, i);
-      if (i > 1) {
-FPB_UNROLL(4)
-        for (int j = 1; j <= i - 1; j++) {
-          float awat = CM(elij, j, i) - (1.f - CV(ep, i)) * CV(clw, i);
-          awat = c_max(0.0f, awat);
-          wdtrain = wdtrain + G * awat * CM(ment, j, i);
-        }
-      }
-      float coeff = COEFFS;
-      CV(wt, i) = OMTSNOW;
-      if (CV(tconv, i) > 273.0f) {
-        coeff = COEFFR;
-        CV(wt, i) = OMTRAIN;
-      }
-      const float qsm = 0.5f * (CV(qconv, i) + CV(qp, i + 1));
-      float afac = coeff * CV(phconv_hpa, i) * (CV(qsconv, i) - qsm) / (1.0e4f + 2.0e3f * CV(phconv_hpa, i) * CV(qsconv, i));
-      afac = c_max(afac, 0.0f);
-      float sigt = CV(sigp, i);
-      sigt = c_max(0.0f, sigt);
-      sigt = c_min(1.0f, sigt);
-      const float b6 = 100.f * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) * sigt * afac / CV(wt, i);
-      const float c6 = (CV(water, i + 1) * CV(wt, i + 1) + wdtrain / SIGD) / CV(wt, i);
-      const float revap = 0.5f * (-b6 + c_sqrt(b6 * b6 + 4.f * c6));
-      CV(evap, i) = sigt * afac * revap;
-      CV(water, i) = revap * revap;
-      if (i != 1) {
-        float dhdp = (CV(h, i) - CV(h, i - 1)) / (CV(pconv_hpa, i - 1) - CV(pconv_hpa, i));
-        dhdp = c_max(dhdp, 10.0f);
-        CV(mp, i) = 100.f * GINV * CV(lv, i) * SIGD * CV(evap, i) / dhdp;
-        CV(mp, i) = c_max(CV(mp, i), 0.0f);
-        const float fac = 20.0f / (CV(phconv_hpa, i - 1) - CV(phconv_hpa, i));
-        CV(mp, i) = (fac * CV(mp, i + 1) + CV(mp, i)) / (1.f + fac);
-        if (CV(pconv_hpa, i) > (0.949f * CV(pconv_hpa, 1))) {
-          jtt = jtt > i ? jtt : i;
-          CV(mp, i) = CV(mp, jtt) * (CV(pconv_hpa, 1) - CV(pconv_hpa, i)) / (CV(pconv_hpa, 1) - CV(pconv_hpa, jtt));
-        }
-      }
-      if (i == inb) continue; // label 400
-      float qstm;
-      if (i == 1) qstm = CV(qsconv, 1);
-      else qstm = CV(qsconv, i - 1);
-      if (CV(mp, i) > CV(mp, i + 1)) {
-        const float rat = CV(mp, i + 1) / CV(mp, i);
-        CV(qp, i) = CV(qp, i + 1) * rat + CV(qconv, i) * (1.0f - rat) +
-                    100.f * GINV * SIGD * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) * (CV(evap, i) / CV(mp, i));
-      } else {
-        if (CV(mp, i + 1) > 0.0f)
-          CV(qp, i) = (CV(gz, i + 1) - CV(gz, i) + CV(qp, i + 1) * (CV(lv, i + 1) + CV(tconv, i + 1) * (CL - CPD)) +
-                       CPD * (CV(tconv, i + 1) - CV(tconv, i))) /
-                      (CV(lv, i) + CV(tconv, i) * (CL - CPD));
-      }
-      CV(qp, i) = c_min(CV(qp, i), qstm);
-      CV(qp, i) = c_max(CV(qp, i), 0.0f);
-    }
-    precip = precip + CV(wt, 1) * SIGD * CV(water, 1) * 3600.f * 24000.f / (ROWL * G);
-  }
-  (void)precip;
-  // net saturated up- and downdraft mass fluxes through each level (:855-913).  The temperature and
-  // humidity tendencies FT, FQ that the scheme also forms there (:867-872,914-934) are not read by
-  // FLEXPART (only FMASS and SUB are) and are left out; IFLAG = 4 (CFL condition on the subsidence)
-  // is kept.  The inner loops are unrolled so that several of the (independent) matrix loads are in
-  // flight at once; the additions keep the reference's order.
-  if (w.mentc) { // (device) the final MENT of the rows that were set, contiguous, for the warp-per-column assembly
-    for (int j = icb; j <= inb; j++)
-      for (int i0 = icb + 1; i0 <= inb; i0 += 8) { // (eight loads in flight)
-        float v[8];
+}
+
+// (device) the final MENT of the rows that were set, once more and contiguous, for the block-per-column flux assembly:
+// columns j0, j0+step, ... of the matrix
+FPB_HD inline void conv_mentc_copy(ConvWork &w, const ConvState &st, int j0, int step) {
+  const int icb = st.icb, inb = st.inb;
+  for (int j = j0; j <= inb; j += step)
+    for (int i0 = icb + 1; i0 <= inb; i0 += 8) { // (eight loads in flight)
+      float v[8];
 FPB_UNROLL(8)
-        for (int u = 0; u < 8; u++) v[u] = CM(ment, (i0 + u <= inb ? i0 + u : inb), j);
+      for (int u = 0; u < 8; u++) v[u] = CM(ment, (i0 + u <= inb ? i0 + u : inb), j);
 FPB_UNROLL(8)
-        for (int u = 0; u < 8; u++)
-          if (i0 + u <= inb) w.mentc[i0 + u + w.ld * j] = v[u];
-      }
-  }
-  (void)frac;
-  st.go = 1; st.iflag = iflag; st.inb = inb; st.icb = icb; st.nk = nk; st.delti = delti;
+      for (int u = 0; u < 8; u++)
+        if (i0 + u <= inb) w.mentc[i0 + u + w.ld * j] = v[u];
+    }
+}
+
+// conv_convect_a: everything up to the flux assembly, one column sequentially (host build, sequential path).
+// The precipitating downdraft (:750-842) is left out like the tendencies FT, FQ (:867-872,914-934) it feeds: WATER,
+// EVAP, MP, QP and PRECIP are read by nothing FLEXPART uses (FMASS, SUB, IFLAG, CBMF); IFLAG = 4 (the CFL condition
+// on the subsidence, in the flux assembly) is kept.
+FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
+  if (!conv_convect_head(w, nl, delt, cbmf, st)) return false;
+  conv_zero_rows(w, st, 1, 1);
+  for (int i = st.icb + 1; i <= st.inb; i++) conv_mix_row(w, st, i);
+  for (int i = st.icb + 1; i <= st.inb; i++) conv_norm_row(w, st, i);
+  if (w.mentc) conv_mentc_copy(w, st, st.icb, 1);
+  st.go = 1;
   return true;
 }
 
@@ -676,7 +640,8 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
 // src/calcmatrix.f90:45-135 (ECMWF branch), like conv_convect in two halves around the flux assembly.
 // cbmf = cbaseflux(ix,jy), in/out.  tconv(1..nuvz-1), qconv(1..nuvz-1) and psconv must be set.
 // conv_calcmatrix_a: pressures, saturation humidity, the scheme up to the flux assembly (st.go: it is due)
-FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvState &st) {
+// head_only: stop in front of the loops over level pairs (the device runs them in conv_mix_kernel)
+FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvState &st, bool head_only = false) {
   const int nuvz = w.nuvz, nconvlev = w.nconvlev;
   CV(phconv, 1) = w.psconv;
   for (int kuvz = 2; kuvz <= nuvz; kuvz++) {
@@ -696,7 +661,7 @@ FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvS
   st.go = 0;
   st.inb = st.icb = st.nk = 0;
   st.delti = 0.f;
-  if (conv_convect_a(w, nconvlev, delt, cbmf, st)) st.go = 1;
+  if (head_only ? conv_convect_head(w, nconvlev, delt, cbmf, st) : conv_convect_a(w, nconvlev, delt, cbmf, st)) st.go = 1;
   st.cbmf = cbmf;
 }
 
