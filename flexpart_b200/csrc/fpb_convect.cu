@@ -7,20 +7,21 @@
 //   [stable LSD radix sort of (key, row), fpb_scatter.cu]
 //   conv_heads_* kernels run heads -> column index of every sorted position, first position and
 //                        key of every column (block scan)
-//   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + convect
-//                        (fpb_convect.cuh) up to the flux assembly, on the column's slice of a work pool.
+//   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + the O(n) part of
+//                        convect (fpb_convect.cuh: conv_convect_head), on the column's slice of a work pool.
 //                        The 32 columns of a warp interleave their slices element by element (stride
 //                        32): the lanes run the same loops, so a warp-wide access to "element e of my
-//                        column" is one 128-byte line instead of 32 scattered sectors.  The kernel is
-//                        bound by the latency of those loads (every warp walks 32 columns, all warps
-//                        are resident at once), so its inner loops request 4-8 elements together
-//                        before working through them in the reference's order.
+//                        column" is one 128-byte line instead of 32 scattered sectors.
+//   conv_mix_kernel      ONE BLOCK PER 32 COLUMNS x 8 ROW RESIDUES: the loops over level pairs (mixing
+//                        fractions, normalisation, redistribution matrix), independent row by row;
+//                        latency-bound, so the inner loops request 4-8 elements together before working
+//                        through them in the reference's order
 //   conv_assembly_kernel ONE BLOCK PER COLUMN: the O(n^3) sums of the flux assembly on the column's
 //                        MENT in shared memory, thread t = level t + 2, each sum in the reference's order
-//   conv_column_tail_kernel  one thread per column again: mass displacement matrix, subsidence,
-//                        redistribution matrix, cbaseflux out, heights of the eta half levels
+//   conv_column_tail_kernel  one thread per column again: subsidence, cbaseflux out, heights of the
+//                        eta half levels
 //   conv_redist_kernel   one thread per particle of the batch's columns: redist
-// Columns are processed in batches (the work pool holds up to 65536 columns, 150-270 KB each at 138
+// Columns are processed in batches (the work pool holds up to 65536 columns, 115-200 KB each at 138
 // levels).  Compiled with --fmad=false; the column arithmetic is bit-comparable with the
 // reference's routines in every math mode (see fpb_convect.cuh).
 #include "fpb_convect.cuh"
@@ -183,12 +184,11 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   static_cast<ConvState *>(a.col_state)[c] = st;
 }
 
-// the loops over level pairs of the scheme (zeroing, mixing fractions, normalisation: conv_zero_rows, conv_mix_row,
-// conv_norm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
+// the loops over level pairs of the scheme (mixing fractions, normalisation: conv_mix_row, conv_norm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
 // still reads "element e of 32 columns" as one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every
 // column.  The rows are independent, so the bits are the sequential loop's; what changes is that a column's chain is
 // 1 / MIX_ROWS as long and MIX_ROWS times as many warps are there to hide the loads.  After a block barrier the same
-// threads write the contiguous copy of MENT, matrix column by matrix column.
+// threads write the contiguous copy of MENT, matrix column by matrix column, and the redistribution matrix row by row.
 constexpr int MIX_ROWS = 8;
 __global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const ConvmixArgs a, int c0, int c1) {
   const int c = c0 + blockIdx.x * 32 + threadIdx.x;
@@ -199,16 +199,20 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const Convmi
   ConvWork w;
   conv_column_work(a, c < c1 ? c - c0 : 0, w);
   if (st.go) {
-    int r0 = (st.icb + 1 + y) % MIX_ROWS; // the rows of this thread, from the first one of the matrix on
-    if (r0 == 0) r0 = MIX_ROWS;
-    conv_zero_rows(w, st, r0, MIX_ROWS);
     for (int i = st.icb + 1 + y; i <= st.inb; i += MIX_ROWS) {
       conv_mix_row(w, st, i);
       conv_norm_row(w, st, i);
     }
   }
   __syncthreads();
-  if (st.go) conv_mentc_copy(w, st, st.icb + y, MIX_ROWS);
+  if (st.go) {
+    conv_mentc_copy(w, st, st.icb + y, MIX_ROWS);
+    // the redistribution matrix (conv_fmass_row), rows 1 + y, + MIX_ROWS, ...: every thread works out nconvtop for itself
+    const float delt = (float)abs(a.cfg.lsynctime);
+    float cbmf;
+    if (conv_calcmatrix_b(w, delt, cbmf, st, false, false))
+      for (int kq = 1 + y; kq <= w.nconvtop; kq += MIX_ROWS) conv_fmass_row(w, st, delt, kq);
+  }
 }
 
 // the flux assembly (src/convect43c.f90:855-913; conv_flux_assembly is its definition) with ONE BLOCK PER COLUMN:
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const Convmi
 }
 #undef WV
 
-// second half: mass displacement matrix, subsidence, the redistribution matrix, heights of the half levels
+// second half: subsidence, cbaseflux out, heights of the half levels
 __global__ void __launch_bounds__(32) conv_column_tail_kernel(const ConvmixArgs a, int c0, int c1) {
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1) return;
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(32) conv_column_tail_kernel(const ConvmixArgs 
   const ConvState st = static_cast<const ConvState *>(a.col_state)[c];
   w.nconvtop = 0;
   float cbmf = st.cbmf;
-  const bool lconv = conv_calcmatrix_b(w, (float)abs(cf.lsynctime), cbmf, st);
+  const bool lconv = conv_calcmatrix_b(w, (float)abs(cf.lsynctime), cbmf, st, false, true); // (rows: conv_mix_kernel)
   a.cbaseflux[g][o2] = cbmf;
   a.col_lconv[c] = lconv ? w.nconvtop : 0;
   if (lconv) conv_uvzlev(w);

@@ -68,7 +68,8 @@ struct ConvWork {
   float *fup, *fdown, *m, *mp, *tvp, *tv, *water, *qp, *ep, *th, *wt, *evap, *clw, *sigp, *tp, *cpn, *lv, *lvcp,
       *h, *hp, *gz, *hm, *uvzlev;
   int *nent;
-  float *ment, *elij, *sij;
+  int *rowtop; // per row i of MENT: max(i, largest j with ment(i,j) > EPSILON), 0: none (conv_norm_row)
+  float *ment, *sij; // (ELIJ is only read by the precipitating downdraft, which is left out: not kept)
   float *mentc; // device: the column's final MENT once more, contiguous (element (i,j) at [i + ld*j]), for the
                 // warp-per-column flux assembly (conv_assembly_kernel); null: not wanted
 };
@@ -85,7 +86,7 @@ constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more
 // floats of one column's slice
 FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
   const size_t lv = (size_t)nuvz + 4, ld = (size_t)nconvlev + 3;
-  return (CONV_NVEC + 1) * lv + 4 * ld * ld;
+  return (CONV_NVEC + 1) * lv + 3 * ld * ld;
 }
 
 // carve the column's slice: `pool` = first float of the slice (for stride 32: of the warp's block of
@@ -101,11 +102,10 @@ FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, 
   float *p = pool;
   for (int k = 0; k < CONV_NVEC - 1; k++) { *vec[k] = p; p += lv; }
   w.nent = reinterpret_cast<int *>(p); p += lv;
-  p += lv; // (spare)
+  w.rowtop = reinterpret_cast<int *>(p); p += lv;
   const size_t ld2 = (size_t)w.ld * w.ld * stride;
   w.fmass = p; p += ld2;
   w.ment = p; p += ld2;
-  w.elij = p; p += ld2;
   w.sij = p;
 }
 
@@ -363,21 +363,15 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   return true;
 }
 
-// The loops over level pairs (:529-545 zeroing, :636-682 mixing fractions, :686-746 normalisation) row by row: row i of
+// The loops over level pairs (:636-682 mixing fractions, :686-746 normalisation) row by row: row i of
 // SIJ / MENT / ELIJ and NENT(i) depend on the column's vectors and on row i alone, so the rows can be worked in any
 // order -- or by different threads (conv_mix_kernel) -- with the reference's bits.
-// conv_zero_rows: FMASS, MENT, ELIJ, SIJ over the part of them that is ever read (calcmatrix / redist go up to
-// nconvtop <= INB+2), rows r0, r0+step, ...  (the reference zeroes (NL+1)^2)
-FPB_HD inline void conv_zero_rows(ConvWork &w, const ConvState &st, int r0, int step) {
-  const int nl = w.nconvlev;
-  const int nz0 = (st.inb + 2) < (nl + 1) ? (st.inb + 2) : (nl + 1);
-  for (int i = r0; i <= nz0; i += step)
-    for (int j = 1; j <= nz0; j++) {
-      CM(fmass, i, j) = 0.0f;
-      CM(ment, i, j) = 0.0f;
-      CM(elij, i, j) = 0.0f;
-      CM(sij, i, j) = 0.0f;
-    }
+// Nothing is zeroed up front (the reference zeroes the four (NL+1)^2 matrices, :529-545): row i of MENT is written in
+// full over the columns ICB..INB it can be set in (the value or 0), the two elements of SIJ the normalisation reads
+// beside that range are set to 0 with the row, every other element of MENT is known to be 0 by its indices
+// (conv_ment_set) and FMASS is written in full over [1, nconvtop]^2 by conv_fmass_row.
+FPB_HD inline bool conv_ment_set(const ConvState &st, int i, int j) { // may MENT(i,j) differ from 0?
+  return i >= st.icb + 1 && i <= st.inb && j >= st.icb && j <= st.inb;
 }
 
 // entrained air mass flux, mixing fractions of row i (:636-682); sij(i,j) is carried in a register while its
@@ -389,6 +383,8 @@ FPB_HD inline void conv_mix_row(ConvWork &w, const ConvState &st, int i) {
   const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
   const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
   int nent_i = CV(nent, i);
+  if (icb > 1) CM(sij, i, icb - 1) = 0.0f;
+  CM(sij, i, inb + 1) = 0.0f;
   // eight levels at a time: their vector elements are requested together (the loop is bound by the latency of
   // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
   for (int j0 = icb; j0 <= inb; j0 += 8) {
@@ -425,10 +421,11 @@ FPB_UNROLL(8)
           altem = s * q_i + (1.f - s) * qti - qs_j;
           altem = altem - (bf2 - 1.f) * cwat;
         }
-        if (s > 0.0f && s < 0.9f) {
-          CM(elij, i, j) = c_max(0.0f, altem);
+        if (s > 0.0f && s < 0.9f) { // (elij(i,j) = max(0, altem) is not kept)
           CM(ment, i, j) = m_i / (1.f - s);
           nent_i = nent_i + 1;
+        } else {
+          CM(ment, i, j) = 0.0f;
         }
         s = c_max(0.0f, s);
         s = c_min(1.0f, s);
@@ -439,15 +436,18 @@ FPB_UNROLL(8)
   CV(nent, i) = nent_i;
   if (nent_i == 0) {
     CM(ment, i, i) = m_i;
-    CM(elij, i, i) = CV(clw, i);
     CM(sij, i, i) = 1.0f;
   }
   if (i == inb) CM(sij, inb, inb) = 1.0f; // (:683, after the loop over i in the reference: row inb is complete here)
 }
 
 // normalise the entrained fluxes of row i (:686-746)
+// and note in rowtop(i) how far the final row reaches above EPSILON (what conv_convect_b's search for nconvtop asks)
 FPB_HD inline void conv_norm_row(ConvWork &w, const ConvState &st, int i) {
+  using namespace k;
   const int icb = st.icb, inb = st.inb, nk = st.nk;
+  int top = 0;           // largest j != i with ment(i,j) > EPSILON
+  float vii = CV(m, i);  // ment(i,i) (nent(i) == 0: the row is 0 but for ment(i,i) = m(i))
   if (CV(nent, i) != 0) {
     const float qp1 = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
     const float anum = CV(h, i) - CV(hp, i) - CV(lv, i) * (qp1 - CV(qsconv, i));
@@ -514,16 +514,20 @@ FPB_UNROLL(4)
           const float v = mv[u] * asij;
           CM(ment, i, j) = v;
           bsum = bsum + v;
+          if (j == i) vii = v;
+          else if (v > EPSILON) top = j;
         }
       }
     }
     if (bsum < 1.0e-18f) {
       CV(nent, i) = 0;
       CM(ment, i, i) = CV(m, i);
-      CM(elij, i, i) = CV(clw, i);
       CM(sij, i, i) = 1.0f;
+      vii = CV(m, i);
     }
   }
+  if (vii > EPSILON && i > top) top = i;
+  CV(rowtop, i) = top > 0 ? (top > i ? top : i) : 0;
 }
 
 // (device) the final MENT of the rows that were set, once more and contiguous, for the block-per-column flux assembly:
@@ -547,7 +551,6 @@ FPB_UNROLL(8)
 // on the subsidence, in the flux assembly) is kept.
 FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   if (!conv_convect_head(w, nl, delt, cbmf, st)) return false;
-  conv_zero_rows(w, st, 1, 1);
   for (int i = st.icb + 1; i <= st.inb; i++) conv_mix_row(w, st, i);
   for (int i = st.icb + 1; i <= st.inb; i++) conv_norm_row(w, st, i);
   if (w.mentc) conv_mentc_copy(w, st, st.icb, 1);
@@ -589,43 +592,32 @@ FPB_UNROLL(8)
   st.iflag = iflag;
 }
 
-// conv_convect_b: mass displacement matrix and compensating subsidence (:972-989); returns iflag
-FPB_HD inline int conv_convect_b(ConvWork &w, const ConvState &st) {
+// conv_convect_b: mass displacement matrix and compensating subsidence (:972-989); returns iflag.  FMASS(j,i) =
+// 0 (+ M(i) when j == NK) + MENT(j,i) itself is formed by conv_fmass_row together with calcmatrix's scaling; here only
+// what the loop finds out about it: nconvtop = 1 + the largest index of an element above EPSILON (rows ICB+1..INB:
+// rowtop; row NK < ICB+1: M(i) alone; every other row is 0).
+FPB_HD inline int conv_convect_b(ConvWork &w, const ConvState &st, bool with_sub = true) {
   using namespace k;
-  const int inb = st.inb, nk = st.nk;
-  const int iflag = st.iflag;
-  // mass displacement matrix and compensating subsidence (:972-989)
-  CV(sub, 1) = 0.f;
+  const int inb = st.inb, icb = st.icb, nk = st.nk;
   int nconvtop = 1;
   for (int i = 1; i <= inb + 1; i++) {
-    const float m_i = CV(m, i);
-    for (int j0 = 1; j0 <= inb + 1; j0 += 4) { // (four elements requested together, then in order)
-      float fv[4], mv[4];
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
-        const int j = j0 + u <= inb + 1 ? j0 + u : inb + 1;
-        fv[u] = CM(fmass, j, i);
-        mv[u] = CM(ment, j, i);
-      }
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
-        const int j = j0 + u;
-        if (j <= inb + 1) {
-          float f = fv[u];
-          if (j == nk) f = f + m_i;
-          f = f + mv[u];
-          CM(fmass, j, i) = f;
-          if (f > EPSILON) {
-            nconvtop = nconvtop > i ? nconvtop : i;
-            nconvtop = nconvtop > j ? nconvtop : j;
-          }
-        }
-      }
+    float f = 0.0f;
+    f = f + CV(m, i);
+    if (f > EPSILON) {
+      nconvtop = nconvtop > i ? nconvtop : i;
+      nconvtop = nconvtop > nk ? nconvtop : nk;
     }
-    if (i > 1) CV(sub, i) = CV(fup, i - 1) - CV(fdown, i);
+  }
+  for (int i = icb + 1; i <= inb; i++) {
+    const int t = CV(rowtop, i);
+    nconvtop = nconvtop > t ? nconvtop : t;
+  }
+  if (with_sub) {
+    CV(sub, 1) = 0.f;
+    for (int i = 2; i <= inb + 1; i++) CV(sub, i) = CV(fup, i - 1) - CV(fdown, i);
   }
   w.nconvtop = nconvtop + 1;
-  return iflag;
+  return st.iflag;
 }
 
 // the whole scheme, sequentially; returns iflag
@@ -665,12 +657,46 @@ FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvS
   st.cbmf = cbmf;
 }
 
-// conv_calcmatrix_b: the rest of the scheme (when the assembly ran) and the redistribution matrix.  Returns lconv.
-FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const ConvState &st) {
+// row kq of fmassfrac (src/calcmatrix.f90:118-131 on the FMASS of :972-985): fmassfrac(kq,kk) = delt*fmass(kq,kk), plus
+// what stays in the level on the diagonal
+FPB_HD inline void conv_fmass_row(ConvWork &w, const ConvState &st, float delt, int kq) {
   const float ga = 9.81f;
+  const int inb = st.inb, nk = st.nk;
+  const float rlevmass = CV(dpr, kq) / ga;
+  float summe = 0.f, vd = 0.f;
+  for (int kk0 = 1; kk0 <= w.nconvtop; kk0 += 4) {
+    float mv[4], ev[4];
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) { // (four elements requested together, then in order)
+      const int kk = kk0 + u;
+      ev[u] = conv_ment_set(st, kq, kk) ? CM(ment, kq, kk) : 0.0f;
+      mv[u] = (kq == nk && kk <= inb + 1) ? CV(m, kk) : 0.0f;
+    }
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) {
+      const int kk = kk0 + u;
+      if (kk <= w.nconvtop) {
+        float f = 0.0f;
+        if (kq == nk && kk <= inb + 1) f = f + mv[u];
+        f = f + ev[u];
+        const float v = delt * f;
+        CM(fmass, kq, kk) = v;
+        summe = summe + v;
+        if (kk == kq) vd = v;
+      }
+    }
+  }
+  CM(fmass, kq, kq) = vd + rlevmass - summe;
+}
+
+// conv_calcmatrix_b: the rest of the scheme (when the assembly ran) and the redistribution matrix.  Returns lconv.
+// rows: also write the matrix (the device has its rows written by conv_mix_kernel); with_sub: also the subsidence
+// (needs FUP / FDOWN of the flux assembly)
+FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const ConvState &st, bool rows = true,
+                                     bool with_sub = true) {
   const float cbmfold = st.cbmfold;
   cbmf = st.cbmf;
-  const int iflag = st.go ? conv_convect_b(w, st) : st.iflag;
+  const int iflag = st.go ? conv_convect_b(w, st, with_sub) : st.iflag;
   if (iflag != 1 && iflag != 4) {
     cbmf = cbmfold;
     return false;
@@ -679,26 +705,8 @@ FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const
     cbmf = cbmfold;
     return false;
   }
-  // fmassfrac(k,kk) = delt*fmass(k,kk) (+ what stays in the level on the diagonal), in place
-  for (int kq = 1; kq <= w.nconvtop; kq++) {
-    const float rlevmass = CV(dpr, kq) / ga;
-    float summe = 0.f;
-    for (int kk0 = 1; kk0 <= w.nconvtop; kk0 += 4) {
-      float fv[4];
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) fv[u] = CM(fmass, kq, (kk0 + u <= w.nconvtop ? kk0 + u : w.nconvtop));
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
-        const int kk = kk0 + u;
-        if (kk <= w.nconvtop) {
-          const float v = delt * fv[u];
-          CM(fmass, kq, kk) = v;
-          summe = summe + v;
-        }
-      }
-    }
-    CM(fmass, kq, kq) = CM(fmass, kq, kq) + rlevmass - summe;
-  }
+  if (rows)
+    for (int kq = 1; kq <= w.nconvtop; kq++) conv_fmass_row(w, st, delt, kq);
   return true;
 }
 
