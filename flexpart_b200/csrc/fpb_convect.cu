@@ -21,7 +21,7 @@
 //   conv_column_tail_kernel  one thread per column again: subsidence, cbaseflux out, heights of the
 //                        eta half levels
 //   conv_redist_kernel   one thread per particle of the batch's columns: redist
-// Columns are processed in batches (the work pool holds up to 65536 columns, 115-200 KB each at 138
+// Columns are processed in batches (the work pool holds up to 65536 columns, 80-140 KB each at 138
 // levels).  Compiled with --fmad=false; the column arithmetic is bit-comparable with the
 // reference's routines in every math mode (see fpb_convect.cuh).
 #include "fpb_convect.cuh"
@@ -184,13 +184,19 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   static_cast<ConvState *>(a.col_state)[c] = st;
 }
 
-// the loops over level pairs of the scheme (mixing fractions, normalisation: conv_mix_row, conv_norm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
+// the loops over level pairs of the scheme (mixing fractions, normalisation: conv_mixnorm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
 // still reads "element e of 32 columns" as one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every
 // column.  The rows are independent, so the bits are the sequential loop's; what changes is that a column's chain is
 // 1 / MIX_ROWS as long and MIX_ROWS times as many warps are there to hide the loads.  After a block barrier the same
 // threads write the contiguous copy of MENT, matrix column by matrix column, and the redistribution matrix row by row.
-constexpr int MIX_ROWS = 8;
-__global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const ConvmixArgs a, int c0, int c1) {
+#ifndef FPB_MIX_ROWS
+#define FPB_MIX_ROWS 8
+#endif
+#ifndef FPB_MIX_MINB
+#define FPB_MIX_MINB 2
+#endif
+constexpr int MIX_ROWS = FPB_MIX_ROWS;
+__global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(const ConvmixArgs a, int c0, int c1) {
   const int c = c0 + blockIdx.x * 32 + threadIdx.x;
   const int y = threadIdx.y;
   ConvState st;
@@ -200,8 +206,7 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const Convmi
   conv_column_work(a, c < c1 ? c - c0 : 0, w);
   if (st.go) {
     for (int i = st.icb + 1 + y; i <= st.inb; i += MIX_ROWS) {
-      conv_mix_row(w, st, i);
-      conv_norm_row(w, st, i);
+      conv_mixnorm_row(w, st, i);
     }
   }
   __syncthreads();
@@ -221,7 +226,10 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, 2) conv_mix_kernel(const Convmi
 // fpb_convmix, profiles/convmix_column_r02.txt)
 constexpr int ASM_THREADS = 128;
 #define WV(a, i) w.a[(size_t)(i) * w.stride]
-__global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const ConvmixArgs a, int c0, int c1) {
+// LT: leading dimension of the shared-memory copy, a compile-time constant (odd: the walk along a row of the matrix is
+// free of bank conflicts) so that the eight loads of an unrolled step are one address register plus immediates;
+// 0: the column's own ld (any number of levels)
+template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const ConvmixArgs a, int c0, int c1) {
   extern __shared__ float smem[];
   const int c = c0 + blockIdx.x;
   ConvState *stp = static_cast<ConvState *>(a.col_state) + c;
@@ -231,13 +239,14 @@ __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const Convmi
   ConvWork w;
   conv_column_work(a, c - c0, w);
   const int ld = w.ld;
-  float *T = smem;                       // MENT, (i,j) at [i + ld*j], rows / columns icb .. inb+1
-  float *mv = smem + (size_t)ld * ld;    // m(1 .. inb+1)
+  const int lt = LT ? LT : ld;
+  float *T = smem;                       // MENT, (i,j) at [i + lt*j], rows / columns icb .. inb+1
+  float *mv = smem + (size_t)lt * lt;    // m(1 .. inb+1)
   float *ph = mv + ld;                   // phconv_hpa(1 .. inb+2)
-  for (int e = threadIdx.x; e < ld * ld; e += ASM_THREADS) {
-    const int i = e % ld, j = e / ld;
-    T[e] = (i >= icb + 1 && i <= inb && j >= icb && j <= inb) ? w.mentc[e] : 0.0f;
-  }
+  // what the sums read: rows and columns icb .. inb+1 (MENT can differ from 0 in rows icb+1 .. inb, columns icb .. inb)
+  for (int j = icb + (threadIdx.x >> 5); j <= inb + 1; j += ASM_THREADS / 32)
+    for (int i = icb + (threadIdx.x & 31); i <= inb + 1; i += 32)
+      T[i + lt * j] = (i >= icb + 1 && i <= inb && j <= inb) ? w.mentc[i + ld * j] : 0.0f;
   for (int i = threadIdx.x; i < ld; i += ASM_THREADS) {
     mv[i] = (i >= 1 && i <= inb + 1) ? WV(m, i) : 0.0f;
     ph[i] = (i >= 1 && i <= inb + 2 && i < ld) ? WV(phconv_hpa, i) : 0.0f;
@@ -258,16 +267,27 @@ __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const Convmi
     float amp1 = 0.0f, ad = 0.0f;
     if (i >= nk)
       for (int kq = i + 1; kq <= inb + 1; kq++) amp1 = amp1 + mv[kq];
-    for (int kq = icb + 1; kq <= i; kq++) {
-#pragma unroll 8
-      for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + T[kq + ld * j];
+    // The two sums walk blocks of the same shape -- amp1: rows icb+1 .. i, columns i+1 .. inb+1 of MENT, row by row;
+    // ad: columns icb .. i-1, rows max(i, icb+1) .. inb, column by column -- so for i > icb they run side by side, two
+    // independent chains of additions per thread, each in the reference's order (i <= icb: both blocks are empty)
+    if (i >= icb + 1) {
+      const int n = inb + 1 - i;
+      for (int o = 0; o < i - icb; o++) {
+        const float *p = T + (icb + 1 + o) + lt * (i + 1);
+        const float *q = T + i + lt * (icb + o);
+        int r = n;
+        for (; r >= 8; r -= 8, p += 8 * lt, q += 8) {
+          float v[8], x[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) { v[u] = p[u * lt]; x[u] = q[u]; }
+#pragma unroll
+          for (int u = 0; u < 8; u++) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
+        }
+        for (; r > 0; r--, p += lt, q++) { amp1 = amp1 + *p; ad = ad + *q; }
+      }
     }
     WV(fup, i) = amp1;
     if ((2.f * G * dpinv * amp1) >= delti) flag4 = 1;
-    for (int kq = icb; kq <= i - 1; kq++) {
-#pragma unroll 8
-      for (int j = (i > icb + 1 ? i : icb + 1); j <= inb; j++) ad = ad + T[j + ld * kq];
-    }
     WV(fdown, i) = ad;
   }
   if (flag4) stp->iflag = 4; // (every writer writes the same value)
@@ -363,15 +383,22 @@ void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *t
 void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) {
   if (c1 <= c0) return;
   const int ld = a.nconvlev + 3;
-  const size_t smem = ((size_t)ld * ld + 2 * (size_t)ld) * sizeof(float);
-  static bool attr_set = false; // (64 KB of dynamic shared memory: above the default limit)
+  const int lt = ld <= 65 ? 65 : ld <= 97 ? 97 : ld <= 129 ? 129 : ld;
+  const size_t smem = ((size_t)lt * lt + 2 * (size_t)ld) * sizeof(float);
+  static bool attr_set = false; // (up to 67 KB of dynamic shared memory and more: above the default limit)
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_assembly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_assembly_kernel<65>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_assembly_kernel<97>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_assembly_kernel<129>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_assembly_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
   conv_mix_kernel<<<(c1 - c0 + 31) / 32, dim3(32, MIX_ROWS), 0, st>>>(a, c0, c1);
-  conv_assembly_kernel<<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
+  if (lt == 65) conv_assembly_kernel<65><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
+  else if (lt == 97) conv_assembly_kernel<97><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
+  else if (lt == 129) conv_assembly_kernel<129><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
+  else conv_assembly_kernel<0><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
   conv_column_tail_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
 }
 size_t fpb_convmix_state_bytes() { return sizeof(fpbconv::ConvState); }

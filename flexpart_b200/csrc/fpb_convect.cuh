@@ -68,8 +68,9 @@ struct ConvWork {
   float *fup, *fdown, *m, *mp, *tvp, *tv, *water, *qp, *ep, *th, *wt, *evap, *clw, *sigp, *tp, *cpn, *lv, *lvcp,
       *h, *hp, *gz, *hm, *uvzlev;
   int *nent;
-  int *rowtop; // per row i of MENT: max(i, largest j with ment(i,j) > EPSILON), 0: none (conv_norm_row)
-  float *ment, *sij; // (ELIJ is only read by the precipitating downdraft, which is left out: not kept)
+  int *rowtop; // per row i of MENT: max(i, largest j with ment(i,j) > EPSILON), 0: none (conv_mixnorm_row)
+  float *ment; // (ELIJ is only read by the precipitating downdraft, which is left out, SIJ only inside conv_mixnorm_row:
+               //  not kept)
   float *mentc; // device: the column's final MENT once more, contiguous (element (i,j) at [i + ld*j]), for the
                 // warp-per-column flux assembly (conv_assembly_kernel); null: not wanted
 };
@@ -86,7 +87,7 @@ constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more
 // floats of one column's slice
 FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
   const size_t lv = (size_t)nuvz + 4, ld = (size_t)nconvlev + 3;
-  return (CONV_NVEC + 1) * lv + 3 * ld * ld;
+  return (CONV_NVEC + 1) * lv + 2 * ld * ld;
 }
 
 // carve the column's slice: `pool` = first float of the slice (for stride 32: of the warp's block of
@@ -105,8 +106,7 @@ FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, 
   w.rowtop = reinterpret_cast<int *>(p); p += lv;
   const size_t ld2 = (size_t)w.ld * w.ld * stride;
   w.fmass = p; p += ld2;
-  w.ment = p; p += ld2;
-  w.sij = p;
+  w.ment = p;
 }
 
 #define CV(a, i) w.a[(size_t)(i) * w.stride]
@@ -367,139 +367,125 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
 // SIJ / MENT / ELIJ and NENT(i) depend on the column's vectors and on row i alone, so the rows can be worked in any
 // order -- or by different threads (conv_mix_kernel) -- with the reference's bits.
 // Nothing is zeroed up front (the reference zeroes the four (NL+1)^2 matrices, :529-545): row i of MENT is written in
-// full over the columns ICB..INB it can be set in (the value or 0), the two elements of SIJ the normalisation reads
-// beside that range are set to 0 with the row, every other element of MENT is known to be 0 by its indices
-// (conv_ment_set) and FMASS is written in full over [1, nconvtop]^2 by conv_fmass_row.
+// full over the columns ICB..INB it can be set in (the value or 0), every other element of MENT is known to be 0 by its
+// indices (conv_ment_set) and FMASS is written in full over [1, nconvtop]^2 by conv_fmass_row.
 FPB_HD inline bool conv_ment_set(const ConvState &st, int i, int j) { // may MENT(i,j) differ from 0?
   return i >= st.icb + 1 && i <= st.inb && j >= st.icb && j <= st.inb;
 }
 
-// entrained air mass flux, mixing fractions of row i (:636-682); sij(i,j) is carried in a register while its
-// statements run instead of being re-read after every store (the stores stay where the reference has them:
-// sij(i,i) = 1 inside the j loop is read back when j == i)
-FPB_HD inline void conv_mix_row(ConvWork &w, const ConvState &st, int i) {
+// Row i of the entrained air mass flux: mixing fractions (:636-682) and normalisation (:686-746) in ONE walk along the
+// row.  The normalisation of element j reads sij(i,j-1), sij(i,j), sij(i,j+1) and ment(i,j) of the mixing loop and
+// nothing else of the matrices, and SIJ is read by nothing after it, so the mixing loop runs one element ahead and
+// hands its values over in registers: SIJ is not stored at all, MENT(i,j) once.  (The reference normalises a row only
+// when nent(i) != 0: with nent(i) == 0 no element of the row has 0 < sij < 0.9 and the walk changes nothing.)
+// rowtop(i) notes how far the final row reaches above EPSILON (what conv_convect_b's search for nconvtop asks).
+#ifndef FPB_MIX_BATCH
+#define FPB_MIX_BATCH 8
+#endif
+constexpr int CONV_MIX_BATCH = FPB_MIX_BATCH;
+FPB_HD inline void conv_mixnorm_row(ConvWork &w, const ConvState &st, int i) {
   using namespace k;
   const int icb = st.icb, inb = st.inb, nk = st.nk;
   const float qti = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
   const float hp_i = CV(hp, i), h_i = CV(h, i), q_i = CV(qconv, i), m_i = CV(m, i);
   int nent_i = CV(nent, i);
-  if (icb > 1) CM(sij, i, icb - 1) = 0.0f;
-  CM(sij, i, inb + 1) = 0.0f;
-  // eight levels at a time: their vector elements are requested together (the loop is bound by the latency of
-  // these loads: one warp walks 32 columns whose vectors do not fit the L1), then worked through in order
-  for (int j0 = icb; j0 <= inb; j0 += 8) {
-    float bf2_[8], t_[8], qs_[8], hj_[8], qj_[8], cw_[8], lv_[8];
-FPB_UNROLL(8)
-    for (int u = 0; u < 8; u++) {
+  // scrit of the normalisation (:690-700; qp1 is the mixing loop's qti)
+  float scrit;
+  {
+    const float lv_i = CV(lv, i), qs_i = CV(qsconv, i);
+    const float anum = h_i - hp_i - lv_i * (qti - qs_i);
+    float denom = h_i - hp_i + lv_i * (q_i - qti);
+    if (fabsf(denom) < 0.01f) denom = 0.01f;
+    scrit = anum / denom;
+    const float alt = qti - qs_i + scrit * (q_i - qti);
+    if (alt < 0.0f) scrit = 1.0f;
+    scrit = c_max(scrit, 0.0f);
+  }
+  float asij = 0.0f, smin = 1.0f;
+  float s_m1 = 0.0f, s_0 = 0.0f, m_0 = 0.0f; // sij(i,j-2), sij(i,j-1), ment(i,j-1) while element j is mixed
+  float php = 0.0f;                          // phconv_hpa(j-1)
+  // CONV_MIX_BATCH levels at a time: their vector elements are requested together (the loop is bound by the latency of
+  // these loads), then worked through in order; element inb+1 only closes the window (sij(i,inb+1) = 0)
+  for (int j0 = icb; j0 <= inb + 1; j0 += CONV_MIX_BATCH) {
+    float bf2_[CONV_MIX_BATCH], t_[CONV_MIX_BATCH], qs_[CONV_MIX_BATCH], hj_[CONV_MIX_BATCH], qj_[CONV_MIX_BATCH],
+        cw_[CONV_MIX_BATCH], lv_[CONV_MIX_BATCH], ph_[CONV_MIX_BATCH];
+FPB_UNROLL(CONV_MIX_BATCH)
+    for (int u = 0; u < CONV_MIX_BATCH; u++) {
       const int j = j0 + u <= inb ? j0 + u : inb;
       bf2_[u] = CV(ft, j); t_[u] = CV(tconv, j); qs_[u] = CV(qsconv, j); hj_[u] = CV(h, j); qj_[u] = CV(qconv, j);
       cw_[u] = CV(fq, j); lv_[u] = CV(lv, j);
+      ph_[u] = CV(phconv_hpa, (j0 + u <= inb + 1 ? j0 + u : inb + 1));
     }
-FPB_UNROLL(8)
-    for (int u = 0; u < 8; u++) {
+FPB_UNROLL(CONV_MIX_BATCH)
+    for (int u = 0; u < CONV_MIX_BATCH; u++) {
       const int j = j0 + u;
-      if (j <= inb) {
-        const float bf2 = bf2_[u];
-        const float t_j = t_[u], qs_j = qs_[u];
-        float anum = hj_[u] - hp_i + (CPV - CPD) * t_j * (qti - qj_[u]);
-        float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
-        float dei = denom;
-        if (fabsf(dei) < 0.01f) dei = 0.01f;
-        float s = anum / dei;
-        CM(sij, i, i) = 1.0f;
-        if (j == i) s = 1.0f;
-        float altem = s * q_i + (1.f - s) * qti - qs_j;
-        altem = altem / bf2;
-        const float cwat = cw_[u];
-        const float stemp = s;
-        if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
-          const float lv_j = lv_[u];
-          anum = anum - lv_j * (qti - qs_j - cwat * bf2);
-          denom = denom + lv_j * (q_i - qti);
-          if (fabsf(denom) < 0.01f) denom = 0.01f;
-          s = anum / denom;
-          altem = s * q_i + (1.f - s) * qti - qs_j;
-          altem = altem - (bf2 - 1.f) * cwat;
-        }
-        if (s > 0.0f && s < 0.9f) { // (elij(i,j) = max(0, altem) is not kept)
-          CM(ment, i, j) = m_i / (1.f - s);
-          nent_i = nent_i + 1;
-        } else {
-          CM(ment, i, j) = 0.0f;
-        }
-        s = c_max(0.0f, s);
-        s = c_min(1.0f, s);
-        CM(sij, i, j) = s;
-      }
-    }
-  }
-  CV(nent, i) = nent_i;
-  if (nent_i == 0) {
-    CM(ment, i, i) = m_i;
-    CM(sij, i, i) = 1.0f;
-  }
-  if (i == inb) CM(sij, inb, inb) = 1.0f; // (:683, after the loop over i in the reference: row inb is complete here)
-}
-
-// normalise the entrained fluxes of row i (:686-746)
-// and note in rowtop(i) how far the final row reaches above EPSILON (what conv_convect_b's search for nconvtop asks)
-FPB_HD inline void conv_norm_row(ConvWork &w, const ConvState &st, int i) {
-  using namespace k;
-  const int icb = st.icb, inb = st.inb, nk = st.nk;
-  int top = 0;           // largest j != i with ment(i,j) > EPSILON
-  float vii = CV(m, i);  // ment(i,i) (nent(i) == 0: the row is 0 but for ment(i,i) = m(i))
-  if (CV(nent, i) != 0) {
-    const float qp1 = CV(qconv, nk) - CV(ep, i) * CV(clw, i);
-    const float anum = CV(h, i) - CV(hp, i) - CV(lv, i) * (qp1 - CV(qsconv, i));
-    float denom = CV(h, i) - CV(hp, i) + CV(lv, i) * (CV(qconv, i) - qp1);
-    if (fabsf(denom) < 0.01f) denom = 0.01f;
-    float scrit = anum / denom;
-    const float alt = qp1 - CV(qsconv, i) + scrit * (CV(qconv, i) - qp1);
-    if (alt < 0.0f) scrit = 1.0f;
-    scrit = c_max(scrit, 0.0f);
-    float asij = 0.0f, smin = 1.0f;
-    // (four levels at a time, their row elements requested together: row i of sij is not written here)
-    for (int j0 = icb; j0 <= inb; j0 += 4) {
-      float sv[6], mv[4], ph[5];
-FPB_UNROLL(6)
-      for (int u = 0; u < 6; u++) {
-        const int jj = j0 - 1 + u;
-        sv[u] = (jj >= 1 && jj <= inb + 1) ? CM(sij, i, jj) : 0.0f;
-      }
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
-FPB_UNROLL(5)
-      for (int u = 0; u < 5; u++) ph[u] = CV(phconv_hpa, (j0 + u <= inb + 1 ? j0 + u : inb + 1));
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
-        const int j = j0 + u;
-        const float s_m1 = sv[u], s_0 = sv[u + 1], s_p1 = sv[u + 2];
-        if (j <= inb && s_0 > 0.0f && s_0 < 0.9f) {
-          float smid, sjmax, sjmin;
-          if (j > i) {
-            smid = c_min(s_0, scrit);
-            sjmax = smid;
-            sjmin = smid;
-            if (smid < smin && s_p1 < smid) {
-              smin = smid;
-              sjmax = c_min(c_min(s_p1, s_0), scrit);
-              sjmin = c_max(s_m1, s_0);
-              sjmin = c_min(sjmin, scrit);
-            }
-          } else {
-            sjmax = c_max(s_p1, scrit);
-            smid = c_max(s_0, scrit);
-            sjmin = 0.0f;
-            if (j > 1) sjmin = s_m1;
-            sjmin = c_max(sjmin, scrit);
+      if (j <= inb + 1) {
+        float s = 0.0f, mraw = 0.0f;
+        if (j <= inb) { // mixing fraction of (i,j)
+          const float bf2 = bf2_[u];
+          const float t_j = t_[u], qs_j = qs_[u];
+          float anum = hj_[u] - hp_i + (CPV - CPD) * t_j * (qti - qj_[u]);
+          float denom = h_i - hp_i + (CPD - CPV) * (q_i - qti) * t_j;
+          float dei = denom;
+          if (fabsf(dei) < 0.01f) dei = 0.01f;
+          s = anum / dei;
+          if (j == i) s = 1.0f; // (sij(i,i) = 1)
+          float altem = s * q_i + (1.f - s) * qti - qs_j;
+          altem = altem / bf2;
+          const float cwat = cw_[u];
+          const float stemp = s;
+          if ((stemp < 0.0f || stemp > 1.0f || altem > cwat) && j > i) {
+            const float lv_j = lv_[u];
+            anum = anum - lv_j * (qti - qs_j - cwat * bf2);
+            denom = denom + lv_j * (q_i - qti);
+            if (fabsf(denom) < 0.01f) denom = 0.01f;
+            s = anum / denom;
           }
-          const float delp = fabsf(sjmax - smid);
-          const float delm = fabsf(sjmin - smid);
-          asij = asij + (delp + delm) * (ph[u] - ph[u + 1]);
-          CM(ment, i, j) = mv[u] * (delp + delm) * (ph[u] - ph[u + 1]);
+          if (s > 0.0f && s < 0.9f) { // (elij(i,j) = max(0, altem) is not kept)
+            mraw = m_i / (1.f - s);
+            nent_i = nent_i + 1;
+          }
+          s = c_max(0.0f, s);
+          s = c_min(1.0f, s);
         }
+        const int jn = j - 1; // normalisation step of (i,jn): window s_m1, s_0, s
+        if (jn >= icb) {
+          float out = m_0;
+          if (s_0 > 0.0f && s_0 < 0.9f) {
+            float smid, sjmax, sjmin;
+            if (jn > i) {
+              smid = c_min(s_0, scrit);
+              sjmax = smid;
+              sjmin = smid;
+              if (smid < smin && s < smid) {
+                smin = smid;
+                sjmax = c_min(c_min(s, s_0), scrit);
+                sjmin = c_max(s_m1, s_0);
+                sjmin = c_min(sjmin, scrit);
+              }
+            } else {
+              sjmax = c_max(s, scrit);
+              smid = c_max(s_0, scrit);
+              sjmin = 0.0f;
+              if (jn > 1) sjmin = s_m1;
+              sjmin = c_max(sjmin, scrit);
+            }
+            const float delp = fabsf(sjmax - smid);
+            const float delm = fabsf(sjmin - smid);
+            asij = asij + (delp + delm) * (php - ph_[u]);
+            out = m_0 * (delp + delm) * (php - ph_[u]);
+          }
+          CM(ment, i, jn) = out;
+        }
+        s_m1 = s_0; s_0 = s; m_0 = mraw; php = ph_[u];
       }
     }
+  }
+  int top = 0;      // largest j != i with ment(i,j) > EPSILON
+  float vii = m_i;  // ment(i,i)
+  if (nent_i == 0) {
+    CM(ment, i, i) = m_i; // (the rest of the row is 0)
+  } else {
     asij = c_max(1.0e-21f, asij);
     asij = 1.0f / asij;
     float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
@@ -520,12 +506,12 @@ FPB_UNROLL(4)
       }
     }
     if (bsum < 1.0e-18f) {
-      CV(nent, i) = 0;
-      CM(ment, i, i) = CV(m, i);
-      CM(sij, i, i) = 1.0f;
-      vii = CV(m, i);
+      nent_i = 0;
+      CM(ment, i, i) = m_i;
+      vii = m_i;
     }
   }
+  CV(nent, i) = nent_i;
   if (vii > EPSILON && i > top) top = i;
   CV(rowtop, i) = top > 0 ? (top > i ? top : i) : 0;
 }
@@ -551,8 +537,7 @@ FPB_UNROLL(8)
 // on the subsidence, in the flux assembly) is kept.
 FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   if (!conv_convect_head(w, nl, delt, cbmf, st)) return false;
-  for (int i = st.icb + 1; i <= st.inb; i++) conv_mix_row(w, st, i);
-  for (int i = st.icb + 1; i <= st.inb; i++) conv_norm_row(w, st, i);
+  for (int i = st.icb + 1; i <= st.inb; i++) conv_mixnorm_row(w, st, i);
   if (w.mentc) conv_mentc_copy(w, st, st.icb, 1);
   st.go = 1;
   return true;
