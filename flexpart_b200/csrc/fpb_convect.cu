@@ -13,11 +13,12 @@
 //                        32): the lanes run the same loops, so a warp-wide access to "element e of my
 //                        column" is one 128-byte line instead of 32 scattered sectors.
 //   conv_mix_kernel      ONE BLOCK PER 32 COLUMNS x 8 ROW RESIDUES: the loops over level pairs (mixing
-//                        fractions, normalisation, redistribution matrix), independent row by row;
+//                        fractions, normalisation), independent row by row;
 //                        latency-bound, so the inner loops request 4-8 elements together before working
 //                        through them in the reference's order
 //   conv_assembly_kernel ONE BLOCK PER COLUMN: the O(n^3) sums of the flux assembly on the column's
-//                        MENT in shared memory, thread t = level t + 2, each sum in the reference's order
+//                        MENT in shared memory, thread t = level t + 2, each sum in the reference's order;
+//                        then the redistribution matrix from the same copy, thread t = row t + 1
 //   conv_column_tail_kernel  one thread per column again: subsidence, cbaseflux out, heights of the
 //                        eta half levels
 //   conv_redist_kernel   one thread per particle of the batch's columns: redist
@@ -138,10 +139,13 @@ __global__ void __launch_bounds__(CB) conv_heads_assign_kernel(const ConvmixArgs
 
 // the column's slice of the work pool: block of 32 slices (q / 32), lane q % 32, elements interleaved
 __device__ __forceinline__ void conv_column_work(const ConvmixArgs &a, int q, ConvWork &w) {
-  const size_t nfl = conv_pool_floats(a.nuvz, a.nconvlev);
-  conv_carve(w, a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32), a.nuvz, a.nconvlev, 32);
+  const size_t nfl = conv_pool_floats(a.nuvz, a.nconvlev, false);
+  conv_carve(w, a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32), a.nuvz, a.nconvlev, 32, false);
   w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
-  w.mentc = a.pool2 + (size_t)q * w.ld * w.ld;
+  // per column and contiguous ((i,j) at [i + ld*j]): the final MENT once more for the flux assembly, and FMASS
+  w.mentc = a.pool2 + (size_t)q * 2 * w.ld * w.ld;
+  w.fmass = w.mentc + (size_t)w.ld * w.ld;
+  w.fstride = 1;
 }
 __device__ __forceinline__ void conv_column_place(const ConvmixArgs &a, int c, int &g, size_t &o2, size_t &plane) {
   const unsigned key = a.col_key[c];
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
 // still reads "element e of 32 columns" as one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every
 // column.  The rows are independent, so the bits are the sequential loop's; what changes is that a column's chain is
 // 1 / MIX_ROWS as long and MIX_ROWS times as many warps are there to hide the loads.  After a block barrier the same
-// threads write the contiguous copy of MENT, matrix column by matrix column, and the redistribution matrix row by row.
+// threads write the contiguous copy of MENT.
 #ifndef FPB_MIX_ROWS
 #define FPB_MIX_ROWS 8
 #endif
@@ -203,20 +207,39 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
   st.go = 0;
   if (c < c1) st = static_cast<const ConvState *>(a.col_state)[c];
   ConvWork w;
-  conv_column_work(a, c < c1 ? c - c0 : 0, w);
+  conv_column_work(a, c - c0, w); // (the pool is whole groups of 32 slices: valid for the idle lanes of the last group too)
   if (st.go) {
     for (int i = st.icb + 1 + y; i <= st.inb; i += MIX_ROWS) {
       conv_mixnorm_row(w, st, i);
     }
   }
   __syncthreads();
-  if (st.go) {
-    conv_mentc_copy(w, st, st.icb + y, MIX_ROWS);
-    // the redistribution matrix (conv_fmass_row), rows 1 + y, + MIX_ROWS, ...: every thread works out nconvtop for itself
-    const float delt = (float)abs(a.cfg.lsynctime);
-    float cbmf;
-    if (conv_calcmatrix_b(w, delt, cbmf, st, false, false))
-      for (int kq = 1 + y; kq <= w.nconvtop; kq += MIX_ROWS) conv_fmass_row(w, st, delt, kq);
+  // the final MENT of the group's columns once more, contiguous per column, for the flux assembly: a transposing copy
+  // through shared memory, tiles of 32 consecutive elements (rows i at one j) x 32 columns, so that both the reads
+  // (element e of 32 columns = one line) and the writes (32 elements of one column = one line) are whole lines.  Every
+  // column is copied over the union of the group's index ranges; what lies outside a column's own range is never read.
+  __shared__ float tile[MIX_ROWS][32][33];
+  const unsigned gomask = __ballot_sync(0xffffffffu, st.go != 0);
+  if (gomask == 0u) return; // (block-uniform: every warp sees the same 32 columns)
+  const int imin = __reduce_min_sync(0xffffffffu, st.go ? st.icb + 1 : 0x7fffffff);
+  const int imax = __reduce_max_sync(0xffffffffu, st.go ? st.inb : 0);
+  const int jmin = imin - 1, jmax = imax;
+  const int nchunk = (imax - imin + 32) / 32;
+  const int ld = w.ld;
+  const float *gment = w.ment - threadIdx.x; // element e of column l of the group at [e * 32 + l]
+  float *gout = a.pool2 + (size_t)(blockIdx.x * 32) * 2 * ld * ld;
+  for (int t = y; t < (jmax - jmin + 1) * nchunk; t += MIX_ROWS) {
+    const int j = jmin + t / nchunk, i0 = imin + 32 * (t % nchunk);
+    const size_t e0 = (size_t)i0 + (size_t)ld * j;
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) tile[y][r][threadIdx.x] = (i0 + r <= imax) ? gment[(e0 + r) * 32 + threadIdx.x] : 0.0f;
+    __syncwarp();
+    if (i0 + (int)threadIdx.x <= imax) {
+#pragma unroll 8
+      for (int l = 0; l < 32; l++)
+        if ((gomask >> l) & 1u) gout[(size_t)l * 2 * ld * ld + e0 + threadIdx.x] = tile[y][threadIdx.x][l];
+    }
+    __syncwarp();
   }
 }
 
@@ -231,9 +254,11 @@ constexpr int ASM_THREADS = 128;
 // 0: the column's own ld (any number of levels)
 template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const ConvmixArgs a, int c0, int c1) {
   extern __shared__ float smem[];
+  __shared__ int s_top;
   const int c = c0 + blockIdx.x;
   ConvState *stp = static_cast<ConvState *>(a.col_state) + c;
   if (!stp->go) return; // block-uniform
+  if (threadIdx.x == 0) s_top = 1;
   const int inb = stp->inb, icb = stp->icb, nk = stp->nk;
   const float delti = stp->delti;
   ConvWork w;
@@ -291,6 +316,27 @@ template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_k
     WV(fdown, i) = ad;
   }
   if (flag4) stp->iflag = 4; // (every writer writes the same value)
+  // the redistribution matrix (conv_fmass_row: calcmatrix's scaling of FMASS = MENT (+ M in row NK)), thread t = rows
+  // 1 + t, ..., from the shared-memory MENT into the column's contiguous FMASS: nconvtop and lconv do not depend on
+  // what the sums above found (IFLAG 1 or 4)
+  ConvState st = *stp;
+  if (!((st.iflag == 1 || st.iflag == 4) && !(st.cbmf <= 0.f && st.cbmfold <= 0.f))) return; // lconv (conv_calcmatrix_b)
+  int top = 0; // conv_convect_b's nconvtop, level by level
+  for (int i = 1 + threadIdx.x; i <= inb + 1; i += ASM_THREADS) {
+    float f = 0.0f;
+    f = f + mv[i];
+    if (f > EPSILON) top = i > nk ? i : nk;
+    if (i >= icb + 1 && i <= inb) {
+      const int t = WV(rowtop, i);
+      top = top > t ? top : t;
+    }
+  }
+  atomicMax(&s_top, top);
+  __syncthreads();
+  w.nconvtop = s_top + 1;
+  const float delt = (float)abs(a.cfg.lsynctime);
+  for (int kq = 1 + threadIdx.x; kq <= w.nconvtop; kq += ASM_THREADS)
+    conv_fmass_row(w, st, delt, kq, [&](int i, int j) { return T[i + lt * j]; });
 }
 #undef WV
 
@@ -329,8 +375,7 @@ __global__ void __launch_bounds__(128) conv_redist_kernel(const ConvmixArgs a, i
   const int nconvtop = a.col_lconv[c];
   if (nconvtop == 0) return; // the column does not convect
   ConvWork w;
-  const int q = c - c0;
-  conv_carve(w, a.pool + (size_t)(q / 32) * 32 * conv_pool_floats(a.nuvz, a.nconvlev) + (q % 32), a.nuvz, a.nconvlev, 32);
+  conv_column_work(a, c - c0, w);
   w.nconvtop = nconvtop;
   const int row = (int)a.sorted_ids[i];
   const int slot = a.p.slot[row];
@@ -405,4 +450,4 @@ size_t fpb_convmix_state_bytes() { return sizeof(fpbconv::ConvState); }
 void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st) {
   if (i1 > i0) conv_redist_kernel<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(a, c0, i0, i1, mode);
 }
-size_t fpb_convmix_pool_floats(int nuvz, int nconvlev) { return fpbconv::conv_pool_floats(nuvz, nconvlev); }
+size_t fpb_convmix_pool_floats(int nuvz, int nconvlev) { return fpbconv::conv_pool_floats(nuvz, nconvlev, false); }

@@ -58,6 +58,7 @@ FPB_HD inline float c_powi(float x, int m) { // real**integer as libgcc's __powi
 // their own column -- the normal case, the lanes run the same loops -- share cache lines.
 struct ConvWork {
   int nuvz, nconvlev, ld, stride;
+  int fstride; // stride of FMASS alone (device: the matrix lives per column, contiguous, outside the interleaved slice)
   const float *akz, *bkz, *akm, *bkm; // 1-based hybrid coefficients (src/com_mod.f90, akz(nuvz) ...)
   // conv_mod
   float *pconv, *phconv, *dpr, *pconv_hpa, *phconv_hpa, *tconv, *qconv, *qsconv, *ft, *fq, *sub;
@@ -72,7 +73,7 @@ struct ConvWork {
   float *ment; // (ELIJ is only read by the precipitating downdraft, which is left out, SIJ only inside conv_mixnorm_row:
                //  not kept)
   float *mentc; // device: the column's final MENT once more, contiguous (element (i,j) at [i + ld*j]), for the
-                // warp-per-column flux assembly (conv_assembly_kernel); null: not wanted
+                // block-per-column flux assembly (conv_assembly_kernel; written by conv_mix_kernel)
 };
 
 // what the two halves of conv_convect / conv_calcmatrix hand over around the flux assembly
@@ -85,14 +86,15 @@ struct ConvState {
 constexpr int CONV_NVEC = 35; // float vectors above (+ nent, stored as one more vector)
 
 // floats of one column's slice
-FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev) {
+FPB_HD inline size_t conv_pool_floats(int nuvz, int nconvlev, bool with_fmass = true) {
   const size_t lv = (size_t)nuvz + 4, ld = (size_t)nconvlev + 3;
-  return (CONV_NVEC + 1) * lv + 2 * ld * ld;
+  return (CONV_NVEC + 1) * lv + (with_fmass ? 2 : 1) * ld * ld;
 }
 
 // carve the column's slice: `pool` = first float of the slice (for stride 32: of the warp's block of
 // 32 slices, plus the lane)
-FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, int stride = 1) {
+// with_fmass = false: w.fmass / w.fstride are the caller's business
+FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, int stride = 1, bool with_fmass = true) {
   const size_t lv = ((size_t)nuvz + 4) * stride;
   w.nuvz = nuvz; w.nconvlev = nconvlev; w.ld = nconvlev + 3; w.stride = stride;
   w.mentc = nullptr;
@@ -105,12 +107,14 @@ FPB_HD inline void conv_carve(ConvWork &w, float *pool, int nuvz, int nconvlev, 
   w.nent = reinterpret_cast<int *>(p); p += lv;
   w.rowtop = reinterpret_cast<int *>(p); p += lv;
   const size_t ld2 = (size_t)w.ld * w.ld * stride;
-  w.fmass = p; p += ld2;
-  w.ment = p;
+  w.ment = p; p += ld2;
+  w.fmass = with_fmass ? p : nullptr;
+  w.fstride = stride;
 }
 
 #define CV(a, i) w.a[(size_t)(i) * w.stride]
 #define CM(a, i, j) w.a[(size_t)((i) + w.ld * (j)) * w.stride]
+#define CF(i, j) w.fmass[(size_t)((i) + w.ld * (j)) * w.fstride]
 
 // src/ew.f90: saturation vapour pressure over water [Pa] (Goff-Gratch)
 FPB_HD inline float conv_ew(float x) {
@@ -516,21 +520,6 @@ FPB_UNROLL(4)
   CV(rowtop, i) = top > 0 ? (top > i ? top : i) : 0;
 }
 
-// (device) the final MENT of the rows that were set, once more and contiguous, for the block-per-column flux assembly:
-// columns j0, j0+step, ... of the matrix
-FPB_HD inline void conv_mentc_copy(ConvWork &w, const ConvState &st, int j0, int step) {
-  const int icb = st.icb, inb = st.inb;
-  for (int j = j0; j <= inb; j += step)
-    for (int i0 = icb + 1; i0 <= inb; i0 += 8) { // (eight loads in flight)
-      float v[8];
-FPB_UNROLL(8)
-      for (int u = 0; u < 8; u++) v[u] = CM(ment, (i0 + u <= inb ? i0 + u : inb), j);
-FPB_UNROLL(8)
-      for (int u = 0; u < 8; u++)
-        if (i0 + u <= inb) w.mentc[i0 + u + w.ld * j] = v[u];
-    }
-}
-
 // conv_convect_a: everything up to the flux assembly, one column sequentially (host build, sequential path).
 // The precipitating downdraft (:750-842) is left out like the tendencies FT, FQ (:867-872,914-934) it feeds: WATER,
 // EVAP, MP, QP and PRECIP are read by nothing FLEXPART uses (FMASS, SUB, IFLAG, CBMF); IFLAG = 4 (the CFL condition
@@ -538,7 +527,6 @@ FPB_UNROLL(8)
 FPB_HD inline bool conv_convect_a(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   if (!conv_convect_head(w, nl, delt, cbmf, st)) return false;
   for (int i = st.icb + 1; i <= st.inb; i++) conv_mixnorm_row(w, st, i);
-  if (w.mentc) conv_mentc_copy(w, st, st.icb, 1);
   st.go = 1;
   return true;
 }
@@ -644,7 +632,9 @@ FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvS
 
 // row kq of fmassfrac (src/calcmatrix.f90:118-131 on the FMASS of :972-985): fmassfrac(kq,kk) = delt*fmass(kq,kk), plus
 // what stays in the level on the diagonal
-FPB_HD inline void conv_fmass_row(ConvWork &w, const ConvState &st, float delt, int kq) {
+// ment_at(i, j): MENT(i,j) where conv_ment_set(st, i, j) (the device reads the shared-memory copy of the flux assembly)
+template <class MentAt>
+FPB_HD inline void conv_fmass_row(ConvWork &w, const ConvState &st, float delt, int kq, MentAt ment_at) {
   const float ga = 9.81f;
   const int inb = st.inb, nk = st.nk;
   const float rlevmass = CV(dpr, kq) / ga;
@@ -654,7 +644,7 @@ FPB_HD inline void conv_fmass_row(ConvWork &w, const ConvState &st, float delt, 
 FPB_UNROLL(4)
     for (int u = 0; u < 4; u++) { // (four elements requested together, then in order)
       const int kk = kk0 + u;
-      ev[u] = conv_ment_set(st, kq, kk) ? CM(ment, kq, kk) : 0.0f;
+      ev[u] = conv_ment_set(st, kq, kk) ? ment_at(kq, kk) : 0.0f;
       mv[u] = (kq == nk && kk <= inb + 1) ? CV(m, kk) : 0.0f;
     }
 FPB_UNROLL(4)
@@ -665,13 +655,13 @@ FPB_UNROLL(4)
         if (kq == nk && kk <= inb + 1) f = f + mv[u];
         f = f + ev[u];
         const float v = delt * f;
-        CM(fmass, kq, kk) = v;
+        CF(kq, kk) = v;
         summe = summe + v;
         if (kk == kq) vd = v;
       }
     }
   }
-  CM(fmass, kq, kq) = vd + rlevmass - summe;
+  CF(kq, kq) = vd + rlevmass - summe;
 }
 
 // conv_calcmatrix_b: the rest of the scheme (when the assembly ran) and the redistribution matrix.  Returns lconv.
@@ -691,7 +681,8 @@ FPB_HD inline bool conv_calcmatrix_b(ConvWork &w, float delt, float &cbmf, const
     return false;
   }
   if (rows)
-    for (int kq = 1; kq <= w.nconvtop; kq++) conv_fmass_row(w, st, delt, kq);
+    for (int kq = 1; kq <= w.nconvtop; kq++)
+      conv_fmass_row(w, st, delt, kq, [&](int i, int j) { return CM(ment, i, j); });
   return true;
 }
 
@@ -747,7 +738,7 @@ FPB_HD inline float conv_redist(const ConvWork &w, float ztold, int levold, floa
   float ffraction = 0.f;
   const float totlevmass = CV(dpr, levold) / ga;
   for (int kq = 1; kq <= w.nconvtop; kq++) {
-    const float f = (ldirect == 1) ? CM(fmass, levold, kq) : CM(fmass, kq, levold);
+    const float f = (ldirect == 1) ? CF(levold, kq) : CF(kq, levold);
     ffraction = ffraction + f / totlevmass;
     if (rn <= ffraction) {
       levnew = kq;
@@ -798,5 +789,6 @@ FPB_HD inline float conv_redist(const ConvWork &w, float ztold, int levold, floa
 
 #undef CV
 #undef CM
+#undef CF
 
 } // namespace fpbconv

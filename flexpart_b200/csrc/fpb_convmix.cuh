@@ -28,7 +28,7 @@ struct ConvmixArgs {
   int32_t *col_start;         // [ncols + 1] first sorted position of every column
   int32_t *col_lconv;         // [ncols] nconvtop when the column convects, else 0
   float *pool;                // work pool: CONV_BATCH columns x conv_pool_floats()
-  float *pool2;               // the columns' final MENT, contiguous per column: CONV_BATCH x (nconvlev + 3)^2
+  float *pool2;               // the columns' final MENT and FMASS, contiguous per column: CONV_BATCH x 2 (nconvlev + 3)^2
   void *col_state;            // [ncols] fpbconv::ConvState: what the halves of the column code hand over
   uint8_t *draws;             // reference RNG: [slot] the particle draws a uniform
   const float *rn_by_slot;    // reference RNG: the uniforms, by slot; null: Philox
