@@ -659,9 +659,10 @@ def next_rows(eng, cb, rel, peak, itime_now, cpu=True):
         t = best(lambda: res.update(n=eng.convmix(itime_now)), n=3)
         out["convmix"] = {"ms": t * 1e3, "occupied_columns": res["n"][0], "convecting_columns": res["n"][1],
                           "particles": c.maxpart, "nconvlev": nconvlev,
-                          "what": "fpb_convmix: column sort, calcmatrix + Emanuel scheme (one thread per occupied column, the flux "
-                                  "assembly one block per "
-                                  "column), redist; synthetic soundings (tests/conv_cases.py)"}
+                          "what": "fpb_convmix: column sort, calcmatrix + Emanuel scheme (O(n) part one thread per occupied "
+                                  "column, level-pair loops row-parallel per group of 32 columns, flux assembly + "
+                                  "redistribution matrix one block per column), redist; synthetic soundings "
+                                  "(tests/conv_cases.py)"}
     except Exception as e:  # (the convection leg must not take the bench line down)
         out["convmix"] = {"error": str(e)}
     # calcpar + verttransform_ecmwf on the device (what getfields does to every new wind field): the raw
