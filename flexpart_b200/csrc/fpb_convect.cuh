@@ -552,7 +552,7 @@ FPB_HD inline void conv_flux_assembly(ConvWork &w, ConvState &st) {
     // (rows 1..ICB of MENT are zero -- only rows ICB+1..INB are ever set -- and x + 0.0 == x)
     for (int kq = icb + 1; kq <= i; kq++) {
 FPB_UNROLL(8)
-      for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + CM(ment, kq, j);
+      for (int j = i + 1; j <= inb + 1; j++) amp1 = amp1 + (j <= inb ? CM(ment, kq, j) : 0.0f); // (column inb+1 is 0)
     }
     CV(fup, i) = amp1;
     if ((2.f * G * dpinv * amp1) >= delti) iflag = 4;

@@ -31,7 +31,43 @@ def hostlib(tmp_path_factory):
     L = C.CDLL(so)
     L.conv_check_column.argtypes = [C.c_int, C.c_int, _pf, _pf, _pf, _pf, _pf, _pf, C.c_float, C.c_float, C.c_float,
                                     C.c_float, _pf, C.c_int, C.c_int, C.c_int, _pf, _pf, _pi, _pi, _pf, _pf, _pf, _pi]
+    L.conv_check_column_rows.argtypes = [C.c_int, C.c_int, _pf, _pf, _pf, _pf, _pf, _pf, C.c_float, C.c_float, _pf, C.c_int,
+                                         _pi, _pf, _pf]
     return L
+
+
+@pytest.mark.parametrize("rows", [1, 8, 5])
+def test_rows_of_the_level_pair_loops_are_independent(hostlib, rows):
+    """What conv_mix_kernel / conv_assembly_kernel rely on: the rows of MENT (mixing fractions + normalisation) and of
+    the redistribution matrix can be worked in any order, on a pool that is not zeroed, with the bits of the
+    sequential routine (which test_column_code_is_bit_identical_to_the_reference_routines pins to the reference)."""
+    nuvz = 138
+    akm, bkm, akz, bkz, nconvlev = conv_cases.hybrid_levels(nuvz)
+    rs = np.random.RandomState(23)
+    L = nconvlev + 3
+    n_conv = 0
+    for col in range(120):
+        tconv, qconv, ps, tt2, td2 = conv_cases.sounding(rs, akz, bkz, nuvz)
+        cbmf0 = np.float32(rs.choice([0.0, 0.004, 0.02]))
+        out = []
+        for which in (0, 1):
+            cb_mf = np.array([cbmf0], np.float32)
+            ntop, ld, used = C.c_int(0), C.c_int(0), C.c_int(0)
+            fm = np.zeros(L * L, np.float32); sub = np.zeros(nuvz + 2, np.float32); uvz = np.zeros(nuvz + 2, np.float32)
+            z = np.zeros(1, np.float32); rn = np.zeros(1, np.float32)
+            if which == 0:
+                lc = hostlib.conv_check_column(nuvz, nconvlev, fp(akz), fp(bkz), fp(akm), fp(bkm), fp(tconv), fp(qconv), ps,
+                                               tt2, td2, 900.0, fp(cb_mf), 1, 900, 0, fp(z), fp(rn), C.byref(used),
+                                               C.byref(ntop), fp(fm), fp(sub), fp(uvz), C.byref(ld))
+            else:
+                lc = hostlib.conv_check_column_rows(nuvz, nconvlev, fp(akz), fp(bkz), fp(akm), fp(bkm), fp(tconv), fp(qconv),
+                                                    ps, 900.0, fp(cb_mf), rows, C.byref(ntop), fp(fm), fp(sub))
+            nt = ntop.value
+            out.append((lc, cb_mf[0].tobytes(), nt, fm.reshape(L, L)[1:nt + 1, 1:nt + 1].tobytes() if lc else b"",
+                        sub[1:nt + 1].tobytes() if lc else b""))
+        assert out[0] == out[1], col
+        n_conv += out[0][0]
+    assert n_conv >= 20, n_conv
 
 
 @pytest.mark.parametrize("ldirect", [1, -1])
