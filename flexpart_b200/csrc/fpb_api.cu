@@ -2629,7 +2629,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   if (!V.pool) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t ld2 = 2 * (size_t)(V.nconvlev + 3) * (V.nconvlev + 3); // + the contiguous MENT of the flux assembly and FMASS
+    const size_t ld2 = fpb_convmix_pool2_floats(V.nconvlev); // + the contiguous MENT of the flux assembly and FMASS
     size_t cols = (free_b / 4) / ((pf + ld2) * sizeof(float));
     cols = std::max<size_t>(256, std::min<size_t>(cols, 65536)) / 32 * 32; // whole blocks of 32 interleaved slices
     DA(V.pool, pf * cols);

@@ -137,14 +137,20 @@ __global__ void __launch_bounds__(CB) conv_heads_assign_kernel(const ConvmixArgs
   if (i + 1 == a.nrows || keys[i + 1] == 0xffffffffu) a.col_start[incl] = i + 1; // end of the last column
 }
 
+// Per column and contiguous (pool2): the final MENT once more, element (i,j) at [i + lt*j] with the leading dimension of
+// the flux assembly's shared-memory copy (conv_lt: odd, so that a walk along a row of the matrix is free of bank
+// conflicts) -- the assembly fetches it as it lies with one bulk copy -- and FMASS, (i,j) at [i + ld*j].
+__host__ __device__ inline int conv_lt(int ld) { return ld <= 65 ? 65 : ld <= 97 ? 97 : ld <= 129 ? 129 : ld; }
+__host__ __device__ inline size_t conv_mentc_floats(int ld) { return ((size_t)conv_lt(ld) * conv_lt(ld) + 3) / 4 * 4; }
+__host__ __device__ inline size_t conv_slab_floats(int ld) { return conv_mentc_floats(ld) + ((size_t)ld * ld + 3) / 4 * 4; }
+
 // the column's slice of the work pool: block of 32 slices (q / 32), lane q % 32, elements interleaved
 __device__ __forceinline__ void conv_column_work(const ConvmixArgs &a, int q, ConvWork &w) {
   const size_t nfl = conv_pool_floats(a.nuvz, a.nconvlev, false);
   conv_carve(w, a.pool + (size_t)(q / 32) * 32 * nfl + (q % 32), a.nuvz, a.nconvlev, 32, false);
   w.akz = a.akz; w.bkz = a.bkz; w.akm = a.akm; w.bkm = a.bkm;
-  // per column and contiguous ((i,j) at [i + ld*j]): the final MENT once more for the flux assembly, and FMASS
-  w.mentc = a.pool2 + (size_t)q * 2 * w.ld * w.ld;
-  w.fmass = w.mentc + (size_t)w.ld * w.ld;
+  w.mentc = a.pool2 + (size_t)q * conv_slab_floats(w.ld);
+  w.fmass = w.mentc + conv_mentc_floats(w.ld);
   w.fstride = 1;
 }
 __device__ __forceinline__ void conv_column_place(const ConvmixArgs &a, int c, int &g, size_t &o2, size_t &plane) {
@@ -227,7 +233,9 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
   const int nchunk = (imax - imin + 32) / 32;
   const int ld = w.ld;
   const float *gment = w.ment - threadIdx.x; // element e of column l of the group at [e * 32 + l]
-  float *gout = a.pool2 + (size_t)(blockIdx.x * 32) * 2 * ld * ld;
+  const int lt = conv_lt(ld);
+  const size_t slab = conv_slab_floats(ld);
+  float *gout = a.pool2 + (size_t)(blockIdx.x * 32) * slab;
   for (int t = y; t < (jmax - jmin + 1) * nchunk; t += MIX_ROWS) {
     const int j = jmin + t / nchunk, i0 = imin + 32 * (t % nchunk);
     const size_t e0 = (size_t)i0 + (size_t)ld * j;
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
     if (i0 + (int)threadIdx.x <= imax) {
 #pragma unroll 8
       for (int l = 0; l < 32; l++)
-        if ((gomask >> l) & 1u) gout[(size_t)l * 2 * ld * ld + e0 + threadIdx.x] = tile[y][threadIdx.x][l];
+        if ((gomask >> l) & 1u) gout[(size_t)l * slab + (size_t)i0 + (size_t)lt * j + threadIdx.x] = tile[y][threadIdx.x][l];
     }
     __syncwarp();
   }
@@ -253,29 +261,53 @@ constexpr int ASM_THREADS = 128;
 // free of bank conflicts) so that the eight loads of an unrolled step are one address register plus immediates;
 // 0: the column's own ld (any number of levels)
 template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_kernel(const ConvmixArgs a, int c0, int c1) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   __shared__ int s_top;
+  __shared__ __align__(8) unsigned long long bar; // mbarrier of the bulk copy
   const int c = c0 + blockIdx.x;
   ConvState *stp = static_cast<ConvState *>(a.col_state) + c;
   if (!stp->go) return; // block-uniform
-  if (threadIdx.x == 0) s_top = 1;
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    s_top = 1;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   const int inb = stp->inb, icb = stp->icb, nk = stp->nk;
   const float delti = stp->delti;
   ConvWork w;
   conv_column_work(a, c - c0, w);
   const int ld = w.ld;
   const int lt = LT ? LT : ld;
-  float *T = smem;                       // MENT, (i,j) at [i + lt*j], rows / columns icb .. inb+1
-  float *mv = smem + (size_t)lt * lt;    // m(1 .. inb+1)
+  float *T = smem;                       // MENT, (i,j) at [i + lt*j]: the image of the column's mentc
+  float *mv = smem + conv_mentc_floats(ld); // m(1 .. inb+1)
   float *ph = mv + ld;                   // phconv_hpa(1 .. inb+2)
-  // what the sums read: rows and columns icb .. inb+1 (MENT can differ from 0 in rows icb+1 .. inb, columns icb .. inb)
-  for (int j = icb + (threadIdx.x >> 5); j <= inb + 1; j += ASM_THREADS / 32)
-    for (int i = icb + (threadIdx.x & 31); i <= inb + 1; i += 32)
-      T[i + lt * j] = (i >= icb + 1 && i <= inb && j <= inb) ? w.mentc[i + ld * j] : 0.0f;
-  for (int i = threadIdx.x; i < ld; i += ASM_THREADS) {
+  // Columns icb .. inb of the matrix as they lie in mentc, with ONE bulk copy (cp.async.bulk, global -> shared memory,
+  // completion on the mbarrier; the range widened to 16-byte boundaries).  The sums read rows icb+1 .. inb of columns
+  // icb .. inb+1: the rows were written for these columns by conv_mix_kernel, column inb+1 (all 0) is set here.
+  const int f0 = (lt * icb) & ~3, f1 = (lt * (inb + 1) + 3) & ~3;
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(f1 - f0) * 4u;
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(T + f0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                 "l"(w.mentc + f0), "r"(bytes), "r"(bar_s)
+                 : "memory");
+  }
+  for (int i = threadIdx.x; i < ld; i += ASM_THREADS) { // (while the copy is in flight)
     mv[i] = (i >= 1 && i <= inb + 1) ? WV(m, i) : 0.0f;
     ph[i] = (i >= 1 && i <= inb + 2 && i < ld) ? WV(phconv_hpa, i) : 0.0f;
   }
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(bar_s), "r"(0u)
+                   : "memory");
+  }
+  for (int i = icb + 1 + threadIdx.x; i <= inb; i += ASM_THREADS) T[i + lt * (inb + 1)] = 0.0f;
   __syncthreads();
   using namespace k;
   int flag4 = 0;
@@ -428,8 +460,8 @@ void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *t
 void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) {
   if (c1 <= c0) return;
   const int ld = a.nconvlev + 3;
-  const int lt = ld <= 65 ? 65 : ld <= 97 ? 97 : ld <= 129 ? 129 : ld;
-  const size_t smem = ((size_t)lt * lt + 2 * (size_t)ld) * sizeof(float);
+  const int lt = conv_lt(ld);
+  const size_t smem = (conv_mentc_floats(ld) + 2 * (size_t)ld) * sizeof(float);
   static bool attr_set = false; // (up to 67 KB of dynamic shared memory and more: above the default limit)
   if (!attr_set) {
     cudaFuncSetAttribute(conv_assembly_kernel<65>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -446,6 +478,7 @@ void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) 
   else conv_assembly_kernel<0><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
   conv_column_tail_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
 }
+size_t fpb_convmix_pool2_floats(int nconvlev) { return conv_slab_floats(nconvlev + 3); }
 size_t fpb_convmix_state_bytes() { return sizeof(fpbconv::ConvState); }
 void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st) {
   if (i1 > i0) conv_redist_kernel<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(a, c0, i0, i1, mode);

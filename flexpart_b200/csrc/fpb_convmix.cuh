@@ -28,7 +28,7 @@ struct ConvmixArgs {
   int32_t *col_start;         // [ncols + 1] first sorted position of every column
   int32_t *col_lconv;         // [ncols] nconvtop when the column convects, else 0
   float *pool;                // work pool: CONV_BATCH columns x conv_pool_floats()
-  float *pool2;               // the columns' final MENT and FMASS, contiguous per column: CONV_BATCH x 2 (nconvlev + 3)^2
+  float *pool2;               // the columns' final MENT and FMASS, contiguous per column: CONV_BATCH x fpb_convmix_pool2_floats()
   void *col_state;            // [ncols] fpbconv::ConvState: what the halves of the column code hand over
   uint8_t *draws;             // reference RNG: [slot] the particle draws a uniform
   const float *rn_by_slot;    // reference RNG: the uniforms, by slot; null: Philox
@@ -40,4 +40,5 @@ void fpb_convmix_heads(const ConvmixArgs &a, const unsigned *sorted_keys, int *t
 void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st);
 void fpb_convmix_redist(const ConvmixArgs &a, int c0, int i0, int i1, int mode, cudaStream_t st);
 size_t fpb_convmix_pool_floats(int nuvz, int nconvlev);
+size_t fpb_convmix_pool2_floats(int nconvlev); // per column: contiguous MENT (assembly layout) + FMASS
 size_t fpb_convmix_state_bytes();
