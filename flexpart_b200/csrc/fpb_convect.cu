@@ -194,19 +194,28 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   static_cast<ConvState *>(a.col_state)[c] = st;
 }
 
-// the loops over level pairs of the scheme (mixing fractions, normalisation: conv_mixnorm_row) with ONE BLOCK PER GROUP OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp
-// still reads "element e of 32 columns" as one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every
-// column.  The rows are independent, so the bits are the sequential loop's; what changes is that a column's chain is
-// 1 / MIX_ROWS as long and MIX_ROWS times as many warps are there to hide the loads.  After a block barrier the same
-// threads write the contiguous copy of MENT.
+// the loops over level pairs of the scheme (mixing fractions, normalisation: conv_mixnorm_row) with ONE BLOCK PER GROUP
+// OF 32 COLUMNS: lane = column of the group (the interleaved layout: a warp still reads "element e of 32 columns" as
+// one line), threadIdx.y = the rows i = icb + 1 + y, + MIX_ROWS, ... of every column.  The rows are independent, so the
+// bits are the sequential loop's; what changes is that a column's chain is 1 / MIX_ROWS as long and MIX_ROWS times as
+// many warps are there to hide the loads.  The eight vectors the walk along a row reads level by level (ft, tconv,
+// qsconv, h, qconv, fq, lv, phconv_hpa) are staged in shared memory first: in the interleaved layout a vector of the
+// group is one contiguous stretch, so each is ONE bulk asynchronous copy (cp.async.bulk, completion on an mbarrier),
+// and the row code reads them through the same pointers, re-based.  After a block barrier the same threads write the
+// contiguous copy of MENT (the staging area becomes the tiles of the transposing copy).
 #ifndef FPB_MIX_ROWS
-#define FPB_MIX_ROWS 8
+#define FPB_MIX_ROWS 16
 #endif
 #ifndef FPB_MIX_MINB
-#define FPB_MIX_MINB 2
+#define FPB_MIX_MINB 1
 #endif
 constexpr int MIX_ROWS = FPB_MIX_ROWS;
-__global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(const ConvmixArgs a, int c0, int c1) {
+constexpr int MIX_NSTAGE = 8; // vectors staged
+constexpr size_t MIX_TILE_BYTES = (size_t)MIX_ROWS * 32 * 33 * sizeof(float);
+// levels_max: levels the launch reserved staging room for (0: no staging)
+__global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(const ConvmixArgs a, int c0, int c1, int levels_max) {
+  extern __shared__ __align__(128) float mixsm[];
+  __shared__ __align__(8) unsigned long long bar;
   const int c = c0 + blockIdx.x * 32 + threadIdx.x;
   const int y = threadIdx.y;
   ConvState st;
@@ -214,6 +223,36 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
   if (c < c1) st = static_cast<const ConvState *>(a.col_state)[c];
   ConvWork w;
   conv_column_work(a, c - c0, w); // (the pool is whole groups of 32 slices: valid for the idle lanes of the last group too)
+  const unsigned gomask = __ballot_sync(0xffffffffu, st.go != 0);
+  if (gomask == 0u) return; // (block-uniform: every warp sees the same 32 columns)
+  const int imax = __reduce_max_sync(0xffffffffu, st.go ? st.inb : 0);
+  const int hi = imax + 1; // levels 1 .. hi are read (phconv_hpa up to inb + 1)
+  if (hi <= levels_max) {
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+    float **vec[MIX_NSTAGE] = {&w.ft, &w.tconv, &w.qsconv, &w.h, &w.qconv, &w.fq, &w.lv, &w.phconv_hpa};
+    if (threadIdx.x == 0 && y == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const unsigned bytes = (unsigned)hi * 32u * 4u; // per vector: element 1 .. hi of the 32 columns
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * MIX_NSTAGE) : "memory");
+#pragma unroll
+      for (int v = 0; v < MIX_NSTAGE; v++) {
+        const unsigned dst_s = (unsigned)__cvta_generic_to_shared(mixsm + (size_t)v * hi * 32);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                     "l"(*vec[v] + 32), "r"(bytes), "r"(bar_s)
+                     : "memory");
+      }
+    }
+    __syncthreads(); // (the barrier is initialised for everyone)
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(bar_s), "r"(0u)
+                   : "memory");
+#pragma unroll
+    for (int v = 0; v < MIX_NSTAGE; v++) *vec[v] = mixsm + (size_t)v * hi * 32 + threadIdx.x - 32; // element e at [e * 32]
+  }
   if (st.go) {
     for (int i = st.icb + 1 + y; i <= st.inb; i += MIX_ROWS) {
       conv_mixnorm_row(w, st, i);
@@ -224,11 +263,8 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
   // through shared memory, tiles of 32 consecutive elements (rows i at one j) x 32 columns, so that both the reads
   // (element e of 32 columns = one line) and the writes (32 elements of one column = one line) are whole lines.  Every
   // column is copied over the union of the group's index ranges; what lies outside a column's own range is never read.
-  __shared__ float tile[MIX_ROWS][32][33];
-  const unsigned gomask = __ballot_sync(0xffffffffu, st.go != 0);
-  if (gomask == 0u) return; // (block-uniform: every warp sees the same 32 columns)
+  float(*tile)[32][33] = reinterpret_cast<float(*)[32][33]>(mixsm);
   const int imin = __reduce_min_sync(0xffffffffu, st.go ? st.icb + 1 : 0x7fffffff);
-  const int imax = __reduce_max_sync(0xffffffffu, st.go ? st.inb : 0);
   const int jmin = imin - 1, jmax = imax;
   const int nchunk = (imax - imin + 32) / 32;
   const int ld = w.ld;
@@ -468,10 +504,16 @@ void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) 
     cudaFuncSetAttribute(conv_assembly_kernel<97>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_assembly_kernel<129>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_assembly_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
-  conv_mix_kernel<<<(c1 - c0 + 31) / 32, dim3(32, MIX_ROWS), 0, st>>>(a, c0, c1);
+  // staging room of the level-pair kernel: eight vectors x levels 1 .. nconvlev + 1 x 32 columns, if that fits
+  size_t mix_smem = (size_t)MIX_NSTAGE * (a.nconvlev + 1) * 32 * sizeof(float);
+  int levels_max = a.nconvlev + 1;
+  if (mix_smem > 200 * 1024) { mix_smem = 0; levels_max = 0; }
+  if (mix_smem < MIX_TILE_BYTES) mix_smem = MIX_TILE_BYTES;
+  conv_mix_kernel<<<(c1 - c0 + 31) / 32, dim3(32, MIX_ROWS), mix_smem, st>>>(a, c0, c1, levels_max);
   if (lt == 65) conv_assembly_kernel<65><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
   else if (lt == 97) conv_assembly_kernel<97><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
   else if (lt == 129) conv_assembly_kernel<129><<<c1 - c0, ASM_THREADS, smem, st>>>(a, c0, c1);
