@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
 // and the row code reads them through the same pointers, re-based.  After a block barrier the same threads write the
 // contiguous copy of MENT (the staging area becomes the tiles of the transposing copy).
 #ifndef FPB_MIX_ROWS
-#define FPB_MIX_ROWS 16
+#define FPB_MIX_ROWS 32 // (A/B with the vectors staged: 16 rows x batch 8: 10.1 ms, 24 x 4: 9.4, 32 x 4: 9.5, 32 x 2: 9.2; gpurun_out/ab_conv_rows.txt)
 #endif
 #ifndef FPB_MIX_MINB
 #define FPB_MIX_MINB 1

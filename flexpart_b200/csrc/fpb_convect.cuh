@@ -384,7 +384,7 @@ FPB_HD inline bool conv_ment_set(const ConvState &st, int i, int j) { // may MEN
 // when nent(i) != 0: with nent(i) == 0 no element of the row has 0 < sij < 0.9 and the walk changes nothing.)
 // rowtop(i) notes how far the final row reaches above EPSILON (what conv_convect_b's search for nconvtop asks).
 #ifndef FPB_MIX_BATCH
-#define FPB_MIX_BATCH 8
+#define FPB_MIX_BATCH 2 // (the device stages these vectors in shared memory: two loads in flight and 64 registers beat eight and 128)
 #endif
 constexpr int CONV_MIX_BATCH = FPB_MIX_BATCH;
 FPB_HD inline void conv_mixnorm_row(ConvWork &w, const ConvState &st, int i) {
