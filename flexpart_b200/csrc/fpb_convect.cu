@@ -209,6 +209,10 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
 #ifndef FPB_MIX_MINB
 #define FPB_MIX_MINB 1
 #endif
+#ifndef FPB_TILE_UNROLL
+#define FPB_TILE_UNROLL 16
+#endif
+constexpr int TILE_UNROLL = FPB_TILE_UNROLL;
 constexpr int MIX_ROWS = FPB_MIX_ROWS;
 constexpr int MIX_NSTAGE = 8; // vectors staged
 constexpr size_t MIX_TILE_BYTES = (size_t)MIX_ROWS * 32 * 33 * sizeof(float);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
   for (int t = y; t < (jmax - jmin + 1) * nchunk; t += MIX_ROWS) {
     const int j = jmin + t / nchunk, i0 = imin + 32 * (t % nchunk);
     const size_t e0 = (size_t)i0 + (size_t)ld * j;
-#pragma unroll 8
+#pragma unroll TILE_UNROLL
     for (int r = 0; r < 32; r++) tile[y][r][threadIdx.x] = (i0 + r <= imax) ? gment[(e0 + r) * 32 + threadIdx.x] : 0.0f;
     __syncwarp();
     if (i0 + (int)threadIdx.x <= imax) {

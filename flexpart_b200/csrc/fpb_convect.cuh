@@ -387,6 +387,10 @@ FPB_HD inline bool conv_ment_set(const ConvState &st, int i, int j) { // may MEN
 #define FPB_MIX_BATCH 2 // (the device stages these vectors in shared memory: two loads in flight and 64 registers beat eight and 128)
 #endif
 constexpr int CONV_MIX_BATCH = FPB_MIX_BATCH;
+#ifndef FPB_SCALE_BATCH
+#define FPB_SCALE_BATCH 8
+#endif
+constexpr int CONV_SCALE_BATCH = FPB_SCALE_BATCH;
 FPB_HD inline void conv_mixnorm_row(ConvWork &w, const ConvState &st, int i) {
   using namespace k;
   const int icb = st.icb, inb = st.inb, nk = st.nk;
@@ -493,12 +497,12 @@ FPB_UNROLL(CONV_MIX_BATCH)
     asij = c_max(1.0e-21f, asij);
     asij = 1.0f / asij;
     float bsum = 0.0f; // (the reference's two loops -- scale the row, then add it up in the same order -- in one)
-    for (int j0 = icb; j0 <= inb; j0 += 4) {
-      float mv[4];
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
-FPB_UNROLL(4)
-      for (int u = 0; u < 4; u++) {
+    for (int j0 = icb; j0 <= inb; j0 += CONV_SCALE_BATCH) { // (the row's elements requested CONV_SCALE_BATCH at a time)
+      float mv[CONV_SCALE_BATCH];
+FPB_UNROLL(CONV_SCALE_BATCH)
+      for (int u = 0; u < CONV_SCALE_BATCH; u++) mv[u] = CM(ment, i, (j0 + u <= inb ? j0 + u : inb));
+FPB_UNROLL(CONV_SCALE_BATCH)
+      for (int u = 0; u < CONV_SCALE_BATCH; u++) {
         const int j = j0 + u;
         if (j <= inb) {
           const float v = mv[u] * asij;
