@@ -2741,7 +2741,7 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
       const int c1 = std::min(ncols, c0 + V.pool_cols);
       fpb_convmix_columns(a, c0, c1, h->stream);
       fpb_convmix_redist(a, c0, col_start[c0], col_start[c1], pass, h->stream);
-      h->launches += 5; // column head, level-pair rows, flux assembly, tail, redist
+      h->launches += 6; // levels, column head, level-pair rows, flux assembly, tail, redist
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));

@@ -7,8 +7,10 @@
 //   [stable LSD radix sort of (key, row), fpb_scatter.cu]
 //   conv_heads_* kernels run heads -> column index of every sorted position, first position and
 //                        key of every column (block scan)
-//   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: sounding (:163-176), calcmatrix + the O(n) part of
-//                        convect (fpb_convect.cuh: conv_convect_head), on the column's slice of a work pool.
+//   conv_pre_kernel      ONE BLOCK PER 32 COLUMNS x 8 LEVEL RESIDUES: sounding (:163-176), calcmatrix's pressures and
+//                        saturation humidity, level by level, on the column's slice of a work pool
+//   conv_column_kernel   ONE THREAD PER OCCUPIED COLUMN: the O(n) part of convect (fpb_convect.cuh:
+//                        conv_convect_head).
 //                        The 32 columns of a warp interleave their slices element by element (stride
 //                        32): the lanes run the same loops, so a warp-wide access to "element e of my
 //                        column" is one 128-byte line instead of 32 scattered sectors.
@@ -162,17 +164,21 @@ __device__ __forceinline__ void conv_column_place(const ConvmixArgs &a, int c, i
   plane = (size_t)a.gnxd[g] * a.gnyd[g];
 }
 
-// first half: sounding, calcmatrix and the Emanuel scheme up to the flux assembly, one thread per column
-__global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
-  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c1) return;
+// what every level of a column gets on its own -- the sounding interpolated in time (src/convmix.f90:163-176), pressures,
+// saturation humidity (conv_calcmatrix_level) -- and the zeroing of the column's vectors, level-parallel: one block per
+// group of 32 columns x PRE_ROWS level residues
+constexpr int PRE_ROWS = 8;
+__global__ void __launch_bounds__(32 * PRE_ROWS) conv_pre_kernel(const ConvmixArgs a, int c0, int c1) {
+  const int c = c0 + blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
   const DevCfg &cf = a.cfg;
   const int nuvz = a.nuvz;
-  const int q = c - c0;
   ConvWork w;
-  conv_column_work(a, q, w);
+  conv_column_work(a, c - c0, w);
   const size_t nvec = (size_t)(CONV_NVEC + 1) * (nuvz + 4);
-  for (size_t k = 0; k < nvec; k++) w.pconv[k * 32] = 0.f; // (the reference's zero-initialised locals; pconv = first vector)
+  for (size_t k = y; k < nvec; k += PRE_ROWS) w.pconv[k * 32] = 0.f; // (the reference's zero-initialised locals; pconv = first vector)
+  __syncthreads();
+  if (c >= c1) return;
   int g;
   size_t o2, plane;
   conv_column_place(a, c, g, o2, plane);
@@ -181,16 +187,31 @@ __global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, in
   const float dtt = 1.f / (dt1 + dt2);
   const float4 s1 = a.CS[g][0][o2], s2 = a.CS[g][1][o2];
   w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
-  w.tt2conv = (s1.y * dt2 + s2.y * dt1) * dtt;
-  w.td2conv = (s1.z * dt2 + s2.z * dt1) * dtt;
-  for (int kz = 1; kz <= nuvz - 1; kz++) {
+  for (int kz = 1 + y; kz <= nuvz - 1; kz += PRE_ROWS) {
     const float2 q1 = a.CT[g][0][(size_t)kz * plane + o2], q2 = a.CT[g][1][(size_t)kz * plane + o2]; // level kz+1
     w.tconv[(size_t)kz * w.stride] = (q1.x * dt2 + q2.x * dt1) * dtt;
     w.qconv[(size_t)kz * w.stride] = (q1.y * dt2 + q2.y * dt1) * dtt;
+    conv_calcmatrix_level(w, kz);
   }
+}
+
+// first half: the O(n) part of the Emanuel scheme up to the loops over level pairs, one thread per column
+__global__ void __launch_bounds__(32) conv_column_kernel(const ConvmixArgs a, int c0, int c1) {
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  const DevCfg &cf = a.cfg;
+  ConvWork w;
+  conv_column_work(a, c - c0, w);
+  int g;
+  size_t o2, plane;
+  conv_column_place(a, c, g, o2, plane);
+  const float dt1 = (float)(cf.itime - cf.memtime[0]), dt2 = (float)(cf.memtime[1] - cf.itime);
+  const float dtt = 1.f / (dt1 + dt2);
+  const float4 s1 = a.CS[g][0][o2], s2 = a.CS[g][1][o2];
+  w.psconv = (s1.x * dt2 + s2.x * dt1) * dtt;
   float cbmf = a.cbaseflux[g][o2];
   ConvState st;
-  conv_calcmatrix_a(w, (float)abs(cf.lsynctime), cbmf, st, true);
+  conv_calcmatrix_a(w, (float)abs(cf.lsynctime), cbmf, st, true, true);
   static_cast<ConvState *>(a.col_state)[c] = st;
 }
 
@@ -511,6 +532,7 @@ void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) 
     cudaFuncSetAttribute(conv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  conv_pre_kernel<<<(c1 - c0 + 31) / 32, dim3(32, PRE_ROWS), 0, st>>>(a, c0, c1);
   conv_column_kernel<<<(c1 - c0 + 31) / 32, 32, 0, st>>>(a, c0, c1);
   // staging room of the level-pair kernel: eight vectors x levels 1 .. nconvlev + 1 x 32 columns, if that fits
   size_t mix_smem = (size_t)MIX_NSTAGE * (a.nconvlev + 1) * 32 * sizeof(float);

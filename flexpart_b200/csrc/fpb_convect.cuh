@@ -203,22 +203,18 @@ FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
 FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbmf, ConvState &st) {
   using namespace k;
   const int MINORIG = 1;
-  const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, SIGS = 0.12f,
-              OMTSNOW = 5.5f, DTMAX = 0.9f, ALPHA = 0.025f, DAMP = 0.1f;
+  const float ELCRIT = .0011f, TLCRIT = -55.0f, ENTP = 1.5f, DTMAX = 0.9f, ALPHA = 0.025f, DAMP = 0.1f;
   int iflag;
   const float delti = 1.0f / delt;
 
   for (int i = 1; i <= nl + 1; i++) {
     CV(ft, i) = 0.0f; CV(fq, i) = 0.0f; CV(fdown, i) = 0.0f; CV(sub, i) = 0.0f; CV(fup, i) = 0.0f;
-    CV(m, i) = 0.0f; CV(mp, i) = 0.0f;
+    CV(m, i) = 0.0f;
   }
   // (FMASS, MENT, ELIJ, SIJ: the reference zeroes them over (NL+1)^2 here and at :529-545; they are
   //  only ever read inside [1, INB+2]^2, so they are zeroed there, below, once INB is known)
-  for (int i = 1; i <= nl + 1; i++) {
-    const float q = CV(qconv, i);
-    const float rdcp = (RD * (1.f - q) + q * RV) / (CPD * (1.f - q) + q * CPV);
-    CV(th, i) = CV(tconv, i) * c_pow(1000.0f / CV(pconv_hpa, i), rdcp);
-  }
+  // (TH, :299-307, is only read by the dry adiabatic adjustment the reference has commented out; like MP, WATER, EVAP,
+  //  WT, QP, SIGP and LVCP -- read by the precipitating downdraft and the tendencies alone -- it is not formed)
   iflag = 0;
 
   // geopotential, heat capacity, static energies (:413-437)
@@ -280,7 +276,6 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   // precipitation efficiencies (:503-520)
   for (int i = 1; i <= nk; i++) {
     CV(ep, i) = 0.0f;
-    CV(sigp, i) = SIGS;
   }
   for (int i = nk + 1; i <= nl; i++) {
     const float tca = CV(tp, i) - 273.15f;
@@ -292,7 +287,6 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
     CV(ep, i) = epmax * (1.0f - elacrit / c_max(CV(clw, i), 1.0e-8f));
     CV(ep, i) = c_max(CV(ep, i), 0.0f);
     CV(ep, i) = c_min(CV(ep, i), epmax);
-    CV(sigp, i) = SIGS;
   }
   for (int i = icb + 1; i <= nl; i++) CV(tvp, i) = CV(tvp, i) - CV(tp, i) * CV(qconv, nk);
   CV(tvp, nl + 1) = CV(tvp, nl) - (CV(gz, nl + 1) - CV(gz, nl)) / CPD;
@@ -300,13 +294,7 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   for (int i = 1; i <= nl + 1; i++) {
     CV(hp, i) = CV(h, i);
     CV(nent, i) = 0;
-    CV(water, i) = 0.0f;
-    CV(evap, i) = 0.0f;
-    CV(wt, i) = OMTSNOW;
-    CV(lvcp, i) = CV(lv, i) / CV(cpn, i);
   }
-  CV(qp, 1) = CV(qconv, 1);
-  for (int i = 2; i <= nl + 1; i++) CV(qp, i) = CV(qconv, i - 1);
   // level of neutral buoyancy (:549-573)
   float cape = 0.0f, capem = 0.0f, byp = 0.0f;
   int inb = icb + 1, inb1 = inb;
@@ -610,22 +598,31 @@ FPB_HD inline int conv_convect(ConvWork &w, int nl, float delt, float &cbmf) {
 // cbmf = cbaseflux(ix,jy), in/out.  tconv(1..nuvz-1), qconv(1..nuvz-1) and psconv must be set.
 // conv_calcmatrix_a: pressures, saturation humidity, the scheme up to the flux assembly (st.go: it is due)
 // head_only: stop in front of the loops over level pairs (the device runs them in conv_mix_kernel)
-FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvState &st, bool head_only = false) {
-  const int nuvz = w.nuvz, nconvlev = w.nconvlev;
-  CV(phconv, 1) = w.psconv;
-  for (int kuvz = 2; kuvz <= nuvz; kuvz++) {
-    const int kq = kuvz - 1;
-    CV(pconv, kq) = (w.akz[kuvz] + w.bkz[kuvz] * w.psconv);
-    CV(phconv, kuvz) = (w.akm[kuvz] + w.bkm[kuvz] * w.psconv);
-    CV(dpr, kq) = CV(phconv, kq) - CV(phconv, kuvz);
-    CV(qsconv, kq) = conv_qvsat(CV(pconv, kq), CV(tconv, kq));
-  }
-  st.cbmfold = cbmf;
-  for (int kq = 1; kq <= nconvlev + 1; kq++) {
+// conv_calcmatrix_level: what calcmatrix (:66-89) works out for level kq = 1 .. nuvz-1, from tconv(kq) and psconv alone
+// (the half-level pressure below is formed again by its own expression instead of being read back), so the levels can
+// go to different threads (conv_pre_kernel)
+FPB_HD inline void conv_calcmatrix_level(ConvWork &w, int kq) {
+  const int kuvz = kq + 1;
+  const float ph_lo = kq == 1 ? w.psconv : (w.akm[kq] + w.bkm[kq] * w.psconv);
+  const float ph_hi = (w.akm[kuvz] + w.bkm[kuvz] * w.psconv);
+  if (kq == 1) CV(phconv, 1) = ph_lo;
+  CV(pconv, kq) = (w.akz[kuvz] + w.bkz[kuvz] * w.psconv);
+  CV(phconv, kuvz) = ph_hi;
+  CV(dpr, kq) = ph_lo - ph_hi;
+  CV(qsconv, kq) = conv_qvsat(CV(pconv, kq), CV(tconv, kq));
+  if (kq <= w.nconvlev + 1) {
     CV(pconv_hpa, kq) = CV(pconv, kq) / 100.f;
-    CV(phconv_hpa, kq) = CV(phconv, kq) / 100.f;
+    CV(phconv_hpa, kq) = ph_lo / 100.f;
   }
-  CV(phconv_hpa, nconvlev + 1) = CV(phconv, nconvlev + 1) / 100.f;
+}
+
+// levels_done: conv_calcmatrix_level has run for every level
+FPB_HD inline void conv_calcmatrix_a(ConvWork &w, float delt, float &cbmf, ConvState &st, bool head_only = false,
+                                     bool levels_done = false) {
+  const int nuvz = w.nuvz, nconvlev = w.nconvlev;
+  if (!levels_done)
+    for (int kq = 1; kq <= nuvz - 1; kq++) conv_calcmatrix_level(w, kq);
+  st.cbmfold = cbmf;
   w.nconvtop = 0;
   st.go = 0;
   st.inb = st.icb = st.nk = 0;
