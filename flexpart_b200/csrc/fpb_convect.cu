@@ -401,7 +401,17 @@ template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_k
 #pragma unroll
           for (int u = 0; u < 8; u++) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
         }
-        for (; r > 0; r--, p += lt, q++) { amp1 = amp1 + *p; ad = ad + *q; }
+        if (r > 0) { // (the last 1 .. 7 elements: requested together like a full step, added in order)
+          float v[7], x[7];
+#pragma unroll
+          for (int u = 0; u < 7; u++) {
+            v[u] = u < r ? p[u * lt] : 0.0f;
+            x[u] = u < r ? q[u] : 0.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 7; u++)
+            if (u < r) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
+        }
       }
     }
     WV(fup, i) = amp1;

@@ -32,7 +32,7 @@ if sub is None:
     base_name = re.search(r"(\w+)<", kname).group(1) if targs else re.search(r"(\w+)\(", kname).group(1)
     frag = base_name
     if targs:
-        frag += "I" + "".join("Lb%dE" % int(a.split(")")[-1]) for a in targs.group(1).split(",")) + "E"
+        frag += "I" + "".join(("Li%dE" if "(int)" in a else "Lb%dE") % int(a.split(")")[-1]) for a in targs.group(1).split(",")) + "E"
     sub = frag
 line_of, cur, inside = {}, None, False
 for l in sass:
