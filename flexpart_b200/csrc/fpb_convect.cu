@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(32 * MIX_ROWS, FPB_MIX_MINB) conv_mix_kernel(c
 // shared memory (the one-thread-per-column walk re-read the matrix from DRAM once per level: two thirds of
 // fpb_convmix, profiles/convmix_column_r02.txt)
 constexpr int ASM_THREADS = 128;
+#ifndef FPB_ASM_U
+#define FPB_ASM_U 8
+#endif
+constexpr int ASM_U = FPB_ASM_U; // elements of a row requested together
 #define WV(a, i) w.a[(size_t)(i) * w.stride]
 // LT: leading dimension of the shared-memory copy, a compile-time constant (odd: the walk along a row of the matrix is
 // free of bank conflicts) so that the eight loads of an unrolled step are one address register plus immediates;
@@ -394,22 +398,22 @@ template <int LT> __global__ void __launch_bounds__(ASM_THREADS) conv_assembly_k
         const float *p = T + (icb + 1 + o) + lt * (i + 1);
         const float *q = T + i + lt * (icb + o);
         int r = n;
-        for (; r >= 8; r -= 8, p += 8 * lt, q += 8) {
-          float v[8], x[8];
+        for (; r >= ASM_U; r -= ASM_U, p += ASM_U * lt, q += ASM_U) {
+          float v[ASM_U], x[ASM_U];
 #pragma unroll
-          for (int u = 0; u < 8; u++) { v[u] = p[u * lt]; x[u] = q[u]; }
+          for (int u = 0; u < ASM_U; u++) { v[u] = p[u * lt]; x[u] = q[u]; }
 #pragma unroll
-          for (int u = 0; u < 8; u++) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
+          for (int u = 0; u < ASM_U; u++) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
         }
-        if (r > 0) { // (the last 1 .. 7 elements: requested together like a full step, added in order)
-          float v[7], x[7];
+        if (r > 0) { // (the last 1 .. ASM_U-1 elements: requested together like a full step, added in order)
+          float v[ASM_U - 1], x[ASM_U - 1];
 #pragma unroll
-          for (int u = 0; u < 7; u++) {
+          for (int u = 0; u < ASM_U - 1; u++) {
             v[u] = u < r ? p[u * lt] : 0.0f;
             x[u] = u < r ? q[u] : 0.0f;
           }
 #pragma unroll
-          for (int u = 0; u < 7; u++)
+          for (int u = 0; u < ASM_U - 1; u++)
             if (u < r) { amp1 = amp1 + v[u]; ad = ad + x[u]; }
         }
       }
