@@ -537,7 +537,10 @@ void fpb_convmix_columns(const ConvmixArgs &a, int c0, int c1, cudaStream_t st) 
   const int ld = a.nconvlev + 3;
   const int lt = conv_lt(ld);
   const size_t smem = (conv_mentc_floats(ld) + 2 * (size_t)ld) * sizeof(float);
-  static bool attr_set = false; // (up to 67 KB of dynamic shared memory and more: above the default limit)
+  static bool attr_set_dev[64] = {}; // (67 / 135 KB of dynamic shared memory: above the default limit; per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool &attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
     cudaFuncSetAttribute(conv_assembly_kernel<65>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_assembly_kernel<97>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
