@@ -288,7 +288,21 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
     CV(ep, i) = c_max(CV(ep, i), 0.0f);
     CV(ep, i) = c_min(CV(ep, i), epmax);
   }
-  for (int i = icb + 1; i <= nl; i++) CV(tvp, i) = CV(tvp, i) - CV(tp, i) * CV(qconv, nk);
+  { // (four levels requested together: a store into one vector keeps the compiler from moving the next level's loads
+    //  ahead of it, and the column kernel is bound by the latency of its loads)
+    const float q_nk = CV(qconv, nk);
+    for (int i0 = icb + 1; i0 <= nl; i0 += 4) {
+      float a_[4], b_[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u <= nl ? i0 + u : nl;
+        a_[u] = CV(tvp, i); b_[u] = CV(tp, i);
+      }
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++)
+        if (i0 + u <= nl) CV(tvp, i0 + u) = a_[u] - b_[u] * q_nk;
+    }
+  }
   CV(tvp, nl + 1) = CV(tvp, nl) - (CV(gz, nl + 1) - CV(gz, nl)) / CPD;
   // initialise the work arrays (:529-545)
   for (int i = 1; i <= nl + 1; i++) {
@@ -298,14 +312,35 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   // level of neutral buoyancy (:549-573)
   float cape = 0.0f, capem = 0.0f, byp = 0.0f;
   int inb = icb + 1, inb1 = inb;
-  for (int i = icb + 1; i <= nl - 1; i++) {
-    const float by = (CV(tvp, i) - CV(tv, i)) * (CV(phconv_hpa, i) - CV(phconv_hpa, i + 1)) / CV(pconv_hpa, i);
-    cape = cape + by;
-    if (by >= 0.0f) inb1 = i + 1;
-    if (cape > 0.0f) {
-      inb = i + 1;
-      byp = (CV(tvp, i + 1) - CV(tv, i + 1)) * (CV(phconv_hpa, i + 1) - CV(phconv_hpa, i + 2)) / CV(pconv_hpa, i + 1);
-      capem = cape;
+  // (the buoyancy terms of five levels at a time, their elements requested together; BYP of level i is the same
+  //  expression as BY of level i+1, so it is that value)
+  for (int i0 = icb + 1; i0 <= nl - 1; i0 += 4) {
+    float by_[5];
+    {
+      float a_[5], b_[5], p_[5], h_[6];
+FPB_UNROLL(5)
+      for (int u = 0; u < 5; u++) {
+        const int i = i0 + u <= nl ? i0 + u : nl;
+        a_[u] = CV(tvp, i); b_[u] = CV(tv, i); p_[u] = CV(pconv_hpa, i);
+      }
+FPB_UNROLL(6)
+      for (int u = 0; u < 6; u++) h_[u] = CV(phconv_hpa, (i0 + u <= nl + 1 ? i0 + u : nl + 1));
+FPB_UNROLL(5)
+      for (int u = 0; u < 5; u++) by_[u] = (a_[u] - b_[u]) * (h_[u] - h_[u + 1]) / p_[u];
+    }
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u;
+      if (i <= nl - 1) {
+        const float by = by_[u];
+        cape = cape + by;
+        if (by >= 0.0f) inb1 = i + 1;
+        if (cape > 0.0f) {
+          inb = i + 1;
+          byp = by_[u + 1];
+          capem = cape;
+        }
+      }
     }
   }
   inb = inb > inb1 ? inb : inb1;
@@ -315,8 +350,20 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   float frac = -cape / defrac;
   frac = c_min(frac, 1.0f);
   frac = c_max(frac, 0.0f);
-  for (int i = icb; i <= inb; i++)
-    CV(hp, i) = CV(h, nk) + (CV(lv, i) + (CPD - CPV) * CV(tconv, i)) * CV(ep, i) * CV(clw, i);
+  {
+    const float h_nk = CV(h, nk);
+    for (int i0 = icb; i0 <= inb; i0 += 4) {
+      float l_[4], t_[4], e_[4], c_[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u <= inb ? i0 + u : inb;
+        l_[u] = CV(lv, i); t_[u] = CV(tconv, i); e_[u] = CV(ep, i); c_[u] = CV(clw, i);
+      }
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++)
+        if (i0 + u <= inb) CV(hp, i0 + u) = h_nk + (l_[u] + (CPD - CPV) * t_[u]) * e_[u] * c_[u];
+    }
+  }
   // cloud base mass flux (:583-611)
   float dbosum = 0.0f;
   const float tvpplcl = CV(tvp, icb - 1) - RD * CV(tvp, icb - 1) * (CV(pconv_hpa, icb - 1) - plcl) /
@@ -346,9 +393,19 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   for (int i = icb + 1; i <= inb; i++) CV(m, i) = CV(m, i) / dbosum;
   // what depends on j alone in the loop over level pairs below -- bf2 and cwat of the reference's inner loop -- is
   // worked out once per level (into the unused ft / fq vectors: the same expressions, so the same bits)
-  for (int j = icb; j <= inb; j++) {
-    CV(ft, j) = 1.f + CV(lv, j) * CV(lv, j) * CV(qsconv, j) / (RV * CV(tconv, j) * CV(tconv, j) * CPD);
-    CV(fq, j) = CV(clw, j) * (1.f - CV(ep, j));
+  for (int j0 = icb; j0 <= inb; j0 += 4) {
+    float l_[4], q_[4], t_[4], c_[4], e_[4];
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) {
+      const int j = j0 + u <= inb ? j0 + u : inb;
+      l_[u] = CV(lv, j); q_[u] = CV(qsconv, j); t_[u] = CV(tconv, j); c_[u] = CV(clw, j); e_[u] = CV(ep, j);
+    }
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++)
+      if (j0 + u <= inb) {
+        CV(ft, j0 + u) = 1.f + l_[u] * l_[u] * q_[u] / (RV * t_[u] * t_[u] * CPD);
+        CV(fq, j0 + u) = c_[u] * (1.f - e_[u]);
+      }
   }
   (void)frac;
   st.iflag = iflag; st.inb = inb; st.icb = icb; st.nk = nk; st.delti = delti;
