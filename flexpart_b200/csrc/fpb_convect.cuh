@@ -226,19 +226,41 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   CV(tv, 1) = CV(tconv, 1) * (1.f + CV(qconv, 1) * EPSI - CV(qconv, 1));
   float ahmin = 1.0e12f;
   int ihmin = nl;
-  for (int i = 2; i <= nl + 1; i++) {
-    const float tvx = CV(tconv, i) * (1.f + CV(qconv, i) * EPSI - CV(qconv, i));
-    const float tvy = CV(tconv, i - 1) * (1.f + CV(qconv, i - 1) * EPSI - CV(qconv, i - 1));
-    CV(gz, i) = CV(gz, i - 1) + 0.5f * RD * (tvx + tvy) * (CV(pconv_hpa, i - 1) - CV(pconv_hpa, i)) / CV(phconv_hpa, i);
-    CV(cpn, i) = CPD * (1.f - CV(qconv, i)) + CPV * CV(qconv, i);
-    CV(h, i) = CV(tconv, i) * CV(cpn, i) + CV(gz, i);
-    CV(lv, i) = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
-    CV(hm, i) = (CPD * (1.f - CV(qconv, i)) + CL * CV(qconv, i)) * (CV(tconv, i) - CV(tconv, 1)) +
-                CV(lv, i) * CV(qconv, i) + CV(gz, i);
-    CV(tv, i) = CV(tconv, i) * (1.f + CV(qconv, i) * EPSI - CV(qconv, i));
-    if (i >= MINORIG && CV(hm, i) < ahmin && CV(hm, i) < CV(hm, i - 1)) {
-      ahmin = CV(hm, i);
-      ihmin = i;
+  { // (the inputs of four levels requested together; what the recurrence carries -- gz, hm and the level below's
+    //  temperature and humidity -- stays in registers instead of being read back after its store)
+    const float t_1 = CV(tconv, 1);
+    float gz_m = 0.0f, hm_m = CV(hm, 1), t_m = t_1, q_m = CV(qconv, 1), p_m = CV(pconv_hpa, 1);
+    for (int i0 = 2; i0 <= nl + 1; i0 += 4) {
+      float t_[4], q_[4], p_[4], ph_[4];
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u <= nl + 1 ? i0 + u : nl + 1;
+        t_[u] = CV(tconv, i); q_[u] = CV(qconv, i); p_[u] = CV(pconv_hpa, i); ph_[u] = CV(phconv_hpa, i);
+      }
+FPB_UNROLL(4)
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u;
+        if (i <= nl + 1) {
+          const float t_i = t_[u], q_i = q_[u];
+          const float tvx = t_i * (1.f + q_i * EPSI - q_i);
+          const float tvy = t_m * (1.f + q_m * EPSI - q_m);
+          const float gz_i = gz_m + 0.5f * RD * (tvx + tvy) * (p_m - p_[u]) / ph_[u];
+          CV(gz, i) = gz_i;
+          const float cpn_i = CPD * (1.f - q_i) + CPV * q_i;
+          CV(cpn, i) = cpn_i;
+          CV(h, i) = t_i * cpn_i + gz_i;
+          const float lv_i = LV0 - CPVMCL * (t_i - 273.15f);
+          CV(lv, i) = lv_i;
+          const float hm_i = (CPD * (1.f - q_i) + CL * q_i) * (t_i - t_1) + lv_i * q_i + gz_i;
+          CV(hm, i) = hm_i;
+          CV(tv, i) = t_i * (1.f + q_i * EPSI - q_i);
+          if (i >= MINORIG && hm_i < ahmin && hm_i < hm_m) {
+            ahmin = hm_i;
+            ihmin = i;
+          }
+          gz_m = gz_i; hm_m = hm_i; t_m = t_i; q_m = q_i; p_m = p_[u];
+        }
+      }
     }
   }
   ihmin = ihmin < nl - 1 ? ihmin : nl - 1;
@@ -277,16 +299,28 @@ FPB_HD inline bool conv_convect_head(ConvWork &w, int nl, float delt, float &cbm
   for (int i = 1; i <= nk; i++) {
     CV(ep, i) = 0.0f;
   }
-  for (int i = nk + 1; i <= nl; i++) {
-    const float tca = CV(tp, i) - 273.15f;
-    float elacrit;
-    if (tca >= 0.0f) elacrit = ELCRIT;
-    else elacrit = ELCRIT * (1.0f - tca / TLCRIT);
-    elacrit = c_max(elacrit, 0.0f);
-    const float epmax = 0.999f;
-    CV(ep, i) = epmax * (1.0f - elacrit / c_max(CV(clw, i), 1.0e-8f));
-    CV(ep, i) = c_max(CV(ep, i), 0.0f);
-    CV(ep, i) = c_min(CV(ep, i), epmax);
+  for (int i0 = nk + 1; i0 <= nl; i0 += 4) { // (four levels requested together; ep(i) formed in a register)
+    float tp_[4], cl_[4];
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u <= nl ? i0 + u : nl;
+      tp_[u] = CV(tp, i); cl_[u] = CV(clw, i);
+    }
+FPB_UNROLL(4)
+    for (int u = 0; u < 4; u++) {
+      if (i0 + u <= nl) {
+        const float tca = tp_[u] - 273.15f;
+        float elacrit;
+        if (tca >= 0.0f) elacrit = ELCRIT;
+        else elacrit = ELCRIT * (1.0f - tca / TLCRIT);
+        elacrit = c_max(elacrit, 0.0f);
+        const float epmax = 0.999f;
+        float ep_i = epmax * (1.0f - elacrit / c_max(cl_[u], 1.0e-8f));
+        ep_i = c_max(ep_i, 0.0f);
+        ep_i = c_min(ep_i, epmax);
+        CV(ep, i0 + u) = ep_i;
+      }
+    }
   }
   { // (four levels requested together: a store into one vector keeps the compiler from moving the next level's loads
     //  ahead of it, and the column kernel is bound by the latency of its loads)
