@@ -170,13 +170,14 @@ FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
     nst = nl;
     nsb = icb + 1;
   }
-  for (int i = nsb; i <= nst; i++) {
-    float tg = CV(tconv, i), qg = CV(qsconv, i);
-    float alv = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
+  for (int i = nsb; i <= nst; i++) { // (the level's inputs read once, tp / clw formed in registers)
+    const float t_i = CV(tconv, i), gz_i = CV(gz, i), p_i = CV(pconv_hpa, i);
+    float tg = t_i, qg = CV(qsconv, i);
+    float alv = LV0 - CPVMCL * (t_i - 273.15f);
     for (int j = 1; j <= 2; j++) {
-      float s = CPD + alv * alv * qg / (RV * CV(tconv, i) * CV(tconv, i));
+      float s = CPD + alv * alv * qg / (RV * t_i * t_i);
       s = 1.f / s;
-      const float ahg = CPD * tg + (CL - CPD) * qnk * CV(tconv, i) + alv * qg + CV(gz, i);
+      const float ahg = CPD * tg + (CL - CPD) * qnk * t_i + alv * qg + gz_i;
       tg = tg + s * (ah0 - ahg);
       tg = c_max(tg, 35.0f);
       const float tc = tg - 273.15f;
@@ -184,14 +185,16 @@ FPB_HD inline void conv_tlift(ConvWork &w, int icb, int nk, int nl, int kk) {
       float es;
       if (tc >= 0.0f) es = 6.112f * c_exp(17.67f * tc / denom);
       else es = c_exp(23.33086f - 6111.72784f / tg + 0.15215f * c_log(tg));
-      qg = EPS0 * es / (CV(pconv_hpa, i) - es * (1.f - EPS0));
+      qg = EPS0 * es / (p_i - es * (1.f - EPS0));
     }
-    alv = LV0 - CPVMCL * (CV(tconv, i) - 273.15f);
-    CV(tp, i) = (ah0 - (CL - CPD) * qnk * CV(tconv, i) - CV(gz, i) - alv * qg) / CPD;
-    CV(clw, i) = qnk - qg;
-    CV(clw, i) = c_max(0.0f, CV(clw, i));
+    alv = LV0 - CPVMCL * (t_i - 273.15f);
+    const float tp_i = (ah0 - (CL - CPD) * qnk * t_i - gz_i - alv * qg) / CPD;
+    CV(tp, i) = tp_i;
+    float clw_i = qnk - qg;
+    clw_i = c_max(0.0f, clw_i);
+    CV(clw, i) = clw_i;
     const float rg = qg / (1.f - qnk);
-    CV(tvp, i) = CV(tp, i) * (1.f + rg * EPSI);
+    CV(tvp, i) = tp_i * (1.f + rg * EPSI);
   }
 }
 
