@@ -2623,8 +2623,9 @@ extern "C" int fpb_convmix(fpb_handle *h, int32_t itime, int32_t *ncolumns, int3
   const int n = h->active_rows >= 0 ? h->active_rows : h->numpart;
   if (n <= 0) return 0;
   const bool refrng = c.rng_mode == FPB_RNG_REFERENCE;
-  // the column kernel is latency-bound (one thread per column walking its own work slice): as many
-  // columns at once as a quarter of the free device memory holds, at most 32768
+  // the column kernels want as many columns at once as possible (fpb_convect.cu): as many as a quarter of
+  // the free device memory holds (80-140 KB of interleaved work slice + 130 KB of per-column matrices each at
+  // 138 levels), at most 65536
   const size_t pf = fpb_convmix_pool_floats(V.nuvz, V.nconvlev);
   if (!V.pool) {
     size_t free_b = 0, total_b = 0;
